@@ -1,0 +1,1099 @@
+"""Mini MJCF compiler: MJCF XML -> MjModel-like numpy object (host side, not the hot path).
+
+The reference delegates model compilation to the `mujoco` C library
+(`/root/reference/mujoco_warp/_src/cli.py:78-100`: MjSpec.from_file -> compile), which is not
+installed in this image.  This module restates the documented MuJoCo compilation semantics for the
+MJCF subset used by the BASELINE scenes (defaults/classes, fromto capsules, spheres, boxes, planes,
+hinge/slide/ball/free joints, motor/position/velocity/general actuators, cameras/lights, keyframes,
+contact excludes, explicit <inertial>).  Its output exposes MjModel-named numpy attributes so that
+`io.put_model` can copy fields by name exactly like `/root/reference/mujoco_warp/_src/io.py:426`.
+
+Constants that need computation rather than parsing (body inertia from geoms, subtreemass,
+rbound/aabb, invweight0, meaninertia, cam/light reference poses, CSR sparsity of M) are derived here;
+SURVEY.md Appendix C lists them.  `put_model` also accepts a real `mujoco.MjModel` when that package
+exists, so this compiler is a stand-in, not a fork of the API.
+"""
+
+from __future__ import annotations
+
+import math
+import os
+import xml.etree.ElementTree as ET
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import constants as C
+
+# ----------------------------------------------------------------------------------------------
+# small math helpers (float64)
+# ----------------------------------------------------------------------------------------------
+
+
+def _vec(s, n=None, default=None):
+  if s is None:
+    return None if default is None else np.array(default, dtype=np.float64)
+  v = np.array([float(x) for x in s.split()], dtype=np.float64)
+  if n is not None and v.size < n and default is not None:
+    d = np.array(default, dtype=np.float64)
+    d[: v.size] = v
+    v = d
+  return v
+
+
+def quat_mul(a, b):
+  return np.array(
+    [
+      a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+      a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+      a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1],
+      a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0],
+    ]
+  )
+
+
+def quat_to_mat(q):
+  w, x, y, z = q
+  return np.array(
+    [
+      [w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+      [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+      [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z],
+    ]
+  )
+
+
+def mat_to_quat(R):
+  """Rotation matrix -> unit quaternion (w,x,y,z), w >= 0 branch-stable."""
+  t = np.trace(R)
+  if t > 0:
+    s = math.sqrt(t + 1.0) * 2
+    q = np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+  elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+    s = math.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2]) * 2
+    q = np.array([(R[2, 1] - R[1, 2]) / s, 0.25 * s, (R[0, 1] + R[1, 0]) / s, (R[0, 2] + R[2, 0]) / s])
+  elif R[1, 1] > R[2, 2]:
+    s = math.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2]) * 2
+    q = np.array([(R[0, 2] - R[2, 0]) / s, (R[0, 1] + R[1, 0]) / s, 0.25 * s, (R[1, 2] + R[2, 1]) / s])
+  else:
+    s = math.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]) * 2
+    q = np.array([(R[1, 0] - R[0, 1]) / s, (R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s])
+  q /= np.linalg.norm(q)
+  if q[0] < 0:
+    q = -q
+  return q
+
+
+def rot_vec(q, v):
+  return quat_to_mat(q) @ v
+
+
+def axis_angle_quat(axis, angle):
+  axis = np.asarray(axis, dtype=np.float64)
+  n = np.linalg.norm(axis)
+  if n < 1e-14:
+    return np.array([1.0, 0, 0, 0])
+  axis = axis / n
+  return np.concatenate([[math.cos(angle / 2)], math.sin(angle / 2) * axis])
+
+
+def z2quat(vec):
+  """Quaternion rotating the z axis onto `vec` (MuJoCo mjuu_z2quat semantics)."""
+  vec = np.asarray(vec, dtype=np.float64)
+  n = np.linalg.norm(vec)
+  if n < 1e-14:
+    return np.array([1.0, 0, 0, 0])
+  vec = vec / n
+  axis = np.cross([0.0, 0.0, 1.0], vec)
+  a = np.linalg.norm(axis)
+  if a < 1e-10:
+    if vec[2] < 0:
+      return np.array([0.0, 1.0, 0.0, 0.0])
+    return np.array([1.0, 0, 0, 0])
+  ang = math.atan2(a, vec[2])
+  return axis_angle_quat(axis / a, ang)
+
+
+def _frame_quat(attr, compiler):
+  """Resolve quat / axisangle / euler / xyaxes / zaxis orientation attributes."""
+  deg = compiler["angle"] == "degree"
+  if "quat" in attr:
+    q = _vec(attr["quat"])
+    return q / np.linalg.norm(q)
+  if "axisangle" in attr:
+    v = _vec(attr["axisangle"])
+    ang = math.radians(v[3]) if deg else v[3]
+    return axis_angle_quat(v[:3], ang)
+  if "euler" in attr:
+    e = _vec(attr["euler"])
+    if deg:
+      e = np.radians(e)
+    seq = compiler["eulerseq"]
+    q = np.array([1.0, 0, 0, 0])
+    for i, ch in enumerate(seq):
+      ax = {"x": [1, 0, 0], "y": [0, 1, 0], "z": [0, 0, 1]}[ch.lower()]
+      qi = axis_angle_quat(ax, e[i])
+      q = quat_mul(q, qi) if ch.islower() else quat_mul(qi, q)
+    return q / np.linalg.norm(q)
+  if "xyaxes" in attr:
+    v = _vec(attr["xyaxes"])
+    x = v[:3] / np.linalg.norm(v[:3])
+    y = v[3:] - x * np.dot(x, v[3:])
+    y = y / np.linalg.norm(y)
+    z = np.cross(x, y)
+    return mat_to_quat(np.stack([x, y, z], axis=1))
+  if "zaxis" in attr:
+    return z2quat(_vec(attr["zaxis"]))
+  return np.array([1.0, 0, 0, 0])
+
+
+# ----------------------------------------------------------------------------------------------
+# geom helpers
+# ----------------------------------------------------------------------------------------------
+
+_GEOM_TYPES = {
+  "plane": C.GEOM_PLANE,
+  "hfield": C.GEOM_HFIELD,
+  "sphere": C.GEOM_SPHERE,
+  "capsule": C.GEOM_CAPSULE,
+  "ellipsoid": C.GEOM_ELLIPSOID,
+  "cylinder": C.GEOM_CYLINDER,
+  "box": C.GEOM_BOX,
+  "mesh": C.GEOM_MESH,
+}
+
+
+def _geom_volume_inertia(gtype, size):
+  """Volume and unit-density principal inertia of a primitive in its own frame."""
+  r = size[0]
+  if gtype == C.GEOM_SPHERE:
+    vol = 4.0 / 3.0 * math.pi * r**3
+    i = 0.4 * vol * r * r
+    return vol, np.array([i, i, i])
+  if gtype == C.GEOM_CAPSULE:
+    h = 2.0 * size[1]
+    vc = math.pi * r * r * h
+    vs = 4.0 / 3.0 * math.pi * r**3
+    ixy = vc * (3 * r * r + h * h) / 12.0 + vs * (0.4 * r * r + 0.375 * r * h + 0.25 * h * h)
+    iz = vc * r * r / 2.0 + vs * 0.4 * r * r
+    return vc + vs, np.array([ixy, ixy, iz])
+  if gtype == C.GEOM_CYLINDER:
+    h = 2.0 * size[1]
+    vol = math.pi * r * r * h
+    ixy = vol * (3 * r * r + h * h) / 12.0
+    return vol, np.array([ixy, ixy, vol * r * r / 2.0])
+  if gtype == C.GEOM_BOX:
+    a, b, c = size
+    vol = 8.0 * a * b * c
+    return vol, vol / 3.0 * np.array([b * b + c * c, a * a + c * c, a * a + b * b])
+  if gtype == C.GEOM_ELLIPSOID:
+    a, b, c = size
+    vol = 4.0 / 3.0 * math.pi * a * b * c
+    return vol, vol / 5.0 * np.array([b * b + c * c, a * a + c * c, a * a + b * b])
+  return 0.0, np.zeros(3)
+
+
+def _geom_rbound(gtype, size):
+  if gtype == C.GEOM_SPHERE:
+    return size[0]
+  if gtype == C.GEOM_CAPSULE:
+    return size[0] + size[1]
+  if gtype == C.GEOM_CYLINDER:
+    return math.sqrt(size[0] ** 2 + size[1] ** 2)
+  if gtype == C.GEOM_ELLIPSOID:
+    return max(size)
+  if gtype == C.GEOM_BOX:
+    return float(np.linalg.norm(size))
+  return 0.0  # plane / hfield: 0 marks "unbounded" (reference collision_driver.py:318-320)
+
+
+def _geom_aabb(gtype, size):
+  """(center[3], halfsize[3]) in the geom frame."""
+  if gtype == C.GEOM_SPHERE:
+    hs = [size[0]] * 3
+  elif gtype == C.GEOM_CAPSULE:
+    hs = [size[0], size[0], size[0] + size[1]]
+  elif gtype == C.GEOM_CYLINDER:
+    hs = [size[0], size[0], size[1]]
+  elif gtype in (C.GEOM_ELLIPSOID, C.GEOM_BOX):
+    hs = list(size)
+  else:
+    hs = [C.MJ_MAXVAL, C.MJ_MAXVAL, C.MJ_MAXVAL]
+  return np.array([0.0, 0.0, 0.0] + hs)
+
+
+# ----------------------------------------------------------------------------------------------
+# defaults
+# ----------------------------------------------------------------------------------------------
+
+_ACT_TAGS = ("general", "motor", "position", "velocity", "intvelocity", "damper", "cylinder", "muscle", "adhesion")
+
+
+class _Defaults:
+  def __init__(self):
+    self.classes = {"main": {}}
+    self.parent = {"main": None}
+
+  def parse(self, elem, parent="main"):
+    name = elem.get("class", "main") if parent is not None else "main"
+    if name not in self.classes:
+      self.classes[name] = {}
+      self.parent[name] = parent
+    for child in elem:
+      if child.tag == "default":
+        self.parse(child, name)
+      else:
+        tag = "actuator" if child.tag in _ACT_TAGS else child.tag
+        self.classes[name].setdefault(tag, {}).update(child.attrib)
+
+  def resolve(self, tag, cls):
+    tag = "actuator" if tag in _ACT_TAGS else tag
+    chain = []
+    c = cls if cls in self.classes else "main"
+    while c is not None:
+      chain.append(c)
+      c = self.parent[c]
+    out = {}
+    for c in reversed(chain):
+      out.update(self.classes[c].get(tag, {}))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# compiler
+# ----------------------------------------------------------------------------------------------
+
+
+def _expand_includes(root, basedir):
+  for parent in list(root.iter()):
+    for i, child in enumerate(list(parent)):
+      if child.tag == "include":
+        sub = ET.parse(os.path.join(basedir, child.get("file"))).getroot()
+        _expand_includes(sub, basedir)
+        parent.remove(child)
+        for j, sc in enumerate(list(sub)):
+          parent.insert(i + j, sc)
+  return root
+
+
+def _merge_toplevel(root):
+  """Merge repeated top-level sections (from includes) into one element per tag."""
+  merged = {}
+  for child in list(root):
+    if child.tag in merged and child.tag in ("worldbody", "asset", "actuator", "keyframe", "contact", "sensor", "default"):
+      tgt = merged[child.tag]
+      for sc in list(child):
+        tgt.append(sc)
+      root.remove(child)
+    else:
+      merged.setdefault(child.tag, child)
+  return root
+
+
+def load(path: str):
+  """Compile an MJCF file into an MjModel-like object."""
+  root = ET.parse(path).getroot()
+  _expand_includes(root, os.path.dirname(os.path.abspath(path)))
+  return compile_xml(root)
+
+
+def load_string(xml: str):
+  return compile_xml(ET.fromstring(xml))
+
+
+def compile_xml(root):
+  # a model included inside <mujoco> contributes its own top-level sections
+  flat = ET.Element("mujoco", root.attrib)
+  for child in list(root):
+    if child.tag == "mujoco":
+      for sc in child:
+        flat.append(sc)
+    else:
+      flat.append(child)
+  root = _merge_toplevel(flat)
+
+  compiler = {"angle": "degree", "eulerseq": "xyz", "autolimits": True, "inertiafromgeom": "auto", "boundmass": 0.0, "boundinertia": 0.0}
+  for ce in root.findall("compiler"):
+    if "angle" in ce.attrib:
+      compiler["angle"] = ce.get("angle")
+    if "eulerseq" in ce.attrib:
+      compiler["eulerseq"] = ce.get("eulerseq")
+    if "autolimits" in ce.attrib:
+      compiler["autolimits"] = ce.get("autolimits") == "true"
+    if "inertiafromgeom" in ce.attrib:
+      compiler["inertiafromgeom"] = ce.get("inertiafromgeom")
+    if "boundmass" in ce.attrib:
+      compiler["boundmass"] = float(ce.get("boundmass"))
+    if "boundinertia" in ce.attrib:
+      compiler["boundinertia"] = float(ce.get("boundinertia"))
+  deg = compiler["angle"] == "degree"
+
+  # ---- options
+  opt = SimpleNamespace(
+    timestep=0.002,
+    tolerance=1e-8,
+    ls_tolerance=0.01,
+    gravity=np.array([0.0, 0.0, -9.81]),
+    integrator=C.INT_EULER,
+    cone=C.CONE_PYRAMIDAL,
+    solver=C.SOL_NEWTON,
+    iterations=100,
+    ls_iterations=50,
+    disableflags=0,
+    enableflags=0,
+    impratio=1.0,
+    jacobian=C.JAC_AUTO,
+  )
+  for oe in root.findall("option"):
+    a = oe.attrib
+    for k in ("timestep", "tolerance", "ls_tolerance", "impratio"):
+      if k in a:
+        setattr(opt, k, float(a[k]))
+    for k in ("iterations", "ls_iterations"):
+      if k in a:
+        setattr(opt, k, int(a[k]))
+    if "gravity" in a:
+      opt.gravity = _vec(a["gravity"])
+    if "integrator" in a:
+      opt.integrator = {"Euler": C.INT_EULER, "RK4": C.INT_RK4, "implicit": C.INT_IMPLICIT, "implicitfast": C.INT_IMPLICITFAST}[a["integrator"]]
+    if "cone" in a:
+      opt.cone = {"pyramidal": C.CONE_PYRAMIDAL, "elliptic": C.CONE_ELLIPTIC}[a["cone"]]
+    if "solver" in a:
+      opt.solver = {"PGS": 0, "CG": C.SOL_CG, "Newton": C.SOL_NEWTON}[a["solver"]]
+    if "jacobian" in a:
+      opt.jacobian = {"dense": C.JAC_DENSE, "sparse": C.JAC_SPARSE, "auto": C.JAC_AUTO}[a["jacobian"]]
+    for fe in oe.findall("flag"):
+      for k, v in fe.attrib.items():
+        if k in C.DISABLE_FLAGS:
+          if v == "disable":
+            opt.disableflags |= C.DISABLE_FLAGS[k]
+        elif k in C.ENABLE_FLAGS:
+          if v == "enable":
+            opt.enableflags |= C.ENABLE_FLAGS[k]
+
+  # ---- defaults
+  dflt = _Defaults()
+  for de in root.findall("default"):
+    dflt.parse(de, None)
+
+  bodies, joints, geoms, sites, cams, lights = [], [], [], [], [], []
+  skipped_mesh_geoms = 0
+
+  def attrs(elem, childclass):
+    cls = elem.get("class", childclass)
+    out = dflt.resolve(elem.tag, cls if cls is not None else "main")
+    out.update(elem.attrib)
+    return out
+
+  def add_body(elem, parentid, childclass):
+    nonlocal skipped_mesh_geoms
+    bid = len(bodies)
+    if parentid < 0:
+      b = dict(name="world", parentid=0, pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]), inertial=None, gravcomp=0.0, mocap=False)
+    else:
+      b = dict(
+        name=elem.get("name", f"body{bid}"),
+        parentid=parentid,
+        pos=_vec(elem.get("pos"), default=[0, 0, 0]),
+        quat=_frame_quat(elem.attrib, compiler),
+        inertial=None,
+        gravcomp=float(elem.get("gravcomp", 0.0)),
+        mocap=elem.get("mocap", "false") == "true",
+      )
+      childclass = elem.get("childclass", childclass)
+    b["jntadr"], b["jntnum"], b["geomadr"], b["geomnum"] = -1, 0, -1, 0
+    bodies.append(b)
+    for child in elem:
+      tag = child.tag
+      if tag == "inertial":
+        a = child.attrib
+        pos = _vec(a.get("pos"), default=[0, 0, 0])
+        quat = _frame_quat(a, compiler)
+        mass = float(a["mass"])
+        if "diaginertia" in a:
+          inertia = _vec(a["diaginertia"])
+        else:
+          f = _vec(a["fullinertia"])
+          full = np.array([[f[0], f[3], f[4]], [f[3], f[1], f[5]], [f[4], f[5], f[2]]])
+          full = quat_to_mat(quat) @ full @ quat_to_mat(quat).T
+          inertia, quat = _principal(full)
+        b["inertial"] = (pos, quat, mass, inertia)
+      elif tag in ("joint", "freejoint"):
+        a = attrs(child, childclass) if tag == "joint" else dict(child.attrib, type="free")
+        jtype = {"free": C.JNT_FREE, "ball": C.JNT_BALL, "slide": C.JNT_SLIDE, "hinge": C.JNT_HINGE}[a.get("type", "hinge")]
+        rng = _vec(a.get("range"), default=[0, 0])
+        if jtype in (C.JNT_HINGE, C.JNT_BALL) and deg:
+          rng = np.radians(rng)
+        lim = a.get("limited", "auto")
+        limited = (lim == "true") or (lim == "auto" and compiler["autolimits"] and "range" in a)
+        afr = _vec(a.get("actuatorfrcrange"), default=[0, 0])
+        afl = a.get("actuatorfrclimited", "auto")
+        actfrclimited = (afl == "true") or (afl == "auto" and compiler["autolimits"] and "actuatorfrcrange" in a)
+        ref = float(a.get("ref", 0.0))
+        sref = float(a.get("springref", 0.0))
+        if jtype == C.JNT_HINGE and deg:
+          ref, sref = math.radians(ref), math.radians(sref)
+        axis = _vec(a.get("axis"), default=[0, 0, 1])
+        if jtype in (C.JNT_FREE, C.JNT_BALL):
+          axis = np.array([0.0, 0.0, 1.0])
+        else:
+          axis = axis / np.linalg.norm(axis)
+        j = dict(
+          name=a.get("name", f"joint{len(joints)}"),
+          type=jtype,
+          bodyid=bid,
+          pos=_vec(a.get("pos"), default=[0, 0, 0]),
+          axis=axis,
+          range=rng,
+          limited=bool(limited),
+          stiffness=float(a.get("stiffness", 0.0)),
+          damping=float(a.get("damping", 0.0)),
+          armature=float(a.get("armature", 0.0)),
+          frictionloss=float(a.get("frictionloss", 0.0)),
+          margin=float(a.get("margin", 0.0)),
+          ref=ref,
+          springref=sref,
+          solreflimit=_vec(a.get("solreflimit"), default=C.DEFAULT_SOLREF),
+          solimplimit=_vec(a.get("solimplimit"), 5, default=C.DEFAULT_SOLIMP),
+          solreffriction=_vec(a.get("solreffriction"), default=C.DEFAULT_SOLREF),
+          solimpfriction=_vec(a.get("solimpfriction"), 5, default=C.DEFAULT_SOLIMP),
+          actfrclimited=bool(actfrclimited),
+          actfrcrange=afr,
+          actgravcomp=a.get("actuatorgravcomp", "false") == "true",
+        )
+        if jtype == C.JNT_FREE:
+          j.update(limited=False, stiffness=float(a.get("stiffness", 0.0)), damping=float(a.get("damping", 0.0)), armature=float(a.get("armature", 0.0)))
+        if b["jntnum"] == 0:
+          b["jntadr"] = len(joints)
+        b["jntnum"] += 1
+        joints.append(j)
+      elif tag == "geom":
+        a = attrs(child, childclass)
+        gtype = _GEOM_TYPES[a.get("type", "sphere")]
+        if "mesh" in a and "type" not in a:
+          gtype = C.GEOM_MESH
+        if gtype == C.GEOM_MESH:
+          # mesh assets are not in the tree (visual STL); only visual (non-colliding, massless) ones can be skipped
+          if int(a.get("contype", 1)) == 0 and int(a.get("conaffinity", 1)) == 0 and (float(a.get("density", 1000)) == 0 or "mass" in a and float(a["mass"]) == 0):
+            skipped_mesh_geoms += 1
+            continue
+          raise NotImplementedError("colliding / massive mesh geoms need mesh assets and convex hulls (SURVEY.md §7: out of scope offline)")
+        size = _vec(a.get("size"), 3, default=[0, 0, 0])
+        pos = _vec(a.get("pos"), default=[0, 0, 0])
+        quat = _frame_quat(a, compiler)
+        if "fromto" in a:
+          ft = _vec(a["fromto"])
+          vec = ft[0:3] - ft[3:6]
+          pos = 0.5 * (ft[0:3] + ft[3:6])
+          quat = z2quat(vec)
+          half = 0.5 * np.linalg.norm(vec)
+          if gtype in (C.GEOM_CAPSULE, C.GEOM_CYLINDER):
+            size = np.array([size[0], half, 0.0])
+          elif gtype in (C.GEOM_BOX, C.GEOM_ELLIPSOID):
+            size = np.array([size[0], size[0], half])
+        fr = _vec(a.get("friction"), 3, default=C.DEFAULT_FRICTION)
+        g = dict(
+          name=a.get("name", f"geom{len(geoms)}"),
+          type=gtype,
+          bodyid=bid,
+          size=size,
+          pos=pos,
+          quat=quat,
+          contype=int(a.get("contype", 1)),
+          conaffinity=int(a.get("conaffinity", 1)),
+          condim=int(a.get("condim", 3)),
+          priority=int(a.get("priority", 0)),
+          friction=fr,
+          solmix=float(a.get("solmix", 1.0)),
+          solref=_vec(a.get("solref"), default=C.DEFAULT_SOLREF),
+          solimp=_vec(a.get("solimp"), 5, default=C.DEFAULT_SOLIMP),
+          margin=float(a.get("margin", 0.0)),
+          gap=float(a.get("gap", 0.0)),
+          density=float(a.get("density", 1000.0)),
+          mass=float(a["mass"]) if "mass" in a else None,
+          group=int(a.get("group", 0)),
+        )
+        if b["geomnum"] == 0:
+          b["geomadr"] = len(geoms)
+        b["geomnum"] += 1
+        geoms.append(g)
+      elif tag == "site":
+        a = attrs(child, childclass)
+        sites.append(dict(name=a.get("name", f"site{len(sites)}"), bodyid=bid, pos=_vec(a.get("pos"), default=[0, 0, 0]), quat=_frame_quat(a, compiler)))
+      elif tag == "camera":
+        a = attrs(child, childclass)
+        cams.append(dict(name=a.get("name", f"cam{len(cams)}"), bodyid=bid, pos=_vec(a.get("pos"), default=[0, 0, 0]), quat=_frame_quat(a, compiler), mode=C.CAMLIGHT_MODES[a.get("mode", "fixed")], target=a.get("target")))
+      elif tag == "light":
+        a = attrs(child, childclass)
+        d = _vec(a.get("dir"), default=[0, 0, -1])
+        lights.append(dict(name=a.get("name", f"light{len(lights)}"), bodyid=bid, pos=_vec(a.get("pos"), default=[0, 0, 0]), dir=d / np.linalg.norm(d), mode=C.CAMLIGHT_MODES[a.get("mode", "fixed")], target=a.get("target")))
+      elif tag == "body":
+        pass
+    for child in elem:
+      if child.tag == "body":
+        add_body(child, bid, childclass)
+
+  # MuJoCo numbers bodies depth-first with all of a body's own elements before its children,
+  # but children are visited in document order AFTER the parent's elements: emulate by recursion.
+  wb = root.find("worldbody")
+  add_body(wb, -1, None)
+
+  nbody, njnt, ngeom = len(bodies), len(joints), len(geoms)
+
+  m = SimpleNamespace()
+  m.opt = opt
+  m.skipped_mesh_geoms = skipped_mesh_geoms
+  m.names = SimpleNamespace(
+    body=[b["name"] for b in bodies], joint=[j["name"] for j in joints], geom=[g["name"] for g in geoms],
+    site=[s["name"] for s in sites], camera=[c["name"] for c in cams], light=[l["name"] for l in lights],
+  )
+
+  # ---- bodies
+  m.nbody = nbody
+  m.body_parentid = np.array([b["parentid"] for b in bodies], dtype=np.int32)
+  m.body_pos = np.array([b["pos"] for b in bodies])
+  m.body_quat = np.array([b["quat"] for b in bodies])
+  m.body_jntnum = np.array([b["jntnum"] for b in bodies], dtype=np.int32)
+  m.body_jntadr = np.array([b["jntadr"] for b in bodies], dtype=np.int32)
+  m.body_geomnum = np.array([b["geomnum"] for b in bodies], dtype=np.int32)
+  m.body_geomadr = np.array([b["geomadr"] for b in bodies], dtype=np.int32)
+  m.body_gravcomp = np.array([b["gravcomp"] for b in bodies])
+  mocapid = -np.ones(nbody, dtype=np.int32)
+  nm = 0
+  for i, b in enumerate(bodies):
+    if b["mocap"]:
+      mocapid[i] = nm
+      nm += 1
+  m.body_mocapid = mocapid
+  m.nmocap = nm
+
+  # ---- joints / dofs
+  m.njnt = njnt
+  m.jnt_type = np.array([j["type"] for j in joints], dtype=np.int32)
+  m.jnt_bodyid = np.array([j["bodyid"] for j in joints], dtype=np.int32)
+  qn = {C.JNT_FREE: 7, C.JNT_BALL: 4, C.JNT_SLIDE: 1, C.JNT_HINGE: 1}
+  vn = {C.JNT_FREE: 6, C.JNT_BALL: 3, C.JNT_SLIDE: 1, C.JNT_HINGE: 1}
+  qadr, dadr = [], []
+  nq = nv = 0
+  for j in joints:
+    qadr.append(nq)
+    dadr.append(nv)
+    nq += qn[j["type"]]
+    nv += vn[j["type"]]
+  m.nq, m.nv = nq, nv
+  m.jnt_qposadr = np.array(qadr, dtype=np.int32)
+  m.jnt_dofadr = np.array(dadr, dtype=np.int32)
+  m.jnt_pos = np.array([j["pos"] for j in joints]).reshape(njnt, 3)
+  m.jnt_axis = np.array([j["axis"] for j in joints]).reshape(njnt, 3)
+  m.jnt_range = np.array([j["range"] for j in joints]).reshape(njnt, 2)
+  m.jnt_limited = np.array([j["limited"] for j in joints], dtype=bool)
+  m.jnt_stiffness = np.array([j["stiffness"] for j in joints])
+  m.jnt_margin = np.array([j["margin"] for j in joints])
+  m.jnt_solref = np.array([j["solreflimit"] for j in joints]).reshape(njnt, 2)
+  m.jnt_solimp = np.array([j["solimplimit"] for j in joints]).reshape(njnt, 5)
+  m.jnt_actfrclimited = np.array([j["actfrclimited"] for j in joints], dtype=bool)
+  m.jnt_actfrcrange = np.array([j["actfrcrange"] for j in joints]).reshape(njnt, 2)
+  m.jnt_actgravcomp = np.array([j["actgravcomp"] for j in joints], dtype=np.int32)
+
+  m.body_dofnum = np.zeros(nbody, dtype=np.int32)
+  m.body_dofadr = -np.ones(nbody, dtype=np.int32)
+  for ji, j in enumerate(joints):
+    b = j["bodyid"]
+    if m.body_dofnum[b] == 0:
+      m.body_dofadr[b] = dadr[ji]
+    m.body_dofnum[b] += vn[j["type"]]
+
+  dof_bodyid, dof_jntid = [], []
+  dof_armature, dof_damping, dof_frictionloss = [], [], []
+  dof_solref, dof_solimp = [], []
+  qpos0 = np.zeros(nq)
+  qpos_spring = np.zeros(nq)
+  for ji, j in enumerate(joints):
+    for _ in range(vn[j["type"]]):
+      dof_bodyid.append(j["bodyid"])
+      dof_jntid.append(ji)
+      dof_armature.append(j["armature"])
+      dof_damping.append(j["damping"])
+      dof_frictionloss.append(j["frictionloss"])
+      dof_solref.append(j["solreffriction"])
+      dof_solimp.append(j["solimpfriction"])
+    qa = qadr[ji]
+    b = bodies[j["bodyid"]]
+    if j["type"] == C.JNT_FREE:
+      qpos0[qa : qa + 3] = b["pos"]
+      qpos0[qa + 3 : qa + 7] = b["quat"]
+      qpos_spring[qa : qa + 7] = qpos0[qa : qa + 7]
+    elif j["type"] == C.JNT_BALL:
+      qpos0[qa : qa + 4] = [1, 0, 0, 0]
+      qpos_spring[qa : qa + 4] = [1, 0, 0, 0]
+    else:
+      qpos0[qa] = j["ref"]
+      qpos_spring[qa] = j["springref"]
+  m.qpos0, m.qpos_spring = qpos0, qpos_spring
+  m.dof_bodyid = np.array(dof_bodyid, dtype=np.int32)
+  m.dof_jntid = np.array(dof_jntid, dtype=np.int32)
+  m.dof_armature = np.array(dof_armature)
+  m.dof_damping = np.array(dof_damping)
+  m.dof_frictionloss = np.array(dof_frictionloss)
+  m.dof_solref = np.array(dof_solref).reshape(nv, 2)
+  m.dof_solimp = np.array(dof_solimp).reshape(nv, 5)
+
+  # dof_parentid: previous dof in the same body, else last dof of the nearest ancestor with dofs
+  dof_parentid = -np.ones(nv, dtype=np.int32)
+  for d in range(nv):
+    b = m.dof_bodyid[d]
+    if d > m.body_dofadr[b]:
+      dof_parentid[d] = d - 1
+    else:
+      p = m.body_parentid[b]
+      while p > 0 and m.body_dofnum[p] == 0:
+        p = m.body_parentid[p]
+      if p > 0 or (p == 0 and m.body_dofnum[0] > 0):
+        if m.body_dofnum[p] > 0:
+          dof_parentid[d] = m.body_dofadr[p] + m.body_dofnum[p] - 1
+  m.dof_parentid = dof_parentid
+
+  # rootid / weldid / treeid
+  rootid = np.zeros(nbody, dtype=np.int32)
+  weldid = np.zeros(nbody, dtype=np.int32)
+  for b in range(1, nbody):
+    p = m.body_parentid[b]
+    rootid[b] = b if p == 0 else rootid[p]
+    weldid[b] = b if m.body_jntnum[b] > 0 else weldid[p]
+  m.body_rootid, m.body_weldid = rootid, weldid
+  treeid = -np.ones(nbody, dtype=np.int32)
+  ntree = 0
+  tree_dofadr, tree_dofnum = [], []
+  for b in range(1, nbody):
+    p = m.body_parentid[b]
+    if m.body_dofnum[b] > 0 and (p == 0 or treeid[p] < 0) and weldid[b] == b:
+      treeid[b] = ntree
+      tree_dofadr.append(int(m.body_dofadr[b]))
+      tree_dofnum.append(0)
+      ntree += 1
+    elif p > 0:
+      treeid[b] = treeid[p]
+  m.ntree = ntree
+  m.body_treeid = treeid
+  m.dof_treeid = np.array([treeid[b] for b in m.dof_bodyid], dtype=np.int32)
+  for d in range(nv):
+    tree_dofnum[m.dof_treeid[d]] += 1
+  m.tree_dofadr = np.array(tree_dofadr, dtype=np.int32)
+  m.tree_dofnum = np.array(tree_dofnum, dtype=np.int32)
+
+  # CSR lower-triangular M: row i holds ancestors of dof i in ascending order, diagonal last
+  rownnz, rowadr, colind = [], [], []
+  adr = 0
+  for i in range(nv):
+    chain = []
+    d = i
+    while d >= 0:
+      chain.append(d)
+      d = dof_parentid[d]
+    chain.reverse()
+    rownnz.append(len(chain))
+    rowadr.append(adr)
+    colind.extend(chain)
+    adr += len(chain)
+  m.M_rownnz = np.array(rownnz, dtype=np.int32)
+  m.M_rowadr = np.array(rowadr, dtype=np.int32)
+  m.M_colind = np.array(colind, dtype=np.int32)
+  m.nC = m.nM = adr
+  m.dof_Madr = (m.M_rowadr + m.M_rownnz - 1).astype(np.int32)
+
+  # ---- geoms
+  m.ngeom = ngeom
+  m.geom_type = np.array([g["type"] for g in geoms], dtype=np.int32)
+  m.geom_bodyid = np.array([g["bodyid"] for g in geoms], dtype=np.int32)
+  m.geom_contype = np.array([g["contype"] for g in geoms], dtype=np.int32)
+  m.geom_conaffinity = np.array([g["conaffinity"] for g in geoms], dtype=np.int32)
+  m.geom_condim = np.array([g["condim"] for g in geoms], dtype=np.int32)
+  m.geom_priority = np.array([g["priority"] for g in geoms], dtype=np.int32)
+  m.geom_dataid = -np.ones(ngeom, dtype=np.int32)
+  m.geom_size = np.array([g["size"] for g in geoms]).reshape(ngeom, 3)
+  m.geom_pos = np.array([g["pos"] for g in geoms]).reshape(ngeom, 3)
+  m.geom_quat = np.array([g["quat"] for g in geoms]).reshape(ngeom, 4)
+  m.geom_friction = np.array([g["friction"] for g in geoms]).reshape(ngeom, 3)
+  m.geom_solmix = np.array([g["solmix"] for g in geoms])
+  m.geom_solref = np.array([g["solref"] for g in geoms]).reshape(ngeom, 2)
+  m.geom_solimp = np.array([g["solimp"] for g in geoms]).reshape(ngeom, 5)
+  m.geom_margin = np.array([g["margin"] for g in geoms])
+  m.geom_gap = np.array([g["gap"] for g in geoms])
+  m.geom_rbound = np.array([_geom_rbound(g["type"], g["size"]) for g in geoms])
+  m.geom_aabb = np.array([_geom_aabb(g["type"], g["size"]) for g in geoms]).reshape(ngeom, 6)
+
+  # ---- body inertial properties
+  mass = np.zeros(nbody)
+  ipos = np.zeros((nbody, 3))
+  iquat = np.tile(np.array([1.0, 0, 0, 0]), (nbody, 1))
+  inertia = np.zeros((nbody, 3))
+  for bi, b in enumerate(bodies):
+    use_geoms = compiler["inertiafromgeom"] == "true" or (compiler["inertiafromgeom"] == "auto" and b["inertial"] is None)
+    if not use_geoms:
+      if b["inertial"] is not None:
+        ipos[bi], iquat[bi], mass[bi], inertia[bi] = b["inertial"]
+      continue
+    if bi == 0:
+      continue
+    gs = [g for g in geoms if g["bodyid"] == bi]
+    tot, com = 0.0, np.zeros(3)
+    parts = []
+    for g in gs:
+      vol, iu = _geom_volume_inertia(g["type"], g["size"])
+      if vol <= 0:
+        continue
+      gm = g["mass"] if g["mass"] is not None else g["density"] * vol
+      if gm <= 0:
+        continue
+      parts.append((gm, g["pos"], quat_to_mat(g["quat"]), iu * (gm / vol)))
+      tot += gm
+      com += gm * g["pos"]
+    if tot <= 0:
+      continue
+    com /= tot
+    full = np.zeros((3, 3))
+    for gm, gp, R, ig in parts:
+      d = gp - com
+      full += R @ np.diag(ig) @ R.T + gm * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+    inertia[bi], iquat[bi] = _principal(full)
+    mass[bi], ipos[bi] = tot, com
+  if compiler["boundmass"] > 0:
+    mass[1:] = np.maximum(mass[1:], compiler["boundmass"])
+  if compiler["boundinertia"] > 0:
+    inertia[1:] = np.maximum(inertia[1:], compiler["boundinertia"])
+  m.body_mass, m.body_ipos, m.body_iquat, m.body_inertia = mass, ipos, iquat, inertia
+  sub = mass.copy()
+  for b in range(nbody - 1, 0, -1):
+    sub[m.body_parentid[b]] += sub[b]
+  m.body_subtreemass = sub
+
+  # ---- sites / cameras / lights
+  m.nsite = len(sites)
+  m.site_bodyid = np.array([s["bodyid"] for s in sites], dtype=np.int32)
+  m.site_pos = np.array([s["pos"] for s in sites]).reshape(m.nsite, 3)
+  m.site_quat = np.array([s["quat"] for s in sites]).reshape(m.nsite, 4)
+
+  def body_id(name):
+    return m.names.body.index(name) if name is not None else -1
+
+  m.ncam = len(cams)
+  m.cam_mode = np.array([c["mode"] for c in cams], dtype=np.int32)
+  m.cam_bodyid = np.array([c["bodyid"] for c in cams], dtype=np.int32)
+  m.cam_targetbodyid = np.array([body_id(c["target"]) for c in cams], dtype=np.int32)
+  m.cam_pos = np.array([c["pos"] for c in cams]).reshape(m.ncam, 3)
+  m.cam_quat = np.array([c["quat"] for c in cams]).reshape(m.ncam, 4)
+  m.nlight = len(lights)
+  m.light_mode = np.array([l["mode"] for l in lights], dtype=np.int32)
+  m.light_bodyid = np.array([l["bodyid"] for l in lights], dtype=np.int32)
+  m.light_targetbodyid = np.array([body_id(l["target"]) for l in lights], dtype=np.int32)
+  m.light_pos = np.array([l["pos"] for l in lights]).reshape(m.nlight, 3)
+  m.light_dir = np.array([l["dir"] for l in lights]).reshape(m.nlight, 3)
+
+  # ---- actuators
+  acts = []
+  ae = root.find("actuator")
+  if ae is not None:
+    for child in ae:
+      if child.tag not in _ACT_TAGS:
+        continue
+      a = dflt.resolve(child.tag, child.get("class", "main"))
+      a.update(child.attrib)
+      acts.append((child.tag, a))
+  nu = len(acts)
+  m.nu = nu
+  m.na = 0
+  m.actuator_trntype = np.zeros(nu, dtype=np.int32)
+  m.actuator_dyntype = np.zeros(nu, dtype=np.int32)
+  m.actuator_gaintype = np.zeros(nu, dtype=np.int32)
+  m.actuator_biastype = np.zeros(nu, dtype=np.int32)
+  m.actuator_trnid = -np.ones((nu, 2), dtype=np.int32)
+  m.actuator_gear = np.zeros((nu, 6))
+  m.actuator_gainprm = np.zeros((nu, 10))
+  m.actuator_biasprm = np.zeros((nu, 10))
+  m.actuator_dynprm = np.zeros((nu, 10))
+  m.actuator_ctrllimited = np.zeros(nu, dtype=bool)
+  m.actuator_ctrlrange = np.zeros((nu, 2))
+  m.actuator_forcelimited = np.zeros(nu, dtype=bool)
+  m.actuator_forcerange = np.zeros((nu, 2))
+  m.actuator_actlimited = np.zeros(nu, dtype=bool)
+  m.actuator_actrange = np.zeros((nu, 2))
+  m.actuator_actadr = -np.ones(nu, dtype=np.int32)
+  m.actuator_actnum = np.zeros(nu, dtype=np.int32)
+  m.names.actuator = []
+  for i, (tag, a) in enumerate(acts):
+    m.names.actuator.append(a.get("name", f"actuator{i}"))
+    if "joint" not in a:
+      raise NotImplementedError(f"actuator transmission other than joint is not supported: {a}")
+    m.actuator_trntype[i] = C.TRN_JOINT
+    m.actuator_trnid[i, 0] = m.names.joint.index(a["joint"])
+    gear = _vec(a.get("gear"), 6, default=[1, 0, 0, 0, 0, 0])
+    m.actuator_gear[i] = gear
+    m.actuator_gainprm[i, 0] = 1.0
+    if tag == "general":
+      if a.get("dyntype", "none") != "none":
+        raise NotImplementedError("stateful actuators (na>0) are not supported")
+      m.actuator_gaintype[i] = {"fixed": C.GAIN_FIXED, "affine": C.GAIN_AFFINE}[a.get("gaintype", "fixed")]
+      m.actuator_biastype[i] = {"none": C.BIAS_NONE, "affine": C.BIAS_AFFINE}[a.get("biastype", "none")]
+      if "gainprm" in a:
+        gp = _vec(a["gainprm"])
+        m.actuator_gainprm[i, :] = 0
+        m.actuator_gainprm[i, : gp.size] = gp
+      if "biasprm" in a:
+        bp = _vec(a["biasprm"])
+        m.actuator_biasprm[i, : bp.size] = bp
+    elif tag == "motor":
+      pass
+    elif tag == "position":
+      kp = float(a.get("kp", 1.0))
+      kv = float(a.get("kv", 0.0))
+      m.actuator_gainprm[i, 0] = kp
+      m.actuator_biastype[i] = C.BIAS_AFFINE
+      m.actuator_biasprm[i, 1] = -kp
+      m.actuator_biasprm[i, 2] = -kv
+    elif tag == "velocity":
+      kv = float(a.get("kv", 1.0))
+      m.actuator_gainprm[i, 0] = kv
+      m.actuator_biastype[i] = C.BIAS_AFFINE
+      m.actuator_biasprm[i, 2] = -kv
+    else:
+      raise NotImplementedError(f"actuator shortcut <{tag}> is not supported")
+    for rng, lim in (("ctrlrange", "ctrllimited"), ("forcerange", "forcelimited")):
+      if rng in a:
+        getattr(m, "actuator_" + rng)[i] = _vec(a[rng])
+      l = a.get(lim, "auto")
+      getattr(m, "actuator_" + lim)[i] = (l == "true") or (l == "auto" and compiler["autolimits"] and rng in a)
+
+  # ---- contact excludes / pairs
+  excl = []
+  ce = root.find("contact")
+  if ce is not None:
+    for child in ce:
+      if child.tag == "exclude":
+        b1, b2 = body_id(child.get("body1")), body_id(child.get("body2"))
+        excl.append((min(b1, b2) << 16) + max(b1, b2))
+        excl.append((max(b1, b2) << 16) + min(b1, b2))
+      elif child.tag == "pair":
+        raise NotImplementedError("explicit contact pairs are not supported")
+  m.exclude_signature = np.array(excl, dtype=np.int64)
+  m.nexclude = len(excl) // 2
+  m.npair = 0
+
+  # unused families (sizes only)
+  m.neq = m.ntendon = m.nflex = m.nmesh = m.nhfield = m.nsensor = m.nsensordata = 0
+  nsens = root.find("sensor")
+  m.nsensor_ignored = 0 if nsens is None else len(list(nsens))
+
+  # ---- keyframes
+  keys = []
+  ke = root.find("keyframe")
+  if ke is not None:
+    for k in ke.findall("key"):
+      keys.append(k)
+  m.nkey = len(keys)
+  m.key_time = np.zeros(m.nkey)
+  m.key_qpos = np.tile(qpos0, (m.nkey, 1)).reshape(m.nkey, nq)
+  m.key_qvel = np.zeros((m.nkey, nv))
+  m.key_ctrl = np.zeros((m.nkey, nu))
+  m.key_act = np.zeros((m.nkey, 0))
+  m.names.key = []
+  for i, k in enumerate(keys):
+    m.names.key.append(k.get("name", f"key{i}"))
+    if "time" in k.attrib:
+      m.key_time[i] = float(k.get("time"))
+    for nm_, arr in (("qpos", m.key_qpos), ("qvel", m.key_qvel), ("ctrl", m.key_ctrl)):
+      if nm_ in k.attrib:
+        v = _vec(k.get(nm_))
+        if v.size != arr.shape[1]:
+          raise ValueError(f"keyframe {i} {nm_} has {v.size} values, expected {arr.shape[1]}")
+        arr[i] = v
+
+  _set_const(m)
+  return m
+
+
+def _principal(full):
+  """Principal inertia (descending) and the quaternion of the principal frame."""
+  w, V = np.linalg.eigh(0.5 * (full + full.T))
+  order = np.argsort(-w)
+  w, V = w[order], V[:, order]
+  if np.linalg.det(V) < 0:
+    V[:, 2] = -V[:, 2]
+  return w, mat_to_quat(V)
+
+
+# ----------------------------------------------------------------------------------------------
+# constants that need a forward pass at qpos0 (MuJoCo mj_setConst semantics; the reference
+# re-derives the same quantities on device in /root/reference/mujoco_warp/_src/set_const.py)
+# ----------------------------------------------------------------------------------------------
+
+
+def kinematics_np(m, qpos):
+  """Host FK at `qpos` (used for make_data static geoms and set_const)."""
+  nb = m.nbody
+  xpos = np.zeros((nb, 3))
+  xquat = np.tile(np.array([1.0, 0, 0, 0]), (nb, 1))
+  xanchor = np.zeros((m.njnt, 3))
+  xaxis = np.zeros((m.njnt, 3))
+  for b in range(1, nb):
+    p = m.body_parentid[b]
+    ja, jn = m.body_jntadr[b], m.body_jntnum[b]
+    if jn == 1 and m.jnt_type[ja] == C.JNT_FREE:
+      qa = m.jnt_qposadr[ja]
+      xpos[b] = qpos[qa : qa + 3]
+      q = qpos[qa + 3 : qa + 7]
+      xquat[b] = q / np.linalg.norm(q)
+      xanchor[ja] = xpos[b]
+      xaxis[ja] = m.jnt_axis[ja]
+      continue
+    pos = rot_vec(xquat[p], m.body_pos[b]) + xpos[p]
+    quat = quat_mul(xquat[p], m.body_quat[b])
+    for j in range(ja, ja + jn):
+      qa = m.jnt_qposadr[j]
+      anchor = rot_vec(quat, m.jnt_pos[j]) + pos
+      axis = rot_vec(quat, m.jnt_axis[j])
+      t = m.jnt_type[j]
+      if t == C.JNT_BALL:
+        ql = qpos[qa : qa + 4]
+        quat = quat_mul(quat, ql / np.linalg.norm(ql))
+        pos = anchor - rot_vec(quat, m.jnt_pos[j])
+      elif t == C.JNT_SLIDE:
+        pos = pos + axis * (qpos[qa] - m.qpos0[qa])
+      elif t == C.JNT_HINGE:
+        quat = quat_mul(quat, axis_angle_quat(m.jnt_axis[j], qpos[qa] - m.qpos0[qa]))
+        pos = anchor - rot_vec(quat, m.jnt_pos[j])
+      xanchor[j], xaxis[j] = anchor, axis
+    xpos[b] = pos
+    xquat[b] = quat / np.linalg.norm(quat)
+  out = SimpleNamespace(xpos=xpos, xquat=xquat, xanchor=xanchor, xaxis=xaxis)
+  out.xmat = np.array([quat_to_mat(q) for q in xquat])
+  out.xipos = np.array([xpos[b] + rot_vec(xquat[b], m.body_ipos[b]) for b in range(nb)])
+  out.ximat = np.array([quat_to_mat(quat_mul(xquat[b], m.body_iquat[b])) for b in range(nb)])
+  out.geom_xpos = np.array([xpos[m.geom_bodyid[g]] + rot_vec(xquat[m.geom_bodyid[g]], m.geom_pos[g]) for g in range(m.ngeom)]).reshape(m.ngeom, 3)
+  out.geom_xmat = np.array([quat_to_mat(quat_mul(xquat[m.geom_bodyid[g]], m.geom_quat[g])) for g in range(m.ngeom)]).reshape(m.ngeom, 3, 3)
+  out.site_xpos = np.array([xpos[m.site_bodyid[s]] + rot_vec(xquat[m.site_bodyid[s]], m.site_pos[s]) for s in range(m.nsite)]).reshape(m.nsite, 3)
+  out.site_xmat = np.array([quat_to_mat(quat_mul(xquat[m.site_bodyid[s]], m.site_quat[s])) for s in range(m.nsite)]).reshape(m.nsite, 3, 3)
+  # subtree com
+  sc = out.xipos * m.body_mass[:, None]
+  for b in range(nb - 1, 0, -1):
+    sc[m.body_parentid[b]] += sc[b]
+  for b in range(nb):
+    if m.body_subtreemass[b] > 0:
+      sc[b] = sc[b] / m.body_subtreemass[b]
+    else:
+      sc[b] = out.xipos[b]
+  out.subtree_com = sc
+  return out
+
+
+def _body_jacobians(m, kin, point_of_body):
+  """World-frame translational/rotational Jacobians (3 x nv each) of point_of_body[b] on body b."""
+  nv = m.nv
+  jacp = np.zeros((m.nbody, 3, nv))
+  jacr = np.zeros((m.nbody, 3, nv))
+  for b in range(1, m.nbody):
+    bb = b
+    while bb > 0:
+      ja, jn = m.body_jntadr[bb], m.body_jntnum[bb]
+      for j in range(ja, ja + jn):
+        d = m.jnt_dofadr[j]
+        t = m.jnt_type[j]
+        r = point_of_body[b] - kin.xanchor[j]
+        if t == C.JNT_FREE:
+          jacp[b, :, d : d + 3] = np.eye(3)
+          R = kin.xmat[bb]
+          for k in range(3):
+            jacr[b, :, d + 3 + k] = R[:, k]
+            jacp[b, :, d + 3 + k] = np.cross(R[:, k], point_of_body[b] - kin.xpos[bb])
+        elif t == C.JNT_BALL:
+          R = kin.xmat[bb]
+          for k in range(3):
+            jacr[b, :, d + k] = R[:, k]
+            jacp[b, :, d + k] = np.cross(R[:, k], r)
+        elif t == C.JNT_SLIDE:
+          jacp[b, :, d] = kin.xaxis[j]
+        else:
+          jacr[b, :, d] = kin.xaxis[j]
+          jacp[b, :, d] = np.cross(kin.xaxis[j], r)
+      bb = m.body_parentid[bb]
+  return jacp, jacr
+
+
+def dense_inertia_np(m, kin):
+  """Joint-space inertia at the configuration in `kin` via sum_b J_b^T I_b J_b (+ armature)."""
+  jacp, jacr = _body_jacobians(m, kin, kin.xipos)
+  M = np.diag(m.dof_armature.astype(np.float64))
+  for b in range(1, m.nbody):
+    Ib = kin.ximat[b] @ np.diag(m.body_inertia[b]) @ kin.ximat[b].T
+    M = M + m.body_mass[b] * jacp[b].T @ jacp[b] + jacr[b].T @ Ib @ jacr[b]
+  return M, jacp, jacr
+
+
+def _set_const(m):
+  kin = kinematics_np(m, m.qpos0)
+  nv = m.nv
+  m.body_invweight0 = np.zeros((m.nbody, 2))
+  m.dof_invweight0 = np.zeros(nv)
+  m.actuator_acc0 = np.zeros(m.nu)
+  if nv > 0:
+    M, jacp, jacr = dense_inertia_np(m, kin)
+    Minv = np.linalg.inv(M)
+    m.stat = SimpleNamespace(meaninertia=max(C.MJ_MINVAL, float(np.trace(M)) / nv))
+    for b in range(1, m.nbody):
+      if m.body_weldid[b] == 0:
+        continue
+      A = jacp[b] @ Minv @ jacp[b].T
+      B = jacr[b] @ Minv @ jacr[b].T
+      m.body_invweight0[b, 0] = np.trace(A) / 3.0
+      m.body_invweight0[b, 1] = np.trace(B) / 3.0
+    dg = np.diag(Minv)
+    for j in range(m.njnt):
+      d = m.jnt_dofadr[j]
+      t = m.jnt_type[j]
+      if t == C.JNT_FREE:
+        m.dof_invweight0[d : d + 3] = dg[d : d + 3].mean()
+        m.dof_invweight0[d + 3 : d + 6] = dg[d + 3 : d + 6].mean()
+      elif t == C.JNT_BALL:
+        m.dof_invweight0[d : d + 3] = dg[d : d + 3].mean()
+      else:
+        m.dof_invweight0[d] = dg[d]
+    for i in range(m.nu):
+      mom = np.zeros(nv)
+      j = m.actuator_trnid[i, 0]
+      mom[m.jnt_dofadr[j]] = m.actuator_gear[i, 0]
+      m.actuator_acc0[i] = np.linalg.norm(Minv @ mom)
+  else:
+    m.stat = SimpleNamespace(meaninertia=1.0)
+
+  # camera / light reference poses at qpos0 (used by track/trackcom modes; reference smooth.py:858-983)
+  cam_xpos = np.array([kin.xpos[m.cam_bodyid[c]] + rot_vec(kin.xquat[m.cam_bodyid[c]], m.cam_pos[c]) for c in range(m.ncam)]).reshape(m.ncam, 3)
+  cam_xmat = np.array([quat_to_mat(quat_mul(kin.xquat[m.cam_bodyid[c]], m.cam_quat[c])) for c in range(m.ncam)]).reshape(m.ncam, 3, 3)
+  m.cam_pos0 = np.array([cam_xpos[c] - kin.xpos[m.cam_bodyid[c]] for c in range(m.ncam)]).reshape(m.ncam, 3)
+  m.cam_poscom0 = np.array([cam_xpos[c] - kin.subtree_com[m.cam_bodyid[c]] for c in range(m.ncam)]).reshape(m.ncam, 3)
+  m.cam_mat0 = cam_xmat
+  l_xpos = np.array([kin.xpos[m.light_bodyid[l]] + rot_vec(kin.xquat[m.light_bodyid[l]], m.light_pos[l]) for l in range(m.nlight)]).reshape(m.nlight, 3)
+  l_xdir = np.array([rot_vec(kin.xquat[m.light_bodyid[l]], m.light_dir[l]) for l in range(m.nlight)]).reshape(m.nlight, 3)
+  m.light_pos0 = np.array([l_xpos[l] - kin.xpos[m.light_bodyid[l]] for l in range(m.nlight)]).reshape(m.nlight, 3)
+  m.light_poscom0 = np.array([l_xpos[l] - kin.subtree_com[m.light_bodyid[l]] for l in range(m.nlight)]).reshape(m.nlight, 3)
+  m.light_dir0 = l_xdir
+
+
+class MjDataLite:
+  """Minimal stand-in for mujoco.MjData: the state inputs put_data reads."""
+
+  def __init__(self, m):
+    self.qpos = m.qpos0.copy()
+    self.qvel = np.zeros(m.nv)
+    self.ctrl = np.zeros(m.nu)
+    self.act = np.zeros(m.na)
+    self.qacc_warmstart = np.zeros(m.nv)
+    self.qfrc_applied = np.zeros(m.nv)
+    self.xfrc_applied = np.zeros((m.nbody, 6))
+    self.time = 0.0
+
+
+def reset_data_keyframe(m, d: MjDataLite, key: int):
+  d.qpos[:] = m.key_qpos[key]
+  d.qvel[:] = m.key_qvel[key]
+  d.ctrl[:] = m.key_ctrl[key]
+  d.time = float(m.key_time[key])
+  d.qacc_warmstart[:] = 0

@@ -1,0 +1,1354 @@
+/* oracle.c -- TEST INFRASTRUCTURE ONLY. CPU restatement of mujoco_warp's batched step.
+ * See oracle.h for scope and the parity-pinning statement. Reference paths are relative to
+ * /root/reference/mujoco_warp/_src/.  Layout conventions: quaternions (w,x,y,z),
+ * spatial vectors (angular[3], linear[3]), vec10 inertia = [Ixx,Iyy,Izz,Ixy,Ixz,Iyz, m*dx,m*dy,m*dz, m],
+ * mat33 row-major, contact frame row 0 = normal (geom1 -> geom2).
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MJ_MINVAL ((real)1e-15)
+#define MJ_MAXVAL ((real)1e10)
+#define MJ_MINIMP ((real)1e-4)
+#define MJ_MAXIMP ((real)0.9999)
+#define MJ_MINMU ((real)1e-5)
+
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { GEOM_PLANE = 0, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH };
+enum { INT_EULER = 0, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST };
+enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
+enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_LIMIT_JOINT = 3, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6, CNSTR_CONTACT_ELLIPTIC = 7 };
+enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
+enum { CAM_FIXED = 0, CAM_TRACK, CAM_TRACKCOM, CAM_TARGETBODY, CAM_TARGETBODYCOM };
+enum { GAIN_FIXED = 0, GAIN_AFFINE = 1 };
+enum { BIAS_NONE = 0, BIAS_AFFINE = 1 };
+enum {
+  DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3, DSBL_CONTACT = 1 << 4,
+  DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7, DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9,
+  DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15
+};
+enum { OVF_NEFC = 1 << 0, OVF_NARROWPHASE = 1 << 3, OVF_ITERATIONS = 1 << 9, OVF_LS_ITERATIONS = 1 << 10, OVF_UNSUPPORTED = 1 << 30 };
+enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
+
+/* ------------------------------------------------------------------ field registries (X-macros) */
+#define MODEL_INTS(X) \
+  X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
+  X(nxn_npair) X(nlimit) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
+  X(disableflags) X(enableflags) X(broadphase_filter)
+#define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia)
+#define MODEL_IARRS(X) \
+  X(body_parentid) X(body_rootid) X(body_weldid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_actfrclimited) X(jnt_actgravcomp) \
+  X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(M_rownnz) X(M_rowadr) X(M_colind) \
+  X(tree_dofadr) X(tree_dofnum) X(qLD_block_adr) \
+  X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
+  X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
+  X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
+  X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(body_isdofancestor)
+#define MODEL_RARRS(X) \
+  X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
+  X(body_inertia) X(body_invweight0) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
+  X(jnt_solimp) X(jnt_actfrcrange) X(dof_armature) X(dof_damping) X(dof_invweight0) X(dof_frictionloss) X(dof_solref) \
+  X(dof_solimp) X(geom_size) X(geom_aabb) X(geom_rbound) X(geom_pos) X(geom_quat) X(geom_friction) X(geom_margin) \
+  X(geom_gap) X(geom_solmix) X(geom_solref) X(geom_solimp) X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) \
+  X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
+  X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat)
+
+/* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
+#define DATA_RARRS(X) \
+  X(time) X(qpos) X(qvel) X(ctrl) X(qacc_warmstart) X(qfrc_applied) X(xfrc_applied) X(qacc) \
+  X(xpos) X(xquat) X(xmat) X(xipos) X(ximat) X(xanchor) X(xaxis) X(geom_xpos) X(geom_xmat) X(site_xpos) X(site_xmat) \
+  X(cam_xpos) X(cam_xmat) X(light_xpos) X(light_xdir) X(subtree_com) X(cdof) X(cinert) X(crb) X(M) X(qLD) \
+  X(actuator_length) X(actuator_moment) X(actuator_velocity) X(cvel) X(cdof_dot) X(qfrc_bias) X(qfrc_spring) \
+  X(qfrc_damper) X(qfrc_gravcomp) X(qfrc_passive) X(actuator_force) X(qfrc_actuator) X(qfrc_smooth) X(qacc_smooth) \
+  X(qfrc_constraint) X(cacc) X(cfrc_int) \
+  X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
+  X(con_dist) X(con_pos) X(con_frame) X(con_includemargin) X(con_friction) X(con_solref) X(con_solreffriction) X(con_solimp)
+#define DATA_IARRS(X) \
+  X(ne) X(nf) X(nl) X(nefc) X(ncon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
+  X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(con_dim) X(con_geom) X(con_efc_address) X(con_geomcollisionid)
+
+struct OrcModel {
+#define X(n) int n;
+  MODEL_INTS(X)
+#undef X
+#define X(n) real n;
+  MODEL_REALS(X)
+#undef X
+#define X(n) const int* n;
+  MODEL_IARRS(X)
+#undef X
+#define X(n) const real* n;
+  MODEL_RARRS(X)
+#undef X
+};
+
+struct OrcData {
+  int nworld, nconmax, njmax;
+#define X(n) real* n;
+  DATA_RARRS(X)
+#undef X
+#define X(n) int* n;
+  DATA_IARRS(X)
+#undef X
+};
+
+static char g_err[256] = "";
+const char* orc_last_error(void) { return g_err; }
+int orc_sizeof_real(void) { return (int)sizeof(real); }
+
+OrcModel* orc_model_create(void) { return (OrcModel*)calloc(1, sizeof(OrcModel)); }
+void orc_model_free(OrcModel* m) { free(m); }
+int orc_model_set_int(OrcModel* m, const char* name, int v) {
+#define X(n) if (!strcmp(name, #n)) { m->n = v; return 0; }
+  MODEL_INTS(X)
+#undef X
+  return -1;
+}
+int orc_model_set_real(OrcModel* m, const char* name, double v) {
+#define X(n) if (!strcmp(name, #n)) { m->n = (real)v; return 0; }
+  MODEL_REALS(X)
+#undef X
+  return -1;
+}
+int orc_model_set_iarr(OrcModel* m, const char* name, const int* p) {
+#define X(n) if (!strcmp(name, #n)) { m->n = p; return 0; }
+  MODEL_IARRS(X)
+#undef X
+  return -1;
+}
+int orc_model_set_rarr(OrcModel* m, const char* name, const real* p) {
+#define X(n) if (!strcmp(name, #n)) { m->n = p; return 0; }
+  MODEL_RARRS(X)
+#undef X
+  return -1;
+}
+OrcData* orc_data_create(int nworld, int nconmax, int njmax) {
+  OrcData* d = (OrcData*)calloc(1, sizeof(OrcData));
+  d->nworld = nworld; d->nconmax = nconmax; d->njmax = njmax;
+  return d;
+}
+void orc_data_free(OrcData* d) { free(d); }
+int orc_data_set_iarr(OrcData* d, const char* name, int* p) {
+#define X(n) if (!strcmp(name, #n)) { d->n = p; return 0; }
+  DATA_IARRS(X)
+#undef X
+  return -1;
+}
+int orc_data_set_rarr(OrcData* d, const char* name, real* p) {
+#define X(n) if (!strcmp(name, #n)) { d->n = p; return 0; }
+  DATA_RARRS(X)
+#undef X
+  return -1;
+}
+
+static int check_fields(const OrcModel* m, const OrcData* d) {
+#define X(n) if (!m->n) { snprintf(g_err, sizeof g_err, "model array '%s' not set", #n); return -1; }
+  MODEL_IARRS(X)
+  MODEL_RARRS(X)
+#undef X
+#define X(n) if (!d->n) { snprintf(g_err, sizeof g_err, "data array '%s' not set", #n); return -1; }
+  DATA_RARRS(X)
+  DATA_IARRS(X)
+#undef X
+  return 0;
+}
+
+/* ------------------------------------------------------------------ math (math.py) */
+static inline real rmin(real a, real b) { return a < b ? a : b; }
+static inline real rmax(real a, real b) { return a > b ? a : b; }
+static inline real rclamp(real x, real lo, real hi) { return rmin(rmax(x, lo), hi); }
+static inline real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void cross3(const real* a, const real* b, real* o) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static inline real len3(const real* a) { return (real)sqrt((double)dot3(a, a)); }
+/* wp.normalize: zero vector stays zero */
+static inline void normalize3(real* a) { real l = len3(a); if (l > 0) { a[0] /= l; a[1] /= l; a[2] /= l; } else { a[0] = a[1] = a[2] = 0; } }
+static inline void normalize4(real* q) {
+  real l = (real)sqrt((double)(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]));
+  if (l > 0) { q[0] /= l; q[1] /= l; q[2] /= l; q[3] /= l; } else { q[0] = q[1] = q[2] = q[3] = 0; }
+}
+/* math.py:24 */
+static inline void mul_quat(const real* u, const real* v, real* o) {
+  real r0 = u[0] * v[0] - u[1] * v[1] - u[2] * v[2] - u[3] * v[3];
+  real r1 = u[0] * v[1] + u[1] * v[0] + u[2] * v[3] - u[3] * v[2];
+  real r2 = u[0] * v[2] - u[1] * v[3] + u[2] * v[0] + u[3] * v[1];
+  real r3 = u[0] * v[3] + u[1] * v[2] - u[2] * v[1] + u[3] * v[0];
+  o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3;
+}
+/* math.py:45 */
+static inline void rot_vec_quat(const real* v, const real* q, real* o) {
+  real s = q[0]; const real* u = q + 1;
+  real uv = dot3(u, v), uu = dot3(u, u), c[3];
+  cross3(u, v, c);
+  for (int i = 0; i < 3; i++) o[i] = 2 * uv * u[i] + (s * s - uu) * v[i] + 2 * s * c[i];
+}
+/* math.py:53 */
+static inline void axis_angle_to_quat(const real* axis, real angle, real* q) {
+  real s = (real)sin((double)angle * 0.5), c = (real)cos((double)angle * 0.5);
+  q[0] = c; q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+/* math.py:60 */
+static inline void quat_to_mat(const real* q, real* m) {
+  real q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  real q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02);
+  m[3] = 2 * (q12 + q03); m[4] = q00 - q11 + q22 - q33; m[5] = 2 * (q23 - q01);
+  m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01); m[8] = q00 - q11 - q22 + q33;
+}
+/* math.py:121 mju_mulInertVec */
+static inline void inert_vec(const real* i, const real* v, real* o) {
+  real r[6];
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+  memcpy(o, r, sizeof r);
+}
+/* math.py:134 */
+static inline void motion_cross(const real* u, const real* v, real* o) {
+  real a[3], b[3], c[3];
+  cross3(u, v, a); cross3(u + 3, v, b); cross3(u, v + 3, c);
+  o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = b[0] + c[0]; o[4] = b[1] + c[1]; o[5] = b[2] + c[2];
+}
+/* math.py:148 */
+static inline void motion_cross_force(const real* v, const real* f, real* o) {
+  real a[3], b[3], c[3];
+  cross3(v, f, a); cross3(v + 3, f + 3, b); cross3(v, f + 3, c);
+  o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; o[3] = c[0]; o[4] = c[1]; o[5] = c[2];
+}
+/* math.py:189 */
+static inline void quat_integrate(real* q, const real* v, real dt) {
+  real ax[3] = {v[0], v[1], v[2]};
+  real n = len3(ax);
+  normalize3(ax);
+  real qr[4], out[4];
+  axis_angle_to_quat(ax, dt * n, qr);
+  normalize4(q);
+  mul_quat(q, qr, out);
+  normalize4(out);
+  memcpy(q, out, sizeof out);
+}
+/* math.py:203 orthogonals + math.py:247 make_frame (rows: a, b, c) */
+static inline void make_frame(const real* a_in, real* frame) {
+  real a[3] = {a_in[0], a_in[1], a_in[2]};
+  normalize3(a);
+  real y[3] = {0, 1, 0}, z[3] = {0, 0, 1}, b[3];
+  const real* s = (-0.5 < a[1] && a[1] < 0.5) ? y : z;
+  real ab = dot3(a, s);
+  for (int i = 0; i < 3; i++) b[i] = s[i] - a[i] * ab;
+  normalize3(b);
+  if (len3(a) == 0) b[0] = b[1] = b[2] = 0;
+  real c[3];
+  cross3(a, b, c);
+  for (int i = 0; i < 3; i++) { frame[i] = a[i]; frame[3 + i] = b[i]; frame[6 + i] = c[i]; }
+}
+static inline real safe_div(real x, real y) { return x / (y != 0 ? y : MJ_MINVAL); }
+/* math.py:269 */
+void orc_closest_segment_point(const real a[3], const real b[3], const real pt[3], real out[3]) {
+  real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, pa[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+  real t = dot3(pa, ab) / (dot3(ab, ab) + (real)1e-6);
+  t = rclamp(t, 0, 1);
+  for (int i = 0; i < 3; i++) out[i] = a[i] + t * ab[i];
+}
+static real seg_pt_dist(const real a[3], const real b[3], const real pt[3], real out[3]) {
+  orc_closest_segment_point(a, b, pt, out);
+  real d[3] = {pt[0] - out[0], pt[1] - out[1], pt[2] - out[2]};
+  return dot3(d, d);
+}
+/* math.py:285 */
+void orc_closest_segment_to_segment_points(const real a0[3], const real a1[3], const real b0[3], const real b1[3], real outa[3], real outb[3]) {
+  real da[3], db[3];
+  for (int i = 0; i < 3; i++) { da[i] = a1[i] - a0[i]; db[i] = b1[i] - b0[i]; }
+  real la = len3(da), lb = len3(db);
+  if (la != 0) for (int i = 0; i < 3; i++) da[i] /= la;
+  if (lb != 0) for (int i = 0; i < 3; i++) db[i] /= lb;
+  real ha = la * (real)0.5, hb = lb * (real)0.5, am[3], bm[3], tr[3];
+  for (int i = 0; i < 3; i++) { am[i] = a0[i] + da[i] * ha; bm[i] = b0[i] + db[i] * hb; tr[i] = am[i] - bm[i]; }
+  real dd = dot3(da, db), dat = dot3(da, tr), dbt = dot3(db, tr), denom = 1 - dd * dd;
+  real ta = (-dat + dd * dbt) / (denom + (real)1e-6), tb = dbt + ta * dd;
+  ta = rclamp(ta, -ha, ha); tb = rclamp(tb, -hb, hb);
+  real ba[3], bb[3], na[3], nb[3];
+  for (int i = 0; i < 3; i++) { ba[i] = am[i] + da[i] * ta; bb[i] = bm[i] + db[i] * tb; }
+  real d1 = seg_pt_dist(a0, a1, bb, na), d2 = seg_pt_dist(b0, b1, ba, nb);
+  if (d1 < d2) { memcpy(outa, na, 3 * sizeof(real)); memcpy(outb, bb, 3 * sizeof(real)); }
+  else { memcpy(outa, ba, 3 * sizeof(real)); memcpy(outb, nb, 3 * sizeof(real)); }
+}
+int orc_upper_tri_index(int n, int i, int j) { return (i * (2 * n - i - 3)) / 2 + j - 1; }
+int orc_upper_trid_index(int n, int i, int j) { if (j < i) { int t = i; i = j; j = t; } return (i * (2 * n - i - 1)) / 2 + j; }
+/* util_misc.py:61 */
+double orc_halton(int index, int base) {
+  int n0 = index; float b = (float)base, f = 1.0f / b, hn = 0.0f;
+  while (n0 > 0) { int n1 = n0 / base; int r = n0 - n1 * base; hn += f * (float)r; f /= b; n0 = n1; }
+  return (double)hn;
+}
+
+/* ------------------------------------------------------------------ per-world view */
+typedef struct {
+  const OrcModel* m;
+  int njmax, nconmax;
+#define X(n) real* n;
+  DATA_RARRS(X)
+#undef X
+#define X(n) int* n;
+  DATA_IARRS(X)
+#undef X
+} W;
+
+static void make_view(const OrcModel* m, const OrcData* d, int w, W* v) {
+  const int nb = m->nbody, nv = m->nv, nj = m->njnt, ng = m->ngeom, nu = m->nu, njm = d->njmax, ncm = d->nconmax;
+  v->m = m; v->njmax = njm; v->nconmax = ncm;
+#define R(n, sz) v->n = d->n + (size_t)w * (size_t)(sz)
+  R(time, 1); R(qpos, m->nq); R(qvel, nv); R(ctrl, nu); R(qacc_warmstart, nv); R(qfrc_applied, nv); R(xfrc_applied, 6 * nb); R(qacc, nv);
+  R(xpos, 3 * nb); R(xquat, 4 * nb); R(xmat, 9 * nb); R(xipos, 3 * nb); R(ximat, 9 * nb); R(xanchor, 3 * nj); R(xaxis, 3 * nj);
+  R(geom_xpos, 3 * ng); R(geom_xmat, 9 * ng); R(site_xpos, 3 * m->nsite); R(site_xmat, 9 * m->nsite);
+  R(cam_xpos, 3 * m->ncam); R(cam_xmat, 9 * m->ncam); R(light_xpos, 3 * m->nlight); R(light_xdir, 3 * m->nlight);
+  R(subtree_com, 3 * nb); R(cdof, 6 * nv); R(cinert, 10 * nb); R(crb, 10 * nb); R(M, m->nC);
+  {
+    int qld = 0;
+    for (int t = 0; t < m->ntree; t++) qld += m->tree_dofnum[t] * m->tree_dofnum[t];
+    R(qLD, qld);
+  }
+  R(actuator_length, nu); R(actuator_moment, m->nJmom); R(actuator_velocity, nu); R(cvel, 6 * nb); R(cdof_dot, 6 * nv);
+  R(qfrc_bias, nv); R(qfrc_spring, nv); R(qfrc_damper, nv); R(qfrc_gravcomp, nv); R(qfrc_passive, nv); R(actuator_force, nu);
+  R(qfrc_actuator, nv); R(qfrc_smooth, nv); R(qacc_smooth, nv); R(qfrc_constraint, nv); R(cacc, 6 * nb); R(cfrc_int, 6 * nb);
+  R(efc_J, njm * nv); R(efc_pos, njm); R(efc_margin, njm); R(efc_D, njm); R(efc_vel, njm); R(efc_aref, njm);
+  R(efc_frictionloss, njm); R(efc_force, njm); R(efc_Ma, nv);
+  R(con_dist, ncm); R(con_pos, 3 * ncm); R(con_frame, 9 * ncm); R(con_includemargin, ncm); R(con_friction, 5 * ncm);
+  R(con_solref, 2 * ncm); R(con_solreffriction, 2 * ncm); R(con_solimp, 5 * ncm);
+  R(ne, 1); R(nf, 1); R(nl, 1); R(nefc, 1); R(ncon, 1); R(ncollision, 1); R(solver_niter, 1); R(overflow, 1);
+  R(efc_type, njm); R(efc_id, njm); R(efc_state, njm); R(moment_rownnz, nu); R(moment_rowadr, nu); R(moment_colind, m->nJmom);
+  R(con_dim, ncm); R(con_geom, 2 * ncm); R(con_efc_address, m->nmaxpyramid * ncm); R(con_geomcollisionid, ncm);
+#undef R
+}
+
+/* ------------------------------------------------------------------ kinematics (smooth.py:46-226) */
+static void kinematics(W* w) {
+  const OrcModel* m = w->m;
+  /* world body */
+  w->xpos[0] = w->xpos[1] = w->xpos[2] = 0;
+  w->xquat[0] = 1; w->xquat[1] = w->xquat[2] = w->xquat[3] = 0;
+  for (int b = 1; b < m->nbody; b++) {
+    int pid = m->body_parentid[b], jntadr = m->body_jntadr[b], jntnum = m->body_jntnum[b];
+    real* xpos = w->xpos + 3 * b; real* xquat = w->xquat + 4 * b;
+    if (jntnum == 1 && m->jnt_type[jntadr] == JNT_FREE) { /* smooth.py:84-97 */
+      int qa = m->jnt_qposadr[jntadr];
+      for (int i = 0; i < 3; i++) xpos[i] = w->qpos[qa + i];
+      for (int i = 0; i < 4; i++) xquat[i] = w->qpos[qa + 3 + i];
+      normalize4(xquat);
+      memcpy(w->xanchor + 3 * jntadr, xpos, 3 * sizeof(real));
+      memcpy(w->xaxis + 3 * jntadr, m->jnt_axis + 3 * jntadr, 3 * sizeof(real));
+      continue;
+    }
+    real pos[3], quat[4];
+    rot_vec_quat(m->body_pos + 3 * b, w->xquat + 4 * pid, pos);
+    for (int i = 0; i < 3; i++) pos[i] += w->xpos[3 * pid + i];
+    mul_quat(w->xquat + 4 * pid, m->body_quat + 4 * b, quat);
+    for (int j = jntadr; j < jntadr + jntnum; j++) { /* smooth.py:116-140 */
+      int qa = m->jnt_qposadr[j], t = m->jnt_type[j];
+      real anchor[3], axis[3], tmp[3];
+      rot_vec_quat(m->jnt_pos + 3 * j, quat, anchor);
+      for (int i = 0; i < 3; i++) anchor[i] += pos[i];
+      rot_vec_quat(m->jnt_axis + 3 * j, quat, axis);
+      if (t == JNT_BALL) {
+        real ql[4] = {w->qpos[qa], w->qpos[qa + 1], w->qpos[qa + 2], w->qpos[qa + 3]}, nq[4];
+        normalize4(ql);
+        mul_quat(quat, ql, nq); memcpy(quat, nq, sizeof nq);
+        rot_vec_quat(m->jnt_pos + 3 * j, quat, tmp);
+        for (int i = 0; i < 3; i++) pos[i] = anchor[i] - tmp[i];
+      } else if (t == JNT_SLIDE) {
+        for (int i = 0; i < 3; i++) pos[i] += axis[i] * (w->qpos[qa] - m->qpos0[qa]);
+      } else if (t == JNT_HINGE) {
+        real ql[4], nq[4];
+        axis_angle_to_quat(m->jnt_axis + 3 * j, w->qpos[qa] - m->qpos0[qa], ql);
+        mul_quat(quat, ql, nq); memcpy(quat, nq, sizeof nq);
+        rot_vec_quat(m->jnt_pos + 3 * j, quat, tmp);
+        for (int i = 0; i < 3; i++) pos[i] = anchor[i] - tmp[i];
+      }
+      memcpy(w->xanchor + 3 * j, anchor, sizeof anchor);
+      memcpy(w->xaxis + 3 * j, axis, sizeof axis);
+    }
+    normalize4(quat);
+    memcpy(xpos, pos, sizeof pos); memcpy(xquat, quat, sizeof quat);
+  }
+  for (int b = 0; b < m->nbody; b++) { /* smooth.py:148-175 */
+    real t[3], q[4];
+    quat_to_mat(w->xquat + 4 * b, w->xmat + 9 * b);
+    rot_vec_quat(m->body_ipos + 3 * b, w->xquat + 4 * b, t);
+    for (int i = 0; i < 3; i++) w->xipos[3 * b + i] = w->xpos[3 * b + i] + t[i];
+    mul_quat(w->xquat + 4 * b, m->body_iquat + 4 * b, q);
+    quat_to_mat(q, w->ximat + 9 * b);
+  }
+  for (int g = 0; g < m->ngeom; g++) { /* smooth.py:178-205: world-welded geoms keep their make_data pose */
+    int b = m->geom_bodyid[g];
+    if (m->body_weldid[b] == 0) continue;
+    real t[3], q[4];
+    rot_vec_quat(m->geom_pos + 3 * g, w->xquat + 4 * b, t);
+    for (int i = 0; i < 3; i++) w->geom_xpos[3 * g + i] = w->xpos[3 * b + i] + t[i];
+    mul_quat(w->xquat + 4 * b, m->geom_quat + 4 * g, q);
+    quat_to_mat(q, w->geom_xmat + 9 * g);
+  }
+  for (int s = 0; s < m->nsite; s++) { /* smooth.py:208-226 */
+    int b = m->site_bodyid[s];
+    real t[3], q[4];
+    rot_vec_quat(m->site_pos + 3 * s, w->xquat + 4 * b, t);
+    for (int i = 0; i < 3; i++) w->site_xpos[3 * s + i] = w->xpos[3 * b + i] + t[i];
+    mul_quat(w->xquat + 4 * b, m->site_quat + 4 * s, q);
+    quat_to_mat(q, w->site_xmat + 9 * s);
+  }
+}
+
+/* ------------------------------------------------------------------ com_pos (smooth.py:686-855) */
+static void com_pos(W* w) {
+  const OrcModel* m = w->m;
+  const int nb = m->nbody;
+  for (int b = 0; b < nb; b++) for (int i = 0; i < 3; i++) w->subtree_com[3 * b + i] = w->xipos[3 * b + i] * m->body_mass[b];
+  for (int b = nb - 1; b >= 1; b--) { int p = m->body_parentid[b]; for (int i = 0; i < 3; i++) w->subtree_com[3 * p + i] += w->subtree_com[3 * b + i]; }
+  for (int b = 0; b < nb; b++) { real ms = m->body_subtreemass[b]; if (ms != 0) for (int i = 0; i < 3; i++) w->subtree_com[3 * b + i] /= ms; }
+  for (int b = 0; b < nb; b++) { /* _cinert smooth.py:733 */
+    const real* mat = w->ximat + 9 * b; const real* inert = m->body_inertia + 3 * b; real mass = m->body_mass[b];
+    real dif[3], tmp[9], *res = w->cinert + 10 * b;
+    for (int i = 0; i < 3; i++) dif[i] = w->xipos[3 * b + i] - w->subtree_com[3 * m->body_rootid[b] + i];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) {
+      real s = 0; for (int k = 0; k < 3; k++) s += mat[3 * r + k] * inert[k] * mat[3 * c + k]; tmp[3 * r + c] = s;
+    }
+    res[0] = tmp[0] + mass * (dif[1] * dif[1] + dif[2] * dif[2]);
+    res[1] = tmp[4] + mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+    res[2] = tmp[8] + mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+    res[3] = tmp[1] - mass * dif[0] * dif[1];
+    res[4] = tmp[2] - mass * dif[0] * dif[2];
+    res[5] = tmp[5] - mass * dif[1] * dif[2];
+    res[6] = mass * dif[0]; res[7] = mass * dif[1]; res[8] = mass * dif[2]; res[9] = mass;
+  }
+  for (int j = 0; j < m->njnt; j++) { /* _cdof smooth.py:779 */
+    int b = m->jnt_bodyid[j], d = m->jnt_dofadr[j], t = m->jnt_type[j];
+    const real* xaxis = w->xaxis + 3 * j; const real* xm = w->xmat + 9 * b;
+    real offset[3], col[3], cr[3];
+    for (int i = 0; i < 3; i++) offset[i] = w->subtree_com[3 * m->body_rootid[b] + i] - w->xanchor[3 * j + i];
+    real* res = w->cdof + 6 * d;
+    if (t == JNT_FREE || t == JNT_BALL) {
+      if (t == JNT_FREE) {
+        memset(res, 0, 18 * sizeof(real));
+        res[3] = 1; res[6 + 4] = 1; res[12 + 5] = 1;
+        res += 18;
+      }
+      for (int k = 0; k < 3; k++) {
+        col[0] = xm[k]; col[1] = xm[3 + k]; col[2] = xm[6 + k]; /* column k of xmat = row k of transpose */
+        cross3(col, offset, cr);
+        for (int i = 0; i < 3; i++) { res[6 * k + i] = col[i]; res[6 * k + 3 + i] = cr[i]; }
+      }
+    } else if (t == JNT_SLIDE) {
+      for (int i = 0; i < 3; i++) { res[i] = 0; res[3 + i] = xaxis[i]; }
+    } else {
+      cross3(xaxis, offset, cr);
+      for (int i = 0; i < 3; i++) { res[i] = xaxis[i]; res[3 + i] = cr[i]; }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ camlight (smooth.py:858-1027) */
+static void camlight(W* w) {
+  const OrcModel* m = w->m;
+  for (int c = 0; c < m->ncam; c++) {
+    int mode = m->cam_mode[c], b = m->cam_bodyid[c], tb = m->cam_targetbodyid[c];
+    real* xp = w->cam_xpos + 3 * c; real* xm = w->cam_xmat + 9 * c;
+    int is_target = mode == CAM_TARGETBODY || mode == CAM_TARGETBODYCOM;
+    real t[3], q[4];
+    if (mode == CAM_TRACK && !(is_target && tb < 0)) {
+      memcpy(xm, m->cam_mat0 + 9 * c, 9 * sizeof(real));
+      for (int i = 0; i < 3; i++) xp[i] = w->xpos[3 * b + i] + m->cam_pos0[3 * c + i];
+    } else if (mode == CAM_TRACKCOM) {
+      memcpy(xm, m->cam_mat0 + 9 * c, 9 * sizeof(real));
+      for (int i = 0; i < 3; i++) xp[i] = w->subtree_com[3 * b + i] + m->cam_poscom0[3 * c + i];
+    } else if (is_target && tb >= 0) {
+      rot_vec_quat(m->cam_pos + 3 * c, w->xquat + 4 * b, t);
+      for (int i = 0; i < 3; i++) xp[i] = w->xpos[3 * b + i] + t[i];
+      const real* pos = (mode == CAM_TARGETBODYCOM) ? w->subtree_com + 3 * tb : w->xpos + 3 * tb;
+      real m3[3] = {xp[0] - pos[0], xp[1] - pos[1], xp[2] - pos[2]}, m1[3], m2[3], z[3] = {0, 0, 1};
+      normalize3(m3); cross3(z, m3, m1); normalize3(m1); cross3(m3, m1, m2); normalize3(m2);
+      for (int i = 0; i < 3; i++) { xm[3 * i] = m1[i]; xm[3 * i + 1] = m2[i]; xm[3 * i + 2] = m3[i]; }
+    } else {
+      rot_vec_quat(m->cam_pos + 3 * c, w->xquat + 4 * b, t);
+      for (int i = 0; i < 3; i++) xp[i] = w->xpos[3 * b + i] + t[i];
+      mul_quat(w->xquat + 4 * b, m->cam_quat + 4 * c, q);
+      quat_to_mat(q, xm);
+    }
+  }
+  for (int l = 0; l < m->nlight; l++) {
+    int mode = m->light_mode[l], b = m->light_bodyid[l], tb = m->light_targetbodyid[l];
+    real* xp = w->light_xpos + 3 * l; real* xd = w->light_xdir + 3 * l;
+    int is_target = mode == CAM_TARGETBODY || mode == CAM_TARGETBODYCOM;
+    real t[3];
+    if (is_target && tb < 0) { /* invalid target: fixed pose, returns before the normalize (smooth.py:951-958) */
+      rot_vec_quat(m->light_pos + 3 * l, w->xquat + 4 * b, t);
+      for (int i = 0; i < 3; i++) xp[i] = w->xpos[3 * b + i] + t[i];
+      rot_vec_quat(m->light_dir + 3 * l, w->xquat + 4 * b, xd);
+      continue;
+    } else if (mode == CAM_TRACK) {
+      memcpy(xd, m->light_dir0 + 3 * l, 3 * sizeof(real));
+      for (int i = 0; i < 3; i++) xp[i] = w->xpos[3 * b + i] + m->light_pos0[3 * l + i];
+    } else if (mode == CAM_TRACKCOM) {
+      memcpy(xd, m->light_dir0 + 3 * l, 3 * sizeof(real));
+      for (int i = 0; i < 3; i++) xp[i] = w->subtree_com[3 * b + i] + m->light_poscom0[3 * l + i];
+    } else if (is_target) {
+      rot_vec_quat(m->light_pos + 3 * l, w->xquat + 4 * b, t);
+      for (int i = 0; i < 3; i++) xp[i] = w->xpos[3 * b + i] + t[i];
+      const real* pos = (mode == CAM_TARGETBODYCOM) ? w->subtree_com + 3 * tb : w->xpos + 3 * tb;
+      for (int i = 0; i < 3; i++) xd[i] = pos[i] - xp[i];
+    } else {
+      rot_vec_quat(m->light_pos + 3 * l, w->xquat + 4 * b, t);
+      for (int i = 0; i < 3; i++) xp[i] = w->xpos[3 * b + i] + t[i];
+      rot_vec_quat(m->light_dir + 3 * l, w->xquat + 4 * b, xd);
+    }
+    normalize3(xd);
+  }
+}
+
+/* ------------------------------------------------------------------ crb (smooth.py:1029-1098) */
+static void crb(W* w) {
+  const OrcModel* m = w->m;
+  memcpy(w->crb, w->cinert, 10 * m->nbody * sizeof(real));
+  for (int b = m->nbody - 1; b >= 1; b--) {
+    int p = m->body_parentid[b];
+    if (p == 0) continue;
+    for (int i = 0; i < 10; i++) w->crb[10 * p + i] += w->crb[10 * b + i];
+  }
+  memset(w->M, 0, m->nC * sizeof(real));
+  for (int d0 = 0; d0 < m->nv; d0++) { /* _M smooth.py:1048 */
+    int b = m->dof_bodyid[d0], madr = m->M_rowadr[d0] + m->M_rownnz[d0] - 1;
+    w->M[madr] = m->dof_armature[d0];
+    real buf[6];
+    inert_vec(w->crb + 10 * b, w->cdof + 6 * d0, buf);
+    for (int d = d0; d >= 0; d = m->dof_parentid[d]) {
+      real s = 0; for (int i = 0; i < 6; i++) s += w->cdof[6 * d + i] * buf[i];
+      w->M[madr] += s; madr--;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ dense per-tree Cholesky (smooth.py:3227-3265, io.py:173-211)
+ * qLD block of tree t: size x size row-major upper factor U (A = U^T U), strictly lower part zero. */
+static void tree_dense(const OrcModel* m, const real* Mcsr, int start, int size, real* A /*size*size*/, const real* diag_add) {
+  memset(A, 0, (size_t)size * size * sizeof(real));
+  for (int i = start; i < start + size; i++) {
+    int adr = m->M_rowadr[i];
+    for (int k = 0; k < m->M_rownnz[i]; k++) {
+      int j = m->M_colind[adr + k];
+      real v = Mcsr[adr + k];
+      A[(i - start) * size + (j - start)] = v;
+      A[(j - start) * size + (i - start)] = v;
+    }
+    if (diag_add) A[(i - start) * size + (i - start)] += diag_add[i];
+  }
+}
+/* in-place upper Cholesky: returns U in the upper triangle (row-major), zeros below */
+static void chol_upper(real* A, int n) {
+  for (int j = 0; j < n; j++) {
+    real s = A[j * n + j];
+    for (int k = 0; k < j; k++) s -= A[k * n + j] * A[k * n + j];
+    real ujj = (real)sqrt((double)s);
+    A[j * n + j] = ujj;
+    for (int i = j + 1; i < n; i++) {
+      real t = A[j * n + i];
+      for (int k = 0; k < j; k++) t -= A[k * n + j] * A[k * n + i];
+      A[j * n + i] = t / ujj;
+    }
+  }
+  for (int i = 1; i < n; i++) for (int j = 0; j < i; j++) A[i * n + j] = 0;
+}
+static void chol_upper_solve(const real* U, int n, const real* b, real* x) {
+  /* U^T y = b ; U x = y */
+  for (int i = 0; i < n; i++) { real s = b[i]; for (int k = 0; k < i; k++) s -= U[k * n + i] * x[k]; x[i] = s / U[i * n + i]; }
+  for (int i = n - 1; i >= 0; i--) { real s = x[i]; for (int k = i + 1; k < n; k++) s -= U[i * n + k] * x[k]; x[i] = s / U[i * n + i]; }
+}
+/* factor_solve_i (smooth.py:3352): factor M (+diag_add) into qLD-like storage L, solve x = (M+diag)^-1 y */
+static void factor_solve_i(W* w, const real* Mcsr, const real* diag_add, real* L, real* x, const real* y) {
+  const OrcModel* m = w->m;
+  for (int t = 0; t < m->ntree; t++) {
+    int start = m->tree_dofadr[t], size = m->tree_dofnum[t];
+    real* blk = L + m->qLD_block_adr[start];
+    tree_dense(m, Mcsr, start, size, blk, diag_add);
+    chol_upper(blk, size);
+    chol_upper_solve(blk, size, y + start, x + start);
+  }
+}
+/* mul_m (support.py:153): res = M vec using the CSR lower triangle */
+static void mul_m(const OrcModel* m, const real* Mcsr, const real* vec, real* res) {
+  for (int i = 0; i < m->nv; i++) res[i] = 0;
+  for (int i = 0; i < m->nv; i++) {
+    int adr = m->M_rowadr[i], n = m->M_rownnz[i];
+    for (int k = 0; k < n; k++) {
+      int j = m->M_colind[adr + k];
+      res[i] += Mcsr[adr + k] * vec[j];
+      if (j != i) res[j] += Mcsr[adr + k] * vec[i];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ transmission (smooth.py:2288-2396; joint transmission only) */
+static void transmission(W* w) {
+  const OrcModel* m = w->m;
+  int nnz = 0;
+  for (int a = 0; a < m->nu; a++) {
+    int j = m->actuator_trnid[2 * a], t = m->jnt_type[j], qa = m->jnt_qposadr[j], va = m->jnt_dofadr[j];
+    const real* gear = m->actuator_gear + 6 * a;
+    if (t == JNT_SLIDE || t == JNT_HINGE) {
+      w->actuator_length[a] = w->qpos[qa] * gear[0];
+      w->moment_rownnz[a] = 1; w->moment_rowadr[a] = nnz;
+      w->moment_colind[nnz] = va; w->actuator_moment[nnz] = gear[0];
+      nnz += 1;
+    } else if (t == JNT_FREE) {
+      w->actuator_length[a] = 0;
+      w->moment_rownnz[a] = 6; w->moment_rowadr[a] = nnz;
+      for (int i = 0; i < 6; i++) { w->moment_colind[nnz + i] = va + i; w->actuator_moment[nnz + i] = gear[i]; }
+      nnz += 6;
+    } else {
+      w->overflow[0] |= OVF_UNSUPPORTED; /* ball-joint transmission not restated */
+      w->moment_rownnz[a] = 0; w->moment_rowadr[a] = nnz; w->actuator_length[a] = 0;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ collision */
+/* collision_driver.py:98-113 */
+static int plane_filter(real size1, real size2, real margin1, real margin2, const real* xpos1, const real* xpos2, const real* xmat1, const real* xmat2) {
+  if (size1 == 0) {
+    real n[3] = {xmat1[2], xmat1[5], xmat1[8]}, d[3] = {xpos2[0] - xpos1[0], xpos2[1] - xpos1[1], xpos2[2] - xpos1[2]};
+    return dot3(d, n) <= size2 + margin1 + margin2;
+  } else if (size2 == 0) {
+    real n[3] = {xmat2[2], xmat2[5], xmat2[8]}, d[3] = {xpos1[0] - xpos2[0], xpos1[1] - xpos2[1], xpos1[2] - xpos2[2]};
+    return dot3(d, n) <= size1 + margin1 + margin2;
+  }
+  return 1;
+}
+/* collision_driver.py:116-121 */
+static int sphere_filter(real size1, real size2, real margin1, real margin2, const real* xpos1, const real* xpos2) {
+  real bound = size1 + size2 + margin1 + margin2, dif[3] = {xpos2[0] - xpos1[0], xpos2[1] - xpos1[1], xpos2[2] - xpos1[2]};
+  return dot3(dif, dif) <= bound * bound;
+}
+static void matvec3(const real* m, const real* v, real* o) {
+  real r0 = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], r1 = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], r2 = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  o[0] = r0; o[1] = r1; o[2] = r2;
+}
+/* collision_driver.py:124-219 */
+static int aabb_filter(const real* c1, const real* c2, const real* s1, const real* s2, real margin1, real margin2, const real* xpos1, const real* xpos2, const real* xmat1, const real* xmat2) {
+  real ce1[3], ce2[3], margin = margin1 + margin2;
+  matvec3(xmat1, c1, ce1); matvec3(xmat2, c2, ce2);
+  for (int i = 0; i < 3; i++) { ce1[i] += xpos1[i]; ce2[i] += xpos2[i]; }
+  real mx1[3] = {-MJ_MAXVAL, -MJ_MAXVAL, -MJ_MAXVAL}, mn1[3] = {MJ_MAXVAL, MJ_MAXVAL, MJ_MAXVAL};
+  real mx2[3] = {-MJ_MAXVAL, -MJ_MAXVAL, -MJ_MAXVAL}, mn2[3] = {MJ_MAXVAL, MJ_MAXVAL, MJ_MAXVAL};
+  real sg[2] = {-1, 1};
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+    real co1[3] = {sg[i] * s1[0], sg[j] * s1[1], sg[k] * s1[2]}, co2[3] = {sg[i] * s2[0], sg[j] * s2[1], sg[k] * s2[2]}, p1[3], p2[3];
+    matvec3(xmat1, co1, p1); matvec3(xmat2, co2, p2);
+    for (int a = 0; a < 3; a++) {
+      if (p1[a] > mx1[a]) mx1[a] = p1[a];
+      if (p1[a] < mn1[a]) mn1[a] = p1[a];
+      if (p2[a] > mx2[a]) mx2[a] = p2[a];
+      if (p2[a] < mn2[a]) mn2[a] = p2[a];
+    }
+  }
+  for (int a = 0; a < 3; a++) {
+    if (ce1[a] + mx1[a] + margin < ce2[a] + mn2[a]) return 0;
+    if (ce2[a] + mx2[a] + margin < ce1[a] + mn1[a]) return 0;
+  }
+  return 1;
+}
+/* collision_driver.py:223-279 */
+static int obb_filter(const real* c1, const real* c2, const real* s1, const real* s2, real margin1, real margin2, const real* xpos1, const real* xpos2, const real* xmat1, const real* xmat2) {
+  real margin = margin1 + margin2, xc[2][3], normal[6][3];
+  matvec3(xmat1, c1, xc[0]); matvec3(xmat2, c2, xc[1]);
+  for (int i = 0; i < 3; i++) { xc[0][i] += xpos1[i]; xc[1][i] += xpos2[i]; }
+  for (int k = 0; k < 3; k++) for (int i = 0; i < 3; i++) { normal[k][i] = xmat1[3 * i + k]; normal[3 + k][i] = xmat2[3 * i + k]; }
+  for (int j = 0; j < 2; j++) for (int k = 0; k < 3; k++) {
+    real proj[2], radius[2];
+    for (int i = 0; i < 2; i++) {
+      const real* size = i == 0 ? s1 : s2;
+      proj[i] = dot3(xc[i], normal[3 * j + k]);
+      radius[i] = (real)fabs((double)(size[0] * dot3(normal[3 * i + 0], normal[3 * j + k]))) + (real)fabs((double)(size[1] * dot3(normal[3 * i + 1], normal[3 * j + k]))) +
+                  (real)fabs((double)(size[2] * dot3(normal[3 * i + 2], normal[3 * j + k])));
+    }
+    if (radius[0] + radius[1] + margin < (real)fabs((double)(proj[1] - proj[0]))) return 0;
+  }
+  return 1;
+}
+/* collision_driver.py:282-334 */
+static int broadphase_filter(const W* w, int g1, int g2) {
+  const OrcModel* m = w->m;
+  real rb1 = m->geom_rbound[g1], rb2 = m->geom_rbound[g2];
+  real em1 = m->geom_margin[g1] + m->geom_gap[g1], em2 = m->geom_margin[g2] + m->geom_gap[g2];
+  const real *xp1 = w->geom_xpos + 3 * g1, *xp2 = w->geom_xpos + 3 * g2, *xm1 = w->geom_xmat + 9 * g1, *xm2 = w->geom_xmat + 9 * g2;
+  int f = m->broadphase_filter;
+  if (rb1 == 0 || rb2 == 0) {
+    if (f & BF_PLANE) return plane_filter(rb1, rb2, em1, em2, xp1, xp2, xm1, xm2);
+  } else {
+    const real *c1 = m->geom_aabb + 6 * g1, *c2 = m->geom_aabb + 6 * g2;
+    if ((f & BF_SPHERE) && !sphere_filter(rb1, rb2, em1, em2, xp1, xp2)) return 0;
+    if ((f & BF_AABB) && !aabb_filter(c1, c2, c1 + 3, c2 + 3, em1, em2, xp1, xp2, xm1, xm2)) return 0;
+    if ((f & BF_OBB) && !obb_filter(c1, c2, c1 + 3, c2 + 3, em1, em2, xp1, xp2, xm1, xm2)) return 0;
+  }
+  return 1;
+}
+
+typedef struct { real margin, gap; int condim; real friction[5], solref[2], solreffriction[2], solimp[5]; } ConParams;
+/* collision_core.py:294-412 (geom pairs only: pairid == -1; adhesion is zero on this path) */
+static void contact_params(const OrcModel* m, int g1, int g2, ConParams* p) {
+  p->margin = m->geom_margin[g1] + m->geom_margin[g2];
+  p->gap = m->geom_gap[g1] + m->geom_gap[g2];
+  real solmix1 = m->geom_solmix[g1], solmix2 = m->geom_solmix[g2], mix;
+  int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2];
+  real fr[3];
+  if (p1 > p2) { mix = 1; p->condim = m->geom_condim[g1]; memcpy(fr, m->geom_friction + 3 * g1, sizeof fr); }
+  else if (p2 > p1) { mix = 0; p->condim = m->geom_condim[g2]; memcpy(fr, m->geom_friction + 3 * g2, sizeof fr); }
+  else {
+    mix = safe_div(solmix1, solmix1 + solmix2);
+    if (solmix1 < MJ_MINVAL && solmix2 < MJ_MINVAL) mix = (real)0.5;
+    if (solmix1 < MJ_MINVAL && solmix2 >= MJ_MINVAL) mix = 0;
+    if (solmix1 >= MJ_MINVAL && solmix2 < MJ_MINVAL) mix = 1;
+    p->condim = m->geom_condim[g1] > m->geom_condim[g2] ? m->geom_condim[g1] : m->geom_condim[g2];
+    for (int i = 0; i < 3; i++) fr[i] = rmax(m->geom_friction[3 * g1 + i], m->geom_friction[3 * g2 + i]);
+  }
+  p->friction[0] = fr[0]; p->friction[1] = fr[0]; p->friction[2] = fr[1]; p->friction[3] = fr[2]; p->friction[4] = fr[2];
+  const real *sr1 = m->geom_solref + 2 * g1, *sr2 = m->geom_solref + 2 * g2;
+  if (sr1[0] > 0 && sr2[0] > 0) for (int i = 0; i < 2; i++) p->solref[i] = mix * sr1[i] + (1 - mix) * sr2[i];
+  else for (int i = 0; i < 2; i++) p->solref[i] = rmin(sr1[i], sr2[i]);
+  p->solreffriction[0] = p->solreffriction[1] = 0;
+  for (int i = 0; i < 5; i++) p->solimp[i] = mix * m->geom_solimp[5 * g1 + i] + (1 - mix) * m->geom_solimp[5 * g2 + i];
+  for (int i = 0; i < 5; i++) p->friction[i] = rmax(MJ_MINMU, p->friction[i]);
+}
+/* collision_core.py:213-291 (per-world slots; pairid[0] == -1, pairid[1] == -1 on this path) */
+static void write_contact(W* w, int id, real dist, const real* pos, const real* frame, const ConParams* p, int g1, int g2) {
+  int detected = dist < p->margin + p->gap;
+  if (!detected) return;
+  int cid = w->ncon[0]++;
+  if (cid >= w->nconmax) { w->overflow[0] |= OVF_NARROWPHASE; return; }
+  const int np = w->m->nmaxpyramid;
+  w->con_dist[cid] = dist;
+  memcpy(w->con_pos + 3 * cid, pos, 3 * sizeof(real));
+  memcpy(w->con_frame + 9 * cid, frame, 9 * sizeof(real));
+  w->con_geom[2 * cid] = g1; w->con_geom[2 * cid + 1] = g2;
+  w->con_includemargin[cid] = p->margin;
+  w->con_dim[cid] = p->condim;
+  memcpy(w->con_friction + 5 * cid, p->friction, 5 * sizeof(real));
+  memcpy(w->con_solref + 2 * cid, p->solref, 2 * sizeof(real));
+  memcpy(w->con_solreffriction + 2 * cid, p->solreffriction, 2 * sizeof(real));
+  memcpy(w->con_solimp + 5 * cid, p->solimp, 5 * sizeof(real));
+  w->con_geomcollisionid[cid] = id;
+  for (int i = 0; i < np; i++) w->con_efc_address[np * cid + i] = -1;
+}
+/* collision_primitive_core.py:47 */
+static real plane_sphere(const real* n, const real* ppos, const real* spos, real r, real* pos) {
+  real d[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
+  real dist = dot3(d, n) - r;
+  for (int i = 0; i < 3; i++) pos[i] = spos[i] - n[i] * (r + (real)0.5 * dist);
+  return dist;
+}
+/* collision_primitive_core.py:55 */
+static real sphere_sphere(const real* pos1, real r1, const real* pos2, real r2, real* pos, real* n) {
+  real dir[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  real dist = len3(dir);
+  if (dist == 0) { n[0] = 1; n[1] = 0; n[2] = 0; } else for (int i = 0; i < 3; i++) n[i] = dir[i] / dist;
+  dist = dist - (r1 + r2);
+  for (int i = 0; i < 3; i++) pos[i] = pos1[i] + n[i] * (r1 + (real)0.5 * dist);
+  return dist;
+}
+static void narrowphase_pair(W* w, int g1, int g2) {
+  const OrcModel* m = w->m;
+  int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+  ConParams p;
+  contact_params(m, g1, g2, &p);
+  const real *pos1 = w->geom_xpos + 3 * g1, *pos2 = w->geom_xpos + 3 * g2, *rot1 = w->geom_xmat + 9 * g1, *rot2 = w->geom_xmat + 9 * g2;
+  const real *size1 = m->geom_size + 3 * g1, *size2 = m->geom_size + 3 * g2;
+  real ax1[3] = {rot1[2], rot1[5], rot1[8]}, ax2[3] = {rot2[2], rot2[5], rot2[8]};
+  real frame[9], pos[3], n[3];
+  if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) { /* collision_primitive.py:281 */
+    real dist = plane_sphere(ax1, pos1, pos2, size2[0], pos);
+    make_frame(ax1, frame);
+    write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+  } else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) { /* collision_primitive_core.py:252, collision_primitive.py:600 */
+    real b[3], c[3], an = dot3(ax1, ax2);
+    for (int i = 0; i < 3; i++) b[i] = ax2[i] - ax1[i] * an;
+    real bn = len3(b);
+    if (bn != 0) for (int i = 0; i < 3; i++) b[i] /= bn;
+    if (bn < 0.5) {
+      if (-0.5 < ax1[1] && ax1[1] < 0.5) { b[0] = 0; b[1] = 1; b[2] = 0; } else { b[0] = 0; b[1] = 0; b[2] = 1; }
+    }
+    cross3(ax1, b, c);
+    for (int i = 0; i < 3; i++) { frame[i] = ax1[i]; frame[3 + i] = b[i]; frame[6 + i] = c[i]; }
+    real e1[3], e2[3], pp1[3], pp2[3];
+    for (int i = 0; i < 3; i++) { e1[i] = pos2[i] + ax2[i] * size2[1]; e2[i] = pos2[i] - ax2[i] * size2[1]; }
+    real d1 = plane_sphere(ax1, pos1, e1, size2[0], pp1), d2 = plane_sphere(ax1, pos1, e2, size2[0], pp2);
+    write_contact(w, 0, d1, pp1, frame, &p, g1, g2);
+    write_contact(w, 1, d2, pp2, frame, &p, g1, g2);
+  } else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) {
+    real dist = sphere_sphere(pos1, size1[0], pos2, size2[0], pos, n);
+    make_frame(n, frame);
+    write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+  } else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) { /* collision_primitive_core.py:87 */
+    real a[3], b[3], pt[3];
+    for (int i = 0; i < 3; i++) { a[i] = pos2[i] - ax2[i] * size2[1]; b[i] = pos2[i] + ax2[i] * size2[1]; }
+    orc_closest_segment_point(a, b, pos1, pt);
+    real dist = sphere_sphere(pos1, size1[0], pt, size2[0], pos, n);
+    make_frame(n, frame);
+    write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+  } else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) { /* collision_primitive_core.py:122-249 */
+    real axis1[3], axis2[3], dif[3], margin = p.margin;
+    for (int i = 0; i < 3; i++) { axis1[i] = ax1[i] * size1[1]; axis2[i] = ax2[i] * size2[1]; dif[i] = pos1[i] - pos2[i]; }
+    real ma = dot3(axis1, axis1), mb = -dot3(axis1, axis2), mc = dot3(axis2, axis2), u = -dot3(axis1, dif), v = dot3(axis2, dif);
+    real det = ma * mc - mb * mb, v1[3], v2[3];
+    real cdist[2] = {INFINITY, INFINITY}, cpos[2][3] = {{0}}, cn[2][3] = {{0}};
+    if (fabs((double)det) >= MJ_MINVAL) {
+      real inv = 1 / det, x1 = (mc * u - mb * v) * inv, x2 = (ma * v - mb * u) * inv;
+      if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; } else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
+      if (x2 > 1) { x2 = 1; x1 = rclamp((u - mb) / ma, -1, 1); } else if (x2 < -1) { x2 = -1; x1 = rclamp((u + mb) / ma, -1, 1); }
+      for (int i = 0; i < 3; i++) { v1[i] = pos1[i] + axis1[i] * x1; v2[i] = pos2[i] + axis2[i] * x2; }
+      real dist = sphere_sphere(v1, size1[0], v2, size2[0], pos, n);
+      if (dist <= margin) { cdist[0] = dist; memcpy(cpos[0], pos, sizeof pos); memcpy(cn[0], n, sizeof n); }
+    } else {
+      int cc = 0; real x1, x2, dist;
+      for (int i = 0; i < 3; i++) v1[i] = pos1[i] + axis1[i];
+      x2 = rclamp((v - mb) / mc, -1, 1);
+      for (int i = 0; i < 3; i++) v2[i] = pos2[i] + axis2[i] * x2;
+      dist = sphere_sphere(v1, size1[0], v2, size2[0], pos, n);
+      if (dist <= margin) { cdist[cc] = dist; memcpy(cpos[cc], pos, sizeof pos); memcpy(cn[cc], n, sizeof n); cc++; }
+      for (int i = 0; i < 3; i++) v1[i] = pos1[i] - axis1[i];
+      x2 = rclamp((v + mb) / mc, -1, 1);
+      for (int i = 0; i < 3; i++) v2[i] = pos2[i] + axis2[i] * x2;
+      dist = sphere_sphere(v1, size1[0], v2, size2[0], pos, n);
+      if (dist <= margin) { cdist[cc] = dist; memcpy(cpos[cc], pos, sizeof pos); memcpy(cn[cc], n, sizeof n); cc++; }
+      if (cc < 2) {
+        for (int i = 0; i < 3; i++) v2[i] = pos2[i] + axis2[i];
+        x1 = rclamp((u - mb) / ma, -1, 1);
+        for (int i = 0; i < 3; i++) v1[i] = pos1[i] + axis1[i] * x1;
+        dist = sphere_sphere(v1, size1[0], v2, size2[0], pos, n);
+        if (dist <= margin) { cdist[cc] = dist; memcpy(cpos[cc], pos, sizeof pos); memcpy(cn[cc], n, sizeof n); cc++; }
+      }
+      if (cc < 2) {
+        for (int i = 0; i < 3; i++) v2[i] = pos2[i] - axis2[i];
+        x1 = rclamp((u + mb) / ma, -1, 1);
+        for (int i = 0; i < 3; i++) v1[i] = pos1[i] + axis1[i] * x1;
+        dist = sphere_sphere(v1, size1[0], v2, size2[0], pos, n);
+        if (dist <= margin) { cdist[cc] = dist; memcpy(cpos[cc], pos, sizeof pos); memcpy(cn[cc], n, sizeof n); }
+      }
+    }
+    for (int i = 0; i < 2; i++) { make_frame(cn[i], frame); write_contact(w, i, cdist[i], cpos[i], frame, &p, g1, g2); }
+  } else {
+    w->overflow[0] |= OVF_UNSUPPORTED;
+  }
+}
+/* collision_driver.py:884-942 with NXN broadphase (:684-770); contacts are written in filtered-pair order */
+static void collision(W* w) {
+  const OrcModel* m = w->m;
+  w->ncon[0] = 0; w->ncollision[0] = 0;
+  if (w->nconmax == 0 || (m->disableflags & (DSBL_CONSTRAINT | DSBL_CONTACT))) return;
+  for (int e = 0; e < m->nxn_npair; e++) {
+    int g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
+    if (!(broadphase_filter(w, g1, g2) || m->nxn_pairid[2 * e + 1] >= 0)) continue;
+    w->ncollision[0]++;
+    if (m->nxn_pairid[2 * e] == -2) continue; /* sensor-only pair: no constraint contact */
+    if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+    narrowphase_pair(w, g1, g2);
+  }
+  if (w->ncon[0] > w->nconmax) w->ncon[0] = w->nconmax;
+}
+
+/* ------------------------------------------------------------------ make_constraint (constraint.py) */
+/* constraint.py:83-152 */
+static void efc_row(W* w, int efcid, real pos_aref, real pos_imp, real invweight, const real* solref, const real* solimp, real margin, real vel, real frictionloss, int type, int id) {
+  const OrcModel* m = w->m;
+  real timeconst = solref[0], dampratio = solref[1], dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  if (!(m->disableflags & DSBL_REFSAFE)) timeconst = rmax(timeconst, 2 * m->timestep);
+  dmin = rclamp(dmin, MJ_MINIMP, MJ_MAXIMP); dmax = rclamp(dmax, MJ_MINIMP, MJ_MAXIMP);
+  width = rmax(MJ_MINVAL, width); mid = rclamp(mid, MJ_MINIMP, MJ_MAXIMP); power = rmax(1, power);
+  real dmax_sq = dmax * dmax;
+  real k = 1 / (dmax_sq * timeconst * timeconst * dampratio * dampratio), b = 2 / (dmax * timeconst);
+  if (solref[0] <= 0) k = -solref[0] / dmax_sq;
+  if (solref[1] <= 0) b = -solref[1] / dmax;
+  real imp_x = (real)fabs((double)pos_imp) / width;
+  real imp_a = (1 / (real)pow((double)mid, (double)power - 1)) * (real)pow((double)imp_x, (double)power);
+  real imp_b = 1 - (1 / (real)pow(1 - (double)mid, (double)power - 1)) * (real)pow(1 - (double)imp_x, (double)power);
+  real imp_y = imp_x < mid ? imp_a : imp_b;
+  real imp = dmin + imp_y * (dmax - dmin);
+  imp = rclamp(imp, dmin, dmax);
+  if (imp_x > 1) imp = dmax;
+  w->efc_D[efcid] = 1 / rmax(invweight * (1 - imp) / imp, MJ_MINVAL);
+  w->efc_vel[efcid] = vel;
+  w->efc_aref[efcid] = -k * imp * pos_aref - b * vel;
+  w->efc_pos[efcid] = pos_aref + margin;
+  w->efc_margin[efcid] = margin;
+  w->efc_frictionloss[efcid] = frictionloss;
+  w->efc_type[efcid] = type;
+  w->efc_id[efcid] = id;
+}
+static void make_constraint(W* w) {
+  const OrcModel* m = w->m;
+  const int nv = m->nv, njmax = w->njmax, np = m->nmaxpyramid;
+  int nefc = 0;
+  w->ne[0] = w->nf[0] = w->nl[0] = 0;
+  if (m->disableflags & DSBL_CONSTRAINT) { w->nefc[0] = 0; return; }
+  /* dof friction (constraint.py:1765) */
+  if (!(m->disableflags & DSBL_FRICTIONLOSS)) {
+    for (int d = 0; d < nv; d++) {
+      if (m->dof_frictionloss[d] <= 0) continue;
+      w->nf[0]++;
+      int efcid = nefc++;
+      if (efcid >= njmax) continue;
+      for (int i = 0; i < nv; i++) w->efc_J[efcid * nv + i] = 0;
+      w->efc_J[efcid * nv + d] = 1;
+      efc_row(w, efcid, 0, 0, m->dof_invweight0[d], m->dof_solref + 2 * d, m->dof_solimp + 5 * d, 0, w->qvel[d], m->dof_frictionloss[d], CNSTR_FRICTION_DOF, d);
+    }
+  }
+  /* joint limits, slide/hinge (constraint.py:1990) */
+  if (!(m->disableflags & DSBL_LIMIT)) {
+    for (int li = 0; li < m->nlimit; li++) {
+      int j = m->jnt_limited_slide_hinge_adr[li];
+      real qpos = w->qpos[m->jnt_qposadr[j]], margin = m->jnt_margin[j];
+      real dist_min = qpos - m->jnt_range[2 * j], dist_max = m->jnt_range[2 * j + 1] - qpos;
+      real pos = rmin(dist_min, dist_max) - margin;
+      if (!(pos < 0)) continue;
+      w->nl[0]++;
+      int efcid = nefc++;
+      if (efcid >= njmax) continue;
+      int d = m->jnt_dofadr[j];
+      real J = (dist_min < dist_max ? (real)1 : (real)0) * 2 - 1;
+      for (int i = 0; i < nv; i++) w->efc_J[efcid * nv + i] = 0;
+      w->efc_J[efcid * nv + d] = J;
+      efc_row(w, efcid, pos, pos, m->dof_invweight0[d], m->jnt_solref + 2 * j, m->jnt_solimp + 5 * j, margin, J * w->qvel[d], 0, CNSTR_LIMIT_JOINT, j);
+    }
+  }
+  /* contacts (constraint.py:2641 init, :3751 dense jac, :4197 update) */
+  if (!(m->disableflags & DSBL_CONTACT)) {
+    for (int c = 0; c < w->ncon[0]; c++) {
+      int condim = w->con_dim[c];
+      real includemargin = w->con_includemargin[c], pos = w->con_dist[c] - includemargin;
+      if (!(pos < 0)) continue;
+      int ndim = (m->cone == CONE_ELLIPTIC) ? condim : (condim == 1 ? 1 : 2 * (condim - 1));
+      int base = nefc; nefc += ndim;
+      int g1 = w->con_geom[2 * c], g2 = w->con_geom[2 * c + 1], b1 = m->geom_bodyid[g1], b2 = m->geom_bodyid[g2];
+      const real* cpos = w->con_pos + 3 * c; const real* frame = w->con_frame + 9 * c; const real* fri = w->con_friction + 5 * c;
+      real off1[3], off2[3];
+      for (int i = 0; i < 3; i++) { off1[i] = cpos[i] - w->subtree_com[3 * m->body_rootid[b1] + i]; off2[i] = cpos[i] - w->subtree_com[3 * m->body_rootid[b2] + i]; }
+      real invweight0 = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
+      for (int dim = 0; dim < ndim; dim++) {
+        int efcid = base + dim;
+        if (efcid >= njmax) { w->con_efc_address[np * c + dim] = -1; continue; }
+        w->con_efc_address[np * c + dim] = efcid;
+        real Jqvel = 0;
+        for (int d = 0; d < nv; d++) {
+          const real* cd = w->cdof + 6 * d;
+          real jp1[3] = {0, 0, 0}, jr1[3] = {0, 0, 0}, jp2[3] = {0, 0, 0}, jr2[3] = {0, 0, 0}, cr[3];
+          if (m->body_isdofancestor[b1 * nv + d]) { cross3(cd, off1, cr); for (int i = 0; i < 3; i++) { jp1[i] = cd[3 + i] + cr[i]; jr1[i] = cd[i]; } }
+          if (m->body_isdofancestor[b2 * nv + d]) { cross3(cd, off2, cr); for (int i = 0; i < 3; i++) { jp2[i] = cd[3 + i] + cr[i]; jr2[i] = cd[i]; } }
+          real jpd[3] = {jp2[0] - jp1[0], jp2[1] - jp1[1], jp2[2] - jp1[2]}, jrd[3] = {jr2[0] - jr1[0], jr2[1] - jr1[1], jr2[2] - jr1[2]};
+          real J;
+          if (m->cone == CONE_ELLIPTIC) {
+            J = dim < 3 ? dot3(jpd, frame + 3 * dim) : dot3(jrd, frame + 3 * (dim - 3));
+          } else {
+            J = dot3(jpd, frame);
+            if (condim > 1) {
+              int dimid2 = dim / 2 + 1;
+              real frii = fri[dimid2 - 1] * (1 - 2 * (real)(dim & 1));
+              if (dimid2 == 1) J += dot3(jpd, frame + 3) * frii;
+              else if (dimid2 == 2) J += dot3(jpd, frame + 6) * frii;
+              else if (dimid2 == 3) J += dot3(jrd, frame) * frii;
+              else if (dimid2 == 4) J += dot3(jrd, frame + 3) * frii;
+              else J += dot3(jrd, frame + 6) * frii;
+            }
+          }
+          w->efc_J[efcid * nv + d] = J;
+          Jqvel += J * w->qvel[d];
+        }
+        real invweight = invweight0, pos_aref = pos; const real* ref = w->con_solref + 2 * c;
+        int type;
+        if (m->cone == CONE_ELLIPTIC) {
+          if (dim > 0) {
+            const real* srf = w->con_solreffriction + 2 * c;
+            if (srf[0] != 0 || srf[1] != 0) ref = srf;
+            invweight = invweight * m->impratio_invsqrt * m->impratio_invsqrt;
+            if (dim > 1) { real f0 = fri[0], fi = fri[dim - 1]; invweight *= f0 * f0 / (fi * fi); }
+            pos_aref = 0;
+          }
+        } else if (condim > 1) {
+          real f0 = fri[0];
+          invweight = invweight + f0 * f0 * invweight;
+          invweight = invweight * 2 * f0 * f0 * m->impratio_invsqrt * m->impratio_invsqrt;
+        }
+        type = condim == 1 ? CNSTR_CONTACT_FRICTIONLESS : (m->cone == CONE_ELLIPTIC ? CNSTR_CONTACT_ELLIPTIC : CNSTR_CONTACT_PYRAMIDAL);
+        efc_row(w, efcid, pos_aref, pos, invweight, ref, w->con_solimp + 5 * c, includemargin, Jqvel, 0, type, c);
+      }
+    }
+  }
+  w->nefc[0] = nefc;
+}
+
+/* ------------------------------------------------------------------ fwd_velocity (forward.py:732-753) */
+static void fwd_velocity(W* w) {
+  const OrcModel* m = w->m;
+  const int nv = m->nv, nb = m->nbody;
+  for (int a = 0; a < m->nu; a++) { /* forward.py:680 */
+    real vel = 0;
+    for (int i = 0; i < w->moment_rownnz[a]; i++) { int s = w->moment_rowadr[a] + i; vel += w->actuator_moment[s] * w->qvel[w->moment_colind[s]]; }
+    w->actuator_velocity[a] = vel;
+  }
+  /* com_vel (smooth.py:2179-2285) */
+  memset(w->cvel, 0, 6 * sizeof(real));
+  for (int b = 1; b < nb; b++) {
+    int pid = m->body_parentid[b], dofid = m->body_dofadr[b], jntid = m->body_jntadr[b], jntnum = m->body_jntnum[b];
+    real cvel[6];
+    memcpy(cvel, w->cvel + 6 * pid, sizeof cvel);
+    for (int j = jntid; j < jntid + jntnum; j++) {
+      int t = m->jnt_type[j];
+      if (t == JNT_FREE) {
+        for (int k = 0; k < 3; k++) for (int i = 0; i < 6; i++) cvel[i] += w->cdof[6 * (dofid + k) + i] * w->qvel[dofid + k];
+        memset(w->cdof_dot + 6 * dofid, 0, 18 * sizeof(real));
+        for (int k = 3; k < 6; k++) motion_cross(cvel, w->cdof + 6 * (dofid + k), w->cdof_dot + 6 * (dofid + k));
+        for (int k = 3; k < 6; k++) for (int i = 0; i < 6; i++) cvel[i] += w->cdof[6 * (dofid + k) + i] * w->qvel[dofid + k];
+        dofid += 6;
+      } else if (t == JNT_BALL) {
+        for (int k = 0; k < 3; k++) motion_cross(cvel, w->cdof + 6 * (dofid + k), w->cdof_dot + 6 * (dofid + k));
+        for (int k = 0; k < 3; k++) for (int i = 0; i < 6; i++) cvel[i] += w->cdof[6 * (dofid + k) + i] * w->qvel[dofid + k];
+        dofid += 3;
+      } else {
+        motion_cross(cvel, w->cdof + 6 * dofid, w->cdof_dot + 6 * dofid);
+        for (int i = 0; i < 6; i++) cvel[i] += w->cdof[6 * dofid + i] * w->qvel[dofid];
+        dofid += 1;
+      }
+    }
+    memcpy(w->cvel + 6 * b, cvel, sizeof cvel);
+  }
+  /* passive (passive.py:73-206,631-667,1257): springs/dampers on slide/hinge; free/ball damping; gravcomp/fluid absent */
+  int dsbl_spring = m->disableflags & DSBL_SPRING, dsbl_damper = m->disableflags & DSBL_DAMPER;
+  for (int d = 0; d < nv; d++) w->qfrc_spring[d] = w->qfrc_damper[d] = w->qfrc_gravcomp[d] = w->qfrc_passive[d] = 0;
+  if (!(dsbl_spring && dsbl_damper)) {
+    for (int j = 0; j < m->njnt; j++) {
+      int d = m->jnt_dofadr[j], t = m->jnt_type[j], qa = m->jnt_qposadr[j];
+      real stiffness = m->jnt_stiffness[j];
+      int has_st = stiffness != 0 && !dsbl_spring;
+      int nd = t == JNT_FREE ? 6 : (t == JNT_BALL ? 3 : 1);
+      if (has_st) {
+        if (t == JNT_SLIDE || t == JNT_HINGE) w->qfrc_spring[d] = -(w->qpos[qa] - m->qpos_spring[qa]) * stiffness;
+        else w->overflow[0] |= OVF_UNSUPPORTED; /* free/ball joint springs not restated */
+      }
+      for (int k = 0; k < nd; k++) {
+        real damping = m->dof_damping[d + k];
+        if (damping != 0 && !dsbl_damper) w->qfrc_damper[d + k] = -w->qvel[d + k] * damping;
+      }
+    }
+    for (int d = 0; d < nv; d++) w->qfrc_passive[d] = w->qfrc_spring[d] + w->qfrc_damper[d];
+  }
+  /* rne (smooth.py:1353-1515), flg_acc = False */
+  memset(w->cacc, 0, 6 * sizeof(real));
+  if (!(m->disableflags & DSBL_GRAVITY)) for (int i = 0; i < 3; i++) w->cacc[3 + i] = -m->gravity[i];
+  for (int b = 1; b < nb; b++) {
+    int pid = m->body_parentid[b];
+    real a[6];
+    memcpy(a, w->cacc + 6 * pid, sizeof a);
+    for (int k = 0; k < m->body_dofnum[b]; k++) { int d = m->body_dofadr[b] + k; for (int i = 0; i < 6; i++) a[i] += w->cdof_dot[6 * d + i] * w->qvel[d]; }
+    memcpy(w->cacc + 6 * b, a, sizeof a);
+  }
+  memset(w->cfrc_int, 0, 6 * sizeof(real));
+  for (int b = 1; b < nb; b++) {
+    real f[6], iv[6], g[6];
+    inert_vec(w->cinert + 10 * b, w->cacc + 6 * b, f);
+    inert_vec(w->cinert + 10 * b, w->cvel + 6 * b, iv);
+    motion_cross_force(w->cvel + 6 * b, iv, g);
+    for (int i = 0; i < 6; i++) w->cfrc_int[6 * b + i] = f[i] + g[i];
+  }
+  for (int b = nb - 1; b >= 1; b--) { int p = m->body_parentid[b]; for (int i = 0; i < 6; i++) w->cfrc_int[6 * p + i] += w->cfrc_int[6 * b + i]; }
+  for (int d = 0; d < nv; d++) { real s = 0; int b = m->dof_bodyid[d]; for (int i = 0; i < 6; i++) s += w->cdof[6 * d + i] * w->cfrc_int[6 * b + i]; w->qfrc_bias[d] = s; }
+}
+
+/* ------------------------------------------------------------------ fwd_actuation (forward.py:756-1252; stateless actuators) */
+static void fwd_actuation(W* w) {
+  const OrcModel* m = w->m;
+  for (int d = 0; d < m->nv; d++) w->qfrc_actuator[d] = 0;
+  if (!m->nu || (m->disableflags & DSBL_ACTUATION)) { for (int a = 0; a < m->nu; a++) w->actuator_force[a] = 0; return; }
+  for (int a = 0; a < m->nu; a++) {
+    real ctrl = w->ctrl[a];
+    if (m->actuator_ctrllimited[a] && !(m->disableflags & DSBL_CLAMPCTRL)) ctrl = rclamp(ctrl, m->actuator_ctrlrange[2 * a], m->actuator_ctrlrange[2 * a + 1]);
+    real length = w->actuator_length[a], velocity = w->actuator_velocity[a];
+    const real *gp = m->actuator_gainprm + 10 * a, *bp = m->actuator_biasprm + 10 * a;
+    real gain = 0, bias = 0;
+    if (m->actuator_gaintype[a] == GAIN_FIXED) gain = gp[0];
+    else if (m->actuator_gaintype[a] == GAIN_AFFINE) gain = gp[0] + gp[1] * length + gp[2] * velocity;
+    if (m->actuator_biastype[a] == BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
+    real force = gain * ctrl + bias;
+    if (m->actuator_forcelimited[a]) force = rclamp(force, m->actuator_forcerange[2 * a], m->actuator_forcerange[2 * a + 1]);
+    w->actuator_force[a] = force;
+  }
+  for (int a = 0; a < m->nu; a++) /* forward.py:1097 */
+    for (int i = 0; i < w->moment_rownnz[a]; i++) { int s = w->moment_rowadr[a] + i; w->qfrc_actuator[w->moment_colind[s]] += w->actuator_moment[s] * w->actuator_force[a]; }
+  int gravity_enabled = !(m->disableflags & DSBL_GRAVITY);
+  for (int d = 0; d < m->nv; d++) { /* forward.py:1120 */
+    int j = m->dof_jntid[d];
+    real q = w->qfrc_actuator[d];
+    if (gravity_enabled && m->jnt_actgravcomp[j]) q += w->qfrc_gravcomp[d];
+    if (m->jnt_actfrclimited[j]) q = rclamp(q, m->jnt_actfrcrange[2 * j], m->jnt_actfrcrange[2 * j + 1]);
+    w->qfrc_actuator[d] = q;
+  }
+}
+
+/* ------------------------------------------------------------------ fwd_acceleration (forward.py:1255-1324, support.py:259-324) */
+static void fwd_acceleration(W* w) {
+  const OrcModel* m = w->m;
+  const int nv = m->nv, nb = m->nbody;
+  for (int d = 0; d < nv; d++) w->qfrc_smooth[d] = w->qfrc_passive[d] - w->qfrc_bias[d] + w->qfrc_actuator[d] + w->qfrc_applied[d];
+  for (int d = 0; d < nv; d++) { /* _apply_ft */
+    const real* cd = w->cdof + 6 * d;
+    int db = m->dof_bodyid[d];
+    real acc = 0;
+    for (int b = db; b < nb; b++) {
+      const real* ft = w->xfrc_applied + 6 * b;
+      if (ft[0] == 0 && ft[1] == 0 && ft[2] == 0 && ft[3] == 0 && ft[4] == 0 && ft[5] == 0) continue;
+      int p = b;
+      while (p != 0 && p != db) p = m->body_parentid[p];
+      if (p == 0) continue;
+      real off[3], cr[3];
+      for (int i = 0; i < 3; i++) off[i] = w->xipos[3 * b + i] - w->subtree_com[3 * m->body_rootid[b] + i];
+      cross3(cd, off, cr);
+      acc += cd[3] * ft[0] + cd[4] * ft[1] + cd[5] * ft[2] + cd[0] * ft[3] + cd[1] * ft[4] + cd[2] * ft[5] + dot3(cr, ft);
+    }
+    w->qfrc_smooth[d] += acc;
+  }
+  factor_solve_i(w, w->M, NULL, w->qLD, w->qacc_smooth, w->qfrc_smooth);
+}
+
+/* ------------------------------------------------------------------ solver (solver.py) -- Newton, full rebuild path
+ * (the reference's incremental-H / stable-state fast path, solver.py:1951,2145-2159, is an algebraically
+ * equivalent optimisation of this exact iteration) */
+typedef struct {
+  real *Jaref, *jv, *grad, *search, *mv, *H, *Hf, *tmp;
+  real search_dot, grad_dot, newton_decrement, improvement;
+} SCtx;
+
+/* solver.py:425-477 (pyramidal / frictionless / limit / friction / equality rows) */
+static void eval_constraint(int is_equality, int is_friction, real jaref, real D, real frictionloss, real* force, int* state) {
+  if (is_equality) { *force = -D * jaref; *state = ST_QUADRATIC; return; }
+  if (is_friction) {
+    real rf = safe_div(frictionloss, D);
+    if (jaref <= -rf) { *force = frictionloss; *state = ST_LINEARNEG; }
+    else if (jaref >= rf) { *force = -frictionloss; *state = ST_LINEARPOS; }
+    else { *force = -D * jaref; *state = ST_QUADRATIC; }
+    return;
+  }
+  if (jaref >= 0) { *force = 0; *state = ST_SATISFIED; } else { *force = -D * jaref; *state = ST_QUADRATIC; }
+}
+/* _update_constraint (solver.py:1698-1822,1912-1948) */
+static void update_constraint(W* w, SCtx* c, int nefc) {
+  const OrcModel* m = w->m; const int nv = m->nv, ne = w->ne[0], nf = w->nf[0];
+  for (int e = 0; e < nefc; e++) {
+    int is_eq = e < ne, is_fr = !is_eq && e < ne + nf;
+    eval_constraint(is_eq, is_fr, c->Jaref[e], w->efc_D[e], is_fr ? w->efc_frictionloss[e] : 0, &w->efc_force[e], &w->efc_state[e]);
+  }
+  for (int d = 0; d < nv; d++) { real s = 0; for (int e = 0; e < nefc; e++) s += w->efc_J[e * nv + d] * w->efc_force[e]; w->qfrc_constraint[d] = s; }
+}
+/* _update_gradient (solver.py:3061-3200): grad, H = M + J^T D_active J, Cholesky, search */
+static void update_gradient(W* w, SCtx* c, int nefc) {
+  const OrcModel* m = w->m; const int nv = m->nv;
+  c->grad_dot = 0;
+  for (int d = 0; d < nv; d++) { real g = w->efc_Ma[d] - w->qfrc_smooth[d] - w->qfrc_constraint[d]; c->grad[d] = g; c->grad_dot += g * g; }
+  memset(c->H, 0, (size_t)nv * nv * sizeof(real));
+  for (int i = 0; i < nv; i++) { /* densify M (upper + lower) */
+    int adr = m->M_rowadr[i];
+    for (int k = 0; k < m->M_rownnz[i]; k++) { int j = m->M_colind[adr + k]; c->H[i * nv + j] = w->M[adr + k]; c->H[j * nv + i] = w->M[adr + k]; }
+  }
+  for (int e = 0; e < nefc; e++) {
+    if (w->efc_state[e] != ST_QUADRATIC) continue;
+    real D = w->efc_D[e]; const real* J = w->efc_J + e * nv;
+    for (int i = 0; i < nv; i++) { if (J[i] == 0) continue; real di = D * J[i]; for (int j = 0; j < nv; j++) c->H[i * nv + j] += di * J[j]; }
+  }
+  memcpy(c->Hf, c->H, (size_t)nv * nv * sizeof(real));
+  chol_upper(c->Hf, nv);
+  chol_upper_solve(c->Hf, nv, c->grad, c->tmp);
+  c->search_dot = 0; c->newton_decrement = 0;
+  for (int d = 0; d < nv; d++) { c->search_dot += c->tmp[d] * c->tmp[d]; c->newton_decrement += c->grad[d] * c->tmp[d]; c->search[d] = -c->tmp[d]; }
+}
+/* (cost(alpha)-cost(0), grad, hess) of one pyramidal row: solver.py:479-517 */
+static void eval_pt_row(int efcid, real alpha, int ne, int nf, real D, real frictionloss, real jaref, real jv, real out[3]) {
+  if (efcid >= ne + nf) {
+    real x = jaref + alpha * jv, quad0 = (real)0.5 * D * jaref * jaref, cost0 = jaref < 0 ? quad0 : 0, offset = quad0 - cost0;
+    if (x < 0) { real jvD = jv * D, h = jv * jvD, ah = alpha * h; out[0] = alpha * (jvD * jaref + (real)0.5 * ah) + offset; out[1] = jvD * jaref + ah; out[2] = h; }
+    else { out[0] = -cost0; out[1] = 0; out[2] = 0; }
+    return;
+  }
+  if (efcid >= ne) {
+    real f = frictionloss, x = jaref + alpha * jv, rf = safe_div(f, D), c0, p[3];
+    if (-rf < jaref && jaref < rf) c0 = (real)0.5 * D * jaref * jaref; else if (jaref <= -rf) c0 = f * ((real)-0.5 * rf - jaref); else c0 = f * ((real)-0.5 * rf + jaref);
+    if (-rf < x && x < rf) { real jvD = jv * D; p[0] = (real)0.5 * D * x * x; p[1] = jvD * x; p[2] = jv * jvD; }
+    else if (x <= -rf) { p[0] = f * ((real)-0.5 * rf - x); p[1] = -f * jv; p[2] = 0; }
+    else { p[0] = f * ((real)-0.5 * rf + x); p[1] = f * jv; p[2] = 0; }
+    out[0] = p[0] - c0; out[1] = p[1]; out[2] = p[2];
+    return;
+  }
+  { real jvD = jv * D, h = jv * jvD, ah = alpha * h; out[0] = alpha * (jvD * jaref + (real)0.5 * ah); out[1] = jvD * jaref + ah; out[2] = h; }
+}
+/* alpha = 0 variant with absolute cost (solver.py:570-592) */
+static void eval_pt_row_zero(int efcid, int ne, int nf, real D, real frictionloss, real jaref, real jv, real out[3]) {
+  out[0] = out[1] = out[2] = 0;
+  if (efcid >= ne + nf) { if (jaref < 0) { real jvD = jv * D; out[0] = (real)0.5 * D * jaref * jaref; out[1] = jvD * jaref; out[2] = jv * jvD; } return; }
+  if (efcid >= ne) {
+    real f = frictionloss, rf = safe_div(f, D), x = jaref;
+    if (-rf < x && x < rf) { real jvD = jv * D; out[0] = (real)0.5 * D * x * x; out[1] = jvD * x; out[2] = jv * jvD; }
+    else if (x <= -rf) { out[0] = f * ((real)-0.5 * rf - x); out[1] = -f * jv; out[2] = 0; }
+    else { out[0] = f * ((real)-0.5 * rf + x); out[1] = f * jv; out[2] = 0; }
+    return;
+  }
+  { real jvD = jv * D; out[0] = (real)0.5 * D * jaref * jaref; out[1] = jvD * jaref; out[2] = jv * jvD; }
+}
+static void eval_total(W* w, SCtx* c, int nefc, real alpha, const real quad_gauss[3], real out[3]) {
+  /* _eval_pt(quad_gauss, alpha) + sum of rows (solver.py:203-211,1113-1169) */
+  const int ne = w->ne[0], nf = w->nf[0];
+  real aq2 = alpha * quad_gauss[2];
+  out[0] = alpha * aq2 + alpha * quad_gauss[1] + quad_gauss[0]; out[1] = 2 * aq2 + quad_gauss[1]; out[2] = 2 * quad_gauss[2];
+  for (int e = 0; e < nefc; e++) { real r[3]; eval_pt_row(e, alpha, ne, nf, w->efc_D[e], w->efc_frictionloss[e], c->Jaref[e], c->jv[e], r); out[0] += r[0]; out[1] += r[1]; out[2] += r[2]; }
+}
+static int in_bracket(const real* x, const real* y) { return (x[1] < y[1] && y[1] < 0) || (x[1] > y[1] && y[1] > 0); }
+#define CP3(d, s) do { (d)[0] = (s)[0]; (d)[1] = (s)[1]; (d)[2] = (s)[2]; } while (0)
+/* _linesearch (solver.py:836-1347, pyramidal path) */
+static void linesearch(W* w, SCtx* c, int nefc) {
+  const OrcModel* m = w->m; const int nv = m->nv, ne = w->ne[0], nf = w->nf[0];
+  mul_m(m, w->M, c->search, c->mv);
+  for (int e = 0; e < nefc; e++) { real s = 0; for (int d = 0; d < nv; d++) s += w->efc_J[e * nv + d] * c->search[d]; c->jv[e] = s; }
+  real snorm = (real)sqrt((double)c->search_dot), scale = m->meaninertia * (real)nv;
+  real gtol = rmax(m->tolerance * m->ls_tolerance * snorm * scale, (real)1e-6);
+  real p0s[3] = {0, 0, 0};
+  for (int e = 0; e < nefc; e++) { real r[3]; eval_pt_row_zero(e, ne, nf, w->efc_D[e], w->efc_frictionloss[e], c->Jaref[e], c->jv[e], r); p0s[0] += r[0]; p0s[1] += r[1]; p0s[2] += r[2]; }
+  real qg[3] = {0, 0, 0};
+  for (int d = 0; d < nv; d++) { qg[1] += c->search[d] * (w->efc_Ma[d] - w->qfrc_smooth[d]); qg[2] += (real)0.5 * c->search[d] * c->mv[d]; }
+  real p0[3] = {qg[0] + p0s[0], qg[1] + p0s[1], 2 * qg[2] + p0s[2]};
+  real p0_delta[3] = {0, p0[1], p0[2]};
+  real lo_alpha_in = -safe_div(p0[1], p0[2]);
+  real lo_in[3];
+  eval_total(w, c, nefc, lo_alpha_in, qg, lo_in);
+  int initial_converged = fabs((double)lo_in[1]) < gtol && lo_in[0] < 0;
+  int ls_converged = initial_converged;
+  real alpha = 0, improvement = 0;
+  if (!initial_converged) {
+    int lo_less = lo_in[1] < p0[1];
+    real lo[3], hi[3], lo_alpha, hi_alpha;
+    if (lo_less) { CP3(lo, lo_in); lo_alpha = lo_alpha_in; CP3(hi, p0_delta); hi_alpha = 0; }
+    else { CP3(lo, p0_delta); lo_alpha = 0; CP3(hi, lo_in); hi_alpha = lo_alpha_in; }
+    for (int it = 0; it < m->ls_iterations; it++) {
+      real lo_next_alpha = lo_alpha - safe_div(lo[1], lo[2]), hi_next_alpha = hi_alpha - safe_div(hi[1], hi[2]), mid_alpha = (real)0.5 * (lo_alpha + hi_alpha);
+      real lo_next[3], hi_next[3], mid[3];
+      eval_total(w, c, nefc, lo_next_alpha, qg, lo_next);
+      eval_total(w, c, nefc, hi_next_alpha, qg, hi_next);
+      eval_total(w, c, nefc, mid_alpha, qg, mid);
+      int s1 = in_bracket(lo, lo_next); if (s1) { CP3(lo, lo_next); lo_alpha = lo_next_alpha; }
+      int s2 = in_bracket(lo, mid); if (s2) { CP3(lo, mid); lo_alpha = mid_alpha; }
+      int s3 = in_bracket(lo, hi_next); if (s3) { CP3(lo, hi_next); lo_alpha = hi_next_alpha; }
+      int swap_lo = s1 || s2 || s3;
+      int h1 = in_bracket(hi, hi_next); if (h1) { CP3(hi, hi_next); hi_alpha = hi_next_alpha; }
+      int h2 = in_bracket(hi, mid); if (h2) { CP3(hi, mid); hi_alpha = mid_alpha; }
+      int h3 = in_bracket(hi, lo_next); if (h3) { CP3(hi, lo_next); hi_alpha = lo_next_alpha; }
+      int swap_hi = h1 || h2 || h3;
+      int ls_done = (!swap_lo && !swap_hi) || (lo[0] < 0 && lo[1] < 0 && lo[1] > -gtol) || (hi[0] < 0 && hi[1] > 0 && hi[1] < gtol);
+      int improved = lo[0] < 0 || hi[0] < 0, lo_better = lo[0] < hi[0];
+      if (improved) { alpha = lo_better ? lo_alpha : hi_alpha; improvement = -(lo_better ? lo[0] : hi[0]); }
+      if (ls_done) { ls_converged = 1; break; }
+    }
+  } else { alpha = lo_alpha_in; improvement = -lo_in[0]; }
+  for (int d = 0; d < nv; d++) { w->qacc[d] += alpha * c->search[d]; w->efc_Ma[d] += alpha * c->mv[d]; }
+  for (int e = 0; e < nefc; e++) c->Jaref[e] += alpha * c->jv[e];
+  c->improvement = improvement;
+  if (!ls_converged) w->overflow[0] |= OVF_LS_ITERATIONS;
+}
+/* solve (solver.py:3671-3743) */
+static void solve(W* w) {
+  const OrcModel* m = w->m; const int nv = m->nv;
+  if (w->njmax == 0 || nv == 0) { memcpy(w->qacc, w->qacc_smooth, nv * sizeof(real)); w->solver_niter[0] = 0; return; }
+  int nefc = w->nefc[0] < w->njmax ? w->nefc[0] : w->njmax;
+  SCtx c;
+  size_t nr = (size_t)(nefc > 0 ? nefc : 1);
+  real* buf = (real*)calloc(2 * nr + 4 * (size_t)nv + 2 * (size_t)nv * nv, sizeof(real));
+  c.Jaref = buf; c.jv = c.Jaref + nr; c.grad = c.jv + nr; c.search = c.grad + nv; c.mv = c.search + nv; c.tmp = c.mv + nv; c.H = c.tmp + nv; c.Hf = c.H + (size_t)nv * nv;
+  const real* start = (m->disableflags & DSBL_WARMSTART) ? w->qacc_smooth : w->qacc_warmstart;
+  memcpy(w->qacc, start, nv * sizeof(real));
+  w->solver_niter[0] = 0;
+  for (int e = 0; e < nefc; e++) { real s = 0; for (int d = 0; d < nv; d++) s += w->efc_J[e * nv + d] * w->qacc[d]; c.Jaref[e] = s - w->efc_aref[e]; }
+  mul_m(m, w->M, w->qacc, w->efc_Ma);
+  update_constraint(w, &c, nefc);
+  update_gradient(w, &c, nefc);
+  real scale = m->meaninertia * (real)nv;
+  int done = m->iterations == 0;
+  while (!done) {
+    linesearch(w, &c, nefc);
+    update_constraint(w, &c, nefc);
+    update_gradient(w, &c, nefc);
+    w->solver_niter[0] += 1; /* _solve_done solver.py:3453 */
+    real improvement = c.improvement / scale, gradient = (real)sqrt((double)c.grad_dot) / scale, model_improvement = (real)0.5 * c.newton_decrement / scale;
+    done = improvement < m->tolerance || gradient < m->tolerance || model_improvement < m->tolerance;
+    if (!done && w->solver_niter[0] == m->iterations) { w->overflow[0] |= OVF_ITERATIONS; done = 1; }
+  }
+  free(buf);
+}
+
+/* ------------------------------------------------------------------ integrators (forward.py:53-131,221-349,387-417) */
+static void advance(W* w, const real* qacc) {
+  const OrcModel* m = w->m;
+  for (int d = 0; d < m->nv; d++) w->qvel[d] += qacc[d] * m->timestep;
+  for (int j = 0; j < m->njnt; j++) {
+    int t = m->jnt_type[j], qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
+    if (t == JNT_FREE) {
+      for (int i = 0; i < 3; i++) w->qpos[qa + i] += m->timestep * w->qvel[da + i];
+      quat_integrate(w->qpos + qa + 3, w->qvel + da + 3, m->timestep);
+    } else if (t == JNT_BALL) {
+      quat_integrate(w->qpos + qa, w->qvel + da, m->timestep);
+    } else {
+      w->qpos[qa] += m->timestep * w->qvel[da];
+    }
+  }
+  w->time[0] += m->timestep;
+  if (w->nefc[0] > w->njmax) w->overflow[0] |= OVF_NEFC;
+  memcpy(w->qacc_warmstart, w->qacc, m->nv * sizeof(real));
+}
+static void euler(W* w) {
+  const OrcModel* m = w->m;
+  if (!(m->disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
+    int qld = 0; for (int t = 0; t < m->ntree; t++) qld += m->tree_dofnum[t] * m->tree_dofnum[t];
+    real* L = (real*)malloc(((size_t)qld + 2 * m->nv) * sizeof(real));
+    real* qacc = L + qld; real* dd = qacc + m->nv;
+    for (int d = 0; d < m->nv; d++) dd[d] = m->timestep * m->dof_damping[d];
+    factor_solve_i(w, w->M, dd, L, qacc, w->efc_Ma);
+    advance(w, qacc);
+    free(L);
+  } else {
+    advance(w, w->qacc);
+  }
+}
+
+static void forward_world(W* w) {
+  kinematics(w); com_pos(w); camlight(w); crb(w);
+  collision(w); make_constraint(w); transmission(w);
+  fwd_velocity(w); fwd_actuation(w); fwd_acceleration(w);
+  solve(w);
+}
+
+static int run(const OrcModel* m, OrcData* d, int nthreads, int do_step) {
+  if (check_fields(m, d)) return -1;
+  if (do_step && m->integrator != INT_EULER) { snprintf(g_err, sizeof g_err, "oracle: only the Euler integrator is restated"); return -1; }
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int wi = 0; wi < d->nworld; wi++) {
+    W w;
+    make_view(m, d, wi, &w);
+    forward_world(&w);
+    if (do_step) euler(&w);
+  }
+  return 0;
+}
+int orc_forward(const OrcModel* m, OrcData* d, int nthreads) { return run(m, d, nthreads, 0); }
+int orc_step(const OrcModel* m, OrcData* d, int nthreads) { return run(m, d, nthreads, 1); }

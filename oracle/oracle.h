@@ -1,0 +1,65 @@
+/* oracle.h -- TEST INFRASTRUCTURE ONLY (not the product path).
+ *
+ * CPU restatement (plain C, one world at a time, OpenMP over worlds) of the batched physics step
+ * of google-deepmind/mujoco_warp: forward.py:1341-1380 (forward/step), smooth.py, collision_driver.py,
+ * collision_primitive*.py, constraint.py, solver.py.  Every function in oracle.c cites the reference
+ * file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.
+ *
+ * PARITY PINNING (see DESIGN.md "Oracle"): the reference's dynamics tests delegate to live MuJoCo C,
+ * which is absent here, so kinematics/CRBA/RNE/constraint/solver values are "parity unpinned" by
+ * upstream goldens; they are pinned instead by (i) the reference's hard-coded vectors that do not need
+ * MuJoCo (math_test.py closest-point cases, collision_driver_test upper_tri_index table, io_test padding),
+ * (ii) physical invariants (M == finite-difference of kinetic energy, RNE consistency, KKT residual of
+ * the solve, energy conservation), all in tests/test_oracle_*.py.
+ *
+ * real = double by default (MuJoCo C precision); -DORC_FLOAT builds an fp32 twin used to study
+ * fp32 rounding (the reference computes in fp32).
+ */
+#ifndef MJB_ORACLE_H
+#define MJB_ORACLE_H
+
+#ifdef ORC_FLOAT
+typedef float real;
+#else
+typedef double real;
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrcModel OrcModel;
+typedef struct OrcData OrcData;
+
+OrcModel* orc_model_create(void);
+void orc_model_free(OrcModel*);
+/* returns 0 on success, -1 if `name` is unknown */
+int orc_model_set_int(OrcModel*, const char* name, int value);
+int orc_model_set_real(OrcModel*, const char* name, double value);
+int orc_model_set_iarr(OrcModel*, const char* name, const int* ptr);
+int orc_model_set_rarr(OrcModel*, const char* name, const real* ptr);
+
+OrcData* orc_data_create(int nworld, int nconmax, int njmax);
+void orc_data_free(OrcData*);
+int orc_data_set_iarr(OrcData*, const char* name, int* ptr);
+int orc_data_set_rarr(OrcData*, const char* name, real* ptr);
+
+/* forward dynamics for all worlds (no integration). nthreads<=0: omp default. returns 0 or -1 (unset field) */
+int orc_forward(const OrcModel*, OrcData*, int nthreads);
+/* forward + integrator (Euler / implicitfast) */
+int orc_step(const OrcModel*, OrcData*, int nthreads);
+const char* orc_last_error(void);
+int orc_sizeof_real(void);
+
+/* exposed math helpers for golden-vector tests (reference math_test.py) */
+void orc_closest_segment_point(const real a[3], const real b[3], const real pt[3], real out[3]);
+void orc_closest_segment_to_segment_points(const real a0[3], const real a1[3], const real b0[3], const real b1[3], real outa[3], real outb[3]);
+int orc_upper_tri_index(int n, int i, int j);
+int orc_upper_trid_index(int n, int i, int j);
+double orc_halton(int index, int base);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
