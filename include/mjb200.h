@@ -1,0 +1,87 @@
+/* mjb200.h -- C ABI of the B200-native batched MuJoCo physics step (libmjb200.so).
+ *
+ * Drop-in boundary for the step path of google-deepmind/mujoco_warp.  Every entry point replaces a
+ * Python function of the reference's public API (paths relative to /root/reference/mujoco_warp/):
+ *
+ *   mjb_model_* / mjb_data_*   <- _src/io.py:259 put_model, :1680 make_data, :1890 put_data (device SoA binding;
+ *                                 the reference binds wp.array pointers into wp.launch argument lists)
+ *   mjb_step                   <- _src/forward.py:1368 step(m, d)
+ *   mjb_forward                <- _src/forward.py:1341 forward(m, d)
+ *   mjb_fwd_position           <- _src/forward.py:635  fwd_position(m, d, factorize=False)
+ *   mjb_kinematics             <- _src/smooth.py:447   kinematics
+ *   mjb_com_pos                <- _src/smooth.py:824   com_pos
+ *   mjb_camlight               <- _src/smooth.py:984   camlight
+ *   mjb_crb                    <- _src/smooth.py:1079  crb
+ *   mjb_transmission           <- _src/smooth.py:2890  transmission
+ *   mjb_collision              <- _src/collision_driver.py:884 collision (NXN broadphase + primitive narrowphase)
+ *   mjb_make_constraint        <- _src/constraint.py:4897 make_constraint
+ *   mjb_fwd_velocity           <- _src/forward.py:732  fwd_velocity (actuator velocity, com_vel, passive, rne)
+ *   mjb_fwd_actuation          <- _src/forward.py:1152 fwd_actuation
+ *   mjb_fwd_acceleration       <- _src/forward.py:1290 fwd_acceleration(factorize=True) (qfrc_smooth, factor M, qacc_smooth)
+ *   mjb_factor_m               <- _src/smooth.py:1340  factor_m
+ *   mjb_solve                  <- _src/solver.py:3671  solve
+ *   mjb_euler                  <- _src/forward.py:387  euler
+ *   mjb_ctrl_noise             <- _src/cli.py:103      _ctrl_noise (harness kernel, untimed in testspeed)
+ *
+ * Conventions: plain pointers and sizes only (no torch / warp types).  All array pointers are DEVICE
+ * pointers owned by the caller for the lifetime of the handle (borrowed, never freed here).  Layout is
+ * the reference's world-major SoA (types.py:2230-2374): a Data field of per-world shape S is a contiguous
+ * (nworld, *S) fp32 / int32 array.  Every call enqueues work on `stream` (a cudaStream_t cast to void*)
+ * and returns immediately; 0 = ok, non-zero = error (see mjb_last_error).  No device synchronisation and
+ * no allocation happen after mjb_data_finalize, so a call sequence is CUDA-graph capturable.
+ * Runtime failures never raise: they set bits in Data.overflow exactly like the reference (types.py:149-176).
+ */
+#ifndef MJB200_H
+#define MJB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mjbModel mjbModel;
+typedef struct mjbData mjbData;
+
+/* ---- Model: build by name, then finalize.  Names are the reference's Model field names. */
+mjbModel* mjb_model_create(void);
+void mjb_model_destroy(mjbModel* m);
+int mjb_model_set_int(mjbModel* m, const char* name, int value);
+int mjb_model_set_float(mjbModel* m, const char* name, float value);
+/* dev_ptr: device array; nbatch: leading (domain-randomisation) dimension, must be 1 in this version */
+int mjb_model_set_array(mjbModel* m, const char* name, const void* dev_ptr, int nbatch);
+int mjb_model_finalize(mjbModel* m);
+
+/* ---- Data */
+mjbData* mjb_data_create(int nworld, int nconmax, int naconmax, int njmax, int njmax_pad, int nv_pad);
+void mjb_data_destroy(mjbData* d);
+int mjb_data_set_array(mjbData* d, const char* name, void* dev_ptr);
+int mjb_data_finalize(mjbData* d, const mjbModel* m);
+
+/* ---- pipeline */
+int mjb_step(const mjbModel* m, mjbData* d, void* stream);
+int mjb_forward(const mjbModel* m, mjbData* d, void* stream);
+int mjb_fwd_position(const mjbModel* m, mjbData* d, void* stream);
+int mjb_kinematics(const mjbModel* m, mjbData* d, void* stream);
+int mjb_com_pos(const mjbModel* m, mjbData* d, void* stream);
+int mjb_camlight(const mjbModel* m, mjbData* d, void* stream);
+int mjb_crb(const mjbModel* m, mjbData* d, void* stream);
+int mjb_transmission(const mjbModel* m, mjbData* d, void* stream);
+int mjb_collision(const mjbModel* m, mjbData* d, void* stream);
+int mjb_make_constraint(const mjbModel* m, mjbData* d, void* stream);
+int mjb_fwd_velocity(const mjbModel* m, mjbData* d, void* stream);
+int mjb_fwd_actuation(const mjbModel* m, mjbData* d, void* stream);
+int mjb_fwd_acceleration(const mjbModel* m, mjbData* d, void* stream);
+int mjb_factor_m(const mjbModel* m, mjbData* d, void* stream);
+int mjb_solve(const mjbModel* m, mjbData* d, void* stream);
+int mjb_euler(const mjbModel* m, mjbData* d, void* stream);
+/* ctrl <- OU noise around ctrl_center (device array of nu floats, or NULL), reference cli.py:103-145 */
+int mjb_ctrl_noise(const mjbModel* m, mjbData* d, const float* ctrl_center, int step, float noise_std, float noise_rate, void* stream);
+
+/* number of kernels the last mjb_* pipeline call launched (for bench.py's gpu_launches) */
+int mjb_last_launch_count(void);
+const char* mjb_last_error(void);
+const char* mjb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

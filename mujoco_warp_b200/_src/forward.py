@@ -1,0 +1,100 @@
+"""Public pipeline functions: step, forward and the individually callable stages.
+
+Same names and `(m, d)` signatures as /root/reference/mujoco_warp/__init__.py:26-123 (forward.py:1368 step, :1341 forward,
+:635 fwd_position, smooth.py kinematics/com_pos/camlight/crb/factor_m/transmission, collision_driver.py:884 collision,
+constraint.py:4897 make_constraint, forward.py:732/1152/1290 fwd_velocity/fwd_actuation/fwd_acceleration, solver.py:3671 solve,
+forward.py:387 euler).  Each is one call through the C-ABI on the current torch CUDA stream; `d` is mutated in place;
+nothing synchronises the device, so sequences are capturable with torch.cuda.graphs.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .types import Data, Model
+
+
+def _call(name: str, m: Model, d: Data):
+  if d._model is not m and d._model._handle != m._handle:
+    raise ValueError("Data was created for a different Model")
+  stream = torch.cuda.current_stream().cuda_stream
+  _lib.check(getattr(_lib.lib(), name)(m._handle, d._handle, stream))
+
+
+def step(m: Model, d: Data):
+  """Advance simulation (forward dynamics + Euler integration)."""
+  _call("mjb_step", m, d)
+
+
+def forward(m: Model, d: Data):
+  """Forward dynamics."""
+  _call("mjb_forward", m, d)
+
+
+def fwd_position(m: Model, d: Data):
+  """Position-dependent computations (kinematics .. make_constraint, transmission)."""
+  _call("mjb_fwd_position", m, d)
+
+
+def kinematics(m: Model, d: Data):
+  _call("mjb_kinematics", m, d)
+
+
+def com_pos(m: Model, d: Data):
+  _call("mjb_com_pos", m, d)
+
+
+def camlight(m: Model, d: Data):
+  _call("mjb_camlight", m, d)
+
+
+def crb(m: Model, d: Data):
+  _call("mjb_crb", m, d)
+
+
+def factor_m(m: Model, d: Data):
+  _call("mjb_factor_m", m, d)
+
+
+def transmission(m: Model, d: Data):
+  _call("mjb_transmission", m, d)
+
+
+def collision(m: Model, d: Data):
+  _call("mjb_collision", m, d)
+
+
+def make_constraint(m: Model, d: Data):
+  _call("mjb_make_constraint", m, d)
+
+
+def fwd_velocity(m: Model, d: Data):
+  _call("mjb_fwd_velocity", m, d)
+
+
+def fwd_actuation(m: Model, d: Data):
+  _call("mjb_fwd_actuation", m, d)
+
+
+def fwd_acceleration(m: Model, d: Data):
+  _call("mjb_fwd_acceleration", m, d)
+
+
+def solve(m: Model, d: Data):
+  _call("mjb_solve", m, d)
+
+
+def euler(m: Model, d: Data):
+  _call("mjb_euler", m, d)
+
+
+def ctrl_noise(m: Model, d: Data, step_index: int, ctrl_center: torch.Tensor | None = None, noise_std: float = 0.01, noise_rate: float = 0.1):
+  """Harness OU control noise (reference cli.py:103-145), deterministic Halton sequence per (step, world, actuator)."""
+  stream = torch.cuda.current_stream().cuda_stream
+  ptr = ctrl_center.data_ptr() if ctrl_center is not None else None
+  _lib.check(_lib.lib().mjb_ctrl_noise(m._handle, d._handle, ptr, int(step_index), float(noise_std), float(noise_rate), stream))
+
+
+def last_launch_count() -> int:
+  return int(_lib.lib().mjb_last_launch_count())

@@ -1,0 +1,502 @@
+"""Host <-> device conversion: put_model, make_data, put_data, reset_data.
+
+Mirrors /root/reference/mujoco_warp/_src/io.py (put_model :259, make_data :1680, put_data :1890, reset_data :2435):
+same signatures, same Model/Data field names and world-major layout, `torch.Tensor` as the device-array container.
+`mjm` is either a real `mujoco.MjModel` (when that package is importable) or the object produced by
+`mujoco_warp_b200.mjcf.load` (MjModel-named numpy attributes); fields are copied by name exactly like io.py:426.
+
+Derived index tables are recomputed here for the warp-per-world kernels (tree levels, child lists, CSR entry rows,
+symmetric gather tables for M*v, per-tree factor offsets, filtered NXN pairs, limited-joint list ...).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import constants as C
+from . import mjcf
+from . import types
+
+_FLOAT_FIELDS = [
+  "qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_subtreemass",
+  "body_inertia", "body_invweight0", "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref",
+  "jnt_solimp", "jnt_actfrcrange", "dof_armature", "dof_damping", "dof_invweight0", "dof_frictionloss", "dof_solref",
+  "dof_solimp", "geom_size", "geom_aabb", "geom_rbound", "geom_pos", "geom_quat", "geom_friction", "geom_margin",
+  "geom_gap", "geom_solmix", "geom_solref", "geom_solimp", "actuator_gear", "actuator_gainprm", "actuator_biasprm",
+  "actuator_ctrlrange", "actuator_forcerange", "cam_pos", "cam_quat", "cam_poscom0", "cam_pos0", "cam_mat0",
+  "light_pos", "light_dir", "light_poscom0", "light_pos0", "light_dir0", "site_pos", "site_quat",
+]
+_INT_FIELDS = [
+  "body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr",
+  "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_actfrclimited", "jnt_actgravcomp",
+  "dof_bodyid", "dof_jntid", "dof_parentid", "M_rownnz", "M_rowadr", "M_colind", "tree_dofadr", "tree_dofnum",
+  "geom_type", "geom_condim", "geom_bodyid", "geom_priority",
+  "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
+  "cam_mode", "cam_bodyid", "cam_targetbodyid", "light_mode", "light_bodyid", "light_targetbodyid", "site_bodyid",
+]
+_SIZES = ["nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "nsite", "ncam", "nlight", "ntree", "nkey", "nmocap", "neq", "ntendon", "nflex"]
+
+_SUPPORTED_PAIRS = {
+  (C.GEOM_PLANE, C.GEOM_SPHERE), (C.GEOM_PLANE, C.GEOM_CAPSULE), (C.GEOM_SPHERE, C.GEOM_SPHERE),
+  (C.GEOM_SPHERE, C.GEOM_CAPSULE), (C.GEOM_CAPSULE, C.GEOM_CAPSULE),
+}
+
+
+def _require_cuda():
+  if not torch.cuda.is_available():
+    raise RuntimeError("mujoco_warp_b200 runs its step path on a CUDA (sm_100a) device only; no CPU fallback exists")
+  return torch.device("cuda", torch.cuda.current_device())
+
+
+def is_sparse(mjm) -> bool:
+  """io.py:153-160."""
+  jac = getattr(mjm.opt, "jacobian", C.JAC_AUTO)
+  if jac == C.JAC_AUTO:
+    return mjm.nv > 32
+  return jac == C.JAC_SPARSE
+
+
+def _get_padded_sizes(nv: int, njmax: int, sparse: bool, tile_size: int = 16, augment_cholesky: bool = False):
+  """io.py:1268-1275."""
+
+  def round_up(x, m):
+    return ((x + m - 1) // m) * m
+
+  njmax_padded = round_up(njmax, tile_size)
+  nv_padded = round_up(nv + int(augment_cholesky), tile_size) if (sparse or nv > 32) else round_up(nv, 4)
+  return njmax_padded, nv_padded
+
+
+def _default_size(base: float) -> int:
+  valid = (2 + (np.arange(19) % 2)) * (2 ** (np.arange(19) // 2 + 3))
+  return int(base) if base > valid[-1] else int(valid[np.searchsorted(valid, base)])
+
+
+def _default_nconmax(mjm) -> int:
+  return _default_size(45)  # io.py:1284-1297 without hfield/flex/sdf terms
+
+
+def _default_njmax(mjm) -> int:
+  return _default_size(53)  # io.py:1299-1311
+
+
+def _np(mjm, name):
+  return np.asarray(getattr(mjm, name))
+
+
+def derive_tables(mjm) -> dict:
+  """Index tables for the kernels (host, numpy)."""
+  nbody, nv, ngeom, njnt, nu = mjm.nbody, mjm.nv, mjm.ngeom, mjm.njnt, mjm.nu
+  parent = _np(mjm, "body_parentid")
+  t = {}
+  # tree levels (reference body_tree, io.py:495-500) and child lists
+  depth = np.zeros(nbody, dtype=np.int32)
+  for b in range(1, nbody):
+    depth[b] = depth[parent[b]] + 1
+  nlevel = int(depth.max()) + 1
+  order = np.argsort(depth, kind="stable").astype(np.int32)
+  t["level_body"] = order
+  t["level_adr"] = np.searchsorted(depth[order], np.arange(nlevel + 1)).astype(np.int32)
+  t["nlevel"] = nlevel
+  t["body_tree"] = [order[t["level_adr"][l] : t["level_adr"][l + 1]] for l in range(nlevel)]
+  children = [[] for _ in range(nbody)]
+  for b in range(1, nbody):
+    children[parent[b]].append(b)
+  t["body_childadr"] = np.concatenate([[0], np.cumsum([len(c) for c in children])]).astype(np.int32)
+  t["body_childid"] = np.array([c for cs in children for c in cs] + ([0] if nbody == 1 else []), dtype=np.int32)
+  # CSR entry rows (reference M_hinit_i) and symmetric gather tables (reference M_mulm_*, io.py:1029-1050)
+  rownnz, rowadr, colind = _np(mjm, "M_rownnz"), _np(mjm, "M_rowadr"), _np(mjm, "M_colind")
+  nC = int(rownnz.sum())
+  entry_row = np.zeros(nC, dtype=np.int32)
+  gather = [[] for _ in range(nv)]
+  for i in range(nv):
+    for k in range(rownnz[i]):
+      e = rowadr[i] + k
+      j = colind[e]
+      entry_row[e] = i
+      gather[i].append((j, e))
+      if j != i:
+        gather[j].append((i, e))
+  t["nC"] = nC
+  t["M_entry_row"] = entry_row
+  t["mulm_rowadr"] = np.concatenate([[0], np.cumsum([len(g) for g in gather])]).astype(np.int32)
+  t["mulm_col"] = np.array([c for g in gather for c, _ in sorted(g)], dtype=np.int32)
+  t["mulm_madr"] = np.array([e for g in gather for _, e in sorted(g)], dtype=np.int32)
+  # per-tree dense factor blocks (io.py:173-211; every block <= M_BLOCK_DENSE_MAX uses the dense path here)
+  tadr, tnum = _np(mjm, "tree_dofadr"), _np(mjm, "tree_dofnum")
+  off, qadr = 0, []
+  for n in tnum:
+    qadr.append(off)
+    off += int(n) * int(n)
+  t["tree_qLDadr"] = np.array(qadr if qadr else [0], dtype=np.int32)
+  t["qld_total"] = off
+  t["maxtree"] = int(tnum.max()) if len(tnum) else 0
+  blk = np.zeros(max(nv, 1), dtype=np.int32)
+  for a, n, q in zip(tadr, tnum, qadr):
+    blk[a : a + n] = q
+  t["qLD_block_adr"] = blk
+  # dof-ancestor mask (io.py:536-549)
+  anc = np.zeros((nbody, nv), dtype=np.int32)
+  dofnum, dofadr, dparent = _np(mjm, "body_dofnum"), _np(mjm, "body_dofadr"), _np(mjm, "dof_parentid")
+  for bodyid in range(nbody):
+    b = bodyid
+    while b > 0 and dofnum[b] == 0:
+      b = parent[b]
+    if dofnum[b] == 0:
+      continue
+    d = dofadr[b] + dofnum[b] - 1
+    while d >= 0:
+      anc[bodyid, d] = 1
+      d = dparent[d]
+  t["body_isdofancestor"] = anc
+  # filtered NXN geom pairs (io.py:551-640)
+  filterparent = not (mjm.opt.disableflags & C.DSBL_FILTERPARENT)
+  g1, g2 = np.triu_indices(ngeom, k=1)
+  gb = _np(mjm, "geom_bodyid")
+  weld = _np(mjm, "body_weldid")
+  b1, b2 = gb[g1], gb[g2]
+  w1, w2 = weld[b1], weld[b2]
+  wp1, wp2 = weld[parent[w1]], weld[parent[w2]]
+  ct, ca = _np(mjm, "geom_contype"), _np(mjm, "geom_conaffinity")
+  mask = ((ct[g1] & ca[g2]) | (ct[g2] & ca[g1])).astype(bool)
+  self_col = w1 == w2
+  parent_child = filterparent & (w1 != 0) & (w2 != 0) & ((w1 == wp2) | (w2 == wp1))
+  excl_sig = np.asarray(getattr(mjm, "exclude_signature", np.zeros(0, dtype=np.int64)))
+  exclude = np.isin((b1.astype(np.int64) << 16) + b2, excl_sig)
+  pairid = -np.ones(len(g1), dtype=np.int32)
+  pairid[~(mask & ~self_col & ~parent_child & ~exclude)] = -2
+  include = pairid > -2
+  t["nxn_geom_pair"] = np.stack((g1, g2), axis=1).astype(np.int32)
+  t["nxn_pairid"] = np.stack((pairid, -np.ones(len(g1), dtype=np.int32)), axis=1).astype(np.int32)
+  t["nxn_geom_pair_filtered"] = t["nxn_geom_pair"][include]
+  t["nxn_pairid_filtered"] = t["nxn_pairid"][include]
+  gt = _np(mjm, "geom_type")
+
+  def trid(i, j):
+    i, j = (j, i) if j < i else (i, j)
+    return (i * (2 * C.NGEOMTYPES - i - 1)) // 2 + j
+
+  counts = np.zeros(C.NGEOMTYPES * (C.NGEOMTYPES + 1) // 2, dtype=int)
+  for a, b in t["nxn_geom_pair_filtered"]:
+    counts[trid(gt[a], gt[b])] += 1
+    key = (min(gt[a], gt[b]), max(gt[a], gt[b]))
+    if key not in _SUPPORTED_PAIRS:
+      raise NotImplementedError(f"collision between geom types {key} is not implemented in this version (supported: {sorted(_SUPPORTED_PAIRS)})")
+  t["geom_pair_type_count"] = tuple(int(c) for c in counts)
+  # constraint source lists
+  jt = _np(mjm, "jnt_type")
+  lim = np.asarray(_np(mjm, "jnt_limited")).astype(bool)
+  t["jnt_limited_slide_hinge_adr"] = np.nonzero(lim & ((jt == C.JNT_SLIDE) | (jt == C.JNT_HINGE)))[0].astype(np.int32)
+  if (lim & (jt == C.JNT_BALL)).any():
+    raise NotImplementedError("ball joint limits are not implemented in this version")
+  t["dof_fricloss_adr"] = np.nonzero(_np(mjm, "dof_frictionloss") > 0)[0].astype(np.int32)
+  # constant sparsity of the actuator moment (joint transmission)
+  trnid = _np(mjm, "actuator_trnid").reshape(nu, 2)
+  jdof = _np(mjm, "jnt_dofadr")
+  nnz_of = {C.JNT_FREE: 6, C.JNT_BALL: 3, C.JNT_SLIDE: 1, C.JNT_HINGE: 1}
+  rn, ra, ci = [], [], []
+  for a in range(nu):
+    if int(_np(mjm, "actuator_trntype")[a]) != C.TRN_JOINT:
+      raise NotImplementedError("only joint transmission is implemented")
+    jtype = int(jt[trnid[a, 0]])
+    if jtype == C.JNT_BALL:
+      raise NotImplementedError("ball-joint actuator transmission is not implemented")
+    n = nnz_of[jtype]
+    ra.append(len(ci))
+    rn.append(n)
+    ci.extend(range(jdof[trnid[a, 0]], jdof[trnid[a, 0]] + n))
+  t["moment_rownnz0"] = np.array(rn if rn else [0], dtype=np.int32)
+  t["moment_rowadr0"] = np.array(ra if ra else [0], dtype=np.int32)
+  t["moment_colind0"] = np.array(ci if ci else [0], dtype=np.int32)
+  t["nJmom"] = len(ci)
+  nmaxcondim = int(_np(mjm, "geom_condim").max()) if ngeom else 1
+  t["nmaxcondim"] = nmaxcondim
+  t["nmaxpyramid"] = max(1, 2 * (nmaxcondim - 1))
+  return t
+
+
+def _validate(mjm):
+  """Feature checks in the spirit of io.py:284-363: fail loudly on anything the kernels do not cover."""
+  o = mjm.opt
+  if o.integrator != C.INT_EULER:
+    raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler only in this version)")
+  if o.cone != C.CONE_PYRAMIDAL:
+    raise NotImplementedError("elliptic friction cones are not implemented in this version")
+  if o.solver != C.SOL_NEWTON:
+    raise NotImplementedError("only the Newton solver is implemented in this version")
+  if is_sparse(mjm):
+    raise NotImplementedError("sparse constraint Jacobians (nv > 32) are not implemented in this version")
+  for n in ("na", "neq", "ntendon", "nflex", "nmocap"):
+    if getattr(mjm, n, 0):
+      raise NotImplementedError(f"{n} > 0 is not supported in this version")
+  if (np.asarray(mjm.body_gravcomp) != 0).any():
+    raise NotImplementedError("gravity compensation is not implemented")
+  jt = np.asarray(mjm.jnt_type)
+  if ((jt == C.JNT_FREE) | (jt == C.JNT_BALL)).any() and (np.asarray(mjm.jnt_stiffness)[(jt == C.JNT_FREE) | (jt == C.JNT_BALL)] != 0).any():
+    raise NotImplementedError("free/ball joint springs are not implemented")
+  if int(np.asarray(mjm.tree_dofnum).max(initial=0)) > 64:
+    raise NotImplementedError("kinematic trees with more than 64 dofs are not supported (dense per-tree Cholesky)")
+
+
+def _ptr_tensor(x: torch.Tensor) -> torch.Tensor:
+  """A contiguous tensor with a valid device pointer (empty tables get a 1-element dummy)."""
+  assert x.is_contiguous()
+  if x.numel() == 0:
+    return torch.zeros(1, dtype=x.dtype, device=x.device)
+  return x
+
+
+def put_model(mjm, batch_sizes=None) -> types.Model:
+  """Creates a device Model from an MjModel-like object (reference io.py:259)."""
+  if batch_sizes:
+    raise NotImplementedError("per-world (batched) Model fields are not supported in this version")
+  dev = _require_cuda()
+  L = _lib.lib()
+  _validate(mjm)
+  t = derive_tables(mjm)
+  sparse = is_sparse(mjm)
+  m = types.Model()
+  for n in _SIZES:
+    setattr(m, n, int(getattr(mjm, n, 0)))
+  m.nC = m.nM = t["nC"]
+  m.nJmom = t["nJmom"]
+  m.nmaxcondim, m.nmaxpyramid = t["nmaxcondim"], t["nmaxpyramid"]
+  m.is_sparse = sparse
+  m.nv_pad = _get_padded_sizes(m.nv, 0, sparse)[1]
+  m.qLD_block_total = t["qld_total"]
+  m.geom_pair_type_count = t["geom_pair_type_count"]
+  m.nbranch = int((t["body_childadr"][1:] - t["body_childadr"][:-1] == 0)[1:].sum()) if m.nbody > 1 else 0
+
+  o = mjm.opt
+  tol = max(float(o.tolerance), 1e-6)  # io.py:401 float32 clamp
+  f32 = lambda x: torch.tensor(np.asarray(x, dtype=np.float32).reshape(1, *np.shape(x)), device=dev)
+  m.opt = types.Option(
+    timestep=f32(o.timestep), tolerance=f32(tol), ls_tolerance=f32(o.ls_tolerance), gravity=f32(np.asarray(o.gravity)),
+    integrator=int(o.integrator), cone=int(o.cone), solver=int(o.solver), iterations=int(o.iterations), ls_iterations=int(o.ls_iterations),
+    disableflags=int(o.disableflags), enableflags=int(o.enableflags), impratio_invsqrt=f32(1.0 / np.sqrt(o.impratio)),
+    broadphase=types.BroadphaseType.NXN, broadphase_filter=int(getattr(o, "broadphase_filter", C.BF_PLANE | C.BF_SPHERE | C.BF_OBB)),
+    graph_conditional=False, run_collision_detection=True, warn_overflow=False,
+  )
+  if len(t["nxn_geom_pair_filtered"]) >= 250_000:
+    raise NotImplementedError("SAP broadphase (>= 250k candidate pairs) is not implemented in this version")
+  m.stat = types.Statistic(meaninertia=f32(mjm.stat.meaninertia))
+
+  keep = []
+
+  def dev_f(arr, batched=True):
+    a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
+    x = torch.from_numpy(a).to(dev)
+    return x.unsqueeze(0).contiguous() if batched else x
+
+  def dev_i(arr):
+    a = np.ascontiguousarray(np.asarray(arr).astype(np.int32))
+    return torch.from_numpy(a).to(dev)
+
+  for n in _FLOAT_FIELDS:
+    setattr(m, n, dev_f(getattr(mjm, n)))
+  for n in _INT_FIELDS:
+    setattr(m, n, dev_i(getattr(mjm, n)))
+  m.jnt_limited = dev_i(np.asarray(mjm.jnt_limited).astype(np.int32))
+  m.body_tree = tuple(dev_i(x) for x in t["body_tree"])
+  for n in ("body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col", "mulm_madr", "tree_qLDadr",
+            "qLD_block_adr", "jnt_limited_slide_hinge_adr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
+            "nxn_geom_pair", "nxn_pairid", "nxn_geom_pair_filtered", "nxn_pairid_filtered"):
+    setattr(m, n, dev_i(t[n]))
+  m.M_hinit_i = m.M_entry_row
+  m.M_mulm_rowadr, m.M_mulm_col, m.M_mulm_madr = m.mulm_rowadr, m.mulm_col, m.mulm_madr
+  anc_pad = np.zeros((m.nbody, m.nv_pad), dtype=np.int32)
+  anc_pad[:, : m.nv] = t["body_isdofancestor"]
+  m.body_isdofancestor = dev_i(anc_pad).reshape(m.nbody, m.nv_pad)
+  m._isdofancestor_nv = dev_i(t["body_isdofancestor"])
+  # host copies the harness reads
+  m._mjm = mjm
+  m._tables = t
+
+  # ---- bind to the C ABI
+  h = L.mjb_model_create()
+  m._handle = h
+  ints = dict(
+    nq=m.nq, nv=m.nv, nu=m.nu, nbody=m.nbody, njnt=m.njnt, ngeom=m.ngeom, nsite=m.nsite, ncam=m.ncam, nlight=m.nlight, nC=m.nC, ntree=m.ntree,
+    nJmom=m.nJmom, nlevel=t["nlevel"], nxn_npair=len(t["nxn_geom_pair_filtered"]), nlimit=len(t["jnt_limited_slide_hinge_adr"]),
+    nfricdof=len(t["dof_fricloss_adr"]), nmaxpyramid=m.nmaxpyramid, integrator=m.opt.integrator, cone=m.opt.cone, solver=m.opt.solver,
+    iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
+    broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
+  )
+  for k, v in ints.items():
+    _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))
+  g = np.asarray(o.gravity, dtype=np.float64)
+  floats = dict(timestep=o.timestep, tolerance=tol, ls_tolerance=o.ls_tolerance, impratio_invsqrt=1.0 / np.sqrt(o.impratio),
+                meaninertia=mjm.stat.meaninertia, gravity_x=g[0], gravity_y=g[1], gravity_z=g[2])
+  for k, v in floats.items():
+    _lib.check(L.mjb_model_set_float(h, k.encode(), float(v)))
+  dev_names = {
+    "jnt_limited_adr": m.jnt_limited_slide_hinge_adr, "nxn_geom_pair": m.nxn_geom_pair_filtered, "nxn_pairid": m.nxn_pairid_filtered,
+    "body_isdofancestor": m._isdofancestor_nv,
+  }
+  for n in _FLOAT_FIELDS + _INT_FIELDS + ["body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col",
+                                         "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0"]:
+    dev_names.setdefault(n, getattr(m, n))
+  for n, x in dev_names.items():
+    x = _ptr_tensor(x)
+    keep.append(x)
+    _lib.check(L.mjb_model_set_array(h, n.encode(), x.data_ptr(), 1))
+  _lib.check(L.mjb_model_finalize(h))
+  m._keep = keep
+  return m
+
+
+# --------------------------------------------------------------------------------------------- Data
+
+
+def _data_spec(m: types.Model, nworld, naconmax, njmax, njmax_pad):
+  """name -> (dtype, shape) for top-level Data fields (reference types.py:2230-2374)."""
+  f, i = torch.float32, torch.int32
+  nb, nv, nq, nu, nj, ng = m.nbody, m.nv, m.nq, m.nu, m.njnt, m.ngeom
+  return {
+    "solver_niter": (i, (nworld,)), "ne": (i, (nworld,)), "nf": (i, (nworld,)), "nl": (i, (nworld,)), "nefc": (i, (nworld,)),
+    "time": (f, (nworld,)), "qpos": (f, (nworld, nq)), "qvel": (f, (nworld, nv)), "act": (f, (nworld, m.na)),
+    "qacc_warmstart": (f, (nworld, nv)), "ctrl": (f, (nworld, nu)), "qfrc_applied": (f, (nworld, nv)), "xfrc_applied": (f, (nworld, nb, 6)),
+    "qacc": (f, (nworld, nv)), "act_dot": (f, (nworld, m.na)), "sensordata": (f, (nworld, 0)),
+    "xpos": (f, (nworld, nb, 3)), "xquat": (f, (nworld, nb, 4)), "xmat": (f, (nworld, nb, 3, 3)), "xipos": (f, (nworld, nb, 3)),
+    "ximat": (f, (nworld, nb, 3, 3)), "xanchor": (f, (nworld, nj, 3)), "xaxis": (f, (nworld, nj, 3)),
+    "geom_xpos": (f, (nworld, ng, 3)), "geom_xmat": (f, (nworld, ng, 3, 3)), "site_xpos": (f, (nworld, m.nsite, 3)), "site_xmat": (f, (nworld, m.nsite, 3, 3)),
+    "cam_xpos": (f, (nworld, m.ncam, 3)), "cam_xmat": (f, (nworld, m.ncam, 3, 3)), "light_xpos": (f, (nworld, m.nlight, 3)), "light_xdir": (f, (nworld, m.nlight, 3)),
+    "subtree_com": (f, (nworld, nb, 3)), "cdof": (f, (nworld, nv, 6)), "cinert": (f, (nworld, nb, 10)),
+    "actuator_length": (f, (nworld, nu)), "moment_rownnz": (i, (nworld, nu)), "moment_rowadr": (i, (nworld, nu)),
+    "moment_colind": (i, (nworld, m.nJmom)), "actuator_moment": (f, (nworld, m.nJmom)),
+    "crb": (f, (nworld, nb, 10)), "M": (f, (nworld, m.nC)), "qLD": (f, (nworld, m.qLD_block_total)), "qLDiagInv": (f, (nworld, nv)),
+    "actuator_velocity": (f, (nworld, nu)), "cvel": (f, (nworld, nb, 6)), "cdof_dot": (f, (nworld, nv, 6)),
+    "qfrc_bias": (f, (nworld, nv)), "qfrc_spring": (f, (nworld, nv)), "qfrc_damper": (f, (nworld, nv)), "qfrc_gravcomp": (f, (nworld, nv)),
+    "qfrc_fluid": (f, (nworld, nv)), "qfrc_adhesion": (f, (nworld, nv)), "qfrc_passive": (f, (nworld, nv)),
+    "actuator_force": (f, (nworld, nu)), "qfrc_actuator": (f, (nworld, nv)), "qfrc_smooth": (f, (nworld, nv)), "qacc_smooth": (f, (nworld, nv)),
+    "qfrc_constraint": (f, (nworld, nv)), "qfrc_inverse": (f, (nworld, nv)), "cacc": (f, (nworld, nb, 6)), "cfrc_int": (f, (nworld, nb, 6)),
+    "cfrc_ext": (f, (nworld, nb, 6)), "energy": (f, (nworld, 2)),
+    "nacon": (i, (1,)), "ncollision": (i, (1,)), "overflow": (i, (nworld,)),
+  }
+
+
+def _contact_spec(m, naconmax):
+  f, i = torch.float32, torch.int32
+  return {
+    "dist": (f, (naconmax,)), "pos": (f, (naconmax, 3)), "frame": (f, (naconmax, 3, 3)), "includemargin": (f, (naconmax,)),
+    "friction": (f, (naconmax, 5)), "solref": (f, (naconmax, 2)), "solreffriction": (f, (naconmax, 2)), "solimp": (f, (naconmax, 5)),
+    "dim": (i, (naconmax,)), "geom": (i, (naconmax, 2)), "efc_address": (i, (naconmax, m.nmaxpyramid)), "worldid": (i, (naconmax,)),
+    "type": (i, (naconmax,)), "geomcollisionid": (i, (naconmax,)),
+  }
+
+
+def _efc_spec(m, nworld, njmax, njmax_pad):
+  f, i = torch.float32, torch.int32
+  return {
+    "type": (i, (nworld, njmax)), "id": (i, (nworld, njmax)), "J": (f, (nworld, njmax_pad, m.nv_pad)), "pos": (f, (nworld, njmax)),
+    "margin": (f, (nworld, njmax)), "D": (f, (nworld, njmax_pad)), "vel": (f, (nworld, njmax)), "aref": (f, (nworld, njmax)),
+    "frictionloss": (f, (nworld, njmax)), "force": (f, (nworld, njmax)), "state": (i, (nworld, njmax_pad)), "Ma": (f, (nworld, nv_of(m))),
+    "Jqvel": (f, (nworld, njmax)),
+  }
+
+
+def nv_of(m):
+  return m.nv
+
+
+_BOUND_TOP = [
+  "time", "qpos", "qvel", "ctrl", "qacc_warmstart", "qfrc_applied", "xfrc_applied", "qacc", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor",
+  "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat", "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert",
+  "crb", "M", "qLD", "actuator_length", "actuator_moment", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
+  "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int",
+  "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind",
+]
+_BOUND_EFC = ["J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "Ma", "type", "id", "state"]
+_BOUND_CONTACT = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "type", "geomcollisionid"]
+
+
+def _alloc(spec, dev):
+  out = {}
+  for name, (dt, shape) in spec.items():
+    out[name] = torch.zeros(shape, dtype=dt, device=dev)
+  return out
+
+
+def make_data(mjm, nworld: int = 1, nconmax=None, nccdmax=None, njmax=None, njmax_nnz=None, naconmax=None, naccdmax=None, nvmax=None, m: types.Model = None) -> types.Data:
+  """Creates a zero-initialised device Data at qpos0 (reference io.py:1680).  `m` (optional) reuses an existing device Model."""
+  dev = _require_cuda()
+  if m is None:
+    m = put_model(mjm)
+  L = _lib.lib()
+  nconmax = _default_nconmax(mjm) if nconmax is None else int(nconmax)
+  njmax = _default_njmax(mjm) if njmax is None else int(njmax)
+  if nworld < 1:
+    raise ValueError("nworld must be >= 1")
+  if nconmax < 0 or njmax < 0:
+    raise ValueError("nconmax and njmax must be >= 0")
+  naconmax = nworld * nconmax if naconmax is None else int(naconmax)
+  njmax_pad, nv_pad = _get_padded_sizes(m.nv, njmax, m.is_sparse)
+  d = types.Data(nworld=nworld, naconmax=naconmax, naccdmax=0, njmax=njmax, njmax_pad=njmax_pad, njmax_nnz=0, nvmax=m.nv, nconmax=nconmax)
+  for k, v in _alloc(_data_spec(m, nworld, naconmax, njmax, njmax_pad), dev).items():
+    setattr(d, k, v)
+  d.contact = types.Contact(**_alloc(_contact_spec(m, max(naconmax, 1)), dev))
+  d.efc = types.Constraint(**_alloc(_efc_spec(m, nworld, max(njmax, 1), max(njmax_pad, 1)), dev))
+  # state at qpos0; static geom poses from one host kinematics pass (io.py:1815-1848)
+  qpos0 = np.asarray(mjm.qpos0, dtype=np.float64)
+  d.qpos.copy_(torch.from_numpy(np.tile(qpos0.astype(np.float32), (nworld, 1))))
+  kin = mjcf.kinematics_np(mjm, qpos0) if hasattr(mjm, "names") else _host_kinematics(mjm, qpos0)
+  d.geom_xpos.copy_(torch.from_numpy(np.tile(kin.geom_xpos.astype(np.float32), (nworld, 1, 1))))
+  d.geom_xmat.copy_(torch.from_numpy(np.tile(kin.geom_xmat.astype(np.float32), (nworld, 1, 1, 1))))
+  d.xquat[..., 0] = 1.0
+  _bind(m, d, L)
+  return d
+
+
+def _host_kinematics(mjm, qpos):
+  import mujoco  # real MjModel path
+
+  mjd = mujoco.MjData(mjm)
+  mjd.qpos[:] = qpos
+  mujoco.mj_kinematics(mjm, mjd)
+  from types import SimpleNamespace
+
+  return SimpleNamespace(geom_xpos=np.array(mjd.geom_xpos), geom_xmat=np.array(mjd.geom_xmat).reshape(-1, 3, 3))
+
+
+def _bind(m: types.Model, d: types.Data, L):
+  h = L.mjb_data_create(d.nworld, d.nconmax, d.naconmax, d.njmax, d.njmax_pad, m.nv_pad)
+  d._handle = h
+  d._model = m
+  d._keep = []
+
+  def reg(cname, x):
+    x = _ptr_tensor(x)
+    d._keep.append(x)
+    _lib.check(L.mjb_data_set_array(h, cname.encode(), x.data_ptr()))
+
+  for n in _BOUND_TOP:
+    reg(n, getattr(d, n))
+  for n in _BOUND_EFC:
+    reg("efc_" + n, getattr(d.efc, n))
+  for n in _BOUND_CONTACT:
+    reg("contact_" + n, getattr(d.contact, n))
+  _lib.check(L.mjb_data_finalize(h, m._handle))
+
+
+def put_data(mjm, mjd, nworld: int = 1, nconmax=None, nccdmax=None, njmax=None, njmax_nnz=None, naconmax=None, naccdmax=None, nvmax=None, m: types.Model = None) -> types.Data:
+  """Moves host state (MjData-like: qpos, qvel, ctrl, qacc_warmstart, time, ...) to a device Data tiled over nworld (io.py:1890)."""
+  d = make_data(mjm, nworld, nconmax, nccdmax, njmax, njmax_nnz, naconmax, naccdmax, nvmax, m=m)
+  for name in ("qpos", "qvel", "ctrl", "qacc_warmstart", "qfrc_applied", "xfrc_applied"):
+    if hasattr(mjd, name):
+      src = np.asarray(getattr(mjd, name), dtype=np.float32)
+      dst = getattr(d, name)
+      dst.copy_(torch.from_numpy(np.broadcast_to(src, (nworld,) + src.shape).copy()).reshape(dst.shape))
+  d.time.fill_(float(getattr(mjd, "time", 0.0)))
+  return d
+
+
+def reset_data(m: types.Model, d: types.Data):
+  """Resets every world to qpos0 with zero velocity/ctrl/time (reference io.py:2435, all worlds)."""
+  mjm = m._mjm
+  d.qpos.copy_(torch.from_numpy(np.tile(np.asarray(mjm.qpos0, dtype=np.float32), (d.nworld, 1))))
+  for n in ("qvel", "ctrl", "qacc_warmstart", "qacc", "qfrc_applied", "xfrc_applied", "time"):
+    getattr(d, n).zero_()
+  for n in ("overflow", "solver_niter", "nefc", "ne", "nf", "nl", "nacon", "ncollision"):
+    getattr(d, n).zero_()

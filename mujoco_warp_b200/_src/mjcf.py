@@ -1097,3 +1097,46 @@ def reset_data_keyframe(m, d: MjDataLite, key: int):
   d.ctrl[:] = m.key_ctrl[key]
   d.time = float(m.key_time[key])
   d.qacc_warmstart[:] = 0
+
+
+# ----------------------------------------------------------------------------------------------
+# compiled-model (de)serialisation: lets a model compiled where the MJCF (or `mujoco`) is available
+# travel as one .npz of MjModel-named arrays (SURVEY.md Appendix C "escape hatch")
+# ----------------------------------------------------------------------------------------------
+
+
+def save_npz(m, path: str):
+  out = {}
+  for k, v in vars(m).items():
+    if k in ("opt", "stat", "names"):
+      for kk, vv in vars(v).items():
+        out[f"{k}.{kk}"] = np.asarray(vv)
+    else:
+      out[k] = np.asarray(v)
+  np.savez_compressed(path, **out)
+
+
+def load_npz(path: str):
+  z = np.load(path, allow_pickle=False)
+  m = SimpleNamespace(opt=SimpleNamespace(), stat=SimpleNamespace(), names=SimpleNamespace())
+  for k in z.files:
+    v = z[k]
+    tgt, name = m, k
+    if "." in k:
+      grp, name = k.split(".", 1)
+      tgt = getattr(m, grp)
+    if grp_is_names(k):
+      v = [str(s) for s in v.tolist()]
+    elif v.ndim == 0:
+      v = v.item()
+    setattr(tgt, name, v)
+  return m
+
+
+def grp_is_names(k: str) -> bool:
+  return k.startswith("names.")
+
+
+def load_any(path: str):
+  """Load a model from .xml (compile) or .npz (precompiled)."""
+  return load_npz(path) if path.endswith(".npz") else load(path)

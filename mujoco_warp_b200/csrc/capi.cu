@@ -1,0 +1,173 @@
+// capi.cu -- extern "C" boundary of libmjb200.so (see include/mjb200.h for the reference interfaces each entry replaces).
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/mjb200.h"
+#include "mjb_types.cuh"
+
+struct mjbModel {
+  ModelDev dev;
+  bool finalized;
+};
+struct mjbData {
+  DataDev dev;
+  bool finalized;
+  size_t smem[6];
+};
+
+namespace {
+thread_local std::string g_err;
+thread_local int g_launches = 0;
+int fail(const std::string& s) { g_err = s; return -1; }
+int check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return fail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+constexpr size_t kMaxSmem = 227 * 1024;
+}  // namespace
+
+extern "C" {
+
+const char* mjb_last_error(void) { return g_err.c_str(); }
+const char* mjb_version(void) { return "mjb200 0.1 (sm_100a)"; }
+int mjb_last_launch_count(void) { return g_launches; }
+
+mjbModel* mjb_model_create(void) {
+  mjbModel* m = new mjbModel();
+  memset(&m->dev, 0, sizeof(ModelDev));
+  m->finalized = false;
+  return m;
+}
+void mjb_model_destroy(mjbModel* m) { delete m; }
+
+int mjb_model_set_int(mjbModel* m, const char* name, int v) {
+#define X(n) if (!strcmp(name, #n)) { m->dev.n = v; return 0; }
+  MJB_MODEL_INTS(X)
+#undef X
+  return fail(std::string("unknown model int field: ") + name);
+}
+int mjb_model_set_float(mjbModel* m, const char* name, float v) {
+#define X(n) if (!strcmp(name, #n)) { m->dev.n = v; return 0; }
+  MJB_MODEL_FLOATS(X)
+#undef X
+  return fail(std::string("unknown model float field: ") + name);
+}
+int mjb_model_set_array(mjbModel* m, const char* name, const void* p, int nbatch) {
+  if (nbatch != 1) return fail(std::string("per-world (batched) Model fields are not supported yet: ") + name);
+#define X(n) if (!strcmp(name, #n)) { m->dev.n = (const int*)p; return 0; }
+  MJB_MODEL_IARRS(X)
+#undef X
+#define X(n) if (!strcmp(name, #n)) { m->dev.n = (const float*)p; return 0; }
+  MJB_MODEL_FARRS(X)
+#undef X
+  return fail(std::string("unknown model array field: ") + name);
+}
+int mjb_model_finalize(mjbModel* m) {
+#define X(n) if (!m->dev.n) return fail(std::string("model array not set: ") + #n);
+  MJB_MODEL_IARRS(X)
+  MJB_MODEL_FARRS(X)
+#undef X
+  if (m->dev.nv <= 0 || m->dev.nbody <= 0) return fail("model has no dofs/bodies");
+  if (m->dev.solver != SOL_NEWTON) return fail("only the Newton solver is implemented");
+  if (m->dev.cone != CONE_PYRAMIDAL) return fail("only the pyramidal friction cone is implemented");
+  if (m->dev.integrator != INT_EULER) return fail("only the Euler integrator is implemented");
+  m->finalized = true;
+  return 0;
+}
+
+mjbData* mjb_data_create(int nworld, int nconmax, int naconmax, int njmax, int njmax_pad, int nv_pad) {
+  mjbData* d = new mjbData();
+  memset(&d->dev, 0, sizeof(DataDev));
+  d->dev.nworld = nworld; d->dev.nconmax = nconmax; d->dev.naconmax = naconmax;
+  d->dev.njmax = njmax; d->dev.njmax_pad = njmax_pad; d->dev.nv_pad = nv_pad;
+  d->finalized = false;
+  return d;
+}
+void mjb_data_destroy(mjbData* d) {
+  if (!d) return;
+  if (d->dev.world_conadr) cudaFree(d->dev.world_conadr);
+  if (d->dev.world_ncon) cudaFree(d->dev.world_ncon);
+  delete d;
+}
+int mjb_data_set_array(mjbData* d, const char* name, void* p) {
+#define X(n) if (!strcmp(name, #n)) { d->dev.n = (float*)p; return 0; }
+  MJB_DATA_FARRS(X)
+#undef X
+#define X(n) if (!strcmp(name, #n)) { d->dev.n = (int*)p; return 0; }
+  MJB_DATA_IARRS(X)
+#undef X
+  return fail(std::string("unknown data array field: ") + name);
+}
+int mjb_data_finalize(mjbData* d, const mjbModel* m) {
+  if (!m || !m->finalized) return fail("model not finalized");
+#define X(n) if (!d->dev.n) return fail(std::string("data array not set: ") + #n);
+  MJB_DATA_FARRS(X)
+  MJB_DATA_IARRS(X)
+#undef X
+  if (d->dev.nv_pad < m->dev.nv) return fail("nv_pad < nv");
+  if (check(cudaMalloc(&d->dev.world_conadr, sizeof(int) * (size_t)d->dev.nworld), "cudaMalloc(world_conadr)")) return -1;
+  if (check(cudaMalloc(&d->dev.world_ncon, sizeof(int) * (size_t)d->dev.nworld), "cudaMalloc(world_ncon)")) return -1;
+  if (check(cudaMemset(d->dev.world_conadr, 0, sizeof(int) * (size_t)d->dev.nworld), "memset")) return -1;
+  if (check(cudaMemset(d->dev.world_ncon, 0, sizeof(int) * (size_t)d->dev.nworld), "memset")) return -1;
+  d->smem[0] = smem_position(m->dev); d->smem[1] = smem_collision(m->dev, d->dev); d->smem[2] = smem_constraint(m->dev, d->dev);
+  d->smem[3] = smem_velocity(m->dev); d->smem[4] = smem_solver(m->dev, d->dev); d->smem[5] = smem_integrate(m->dev);
+  static const char* names[6] = {"position", "collision", "constraint", "velocity", "solver", "integrate"};
+  for (int i = 0; i < 6; i++)
+    if (d->smem[i] > kMaxSmem) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "%s kernel needs %zu B of shared memory per block (> %zu): model/njmax too large for this version", names[i], d->smem[i], kMaxSmem);
+      return fail(buf);
+    }
+  d->finalized = true;
+  return 0;
+}
+
+#define MJB_ENTER()                                                                 \
+  if (!m || !d || !m->finalized || !d->finalized) return fail("model/data not finalized"); \
+  cudaStream_t s = (cudaStream_t)stream;                                             \
+  g_launches = 0;
+#define MJB_LAUNCH(call, n) do { if (check((call), #call)) return -1; g_launches += (n); } while (0)
+
+int mjb_kinematics(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_KINEMATICS, s), 1); return 0; }
+int mjb_com_pos(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_COM_POS, s), 1); return 0; }
+int mjb_camlight(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_CAMLIGHT, s), 1); return 0; }
+int mjb_crb(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_CRB, s), 1); return 0; }
+int mjb_transmission(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_TRANSMISSION, s), 1); return 0; }
+int mjb_collision(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1); return 0; }
+int mjb_make_constraint(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1); return 0; }
+int mjb_fwd_velocity(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_VELOCITY, s), 1); return 0; }
+int mjb_fwd_actuation(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_ACTUATION, s), 1); return 0; }
+int mjb_fwd_acceleration(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_ACCELERATION, s), 1); return 0; }
+int mjb_factor_m(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_FACTOR_ONLY, s), 1); return 0; }
+int mjb_solve(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1); return 0; }
+int mjb_euler(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1); return 0; }
+
+static int fwd_position_impl(const mjbModel* m, mjbData* d, cudaStream_t s) {
+  // forward.py:635-677 with factorize=False: kinematics, com_pos, camlight, crb, collision, make_constraint, transmission
+  MJB_LAUNCH(launch_position(m->dev, d->dev, STG_KINEMATICS | STG_COM_POS | STG_CAMLIGHT | STG_CRB | STG_TRANSMISSION, s), 1);
+  MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1);
+  MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1);
+  return 0;
+}
+static int forward_impl(const mjbModel* m, mjbData* d, cudaStream_t s) {
+  if (fwd_position_impl(m, d, s)) return -1;
+  MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_VELOCITY | STG_ACTUATION | STG_ACCELERATION, s), 1);
+  MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1);
+  return 0;
+}
+int mjb_fwd_position(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return fwd_position_impl(m, d, s); }
+int mjb_forward(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return forward_impl(m, d, s); }
+int mjb_step(const mjbModel* m, mjbData* d, void* stream) {
+  MJB_ENTER();
+  if (forward_impl(m, d, s)) return -1;
+  MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1);
+  return 0;
+}
+int mjb_ctrl_noise(const mjbModel* m, mjbData* d, const float* ctrl_center, int step, float noise_std, float noise_rate, void* stream) {
+  MJB_ENTER();
+  MJB_LAUNCH(launch_ctrl_noise(m->dev, d->dev, ctrl_center, step, noise_std, noise_rate, s), 1);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// k_integrate.cu -- Euler integrator (+ optional implicit joint damping) and the harness ctrl-noise kernel.
+//
+// Replaces (reference, /root/reference/mujoco_warp/_src/): forward.py:387-417 euler, :276-349 _advance
+// (_next_velocity :117, _next_position :53, _next_time :221, qacc_warmstart copy :343) and, for models without
+// eulerdamp=disable, the (M + dt*diag(damping)) factor-solve (:391-415).  cli.py:103-145 _ctrl_noise.
+#include "mjb_chol.cuh"
+#include "mjb_math.cuh"
+#include "mjb_types.cuh"
+
+namespace {
+
+__host__ __device__ inline int chol_ld(int n) { return (n | 1); }
+__host__ __device__ inline int int_words(const ModelDev& m) {
+  const bool damp = !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
+  int o = 2 * m.nv;  // qacc, qvel
+  if (damp) o += m.maxtree * chol_ld(m.maxtree) + m.maxtree;
+  return (o + 3) & ~3;
+}
+
+__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
+k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  if (w >= d.nworld) return;
+  float* S = smem + warp * int_words(m);
+  float *qacc = S, *qvel = S + m.nv, *A = S + 2 * m.nv, *x = A + m.maxtree * chol_ld(m.maxtree);
+  const int nv = m.nv;
+  const size_t wb = (size_t)w;
+  const float dt = m.timestep;
+
+  warp_copy(qacc, d.qacc + wb * nv, nv, lane);
+  warp_copy(qvel, d.qvel + wb * nv, nv, lane);
+  __syncwarp();
+  warp_copy(d.qacc_warmstart + wb * nv, qacc, nv, lane);  // warmstart <- solver qacc (forward.py:343)
+
+  if (!(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
+    // qacc <- (M + dt*diag(damping))^-1 * Ma  (forward.py:391-415)
+    const float* Mw = d.M + wb * m.nC;
+    for (int t = 0; t < m.ntree; t++) {
+      const int start = m.tree_dofadr[t], n = m.tree_dofnum[t], ld = chol_ld(n);
+      for (int i = lane; i < n * ld; i += 32) A[i] = 0.f;
+      __syncwarp();
+      for (int r = start; r < start + n; r++) {
+        const int adr = m.M_rowadr[r], nnz = m.M_rownnz[r];
+        for (int k = lane; k < nnz; k += 32) {
+          const int col = m.M_colind[adr + k];
+          A[(r - start) * ld + (col - start)] = Mw[adr + k] + (col == r ? dt * m.dof_damping[r] : 0.f);
+        }
+      }
+      for (int i = lane; i < n; i += 32) x[i] = d.efc_Ma[wb * nv + start + i];
+      __syncwarp();
+      warp_cholesky(A, n, ld, lane);
+      warp_chol_solve(A, n, ld, x, lane);
+      for (int i = lane; i < n; i += 32) qacc[start + i] = x[i];
+      __syncwarp();
+    }
+  }
+  for (int dd = lane; dd < nv; dd += 32) { const float v = qvel[dd] + qacc[dd] * dt; qvel[dd] = v; d.qvel[wb * nv + dd] = v; }
+  __syncwarp();
+  float* qpos = d.qpos + wb * m.nq;
+  for (int j = lane; j < m.njnt; j += 32) {
+    const int t = m.jnt_type[j], qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+    if (t == JNT_FREE) {
+      for (int k = 0; k < 3; k++) qpos[qa + k] += dt * qvel[da + k];
+      stq(qpos + qa + 3, quat_integrate(ldq(qpos + qa + 3), ld3(qvel + da + 3), dt));
+    } else if (t == JNT_BALL) {
+      stq(qpos + qa, quat_integrate(ldq(qpos + qa), ld3(qvel + da), dt));
+    } else {
+      qpos[qa] += dt * qvel[da];
+    }
+  }
+  if (lane == 0) {  // _next_time (forward.py:221-271)
+    d.time[w] += dt;
+    int ovf = 0;
+    if (d.nefc[w] > d.njmax) ovf |= OVF_NEFC;
+    if (d.ncollision[0] > d.naconmax) ovf |= OVF_BROADPHASE;
+    if (d.nacon[0] > d.naconmax) ovf |= OVF_NARROWPHASE;
+    if (ovf) d.overflow[w] |= ovf;
+  }
+}
+
+// deterministic Halton value (reference util_misc.py:61-76)
+__device__ __forceinline__ float halton(int index, int base) {
+  int n0 = index;
+  const float b = (float)base;
+  float f = 1.0f / b, hn = 0.f;
+  while (n0 > 0) { const int n1 = n0 / base, r = n0 - n1 * base; hn += f * (float)r; f /= b; n0 = n1; }
+  return hn;
+}
+
+__global__ void k_ctrl_noise(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, const float* __restrict__ ctrl_center, int step, float noise_std, float noise_rate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nworld * m.nu) return;
+  const int w = i / m.nu, a = i - w * m.nu;
+  const float rate = expf(-m.timestep / noise_rate), scale = noise_std * sqrtf(1.0f - rate * rate);
+  float midpoint = 0.f, halfrange = 1.f;
+  const float lo = m.actuator_ctrlrange[2 * a], hi = m.actuator_ctrlrange[2 * a + 1];
+  const bool limited = m.actuator_ctrllimited[a];
+  if (limited) { midpoint = 0.5f * (hi + lo); halfrange = 0.5f * (hi - lo); }
+  if (ctrl_center) midpoint = ctrl_center[a];
+  float ctrl = rate * d.ctrl[i] + (1.0f - rate) * midpoint;
+  ctrl += scale * halfrange * (2.0f * halton((step + 1) * (w + 1), a + 2) - 1.0f);
+  if (limited) ctrl = clampf(ctrl, lo, hi);
+  d.ctrl[i] = ctrl;
+}
+
+}  // namespace
+
+size_t smem_integrate(const ModelDev& m) { return (size_t)int_words(m) * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+
+cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s) {
+  const size_t smem = smem_integrate(m);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_euler, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  k_euler<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ctrl_noise(const ModelDev& m, const DataDev& d, const float* ctrl_center, int step, float std, float rate, cudaStream_t s) {
+  const int n = d.nworld * m.nu;
+  if (n == 0) return cudaSuccess;
+  k_ctrl_noise<<<(n + 255) / 256, 256, 0, s>>>(m, d, ctrl_center, step, std, rate);
+  return cudaGetLastError();
+}

@@ -1,0 +1,332 @@
+// k_solver.cu -- Newton constraint solver as ONE persistent launch (one warp per world, all state in shared memory).
+//
+// Replaces (reference, /root/reference/mujoco_warp/_src/solver.py): :3671 solve / :3689 _solve, :3622 init_context,
+// :1566 _solve_init_dof, :1609 _solve_init_jaref, support.py:153 mul_m, :1698 _update_constraint_efc,
+// :1912 qfrc_constraint, :2119-2199 gradient, :2366 _update_gradient_JTDAJ_dense_tiled, :1951 _update_gradient_h_incremental,
+// :2567 _update_gradient_cholesky, :836-1347 _linesearch_iterative_kernel, :3453 _solve_done, and the CUDA-graph `while`
+// node (:3717-3726) that relaunches ~10 kernels per iteration until every world is done.
+//
+// Here a world's Jacobian (nefc x nv), Hessian, its Cholesky factor, CSR inertia and all solver vectors live in the
+// warp's shared-memory slice for the whole solve; iterations are a device-side loop, so a world stops as soon as IT has
+// converged (no global `nsolving` counter, no graph conditional).  Reductions are warp shuffles; the Hessian is updated
+// incrementally from the rows whose QUADRATIC flag flipped (exactly the reference's rule) and refactored in place.
+// Algorithm and tolerances follow the reference: exact Newton with the iterative bracketing line search on the
+// shifted (cost(alpha) - cost(0)) piecewise-quadratic 1-D cost.  Pyramidal / frictionless / limit / dof-friction rows.
+#include "mjb_chol.cuh"
+#include "mjb_math.cuh"
+#include "mjb_types.cuh"
+
+namespace {
+
+struct SolLayout { int J, H, Lf, M, vec, rowf, rowi, ldJ, ldH, total; };
+__host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d) {
+  SolLayout L;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += n; return r; };
+  L.ldJ = m.nv | 1; L.ldH = m.nv | 1;
+  L.J = take(d.njmax * L.ldJ);
+  L.H = take(m.nv * L.ldH); L.Lf = take(m.nv * L.ldH);
+  L.M = take(m.nC);
+  L.vec = take(8 * m.nv);
+  L.rowf = take(6 * d.njmax);
+  L.rowi = take(2 * d.njmax);
+  L.total = (o + 3) & ~3;
+  return L;
+}
+
+struct P3 { float c, g, h; };
+__device__ __forceinline__ P3 mkp(float c, float g, float h) { P3 p; p.c = c; p.g = g; p.h = h; return p; }
+__device__ __forceinline__ P3 operator+(P3 a, P3 b) { return mkp(a.c + b.c, a.g + b.g, a.h + b.h); }
+__device__ __forceinline__ P3 warp_sum3(P3 p) { return mkp(warp_sum(p.c), warp_sum(p.g), warp_sum(p.h)); }
+
+// row kinds by position (solver.py:1751-1755): [0,ne) equality, [ne,ne+nf) friction loss, rest inequality
+// shifted evaluation: (cost(alpha) - cost(0), grad, hess) -- solver.py:479-517
+__device__ __forceinline__ P3 eval_row(int r, float alpha, int ne, int nf, float D, float f, float jaref, float jv) {
+  if (r >= ne + nf) {
+    const float x = jaref + alpha * jv, quad0 = 0.5f * D * jaref * jaref, cost0 = jaref < 0.f ? quad0 : 0.f, offset = quad0 - cost0;
+    if (x < 0.f) { const float jvD = jv * D, h = jv * jvD, ah = alpha * h; return mkp(alpha * (jvD * jaref + 0.5f * ah) + offset, jvD * jaref + ah, h); }
+    return mkp(-cost0, 0.f, 0.f);
+  }
+  if (r >= ne) {
+    const float x = jaref + alpha * jv, rf = safe_div(f, D);
+    float c0;
+    if (-rf < jaref && jaref < rf) c0 = 0.5f * D * jaref * jaref; else if (jaref <= -rf) c0 = f * (-0.5f * rf - jaref); else c0 = f * (-0.5f * rf + jaref);
+    if (-rf < x && x < rf) { const float jvD = jv * D; return mkp(0.5f * D * x * x - c0, jvD * x, jv * jvD); }
+    if (x <= -rf) return mkp(f * (-0.5f * rf - x) - c0, -f * jv, 0.f);
+    return mkp(f * (-0.5f * rf + x) - c0, f * jv, 0.f);
+  }
+  const float jvD = jv * D, h = jv * jvD, ah = alpha * h;
+  return mkp(alpha * (jvD * jaref + 0.5f * ah), jvD * jaref + ah, h);
+}
+// absolute evaluation at alpha = 0 (solver.py:570-592)
+__device__ __forceinline__ P3 eval_row_zero(int r, int ne, int nf, float D, float f, float jaref, float jv) {
+  if (r >= ne + nf) {
+    if (jaref < 0.f) { const float jvD = jv * D; return mkp(0.5f * D * jaref * jaref, jvD * jaref, jv * jvD); }
+    return mkp(0.f, 0.f, 0.f);
+  }
+  if (r >= ne) {
+    const float rf = safe_div(f, D), x = jaref;
+    if (-rf < x && x < rf) { const float jvD = jv * D; return mkp(0.5f * D * x * x, jvD * x, jv * jvD); }
+    if (x <= -rf) return mkp(f * (-0.5f * rf - x), -f * jv, 0.f);
+    return mkp(f * (-0.5f * rf + x), f * jv, 0.f);
+  }
+  const float jvD = jv * D;
+  return mkp(0.5f * D * jaref * jaref, jvD * jaref, jv * jvD);
+}
+__device__ __forceinline__ P3 eval_gauss(float q0, float q1, float q2, float alpha) {  // _eval_pt solver.py:203
+  const float aq2 = alpha * q2;
+  return mkp(alpha * aq2 + alpha * q1 + q0, 2.0f * aq2 + q1, 2.0f * q2);
+}
+__device__ __forceinline__ bool in_bracket(P3 x, P3 y) { return (x.g < y.g && y.g < 0.f) || (x.g > y.g && y.g > 0.f); }
+
+struct Ctx {
+  const ModelDev* m;
+  int lane, nv, nefc, ne, nf, ldJ, ldH;
+  float *J, *H, *Lf, *M, *qacc, *Ma, *grad, *search, *mv, *qfs, *x, *qfc;
+  float *Jaref, *jv, *D, *force, *floss, *hw;
+  int *state, *hidx;
+  float search_dot, grad_dot, newton_decrement, improvement;
+};
+
+// res = M vec via the symmetric gather tables (support.py:153 mul_m; tables io.py:1029-1050)
+__device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res) {
+  const ModelDev& m = *c.m;
+  for (int i = c.lane; i < c.nv; i += 32) {
+    float acc = 0.f;
+    for (int k = m.mulm_rowadr[i]; k < m.mulm_rowadr[i + 1]; k++) acc += c.M[m.mulm_madr[k]] * vec[m.mulm_col[k]];
+    res[i] = acc;
+  }
+}
+
+// force/state per row, qfrc_constraint = J^T force, and the list of rows whose QUADRATIC flag changed
+// (init=true: list every QUADRATIC row with weight +D).  Returns the list length.
+__device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
+  int nlist = 0;
+  for (int r0 = 0; r0 < c.nefc; r0 += 32) {
+    const int r = r0 + c.lane;
+    bool flip = false;
+    float wgt = 0.f;
+    if (r < c.nefc) {
+      const float jaref = c.Jaref[r], D = c.D[r];
+      const int old = c.state[r];
+      float force; int st;
+      if (r < c.ne) { force = -D * jaref; st = ST_QUADRATIC; }
+      else if (r < c.ne + c.nf) {
+        const float f = c.floss[r], rf = safe_div(f, D);
+        if (jaref <= -rf) { force = f; st = ST_LINEARNEG; } else if (jaref >= rf) { force = -f; st = ST_LINEARPOS; } else { force = -D * jaref; st = ST_QUADRATIC; }
+      } else if (jaref >= 0.f) { force = 0.f; st = ST_SATISFIED; }
+      else { force = -D * jaref; st = ST_QUADRATIC; }
+      c.force[r] = force; c.state[r] = st;
+      const bool nq = st == ST_QUADRATIC, oq = (!init) && old == ST_QUADRATIC;
+      flip = nq != oq;
+      wgt = nq ? D : -D;
+    }
+    const unsigned bal = __ballot_sync(FULL_MASK, flip);
+    if (flip) { const int p = nlist + __popc(bal & ((1u << c.lane) - 1u)); c.hidx[p] = r; c.hw[p] = wgt; }
+    nlist += __popc(bal);
+  }
+  __syncwarp();
+  for (int dd = c.lane; dd < c.nv; dd += 32) {
+    float s = 0.f;
+    for (int r = 0; r < c.nefc; r++) s += c.J[r * c.ldJ + dd] * c.force[r];
+    c.qfc[dd] = s;
+  }
+  __syncwarp();
+  return nlist;
+}
+
+// grad, H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad
+__device__ __forceinline__ void update_gradient(Ctx& c, int nlist) {
+  const int nv = c.nv;
+  float gd = 0.f;
+  for (int dd = c.lane; dd < nv; dd += 32) { const float g = c.Ma[dd] - c.qfs[dd] - c.qfc[dd]; c.grad[dd] = g; c.x[dd] = g; gd += g * g; }
+  c.grad_dot = warp_sum(gd);
+  const int ntri = nv * (nv + 1) / 2;
+  if (nlist > 0) {
+    for (int e = c.lane; e < ntri; e += 32) {
+      int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((i + 1) * (i + 2) / 2 <= e) i++;
+      while (i * (i + 1) / 2 > e) i--;
+      const int j = e - i * (i + 1) / 2;
+      float acc = 0.f;
+      for (int k = 0; k < nlist; k++) { const float* Jr = c.J + c.hidx[k] * c.ldJ; acc += c.hw[k] * Jr[i] * Jr[j]; }
+      c.H[i * c.ldH + j] += acc;
+    }
+    __syncwarp();
+  }
+  for (int e = c.lane; e < nv * c.ldH; e += 32) c.Lf[e] = c.H[e];
+  __syncwarp();
+  warp_cholesky(c.Lf, nv, c.ldH, c.lane);
+  warp_chol_solve(c.Lf, nv, c.ldH, c.x, c.lane);
+  float sd = 0.f, nd = 0.f;
+  for (int dd = c.lane; dd < nv; dd += 32) { const float xx = c.x[dd]; sd += xx * xx; nd += c.grad[dd] * xx; c.search[dd] = -xx; }
+  c.search_dot = warp_sum(sd);
+  c.newton_decrement = warp_sum(nd);
+  __syncwarp();
+}
+
+__device__ __forceinline__ P3 eval_total(const Ctx& c, float alpha, float q0, float q1, float q2) {
+  P3 s = mkp(0.f, 0.f, 0.f);
+  for (int r = c.lane; r < c.nefc; r += 32) s = s + eval_row(r, alpha, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
+  return eval_gauss(q0, q1, q2, alpha) + warp_sum3(s);
+}
+
+// solver.py:836-1347; returns true when the line search converged
+__device__ __forceinline__ bool linesearch(Ctx& c) {
+  const ModelDev& m = *c.m;
+  const int nv = c.nv;
+  mul_m(c, c.search, c.mv);
+  for (int r = c.lane; r < c.nefc; r += 32) {
+    const float* Jr = c.J + r * c.ldJ;
+    float s = 0.f;
+    for (int dd = 0; dd < nv; dd++) s += Jr[dd] * c.search[dd];
+    c.jv[r] = s;
+  }
+  __syncwarp();
+  const float snorm = sqrtf(c.search_dot), scale = m.meaninertia * (float)nv;
+  const float gtol = fmaxf(m.tolerance * m.ls_tolerance * snorm * scale, 1e-6f);
+  P3 p0s = mkp(0.f, 0.f, 0.f);
+  for (int r = c.lane; r < c.nefc; r += 32) p0s = p0s + eval_row_zero(r, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
+  p0s = warp_sum3(p0s);
+  float g1 = 0.f, g2 = 0.f;
+  for (int dd = c.lane; dd < nv; dd += 32) { const float s = c.search[dd]; g1 += s * (c.Ma[dd] - c.qfs[dd]); g2 += 0.5f * s * c.mv[dd]; }
+  const float q0 = 0.f, q1 = warp_sum(g1), q2 = warp_sum(g2);
+  const P3 p0 = mkp(q0 + p0s.c, q1 + p0s.g, 2.0f * q2 + p0s.h);
+  const P3 p0_delta = mkp(0.f, p0.g, p0.h);
+  const float lo_alpha_in = -safe_div(p0.g, p0.h);
+  const P3 lo_in = eval_total(c, lo_alpha_in, q0, q1, q2);
+  const bool initial_converged = fabsf(lo_in.g) < gtol && lo_in.c < 0.f;
+  bool ls_converged = initial_converged;
+  float alpha = 0.f, improvement = 0.f;
+  if (!initial_converged) {
+    const bool lo_less = lo_in.g < p0.g;
+    P3 lo = lo_less ? lo_in : p0_delta, hi = lo_less ? p0_delta : lo_in;
+    float lo_alpha = lo_less ? lo_alpha_in : 0.f, hi_alpha = lo_less ? 0.f : lo_alpha_in;
+    for (int it = 0; it < m.ls_iterations; it++) {
+      const float lo_next_alpha = lo_alpha - safe_div(lo.g, lo.h), hi_next_alpha = hi_alpha - safe_div(hi.g, hi.h), mid_alpha = 0.5f * (lo_alpha + hi_alpha);
+      P3 sl = mkp(0.f, 0.f, 0.f), sh = sl, sm = sl;
+      for (int r = c.lane; r < c.nefc; r += 32) {
+        const float D = c.D[r], f = c.floss[r], ja = c.Jaref[r], jv = c.jv[r];
+        sl = sl + eval_row(r, lo_next_alpha, c.ne, c.nf, D, f, ja, jv);
+        sh = sh + eval_row(r, hi_next_alpha, c.ne, c.nf, D, f, ja, jv);
+        sm = sm + eval_row(r, mid_alpha, c.ne, c.nf, D, f, ja, jv);
+      }
+      const P3 lo_next = eval_gauss(q0, q1, q2, lo_next_alpha) + warp_sum3(sl);
+      const P3 hi_next = eval_gauss(q0, q1, q2, hi_next_alpha) + warp_sum3(sh);
+      const P3 mid = eval_gauss(q0, q1, q2, mid_alpha) + warp_sum3(sm);
+      const bool s1 = in_bracket(lo, lo_next); if (s1) { lo = lo_next; lo_alpha = lo_next_alpha; }
+      const bool s2 = in_bracket(lo, mid); if (s2) { lo = mid; lo_alpha = mid_alpha; }
+      const bool s3 = in_bracket(lo, hi_next); if (s3) { lo = hi_next; lo_alpha = hi_next_alpha; }
+      const bool h1 = in_bracket(hi, hi_next); if (h1) { hi = hi_next; hi_alpha = hi_next_alpha; }
+      const bool h2 = in_bracket(hi, mid); if (h2) { hi = mid; hi_alpha = mid_alpha; }
+      const bool h3 = in_bracket(hi, lo_next); if (h3) { hi = lo_next; hi_alpha = lo_next_alpha; }
+      const bool swap_lo = s1 || s2 || s3, swap_hi = h1 || h2 || h3;
+      const bool ls_done = (!swap_lo && !swap_hi) || (lo.c < 0.f && lo.g < 0.f && lo.g > -gtol) || (hi.c < 0.f && hi.g > 0.f && hi.g < gtol);
+      const bool improved = lo.c < 0.f || hi.c < 0.f, lo_better = lo.c < hi.c;
+      if (improved) { alpha = lo_better ? lo_alpha : hi_alpha; improvement = -(lo_better ? lo.c : hi.c); }
+      if (ls_done) { ls_converged = true; break; }
+    }
+  } else {
+    alpha = lo_alpha_in; improvement = -lo_in.c;
+  }
+  for (int dd = c.lane; dd < nv; dd += 32) { c.qacc[dd] += alpha * c.search[dd]; c.Ma[dd] += alpha * c.mv[dd]; }
+  for (int r = c.lane; r < c.nefc; r += 32) c.Jaref[r] += alpha * c.jv[r];
+  c.improvement = improvement;
+  __syncwarp();
+  return ls_converged;
+}
+
+__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
+k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  if (w >= d.nworld) return;
+  const SolLayout L = sol_layout(m, d);
+  float* S = smem + warp * L.total;
+  const int nv = m.nv, njmax = d.njmax, nvp = d.nv_pad;
+  const size_t wb = (size_t)w;
+  Ctx c;
+  c.m = &m; c.lane = lane; c.nv = nv; c.ldJ = L.ldJ; c.ldH = L.ldH;
+  c.J = S + L.J; c.H = S + L.H; c.Lf = S + L.Lf; c.M = S + L.M;
+  float* v = S + L.vec;
+  c.qacc = v; c.Ma = v + nv; c.grad = v + 2 * nv; c.search = v + 3 * nv; c.mv = v + 4 * nv; c.qfs = v + 5 * nv; c.x = v + 6 * nv; c.qfc = v + 7 * nv;
+  float* rf = S + L.rowf;
+  c.Jaref = rf; c.jv = rf + njmax; c.D = rf + 2 * njmax; c.force = rf + 3 * njmax; c.floss = rf + 4 * njmax; c.hw = rf + 5 * njmax;
+  int* ri = (int*)(S + L.rowi);
+  c.state = ri; c.hidx = ri + njmax;
+
+  if (njmax == 0 || nv == 0) {
+    for (int dd = lane; dd < nv; dd += 32) d.qacc[wb * nv + dd] = d.qacc_smooth[wb * nv + dd];
+    if (lane == 0) d.solver_niter[w] = 0;
+    return;
+  }
+  const int nefc = min(d.nefc[w], njmax);
+  c.nefc = nefc; c.ne = d.ne[w]; c.nf = d.nf[w];
+
+  // ---- stage the world's problem in shared memory
+  {
+    const float* Jg = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
+    for (int i = lane; i < nefc * nvp; i += 32) { const int r = i / nvp, col = i - r * nvp; if (col < nv) c.J[r * c.ldJ + col] = Jg[i]; }
+    for (int r = lane; r < nefc; r += 32) {
+      c.D[r] = d.efc_D[wb * d.njmax_pad + r];
+      c.floss[r] = d.efc_frictionloss[wb * njmax + r];
+      c.state[r] = ST_SATISFIED;
+    }
+    warp_copy(c.M, d.M + wb * m.nC, m.nC, lane);
+    warp_copy(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
+    const float* start = (m.disableflags & DSBL_WARMSTART) ? d.qacc_smooth : d.qacc_warmstart;
+    warp_copy(c.qacc, start + wb * nv, nv, lane);
+    for (int e = lane; e < nv * c.ldH; e += 32) c.H[e] = 0.f;
+  }
+  __syncwarp();
+  for (int e = lane; e < m.nC; e += 32) c.H[m.M_entry_row[e] * c.ldH + m.M_colind[e]] = c.M[e];  // lower triangle of M
+  for (int r = lane; r < nefc; r += 32) {  // Jaref = J qacc - aref
+    const float* Jr = c.J + r * c.ldJ;
+    float s = 0.f;
+    for (int dd = 0; dd < nv; dd++) s += Jr[dd] * c.qacc[dd];
+    c.Jaref[r] = s - d.efc_aref[wb * njmax + r];
+  }
+  mul_m(c, c.qacc, c.Ma);
+  __syncwarp();
+
+  int nlist = update_constraint(c, true);
+  update_gradient(c, nlist);
+
+  const float scale = m.meaninertia * (float)nv;
+  int niter = 0, ovf = 0;
+  bool done = m.iterations == 0;
+  while (!done) {
+    if (!linesearch(c)) ovf |= OVF_LS_ITERATIONS;
+    nlist = update_constraint(c, false);
+    update_gradient(c, nlist);
+    niter++;
+    const float improvement = c.improvement / scale, gradient = sqrtf(c.grad_dot) / scale, model_improvement = 0.5f * c.newton_decrement / scale;
+    done = improvement < m.tolerance || gradient < m.tolerance || model_improvement < m.tolerance;
+    if (!done && niter == m.iterations) { ovf |= OVF_ITERATIONS; done = true; }
+  }
+
+  // ---- results
+  warp_copy(d.qacc + wb * nv, c.qacc, nv, lane);
+  warp_copy(d.efc_Ma + wb * nv, c.Ma, nv, lane);
+  warp_copy(d.qfrc_constraint + wb * nv, c.qfc, nv, lane);
+  for (int r = lane; r < nefc; r += 32) { d.efc_force[wb * njmax + r] = c.force[r]; d.efc_state[wb * d.njmax_pad + r] = c.state[r]; }
+  if (lane == 0) { d.solver_niter[w] = niter; if (ovf) d.overflow[w] |= ovf; }
+}
+
+}  // namespace
+
+size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_layout(m, d).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+
+cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
+  const size_t smem = smem_solver(m, d);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_solver, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  k_solver<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  return cudaGetLastError();
+}

@@ -1,0 +1,124 @@
+// mjb_types.cuh -- device-side Model / Data descriptors (plain structs of pointers + sizes).
+// Field names follow the reference's Model/Data dataclasses (/root/reference/mujoco_warp/_src/types.py:982,2075).
+// The X-macro lists below are the single source of truth for the by-name C-ABI setters in capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+// ---------------------------------------------------------------- Model
+#define MJB_MODEL_INTS(X) \
+  X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) X(nlevel) \
+  X(nxn_npair) X(nlimit) X(nfricdof) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) \
+  X(ls_iterations) X(disableflags) X(enableflags) X(broadphase_filter) X(qld_total) X(maxtree)
+#define MJB_MODEL_FLOATS(X) \
+  X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(gravity_x) X(gravity_y) X(gravity_z)
+#define MJB_MODEL_IARRS(X) \
+  X(body_parentid) X(body_rootid) X(body_weldid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
+  X(body_childadr) X(body_childid) X(level_adr) X(level_body) \
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_actfrclimited) X(jnt_actgravcomp) X(jnt_limited_adr) \
+  X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(dof_fricloss_adr) X(M_rownnz) X(M_rowadr) X(M_colind) X(M_entry_row) X(mulm_rowadr) X(mulm_col) X(mulm_madr) \
+  X(tree_dofadr) X(tree_dofnum) X(tree_qLDadr) \
+  X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
+  X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
+  X(moment_rownnz0) X(moment_rowadr0) X(moment_colind0) \
+  X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
+  X(nxn_geom_pair) X(nxn_pairid) X(body_isdofancestor)
+#define MJB_MODEL_FARRS(X) \
+  X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
+  X(body_inertia) X(body_invweight0) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
+  X(jnt_solimp) X(jnt_actfrcrange) X(dof_armature) X(dof_damping) X(dof_invweight0) X(dof_frictionloss) X(dof_solref) \
+  X(dof_solimp) X(geom_size) X(geom_aabb) X(geom_rbound) X(geom_pos) X(geom_quat) X(geom_friction) X(geom_margin) \
+  X(geom_gap) X(geom_solmix) X(geom_solref) X(geom_solimp) X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) \
+  X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
+  X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat)
+
+struct ModelDev {
+#define X(n) int n;
+  MJB_MODEL_INTS(X)
+#undef X
+#define X(n) float n;
+  MJB_MODEL_FLOATS(X)
+#undef X
+#define X(n) const int* __restrict__ n;
+  MJB_MODEL_IARRS(X)
+#undef X
+#define X(n) const float* __restrict__ n;
+  MJB_MODEL_FARRS(X)
+#undef X
+};
+
+// ---------------------------------------------------------------- Data
+#define MJB_DATA_FARRS(X) \
+  X(time) X(qpos) X(qvel) X(ctrl) X(qacc_warmstart) X(qfrc_applied) X(xfrc_applied) X(qacc) \
+  X(xpos) X(xquat) X(xmat) X(xipos) X(ximat) X(xanchor) X(xaxis) X(geom_xpos) X(geom_xmat) X(site_xpos) X(site_xmat) \
+  X(cam_xpos) X(cam_xmat) X(light_xpos) X(light_xdir) X(subtree_com) X(cdof) X(cinert) X(crb) X(M) X(qLD) \
+  X(actuator_length) X(actuator_moment) X(actuator_velocity) X(cvel) X(cdof_dot) X(qfrc_bias) X(qfrc_spring) \
+  X(qfrc_damper) X(qfrc_gravcomp) X(qfrc_passive) X(actuator_force) X(qfrc_actuator) X(qfrc_smooth) X(qacc_smooth) \
+  X(qfrc_constraint) X(cacc) X(cfrc_int) \
+  X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
+  X(contact_dist) X(contact_pos) X(contact_frame) X(contact_includemargin) X(contact_friction) X(contact_solref) \
+  X(contact_solreffriction) X(contact_solimp)
+#define MJB_DATA_IARRS(X) \
+  X(ne) X(nf) X(nl) X(nefc) X(nacon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
+  X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(contact_dim) X(contact_geom) X(contact_efc_address) \
+  X(contact_worldid) X(contact_type) X(contact_geomcollisionid)
+
+struct DataDev {
+  int nworld, nconmax, naconmax, njmax, njmax_pad, nv_pad;
+#define X(n) float* __restrict__ n;
+  MJB_DATA_FARRS(X)
+#undef X
+#define X(n) int* __restrict__ n;
+  MJB_DATA_IARRS(X)
+#undef X
+  // internal scratch (allocated by mjb_data_finalize; not part of the reference's Data)
+  int* world_conadr;  // (nworld) first contact-pool slot of each world's contiguous block
+  int* world_ncon;    // (nworld) number of contacts the world wrote this step
+};
+
+// ---------------------------------------------------------------- enums (MuJoCo values; see constants.py)
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { GEOM_PLANE = 0, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH };
+enum { INT_EULER = 0, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST };
+enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
+enum { SOL_CG = 1, SOL_NEWTON = 2 };
+enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_LIMIT_JOINT = 3, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6, CNSTR_CONTACT_ELLIPTIC = 7 };
+enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
+enum { CAM_FIXED = 0, CAM_TRACK, CAM_TRACKCOM, CAM_TARGETBODY, CAM_TARGETBODYCOM };
+enum { GAIN_FIXED = 0, GAIN_AFFINE = 1 };
+enum { BIAS_NONE = 0, BIAS_AFFINE = 1 };
+enum {
+  DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3, DSBL_CONTACT = 1 << 4,
+  DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7, DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9,
+  DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15
+};
+enum { OVF_NEFC = 1 << 0, OVF_BROADPHASE = 1 << 2, OVF_NARROWPHASE = 1 << 3, OVF_ITERATIONS = 1 << 9, OVF_LS_ITERATIONS = 1 << 10 };
+enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
+enum { CONTACT_TYPE_CONSTRAINT = 1, CONTACT_TYPE_SENSOR = 2 };
+
+#define MJ_MINVAL 1e-15f
+#define MJ_MAXVAL 1e10f
+#define MJ_MINIMP 1e-4f
+#define MJ_MAXIMP 0.9999f
+#define MJ_MINMU 1e-5f
+
+// stage bits for the fused position kernel
+enum { STG_KINEMATICS = 1, STG_COM_POS = 2, STG_CAMLIGHT = 4, STG_CRB = 8, STG_TRANSMISSION = 16 };
+// stage bits for the fused velocity kernel
+enum { STG_VELOCITY = 1, STG_ACTUATION = 2, STG_ACCELERATION = 4, STG_FACTOR_ONLY = 8 };
+
+constexpr int MJB_WARPS_PER_BLOCK = 4;
+
+// launchers (one per .cu); each returns the cudaError of the launch
+cudaError_t launch_position(const ModelDev& m, const DataDev& d, int stage_mask, cudaStream_t s);
+cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s);
+cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s);
+cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int stage_mask, cudaStream_t s);
+cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s);
+cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s);
+cudaError_t launch_ctrl_noise(const ModelDev& m, const DataDev& d, const float* ctrl_center, int step, float std, float rate, cudaStream_t s);
+size_t smem_position(const ModelDev& m);
+size_t smem_collision(const ModelDev& m, const DataDev& d);
+size_t smem_constraint(const ModelDev& m, const DataDev& d);
+size_t smem_velocity(const ModelDev& m);
+size_t smem_solver(const ModelDev& m, const DataDev& d);
+size_t smem_integrate(const ModelDev& m);
