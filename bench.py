@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched physics step on humanoid.xml (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nworld 8192]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], reference benchmarks/humanoid/__init__.py): humanoid, nworld=8192 per GPU, nconmax=24,
+njmax=64, keyframe 0 (squat), Newton / pyramidal / Euler, deterministic Ornstein-Uhlenbeck ctrl noise (cli.py:103-145).
+A "step" is one pass of the hot path (ctrl-noise kernel + mjb_step) over all worlds of the rank.  Weak scaling: every rank
+owns its own 8192 worlds on its own GPU, no collective inside the step; the timed region is bracketed by barrier +
+synchronize, timed with CUDA events, MAX over ranks.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the roofline / algorithmic-bytes definitions.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NCONMAX, NJMAX = 24, 64
+METRIC = "env-steps/sec (whole box) on humanoid.xml at nworld=8192 per GPU"
+
+
+def parse():
+  p = argparse.ArgumentParser()
+  p.add_argument("--gpus", type=int, default=1)
+  p.add_argument("--steps", type=int, default=200)
+  p.add_argument("--warmup", type=int, default=20)
+  p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  p.add_argument("--nworld", type=int, default=8192, help="worlds per GPU")
+  p.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
+  p.add_argument("--cpu-sample-worlds", type=int, default=1024)
+  return p.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- clocks
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+  Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+  def __init__(self, gpu_index):
+    self.gpu, self.rows, self.proc = gpu_index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+    mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+    reasons = set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      if len(r) >= 9:
+        for n, v in zip(names, r[5:9]):
+          if v.lower().startswith("active"):
+            reasons.add(n)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- algorithmic bytes
+
+
+def algorithmic_words(mjm, tabs, ncon_mean, nefc_mean, nv_pad):
+  """Per-env-step algorithmic fp32/int32 words per kernel: every Data output written once, every input read once;
+  Model constants and workspace count zero."""
+  nq, nv, nu, nb, nj, ng = mjm.nq, mjm.nv, mjm.nu, mjm.nbody, mjm.njnt, mjm.ngeom
+  ng_dyn = int((np.asarray(mjm.body_weldid)[np.asarray(mjm.geom_bodyid)] != 0).sum())
+  nC, nJ, qld = tabs["nC"], tabs["nJmom"], tabs["qld_total"]
+  w = {}
+  w["position"] = nq + (3 + 4 + 9 + 3 + 9) * nb + 6 * nj + 12 * ng_dyn + 12 * mjm.nsite + 12 * mjm.ncam + 6 * mjm.nlight + (3 + 10) * nb + 6 * nv + 10 * nb + nC + 3 * nu + 2 * nJ
+  w["collision"] = 12 * ng + 39 * ncon_mean + 2
+  w["constraint"] = nq + nv + 6 * nv + 3 * nb + 39 * ncon_mean + nefc_mean * nv_pad + 8 * nefc_mean + 4 * ncon_mean + 4
+  w["velocity"] = nv + 6 * nv + 10 * nb + nu + nC + 2 * nJ + nu + nu + 6 * nb + 6 * nv + 6 * nv + 12 * nb + nu + qld + nv + nv
+  w["solver"] = nefc_mean * nv_pad + 3 * nefc_mean + nC + 2 * nv + 3 * nv + 2 * nefc_mean + 1
+  w["integrate"] = nq + 2 * nv + nq + 2 * nv + 1
+  return w
+
+
+# --------------------------------------------------------------------------------------------- CPU arm (oracle)
+
+
+def cpu_run(mjm, nworld, nsteps, nthreads):
+  """Times the CPU restatement (oracle, fp64, OpenMP over worlds) on a bounded sample; returns env-steps/s."""
+  from tests import util
+  from oracle import orc  # noqa: F401  (bench.py's cpu_baseline / --impl reference legs are allowed to use the oracle)
+
+  o = util.make_oracle(mjm, nworld, NCONMAX, NJMAX)
+  o.set_state(qpos=mjm.key_qpos[0], ctrl=mjm.key_ctrl[0])
+  rng = np.random.default_rng(0)
+  o.step(nthreads)
+  t0 = time.perf_counter()
+  for _ in range(nsteps):
+    o.d["ctrl"][:] = np.clip(o.d["ctrl"] + 0.01 * rng.uniform(-1, 1, o.d["ctrl"].shape), -1, 1)
+    o.step(nthreads)
+  dt = time.perf_counter() - t0
+  return nworld * nsteps / dt, dt
+
+
+def run_reference(args):
+  """--impl reference: the reference's algorithm on the box's host cores.  The reference itself (Warp + mujoco) cannot be
+  installed here (no wheels, no network: DESIGN.md), so this arm times the CPU restatement in oracle/ (kind = "port")."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  from mujoco_warp_b200._src import mjcf
+  from tests import util
+
+  mjm = mjcf.load_any(util.HUMANOID)
+  cores = os.cpu_count() or 1
+  nw = args.cpu_sample_worlds
+  for _ in range(max(1, min(args.warmup, 3))):
+    cpu_run(mjm, nw, 1, cores)
+  t0 = time.perf_counter()
+  rate, dt = cpu_run(mjm, nw, args.steps, cores)
+  sample = f"{nw} worlds x {args.steps} steps of the oracle (fp64 C, OpenMP {cores} threads) per run"
+  line = {
+    "impl": "reference", "metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    "config": {"workload": f"humanoid nworld={nw} per CPU step (bounded sample of nworld={args.nworld}/GPU), nconmax={NCONMAX}, njmax={NJMAX}, keyframe squat, random-walk ctrl"},
+    "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+    "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+
+
+def run_ours(args):
+  import torch
+
+  import mujoco_warp_b200 as mjw
+  from mujoco_warp_b200._src import io as mio
+  from tests import util
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+  def barrier():
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  tabs = mio.derive_tables(mjm)
+  m = mjw.put_model(mjm)
+  nworld = args.nworld
+  from mujoco_warp_b200._src.mjcf import MjDataLite, reset_data_keyframe
+
+  mjd = MjDataLite(mjm)
+  reset_data_keyframe(mjm, mjd, 0)
+  d = mjw.put_data(mjm, mjd, nworld=nworld, nconmax=NCONMAX, njmax=NJMAX, m=m)
+  center = torch.from_numpy(np.asarray(mjm.key_ctrl[0], dtype=np.float32)).cuda()
+  # ranks use shifted Halton step indices so their noise streams differ
+  world_offset = rank * nworld
+
+  stream = torch.cuda.Stream()
+  graph = None
+  step_idx = [0]
+
+  def one_step():
+    mjw.ctrl_noise(m, d, step_idx[0] + world_offset, center)
+    if graph is not None:
+      graph.replay()
+    else:
+      mjw.step(m, d)
+    step_idx[0] += 1
+
+  with torch.cuda.stream(stream):
+    for _ in range(3):
+      one_step()
+    stream.synchronize()
+    launches_per_step = 1 + mjw.last_launch_count()
+    if not args.no_graph:
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g, stream=stream):
+        mjw.step(m, d)
+      graph = g
+    for _ in range(args.warmup):
+      one_step()
+    stream.synchronize()
+
+    # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    if rank == 0:
+      sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    niter_sum = torch.zeros((), device="cuda", dtype=torch.float64)
+    e0.record(stream)
+    for _ in range(args.steps):
+      one_step()
+    e1.record(stream)
+    stream.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+
+    # ---- statistics of the run (untimed)
+    ncon_mean = float(d.nacon.cpu()[0]) / nworld
+    nefc_mean = float(d.nefc.float().mean().cpu())
+    niter_mean = float(d.solver_niter.float().mean().cpu())
+    ovf = int((d.overflow != 0).sum().cpu())
+    nan_worlds = int(torch.isnan(d.qpos).any(dim=1).sum().cpu())
+
+    # ---- per-kernel durations (separate pass with event pairs around each kernel)
+    nprof = 20
+    acc = None
+    for _ in range(nprof):
+      mjw.ctrl_noise(m, d, step_idx[0] + world_offset, center)
+      step_idx[0] += 1
+      r = mjw.step_profile(m, d)
+      acc = r if acc is None else {k: acc[k] + r[k] for k in r}
+    kms = {k: v / nprof for k, v in acc.items()}
+
+    # ---- e2e: same metric through the public API with HOST buffers: per step H2D of ctrl (pinned), step, D2H of qpos+qvel
+    ctrl_host = torch.empty((nworld, mjm.nu), dtype=torch.float32).pin_memory()
+    ctrl_host.copy_(d.ctrl.cpu())
+    out_host = torch.empty((nworld, mjm.nq + mjm.nv), dtype=torch.float32).pin_memory()
+    e2e_steps = max(10, args.steps // 2)
+    rng = np.random.default_rng(rank)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+      d.ctrl.copy_(ctrl_host, non_blocking=True)
+      if graph is not None:
+        graph.replay()
+      else:
+        mjw.step(m, d)
+      out_host[:, : mjm.nq].copy_(d.qpos, non_blocking=True)
+      out_host[:, mjm.nq :].copy_(d.qvel, non_blocking=True)
+      stream.synchronize()
+      # host-side policy stand-in: nudge controls using the state just read back
+      ctrl_host.add_(0.001 * float(out_host[0, 2])).clamp_(-1, 1)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+  t_max = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+  if dist is not None:
+    dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+  ms_max, e2e_ms_max = float(t_max[0]), float(t_max[1])
+  total_worlds = nworld * world
+  value = total_worlds * args.steps / (ms_max * 1e-3)
+  e2e_value = total_worlds * e2e_steps / (e2e_ms_max * 1e-3)
+
+  if rank == 0:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+      pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    words = algorithmic_words(mjm, tabs, ncon_mean, nefc_mean, m.nv_pad)
+    top = max(kms, key=kms.get)
+    bytes_launch = 4.0 * words[top] * nworld
+    achieved = bytes_launch / (kms[top] * 1e-3) / 1e9
+    step_bytes = 4.0 * sum(words.values()) * nworld
+    cpu = None
+    if world == 1 or True:
+      cores = os.cpu_count() or 1
+      rate, dt = cpu_run(mjm, args.cpu_sample_worlds, 20, cores)
+      cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+             "sample": f"{args.cpu_sample_worlds} worlds x 20 steps of the fp64 C oracle (OpenMP {cores} threads), {dt:.1f} s"}
+    line = {
+      "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 2729192.0,
+      "dtype": "f32", "data": "synthetic",
+      "config": {
+        "workload": f"humanoid.xml nworld={nworld}/GPU nconmax={NCONMAX} njmax={NJMAX} keyframe=squat Newton/pyramidal/Euler, OU ctrl noise (Halton)",
+        "cuda_graph": graph is not None, "l2": "per-step Data working set (~175 MB at 8192 worlds incl. efc.J rows) exceeds the 126 MB L2; no explicit flush",
+        "vs_baseline_note": "2,729,192 steps/s is the reference's only published number (benchmarks/README.md:48), hardware unstated",
+        "ncon_mean": ncon_mean, "nefc_mean": nefc_mean, "solver_niter_mean": niter_mean, "overflow_worlds": ovf, "nan_worlds": nan_worlds,
+      },
+      "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(nworld * mjm.nu * 4), "d2h_bytes_per_step": int(nworld * (mjm.nq + mjm.nv) * 4), "steps": e2e_steps},
+      "gpu_launches": launches_per_step * args.steps,
+      "kernel_ms": kms,
+      "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                   "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                   "algorithmic_bytes_per_launch": bytes_launch, "step_algorithmic_bytes": step_bytes,
+                   "step_frac": step_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak},
+      "cpu_baseline": cpu,
+      "clocks": clocks,
+    }
+    print(json.dumps(line))
+  if dist is not None:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  a = parse()
+  if a.impl == "reference":
+    run_reference(a)
+  else:
+    run_ours(a)

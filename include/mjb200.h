@@ -76,6 +76,10 @@ int mjb_euler(const mjbModel* m, mjbData* d, void* stream);
 /* ctrl <- OU noise around ctrl_center (device array of nu floats, or NULL), reference cli.py:103-145 */
 int mjb_ctrl_noise(const mjbModel* m, mjbData* d, const float* ctrl_center, int step, float noise_std, float noise_rate, void* stream);
 
+/* profiling aid: runs ONE step with a CUDA-event pair around each of the 6 kernels (position, collision, constraint,
+ * velocity, solver, integrate), synchronises, and writes the 6 durations in ms to ms_out (host pointer). */
+int mjb_step_profile(const mjbModel* m, mjbData* d, void* stream, float* ms_out);
+
 /* number of kernels the last mjb_* pipeline call launched (for bench.py's gpu_launches) */
 int mjb_last_launch_count(void);
 const char* mjb_last_error(void);

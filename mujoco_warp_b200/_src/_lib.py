@@ -75,6 +75,7 @@ def lib():
     getattr(L, f).argtypes = [vp, vp, vp]
     getattr(L, f).restype = ci
   L.mjb_ctrl_noise.argtypes = [vp, vp, vp, ci, cf, cf, vp]
+  L.mjb_step_profile.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_float)]
   L.mjb_last_launch_count.restype = ci
   _lib = L
   return L

@@ -98,3 +98,16 @@ def ctrl_noise(m: Model, d: Data, step_index: int, ctrl_center: torch.Tensor | N
 
 def last_launch_count() -> int:
   return int(_lib.lib().mjb_last_launch_count())
+
+
+KERNEL_NAMES = ("position", "collision", "constraint", "velocity", "solver", "integrate")
+
+
+def step_profile(m: Model, d: Data):
+  """One step with per-kernel CUDA-event timing; returns {kernel: ms}. Synchronises (profiling aid)."""
+  import ctypes
+
+  out = (ctypes.c_float * 6)()
+  stream = torch.cuda.current_stream().cuda_stream
+  _lib.check(_lib.lib().mjb_step_profile(m._handle, d._handle, stream, out))
+  return dict(zip(KERNEL_NAMES, [float(x) for x in out]))

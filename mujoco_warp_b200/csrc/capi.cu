@@ -164,6 +164,29 @@ int mjb_step(const mjbModel* m, mjbData* d, void* stream) {
   MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1);
   return 0;
 }
+int mjb_step_profile(const mjbModel* m, mjbData* d, void* stream, float* ms_out) {
+  // one step with a CUDA event pair around every kernel; synchronises (profiling aid, not the hot path)
+  MJB_ENTER();
+  cudaEvent_t ev[7];
+  for (int i = 0; i < 7; i++) if (check(cudaEventCreate(&ev[i]), "cudaEventCreate")) return -1;
+  cudaEventRecord(ev[0], s);
+  MJB_LAUNCH(launch_position(m->dev, d->dev, STG_KINEMATICS | STG_COM_POS | STG_CAMLIGHT | STG_CRB | STG_TRANSMISSION, s), 1);
+  cudaEventRecord(ev[1], s);
+  MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1);
+  cudaEventRecord(ev[2], s);
+  MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1);
+  cudaEventRecord(ev[3], s);
+  MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_VELOCITY | STG_ACTUATION | STG_ACCELERATION, s), 1);
+  cudaEventRecord(ev[4], s);
+  MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1);
+  cudaEventRecord(ev[5], s);
+  MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1);
+  cudaEventRecord(ev[6], s);
+  if (check(cudaEventSynchronize(ev[6]), "cudaEventSynchronize")) return -1;
+  for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (int i = 0; i < 7; i++) cudaEventDestroy(ev[i]);
+  return 0;
+}
 int mjb_ctrl_noise(const mjbModel* m, mjbData* d, const float* ctrl_center, int step, float noise_std, float noise_rate, void* stream) {
   MJB_ENTER();
   MJB_LAUNCH(launch_ctrl_noise(m->dev, d->dev, ctrl_center, step, noise_std, noise_rate, s), 1);

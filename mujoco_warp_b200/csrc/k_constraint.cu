@@ -38,9 +38,14 @@ __device__ void efc_row(const ModelDev& m, const DataDev& d, int w, int efcid, f
   if (solref[0] <= 0.f) k = -solref[0] / dmax_sq;
   if (solref[1] <= 0.f) b = -solref[1] / dmax;
   const float imp_x = fabsf(pos_imp) / width;
-  const float imp_a = (1.0f / powf(mid, power - 1.0f)) * powf(imp_x, power);
-  const float imp_b = 1.0f - (1.0f / powf(1.0f - mid, power - 1.0f)) * powf(1.0f - imp_x, power);
-  const float imp_y = imp_x < mid ? imp_a : imp_b;
+  // x^power / c^(power-1) on the lower branch, mirrored on the upper one; power == 2 (MuJoCo default) and 1 avoid powf
+  const bool lower = imp_x < mid;
+  const float bx = lower ? imp_x : 1.0f - imp_x, bc = lower ? mid : 1.0f - mid;
+  float t;
+  if (power == 2.0f) t = bx * bx / bc;
+  else if (power == 1.0f) t = bx;
+  else t = (1.0f / powf(bc, power - 1.0f)) * powf(bx, power);
+  const float imp_y = lower ? t : 1.0f - t;
   float imp = clampf(dmin + imp_y * (dmax - dmin), dmin, dmax);
   if (imp_x > 1.0f) imp = dmax;
   const size_t r = (size_t)w * d.njmax + efcid;

@@ -41,17 +41,23 @@ k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
       const int start = m.tree_dofadr[t], n = m.tree_dofnum[t], ld = chol_ld(n);
       for (int i = lane; i < n * ld; i += 32) A[i] = 0.f;
       __syncwarp();
-      for (int r = start; r < start + n; r++) {
-        const int adr = m.M_rowadr[r], nnz = m.M_rownnz[r];
-        for (int k = lane; k < nnz; k += 32) {
-          const int col = m.M_colind[adr + k];
-          A[(r - start) * ld + (col - start)] = Mw[adr + k] + (col == r ? dt * m.dof_damping[r] : 0.f);
-        }
+      const int e0 = m.M_rowadr[start], e1 = m.M_rowadr[start + n - 1] + m.M_rownnz[start + n - 1];
+      for (int e = e0 + lane; e < e1; e += 32) {
+        const int r = m.M_entry_row[e], col = m.M_colind[e];
+        A[(r - start) * ld + (col - start)] = Mw[e] + (col == r ? dt * m.dof_damping[r] : 0.f);
       }
-      for (int i = lane; i < n; i += 32) x[i] = d.efc_Ma[wb * nv + start + i];
       __syncwarp();
-      warp_cholesky(A, n, ld, lane);
-      warp_chol_solve(A, n, ld, x, lane);
+      if (n <= 32) {
+        const float b = lane < n ? d.efc_Ma[wb * nv + start + lane] : 0.f;
+        const float xx = chol_solve_reg_any(A, ld, n, b, A, ld, lane);
+        if (lane < n) x[lane] = xx;
+        __syncwarp();
+      } else {
+        for (int i = lane; i < n; i += 32) x[i] = d.efc_Ma[wb * nv + start + i];
+        __syncwarp();
+        warp_cholesky(A, n, ld, lane);
+        warp_chol_solve(A, n, ld, x, lane);
+      }
       for (int i = lane; i < n; i += 32) qacc[start + i] = x[i];
       __syncwarp();
     }

@@ -135,12 +135,17 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
   return nlist;
 }
 
-// grad, H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad
-__device__ __forceinline__ void update_gradient(Ctx& c, int nlist) {
-  const int nv = c.nv;
+// grad = Ma - qfrc_smooth - qfrc_constraint and its squared norm
+__device__ __forceinline__ void update_grad(Ctx& c) {
   float gd = 0.f;
-  for (int dd = c.lane; dd < nv; dd += 32) { const float g = c.Ma[dd] - c.qfs[dd] - c.qfc[dd]; c.grad[dd] = g; c.x[dd] = g; gd += g * g; }
+  for (int dd = c.lane; dd < c.nv; dd += 32) { const float g = c.Ma[dd] - c.qfs[dd] - c.qfc[dd]; c.grad[dd] = g; gd += g * g; }
   c.grad_dot = warp_sum(gd);
+  __syncwarp();
+}
+
+// H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
+__device__ __forceinline__ void update_search(Ctx& c, int nlist) {
+  const int nv = c.nv;
   const int ntri = nv * (nv + 1) / 2;
   if (nlist > 0) {
     for (int e = c.lane; e < ntri; e += 32) {
@@ -154,12 +159,20 @@ __device__ __forceinline__ void update_gradient(Ctx& c, int nlist) {
     }
     __syncwarp();
   }
-  for (int e = c.lane; e < nv * c.ldH; e += 32) c.Lf[e] = c.H[e];
-  __syncwarp();
-  warp_cholesky(c.Lf, nv, c.ldH, c.lane);
-  warp_chol_solve(c.Lf, nv, c.ldH, c.x, c.lane);
   float sd = 0.f, nd = 0.f;
-  for (int dd = c.lane; dd < nv; dd += 32) { const float xx = c.x[dd]; sd += xx * xx; nd += c.grad[dd] * xx; c.search[dd] = -xx; }
+  if (nv <= 32) {
+    const float g = c.lane < nv ? c.grad[c.lane] : 0.f;
+    const float xx = chol_solve_reg_any(c.H, c.ldH, nv, g, c.Lf, c.ldH, c.lane);
+    sd = xx * xx; nd = g * xx;
+    if (c.lane < nv) c.search[c.lane] = -xx;
+  } else {
+    for (int dd = c.lane; dd < nv; dd += 32) c.x[dd] = c.grad[dd];
+    for (int e = c.lane; e < nv * c.ldH; e += 32) c.Lf[e] = c.H[e];
+    __syncwarp();
+    warp_cholesky(c.Lf, nv, c.ldH, c.lane);
+    warp_chol_solve(c.Lf, nv, c.ldH, c.x, c.lane);
+    for (int dd = c.lane; dd < nv; dd += 32) { const float xx = c.x[dd]; sd += xx * xx; nd += c.grad[dd] * xx; c.search[dd] = -xx; }
+  }
   c.search_dot = warp_sum(sd);
   c.newton_decrement = warp_sum(nd);
   __syncwarp();
@@ -290,20 +303,25 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   mul_m(c, c.qacc, c.Ma);
   __syncwarp();
 
-  int nlist = update_constraint(c, true);
-  update_gradient(c, nlist);
-
+  // One call site per phase: iteration -1 is init_context (solver.py:3622), iterations >= 0 are _solver_iteration (:3526).
+  // _solve_done's three criteria are OR-ed (:3483-3486), so when `improvement` or `gradient` already satisfies the
+  // tolerance the Hessian refactorisation (whose only consumer is the next line search) is skipped.
   const float scale = m.meaninertia * (float)nv;
   int niter = 0, ovf = 0;
-  bool done = m.iterations == 0;
-  while (!done) {
-    if (!linesearch(c)) ovf |= OVF_LS_ITERATIONS;
-    nlist = update_constraint(c, false);
-    update_gradient(c, nlist);
-    niter++;
-    const float improvement = c.improvement / scale, gradient = sqrtf(c.grad_dot) / scale, model_improvement = 0.5f * c.newton_decrement / scale;
-    done = improvement < m.tolerance || gradient < m.tolerance || model_improvement < m.tolerance;
-    if (!done && niter == m.iterations) { ovf |= OVF_ITERATIONS; done = true; }
+  for (int it = -1;; it++) {
+    if (it >= 0 && !linesearch(c)) ovf |= OVF_LS_ITERATIONS;
+    const int nlist = update_constraint(c, it < 0);
+    update_grad(c);
+    if (it >= 0) {
+      niter++;
+      const float improvement = c.improvement / scale, gradient = sqrtf(c.grad_dot) / scale;
+      if (improvement < m.tolerance || gradient < m.tolerance) break;
+    } else if (m.iterations == 0) break;
+    update_search(c, nlist);
+    if (it >= 0) {
+      if (0.5f * c.newton_decrement / scale < m.tolerance) break;
+      if (niter == m.iterations) { ovf |= OVF_ITERATIONS; break; }
+    }
   }
 
   // ---- results

@@ -254,20 +254,25 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       const int start = m.tree_dofadr[t], n = m.tree_dofnum[t], ld = chol_ld(n);
       for (int i = lane; i < n * ld; i += 32) A[i] = 0.f;
       __syncwarp();
-      for (int r = start; r < start + n; r++) {
-        const int adr = m.M_rowadr[r], nnz = m.M_rownnz[r];
-        for (int k = lane; k < nnz; k += 32) A[(r - start) * ld + (m.M_colind[adr + k] - start)] = Mw[adr + k];
-      }
+      const int e0 = m.M_rowadr[start], e1 = m.M_rowadr[start + n - 1] + m.M_rownnz[start + n - 1];
+      for (int e = e0 + lane; e < e1; e += 32) A[(m.M_entry_row[e] - start) * ld + (m.M_colind[e] - start)] = Mw[e];
       __syncwarp();
-      warp_cholesky(A, n, ld, lane);
       float* qld = d.qLD + wb * m.qld_total + m.tree_qLDadr[t];
-      for (int i = lane; i < n * n; i += 32) { const int r = i / n, c = i - r * n; qld[i] = c >= r ? A[c * ld + r] : 0.f; }
-      if (mask & STG_ACCELERATION) {
-        for (int i = lane; i < n; i += 32) x[i] = q_smooth[start + i];
+      if (n <= 32) {
+        const float b = ((mask & STG_ACCELERATION) && lane < n) ? q_smooth[start + lane] : 0.f;
+        const float xx = chol_solve_reg_any(A, ld, n, b, A, ld, lane);
         __syncwarp();
-        warp_chol_solve(A, n, ld, x, lane);
-        for (int i = lane; i < n; i += 32) d.qacc_smooth[wb * nv + start + i] = x[i];
+        if ((mask & STG_ACCELERATION) && lane < n) d.qacc_smooth[wb * nv + start + lane] = xx;
+      } else {
+        warp_cholesky(A, n, ld, lane);
+        if (mask & STG_ACCELERATION) {
+          for (int i = lane; i < n; i += 32) x[i] = q_smooth[start + i];
+          __syncwarp();
+          warp_chol_solve(A, n, ld, x, lane);
+          for (int i = lane; i < n; i += 32) d.qacc_smooth[wb * nv + start + i] = x[i];
+        }
       }
+      for (int i = lane; i < n * n; i += 32) { const int r = i / n, c = i - r * n; qld[i] = c >= r ? A[c * ld + r] : 0.f; }
       __syncwarp();
     }
   }

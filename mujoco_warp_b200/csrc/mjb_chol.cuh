@@ -44,3 +44,61 @@ __device__ __forceinline__ void warp_chol_solve(const float* L, int n, int ld, f
     __syncwarp();
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Register-resident Cholesky for n <= 32: lane i keeps row i of the matrix in registers, columns are eliminated
+// right-looking with warp shuffles (no shared-memory round trips, no __syncwarp per column), the forward substitution of
+// one right-hand side is folded into the same sweep, the factor is written once to shared memory (for the caller and for
+// the transposed read of the backward substitution).  ~N^2/2 SHFL + FFMA instead of ~N^2/2 dependent LDS chains.
+//   Hs  : shared, n x n, leading dim ld, lower triangle valid
+//   b   : right-hand side element of row `lane` (0 for lane >= n)
+//   Ls  : shared scratch (n rows x ldL), receives L (lower triangle); may alias Hs when ldL == ld (each lane only
+//         reads and writes its own row)
+// returns x[lane] of (L L^T) x = b.
+template <int N>
+__device__ __forceinline__ float chol_solve_reg(const float* Hs, int ld, int n, float b, float* Ls, int ldL, int lane) {
+  float a[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    float v = (k == lane) ? 1.0f : 0.f;                      // identity padding for rows/cols >= n
+    if (lane < n && k <= lane) v = Hs[lane * ld + k];
+    a[k] = v;
+  }
+  float myinv = 1.0f;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    const float ajj = __shfl_sync(FULL_MASK, a[j], j);
+    const float inv = rsqrtf(fmaxf(ajj, MJ_MINVAL));
+    a[j] *= inv;
+    if (lane == j) myinv = inv;
+    const float yj = __shfl_sync(FULL_MASK, b, j) * inv;
+    b = lane > j ? b - a[j] * yj : (lane == j ? yj : b);
+#pragma unroll
+    for (int k = j + 1; k < N; k++) {
+      const float lkj = __shfl_sync(FULL_MASK, a[j], k);
+      a[k] -= a[j] * lkj;
+    }
+  }
+  if (lane < n) {  // rows >= n are identity padding and are not stored
+#pragma unroll
+    for (int k = 0; k < N; k++)
+      if (k <= lane) Ls[lane * ldL + k] = a[k];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = N - 1; j >= 0; j--) {
+    const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
+    const float ltj = (lane < j && j < n) ? Ls[j * ldL + lane] : 0.f;
+    b = lane < j ? b - ltj * xj : (lane == j ? xj : b);
+  }
+  return b;
+}
+
+// n <= 32 dispatch over padded sizes (warp-uniform branch)
+__device__ __forceinline__ float chol_solve_reg_any(const float* Hs, int ld, int n, float b, float* Ls, int ldL, int lane) {
+  if (n <= 8) return chol_solve_reg<8>(Hs, ld, n, b, Ls, ldL, lane);
+  if (n <= 16) return chol_solve_reg<16>(Hs, ld, n, b, Ls, ldL, lane);
+  if (n <= 24) return chol_solve_reg<24>(Hs, ld, n, b, Ls, ldL, lane);
+  if (n <= 28) return chol_solve_reg<28>(Hs, ld, n, b, Ls, ldL, lane);
+  return chol_solve_reg<32>(Hs, ld, n, b, Ls, ldL, lane);
+}
