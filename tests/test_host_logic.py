@@ -1,0 +1,170 @@
+"""CPU tests of the host side: constants, MJCF compiler, derived index tables, C-ABI library symbols, no-CUDA behaviour."""
+
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from tests import util
+
+
+@pytest.fixture(scope="module")
+def mjm(built):
+  from mujoco_warp_b200._src import mjcf
+
+  return mjcf.load_any(util.HUMANOID)
+
+
+def test_constants_self_consistent():
+  from mujoco_warp_b200._src import constants as C
+  from mujoco_warp_b200._src import types as T
+
+  assert [int(x) for x in T.JointType] == [0, 1, 2, 3]
+  assert T.GeomType.PLANE == 0 and T.GeomType.CAPSULE == 3 and T.GeomType.BOX == 6 and T.GeomType.MESH == 7
+  assert T.SolverType.NEWTON == 2 and T.ConeType.PYRAMIDAL == 0 and T.IntegratorType.IMPLICITFAST == 3
+  assert T.ConstraintType.LIMIT_JOINT == 3 and T.ConstraintType.CONTACT_PYRAMIDAL == 6
+  assert T.ConstraintState.QUADRATIC == 1
+  bits = list(C.DISABLE_FLAGS.values())
+  assert len(set(bits)) == len(bits) and all(b & (b - 1) == 0 for b in bits)
+  assert T.OverflowType.ITERATIONS == 1 << 9 and T.OverflowType.LS_ITERATIONS == 1 << 10  # reference types.py:149-176
+  try:
+    import mujoco
+  except ImportError:
+    return
+  assert C.MJ_MINVAL == mujoco.mjMINVAL and C.MJ_MINIMP == mujoco.mjMINIMP and C.MJ_MINMU == mujoco.mjMINMU
+  assert C.DSBL_EULERDAMP == mujoco.mjtDisableBit.mjDSBL_EULERDAMP and C.JNT_HINGE == mujoco.mjtJoint.mjJNT_HINGE
+
+
+def test_capi_library_exports_every_header_symbol(built):
+  from mujoco_warp_b200._src import _lib
+
+  names = _lib.exported_symbols_in_header()
+  assert len(names) >= 30
+  L = ctypes.CDLL(_lib.LIB_PATH)
+  missing = [n for n in names if not hasattr(L, n)]
+  assert not missing, missing
+  L.mjb_version.restype = ctypes.c_char_p
+  assert b"sm_100a" in L.mjb_version()
+
+
+def test_capi_name_registry_without_gpu(built):
+  """Model build-by-name works on the host (no device calls): unknown names and bad batch sizes are rejected."""
+  from mujoco_warp_b200._src import _lib
+
+  L = _lib.lib()
+  h = L.mjb_model_create()
+  assert L.mjb_model_set_int(h, b"nv", 27) == 0
+  assert L.mjb_model_set_int(h, b"not_a_field", 1) != 0 and b"unknown" in L.mjb_last_error()
+  assert L.mjb_model_set_float(h, b"timestep", 0.005) == 0
+  assert L.mjb_model_set_array(h, b"body_pos", 0x1000, 2) != 0  # batched model fields unsupported
+  assert L.mjb_model_finalize(h) != 0 and b"not set" in L.mjb_last_error()
+  L.mjb_model_destroy(h)
+
+
+def test_product_path_fails_loudly_without_cuda(mjm):
+  import torch
+
+  import mujoco_warp_b200 as mjw
+
+  if torch.cuda.is_available():
+    pytest.skip("CUDA present")
+  with pytest.raises(RuntimeError, match="CUDA"):
+    mjw.put_model(mjm)
+
+
+def test_product_package_never_imports_oracle():
+  import re
+
+  pkg = os.path.join(util.ROOT, "mujoco_warp_b200")
+  for dp, _, fs in os.walk(pkg):
+    for f in fs:
+      if f.endswith((".py", ".cu", ".cuh", ".h")):
+        txt = open(os.path.join(dp, f)).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+
+
+def test_mjcf_compiler_matches_fixture(mjm):
+  """When the reference tree is mounted, compiling its XML reproduces the committed .npz fixture exactly."""
+  from mujoco_warp_b200._src import mjcf
+
+  xml = "/root/reference/benchmarks/humanoid/humanoid.xml"
+  if not os.path.exists(xml):
+    pytest.skip("reference tree not mounted (GPU box)")
+  a = mjcf.load(xml)
+  for k in ("body_mass", "body_inertia", "body_ipos", "body_iquat", "geom_size", "geom_pos", "geom_quat", "jnt_range", "dof_invweight0", "body_invweight0", "key_qpos", "M_colind"):
+    np.testing.assert_array_equal(np.asarray(getattr(a, k)), np.asarray(getattr(mjm, k)), err_msg=k)
+
+
+def test_compiled_humanoid_physical_sanity(mjm):
+  assert mjm.body_mass.sum() == pytest.approx(40.84, abs=0.01)  # density-1000 capsule humanoid
+  names = mjm.names.body
+  for side in ("thigh", "shin", "foot", "upper_arm", "lower_arm", "hand"):
+    r, l = names.index(side + "_right"), names.index(side + "_left")
+    assert mjm.body_mass[r] == pytest.approx(mjm.body_mass[l], rel=1e-12)
+    np.testing.assert_allclose(np.sort(mjm.body_inertia[r]), np.sort(mjm.body_inertia[l]), rtol=1e-9)
+  assert (mjm.body_inertia[1:] > 0).all()
+  assert mjm.jnt_limited.sum() == 21 and mjm.nkey == 3
+  assert mjm.opt.disableflags == 1 << 15 and mjm.opt.timestep == 0.005 and mjm.opt.iterations == 100
+  # capsule geom: rbound = radius + half length; plane rbound 0 (collision_driver.py:318-320)
+  assert mjm.geom_rbound[0] == 0 and mjm.geom_rbound[1] == pytest.approx(0.07 + 0.07)
+  # triangle inequality of principal inertias
+  I = np.sort(mjm.body_inertia[1:], axis=1)
+  assert (I[:, 0] + I[:, 1] >= I[:, 2] - 1e-12).all()
+
+
+def test_derived_tables(mjm):
+  from mujoco_warp_b200._src import io as mio
+
+  t = mio.derive_tables(mjm)
+  # levels partition the bodies, parents sit one level above
+  assert sorted(t["level_body"].tolist()) == list(range(mjm.nbody))
+  depth = np.zeros(mjm.nbody, int)
+  for l in range(t["nlevel"]):
+    depth[t["level_body"][t["level_adr"][l] : t["level_adr"][l + 1]]] = l
+  assert (depth[1:] == depth[mjm.body_parentid[1:]] + 1).all()
+  # child lists invert body_parentid
+  for b in range(mjm.nbody):
+    kids = t["body_childid"][t["body_childadr"][b] : t["body_childadr"][b + 1]]
+    assert sorted(kids.tolist()) == [c for c in range(1, mjm.nbody) if mjm.body_parentid[c] == b]
+  # symmetric gather tables reproduce dense M @ v
+  rng = np.random.default_rng(0)
+  Mcsr = rng.normal(size=t["nC"])
+  v = rng.normal(size=mjm.nv)
+  M = np.zeros((mjm.nv, mjm.nv))
+  for e in range(t["nC"]):
+    i, j = t["M_entry_row"][e], mjm.M_colind[e]
+    M[i, j] = M[j, i] = Mcsr[e]
+  got = np.array([sum(Mcsr[t["mulm_madr"][k]] * v[t["mulm_col"][k]] for k in range(t["mulm_rowadr"][i], t["mulm_rowadr"][i + 1])) for i in range(mjm.nv)])
+  np.testing.assert_allclose(got, M @ v, atol=1e-12)
+  # NXN pairs: humanoid keeps floor-vs-body and non-adjacent body pairs, excludes parent-child and same-body pairs
+  pairs = t["nxn_geom_pair_filtered"]
+  assert 0 < len(pairs) <= 190
+  b = mjm.geom_bodyid
+  assert all(b[p] != b[q] for p, q in pairs)
+  assert all(mjm.body_parentid[b[p]] != b[q] and mjm.body_parentid[b[q]] != b[p] or 0 in (b[p], b[q]) for p, q in pairs)
+  assert t["nmaxpyramid"] == 4 and t["nJmom"] == mjm.nu and len(t["jnt_limited_slide_hinge_adr"]) == 21
+  assert mio.is_sparse(mjm) is False
+
+
+def test_unsupported_features_raise():
+  from mujoco_warp_b200._src import io as mio
+  from mujoco_warp_b200._src import mjcf
+
+  xml = """<mujoco><option cone="elliptic"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
+  with pytest.raises(NotImplementedError, match="elliptic"):
+    mio._validate(mjcf.load_string(xml))
+  xml = """<mujoco><worldbody><geom type="plane" size="1 1 1"/><body pos="0 0 1"><freejoint/><geom type="box" size=".1 .1 .1"/></body></worldbody></mujoco>"""
+  with pytest.raises(NotImplementedError, match="collision between geom types"):
+    mio.derive_tables(mjcf.load_string(xml))
+
+
+def test_shard_worlds():
+  from mujoco_warp_b200._src import shard
+
+  for total, ws in ((65536, 8), (10, 3), (7, 8)):
+    blocks = [shard.shard_worlds(total, ws, r) for r in range(ws)]
+    assert sum(c for _, c in blocks) == total
+    assert all(blocks[r][0] + blocks[r][1] == blocks[r + 1][0] for r in range(ws - 1))
+    assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+  assert shard.whole_job_rate(8192 * 100, 0.5, world_size=8) == 8 * 8192 * 100 / 0.5

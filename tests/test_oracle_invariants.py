@@ -1,0 +1,155 @@
+"""Physical invariants that pin the oracle's dynamics (the reference's own dynamics tests delegate to live MuJoCo, which is
+unavailable here -- see oracle.h).  Each invariant is a property the true algorithm must satisfy independent of any
+implementation: symmetric positive-definite M equal to the kinetic-energy Hessian, inverse-dynamics consistency, KKT
+optimality of the constraint solve, momentum/energy behaviour of a free-falling humanoid."""
+
+import numpy as np
+import pytest
+
+from tests import util
+
+
+@pytest.fixture(scope="module")
+def scene(built):
+  from mujoco_warp_b200._src import mjcf
+
+  return mjcf.load_any(util.HUMANOID)
+
+
+def dense_M(mjm, Mcsr):
+  M = np.zeros((mjm.nv, mjm.nv))
+  for i in range(mjm.nv):
+    for k in range(mjm.M_rownnz[i]):
+      j = mjm.M_colind[mjm.M_rowadr[i] + k]
+      M[i, j] = M[j, i] = Mcsr[mjm.M_rowadr[i] + k]
+  return M
+
+
+def test_M_is_spd_and_matches_kinetic_energy(scene):
+  mjm = scene
+  nw = 4
+  o = util.make_oracle(mjm, nw, 24, 64)
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, nw)
+  o.set_state(qpos=qpos, qvel=qvel)
+  o.forward()
+  for w in range(nw):
+    M = dense_M(mjm, o.d["M"][w])
+    assert np.linalg.eigvalsh(M).min() > 0
+    # kinetic energy two ways: 0.5 v'Mv  ==  sum_b 0.5 cvel' I_c cvel (cinert in the com frame)
+    v = o.d["qvel"][w]
+    ke_joint = 0.5 * v @ M @ v - 0.5 * np.sum(mjm.dof_armature * v * v)
+    ke_body = 0.0
+    for b in range(1, mjm.nbody):
+      ci, cv = o.d["cinert"][w, b], o.d["cvel"][w, b]
+      I = np.array([[ci[0], ci[3], ci[4]], [ci[3], ci[1], ci[5]], [ci[4], ci[5], ci[2]]])
+      mc, mass = ci[6:9], ci[9]
+      wv, lv = cv[:3], cv[3:]
+      ke_body += 0.5 * (wv @ I @ wv) + lv @ np.cross(wv, mc) * 1.0 + 0.5 * mass * lv @ lv
+    assert ke_joint == pytest.approx(ke_body, rel=1e-9, abs=1e-10)
+    # qLD: M = U^T U
+    U = o.d["qLD"][w].reshape(mjm.nv, mjm.nv)
+    np.testing.assert_allclose(U.T @ U, M, atol=1e-9)
+
+
+def test_smooth_dynamics_consistency(scene):
+  """M qacc_smooth + qfrc_bias == qfrc_passive + qfrc_actuator + qfrc_applied  (forward.py:1255-1324)."""
+  mjm = scene
+  nw = 4
+  o = util.make_oracle(mjm, nw, 24, 64)
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, nw)
+  o.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl)
+  o.forward()
+  for w in range(nw):
+    M = dense_M(mjm, o.d["M"][w])
+    lhs = M @ o.d["qacc_smooth"][w] + o.d["qfrc_bias"][w]
+    rhs = o.d["qfrc_passive"][w] + o.d["qfrc_actuator"][w]
+    np.testing.assert_allclose(lhs, rhs, atol=1e-8, rtol=1e-9)
+    np.testing.assert_allclose(o.d["qfrc_actuator"][w][6:], (np.clip(ctrl[w], -1, 1) * mjm.actuator_gear[:, 0])[np.argsort(mjm.jnt_dofadr[mjm.actuator_trnid[:, 0]])], atol=1e-12)
+
+
+def test_bias_force_is_gravity_for_static_pose(scene):
+  """With zero velocity, qfrc_bias = -J_com^T m g summed over bodies: the root's vertical translational dof carries total weight."""
+  mjm = scene
+  o = util.make_oracle(mjm, 1, 24, 64)
+  o.set_state(qpos=mjm.key_qpos[2])  # no_efc keyframe
+  o.forward()
+  total_mass = mjm.body_mass.sum()
+  assert o.d["qfrc_bias"][0, 2] == pytest.approx(total_mass * 9.81, rel=1e-12)
+  assert o.d["nefc"][0] == 0 and o.d["ncon"][0] == 0
+  # free fall: root linear acceleration = gravity, solver leaves qacc = qacc_smooth
+  np.testing.assert_allclose(o.d["qacc"][0], o.d["qacc_smooth"][0], atol=1e-9)
+  assert o.d["qacc_smooth"][0, 2] == pytest.approx(-9.81, abs=0.5)  # joint springs couple slightly into the root
+
+
+def test_solver_kkt(scene):
+  """At the solution of the convex problem the gradient vanishes: M qacc - qfrc_smooth - J^T f = 0, with per-row forces
+  consistent with the row states (solver.py:425-477) and non-negative normal cone combinations."""
+  mjm = scene
+  nw = 8
+  o = util.make_oracle(mjm, nw, 24, 64)
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, nw)
+  o.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, qacc_warmstart=warm)
+  o.forward()
+  assert (o.d["overflow"] == 0).all()
+  for w in range(nw):
+    ne = o.d["nefc"][w]
+    assert ne > 0
+    M = dense_M(mjm, o.d["M"][w])
+    J, f = o.d["efc_J"][w, :ne], o.d["efc_force"][w, :ne]
+    grad = M @ o.d["qacc"][w] - o.d["qfrc_smooth"][w] - J.T @ f
+    scale = mjm.stat.meaninertia * mjm.nv
+    assert np.linalg.norm(grad) / scale < 1e-6
+    np.testing.assert_allclose(o.d["qfrc_constraint"][w], J.T @ f, atol=1e-9)
+    np.testing.assert_allclose(o.d["efc_Ma"][w], M @ o.d["qacc"][w], atol=1e-7)
+    jar = J @ o.d["qacc"][w] - o.d["efc_aref"][w, :ne]
+    st = o.d["efc_state"][w, :ne]
+    assert ((st == 1) == (jar < 0)).all()
+    np.testing.assert_allclose(f, np.where(jar < 0, -o.d["efc_D"][w, :ne] * jar, 0.0), atol=1e-9)
+    assert (f >= 0).all()
+
+
+def test_contacts_squat_keyframe(scene):
+  """Squat keyframe: 4 foot capsules on the floor, 2 plane-capsule contacts each, condim 3 -> 4 pyramid rows per contact."""
+  mjm = scene
+  o = util.make_oracle(mjm, 1, 24, 64)
+  o.set_state(qpos=mjm.key_qpos[0])
+  o.forward()
+  assert o.d["ncon"][0] == 8 and o.d["nefc"][0] == 32 and o.d["nl"][0] == 0
+  g = o.d["con_geom"][0, :8]
+  assert (g[:, 0] == 0).all()
+  assert sorted(set(g[:, 1])) == sorted(mjm.names.geom.index(n) for n in ("foot1_right", "foot2_right", "foot1_left", "foot2_left"))
+  assert (o.d["con_dim"][0, :8] == 3).all()
+  np.testing.assert_allclose(o.d["con_frame"][0, :8, 0], [[0, 0, 1]] * 8, atol=1e-12)
+  assert (o.d["efc_type"][0, :32] == 6).all()
+
+
+def test_free_fall_conserves_momentum_and_energy(scene):
+  """no_efc keyframe, gravity only (no damping on the root): horizontal momentum stays 0, the CoM falls as g t^2 / 2."""
+  mjm = scene
+  o = util.make_oracle(mjm, 1, 24, 64)
+  o.set_state(qpos=mjm.key_qpos[2])
+  o.forward()
+  com0 = o.d["subtree_com"][0, 1].copy()
+  n = 40
+  for _ in range(n):
+    o.step()
+  o.forward()
+  t = n * mjm.opt.timestep
+  com = o.d["subtree_com"][0, 1]
+  np.testing.assert_allclose(com[:2], com0[:2], atol=1e-9)
+  # semi-implicit Euler: z(t) = z0 - g dt^2 n(n+1)/2
+  assert com[2] - com0[2] == pytest.approx(-9.81 * mjm.opt.timestep**2 * n * (n + 1) / 2, rel=1e-6)
+  assert o.d["time"][0] == pytest.approx(t)
+
+
+def test_fp32_oracle_tracks_fp64(scene):
+  mjm = scene
+  nw = 4
+  o64 = util.make_oracle(mjm, nw, 24, 64, dtype=np.float64)
+  o32 = util.make_oracle(mjm, nw, 24, 64, dtype=np.float32)
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, nw)
+  for o in (o64, o32):
+    o.set_state(qpos=qpos.astype(np.float32), qvel=qvel.astype(np.float32), ctrl=ctrl.astype(np.float32), qacc_warmstart=warm.astype(np.float32))
+    o.forward()
+  np.testing.assert_array_equal(o32.d["nefc"], o64.d["nefc"])
+  np.testing.assert_allclose(o32.d["qacc"], o64.d["qacc"], atol=5e-3 * np.abs(o64.d["qacc"]).max())
