@@ -123,8 +123,8 @@ __device__ void contact_params(const ModelDev& m, int g1, int g2, ConParams* p) 
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
+  const int w = blockIdx.x;
   if (w >= d.nworld) return;
   const ColLayout L = col_layout(m, d);
   float* S = smem + warp * L.total;
@@ -143,6 +143,7 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
 
   // ---- broadphase: lanes over the filtered pair list, ordered compaction of survivors
   int nsurv = 0, ntotal = 0;
+#pragma unroll 1
   for (int e0 = 0; e0 < m.nxn_npair; e0 += 32) {
     const int e = e0 + lane;
     bool pass = false;
@@ -182,6 +183,7 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
 
   // ---- narrowphase on the compacted list; contacts staged in shared memory in (pair, contact id) order
   int ncon = 0;
+#pragma unroll 1
   for (int s0 = 0; s0 < nsurv; s0 += 32) {
     const int si = s0 + lane;
     float cd[2] = {INFINITY, INFINITY};
@@ -281,6 +283,7 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
     if (ovf) d.overflow[w] |= ovf;
   }
   const int np = m.nmaxpyramid;
+#pragma unroll 1
   for (int c = lane; c < nwrite; c += 32) {
     const int cid = base + c, g1 = sgeom[3 * c], g2 = sgeom[3 * c + 1];
     const float* st = stage + STAGE_WORDS * c;

@@ -62,8 +62,8 @@ __device__ void efc_row(const ModelDev& m, const DataDev& d, int w, int efcid, f
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
+  const int w = blockIdx.x;
   if (w >= d.nworld) return;
   const ConLayout L = con_layout(m);
   float* S = smem + warp * L.total;
@@ -89,6 +89,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
     for (int i = 0; i < nf; i++) {
       const int efcid = nefc + i, dof = m.dof_fricloss_adr[i];
       if (efcid >= njmax) break;
+#pragma unroll 1
       for (int c = lane; c < nvp; c += 32) Jw[(size_t)efcid * nvp + c] = c == dof ? 1.0f : 0.f;
       if (lane == 0)
         efc_row(m, d, w, efcid, 0.f, 0.f, m.dof_invweight0[dof], m.dof_solref + 2 * dof, m.dof_solimp + 5 * dof, 0.f, qvel[dof],
@@ -99,6 +100,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
 
   // ---- joint limits (slide / hinge)
   if (!(m.disableflags & DSBL_LIMIT)) {
+#pragma unroll 1
     for (int l0 = 0; l0 < m.nlimit; l0 += 32) {
       const int li = l0 + lane;
       bool active = false;
@@ -126,6 +128,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
         const int r = __shfl_sync(FULL_MASK, efcid, src), dcol = __shfl_sync(FULL_MASK, dofadr, src);
         const float jv = __shfl_sync(FULL_MASK, Jv, src);
         if (r < njmax)
+#pragma unroll 1
           for (int c = lane; c < nvp; c += 32) Jw[(size_t)r * nvp + c] = c == dcol ? jv : 0.f;
       }
       const int n = __popc(bal);
@@ -137,6 +140,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
   if (!(m.disableflags & DSBL_CONTACT)) {
     const int cbase = d.world_conadr[w], ncon = d.world_ncon[w], np = m.nmaxpyramid;
     const bool elliptic = m.cone == CONE_ELLIPTIC;
+#pragma unroll 1
     for (int c = 0; c < ncon; c++) {
       const int cid = cbase + c;
       const float includemargin = d.contact_includemargin[cid], pos = d.contact_dist[cid] - includemargin;
@@ -154,6 +158,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
       float velp[10];
 #pragma unroll
       for (int k = 0; k < 10; k++) velp[k] = 0.f;
+#pragma unroll 1
       for (int dd = lane; dd < nvp; dd += 32) {
         v3 jpd = mk3(0.f, 0.f, 0.f), jrd = mk3(0.f, 0.f, 0.f);
         float qv = 0.f;

@@ -20,8 +20,8 @@ __host__ __device__ inline int int_words(const ModelDev& m) {
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
+  const int w = blockIdx.x;
   if (w >= d.nworld) return;
   float* S = smem + warp * int_words(m);
   float *qacc = S, *qvel = S + m.nv, *A = S + 2 * m.nv, *x = A + m.maxtree * chol_ld(m.maxtree);
@@ -37,11 +37,14 @@ k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   if (!(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
     // qacc <- (M + dt*diag(damping))^-1 * Ma  (forward.py:391-415)
     const float* Mw = d.M + wb * m.nC;
+#pragma unroll 1
     for (int t = 0; t < m.ntree; t++) {
       const int start = m.tree_dofadr[t], n = m.tree_dofnum[t], ld = chol_ld(n);
+#pragma unroll 1
       for (int i = lane; i < n * ld; i += 32) A[i] = 0.f;
       __syncwarp();
       const int e0 = m.M_rowadr[start], e1 = m.M_rowadr[start + n - 1] + m.M_rownnz[start + n - 1];
+#pragma unroll 1
       for (int e = e0 + lane; e < e1; e += 32) {
         const int r = m.M_entry_row[e], col = m.M_colind[e];
         A[(r - start) * ld + (col - start)] = Mw[e] + (col == r ? dt * m.dof_damping[r] : 0.f);
@@ -53,18 +56,22 @@ k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
         if (lane < n) x[lane] = xx;
         __syncwarp();
       } else {
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) x[i] = d.efc_Ma[wb * nv + start + i];
         __syncwarp();
         warp_cholesky(A, n, ld, lane);
         warp_chol_solve(A, n, ld, x, lane);
       }
+#pragma unroll 1
       for (int i = lane; i < n; i += 32) qacc[start + i] = x[i];
       __syncwarp();
     }
   }
+#pragma unroll 1
   for (int dd = lane; dd < nv; dd += 32) { const float v = qvel[dd] + qacc[dd] * dt; qvel[dd] = v; d.qvel[wb * nv + dd] = v; }
   __syncwarp();
   float* qpos = d.qpos + wb * m.nq;
+#pragma unroll 1
   for (int j = lane; j < m.njnt; j += 32) {
     const int t = m.jnt_type[j], qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
     if (t == JNT_FREE) {

@@ -34,8 +34,8 @@ __host__ __device__ inline PosLayout pos_layout(const ModelDev& m) {
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
+  const int w = blockIdx.x;
   if (w >= d.nworld) return;
   const PosLayout L = pos_layout(m);
   float* S = smem + warp * L.total;
@@ -51,7 +51,9 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
   if (mask & STG_KINEMATICS) {
     if (lane == 0) { xpos[0] = xpos[1] = xpos[2] = 0.f; xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f; }
     __syncwarp();
+#pragma unroll 1
     for (int l = 1; l < m.nlevel; l++) {
+#pragma unroll 1
       for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
         const int b = m.level_body[i], pid = m.body_parentid[b], jntadr = m.body_jntadr[b], jntnum = m.body_jntnum[b];
         if (jntnum == 1 && m.jnt_type[jntadr] == JNT_FREE) {
@@ -65,6 +67,7 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         q4 pq = ldq(xquat + 4 * pid);
         v3 pos = qrot(pq, ld3(m.body_pos + 3 * b)) + ld3(xpos + 3 * pid);
         q4 quat = qmul(pq, ldq(m.body_quat + 4 * b));
+#pragma unroll 1
         for (int j = jntadr; j < jntadr + jntnum; j++) {
           const int qa = m.jnt_qposadr[j], t = m.jnt_type[j];
           v3 jpos = ld3(m.jnt_pos + 3 * j), jax = ld3(m.jnt_axis + 3 * j);
@@ -84,12 +87,14 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
+#pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       q4 q = ldq(xquat + 4 * b);
       quat_to_mat(q, xmat + 9 * b);
       st3(xipos + 3 * b, ld3(xpos + 3 * b) + qrot(q, ld3(m.body_ipos + 3 * b)));
       quat_to_mat(qmul(q, ldq(m.body_iquat + 4 * b)), ximat + 9 * b);
     }
+#pragma unroll 1
     for (int g = lane; g < ng; g += 32) {
       const int b = m.geom_bodyid[g];
       if (m.body_weldid[b] == 0) {  // static geom: keeps the pose computed at make_data (smooth.py:197-200)
@@ -101,6 +106,7 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         quat_to_mat(qmul(q, ldq(m.geom_quat + 4 * g)), gxmat + 9 * g);
       }
     }
+#pragma unroll 1
     for (int s = lane; s < m.nsite; s += 32) {
       const int b = m.site_bodyid[s];
       q4 q = ldq(xquat + 4 * b);
@@ -132,9 +138,12 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
   // ------------------------------------------------------------------ com_pos
   if (mask & STG_COM_POS) {
+#pragma unroll 1
     for (int b = lane; b < nb; b += 32) st3(scom + 3 * b, ld3(xipos + 3 * b) * m.body_mass[b]);
     __syncwarp();
+#pragma unroll 1
     for (int l = m.nlevel - 2; l >= 0; l--) {
+#pragma unroll 1
       for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
         const int b = m.level_body[i];
         v3 acc = ld3(scom + 3 * b);
@@ -143,11 +152,13 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
+#pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       const float ms = m.body_subtreemass[b];
       if (ms != 0.f) st3(scom + 3 * b, ld3(scom + 3 * b) * (1.0f / ms));
     }
     __syncwarp();
+#pragma unroll 1
     for (int b = lane; b < nb; b += 32) {  // cinert (smooth.py:733)
       const float* mat = ximat + 9 * b;
       const v3 inert = ld3(m.body_inertia + 3 * b);
@@ -166,6 +177,7 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       r[5] = b0 * mat[6] + b1 * mat[7] + b2 * mat[8] - mass * dif.y * dif.z;
       r[6] = mass * dif.x; r[7] = mass * dif.y; r[8] = mass * dif.z; r[9] = mass;
     }
+#pragma unroll 1
     for (int j = lane; j < nj; j += 32) {  // cdof (smooth.py:779)
       const int b = m.jnt_bodyid[j], t = m.jnt_type[j];
       int dof = m.jnt_dofadr[j];
@@ -201,6 +213,7 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
   // ------------------------------------------------------------------ camlight (smooth.py:858-1027)
   if (mask & STG_CAMLIGHT) {
+#pragma unroll 1
     for (int c = lane; c < m.ncam; c += 32) {
       const int mode = m.cam_mode[c], b = m.cam_bodyid[c], tb = m.cam_targetbodyid[c];
       const bool is_target = mode == CAM_TARGETBODY || mode == CAM_TARGETBODYCOM;
@@ -225,6 +238,7 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       st3(d.cam_xpos + (wb * m.ncam + c) * 3, p);
       for (int k = 0; k < 9; k++) d.cam_xmat[(wb * m.ncam + c) * 9 + k] = mat[k];
     }
+#pragma unroll 1
     for (int l = lane; l < m.nlight; l += 32) {
       const int mode = m.light_mode[l], b = m.light_bodyid[l], tb = m.light_targetbodyid[l];
       const bool is_target = mode == CAM_TARGETBODY || mode == CAM_TARGETBODYCOM;
@@ -252,14 +266,18 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
   // ------------------------------------------------------------------ crb + M (smooth.py:1029-1098)
   if (mask & STG_CRB) {
+#pragma unroll 1
     for (int i = lane; i < 10 * nb; i += 32) crb[i] = cinert[i];
     __syncwarp();
+#pragma unroll 1
     for (int l = m.nlevel - 2; l >= 1; l--) {
+#pragma unroll 1
       for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
         const int b = m.level_body[i];
         float acc[10];
 #pragma unroll
         for (int k = 0; k < 10; k++) acc[k] = crb[10 * b + k];
+#pragma unroll 1
         for (int c = m.body_childadr[b]; c < m.body_childadr[b + 1]; c++) {
           const float* cc = crb + 10 * m.body_childid[c];
 #pragma unroll
@@ -270,8 +288,10 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
+#pragma unroll 1
     for (int dd = lane; dd < nv; dd += 32) inert_vec(crb + 10 * m.dof_bodyid[dd], cdof + 6 * dd, buf + 6 * dd);
     __syncwarp();
+#pragma unroll 1
     for (int e = lane; e < m.nC; e += 32) {
       const int i = m.M_entry_row[e], j = m.M_colind[e];
       float v = dot6(cdof + 6 * j, buf + 6 * i);
@@ -285,12 +305,14 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
   // ------------------------------------------------------------------ transmission (joint transmission; smooth.py:2288-2396)
   if (mask & STG_TRANSMISSION) {
+#pragma unroll 1
     for (int a = lane; a < m.nu; a += 32) {
       const int j = m.actuator_trnid[2 * a], t = m.jnt_type[j], adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a];
       const float* gear = m.actuator_gear + 6 * a;
       d.actuator_length[wb * m.nu + a] = (t == JNT_SLIDE || t == JNT_HINGE) ? qpos[m.jnt_qposadr[j]] * gear[0] : 0.f;
       d.moment_rownnz[wb * m.nu + a] = nnz;
       d.moment_rowadr[wb * m.nu + a] = adr;
+#pragma unroll 1
       for (int k = 0; k < nnz; k++) {
         d.moment_colind[wb * m.nJmom + adr + k] = m.moment_colind0[adr + k];
         d.actuator_moment[wb * m.nJmom + adr + k] = gear[k];

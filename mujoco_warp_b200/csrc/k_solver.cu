@@ -91,6 +91,7 @@ struct Ctx {
 // res = M vec via the symmetric gather tables (support.py:153 mul_m; tables io.py:1029-1050)
 __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res) {
   const ModelDev& m = *c.m;
+#pragma unroll 1
   for (int i = c.lane; i < c.nv; i += 32) {
     float acc = 0.f;
     for (int k = m.mulm_rowadr[i]; k < m.mulm_rowadr[i + 1]; k++) acc += c.M[m.mulm_madr[k]] * vec[m.mulm_col[k]];
@@ -102,6 +103,7 @@ __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res
 // (init=true: list every QUADRATIC row with weight +D).  Returns the list length.
 __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
   int nlist = 0;
+#pragma unroll 1
   for (int r0 = 0; r0 < c.nefc; r0 += 32) {
     const int r = r0 + c.lane;
     bool flip = false;
@@ -126,6 +128,7 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
     nlist += __popc(bal);
   }
   __syncwarp();
+#pragma unroll 1
   for (int dd = c.lane; dd < c.nv; dd += 32) {
     float s = 0.f;
     for (int r = 0; r < c.nefc; r++) s += c.J[r * c.ldJ + dd] * c.force[r];
@@ -138,6 +141,7 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
 // grad = Ma - qfrc_smooth - qfrc_constraint and its squared norm
 __device__ __forceinline__ void update_grad(Ctx& c) {
   float gd = 0.f;
+#pragma unroll 1
   for (int dd = c.lane; dd < c.nv; dd += 32) { const float g = c.Ma[dd] - c.qfs[dd] - c.qfc[dd]; c.grad[dd] = g; gd += g * g; }
   c.grad_dot = warp_sum(gd);
   __syncwarp();
@@ -148,6 +152,7 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   const int nv = c.nv;
   const int ntri = nv * (nv + 1) / 2;
   if (nlist > 0) {
+#pragma unroll 1
     for (int e = c.lane; e < ntri; e += 32) {
       int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
       while ((i + 1) * (i + 2) / 2 <= e) i++;
@@ -166,11 +171,14 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
     sd = xx * xx; nd = g * xx;
     if (c.lane < nv) c.search[c.lane] = -xx;
   } else {
+#pragma unroll 1
     for (int dd = c.lane; dd < nv; dd += 32) c.x[dd] = c.grad[dd];
+#pragma unroll 1
     for (int e = c.lane; e < nv * c.ldH; e += 32) c.Lf[e] = c.H[e];
     __syncwarp();
     warp_cholesky(c.Lf, nv, c.ldH, c.lane);
     warp_chol_solve(c.Lf, nv, c.ldH, c.x, c.lane);
+#pragma unroll 1
     for (int dd = c.lane; dd < nv; dd += 32) { const float xx = c.x[dd]; sd += xx * xx; nd += c.grad[dd] * xx; c.search[dd] = -xx; }
   }
   c.search_dot = warp_sum(sd);
@@ -180,6 +188,7 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
 
 __device__ __forceinline__ P3 eval_total(const Ctx& c, float alpha, float q0, float q1, float q2) {
   P3 s = mkp(0.f, 0.f, 0.f);
+#pragma unroll 1
   for (int r = c.lane; r < c.nefc; r += 32) s = s + eval_row(r, alpha, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
   return eval_gauss(q0, q1, q2, alpha) + warp_sum3(s);
 }
@@ -189,6 +198,7 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   const ModelDev& m = *c.m;
   const int nv = c.nv;
   mul_m(c, c.search, c.mv);
+#pragma unroll 1
   for (int r = c.lane; r < c.nefc; r += 32) {
     const float* Jr = c.J + r * c.ldJ;
     float s = 0.f;
@@ -199,9 +209,11 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   const float snorm = sqrtf(c.search_dot), scale = m.meaninertia * (float)nv;
   const float gtol = fmaxf(m.tolerance * m.ls_tolerance * snorm * scale, 1e-6f);
   P3 p0s = mkp(0.f, 0.f, 0.f);
+#pragma unroll 1
   for (int r = c.lane; r < c.nefc; r += 32) p0s = p0s + eval_row_zero(r, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
   p0s = warp_sum3(p0s);
   float g1 = 0.f, g2 = 0.f;
+#pragma unroll 1
   for (int dd = c.lane; dd < nv; dd += 32) { const float s = c.search[dd]; g1 += s * (c.Ma[dd] - c.qfs[dd]); g2 += 0.5f * s * c.mv[dd]; }
   const float q0 = 0.f, q1 = warp_sum(g1), q2 = warp_sum(g2);
   const P3 p0 = mkp(q0 + p0s.c, q1 + p0s.g, 2.0f * q2 + p0s.h);
@@ -215,9 +227,11 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
     const bool lo_less = lo_in.g < p0.g;
     P3 lo = lo_less ? lo_in : p0_delta, hi = lo_less ? p0_delta : lo_in;
     float lo_alpha = lo_less ? lo_alpha_in : 0.f, hi_alpha = lo_less ? 0.f : lo_alpha_in;
+#pragma unroll 1
     for (int it = 0; it < m.ls_iterations; it++) {
       const float lo_next_alpha = lo_alpha - safe_div(lo.g, lo.h), hi_next_alpha = hi_alpha - safe_div(hi.g, hi.h), mid_alpha = 0.5f * (lo_alpha + hi_alpha);
       P3 sl = mkp(0.f, 0.f, 0.f), sh = sl, sm = sl;
+#pragma unroll 1
       for (int r = c.lane; r < c.nefc; r += 32) {
         const float D = c.D[r], f = c.floss[r], ja = c.Jaref[r], jv = c.jv[r];
         sl = sl + eval_row(r, lo_next_alpha, c.ne, c.nf, D, f, ja, jv);
@@ -242,7 +256,9 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   } else {
     alpha = lo_alpha_in; improvement = -lo_in.c;
   }
+#pragma unroll 1
   for (int dd = c.lane; dd < nv; dd += 32) { c.qacc[dd] += alpha * c.search[dd]; c.Ma[dd] += alpha * c.mv[dd]; }
+#pragma unroll 1
   for (int r = c.lane; r < c.nefc; r += 32) c.Jaref[r] += alpha * c.jv[r];
   c.improvement = improvement;
   __syncwarp();
@@ -252,8 +268,8 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
+  const int w = blockIdx.x;
   if (w >= d.nworld) return;
   const SolLayout L = sol_layout(m, d);
   float* S = smem + warp * L.total;
@@ -270,6 +286,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   c.state = ri; c.hidx = ri + njmax;
 
   if (njmax == 0 || nv == 0) {
+#pragma unroll 1
     for (int dd = lane; dd < nv; dd += 32) d.qacc[wb * nv + dd] = d.qacc_smooth[wb * nv + dd];
     if (lane == 0) d.solver_niter[w] = 0;
     return;
@@ -280,7 +297,9 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   // ---- stage the world's problem in shared memory
   {
     const float* Jg = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
+#pragma unroll 1
     for (int i = lane; i < nefc * nvp; i += 32) { const int r = i / nvp, col = i - r * nvp; if (col < nv) c.J[r * c.ldJ + col] = Jg[i]; }
+#pragma unroll 1
     for (int r = lane; r < nefc; r += 32) {
       c.D[r] = d.efc_D[wb * d.njmax_pad + r];
       c.floss[r] = d.efc_frictionloss[wb * njmax + r];
@@ -290,10 +309,13 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     warp_copy(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
     const float* start = (m.disableflags & DSBL_WARMSTART) ? d.qacc_smooth : d.qacc_warmstart;
     warp_copy(c.qacc, start + wb * nv, nv, lane);
+#pragma unroll 1
     for (int e = lane; e < nv * c.ldH; e += 32) c.H[e] = 0.f;
   }
   __syncwarp();
+#pragma unroll 1
   for (int e = lane; e < m.nC; e += 32) c.H[m.M_entry_row[e] * c.ldH + m.M_colind[e]] = c.M[e];  // lower triangle of M
+#pragma unroll 1
   for (int r = lane; r < nefc; r += 32) {  // Jaref = J qacc - aref
     const float* Jr = c.J + r * c.ldJ;
     float s = 0.f;
@@ -328,6 +350,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   warp_copy(d.qacc + wb * nv, c.qacc, nv, lane);
   warp_copy(d.efc_Ma + wb * nv, c.Ma, nv, lane);
   warp_copy(d.qfrc_constraint + wb * nv, c.qfc, nv, lane);
+#pragma unroll 1
   for (int r = lane; r < nefc; r += 32) { d.efc_force[wb * njmax + r] = c.force[r]; d.efc_state[wb * d.njmax_pad + r] = c.state[r]; }
   if (lane == 0) { d.solver_niter[w] = niter; if (ovf) d.overflow[w] |= ovf; }
 }

@@ -31,8 +31,8 @@ __host__ __device__ inline VelLayout vel_layout(const ModelDev& m) {
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = blockIdx.x * MJB_WARPS_PER_BLOCK + warp;
+  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
+  const int w = blockIdx.x;
   if (w >= d.nworld) return;
   const VelLayout L = vel_layout(m);
   float* S = smem + warp * L.total;
@@ -49,6 +49,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
   // ------------------------------------------------------------------ fwd_velocity
   if (mask & STG_VELOCITY) {
     warp_copy(cinert, d.cinert + wb * 10 * nb, 10 * nb, lane);
+#pragma unroll 1
     for (int a = lane; a < nu; a += 32) {  // actuator velocity = moment . qvel
       const int nnz = d.moment_rownnz[wb * nu + a], adr = d.moment_rowadr[wb * nu + a];
       float vel = 0.f;
@@ -58,13 +59,16 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     // com_vel: level-synchronous forward pass
     if (lane < 6) cvel[lane] = 0.f;
     __syncwarp();
+#pragma unroll 1
     for (int l = 1; l < m.nlevel; l++) {
+#pragma unroll 1
       for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
         const int b = m.level_body[i], pid = m.body_parentid[b], jntadr = m.body_jntadr[b], jntnum = m.body_jntnum[b];
         int dof = m.body_dofadr[b];
         float cv[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) cv[k] = cvel[6 * pid + k];
+#pragma unroll 1
         for (int j = jntadr; j < jntadr + jntnum; j++) {
           const int t = m.jnt_type[j];
           if (t == JNT_FREE) {
@@ -94,6 +98,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     // passive: joint springs (slide/hinge) and dampers
     {
       const bool dsbl_spring = m.disableflags & DSBL_SPRING, dsbl_damper = m.disableflags & DSBL_DAMPER;
+#pragma unroll 1
       for (int dd = lane; dd < nv; dd += 32) {
         const int j = m.dof_jntid[dd], t = m.jnt_type[j];
         float spring = 0.f, damper = 0.f;
@@ -116,12 +121,15 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     // rne: cacc forward, cfrc per body, backward accumulation, projection
     if (lane < 6) cacc[lane] = lane < 3 ? 0.f : ((m.disableflags & DSBL_GRAVITY) ? 0.f : -(lane == 3 ? m.gravity_x : lane == 4 ? m.gravity_y : m.gravity_z));
     __syncwarp();
+#pragma unroll 1
     for (int l = 1; l < m.nlevel; l++) {
+#pragma unroll 1
       for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
         const int b = m.level_body[i], pid = m.body_parentid[b];
         float a[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) a[k] = cacc[6 * pid + k];
+#pragma unroll 1
         for (int q = 0; q < m.body_dofnum[b]; q++) {
           const int dof = m.body_dofadr[b] + q;
           const float v = qvel[dof];
@@ -133,6 +141,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
+#pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (b > 0) {
@@ -147,12 +156,15 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       for (int k = 0; k < 6; k++) cfrc[6 * b + k] = f[k];
     }
     __syncwarp();
+#pragma unroll 1
     for (int l = m.nlevel - 2; l >= 0; l--) {
+#pragma unroll 1
       for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
         const int b = m.level_body[i];
         float acc[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) acc[k] = cfrc[6 * b + k];
+#pragma unroll 1
         for (int c = m.body_childadr[b]; c < m.body_childadr[b + 1]; c++) {
           const float* cc = cfrc + 6 * m.body_childid[c];
 #pragma unroll
@@ -163,6 +175,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
+#pragma unroll 1
     for (int dd = lane; dd < nv; dd += 32) {
       const float v = dot6(cdof + 6 * dd, cfrc + 6 * m.dof_bodyid[dd]);
       q_bias[dd] = v;
@@ -178,10 +191,12 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
   // ------------------------------------------------------------------ fwd_actuation
   if (mask & STG_ACTUATION) {
+#pragma unroll 1
     for (int dd = lane; dd < nv; dd += 32) q_act[dd] = 0.f;
     __syncwarp();
     const bool enabled = nu > 0 && !(m.disableflags & DSBL_ACTUATION);
     // actuator forces; scatter moment^T force by a per-dof gather loop over actuators (deterministic, no atomics)
+#pragma unroll 1
     for (int a = lane; a < nu; a += 32) {
       float force = 0.f;
       if (enabled) {
@@ -200,8 +215,10 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     }
     __syncwarp();
     if (enabled) {
+#pragma unroll 1
       for (int dd = lane; dd < nv; dd += 32) {
         float q = 0.f;
+#pragma unroll 1
         for (int a = 0; a < nu; a++) {  // actuators in index order -> fixed summation order
           const int adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a];
           for (int k = 0; k < nnz; k++)
@@ -223,11 +240,14 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
   // ------------------------------------------------------------------ fwd_acceleration (factorize=True)
   if (mask & (STG_ACCELERATION | STG_FACTOR_ONLY)) {
     if (mask & STG_ACCELERATION) {
+#pragma unroll 1
       for (int dd = lane; dd < nv; dd += 32) q_smooth[dd] = q_passive[dd] - q_bias[dd] + q_act[dd] + d.qfrc_applied[wb * nv + dd];
       // xfrc_applied: skipped entirely when the world's applied wrenches are all zero (the common case)
       bool any = false;
+#pragma unroll 1
       for (int i = lane; i < 6 * nb; i += 32) any |= d.xfrc_applied[wb * 6 * nb + i] != 0.f;
       if (__any_sync(FULL_MASK, any)) {
+#pragma unroll 1
         for (int dd = lane; dd < nv; dd += 32) {
           const float* cd = cdof + 6 * dd;
           const int db = m.dof_bodyid[dd];
@@ -250,11 +270,14 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     }
     // per-tree dense Cholesky of M, qLD block = upper factor U (row-major, zeros below), qacc_smooth = M^-1 qfrc_smooth
     const float* Mw = d.M + wb * m.nC;
+#pragma unroll 1
     for (int t = 0; t < m.ntree; t++) {
       const int start = m.tree_dofadr[t], n = m.tree_dofnum[t], ld = chol_ld(n);
+#pragma unroll 1
       for (int i = lane; i < n * ld; i += 32) A[i] = 0.f;
       __syncwarp();
       const int e0 = m.M_rowadr[start], e1 = m.M_rowadr[start + n - 1] + m.M_rownnz[start + n - 1];
+#pragma unroll 1
       for (int e = e0 + lane; e < e1; e += 32) A[(m.M_entry_row[e] - start) * ld + (m.M_colind[e] - start)] = Mw[e];
       __syncwarp();
       float* qld = d.qLD + wb * m.qld_total + m.tree_qLDadr[t];
@@ -266,12 +289,15 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       } else {
         warp_cholesky(A, n, ld, lane);
         if (mask & STG_ACCELERATION) {
+#pragma unroll 1
           for (int i = lane; i < n; i += 32) x[i] = q_smooth[start + i];
           __syncwarp();
           warp_chol_solve(A, n, ld, x, lane);
+#pragma unroll 1
           for (int i = lane; i < n; i += 32) d.qacc_smooth[wb * nv + start + i] = x[i];
         }
       }
+#pragma unroll 1
       for (int i = lane; i < n * n; i += 32) { const int r = i / n, c = i - r * n; qld[i] = c >= r ? A[c * ld + r] : 0.f; }
       __syncwarp();
     }
