@@ -42,6 +42,18 @@ def parse():
   return p.parse_args()
 
 
+def usable_cores() -> int:
+  """Host cores this process may actually use: min(affinity mask, cgroup cpu quota)."""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+  try:
+    quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+    if quota != "max":
+      n = min(n, max(1, int(int(quota) / int(period))))
+  except Exception:
+    pass
+  return n
+
+
 # --------------------------------------------------------------------------------------------- clocks
 
 
@@ -135,7 +147,7 @@ def run_reference(args):
   from tests import util
 
   mjm = mjcf.load_any(util.HUMANOID)
-  cores = os.cpu_count() or 1
+  cores = usable_cores()
   nw = args.cpu_sample_worlds
   for _ in range(max(1, min(args.warmup, 3))):
     cpu_run(mjm, nw, 1, cores)
@@ -159,6 +171,7 @@ def run_reference(args):
 def run_ours(args):
   import torch
 
+  torch.set_num_threads(max(1, min(4, usable_cores())))  # host-side tensor ops in the e2e loop stay within the cpu quota
   import mujoco_warp_b200 as mjw
   from mujoco_warp_b200._src import io as mio
   from tests import util
@@ -294,7 +307,7 @@ def run_ours(args):
     step_bytes = 4.0 * sum(words.values()) * nworld
     cpu = None
     if world == 1 or True:
-      cores = os.cpu_count() or 1
+      cores = usable_cores()
       rate, dt = cpu_run(mjm, args.cpu_sample_worlds, 10, cores)
       cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
              "sample": f"{args.cpu_sample_worlds} worlds x 10 steps of the fp64 C oracle (OpenMP {cores} threads), {dt:.1f} s"}

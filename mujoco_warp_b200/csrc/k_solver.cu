@@ -18,19 +18,22 @@
 
 namespace {
 
-struct SolLayout { int J, H, Lf, M, vec, rowf, rowi, ldJ, ldH, total; };
+// Shared-memory slice of one world.  J rows keep the global stride nv_pad (a multiple of 4 floats), so a row is 16-byte
+// aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
+// rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
+struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, total; };
 __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d) {
   SolLayout L;
   int o = 0;
-  auto take = [&](int n) { int r = o; o += n; return r; };
-  L.ldJ = m.nv | 1; L.ldH = m.nv | 1;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  L.nvp = d.nv_pad; L.ldJ = d.nv_pad; L.ldH = m.nv | 1;
   L.J = take(d.njmax * L.ldJ);
+  L.vec = take(8 * L.nvp);
   L.H = take(m.nv * L.ldH); L.Lf = take(m.nv * L.ldH);
   L.M = take(m.nC);
-  L.vec = take(8 * m.nv);
   L.rowf = take(6 * d.njmax);
   L.rowi = take(2 * d.njmax);
-  L.total = (o + 3) & ~3;
+  L.total = o;
   return L;
 }
 
@@ -79,9 +82,20 @@ __device__ __forceinline__ P3 eval_gauss(float q0, float q1, float q2, float alp
 }
 __device__ __forceinline__ bool in_bracket(P3 x, P3 y) { return (x.g < y.g && y.g < 0.f) || (x.g > y.g && y.g > 0.f); }
 
+// dot of a 16B-aligned J row with a zero-padded, 16B-aligned per-dof vector
+__device__ __forceinline__ float row_dot(const float* Jr, const float* vec, int nvp) {
+  float s = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < nvp; k += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(Jr + k), b = *reinterpret_cast<const float4*>(vec + k);
+    s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  }
+  return s;
+}
+
 struct Ctx {
   const ModelDev* m;
-  int lane, nv, nefc, ne, nf, ldJ, ldH;
+  int lane, nv, nvp, nefc, ne, nf, ldJ, ldH;
   float *J, *H, *Lf, *M, *qacc, *Ma, *grad, *search, *mv, *qfs, *x, *qfc;
   float *Jaref, *jv, *D, *force, *floss, *hw;
   int *state, *hidx;
@@ -147,30 +161,63 @@ __device__ __forceinline__ void update_grad(Ctx& c) {
   __syncwarp();
 }
 
+// Newton direction for nv <= 32: lane i keeps row i of H in registers, adds w * J_r[i] * J_r[:] for every listed row r
+// (J_r[:] read with broadcast LDS.128), stores the updated row back, and hands the registers straight to the Cholesky sweep.
+template <int N>
+__device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g) {
+  const int lane = c.lane, nv = c.nv;
+  float a[N];
+  chol_load_rows<N>(a, c.H, c.ldH, nv, lane);
+  if (nlist > 0) {
+#pragma unroll 1
+    for (int t = 0; t < nlist; t++) {
+      const float* Jr = c.J + c.hidx[t] * c.ldJ;
+      const float sc = lane < nv ? c.hw[t] * Jr[lane] : 0.f;
+#pragma unroll
+      for (int k = 0; k < N; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(Jr + k);
+        a[k] += sc * v.x; a[k + 1] += sc * v.y; a[k + 2] += sc * v.z; a[k + 3] += sc * v.w;
+      }
+    }
+    if (lane < nv) {
+#pragma unroll
+      for (int k = 0; k < N; k++)
+        if (k <= lane) c.H[lane * c.ldH + k] = a[k];
+    }
+    // columns >= nv of rows < nv only ever hold the unused upper triangle; rows >= nv stay identity (sc == 0)
+  }
+  return chol_solve_rows<N>(a, nv, g, c.Lf, c.ldH, lane);
+}
+
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
 __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   const int nv = c.nv;
-  const int ntri = nv * (nv + 1) / 2;
-  if (nlist > 0) {
-#pragma unroll 1
-    for (int e = c.lane; e < ntri; e += 32) {
-      int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-      while ((i + 1) * (i + 2) / 2 <= e) i++;
-      while (i * (i + 1) / 2 > e) i--;
-      const int j = e - i * (i + 1) / 2;
-      float acc = 0.f;
-      for (int k = 0; k < nlist; k++) { const float* Jr = c.J + c.hidx[k] * c.ldJ; acc += c.hw[k] * Jr[i] * Jr[j]; }
-      c.H[i * c.ldH + j] += acc;
-    }
-    __syncwarp();
-  }
   float sd = 0.f, nd = 0.f;
   if (nv <= 32) {
     const float g = c.lane < nv ? c.grad[c.lane] : 0.f;
-    const float xx = chol_solve_reg_any(c.H, c.ldH, nv, g, c.Lf, c.ldH, c.lane);
+    float xx;
+    if (nv <= 8) xx = newton_direction_reg<8>(c, nlist, g);
+    else if (nv <= 16) xx = newton_direction_reg<16>(c, nlist, g);
+    else if (nv <= 24) xx = newton_direction_reg<24>(c, nlist, g);
+    else if (nv <= 28) xx = newton_direction_reg<28>(c, nlist, g);
+    else xx = newton_direction_reg<32>(c, nlist, g);
     sd = xx * xx; nd = g * xx;
     if (c.lane < nv) c.search[c.lane] = -xx;
   } else {
+    const int ntri = nv * (nv + 1) / 2;
+    if (nlist > 0) {
+#pragma unroll 1
+      for (int e = c.lane; e < ntri; e += 32) {
+        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= e) i++;
+        while (i * (i + 1) / 2 > e) i--;
+        const int j = e - i * (i + 1) / 2;
+        float acc = 0.f;
+        for (int k = 0; k < nlist; k++) { const float* Jr = c.J + c.hidx[k] * c.ldJ; acc += c.hw[k] * Jr[i] * Jr[j]; }
+        c.H[i * c.ldH + j] += acc;
+      }
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int dd = c.lane; dd < nv; dd += 32) c.x[dd] = c.grad[dd];
 #pragma unroll 1
@@ -200,10 +247,7 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   mul_m(c, c.search, c.mv);
 #pragma unroll 1
   for (int r = c.lane; r < c.nefc; r += 32) {
-    const float* Jr = c.J + r * c.ldJ;
-    float s = 0.f;
-    for (int dd = 0; dd < nv; dd++) s += Jr[dd] * c.search[dd];
-    c.jv[r] = s;
+    c.jv[r] = row_dot(c.J + r * c.ldJ, c.search, c.nvp);
   }
   __syncwarp();
   const float snorm = sqrtf(c.search_dot), scale = m.meaninertia * (float)nv;
@@ -276,10 +320,11 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const int nv = m.nv, njmax = d.njmax, nvp = d.nv_pad;
   const size_t wb = (size_t)w;
   Ctx c;
-  c.m = &m; c.lane = lane; c.nv = nv; c.ldJ = L.ldJ; c.ldH = L.ldH;
+  c.m = &m; c.lane = lane; c.nv = nv; c.nvp = L.nvp; c.ldJ = L.ldJ; c.ldH = L.ldH;
   c.J = S + L.J; c.H = S + L.H; c.Lf = S + L.Lf; c.M = S + L.M;
   float* v = S + L.vec;
-  c.qacc = v; c.Ma = v + nv; c.grad = v + 2 * nv; c.search = v + 3 * nv; c.mv = v + 4 * nv; c.qfs = v + 5 * nv; c.x = v + 6 * nv; c.qfc = v + 7 * nv;
+  const int vp = L.nvp;
+  c.qacc = v; c.Ma = v + vp; c.grad = v + 2 * vp; c.search = v + 3 * vp; c.mv = v + 4 * vp; c.qfs = v + 5 * vp; c.x = v + 6 * vp; c.qfc = v + 7 * vp;
   float* rf = S + L.rowf;
   c.Jaref = rf; c.jv = rf + njmax; c.D = rf + 2 * njmax; c.force = rf + 3 * njmax; c.floss = rf + 4 * njmax; c.hw = rf + 5 * njmax;
   int* ri = (int*)(S + L.rowi);
@@ -296,9 +341,12 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
 
   // ---- stage the world's problem in shared memory
   {
-    const float* Jg = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
+    const float4* Jg = reinterpret_cast<const float4*>(d.efc_J + wb * (size_t)d.njmax_pad * nvp);
+    float4* Js = reinterpret_cast<float4*>(c.J);
 #pragma unroll 1
-    for (int i = lane; i < nefc * nvp; i += 32) { const int r = i / nvp, col = i - r * nvp; if (col < nv) c.J[r * c.ldJ + col] = Jg[i]; }
+    for (int i = lane; i < nefc * nvp / 4; i += 32) Js[i] = Jg[i];
+    for (int i = lane; i < 8 * vp; i += 32) v[i] = 0.f;  // zero padding of every per-dof vector
+    __syncwarp();
 #pragma unroll 1
     for (int r = lane; r < nefc; r += 32) {
       c.D[r] = d.efc_D[wb * d.njmax_pad + r];
@@ -317,10 +365,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   for (int e = lane; e < m.nC; e += 32) c.H[m.M_entry_row[e] * c.ldH + m.M_colind[e]] = c.M[e];  // lower triangle of M
 #pragma unroll 1
   for (int r = lane; r < nefc; r += 32) {  // Jaref = J qacc - aref
-    const float* Jr = c.J + r * c.ldJ;
-    float s = 0.f;
-    for (int dd = 0; dd < nv; dd++) s += Jr[dd] * c.qacc[dd];
-    c.Jaref[r] = s - d.efc_aref[wb * njmax + r];
+    c.Jaref[r] = row_dot(c.J + r * c.ldJ, c.qacc, c.nvp) - d.efc_aref[wb * njmax + r];
   }
   mul_m(c, c.qacc, c.Ma);
   __syncwarp();

@@ -55,15 +55,20 @@ __device__ __forceinline__ void warp_chol_solve(const float* L, int n, int ld, f
 //   Ls  : shared scratch (n rows x ldL), receives L (lower triangle); may alias Hs when ldL == ld (each lane only
 //         reads and writes its own row)
 // returns x[lane] of (L L^T) x = b.
+// Row loader: a[k] = H[lane][k] for k <= lane < n, identity padding elsewhere.
 template <int N>
-__device__ __forceinline__ float chol_solve_reg(const float* Hs, int ld, int n, float b, float* Ls, int ldL, int lane) {
-  float a[N];
+__device__ __forceinline__ void chol_load_rows(float (&a)[N], const float* Hs, int ld, int n, int lane) {
 #pragma unroll
   for (int k = 0; k < N; k++) {
-    float v = (k == lane) ? 1.0f : 0.f;                      // identity padding for rows/cols >= n
+    float v = (k == lane) ? 1.0f : 0.f;
     if (lane < n && k <= lane) v = Hs[lane * ld + k];
     a[k] = v;
   }
+}
+
+// Factor + solve on rows already held in registers (consumes a[]).
+template <int N>
+__device__ __forceinline__ float chol_solve_rows(float (&a)[N], int n, float b, float* Ls, int ldL, int lane) {
   float myinv = 1.0f;
 #pragma unroll
   for (int j = 0; j < N; j++) {
@@ -92,6 +97,13 @@ __device__ __forceinline__ float chol_solve_reg(const float* Hs, int ld, int n, 
     b = lane < j ? b - ltj * xj : (lane == j ? xj : b);
   }
   return b;
+}
+
+template <int N>
+__device__ __forceinline__ float chol_solve_reg(const float* Hs, int ld, int n, float b, float* Ls, int ldL, int lane) {
+  float a[N];
+  chol_load_rows<N>(a, Hs, ld, n, lane);
+  return chol_solve_rows<N>(a, n, b, Ls, ldL, lane);
 }
 
 // n <= 32 dispatch over padded sizes (warp-uniform branch)
