@@ -211,6 +211,14 @@ def derive_tables(mjm) -> dict:
   t["moment_rowadr0"] = np.array(ra if ra else [0], dtype=np.int32)
   t["moment_colind0"] = np.array(ci if ci else [0], dtype=np.int32)
   t["nJmom"] = len(ci)
+  # reverse table: for every dof the (actuator, moment index) pairs that act on it, in actuator order
+  rev = [[] for _ in range(nv)]
+  for a in range(nu):
+    for k in range(rn[a]):
+      rev[ci[ra[a] + k]].append((a, ra[a] + k))
+  t["dofact_adr"] = np.concatenate([[0], np.cumsum([len(r) for r in rev])]).astype(np.int32)
+  t["dofact_act"] = np.array([a for r in rev for a, _ in r] or [0], dtype=np.int32)
+  t["dofact_mom"] = np.array([i for r in rev for _, i in r] or [0], dtype=np.int32)
   nmaxcondim = int(_np(mjm, "geom_condim").max()) if ngeom else 1
   t["nmaxcondim"] = nmaxcondim
   t["nmaxpyramid"] = max(1, 2 * (nmaxcondim - 1))
@@ -302,6 +310,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.body_tree = tuple(dev_i(x) for x in t["body_tree"])
   for n in ("body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col", "mulm_madr", "tree_qLDadr",
             "qLD_block_adr", "jnt_limited_slide_hinge_adr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
+            "dofact_adr", "dofact_act", "dofact_mom",
             "nxn_geom_pair", "nxn_pairid", "nxn_geom_pair_filtered", "nxn_pairid_filtered"):
     setattr(m, n, dev_i(t[n]))
   m.M_hinit_i = m.M_entry_row
@@ -336,7 +345,8 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     "body_isdofancestor": m._isdofancestor_nv,
   }
   for n in _FLOAT_FIELDS + _INT_FIELDS + ["body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col",
-                                         "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0"]:
+                                         "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
+                                         "dofact_adr", "dofact_act", "dofact_mom"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)

@@ -28,10 +28,13 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   L.nvp = d.nv_pad; L.ldJ = d.nv_pad; L.ldH = m.nv | 1;
   L.J = take(d.njmax * L.ldJ);
-  L.vec = take(8 * L.nvp);
-  L.H = take(m.nv * L.ldH); L.Lf = take(m.nv * L.ldH);
+  L.vec = take(7 * L.nvp);  // qacc, Ma, grad, search, mv (= x scratch of the nv > 32 path), qfs, qfc
+  // nv <= 32: H and its factor are stored as packed lower triangles (register Cholesky path); larger nv keeps nv x ldH
+  const int hsz = m.nv <= 32 ? m.nv * (m.nv + 1) / 2 : m.nv * L.ldH;
+  L.H = take(hsz); L.Lf = take(hsz);
   L.M = take(m.nC);
-  L.rowf = take(6 * d.njmax);
+  // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
+  L.rowf = take((m.nfricdof > 0 ? 5 : 4) * d.njmax);
   L.rowi = take(2 * d.njmax);
   L.total = o;
   return L;
@@ -167,7 +170,7 @@ template <int N>
 __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g) {
   const int lane = c.lane, nv = c.nv;
   float a[N];
-  chol_load_rows<N>(a, c.H, c.ldH, nv, lane);
+  chol_load_rows<N, true>(a, c.H, c.ldH, nv, lane);
   if (nlist > 0) {
 #pragma unroll 1
     for (int t = 0; t < nlist; t++) {
@@ -180,13 +183,14 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
       }
     }
     if (lane < nv) {
+      const int base = (lane * (lane + 1)) / 2;
 #pragma unroll
       for (int k = 0; k < N; k++)
-        if (k <= lane) c.H[lane * c.ldH + k] = a[k];
+        if (k <= lane) c.H[base + k] = a[k];
     }
     // columns >= nv of rows < nv only ever hold the unused upper triangle; rows >= nv stay identity (sc == 0)
   }
-  return chol_solve_rows<N>(a, nv, g, c.Lf, c.ldH, lane);
+  return chol_solve_rows<N, true>(a, nv, g, c.Lf, c.ldH, lane);
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
@@ -324,9 +328,10 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   c.J = S + L.J; c.H = S + L.H; c.Lf = S + L.Lf; c.M = S + L.M;
   float* v = S + L.vec;
   const int vp = L.nvp;
-  c.qacc = v; c.Ma = v + vp; c.grad = v + 2 * vp; c.search = v + 3 * vp; c.mv = v + 4 * vp; c.qfs = v + 5 * vp; c.x = v + 6 * vp; c.qfc = v + 7 * vp;
+  c.qacc = v; c.Ma = v + vp; c.grad = v + 2 * vp; c.search = v + 3 * vp; c.mv = v + 4 * vp; c.x = c.mv; c.qfs = v + 5 * vp; c.qfc = v + 6 * vp;
   float* rf = S + L.rowf;
-  c.Jaref = rf; c.jv = rf + njmax; c.D = rf + 2 * njmax; c.force = rf + 3 * njmax; c.floss = rf + 4 * njmax; c.hw = rf + 5 * njmax;
+  c.Jaref = rf; c.jv = rf + njmax; c.hw = c.jv; c.D = rf + 2 * njmax; c.force = rf + 3 * njmax;
+  c.floss = m.nfricdof > 0 ? rf + 4 * njmax : c.D;  // never interpreted when the world has no friction rows
   int* ri = (int*)(S + L.rowi);
   c.state = ri; c.hidx = ri + njmax;
 
@@ -345,24 +350,28 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     float4* Js = reinterpret_cast<float4*>(c.J);
 #pragma unroll 1
     for (int i = lane; i < nefc * nvp / 4; i += 32) Js[i] = Jg[i];
-    for (int i = lane; i < 8 * vp; i += 32) v[i] = 0.f;  // zero padding of every per-dof vector
+    for (int i = lane; i < 7 * vp; i += 32) v[i] = 0.f;  // zero padding of every per-dof vector
     __syncwarp();
 #pragma unroll 1
     for (int r = lane; r < nefc; r += 32) {
       c.D[r] = d.efc_D[wb * d.njmax_pad + r];
-      c.floss[r] = d.efc_frictionloss[wb * njmax + r];
+      if (m.nfricdof > 0) c.floss[r] = d.efc_frictionloss[wb * njmax + r];
       c.state[r] = ST_SATISFIED;
     }
     warp_copy(c.M, d.M + wb * m.nC, m.nC, lane);
     warp_copy(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
     const float* start = (m.disableflags & DSBL_WARMSTART) ? d.qacc_smooth : d.qacc_warmstart;
     warp_copy(c.qacc, start + wb * nv, nv, lane);
+    const int hsz = nv <= 32 ? nv * (nv + 1) / 2 : nv * c.ldH;
 #pragma unroll 1
-    for (int e = lane; e < nv * c.ldH; e += 32) c.H[e] = 0.f;
+    for (int e = lane; e < hsz; e += 32) c.H[e] = 0.f;
   }
   __syncwarp();
 #pragma unroll 1
-  for (int e = lane; e < m.nC; e += 32) c.H[m.M_entry_row[e] * c.ldH + m.M_colind[e]] = c.M[e];  // lower triangle of M
+  for (int e = lane; e < m.nC; e += 32) {  // lower triangle of M
+    const int r = m.M_entry_row[e], col = m.M_colind[e];
+    c.H[nv <= 32 ? (r * (r + 1)) / 2 + col : r * c.ldH + col] = c.M[e];
+  }
 #pragma unroll 1
   for (int r = lane; r < nefc; r += 32) {  // Jaref = J qacc - aref
     c.Jaref[r] = row_dot(c.J + r * c.ldJ, c.qacc, c.nvp) - d.efc_aref[wb * njmax + r];

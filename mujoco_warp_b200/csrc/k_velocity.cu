@@ -14,7 +14,7 @@
 
 namespace {
 
-struct VelLayout { int qvel, cdof, cinert, cvel, cdofdot, cacc, cfrc, qf, A, x, total; };
+struct VelLayout { int qvel, cdof, cinert, cvel, cdofdot, cacc, cfrc, qf, A, x, af, total; };
 __host__ __device__ inline int chol_ld(int n) { return (n | 1); }  // odd leading dimension
 __host__ __device__ inline VelLayout vel_layout(const ModelDev& m) {
   VelLayout L;
@@ -23,7 +23,7 @@ __host__ __device__ inline VelLayout vel_layout(const ModelDev& m) {
   L.qvel = take(m.nv); L.cdof = take(6 * m.nv); L.cinert = take(10 * m.nbody); L.cvel = take(6 * m.nbody);
   L.cdofdot = take(6 * m.nv); L.cacc = take(6 * m.nbody); L.cfrc = take(6 * m.nbody);
   L.qf = take(4 * m.nv);  // passive, bias, actuator, smooth
-  L.A = take(m.maxtree * chol_ld(m.maxtree)); L.x = take(m.maxtree);
+  L.A = take(m.maxtree * chol_ld(m.maxtree)); L.x = take(m.maxtree); L.af = take(m.nu);
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -37,7 +37,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
   const VelLayout L = vel_layout(m);
   float* S = smem + warp * L.total;
   float *qvel = S + L.qvel, *cdof = S + L.cdof, *cinert = S + L.cinert, *cvel = S + L.cvel, *cdofdot = S + L.cdofdot,
-        *cacc = S + L.cacc, *cfrc = S + L.cfrc, *A = S + L.A, *x = S + L.x;
+        *cacc = S + L.cacc, *cfrc = S + L.cfrc, *A = S + L.A, *x = S + L.x, *aforce = S + L.af;
   float *q_passive = S + L.qf, *q_bias = q_passive + m.nv, *q_act = q_bias + m.nv, *q_smooth = q_act + m.nv;
   const int nv = m.nv, nb = m.nbody, nu = m.nu;
   const size_t wb = (size_t)w;
@@ -212,18 +212,15 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         if (m.actuator_forcelimited[a]) force = clampf(force, m.actuator_forcerange[2 * a], m.actuator_forcerange[2 * a + 1]);
       }
       d.actuator_force[wb * nu + a] = force;
+      aforce[a] = force;
     }
     __syncwarp();
     if (enabled) {
 #pragma unroll 1
       for (int dd = lane; dd < nv; dd += 32) {
         float q = 0.f;
-#pragma unroll 1
-        for (int a = 0; a < nu; a++) {  // actuators in index order -> fixed summation order
-          const int adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a];
-          for (int k = 0; k < nnz; k++)
-            if (m.moment_colind0[adr + k] == dd) q += d.actuator_moment[wb * m.nJmom + adr + k] * d.actuator_force[wb * nu + a];
-        }
+        // moment^T force through the per-dof reverse table (entries in actuator order -> fixed summation order, no atomics)
+        for (int k = m.dofact_adr[dd]; k < m.dofact_adr[dd + 1]; k++) q += d.actuator_moment[wb * m.nJmom + m.dofact_mom[k]] * aforce[m.dofact_act[k]];
         const int j = m.dof_jntid[dd];
         if (!(m.disableflags & DSBL_GRAVITY) && m.jnt_actgravcomp[j]) q += d.qfrc_gravcomp[wb * nv + dd];
         if (m.jnt_actfrclimited[j]) q = clampf(q, m.jnt_actfrcrange[2 * j], m.jnt_actfrcrange[2 * j + 1]);
@@ -298,7 +295,8 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         }
       }
 #pragma unroll 1
-      for (int i = lane; i < n * n; i += 32) { const int r = i / n, c = i - r * n; qld[i] = c >= r ? A[c * ld + r] : 0.f; }
+      for (int r = 0; r < n; r++)
+        for (int c = lane; c < n; c += 32) qld[r * n + c] = c >= r ? A[c * ld + r] : 0.f;
       __syncwarp();
     }
   }

@@ -55,19 +55,26 @@ __device__ __forceinline__ void warp_chol_solve(const float* L, int n, int ld, f
 //   Ls  : shared scratch (n rows x ldL), receives L (lower triangle); may alias Hs when ldL == ld (each lane only
 //         reads and writes its own row)
 // returns x[lane] of (L L^T) x = b.
+// Lower-triangular element address.  PACKED rows start at the triangular number r(r+1)/2: triangular numbers are distinct
+// mod 32 for r < 32, so both the row-wise access (lane = row) and the transposed access (lane = column) stay bank-conflict
+// free while the matrix takes n(n+1)/2 words instead of n*ld.
+template <bool PACKED>
+__device__ __forceinline__ int tri_at(int r, int c, int ld) { return PACKED ? (r * (r + 1)) / 2 + c : r * ld + c; }
+
 // Row loader: a[k] = H[lane][k] for k <= lane < n, identity padding elsewhere.
-template <int N>
+template <int N, bool PACKED = false>
 __device__ __forceinline__ void chol_load_rows(float (&a)[N], const float* Hs, int ld, int n, int lane) {
+  const int base = tri_at<PACKED>(lane, 0, ld);
 #pragma unroll
   for (int k = 0; k < N; k++) {
     float v = (k == lane) ? 1.0f : 0.f;
-    if (lane < n && k <= lane) v = Hs[lane * ld + k];
+    if (lane < n && k <= lane) v = Hs[base + k];
     a[k] = v;
   }
 }
 
 // Factor + solve on rows already held in registers (consumes a[]).
-template <int N>
+template <int N, bool PACKED = false>
 __device__ __forceinline__ float chol_solve_rows(float (&a)[N], int n, float b, float* Ls, int ldL, int lane) {
   float myinv = 1.0f;
 #pragma unroll
@@ -85,15 +92,16 @@ __device__ __forceinline__ float chol_solve_rows(float (&a)[N], int n, float b, 
     }
   }
   if (lane < n) {  // rows >= n are identity padding and are not stored
+    const int base = tri_at<PACKED>(lane, 0, ldL);
 #pragma unroll
     for (int k = 0; k < N; k++)
-      if (k <= lane) Ls[lane * ldL + k] = a[k];
+      if (k <= lane) Ls[base + k] = a[k];
   }
   __syncwarp();
 #pragma unroll
   for (int j = N - 1; j >= 0; j--) {
     const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
-    const float ltj = (lane < j && j < n) ? Ls[j * ldL + lane] : 0.f;
+    const float ltj = (lane < j && j < n) ? Ls[tri_at<PACKED>(j, lane, ldL)] : 0.f;
     b = lane < j ? b - ltj * xj : (lane == j ? xj : b);
   }
   return b;

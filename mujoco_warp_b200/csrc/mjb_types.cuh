@@ -19,7 +19,7 @@
   X(tree_dofadr) X(tree_dofnum) X(tree_qLDadr) \
   X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
-  X(moment_rownnz0) X(moment_rowadr0) X(moment_colind0) \
+  X(moment_rownnz0) X(moment_rowadr0) X(moment_colind0) X(dofact_adr) X(dofact_act) X(dofact_mom) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(body_isdofancestor)
 #define MJB_MODEL_FARRS(X) \
