@@ -228,14 +228,14 @@ def derive_tables(mjm) -> dict:
 def _validate(mjm):
   """Feature checks in the spirit of io.py:284-363: fail loudly on anything the kernels do not cover."""
   o = mjm.opt
-  if o.integrator != C.INT_EULER:
-    raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler only in this version)")
+  if o.integrator not in (C.INT_EULER, C.INT_IMPLICITFAST):
+    raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler and implicitfast only in this version)")
   if o.cone != C.CONE_PYRAMIDAL:
     raise NotImplementedError("elliptic friction cones are not implemented in this version")
   if o.solver != C.SOL_NEWTON:
     raise NotImplementedError("only the Newton solver is implemented in this version")
-  if is_sparse(mjm):
-    raise NotImplementedError("sparse constraint Jacobians (nv > 32) are not implemented in this version")
+  if mjm.nv > 64:
+    raise NotImplementedError("nv > 64 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
   for n in ("na", "neq", "ntendon", "nflex", "nmocap"):
     if getattr(mjm, n, 0):
       raise NotImplementedError(f"{n} > 0 is not supported in this version")
@@ -264,7 +264,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   L = _lib.lib()
   _validate(mjm)
   t = derive_tables(mjm)
-  sparse = is_sparse(mjm)
+  # The reference switches to a CSR constraint Jacobian for nv > 32 (io.py:153-160).  This version keeps the DENSE efc.J
+  # layout for every supported nv (<= 64); Model.is_sparse is therefore always False (documented deviation for e.g. the G1).
+  sparse = False
   m = types.Model()
   for n in _SIZES:
     setattr(m, n, int(getattr(mjm, n, 0)))
@@ -510,3 +512,33 @@ def reset_data(m: types.Model, d: types.Data):
     getattr(d, n).zero_()
   for n in ("overflow", "solver_niter", "nefc", "ne", "nf", "nl", "nacon", "ncollision"):
     getattr(d, n).zero_()
+
+
+def load_trajectory(npz_path: str, mjm, mjd) -> np.ndarray:
+  """Loads a ctrl sequence and samples it on the model timestep with zero-order hold (reference io.py:3067-3113).
+
+  Sets mjd.qpos/qvel from the file's first frame when present.  `times` holds one timestamp per control or the
+  interval boundaries (one extra)."""
+  data = np.load(npz_path)
+  ctrl, times = data["ctrl"], data["times"]
+  if ctrl.ndim != 2 or len(ctrl) == 0:
+    raise ValueError(f"ctrl must have shape (nstep, nu) with nstep > 0, got {ctrl.shape}")
+  if ctrl.shape[1] != mjm.nu:
+    raise ValueError(f"ctrl shape {ctrl.shape} does not match model nu={mjm.nu}")
+  if times.ndim != 1 or len(times) not in (len(ctrl), len(ctrl) + 1):
+    raise ValueError(f"times shape {times.shape} must contain {len(ctrl)} or {len(ctrl) + 1} timestamps")
+  if not np.all(np.isfinite(times)):
+    raise ValueError("times must be finite")
+  intervals = np.diff(times)
+  if np.any(intervals <= 0):
+    raise ValueError("times must be strictly increasing")
+  if "qpos" in data and data["qpos"].shape[1] == mjm.nq:
+    mjd.qpos[:] = data["qpos"][0]
+  if "qvel" in data and data["qvel"].shape[1] == mjm.nv:
+    mjd.qvel[:] = data["qvel"][0]
+  if len(times) == len(ctrl):
+    final_dt = intervals[-1] if len(intervals) else mjm.opt.timestep
+    times = np.append(times, times[-1] + final_dt)
+  n_steps = int(np.round((times[-1] - times[0]) / mjm.opt.timestep))
+  sample_times = times[0] + (np.arange(n_steps) + 1e-7) * mjm.opt.timestep
+  return ctrl[np.searchsorted(times, sample_times, side="right") - 1]

@@ -1,8 +1,10 @@
-// k_integrate.cu -- Euler integrator (+ optional implicit joint damping) and the harness ctrl-noise kernel.
+// k_integrate.cu -- Euler (+ optional implicit joint damping) and implicitfast integrators, harness ctrl-noise kernel.
 //
 // Replaces (reference, /root/reference/mujoco_warp/_src/): forward.py:387-417 euler, :276-349 _advance
 // (_next_velocity :117, _next_position :53, _next_time :221, qacc_warmstart copy :343) and, for models without
-// eulerdamp=disable, the (M + dt*diag(damping)) factor-solve (:391-415).  cli.py:103-145 _ctrl_noise.
+// eulerdamp=disable, the (M + dt*diag(damping)) factor-solve (:391-415).  implicitfast (forward.py:602-610 with
+// derivative.py:38-176 _qderiv_actuator_passive_vel, :178-245 moment^T vel moment scatter, :221-245 damping) factors
+// M - dt*qDeriv instead.  cli.py:103-145 _ctrl_noise.
 #include "mjb_chol.cuh"
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
@@ -11,7 +13,7 @@ namespace {
 
 __host__ __device__ inline int chol_ld(int n) { return (n | 1); }
 __host__ __device__ inline int int_words(const ModelDev& m) {
-  const bool damp = !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
+  const bool damp = m.integrator == INT_IMPLICITFAST || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
   int o = 2 * m.nv;  // qacc, qvel
   if (damp) o += m.maxtree * chol_ld(m.maxtree) + m.maxtree;
   return (o + 3) & ~3;
@@ -34,8 +36,10 @@ k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   __syncwarp();
   warp_copy(d.qacc_warmstart + wb * nv, qacc, nv, lane);  // warmstart <- solver qacc (forward.py:343)
 
-  if (!(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
-    // qacc <- (M + dt*diag(damping))^-1 * Ma  (forward.py:391-415)
+  const bool implicitfast = m.integrator == INT_IMPLICITFAST;
+  if (implicitfast || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
+    // Euler: qacc <- (M + dt*diag(damping))^-1 * Ma  (forward.py:391-415); implicitfast: (M - dt*qDeriv)^-1 * Ma
+    const bool damper = !(m.disableflags & DSBL_DAMPER);
     const float* Mw = d.M + wb * m.nC;
 #pragma unroll 1
     for (int t = 0; t < m.ntree; t++) {
@@ -47,9 +51,32 @@ k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
 #pragma unroll 1
       for (int e = e0 + lane; e < e1; e += 32) {
         const int r = m.M_entry_row[e], col = m.M_colind[e];
-        A[(r - start) * ld + (col - start)] = Mw[e] + (col == r ? dt * m.dof_damping[r] : 0.f);
+        A[(r - start) * ld + (col - start)] = Mw[e] + ((col == r && damper) ? dt * m.dof_damping[r] : 0.f);
       }
       __syncwarp();
+      if (implicitfast && m.nu > 0 && !(m.disableflags & DSBL_ACTUATION)) {
+#pragma unroll 1
+        for (int a = 0; a < m.nu; a++) {  // actuators one after the other: fixed accumulation order, no atomics
+          const int adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a], d0 = m.moment_colind0[adr];
+          if (d0 < start || d0 >= start + n) continue;
+          const float gain = m.actuator_gaintype[a] == GAIN_AFFINE ? m.actuator_gainprm[10 * a + 2] : 0.f;
+          const float bias = m.actuator_biastype[a] == BIAS_AFFINE ? m.actuator_biasprm[10 * a + 2] : 0.f;
+          if (bias == 0.f && gain == 0.f) continue;
+          if (m.actuator_forcelimited[a]) {
+            const float f = d.actuator_force[wb * m.nu + a];
+            if (f <= m.actuator_forcerange[2 * a] || f >= m.actuator_forcerange[2 * a + 1]) continue;
+          }
+          const float vel = bias + (gain != 0.f ? gain * d.ctrl[wb * m.nu + a] : 0.f);
+          for (int p = lane; p < nnz * nnz; p += 32) {
+            const int i = p / nnz, j = p - i * nnz;
+            if (j <= i) {
+              const float mi = d.actuator_moment[wb * m.nJmom + adr + i], mj = d.actuator_moment[wb * m.nJmom + adr + j];
+              A[(m.moment_colind0[adr + i] - start) * ld + (m.moment_colind0[adr + j] - start)] -= dt * mi * mj * vel;
+            }
+          }
+          __syncwarp();
+        }
+      }
       if (n <= 32) {
         const float b = lane < n ? d.efc_Ma[wb * nv + start + lane] : 0.f;
         const float xx = chol_solve_reg_any(A, ld, n, b, A, ld, lane);

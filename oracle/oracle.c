@@ -1328,6 +1328,42 @@ static void euler(W* w) {
   }
 }
 
+/* implicitfast (forward.py:602-610; derivative.py:38-176,178-245,1116-1200): qacc = (M - dt*qDeriv)^-1 Ma with
+ * qDeriv = sum_act moment^T (d force / d velocity) moment  -  diag(damping), stateless actuators only */
+static void implicitfast(W* w) {
+  const OrcModel* m = w->m;
+  const int nv = m->nv;
+  int qld = 0; for (int t = 0; t < m->ntree; t++) qld += m->tree_dofnum[t] * m->tree_dofnum[t];
+  real* buf = (real*)calloc((size_t)qld + nv + m->nC, sizeof(real));
+  real *L = buf, *qacc = buf + qld, *Mi = qacc + nv;
+  memcpy(Mi, w->M, m->nC * sizeof(real));
+  if (m->nu && !(m->disableflags & DSBL_ACTUATION)) {
+    for (int a = 0; a < m->nu; a++) {
+      real gain = m->actuator_gaintype[a] == GAIN_AFFINE ? m->actuator_gainprm[10 * a + 2] : 0;
+      real bias = m->actuator_biastype[a] == BIAS_AFFINE ? m->actuator_biasprm[10 * a + 2] : 0;
+      if (bias == 0 && gain == 0) continue;
+      if (m->actuator_forcelimited[a]) {
+        real f = w->actuator_force[a];
+        if (f <= m->actuator_forcerange[2 * a] || f >= m->actuator_forcerange[2 * a + 1]) continue;
+      }
+      real vel = bias + (gain != 0 ? gain * w->ctrl[a] : 0);
+      if (vel == 0) continue;
+      int adr = w->moment_rowadr[a], nnz = w->moment_rownnz[a];
+      for (int i = 0; i < nnz; i++) for (int j = 0; j <= i; j++) {
+        int di = w->moment_colind[adr + i], dj = w->moment_colind[adr + j];
+        /* CSR address of (di, dj): dj must be an ancestor dof of di (M_elemid >= 0) */
+        for (int k = 0; k < m->M_rownnz[di]; k++)
+          if (m->M_colind[m->M_rowadr[di] + k] == dj) Mi[m->M_rowadr[di] + k] -= m->timestep * w->actuator_moment[adr + i] * w->actuator_moment[adr + j] * vel;
+      }
+    }
+  }
+  if (!(m->disableflags & DSBL_DAMPER))
+    for (int d = 0; d < nv; d++) Mi[m->M_rowadr[d] + m->M_rownnz[d] - 1] += m->timestep * m->dof_damping[d];
+  factor_solve_i(w, Mi, NULL, L, qacc, w->efc_Ma);
+  advance(w, qacc);
+  free(buf);
+}
+
 static void forward_world(W* w) {
   kinematics(w); com_pos(w); camlight(w); crb(w);
   collision(w); make_constraint(w); transmission(w);
@@ -1337,7 +1373,7 @@ static void forward_world(W* w) {
 
 static int run(const OrcModel* m, OrcData* d, int nthreads, int do_step) {
   if (check_fields(m, d)) return -1;
-  if (do_step && m->integrator != INT_EULER) { snprintf(g_err, sizeof g_err, "oracle: only the Euler integrator is restated"); return -1; }
+  if (do_step && m->integrator != INT_EULER && m->integrator != INT_IMPLICITFAST) { snprintf(g_err, sizeof g_err, "oracle: only the Euler and implicitfast integrators are restated"); return -1; }
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -1346,7 +1382,7 @@ static int run(const OrcModel* m, OrcData* d, int nthreads, int do_step) {
     W w;
     make_view(m, d, wi, &w);
     forward_world(&w);
-    if (do_step) euler(&w);
+    if (do_step) { if (m->integrator == INT_IMPLICITFAST) implicitfast(&w); else euler(&w); }
   }
   return 0;
 }

@@ -142,3 +142,39 @@ def test_determinism(scene):
     outs.append((d.qpos.cpu().numpy().copy(), d.qvel.cpu().numpy().copy(), d.efc.force.cpu().numpy().copy()))
   for a, b in zip(outs[0], outs[1]):
     np.testing.assert_array_equal(a, b)
+
+
+# --------------------------------------------------------------------------------------------- unitree G1 (BASELINE configs[2])
+
+
+def test_g1_replay_matches_oracle(built):
+  """unitree_g1 scene_flat: nv=35 (dense J in this version), implicitfast, position actuators, replayed shuffle_dance ctrl.
+  100 steps from the trajectory's first frame; per-step contact/constraint counts identical, state within tolerance."""
+  import mujoco_warp_b200 as mjw
+  from mujoco_warp_b200._src.mjcf import MjDataLite
+
+  mjm = mjw.mjcf.load_any(util.G1)
+  mjd = MjDataLite(mjm)
+  ctrls = mjw.load_trajectory(util.G1_TRAJ, mjm, mjd)
+  nworld, nconmax, njmax = 8, 48, 192
+  m = mjw.put_model(mjm)
+  d = mjw.put_data(mjm, mjd, nworld=nworld, nconmax=nconmax, njmax=njmax, m=m)
+  o = util.make_oracle(mjm, nworld, nconmax, njmax)
+  o.set_state(qpos=mjd.qpos.astype(np.float32), qvel=mjd.qvel.astype(np.float32))
+  rng = np.random.default_rng(5)
+  jitter = (0.02 * rng.uniform(-1, 1, (nworld, mjm.nu))).astype(np.float32)
+  jitter[0] = 0
+  mismatched = 0
+  for i in range(100):
+    c = (ctrls[i][None, :] + jitter).astype(np.float32)
+    d.ctrl.copy_(torch.from_numpy(c))
+    o.d["ctrl"][:] = c
+    mjw.step(m, d)
+    o.step()
+    torch.cuda.synchronize()
+    mismatched += int((d.nefc.cpu().numpy() != o.d["nefc"]).sum())
+    util.assert_close(f"g1 qpos@{i}", d.qpos.cpu().numpy(), o.d["qpos"], atol=2e-3, rtol=2e-3)
+  util.assert_close("g1 qvel", d.qvel.cpu().numpy(), o.d["qvel"], atol=5e-2, rtol=2e-2)
+  # contact make/break decisions happen at |dist - margin| ~ 1e-7 boundaries; allow a handful of one-step disagreements
+  assert mismatched <= 8, mismatched
+  assert not (d.overflow.cpu().numpy() & ~int(mjw.OverflowType.LS_ITERATIONS)).any()

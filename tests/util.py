@@ -7,6 +7,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = os.path.join(ROOT, "mujoco_warp_b200", "test_data")
 HUMANOID = os.path.join(SCENES, "humanoid.npz")
+G1 = os.path.join(SCENES, "unitree_g1_flat.npz")
+G1_TRAJ = os.path.join(SCENES, "unitree_g1_shuffle_dance.npz")
 
 
 def seeded_state(mjm, nworld, key=0, seed=42, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=0.5):

@@ -18,7 +18,10 @@ OUT = os.path.join(ROOT, "mujoco_warp_b200", "test_data")
 
 SCENES = {
   "humanoid": "benchmarks/humanoid/humanoid.xml",  # BASELINE configs[1]: iterations=100, ls_iterations=50
+  "unitree_g1_flat": "benchmarks/unitree_g1/scene_flat.xml",  # BASELINE configs[2] (visual mesh geoms skipped: STL not in tree)
 }
+# replay trajectories are benchmark INPUT data (ctrl sequences), copied verbatim
+TRAJECTORIES = {"unitree_g1_shuffle_dance.npz": "benchmarks/unitree_g1/shuffle_dance.npz"}
 
 if __name__ == "__main__":
   os.makedirs(OUT, exist_ok=True)
@@ -26,3 +29,8 @@ if __name__ == "__main__":
     m = mjcf.load(os.path.join(REF, rel))
     mjcf.save_npz(m, os.path.join(OUT, name + ".npz"))
     print(name, "nq", m.nq, "nv", m.nv, "nbody", m.nbody, "ngeom", m.ngeom, "->", os.path.join(OUT, name + ".npz"))
+  import shutil
+
+  for dst, rel in TRAJECTORIES.items():
+    shutil.copyfile(os.path.join(REF, rel), os.path.join(OUT, dst))
+    print("copied", rel, "->", dst)
