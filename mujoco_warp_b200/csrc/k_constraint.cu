@@ -14,12 +14,20 @@
 
 namespace {
 
-struct ConLayout { int cdof, scom, qvel, total; };
-__host__ __device__ inline ConLayout con_layout(const ModelDev& m) {
+// Per-contact record prepared by ONE lane per contact (phase A: every dependent lookup -- pool fields, geom -> body ->
+// root -> subtree_com, invweight -- happens in parallel across contacts), then consumed by the whole warp (phase B: lanes =
+// dofs).  The reference does the same work with one thread per contact (_efc_contact_init) and one tile per world
+// (_efc_contact_jac_dense), re-reading the pool from global memory in every kernel.
+constexpr int CR_FRAME = 0, CR_FRI = 9, CR_OFF1 = 14, CR_OFF2 = 17, CR_POS = 20, CR_INC = 21, CR_INVW = 22, CR_SOLREF = 23,
+              CR_SOLREFF = 25, CR_SOLIMP = 27, CR_B1 = 32, CR_B2 = 33, CR_BASE = 34, CR_NDIM = 35, CR_CONDIM = 36, CR_WORDS = 37;
+__host__ __device__ inline int con_cap(const DataDev& d) { return 2 * d.nconmax > 32 ? 2 * d.nconmax : 32; }  // = collision's per-world cap
+
+struct ConLayout { int cdof, scom, qvel, rec, total; };
+__host__ __device__ inline ConLayout con_layout(const ModelDev& m, const DataDev& d) {
   ConLayout L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
-  L.cdof = take(6 * m.nv); L.scom = take(3 * m.nbody); L.qvel = take(m.nv);
+  L.cdof = take(6 * m.nv); L.scom = take(3 * m.nbody); L.qvel = take(m.nv); L.rec = take(CR_WORDS * con_cap(d));
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -65,9 +73,9 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
   const int w = blockIdx.x;
   if (w >= d.nworld) return;
-  const ConLayout L = con_layout(m);
+  const ConLayout L = con_layout(m, d);
   float* S = smem + warp * L.total;
-  float *cdof = S + L.cdof, *scom = S + L.scom, *qvel = S + L.qvel;
+  float *cdof = S + L.cdof, *scom = S + L.scom, *qvel = S + L.qvel, *rec = S + L.rec;
   const int nv = m.nv, nb = m.nbody, njmax = d.njmax, nvp = d.nv_pad;
   const size_t wb = (size_t)w;
   float* Jw = d.efc_J + wb * (size_t)d.njmax_pad * nvp;   // (nworld, njmax_pad, nv_pad)
@@ -138,23 +146,56 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
 
   // ---- contacts
   if (!(m.disableflags & DSBL_CONTACT)) {
-    const int cbase = d.world_conadr[w], ncon = d.world_ncon[w], np = m.nmaxpyramid;
+    const int cbase = d.world_conadr[w], ncon = min(d.world_ncon[w], con_cap(d)), np = m.nmaxpyramid;
     const bool elliptic = m.cone == CONE_ELLIPTIC;
+    // ---- phase A: lane = contact
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncon; c0 += 32) {
+      const int c = c0 + lane, cid = cbase + c;
+      int ndim = 0, condim = 0;
+      float includemargin = 0.f, pos = 0.f;
+      if (c < ncon) {
+        includemargin = d.contact_includemargin[cid];
+        pos = d.contact_dist[cid] - includemargin;
+        condim = d.contact_dim[cid];
+        if (pos < 0.f) ndim = elliptic ? condim : (condim == 1 ? 1 : 2 * (condim - 1));
+      }
+      const int base = nefc + warp_excl_scan(ndim, lane);
+      nefc += warp_sum_i(ndim);
+      if (c < ncon) {
+        float* r = rec + CR_WORDS * c;
+        r[CR_NDIM] = __int_as_float(ndim);
+        if (ndim > 0) {
+          const int g1 = d.contact_geom[2 * cid], g2 = d.contact_geom[2 * cid + 1], b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
+          const v3 cpos = ld3(d.contact_pos + 3 * cid);
+          for (int k = 0; k < 9; k++) r[CR_FRAME + k] = d.contact_frame[9 * (size_t)cid + k];
+          for (int k = 0; k < 5; k++) { r[CR_FRI + k] = d.contact_friction[5 * cid + k]; r[CR_SOLIMP + k] = d.contact_solimp[5 * cid + k]; }
+          st3(r + CR_OFF1, cpos - ld3(scom + 3 * m.body_rootid[b1]));
+          st3(r + CR_OFF2, cpos - ld3(scom + 3 * m.body_rootid[b2]));
+          r[CR_POS] = pos; r[CR_INC] = includemargin;
+          r[CR_INVW] = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
+          r[CR_SOLREF] = d.contact_solref[2 * cid]; r[CR_SOLREF + 1] = d.contact_solref[2 * cid + 1];
+          r[CR_SOLREFF] = d.contact_solreffriction[2 * cid]; r[CR_SOLREFF + 1] = d.contact_solreffriction[2 * cid + 1];
+          r[CR_B1] = __int_as_float(b1); r[CR_B2] = __int_as_float(b2);
+          r[CR_BASE] = __int_as_float(base); r[CR_CONDIM] = __int_as_float(condim);
+          for (int k = 0; k < ndim; k++) d.contact_efc_address[np * cid + k] = base + k < njmax ? base + k : -1;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- phase B: lanes = dofs, contacts one after the other, every operand already in shared memory
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {
-      const int cid = cbase + c;
-      const float includemargin = d.contact_includemargin[cid], pos = d.contact_dist[cid] - includemargin;
-      if (!(pos < 0.f)) continue;
-      const int condim = d.contact_dim[cid];
-      const int ndim = elliptic ? condim : (condim == 1 ? 1 : 2 * (condim - 1));
-      const int base = nefc;
-      nefc += ndim;
-      const int g1 = d.contact_geom[2 * cid], g2 = d.contact_geom[2 * cid + 1], b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
-      const v3 cpos = ld3(d.contact_pos + 3 * cid);
+      const float* r = rec + CR_WORDS * c;
+      const int ndim = __float_as_int(r[CR_NDIM]);
+      if (ndim == 0) continue;
+      const int cid = cbase + c, base = __float_as_int(r[CR_BASE]), condim = __float_as_int(r[CR_CONDIM]);
+      const int b1 = __float_as_int(r[CR_B1]), b2 = __float_as_int(r[CR_B2]);
+      const float pos = r[CR_POS], includemargin = r[CR_INC];
       float frame[9], fri[5];
-      for (int k = 0; k < 9; k++) frame[k] = d.contact_frame[9 * cid + k];
-      for (int k = 0; k < 5; k++) fri[k] = d.contact_friction[5 * cid + k];
-      const v3 off1 = cpos - ld3(scom + 3 * m.body_rootid[b1]), off2 = cpos - ld3(scom + 3 * m.body_rootid[b2]);
+      for (int k = 0; k < 9; k++) frame[k] = r[CR_FRAME + k];
+      for (int k = 0; k < 5; k++) fri[k] = r[CR_FRI + k];
+      const v3 off1 = ld3(r + CR_OFF1), off2 = ld3(r + CR_OFF2);
       float velp[10];
 #pragma unroll
       for (int k = 0; k < 10; k++) velp[k] = 0.f;
@@ -198,18 +239,15 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
       }
       if (lane < ndim) {  // constraint.py:4197-4343
         const int dim = lane, efcid = base + dim;
-        if (efcid >= njmax) {
-          d.contact_efc_address[np * cid + dim] = -1;
-        } else {
-          d.contact_efc_address[np * cid + dim] = efcid;
-          float invweight = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
+        if (efcid < njmax) {
+          float invweight = r[CR_INVW];
           float pos_aref = pos;
-          float ref[2] = {d.contact_solref[2 * cid], d.contact_solref[2 * cid + 1]};
+          float ref[2] = {r[CR_SOLREF], r[CR_SOLREF + 1]};
           float imp5[5];
-          for (int k = 0; k < 5; k++) imp5[k] = d.contact_solimp[5 * cid + k];
+          for (int k = 0; k < 5; k++) imp5[k] = r[CR_SOLIMP + k];
           if (elliptic) {
             if (dim > 0) {
-              const float s0 = d.contact_solreffriction[2 * cid], s1 = d.contact_solreffriction[2 * cid + 1];
+              const float s0 = r[CR_SOLREFF], s1 = r[CR_SOLREFF + 1];
               if (s0 != 0.f || s1 != 0.f) { ref[0] = s0; ref[1] = s1; }
               invweight = invweight * m.impratio_invsqrt * m.impratio_invsqrt;
               if (dim > 1) invweight *= fri[0] * fri[0] / (fri[dim - 1] * fri[dim - 1]);
@@ -231,7 +269,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
 
 }  // namespace
 
-size_t smem_constraint(const ModelDev& m, const DataDev&) { return (size_t)con_layout(m).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+size_t smem_constraint(const ModelDev& m, const DataDev& d) { return (size_t)con_layout(m, d).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
 
 cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_constraint(m, d);
