@@ -190,7 +190,11 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
     }
     // columns >= nv of rows < nv only ever hold the unused upper triangle; rows >= nv stay identity (sc == 0)
   }
+#ifdef MJB_CHOL_UNROLLED
   return chol_solve_rows<N, true>(a, nv, g, c.Lf, c.ldH, lane);
+#else
+  return chol_solve_rows_rolled<N, true>(a, nv, g, c.Lf, c.ldH, lane);
+#endif
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement

@@ -107,6 +107,39 @@ __device__ __forceinline__ float chol_solve_rows(float (&a)[N], int n, float b, 
   return b;
 }
 
+// Same factor + solve with a ROLLED column loop: after eliminating a column every lane rotates its row registers by one
+// (a[k-1] <- a[k] - l_ij * l_kj), so the pivot column always sits in a[0] and the loop body is identical for every column.
+// Executes ~n*N instead of ~N^2/2 SHFL/FFMA pairs but is ~25x smaller: the fully unrolled sweep (30 KB of SASS for N = 28)
+// thrashed the instruction cache (ncu: `no_instruction` was the top stall of k_solver).
+template <int N, bool PACKED = false>
+__device__ __forceinline__ float chol_solve_rows_rolled(float (&a)[N], int n, float b, float* Ls, int ldL, int lane) {
+  float myinv = 1.0f;
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    const float ajj = __shfl_sync(FULL_MASK, a[0], j);
+    const float inv = rsqrtf(fmaxf(ajj, MJ_MINVAL));
+    const float lij = a[0] * inv;  // column j of L (meaningful for lanes >= j)
+    if (lane == j) myinv = inv;
+    const float yj = __shfl_sync(FULL_MASK, b, j) * inv;
+    b = lane > j ? b - lij * yj : (lane == j ? yj : b);
+    if (lane >= j && lane < n) Ls[tri_at<PACKED>(lane, j, ldL)] = lij;
+#pragma unroll
+    for (int k = 1; k < N; k++) {
+      const float lkj = __shfl_sync(FULL_MASK, lij, (j + k) & 31);
+      a[k - 1] = a[k] - lij * lkj;
+    }
+    a[N - 1] = 0.f;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int j = n - 1; j >= 0; j--) {
+    const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
+    const float ltj = lane < j ? Ls[tri_at<PACKED>(j, lane, ldL)] : 0.f;
+    b = lane < j ? b - ltj * xj : (lane == j ? xj : b);
+  }
+  return b;
+}
+
 template <int N>
 __device__ __forceinline__ float chol_solve_reg(const float* Hs, int ld, int n, float b, float* Ls, int ldL, int lane) {
   float a[N];
