@@ -1,5 +1,6 @@
 // capi.cu -- extern "C" boundary of libmjb200.so (see include/mjb200.h for the reference interfaces each entry replaces).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -14,6 +15,11 @@ struct mjbData {
   DataDev dev;
   bool finalized;
   size_t smem[6];
+  // step pipelining over two world halves on two internal streams (overlaps each kernel's partial last wave with the
+  // other half's kernels; worlds never interact, so the halves are independent apart from the shared contact-pool counter)
+  cudaStream_t aux[2];
+  cudaEvent_t ev_fork, ev_join[2];
+  int nsplit;
 };
 
 namespace {
@@ -81,13 +87,19 @@ mjbData* mjb_data_create(int nworld, int nconmax, int naconmax, int njmax, int n
   memset(&d->dev, 0, sizeof(DataDev));
   d->dev.nworld = nworld; d->dev.nconmax = nconmax; d->dev.naconmax = naconmax;
   d->dev.njmax = njmax; d->dev.njmax_pad = njmax_pad; d->dev.nv_pad = nv_pad;
+  d->dev.w0 = 0; d->dev.wn = nworld;
   d->finalized = false;
+  d->nsplit = 1;
   return d;
 }
 void mjb_data_destroy(mjbData* d) {
   if (!d) return;
   if (d->dev.world_conadr) cudaFree(d->dev.world_conadr);
   if (d->dev.world_ncon) cudaFree(d->dev.world_ncon);
+  if (d->nsplit > 1) {
+    for (int i = 0; i < 2; i++) { cudaStreamDestroy(d->aux[i]); cudaEventDestroy(d->ev_join[i]); }
+    cudaEventDestroy(d->ev_fork);
+  }
   delete d;
 }
 int mjb_data_set_array(mjbData* d, const char* name, void* p) {
@@ -119,6 +131,18 @@ int mjb_data_finalize(mjbData* d, const mjbModel* m) {
       snprintf(buf, sizeof buf, "%s kernel needs %zu B of shared memory per block (> %zu): model/njmax too large for this version", names[i], d->smem[i], kMaxSmem);
       return fail(buf);
     }
+  {
+    const char* e = getenv("MJB_SPLIT");
+    const int want = e ? atoi(e) : 2;
+    if (want >= 2 && d->dev.nworld >= 1024) {
+      for (int i = 0; i < 2; i++) {
+        if (check(cudaStreamCreateWithFlags(&d->aux[i], cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
+        if (check(cudaEventCreateWithFlags(&d->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return -1;
+      }
+      if (check(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return -1;
+      d->nsplit = 2;
+    }
+  }
   d->finalized = true;
   return 0;
 }
@@ -134,7 +158,7 @@ int mjb_com_pos(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_
 int mjb_camlight(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_CAMLIGHT, s), 1); return 0; }
 int mjb_crb(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_CRB, s), 1); return 0; }
 int mjb_transmission(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_TRANSMISSION, s), 1); return 0; }
-int mjb_collision(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1); return 0; }
+int mjb_collision(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(reset_contact_counters(d->dev, s), 0); MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1); return 0; }
 int mjb_make_constraint(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1); return 0; }
 int mjb_fwd_velocity(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_VELOCITY, s), 1); return 0; }
 int mjb_fwd_actuation(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_ACTUATION, s), 1); return 0; }
@@ -143,26 +167,44 @@ int mjb_factor_m(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB
 int mjb_solve(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1); return 0; }
 int mjb_euler(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1); return 0; }
 
-static int fwd_position_impl(const mjbModel* m, mjbData* d, cudaStream_t s) {
-  // forward.py:635-677 with factorize=False: kinematics, com_pos, camlight, crb, collision, make_constraint, transmission
-  MJB_LAUNCH(launch_position(m->dev, d->dev, STG_KINEMATICS | STG_COM_POS | STG_CAMLIGHT | STG_CRB | STG_TRANSMISSION, s), 1);
-  MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1);
-  MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1);
+// which stages a pipeline call runs
+enum { RUN_POSITION = 1, RUN_VELOCITY = 2, RUN_SOLVER = 4, RUN_EULER = 8 };
+
+static int chain(const mjbModel* m, const DataDev& dd, int what, cudaStream_t s) {
+  if (what & RUN_POSITION) {
+    // forward.py:635-677 with factorize=False: kinematics, com_pos, camlight, crb, collision, make_constraint, transmission
+    MJB_LAUNCH(launch_position(m->dev, dd, STG_KINEMATICS | STG_COM_POS | STG_CAMLIGHT | STG_CRB | STG_TRANSMISSION, s), 1);
+    MJB_LAUNCH(launch_collision(m->dev, dd, s), 1);
+    MJB_LAUNCH(launch_constraint(m->dev, dd, s), 1);
+  }
+  if (what & RUN_VELOCITY) MJB_LAUNCH(launch_velocity(m->dev, dd, STG_VELOCITY | STG_ACTUATION | STG_ACCELERATION, s), 1);
+  if (what & RUN_SOLVER) MJB_LAUNCH(launch_solver(m->dev, dd, s), 1);
+  if (what & RUN_EULER) MJB_LAUNCH(launch_integrate(m->dev, dd, s), 1);
   return 0;
 }
-static int forward_impl(const mjbModel* m, mjbData* d, cudaStream_t s) {
-  if (fwd_position_impl(m, d, s)) return -1;
-  MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_VELOCITY | STG_ACTUATION | STG_ACCELERATION, s), 1);
-  MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1);
+
+static int pipeline(const mjbModel* m, mjbData* d, int what, cudaStream_t s) {
+  if (what & RUN_POSITION) MJB_LAUNCH(reset_contact_counters(d->dev, s), 0);
+  if (d->nsplit < 2) return chain(m, d->dev, what, s);
+  // fork: both halves wait for everything queued on the caller's stream, run their own kernel chain, and are joined back
+  if (check(cudaEventRecord(d->ev_fork, s), "cudaEventRecord")) return -1;
+  const int half = (d->dev.nworld + 1) / 2;
+  for (int h = 0; h < 2; h++) {
+    DataDev dd = d->dev;
+    dd.w0 = h * half;
+    dd.wn = h == 0 ? half : d->dev.nworld - half;
+    if (check(cudaStreamWaitEvent(d->aux[h], d->ev_fork, 0), "cudaStreamWaitEvent")) return -1;
+    if (chain(m, dd, what, d->aux[h])) return -1;
+    if (check(cudaEventRecord(d->ev_join[h], d->aux[h]), "cudaEventRecord")) return -1;
+    if (check(cudaStreamWaitEvent(s, d->ev_join[h], 0), "cudaStreamWaitEvent")) return -1;
+  }
   return 0;
 }
-int mjb_fwd_position(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return fwd_position_impl(m, d, s); }
-int mjb_forward(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return forward_impl(m, d, s); }
+int mjb_fwd_position(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return pipeline(m, d, RUN_POSITION, s); }
+int mjb_forward(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER, s); }
 int mjb_step(const mjbModel* m, mjbData* d, void* stream) {
   MJB_ENTER();
-  if (forward_impl(m, d, s)) return -1;
-  MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1);
-  return 0;
+  return pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER | RUN_EULER, s);
 }
 int mjb_step_profile(const mjbModel* m, mjbData* d, void* stream, float* ms_out) {
   // one step with a CUDA event pair around every kernel; synchronises (profiling aid, not the hot path)
@@ -172,6 +214,7 @@ int mjb_step_profile(const mjbModel* m, mjbData* d, void* stream, float* ms_out)
   cudaEventRecord(ev[0], s);
   MJB_LAUNCH(launch_position(m->dev, d->dev, STG_KINEMATICS | STG_COM_POS | STG_CAMLIGHT | STG_CRB | STG_TRANSMISSION, s), 1);
   cudaEventRecord(ev[1], s);
+  MJB_LAUNCH(reset_contact_counters(d->dev, s), 0);
   MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1);
   cudaEventRecord(ev[2], s);
   MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1);

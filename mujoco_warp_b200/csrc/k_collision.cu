@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x;
+  const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   const ColLayout L = col_layout(m, d);
   float* S = smem + warp * L.total;
@@ -310,11 +310,14 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
 
 size_t smem_collision(const ModelDev& m, const DataDev& d) { return (size_t)col_layout(m, d).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
 
-cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s) {
+cudaError_t reset_contact_counters(const DataDev& d, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(d.nacon, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(d.ncollision, 0, sizeof(int), s);
-  if (e != cudaSuccess) return e;
+  return cudaMemsetAsync(d.ncollision, 0, sizeof(int), s);
+}
+
+cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s) {
+  cudaError_t e;
   const size_t smem = smem_collision(m, d);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -322,7 +325,7 @@ cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  const int grid = d.wn;
   k_collision<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

@@ -27,7 +27,7 @@ __host__ __device__ inline ConLayout con_layout(const ModelDev& m, const DataDev
   ConLayout L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
-  L.cdof = take(6 * m.nv); L.scom = take(3 * m.nbody); L.qvel = take(m.nv); L.rec = take(CR_WORDS * con_cap(d));
+  L.cdof = take(6 * m.nv); L.scom = take(3 * m.nbody); L.qvel = take(m.nv); L.rec = take(CR_WORDS * 32);  // one 32-contact batch at a time
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -67,11 +67,11 @@ __device__ void efc_row(const ModelDev& m, const DataDev& d, int w, int efcid, f
   d.efc_id[r] = id;
 }
 
-__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32, 28)
 k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x;
+  const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   const ConLayout L = con_layout(m, d);
   float* S = smem + warp * L.total;
@@ -148,9 +148,9 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
   if (!(m.disableflags & DSBL_CONTACT)) {
     const int cbase = d.world_conadr[w], ncon = min(d.world_ncon[w], con_cap(d)), np = m.nmaxpyramid;
     const bool elliptic = m.cone == CONE_ELLIPTIC;
-    // ---- phase A: lane = contact
 #pragma unroll 1
     for (int c0 = 0; c0 < ncon; c0 += 32) {
+      // ---- phase A: lane = contact (batch of 32)
       const int c = c0 + lane, cid = cbase + c;
       int ndim = 0, condim = 0;
       float includemargin = 0.f, pos = 0.f;
@@ -163,7 +163,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
       const int base = nefc + warp_excl_scan(ndim, lane);
       nefc += warp_sum_i(ndim);
       if (c < ncon) {
-        float* r = rec + CR_WORDS * c;
+        float* r = rec + CR_WORDS * lane;
         r[CR_NDIM] = __int_as_float(ndim);
         if (ndim > 0) {
           const int g1 = d.contact_geom[2 * cid], g2 = d.contact_geom[2 * cid + 1], b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
@@ -181,15 +181,15 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
           for (int k = 0; k < ndim; k++) d.contact_efc_address[np * cid + k] = base + k < njmax ? base + k : -1;
         }
       }
-    }
-    __syncwarp();
-    // ---- phase B: lanes = dofs, contacts one after the other, every operand already in shared memory
+      __syncwarp();
+      // ---- phase B: lanes = dofs, the batch's contacts one after the other, every operand already in shared memory
+      const int nb_ = min(32, ncon - c0);
 #pragma unroll 1
-    for (int c = 0; c < ncon; c++) {
-      const float* r = rec + CR_WORDS * c;
+      for (int cb = 0; cb < nb_; cb++) {
+      const float* r = rec + CR_WORDS * cb;
       const int ndim = __float_as_int(r[CR_NDIM]);
       if (ndim == 0) continue;
-      const int cid = cbase + c, base = __float_as_int(r[CR_BASE]), condim = __float_as_int(r[CR_CONDIM]);
+      const int cid = cbase + c0 + cb, base = __float_as_int(r[CR_BASE]), condim = __float_as_int(r[CR_CONDIM]);
       const int b1 = __float_as_int(r[CR_B1]), b2 = __float_as_int(r[CR_B2]);
       const float pos = r[CR_POS], includemargin = r[CR_INC];
       float frame[9], fri[5];
@@ -262,6 +262,8 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
           efc_row(m, d, w, efcid, pos_aref, pos, invweight, ref, imp5, includemargin, myvel, 0.f, type, cid);
         }
       }
+      }
+      __syncwarp();
     }
   }
   if (lane == 0) { d.ne[w] = 0; d.nf[w] = nf; d.nl[w] = nl; d.nefc[w] = nefc; }
@@ -279,7 +281,7 @@ cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t 
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  const int grid = d.wn;
   k_constraint<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

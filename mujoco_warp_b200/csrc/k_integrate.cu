@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x;
+  const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   float* S = smem + warp * int_words(m);
   float *qacc = S, *qvel = S + m.nv, *A = S + 2 * m.nv, *x = A + m.maxtree * chol_ld(m.maxtree);
@@ -157,7 +157,7 @@ cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  const int grid = d.wn;
   k_euler<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

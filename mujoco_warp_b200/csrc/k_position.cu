@@ -26,7 +26,10 @@ __host__ __device__ inline PosLayout pos_layout(const ModelDev& m) {
   L.xanchor = take(3 * m.njnt); L.xaxis = take(3 * m.njnt);
   L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom);
   L.scom = take(3 * m.nbody); L.cinert = take(10 * m.nbody); L.crb = take(10 * m.nbody);
-  L.cdof = take(6 * m.nv); L.buf = take(6 * m.nv); L.M = take(m.nC);
+  L.cdof = take(6 * m.nv); L.M = take(m.nC);
+  // crb*cdof scratch (6 nv) reuses the geom_xmat staging area, which is dead once kinematics has been written out
+  L.buf = L.gxmat;
+  if (6 * m.nv > 9 * m.ngeom) L.buf = take(6 * m.nv);
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x;
+  const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   const PosLayout L = pos_layout(m);
   float* S = smem + warp * L.total;
@@ -333,7 +336,7 @@ cudaError_t launch_position(const ModelDev& m, const DataDev& d, int mask, cudaS
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  const int grid = d.wn;
   k_position<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, mask);
   return cudaGetLastError();
 }

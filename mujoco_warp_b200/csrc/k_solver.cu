@@ -88,7 +88,7 @@ __device__ __forceinline__ bool in_bracket(P3 x, P3 y) { return (x.g < y.g && y.
 // dot of a 16B-aligned J row with a zero-padded, 16B-aligned per-dof vector
 __device__ __forceinline__ float row_dot(const float* Jr, const float* vec, int nvp) {
   float s = 0.f;
-#pragma unroll 1
+#pragma unroll 4
   for (int k = 0; k < nvp; k += 4) {
     const float4 a = *reinterpret_cast<const float4*>(Jr + k), b = *reinterpret_cast<const float4*>(vec + k);
     s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
@@ -111,6 +111,7 @@ __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res
 #pragma unroll 1
   for (int i = c.lane; i < c.nv; i += 32) {
     float acc = 0.f;
+#pragma unroll 4
     for (int k = m.mulm_rowadr[i]; k < m.mulm_rowadr[i + 1]; k++) acc += c.M[m.mulm_madr[k]] * vec[m.mulm_col[k]];
     res[i] = acc;
   }
@@ -148,6 +149,7 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
 #pragma unroll 1
   for (int dd = c.lane; dd < c.nv; dd += 32) {
     float s = 0.f;
+#pragma unroll 8
     for (int r = 0; r < c.nefc; r++) s += c.J[r * c.ldJ + dd] * c.force[r];
     c.qfc[dd] = s;
   }
@@ -172,7 +174,7 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
   float a[N];
   chol_load_rows<N, true>(a, c.H, c.ldH, nv, lane);
   if (nlist > 0) {
-#pragma unroll 1
+#pragma unroll 2
     for (int t = 0; t < nlist; t++) {
       const float* Jr = c.J + c.hidx[t] * c.ldJ;
       const float sc = lane < nv ? c.hw[t] * Jr[lane] : 0.f;
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x;
+  const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   const SolLayout L = sol_layout(m, d);
   float* S = smem + warp * L.total;
@@ -425,7 +427,7 @@ cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  const int grid = d.wn;
   k_solver<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

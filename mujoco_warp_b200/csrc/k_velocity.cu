@@ -28,11 +28,12 @@ __host__ __device__ inline VelLayout vel_layout(const ModelDev& m) {
   return L;
 }
 
-__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
+// 28 resident one-warp blocks per SM make 8192 worlds exactly two full waves on 148 SMs (caps registers at 72)
+__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32, 28)
 k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x;
+  const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   const VelLayout L = vel_layout(m);
   float* S = smem + warp * L.total;
@@ -314,7 +315,7 @@ cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int mask, cudaS
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int grid = (d.nworld + MJB_WARPS_PER_BLOCK - 1) / MJB_WARPS_PER_BLOCK;
+  const int grid = d.wn;
   k_velocity<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, mask);
   return cudaGetLastError();
 }

@@ -123,12 +123,21 @@ __device__ __forceinline__ float chol_solve_rows_rolled(float (&a)[N], int n, fl
     const float yj = __shfl_sync(FULL_MASK, b, j) * inv;
     b = lane > j ? b - lij * yj : (lane == j ? yj : b);
     if (lane >= j && lane < n) Ls[tri_at<PACKED>(lane, j, ldL)] = lij;
+    // trailing update of the n-1-j columns to the right, in chunks of 4 with a warp-uniform early exit (registers past the
+    // matrix edge are never read again, so they need not be shifted); srcLane >= 32 wraps modulo 32 by definition of SHFL
+    const int rem = n - 1 - j;
 #pragma unroll
-    for (int k = 1; k < N; k++) {
-      const float lkj = __shfl_sync(FULL_MASK, lij, (j + k) & 31);
-      a[k - 1] = a[k] - lij * lkj;
+    for (int k0 = 1; k0 < N; k0 += 4) {
+      if (k0 > rem) break;
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const int k = k0 + kk;
+        if (k < N) {
+          const float lkj = __shfl_sync(FULL_MASK, lij, j + k);
+          a[k - 1] = a[k] - lij * lkj;
+        }
+      }
     }
-    a[N - 1] = 0.f;
   }
   __syncwarp();
 #pragma unroll 1

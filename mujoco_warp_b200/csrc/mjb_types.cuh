@@ -64,6 +64,7 @@ struct ModelDev {
 
 struct DataDev {
   int nworld, nconmax, naconmax, njmax, njmax_pad, nv_pad;
+  int w0, wn;  // world range [w0, w0 + wn) processed by one launch (the step is pipelined over two world halves)
 #define X(n) float* __restrict__ n;
   MJB_DATA_FARRS(X)
 #undef X
@@ -113,6 +114,7 @@ constexpr int MJB_WARPS_PER_BLOCK = 1;
 // launchers (one per .cu); each returns the cudaError of the launch
 cudaError_t launch_position(const ModelDev& m, const DataDev& d, int stage_mask, cudaStream_t s);
 cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s);
+cudaError_t reset_contact_counters(const DataDev& d, cudaStream_t s);
 cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s);
 cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int stage_mask, cudaStream_t s);
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s);
