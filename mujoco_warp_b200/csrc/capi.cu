@@ -1,7 +1,9 @@
 // capi.cu -- extern "C" boundary of libmjb200.so (see include/mjb200.h for the reference interfaces each entry replaces).
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+using std::min;
 #include <string>
 
 #include "../../include/mjb200.h"
@@ -17,8 +19,8 @@ struct mjbData {
   size_t smem[6];
   // step pipelining over two world halves on two internal streams (overlaps each kernel's partial last wave with the
   // other half's kernels; worlds never interact, so the halves are independent apart from the shared contact-pool counter)
-  cudaStream_t aux[2];
-  cudaEvent_t ev_fork, ev_join[2];
+  cudaStream_t aux[8];
+  cudaEvent_t ev_fork, ev_join[8];
   int nsplit;
 };
 
@@ -97,7 +99,7 @@ void mjb_data_destroy(mjbData* d) {
   if (d->dev.world_conadr) cudaFree(d->dev.world_conadr);
   if (d->dev.world_ncon) cudaFree(d->dev.world_ncon);
   if (d->nsplit > 1) {
-    for (int i = 0; i < 2; i++) { cudaStreamDestroy(d->aux[i]); cudaEventDestroy(d->ev_join[i]); }
+    for (int i = 0; i < d->nsplit; i++) { cudaStreamDestroy(d->aux[i]); cudaEventDestroy(d->ev_join[i]); }
     cudaEventDestroy(d->ev_fork);
   }
   delete d;
@@ -135,12 +137,13 @@ int mjb_data_finalize(mjbData* d, const mjbModel* m) {
     const char* e = getenv("MJB_SPLIT");
     const int want = e ? atoi(e) : 2;
     if (want >= 2 && d->dev.nworld >= 1024) {
-      for (int i = 0; i < 2; i++) {
+      const int ns = want > 8 ? 8 : want;
+      for (int i = 0; i < ns; i++) {
         if (check(cudaStreamCreateWithFlags(&d->aux[i], cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
         if (check(cudaEventCreateWithFlags(&d->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return -1;
       }
       if (check(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return -1;
-      d->nsplit = 2;
+      d->nsplit = ns;
     }
   }
   d->finalized = true;
@@ -188,11 +191,12 @@ static int pipeline(const mjbModel* m, mjbData* d, int what, cudaStream_t s) {
   if (d->nsplit < 2) return chain(m, d->dev, what, s);
   // fork: both halves wait for everything queued on the caller's stream, run their own kernel chain, and are joined back
   if (check(cudaEventRecord(d->ev_fork, s), "cudaEventRecord")) return -1;
-  const int half = (d->dev.nworld + 1) / 2;
-  for (int h = 0; h < 2; h++) {
+  const int part = (d->dev.nworld + d->nsplit - 1) / d->nsplit;
+  for (int h = 0; h < d->nsplit; h++) {
     DataDev dd = d->dev;
-    dd.w0 = h * half;
-    dd.wn = h == 0 ? half : d->dev.nworld - half;
+    dd.w0 = h * part;
+    dd.wn = min(part, d->dev.nworld - dd.w0);
+    if (dd.wn <= 0) break;
     if (check(cudaStreamWaitEvent(d->aux[h], d->ev_fork, 0), "cudaStreamWaitEvent")) return -1;
     if (chain(m, dd, what, d->aux[h])) return -1;
     if (check(cudaEventRecord(d->ev_join[h], d->aux[h]), "cudaEventRecord")) return -1;

@@ -178,3 +178,76 @@ def test_g1_replay_matches_oracle(built):
   # contact make/break decisions happen at |dist - margin| ~ 1e-7 boundaries; allow a handful of one-step disagreements
   assert mismatched <= 8, mismatched
   assert not (d.overflow.cpu().numpy() & ~int(mjw.OverflowType.LS_ITERATIONS)).any()
+
+
+# --------------------------------------------------------------------------------------------- mixed-feature scene
+
+
+@pytest.fixture(scope="module")
+def mixed(built):
+  import mujoco_warp_b200 as mjw
+
+  mjm = mjw.mjcf.load_string(util.MIXED_XML)
+  return mjw, mjm, mjw.put_model(mjm)
+
+
+def test_mixed_scene_forward_and_rollout(mixed):
+  """Own scene covering the remaining code paths: slide / ball joints, several trees, dof friction-loss rows, joint limits on a
+  slide joint, implicit Euler damping (eulerdamp on), position / velocity / motor actuators with force and joint-force
+  clamps, sphere-sphere, sphere-capsule, capsule-capsule (incl. the parallel two-contact case), plane-sphere contacts,
+  condim 1 / 3 / 4 / 6 pyramids, geom priority / solmix / margin / gap mixing, applied wrenches and joint forces."""
+  mjw, mjm, m = mixed
+  assert mjm.ntree == 7 and mjm.nv == 41 and (mjm.dof_frictionloss > 0).sum() == 2
+  nworld, nconmax, njmax = 16, 32, 128
+  d = mjw.make_data(mjm, nworld=nworld, nconmax=nconmax, njmax=njmax, m=m)
+  o = util.make_oracle(mjm, nworld, nconmax, njmax)
+  # every world is perturbed: at the exact keyframe two capsule pairs are perfectly parallel, where the reference's
+  # `abs(det) >= MJ_MINVAL` branch (collision_primitive_core.py:158) is decided by fp32/FMA rounding noise
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, nworld, key=0, seed=9, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  rng = np.random.default_rng(2)
+  xfrc = np.zeros((nworld, mjm.nbody, 6), dtype=np.float32)
+  xfrc[1::2, 1] = rng.uniform(-1, 1, (nworld // 2, 6))  # wrench on ball0 in every second world
+  xfrc[:, 9, :3] = rng.uniform(-0.5, 0.5, (nworld, 3))  # force on the pendulum
+  qapp = (0.2 * rng.uniform(-1, 1, (nworld, mjm.nv))).astype(np.float32)
+  f32 = lambda a: a.astype(np.float32)
+  for name, val in (("qpos", qpos), ("qvel", qvel), ("ctrl", ctrl), ("qacc_warmstart", warm), ("xfrc_applied", xfrc), ("qfrc_applied", qapp)):
+    getattr(d, name).copy_(torch.from_numpy(f32(val)).reshape(getattr(d, name).shape))
+  o.set_state(qpos=f32(qpos), qvel=f32(qvel), ctrl=f32(ctrl), qacc_warmstart=f32(warm))
+  o.d["xfrc_applied"][:] = xfrc
+  o.d["qfrc_applied"][:] = qapp
+  mjw.forward(m, d)
+  o.forward()
+  torch.cuda.synchronize()
+  od = o.d
+  assert od["nf"].min() == 2 and od["ncon"].max() >= 5 and (od["con_dim"][0, : od["ncon"][0]] == 6).any()
+  for name in util.SMOOTH_FIELDS + ["site_xpos", "site_xmat"]:
+    util.assert_close(name, getattr(d, name).cpu().numpy().reshape(od[name].shape), od[name], atol=5e-4, rtol=5e-4)
+  for name in ("ne", "nf", "nl", "nefc"):
+    np.testing.assert_array_equal(getattr(d, name).cpu().numpy(), od[name], err_msg=name)
+  J = d.efc.J.cpu().numpy()
+  for w in range(nworld):
+    ids = util.world_contacts(d, w)
+    n = int(od["ncon"][w])
+    assert len(ids) == n
+    np.testing.assert_array_equal(d.contact.geom[ids].cpu().numpy(), od["con_geom"][w, :n])
+    np.testing.assert_array_equal(d.contact.dim[ids].cpu().numpy(), od["con_dim"][w, :n])
+    for f, of in (("dist", "con_dist"), ("pos", "con_pos"), ("frame", "con_frame"), ("friction", "con_friction"), ("solref", "con_solref"), ("solimp", "con_solimp"), ("includemargin", "con_includemargin")):
+      util.assert_close(f"contact.{f}[w{w}]", getattr(d.contact, f)[ids].cpu().numpy(), od[of][w, :n], atol=5e-4, rtol=5e-4)
+    ne = int(od["nefc"][w])
+    np.testing.assert_array_equal(d.efc.type[w, :ne].cpu().numpy(), od["efc_type"][w, :ne])
+    util.assert_close(f"efc.J[w{w}]", J[w, :ne, : mjm.nv], od["efc_J"][w, :ne], atol=5e-4, rtol=5e-4)
+    for f in ("pos", "margin", "vel", "frictionloss"):
+      util.assert_close(f"efc.{f}[w{w}]", getattr(d.efc, f)[w, :ne].cpu().numpy(), od["efc_" + f][w, :ne], atol=5e-4, rtol=5e-4)
+    util.assert_close(f"efc.D[w{w}]", d.efc.D[w, :ne].cpu().numpy(), od["efc_D"][w, :ne], atol=1e-3, rtol=2e-3)
+    util.assert_close(f"efc.aref[w{w}]", d.efc.aref[w, :ne].cpu().numpy(), od["efc_aref"][w, :ne], atol=2e-3, rtol=2e-3)
+  scale = max(1.0, float(np.abs(od["qacc"]).max()))
+  util.assert_close("qacc", d.qacc.cpu().numpy(), od["qacc"], atol=1e-2 * scale, rtol=0)
+  # rollout with implicit joint damping in the Euler step
+  mismatched = 0
+  for i in range(30):
+    mjw.step(m, d)
+    o.step()
+    torch.cuda.synchronize()
+    mismatched += int((d.nefc.cpu().numpy() != od["nefc"]).sum())
+    util.assert_close(f"qpos@{i}", d.qpos.cpu().numpy(), od["qpos"], atol=3e-3, rtol=3e-3)
+  assert mismatched <= 10, mismatched

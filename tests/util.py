@@ -11,15 +11,15 @@ G1 = os.path.join(SCENES, "unitree_g1_flat.npz")
 G1_TRAJ = os.path.join(SCENES, "unitree_g1_shuffle_dance.npz")
 
 
-def seeded_state(mjm, nworld, key=0, seed=42, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=0.5):
+def seeded_state(mjm, nworld, key=0, seed=42, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=True):
   """Per-world states around a keyframe, like the reference fixture's seeded uniform noise (test_data/__init__.py:82-98)."""
   from mujoco_warp_b200._src import constants as C
 
   rng = np.random.default_rng(seed)
   qpos = np.tile(mjm.key_qpos[key] if key is not None and mjm.nkey > key else mjm.qpos0, (nworld, 1)).astype(np.float64)
   qpos += qpos_noise * rng.uniform(-1, 1, qpos.shape)
-  # world 0 stays exactly at the keyframe
-  qpos[0] = mjm.key_qpos[key] if key is not None and mjm.nkey > key else mjm.qpos0
+  if exact_world0:  # world 0 stays exactly at the keyframe
+    qpos[0] = mjm.key_qpos[key] if key is not None and mjm.nkey > key else mjm.qpos0
   for j in range(mjm.njnt):
     qa = mjm.jnt_qposadr[j]
     if mjm.jnt_type[j] == C.JNT_FREE:
@@ -27,7 +27,8 @@ def seeded_state(mjm, nworld, key=0, seed=42, qpos_noise=0.05, qvel_noise=0.5, c
     elif mjm.jnt_type[j] == C.JNT_BALL:
       qpos[:, qa : qa + 4] /= np.linalg.norm(qpos[:, qa : qa + 4], axis=1, keepdims=True)
   qvel = qvel_noise * rng.uniform(-1, 1, (nworld, mjm.nv))
-  qvel[0] = 0
+  if exact_world0:
+    qvel[0] = 0
   ctrl = ctrl_noise * rng.uniform(-1, 1, (nworld, mjm.nu))
   warm = rng.uniform(-1, 1, (nworld, mjm.nv))
   return qpos, qvel, ctrl, warm
@@ -63,3 +64,64 @@ def assert_close(name, a, b, atol, rtol):
   if not (err <= tol).all():
     i = np.unravel_index(np.argmax(err - tol), err.shape)
     raise AssertionError(f"{name}: max violation at {i}: got {a[i]:.8g}, want {b[i]:.8g} (|err|={err[i]:.3g}, tol={tol[i]:.3g})")
+
+
+MIXED_XML = """
+<mujoco model="mixed">
+  <option timestep="0.004" iterations="50" ls_iterations="30"/>
+  <default>
+    <geom friction="0.8 0.01 0.002" solref="0.02 1"/>
+  </default>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05" condim="3" margin="0.002"/>
+    <light name="l0" pos="0 0 3" mode="fixed"/>
+    <camera name="c0" pos="2 0 1" mode="targetbody" target="ball0"/>
+    <body name="ball0" pos="0 0 0.12">
+      <freejoint/>
+      <geom name="s0" type="sphere" size="0.1" condim="4" priority="1"/>
+      <site name="st0" pos="0.05 0 0"/>
+    </body>
+    <body name="ball1" pos="0.17 0 0.13">
+      <freejoint/>
+      <geom name="s1" type="sphere" size="0.1" condim="1" solmix="2" margin="0.004" gap="0.001"/>
+    </body>
+    <body name="cap0" pos="0 0.3 0.09" euler="0 80 10">
+      <freejoint/>
+      <geom name="c0" type="capsule" size="0.06 0.15" condim="6"/>
+    </body>
+    <body name="cap1" pos="0.05 0.32 0.2" euler="0 85 40">
+      <freejoint/>
+      <geom name="c1" type="capsule" size="0.05 0.12" condim="3"/>
+    </body>
+    <body name="cap2" pos="0.5 0.5 0.3" euler="0 90 0">
+      <freejoint/>
+      <geom name="c2" type="capsule" size="0.04 0.1"/>
+    </body>
+    <body name="cap3" pos="0.5 0.5 0.385" euler="0 90 0">
+      <freejoint/>
+      <geom name="c3" type="capsule" size="0.04 0.1"/>
+    </body>
+    <body name="arm" pos="-0.6 0 0.6">
+      <joint name="slide" type="slide" axis="0 0 1" range="-0.2 0.05" limited="true" damping="2" frictionloss="0.3" stiffness="5" springref="0.02"/>
+      <geom type="capsule" fromto="0 0 0 0.2 0 0" size="0.03" mass="0.8"/>
+      <body name="fore" pos="0.2 0 0">
+        <joint name="hinge" type="hinge" axis="0 1 0" range="-40 60" limited="true" damping="0.1" armature="0.01" frictionloss="0.05" actuatorfrcrange="-3 3"/>
+        <geom type="capsule" fromto="0 0 0 0.25 0 0" size="0.025" mass="0.4"/>
+        <body name="pend" pos="0.25 0 0">
+          <joint name="ball" type="ball" damping="0.05"/>
+          <geom type="capsule" fromto="0 0 0 0 0 -0.2" size="0.02" mass="0.3"/>
+          <geom name="tip" type="sphere" pos="0 0 -0.22" size="0.04" mass="0.2"/>
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <motor name="m_slide" joint="slide" gear="10" ctrlrange="-1 1" ctrllimited="true"/>
+    <position name="p_hinge" joint="hinge" kp="20" kv="1" forcerange="-4 4" forcelimited="true"/>
+    <velocity name="v_hinge" joint="hinge" kv="0.5"/>
+  </actuator>
+  <keyframe>
+    <key name="k0" qpos="0 0 0.099 1 0 0 0  0.195 0 0.1 1 0 0 0  0 0.3 0.0595 0.7071 0 0.7071 0  0.02 0.3 0.1675 0.5 0.5 0.5 0.5  0.5 0.5 0.039 0.7071 0 0.7071 0  0.5 0.5 0.118 0.7071 0 0.7071 0  0.06 0.5  0.98 0.1 0.1 0.1"/>
+  </keyframe>
+</mujoco>
+"""
