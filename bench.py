@@ -304,6 +304,12 @@ def run_ours(args):
     top = max(kms, key=kms.get)
     bytes_launch = 4.0 * words[top] * nworld
     achieved = bytes_launch / (kms[top] * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/r01_final_kernels.md)
+      traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["traffic_bytes"].get("k_" + top)
+      traffic = traffic * nworld / 8192.0 if traffic is not None else None
+    except Exception:
+      pass
     step_bytes = 4.0 * sum(words.values()) * nworld
     cpu = None
     if world == 1 or True:
@@ -325,7 +331,7 @@ def run_ours(args):
       "gpu_launches": launches_per_step * args.steps,
       "kernel_ms": kms,
       "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                   "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                   "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                    "algorithmic_bytes_per_launch": bytes_launch, "step_algorithmic_bytes": step_bytes,
                    "step_frac": step_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak},
       "cpu_baseline": cpu,
