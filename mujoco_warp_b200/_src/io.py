@@ -230,8 +230,8 @@ def _validate(mjm):
   o = mjm.opt
   if o.integrator not in (C.INT_EULER, C.INT_IMPLICITFAST):
     raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler and implicitfast only in this version)")
-  if o.cone != C.CONE_PYRAMIDAL:
-    raise NotImplementedError("elliptic friction cones are not implemented in this version")
+  if o.cone not in (C.CONE_PYRAMIDAL, C.CONE_ELLIPTIC):
+    raise NotImplementedError(f"unknown friction cone {o.cone}")
   if o.solver != C.SOL_NEWTON:
     raise NotImplementedError("only the Newton solver is implemented in this version")
   if mjm.nv > 64:

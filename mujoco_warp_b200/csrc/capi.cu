@@ -78,7 +78,7 @@ int mjb_model_finalize(mjbModel* m) {
 #undef X
   if (m->dev.nv <= 0 || m->dev.nbody <= 0) return fail("model has no dofs/bodies");
   if (m->dev.solver != SOL_NEWTON) return fail("only the Newton solver is implemented");
-  if (m->dev.cone != CONE_PYRAMIDAL) return fail("only the pyramidal friction cone is implemented");
+  if (m->dev.cone != CONE_PYRAMIDAL && m->dev.cone != CONE_ELLIPTIC) return fail("unknown friction cone type");
   if (m->dev.integrator != INT_EULER && m->dev.integrator != INT_IMPLICITFAST) return fail("only the Euler and implicitfast integrators are implemented");
   m->finalized = true;
   return 0;

@@ -11,7 +11,9 @@
 // converged (no global `nsolving` counter, no graph conditional).  Reductions are warp shuffles; the Hessian is updated
 // incrementally from the rows whose QUADRATIC flag flipped (exactly the reference's rule) and refactored in place.
 // Algorithm and tolerances follow the reference: exact Newton with the iterative bracketing line search on the
-// shifted (cost(alpha) - cost(0)) piecewise-quadratic 1-D cost.  Pyramidal / frictionless / limit / dof-friction rows.
+// shifted (cost(alpha) - cost(0)) piecewise-quadratic 1-D cost.  Pyramidal / frictionless / limit / dof-friction rows
+// in the default instantiation; k_solver<true> adds elliptic cones (solver.py:286-477 zones, :957-1015 per-contact
+// quads, :2443-2565 cone Hessian) with the Hessian rebuilt from M every iteration like the reference's elliptic path.
 #include "mjb_chol.cuh"
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
@@ -21,7 +23,7 @@ namespace {
 // Shared-memory slice of one world.  J rows keep the global stride nv_pad (a multiple of 4 floats), so a row is 16-byte
 // aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
 // rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
-struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, total; };
+struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, total; };
 __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d) {
   SolLayout L;
   int o = 0;
@@ -34,8 +36,11 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   L.H = take(hsz); L.Lf = take(hsz);
   L.M = take(m.nC);
   // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
-  L.rowf = take((m.nfricdof > 0 ? 5 : 4) * d.njmax);
-  L.rowi = take(2 * d.njmax);
+  // elliptic cones add: per-row friction scale, 3 quad words per row (solver.py:1008-1015 layout), row->contact info
+  const bool ell = m.cone == CONE_ELLIPTIC;
+  L.nrowf = (m.nfricdof > 0 ? 5 : 4);
+  L.rowf = take((L.nrowf + (ell ? 4 : 0)) * d.njmax);
+  L.rowi = take((ell ? 3 : 2) * d.njmax);
   L.total = o;
   return L;
 }
@@ -85,6 +90,58 @@ __device__ __forceinline__ P3 eval_gauss(float q0, float q1, float q2, float alp
 }
 __device__ __forceinline__ bool in_bracket(P3 x, P3 y) { return (x.g < y.g && y.g < 0.f) || (x.g > y.g && y.g > 0.f); }
 
+// ---- elliptic cone, one contact (quad = cost polynomial of all its rows, (u0, v0, uu), (uv, vv, dm))
+struct EllQ { float q0, q1, q2, u0, v0, uu, uv, vv, dm; };
+struct EllRef { float cost0, T0, r0; int st; };
+// cost / tangential norm / residual / zone at alpha = 0 (solver.py:286-305)
+__device__ __forceinline__ EllRef ell_reference(float mu, const EllQ& q) {
+  EllRef e; e.T0 = 0.f; e.r0 = 0.f;
+  if (q.uu <= 0.f) { const bool neg = q.u0 < 0.f; e.cost0 = neg ? q.q0 : 0.f; e.st = neg ? ST_QUADRATIC : ST_SATISFIED; return e; }
+  e.T0 = sqrtf(q.uu);
+  if (q.u0 >= mu * e.T0) { e.cost0 = 0.f; e.st = ST_SATISFIED; return e; }
+  if (mu * q.u0 + e.T0 <= 0.f) { e.cost0 = q.q0; e.st = ST_QUADRATIC; return e; }
+  e.r0 = q.u0 - mu * e.T0; e.cost0 = 0.5f * q.dm * e.r0 * e.r0; e.st = ST_CONE;
+  return e;
+}
+// shifted (cost(alpha) - cost(0), grad, hess) of one elliptic contact (solver.py:329-404)
+__device__ __forceinline__ P3 ell_shifted(float mu, const EllQ& q, const EllRef& e, float alpha) {
+  const float N = q.u0 + alpha * q.v0, Tsqr_delta = alpha * (2.0f * q.uv + alpha * q.vv), Tsqr = q.uu + Tsqr_delta;
+  bool bottom = false;
+  float T = 0.f;
+  if (Tsqr <= 0.f) bottom = N < 0.f;
+  else {
+    T = sqrtf(Tsqr);
+    if (N >= mu * T) {}  // top zone
+    else if (mu * N + T <= 0.f) bottom = true;
+    else {
+      const float Tinv = 1.0f / T, T1 = (q.uv + alpha * q.vv) * Tinv, T2 = (q.vv - T1 * T1) * Tinv, r = N - mu * T, r1 = q.v0 - mu * T1;
+      float cost;
+      if (e.st == ST_CONE) { const float Td = Tsqr_delta / (T + e.T0), rd = alpha * q.v0 - mu * Td; cost = 0.5f * q.dm * rd * (2.0f * e.r0 + rd); }
+      else if (e.st == ST_QUADRATIC) { const float aq2 = alpha * q.q2, b = mu * N + T; cost = alpha * (aq2 + q.q1) - 0.5f * q.dm * b * b; }
+      else cost = 0.5f * q.dm * r * r;
+      return mkp(cost, q.dm * r * r1, q.dm * (r1 * r1 + r * (-mu * T2)));
+    }
+  }
+  if (bottom) {
+    const float aq2 = alpha * q.q2;
+    float cost = alpha * (aq2 + q.q1);
+    if (e.st == ST_CONE) { const float b = mu * q.u0 + e.T0; cost += 0.5f * q.dm * b * b; }
+    else if (e.st == ST_SATISFIED) cost = 0.5f * q.dm * (1.0f + mu * mu) * (N * N + fmaxf(Tsqr, 0.f));
+    return mkp(cost, 2.0f * aq2 + q.q1, 2.0f * q.q2);
+  }
+  return mkp(-e.cost0, 0.f, 0.f);
+}
+// absolute value at alpha = 0 (solver.py:308-320)
+__device__ __forceinline__ P3 ell_zero(float mu, const EllQ& q) {
+  const EllRef e = ell_reference(mu, q);
+  if (e.st == ST_QUADRATIC) return mkp(q.q0, q.q1, 2.0f * q.q2);
+  if (e.st == ST_CONE) {
+    const float Tinv = 1.0f / e.T0, T1 = q.uv * Tinv, T2 = (q.vv - T1 * T1) * Tinv, r1 = q.v0 - mu * T1;
+    return mkp(e.cost0, q.dm * e.r0 * r1, q.dm * (r1 * r1 - mu * e.r0 * T2));
+  }
+  return mkp(0.f, 0.f, 0.f);
+}
+
 // dot of a 16B-aligned J row with a zero-padded, 16B-aligned per-dof vector
 __device__ __forceinline__ float row_dot(const float* Jr, const float* vec, int nvp) {
   float s = 0.f;
@@ -103,7 +160,15 @@ struct Ctx {
   float *Jaref, *jv, *D, *force, *floss, *hw;
   int *state, *hidx;
   float search_dot, grad_dot, newton_decrement, improvement;
+  // elliptic only: rinfo[r] = -1 (not an elliptic row) | -2 (contact cut by njmax) | (dim << 4) | j;  rfri[r] = mu (j = 0)
+  // or friction[j-1];  quad = 3 words per row;  the CONE contacts' primary rows are listed from the END of hidx
+  int* rinfo; float *rfri, *quad; int njmax, ncone;
 };
+__device__ __forceinline__ EllQ ell_load(const Ctx& c, int r) {
+  const float* q = c.quad + 3 * r;
+  EllQ e; e.q0 = q[0]; e.q1 = q[1]; e.q2 = q[2]; e.u0 = q[3]; e.v0 = q[4]; e.uu = q[5]; e.uv = q[6]; e.vv = q[7]; e.dm = q[8];
+  return e;
+}
 
 // res = M vec via the symmetric gather tables (support.py:153 mul_m; tables io.py:1029-1050)
 __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res) {
@@ -119,12 +184,14 @@ __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res
 
 // force/state per row, qfrc_constraint = J^T force, and the list of rows whose QUADRATIC flag changed
 // (init=true: list every QUADRATIC row with weight +D).  Returns the list length.
+template <bool ELL>
 __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
-  int nlist = 0;
+  int nlist = 0, ncone = 0;
+  if (ELL) init = true;  // elliptic: H is rebuilt from M, so every QUADRATIC row is listed
 #pragma unroll 1
   for (int r0 = 0; r0 < c.nefc; r0 += 32) {
     const int r = r0 + c.lane;
-    bool flip = false;
+    bool flip = false, cone0 = false;
     float wgt = 0.f;
     if (r < c.nefc) {
       const float jaref = c.Jaref[r], D = c.D[r];
@@ -134,6 +201,24 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
       else if (r < c.ne + c.nf) {
         const float f = c.floss[r], rf = safe_div(f, D);
         if (jaref <= -rf) { force = f; st = ST_LINEARNEG; } else if (jaref >= rf) { force = -f; st = ST_LINEARPOS; } else { force = -D * jaref; st = ST_QUADRATIC; }
+      } else if (ELL && c.rinfo[r] != -1) {  // solver.py:455-472
+        const int info = c.rinfo[r];
+        force = 0.f; st = ST_SATISFIED;
+        if (info >= 0) {
+          const int j = info & 15, dim = info >> 4, e0 = r - j;
+          const float mu = c.rfri[e0], N = c.Jaref[e0] * mu;
+          float TT = 0.f;
+          for (int i = 1; i < dim; i++) { const float u = c.Jaref[e0 + i] * c.rfri[e0 + i]; TT += u * u; }
+          const float T = TT <= 0.f ? 0.f : sqrtf(TT);
+          if ((N >= mu * T) || (T <= 0.f && N >= 0.f)) {}
+          else if ((mu * N + T <= 0.f) || (T <= 0.f && N < 0.f)) { force = -D * jaref; st = ST_QUADRATIC; }
+          else {
+            const float dm = safe_div(c.D[e0], mu * mu * (1.0f + mu * mu)), fn = -dm * (N - mu * T) * mu, fr = c.rfri[r];
+            force = j == 0 ? fn : -safe_div(fn, T) * (jaref * fr * fr);
+            st = ST_CONE;
+            cone0 = j == 0;
+          }
+        }
       } else if (jaref >= 0.f) { force = 0.f; st = ST_SATISFIED; }
       else { force = -D * jaref; st = ST_QUADRATIC; }
       c.force[r] = force; c.state[r] = st;
@@ -144,7 +229,13 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
     const unsigned bal = __ballot_sync(FULL_MASK, flip);
     if (flip) { const int p = nlist + __popc(bal & ((1u << c.lane) - 1u)); c.hidx[p] = r; c.hw[p] = wgt; }
     nlist += __popc(bal);
+    if (ELL) {
+      const unsigned cb = __ballot_sync(FULL_MASK, cone0);
+      if (cone0) c.hidx[c.njmax - 1 - (ncone + __popc(cb & ((1u << c.lane) - 1u)))] = r;
+      ncone += __popc(cb);
+    }
   }
+  c.ncone = ncone;
   __syncwarp();
 #pragma unroll 1
   for (int dd = c.lane; dd < c.nv; dd += 32) {
@@ -168,7 +259,31 @@ __device__ __forceinline__ void update_grad(Ctx& c) {
 
 // Newton direction for nv <= 32: lane i keeps row i of H in registers, adds w * J_r[i] * J_r[:] for every listed row r
 // (J_r[:] read with broadcast LDS.128), stores the updated row back, and hands the registers straight to the Cholesky sweep.
-template <int N>
+// Elliptic cone term of one CONE-state contact as `dim` rank-1 updates (solver.py:2443-2565 regrouped): with
+// z0 = mu J0, p = sum_j u_j s_j J_j (u_j = Jaref_j s_j, s_j = friction_j-1),
+//   dH = dm [ z0 z0^T - mu/t (z0 p^T + p z0^T) + mu n / t^3 p p^T + (mu^2 - n mu / t) sum_j s_j^2 J_j J_j^T ]
+// so row i receives cA_i J0[:] + sum_j c_ji J_j[:].  Returns the per-contact scalars; the caller applies the updates.
+struct ConeK { float dm, mu, mu_tinv, munttt, tdiag; int dim; };
+__device__ __forceinline__ ConeK cone_scalars(const Ctx& c, int e0) {
+  ConeK k;
+  k.dim = c.rinfo[e0] >> 4; k.mu = c.rfri[e0];
+  const float mu2 = k.mu * k.mu;
+  k.dm = safe_div(c.D[e0], mu2 * (1.0f + mu2));
+  const float n = c.Jaref[e0] * k.mu;
+  float tt = 0.f;
+  for (int j = 1; j < k.dim; j++) { const float u = c.Jaref[e0 + j] * c.rfri[e0 + j]; tt += u * u; }
+  const float t = fmaxf(sqrtf(tt), MJ_MINVAL), ttt = fmaxf(t * t * t, MJ_MINVAL);
+  k.mu_tinv = safe_div(k.mu, t); k.munttt = k.mu * safe_div(n, ttt); k.tdiag = mu2 - n * k.mu_tinv;
+  return k;
+}
+// coefficient of row e0 + j's rank-1 update for Hessian row i, given J0[i], p_i
+__device__ __forceinline__ float cone_coef(const Ctx& c, const ConeK& k, int e0, int j, float J0i, float pi, float Jji) {
+  if (j == 0) return k.dm * k.mu * (k.mu * J0i - k.mu_tinv * pi);
+  const float s = c.rfri[e0 + j], us = c.Jaref[e0 + j] * s * s;
+  return k.dm * ((k.munttt * pi - k.mu_tinv * k.mu * J0i) * us + k.tdiag * s * s * Jji);
+}
+
+template <int N, bool ELL>
 __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g) {
   const int lane = c.lane, nv = c.nv;
   float a[N];
@@ -184,13 +299,35 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
         a[k] += sc * v.x; a[k + 1] += sc * v.y; a[k + 2] += sc * v.z; a[k + 3] += sc * v.w;
       }
     }
-    if (lane < nv) {
+    if (!ELL && lane < nv) {  // elliptic keeps c.H == M: the next iteration rebuilds from it
       const int base = (lane * (lane + 1)) / 2;
 #pragma unroll
       for (int k = 0; k < N; k++)
         if (k <= lane) c.H[base + k] = a[k];
     }
     // columns >= nv of rows < nv only ever hold the unused upper triangle; rows >= nv stay identity (sc == 0)
+  }
+  if (ELL) {
+#pragma unroll 1
+    for (int t = 0; t < c.ncone; t++) {
+      const int e0 = c.hidx[c.njmax - 1 - t];
+      const ConeK k = cone_scalars(c, e0);
+      if (k.dm == 0.f) continue;
+      const float* J0 = c.J + e0 * c.ldJ;
+      const float J0i = lane < nv ? J0[lane] : 0.f;
+      float pi = 0.f;
+      for (int j = 1; j < k.dim; j++) pi += c.Jaref[e0 + j] * c.rfri[e0 + j] * c.rfri[e0 + j] * (lane < nv ? J0[j * c.ldJ + lane] : 0.f);
+#pragma unroll 1
+      for (int j = 0; j < k.dim; j++) {
+        const float* Jr = J0 + j * c.ldJ;
+        const float sc = lane < nv ? cone_coef(c, k, e0, j, J0i, pi, Jr[lane]) : 0.f;
+#pragma unroll
+        for (int q = 0; q < N; q += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Jr + q);
+          a[q] += sc * v.x; a[q + 1] += sc * v.y; a[q + 2] += sc * v.z; a[q + 3] += sc * v.w;
+        }
+      }
+    }
   }
 #ifdef MJB_CHOL_UNROLLED
   return chol_solve_rows<N, true>(a, nv, g, c.Lf, c.ldH, lane);
@@ -200,38 +337,61 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
+template <bool ELL>
 __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   const int nv = c.nv;
   float sd = 0.f, nd = 0.f;
   if (nv <= 32) {
     const float g = c.lane < nv ? c.grad[c.lane] : 0.f;
     float xx;
-    if (nv <= 8) xx = newton_direction_reg<8>(c, nlist, g);
-    else if (nv <= 16) xx = newton_direction_reg<16>(c, nlist, g);
-    else if (nv <= 24) xx = newton_direction_reg<24>(c, nlist, g);
-    else if (nv <= 28) xx = newton_direction_reg<28>(c, nlist, g);
-    else xx = newton_direction_reg<32>(c, nlist, g);
+    if (nv <= 8) xx = newton_direction_reg<8, ELL>(c, nlist, g);
+    else if (nv <= 16) xx = newton_direction_reg<16, ELL>(c, nlist, g);
+    else if (nv <= 24) xx = newton_direction_reg<24, ELL>(c, nlist, g);
+    else if (nv <= 28) xx = newton_direction_reg<28, ELL>(c, nlist, g);
+    else xx = newton_direction_reg<32, ELL>(c, nlist, g);
     sd = xx * xx; nd = g * xx;
     if (c.lane < nv) c.search[c.lane] = -xx;
   } else {
     const int ntri = nv * (nv + 1) / 2;
-    if (nlist > 0) {
+    if (!ELL) {
+      if (nlist > 0) {
+#pragma unroll 1
+        for (int e = c.lane; e < ntri; e += 32) {
+          int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+          while ((i + 1) * (i + 2) / 2 <= e) i++;
+          while (i * (i + 1) / 2 > e) i--;
+          const int j = e - i * (i + 1) / 2;
+          float acc = 0.f;
+          for (int k = 0; k < nlist; k++) { const float* Jr = c.J + c.hidx[k] * c.ldJ; acc += c.hw[k] * Jr[i] * Jr[j]; }
+          c.H[i * c.ldH + j] += acc;
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int e = c.lane; e < nv * c.ldH; e += 32) c.Lf[e] = c.H[e];
+    } else {  // elliptic: Lf = M + sum_quadratic D J J^T + cone terms, c.H stays M
 #pragma unroll 1
       for (int e = c.lane; e < ntri; e += 32) {
         int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
         while ((i + 1) * (i + 2) / 2 <= e) i++;
         while (i * (i + 1) / 2 > e) i--;
         const int j = e - i * (i + 1) / 2;
-        float acc = 0.f;
+        float acc = c.H[i * c.ldH + j];
         for (int k = 0; k < nlist; k++) { const float* Jr = c.J + c.hidx[k] * c.ldJ; acc += c.hw[k] * Jr[i] * Jr[j]; }
-        c.H[i * c.ldH + j] += acc;
+        for (int t = 0; t < c.ncone; t++) {
+          const int e0 = c.hidx[c.njmax - 1 - t];
+          const ConeK k = cone_scalars(c, e0);
+          if (k.dm == 0.f) continue;
+          const float* J0 = c.J + e0 * c.ldJ;
+          float pi = 0.f;
+          for (int q = 1; q < k.dim; q++) pi += c.Jaref[e0 + q] * c.rfri[e0 + q] * c.rfri[e0 + q] * J0[q * c.ldJ + i];
+          for (int q = 0; q < k.dim; q++) acc += cone_coef(c, k, e0, q, J0[i], pi, J0[q * c.ldJ + i]) * J0[q * c.ldJ + j];
+        }
+        c.Lf[i * c.ldH + j] = acc;
       }
-      __syncwarp();
     }
 #pragma unroll 1
     for (int dd = c.lane; dd < nv; dd += 32) c.x[dd] = c.grad[dd];
-#pragma unroll 1
-    for (int e = c.lane; e < nv * c.ldH; e += 32) c.Lf[e] = c.H[e];
     __syncwarp();
     warp_cholesky(c.Lf, nv, c.ldH, c.lane);
     warp_chol_solve(c.Lf, nv, c.ldH, c.x, c.lane);
@@ -243,14 +403,20 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   __syncwarp();
 }
 
+template <bool ELL>
 __device__ __forceinline__ P3 eval_total(const Ctx& c, float alpha, float q0, float q1, float q2) {
   P3 s = mkp(0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int r = c.lane; r < c.nefc; r += 32) s = s + eval_row(r, alpha, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
+  for (int r = c.lane; r < c.nefc; r += 32) {
+    if (ELL && c.rinfo[r] != -1) {
+      if (c.rinfo[r] >= 0 && (c.rinfo[r] & 15) == 0) { const EllQ q = ell_load(c, r); const float mu = c.rfri[r]; s = s + ell_shifted(mu, q, ell_reference(mu, q), alpha); }
+    } else s = s + eval_row(r, alpha, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
+  }
   return eval_gauss(q0, q1, q2, alpha) + warp_sum3(s);
 }
 
 // solver.py:836-1347; returns true when the line search converged
+template <bool ELL>
 __device__ __forceinline__ bool linesearch(Ctx& c) {
   const ModelDev& m = *c.m;
   const int nv = c.nv;
@@ -263,8 +429,32 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   const float snorm = sqrtf(c.search_dot), scale = m.meaninertia * (float)nv;
   const float gtol = fmaxf(m.tolerance * m.ls_tolerance * snorm * scale, 1e-6f);
   P3 p0s = mkp(0.f, 0.f, 0.f);
+  if (ELL) {  // per-contact quads at the primary rows (solver.py:957-1015)
 #pragma unroll 1
-  for (int r = c.lane; r < c.nefc; r += 32) p0s = p0s + eval_row_zero(r, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
+    for (int r = c.lane; r < c.nefc; r += 32) {
+      const int info = c.rinfo[r];
+      if (info < 0 || (info & 15) != 0) continue;
+      const int dim = info >> 4;
+      const float mu = c.rfri[r], ja = c.Jaref[r], jv = c.jv[r], D = c.D[r], jvD = jv * D;
+      float q0 = 0.5f * ja * ja * D, q1 = jvD * ja, q2 = 0.5f * jv * jvD, uu = 0.f, uv = 0.f, vv = 0.f;
+      for (int j = 1; j < dim; j++) {
+        const float jvj = c.jv[r + j], jaj = c.Jaref[r + j], dj = c.D[r + j], DJ = dj * jaj, fj = c.rfri[r + j];
+        q0 += 0.5f * jaj * DJ; q1 += jvj * DJ; q2 += 0.5f * jvj * dj * jvj;
+        const float uj = jaj * fj, vj = jvj * fj;
+        uu += uj * uj; uv += uj * vj; vv += vj * vj;
+      }
+      float* q = c.quad + 3 * r;
+      const float mu2 = mu * mu;
+      q[0] = q0; q[1] = q1; q[2] = q2; q[3] = ja * mu; q[4] = jv * mu; q[5] = uu; q[6] = uv; q[7] = vv; q[8] = D / (mu2 * (1.0f + mu2));
+    }
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int r = c.lane; r < c.nefc; r += 32) {
+    if (ELL && c.rinfo[r] != -1) {
+      if (c.rinfo[r] >= 0 && (c.rinfo[r] & 15) == 0) p0s = p0s + ell_zero(c.rfri[r], ell_load(c, r));
+    } else p0s = p0s + eval_row_zero(r, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
+  }
   p0s = warp_sum3(p0s);
   float g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
@@ -273,7 +463,7 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   const P3 p0 = mkp(q0 + p0s.c, q1 + p0s.g, 2.0f * q2 + p0s.h);
   const P3 p0_delta = mkp(0.f, p0.g, p0.h);
   const float lo_alpha_in = -safe_div(p0.g, p0.h);
-  const P3 lo_in = eval_total(c, lo_alpha_in, q0, q1, q2);
+  const P3 lo_in = eval_total<ELL>(c, lo_alpha_in, q0, q1, q2);
   const bool initial_converged = fabsf(lo_in.g) < gtol && lo_in.c < 0.f;
   bool ls_converged = initial_converged;
   float alpha = 0.f, improvement = 0.f;
@@ -287,6 +477,13 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
       P3 sl = mkp(0.f, 0.f, 0.f), sh = sl, sm = sl;
 #pragma unroll 1
       for (int r = c.lane; r < c.nefc; r += 32) {
+        if (ELL && c.rinfo[r] != -1) {
+          if (c.rinfo[r] >= 0 && (c.rinfo[r] & 15) == 0) {
+            const EllQ q = ell_load(c, r); const float mu = c.rfri[r]; const EllRef e = ell_reference(mu, q);
+            sl = sl + ell_shifted(mu, q, e, lo_next_alpha); sh = sh + ell_shifted(mu, q, e, hi_next_alpha); sm = sm + ell_shifted(mu, q, e, mid_alpha);
+          }
+          continue;
+        }
         const float D = c.D[r], f = c.floss[r], ja = c.Jaref[r], jv = c.jv[r];
         sl = sl + eval_row(r, lo_next_alpha, c.ne, c.nf, D, f, ja, jv);
         sh = sh + eval_row(r, hi_next_alpha, c.ne, c.nf, D, f, ja, jv);
@@ -319,6 +516,7 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   return ls_converged;
 }
 
+template <bool ELL>
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -340,6 +538,8 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   c.floss = m.nfricdof > 0 ? rf + 4 * njmax : c.D;  // never interpreted when the world has no friction rows
   int* ri = (int*)(S + L.rowi);
   c.state = ri; c.hidx = ri + njmax;
+  c.njmax = njmax; c.ncone = 0;
+  c.rfri = rf + L.nrowf * njmax; c.quad = c.rfri + njmax; c.rinfo = ri + 2 * njmax;
 
   if (njmax == 0 || nv == 0) {
 #pragma unroll 1
@@ -363,6 +563,15 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
       c.D[r] = d.efc_D[wb * d.njmax_pad + r];
       if (m.nfricdof > 0) c.floss[r] = d.efc_frictionloss[wb * njmax + r];
       c.state[r] = ST_SATISFIED;
+      if (ELL) {  // row -> (contact, component) map; a contact's rows are consecutive (k_constraint.cu)
+        int info = -1; float fr = 0.f;
+        if (d.efc_type[wb * njmax + r] == CNSTR_CONTACT_ELLIPTIC) {
+          const int cid = d.efc_id[wb * njmax + r], e0 = d.contact_efc_address[(size_t)cid * m.nmaxpyramid], dim = d.contact_dim[cid], j = r - e0;
+          info = (e0 < 0 || e0 + dim > nefc) ? -2 : ((dim << 4) | j);
+          fr = j == 0 ? d.contact_friction[5 * (size_t)cid] * m.impratio_invsqrt : d.contact_friction[5 * (size_t)cid + j - 1];
+        }
+        c.rinfo[r] = info; c.rfri[r] = fr;
+      }
     }
     warp_copy(c.M, d.M + wb * m.nC, m.nC, lane);
     warp_copy(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
@@ -391,15 +600,15 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const float scale = m.meaninertia * (float)nv;
   int niter = 0, ovf = 0;
   for (int it = -1;; it++) {
-    if (it >= 0 && !linesearch(c)) ovf |= OVF_LS_ITERATIONS;
-    const int nlist = update_constraint(c, it < 0);
+    if (it >= 0 && !linesearch<ELL>(c)) ovf |= OVF_LS_ITERATIONS;
+    const int nlist = update_constraint<ELL>(c, it < 0);
     update_grad(c);
     if (it >= 0) {
       niter++;
       const float improvement = c.improvement / scale, gradient = sqrtf(c.grad_dot) / scale;
       if (improvement < m.tolerance || gradient < m.tolerance) break;
     } else if (m.iterations == 0) break;
-    update_search(c, nlist);
+    update_search<ELL>(c, nlist);
     if (it >= 0) {
       if (0.5f * c.newton_decrement / scale < m.tolerance) break;
       if (niter == m.iterations) { ovf |= OVF_ITERATIONS; break; }
@@ -421,13 +630,16 @@ size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_lay
 
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_solver(m, d);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_solver, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured[2] = {0, 0};
+  const bool ell = m.cone == CONE_ELLIPTIC;
+  if (smem > 48 * 1024 && smem > configured[ell]) {
+    cudaError_t e = ell ? cudaFuncSetAttribute(k_solver<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(k_solver<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[ell] = smem;
   }
   const int grid = d.wn;
-  k_solver<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  if (ell) k_solver<true><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  else k_solver<false><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

@@ -1130,6 +1130,8 @@ static void fwd_acceleration(W* w) {
 typedef struct {
   real *Jaref, *jv, *grad, *search, *mv, *H, *Hf, *tmp;
   real search_dot, grad_dot, newton_decrement, improvement;
+  /* elliptic cones: per contact quad (3), quad1 (u0, v0, uu), quad2 (uv, vv, dm) -- solver.py:957-1015 */
+  real* quad;
 } SCtx;
 
 /* solver.py:425-477 (pyramidal / frictionless / limit / friction / equality rows) */
@@ -1144,12 +1146,35 @@ static void eval_constraint(int is_equality, int is_friction, real jaref, real D
   }
   if (jaref >= 0) { *force = 0; *state = ST_SATISFIED; } else { *force = -D * jaref; *state = ST_QUADRATIC; }
 }
-/* _update_constraint (solver.py:1698-1822,1912-1948) */
+/* _update_constraint (solver.py:1698-1822,1912-1948); elliptic rows follow _eval_constraint :425-477 and _eval_elliptic_middle :407-422 */
 static void update_constraint(W* w, SCtx* c, int nefc) {
-  const OrcModel* m = w->m; const int nv = m->nv, ne = w->ne[0], nf = w->nf[0];
+  const OrcModel* m = w->m; const int nv = m->nv, ne = w->ne[0], nf = w->nf[0], np = m->nmaxpyramid;
   for (int e = 0; e < nefc; e++) {
+    if (w->efc_type[e] == CNSTR_CONTACT_ELLIPTIC) continue; /* handled per contact below */
     int is_eq = e < ne, is_fr = !is_eq && e < ne + nf;
     eval_constraint(is_eq, is_fr, c->Jaref[e], w->efc_D[e], is_fr ? w->efc_frictionloss[e] : 0, &w->efc_force[e], &w->efc_state[e]);
+  }
+  if (m->cone == CONE_ELLIPTIC) {
+    for (int k = 0; k < w->ncon[0]; k++) {
+      int dim = w->con_dim[k], e0 = w->con_efc_address[np * k];
+      if (dim == 1 || e0 < 0 || e0 >= nefc) continue;
+      const real* fri = w->con_friction + 5 * k;
+      real mu = fri[0] * m->impratio_invsqrt, N = c->Jaref[e0] * mu, TT = 0;
+      for (int j = 1; j < dim; j++) { int ej = w->con_efc_address[np * k + j]; real uj = c->Jaref[ej] * fri[j - 1]; TT += uj * uj; }
+      real T = TT <= 0 ? 0 : (real)sqrt((double)TT);
+      for (int j = 0; j < dim; j++) {
+        int e = w->con_efc_address[np * k + j];
+        real jaref = c->Jaref[e], D = w->efc_D[e];
+        if ((N >= mu * T) || (T <= 0 && N >= 0)) { w->efc_force[e] = 0; w->efc_state[e] = ST_SATISFIED; }
+        else if ((mu * N + T <= 0) || (T <= 0 && N < 0)) { w->efc_force[e] = -D * jaref; w->efc_state[e] = ST_QUADRATIC; }
+        else {
+          real dm = safe_div(w->efc_D[e0], mu * mu * (1 + mu * mu)), nmt = N - mu * T, fn = -dm * nmt * mu;
+          if (j == 0) w->efc_force[e] = fn;
+          else { real uf = jaref * fri[j - 1] * fri[j - 1]; w->efc_force[e] = -safe_div(fn, T) * uf; }
+          w->efc_state[e] = ST_CONE;
+        }
+      }
+    }
   }
   for (int d = 0; d < nv; d++) { real s = 0; for (int e = 0; e < nefc; e++) s += w->efc_J[e * nv + d] * w->efc_force[e]; w->qfrc_constraint[d] = s; }
 }
@@ -1167,6 +1192,29 @@ static void update_gradient(W* w, SCtx* c, int nefc) {
     if (w->efc_state[e] != ST_QUADRATIC) continue;
     real D = w->efc_D[e]; const real* J = w->efc_J + e * nv;
     for (int i = 0; i < nv; i++) { if (J[i] == 0) continue; real di = D * J[i]; for (int j = 0; j < nv; j++) c->H[i * nv + j] += di * J[j]; }
+  }
+  if (m->cone == CONE_ELLIPTIC) { /* JTCJ, solver.py:2443-2565 */
+    const int np = m->nmaxpyramid;
+    for (int k = 0; k < w->ncon[0]; k++) {
+      int dim = w->con_dim[k], e0 = w->con_efc_address[np * k];
+      if (dim == 1 || e0 < 0 || e0 >= nefc || w->efc_state[e0] != ST_CONE) continue;
+      const real* fri = w->con_friction + 5 * k;
+      real mu = fri[0] * m->impratio_invsqrt, mu2 = mu * mu, dm = safe_div(w->efc_D[e0], mu2 * (1 + mu2));
+      if (dm == 0) continue;
+      real n = c->Jaref[e0] * mu, tt = 0;
+      for (int j = 1; j < dim; j++) { int ej = w->con_efc_address[np * k + j]; real u = c->Jaref[ej] * fri[j - 1]; tt += u * u; }
+      real t = rmax((real)sqrt((double)tt), MJ_MINVAL), ttt = rmax(t * t * t, MJ_MINVAL), mu_tinv = safe_div(mu, t);
+      real mu_n_over_ttt = mu * safe_div(n, ttt), tangent_diag = mu2 - n * mu_tinv;
+      for (int d1 = 0; d1 < nv; d1++) for (int d2 = 0; d2 < nv; d2++) {
+        real z01 = mu * w->efc_J[e0 * nv + d1], z02 = mu * w->efc_J[e0 * nv + d2], p1 = 0, p2 = 0, td = 0;
+        for (int j = 1; j < dim; j++) {
+          int ej = w->con_efc_address[np * k + j]; real sc = fri[j - 1], u = c->Jaref[ej] * sc;
+          real z1 = sc * w->efc_J[ej * nv + d1], z2 = sc * w->efc_J[ej * nv + d2];
+          p1 += u * z1; p2 += u * z2; td += z1 * z2;
+        }
+        c->H[d1 * nv + d2] += dm * (z01 * z02 - mu_tinv * (z01 * p2 + z02 * p1) + mu_n_over_ttt * p1 * p2 + tangent_diag * td);
+      }
+    }
   }
   memcpy(c->Hf, c->H, (size_t)nv * nv * sizeof(real));
   chol_upper(c->Hf, nv);
@@ -1206,12 +1254,98 @@ static void eval_pt_row_zero(int efcid, int ne, int nf, real D, real frictionlos
   }
   { real jvD = jv * D; out[0] = (real)0.5 * D * jaref * jaref; out[1] = jvD * jaref; out[2] = jv * jvD; }
 }
+/* _eval_elliptic_reference (solver.py:286-305): cost, T, r and state of a contact at alpha = 0 */
+static void ell_reference(real mu, const real* q, const real* q1, const real* q2, real* cost0, real* T0, real* r0, int* state0) {
+  real u0 = q1[0], uu = q1[2], dm = q2[2];
+  if (uu <= 0) { *T0 = 0; *r0 = 0; if (u0 < 0) { *cost0 = q[0]; *state0 = ST_QUADRATIC; } else { *cost0 = 0; *state0 = ST_SATISFIED; } return; }
+  *T0 = (real)sqrt((double)uu);
+  if (u0 >= mu * *T0) { *cost0 = 0; *r0 = 0; *state0 = ST_SATISFIED; return; }
+  if (mu * u0 + *T0 <= 0) { *cost0 = q[0]; *r0 = 0; *state0 = ST_QUADRATIC; return; }
+  *r0 = u0 - mu * *T0; *cost0 = (real)0.5 * dm * *r0 * *r0; *state0 = ST_CONE;
+}
+/* quadratic-zone value shifted by the alpha = 0 cost (solver.py:329-350) */
+static void ell_quadratic_shifted(real mu, const real* q, real alpha, real N, real Tsqr, real u0, real T0, real dm, int state0, real out[3]) {
+  real aq2 = alpha * q[2], cost = alpha * (aq2 + q[1]);
+  if (state0 == ST_CONE) { real b = mu * u0 + T0; cost += (real)0.5 * dm * b * b; }
+  else if (state0 == ST_SATISFIED) cost = (real)0.5 * dm * (1 + mu * mu) * (N * N + rmax(Tsqr, 0));
+  out[0] = cost; out[1] = 2 * aq2 + q[1]; out[2] = 2 * q[2];
+}
+/* _eval_elliptic_shifted (solver.py:353-404): (cost(alpha) - cost(0), grad, hess) of one elliptic contact */
+static void ell_shifted(real mu, const real* q, const real* q1, const real* q2, real alpha, real cost0, real T0, real r0, int state0, real out[3]) {
+  real u0 = q1[0], v0 = q1[1], uu = q1[2], uv = q2[0], vv = q2[1], dm = q2[2];
+  real N = u0 + alpha * v0, Tsqr_delta = alpha * (2 * uv + alpha * vv), Tsqr = uu + Tsqr_delta;
+  if (Tsqr <= 0) {
+    if (N < 0) { ell_quadratic_shifted(mu, q, alpha, N, Tsqr, u0, T0, dm, state0, out); return; }
+  } else {
+    real T = (real)sqrt((double)Tsqr);
+    if (N >= mu * T) { /* top zone: satisfied */ }
+    else if (mu * N + T <= 0) { ell_quadratic_shifted(mu, q, alpha, N, Tsqr, u0, T0, dm, state0, out); return; }
+    else {
+      real T1 = (uv + alpha * vv) / T, T2 = (vv - T1 * T1) / T, r = N - mu * T, r1 = v0 - mu * T1, cost;
+      if (state0 == ST_CONE) { real Td = Tsqr_delta / (T + T0), rd = alpha * v0 - mu * Td; cost = (real)0.5 * dm * rd * (2 * r0 + rd); }
+      else if (state0 == ST_QUADRATIC) { real aq2 = alpha * q[2], b = mu * N + T; cost = alpha * (aq2 + q[1]) - (real)0.5 * dm * b * b; }
+      else cost = (real)0.5 * dm * r * r;
+      out[0] = cost; out[1] = dm * r * r1; out[2] = dm * (r1 * r1 + r * (-mu * T2));
+      return;
+    }
+  }
+  out[0] = -cost0; out[1] = 0; out[2] = 0;
+}
+/* absolute value at alpha = 0 (solver.py:308-320) */
+static void ell_alpha_zero(real mu, const real* q, const real* q1, const real* q2, real out[3]) {
+  real cost0, T0, r0; int st;
+  ell_reference(mu, q, q1, q2, &cost0, &T0, &r0, &st);
+  out[0] = out[1] = out[2] = 0;
+  if (st == ST_QUADRATIC) { out[0] = q[0]; out[1] = q[1]; out[2] = 2 * q[2]; }
+  else if (st == ST_CONE) {
+    real T1 = q2[0] / T0, T2 = (q2[1] - T1 * T1) / T0, r1 = q1[1] - mu * T1, dm = q2[2];
+    out[0] = cost0; out[1] = dm * r0 * r1; out[2] = dm * (r1 * r1 - mu * r0 * T2);
+  }
+}
+/* per-contact quad / quad1 / quad2 for the current (Jaref, jv) -- solver.py:957-1015 */
+static void ell_prepare(W* w, SCtx* c, int nefc) {
+  const OrcModel* m = w->m; const int np = m->nmaxpyramid;
+  for (int k = 0; k < w->ncon[0]; k++) {
+    real* Q = c->quad + 9 * k;
+    for (int i = 0; i < 9; i++) Q[i] = 0;
+    int dim = w->con_dim[k], e0 = w->con_efc_address[np * k];
+    if (dim == 1 || e0 < 0 || e0 >= nefc) continue;
+    const real* fri = w->con_friction + 5 * k;
+    real mu = fri[0] * m->impratio_invsqrt, ja = c->Jaref[e0], jv = c->jv[e0], D = w->efc_D[e0], jvD = jv * D;
+    Q[0] = (real)0.5 * ja * ja * D; Q[1] = jvD * ja; Q[2] = (real)0.5 * jv * jvD;
+    real uu = 0, uv = 0, vv = 0;
+    for (int j = 1; j < dim; j++) {
+      int ej = w->con_efc_address[np * k + j];
+      real jvj = c->jv[ej], jaj = c->Jaref[ej], dj = w->efc_D[ej], DJ = dj * jaj;
+      Q[0] += (real)0.5 * jaj * DJ; Q[1] += jvj * DJ; Q[2] += (real)0.5 * jvj * dj * jvj;
+      real uj = jaj * fri[j - 1], vj = jvj * fri[j - 1];
+      uu += uj * uj; uv += uj * vj; vv += vj * vj;
+    }
+    Q[3] = ja * mu; Q[4] = jv * mu; Q[5] = uu;
+    Q[6] = uv; Q[7] = vv; Q[8] = D / (mu * mu * (1 + mu * mu));
+  }
+}
+static void ell_total(W* w, SCtx* c, int nefc, real alpha, int zero, real out[3]) {
+  const OrcModel* m = w->m; const int np = m->nmaxpyramid;
+  for (int k = 0; k < w->ncon[0]; k++) {
+    int dim = w->con_dim[k], e0 = w->con_efc_address[np * k];
+    if (dim == 1 || e0 < 0 || e0 >= nefc) continue;
+    const real* Q = c->quad + 9 * k; real r[3], mu = w->con_friction[5 * k] * m->impratio_invsqrt;
+    if (zero) ell_alpha_zero(mu, Q, Q + 3, Q + 6, r);
+    else { real c0, T0, r0; int st; ell_reference(mu, Q, Q + 3, Q + 6, &c0, &T0, &r0, &st); ell_shifted(mu, Q, Q + 3, Q + 6, alpha, c0, T0, r0, st, r); }
+    out[0] += r[0]; out[1] += r[1]; out[2] += r[2];
+  }
+}
 static void eval_total(W* w, SCtx* c, int nefc, real alpha, const real quad_gauss[3], real out[3]) {
   /* _eval_pt(quad_gauss, alpha) + sum of rows (solver.py:203-211,1113-1169) */
   const int ne = w->ne[0], nf = w->nf[0];
   real aq2 = alpha * quad_gauss[2];
   out[0] = alpha * aq2 + alpha * quad_gauss[1] + quad_gauss[0]; out[1] = 2 * aq2 + quad_gauss[1]; out[2] = 2 * quad_gauss[2];
-  for (int e = 0; e < nefc; e++) { real r[3]; eval_pt_row(e, alpha, ne, nf, w->efc_D[e], w->efc_frictionloss[e], c->Jaref[e], c->jv[e], r); out[0] += r[0]; out[1] += r[1]; out[2] += r[2]; }
+  for (int e = 0; e < nefc; e++) {
+    if (w->efc_type[e] == CNSTR_CONTACT_ELLIPTIC) continue;
+    real r[3]; eval_pt_row(e, alpha, ne, nf, w->efc_D[e], w->efc_frictionloss[e], c->Jaref[e], c->jv[e], r); out[0] += r[0]; out[1] += r[1]; out[2] += r[2];
+  }
+  if (w->m->cone == CONE_ELLIPTIC) ell_total(w, c, nefc, alpha, 0, out);
 }
 static int in_bracket(const real* x, const real* y) { return (x[1] < y[1] && y[1] < 0) || (x[1] > y[1] && y[1] > 0); }
 #define CP3(d, s) do { (d)[0] = (s)[0]; (d)[1] = (s)[1]; (d)[2] = (s)[2]; } while (0)
@@ -1223,7 +1357,12 @@ static void linesearch(W* w, SCtx* c, int nefc) {
   real snorm = (real)sqrt((double)c->search_dot), scale = m->meaninertia * (real)nv;
   real gtol = rmax(m->tolerance * m->ls_tolerance * snorm * scale, (real)1e-6);
   real p0s[3] = {0, 0, 0};
-  for (int e = 0; e < nefc; e++) { real r[3]; eval_pt_row_zero(e, ne, nf, w->efc_D[e], w->efc_frictionloss[e], c->Jaref[e], c->jv[e], r); p0s[0] += r[0]; p0s[1] += r[1]; p0s[2] += r[2]; }
+  if (m->cone == CONE_ELLIPTIC) ell_prepare(w, c, nefc);
+  for (int e = 0; e < nefc; e++) {
+    if (w->efc_type[e] == CNSTR_CONTACT_ELLIPTIC) continue;
+    real r[3]; eval_pt_row_zero(e, ne, nf, w->efc_D[e], w->efc_frictionloss[e], c->Jaref[e], c->jv[e], r); p0s[0] += r[0]; p0s[1] += r[1]; p0s[2] += r[2];
+  }
+  if (m->cone == CONE_ELLIPTIC) ell_total(w, c, nefc, 0, 1, p0s);
   real qg[3] = {0, 0, 0};
   for (int d = 0; d < nv; d++) { qg[1] += c->search[d] * (w->efc_Ma[d] - w->qfrc_smooth[d]); qg[2] += (real)0.5 * c->search[d] * c->mv[d]; }
   real p0[3] = {qg[0] + p0s[0], qg[1] + p0s[1], 2 * qg[2] + p0s[2]};
@@ -1271,7 +1410,8 @@ static void solve(W* w) {
   int nefc = w->nefc[0] < w->njmax ? w->nefc[0] : w->njmax;
   SCtx c;
   size_t nr = (size_t)(nefc > 0 ? nefc : 1);
-  real* buf = (real*)calloc(2 * nr + 4 * (size_t)nv + 2 * (size_t)nv * nv, sizeof(real));
+  real* buf = (real*)calloc(2 * nr + 4 * (size_t)nv + 2 * (size_t)nv * nv + 9 * (size_t)(w->nconmax + 1), sizeof(real));
+  c.quad = buf + 2 * nr + 4 * (size_t)nv + 2 * (size_t)nv * nv;
   c.Jaref = buf; c.jv = c.Jaref + nr; c.grad = c.jv + nr; c.search = c.grad + nv; c.mv = c.search + nv; c.tmp = c.mv + nv; c.H = c.tmp + nv; c.Hf = c.H + (size_t)nv * nv;
   const real* start = (m->disableflags & DSBL_WARMSTART) ? w->qacc_smooth : w->qacc_warmstart;
   memcpy(w->qacc, start, nv * sizeof(real));

@@ -183,12 +183,52 @@ def test_g1_replay_matches_oracle(built):
 # --------------------------------------------------------------------------------------------- mixed-feature scene
 
 
-@pytest.fixture(scope="module")
-def mixed(built):
+@pytest.fixture(scope="module", params=["pyramidal", "elliptic"])
+def mixed(built, request):
   import mujoco_warp_b200 as mjw
 
-  mjm = mjw.mjcf.load_string(util.MIXED_XML)
+  xml = util.MIXED_XML
+  if request.param == "elliptic":  # elliptic cones + impratio != 1 + a friction-specific solref on every contact
+    xml = xml.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"')
+    assert "elliptic" in xml
+  mjm = mjw.mjcf.load_string(xml)
   return mjw, mjm, mjw.put_model(mjm)
+
+
+@pytest.fixture(scope="module")
+def scene_elliptic(built):
+  import mujoco_warp_b200 as mjw
+  from mujoco_warp_b200._src import constants as C
+
+  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  mjm.opt.cone = C.CONE_ELLIPTIC
+  return mjw, mjm, mjw.put_model(mjm)
+
+
+def test_elliptic_humanoid_forward_and_rollout(scene_elliptic):
+  """Elliptic friction cones on the benchmark scene (nv <= 32 register path): row layout (condim rows per contact, type
+  CONTACT_ELLIPTIC), cone-zone forces/states and the Newton solution match the oracle; then a 20-step rollout."""
+  mjw, mjm, m = scene_elliptic
+  d, o = _setup(scene_elliptic, seed=11)
+  mjw.forward(m, d)
+  o.forward()
+  _compare_forward(scene_elliptic, d, o)
+  od = o.d
+  assert (od["efc_type"] == 7).any() and (od["efc_state"] == 4).any(), "scene must exercise the CONE zone"
+  st = d.efc.state.cpu().numpy()
+  agree = total = 0
+  for w in range(d.nworld):
+    ne = int(od["nefc"][w])
+    agree += int((st[w, :ne] == od["efc_state"][w, :ne]).sum()); total += ne
+  assert agree >= 0.98 * total, (agree, total)  # zone boundaries can flip on fp32 rounding
+  for i in range(20):
+    mjw.step(m, d)
+    o.step()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d.nefc.cpu().numpy(), od["nefc"], err_msg=f"nefc at step {i}")
+    util.assert_close(f"qpos@{i}", d.qpos.cpu().numpy(), od["qpos"], atol=1e-3, rtol=1e-3)
+    util.assert_close(f"qvel@{i}", d.qvel.cpu().numpy(), od["qvel"], atol=2e-2, rtol=1e-2)
+  assert (d.overflow.cpu().numpy() == 0).all()
 
 
 def test_mixed_scene_forward_and_rollout(mixed):

@@ -153,3 +153,85 @@ def test_fp32_oracle_tracks_fp64(scene):
     o.forward()
   np.testing.assert_array_equal(o32.d["nefc"], o64.d["nefc"])
   np.testing.assert_allclose(o32.d["qacc"], o64.d["qacc"], atol=5e-3 * np.abs(o64.d["qacc"]).max())
+
+
+def _elliptic_cost(mjm, od, w, qacc):
+  """Convex objective of the elliptic-cone problem written from its definition (Gauss term + per-contact cone penalty:
+  0 in the top zone, full quadratic in the bottom zone, 0.5 dm (N - mu T)^2 in between)."""
+  ne = od["nefc"][w]
+  M = dense_M(mjm, od["M"][w])
+  J, D, aref = od["efc_J"][w, :ne], od["efc_D"][w, :ne], od["efc_aref"][w, :ne]
+  typ, eid = od["efc_type"][w, :ne], od["efc_id"][w, :ne]
+  jar = J @ qacc - aref
+  dq = qacc - od["qacc_smooth"][w]
+  cost = 0.5 * dq @ M @ dq
+  done = set()
+  for r in range(ne):
+    if typ[r] != 7:  # limit / frictionless contact rows
+      cost += 0.5 * D[r] * jar[r] ** 2 if jar[r] < 0 else 0.0
+      continue
+    c = eid[r]
+    if c in done:
+      continue
+    done.add(c)
+    dim, fri = od["con_dim"][w, c], od["con_friction"][w, c]
+    mu = fri[0] / np.sqrt(mjm.opt.impratio)
+    rows = np.arange(r, r + dim)
+    N = jar[r] * mu
+    T = np.sqrt(((jar[rows[1:]] * fri[: dim - 1]) ** 2).sum())
+    if N >= mu * T:
+      continue
+    if mu * N + T <= 0:
+      cost += 0.5 * (D[rows] * jar[rows] ** 2).sum()
+    else:
+      cost += 0.5 * D[r] / (mu * mu * (1 + mu * mu)) * (N - mu * T) ** 2
+  return cost
+
+
+def test_solver_elliptic_minimises_cone_cost(scene):
+  """Elliptic cones: the oracle's Newton solution is the minimiser of the independently written convex objective (finite-
+  difference gradient ~ 0, random perturbations never decrease it), forces obey the friction cone, and the CONE zone is hit."""
+  import copy
+
+  from mujoco_warp_b200._src import constants as C
+
+  mjm = copy.deepcopy(scene)
+  mjm.opt.cone = C.CONE_ELLIPTIC
+  mjm.opt.tolerance = 1e-10
+  nw = 8
+  o = util.make_oracle(mjm, nw, 24, 64)
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, nw, seed=5)
+  o.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, qacc_warmstart=warm)
+  o.forward()
+  od = o.d
+  assert (od["overflow"] == 0).all()
+  assert (od["efc_state"] == 4).any() and (od["efc_type"] == 7).any()
+  rng = np.random.default_rng(0)
+  for w in range(nw):
+    ne = od["nefc"][w]
+    if ne == 0:
+      continue
+    M = dense_M(mjm, od["M"][w])
+    J, f = od["efc_J"][w, :ne], od["efc_force"][w, :ne]
+    grad = M @ od["qacc"][w] - od["qfrc_smooth"][w] - J.T @ f
+    scale = mjm.stat.meaninertia * mjm.nv
+    assert np.linalg.norm(grad) / scale < 1e-6
+    q = od["qacc"][w].copy()
+    c0 = _elliptic_cost(mjm, od, w, q)
+    # the analytic force is minus the cost gradient wrt Jaref: check by central differences along random directions
+    for _ in range(6):
+      dq = rng.standard_normal(mjm.nv)
+      h = 1e-4
+      num = (_elliptic_cost(mjm, od, w, q + h * dq) - _elliptic_cost(mjm, od, w, q - h * dq)) / (2 * h)
+      assert abs(num) < 1e-4 * max(1.0, abs(c0)), (w, num, c0)
+      assert _elliptic_cost(mjm, od, w, q + 1e-2 * dq) >= c0 - 1e-9 * max(1.0, abs(c0))
+    # friction cone on the contact forces (impratio = 1): f_n >= 0 and sum (f_j / mu_j)^2 <= f_n^2
+    typ, eid = od["efc_type"][w, :ne], od["efc_id"][w, :ne]
+    for r in range(ne):
+      if typ[r] == 7 and (r == 0 or eid[r - 1] != eid[r] or typ[r - 1] != 7):
+        c = eid[r]
+        dim, fri = od["con_dim"][w, c], od["con_friction"][w, c]
+        ft = f[r + 1 : r + dim] / fri[: dim - 1]
+        assert f[r] >= -1e-9
+        if od["efc_state"][w, r] == 4:
+          np.testing.assert_allclose(np.sqrt((ft**2).sum()), f[r], rtol=1e-6, atol=1e-9)
