@@ -32,7 +32,7 @@ enum { BIAS_NONE = 0, BIAS_AFFINE = 1 };
 enum {
   DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3, DSBL_CONTACT = 1 << 4,
   DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7, DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9,
-  DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15
+  DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15, DSBL_NATIVECCD = 1 << 17
 };
 enum { OVF_NEFC = 1 << 0, OVF_NARROWPHASE = 1 << 3, OVF_ITERATIONS = 1 << 9, OVF_LS_ITERATIONS = 1 << 10, OVF_UNSUPPORTED = 1 << 30 };
 enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
@@ -763,6 +763,476 @@ static real sphere_sphere(const real* pos1, real r1, const real* pos2, real r2, 
   for (int i = 0; i < 3; i++) pos[i] = pos1[i] + n[i] * (r1 + (real)0.5 * dist);
   return dist;
 }
+/* ------------------------------------------------------------------ box / cylinder / ellipsoid primitives
+ * (collision_primitive_core.py:305-1433).  Outputs use MAXVAL for unpopulated contact slots like the reference. */
+#define ORC_MAXVAL ((real)1e10)
+static inline void matT_vec3(const real* m, const real* v, real* o) {
+  for (int j = 0; j < 3; j++) o[j] = m[j] * v[0] + m[3 + j] * v[1] + m[6 + j] * v[2];
+}
+static inline void mat_mul3(const real* a, const real* b, real* c) {
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+static inline void mat_T3(const real* a, real* t) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * j + i]; }
+static inline real rabs(real x) { return x < 0 ? -x : x; }
+/* collision_primitive_core.py:305 */
+static real plane_ellipsoid(const real* n, const real* ppos, const real* epos, const real* erot, const real* esize, real* pos) {
+  real loc[3], sup[3], off[3];
+  matT_vec3(erot, n, loc);
+  for (int i = 0; i < 3; i++) loc[i] *= esize[i];
+  normalize3(loc);
+  for (int i = 0; i < 3; i++) sup[i] = -loc[i] * esize[i];
+  matvec3(erot, sup, off);
+  for (int i = 0; i < 3; i++) pos[i] = epos[i] + off[i];
+  real d[3] = {pos[0] - ppos[0], pos[1] - ppos[1], pos[2] - ppos[2]};
+  real dist = dot3(n, d);
+  for (int i = 0; i < 3; i++) pos[i] -= n[i] * dist * (real)0.5;
+  return dist;
+}
+/* collision_primitive_core.py:336: all 8 corners, the caller keeps those within margin */
+static void plane_box(const real* n, const real* ppos, const real* bpos, const real* brot, const real* bsize, real dist[8], real pos[8][3]) {
+  real d[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
+  real center_dist = dot3(d, n);
+  for (int i = 0; i < 8; i++) {
+    real cl[3] = {(i & 1) ? bsize[0] : -bsize[0], (i & 2) ? bsize[1] : -bsize[1], (i & 4) ? bsize[2] : -bsize[2]}, c[3];
+    matvec3(brot, cl, c);
+    real cdist = center_dist + dot3(n, c);
+    dist[i] = cdist;
+    for (int k = 0; k < 3; k++) pos[i][k] = c[k] + bpos[k] - (real)0.5 * n[k] * cdist;
+  }
+}
+/* collision_primitive_core.py:387 */
+static real sphere_cylinder(const real* spos, real sr, const real* cpos, const real* caxis, real cr, real chh, real* pos, real* nrm) {
+  real vec[3] = {spos[0] - cpos[0], spos[1] - cpos[1], spos[2] - cpos[2]};
+  real x = dot3(vec, caxis), a_proj[3], p_proj[3];
+  for (int i = 0; i < 3; i++) { a_proj[i] = caxis[i] * x; p_proj[i] = vec[i] - a_proj[i]; }
+  real p_proj_sqr = dot3(p_proj, p_proj);
+  int collide_side = rabs(x) < chh, collide_cap = p_proj_sqr < cr * cr;
+  if (collide_side && collide_cap) {
+    real dist_cap = chh - rabs(x), dist_radius = cr - (real)sqrt((double)p_proj_sqr);
+    if (dist_cap < dist_radius) collide_side = 0; else collide_cap = 0;
+  }
+  if (collide_side) {
+    real tgt[3] = {cpos[0] + a_proj[0], cpos[1] + a_proj[1], cpos[2] + a_proj[2]};
+    return sphere_sphere(spos, sr, tgt, cr, pos, nrm);
+  } else if (collide_cap) {
+    real sgn = x > 0 ? (real)1 : (real)-1, pcap[3], pn[3];
+    for (int i = 0; i < 3; i++) { pcap[i] = cpos[i] + sgn * caxis[i] * chh; pn[i] = sgn * caxis[i]; }
+    real dist = plane_sphere(pn, pcap, spos, sr, pos);
+    for (int i = 0; i < 3; i++) nrm[i] = -pn[i];
+    return dist;
+  }
+  real inv_len = safe_div(1, (real)sqrt((double)p_proj_sqr)), sgn = x > 0 ? (real)1 : (x < 0 ? (real)-1 : (real)0), corner[3];
+  for (int i = 0; i < 3; i++) corner[i] = cpos[i] + caxis[i] * (sgn * chh) + p_proj[i] * (cr * inv_len);
+  return sphere_sphere(spos, sr, corner, 0, pos, nrm);
+}
+/* collision_primitive_core.py:459: two rim points + a triangle on the near cap */
+static void plane_cylinder(const real* n, const real* ppos, const real* center, const real* caxis, real cr, real chh, real dist[4], real pos[4][3]) {
+  real axis[3] = {caxis[0], caxis[1], caxis[2]};
+  real prjaxis = dot3(n, axis);
+  if (prjaxis > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; prjaxis = -prjaxis; }
+  real d0v[3] = {center[0] - ppos[0], center[1] - ppos[1], center[2] - ppos[2]};
+  real dist0 = dot3(d0v, n), vec[3];
+  for (int i = 0; i < 3; i++) vec[i] = axis[i] * prjaxis - n[i];
+  real len_sqr = dot3(vec, vec);
+  if (len_sqr >= (real)1e-12) { real sc = safe_div(cr, (real)sqrt((double)len_sqr)); for (int i = 0; i < 3; i++) vec[i] *= sc; }
+  else { vec[0] = cr; vec[1] = 0; vec[2] = 0; }
+  real prjvec = dot3(vec, n);
+  for (int i = 0; i < 3; i++) axis[i] *= chh;
+  prjaxis *= chh;
+  real dist1 = dist0 + prjaxis + prjvec, dist2 = dist0 - prjaxis + prjvec;
+  for (int i = 0; i < 3; i++) { pos[0][i] = center[i] + vec[i] + axis[i] - n[i] * (dist1 * (real)0.5); pos[1][i] = center[i] + vec[i] - axis[i] - n[i] * (dist2 * (real)0.5); }
+  dist[0] = dist1; dist[1] = dist2;
+  real prjvec1 = -prjvec * (real)0.5, dist3 = dist0 + prjaxis + prjvec1, vec1[3];
+  cross3(vec, axis, vec1);
+  normalize3(vec1);
+  real sc = cr * (real)sqrt(3.0) * (real)0.5;
+  for (int i = 0; i < 3; i++) vec1[i] *= sc;
+  for (int i = 0; i < 3; i++) {
+    pos[2][i] = center[i] + vec1[i] + axis[i] - vec[i] * (real)0.5 - n[i] * (dist3 * (real)0.5);
+    pos[3][i] = center[i] - vec1[i] + axis[i] - vec[i] * (real)0.5 - n[i] * (dist3 * (real)0.5);
+  }
+  dist[2] = dist3; dist[3] = dist3;
+}
+/* collision_primitive_core.py:1043 */
+static real sphere_box(const real* spos, real sr, const real* bpos, const real* brot, const real* bsize, real* cpos, real* nrm) {
+  real rel[3] = {spos[0] - bpos[0], spos[1] - bpos[1], spos[2] - bpos[2]}, center[3], clamped[3], dir[3], pos[3], cdist;
+  matT_vec3(brot, rel, center);
+  for (int i = 0; i < 3; i++) { clamped[i] = rmax(-bsize[i], rmin(bsize[i], center[i])); dir[i] = clamped[i] - center[i]; }
+  real dist = len3(dir);
+  if (dist <= MJ_MINVAL) { /* centre inside the box: push out through the nearest face */
+    real closest = 2 * (bsize[0] + bsize[1] + bsize[2]); int k = 0;
+    for (int i = 0; i < 6; i++) {
+      real face_dist = rabs(((i % 2) ? (real)1 : (real)-1) * bsize[i / 2] - center[i / 2]);
+      if (closest > face_dist) { closest = face_dist; k = i; }
+    }
+    real nearest[3] = {0, 0, 0};
+    nearest[k / 2] = (k % 2) ? (real)-1 : (real)1;
+    for (int i = 0; i < 3; i++) pos[i] = center[i] + nearest[i] * (sr - closest) / 2;
+    matvec3(brot, nearest, nrm);
+    cdist = -closest - sr;
+  } else {
+    for (int i = 0; i < 3; i++) dir[i] /= dist;
+    for (int i = 0; i < 3; i++) pos[i] = (real)0.5 * (clamped[i] + center[i] + dir[i] * sr);
+    matvec3(brot, dir, nrm);
+    cdist = dist - sr;
+  }
+  real g[3]; matvec3(brot, pos, g);
+  for (int i = 0; i < 3; i++) cpos[i] = bpos[i] + g[i];
+  return cdist;
+}
+/* collision_primitive_core.py:1098 (after MuJoCo's mjc_CapsuleBox): closest feature search, then an optional second
+ * contact further along the capsule; both contacts are sphere-box tests at the chosen segment points */
+static void capsule_box(const real* cpos_in, const real* caxis, real crad, real chl, const real* bpos, const real* brot, const real* bsize,
+                        real dist[2], real cpos[2][3], real cnrm[2][3]) {
+  real rel[3] = {cpos_in[0] - bpos[0], cpos_in[1] - bpos[1], cpos_in[2] - bpos[2]}, pos[3], axis[3], halfaxis[3];
+  matT_vec3(brot, rel, pos);
+  matT_vec3(brot, caxis, axis);
+  for (int i = 0; i < 3; i++) halfaxis[i] = axis[i] * chl;
+  int axisdir = (halfaxis[0] > 0) + 2 * (halfaxis[1] > 0) + 4 * (halfaxis[2] > 0);
+  real bestdist = (real)1e32, bestsegmentpos = -12;
+  int cltype = -4, clface = -12;
+  for (int i = -1; i <= 1; i += 2) { /* a capsule tip closest to a face */
+    real tip[3], bp[3]; int n_out = 0, ax_out = -1;
+    for (int j = 0; j < 3; j++) { tip[j] = pos[j] + (real)i * halfaxis[j]; bp[j] = tip[j]; }
+    for (int j = 0; j < 3; j++) {
+      if (bp[j] < -bsize[j]) { n_out++; ax_out = j; bp[j] = -bsize[j]; }
+      else if (bp[j] > bsize[j]) { n_out++; ax_out = j; bp[j] = bsize[j]; }
+    }
+    if (n_out > 1) continue;
+    real dd[3] = {bp[0] - tip[0], bp[1] - tip[1], bp[2] - tip[2]}, ds = dot3(dd, dd);
+    if (ds < bestdist) { bestdist = ds; bestsegmentpos = (real)i; cltype = -2 + i; clface = ax_out; }
+  }
+  int clcorner = -123, cledge = -123; real bestboxpos = 0;
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 3; j++) { /* box edges (corner i, direction j) */
+    if (i & (1 << j)) continue;
+    real box_pt[3] = {((i & 1) ? 1 : -1) * bsize[0], ((i & 2) ? 1 : -1) * bsize[1], ((i & 4) ? 1 : -1) * bsize[2]}, dif[3];
+    box_pt[j] = 0;
+    for (int k = 0; k < 3; k++) dif[k] = box_pt[k] - pos[k];
+    real u = -bsize[j] * dif[j], v = dot3(halfaxis, dif), ma = bsize[j] * bsize[j], mb = -bsize[j] * halfaxis[j], mc = chl * chl;
+    real det = ma * mc - mb * mb;
+    if (rabs(det) < MJ_MINVAL) continue;
+    real idet = 1 / det, x1 = (mc * u - mb * v) * idet, x2 = (ma * v - mb * u) * idet;
+    int s1 = 1, s2 = 1;
+    if (x1 > 1) { x1 = 1; s1 = 2; x2 = safe_div(v - mb, mc); }
+    else if (x1 < -1) { x1 = -1; s1 = 0; x2 = safe_div(v + mb, mc); }
+    int x2_over = x2 > 1;
+    if (x2_over || x2 < -1) {
+      if (x2_over) { x2 = 1; s2 = 2; x1 = safe_div(u - mb, ma); } else { x2 = -1; s2 = 0; x1 = safe_div(u + mb, ma); }
+      if (x1 > 1) { x1 = 1; s1 = 2; } else if (x1 < -1) { x1 = -1; s1 = 0; }
+    }
+    for (int k = 0; k < 3; k++) dif[k] -= halfaxis[k] * x2;
+    dif[j] += bsize[j] * x1;
+    int ct = s1 * 3 + s2;
+    real dsq = dot3(dif, dif);
+    if (dsq < bestdist - MJ_MINVAL) {
+      bestdist = dsq; bestsegmentpos = x2; bestboxpos = x1;
+      int c2 = ct / 6;
+      clcorner = i + (1 << j) * c2; cledge = j; cltype = ct;
+    }
+  }
+  dist[0] = dist[1] = ORC_MAXVAL;
+  memset(cpos, 0, 6 * sizeof(real)); memset(cnrm, 0, 6 * sizeof(real));
+  if (cltype == -4) return;
+  real secondpos = -4;
+  if (cltype >= 0 && cltype / 3 != 1) { /* a box corner is closest */
+    int c1 = axisdir ^ clcorner;
+    if (c1 != 0 && c1 != 7) {
+      int mul, ax = 0, ax1 = 1, ax2 = 2;
+      if (c1 == 1 || c1 == 2 || c1 == 4) mul = 1; else { mul = -1; c1 = 7 - c1; }
+      if (c1 == 1) { ax = 0; ax1 = 1; ax2 = 2; } else if (c1 == 2) { ax = 1; ax1 = 2; ax2 = 0; } else if (c1 == 4) { ax = 2; ax1 = 0; ax2 = 1; }
+      if (axis[ax] * axis[ax] > (real)0.5) {
+        real mm = 2 * safe_div(bsize[ax], rabs(halfaxis[ax]));
+        secondpos = rmin(1 - (real)mul * bestsegmentpos, mm);
+      } else {
+        real mm = 2 * rmin(safe_div(bsize[ax1], rabs(halfaxis[ax1])), safe_div(bsize[ax2], rabs(halfaxis[ax2])));
+        secondpos = -rmin(1 + (real)mul * bestsegmentpos, mm);
+      }
+      secondpos *= (real)mul;
+    }
+  } else if (cltype >= 0 && cltype / 3 == 1) { /* the interior of a box edge is closest */
+    int c1 = axisdir ^ clcorner;
+    c1 &= 7 - (1 << cledge);
+    if (c1 == 1 || c1 == 2 || c1 == 4) {
+      int ax = cledge, ax1 = (cledge + 1) % 3, ax2 = (cledge + 2) % 3, mul;
+      if (rabs(axis[ax1]) > rabs(axis[ax2])) ax1 = ax2;
+      ax2 = 3 - ax - ax1;
+      if (c1 & (1 << ax2)) { mul = 1; secondpos = 1 - bestsegmentpos; } else { mul = -1; secondpos = 1 + bestsegmentpos; }
+      real e1 = 2 * safe_div(bsize[ax2], rabs(halfaxis[ax2])), e2;
+      secondpos = rmin(e1, secondpos);
+      if (((axisdir & (1 << ax)) != 0) == ((c1 & (1 << ax2)) != 0)) e2 = 1 - bestboxpos; else e2 = 1 + bestboxpos;
+      e1 = bsize[ax] * safe_div(e2, rabs(halfaxis[ax]));
+      secondpos = rmin(e1, secondpos);
+      secondpos *= (real)mul;
+    }
+  } else if (cltype < 0) { /* a capsule tip over a face: the second point is the far end clamped to the face */
+    if (clface != -1) {
+      int mul = cltype == -3 ? 1 : -1;
+      secondpos = 2;
+      real tmp1[3];
+      for (int i = 0; i < 3; i++) tmp1[i] = pos[i] - halfaxis[i] * (real)mul;
+      for (int i = 0; i < 3; i++) {
+        if (i == clface) continue;
+        real ha_r = safe_div((real)mul, halfaxis[i]);
+        real e1 = (bsize[i] - tmp1[i]) * ha_r;
+        if (0 < e1 && e1 < secondpos) secondpos = e1;
+        e1 = (-bsize[i] - tmp1[i]) * ha_r;
+        if (0 < e1 && e1 < secondpos) secondpos = e1;
+      }
+      secondpos *= (real)mul;
+    }
+  }
+  real sl[3], sg[3];
+  for (int i = 0; i < 3; i++) sl[i] = pos[i] + halfaxis[i] * bestsegmentpos;
+  matvec3(brot, sl, sg);
+  for (int i = 0; i < 3; i++) sg[i] += bpos[i];
+  dist[0] = sphere_box(sg, crad, bpos, brot, bsize, cpos[0], cnrm[0]);
+  if (secondpos > -3) {
+    for (int i = 0; i < 3; i++) sl[i] = pos[i] + halfaxis[i] * (secondpos + bestsegmentpos);
+    matvec3(brot, sl, sg);
+    for (int i = 0; i < 3; i++) sg[i] += bpos[i];
+    dist[1] = sphere_box(sg, crad, bpos, brot, bsize, cpos[1], cnrm[1]);
+  }
+}
+/* collision_primitive_core.py:556 */
+static void rotmore_of(int face, real* r) {
+  for (int i = 0; i < 9; i++) r[i] = 0;
+  switch (face) {
+    case 0: r[2] = -1; r[4] = 1; r[6] = 1; break;
+    case 1: r[0] = 1; r[5] = -1; r[7] = 1; break;
+    case 2: r[0] = 1; r[4] = 1; r[8] = 1; break;
+    case 3: r[2] = 1; r[4] = 1; r[6] = -1; break;
+    case 4: r[0] = 1; r[5] = 1; r[7] = -1; break;
+    case 5: r[0] = -1; r[4] = 1; r[8] = -1; break;
+  }
+}
+/* collision_primitive_core.py:588 (after MuJoCo's mjc_BoxBox): separating-axis search over 6 face normals and 9 edge
+ * cross products, then clipping of the incident face / edge against the reference face.  Returns the contact count. */
+static int box_box(const real* pos1, const real* rot1, const real* size1, const real* pos2, const real* rot2, const real* size2, real margin,
+                   real cdist[8], real cpos[8][3], real cnormal[3]) {
+  real d21[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]}, d12[3] = {-d21[0], -d21[1], -d21[2]};
+  real pos21[3], pos12[3], rot1T[9], rot21[9], rot12[9], rot21abs[9], rot12abs[9], plen1[3], plen2[3];
+  matT_vec3(rot1, d21, pos21);
+  matT_vec3(rot2, d12, pos12);
+  mat_T3(rot1, rot1T);
+  mat_mul3(rot1T, rot2, rot21);
+  mat_T3(rot21, rot12);
+  for (int i = 0; i < 9; i++) rot21abs[i] = rabs(rot21[i]);
+  mat_T3(rot21abs, rot12abs);
+  matvec3(rot21abs, size2, plen2);
+  matvec3(rot12abs, size1, plen1);
+  real separation = margin + 3 * (size1[0] + size2[0]) + 3 * (size1[1] + size2[1]) + 3 * (size1[2] + size2[2]);
+  int axis_code = -1;
+  for (int i = 0; i < 3; i++) {
+    real c1 = -rabs(pos21[i]) + size1[i] + plen2[i], c2 = -rabs(pos12[i]) + size2[i] + plen1[i];
+    if (c1 < -margin || c2 < -margin) return 0;
+    if (c1 < separation) { separation = c1; axis_code = i + 3 * (pos21[i] < 0); }
+    if (c2 < separation) { separation = c2; axis_code = i + 3 * (pos12[i] < 0) + 6; }
+  }
+  real clnorm[3] = {0, 0, 0}; int inv = 0, cle1 = 0, cle2 = 0;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    const real* a = rot12 + 3 * j; real ca[3];
+    if (i == 0) { ca[0] = 0; ca[1] = -a[2]; ca[2] = a[1]; } else if (i == 1) { ca[0] = a[2]; ca[1] = 0; ca[2] = -a[0]; } else { ca[0] = -a[1]; ca[1] = a[0]; ca[2] = 0; }
+    real cl = len3(ca);
+    if (cl < MJ_MINVAL) continue;
+    for (int k = 0; k < 3; k++) ca[k] /= cl;
+    real box_dist = dot3(pos21, ca), c3 = 0;
+    for (int k = 0; k < 3; k++) {
+      if (k != i) c3 += size1[k] * rabs(ca[k]);
+      if (k != j) c3 += size2[k] * rot21abs[3 * i + (3 - k - j)] / cl;
+    }
+    c3 -= rabs(box_dist);
+    if (c3 < -margin) return 0;
+    if (c3 < separation * ((real)1 - (real)1e-12)) {
+      separation = c3; cle1 = 0; cle2 = 0;
+      for (int k = 0; k < 3; k++) {
+        if (k != i && ((ca[k] > 0) ^ (box_dist < 0))) cle1 += 1 << k;
+        if (k != j && ((rot21[3 * i + (3 - k - j)] > 0) ^ (box_dist < 0) ^ ((k - j + 3) % 3 == 1))) cle2 += 1 << k;
+      }
+      axis_code = 12 + i * 3 + j;
+      memcpy(clnorm, ca, sizeof ca);
+      inv = box_dist < 0;
+    }
+  }
+  if (axis_code == -1) return 0;
+  real points[8][3], depth[8], rotmore[9], rw[9], pw[3], normal[3], hz, rmT[9];
+  int n = 0;
+  memset(points, 0, sizeof points); memset(depth, 0, sizeof depth);
+  if (axis_code < 12) { /* face of one box against the vertices / edges of the other */
+    int face_idx = axis_code % 6, box_idx = axis_code / 6;
+    rotmore_of(face_idx, rotmore);
+    real r[9], p[3], ss[3], rt[9], tmp[3];
+    const real* s = box_idx ? size1 : size2;
+    mat_mul3(rotmore, box_idx ? rot12 : rot21, r);
+    matvec3(rotmore, box_idx ? pos12 : pos21, p);
+    matvec3(rotmore, box_idx ? size2 : size1, tmp);
+    for (int i = 0; i < 3; i++) ss[i] = rabs(tmp[i]);
+    mat_T3(r, rt);
+    real lx = ss[0], ly = ss[1];
+    hz = ss[2];
+    p[2] -= hz;
+    int clcorner = 0;
+    for (int i = 0; i < 3; i++) if (r[6 + i] < 0) clcorner += 1 << i;
+    real lp[3] = {p[0], p[1], p[2]};
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) lp[k] += rt[3 * i + k] * s[i] * ((clcorner & (1 << i)) ? (real)1 : (real)-1);
+    int dirs = 0;
+    real cn1[3] = {0, 0, 0}, cn2[3] = {0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+      if (rabs(r[6 + i]) < (real)0.5) {
+        real* cn = dirs ? cn2 : cn1;
+        for (int k = 0; k < 3; k++) cn[k] = rt[3 * i + k] * s[i] * ((clcorner & (1 << i)) ? (real)-2 : (real)2);
+        dirs++;
+      }
+    }
+    int kk = dirs * dirs;
+    for (int i = 0; i < kk; i++) for (int q = 0; q < 2; q++) { /* incident-face edges against the reference rectangle's sides */
+      real lav[3], lbv[3];
+      for (int k = 0; k < 3; k++) { lav[k] = lp[k] + (i < 2 ? 0 : (i == 2 ? cn1[k] : cn2[k])); lbv[k] = (i == 0 || i == 3) ? cn1[k] : cn2[k]; }
+      if (rabs(lbv[q]) > MJ_MINVAL) {
+        real br = 1 / lbv[q];
+        for (int j = -1; j <= 1; j += 2) {
+          real l = ss[q] * (real)j, c1 = (l - lav[q]) * br;
+          if (c1 < 0 || c1 > 1) continue;
+          real c2 = lav[1 - q] + lbv[1 - q] * c1;
+          if (rabs(c2) > ss[1 - q]) continue;
+          if (n < 8) { for (int k = 0; k < 3; k++) points[n][k] = lav[k] + c1 * lbv[k]; n++; }
+        }
+      }
+    }
+    if (dirs == 2) { /* reference-face corners inside the incident parallelogram */
+      real ax = cn1[0], bx = cn2[0], ay = cn1[1], by = cn2[1], C = safe_div(1, ax * by - bx * ay);
+      for (int i = 0; i < 4; i++) {
+        real llx = (i / 2) ? lx : -lx, lly = (i % 2) ? ly : -ly, x = llx - lp[0], y = lly - lp[1];
+        real u = (x * by - y * bx) * C, v = (y * ax - x * ay) * C;
+        if (u > 0 && v > 0 && u < 1 && v < 1 && n < 8) { points[n][0] = llx; points[n][1] = lly; points[n][2] = lp[2] + u * cn1[2] + v * cn2[2]; n++; }
+      }
+    }
+    for (int i = 0; i < (1 << dirs); i++) { /* incident corners inside the reference rectangle */
+      real t[3];
+      for (int k = 0; k < 3; k++) t[k] = lp[k] + (real)(i & 1) * cn1[k] + (real)((i & 2) != 0) * cn2[k];
+      if (t[0] > -lx && t[0] < lx && t[1] > -ly && t[1] < ly && n < 8) { memcpy(points[n], t, sizeof t); n++; }
+    }
+    int m = n; n = 0;
+    for (int i = 0; i < m; i++) {
+      if (points[i][2] > margin) continue;
+      if (i != n) memcpy(points[n], points[i], 3 * sizeof(real));
+      depth[n] = points[n][2];
+      points[n][2] *= (real)0.5;
+      n++;
+    }
+    mat_T3(rotmore, rmT);
+    mat_mul3(box_idx ? rot2 : rot1, rmT, rw);
+    memcpy(pw, box_idx ? pos2 : pos1, 3 * sizeof(real));
+    for (int k = 0; k < 3; k++) normal[k] = (box_idx ? (real)-1 : (real)1) * rw[3 * k + 2];
+  } else { /* edge of box1 against edge of box2 */
+    int edge1 = (axis_code - 12) / 3, edge2 = (axis_code - 12) % 3;
+    int ax1 = 1 - (edge2 & 1), ax2 = 2 - (edge2 & 2), pax1 = 1 - (edge1 & 1), pax2 = 2 - (edge1 & 2);
+    if (rot21abs[3 * edge1 + ax1] < rot21abs[3 * edge1 + ax2]) { int t = ax1; ax1 = ax2; ax2 = t; }
+    if (rot12abs[3 * edge2 + pax1] < rot12abs[3 * edge2 + pax2]) { int t = pax1; pax1 = pax2; pax2 = t; }
+    rotmore_of((cle1 & (1 << pax2)) ? pax2 : pax2 + 3, rotmore);
+    real p[3], rnorm[3], r[9], rt[9], s[3], tmp[3];
+    matvec3(rotmore, pos21, p);
+    matvec3(rotmore, clnorm, rnorm);
+    mat_mul3(rotmore, rot21, r);
+    mat_T3(r, rt);
+    mat_T3(rotmore, rmT);
+    matvec3(rmT, size1, tmp);
+    for (int i = 0; i < 3; i++) s[i] = rabs(tmp[i]);
+    real lx = s[0], ly = s[1];
+    hz = s[2];
+    p[2] -= hz;
+    real sg1 = (cle2 & (1 << ax1)) ? (real)1 : (real)-1, sg2 = (cle2 & (1 << ax2)) ? (real)1 : (real)-1;
+    for (int k = 0; k < 3; k++) {
+      real base0 = p[k] + rt[3 * ax1 + k] * size2[ax1] * sg1 + rt[3 * ax2 + k] * size2[ax2] * sg2;
+      real base2 = p[k] - rt[3 * ax1 + k] * size2[ax1] * sg1 + rt[3 * ax2 + k] * size2[ax2] * sg2;
+      real e = rt[3 * edge2 + k] * size2[edge2];
+      points[0][k] = base0 + e; points[1][k] = base0 - e; points[2][k] = base2 + e; points[3][k] = base2 - e;
+    }
+    real axi_lp[3], axi_cn1[3], axi_cn2[3];
+    for (int k = 0; k < 3; k++) { axi_lp[k] = points[0][k]; axi_cn1[k] = points[1][k] - points[0][k]; axi_cn2[k] = points[2][k] - points[0][k]; }
+    if (rabs(rnorm[2]) < MJ_MINVAL) return 0;
+    real sgn = inv ? (real)-1 : (real)1, innorm = sgn / rnorm[2], pu[4][3];
+    for (int i = 0; i < 4; i++) {
+      memcpy(pu[i], points[i], 3 * sizeof(real));
+      real c_scl = points[i][2] * sgn * innorm;
+      for (int k = 0; k < 3; k++) points[i][k] -= rnorm[k] * c_scl;
+    }
+    real pts_lp[3], pts_cn1[3], pts_cn2[3];
+    for (int k = 0; k < 3; k++) { pts_lp[k] = points[0][k]; pts_cn1[k] = points[1][k] - points[0][k]; pts_cn2[k] = points[2][k] - points[0][k]; }
+    n = 0;
+    for (int i = 0; i < 4; i++) for (int q = 0; q < 2; q++) {
+      real la = pts_lp[q] + (i < 2 ? 0 : (i == 2 ? pts_cn1[q] : pts_cn2[q])), lb = (i == 0 || i == 3) ? pts_cn1[q] : pts_cn2[q];
+      real lc = pts_lp[1 - q] + (i < 2 ? 0 : (i == 2 ? pts_cn1[1 - q] : pts_cn2[1 - q])), ld = (i == 0 || i == 3) ? pts_cn1[1 - q] : pts_cn2[1 - q];
+      real lua[3], lub[3];
+      for (int k = 0; k < 3; k++) { lua[k] = axi_lp[k] + (i < 2 ? 0 : (i == 2 ? axi_cn1[k] : axi_cn2[k])); lub[k] = (i == 0 || i == 3) ? axi_cn1[k] : axi_cn2[k]; }
+      if (rabs(lb) > MJ_MINVAL) {
+        real br = 1 / lb;
+        for (int j = -1; j <= 1; j += 2) {
+          if (n == 8) break;
+          real l = s[q] * (real)j, c1 = (l - la) * br;
+          if (c1 < 0 || c1 > 1) continue;
+          real c2 = lc + ld * c1;
+          if (rabs(c2) > s[1 - q]) continue;
+          if ((lua[2] + lub[2] * c1) * innorm > margin) continue;
+          for (int k = 0; k < 3; k++) points[n][k] = lua[k] * (real)0.5 + c1 * lub[k] * (real)0.5;
+          points[n][q] += (real)0.5 * l;
+          points[n][1 - q] += (real)0.5 * c2;
+          depth[n] = points[n][2] * innorm * 2;
+          n++;
+        }
+      }
+    }
+    int nl = n;
+    real ax = pts_cn1[0], bx = pts_cn2[0], ay = pts_cn1[1], by = pts_cn2[1], C = safe_div(1, ax * by - bx * ay);
+    for (int i = 0; i < 4; i++) {
+      if (n == 8) break;
+      real llx = (i / 2) ? lx : -lx, lly = (i % 2) ? ly : -ly, x = llx - pts_lp[0], y = lly - pts_lp[1];
+      real u = (x * by - y * bx) * C, v = (y * ax - x * ay) * C;
+      if (nl == 0) { if ((u < 0 || u > 1) && (v < 0 || v > 1)) continue; }
+      else if (u < 0 || v < 0 || u > 1 || v > 1) continue;
+      u = rclamp(u, 0, 1); v = rclamp(v, 0, 1);
+      real wgt = 1 - u - v, vtmp[3], pt[3] = {llx, lly, 0}, tc1 = 0;
+      for (int k = 0; k < 3; k++) { vtmp[k] = pu[0][k] * wgt + pu[1][k] * u + pu[2][k] * v; tc1 += (pt[k] - vtmp[k]) * (pt[k] - vtmp[k]); }
+      if (vtmp[2] > 0 && tc1 > margin * margin) continue;
+      for (int k = 0; k < 3; k++) points[n][k] = (real)0.5 * (pt[k] + vtmp[k]);
+      depth[n] = (real)sqrt((double)tc1) * (vtmp[2] < 0 ? (real)-1 : (real)1);
+      n++;
+    }
+    int nf = n;
+    for (int i = 0; i < 4; i++) {
+      if (n >= 8) break;
+      real x = pu[i][0], y = pu[i][1];
+      if (nl == 0 && nf != 0) { if ((x < -lx || x > lx) && (y < -ly || y > ly)) continue; }
+      else if (x < -lx || x > lx || y < -ly || y > ly) continue;
+      real c1 = 0;
+      for (int j = 0; j < 2; j++) {
+        if (pu[i][j] < -s[j]) c1 += (pu[i][j] + s[j]) * (pu[i][j] + s[j]);
+        else if (pu[i][j] > s[j]) c1 += (pu[i][j] - s[j]) * (pu[i][j] - s[j]);
+      }
+      c1 += pu[i][2] * innorm * pu[i][2] * innorm;
+      if (pu[i][2] > 0 && c1 > margin * margin) continue;
+      real tp[3] = {pu[i][0], pu[i][1], 0};
+      for (int j = 0; j < 2; j++) {
+        if (pu[i][j] < -s[j]) tp[j] = -s[j] * (real)0.5;
+        else if (pu[i][j] > s[j]) tp[j] = s[j] * (real)0.5;
+      }
+      for (int k = 0; k < 3; k++) points[n][k] = (tp[k] + pu[i][k]) * (real)0.5;
+      depth[n] = (real)sqrt((double)c1) * (pu[i][2] < 0 ? (real)-1 : (real)1);
+      n++;
+    }
+    mat_mul3(rot1, rmT, rw);
+    memcpy(pw, pos1, 3 * sizeof(real));
+    real nn[3]; matvec3(rw, rnorm, nn);
+    for (int k = 0; k < 3; k++) normal[k] = sgn * nn[k];
+  }
+  for (int i = 0; i < n; i++) {
+    points[i][2] += hz;
+    real g[3]; matvec3(rw, points[i], g);
+    for (int k = 0; k < 3; k++) cpos[i][k] = g[k] + pw[k];
+    cdist[i] = depth[i];
+  }
+  memcpy(cnormal, normal, sizeof normal);
+  return n;
+}
 static void narrowphase_pair(W* w, int g1, int g2) {
   const OrcModel* m = w->m;
   int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
@@ -843,6 +1313,37 @@ static void narrowphase_pair(W* w, int g1, int g2) {
       }
     }
     for (int i = 0; i < 2; i++) { make_frame(cn[i], frame); write_contact(w, i, cdist[i], cpos[i], frame, &p, g1, g2); }
+  } else if (t1 == GEOM_PLANE && t2 == GEOM_ELLIPSOID) { /* collision_primitive.py:686 */
+    real dist = plane_ellipsoid(ax1, pos1, pos2, rot2, size2, pos);
+    make_frame(ax1, frame);
+    write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+  } else if (t1 == GEOM_PLANE && t2 == GEOM_CYLINDER) { /* collision_primitive.py:1000 */
+    real d4[4], p4[4][3];
+    plane_cylinder(ax1, pos1, pos2, ax2, size2[0], size2[1], d4, p4);
+    make_frame(ax1, frame);
+    for (int i = 0; i < 4; i++) write_contact(w, i, d4[i], p4[i], frame, &p, g1, g2);
+  } else if (t1 == GEOM_PLANE && t2 == GEOM_BOX) { /* collision_primitive.py:761 */
+    real d8[8], p8[8][3];
+    plane_box(ax1, pos1, pos2, rot2, size2, d8, p8);
+    make_frame(ax1, frame);
+    for (int i = 0; i < 8; i++) write_contact(w, i, d8[i], p8[i], frame, &p, g1, g2);
+  } else if (t1 == GEOM_SPHERE && t2 == GEOM_CYLINDER) { /* collision_primitive.py:915 */
+    real dist = sphere_cylinder(pos1, size1[0], pos2, ax2, size2[0], size2[1], pos, n);
+    make_frame(n, frame);
+    write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+  } else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) { /* collision_primitive.py:1087 */
+    real dist = sphere_box(pos1, size1[0], pos2, rot2, size2, pos, n);
+    make_frame(n, frame);
+    write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+  } else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) { /* collision_primitive.py:1161 */
+    real d2[2], p2[2][3], n2[2][3];
+    capsule_box(pos1, ax1, size1[0], size1[1], pos2, rot2, size2, d2, p2, n2);
+    for (int i = 0; i < 2; i++) { make_frame(n2[i], frame); write_contact(w, i, d2[i], p2[i], frame, &p, g1, g2); }
+  } else if (t1 == GEOM_BOX && t2 == GEOM_BOX && (m->disableflags & DSBL_NATIVECCD)) { /* collision_primitive.py:1250; primitive only with nativeccd off (collision_driver.py:868) */
+    real d8[8], p8[8][3], nn[3];
+    int nc = box_box(pos1, rot1, size1, pos2, rot2, size2, p.margin, d8, p8, nn);
+    make_frame(nn, frame);
+    for (int i = 0; i < nc; i++) write_contact(w, i, d8[i], p8[i], frame, &p, g1, g2);
   } else {
     w->overflow[0] |= OVF_UNSUPPORTED;
   }
