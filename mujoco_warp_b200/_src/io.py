@@ -41,6 +41,9 @@ _SIZES = ["nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "nsite", "ncam", "nl
 _SUPPORTED_PAIRS = {
   (C.GEOM_PLANE, C.GEOM_SPHERE), (C.GEOM_PLANE, C.GEOM_CAPSULE), (C.GEOM_SPHERE, C.GEOM_SPHERE),
   (C.GEOM_SPHERE, C.GEOM_CAPSULE), (C.GEOM_CAPSULE, C.GEOM_CAPSULE),
+  # box / cylinder / ellipsoid primitives (collision_driver.py:47-81: the pairs the reference routes to primitive functions)
+  (C.GEOM_PLANE, C.GEOM_ELLIPSOID), (C.GEOM_PLANE, C.GEOM_CYLINDER), (C.GEOM_PLANE, C.GEOM_BOX),
+  (C.GEOM_SPHERE, C.GEOM_CYLINDER), (C.GEOM_SPHERE, C.GEOM_BOX), (C.GEOM_CAPSULE, C.GEOM_BOX),
 }
 
 
@@ -182,7 +185,11 @@ def derive_tables(mjm) -> dict:
   for a, b in t["nxn_geom_pair_filtered"]:
     counts[trid(gt[a], gt[b])] += 1
     key = (min(gt[a], gt[b]), max(gt[a], gt[b]))
-    if key not in _SUPPORTED_PAIRS:
+    if key == (C.GEOM_BOX, C.GEOM_BOX):
+      # box-box is a primitive pair only with native CCD disabled (collision_driver.py:868-870); GJK/EPA is not implemented here
+      if not (int(mjm.opt.disableflags) & C.DSBL_NATIVECCD):
+        raise NotImplementedError('box-box collisions need <flag nativeccd="disable"/> (primitive box-box); the GJK/EPA convex path is not implemented')
+    elif key not in _SUPPORTED_PAIRS:
       raise NotImplementedError(f"collision between geom types {key} is not implemented in this version (supported: {sorted(_SUPPORTED_PAIRS)})")
   t["geom_pair_type_count"] = tuple(int(c) for c in counts)
   # constraint source lists
@@ -334,6 +341,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     nfricdof=len(t["dof_fricloss_adr"]), nmaxpyramid=m.nmaxpyramid, integrator=m.opt.integrator, cone=m.opt.cone, solver=m.opt.solver,
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
+    has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))

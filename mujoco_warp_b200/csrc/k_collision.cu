@@ -3,8 +3,9 @@
 // Replaces (reference, /root/reference/mujoco_warp/_src/): collision_driver.py:684-770 (_nxn_broadphase: one thread
 // per (world, pair), one global atomic per surviving pair), :98-334 (plane/sphere/AABB/OBB filters),
 // collision_primitive.py:1352-1513 (_primitive_narrowphase: naconmax threads, most idle), collision_primitive_core.py:47-302
-// (plane-sphere, sphere-sphere, sphere-capsule, capsule-capsule, plane-capsule), collision_core.py:213-470 (write_contact,
-// contact parameter mixing).
+// (plane-sphere, sphere-sphere, sphere-capsule, capsule-capsule, plane-capsule), :305-1433 (ellipsoid / cylinder / box pairs,
+// mjb_colliders.cuh; only in the k_collision<8> instantiation, chosen when the model has such geoms),
+// collision_core.py:213-470 (write_contact, contact parameter mixing).
 //
 // B200 design: one warp owns one world.  Lanes test the model's precomputed pair list, survivors are compacted with
 // ballot/popc in pair order, narrowphase runs densely on the compacted list, contacts are staged in shared memory and the
@@ -12,6 +13,7 @@
 // per pair and one per contact).  Within a world the contact order is deterministic (pair order, then contact index);
 // only the position of a world's block inside the pool depends on scheduling.  Data.contact keeps the reference's global
 // pool layout (types.py:1975-2018) so [0, nacon) is densely packed.
+#include "mjb_colliders.cuh"
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
 
@@ -120,6 +122,9 @@ __device__ void contact_params(const ModelDev& m, int g1, int g2, ConParams* p) 
   for (int i = 0; i < 5; i++) p->solimp[i] = mix * m.geom_solimp[5 * g1 + i] + (1.f - mix) * m.geom_solimp[5 * g2 + i];
 }
 
+// MAXC = contacts one geom pair can produce: 2 for plane/sphere/capsule-only models (everything stays in registers),
+// 8 once boxes, cylinders or ellipsoids are present.
+template <int MAXC>
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -186,8 +191,10 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
 #pragma unroll 1
   for (int s0 = 0; s0 < nsurv; s0 += 32) {
     const int si = s0 + lane;
-    float cd[2] = {INFINITY, INFINITY};
-    v3 cp[2], cn[2];
+    float cd[MAXC];
+    v3 cp[MAXC], cn[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) cd[k] = INFINITY;
     float frame0[9];
     bool shared_frame = false;
     int g1 = 0, g2 = 0;
@@ -247,15 +254,37 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
             if (dist <= margin) { cd[cc] = dist; cp[cc] = p; cn[cc] = n; }
           }
         }
+      } else if (MAXC >= 8) {
+        const float *rot1 = gxmat + 9 * g1, *rot2 = gxmat + 9 * g2;
+        if (t1 == GEOM_PLANE && t2 == GEOM_ELLIPSOID) {
+          cd[0] = plane_ellipsoid(ax1, pos1, pos2, rot2, size2, &cp[0]); cn[0] = ax1;
+        } else if (t1 == GEOM_PLANE && t2 == GEOM_CYLINDER) {
+          plane_cylinder(ax1, pos1, pos2, ax2, size2.x, size2.y, cd, cp);
+          for (int k = 0; k < 4; k++) cn[k] = ax1;
+        } else if (t1 == GEOM_PLANE && t2 == GEOM_BOX) {
+          plane_box(ax1, pos1, pos2, rot2, size2, cd, cp);
+          for (int k = 0; k < MAXC; k++) cn[k] = ax1;
+        } else if (t1 == GEOM_SPHERE && t2 == GEOM_CYLINDER) {
+          cd[0] = sphere_cylinder(pos1, size1.x, pos2, ax2, size2.x, size2.y, &cp[0], &cn[0]);
+        } else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) {
+          cd[0] = sphere_box(pos1, size1.x, pos2, rot2, size2, &cp[0], &cn[0]);
+        } else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) {
+          capsule_box(pos1, ax1, size1.x, size1.y, pos2, rot2, size2, cd, cp, cn);
+        } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {  // primitive box-box: put_model requires the nativeccd disable flag
+          v3 nn;
+          const int nc = box_box(pos1, rot1, size1, pos2, rot2, size2, margin, cd, cp, &nn);
+          for (int k = 0; k < MAXC; k++) { cn[k] = nn; if (k >= nc) cd[k] = INFINITY; }
+        }
       }
     }
-    const bool v0 = cd[0] < inc, v1 = cd[1] < inc;  // write_contact: detected = dist < margin + gap
-    const int cnt = (int)v0 + (int)v1;
+    int cnt = 0;  // write_contact: detected = dist < margin + gap
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) cnt += cd[k] < inc ? 1 : 0;
     int off = ncon + warp_excl_scan(cnt, lane);
     ncon += warp_sum_i(cnt);
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      if (k == 0 ? v0 : v1) {
+    for (int k = 0; k < MAXC; k++) {
+      if (cd[k] < inc) {
         if (off < ccap) {
           float* st = stage + STAGE_WORDS * off;
           st[0] = cd[k]; st3(st + 1, cp[k]);
@@ -319,13 +348,16 @@ cudaError_t reset_contact_counters(const DataDev& d, cudaStream_t s) {
 cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   cudaError_t e;
   const size_t smem = smem_collision(m, d);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    e = cudaFuncSetAttribute(k_collision, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured[2] = {0, 0};
+  const int full = m.has_multicontact_geom ? 1 : 0;
+  if (smem > 48 * 1024 && smem > configured[full]) {
+    e = full ? cudaFuncSetAttribute(k_collision<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+             : cudaFuncSetAttribute(k_collision<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[full] = smem;
   }
   const int grid = d.wn;
-  k_collision<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  if (full) k_collision<8><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  else k_collision<2><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }
