@@ -153,7 +153,7 @@ class Oracle:
   o = Oracle(mjm, nworld=4, nconmax=24, njmax=64); o.d["qpos"][:] = ...; o.forward(); o.d["qacc"]
   """
 
-  def __init__(self, mjm, nworld=1, nconmax=24, njmax=64, dtype=np.float64, static_kin=None):
+  def __init__(self, mjm, nworld=1, nconmax=24, njmax=64, dtype=np.float64, static_kin=None, clamp_tolerance=True):
     self.real = np.dtype(dtype)
     self.lib = _lib(self.real.itemsize)
     self.mjm, self.nworld, self.nconmax, self.njmax = mjm, nworld, nconmax, njmax
@@ -187,8 +187,9 @@ class Oracle:
     seti("ls_iterations", o.ls_iterations); seti("disableflags", o.disableflags); seti("enableflags", o.enableflags)
     seti("broadphase_filter", getattr(o, "broadphase_filter", 1 | 2 | 8))  # io.py:405 default PLANE|SPHERE|OBB
     tol = float(o.tolerance)
-    if self.real.itemsize == 4:
-      tol = max(tol, 1e-6)  # io.py:401: tolerance clamped for float32
+    if clamp_tolerance:
+      tol = max(tol, 1e-6)  # io.py:401: put_model clamps the solver tolerance (chosen for float32) whatever the host precision;
+      # clamp_tolerance=False lets invariant tests converge the fp64 build fully
     self.tolerance = tol
     setr("timestep", o.timestep); setr("tolerance", tol); setr("ls_tolerance", o.ls_tolerance)
     setr("impratio_invsqrt", 1.0 / np.sqrt(o.impratio)); setr("meaninertia", mjm.stat.meaninertia)

@@ -1,0 +1,85 @@
+"""CUDA path (through the C-ABI) vs the trajectories produced by the reference's own pipeline
+(tests/golden/pipeline_*.npz, see tools/make_pipeline_goldens.py).  fp32 kernels against the reference evaluated in double:
+smooth / constraint quantities within 5e-4 (the reference's own test tolerance, smooth_test.py:32), solver outputs within
+5e-3 of the force scale, integer outputs exact."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+from tests.test_oracle_golden_pipeline import GOLD_DIR, SCENES, SMOOTH, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def close(name, got, want, atol, rtol=0.0):
+  got = np.asarray(got, dtype=np.float64)
+  want = np.asarray(want, dtype=np.float64).reshape(got.shape)
+  util.assert_close(name, got, want, atol=atol, rtol=rtol)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_gpu_matches_reference_pipeline(built, name):
+  import mujoco_warp_b200 as mjw
+
+  g = np.load(os.path.join(GOLD_DIR, f"pipeline_{name}.npz"))
+  mjm = load_scene(name)
+  m = mjw.put_model(mjm)
+  nworld = g["in/qpos"].shape[0]
+  d = mjw.make_data(mjm, nworld=nworld, nconmax=int(g["in/nconmax"]), njmax=int(g["in/njmax"]), m=m)
+  f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+  d.qpos.copy_(f32(g["in/qpos"])); d.qvel.copy_(f32(g["in/qvel"])); d.qacc_warmstart.copy_(f32(g["in/qacc_warmstart"]))
+  if mjm.nu:
+    d.ctrl.copy_(f32(g["in/ctrl"]))
+  mjw.forward(m, d)
+  torch.cuda.synchronize()
+  assert (d.overflow.cpu().numpy() == 0).all()
+  nv, tag = mjm.nv, "forward"
+  for f in SMOOTH:
+    k = f"{tag}/{f}"
+    if k not in g or not g[k].size or not hasattr(d, f):
+      continue
+    got = getattr(d, f).cpu().numpy().reshape(nworld, -1)
+    want = g[k]
+    if f == "M":
+      want = want[:, : mjm.nC]
+    want = want.reshape(nworld, -1)[:, : got.shape[1]]
+    scale = max(1.0, float(np.abs(want).max()))
+    close(k, got, want, atol=5e-4 * scale)
+  for f in ("ne", "nf", "nl", "nefc"):
+    np.testing.assert_array_equal(getattr(d, f).cpu().numpy().reshape(-1), g[f"{tag}/{f}"].reshape(-1), err_msg=f)
+  assert int(d.nacon.cpu()[0]) == int(g[f"{tag}/nacon"])
+  wid = g[f"{tag}/con_worldid"]
+  J = d.efc.J.cpu().numpy()
+  fscale = max(1.0, float(np.abs(g[f"{tag}/efc_force"]).max()))
+  for w in range(nworld):
+    ids = util.world_contacts(d, w)
+    ref_ids = np.nonzero(wid == w)[0]
+    assert len(ids) == len(ref_ids)
+    c = d.contact
+    np.testing.assert_array_equal(c.geom[ids].cpu().numpy(), g[f"{tag}/con_geom"][ref_ids])
+    np.testing.assert_array_equal(c.dim[ids].cpu().numpy(), g[f"{tag}/con_dim"][ref_ids])
+    np.testing.assert_array_equal(c.geomcollisionid[ids].cpu().numpy(), g[f"{tag}/con_geomcollisionid"][ref_ids])
+    for f in ("dist", "pos", "frame", "includemargin", "friction", "solref", "solimp"):
+      close(f"con_{f}[w{w}]", getattr(c, f)[ids].cpu().numpy().reshape(len(ids), -1), g[f"{tag}/con_{f}"][ref_ids].reshape(len(ids), -1), atol=5e-4, rtol=5e-4)
+    ne = int(g[f"{tag}/nefc"].reshape(-1)[w])
+    np.testing.assert_array_equal(d.efc.type[w, :ne].cpu().numpy(), g[f"{tag}/efc_type"][w, :ne])
+    close(f"efc_J[w{w}]", J[w, :ne, :nv], g[f"{tag}/efc_J"][w, :ne, :nv], atol=5e-4, rtol=5e-4)
+    for f in ("pos", "margin", "vel", "frictionloss"):
+      close(f"efc_{f}[w{w}]", getattr(d.efc, f)[w, :ne].cpu().numpy(), g[f"{tag}/efc_{f}"][w, :ne], atol=5e-4, rtol=5e-4)
+    close(f"efc_D[w{w}]", d.efc.D[w, :ne].cpu().numpy(), g[f"{tag}/efc_D"][w, :ne], atol=1e-3, rtol=2e-3)
+    close(f"efc_aref[w{w}]", d.efc.aref[w, :ne].cpu().numpy(), g[f"{tag}/efc_aref"][w, :ne], atol=2e-3, rtol=2e-3)
+    close(f"efc_force[w{w}]", d.efc.force[w, :ne].cpu().numpy(), g[f"{tag}/efc_force"][w, :ne], atol=5e-3 * fscale)
+  scale = max(1.0, float(np.abs(g[f"{tag}/qacc"]).max()))
+  close("qacc", d.qacc.cpu().numpy(), g[f"{tag}/qacc"], atol=5e-3 * scale)
+  s = 0
+  while f"step{s}/qpos" in g:
+    mjw.step(m, d)
+    torch.cuda.synchronize()
+    close(f"step{s}/qpos", d.qpos.cpu().numpy(), g[f"step{s}/qpos"], atol=2e-4, rtol=2e-4)
+    close(f"step{s}/qvel", d.qvel.cpu().numpy(), g[f"step{s}/qvel"], atol=1e-2, rtol=5e-3)
+    s += 1
+  assert s >= 3 and (d.overflow.cpu().numpy() == 0).all()

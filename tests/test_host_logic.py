@@ -151,10 +151,16 @@ def test_unsupported_features_raise():
   from mujoco_warp_b200._src import io as mio
   from mujoco_warp_b200._src import mjcf
 
-  xml = """<mujoco><option cone="elliptic"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
-  with pytest.raises(NotImplementedError, match="elliptic"):
+  xml = """<mujoco><option integrator="RK4"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
+  with pytest.raises(NotImplementedError, match="integrator"):
     mio._validate(mjcf.load_string(xml))
-  xml = """<mujoco><worldbody><geom type="plane" size="1 1 1"/><body pos="0 0 1"><freejoint/><geom type="box" size=".1 .1 .1"/></body></worldbody></mujoco>"""
+  # box-box is a primitive pair only with nativeccd disabled; cylinder-box always needs the (unimplemented) convex path
+  two = '<body pos="0 0 1"><freejoint/><geom type="box" size=".1 .1 .1"/></body><body pos="0 0 2"><freejoint/><geom type="{t}" size=".1 .1 .1"/></body>'
+  xml = "<mujoco><worldbody>" + two.format(t="box") + "</worldbody></mujoco>"
+  with pytest.raises(NotImplementedError, match="nativeccd"):
+    mio.derive_tables(mjcf.load_string(xml))
+  mio.derive_tables(mjcf.load_string(xml.replace("<worldbody>", '<option><flag nativeccd="disable"/></option><worldbody>')))
+  xml = "<mujoco><worldbody>" + two.format(t="cylinder") + "</worldbody></mujoco>"
   with pytest.raises(NotImplementedError, match="collision between geom types"):
     mio.derive_tables(mjcf.load_string(xml))
 

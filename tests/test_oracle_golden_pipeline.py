@@ -1,0 +1,116 @@
+"""fp64 oracle vs trajectories produced by the reference's own pipeline (tools/make_pipeline_goldens.py: unmodified
+reference sources executed on the CPU through tools/warp_shim.py).  forward() fields, constraint rows, solver output and
+NSTEP steps of state, per scene."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from tests import util
+
+GOLD_DIR = os.path.join(os.path.dirname(__file__), "golden")
+SCENES = sorted(os.path.basename(p)[len("pipeline_"):-4] for p in glob.glob(os.path.join(GOLD_DIR, "pipeline_*.npz")))
+
+SMOOTH = ["xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
+          "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert", "crb", "M", "actuator_length", "actuator_moment", "actuator_velocity", "cvel",
+          "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth"]
+
+
+def load_scene(name):
+  from mujoco_warp_b200._src import constants as C
+  from mujoco_warp_b200._src import mjcf
+  from tests.test_gpu_colliders import BOX_XML
+
+  if name.startswith("humanoid"):
+    mjm = mjcf.load_any(util.HUMANOID)
+    if name.endswith("elliptic"):
+      mjm.opt.cone = C.CONE_ELLIPTIC
+  elif name == "mixed":
+    mjm = mjcf.load_string(util.MIXED_XML)
+  elif name == "mixed_elliptic":
+    mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"'))
+  elif name == "boxes":
+    mjm = mjcf.load_string(BOX_XML)
+  elif name == "g1":
+    mjm = mjcf.load_any(util.G1)
+  else:
+    raise KeyError(name)
+  return mjm
+
+
+def close(name, got, want, tol):
+  got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+  want = want.reshape(got.shape)
+  scale = max(1.0, float(np.abs(want).max(initial=0.0)))
+  err = float(np.abs(got - want).max(initial=0.0))
+  assert err <= tol * scale, f"{name}: max |diff| {err:.3e} (scale {scale:.3e})"
+
+
+def compare(tag, g, od, mjm, nworld, tol):
+  nv = mjm.nv
+  for f in SMOOTH:
+    k = f"{tag}/{f}"
+    if k in g and f in od and g[k].size:
+      want = g[k]
+      if f == "M":
+        want = want[:, : mjm.nC] if want.ndim == 2 else want
+      if f == "actuator_moment":
+        want = want.reshape(nworld, -1)[:, : od[f].reshape(nworld, -1).shape[1]]
+      close(k, od[f].reshape(nworld, -1), want.reshape(nworld, -1), tol)
+  for f in ("ne", "nf", "nl", "nefc"):
+    np.testing.assert_array_equal(od[f].reshape(-1), g[f"{tag}/{f}"].reshape(-1), err_msg=f"{tag}/{f}")
+  wid = g[f"{tag}/con_worldid"]
+  for w in range(nworld):
+    ids = np.nonzero(wid == w)[0]
+    n = int(od["ncon"][w])
+    assert n == len(ids), f"{tag} world {w}: {n} contacts, reference {len(ids)}"
+    np.testing.assert_array_equal(od["con_geom"][w, :n], g[f"{tag}/con_geom"][ids])
+    np.testing.assert_array_equal(od["con_dim"][w, :n], g[f"{tag}/con_dim"][ids])
+    np.testing.assert_array_equal(od["con_geomcollisionid"][w, :n], g[f"{tag}/con_geomcollisionid"][ids])
+    for f in ("dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp"):
+      close(f"{tag}/con_{f}[w{w}]", od["con_" + f][w, :n], g[f"{tag}/con_{f}"][ids], tol)
+    ne = int(od["nefc"][w])
+    np.testing.assert_array_equal(od["efc_type"][w, :ne], g[f"{tag}/efc_type"][w, :ne])
+    eid = g[f"{tag}/efc_id"][w, :ne].copy()
+    is_con = od["efc_type"][w, :ne] >= 5
+    if n:
+      eid[is_con] -= ids[0]  # the reference's contact ids index the global pool
+    np.testing.assert_array_equal(od["efc_id"][w, :ne], eid)
+    np.testing.assert_array_equal(od["con_efc_address"][w, :n, : g[f"{tag}/con_efc_address"].shape[1]], g[f"{tag}/con_efc_address"][ids][:, : od["con_efc_address"].shape[2]])
+    close(f"{tag}/efc_J[w{w}]", od["efc_J"][w, :ne], g[f"{tag}/efc_J"][w, :ne, :nv], tol)
+    for f in ("pos", "margin", "D", "vel", "aref", "frictionloss"):
+      close(f"{tag}/efc_{f}[w{w}]", od["efc_" + f][w, :ne], g[f"{tag}/efc_{f}"][w, :ne], tol)
+    # solver: both sides iterate the same algorithm in double precision
+    close(f"{tag}/efc_force[w{w}]", od["efc_force"][w, :ne], g[f"{tag}/efc_force"][w, :ne], 1e-7)
+    np.testing.assert_array_equal(od["efc_state"][w, :ne], g[f"{tag}/efc_state"][w, :ne])
+  close(f"{tag}/qacc", od["qacc"], g[f"{tag}/qacc"], 1e-7)
+  close(f"{tag}/qfrc_constraint", od["qfrc_constraint"], g[f"{tag}/qfrc_constraint"], 1e-7)
+  np.testing.assert_array_equal(od["solver_niter"].reshape(-1), g[f"{tag}/solver_niter"].reshape(-1), err_msg=f"{tag}/solver_niter")
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_oracle_matches_reference_pipeline(built, name):
+  g = np.load(os.path.join(GOLD_DIR, f"pipeline_{name}.npz"))
+  mjm = load_scene(name)
+  nworld = g["in/qpos"].shape[0]
+  o = util.make_oracle(mjm, nworld, int(g["in/nconmax"]), int(g["in/njmax"]))
+  o.set_state(qpos=g["in/qpos"], qvel=g["in/qvel"], qacc_warmstart=g["in/qacc_warmstart"])
+  if mjm.nu:
+    o.set_state(ctrl=g["in/ctrl"])
+  o.forward()
+  assert (o.d["overflow"] == 0).all()
+  compare("forward", g, o.d, mjm, nworld, 1e-9)
+  s = 0
+  while f"step{s}/qpos" in g:
+    o.step()
+    close(f"step{s}/qpos", o.d["qpos"], g[f"step{s}/qpos"], 1e-6)
+    # after the first step the two sides' inputs differ at rounding level, which can flip a borderline termination test
+    # (one Newton iteration more or less); both results are converged to the solver tolerance (1e-6, scaled)
+    close(f"step{s}/qvel", o.d["qvel"], g[f"step{s}/qvel"], 1e-4)
+    close(f"step{s}/qacc_warmstart", o.d["qacc_warmstart"], g[f"step{s}/qacc_warmstart"], 2e-4)
+    close(f"step{s}/time", o.d["time"], g[f"step{s}/time"], 1e-12)
+    np.testing.assert_array_equal(o.d["nefc"].reshape(-1), g[f"step{s}/nefc"].reshape(-1), err_msg=f"step{s}/nefc")
+    s += 1
+  assert s >= 3

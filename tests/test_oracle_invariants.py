@@ -199,7 +199,7 @@ def test_solver_elliptic_minimises_cone_cost(scene):
   mjm.opt.cone = C.CONE_ELLIPTIC
   mjm.opt.tolerance = 1e-10
   nw = 8
-  o = util.make_oracle(mjm, nw, 24, 64)
+  o = util.make_oracle(mjm, nw, 24, 64, clamp_tolerance=False)
   qpos, qvel, ctrl, warm = util.seeded_state(mjm, nw, seed=5)
   o.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, qacc_warmstart=warm)
   o.forward()

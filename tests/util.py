@@ -34,12 +34,12 @@ def seeded_state(mjm, nworld, key=0, seed=42, qpos_noise=0.05, qvel_noise=0.5, c
   return qpos, qvel, ctrl, warm
 
 
-def make_oracle(mjm, nworld, nconmax, njmax, dtype=np.float64):
+def make_oracle(mjm, nworld, nconmax, njmax, dtype=np.float64, clamp_tolerance=True):
   from mujoco_warp_b200._src import mjcf
   from oracle import orc
 
   kin = mjcf.kinematics_np(mjm, mjm.qpos0)
-  return orc.Oracle(mjm, nworld=nworld, nconmax=nconmax, njmax=njmax, dtype=dtype, static_kin=kin)
+  return orc.Oracle(mjm, nworld=nworld, nconmax=nconmax, njmax=njmax, dtype=dtype, static_kin=kin, clamp_tolerance=clamp_tolerance)
 
 
 def world_contacts(d, w):

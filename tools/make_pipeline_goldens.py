@@ -1,0 +1,104 @@
+"""Golden trajectories from the reference's own step pipeline, executed on the CPU through tools/warp_shim.py.
+
+  python tools/make_pipeline_goldens.py          # writes tests/golden/pipeline_<scene>.npz
+
+For every scene the UNMODIFIED reference code (io.put_model -> io.make_data -> forward.forward / forward.step and every
+kernel they launch: smooth.py, collision_driver.py, collision_primitive.py, constraint.py, passive.py, solver.py,
+derivative.py) runs in double precision on a model compiled by mujoco_warp_b200._src.mjcf, from seeded states.  The fixture
+stores the inputs and every Data field the parity tests compare, after forward() and after each of NSTEP step() calls.
+tests/test_oracle_golden_pipeline.py holds the fp64 oracle to these numbers.
+"""
+
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mujoco_warp_b200._src import constants as C  # noqa: E402
+from mujoco_warp_b200._src import mjcf  # noqa: E402
+from tests import util  # noqa: E402
+from tests.test_gpu_colliders import BOX_XML  # noqa: E402
+from tools import ref_runner  # noqa: E402
+
+NWORLD, NSTEP = 3, 4
+
+FIELDS = [
+  "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
+  "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert", "crb", "M", "actuator_length", "actuator_moment", "actuator_velocity", "cvel",
+  "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth",
+  "qacc", "qfrc_constraint", "ne", "nf", "nl", "nefc", "solver_niter",
+]
+EFC = ["type", "id", "J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "state"]
+CON = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "geomcollisionid"]
+
+
+def scenes():
+  hum = mjcf.load_any(util.HUMANOID)
+  yield "humanoid", hum, dict(nconmax=24, njmax=128, key=0, qpos_noise=0.003, exact_world0=False)
+  hum_e = mjcf.load_any(util.HUMANOID)
+  hum_e.opt.cone = C.CONE_ELLIPTIC
+  yield "humanoid_elliptic", hum_e, dict(nconmax=24, njmax=128, key=0, qpos_noise=0.003, exact_world0=False)
+  yield "mixed", mjcf.load_string(util.MIXED_XML), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  ell = util.MIXED_XML.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"')
+  yield "mixed_elliptic", mjcf.load_string(ell), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  yield "boxes", mjcf.load_string(BOX_XML), dict(nconmax=48, njmax=200, key=None, qpos_noise=0.003, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
+  yield "g1", mjcf.load_any(util.G1), dict(nconmax=48, njmax=192, key=0, qpos_noise=0.02, qvel_noise=0.2, ctrl_noise=0.3)
+
+
+def snapshot(mjm, d, out, tag):
+  for f in FIELDS:
+    a = getattr(d, f, None)
+    if a is not None and a.a is not None:
+      out[f"{tag}/{f}"] = a.numpy()
+  for f in EFC:
+    a = getattr(d.efc, f)
+    if a is not None and a.a is not None:
+      out[f"{tag}/efc_{f}"] = a.numpy()
+  nacon = int(d.nacon.numpy()[0])
+  out[f"{tag}/nacon"] = np.array(nacon)
+  for f in CON:
+    out[f"{tag}/con_{f}"] = getattr(d.contact, f).numpy()[:nacon]
+  for f in ("qpos", "qvel", "qacc_warmstart", "time", "act"):
+    a = getattr(d, f, None)
+    if a is not None and a.a is not None:
+      out[f"{tag}/{f}"] = a.numpy()
+
+
+def main(only=None):
+  wp, ref = ref_runner.setup()
+  io, fwd = ref["io"], ref["forward"]
+  for name, mjm, cfg in scenes():
+    if only and name not in only:
+      continue
+    t0 = time.time()
+    nconmax, njmax = cfg.pop("nconmax"), cfg.pop("njmax")
+    key = cfg.pop("key")
+    qpos, qvel, ctrl, warm = util.seeded_state(mjm, NWORLD, key=key, seed=1234, **cfg)
+    if name.startswith("humanoid"):  # keep the feet on the floor: exact root pose, pushed 0.5 mm deeper per world
+      qpos[:, :7] = mjm.key_qpos[0][:7]
+      qpos[:, 2] -= 0.0005 * np.arange(NWORLD)
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)  # inputs exactly representable in fp32
+    qpos, qvel, ctrl, warm = f32(qpos), f32(qvel), f32(ctrl), f32(warm)
+    ad = ref_runner.MjModelAdapter(mjm)
+    m = io.put_model(ad)
+    d = io.make_data(ad, nworld=NWORLD, nconmax=nconmax, njmax=njmax)
+    d.qpos.a[...] = qpos; d.qvel.a[...] = qvel; d.qacc_warmstart.a[...] = warm
+    if mjm.nu:
+      d.ctrl.a[...] = ctrl
+    out = {"in/qpos": qpos, "in/qvel": qvel, "in/ctrl": ctrl, "in/qacc_warmstart": warm, "in/nconmax": np.array(nconmax), "in/njmax": np.array(njmax)}
+    fwd.forward(m, d)
+    snapshot(mjm, d, out, "forward")
+    for s in range(NSTEP):
+      fwd.step(m, d)
+      snapshot(mjm, d, out, f"step{s}")
+    path = os.path.join(ROOT, "tests", "golden", f"pipeline_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: nefc {out['forward/nefc'].ravel()}, nacon {int(out['forward/nacon'])}, niter {out['forward/solver_niter'].ravel()}, "
+          f"{os.path.getsize(path) // 1024} KiB, {time.time() - t0:.1f} s; MjModel fallbacks: {len(ad.missing)}")
+
+
+if __name__ == "__main__":
+  main(sys.argv[1:])
