@@ -6,12 +6,13 @@
  * file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.
  *
- * PARITY PINNING (see DESIGN.md "Oracle"): the reference's dynamics tests delegate to live MuJoCo C,
- * which is absent here, so kinematics/CRBA/RNE/constraint/solver values are "parity unpinned" by
- * upstream goldens; they are pinned instead by (i) the reference's hard-coded vectors that do not need
- * MuJoCo (math_test.py closest-point cases, collision_driver_test upper_tri_index table, io_test padding),
- * (ii) physical invariants (M == finite-difference of kinetic energy, RNE consistency, KKT residual of
- * the solve, energy conservation), all in tests/test_oracle_*.py.
+ * PARITY PINNING: pinned against outputs of the reference itself.  The reference's unmodified
+ * Python sources are executed on the CPU through tools/warp_shim.py (a pure-Python stand-in for the warp API), which
+ * yields (i) tests/golden/reference_colliders.json -- every primitive pair function of collision_primitive_core.py --
+ * and (ii) tests/golden/pipeline_*.npz -- io.put_model -> make_data -> forward()/step() on six scenes.  The fp64 build
+ * of this file reproduces them to 1e-9 (tests/test_oracle_golden_colliders.py, tests/test_oracle_golden_pipeline.py).
+ * Also kept: the reference's hard-coded vectors that need no MuJoCo and physical invariants (tests/test_oracle_*.py).
+ * Outside the pin: the MJCF compiler (MuJoCo's C compiler is absent; the fixtures pin step(m, d) given the model arrays).
  *
  * real = double by default (MuJoCo C precision); -DORC_FLOAT builds an fp32 twin used to study
  * fp32 rounding (the reference computes in fp32).
