@@ -104,3 +104,7 @@ CONTACT_TYPE_CONSTRAINT, CONTACT_TYPE_SENSOR = 1, 2
 DEFAULT_SOLREF = [0.02, 1.0]
 DEFAULT_SOLIMP = [0.9, 0.95, 0.001, 0.5, 2.0]
 DEFAULT_FRICTION = [1.0, 0.005, 0.0001]
+
+# mjtEq / mjtObj (the members the equality path uses)
+EQ_CONNECT, EQ_WELD, EQ_JOINT, EQ_TENDON, EQ_FLEX = 0, 1, 2, 3, 4
+OBJ_BODY, OBJ_JOINT, OBJ_SITE = 1, 3, 6

@@ -196,8 +196,7 @@ def derive_tables(mjm) -> dict:
   jt = _np(mjm, "jnt_type")
   lim = np.asarray(_np(mjm, "jnt_limited")).astype(bool)
   t["jnt_limited_slide_hinge_adr"] = np.nonzero(lim & ((jt == C.JNT_SLIDE) | (jt == C.JNT_HINGE)))[0].astype(np.int32)
-  if (lim & (jt == C.JNT_BALL)).any():
-    raise NotImplementedError("ball joint limits are not implemented in this version")
+  t["jnt_limited_ball_adr"] = np.nonzero(lim & (jt == C.JNT_BALL))[0].astype(np.int32)
   t["dof_fricloss_adr"] = np.nonzero(_np(mjm, "dof_frictionloss") > 0)[0].astype(np.int32)
   # constant sparsity of the actuator moment (joint transmission)
   trnid = _np(mjm, "actuator_trnid").reshape(nu, 2)
@@ -243,9 +242,15 @@ def _validate(mjm):
     raise NotImplementedError("only the Newton solver is implemented in this version")
   if mjm.nv > 64:
     raise NotImplementedError("nv > 64 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
-  for n in ("na", "neq", "ntendon", "nflex", "nmocap"):
+  for n in ("na", "ntendon", "nflex", "nmocap"):
     if getattr(mjm, n, 0):
       raise NotImplementedError(f"{n} > 0 is not supported in this version")
+  if getattr(mjm, "neq", 0):
+    et, ot = np.asarray(mjm.eq_type), np.asarray(mjm.eq_objtype)
+    if not np.isin(et, (C.EQ_CONNECT, C.EQ_WELD, C.EQ_JOINT)).all():
+      raise NotImplementedError("only connect / weld / joint equality constraints are implemented")
+    if (ot[np.isin(et, (C.EQ_CONNECT, C.EQ_WELD))] != C.OBJ_BODY).any():
+      raise NotImplementedError("site-based connect / weld equality constraints are not implemented")
   if (np.asarray(mjm.body_gravcomp) != 0).any():
     raise NotImplementedError("gravity compensation is not implemented")
   jt = np.asarray(mjm.jnt_type)
@@ -318,11 +323,21 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.jnt_limited = dev_i(np.asarray(mjm.jnt_limited).astype(np.int32))
   m.body_tree = tuple(dev_i(x) for x in t["body_tree"])
   for n in ("body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col", "mulm_madr", "tree_qLDadr",
-            "qLD_block_adr", "jnt_limited_slide_hinge_adr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
+            "qLD_block_adr", "jnt_limited_slide_hinge_adr", "jnt_limited_ball_adr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
             "dofact_adr", "dofact_act", "dofact_mom",
             "nxn_geom_pair", "nxn_pairid", "nxn_geom_pair_filtered", "nxn_pairid_filtered"):
     setattr(m, n, dev_i(t[n]))
   m.M_hinit_i = m.M_entry_row
+  # equality constraints (connect / weld / joint): eq_* as in the reference Model (types.py), data per world-batch slot 0
+  neq = int(getattr(mjm, "neq", 0))
+  m.neq = neq
+  m.eq_type = dev_i(mjm.eq_type if neq else np.zeros(0))
+  m.eq_obj1id = dev_i(mjm.eq_obj1id if neq else np.zeros(0))
+  m.eq_obj2id = dev_i(mjm.eq_obj2id if neq else np.zeros(0))
+  m.eq_objtype = dev_i(mjm.eq_objtype if neq else np.zeros(0))
+  m.eq_solref = dev_f(np.asarray(mjm.eq_solref).reshape(neq, 2) if neq else np.zeros((0, 2)))
+  m.eq_solimp = dev_f(np.asarray(mjm.eq_solimp).reshape(neq, 5) if neq else np.zeros((0, 5)))
+  m.eq_data = dev_f(np.asarray(mjm.eq_data).reshape(neq, 11) if neq else np.zeros((0, 11)))
   m.M_mulm_rowadr, m.M_mulm_col, m.M_mulm_madr = m.mulm_rowadr, m.mulm_col, m.mulm_madr
   anc_pad = np.zeros((m.nbody, m.nv_pad), dtype=np.int32)
   anc_pad[:, : m.nv] = t["body_isdofancestor"]
@@ -342,6 +357,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
+    neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))
@@ -356,7 +372,8 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   }
   for n in _FLOAT_FIELDS + _INT_FIELDS + ["body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col",
                                          "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
-                                         "dofact_adr", "dofact_act", "dofact_mom"]:
+                                         "dofact_adr", "dofact_act", "dofact_mom", "eq_type", "eq_obj1id", "eq_obj2id", "eq_solref", "eq_solimp", "eq_data",
+                                         "jnt_limited_ball_adr"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)
@@ -394,6 +411,7 @@ def _data_spec(m: types.Model, nworld, naconmax, njmax, njmax_pad):
     "qfrc_constraint": (f, (nworld, nv)), "qfrc_inverse": (f, (nworld, nv)), "cacc": (f, (nworld, nb, 6)), "cfrc_int": (f, (nworld, nb, 6)),
     "cfrc_ext": (f, (nworld, nb, 6)), "energy": (f, (nworld, 2)),
     "nacon": (i, (1,)), "ncollision": (i, (1,)), "overflow": (i, (nworld,)),
+    "eq_active": (i, (nworld, getattr(m, "neq", 0))),  # the reference stores bool; int32 0/1 here (one word per flag)
   }
 
 
@@ -426,7 +444,7 @@ _BOUND_TOP = [
   "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat", "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert",
   "crb", "M", "qLD", "actuator_length", "actuator_moment", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
   "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int",
-  "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind",
+  "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active",
 ]
 _BOUND_EFC = ["J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "Ma", "type", "id", "state"]
 _BOUND_CONTACT = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "type", "geomcollisionid"]
@@ -465,6 +483,8 @@ def make_data(mjm, nworld: int = 1, nconmax=None, nccdmax=None, njmax=None, njma
   d.geom_xpos.copy_(torch.from_numpy(np.tile(kin.geom_xpos.astype(np.float32), (nworld, 1, 1))))
   d.geom_xmat.copy_(torch.from_numpy(np.tile(kin.geom_xmat.astype(np.float32), (nworld, 1, 1, 1))))
   d.xquat[..., 0] = 1.0
+  if getattr(m, "neq", 0):
+    d.eq_active.copy_(torch.from_numpy(np.tile(np.asarray(mjm.eq_active0).astype(np.int32), (nworld, 1))))
   _bind(m, d, L)
   return d
 
@@ -520,6 +540,8 @@ def reset_data(m: types.Model, d: types.Data):
     getattr(d, n).zero_()
   for n in ("overflow", "solver_niter", "nefc", "ne", "nf", "nl", "nacon", "ncollision"):
     getattr(d, n).zero_()
+  if getattr(m, "neq", 0):
+    d.eq_active.copy_(torch.from_numpy(np.tile(np.asarray(mjm.eq_active0).astype(np.int32), (d.nworld, 1))))
 
 
 def load_trajectory(npz_path: str, mjm, mjd) -> np.ndarray:

@@ -878,8 +878,49 @@ def compile_xml(root):
   m.nexclude = len(excl) // 2
   m.npair = 0
 
+  # ---- equality constraints: connect / weld between bodies, joint coupling (tendon / flex equalities are not compiled)
+  eqs = []
+  ee = root.find("equality")
+  if ee is not None:
+    for child in ee:
+      if child.tag not in ("connect", "weld", "joint"):
+        raise NotImplementedError(f"equality type <{child.tag}> is not supported")
+      a = dflt.resolve("equality", child.get("class", "main"))
+      a.update(child.attrib)
+      data = np.zeros(11)
+      if child.tag == "joint":
+        etype, otype = C.EQ_JOINT, C.OBJ_JOINT
+        o1 = m.names.joint.index(a["joint1"])
+        o2 = m.names.joint.index(a["joint2"]) if "joint2" in a else -1
+        data[:5] = _vec(a.get("polycoef", "0 1 0 0 0"))
+      else:
+        if "site1" in a:
+          raise NotImplementedError("site-based connect / weld equalities are not supported")
+        etype, otype = (C.EQ_CONNECT if child.tag == "connect" else C.EQ_WELD), C.OBJ_BODY
+        o1 = m.names.body.index(a["body1"])
+        o2 = m.names.body.index(a["body2"]) if "body2" in a else 0
+        if child.tag == "connect":
+          data[:3] = _vec(a["anchor"])
+        else:
+          data[:3] = _vec(a.get("anchor", "0 0 0"))
+          if "relpose" in a:
+            rp = _vec(a["relpose"])
+            data[3:6], data[6:10] = rp[:3], rp[3:7]
+          data[10] = float(a.get("torquescale", 1.0))
+      eqs.append(dict(type=etype, objtype=otype, obj1=o1, obj2=o2, data=data, active=a.get("active", "true") == "true",
+                      solref=_vec(a.get("solref", "0.02 1")), solimp=_vec(a.get("solimp", "0.9 0.95 0.001 0.5 2"))))
+  m.neq = len(eqs)
+  m.eq_type = np.array([e["type"] for e in eqs], dtype=np.int32)
+  m.eq_objtype = np.array([e["objtype"] for e in eqs], dtype=np.int32)
+  m.eq_obj1id = np.array([e["obj1"] for e in eqs], dtype=np.int32)
+  m.eq_obj2id = np.array([e["obj2"] for e in eqs], dtype=np.int32)
+  m.eq_active0 = np.array([e["active"] for e in eqs], dtype=bool)
+  m.eq_solref = np.array([e["solref"] for e in eqs], dtype=np.float64).reshape(m.neq, 2)
+  m.eq_solimp = np.array([e["solimp"] for e in eqs], dtype=np.float64).reshape(m.neq, 5)
+  m.eq_data = np.array([e["data"] for e in eqs], dtype=np.float64).reshape(m.neq, 11)
+
   # unused families (sizes only)
-  m.neq = m.ntendon = m.nflex = m.nmesh = m.nhfield = m.nsensor = m.nsensordata = 0
+  m.ntendon = m.nflex = m.nmesh = m.nhfield = m.nsensor = m.nsensordata = 0
   nsens = root.find("sensor")
   m.nsensor_ignored = 0 if nsens is None else len(list(nsens))
 
@@ -1028,9 +1069,30 @@ def dense_inertia_np(m, kin):
   return M, jacp, jacr
 
 
+def _set_eq_data0(m, kin):
+  """Connect / weld anchors and relative pose at qpos0 (reference set_const.py:78-153, MuJoCo mj_setConst)."""
+  xmat = np.asarray(kin.xmat).reshape(m.nbody, 3, 3)
+  for e in range(m.neq):
+    o1, o2, data = int(m.eq_obj1id[e]), int(m.eq_obj2id[e]), m.eq_data[e]
+    if m.eq_type[e] == C.EQ_CONNECT:
+      pos = kin.xpos[o1] + xmat[o1] @ data[0:3]  # anchor given in body1's frame
+      data[3:6] = xmat[o2].T @ (pos - kin.xpos[o2])
+    elif m.eq_type[e] == C.EQ_WELD:
+      quat = data[6:10]
+      if quat @ quat > 0:
+        data[6:10] = quat / np.linalg.norm(quat)
+      else:
+        pos = kin.xpos[o2] + xmat[o2] @ data[0:3]  # anchor given in body2's frame
+        data[3:6] = xmat[o1].T @ (pos - kin.xpos[o1])
+        q1 = kin.xquat[o1]
+        data[6:10] = quat_mul(np.array([q1[0], -q1[1], -q1[2], -q1[3]]), kin.xquat[o2])
+
+
 def _set_const(m):
   kin = kinematics_np(m, m.qpos0)
   nv = m.nv
+  if getattr(m, "neq", 0):
+    _set_eq_data0(m, kin)
   m.body_invweight0 = np.zeros((m.nbody, 2))
   m.dof_invweight0 = np.zeros(nv)
   m.actuator_acc0 = np.zeros(m.nu)

@@ -1,6 +1,8 @@
-// k_constraint.cu -- fused make_constraint: dof-friction rows, joint-limit rows, contact rows (dense Jacobian).
+// k_constraint.cu -- fused make_constraint: equality rows (connect / weld / joint), dof-friction rows, joint-limit rows
+// (ball, slide / hinge), contact rows (dense Jacobian).
 //
-// Replaces (reference, /root/reference/mujoco_warp/_src/constraint.py): :61 _zero_constraint_counts, :1765 _friction_dof,
+// Replaces (reference, /root/reference/mujoco_warp/_src/constraint.py): :61 _zero_constraint_counts, :156 _equality_connect,
+// :966 _equality_weld, :500 _equality_joint (+ support.py:506 jac_dof, :615 jac_dot_dof), :2107 _limit_ball, :1765 _friction_dof,
 // :1990 _limit_slide_hinge, :2641 _efc_contact_init, :3751 _efc_contact_jac_dense, :4197 _efc_contact_update and the row
 // builder :83-152 _efc_row -- ~16 launches with per-row atomics there, one launch here.
 //
@@ -67,6 +69,36 @@ __device__ void efc_row(const ModelDev& m, const DataDev& d, int w, int efcid, f
   d.efc_id[r] = id;
 }
 
+
+// support.py:506 / :615 -- Jacobian column of a point on body b for dof `dof`, and its time derivative.  cvel / cdof_dot
+// are read from Data as the previous velocity stage left them (the reference builds constraints before fwd_velocity too).
+__device__ __forceinline__ void jac_cols(const ModelDev& m, const DataDev& d, size_t wb, const float* cdof, const float* scom, v3 point, int b,
+                                         int dof, v3* jp, v3* jr, v3* dp, v3* dr) {
+  *jp = *jr = *dp = *dr = mk3(0.f, 0.f, 0.f);
+  if (!m.body_isdofancestor[b * m.nv + dof]) return;
+  const v3 off = point - ld3(scom + 3 * m.body_rootid[b]);
+  const float* cd = cdof + 6 * dof;
+  const v3 cang = ld3(cd), clin = ld3(cd + 3);
+  *jp = clin + cross(cang, off);
+  *jr = cang;
+  const float* cv = d.cvel + (wb * m.nbody + b) * 6;
+  const v3 pvel = ld3(cv + 3) - cross(off, ld3(cv));
+  float cdd[6];
+  const int j = m.dof_jntid[dof], jt = m.jnt_type[j];
+  if (jt == JNT_BALL || (jt == JNT_FREE && dof >= m.jnt_dofadr[j] + 3)) motion_cross(d.cvel + (wb * m.nbody + m.dof_bodyid[dof]) * 6, cd, cdd);
+  else for (int i = 0; i < 6; i++) cdd[i] = d.cdof_dot[(wb * m.nv + dof) * 6 + i];
+  *dp = ld3(cdd + 3) + cross(ld3(cdd), off) + cross(cang, pvel);
+  *dr = ld3(cdd);
+}
+__device__ __forceinline__ float comp3(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__device__ __forceinline__ q4 quat_mul_axis(q4 q, v3 a) {  // math.py:33
+  return mkq(-q.x * a.x - q.y * a.y - q.z * a.z, q.w * a.x + q.y * a.z - q.z * a.y, q.w * a.y + q.z * a.x - q.x * a.z, q.w * a.z + q.x * a.y - q.y * a.x);
+}
+__device__ __forceinline__ q4 qscale(q4 q, float s) { return mkq(q.w * s, q.x * s, q.y * s, q.z * s); }
+__device__ __forceinline__ q4 qconj(q4 q) { return mkq(q.w, -q.x, -q.y, -q.z); }
+__device__ __forceinline__ v3 qvec(q4 q) { return mk3(q.x, q.y, q.z); }
+__device__ __forceinline__ v3 warp_sum3v(v3 a) { return mk3(warp_sum(a.x), warp_sum(a.y), warp_sum(a.z)); }
+
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32, 28)
 k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -89,7 +121,102 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
   warp_copy(qvel, d.qvel + wb * nv, nv, lane);
   __syncwarp();
 
-  int nefc = 0, nf = 0, nl = 0;
+  int nefc = 0, ne = 0, nf = 0, nl = 0;
+
+  // ---- equality rows, in the reference's launch order: connect, weld, joint (constraint.py:4911-5080).  The warp walks
+  // the (few) equalities together; lanes map to dofs for the Jacobian rows and the J*qvel / Jdot*qvel reductions.
+  if (m.neq > 0 && !(m.disableflags & DSBL_EQUALITY)) {
+#pragma unroll 1
+    for (int pass = 0; pass < 3; pass++) {
+#pragma unroll 1
+      for (int e = 0; e < m.neq; e++) {
+        const int type = m.eq_type[e];
+        if (type != (pass == 0 ? EQ_CONNECT : pass == 1 ? EQ_WELD : EQ_JOINT) || !d.eq_active[wb * m.neq + e]) continue;
+        const float* data = m.eq_data + 11 * e;
+        const int o1 = m.eq_obj1id[e], o2 = m.eq_obj2id[e];
+        if (type == EQ_JOINT) {
+          const int efcid = nefc;
+          nefc += 1; ne += 1;
+          if (efcid >= njmax) continue;
+          const int d1 = m.jnt_dofadr[o1], q1 = m.jnt_qposadr[o1];
+          int d2 = -1;
+          float pos, Jqvel, invweight, deriv2 = 0.f;
+          if (o2 > -1) {
+            const int q2 = m.jnt_qposadr[o2];
+            d2 = m.jnt_dofadr[o2];
+            const float dif = d.qpos[wb * m.nq + q2] - m.qpos0[q2];
+            const float rhs = data[0] + dif * (data[1] + dif * (data[2] + dif * (data[3] + dif * data[4])));
+            deriv2 = data[1] + dif * (2.0f * data[2] + dif * (3.0f * data[3] + dif * 4.0f * data[4]));
+            pos = d.qpos[wb * m.nq + q1] - m.qpos0[q1] - rhs;
+            Jqvel = qvel[d1] - qvel[d2] * deriv2;
+            invweight = m.dof_invweight0[d1] + m.dof_invweight0[d2];
+          } else {
+            pos = d.qpos[wb * m.nq + q1] - m.qpos0[q1] - data[0];
+            Jqvel = qvel[d1];
+            invweight = m.dof_invweight0[d1];
+          }
+#pragma unroll 1
+          for (int c = lane; c < nvp; c += 32) Jw[(size_t)efcid * nvp + c] = c == d1 ? 1.0f : (c == d2 ? -deriv2 : 0.f);
+          if (lane == 0) efc_row(m, d, w, efcid, pos, pos, invweight, m.eq_solref + 2 * e, m.eq_solimp + 5 * e, 0.f, Jqvel, 0.f, CNSTR_EQUALITY, e);
+          continue;
+        }
+        const int nrow = type == EQ_CONNECT ? 3 : 6, efcid = nefc;
+        nefc += nrow; ne += nrow;
+        if (efcid >= njmax - nrow) continue;
+        const int b1 = o1, b2 = o2;
+        const v3 a1 = ld3(data), a2 = ld3(data + 3);  // connect: a1 in body1, a2 in body2; weld: data[0:3] is in body2's frame
+        const v3 pos1 = ld3(d.xpos + (wb * nb + b1) * 3) + matvec(d.xmat + (wb * nb + b1) * 9, type == EQ_CONNECT ? a1 : a2);
+        const v3 pos2 = ld3(d.xpos + (wb * nb + b2) * 3) + matvec(d.xmat + (wb * nb + b2) * 9, type == EQ_CONNECT ? a2 : a1);
+        q4 quat = mkq(1.f, 0.f, 0.f, 0.f), quat1 = quat;
+        const q4 xq1 = ldq(d.xquat + (wb * nb + b1) * 4), xq2 = ldq(d.xquat + (wb * nb + b2) * 4), relpose = ldq(data + 6);
+        float torquescale = 0.f;
+        if (type == EQ_WELD) { torquescale = data[10]; quat = qmul(xq1, relpose); quat1 = qconj(xq2); }
+        v3 Jqvelp = mk3(0.f, 0.f, 0.f), Jqvelr = Jqvelp, Jdotvp = Jqvelp, Jdotvr0 = Jqvelp;
+#pragma unroll 1
+        for (int c = lane; c < nvp; c += 32) {
+          v3 jdp = mk3(0.f, 0.f, 0.f), jdr = jdp;
+          if (c < nv) {
+            v3 jp1, jr1, dp1, dr1, jp2, jr2, dp2, dr2;
+            jac_cols(m, d, wb, cdof, scom, pos1, b1, c, &jp1, &jr1, &dp1, &dr1);
+            jac_cols(m, d, wb, cdof, scom, pos2, b2, c, &jp2, &jr2, &dp2, &dr2);
+            const float qv = qvel[c];
+            jdp = jp1 - jp2;
+            Jqvelp = Jqvelp + jdp * qv; Jdotvp = Jdotvp + (dp1 - dp2) * qv;
+            if (type == EQ_WELD) {
+              jdr = qvec(qmul(quat_mul_axis(quat1, (jr1 - jr2) * torquescale), quat)) * 0.5f;
+              Jqvelr = Jqvelr + jdr * qv; Jdotvr0 = Jdotvr0 + (dr1 - dr2) * qv;
+            }
+          }
+          Jw[(size_t)(efcid + 0) * nvp + c] = jdp.x; Jw[(size_t)(efcid + 1) * nvp + c] = jdp.y; Jw[(size_t)(efcid + 2) * nvp + c] = jdp.z;
+          if (type == EQ_WELD) { Jw[(size_t)(efcid + 3) * nvp + c] = jdr.x; Jw[(size_t)(efcid + 4) * nvp + c] = jdr.y; Jw[(size_t)(efcid + 5) * nvp + c] = jdr.z; }
+        }
+        Jqvelp = warp_sum3v(Jqvelp); Jdotvp = warp_sum3v(Jdotvp);
+        const v3 cpos = pos1 - pos2;
+        const float invw_t = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
+        v3 crot = mk3(0.f, 0.f, 0.f), Jdotvr = crot;
+        if (type == EQ_WELD) {
+          Jqvelr = warp_sum3v(Jqvelr); Jdotvr0 = warp_sum3v(Jdotvr0);
+          crot = qvec(qmul(quat1, quat)) * torquescale;
+          // rotational Jdot*v through the quaternion product rule (constraint.py:1085-1117, 1381-1395)
+          const v3 om1 = ld3(d.cvel + (wb * nb + b1) * 6), om2 = ld3(d.cvel + (wb * nb + b2) * 6), dom = om1 - om2;
+          const q4 om1q = mkq(0.f, om1.x, om1.y, om1.z), om2q = mkq(0.f, om2.x, om2.y, om2.z), domq = mkq(0.f, dom.x, dom.y, dom.z);
+          const q4 qdot0r = qmul(qscale(qmul(om1q, xq1), 0.5f), relpose), qdot1 = qscale(qmul(om2q, xq2), 0.5f);
+          const q4 negqdot1 = qconj(qdot1), negq1 = qconj(xq2), djq = mkq(0.f, Jdotvr0.x, Jdotvr0.y, Jdotvr0.z);
+          const v3 t1 = qvec(qmul(qmul(negqdot1, domq), quat)), t2 = qvec(qmul(qmul(negq1, djq), quat)), t3 = qvec(qmul(qmul(negq1, domq), qdot0r));
+          Jdotvr = (t1 + t2 + t3) * (0.5f * torquescale);
+        }
+        const float pos_imp = sqrtf(dot(cpos, cpos) + dot(crot, crot));
+        if (lane < nrow) {
+          const bool rot = lane >= 3;
+          const int k = rot ? lane - 3 : lane;
+          const float invw = rot ? m.body_invweight0[2 * b1 + 1] + m.body_invweight0[2 * b2 + 1] : invw_t;
+          efc_row(m, d, w, efcid + lane, comp3(rot ? crot : cpos, k), pos_imp, invw, m.eq_solref + 2 * e, m.eq_solimp + 5 * e, 0.f,
+                  comp3(rot ? Jqvelr : Jqvelp, k), 0.f, CNSTR_EQUALITY, e);
+          d.efc_aref[wb * njmax + efcid + lane] -= comp3(rot ? Jdotvr : Jdotvp, k);
+        }
+      }
+    }
+  }
 
   // ---- dof friction loss rows (always present when frictionloss > 0)
   if (!(m.disableflags & DSBL_FRICTIONLOSS)) {
@@ -106,8 +233,33 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
     nefc += nf;
   }
 
-  // ---- joint limits (slide / hinge)
+  // ---- joint limits: ball joints first (constraint.py:2107), then slide / hinge -- the reference's launch order
   if (!(m.disableflags & DSBL_LIMIT)) {
+#pragma unroll 1
+    for (int li = 0; li < m.nlimit_ball; li++) {
+      const int j = m.jnt_limited_ball_adr[li], qa = m.jnt_qposadr[j], dofadr = m.jnt_dofadr[j];
+      const q4 q = qnormalize(ldq(d.qpos + wb * m.nq + qa));
+      v3 axis = mk3(0.f, 0.f, 0.f);
+      float angle = 0.f;
+      const float s2 = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+      if (s2 != 0.f) {  // math.py:161 quat_to_vel, then normalize_with_norm
+        float speed = 2.0f * atan2f(s2, q.w);
+        if (speed > 3.14159265358979f) speed -= 2.0f * 3.14159265358979f;
+        const v3 v = mk3(q.x, q.y, q.z) * (speed / s2);
+        angle = length(v);
+        axis = angle == 0.f ? v : v * (1.0f / angle);
+      }
+      const float margin = m.jnt_margin[j], pos = fmaxf(m.jnt_range[2 * j], m.jnt_range[2 * j + 1]) - angle - margin;
+      if (!(pos < 0.f)) continue;
+      const int efcid = nefc;
+      nefc += 1; nl += 1;
+      if (efcid >= njmax) continue;
+#pragma unroll 1
+      for (int c = lane; c < nvp; c += 32) Jw[(size_t)efcid * nvp + c] = (c >= dofadr && c < dofadr + 3) ? -comp3(axis, c - dofadr) : 0.f;
+      if (lane == 0)
+        efc_row(m, d, w, efcid, pos, pos, m.dof_invweight0[dofadr], m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, margin,
+                -(axis.x * qvel[dofadr] + axis.y * qvel[dofadr + 1] + axis.z * qvel[dofadr + 2]), 0.f, CNSTR_LIMIT_JOINT, j);
+    }
 #pragma unroll 1
     for (int l0 = 0; l0 < m.nlimit; l0 += 32) {
       const int li = l0 + lane;
@@ -266,7 +418,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
       __syncwarp();
     }
   }
-  if (lane == 0) { d.ne[w] = 0; d.nf[w] = nf; d.nl[w] = nl; d.nefc[w] = nefc; }
+  if (lane == 0) { d.ne[w] = ne; d.nf[w] = nf; d.nl[w] = nl; d.nefc[w] = nefc; }
 }
 
 }  // namespace

@@ -24,6 +24,7 @@ enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { GEOM_PLANE = 0, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH };
 enum { INT_EULER = 0, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST };
 enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
+enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
 enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_LIMIT_JOINT = 3, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6, CNSTR_CONTACT_ELLIPTIC = 7 };
 enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
 enum { CAM_FIXED = 0, CAM_TRACK, CAM_TRACKCOM, CAM_TARGETBODY, CAM_TARGETBODYCOM };
@@ -40,7 +41,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 /* ------------------------------------------------------------------ field registries (X-macros) */
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
-  X(nxn_npair) X(nlimit) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
+  X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
   X(disableflags) X(enableflags) X(broadphase_filter)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia)
 #define MODEL_IARRS(X) \
@@ -51,7 +52,8 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
-  X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(body_isdofancestor)
+  X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
+  X(eq_type) X(eq_obj1id) X(eq_obj2id)
 #define MODEL_RARRS(X) \
   X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
   X(body_inertia) X(body_invweight0) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
@@ -59,7 +61,8 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(dof_solimp) X(geom_size) X(geom_aabb) X(geom_rbound) X(geom_pos) X(geom_quat) X(geom_friction) X(geom_margin) \
   X(geom_gap) X(geom_solmix) X(geom_solref) X(geom_solimp) X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) \
   X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
-  X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat)
+  X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat) \
+  X(eq_solref) X(eq_solimp) X(eq_data)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -73,7 +76,8 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(con_dist) X(con_pos) X(con_frame) X(con_includemargin) X(con_friction) X(con_solref) X(con_solreffriction) X(con_solimp)
 #define DATA_IARRS(X) \
   X(ne) X(nf) X(nl) X(nefc) X(ncon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
-  X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(con_dim) X(con_geom) X(con_efc_address) X(con_geomcollisionid)
+  X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(con_dim) X(con_geom) X(con_efc_address) X(con_geomcollisionid) \
+  X(eq_active)
 
 struct OrcModel {
 #define X(n) int n;
@@ -330,6 +334,7 @@ static void make_view(const OrcModel* m, const OrcData* d, int w, W* v) {
   R(ne, 1); R(nf, 1); R(nl, 1); R(nefc, 1); R(ncon, 1); R(ncollision, 1); R(solver_niter, 1); R(overflow, 1);
   R(efc_type, njm); R(efc_id, njm); R(efc_state, njm); R(moment_rownnz, nu); R(moment_rowadr, nu); R(moment_colind, m->nJmom);
   R(con_dim, ncm); R(con_geom, 2 * ncm); R(con_efc_address, m->nmaxpyramid * ncm); R(con_geomcollisionid, ncm);
+  R(eq_active, m->neq);
 #undef R
 }
 
@@ -1392,12 +1397,155 @@ static void efc_row(W* w, int efcid, real pos_aref, real pos_imp, real invweight
   w->efc_type[efcid] = type;
   w->efc_id[efcid] = id;
 }
+/* support.py:506 jac_dof / :615 jac_dot_dof: translational and rotational Jacobian column (and its time derivative)
+ * of a point attached to body `b` for dof `d`; cvel / cdof_dot are whatever the last velocity stage left in Data */
+static void jac_dof(const W* w, const real* point, int b, int d, real* jp, real* jr) {
+  const OrcModel* m = w->m;
+  for (int i = 0; i < 3; i++) { jp[i] = 0; jr[i] = 0; }
+  if (!m->body_isdofancestor[b * m->nv + d]) return;
+  const real* com = w->subtree_com + 3 * m->body_rootid[b]; const real* cd = w->cdof + 6 * d;
+  real off[3] = {point[0] - com[0], point[1] - com[1], point[2] - com[2]}, cr[3];
+  cross3(cd, off, cr);
+  for (int i = 0; i < 3; i++) { jp[i] = cd[3 + i] + cr[i]; jr[i] = cd[i]; }
+}
+static void jac_dot_dof(const W* w, const real* point, int b, int d, real* jp, real* jr) {
+  const OrcModel* m = w->m;
+  for (int i = 0; i < 3; i++) { jp[i] = 0; jr[i] = 0; }
+  if (!m->body_isdofancestor[b * m->nv + d]) return;
+  const real* com = w->subtree_com + 3 * m->body_rootid[b];
+  real off[3] = {point[0] - com[0], point[1] - com[1], point[2] - com[2]};
+  const real* cvel = w->cvel + 6 * b; const real* cd = w->cdof + 6 * d;
+  real t[3], pvel[3], cdd[6];
+  cross3(off, cvel, t);
+  for (int i = 0; i < 3; i++) pvel[i] = cvel[3 + i] - t[i];
+  memcpy(cdd, w->cdof_dot + 6 * d, sizeof cdd);
+  int j = m->dof_jntid[d], jt = m->jnt_type[j];
+  if (jt == JNT_BALL || (jt == JNT_FREE && d >= m->jnt_dofadr[j] + 3)) motion_cross(w->cvel + 6 * m->dof_bodyid[d], cd, cdd);
+  real c1[3], c2[3];
+  cross3(cdd, off, c1);
+  cross3(cd, pvel, c2);
+  for (int i = 0; i < 3; i++) { jp[i] = cdd[3 + i] + c1[i] + c2[i]; jr[i] = cdd[i]; }
+}
+static inline void quat_mul_axis(const real* q, const real* a, real* o) { /* math.py:33 */
+  o[0] = -q[1] * a[0] - q[2] * a[1] - q[3] * a[2];
+  o[1] = q[0] * a[0] + q[2] * a[2] - q[3] * a[1];
+  o[2] = q[0] * a[1] + q[3] * a[0] - q[1] * a[2];
+  o[3] = q[0] * a[2] + q[1] * a[1] - q[2] * a[0];
+}
+/* constraint.py:156 connect (3 rows), :966 weld (6 rows), :500 joint (1 row); body-based anchors only */
+static int equality_rows(W* w, int nefc) {
+  const OrcModel* m = w->m; const int nv = m->nv, njmax = w->njmax;
+  for (int pass = 0; pass < 3; pass++) for (int e = 0; e < m->neq; e++) { /* launch order: connect, weld, joint */
+    int type = m->eq_type[e];
+    if (type != (pass == 0 ? EQ_CONNECT : pass == 1 ? EQ_WELD : EQ_JOINT) || !w->eq_active[e]) continue;
+    const real* data = m->eq_data + 11 * e; const real* solref = m->eq_solref + 2 * e; const real* solimp = m->eq_solimp + 5 * e;
+    int o1 = m->eq_obj1id[e], o2 = m->eq_obj2id[e];
+    if (type == EQ_JOINT) {
+      w->ne[0] += 1;
+      int efcid = nefc; nefc += 1;
+      if (efcid >= njmax) continue;
+      int d1 = m->jnt_dofadr[o1], q1 = m->jnt_qposadr[o1];
+      real* J = w->efc_J + (size_t)efcid * nv, pos, Jqvel, invweight;
+      for (int i = 0; i < nv; i++) J[i] = 0;
+      J[d1] = 1;
+      if (o2 > -1) {
+        int q2 = m->jnt_qposadr[o2], d2 = m->jnt_dofadr[o2];
+        real dif = w->qpos[q2] - m->qpos0[q2];
+        real rhs = data[0] + dif * (data[1] + dif * (data[2] + dif * (data[3] + dif * data[4])));
+        real deriv2 = data[1] + dif * (2 * data[2] + dif * (3 * data[3] + dif * 4 * data[4]));
+        pos = w->qpos[q1] - m->qpos0[q1] - rhs;
+        Jqvel = w->qvel[d1] - w->qvel[d2] * deriv2;
+        invweight = m->dof_invweight0[d1] + m->dof_invweight0[d2];
+        J[d2] = -deriv2;
+      } else {
+        pos = w->qpos[q1] - m->qpos0[q1] - data[0];
+        Jqvel = w->qvel[d1];
+        invweight = m->dof_invweight0[d1];
+      }
+      efc_row(w, efcid, pos, pos, invweight, solref, solimp, 0, Jqvel, 0, CNSTR_EQUALITY, e);
+      continue;
+    }
+    const int nrow = type == EQ_CONNECT ? 3 : 6;
+    w->ne[0] += nrow;
+    int efcid = nefc; nefc += nrow;
+    if (efcid >= njmax - nrow) continue;
+    const int b1 = o1, b2 = o2;
+    const real *a1 = data, *a2 = data + 3; /* connect: anchor1 in body1, anchor2 in body2; weld: data[0:3] lives in body2 */
+    real pos1[3], pos2[3], t[3];
+    matvec3(w->xmat + 9 * b1, type == EQ_CONNECT ? a1 : a2, t);
+    for (int i = 0; i < 3; i++) pos1[i] = w->xpos[3 * b1 + i] + t[i];
+    matvec3(w->xmat + 9 * b2, type == EQ_CONNECT ? a2 : a1, t);
+    for (int i = 0; i < 3; i++) pos2[i] = w->xpos[3 * b2 + i] + t[i];
+    real quat[4] = {1, 0, 0, 0}, quat1[4] = {1, 0, 0, 0}, torquescale = 0;
+    if (type == EQ_WELD) {
+      torquescale = data[10];
+      mul_quat(w->xquat + 4 * b1, data + 6, quat);
+      const real* q2 = w->xquat + 4 * b2;
+      quat1[0] = q2[0]; quat1[1] = -q2[1]; quat1[2] = -q2[2]; quat1[3] = -q2[3];
+    }
+    real Jqvelp[3] = {0, 0, 0}, Jqvelr[3] = {0, 0, 0}, Jdotvp[3] = {0, 0, 0}, Jdotvr0[3] = {0, 0, 0};
+    for (int d = 0; d < nv; d++) {
+      real jp1[3], jr1[3], jp2[3], jr2[3], dp1[3], dr1[3], dp2[3], dr2[3];
+      jac_dof(w, pos1, b1, d, jp1, jr1); jac_dof(w, pos2, b2, d, jp2, jr2);
+      jac_dot_dof(w, pos1, b1, d, dp1, dr1); jac_dot_dof(w, pos2, b2, d, dp2, dr2);
+      real qv = w->qvel[d];
+      for (int i = 0; i < 3; i++) {
+        real jd = jp1[i] - jp2[i];
+        w->efc_J[(size_t)(efcid + i) * nv + d] = jd;
+        Jqvelp[i] += jd * qv; Jdotvp[i] += (dp1[i] - dp2[i]) * qv;
+      }
+      if (type == EQ_WELD) {
+        real jdr[3] = {(jr1[0] - jr2[0]) * torquescale, (jr1[1] - jr2[1]) * torquescale, (jr1[2] - jr2[2]) * torquescale}, qa[4], qb[4];
+        quat_mul_axis(quat1, jdr, qa);
+        mul_quat(qa, quat, qb);
+        for (int i = 0; i < 3; i++) {
+          real jr = (real)0.5 * qb[1 + i];
+          w->efc_J[(size_t)(efcid + 3 + i) * nv + d] = jr;
+          Jqvelr[i] += jr * qv; Jdotvr0[i] += (dr1[i] - dr2[i]) * qv;
+        }
+      }
+    }
+    real cpos[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+    real invw_t = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
+    if (type == EQ_CONNECT) {
+      real pos_imp = len3(cpos);
+      for (int i = 0; i < 3; i++) { efc_row(w, efcid + i, cpos[i], pos_imp, invw_t, solref, solimp, 0, Jqvelp[i], 0, CNSTR_EQUALITY, e); w->efc_aref[efcid + i] -= Jdotvp[i]; }
+      continue;
+    }
+    real crotq[4], crot[3];
+    mul_quat(quat1, quat, crotq);
+    for (int i = 0; i < 3; i++) crot[i] = crotq[1 + i] * torquescale;
+    real pos_imp = (real)sqrt((double)(dot3(cpos, cpos) + dot3(crot, crot)));
+    /* rotational Jdotv from the quaternion product rule (constraint.py:1085-1117, 1381-1395) */
+    const real *om1 = w->cvel + 6 * b1, *om2 = w->cvel + 6 * b2;
+    real om1q[4] = {0, om1[0], om1[1], om1[2]}, om2q[4] = {0, om2[0], om2[1], om2[2]}, domq[4] = {0, om1[0] - om2[0], om1[1] - om2[1], om1[2] - om2[2]};
+    real qdot0[4], qdot0r[4], qdot1[4], negqdot1[4], negq1[4], dj[4] = {0, Jdotvr0[0], Jdotvr0[1], Jdotvr0[2]}, ta[4], t1[4], t2[4], t3[4];
+    mul_quat(om1q, w->xquat + 4 * b1, qdot0);
+    for (int i = 0; i < 4; i++) qdot0[i] *= (real)0.5;
+    mul_quat(qdot0, data + 6, qdot0r);
+    mul_quat(om2q, w->xquat + 4 * b2, qdot1);
+    for (int i = 0; i < 4; i++) qdot1[i] *= (real)0.5;
+    negqdot1[0] = qdot1[0]; negq1[0] = w->xquat[4 * b2];
+    for (int i = 1; i < 4; i++) { negqdot1[i] = -qdot1[i]; negq1[i] = -w->xquat[4 * b2 + i]; }
+    mul_quat(negqdot1, domq, ta); mul_quat(ta, quat, t1);
+    mul_quat(negq1, dj, ta); mul_quat(ta, quat, t2);
+    mul_quat(negq1, domq, ta); mul_quat(ta, qdot0r, t3);
+    real invw_r = m->body_invweight0[2 * b1 + 1] + m->body_invweight0[2 * b2 + 1];
+    for (int i = 0; i < 3; i++) { efc_row(w, efcid + i, cpos[i], pos_imp, invw_t, solref, solimp, 0, Jqvelp[i], 0, CNSTR_EQUALITY, e); w->efc_aref[efcid + i] -= Jdotvp[i]; }
+    for (int i = 0; i < 3; i++) {
+      efc_row(w, efcid + 3 + i, crot[i], pos_imp, invw_r, solref, solimp, 0, Jqvelr[i], 0, CNSTR_EQUALITY, e);
+      w->efc_aref[efcid + 3 + i] -= (t1[1 + i] + t2[1 + i] + t3[1 + i]) * (real)0.5 * torquescale;
+    }
+  }
+  return nefc;
+}
 static void make_constraint(W* w) {
   const OrcModel* m = w->m;
   const int nv = m->nv, njmax = w->njmax, np = m->nmaxpyramid;
   int nefc = 0;
   w->ne[0] = w->nf[0] = w->nl[0] = 0;
   if (m->disableflags & DSBL_CONSTRAINT) { w->nefc[0] = 0; return; }
+  if (!(m->disableflags & DSBL_EQUALITY)) nefc = equality_rows(w, nefc);
   /* dof friction (constraint.py:1765) */
   if (!(m->disableflags & DSBL_FRICTIONLOSS)) {
     for (int d = 0; d < nv; d++) {
@@ -1410,8 +1558,31 @@ static void make_constraint(W* w) {
       efc_row(w, efcid, 0, 0, m->dof_invweight0[d], m->dof_solref + 2 * d, m->dof_solimp + 5 * d, 0, w->qvel[d], m->dof_frictionloss[d], CNSTR_FRICTION_DOF, d);
     }
   }
-  /* joint limits, slide/hinge (constraint.py:1990) */
+  /* joint limits: ball (constraint.py:2107) first, then slide/hinge (:1990) -- the reference's launch order */
   if (!(m->disableflags & DSBL_LIMIT)) {
+    for (int li = 0; li < m->nlimit_ball; li++) {
+      int j = m->jnt_limited_ball_adr[li], qa = m->jnt_qposadr[j];
+      real q[4] = {w->qpos[qa], w->qpos[qa + 1], w->qpos[qa + 2], w->qpos[qa + 3]}, axis[3] = {0, 0, 0}, angle = 0;
+      normalize4(q);
+      real s2 = (real)sqrt((double)(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]));
+      if (s2 != 0) { /* math.py:161 quat_to_vel, then normalize_with_norm */
+        real speed = 2 * (real)atan2((double)s2, (double)q[0]);
+        if (speed > (real)3.14159265358979323846) speed -= 2 * (real)3.14159265358979323846;
+        real v[3] = {q[1] * speed / s2, q[2] * speed / s2, q[3] * speed / s2};
+        angle = len3(v);
+        for (int i = 0; i < 3; i++) axis[i] = angle == 0 ? v[i] : v[i] / angle;
+      }
+      real margin = m->jnt_margin[j], pos = rmax(m->jnt_range[2 * j], m->jnt_range[2 * j + 1]) - angle - margin;
+      if (!(pos < 0)) continue;
+      w->nl[0]++;
+      int efcid = nefc++;
+      if (efcid >= njmax) continue;
+      int d = m->jnt_dofadr[j];
+      real Jqvel = 0;
+      for (int i = 0; i < nv; i++) w->efc_J[efcid * nv + i] = 0;
+      for (int i = 0; i < 3; i++) { w->efc_J[efcid * nv + d + i] = -axis[i]; Jqvel -= axis[i] * w->qvel[d + i]; }
+      efc_row(w, efcid, pos, pos, m->dof_invweight0[d], m->jnt_solref + 2 * j, m->jnt_solimp + 5 * j, margin, Jqvel, 0, CNSTR_LIMIT_JOINT, j);
+    }
     for (int li = 0; li < m->nlimit; li++) {
       int j = m->jnt_limited_slide_hinge_adr[li];
       real qpos = w->qpos[m->jnt_qposadr[j]], margin = m->jnt_margin[j];

@@ -104,6 +104,7 @@ def derived_tables(mjm):
   pairs = np.stack((g1, g2), axis=1)[include].astype(np.int32)
   pid = np.stack((pairid[include], -np.ones(include.sum(), dtype=np.int32)), axis=1).astype(np.int32)
   limited = np.nonzero(np.asarray(mjm.jnt_limited).astype(bool) & ((mjm.jnt_type == 2) | (mjm.jnt_type == 3)))[0].astype(np.int32)
+  limited_ball = np.nonzero(np.asarray(mjm.jnt_limited).astype(bool) & (mjm.jnt_type == 1))[0].astype(np.int32)
   blk = np.zeros(max(nv, 1), dtype=np.int32)
   off = 0
   for adr, num in zip(mjm.tree_dofadr, mjm.tree_dofnum):
@@ -114,7 +115,7 @@ def derived_tables(mjm):
     t = mjm.jnt_type[mjm.actuator_trnid[i, 0]]
     nJmom += {0: 6, 1: 3, 2: 1, 3: 1}[int(t)]
   nmaxcondim = int(mjm.geom_condim.max()) if ngeom else 1
-  return dict(body_isdofancestor=anc, nxn_geom_pair=pairs, nxn_pairid=pid, jnt_limited_slide_hinge_adr=limited,
+  return dict(body_isdofancestor=anc, nxn_geom_pair=pairs, nxn_pairid=pid, jnt_limited_slide_hinge_adr=limited, jnt_limited_ball_adr=limited_ball,
               qLD_block_adr=blk, qld_total=off, nJmom=nJmom, nmaxpyramid=max(1, 2 * (nmaxcondim - 1)))
 
 
@@ -143,6 +144,7 @@ def data_spec(mjm, tabs, nconmax, njmax):
     "ne": (I, ()), "nf": (I, ()), "nl": (I, ()), "nefc": (I, ()), "ncon": (I, ()), "ncollision": (I, ()), "solver_niter": (I, ()), "overflow": (I, ()),
     "efc_type": (I, (njmax,)), "efc_id": (I, (njmax,)), "efc_state": (I, (njmax,)),
     "moment_rownnz": (I, (nu,)), "moment_rowadr": (I, (nu,)), "moment_colind": (I, (tabs["nJmom"],)),
+    "eq_active": (I, (int(getattr(mjm, "neq", 0)),)),
     "con_dim": (I, (nconmax,)), "con_geom": (I, (nconmax, 2)), "con_efc_address": (I, (nconmax, npyr)), "con_geomcollisionid": (I, (nconmax,)),
   }
 
@@ -183,6 +185,8 @@ class Oracle:
     o = mjm.opt
     seti("nJmom", self.tabs["nJmom"]); seti("nxn_npair", len(self.tabs["nxn_geom_pair"])); seti("nlimit", len(self.tabs["jnt_limited_slide_hinge_adr"]))
     seti("nmaxpyramid", self.tabs["nmaxpyramid"])
+    neq = int(getattr(mjm, "neq", 0))
+    seti("nlimit_ball", len(self.tabs["jnt_limited_ball_adr"])); seti("neq", neq)
     seti("integrator", o.integrator); seti("cone", o.cone); seti("solver", o.solver); seti("iterations", o.iterations)
     seti("ls_iterations", o.ls_iterations); seti("disableflags", o.disableflags); seti("enableflags", o.enableflags)
     seti("broadphase_filter", getattr(o, "broadphase_filter", 1 | 2 | 8))  # io.py:405 default PLANE|SPHERE|OBB
@@ -198,8 +202,12 @@ class Oracle:
     for n in MODEL_RARRS:
       setra(n, getattr(mjm, n))
     setra("gravity", o.gravity)
-    for n in ("nxn_geom_pair", "nxn_pairid", "jnt_limited_slide_hinge_adr", "body_isdofancestor", "qLD_block_adr"):
+    for n in ("nxn_geom_pair", "nxn_pairid", "jnt_limited_slide_hinge_adr", "jnt_limited_ball_adr", "body_isdofancestor", "qLD_block_adr"):
       setia(n, self.tabs[n])
+    for n in ("eq_type", "eq_obj1id", "eq_obj2id"):
+      setia(n, getattr(mjm, n) if neq else np.zeros(1, dtype=np.int32))
+    for n, k in (("eq_solref", 2), ("eq_solimp", 5), ("eq_data", 11)):
+      setra(n, getattr(mjm, n) if neq else np.zeros(k))
 
     self.spec = data_spec(mjm, self.tabs, nconmax, njmax)
     self.dptr = ctypes.c_void_p(lib.orc_data_create(nworld, nconmax, njmax))
@@ -211,6 +219,8 @@ class Oracle:
       assert fn(self.dptr, name.encode(), a.ctypes.data) == 0, name
     # initial state: qpos0, static geom poses from host kinematics (io.py:1815-1843)
     self.d["qpos"][:] = np.asarray(mjm.qpos0)
+    if neq:
+      self.d["eq_active"][:] = np.asarray(mjm.eq_active0).astype(np.int32)
     if static_kin is not None:
       self.d["geom_xpos"][:] = static_kin.geom_xpos
       self.d["geom_xmat"][:] = static_kin.geom_xmat

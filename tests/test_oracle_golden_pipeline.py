@@ -33,6 +33,8 @@ def load_scene(name):
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"'))
   elif name == "boxes":
     mjm = mjcf.load_string(BOX_XML)
+  elif name == "equality":
+    mjm = mjcf.load_string(util.EQUALITY_XML)
   elif name == "g1":
     mjm = mjcf.load_any(util.G1)
   else:

@@ -125,3 +125,49 @@ MIXED_XML = """
   </keyframe>
 </mujoco>
 """
+
+
+EQUALITY_XML = """
+<mujoco model="equality">
+  <option timestep="0.002" iterations="50"/>
+  <worldbody>
+    <geom type="plane" size="0 0 .05"/>
+    <body name="a1" pos="0 0 1">
+      <joint name="h1" type="hinge" axis="0 1 0" damping="0.1"/>
+      <geom type="capsule" fromto="0 0 0 0.3 0 0" size="0.02"/>
+      <body name="a2" pos="0.3 0 0">
+        <joint name="h2" type="hinge" axis="0 1 0" damping="0.1"/>
+        <geom type="capsule" fromto="0 0 0 0 0 -0.3" size="0.02"/>
+      </body>
+    </body>
+    <body name="b1" pos="0 0 0.7">
+      <joint name="h3" type="hinge" axis="0 1 0"/>
+      <geom type="capsule" fromto="0 0 0 0.3 0 0" size="0.02" contype="0" conaffinity="0"/>
+    </body>
+    <body name="ballarm" pos="0 0.5 1">
+      <joint name="bj" type="ball" limited="true" range="0 30" damping="0.05"/>
+      <geom type="capsule" fromto="0 0 0 0 0 -0.3" size="0.03"/>
+    </body>
+    <body name="f1" pos="0.6 0.5 0.5"><freejoint/><geom type="sphere" size="0.05"/></body>
+    <body name="f2" pos="0.8 0.5 0.5"><freejoint/><geom type="box" size="0.04 0.04 0.04"/></body>
+    <body name="s1" pos="-0.5 0 0.5"><joint name="sl1" type="slide" axis="0 0 1"/><geom type="sphere" size="0.04"/></body>
+    <body name="s2" pos="-0.7 0 0.5"><joint name="sl2" type="slide" axis="0 0 1" damping="1"/><geom type="sphere" size="0.04"/></body>
+    <body name="s3" pos="-0.9 0 0.5"><joint name="sl3" type="slide" axis="1 0 0"/><geom type="sphere" size="0.04"/></body>
+  </worldbody>
+  <equality>
+    <connect body1="a2" body2="b1" anchor="0 0 -0.3"/>
+    <weld body1="f1" body2="f2" torquescale="0.8"/>
+    <joint joint1="sl1" joint2="sl2" polycoef="0 0.5 0.1 0 0"/>
+    <joint joint1="sl3" polycoef="0.05 0 0 0 0" solref="0.03 1"/>
+    <connect body1="s2" anchor="0.1 0 0" solimp="0.8 0.9 0.01 0.5 2"/>
+    <weld body1="s1" body2="s3" active="false"/>
+  </equality>
+  <actuator>
+    <motor joint="h1" gear="2"/>
+    <motor joint="sl1" gear="5"/>
+  </actuator>
+  <keyframe>
+    <key name="k0" qpos="0 0 0  0.9396926 0.3420201 0 0  0.6 0.5 0.5 1 0 0 0  0.8 0.5 0.5 1 0 0 0  0 0 0"/>
+  </keyframe>
+</mujoco>
+"""
