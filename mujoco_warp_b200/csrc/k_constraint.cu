@@ -99,6 +99,9 @@ __device__ __forceinline__ q4 qconj(q4 q) { return mkq(q.w, -q.x, -q.y, -q.z); }
 __device__ __forceinline__ v3 qvec(q4 q) { return mk3(q.x, q.y, q.z); }
 __device__ __forceinline__ v3 warp_sum3v(v3 a) { return mk3(warp_sum(a.x), warp_sum(a.y), warp_sum(a.z)); }
 
+// EQ = the model has equality constraints or limited ball joints; plain articulated models (humanoid) use the leaner
+// instantiation without that code.
+template <bool EQ>
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32, 28)
 k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -125,7 +128,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
 
   // ---- equality rows, in the reference's launch order: connect, weld, joint (constraint.py:4911-5080).  The warp walks
   // the (few) equalities together; lanes map to dofs for the Jacobian rows and the J*qvel / Jdot*qvel reductions.
-  if (m.neq > 0 && !(m.disableflags & DSBL_EQUALITY)) {
+  if (EQ && m.neq > 0 && !(m.disableflags & DSBL_EQUALITY)) {
 #pragma unroll 1
     for (int pass = 0; pass < 3; pass++) {
 #pragma unroll 1
@@ -236,7 +239,7 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
   // ---- joint limits: ball joints first (constraint.py:2107), then slide / hinge -- the reference's launch order
   if (!(m.disableflags & DSBL_LIMIT)) {
 #pragma unroll 1
-    for (int li = 0; li < m.nlimit_ball; li++) {
+    for (int li = 0; li < (EQ ? m.nlimit_ball : 0); li++) {
       const int j = m.jnt_limited_ball_adr[li], qa = m.jnt_qposadr[j], dofadr = m.jnt_dofadr[j];
       const q4 q = qnormalize(ldq(d.qpos + wb * m.nq + qa));
       v3 axis = mk3(0.f, 0.f, 0.f);
@@ -427,13 +430,15 @@ size_t smem_constraint(const ModelDev& m, const DataDev& d) { return (size_t)con
 
 cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_constraint(m, d);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_constraint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured[2] = {0, 0};
+  const int eq = (m.neq > 0 || m.nlimit_ball > 0) ? 1 : 0;
+  void (*kern)(ModelDev, DataDev) = eq ? k_constraint<true> : k_constraint<false>;
+  if (smem > 48 * 1024 && smem > configured[eq]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[eq] = smem;
   }
   const int grid = d.wn;
-  k_constraint<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  kern<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

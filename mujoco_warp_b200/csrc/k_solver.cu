@@ -23,16 +23,21 @@ namespace {
 // Shared-memory slice of one world.  J rows keep the global stride nv_pad (a multiple of 4 floats), so a row is 16-byte
 // aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
 // rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
-struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, total; };
+struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, total; };
 __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d) {
   SolLayout L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   L.nvp = d.nv_pad; L.ldJ = d.nv_pad; L.ldH = m.nv | 1;
-  L.J = take(d.njmax * L.ldJ);
+  // nv > 32 ("big" models, e.g. unitree G1): only the first jcap Jacobian rows are staged in shared memory, later rows are
+  // read from global memory (they are L2 hits; nefc is usually far below njmax) -- keeps the per-world slice small enough for
+  // >= 12 resident warps per SM instead of 5
+  L.jcap = m.nv > 32 ? (d.njmax < 48 ? d.njmax : 48) : d.njmax;
+  L.J = take(L.jcap * L.ldJ);
   L.vec = take(7 * L.nvp);  // qacc, Ma, grad, search, mv (= x scratch of the nv > 32 path), qfs, qfc
   // nv <= 32: H and its factor are stored as packed lower triangles (register Cholesky path); larger nv keeps nv x ldH
-  const int hsz = m.nv <= 32 ? m.nv * (m.nv + 1) / 2 : m.nv * L.ldH;
+  // H and its factor are packed lower triangles (register Cholesky for nv <= 32, shared-memory Cholesky above)
+  const int hsz = m.nv * (m.nv + 1) / 2;
   L.H = take(hsz); L.Lf = take(hsz);
   L.M = take(m.nC);
   // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
@@ -163,7 +168,13 @@ struct Ctx {
   // elliptic only: rinfo[r] = -1 (not an elliptic row) | -2 (contact cut by njmax) | (dim << 4) | j;  rfri[r] = mu (j = 0)
   // or friction[j-1];  quad = 3 words per row;  the CONE contacts' primary rows are listed from the END of hidx
   int* rinfo; float *rfri, *quad; int njmax, ncone;
+  const float* Jg; int jcap;  // big models: rows >= jcap live in global memory (same leading dimension)
 };
+template <bool BIG>
+__device__ __forceinline__ const float* jrow(const Ctx& c, int r) {
+  if (BIG && r >= c.jcap) return c.Jg + (size_t)r * c.ldJ;
+  return c.J + r * c.ldJ;
+}
 __device__ __forceinline__ EllQ ell_load(const Ctx& c, int r) {
   const float* q = c.quad + 3 * r;
   EllQ e; e.q0 = q[0]; e.q1 = q[1]; e.q2 = q[2]; e.u0 = q[3]; e.v0 = q[4]; e.uu = q[5]; e.uv = q[6]; e.vv = q[7]; e.dm = q[8];
@@ -184,7 +195,7 @@ __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res
 
 // force/state per row, qfrc_constraint = J^T force, and the list of rows whose QUADRATIC flag changed
 // (init=true: list every QUADRATIC row with weight +D).  Returns the list length.
-template <bool ELL>
+template <bool ELL, bool BIG>
 __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
   int nlist = 0, ncone = 0;
   if (ELL) init = true;  // elliptic: H is rebuilt from M, so every QUADRATIC row is listed
@@ -241,7 +252,7 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
   for (int dd = c.lane; dd < c.nv; dd += 32) {
     float s = 0.f;
 #pragma unroll 8
-    for (int r = 0; r < c.nefc; r++) s += c.J[r * c.ldJ + dd] * c.force[r];
+    for (int r = 0; r < c.nefc; r++) s += jrow<BIG>(c, r)[dd] * c.force[r];
     c.qfc[dd] = s;
   }
   __syncwarp();
@@ -337,11 +348,11 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
-template <bool ELL>
+template <bool ELL, bool BIG>
 __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   const int nv = c.nv;
   float sd = 0.f, nd = 0.f;
-  if (nv <= 32) {
+  if (!BIG) {  // nv <= 32 (launch_solver picks the instantiation)
     const float g = c.lane < nv ? c.grad[c.lane] : 0.f;
     float xx;
     if (nv <= 8) xx = newton_direction_reg<8, ELL>(c, nlist, g);
@@ -352,49 +363,57 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
     sd = xx * xx; nd = g * xx;
     if (c.lane < nv) c.search[c.lane] = -xx;
   } else {
+    // 32 < nv <= 64: lane owns Hessian rows `lane` and `lane + 32` of the packed lower triangle in shared memory
     const int ntri = nv * (nv + 1) / 2;
-    if (!ELL) {
-      if (nlist > 0) {
+    float* Hd = ELL ? c.Lf : c.H;  // elliptic: rebuild into Lf from M (c.H) every iteration
+    if (ELL) {
 #pragma unroll 1
-        for (int e = c.lane; e < ntri; e += 32) {
-          int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-          while ((i + 1) * (i + 2) / 2 <= e) i++;
-          while (i * (i + 1) / 2 > e) i--;
-          const int j = e - i * (i + 1) / 2;
-          float acc = 0.f;
-          for (int k = 0; k < nlist; k++) { const float* Jr = c.J + c.hidx[k] * c.ldJ; acc += c.hw[k] * Jr[i] * Jr[j]; }
-          c.H[i * c.ldH + j] += acc;
-        }
-        __syncwarp();
+      for (int e = c.lane; e < ntri; e += 32) c.Lf[e] = c.H[e];
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int t = 0; t < nlist; t++) {
+      const float* Jr = jrow<true>(c, c.hidx[t]);
+      const float wt = c.hw[t];
+#pragma unroll 1
+      for (int i = c.lane; i < nv; i += 32) {
+        const float sc = wt * Jr[i];
+        float* Hi = Hd + (i * (i + 1)) / 2;
+        if (sc != 0.f)
+#pragma unroll 4
+          for (int k = 0; k <= i; k++) Hi[k] += sc * Jr[k];
       }
+    }
+    if (ELL) {
 #pragma unroll 1
-      for (int e = c.lane; e < nv * c.ldH; e += 32) c.Lf[e] = c.H[e];
-    } else {  // elliptic: Lf = M + sum_quadratic D J J^T + cone terms, c.H stays M
+      for (int t = 0; t < c.ncone; t++) {
+        const int e0 = c.hidx[c.njmax - 1 - t];
+        const ConeK k = cone_scalars(c, e0);
+        if (k.dm == 0.f) continue;
+        const float* J0 = jrow<true>(c, e0);
 #pragma unroll 1
-      for (int e = c.lane; e < ntri; e += 32) {
-        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while ((i + 1) * (i + 2) / 2 <= e) i++;
-        while (i * (i + 1) / 2 > e) i--;
-        const int j = e - i * (i + 1) / 2;
-        float acc = c.H[i * c.ldH + j];
-        for (int k = 0; k < nlist; k++) { const float* Jr = c.J + c.hidx[k] * c.ldJ; acc += c.hw[k] * Jr[i] * Jr[j]; }
-        for (int t = 0; t < c.ncone; t++) {
-          const int e0 = c.hidx[c.njmax - 1 - t];
-          const ConeK k = cone_scalars(c, e0);
-          if (k.dm == 0.f) continue;
-          const float* J0 = c.J + e0 * c.ldJ;
+        for (int i = c.lane; i < nv; i += 32) {
           float pi = 0.f;
-          for (int q = 1; q < k.dim; q++) pi += c.Jaref[e0 + q] * c.rfri[e0 + q] * c.rfri[e0 + q] * J0[q * c.ldJ + i];
-          for (int q = 0; q < k.dim; q++) acc += cone_coef(c, k, e0, q, J0[i], pi, J0[q * c.ldJ + i]) * J0[q * c.ldJ + j];
+          for (int q = 1; q < k.dim; q++) pi += c.Jaref[e0 + q] * c.rfri[e0 + q] * c.rfri[e0 + q] * jrow<true>(c, e0 + q)[i];
+          float* Hi = Hd + (i * (i + 1)) / 2;
+          for (int q = 0; q < k.dim; q++) {
+            const float* Jq = jrow<true>(c, e0 + q);
+            const float sc = cone_coef(c, k, e0, q, J0[i], pi, Jq[i]);
+            for (int kk = 0; kk <= i; kk++) Hi[kk] += sc * Jq[kk];
+          }
         }
-        c.Lf[i * c.ldH + j] = acc;
       }
+    }
+    __syncwarp();
+    if (!ELL) {
+#pragma unroll 1
+      for (int e = c.lane; e < ntri; e += 32) c.Lf[e] = c.H[e];
     }
 #pragma unroll 1
     for (int dd = c.lane; dd < nv; dd += 32) c.x[dd] = c.grad[dd];
     __syncwarp();
-    warp_cholesky(c.Lf, nv, c.ldH, c.lane);
-    warp_chol_solve(c.Lf, nv, c.ldH, c.x, c.lane);
+    warp_cholesky_packed(c.Lf, nv, c.lane);
+    warp_chol_solve_packed(c.Lf, nv, c.x, c.lane);
 #pragma unroll 1
     for (int dd = c.lane; dd < nv; dd += 32) { const float xx = c.x[dd]; sd += xx * xx; nd += c.grad[dd] * xx; c.search[dd] = -xx; }
   }
@@ -416,14 +435,14 @@ __device__ __forceinline__ P3 eval_total(const Ctx& c, float alpha, float q0, fl
 }
 
 // solver.py:836-1347; returns true when the line search converged
-template <bool ELL>
+template <bool ELL, bool BIG>
 __device__ __forceinline__ bool linesearch(Ctx& c) {
   const ModelDev& m = *c.m;
   const int nv = c.nv;
   mul_m(c, c.search, c.mv);
 #pragma unroll 1
   for (int r = c.lane; r < c.nefc; r += 32) {
-    c.jv[r] = row_dot(c.J + r * c.ldJ, c.search, c.nvp);
+    c.jv[r] = row_dot(jrow<BIG>(c, r), c.search, c.nvp);
   }
   __syncwarp();
   const float snorm = sqrtf(c.search_dot), scale = m.meaninertia * (float)nv;
@@ -516,7 +535,7 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   return ls_converged;
 }
 
-template <bool ELL>
+template <bool ELL, bool BIG>
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -539,6 +558,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   int* ri = (int*)(S + L.rowi);
   c.state = ri; c.hidx = ri + njmax;
   c.njmax = njmax; c.ncone = 0;
+  c.jcap = L.jcap; c.Jg = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
   c.rfri = rf + L.nrowf * njmax; c.quad = c.rfri + njmax; c.rinfo = ri + 2 * njmax;
 
   if (njmax == 0 || nv == 0) {
@@ -555,7 +575,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     const float4* Jg = reinterpret_cast<const float4*>(d.efc_J + wb * (size_t)d.njmax_pad * nvp);
     float4* Js = reinterpret_cast<float4*>(c.J);
 #pragma unroll 1
-    for (int i = lane; i < nefc * nvp / 4; i += 32) Js[i] = Jg[i];
+    for (int i = lane; i < min(nefc, L.jcap) * nvp / 4; i += 32) Js[i] = Jg[i];
     for (int i = lane; i < 7 * vp; i += 32) v[i] = 0.f;  // zero padding of every per-dof vector
     __syncwarp();
 #pragma unroll 1
@@ -577,7 +597,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     warp_copy(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
     const float* start = (m.disableflags & DSBL_WARMSTART) ? d.qacc_smooth : d.qacc_warmstart;
     warp_copy(c.qacc, start + wb * nv, nv, lane);
-    const int hsz = nv <= 32 ? nv * (nv + 1) / 2 : nv * c.ldH;
+    const int hsz = nv * (nv + 1) / 2;
 #pragma unroll 1
     for (int e = lane; e < hsz; e += 32) c.H[e] = 0.f;
   }
@@ -585,11 +605,11 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
 #pragma unroll 1
   for (int e = lane; e < m.nC; e += 32) {  // lower triangle of M
     const int r = m.M_entry_row[e], col = m.M_colind[e];
-    c.H[nv <= 32 ? (r * (r + 1)) / 2 + col : r * c.ldH + col] = c.M[e];
+    c.H[(r * (r + 1)) / 2 + col] = c.M[e];
   }
 #pragma unroll 1
   for (int r = lane; r < nefc; r += 32) {  // Jaref = J qacc - aref
-    c.Jaref[r] = row_dot(c.J + r * c.ldJ, c.qacc, c.nvp) - d.efc_aref[wb * njmax + r];
+    c.Jaref[r] = row_dot(jrow<BIG>(c, r), c.qacc, c.nvp) - d.efc_aref[wb * njmax + r];
   }
   mul_m(c, c.qacc, c.Ma);
   __syncwarp();
@@ -600,15 +620,15 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const float scale = m.meaninertia * (float)nv;
   int niter = 0, ovf = 0;
   for (int it = -1;; it++) {
-    if (it >= 0 && !linesearch<ELL>(c)) ovf |= OVF_LS_ITERATIONS;
-    const int nlist = update_constraint<ELL>(c, it < 0);
+    if (it >= 0 && !linesearch<ELL, BIG>(c)) ovf |= OVF_LS_ITERATIONS;
+    const int nlist = update_constraint<ELL, BIG>(c, it < 0);
     update_grad(c);
     if (it >= 0) {
       niter++;
       const float improvement = c.improvement / scale, gradient = sqrtf(c.grad_dot) / scale;
       if (improvement < m.tolerance || gradient < m.tolerance) break;
     } else if (m.iterations == 0) break;
-    update_search<ELL>(c, nlist);
+    update_search<ELL, BIG>(c, nlist);
     if (it >= 0) {
       if (0.5f * c.newton_decrement / scale < m.tolerance) break;
       if (niter == m.iterations) { ovf |= OVF_ITERATIONS; break; }
@@ -630,16 +650,15 @@ size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_lay
 
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_solver(m, d);
-  static size_t configured[2] = {0, 0};
-  const bool ell = m.cone == CONE_ELLIPTIC;
-  if (smem > 48 * 1024 && smem > configured[ell]) {
-    cudaError_t e = ell ? cudaFuncSetAttribute(k_solver<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(k_solver<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured[4] = {0, 0, 0, 0};
+  const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = m.nv > 32 ? 1 : 0, which = 2 * big + ell;
+  void (*kern)(ModelDev, DataDev) = which == 0 ? k_solver<false, false> : which == 1 ? k_solver<true, false> : which == 2 ? k_solver<false, true> : k_solver<true, true>;
+  if (smem > 48 * 1024 && smem > configured[which]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[ell] = smem;
+    configured[which] = smem;
   }
   const int grid = d.wn;
-  if (ell) k_solver<true><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
-  else k_solver<false><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  kern<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

@@ -45,6 +45,46 @@ __device__ __forceinline__ void warp_chol_solve(const float* L, int n, int ld, f
   }
 }
 
+// Packed-lower-triangle variants (row r starts at r(r+1)/2), used for 32 < n <= 64 where the matrix must stay small enough
+// in shared memory for a healthy number of resident warps.
+__device__ __forceinline__ void warp_cholesky_packed(float* A, int n, int lane) {
+  for (int j = 0; j < n; j++) {
+    const float* rj = A + (j * (j + 1)) / 2;
+    float s = 0.f;
+    for (int k = lane; k < j; k += 32) s += rj[k] * rj[k];
+    s = warp_sum(s);
+    const float ljj = sqrtf(fmaxf(rj[j] - s, MJ_MINVAL));
+    const float inv = 1.0f / ljj;
+    for (int i = j + 1 + lane; i < n; i += 32) {
+      float* ri = A + (i * (i + 1)) / 2;
+      float t = ri[j];
+#pragma unroll 4
+      for (int k = 0; k < j; k++) t -= ri[k] * rj[k];
+      ri[j] = t * inv;
+    }
+    __syncwarp();
+    if (lane == 0) A[(j * (j + 1)) / 2 + j] = ljj;
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void warp_chol_solve_packed(const float* L, int n, float* x, int lane) {
+  for (int j = 0; j < n; j++) {  // forward: L y = b
+    const float yj = x[j] / L[(j * (j + 1)) / 2 + j];
+    __syncwarp();
+    for (int i = j + 1 + lane; i < n; i += 32) x[i] -= L[(i * (i + 1)) / 2 + j] * yj;
+    if (lane == 0) x[j] = yj;
+    __syncwarp();
+  }
+  for (int j = n - 1; j >= 0; j--) {  // backward: L^T x = y
+    const float* rj = L + (j * (j + 1)) / 2;
+    const float xj = x[j] / rj[j];
+    __syncwarp();
+    for (int i = lane; i < j; i += 32) x[i] -= rj[i] * xj;
+    if (lane == 0) x[j] = xj;
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Register-resident Cholesky for n <= 32: lane i keeps row i of the matrix in registers, columns are eliminated
 // right-looking with warp shuffles (no shared-memory round trips, no __syncwarp per column), the forward substitution of
