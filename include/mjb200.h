@@ -19,6 +19,11 @@
  *   mjb_fwd_actuation          <- _src/forward.py:1152 fwd_actuation
  *   mjb_fwd_acceleration       <- _src/forward.py:1290 fwd_acceleration(factorize=True) (qfrc_smooth, factor M, qacc_smooth)
  *   mjb_factor_m               <- _src/smooth.py:1340  factor_m
+ *   mjb_com_vel                <- _src/smooth.py:2261  com_vel
+ *   mjb_passive                <- _src/passive.py:1257 passive (joint springs and dampers)
+ *   mjb_rne                    <- _src/smooth.py:1499  rne(flg_acc=False)
+ *   mjb_solve_m                <- _src/smooth.py:3214  solve_m(m, d, x, y): x = M^-1 y through Data.qLD
+ *   mjb_mul_m                  <- _src/support.py:153  mul_m(m, d, res, vec): res = M vec
  *   mjb_solve                  <- _src/solver.py:3671  solve
  *   mjb_euler                  <- _src/forward.py:387  euler
  *   mjb_ctrl_noise             <- _src/cli.py:103      _ctrl_noise (harness kernel, untimed in testspeed)
@@ -71,6 +76,12 @@ int mjb_fwd_velocity(const mjbModel* m, mjbData* d, void* stream);
 int mjb_fwd_actuation(const mjbModel* m, mjbData* d, void* stream);
 int mjb_fwd_acceleration(const mjbModel* m, mjbData* d, void* stream);
 int mjb_factor_m(const mjbModel* m, mjbData* d, void* stream);
+int mjb_com_vel(const mjbModel* m, mjbData* d, void* stream);
+int mjb_passive(const mjbModel* m, mjbData* d, void* stream);
+int mjb_rne(const mjbModel* m, mjbData* d, void* stream);
+/* x, y, res, vec: device arrays (nworld, nv) fp32 */
+int mjb_solve_m(const mjbModel* m, mjbData* d, float* x, const float* y, void* stream);
+int mjb_mul_m(const mjbModel* m, mjbData* d, float* res, const float* vec, void* stream);
 int mjb_solve(const mjbModel* m, mjbData* d, void* stream);
 int mjb_euler(const mjbModel* m, mjbData* d, void* stream);
 /* ctrl <- OU noise around ctrl_center (device array of nu floats, or NULL), reference cli.py:103-145 */

@@ -89,6 +89,76 @@ def euler(m: Model, d: Data):
   _call("mjb_euler", m, d)
 
 
+def implicit(m: Model, d: Data):
+  """Integrates with the implicit-in-velocity scheme the model selects (reference forward.py:578; implicitfast only here)."""
+  from . import constants as C
+
+  if m.opt.integrator != C.INT_IMPLICITFAST:
+    raise NotImplementedError("implicit(): only the implicitfast integrator is implemented")
+  _call("mjb_euler", m, d)  # the integrate kernel dispatches on m.opt.integrator
+
+
+def fwd_kinematics(m: Model, d: Data):
+  """kinematics, com_pos, camlight (reference forward.py:613-632; no flex / tendon in this version)."""
+  kinematics(m, d)
+  com_pos(m, d)
+  camlight(m, d)
+
+
+def com_vel(m: Model, d: Data):
+  """Body velocities cvel and cdof_dot (reference smooth.py:2261)."""
+  _call("mjb_com_vel", m, d)
+
+
+def passive(m: Model, d: Data):
+  """Passive joint forces: springs and dampers (reference passive.py:1257)."""
+  _call("mjb_passive", m, d)
+
+
+def rne(m: Model, d: Data, flg_acc: bool = False):
+  """Bias forces by recursive Newton-Euler (reference smooth.py:1499)."""
+  if flg_acc:
+    raise NotImplementedError("rne(flg_acc=True) is not implemented")
+  _call("mjb_rne", m, d)
+
+
+def _vec_call(name: str, m: Model, d: Data, out: torch.Tensor, inp: torch.Tensor):
+  for t in (out, inp):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (d.nworld, m.nv):
+      raise ValueError(f"expected a contiguous CUDA float32 tensor of shape ({d.nworld}, {m.nv})")
+  stream = torch.cuda.current_stream().cuda_stream
+  _lib.check(getattr(_lib.lib(), name)(m._handle, d._handle, out.data_ptr(), inp.data_ptr(), stream))
+
+
+def solve_m(m: Model, d: Data, x: torch.Tensor, y: torch.Tensor):
+  """x = M^-1 y using the factor in d.qLD (reference smooth.py:3214)."""
+  _vec_call("mjb_solve_m", m, d, x, y)
+
+
+def mul_m(m: Model, d: Data, res: torch.Tensor, vec: torch.Tensor):
+  """res = M vec (reference support.py:153)."""
+  _vec_call("mjb_mul_m", m, d, res, vec)
+
+
+def step1(m: Model, d: Data):
+  """First half of a split step, before the user sets controls (reference forward.py step1; no sensors / energy here)."""
+  fwd_position(m, d)
+  fwd_velocity(m, d)
+
+
+def step2(m: Model, d: Data):
+  """Second half of a split step (reference forward.py step2)."""
+  from . import constants as C
+
+  fwd_actuation(m, d)
+  fwd_acceleration(m, d)
+  solve(m, d)
+  if m.opt.integrator == C.INT_IMPLICITFAST:
+    implicit(m, d)
+  else:
+    euler(m, d)
+
+
 def ctrl_noise(m: Model, d: Data, step_index: int, ctrl_center: torch.Tensor | None = None, noise_std: float = 0.01, noise_rate: float = 0.1):
   """Harness OU control noise (reference cli.py:103-145), deterministic Halton sequence per (step, world, actuator)."""
   stream = torch.cuda.current_stream().cuda_stream

@@ -544,6 +544,84 @@ def reset_data(m: types.Model, d: types.Data):
     d.eq_active.copy_(torch.from_numpy(np.tile(np.asarray(mjm.eq_active0).astype(np.int32), (d.nworld, 1))))
 
 
+def reset_data_keyframe(m: types.Model, d: types.Data, key):
+  """Resets worlds to a keyframe (reference io.py:2797): an int resets every world (ValueError if out of range); an integer
+  tensor of shape (nworld,) resets each world to its own keyframe and leaves worlds with an out-of-range index untouched."""
+  mjm = m._mjm
+  nkey = int(mjm.nkey)
+  if isinstance(key, (int, np.integer)):
+    if key < 0 or key >= nkey:
+      raise ValueError(f"key ({int(key)}) must be in [0, {nkey}).")
+    keys = torch.full((d.nworld,), int(key), dtype=torch.int64, device=d.qpos.device)
+  elif isinstance(key, torch.Tensor):
+    if tuple(key.shape) != (d.nworld,):
+      raise ValueError(f"key array must have shape ({d.nworld},), got {tuple(key.shape)}.")
+    if key.dtype not in (torch.int32, torch.int64):
+      raise ValueError(f"key array must be of integer type, got {key.dtype}.")
+    keys = key.to(device=d.qpos.device, dtype=torch.int64)
+  else:
+    raise ValueError(f"key must be an int or a tensor, got {type(key)}.")
+  valid = (keys >= 0) & (keys < nkey)
+  if not bool(valid.any()):
+    return
+  idx = keys.clamp(0, max(nkey - 1, 0))
+  dev = d.qpos.device
+  f32 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(dev)
+  sel = lambda new, old: torch.where(valid.reshape((-1,) + (1,) * (old.dim() - 1)), new, old)
+  d.qpos.copy_(sel(f32(mjm.key_qpos)[idx], d.qpos))
+  d.qvel.copy_(sel(f32(mjm.key_qvel)[idx], d.qvel))
+  if m.nu:
+    d.ctrl.copy_(sel(f32(mjm.key_ctrl)[idx], d.ctrl))
+  d.time.copy_(sel(f32(mjm.key_time)[idx], d.time))
+  for n in ("qacc_warmstart", "qacc", "qfrc_applied", "xfrc_applied"):
+    t = getattr(d, n)
+    t.copy_(sel(torch.zeros_like(t), t))
+  for n in ("overflow", "solver_niter", "nefc", "ne", "nf", "nl"):
+    t = getattr(d, n)
+    t.copy_(sel(torch.zeros_like(t), t))
+  if getattr(m, "neq", 0):
+    d.eq_active.copy_(sel(torch.from_numpy(np.asarray(mjm.eq_active0).astype(np.int32)).to(dev).expand(d.nworld, -1), d.eq_active))
+
+
+_GET_FIELDS = (
+  "qpos", "qvel", "ctrl", "qacc_warmstart", "qfrc_applied", "xfrc_applied", "qacc", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis",
+  "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat", "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert", "crb",
+  "actuator_length", "actuator_velocity", "actuator_force", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper", "qfrc_passive",
+  "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int", "qLD", "actuator_moment",
+)
+
+
+def get_data_into(result, mjm, d: types.Data, world_id: int = 0):
+  """Copies one world of a device Data into a host MjData-like object (reference io.py:2184): state and every computed field
+  by MjData name, `M` as MuJoCo's CSR values, the world's contacts (`result.contact` as a dict of arrays, in pool order) and
+  its constraint rows (`efc_*`, with `efc_J` dense nefc x nv); `ncon`, `nefc`, `ne`, `nf`, `nl`, `time`, `solver_niter`."""
+  w = int(world_id)
+  if not 0 <= w < d.nworld:
+    raise ValueError(f"world_id {w} out of range [0, {d.nworld})")
+  nacon = min(int(d.nacon.cpu()[0]), d.naconmax)
+  nefc = min(int(d.nefc[w].cpu()), d.njmax)
+  for name in _GET_FIELDS:
+    setattr(result, name, getattr(d, name)[w].cpu().numpy().astype(np.float64))
+  result.qM = d.M[w].cpu().numpy().astype(np.float64)
+  result.M = result.qM
+  result.time = float(d.time[w].cpu())
+  result.solver_niter = int(d.solver_niter[w].cpu())
+  result.ne, result.nf, result.nl, result.nefc = int(d.ne[w].cpu()), int(d.nf[w].cpu()), int(d.nl[w].cpu()), nefc
+  ids = torch.nonzero(d.contact.worldid[:nacon] == w).reshape(-1)
+  result.ncon = int(ids.numel())
+  con = {}
+  for name in ("dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address"):
+    con[name] = getattr(d.contact, name)[ids].cpu().numpy()
+  result.contact = con
+  nv = mjm.nv
+  result.efc_J = d.efc.J[w, :nefc, :nv].cpu().numpy().astype(np.float64)
+  for name in ("pos", "margin", "D", "vel", "aref", "frictionloss", "force"):
+    setattr(result, "efc_" + name, getattr(d.efc, name)[w, :nefc].cpu().numpy().astype(np.float64))
+  for name in ("type", "id", "state"):
+    setattr(result, "efc_" + name, getattr(d.efc, name)[w, :nefc].cpu().numpy())
+  return result
+
+
 def load_trajectory(npz_path: str, mjm, mjd) -> np.ndarray:
   """Loads a ctrl sequence and samples it on the model timestep with zero-order hold (reference io.py:3067-3113).
 

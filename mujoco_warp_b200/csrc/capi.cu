@@ -167,6 +167,21 @@ int mjb_fwd_velocity(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER();
 int mjb_fwd_actuation(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_ACTUATION, s), 1); return 0; }
 int mjb_fwd_acceleration(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_ACCELERATION, s), 1); return 0; }
 int mjb_factor_m(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_FACTOR_ONLY, s), 1); return 0; }
+int mjb_com_vel(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_COMVEL, s), 1); return 0; }
+int mjb_passive(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_PASSIVE, s), 1); return 0; }
+int mjb_rne(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_RNE, s), 1); return 0; }
+int mjb_solve_m(const mjbModel* m, mjbData* d, float* x, const float* y, void* stream) {
+  MJB_ENTER();
+  if (!x || !y) return fail("mjb_solve_m: null vector");
+  MJB_LAUNCH(launch_solve_m(m->dev, d->dev, x, y, s), 1);
+  return 0;
+}
+int mjb_mul_m(const mjbModel* m, mjbData* d, float* res, const float* vec, void* stream) {
+  MJB_ENTER();
+  if (!res || !vec) return fail("mjb_mul_m: null vector");
+  MJB_LAUNCH(launch_mul_m(m->dev, d->dev, res, vec, s), 1);
+  return 0;
+}
 int mjb_solve(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1); return 0; }
 int mjb_euler(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1); return 0; }
 

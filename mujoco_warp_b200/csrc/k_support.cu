@@ -1,0 +1,72 @@
+// k_support.cu -- small public utilities that operate on a finished position stage: solve_m and mul_m.
+//
+// Replaces (reference, /root/reference/mujoco_warp/_src/): smooth.py:3214 solve_m (x = M^-1 y through the per-tree factor kept
+// in Data.qLD; the reference launches one tile kernel per block size) and support.py:153-256 mul_m (res = M vec through the
+// symmetric gather tables of io.py:1029-1050).  One warp per world, like every other stage.
+#include "mjb_math.cuh"
+#include "mjb_types.cuh"
+
+namespace {
+
+// qLD holds, per kinematic tree, the dense upper factor U (row-major n x n, zeros below the diagonal) with M = U^T U.
+__global__ void __launch_bounds__(32)
+k_solve_m(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, float* __restrict__ xo, const float* __restrict__ yi) {
+  extern __shared__ float x[];
+  const int lane = threadIdx.x, w = blockIdx.x + d.w0;
+  if (w >= d.nworld) return;
+  const size_t wb = (size_t)w;
+  const int nv = m.nv;
+  warp_copy(x, yi + wb * nv, nv, lane);
+  __syncwarp();
+#pragma unroll 1
+  for (int t = 0; t < m.ntree; t++) {
+    const int start = m.tree_dofadr[t], n = m.tree_dofnum[t];
+    const float* U = d.qLD + wb * m.qld_total + m.tree_qLDadr[t];
+    float* xt = x + start;
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {  // U^T z = y (forward)
+      const float zj = xt[j] / U[j * n + j];
+      __syncwarp();
+      for (int i = j + 1 + lane; i < n; i += 32) xt[i] -= U[j * n + i] * zj;
+      if (lane == 0) xt[j] = zj;
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int j = n - 1; j >= 0; j--) {  // U x = z (backward)
+      const float xj = xt[j] / U[j * n + j];
+      __syncwarp();
+      for (int i = lane; i < j; i += 32) xt[i] -= U[i * n + j] * xj;
+      if (lane == 0) xt[j] = xj;
+      __syncwarp();
+    }
+  }
+  warp_copy(xo + wb * nv, x, nv, lane);
+}
+
+__global__ void __launch_bounds__(32)
+k_mul_m(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, float* __restrict__ res, const float* __restrict__ vec) {
+  extern __shared__ float v[];
+  const int lane = threadIdx.x, w = blockIdx.x + d.w0;
+  if (w >= d.nworld) return;
+  const size_t wb = (size_t)w;
+  warp_copy(v, vec + wb * m.nv, m.nv, lane);
+  __syncwarp();
+  const float* M = d.M + wb * m.nC;
+#pragma unroll 1
+  for (int i = lane; i < m.nv; i += 32) {
+    float acc = 0.f;
+    for (int k = m.mulm_rowadr[i]; k < m.mulm_rowadr[i + 1]; k++) acc += M[m.mulm_madr[k]] * v[m.mulm_col[k]];
+    res[wb * m.nv + i] = acc;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_solve_m(const ModelDev& m, const DataDev& d, float* x, const float* y, cudaStream_t s) {
+  k_solve_m<<<d.wn, 32, (m.nv + 4) * sizeof(float), s>>>(m, d, x, y);
+  return cudaGetLastError();
+}
+cudaError_t launch_mul_m(const ModelDev& m, const DataDev& d, float* res, const float* vec, cudaStream_t s) {
+  k_mul_m<<<d.wn, 32, (m.nv + 4) * sizeof(float), s>>>(m, d, res, vec);
+  return cudaGetLastError();
+}

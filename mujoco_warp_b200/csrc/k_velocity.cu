@@ -48,8 +48,10 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
   __syncwarp();
 
   // ------------------------------------------------------------------ fwd_velocity
-  if (mask & STG_VELOCITY) {
-    warp_copy(cinert, d.cinert + wb * 10 * nb, 10 * nb, lane);
+  const bool v_all = mask & STG_VELOCITY;  // the sub-stage bits serve the individually callable com_vel / passive / rne
+  if (mask & (STG_VELOCITY | STG_COMVEL | STG_PASSIVE | STG_RNE)) {
+    if (v_all || (mask & STG_RNE)) warp_copy(cinert, d.cinert + wb * 10 * nb, 10 * nb, lane);
+    if (v_all)
 #pragma unroll 1
     for (int a = lane; a < nu; a += 32) {  // actuator velocity = moment . qvel
       const int nnz = d.moment_rownnz[wb * nu + a], adr = d.moment_rowadr[wb * nu + a];
@@ -58,6 +60,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       d.actuator_velocity[wb * nu + a] = vel;
     }
     // com_vel: level-synchronous forward pass
+    if (v_all || (mask & STG_COMVEL)) {
     if (lane < 6) cvel[lane] = 0.f;
     __syncwarp();
 #pragma unroll 1
@@ -95,9 +98,14 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     }
     warp_copy(d.cvel + wb * 6 * nb, cvel, 6 * nb, lane);
     warp_copy(d.cdof_dot + wb * 6 * nv, cdofdot, 6 * nv, lane);
+    } else if (mask & STG_RNE) {
+      warp_copy(cvel, d.cvel + wb * 6 * nb, 6 * nb, lane);
+      warp_copy(cdofdot, d.cdof_dot + wb * 6 * nv, 6 * nv, lane);
+      __syncwarp();
+    }
 
     // passive: joint springs (slide/hinge) and dampers
-    {
+    if (v_all || (mask & STG_PASSIVE)) {
       const bool dsbl_spring = m.disableflags & DSBL_SPRING, dsbl_damper = m.disableflags & DSBL_DAMPER;
 #pragma unroll 1
       for (int dd = lane; dd < nv; dd += 32) {
@@ -120,6 +128,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
     }
     // rne: cacc forward, cfrc per body, backward accumulation, projection
+    if (v_all || (mask & STG_RNE)) {
     if (lane < 6) cacc[lane] = lane < 3 ? 0.f : ((m.disableflags & DSBL_GRAVITY) ? 0.f : -(lane == 3 ? m.gravity_x : lane == 4 ? m.gravity_y : m.gravity_z));
     __syncwarp();
 #pragma unroll 1
@@ -184,6 +193,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     }
     warp_copy(d.cacc + wb * 6 * nb, cacc, 6 * nb, lane);
     warp_copy(d.cfrc_int + wb * 6 * nb, cfrc, 6 * nb, lane);
+    }
   } else if (mask & STG_ACCELERATION) {
     warp_copy(q_passive, d.qfrc_passive + wb * nv, nv, lane);
     warp_copy(q_bias, d.qfrc_bias + wb * nv, nv, lane);

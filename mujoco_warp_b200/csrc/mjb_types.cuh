@@ -107,7 +107,8 @@ enum { CONTACT_TYPE_CONSTRAINT = 1, CONTACT_TYPE_SENSOR = 2 };
 // stage bits for the fused position kernel
 enum { STG_KINEMATICS = 1, STG_COM_POS = 2, STG_CAMLIGHT = 4, STG_CRB = 8, STG_TRANSMISSION = 16 };
 // stage bits for the fused velocity kernel
-enum { STG_VELOCITY = 1, STG_ACTUATION = 2, STG_ACCELERATION = 4, STG_FACTOR_ONLY = 8 };
+enum { STG_VELOCITY = 1, STG_ACTUATION = 2, STG_ACCELERATION = 4, STG_FACTOR_ONLY = 8,
+       STG_COMVEL = 16, STG_PASSIVE = 32, STG_RNE = 64 };  // single sub-stages of fwd_velocity (smooth.com_vel, passive.passive, smooth.rne)
 
 // One warp per block: blockIdx.x IS the world, so every world-dependent branch and address is warp-uniform by construction
 // (ptxas keeps them on the uniform datapath and drops the WARPSYNC it otherwise emits around each SHFL).
@@ -119,6 +120,8 @@ cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s
 cudaError_t reset_contact_counters(const DataDev& d, cudaStream_t s);
 cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s);
 cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int stage_mask, cudaStream_t s);
+cudaError_t launch_solve_m(const ModelDev& m, const DataDev& d, float* x, const float* y, cudaStream_t s);
+cudaError_t launch_mul_m(const ModelDev& m, const DataDev& d, float* res, const float* vec, cudaStream_t s);
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s);
 cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s);
 cudaError_t launch_ctrl_noise(const ModelDev& m, const DataDev& d, const float* ctrl_center, int step, float std, float rate, cudaStream_t s);
