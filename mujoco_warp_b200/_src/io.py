@@ -238,8 +238,8 @@ def _validate(mjm):
     raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler and implicitfast only in this version)")
   if o.cone not in (C.CONE_PYRAMIDAL, C.CONE_ELLIPTIC):
     raise NotImplementedError(f"unknown friction cone {o.cone}")
-  if o.solver != C.SOL_NEWTON:
-    raise NotImplementedError("only the Newton solver is implemented in this version")
+  if o.solver not in (C.SOL_NEWTON, C.SOL_CG):
+    raise NotImplementedError("only the Newton and CG solvers are implemented in this version (no PGS)")
   if mjm.nv > 64:
     raise NotImplementedError("nv > 64 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
   for n in ("na", "ntendon", "nflex", "nmocap"):

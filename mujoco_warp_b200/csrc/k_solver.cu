@@ -23,7 +23,7 @@ namespace {
 // Shared-memory slice of one world.  J rows keep the global stride nv_pad (a multiple of 4 floats), so a row is 16-byte
 // aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
 // rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
-struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, total; };
+struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, cgv, total; };
 __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d) {
   SolLayout L;
   int o = 0;
@@ -35,6 +35,7 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   L.jcap = m.nv > 32 ? (d.njmax < 48 ? d.njmax : 48) : d.njmax;
   L.J = take(L.jcap * L.ldJ);
   L.vec = take(7 * L.nvp);  // qacc, Ma, grad, search, mv (= x scratch of the nv > 32 path), qfs, qfc
+  L.cgv = take(m.solver == SOL_CG ? 3 * L.nvp : 0);  // CG only: Mgrad, prev_grad, prev_Mgrad
   // nv <= 32: H and its factor are stored as packed lower triangles (register Cholesky path); larger nv keeps nv x ldH
   // H and its factor are packed lower triangles (register Cholesky for nv <= 32, shared-memory Cholesky above)
   const int hsz = m.nv * (m.nv + 1) / 2;
@@ -169,6 +170,7 @@ struct Ctx {
   // or friction[j-1];  quad = 3 words per row;  the CONE contacts' primary rows are listed from the END of hidx
   int* rinfo; float *rfri, *quad; int njmax, ncone;
   const float* Jg; int jcap;  // big models: rows >= jcap live in global memory (same leading dimension)
+  float* cgv;                 // CG only: Mgrad, prev_grad, prev_Mgrad (nvp each)
 };
 template <bool BIG>
 __device__ __forceinline__ const float* jrow(const Ctx& c, int r) {
@@ -535,7 +537,56 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   return ls_converged;
 }
 
-template <bool ELL, bool BIG>
+// Conjugate-gradient direction (solver.py:1665 _solve_init_search_cg, :3295 beta, :3360 search update): Mgrad = M^-1 grad
+// through the per-tree factor U (M = U^T U) that fwd_acceleration left in Data.qLD, Polak-Ribiere beta, search update.
+// Only the CG instantiations of the kernel contain it.
+__device__ __forceinline__ void cg_direction(Ctx& c, const ModelDev& m, const DataDev& d, size_t wb, bool init) {
+  const int nv = c.nv, lane = c.lane;
+  float *Mg = c.cgv, *pg = c.cgv + c.nvp, *pMg = c.cgv + 2 * c.nvp;
+#pragma unroll 1
+  for (int dd = lane; dd < nv; dd += 32) Mg[dd] = c.grad[dd];
+  __syncwarp();
+#pragma unroll 1
+  for (int t = 0; t < m.ntree; t++) {
+    const int start = m.tree_dofadr[t], n = m.tree_dofnum[t];
+    const float* U = d.qLD + wb * m.qld_total + m.tree_qLDadr[t];
+    float* xt = Mg + start;
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+      const float zj = xt[j] / U[j * n + j];
+      __syncwarp();
+      for (int i = j + 1 + lane; i < n; i += 32) xt[i] -= U[j * n + i] * zj;
+      if (lane == 0) xt[j] = zj;
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int j = n - 1; j >= 0; j--) {
+      const float xj = xt[j] / U[j * n + j];
+      __syncwarp();
+      for (int i = lane; i < j; i += 32) xt[i] -= U[i * n + j] * xj;
+      if (lane == 0) xt[j] = xj;
+      __syncwarp();
+    }
+  }
+  float beta = 0.f;
+  if (!init) {
+    float num = 0.f, den = 0.f;
+#pragma unroll 1
+    for (int dd = lane; dd < nv; dd += 32) { num += c.grad[dd] * (Mg[dd] - pMg[dd]); den += pg[dd] * pMg[dd]; }
+    beta = fmaxf(0.f, warp_sum(num) / fmaxf(MJ_MINVAL, warp_sum(den)));
+  }
+  float sd = 0.f;
+#pragma unroll 1
+  for (int dd = lane; dd < nv; dd += 32) {
+    const float sv = -Mg[dd] + beta * c.search[dd];
+    c.search[dd] = sv; sd += sv * sv;
+    pg[dd] = c.grad[dd]; pMg[dd] = Mg[dd];
+  }
+  c.search_dot = warp_sum(sd);
+  __syncwarp();
+}
+
+template <bool ELL, bool BIG, bool CG>
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -559,6 +610,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   c.state = ri; c.hidx = ri + njmax;
   c.njmax = njmax; c.ncone = 0;
   c.jcap = L.jcap; c.Jg = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
+  c.cgv = S + L.cgv;
   c.rfri = rf + L.nrowf * njmax; c.quad = c.rfri + njmax; c.rinfo = ri + 2 * njmax;
 
   if (njmax == 0 || nv == 0) {
@@ -628,7 +680,12 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
       const float improvement = c.improvement / scale, gradient = sqrtf(c.grad_dot) / scale;
       if (improvement < m.tolerance || gradient < m.tolerance) break;
     } else if (m.iterations == 0) break;
-    update_search<ELL, BIG>(c, nlist);
+    if (CG) {
+      if (it >= 0 && niter == m.iterations) { ovf |= OVF_ITERATIONS; break; }
+      cg_direction(c, m, d, wb, it < 0);
+      continue;
+    }
+    if (!CG) update_search<ELL, BIG>(c, nlist);
     if (it >= 0) {
       if (0.5f * c.newton_decrement / scale < m.tolerance) break;
       if (niter == m.iterations) { ovf |= OVF_ITERATIONS; break; }
@@ -650,9 +707,12 @@ size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_lay
 
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_solver(m, d);
-  static size_t configured[4] = {0, 0, 0, 0};
-  const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = m.nv > 32 ? 1 : 0, which = 2 * big + ell;
-  void (*kern)(ModelDev, DataDev) = which == 0 ? k_solver<false, false> : which == 1 ? k_solver<true, false> : which == 2 ? k_solver<false, true> : k_solver<true, true>;
+  static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = m.nv > 32 ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0, which = 4 * cg + 2 * big + ell;
+  static void (*const kerns[8])(ModelDev, DataDev) = {
+    k_solver<false, false, false>, k_solver<true, false, false>, k_solver<false, true, false>, k_solver<true, true, false>,
+    k_solver<false, false, true>,  k_solver<true, false, true>,  k_solver<false, true, true>,  k_solver<true, true, true>};
+  void (*kern)(ModelDev, DataDev) = kerns[which];
   if (smem > 48 * 1024 && smem > configured[which]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -24,6 +24,7 @@ enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { GEOM_PLANE = 0, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH };
 enum { INT_EULER = 0, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST };
 enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
+enum { SOL_CG = 1, SOL_NEWTON = 2 };
 enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
 enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_LIMIT_JOINT = 3, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6, CNSTR_CONTACT_ELLIPTIC = 7 };
 enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
@@ -1800,7 +1801,7 @@ static void fwd_acceleration(W* w) {
  * (the reference's incremental-H / stable-state fast path, solver.py:1951,2145-2159, is an algebraically
  * equivalent optimisation of this exact iteration) */
 typedef struct {
-  real *Jaref, *jv, *grad, *search, *mv, *H, *Hf, *tmp;
+  real *Jaref, *jv, *grad, *search, *mv, *H, *Hf, *tmp, *Mgrad, *prev_grad, *prev_Mgrad;
   real search_dot, grad_dot, newton_decrement, improvement;
   /* elliptic cones: per contact quad (3), quad1 (u0, v0, uu), quad2 (uv, vv, dm) -- solver.py:957-1015 */
   real* quad;
@@ -1855,6 +1856,13 @@ static void update_gradient(W* w, SCtx* c, int nefc) {
   const OrcModel* m = w->m; const int nv = m->nv;
   c->grad_dot = 0;
   for (int d = 0; d < nv; d++) { real g = w->efc_Ma[d] - w->qfrc_smooth[d] - w->qfrc_constraint[d]; c->grad[d] = g; c->grad_dot += g * g; }
+  if (m->solver == SOL_CG) { /* Mgrad = M^-1 grad through the factor of M (smooth.solve_m, solver.py:3086) */
+    for (int t = 0; t < m->ntree; t++) {
+      int start = m->tree_dofadr[t], size = m->tree_dofnum[t];
+      chol_upper_solve(w->qLD + m->qLD_block_adr[start], size, c->grad + start, c->Mgrad + start);
+    }
+    return;
+  }
   memset(c->H, 0, (size_t)nv * nv * sizeof(real));
   for (int i = 0; i < nv; i++) { /* densify M (upper + lower) */
     int adr = m->M_rowadr[i];
@@ -2080,10 +2088,11 @@ static void solve(W* w) {
   const OrcModel* m = w->m; const int nv = m->nv;
   if (w->njmax == 0 || nv == 0) { memcpy(w->qacc, w->qacc_smooth, nv * sizeof(real)); w->solver_niter[0] = 0; return; }
   int nefc = w->nefc[0] < w->njmax ? w->nefc[0] : w->njmax;
-  SCtx c;
+  SCtx c; memset(&c, 0, sizeof c);
   size_t nr = (size_t)(nefc > 0 ? nefc : 1);
-  real* buf = (real*)calloc(2 * nr + 4 * (size_t)nv + 2 * (size_t)nv * nv + 9 * (size_t)(w->nconmax + 1), sizeof(real));
+  real* buf = (real*)calloc(2 * nr + 7 * (size_t)nv + 2 * (size_t)nv * nv + 9 * (size_t)(w->nconmax + 1), sizeof(real));
   c.quad = buf + 2 * nr + 4 * (size_t)nv + 2 * (size_t)nv * nv;
+  c.Mgrad = c.quad + 9 * (size_t)(w->nconmax + 1); c.prev_grad = c.Mgrad + nv; c.prev_Mgrad = c.prev_grad + nv;
   c.Jaref = buf; c.jv = c.Jaref + nr; c.grad = c.jv + nr; c.search = c.grad + nv; c.mv = c.search + nv; c.tmp = c.mv + nv; c.H = c.tmp + nv; c.Hf = c.H + (size_t)nv * nv;
   const real* start = (m->disableflags & DSBL_WARMSTART) ? w->qacc_smooth : w->qacc_warmstart;
   memcpy(w->qacc, start, nv * sizeof(real));
@@ -2092,14 +2101,31 @@ static void solve(W* w) {
   mul_m(m, w->M, w->qacc, w->efc_Ma);
   update_constraint(w, &c, nefc);
   update_gradient(w, &c, nefc);
+  const int cg = m->solver == SOL_CG;
+  if (cg) { /* _solve_init_search_cg (solver.py:1665): search = -Mgrad */
+    c.search_dot = 0;
+    for (int d = 0; d < nv; d++) { c.search[d] = -c.Mgrad[d]; c.search_dot += c.search[d] * c.search[d]; c.prev_grad[d] = c.grad[d]; c.prev_Mgrad[d] = c.Mgrad[d]; }
+  }
   real scale = m->meaninertia * (real)nv;
   int done = m->iterations == 0;
   while (!done) {
     linesearch(w, &c, nefc);
     update_constraint(w, &c, nefc);
     update_gradient(w, &c, nefc);
-    w->solver_niter[0] += 1; /* _solve_done solver.py:3453 */
+    w->solver_niter[0] += 1; /* _solve_done solver.py:3453 / _solve_cg_finalize :3402 */
     real improvement = c.improvement / scale, gradient = (real)sqrt((double)c.grad_dot) / scale, model_improvement = (real)0.5 * c.newton_decrement / scale;
+    if (cg) { /* Polak-Ribiere (solver.py:3295-3333, 3360-3398) */
+      real num = 0, den = 0;
+      for (int d = 0; d < nv; d++) { num += c.grad[d] * (c.Mgrad[d] - c.prev_Mgrad[d]); den += c.prev_grad[d] * c.prev_Mgrad[d]; }
+      real beta = rmax(0, num / rmax(MJ_MINVAL, den));
+      done = improvement < m->tolerance || gradient < m->tolerance;
+      if (!done && w->solver_niter[0] == m->iterations) { w->overflow[0] |= OVF_ITERATIONS; done = 1; }
+      if (!done) {
+        c.search_dot = 0;
+        for (int d = 0; d < nv; d++) { c.search[d] = -c.Mgrad[d] + beta * c.search[d]; c.search_dot += c.search[d] * c.search[d]; c.prev_grad[d] = c.grad[d]; c.prev_Mgrad[d] = c.Mgrad[d]; }
+      }
+      continue;
+    }
     done = improvement < m->tolerance || gradient < m->tolerance || model_improvement < m->tolerance;
     if (!done && w->solver_niter[0] == m->iterations) { w->overflow[0] |= OVF_ITERATIONS; done = 1; }
   }

@@ -27,6 +27,10 @@ def load_scene(name):
     mjm = mjcf.load_any(util.HUMANOID)
     if name.endswith("elliptic"):
       mjm.opt.cone = C.CONE_ELLIPTIC
+    if name.endswith("cg"):
+      mjm.opt.solver = C.SOL_CG
+  elif name == "mixed_elliptic_cg":
+    mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option solver="CG" cone="elliptic" timestep="0.004"'))
   elif name == "mixed":
     mjm = mjcf.load_string(util.MIXED_XML)
   elif name == "mixed_elliptic":
@@ -50,7 +54,7 @@ def close(name, got, want, tol):
   assert err <= tol * scale, f"{name}: max |diff| {err:.3e} (scale {scale:.3e})"
 
 
-def compare(tag, g, od, mjm, nworld, tol):
+def compare(tag, g, od, mjm, nworld, tol, solver_tol=1e-7, exact_iterations=True):
   nv = mjm.nv
   for f in SMOOTH:
     k = f"{tag}/{f}"
@@ -85,11 +89,13 @@ def compare(tag, g, od, mjm, nworld, tol):
     for f in ("pos", "margin", "D", "vel", "aref", "frictionloss"):
       close(f"{tag}/efc_{f}[w{w}]", od["efc_" + f][w, :ne], g[f"{tag}/efc_{f}"][w, :ne], tol)
     # solver: both sides iterate the same algorithm in double precision
-    close(f"{tag}/efc_force[w{w}]", od["efc_force"][w, :ne], g[f"{tag}/efc_force"][w, :ne], 1e-7)
-    np.testing.assert_array_equal(od["efc_state"][w, :ne], g[f"{tag}/efc_state"][w, :ne])
-  close(f"{tag}/qacc", od["qacc"], g[f"{tag}/qacc"], 1e-7)
-  close(f"{tag}/qfrc_constraint", od["qfrc_constraint"], g[f"{tag}/qfrc_constraint"], 1e-7)
-  np.testing.assert_array_equal(od["solver_niter"].reshape(-1), g[f"{tag}/solver_niter"].reshape(-1), err_msg=f"{tag}/solver_niter")
+    close(f"{tag}/efc_force[w{w}]", od["efc_force"][w, :ne], g[f"{tag}/efc_force"][w, :ne], solver_tol)
+    if exact_iterations:
+      np.testing.assert_array_equal(od["efc_state"][w, :ne], g[f"{tag}/efc_state"][w, :ne])
+  close(f"{tag}/qacc", od["qacc"], g[f"{tag}/qacc"], solver_tol)
+  close(f"{tag}/qfrc_constraint", od["qfrc_constraint"], g[f"{tag}/qfrc_constraint"], solver_tol)
+  if exact_iterations:
+    np.testing.assert_array_equal(od["solver_niter"].reshape(-1), g[f"{tag}/solver_niter"].reshape(-1), err_msg=f"{tag}/solver_niter")
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -103,15 +109,20 @@ def test_oracle_matches_reference_pipeline(built, name):
     o.set_state(ctrl=g["in/ctrl"])
   o.forward()
   assert (o.d["overflow"] == 0).all()
-  compare("forward", g, o.d, mjm, nworld, 1e-9)
+  # CG takes tens of iterations: rounding differences grow along the conjugate directions, so iteration counts can differ by
+  # a few and the two (equally converged) answers agree to the solver tolerance rather than to rounding
+  cg = name.endswith("cg")
+  compare("forward", g, o.d, mjm, nworld, 1e-9, solver_tol=5e-3 if cg else 1e-7, exact_iterations=not cg)
+  if cg:
+    assert (np.abs(o.d["solver_niter"].reshape(-1) - g["forward/solver_niter"].reshape(-1)) <= 5).all()
   s = 0
   while f"step{s}/qpos" in g:
     o.step()
-    close(f"step{s}/qpos", o.d["qpos"], g[f"step{s}/qpos"], 1e-6)
+    close(f"step{s}/qpos", o.d["qpos"], g[f"step{s}/qpos"], 1e-5 if cg else 1e-6)
     # after the first step the two sides' inputs differ at rounding level, which can flip a borderline termination test
     # (one Newton iteration more or less); both results are converged to the solver tolerance (1e-6, scaled)
-    close(f"step{s}/qvel", o.d["qvel"], g[f"step{s}/qvel"], 1e-4)
-    close(f"step{s}/qacc_warmstart", o.d["qacc_warmstart"], g[f"step{s}/qacc_warmstart"], 2e-4)
+    close(f"step{s}/qvel", o.d["qvel"], g[f"step{s}/qvel"], 2e-3 if cg else 1e-4)
+    close(f"step{s}/qacc_warmstart", o.d["qacc_warmstart"], g[f"step{s}/qacc_warmstart"], 5e-3 if cg else 2e-4)
     close(f"step{s}/time", o.d["time"], g[f"step{s}/time"], 1e-12)
     np.testing.assert_array_equal(o.d["nefc"].reshape(-1), g[f"step{s}/nefc"].reshape(-1), err_msg=f"step{s}/nefc")
     s += 1

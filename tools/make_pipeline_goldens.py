@@ -41,9 +41,14 @@ def scenes():
   hum_e = mjcf.load_any(util.HUMANOID)
   hum_e.opt.cone = C.CONE_ELLIPTIC
   yield "humanoid_elliptic", hum_e, dict(nconmax=24, njmax=128, key=0, qpos_noise=0.003, exact_world0=False)
+  hum_cg = mjcf.load_any(util.HUMANOID)
+  hum_cg.opt.solver = C.SOL_CG
+  yield "humanoid_cg", hum_cg, dict(nconmax=24, njmax=128, key=0, qpos_noise=0.003, exact_world0=False)
   yield "mixed", mjcf.load_string(util.MIXED_XML), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   ell = util.MIXED_XML.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"')
   yield "mixed_elliptic", mjcf.load_string(ell), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  cg = util.MIXED_XML.replace('<option timestep="0.004"', '<option solver="CG" cone="elliptic" timestep="0.004"')
+  yield "mixed_elliptic_cg", mjcf.load_string(cg), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   yield "boxes", mjcf.load_string(BOX_XML), dict(nconmax=48, njmax=200, key=None, qpos_noise=0.003, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
   yield "g1", mjcf.load_any(util.G1), dict(nconmax=48, njmax=192, key=0, qpos_noise=0.02, qvel_noise=0.2, ctrl_noise=0.3)
