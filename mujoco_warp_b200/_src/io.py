@@ -21,7 +21,7 @@ from . import types
 
 _FLOAT_FIELDS = [
   "qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_subtreemass",
-  "body_inertia", "body_invweight0", "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref",
+  "body_inertia", "body_invweight0", "body_gravcomp", "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref",
   "jnt_solimp", "jnt_actfrcrange", "dof_armature", "dof_damping", "dof_invweight0", "dof_frictionloss", "dof_solref",
   "dof_solimp", "geom_size", "geom_aabb", "geom_rbound", "geom_pos", "geom_quat", "geom_friction", "geom_margin",
   "geom_gap", "geom_solmix", "geom_solref", "geom_solimp", "actuator_gear", "actuator_gainprm", "actuator_biasprm",
@@ -251,11 +251,6 @@ def _validate(mjm):
       raise NotImplementedError("only connect / weld / joint equality constraints are implemented")
     if (ot[np.isin(et, (C.EQ_CONNECT, C.EQ_WELD))] != C.OBJ_BODY).any():
       raise NotImplementedError("site-based connect / weld equality constraints are not implemented")
-  if (np.asarray(mjm.body_gravcomp) != 0).any():
-    raise NotImplementedError("gravity compensation is not implemented")
-  jt = np.asarray(mjm.jnt_type)
-  if ((jt == C.JNT_FREE) | (jt == C.JNT_BALL)).any() and (np.asarray(mjm.jnt_stiffness)[(jt == C.JNT_FREE) | (jt == C.JNT_BALL)] != 0).any():
-    raise NotImplementedError("free/ball joint springs are not implemented")
   if int(np.asarray(mjm.tree_dofnum).max(initial=0)) > 64:
     raise NotImplementedError("kinematic trees with more than 64 dofs are not supported (dense per-tree Cholesky)")
 
@@ -357,7 +352,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
-    neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]),
+    neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any()),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))

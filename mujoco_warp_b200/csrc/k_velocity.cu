@@ -104,27 +104,52 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       __syncwarp();
     }
 
-    // passive: joint springs (slide/hinge) and dampers
+    // passive: joint springs (slide / hinge; ball and free joints through quat_sub) and dampers, gravity compensation
     if (v_all || (mask & STG_PASSIVE)) {
       const bool dsbl_spring = m.disableflags & DSBL_SPRING, dsbl_damper = m.disableflags & DSBL_DAMPER;
+      const bool gravcomp = m.has_gravcomp && !(m.disableflags & DSBL_GRAVITY) && !(dsbl_spring && dsbl_damper);
 #pragma unroll 1
       for (int dd = lane; dd < nv; dd += 32) {
         const int j = m.dof_jntid[dd], t = m.jnt_type[j];
-        float spring = 0.f, damper = 0.f;
+        float spring = 0.f, damper = 0.f, gc = 0.f;
         if (!(dsbl_spring && dsbl_damper)) {
           const float stiffness = m.jnt_stiffness[j];
-          if (stiffness != 0.f && !dsbl_spring && (t == JNT_SLIDE || t == JNT_HINGE)) {
-            const int qa = m.jnt_qposadr[j];
-            spring = -(d.qpos[wb * m.nq + qa] - m.qpos_spring[qa]) * stiffness;
+          if (stiffness != 0.f && !dsbl_spring) {
+            const int qa = m.jnt_qposadr[j], k = dd - m.jnt_dofadr[j];
+            if (t == JNT_SLIDE || t == JNT_HINGE) spring = -(d.qpos[wb * m.nq + qa] - m.qpos_spring[qa]) * stiffness;
+            else if (t == JNT_FREE && k < 3) spring = -stiffness * (d.qpos[wb * m.nq + qa + k] - m.qpos_spring[qa + k]);
+            else {  // rotational part: -k * quat_sub(q, q_spring) (passive.py:141-183, math.py:161-186)
+              const int ra = t == JNT_FREE ? qa + 3 : qa, kk = t == JNT_FREE ? k - 3 : k;
+              const q4 rot = qnormalize(ldq(d.qpos + wb * m.nq + ra)), ref = ldq(m.qpos_spring + ra);
+              const q4 qd = qmul(mkq(ref.w, -ref.x, -ref.y, -ref.z), rot);
+              const float s2 = sqrtf(qd.x * qd.x + qd.y * qd.y + qd.z * qd.z);
+              if (s2 != 0.f) {
+                float speed = 2.0f * atan2f(s2, qd.w);
+                if (speed > 3.14159265358979f) speed -= 2.0f * 3.14159265358979f;
+                spring = -stiffness * (kk == 0 ? qd.x : kk == 1 ? qd.y : qd.z) * (speed / s2);
+              }
+            }
           }
           const float damping = m.dof_damping[dd];
           if (damping != 0.f && !dsbl_damper) damper = -qvel[dd] * damping;
         }
+        if (gravcomp) {  // passive.py:275-303: -gravity * mass * gravcomp at the body's inertial origin, projected on this dof
+#pragma unroll 1
+          for (int b = 1; b < nb; b++) {
+            const float g = m.body_gravcomp[b];
+            if (g == 0.f || !m.body_isdofancestor[b * nv + dd]) continue;
+            const float sc = -m.body_mass[b] * g;
+            const v3 off = ld3(d.xipos + (wb * nb + b) * 3) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3);
+            const v3 jp = ld3(cdof + 6 * dd + 3) + cross(ld3(cdof + 6 * dd), off);
+            gc += sc * (jp.x * m.gravity_x + jp.y * m.gravity_y + jp.z * m.gravity_z);
+          }
+        }
         d.qfrc_spring[wb * nv + dd] = spring;
         d.qfrc_damper[wb * nv + dd] = damper;
-        d.qfrc_gravcomp[wb * nv + dd] = 0.f;
-        q_passive[dd] = spring + damper;
-        d.qfrc_passive[wb * nv + dd] = spring + damper;
+        d.qfrc_gravcomp[wb * nv + dd] = gc;
+        const float passive = spring + damper + (m.jnt_actgravcomp[j] ? 0.f : gc);
+        q_passive[dd] = passive;
+        d.qfrc_passive[wb * nv + dd] = passive;
       }
     }
     // rne: cacc forward, cfrc per body, backward accumulation, projection

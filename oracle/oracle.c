@@ -57,7 +57,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(eq_type) X(eq_obj1id) X(eq_obj2id)
 #define MODEL_RARRS(X) \
   X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
-  X(body_inertia) X(body_invweight0) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
+  X(body_inertia) X(body_invweight0) X(body_gravcomp) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
   X(jnt_solimp) X(jnt_actfrcrange) X(dof_armature) X(dof_damping) X(dof_invweight0) X(dof_frictionloss) X(dof_solref) \
   X(dof_solimp) X(geom_size) X(geom_aabb) X(geom_rbound) X(geom_pos) X(geom_quat) X(geom_friction) X(geom_margin) \
   X(geom_gap) X(geom_solmix) X(geom_solref) X(geom_solimp) X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) \
@@ -1709,9 +1709,26 @@ static void fwd_velocity(W* w) {
       real stiffness = m->jnt_stiffness[j];
       int has_st = stiffness != 0 && !dsbl_spring;
       int nd = t == JNT_FREE ? 6 : (t == JNT_BALL ? 3 : 1);
-      if (has_st) {
+      if (has_st) { /* passive.py:125-206; polynomial stiffness terms are zero on this path */
         if (t == JNT_SLIDE || t == JNT_HINGE) w->qfrc_spring[d] = -(w->qpos[qa] - m->qpos_spring[qa]) * stiffness;
-        else w->overflow[0] |= OVF_UNSUPPORTED; /* free/ball joint springs not restated */
+        else {
+          int ra = qa, rd = d;
+          if (t == JNT_FREE) {
+            for (int i = 0; i < 3; i++) w->qfrc_spring[d + i] = -stiffness * (w->qpos[qa + i] - m->qpos_spring[qa + i]);
+            ra = qa + 3; rd = d + 3;
+          }
+          real rot[4] = {w->qpos[ra], w->qpos[ra + 1], w->qpos[ra + 2], w->qpos[ra + 3]}, qneg[4], qdif[4], dif[3] = {0, 0, 0};
+          normalize4(rot);
+          qneg[0] = m->qpos_spring[ra]; for (int i = 1; i < 4; i++) qneg[i] = -m->qpos_spring[ra + i];
+          mul_quat(qneg, rot, qdif); /* math.py:178 quat_sub, :161 quat_to_vel */
+          real s2 = (real)sqrt((double)(qdif[1] * qdif[1] + qdif[2] * qdif[2] + qdif[3] * qdif[3]));
+          if (s2 != 0) {
+            real speed = 2 * (real)atan2((double)s2, (double)qdif[0]);
+            if (speed > (real)3.14159265358979323846) speed -= 2 * (real)3.14159265358979323846;
+            for (int i = 0; i < 3; i++) dif[i] = qdif[1 + i] * speed / s2;
+          }
+          for (int i = 0; i < 3; i++) w->qfrc_spring[rd + i] = -stiffness * dif[i];
+        }
       }
       for (int k = 0; k < nd; k++) {
         real damping = m->dof_damping[d + k];
@@ -1719,6 +1736,25 @@ static void fwd_velocity(W* w) {
       }
     }
     for (int d = 0; d < nv; d++) w->qfrc_passive[d] = w->qfrc_spring[d] + w->qfrc_damper[d];
+  }
+  /* gravity compensation (passive.py:275-303): -gravity * mass * gravcomp applied at the body's inertial frame origin;
+   * added to qfrc_passive unless the joint routes it through the actuators (passive.py:650-653) */
+  if (!(m->disableflags & DSBL_GRAVITY) && !(dsbl_spring && dsbl_damper)) { /* passive() returns early when both are disabled (:1263) */
+    int any = 0;
+    for (int b = 1; b < nb; b++) {
+      real gc = m->body_gravcomp[b];
+      if (gc == 0) continue;
+      any = 1;
+      real force[3] = {-m->gravity[0] * m->body_mass[b] * gc, -m->gravity[1] * m->body_mass[b] * gc, -m->gravity[2] * m->body_mass[b] * gc};
+      for (int d = 0; d < nv; d++) {
+        if (!m->body_isdofancestor[b * nv + d]) continue;
+        const real* com = w->subtree_com + 3 * m->body_rootid[b]; const real* cd = w->cdof + 6 * d;
+        real off[3] = {w->xipos[3 * b] - com[0], w->xipos[3 * b + 1] - com[1], w->xipos[3 * b + 2] - com[2]}, cr[3];
+        cross3(cd, off, cr);
+        w->qfrc_gravcomp[d] += (cd[3] + cr[0]) * force[0] + (cd[4] + cr[1]) * force[1] + (cd[5] + cr[2]) * force[2];
+      }
+    }
+    if (any) for (int d = 0; d < nv; d++) if (!m->jnt_actgravcomp[m->dof_jntid[d]]) w->qfrc_passive[d] += w->qfrc_gravcomp[d];
   }
   /* rne (smooth.py:1353-1515), flg_acc = False */
   memset(w->cacc, 0, 6 * sizeof(real));

@@ -171,3 +171,19 @@ EQUALITY_XML = """
   </keyframe>
 </mujoco>
 """
+
+
+def passive_xml():
+  """MIXED_XML with the remaining passive-force features switched on: gravity compensation (one body routed through the
+  actuators with actuatorgravcomp), a ball-joint spring and a free-joint spring / damper."""
+  x = MIXED_XML
+  for a, b in (
+    ('<body name="pend" pos="0.25 0 0">', '<body name="pend" pos="0.25 0 0" gravcomp="0.7">'),
+    ('<joint name="ball" type="ball" damping="0.05"/>', '<joint name="ball" type="ball" damping="0.05" stiffness="2"/>'),
+    ('<body name="ball0" pos="0 0 0.12">\n      <freejoint/>', '<body name="ball0" pos="0 0 0.12" gravcomp="0.3">\n      <joint type="free" stiffness="3" damping="0.2"/>'),
+    ('<body name="arm" pos="-0.6 0 0.6">', '<body name="arm" pos="-0.6 0 0.6" gravcomp="1">'),
+    ('<joint name="slide" type="slide" axis="0 0 1"', '<joint name="slide" type="slide" actuatorgravcomp="true" axis="0 0 1"'),
+  ):
+    assert a in x, a
+    x = x.replace(a, b)
+  return x
