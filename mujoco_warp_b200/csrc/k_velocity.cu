@@ -29,6 +29,8 @@ __host__ __device__ inline VelLayout vel_layout(const ModelDev& m) {
 }
 
 // 28 resident one-warp blocks per SM make 8192 worlds exactly two full waves on 148 SMs (caps registers at 72)
+// PEXT = the model uses gravity compensation or free / ball joint springs (kept out of the plain instantiation)
+template <bool PEXT>
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32, 28)
 k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
   extern __shared__ float smem[];
@@ -107,7 +109,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     // passive: joint springs (slide / hinge; ball and free joints through quat_sub) and dampers, gravity compensation
     if (v_all || (mask & STG_PASSIVE)) {
       const bool dsbl_spring = m.disableflags & DSBL_SPRING, dsbl_damper = m.disableflags & DSBL_DAMPER;
-      const bool gravcomp = m.has_gravcomp && !(m.disableflags & DSBL_GRAVITY) && !(dsbl_spring && dsbl_damper);
+      const bool gravcomp = PEXT && m.has_gravcomp && !(m.disableflags & DSBL_GRAVITY) && !(dsbl_spring && dsbl_damper);
 #pragma unroll 1
       for (int dd = lane; dd < nv; dd += 32) {
         const int j = m.dof_jntid[dd], t = m.jnt_type[j];
@@ -117,6 +119,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
           if (stiffness != 0.f && !dsbl_spring) {
             const int qa = m.jnt_qposadr[j], k = dd - m.jnt_dofadr[j];
             if (t == JNT_SLIDE || t == JNT_HINGE) spring = -(d.qpos[wb * m.nq + qa] - m.qpos_spring[qa]) * stiffness;
+            else if (!PEXT) {}
             else if (t == JNT_FREE && k < 3) spring = -stiffness * (d.qpos[wb * m.nq + qa + k] - m.qpos_spring[qa + k]);
             else {  // rotational part: -k * quat_sub(q, q_spring) (passive.py:141-183, math.py:161-186)
               const int ra = t == JNT_FREE ? qa + 3 : qa, kk = t == JNT_FREE ? k - 3 : k;
@@ -344,13 +347,15 @@ size_t smem_velocity(const ModelDev& m) { return (size_t)vel_layout(m).total * s
 
 cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int mask, cudaStream_t s) {
   const size_t smem = smem_velocity(m);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured[2] = {0, 0};
+  const int ext = m.has_gravcomp ? 1 : 0;  // has_gravcomp also flags free / ball joint springs (io.py put_model)
+  void (*kern)(ModelDev, DataDev, int) = ext ? k_velocity<true> : k_velocity<false>;
+  if (smem > 48 * 1024 && smem > configured[ext]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[ext] = smem;
   }
   const int grid = d.wn;
-  k_velocity<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, mask);
+  kern<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, mask);
   return cudaGetLastError();
 }
