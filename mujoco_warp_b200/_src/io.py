@@ -29,7 +29,7 @@ _FLOAT_FIELDS = [
   "light_pos", "light_dir", "light_poscom0", "light_pos0", "light_dir0", "site_pos", "site_quat",
 ]
 _INT_FIELDS = [
-  "body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr",
+  "body_parentid", "body_rootid", "body_weldid", "body_mocapid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr",
   "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_actfrclimited", "jnt_actgravcomp",
   "dof_bodyid", "dof_jntid", "dof_parentid", "M_rownnz", "M_rowadr", "M_colind", "tree_dofadr", "tree_dofnum",
   "geom_type", "geom_condim", "geom_bodyid", "geom_priority",
@@ -242,7 +242,7 @@ def _validate(mjm):
     raise NotImplementedError("only the Newton and CG solvers are implemented in this version (no PGS)")
   if mjm.nv > 64:
     raise NotImplementedError("nv > 64 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
-  for n in ("na", "ntendon", "nflex", "nmocap"):
+  for n in ("na", "ntendon", "nflex"):
     if getattr(mjm, n, 0):
       raise NotImplementedError(f"{n} > 0 is not supported in this version")
   if getattr(mjm, "neq", 0):
@@ -352,7 +352,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
-    neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
+    nmocap=int(getattr(mjm, "nmocap", 0)), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))
@@ -407,6 +407,7 @@ def _data_spec(m: types.Model, nworld, naconmax, njmax, njmax_pad):
     "cfrc_ext": (f, (nworld, nb, 6)), "energy": (f, (nworld, 2)),
     "nacon": (i, (1,)), "ncollision": (i, (1,)), "overflow": (i, (nworld,)),
     "eq_active": (i, (nworld, getattr(m, "neq", 0))),  # the reference stores bool; int32 0/1 here (one word per flag)
+    "mocap_pos": (f, (nworld, m.nmocap, 3)), "mocap_quat": (f, (nworld, m.nmocap, 4)),
   }
 
 
@@ -439,7 +440,7 @@ _BOUND_TOP = [
   "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat", "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert",
   "crb", "M", "qLD", "actuator_length", "actuator_moment", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
   "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int",
-  "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active",
+  "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active", "mocap_pos", "mocap_quat",
 ]
 _BOUND_EFC = ["J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "Ma", "type", "id", "state"]
 _BOUND_CONTACT = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "type", "geomcollisionid"]
@@ -480,8 +481,20 @@ def make_data(mjm, nworld: int = 1, nconmax=None, nccdmax=None, njmax=None, njma
   d.xquat[..., 0] = 1.0
   if getattr(m, "neq", 0):
     d.eq_active.copy_(torch.from_numpy(np.tile(np.asarray(mjm.eq_active0).astype(np.int32), (nworld, 1))))
+  _reset_mocap(mjm, d)
   _bind(m, d, L)
   return d
+
+
+def _reset_mocap(mjm, d):
+  """mocap poses start at the bodies' model pose (reference io.py:1824-1846)"""
+  if not getattr(mjm, "nmocap", 0):
+    return
+  mid = np.asarray(mjm.body_mocapid)
+  mb = np.nonzero(mid >= 0)[0]
+  order = mb[np.argsort(mid[mb])]
+  d.mocap_pos.copy_(torch.from_numpy(np.tile(np.asarray(mjm.body_pos, dtype=np.float32)[order], (d.nworld, 1, 1))))
+  d.mocap_quat.copy_(torch.from_numpy(np.tile(np.asarray(mjm.body_quat, dtype=np.float32)[order], (d.nworld, 1, 1))))
 
 
 def _host_kinematics(mjm, qpos):
@@ -537,6 +550,7 @@ def reset_data(m: types.Model, d: types.Data):
     getattr(d, n).zero_()
   if getattr(m, "neq", 0):
     d.eq_active.copy_(torch.from_numpy(np.tile(np.asarray(mjm.eq_active0).astype(np.int32), (d.nworld, 1))))
+  _reset_mocap(mjm, d)
 
 
 def reset_data_keyframe(m: types.Model, d: types.Data, key):

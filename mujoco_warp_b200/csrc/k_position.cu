@@ -68,8 +68,12 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
           continue;
         }
         q4 pq = ldq(xquat + 4 * pid);
-        v3 pos = qrot(pq, ld3(m.body_pos + 3 * b)) + ld3(xpos + 3 * pid);
-        q4 quat = qmul(pq, ldq(m.body_quat + 4 * b));
+        // mocap bodies take their pose from Data.mocap_pos / mocap_quat (smooth.py:104-110)
+        const int mc = m.nmocap > 0 ? m.body_mocapid[b] : -1;
+        const v3 bpos = mc >= 0 ? ld3(d.mocap_pos + (wb * m.nmocap + mc) * 3) : ld3(m.body_pos + 3 * b);
+        const q4 bquat = mc >= 0 ? ldq(d.mocap_quat + (wb * m.nmocap + mc) * 4) : ldq(m.body_quat + 4 * b);
+        v3 pos = qrot(pq, bpos) + ld3(xpos + 3 * pid);
+        q4 quat = qmul(pq, bquat);
 #pragma unroll 1
         for (int j = jntadr; j < jntadr + jntnum; j++) {
           const int qa = m.jnt_qposadr[j], t = m.jnt_type[j];
@@ -100,7 +104,7 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 #pragma unroll 1
     for (int g = lane; g < ng; g += 32) {
       const int b = m.geom_bodyid[g];
-      if (m.body_weldid[b] == 0) {  // static geom: keeps the pose computed at make_data (smooth.py:197-200)
+      if (m.body_weldid[b] == 0 && (m.nmocap == 0 || m.body_mocapid[m.body_rootid[b]] == -1)) {  // static geom: keeps the pose computed at make_data (smooth.py:197-200)
         for (int k = 0; k < 3; k++) gxpos[3 * g + k] = d.geom_xpos[(wb * ng + g) * 3 + k];
         for (int k = 0; k < 9; k++) gxmat[9 * g + k] = d.geom_xmat[(wb * ng + g) * 9 + k];
       } else {

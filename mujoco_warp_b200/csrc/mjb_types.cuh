@@ -8,11 +8,11 @@
 #define MJB_MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) X(nlevel) \
   X(nxn_npair) X(nlimit) X(nfricdof) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) \
-  X(ls_iterations) X(disableflags) X(enableflags) X(broadphase_filter) X(qld_total) X(maxtree) X(has_multicontact_geom) X(neq) X(nlimit_ball) X(has_gravcomp)
+  X(ls_iterations) X(disableflags) X(enableflags) X(broadphase_filter) X(qld_total) X(maxtree) X(has_multicontact_geom) X(neq) X(nlimit_ball) X(has_gravcomp) X(nmocap)
 #define MJB_MODEL_FLOATS(X) \
   X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(gravity_x) X(gravity_y) X(gravity_z)
 #define MJB_MODEL_IARRS(X) \
-  X(body_parentid) X(body_rootid) X(body_weldid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
+  X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
   X(body_childadr) X(body_childid) X(level_adr) X(level_body) \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_actfrclimited) X(jnt_actgravcomp) X(jnt_limited_adr) \
   X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(dof_fricloss_adr) X(M_rownnz) X(M_rowadr) X(M_colind) X(M_entry_row) X(mulm_rowadr) X(mulm_col) X(mulm_madr) \
@@ -57,7 +57,7 @@ struct ModelDev {
   X(qfrc_constraint) X(cacc) X(cfrc_int) \
   X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
   X(contact_dist) X(contact_pos) X(contact_frame) X(contact_includemargin) X(contact_friction) X(contact_solref) \
-  X(contact_solreffriction) X(contact_solimp)
+  X(contact_solreffriction) X(contact_solimp) X(mocap_pos) X(mocap_quat)
 #define MJB_DATA_IARRS(X) \
   X(ne) X(nf) X(nl) X(nefc) X(nacon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
   X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(contact_dim) X(contact_geom) X(contact_efc_address) \

@@ -41,12 +41,12 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 
 /* ------------------------------------------------------------------ field registries (X-macros) */
 #define MODEL_INTS(X) \
-  X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
+  X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
   X(disableflags) X(enableflags) X(broadphase_filter)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia)
 #define MODEL_IARRS(X) \
-  X(body_parentid) X(body_rootid) X(body_weldid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
+  X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_actfrclimited) X(jnt_actgravcomp) \
   X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(M_rownnz) X(M_rowadr) X(M_colind) \
   X(tree_dofadr) X(tree_dofnum) X(qLD_block_adr) \
@@ -67,7 +67,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
-  X(time) X(qpos) X(qvel) X(ctrl) X(qacc_warmstart) X(qfrc_applied) X(xfrc_applied) X(qacc) \
+  X(time) X(qpos) X(qvel) X(ctrl) X(qacc_warmstart) X(qfrc_applied) X(xfrc_applied) X(qacc) X(mocap_pos) X(mocap_quat) \
   X(xpos) X(xquat) X(xmat) X(xipos) X(ximat) X(xanchor) X(xaxis) X(geom_xpos) X(geom_xmat) X(site_xpos) X(site_xmat) \
   X(cam_xpos) X(cam_xmat) X(light_xpos) X(light_xdir) X(subtree_com) X(cdof) X(cinert) X(crb) X(M) X(qLD) \
   X(actuator_length) X(actuator_moment) X(actuator_velocity) X(cvel) X(cdof_dot) X(qfrc_bias) X(qfrc_spring) \
@@ -315,6 +315,7 @@ static void make_view(const OrcModel* m, const OrcData* d, int w, W* v) {
   const int nb = m->nbody, nv = m->nv, nj = m->njnt, ng = m->ngeom, nu = m->nu, njm = d->njmax, ncm = d->nconmax;
   v->m = m; v->njmax = njm; v->nconmax = ncm;
 #define R(n, sz) v->n = d->n + (size_t)w * (size_t)(sz)
+  R(mocap_pos, 3 * m->nmocap); R(mocap_quat, 4 * m->nmocap);
   R(time, 1); R(qpos, m->nq); R(qvel, nv); R(ctrl, nu); R(qacc_warmstart, nv); R(qfrc_applied, nv); R(xfrc_applied, 6 * nb); R(qacc, nv);
   R(xpos, 3 * nb); R(xquat, 4 * nb); R(xmat, 9 * nb); R(xipos, 3 * nb); R(ximat, 9 * nb); R(xanchor, 3 * nj); R(xaxis, 3 * nj);
   R(geom_xpos, 3 * ng); R(geom_xmat, 9 * ng); R(site_xpos, 3 * m->nsite); R(site_xmat, 9 * m->nsite);
@@ -358,9 +359,13 @@ static void kinematics(W* w) {
       continue;
     }
     real pos[3], quat[4];
-    rot_vec_quat(m->body_pos + 3 * b, w->xquat + 4 * pid, pos);
+    /* mocap bodies take their pose from Data.mocap_pos / mocap_quat instead of body_pos / body_quat (smooth.py:104-110) */
+    int mc = m->body_mocapid[b];
+    const real* bpos = mc >= 0 ? w->mocap_pos + 3 * mc : m->body_pos + 3 * b;
+    const real* bquat = mc >= 0 ? w->mocap_quat + 4 * mc : m->body_quat + 4 * b;
+    rot_vec_quat(bpos, w->xquat + 4 * pid, pos);
     for (int i = 0; i < 3; i++) pos[i] += w->xpos[3 * pid + i];
-    mul_quat(w->xquat + 4 * pid, m->body_quat + 4 * b, quat);
+    mul_quat(w->xquat + 4 * pid, bquat, quat);
     for (int j = jntadr; j < jntadr + jntnum; j++) { /* smooth.py:116-140 */
       int qa = m->jnt_qposadr[j], t = m->jnt_type[j];
       real anchor[3], axis[3], tmp[3];
@@ -398,7 +403,7 @@ static void kinematics(W* w) {
   }
   for (int g = 0; g < m->ngeom; g++) { /* smooth.py:178-205: world-welded geoms keep their make_data pose */
     int b = m->geom_bodyid[g];
-    if (m->body_weldid[b] == 0) continue;
+    if (m->body_weldid[b] == 0 && m->body_mocapid[m->body_rootid[b]] == -1) continue; /* unless it hangs off a mocap body */
     real t[3], q[4];
     rot_vec_quat(m->geom_pos + 3 * g, w->xquat + 4 * b, t);
     for (int i = 0; i < 3; i++) w->geom_xpos[3 * g + i] = w->xpos[3 * b + i] + t[i];

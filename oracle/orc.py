@@ -55,9 +55,9 @@ def _lib(real_bytes: int):
   return _LIBS[real_bytes]
 
 
-MODEL_INTS = ["nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "ncam", "nlight", "nC", "ntree"]
+MODEL_INTS = ["nq", "nv", "nu", "nbody", "nmocap", "njnt", "ngeom", "nsite", "ncam", "nlight", "nC", "ntree"]
 MODEL_IARRS = [
-  "body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr",
+  "body_parentid", "body_rootid", "body_weldid", "body_mocapid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr",
   "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_actfrclimited", "jnt_actgravcomp",
   "dof_bodyid", "dof_jntid", "dof_parentid", "M_rownnz", "M_rowadr", "M_colind", "tree_dofadr", "tree_dofnum",
   "geom_type", "geom_condim", "geom_bodyid", "geom_priority",
@@ -127,6 +127,7 @@ def data_spec(mjm, tabs, nconmax, njmax):
   return {
     "time": (R, ()), "qpos": (R, (nq,)), "qvel": (R, (nv,)), "ctrl": (R, (nu,)), "qacc_warmstart": (R, (nv,)),
     "qfrc_applied": (R, (nv,)), "xfrc_applied": (R, (nb, 6)), "qacc": (R, (nv,)),
+    "mocap_pos": (R, (int(getattr(mjm, "nmocap", 0)), 3)), "mocap_quat": (R, (int(getattr(mjm, "nmocap", 0)), 4)),
     "xpos": (R, (nb, 3)), "xquat": (R, (nb, 4)), "xmat": (R, (nb, 3, 3)), "xipos": (R, (nb, 3)), "ximat": (R, (nb, 3, 3)),
     "xanchor": (R, (nj, 3)), "xaxis": (R, (nj, 3)), "geom_xpos": (R, (ng, 3)), "geom_xmat": (R, (ng, 3, 3)),
     "site_xpos": (R, (mjm.nsite, 3)), "site_xmat": (R, (mjm.nsite, 3, 3)),
@@ -221,6 +222,11 @@ class Oracle:
     self.d["qpos"][:] = np.asarray(mjm.qpos0)
     if neq:
       self.d["eq_active"][:] = np.asarray(mjm.eq_active0).astype(np.int32)
+    if getattr(mjm, "nmocap", 0):  # io.py:1824-1846: mocap poses start at the bodies' model pose
+      mb = np.nonzero(np.asarray(mjm.body_mocapid) >= 0)[0]
+      order = mb[np.argsort(np.asarray(mjm.body_mocapid)[mb])]
+      self.d["mocap_pos"][:] = np.asarray(mjm.body_pos)[order]
+      self.d["mocap_quat"][:] = np.asarray(mjm.body_quat)[order]
     if static_kin is not None:
       self.d["geom_xpos"][:] = static_kin.geom_xpos
       self.d["geom_xmat"][:] = static_kin.geom_xmat

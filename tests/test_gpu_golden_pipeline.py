@@ -34,6 +34,8 @@ def test_gpu_matches_reference_pipeline(built, name):
   d.qpos.copy_(f32(g["in/qpos"])); d.qvel.copy_(f32(g["in/qvel"])); d.qacc_warmstart.copy_(f32(g["in/qacc_warmstart"]))
   if mjm.nu:
     d.ctrl.copy_(f32(g["in/ctrl"]))
+  if "in/mocap_pos" in g:
+    d.mocap_pos.copy_(f32(g["in/mocap_pos"])); d.mocap_quat.copy_(f32(g["in/mocap_quat"]))
   mjw.forward(m, d)
   torch.cuda.synchronize()
   assert (d.overflow.cpu().numpy() == 0).all()

@@ -112,6 +112,8 @@ def test_oracle_matches_reference_pipeline(built, name):
   o.set_state(qpos=g["in/qpos"], qvel=g["in/qvel"], qacc_warmstart=g["in/qacc_warmstart"])
   if mjm.nu:
     o.set_state(ctrl=g["in/ctrl"])
+  if "in/mocap_pos" in g:
+    o.d["mocap_pos"][:] = g["in/mocap_pos"]; o.d["mocap_quat"][:] = g["in/mocap_quat"]
   o.forward()
   assert (o.d["overflow"] == 0).all()
   # CG takes tens of iterations: rounding differences grow along the conjugate directions, so iteration counts can differ by

@@ -153,6 +153,12 @@ EQUALITY_XML = """
     <body name="s1" pos="-0.5 0 0.5"><joint name="sl1" type="slide" axis="0 0 1"/><geom type="sphere" size="0.04"/></body>
     <body name="s2" pos="-0.7 0 0.5"><joint name="sl2" type="slide" axis="0 0 1" damping="1"/><geom type="sphere" size="0.04"/></body>
     <body name="s3" pos="-0.9 0 0.5"><joint name="sl3" type="slide" axis="1 0 0"/><geom type="sphere" size="0.04"/></body>
+    <body name="target" mocap="true" pos="0.3 -0.5 0.4" quat="0.9238795 0 0.3826834 0">
+      <geom name="paddle" type="box" size="0.15 0.15 0.01" contype="2" conaffinity="2"/>
+      <body name="target_child" pos="0 0 0.1"><geom type="sphere" size="0.03" contype="0" conaffinity="0"/></body>
+    </body>
+    <body name="puck" pos="0.3 -0.5 0.47"><freejoint/><geom type="sphere" size="0.05" contype="2" conaffinity="2"/></body>
+    <body name="follower" pos="0.3 -0.9 0.4"><freejoint/><geom type="sphere" size="0.04" contype="0" conaffinity="0"/></body>
   </worldbody>
   <equality>
     <connect body1="a2" body2="b1" anchor="0 0 -0.3"/>
@@ -161,13 +167,14 @@ EQUALITY_XML = """
     <joint joint1="sl3" polycoef="0.05 0 0 0 0" solref="0.03 1"/>
     <connect body1="s2" anchor="0.1 0 0" solimp="0.8 0.9 0.01 0.5 2"/>
     <weld body1="s1" body2="s3" active="false"/>
+    <weld body1="follower" body2="target_child" solref="0.01 1"/>
   </equality>
   <actuator>
     <motor joint="h1" gear="2"/>
     <motor joint="sl1" gear="5"/>
   </actuator>
   <keyframe>
-    <key name="k0" qpos="0 0 0  0.9396926 0.3420201 0 0  0.6 0.5 0.5 1 0 0 0  0.8 0.5 0.5 1 0 0 0  0 0 0"/>
+    <key name="k0" qpos="0 0 0  0.9396926 0.3420201 0 0  0.6 0.5 0.5 1 0 0 0  0.8 0.5 0.5 1 0 0 0  0 0 0  0.3 -0.5 0.47 1 0 0 0  0.3 -0.9 0.4 1 0 0 0"/>
   </keyframe>
 </mujoco>
 """

@@ -95,7 +95,15 @@ def main(only=None):
     d.qpos.a[...] = qpos; d.qvel.a[...] = qvel; d.qacc_warmstart.a[...] = warm
     if mjm.nu:
       d.ctrl.a[...] = ctrl
-    out = {"in/qpos": qpos, "in/qvel": qvel, "in/ctrl": ctrl, "in/qacc_warmstart": warm, "in/nconmax": np.array(nconmax), "in/njmax": np.array(njmax)}
+    extra = {}
+    if getattr(mjm, "nmocap", 0):  # move the mocap bodies away from their model pose, differently per world
+      rng = np.random.default_rng(77)
+      mp = d.mocap_pos.numpy() + f32(0.03 * rng.uniform(-1, 1, (NWORLD, mjm.nmocap, 3)))
+      mq = d.mocap_quat.numpy() + f32(0.1 * rng.uniform(-1, 1, (NWORLD, mjm.nmocap, 4)))
+      mq = f32(mq / np.linalg.norm(mq, axis=-1, keepdims=True))
+      d.mocap_pos.a[...] = mp; d.mocap_quat.a[...] = mq
+      extra = {"in/mocap_pos": mp, "in/mocap_quat": mq}
+    out = {**extra, "in/qpos": qpos, "in/qvel": qvel, "in/ctrl": ctrl, "in/qacc_warmstart": warm, "in/nconmax": np.array(nconmax), "in/njmax": np.array(njmax)}
     fwd.forward(m, d)
     snapshot(mjm, d, out, "forward")
     for s in range(NSTEP):

@@ -253,6 +253,7 @@ import itertools as _it
 import numpy as _np
 
 _STATE = {"tid": (0,), "block_dim": 1}
+_CPU = _t.SimpleNamespace(is_cpu=True, is_cuda=False, sm_count=1, ordinal=0, arch=0)
 
 
 def _inner(dtype):
@@ -273,7 +274,7 @@ class array:
   def __init__(self, data=None, dtype=None, shape=None, ndim=None, device=None, **kw):
     self.dtype = dtype if dtype is not None else float
     self._is_batched = False
-    self.device = "cpu"
+    self.device = _CPU
     inner = _inner(self.dtype)
     if kw.get("ptr") is not None:  # reinterpretation of another array's storage (same bytes, new dtype / shape)
       self.a = kw["ptr"].a.reshape(tuple(_shape_t(shape)) + inner)
@@ -302,7 +303,7 @@ class array:
   @classmethod
   def _view(cls, a, dtype):
     o = cls.__new__(cls)
-    o.dtype, o.a, o._is_batched, o.device = dtype, a, False, "cpu"
+    o.dtype, o.a, o._is_batched, o.device = dtype, a, False, _CPU
     inner = _inner(dtype)
     o.shape = a.shape[: a.ndim - len(inner)]
     o.ndim = len(o.shape)
