@@ -170,6 +170,9 @@ def derive_tables(mjm) -> dict:
   exclude = np.isin((b1.astype(np.int64) << 16) + b2, excl_sig)
   pairid = -np.ones(len(g1), dtype=np.int32)
   pairid[~(mask & ~self_col & ~parent_child & ~exclude)] = -2
+  for i in range(int(getattr(mjm, "npair", 0))):  # explicit <pair>s override the filters (reference io.py:577-583)
+    a, b = sorted((int(mjm.pair_geom1[i]), int(mjm.pair_geom2[i])))
+    pairid[(a * (2 * ngeom - a - 3)) // 2 + b - 1] = i
   include = pairid > -2
   t["nxn_geom_pair"] = np.stack((g1, g2), axis=1).astype(np.int32)
   t["nxn_pairid"] = np.stack((pairid, -np.ones(len(g1), dtype=np.int32)), axis=1).astype(np.int32)
@@ -226,6 +229,8 @@ def derive_tables(mjm) -> dict:
   t["dofact_act"] = np.array([a for r in rev for a, _ in r] or [0], dtype=np.int32)
   t["dofact_mom"] = np.array([i for r in rev for _, i in r] or [0], dtype=np.int32)
   nmaxcondim = int(_np(mjm, "geom_condim").max()) if ngeom else 1
+  if getattr(mjm, "npair", 0):
+    nmaxcondim = max(nmaxcondim, int(np.asarray(mjm.pair_dim).max()))
   t["nmaxcondim"] = nmaxcondim
   t["nmaxpyramid"] = max(1, 2 * (nmaxcondim - 1))
   return t
@@ -333,6 +338,16 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.eq_solref = dev_f(np.asarray(mjm.eq_solref).reshape(neq, 2) if neq else np.zeros((0, 2)))
   m.eq_solimp = dev_f(np.asarray(mjm.eq_solimp).reshape(neq, 5) if neq else np.zeros((0, 5)))
   m.eq_data = dev_f(np.asarray(mjm.eq_data).reshape(neq, 11) if neq else np.zeros((0, 11)))
+  # explicit contact pairs (reference Model.pair_*)
+  npair = int(getattr(mjm, "npair", 0))
+  m.npair = npair
+  m.pair_dim = dev_i(mjm.pair_dim if npair else np.zeros(0))
+  m.pair_geom1 = dev_i(mjm.pair_geom1 if npair else np.zeros(0))
+  m.pair_geom2 = dev_i(mjm.pair_geom2 if npair else np.zeros(0))
+  for n, k in (("pair_friction", 5), ("pair_solref", 2), ("pair_solreffriction", 2), ("pair_solimp", 5)):
+    setattr(m, n, dev_f(np.asarray(getattr(mjm, n)).reshape(npair, k) if npair else np.zeros((0, k))))
+  for n in ("pair_margin", "pair_gap"):
+    setattr(m, n, dev_f(np.asarray(getattr(mjm, n)) if npair else np.zeros(0)))
   m.M_mulm_rowadr, m.M_mulm_col, m.M_mulm_madr = m.mulm_rowadr, m.mulm_col, m.mulm_madr
   anc_pad = np.zeros((m.nbody, m.nv_pad), dtype=np.int32)
   anc_pad[:, : m.nv] = t["body_isdofancestor"]
@@ -352,7 +367,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
-    nmocap=int(getattr(mjm, "nmocap", 0)), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
+    nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))
@@ -368,7 +383,8 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   for n in _FLOAT_FIELDS + _INT_FIELDS + ["body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col",
                                          "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
                                          "dofact_adr", "dofact_act", "dofact_mom", "eq_type", "eq_obj1id", "eq_obj2id", "eq_solref", "eq_solimp", "eq_data",
-                                         "jnt_limited_ball_adr"]:
+                                         "jnt_limited_ball_adr", "pair_dim", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp",
+                                         "pair_margin", "pair_gap"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)

@@ -864,7 +864,7 @@ def compile_xml(root):
       getattr(m, "actuator_" + lim)[i] = (l == "true") or (l == "auto" and compiler["autolimits"] and rng in a)
 
   # ---- contact excludes / pairs
-  excl = []
+  excl, pairs = [], []
   ce = root.find("contact")
   if ce is not None:
     for child in ce:
@@ -873,10 +873,37 @@ def compile_xml(root):
         excl.append((min(b1, b2) << 16) + max(b1, b2))
         excl.append((max(b1, b2) << 16) + min(b1, b2))
       elif child.tag == "pair":
-        raise NotImplementedError("explicit contact pairs are not supported")
+        a = dflt.resolve("pair", child.get("class", "main"))
+        a.update(child.attrib)
+        g1, g2 = m.names.geom.index(a["geom1"]), m.names.geom.index(a["geom2"])
+        # attributes left unset are derived from the two geoms the way MuJoCo's compiler does for explicit pairs:
+        # condim / friction = max, solref / solimp mixed by solmix, margin / gap = max
+        mix = m.geom_solmix[g1] / max(m.geom_solmix[g1] + m.geom_solmix[g2], C.MJ_MINVAL)
+        fmax = np.maximum(m.geom_friction[g1], m.geom_friction[g2])
+        fr = _vec(a.get("friction"), 5, [fmax[0], fmax[0], fmax[1], fmax[2], fmax[2]])
+        if "friction" in a:
+          given = len(a["friction"].split())
+          if given == 1:
+            fr[1] = fr[0]
+        pairs.append(dict(
+          geom1=g1, geom2=g2, dim=int(a.get("condim", max(m.geom_condim[g1], m.geom_condim[g2]))), friction=fr,
+          solref=_vec(a.get("solref"), 2, mix * m.geom_solref[g1] + (1 - mix) * m.geom_solref[g2]),
+          solreffriction=_vec(a.get("solreffriction"), 2, [0.0, 0.0]),
+          solimp=_vec(a.get("solimp"), 5, mix * m.geom_solimp[g1] + (1 - mix) * m.geom_solimp[g2]),
+          margin=float(a.get("margin", max(m.geom_margin[g1], m.geom_margin[g2]))), gap=float(a.get("gap", max(m.geom_gap[g1], m.geom_gap[g2]))),
+        ))
   m.exclude_signature = np.array(excl, dtype=np.int64)
   m.nexclude = len(excl) // 2
-  m.npair = 0
+  m.npair = len(pairs)
+  m.pair_geom1 = np.array([p["geom1"] for p in pairs], dtype=np.int32)
+  m.pair_geom2 = np.array([p["geom2"] for p in pairs], dtype=np.int32)
+  m.pair_dim = np.array([p["dim"] for p in pairs], dtype=np.int32)
+  m.pair_friction = np.array([p["friction"] for p in pairs], dtype=np.float64).reshape(m.npair, 5)
+  m.pair_solref = np.array([p["solref"] for p in pairs], dtype=np.float64).reshape(m.npair, 2)
+  m.pair_solreffriction = np.array([p["solreffriction"] for p in pairs], dtype=np.float64).reshape(m.npair, 2)
+  m.pair_solimp = np.array([p["solimp"] for p in pairs], dtype=np.float64).reshape(m.npair, 5)
+  m.pair_margin = np.array([p["margin"] for p in pairs], dtype=np.float64)
+  m.pair_gap = np.array([p["gap"] for p in pairs], dtype=np.float64)
 
   # ---- equality constraints: connect / weld between bodies, joint coupling (tendon / flex equalities are not compiled)
   eqs = []

@@ -32,7 +32,7 @@ __host__ __device__ inline ColLayout col_layout(const ModelDev& m, const DataDev
   L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom);
   L.surv = take(surv_cap(m));
   L.stage = take(STAGE_WORDS * world_con_cap(d));
-  L.sgeom = take(3 * world_con_cap(d));  // g1, g2, geomcollisionid
+  L.sgeom = take(4 * world_con_cap(d));  // g1, g2, geomcollisionid, pairid
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -91,7 +91,14 @@ __device__ __forceinline__ float sphere_sphere(v3 pos1, float r1, v3 pos2, float
 struct ConParams { float margin, gap; int condim; float friction[5], solref[2], solreffriction[2], solimp[5]; };
 
 // collision_core.py:294-412 for geom pairs (pairid == -1)
-__device__ void contact_params(const ModelDev& m, int g1, int g2, ConParams* p) {
+__device__ void contact_params(const ModelDev& m, int g1, int g2, int pairid, ConParams* p) {
+  if (pairid > -1) {  // explicit <pair>: every parameter comes from the pair (collision_core.py:305-307, 343-349)
+    p->margin = m.pair_margin[pairid]; p->gap = m.pair_gap[pairid]; p->condim = m.pair_dim[pairid];
+    for (int i = 0; i < 5; i++) { p->friction[i] = fmaxf(MJ_MINMU, m.pair_friction[5 * pairid + i]); p->solimp[i] = m.pair_solimp[5 * pairid + i]; }
+    for (int i = 0; i < 2; i++) { p->solref[i] = m.pair_solref[2 * pairid + i]; p->solreffriction[i] = m.pair_solreffriction[2 * pairid + i]; }
+    return;
+  }
+  p->solreffriction[0] = 0.f; p->solreffriction[1] = 0.f;
   p->margin = m.geom_margin[g1] + m.geom_margin[g2];
   p->gap = m.geom_gap[g1] + m.geom_gap[g2];
   const float solmix1 = m.geom_solmix[g1], solmix2 = m.geom_solmix[g2];
@@ -199,13 +206,15 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
     bool shared_frame = false;
     int g1 = 0, g2 = 0;
     float inc = 0.f;  // margin + gap
+    int pid = -1;     // explicit pair id of this geom pair, -1 for dynamically generated pairs
     if (si < nsurv) {
       const int e = surv[si];
       g1 = m.nxn_geom_pair[2 * e]; g2 = m.nxn_geom_pair[2 * e + 1];
       if (m.geom_type[g1] > m.geom_type[g2]) { const int t = g1; g1 = g2; g2 = t; }
       const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-      const float margin = m.geom_margin[g1] + m.geom_margin[g2];
-      inc = margin + m.geom_gap[g1] + m.geom_gap[g2];
+      pid = m.npair > 0 ? m.nxn_pairid[2 * e] : -1;
+      const float margin = pid > -1 ? m.pair_margin[pid] : m.geom_margin[g1] + m.geom_margin[g2];
+      inc = margin + (pid > -1 ? m.pair_gap[pid] : m.geom_gap[g1] + m.geom_gap[g2]);
       const v3 pos1 = ld3(gxpos + 3 * g1), pos2 = ld3(gxpos + 3 * g2);
       const v3 ax1 = matcol(gxmat + 9 * g1, 2), ax2 = matcol(gxmat + 9 * g2, 2);
       const v3 size1 = ld3(m.geom_size + 3 * g1), size2 = ld3(m.geom_size + 3 * g2);
@@ -289,7 +298,7 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
           float* st = stage + STAGE_WORDS * off;
           st[0] = cd[k]; st3(st + 1, cp[k]);
           if (shared_frame) { for (int q = 0; q < 9; q++) st[4 + q] = frame0[q]; } else make_frame(cn[k], st + 4);
-          sgeom[3 * off] = g1; sgeom[3 * off + 1] = g2; sgeom[3 * off + 2] = k;
+          sgeom[4 * off] = g1; sgeom[4 * off + 1] = g2; sgeom[4 * off + 2] = k; sgeom[4 * off + 3] = pid;
         }
         off++;
       }
@@ -314,24 +323,24 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
   const int np = m.nmaxpyramid;
 #pragma unroll 1
   for (int c = lane; c < nwrite; c += 32) {
-    const int cid = base + c, g1 = sgeom[3 * c], g2 = sgeom[3 * c + 1];
+    const int cid = base + c, g1 = sgeom[4 * c], g2 = sgeom[4 * c + 1];
     const float* st = stage + STAGE_WORDS * c;
     ConParams p;
-    contact_params(m, g1, g2, &p);
+    contact_params(m, g1, g2, sgeom[4 * c + 3], &p);
     d.contact_dist[cid] = st[0];
     for (int k = 0; k < 3; k++) d.contact_pos[3 * cid + k] = st[1 + k];
     for (int k = 0; k < 9; k++) d.contact_frame[9 * cid + k] = st[4 + k];
     d.contact_includemargin[cid] = p.margin;
     for (int k = 0; k < 5; k++) d.contact_friction[5 * cid + k] = p.friction[k];
     d.contact_solref[2 * cid] = p.solref[0]; d.contact_solref[2 * cid + 1] = p.solref[1];
-    d.contact_solreffriction[2 * cid] = 0.f; d.contact_solreffriction[2 * cid + 1] = 0.f;
+    d.contact_solreffriction[2 * cid] = p.solreffriction[0]; d.contact_solreffriction[2 * cid + 1] = p.solreffriction[1];
     for (int k = 0; k < 5; k++) d.contact_solimp[5 * cid + k] = p.solimp[k];
     d.contact_dim[cid] = p.condim;
     d.contact_geom[2 * cid] = g1; d.contact_geom[2 * cid + 1] = g2;
     for (int k = 0; k < np; k++) d.contact_efc_address[np * cid + k] = -1;
     d.contact_worldid[cid] = w;
     d.contact_type[cid] = CONTACT_TYPE_CONSTRAINT;
-    d.contact_geomcollisionid[cid] = sgeom[3 * c + 2];
+    d.contact_geomcollisionid[cid] = sgeom[4 * c + 2];
   }
 }
 

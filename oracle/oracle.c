@@ -54,7 +54,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
-  X(eq_type) X(eq_obj1id) X(eq_obj2id)
+  X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim)
 #define MODEL_RARRS(X) \
   X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
   X(body_inertia) X(body_invweight0) X(body_gravcomp) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
@@ -63,7 +63,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(geom_gap) X(geom_solmix) X(geom_solref) X(geom_solimp) X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) \
   X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
   X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat) \
-  X(eq_solref) X(eq_solimp) X(eq_data)
+  X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -714,7 +714,13 @@ static int broadphase_filter(const W* w, int g1, int g2) {
 
 typedef struct { real margin, gap; int condim; real friction[5], solref[2], solreffriction[2], solimp[5]; } ConParams;
 /* collision_core.py:294-412 (geom pairs only: pairid == -1; adhesion is zero on this path) */
-static void contact_params(const OrcModel* m, int g1, int g2, ConParams* p) {
+static void contact_params(const OrcModel* m, int g1, int g2, int pairid, ConParams* p) {
+  if (pairid > -1) { /* explicit <pair>: parameters come from the pair (collision_core.py:305-307, 343-349) */
+    p->margin = m->pair_margin[pairid]; p->gap = m->pair_gap[pairid]; p->condim = m->pair_dim[pairid];
+    for (int i = 0; i < 5; i++) { p->friction[i] = rmax(MJ_MINMU, m->pair_friction[5 * pairid + i]); p->solimp[i] = m->pair_solimp[5 * pairid + i]; }
+    for (int i = 0; i < 2; i++) { p->solref[i] = m->pair_solref[2 * pairid + i]; p->solreffriction[i] = m->pair_solreffriction[2 * pairid + i]; }
+    return;
+  }
   p->margin = m->geom_margin[g1] + m->geom_margin[g2];
   p->gap = m->geom_gap[g1] + m->geom_gap[g2];
   real solmix1 = m->geom_solmix[g1], solmix2 = m->geom_solmix[g2], mix;
@@ -1244,11 +1250,11 @@ static int box_box(const real* pos1, const real* rot1, const real* size1, const 
   memcpy(cnormal, normal, sizeof normal);
   return n;
 }
-static void narrowphase_pair(W* w, int g1, int g2) {
+static void narrowphase_pair(W* w, int g1, int g2, int pairid) {
   const OrcModel* m = w->m;
   int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
   ConParams p;
-  contact_params(m, g1, g2, &p);
+  contact_params(m, g1, g2, pairid, &p);
   const real *pos1 = w->geom_xpos + 3 * g1, *pos2 = w->geom_xpos + 3 * g2, *rot1 = w->geom_xmat + 9 * g1, *rot2 = w->geom_xmat + 9 * g2;
   const real *size1 = m->geom_size + 3 * g1, *size2 = m->geom_size + 3 * g2;
   real ax1[3] = {rot1[2], rot1[5], rot1[8]}, ax2[3] = {rot2[2], rot2[5], rot2[8]};
@@ -1370,7 +1376,7 @@ static void collision(W* w) {
     w->ncollision[0]++;
     if (m->nxn_pairid[2 * e] == -2) continue; /* sensor-only pair: no constraint contact */
     if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
-    narrowphase_pair(w, g1, g2);
+    narrowphase_pair(w, g1, g2, m->nxn_pairid[2 * e]);
   }
   if (w->ncon[0] > w->nconmax) w->ncon[0] = w->nconmax;
 }

@@ -100,6 +100,9 @@ def derived_tables(mjm):
   exclude = np.isin((b1.astype(np.int64) << 16) + b2, mjm.exclude_signature)
   pairid = -np.ones(len(g1), dtype=np.int32)
   pairid[~(mask & ~self_col & ~parent_child & ~exclude)] = -2
+  for i in range(int(getattr(mjm, "npair", 0))):  # explicit pairs override the filters (io.py:577-583)
+    a, b = sorted((int(mjm.pair_geom1[i]), int(mjm.pair_geom2[i])))
+    pairid[(a * (2 * ngeom - a - 3)) // 2 + b - 1] = i
   include = pairid > -2
   pairs = np.stack((g1, g2), axis=1)[include].astype(np.int32)
   pid = np.stack((pairid[include], -np.ones(include.sum(), dtype=np.int32)), axis=1).astype(np.int32)
@@ -115,6 +118,8 @@ def derived_tables(mjm):
     t = mjm.jnt_type[mjm.actuator_trnid[i, 0]]
     nJmom += {0: 6, 1: 3, 2: 1, 3: 1}[int(t)]
   nmaxcondim = int(mjm.geom_condim.max()) if ngeom else 1
+  if getattr(mjm, "npair", 0):
+    nmaxcondim = max(nmaxcondim, int(np.asarray(mjm.pair_dim).max()))
   return dict(body_isdofancestor=anc, nxn_geom_pair=pairs, nxn_pairid=pid, jnt_limited_slide_hinge_adr=limited, jnt_limited_ball_adr=limited_ball,
               qLD_block_adr=blk, qld_total=off, nJmom=nJmom, nmaxpyramid=max(1, 2 * (nmaxcondim - 1)))
 
@@ -207,6 +212,10 @@ class Oracle:
       setia(n, self.tabs[n])
     for n in ("eq_type", "eq_obj1id", "eq_obj2id"):
       setia(n, getattr(mjm, n) if neq else np.zeros(1, dtype=np.int32))
+    npair = int(getattr(mjm, "npair", 0))
+    setia("pair_dim", mjm.pair_dim if npair else np.zeros(1, dtype=np.int32))
+    for n, k in (("pair_friction", 5), ("pair_solref", 2), ("pair_solreffriction", 2), ("pair_solimp", 5), ("pair_margin", 1), ("pair_gap", 1)):
+      setra(n, getattr(mjm, n) if npair else np.zeros(k))
     for n, k in (("eq_solref", 2), ("eq_solimp", 5), ("eq_data", 11)):
       setra(n, getattr(mjm, n) if neq else np.zeros(k))
 

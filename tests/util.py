@@ -180,6 +180,18 @@ EQUALITY_XML = """
 """
 
 
+def pairs_xml():
+  """MIXED_XML plus explicit contact pairs: a fully specified pair that overrides two colliding capsules (own condim,
+  5-vector friction, solref / solreffriction / solimp, margin, gap) and a pair between geoms the contype filter would drop."""
+  x = MIXED_XML.replace("</actuator>", """</actuator>
+  <contact>
+    <pair geom1="c0" geom2="c1" condim="4" friction="0.6 0.5 0.02 0.003 0.004" solref="0.015 0.9" solreffriction="0.03 1.1"
+          solimp="0.85 0.97 0.002 0.4 2" margin="0.01" gap="0.003"/>
+    <pair geom1="floor" geom2="s1" condim="3" friction="1.1 1.1 0.01 0.001 0.001" solref="0.02 1" solimp="0.9 0.95 0.001 0.5 2" margin="0.006" gap="0"/>
+  </contact>""")
+  return x.replace('<option timestep="0.004"', '<option cone="elliptic" timestep="0.004"')
+
+
 def passive_xml():
   """MIXED_XML with the remaining passive-force features switched on: gravity compensation (one body routed through the
   actuators with actuatorgravcomp), a ball-joint spring and a free-joint spring / damper."""
