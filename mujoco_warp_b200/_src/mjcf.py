@@ -337,6 +337,8 @@ def compile_xml(root):
     integrator=C.INT_EULER,
     cone=C.CONE_PYRAMIDAL,
     solver=C.SOL_NEWTON,
+    ccd_iterations=35,
+    ccd_tolerance=1e-6,
     iterations=100,
     ls_iterations=50,
     disableflags=0,
@@ -346,7 +348,9 @@ def compile_xml(root):
   )
   for oe in root.findall("option"):
     a = oe.attrib
-    for k in ("timestep", "tolerance", "ls_tolerance", "impratio"):
+    if "ccd_iterations" in a:
+      opt.ccd_iterations = int(a["ccd_iterations"])
+    for k in ("timestep", "tolerance", "ls_tolerance", "impratio", "ccd_tolerance"):
       if k in a:
         setattr(opt, k, float(a[k]))
     for k in ("iterations", "ls_iterations"):

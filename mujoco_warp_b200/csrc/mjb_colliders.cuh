@@ -79,7 +79,7 @@ __device__ __forceinline__ float sphere_cylinder(v3 spos, float sr, v3 cpos, v3 
     *nrm = pn * -1.0f;
     return dist;
   }
-  const float inv_len = safe_div(1.0f, sqrtf(p_sqr)), sgn = x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f);
+  const float inv_len = safe_div(1.0f, sqrtf(p_sqr)), sgn = x < 0.f ? -1.f : 1.f;  // wp.sign(0) = +1
   return col_sphere_sphere(spos, sr, cpos + caxis * (sgn * chh) + p_proj * (cr * inv_len), 0.f, pos, nrm);
 }
 

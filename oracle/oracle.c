@@ -36,15 +36,15 @@ enum {
   DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7, DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9,
   DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15, DSBL_NATIVECCD = 1 << 17
 };
-enum { OVF_NEFC = 1 << 0, OVF_NARROWPHASE = 1 << 3, OVF_ITERATIONS = 1 << 9, OVF_LS_ITERATIONS = 1 << 10, OVF_UNSUPPORTED = 1 << 30 };
+enum { OVF_NEFC = 1 << 0, OVF_NARROWPHASE = 1 << 3, OVF_CCD = 1 << 4, OVF_EPA_HORIZON = 1 << 8, OVF_ITERATIONS = 1 << 9, OVF_LS_ITERATIONS = 1 << 10, OVF_UNSUPPORTED = 1 << 30 };
 enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 
 /* ------------------------------------------------------------------ field registries (X-macros) */
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
-  X(disableflags) X(enableflags) X(broadphase_filter)
-#define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia)
+  X(disableflags) X(enableflags) X(broadphase_filter) X(ccd_iterations)
+#define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(ccd_tolerance)
 #define MODEL_IARRS(X) \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_actfrclimited) X(jnt_actgravcomp) \
@@ -838,7 +838,7 @@ static real sphere_cylinder(const real* spos, real sr, const real* cpos, const r
     for (int i = 0; i < 3; i++) nrm[i] = -pn[i];
     return dist;
   }
-  real inv_len = safe_div(1, (real)sqrt((double)p_proj_sqr)), sgn = x > 0 ? (real)1 : (x < 0 ? (real)-1 : (real)0), corner[3];
+  real inv_len = safe_div(1, (real)sqrt((double)p_proj_sqr)), sgn = x < 0 ? (real)-1 : (real)1 /* wp.sign(0) = +1 */, corner[3];
   for (int i = 0; i < 3; i++) corner[i] = cpos[i] + caxis[i] * (sgn * chh) + p_proj[i] * (cr * inv_len);
   return sphere_sphere(spos, sr, corner, 0, pos, nrm);
 }
@@ -1250,6 +1250,39 @@ static int box_box(const real* pos1, const real* rot1, const real* size1, const 
   memcpy(cnormal, normal, sizeof normal);
   return n;
 }
+#include "oracle_ccd.h"
+
+/* collision_driver.py:47-81: pair types the reference sends to the convex (GJK / EPA) path, in MJ_COLLISION_TABLE order,
+ * restricted to analytic geoms.  Box-box is convex unless the nativeccd disable flag routes it to the primitive. */
+static const int CONVEX_PAIRS[][2] = {{GEOM_SPHERE, GEOM_ELLIPSOID}, {GEOM_CAPSULE, GEOM_ELLIPSOID}, {GEOM_CAPSULE, GEOM_CYLINDER},
+  {GEOM_ELLIPSOID, GEOM_ELLIPSOID}, {GEOM_ELLIPSOID, GEOM_CYLINDER}, {GEOM_ELLIPSOID, GEOM_BOX}, {GEOM_CYLINDER, GEOM_CYLINDER},
+  {GEOM_CYLINDER, GEOM_BOX}};
+#define N_CONVEX_PAIRS ((int)(sizeof CONVEX_PAIRS / sizeof CONVEX_PAIRS[0]))
+static int convex_pair_rank(int t1, int t2) {
+  for (int i = 0; i < N_CONVEX_PAIRS; i++) if (CONVEX_PAIRS[i][0] == t1 && CONVEX_PAIRS[i][1] == t2) return i;
+  return -1;
+}
+/* collision_convex.py:739-968 eval_ccd_write_contact (single contact; multi-contact applies to box / mesh pairs only) */
+static void convex_pair(W* w, int g1, int g2, int pairid) {
+  const OrcModel* m = w->m;
+  ConParams p;
+  contact_params(m, g1, g2, pairid, &p);
+  CGeom a, b;
+  memcpy(a.pos, w->geom_xpos + 3 * g1, sizeof a.pos); memcpy(a.rot, w->geom_xmat + 9 * g1, sizeof a.rot); memcpy(a.size, m->geom_size + 3 * g1, sizeof a.size);
+  memcpy(b.pos, w->geom_xpos + 3 * g2, sizeof b.pos); memcpy(b.rot, w->geom_xmat + 9 * g2, sizeof b.rot); memcpy(b.size, m->geom_size + 3 * g2, sizeof b.size);
+  a.type = m->geom_type[g1]; b.type = m->geom_type[g2];
+  a.margin = b.margin = p.margin;
+  real dist, x1[3], x2[3], frame[9], nrm[3], pos[3]; int ovf = 0;
+  int ncon = ccd_pair(m->ccd_tolerance, p.gap, m->ccd_iterations, a, b, &dist, x1, x2, &ovf);
+  if (ovf) w->overflow[0] |= OVF_EPA_HORIZON;
+  if (ncon == 0 || dist >= p.gap) return;
+  dist += p.margin; /* back to the distance between the un-inflated surfaces (collision_convex.py:862-868) */
+  if (dist <= p.margin) v3sub(x1, x2, nrm); else v3sub(x2, x1, nrm);
+  make_frame(nrm, frame);
+  for (int i = 0; i < 3; i++) pos[i] = (real)0.5 * (x1[i] + x2[i]);
+  write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+}
+
 static void narrowphase_pair(W* w, int g1, int g2, int pairid) {
   const OrcModel* m = w->m;
   int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
@@ -1370,14 +1403,28 @@ static void collision(W* w) {
   const OrcModel* m = w->m;
   w->ncon[0] = 0; w->ncollision[0] = 0;
   if (w->nconmax == 0 || (m->disableflags & (DSBL_CONSTRAINT | DSBL_CONTACT))) return;
+  /* Contact order of the reference under sequential execution: the convex narrowphase runs first, one launch per pair type
+   * in table order (collision_driver.py:877, collision_convex.py:1369), then the primitive narrowphase; within a launch,
+   * broadphase (pair-list) order.  Pass -1 is the broadphase itself. */
+  unsigned char* pass = (unsigned char*)calloc((size_t)(m->nxn_npair > 0 ? m->nxn_npair : 1), 1);
   for (int e = 0; e < m->nxn_npair; e++) {
     int g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
     if (!(broadphase_filter(w, g1, g2) || m->nxn_pairid[2 * e + 1] >= 0)) continue;
     w->ncollision[0]++;
     if (m->nxn_pairid[2 * e] == -2) continue; /* sensor-only pair: no constraint contact */
-    if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
-    narrowphase_pair(w, g1, g2, m->nxn_pairid[2 * e]);
+    pass[e] = 1;
   }
+  for (int rank = 0; rank <= N_CONVEX_PAIRS; rank++) {
+    for (int e = 0; e < m->nxn_npair; e++) {
+      if (!pass[e]) continue;
+      int g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
+      if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+      int cr = convex_pair_rank(m->geom_type[g1], m->geom_type[g2]);
+      if (rank < N_CONVEX_PAIRS) { if (cr == rank) convex_pair(w, g1, g2, m->nxn_pairid[2 * e]); }
+      else if (cr < 0) narrowphase_pair(w, g1, g2, m->nxn_pairid[2 * e]);
+    }
+  }
+  free(pass);
   if (w->ncon[0] > w->nconmax) w->ncon[0] = w->nconmax;
 }
 

@@ -1,0 +1,421 @@
+/* oracle_ccd.h -- TEST INFRASTRUCTURE ONLY: CPU restatement of the reference's general convex collision path for analytic
+ * convex geoms (sphere, capsule, ellipsoid, cylinder, box; no mesh / hfield, no multi-contact):
+ * /root/reference/mujoco_warp/_src/collision_gjk.py :115 support, :281-594 distance sub-algorithm (S1D / S2D / S3D),
+ * :635 gjk, :1021-1286 polytope construction, :1319 _epa, :947 _epa_witness, :2303 _inflate, :2350 gjk_phase, :2421 epa_phase;
+ * driver collision_convex.py:739-968 (eval_ccd_write_contact).  Included by oracle.c (single translation unit). */
+
+#define CCD_FLOAT_MAX ((real)1e30)
+#define CCD_MINVAL ((real)1e-15)
+#define CCD_MIN_DIST2 ((real)1e-10)
+#define CCD_MIN_DIST3 ((real)1e-10)
+#define CCD_MIN_DIST4 ((real)1e-17)
+#define CCD_MAX_EPAFACES 5
+#define CCD_MAX_EPAHORIZON 24
+
+typedef struct { real pos[3], rot[9], size[3], margin; int type; } CGeom;
+typedef struct {
+  int separated, dim; real dist, x1[3], x2[3];
+  real simplex[4][3], simplex1[4][3], simplex2[4][3]; int index1[4], index2[4];
+} GjkResult;
+typedef struct {
+  int status, nvert, nface, nhorizon, maxvert, maxface;
+  real (*vert)[3]; int* vert_index; real center[3];
+  unsigned* face; real (*face_pr)[3]; real* face_norm2; int horizon[CCD_MAX_EPAHORIZON];
+} Polytope;
+
+static inline real csign(real x) { return x < 0 ? (real)-1 : (real)1; } /* warp: sign(0) = +1 */
+static inline void v3sub(const real* a, const real* b, real* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static inline void v3cpy(real* d, const real* s) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+
+/* collision_gjk.py:115 support point of a geom inflated by half its margin; *vidx = box corner id or -1 */
+static void ccd_support(const CGeom* g, const real* dir, real* out, int* vidx) {
+  *vidx = -1;
+  if (g->type == GEOM_SPHERE) { for (int i = 0; i < 3; i++) out[i] = g->pos[i] + (g->size[0] + (real)0.5 * g->margin) * dir[i]; return; }
+  real ld[3], res[3] = {0, 0, 0};
+  matT_vec3(g->rot, dir, ld);
+  if (g->type == GEOM_BOX) {
+    real t[3] = {csign(ld[0]), csign(ld[1]), csign(ld[2])};
+    for (int i = 0; i < 3; i++) res[i] = t[i] * g->size[i];
+    *vidx = (t[0] > 0 ? 1 : 0) + (t[1] > 0 ? 2 : 0) + (t[2] > 0 ? 4 : 0);
+  } else if (g->type == GEOM_CAPSULE) {
+    for (int i = 0; i < 3; i++) res[i] = ld[i] * g->size[0];
+    res[2] += csign(ld[2]) * g->size[1];
+  } else if (g->type == GEOM_ELLIPSOID) {
+    for (int i = 0; i < 3; i++) res[i] = ld[i] * g->size[i];
+    normalize3(res);
+    for (int i = 0; i < 3; i++) res[i] *= g->size[i];
+  } else if (g->type == GEOM_CYLINDER) {
+    real d = (real)sqrt((double)(ld[0] * ld[0] + ld[1] * ld[1]));
+    if (d > CCD_MINVAL) { real scl = g->size[0] / d; res[0] = ld[0] * scl; res[1] = ld[1] * scl; }
+    res[2] = csign(ld[2]) * g->size[1];
+  }
+  matvec3(g->rot, res, out);
+  for (int i = 0; i < 3; i++) out[i] += g->pos[i];
+  if (g->margin > 0) for (int i = 0; i < 3; i++) out[i] += dir[i] * ((real)0.5 * g->margin);
+}
+
+static inline real det3(const real* a, const real* b, const real* c) { real t[3]; cross3(b, c, t); return dot3(a, t); }
+static inline int same_sign(real a, real b) { if (a > 0 && b > 0) return 1; if (a < 0 && b < 0) return -1; return 0; }
+static void project_origin_line(const real* v1, const real* v2, real* o) {
+  real diff[3]; v3sub(v2, v1, diff);
+  real scl = -(dot3(v2, diff) / dot3(diff, diff));
+  for (int i = 0; i < 3; i++) o[i] = v2[i] + scl * diff[i];
+}
+static int project_origin_plane(const real* v1, const real* v2, const real* v3, real* o) {
+  real d21[3], d31[3], d32[3], n[3], nv, nn;
+  v3sub(v2, v1, d21); v3sub(v3, v1, d31); v3sub(v3, v2, d32);
+  o[0] = o[1] = o[2] = 0;
+  cross3(d32, d21, n); nv = dot3(n, v2); nn = dot3(n, n);
+  if (nn == 0) return 1;
+  if (nv != 0 && nn > CCD_MINVAL) { for (int i = 0; i < 3; i++) o[i] = (nv / nn) * n[i]; return 0; }
+  cross3(d21, d31, n); nv = dot3(n, v1); nn = dot3(n, n);
+  if (nn == 0) return 1;
+  if (nv != 0 && nn > CCD_MINVAL) { for (int i = 0; i < 3; i++) o[i] = (nv / nn) * n[i]; return 0; }
+  cross3(d31, d32, n); nv = dot3(n, v3); nn = dot3(n, n);
+  for (int i = 0; i < 3; i++) o[i] = (nv / nn) * n[i];
+  return 0;
+}
+static void S1D(const real* s1, const real* s2, real* l) {
+  real po[3]; project_origin_line(s1, s2, po);
+  real mu_max = s1[0] - s2[0]; int index = 0;
+  real mu = s1[1] - s2[1]; if (rabs(mu) >= rabs(mu_max)) { mu_max = mu; index = 1; }
+  mu = s1[2] - s2[2]; if (rabs(mu) >= rabs(mu_max)) { mu_max = mu; index = 2; }
+  real C1 = po[index] - s2[index], C2 = s1[index] - po[index];
+  if (same_sign(mu_max, C1) && same_sign(mu_max, C2)) { l[0] = C1 / mu_max; l[1] = C2 / mu_max; return; }
+  l[0] = 0; l[1] = 1;
+}
+static void tri_minors(const real* s1, const real* s2, const real* s3, real* M14, real* M24, real* M34) {
+  *M14 = s2[1] * s3[2] - s2[2] * s3[1] - s1[1] * s3[2] + s1[2] * s3[1] + s1[1] * s2[2] - s1[2] * s2[1];
+  *M24 = s2[0] * s3[2] - s2[2] * s3[0] - s1[0] * s3[2] + s1[2] * s3[0] + s1[0] * s2[2] - s1[2] * s2[0];
+  *M34 = s2[0] * s3[1] - s2[1] * s3[0] - s1[0] * s3[1] + s1[1] * s3[0] + s1[0] * s2[1] - s1[1] * s2[0];
+}
+/* signed areas of (p, b, c), (p, a, c), (p, a, b) in the 2-D projection that drops the axis with the largest minor */
+static real tri_cofactors(const real* s1, const real* s2, const real* s3, const real* p, real C[3]) {
+  real M14, M24, M34, Mmax; int x, y;
+  tri_minors(s1, s2, s3, &M14, &M24, &M34);
+  real mu1 = rabs(M14), mu2 = rabs(M24), mu3 = rabs(M34);
+  if (mu1 >= mu2 && mu1 >= mu3) { Mmax = M14; x = 1; y = 2; } else if (mu2 >= mu3) { Mmax = M24; x = 0; y = 2; } else { Mmax = M34; x = 0; y = 1; }
+  C[0] = p[x] * s2[y] + p[y] * s3[x] + s2[x] * s3[y] - p[x] * s3[y] - p[y] * s2[x] - s3[x] * s2[y];
+  C[1] = p[x] * s3[y] + p[y] * s1[x] + s3[x] * s1[y] - p[x] * s1[y] - p[y] * s3[x] - s1[x] * s3[y];
+  C[2] = p[x] * s1[y] + p[y] * s2[x] + s1[x] * s2[y] - p[x] * s2[y] - p[y] * s1[x] - s2[x] * s1[y];
+  return Mmax;
+}
+static void S2D(const real* s1, const real* s2, const real* s3, real* l) {
+  real po[3];
+  if (project_origin_plane(s1, s2, s3, po)) { real v[2]; S1D(s1, s2, v); l[0] = v[0]; l[1] = v[1]; l[2] = 0; return; }
+  real C[3], Mmax = tri_cofactors(s1, s2, s3, po, C);
+  int c1 = same_sign(Mmax, C[0]), c2 = same_sign(Mmax, C[1]), c3 = same_sign(Mmax, C[2]);
+  if (c1 && c2 && c3) { for (int i = 0; i < 3; i++) l[i] = C[i] / Mmax; return; }
+  real dmin = CCD_FLOAT_MAX, sub[2], x[3], d;
+  l[0] = l[1] = l[2] = 0;
+  if (!c1) { S1D(s2, s3, sub); for (int i = 0; i < 3; i++) x[i] = sub[0] * s2[i] + sub[1] * s3[i]; d = dot3(x, x); l[0] = 0; l[1] = sub[0]; l[2] = sub[1]; dmin = d; }
+  if (!c2) { S1D(s1, s3, sub); for (int i = 0; i < 3; i++) x[i] = sub[0] * s1[i] + sub[1] * s3[i]; d = dot3(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = 0; l[2] = sub[1]; dmin = d; } }
+  if (!c3) { S1D(s1, s2, sub); for (int i = 0; i < 3; i++) x[i] = sub[0] * s1[i] + sub[1] * s2[i]; d = dot3(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = 0; } }
+}
+static void S3D(const real* s1, const real* s2, const real* s3, const real* s4, real* l) {
+  real C41 = -det3(s2, s3, s4), C42 = det3(s1, s3, s4), C43 = -det3(s1, s2, s4), C44 = det3(s1, s2, s3);
+  real m_det = C41 + C42 + C43 + C44;
+  int c1 = same_sign(m_det, C41), c2 = same_sign(m_det, C42), c3 = same_sign(m_det, C43), c4 = same_sign(m_det, C44);
+  if (c1 && c2 && c3 && c4) { l[0] = C41 / m_det; l[1] = C42 / m_det; l[2] = C43 / m_det; l[3] = C44 / m_det; return; }
+  real dmin = CCD_FLOAT_MAX, sub[3], x[3], d;
+  l[0] = l[1] = l[2] = l[3] = 0;
+  if (!c1) { S2D(s2, s3, s4, sub); for (int i = 0; i < 3; i++) x[i] = sub[0] * s2[i] + sub[1] * s3[i] + sub[2] * s4[i]; d = dot3(x, x); l[0] = 0; l[1] = sub[0]; l[2] = sub[1]; l[3] = sub[2]; dmin = d; }
+  if (!c2) { S2D(s1, s3, s4, sub); for (int i = 0; i < 3; i++) x[i] = sub[0] * s1[i] + sub[1] * s3[i] + sub[2] * s4[i]; d = dot3(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = 0; l[2] = sub[1]; l[3] = sub[2]; dmin = d; } }
+  if (!c3) { S2D(s1, s2, s4, sub); for (int i = 0; i < 3; i++) x[i] = sub[0] * s1[i] + sub[1] * s2[i] + sub[2] * s4[i]; d = dot3(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = 0; l[3] = sub[2]; dmin = d; } }
+  if (!c4) { S2D(s1, s2, s3, sub); for (int i = 0; i < 3; i++) x[i] = sub[0] * s1[i] + sub[1] * s2[i] + sub[2] * s3[i]; d = dot3(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = sub[2]; l[3] = 0; } }
+}
+static void subdistance(int n, real s[4][3], real* l) {
+  l[0] = 1; l[1] = l[2] = l[3] = 0;
+  if (n == 4) S3D(s[0], s[1], s[2], s[3], l);
+  else if (n == 3) { real t[3]; S2D(s[0], s[1], s[2], t); l[0] = t[0]; l[1] = t[1]; l[2] = t[2]; l[3] = 0; }
+  else if (n == 2) { real t[2]; S1D(s[0], s[1], t); l[0] = t[0]; l[1] = t[1]; l[2] = l[3] = 0; }
+}
+static void linear_combine(int n, const real* l, real m[4][3], real* o) {
+  o[0] = o[1] = o[2] = 0;
+  for (int k = 0; k < (n < 1 ? 1 : n); k++) for (int i = 0; i < 3; i++) o[i] += l[k] * m[k][i];
+}
+
+/* collision_gjk.py:635 (is_discrete = false for analytic geoms: no direction tuning, tolerance-based stop) */
+static void ccd_gjk(real tolerance, int iterations, const CGeom* g1, const CGeom* g2, const real* x1_0, const real* x2_0, real cutoff, GjkResult* r) {
+  real lmbda[4] = {1, 0, 0, 0}, x_k[3], epsilon = (real)0.5 * tolerance * tolerance, min_norm = tolerance;
+  int n = 0;
+  memset(r, 0, sizeof *r);
+  v3sub(x1_0, x2_0, x_k);
+  real xnorm = (real)sqrt((double)dot3(x_k, x_k)), xnorm_prev = 0;
+  for (int it = 0; it < iterations; it++) {
+    if (xnorm < min_norm || rabs(xnorm_prev - xnorm) < CCD_MINVAL) break;
+    real dir_neg[3] = {x_k[0] / xnorm, x_k[1] / xnorm, x_k[2] / xnorm}, dpos[3] = {-dir_neg[0], -dir_neg[1], -dir_neg[2]};
+    ccd_support(g1, dpos, r->simplex1[n], &r->index1[n]);
+    ccd_support(g2, dir_neg, r->simplex2[n], &r->index2[n]);
+    v3sub(r->simplex1[n], r->simplex2[n], r->simplex[n]);
+    real dk[3]; v3sub(x_k, r->simplex[n], dk);
+    if (dot3(x_k, dk) < epsilon) break;
+    real lower = dot3(x_k, r->simplex[n]);
+    if (cutoff == 0) { if (lower > 0) { r->separated = 1; r->dim = 0; r->dist = CCD_FLOAT_MAX; return; } }
+    else if (cutoff < CCD_FLOAT_MAX) { if (lower > 0 && lower >= cutoff * xnorm) { r->separated = 1; r->dim = 0; r->dist = CCD_FLOAT_MAX; return; } }
+    subdistance(n + 1, r->simplex, lmbda);
+    n = 0;
+    for (int i = 0; i < 4; i++) {
+      if (lmbda[i] == 0) continue;
+      v3cpy(r->simplex[n], r->simplex[i]); v3cpy(r->simplex1[n], r->simplex1[i]); v3cpy(r->simplex2[n], r->simplex2[i]);
+      r->index1[n] = r->index1[i]; r->index2[n] = r->index2[i]; lmbda[n] = lmbda[i];
+      n++;
+    }
+    if (n < 1) break;
+    linear_combine(n, lmbda, r->simplex, x_k);
+    xnorm_prev = xnorm;
+    xnorm = (real)sqrt((double)dot3(x_k, x_k));
+    if (n == 4) break;
+  }
+  r->separated = 0;
+  if (n == 0) { v3cpy(r->x1, x1_0); v3cpy(r->x2, x2_0); } else { linear_combine(n, lmbda, r->simplex1, r->x1); linear_combine(n, lmbda, r->simplex2, r->x2); }
+  if (xnorm > 0) {
+    real dir[3] = {x_k[0] / xnorm, x_k[1] / xnorm, x_k[2] / xnorm}, nd[3] = {-dir[0], -dir[1], -dir[2]}, p1[3], p2[3], dd[3]; int vi;
+    ccd_support(g1, nd, p1, &vi); ccd_support(g2, dir, p2, &vi);
+    v3sub(p1, p2, dd);
+    r->separated = dot3(x_k, dd) > 0;
+  }
+  r->dist = (n == 4 && !r->separated) ? 0 : xnorm;
+  r->dim = n;
+}
+
+/* ---- EPA */
+static int same_side(const real* p0, const real* p1, const real* p2, const real* p3) {
+  real a[3], b[3], n[3], c[3], neg[3] = {-p0[0], -p0[1], -p0[2]};
+  v3sub(p1, p0, a); v3sub(p2, p0, b); cross3(a, b, n); v3sub(p3, p0, c);
+  real d1 = dot3(n, c), d2 = dot3(n, neg);
+  return (d1 > 0 && d2 > 0) || (d1 < 0 && d2 < 0);
+}
+static int test_tetra(const real* p0, const real* p1, const real* p2, const real* p3) {
+  return same_side(p0, p1, p2, p3) && same_side(p1, p2, p3, p0) && same_side(p2, p3, p0, p1) && same_side(p3, p0, p1, p2);
+}
+static void tri_affine_coord(const real* v1, const real* v2, const real* v3, const real* p, real* l) {
+  real C[3], Mmax = tri_cofactors(v1, v2, v3, p, C);
+  for (int i = 0; i < 3; i++) l[i] = C[i] / Mmax;
+}
+static int tri_point_intersect(const real* v1, const real* v2, const real* v3, const real* p) {
+  real l[3]; tri_affine_coord(v1, v2, v3, p, l);
+  if (l[0] < 0 || l[1] < 0 || l[2] < 0) return 0;
+  real pr[3], d[3];
+  for (int i = 0; i < 3; i++) pr[i] = v1[i] * l[0] + v2[i] * l[1] + v3[i] * l[2];
+  v3sub(pr, p, d);
+  return len3(d) < CCD_MINVAL;
+}
+static void pt_mink(const Polytope* pt, int v, real* o) { v3sub(pt->vert[2 * v], pt->vert[2 * v + 1], o); }
+static real attach_face(Polytope* pt, int idx, int v1, int v2, int v3) {
+  if (pt->nface == pt->maxface) return 0;
+  real p1[3], p2[3], p3[3], r[3], d[3];
+  pt_mink(pt, v1, p1); pt_mink(pt, v2, p2); pt_mink(pt, v3, p3);
+  if (project_origin_plane(p3, p2, p1, r)) return 0;
+  v3sub(p1, pt->center, d);
+  if (dot3(r, d) < 0) for (int i = 0; i < 3; i++) r[i] = -r[i];
+  pt->face[idx] = (unsigned)(v1 + (v2 << 10) + (v3 << 20));
+  v3cpy(pt->face_pr[idx], r);
+  pt->face_norm2[idx] = dot3(r, r);
+  return pt->face_norm2[idx];
+}
+static void epa_support(Polytope* pt, int idx, const CGeom* g1, const CGeom* g2, const real* dir) {
+  real nd[3] = {-dir[0], -dir[1], -dir[2]};
+  ccd_support(g1, dir, pt->vert[2 * idx], &pt->vert_index[2 * idx]);
+  ccd_support(g2, nd, pt->vert[2 * idx + 1], &pt->vert_index[2 * idx + 1]);
+}
+static void replace_simplex3(const Polytope* pt, int v1, int v2, int v3, GjkResult* r) {
+  int v[3] = {v1, v2, v3};
+  for (int k = 0; k < 3; k++) {
+    v3cpy(r->simplex1[k], pt->vert[2 * v[k]]); v3cpy(r->simplex2[k], pt->vert[2 * v[k] + 1]);
+    v3sub(r->simplex1[k], r->simplex2[k], r->simplex[k]);
+    r->index1[k] = pt->vert_index[2 * v[k]]; r->index2[k] = pt->vert_index[2 * v[k] + 1];
+  }
+}
+static int ray_triangle(const real* v1, const real* v2, const real* v3, const real* v4, const real* v5) {
+  real a[3], b[3], c[3], d[3];
+  v3sub(v3, v1, a); v3sub(v4, v1, b); v3sub(v5, v1, c); v3sub(v2, v1, d);
+  real vol1 = det3(a, b, d), vol2 = det3(b, c, d), vol3 = det3(c, a, d);
+  if (vol1 >= 0 && vol2 >= 0 && vol3 >= 0) return 1;
+  if (vol1 <= 0 && vol2 <= 0 && vol3 <= 0) return -1;
+  return 0;
+}
+static void load_simplex(Polytope* pt, const GjkResult* r, int n) {
+  for (int k = 0; k < n; k++) { v3cpy(pt->vert[2 * k], r->simplex1[k]); v3cpy(pt->vert[2 * k + 1], r->simplex2[k]); pt->vert_index[2 * k] = r->index1[k]; pt->vert_index[2 * k + 1] = r->index2[k]; }
+}
+/* :1021 hexahedron from a 1-simplex; status -1 = fall back to the 2-simplex written into r */
+static void polytope2(Polytope* pt, GjkResult* r, const CGeom* g1, const CGeom* g2) {
+  real diff[3]; v3sub(r->simplex[1], r->simplex[0], diff);
+  for (int i = 0; i < 3; i++) pt->center[i] = (real)0.5 * (r->simplex[0][i] + r->simplex[1][i]);
+  real value = CCD_FLOAT_MAX; int index = 0;
+  for (int i = 0; i < 3; i++) if (rabs(diff[i]) < value) { value = rabs(diff[i]); index = i; }
+  real e[3] = {0, 0, 0}, d1[3], d2[3], d3[3], R[9];
+  e[index] = 1;
+  cross3(e, diff, d1);
+  { real n = len3(diff), u1 = diff[0] / n, u2 = diff[1] / n, u3 = diff[2] / n, s = (real)0.86602540378, c = (real)-0.5; /* :885 rotation by 120 deg */
+    R[0] = c + u1 * u1 * (1 - c); R[1] = u1 * u2 * (1 - c) - u3 * s; R[2] = u1 * u3 * (1 - c) + u2 * s;
+    R[3] = u2 * u1 * (1 - c) + u3 * s; R[4] = c + u2 * u2 * (1 - c); R[5] = u2 * u3 * (1 - c) - u1 * s;
+    R[6] = u1 * u3 * (1 - c) - u2 * s; R[7] = u2 * u3 * (1 - c) + u1 * s; R[8] = c + u3 * u3 * (1 - c); }
+  matvec3(R, d1, d2); matvec3(R, d2, d3);
+  load_simplex(pt, r, 2);
+  real t[3], nn;
+  nn = len3(d1); for (int i = 0; i < 3; i++) t[i] = d1[i] / nn; epa_support(pt, 2, g1, g2, t);
+  nn = len3(d2); for (int i = 0; i < 3; i++) t[i] = d2[i] / nn; epa_support(pt, 3, g1, g2, t);
+  nn = len3(d3); for (int i = 0; i < 3; i++) t[i] = d3[i] / nn; epa_support(pt, 4, g1, g2, t);
+  static const int F[6][3] = {{0, 2, 3}, {0, 4, 2}, {0, 3, 4}, {1, 3, 2}, {1, 2, 4}, {1, 4, 3}};
+  for (int f = 0; f < 6; f++)
+    if (attach_face(pt, f, F[f][0], F[f][1], F[f][2]) < CCD_MIN_DIST2) { pt->status = -1; replace_simplex3(pt, F[f][0], F[f][1], F[f][2], r); return; }
+  real v2[3], v3[3], v4[3];
+  pt_mink(pt, 2, v2); pt_mink(pt, 3, v3); pt_mink(pt, 4, v4);
+  if (!ray_triangle(r->simplex[0], r->simplex[1], v2, v3, v4)) { pt->status = 1; return; }
+  pt->nvert = 5; pt->nface = 6; pt->status = 0;
+}
+/* :1114 hexahedron from a 2-simplex */
+static void polytope3(Polytope* pt, const GjkResult* r, const CGeom* g1, const CGeom* g2) {
+  for (int i = 0; i < 3; i++) pt->center[i] = (r->simplex[0][i] + r->simplex[1][i] + r->simplex[2][i]) * (real)(1.0 / 3.0);
+  real a[3], b[3], n[3];
+  v3sub(r->simplex[1], r->simplex[0], a); v3sub(r->simplex[2], r->simplex[0], b); cross3(a, b, n);
+  real norm = len3(n);
+  if (norm < CCD_MINVAL) { pt->status = 2; return; }
+  for (int i = 0; i < 3; i++) n[i] /= norm;
+  load_simplex(pt, r, 3);
+  real nn[3] = {-n[0], -n[1], -n[2]};
+  epa_support(pt, 3, g1, g2, nn);
+  epa_support(pt, 4, g1, g2, n);
+  const real *v1 = r->simplex[0], *v2 = r->simplex[1], *v3 = r->simplex[2];
+  real v4[3], v5[3];
+  pt_mink(pt, 3, v4); pt_mink(pt, 4, v5);
+  if (tri_point_intersect(v1, v2, v3, v4)) { pt->status = 3; return; }
+  if (tri_point_intersect(v1, v2, v3, v5)) { pt->status = 4; return; }
+  if (r->dist > (real)1e-5 && !test_tetra(v1, v2, v3, v4) && !test_tetra(v1, v2, v3, v5)) { pt->status = 5; return; }
+  static const int F[6][3] = {{4, 0, 1}, {4, 2, 0}, {4, 1, 2}, {3, 1, 0}, {3, 0, 2}, {3, 2, 1}};
+  for (int f = 0; f < 6; f++) if (attach_face(pt, f, F[f][0], F[f][1], F[f][2]) < CCD_MIN_DIST3) { pt->status = 6 + f; return; }
+  pt->nvert = 5; pt->nface = 6; pt->status = 0;
+}
+/* :1207 tetrahedron from a 3-simplex */
+static void polytope4(Polytope* pt, GjkResult* r) {
+  for (int i = 0; i < 3; i++) pt->center[i] = (real)0.25 * (r->simplex[0][i] + r->simplex[1][i] + r->simplex[2][i] + r->simplex[3][i]);
+  load_simplex(pt, r, 4);
+  static const int F[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {3, 2, 1}};
+  real dist[4]; int idx = 0;
+  for (int f = 0; f < 4; f++) {
+    dist[f] = attach_face(pt, f, F[f][0], F[f][1], F[f][2]);
+    if (dist[f] < CCD_MIN_DIST4) { pt->status = -1; replace_simplex3(pt, F[f][0], F[f][1], F[f][2], r); return; }
+    if (f == 1) idx = dist[0] < dist[1] ? 0 : 1;
+    else if (f > 1) idx = dist[f] < dist[idx] ? f : idx;
+  }
+  if (!test_tetra(r->simplex[0], r->simplex[1], r->simplex[2], r->simplex[3])) {
+    if (dist[idx] > CCD_MINVAL) { pt->status = 12; return; }
+    pt->status = -1; replace_simplex3(pt, F[idx][0], F[idx][1], F[idx][2], r); return;
+  }
+  pt->nvert = 4; pt->nface = 4; pt->status = 0;
+}
+#define FACE_DELETED 0x80000000u
+#define FACE_INVALID 0x40000000u
+static int add_edge(Polytope* pt, int e1, int e2) {
+  int n = pt->nhorizon;
+  if (n < 0) return -1;
+  int edge = ((e1 < e2 ? e1 : e2) << 10) | (e1 < e2 ? e2 : e1);
+  for (int i = 0; i < n; i++) if (edge == pt->horizon[i]) { pt->horizon[i] = pt->horizon[n - 1]; return n - 1; }
+  if (n == CCD_MAX_EPAHORIZON) return -1;
+  pt->horizon[n] = edge;
+  return n + 1;
+}
+/* :1319; returns the index of the closest face (or -1) and writes the witness points / distance */
+static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1, const CGeom* g2, real* dist, real* x1, real* x2, int* ovf) {
+  real upper = CCD_FLOAT_MAX, upper2 = CCD_FLOAT_MAX, epsilon = tolerance;
+  int idx = -1, pidx = -1, nvalid = pt->nface;
+  if (iterations > 1000) iterations = 1000;
+  for (int it = 0; it < iterations; it++) {
+    pidx = idx; idx = -1;
+    real lower2 = CCD_FLOAT_MAX;
+    for (int i = 0; i < pt->nface; i++) if (!(pt->face[i] & (FACE_DELETED | FACE_INVALID)) && pt->face_norm2[i] < lower2) { idx = i; lower2 = pt->face_norm2[i]; }
+    if (lower2 > upper2 || idx < 0) { idx = pidx; break; }
+    if (lower2 <= 0) break;
+    real lower = (real)sqrt((double)lower2), fp[3], dir[3], w[3];
+    int wi = pt->nvert;
+    v3cpy(fp, pt->face_pr[idx]);
+    for (int i = 0; i < 3; i++) dir[i] = fp[i] / lower;
+    epa_support(pt, wi, g1, g2, dir);
+    pt_mink(pt, wi, w);
+    pt->nvert++;
+    real upper_k = dot3(fp, w) / lower;
+    if (upper_k < upper) { upper = upper_k; upper2 = upper * upper; }
+    if (upper - lower < epsilon) break;
+    nvalid--;
+    pt->face[idx] |= FACE_DELETED;
+    { unsigned f = pt->face[idx]; int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
+      pt->nhorizon = add_edge(pt, a, b); pt->nhorizon = add_edge(pt, b, c); pt->nhorizon = add_edge(pt, c, a); }
+    if (pt->nhorizon == -1) { *ovf = 1; idx = -1; break; }
+    for (int i = 0; i < pt->nface; i++) {
+      if (pt->face[i] & FACE_DELETED) continue;
+      if (dot3(pt->face_pr[i], w) - pt->face_norm2[i] > (real)1e-10) {
+        if (!(pt->face[i] & (FACE_DELETED | FACE_INVALID))) nvalid--;
+        pt->face[i] |= FACE_DELETED;
+        unsigned f = pt->face[i]; int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
+        pt->nhorizon = add_edge(pt, a, b); pt->nhorizon = add_edge(pt, b, c); pt->nhorizon = add_edge(pt, c, a);
+        if (pt->nhorizon == -1) { *ovf = 1; idx = -1; break; }
+      }
+    }
+    for (int i = 0; i < pt->nhorizon; i++) {
+      int e = pt->horizon[i];
+      real dist2 = attach_face(pt, pt->nface, wi, e & 0x3FF, (e >> 10) & 0x3FF);
+      if (dist2 == 0) { idx = -1; break; }
+      pt->nface++;
+      if (dist2 >= lower2 && dist2 <= upper2) nvalid++; else pt->face[pt->nface - 1] |= FACE_INVALID;
+    }
+    if (nvalid == 0 || idx == -1) break;
+    pt->nhorizon = 0;
+  }
+  if (idx > -1) { /* :947 witness points from the barycentric coordinates of the projection on the closest face */
+    unsigned f = pt->face[idx]; int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
+    real v1[3], v2[3], v3[3], l[3];
+    pt_mink(pt, a, v1); pt_mink(pt, b, v2); pt_mink(pt, c, v3);
+    tri_affine_coord(v1, v2, v3, pt->face_pr[idx], l);
+    for (int i = 0; i < 3; i++) {
+      x2[i] = pt->vert[2 * a + 1][i] * l[0] + pt->vert[2 * b + 1][i] * l[1] + pt->vert[2 * c + 1][i] * l[2];
+      x1[i] = pt->vert[2 * a][i] * l[0] + pt->vert[2 * b][i] * l[1] + pt->vert[2 * c][i] * l[2];
+    }
+    *dist = -(real)sqrt((double)pt->face_norm2[idx]);
+    return idx;
+  }
+  *dist = 0; x1[0] = x1[1] = x1[2] = x2[0] = x2[1] = x2[2] = 0;
+  return -1;
+}
+
+/* gjk_phase (:2350) + epa_phase (:2421): returns the number of contacts (0 or 1); dist is relative to the margin-inflated shapes */
+static int ccd_pair(real tolerance, real cutoff, int iterations, CGeom g1, CGeom g2, real* dist, real* x1, real* x2, int* ovf) {
+  const CGeom o1 = g1, o2 = g2;
+  real full1 = 0, full2 = 0, size1 = 0, size2 = 0;
+  GjkResult r;
+  if (g1.type == GEOM_SPHERE || g1.type == GEOM_CAPSULE) { size1 = g1.size[0]; full1 = size1 + (real)0.5 * g1.margin; g1.margin = 0; g1.size[0] = 0; }
+  if (g2.type == GEOM_SPHERE || g2.type == GEOM_CAPSULE) { size2 = g2.size[0]; full2 = size2 + (real)0.5 * g2.margin; g2.margin = 0; g2.size[0] = 0; }
+  if (size1 + size2 > 0) {
+    cutoff += full1 + full2;
+    ccd_gjk(tolerance, iterations, &g1, &g2, g1.pos, g2.pos, cutoff, &r);
+    if (r.dist > tolerance) {
+      v3cpy(x1, r.x1); v3cpy(x2, r.x2);
+      if (r.dist == CCD_FLOAT_MAX) { *dist = r.dist; return 1; }
+      real n[3]; v3sub(x2, x1, n); normalize3(n); /* :2303 _inflate */
+      if (full1 > 0) for (int i = 0; i < 3; i++) x1[i] += full1 * n[i];
+      if (full2 > 0) for (int i = 0; i < 3; i++) x2[i] -= full2 * n[i];
+      *dist = r.dist - (full1 + full2);
+      return 1;
+    }
+    g1 = o1; g2 = o2;
+    cutoff -= full1 + full2;
+  }
+  ccd_gjk(tolerance, iterations, &g1, &g2, g1.pos, g2.pos, cutoff, &r);
+  if (r.dist > tolerance || r.dim < 2 || r.separated) { *dist = r.dist; v3cpy(x1, r.x1); v3cpy(x2, r.x2); return 1; }
+  /* epa_phase */
+  enum { MAXV = 10 + 2 * 1000 };
+  int maxvert = 10 + 2 * iterations, maxface = 6 + CCD_MAX_EPAFACES * iterations;
+  Polytope pt; memset(&pt, 0, sizeof pt);
+  pt.maxvert = maxvert; pt.maxface = maxface;
+  pt.vert = (real(*)[3])calloc((size_t)maxvert, 3 * sizeof(real)); pt.vert_index = (int*)calloc((size_t)maxvert, sizeof(int));
+  pt.face = (unsigned*)calloc((size_t)maxface, sizeof(unsigned)); pt.face_pr = (real(*)[3])calloc((size_t)maxface, 3 * sizeof(real));
+  pt.face_norm2 = (real*)calloc((size_t)maxface, sizeof(real));
+  int ncon = 1;
+  if (r.dim == 2) { polytope2(&pt, &r, &g1, &g2); if (pt.status == -1) r.dim = 3; }
+  else if (r.dim == 4) { polytope4(&pt, &r); if (pt.status == -1) r.dim = 3; }
+  if (r.dim == 3) { pt.status = 0; polytope3(&pt, &r, &g1, &g2); }
+  if (pt.status) { *dist = r.dist; v3cpy(x1, r.x1); v3cpy(x2, r.x2); }
+  else if (ccd_epa(tolerance, iterations, &pt, &g1, &g2, dist, x1, x2, ovf) == -1) { *dist = CCD_FLOAT_MAX; ncon = 0; }
+  free(pt.vert); free(pt.vert_index); free(pt.face); free(pt.face_pr); free(pt.face_norm2);
+  return ncon;
+}

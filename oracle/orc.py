@@ -196,6 +196,7 @@ class Oracle:
     seti("integrator", o.integrator); seti("cone", o.cone); seti("solver", o.solver); seti("iterations", o.iterations)
     seti("ls_iterations", o.ls_iterations); seti("disableflags", o.disableflags); seti("enableflags", o.enableflags)
     seti("broadphase_filter", getattr(o, "broadphase_filter", 1 | 2 | 8))  # io.py:405 default PLANE|SPHERE|OBB
+    seti("ccd_iterations", getattr(o, "ccd_iterations", 35)); setr("ccd_tolerance", getattr(o, "ccd_tolerance", 1e-6))
     tol = float(o.tolerance)
     if clamp_tolerance:
       tol = max(tol, 1e-6)  # io.py:401: put_model clamps the solver tolerance (chosen for float32) whatever the host precision;

@@ -37,6 +37,8 @@ def load_scene(name):
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"'))
   elif name == "boxes":
     mjm = mjcf.load_string(BOX_XML)
+  elif name == "convex":
+    mjm = mjcf.load_string(util.CONVEX_XML)
   elif name == "pairs":
     mjm = mjcf.load_string(util.pairs_xml())
   elif name == "passive":
@@ -85,8 +87,9 @@ def compare(tag, g, od, mjm, nworld, tol, solver_tol=1e-7, exact_iterations=True
     np.testing.assert_array_equal(od["efc_type"][w, :ne], g[f"{tag}/efc_type"][w, :ne])
     eid = g[f"{tag}/efc_id"][w, :ne].copy()
     is_con = od["efc_type"][w, :ne] >= 5
-    if n:
-      eid[is_con] -= ids[0]  # the reference's contact ids index the global pool
+    if n:  # the reference's contact ids index the global pool (a world's contacts need not be contiguous there)
+      local = {int(p): k for k, p in enumerate(ids)}
+      eid[is_con] = [local[int(p)] for p in eid[is_con]]
     np.testing.assert_array_equal(od["efc_id"][w, :ne], eid)
     np.testing.assert_array_equal(od["con_efc_address"][w, :n, : g[f"{tag}/con_efc_address"].shape[1]], g[f"{tag}/con_efc_address"][ids][:, : od["con_efc_address"].shape[2]])
     close(f"{tag}/efc_J[w{w}]", od["efc_J"][w, :ne], g[f"{tag}/efc_J"][w, :ne, :nv], tol)

@@ -206,3 +206,29 @@ def passive_xml():
     assert a in x, a
     x = x.replace(a, b)
   return x
+
+
+CONVEX_XML = """
+<mujoco model="convex">
+  <option timestep="0.002" iterations="50"/>
+  <default><geom friction="0.9 0.01 0.002"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05" condim="3"/>
+    <body name="box_static" pos="0 0 0.099"><geom type="box" size="0.25 0.25 0.1" density="500"/></body>
+    <body name="cyl_on_box" pos="0.05 0.02 0.277"><freejoint/><geom type="cylinder" size="0.07 0.08"/></body>
+    <body name="ell_on_box" pos="-0.1 -0.1 0.247"><freejoint/><geom type="ellipsoid" size="0.06 0.09 0.05"/></body>
+    <body name="cyl_a_static" pos="0.8 0 0.099"><geom type="cylinder" size="0.1 0.1"/></body>
+    <body name="cyl_b" pos="0.82 0.03 0.277" euler="0 90 0"><freejoint/><geom type="cylinder" size="0.08 0.12"/></body>
+    <body name="cap_on_cyl" pos="0.8 0.45 0.247" euler="90 0 0"><freejoint/><geom type="capsule" size="0.05 0.12"/></body>
+    <body name="cyl_c_static" pos="0.8 0.45 0.099"><geom type="cylinder" size="0.12 0.1"/></body>
+    <body name="ell_a_static" pos="-0.8 0 0.059"><geom type="ellipsoid" size="0.15 0.1 0.06"/></body>
+    <body name="ell_b" pos="-0.78 0.02 0.165" euler="10 0 30"><freejoint/><geom type="ellipsoid" size="0.08 0.06 0.05"/></body>
+    <body name="sph_on_ell" pos="-0.8 0.5 0.166"><freejoint/><geom type="sphere" size="0.05"/></body>
+    <body name="ell_c_static" pos="-0.8 0.5 0.059"><geom type="ellipsoid" size="0.12 0.12 0.06"/></body>
+    <body name="cap_on_ell" pos="-0.8 -0.5 0.205" euler="0 90 0"><freejoint/><geom type="capsule" size="0.04 0.1"/></body>
+    <body name="ell_d_static" pos="-0.8 -0.5 0.079"><geom type="ellipsoid" size="0.15 0.1 0.08" margin="0.004"/></body>
+    <body name="ell_on_cyl" pos="0 0.8 0.236"><freejoint/><geom type="ellipsoid" size="0.07 0.07 0.04"/></body>
+    <body name="cyl_d_static" pos="0 0.8 0.099"><geom type="cylinder" size="0.1 0.1"/></body>
+  </worldbody>
+</mujoco>
+"""

@@ -51,6 +51,7 @@ def scenes():
   yield "mixed_elliptic_cg", mjcf.load_string(cg), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   yield "pairs", mjcf.load_string(util.pairs_xml()), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   yield "passive", mjcf.load_string(util.passive_xml()), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  yield "convex", mjcf.load_string(util.CONVEX_XML), dict(nconmax=64, njmax=256, key=None, qpos_noise=0.004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "boxes", mjcf.load_string(BOX_XML), dict(nconmax=48, njmax=200, key=None, qpos_noise=0.003, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
   yield "g1", mjcf.load_any(util.G1), dict(nconmax=48, njmax=192, key=0, qpos_noise=0.02, qvel_noise=0.2, ctrl_noise=0.3)

@@ -182,7 +182,7 @@ def _build_warp():
 
   wp.func = func
   wp.kernel = lambda f=None, **k: f if f is not None else (lambda g: g)
-  wp.struct = lambda c: c
+  wp.struct = _struct
   wp.set_module_options = lambda *a, **k: None
   wp.static = lambda x: x
   wp.vec2, wp.vec3, wp.vec4 = _vec_cls(2), _vec_cls(3), _vec_cls(4)
@@ -235,7 +235,7 @@ def _build_warp():
   wp.normalize = normalize
   wp.cw_mul = lambda a, b: a._new([p * q for p, q in zip(a.v, b.v)])
   wp.sqrt, wp.sin, wp.cos, wp.atan2, wp.acos, wp.exp, wp.log, wp.pow = _m.sqrt, _m.sin, _m.cos, _m.atan2, _m.acos, _m.exp, _m.log, _m.pow
-  wp.sign = lambda x: -1.0 if x < 0 else 1.0  # warp: sign(0) = +1
+  wp.sign = lambda x: x._new([-1.0 if a < 0 else 1.0 for a in x.v]) if isinstance(x, Vec) else (-1.0 if x < 0 else 1.0)  # warp: sign(0) = +1
   wp.clamp = lambda x, lo, hi: min(max(x, lo), hi)
   wp.transpose = lambda a: _mat_cls(len(a.m[0]), len(a.m))._from_rows([list(c) for c in zip(*a.m)])
   wp.matrix_from_rows = lambda *rows: _mat_cls(len(rows), len(rows[0].v))._from_rows([list(r.v) for r in rows])
@@ -746,12 +746,42 @@ def _wp_mod(a, b):
 
 
 def _wp_copy(x):
-  """`a = b` copies vectors / matrices in warp (value types); Python would alias them"""
+  """`a = b` copies vectors / matrices / structs in warp (value types); Python would alias them"""
   if isinstance(x, Vec):
     return x._new(list(x.v))
   if isinstance(x, Mat):
     return x._new([list(r) for r in x.m])
+  if getattr(type(x), "_wp_struct", False):
+    o = type(x).__new__(type(x))
+    for k, v in x.__dict__.items():
+      o.__dict__[k] = _wp_copy(v) if isinstance(v, (Vec, Mat)) or getattr(type(v), "_wp_struct", False) else v
+    return o
   return x
+
+
+def _struct(cls):
+  """@wp.struct: fields are zero-initialised on construction, instances have value semantics (see _wp_copy)"""
+  import typing
+
+  def __init__(self):
+    for name, tp in typing.get_type_hints(cls, include_extras=False).items() if False else cls.__annotations__.items():
+      if tp is bool:
+        v = False
+      elif tp is int:
+        v = 0
+      elif tp is float:
+        v = 0.0
+      elif isinstance(tp, type) and issubclass(tp, (Vec, Mat)):
+        v = tp()
+      elif isinstance(tp, type) and getattr(tp, "_wp_struct", False):
+        v = tp()
+      else:
+        v = None  # arrays are bound by the caller
+      setattr(self, name, v)
+
+  cls.__init__ = __init__
+  cls._wp_struct = True
+  return cls
 
 
 _bi.__wp_div__, _bi.__wp_mod__, _bi.__wp_copy__ = _wp_div, _wp_mod, _wp_copy
