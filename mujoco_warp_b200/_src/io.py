@@ -45,6 +45,11 @@ _SUPPORTED_PAIRS = {
   (C.GEOM_PLANE, C.GEOM_ELLIPSOID), (C.GEOM_PLANE, C.GEOM_CYLINDER), (C.GEOM_PLANE, C.GEOM_BOX),
   (C.GEOM_SPHERE, C.GEOM_CYLINDER), (C.GEOM_SPHERE, C.GEOM_BOX), (C.GEOM_CAPSULE, C.GEOM_BOX),
 }
+# pairs the reference sends to GJK / EPA (collision_driver.py:47-81) that are built here: analytic convex geoms, single contact
+_CONVEX_PAIRS = {
+  (C.GEOM_SPHERE, C.GEOM_ELLIPSOID), (C.GEOM_CAPSULE, C.GEOM_ELLIPSOID), (C.GEOM_CAPSULE, C.GEOM_CYLINDER), (C.GEOM_ELLIPSOID, C.GEOM_ELLIPSOID),
+  (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER), (C.GEOM_ELLIPSOID, C.GEOM_BOX), (C.GEOM_CYLINDER, C.GEOM_CYLINDER), (C.GEOM_CYLINDER, C.GEOM_BOX),
+}
 
 
 def _require_cuda():
@@ -184,6 +189,7 @@ def derive_tables(mjm) -> dict:
     i, j = (j, i) if j < i else (i, j)
     return (i * (2 * C.NGEOMTYPES - i - 1)) // 2 + j
 
+  t["has_convex_pair"] = 0
   counts = np.zeros(C.NGEOMTYPES * (C.NGEOMTYPES + 1) // 2, dtype=int)
   for a, b in t["nxn_geom_pair_filtered"]:
     counts[trid(gt[a], gt[b])] += 1
@@ -192,8 +198,10 @@ def derive_tables(mjm) -> dict:
       # box-box is a primitive pair only with native CCD disabled (collision_driver.py:868-870); GJK/EPA is not implemented here
       if not (int(mjm.opt.disableflags) & C.DSBL_NATIVECCD):
         raise NotImplementedError('box-box collisions need <flag nativeccd="disable"/> (primitive box-box); the GJK/EPA convex path is not implemented')
+    elif key in _CONVEX_PAIRS:
+      t["has_convex_pair"] = 1
     elif key not in _SUPPORTED_PAIRS:
-      raise NotImplementedError(f"collision between geom types {key} is not implemented in this version (supported: {sorted(_SUPPORTED_PAIRS)})")
+      raise NotImplementedError(f"collision between geom types {key} is not implemented in this version (supported: {sorted(_SUPPORTED_PAIRS | _CONVEX_PAIRS)})")
   t["geom_pair_type_count"] = tuple(int(c) for c in counts)
   # constraint source lists
   jt = _np(mjm, "jnt_type")
@@ -367,13 +375,13 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
-    nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
+    nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))
   g = np.asarray(o.gravity, dtype=np.float64)
   floats = dict(timestep=o.timestep, tolerance=tol, ls_tolerance=o.ls_tolerance, impratio_invsqrt=1.0 / np.sqrt(o.impratio),
-                meaninertia=mjm.stat.meaninertia, gravity_x=g[0], gravity_y=g[1], gravity_z=g[2])
+                meaninertia=mjm.stat.meaninertia, gravity_x=g[0], gravity_y=g[1], gravity_z=g[2], ccd_tolerance=float(getattr(o, "ccd_tolerance", 1e-6)))
   for k, v in floats.items():
     _lib.check(L.mjb_model_set_float(h, k.encode(), float(v)))
   dev_names = {

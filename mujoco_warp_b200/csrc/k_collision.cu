@@ -13,6 +13,7 @@
 // per pair and one per contact).  Within a world the contact order is deterministic (pair order, then contact index);
 // only the position of a world's block inside the pool depends on scheduling.  Data.contact keeps the reference's global
 // pool layout (types.py:1975-2018) so [0, nacon) is densely packed.
+#include "mjb_ccd.cuh"
 #include "mjb_colliders.cuh"
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
@@ -24,7 +25,9 @@ constexpr int STAGE_WORDS = 13;  // dist, pos[3], frame[9]
 __host__ __device__ inline int world_con_cap(const DataDev& d) { return 2 * d.nconmax > 32 ? 2 * d.nconmax : 32; }
 __host__ __device__ inline int surv_cap(const ModelDev& m) { return m.nxn_npair < 1024 ? m.nxn_npair : 1024; }
 
-struct ColLayout { int gxpos, gxmat, surv, stage, sgeom, total; };
+constexpr int CCD_LANES = 4;  // geom pairs that run GJK / EPA concurrently in one warp (each needs a polytope in shared memory)
+
+struct ColLayout { int gxpos, gxmat, surv, stage, sgeom, ccd, total; };
 __host__ __device__ inline ColLayout col_layout(const ModelDev& m, const DataDev& d) {
   ColLayout L;
   int o = 0;
@@ -33,6 +36,7 @@ __host__ __device__ inline ColLayout col_layout(const ModelDev& m, const DataDev
   L.surv = take(surv_cap(m));
   L.stage = take(STAGE_WORDS * world_con_cap(d));
   L.sgeom = take(4 * world_con_cap(d));  // g1, g2, geomcollisionid, pairid
+  L.ccd = take(m.has_convex_pair ? CCD_LANES * ccd_scratch_words(m.ccd_iterations) : 0);
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -193,8 +197,70 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
   if (nsurv > scap) { nsurv = scap; ovf |= OVF_BROADPHASE; }
   __syncwarp();
 
-  // ---- narrowphase on the compacted list; contacts staged in shared memory in (pair, contact id) order
+  // ---- narrowphase on the compacted list; contacts staged in shared memory.  Order inside a world: convex (GJK / EPA) pairs
+  // first, by pair type in the reference's table order, then primitive pairs (the order the reference produces when its
+  // launches run sequentially: collision_driver.py:877, collision_convex.py:1369); within a type, pair-list order.
   int ncon = 0;
+  if (MAXC >= 8 && m.has_convex_pair) {
+    float* ccd_scratch = S + L.ccd;
+    const int sw = ccd_scratch_words(m.ccd_iterations);
+#pragma unroll 1
+    for (int rank = 0; rank < 8; rank++) {
+#pragma unroll 1
+      for (int s0 = 0; s0 < nsurv; s0 += 32) {
+        const int si = s0 + lane;
+        int g1 = 0, g2 = 0, pid = -1;
+        bool mine = false;
+        if (si < nsurv) {
+          const int e = surv[si];
+          g1 = m.nxn_geom_pair[2 * e]; g2 = m.nxn_geom_pair[2 * e + 1];
+          if (m.geom_type[g1] > m.geom_type[g2]) { const int t = g1; g1 = g2; g2 = t; }
+          mine = convex_rank(m.geom_type[g1], m.geom_type[g2]) == rank;
+          pid = m.npair > 0 ? m.nxn_pairid[2 * e] : -1;
+        }
+        unsigned todo = __ballot_sync(FULL_MASK, mine);
+        while (todo) {
+          unsigned batch = 0, t = todo;
+          for (int k = 0; k < CCD_LANES && t; k++) { batch |= t & (0u - t); t &= t - 1; }
+          todo &= ~batch;
+          const bool active = (batch >> lane) & 1u;
+          bool hit = false;
+          float dist = 0.f;
+          v3 pos = mk3(0.f, 0.f, 0.f), nrm = mk3(1.f, 0.f, 0.f);
+          if (active) {
+            const int slot = __popc(batch & ((1u << lane) - 1u));
+            const float margin = pid > -1 ? m.pair_margin[pid] : m.geom_margin[g1] + m.geom_margin[g2];
+            const float gap = pid > -1 ? m.pair_gap[pid] : m.geom_gap[g1] + m.geom_gap[g2];
+            CGeom a, b;
+            a.pos = ld3(gxpos + 3 * g1); a.rot = gxmat + 9 * g1; a.size = ld3(m.geom_size + 3 * g1); a.margin = margin; a.type = m.geom_type[g1];
+            b.pos = ld3(gxpos + 3 * g2); b.rot = gxmat + 9 * g2; b.size = ld3(m.geom_size + 3 * g2); b.margin = margin; b.type = m.geom_type[g2];
+            v3 x1, x2;
+            bool eovf = false;
+            const int nc = ccd_pair(m.ccd_tolerance, gap, m.ccd_iterations, a, b, ccd_scratch + slot * sw, &dist, &x1, &x2, &eovf);
+            if (eovf) ovf |= OVF_EPA_HORIZON;
+            if (nc > 0 && dist < gap) {  // collision_convex.py:860-868, 935-940
+              dist += margin;
+              nrm = dist <= margin ? x1 - x2 : x2 - x1;
+              pos = (x1 + x2) * 0.5f;
+              hit = dist < margin + gap;  // write_contact
+            }
+          }
+          const unsigned hb = __ballot_sync(FULL_MASK, hit);
+          if (hit) {
+            const int off = ncon + __popc(hb & ((1u << lane) - 1u));
+            if (off < ccap) {
+              float* st = stage + STAGE_WORDS * off;
+              st[0] = dist; st3(st + 1, pos);
+              make_frame(nrm, st + 4);
+              sgeom[4 * off] = g1; sgeom[4 * off + 1] = g2; sgeom[4 * off + 2] = 0; sgeom[4 * off + 3] = pid;
+            }
+          }
+          ncon += __popc(hb);
+        }
+      }
+    }
+    ovf = __reduce_or_sync(FULL_MASK, (unsigned)ovf);
+  }
 #pragma unroll 1
   for (int s0 = 0; s0 < nsurv; s0 += 32) {
     const int si = s0 + lane;

@@ -1,0 +1,409 @@
+// mjb_ccd.cuh -- general convex collision (GJK + EPA) for analytic convex geoms, one lane per geom pair.
+//
+// Replaces /root/reference/mujoco_warp/_src/collision_gjk.py: :115 support, :281-594 distance sub-algorithm (S1D / S2D / S3D),
+// :635 gjk, :1021-1286 polytope construction, :1319 _epa, :947 _epa_witness, :2303 _inflate, :2350 gjk_phase,
+// :2421 epa_phase (sphere, capsule, ellipsoid, cylinder, box; meshes, height fields and the multi-contact clipping of
+// box / mesh pairs are not built yet).  The EPA polytope lives in a per-lane slice of shared memory supplied by the caller.
+#pragma once
+#include "mjb_colliders.cuh"
+#include "mjb_math.cuh"
+#include "mjb_types.cuh"
+
+#define CCD_FLOAT_MAX 1e30f
+#define CCD_MINVAL 1e-15f
+#define CCD_MIN_DIST2 1e-10f
+#define CCD_MIN_DIST3 1e-10f
+#define CCD_MIN_DIST4 1e-17f
+#define CCD_MAX_EPAFACES 5
+#define CCD_MAX_EPAHORIZON 24
+#define CCD_FACE_DELETED 0x80000000u
+#define CCD_FACE_INVALID 0x40000000u
+
+// Geom-type pairs the reference routes to the convex path (collision_driver.py:47-81), analytic geoms only, in table order.
+// Box-box is convex there too but needs the multi-contact clipping; put_model only admits it with nativeccd disabled
+// (primitive box_box).
+__host__ __device__ inline int convex_rank(int t1, int t2) {
+  if (t1 == GEOM_SPHERE && t2 == GEOM_ELLIPSOID) return 0;
+  if (t1 == GEOM_CAPSULE && t2 == GEOM_ELLIPSOID) return 1;
+  if (t1 == GEOM_CAPSULE && t2 == GEOM_CYLINDER) return 2;
+  if (t1 == GEOM_ELLIPSOID && t2 == GEOM_ELLIPSOID) return 3;
+  if (t1 == GEOM_ELLIPSOID && t2 == GEOM_CYLINDER) return 4;
+  if (t1 == GEOM_ELLIPSOID && t2 == GEOM_BOX) return 5;
+  if (t1 == GEOM_CYLINDER && t2 == GEOM_CYLINDER) return 6;
+  if (t1 == GEOM_CYLINDER && t2 == GEOM_BOX) return 7;
+  return -1;
+}
+
+struct CGeom { v3 pos; const float* rot; v3 size; float margin; int type; };
+struct GjkRes { bool separated; int dim; float dist; v3 x1, x2, s[4], s1[4], s2[4]; };
+// words of shared memory one lane's polytope needs: vertices (2 per support pair), faces, face projections, squared norms, horizon
+__host__ __device__ inline int ccd_scratch_words(int iterations) {
+  return 3 * (10 + 2 * iterations) + 5 * (6 + CCD_MAX_EPAFACES * iterations) + CCD_MAX_EPAHORIZON;
+}
+struct Polytope {
+  int status, nvert, nface, nhorizon, maxface;
+  v3 center;
+  float* vert;       // 3 * (10 + 2 it)
+  unsigned* face;    // maxface
+  float* face_pr;    // 3 * maxface
+  float* face_norm2; // maxface
+  int* horizon;      // CCD_MAX_EPAHORIZON
+};
+
+__device__ __forceinline__ float csign(float x) { return x < 0.f ? -1.f : 1.f; }  // wp.sign(0) = +1
+
+__device__ v3 ccd_support(const CGeom& g, v3 dir) {
+  if (g.type == GEOM_SPHERE) return g.pos + dir * (g.size.x + 0.5f * g.margin);
+  const v3 ld = mat_t_vec(g.rot, dir);
+  v3 res = mk3(0.f, 0.f, 0.f);
+  if (g.type == GEOM_BOX) res = mk3(csign(ld.x) * g.size.x, csign(ld.y) * g.size.y, csign(ld.z) * g.size.z);
+  else if (g.type == GEOM_CAPSULE) { res = ld * g.size.x; res.z += csign(ld.z) * g.size.y; }
+  else if (g.type == GEOM_ELLIPSOID) res = cw_mul(normalize(cw_mul(ld, g.size)), g.size);
+  else if (g.type == GEOM_CYLINDER) {
+    const float d = sqrtf(ld.x * ld.x + ld.y * ld.y);
+    if (d > CCD_MINVAL) { const float scl = g.size.x / d; res.x = ld.x * scl; res.y = ld.y * scl; }
+    res.z = csign(ld.z) * g.size.y;
+  }
+  v3 out = matvec(g.rot, res) + g.pos;
+  if (g.margin > 0.f) out = out + dir * (0.5f * g.margin);
+  return out;
+}
+
+__device__ __forceinline__ float det3(v3 a, v3 b, v3 c) { return dot(a, cross(b, c)); }
+__device__ __forceinline__ int same_sign(float a, float b) { return (a > 0.f && b > 0.f) ? 1 : ((a < 0.f && b < 0.f) ? -1 : 0); }
+__device__ __forceinline__ v3 project_origin_line(v3 v1, v3 v2) {
+  const v3 diff = v2 - v1;
+  return v2 + diff * (-(dot(v2, diff) / dot(diff, diff)));
+}
+__device__ int project_origin_plane(v3 v1, v3 v2, v3 v3_, v3* o) {
+  const v3 d21 = v2 - v1, d31 = v3_ - v1, d32 = v3_ - v2;
+  *o = mk3(0.f, 0.f, 0.f);
+  v3 n = cross(d32, d21);
+  float nv = dot(n, v2), nn = dot(n, n);
+  if (nn == 0.f) return 1;
+  if (nv != 0.f && nn > CCD_MINVAL) { *o = n * (nv / nn); return 0; }
+  n = cross(d21, d31); nv = dot(n, v1); nn = dot(n, n);
+  if (nn == 0.f) return 1;
+  if (nv != 0.f && nn > CCD_MINVAL) { *o = n * (nv / nn); return 0; }
+  n = cross(d31, d32); nv = dot(n, v3_); nn = dot(n, n);
+  *o = n * (nv / nn);
+  return 0;
+}
+__device__ void S1D(v3 s1, v3 s2, float* l) {
+  const v3 po = project_origin_line(s1, s2);
+  float mu_max = s1.x - s2.x;
+  int index = 0;
+  float mu = s1.y - s2.y;
+  if (fabsf(mu) >= fabsf(mu_max)) { mu_max = mu; index = 1; }
+  mu = s1.z - s2.z;
+  if (fabsf(mu) >= fabsf(mu_max)) { mu_max = mu; index = 2; }
+  const float C1 = comp(po, index) - comp(s2, index), C2 = comp(s1, index) - comp(po, index);
+  if (same_sign(mu_max, C1) && same_sign(mu_max, C2)) { l[0] = C1 / mu_max; l[1] = C2 / mu_max; return; }
+  l[0] = 0.f; l[1] = 1.f;
+}
+// signed areas of (p, s2, s3), (p, s1, s3), (p, s1, s2) in the projection that drops the axis with the largest minor; returns that minor
+__device__ float tri_cofactors(v3 s1, v3 s2, v3 s3, v3 p, float* C) {
+  const float M14 = s2.y * s3.z - s2.z * s3.y - s1.y * s3.z + s1.z * s3.y + s1.y * s2.z - s1.z * s2.y;
+  const float M24 = s2.x * s3.z - s2.z * s3.x - s1.x * s3.z + s1.z * s3.x + s1.x * s2.z - s1.z * s2.x;
+  const float M34 = s2.x * s3.y - s2.y * s3.x - s1.x * s3.y + s1.y * s3.x + s1.x * s2.y - s1.y * s2.x;
+  const float mu1 = fabsf(M14), mu2 = fabsf(M24), mu3 = fabsf(M34);
+  float Mmax; int x, y;
+  if (mu1 >= mu2 && mu1 >= mu3) { Mmax = M14; x = 1; y = 2; } else if (mu2 >= mu3) { Mmax = M24; x = 0; y = 2; } else { Mmax = M34; x = 0; y = 1; }
+  const float px = comp(p, x), py = comp(p, y), ax = comp(s1, x), ay = comp(s1, y), bx = comp(s2, x), by = comp(s2, y), cx = comp(s3, x), cy = comp(s3, y);
+  C[0] = px * by + py * cx + bx * cy - px * cy - py * bx - cx * by;
+  C[1] = px * cy + py * ax + cx * ay - px * ay - py * cx - ax * cy;
+  C[2] = px * ay + py * bx + ax * by - px * by - py * ax - bx * ay;
+  return Mmax;
+}
+__device__ void S2D(v3 s1, v3 s2, v3 s3, float* l) {
+  v3 po;
+  if (project_origin_plane(s1, s2, s3, &po)) { S1D(s1, s2, l); l[2] = 0.f; return; }
+  float C[3];
+  const float Mmax = tri_cofactors(s1, s2, s3, po, C);
+  const int c1 = same_sign(Mmax, C[0]), c2 = same_sign(Mmax, C[1]), c3 = same_sign(Mmax, C[2]);
+  if (c1 && c2 && c3) { l[0] = C[0] / Mmax; l[1] = C[1] / Mmax; l[2] = C[2] / Mmax; return; }
+  float dmin = CCD_FLOAT_MAX, sub[2];
+  l[0] = l[1] = l[2] = 0.f;
+  if (!c1) { S1D(s2, s3, sub); const v3 x = s2 * sub[0] + s3 * sub[1]; l[0] = 0.f; l[1] = sub[0]; l[2] = sub[1]; dmin = dot(x, x); }
+  if (!c2) { S1D(s1, s3, sub); const v3 x = s1 * sub[0] + s3 * sub[1]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = 0.f; l[2] = sub[1]; dmin = d; } }
+  if (!c3) { S1D(s1, s2, sub); const v3 x = s1 * sub[0] + s2 * sub[1]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = 0.f; } }
+}
+__device__ void S3D(v3 s1, v3 s2, v3 s3, v3 s4, float* l) {
+  const float C41 = -det3(s2, s3, s4), C42 = det3(s1, s3, s4), C43 = -det3(s1, s2, s4), C44 = det3(s1, s2, s3);
+  const float m_det = C41 + C42 + C43 + C44;
+  const int c1 = same_sign(m_det, C41), c2 = same_sign(m_det, C42), c3 = same_sign(m_det, C43), c4 = same_sign(m_det, C44);
+  if (c1 && c2 && c3 && c4) { l[0] = C41 / m_det; l[1] = C42 / m_det; l[2] = C43 / m_det; l[3] = C44 / m_det; return; }
+  float dmin = CCD_FLOAT_MAX, sub[3];
+  l[0] = l[1] = l[2] = l[3] = 0.f;
+  if (!c1) { S2D(s2, s3, s4, sub); const v3 x = s2 * sub[0] + s3 * sub[1] + s4 * sub[2]; l[0] = 0.f; l[1] = sub[0]; l[2] = sub[1]; l[3] = sub[2]; dmin = dot(x, x); }
+  if (!c2) { S2D(s1, s3, s4, sub); const v3 x = s1 * sub[0] + s3 * sub[1] + s4 * sub[2]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = 0.f; l[2] = sub[1]; l[3] = sub[2]; dmin = d; } }
+  if (!c3) { S2D(s1, s2, s4, sub); const v3 x = s1 * sub[0] + s2 * sub[1] + s4 * sub[2]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = 0.f; l[3] = sub[2]; dmin = d; } }
+  if (!c4) { S2D(s1, s2, s3, sub); const v3 x = s1 * sub[0] + s2 * sub[1] + s3 * sub[2]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = sub[2]; l[3] = 0.f; } }
+}
+__device__ __forceinline__ v3 lin_comb(int n, const float* l, const v3* m) {
+  v3 o = m[0] * l[0];
+  for (int k = 1; k < n; k++) o = o + m[k] * l[k];
+  return o;
+}
+
+// collision_gjk.py:635 with is_discrete = false (analytic geoms)
+__device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const CGeom& g2, float cutoff, GjkRes& r) {
+  float lmbda[4] = {1.f, 0.f, 0.f, 0.f};
+  const float epsilon = 0.5f * tolerance * tolerance;
+  int n = 0;
+  v3 x_k = g1.pos - g2.pos;
+  float xnorm = sqrtf(dot(x_k, x_k)), xnorm_prev = 0.f;
+  r.separated = false; r.dim = 0; r.dist = 0.f; r.x1 = r.x2 = mk3(0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int it = 0; it < iterations; it++) {
+    if (xnorm < tolerance || fabsf(xnorm_prev - xnorm) < CCD_MINVAL) break;
+    const v3 dir_neg = x_k * (1.0f / xnorm);
+    r.s1[n] = ccd_support(g1, dir_neg * -1.0f);
+    r.s2[n] = ccd_support(g2, dir_neg);
+    r.s[n] = r.s1[n] - r.s2[n];
+    if (dot(x_k, x_k - r.s[n]) < epsilon) break;
+    const float lower = dot(x_k, r.s[n]);
+    if (cutoff == 0.f) { if (lower > 0.f) { r.separated = true; r.dist = CCD_FLOAT_MAX; return; } }
+    else if (cutoff < CCD_FLOAT_MAX) { if (lower > 0.f && lower >= cutoff * xnorm) { r.separated = true; r.dist = CCD_FLOAT_MAX; return; } }
+    if (n == 3) S3D(r.s[0], r.s[1], r.s[2], r.s[3], lmbda);
+    else if (n == 2) { S2D(r.s[0], r.s[1], r.s[2], lmbda); lmbda[3] = 0.f; }
+    else if (n == 1) { S1D(r.s[0], r.s[1], lmbda); lmbda[2] = lmbda[3] = 0.f; }
+    else { lmbda[0] = 1.f; lmbda[1] = lmbda[2] = lmbda[3] = 0.f; }
+    n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (lmbda[i] == 0.f) continue;
+      r.s[n] = r.s[i]; r.s1[n] = r.s1[i]; r.s2[n] = r.s2[i]; lmbda[n] = lmbda[i];
+      n++;
+    }
+    if (n < 1) break;
+    x_k = lin_comb(n, lmbda, r.s);
+    xnorm_prev = xnorm;
+    xnorm = sqrtf(dot(x_k, x_k));
+    if (n == 4) break;
+  }
+  if (n == 0) { r.x1 = g1.pos; r.x2 = g2.pos; } else { r.x1 = lin_comb(n, lmbda, r.s1); r.x2 = lin_comb(n, lmbda, r.s2); }
+  if (xnorm > 0.f) {
+    const v3 dir = x_k * (1.0f / xnorm);
+    r.separated = dot(x_k, ccd_support(g1, dir * -1.0f) - ccd_support(g2, dir)) > 0.f;
+  }
+  r.dist = (n == 4 && !r.separated) ? 0.f : xnorm;
+  r.dim = n;
+}
+
+__device__ __forceinline__ v3 pt_v1(const Polytope& pt, int v) { return ld3(pt.vert + 6 * v); }
+__device__ __forceinline__ v3 pt_v2(const Polytope& pt, int v) { return ld3(pt.vert + 6 * v + 3); }
+__device__ __forceinline__ v3 pt_mink(const Polytope& pt, int v) { return pt_v1(pt, v) - pt_v2(pt, v); }
+__device__ bool same_side(v3 p0, v3 p1, v3 p2, v3 p3) {
+  const v3 n = cross(p1 - p0, p2 - p0);
+  const float d1 = dot(n, p3 - p0), d2 = dot(n, p0 * -1.0f);
+  return (d1 > 0.f && d2 > 0.f) || (d1 < 0.f && d2 < 0.f);
+}
+__device__ bool test_tetra(v3 p0, v3 p1, v3 p2, v3 p3) {
+  return same_side(p0, p1, p2, p3) && same_side(p1, p2, p3, p0) && same_side(p2, p3, p0, p1) && same_side(p3, p0, p1, p2);
+}
+__device__ bool tri_point_intersect(v3 v1, v3 v2, v3 v3_, v3 p) {
+  float C[3];
+  const float Mmax = tri_cofactors(v1, v2, v3_, p, C);
+  const float l1 = C[0] / Mmax, l2 = C[1] / Mmax, l3 = C[2] / Mmax;
+  if (l1 < 0.f || l2 < 0.f || l3 < 0.f) return false;
+  return length(v1 * l1 + v2 * l2 + v3_ * l3 - p) < CCD_MINVAL;
+}
+__device__ float attach_face(Polytope& pt, int idx, int v1, int v2, int v3_) {
+  if (pt.nface == pt.maxface) return 0.f;
+  const v3 p1 = pt_mink(pt, v1), p2 = pt_mink(pt, v2), p3 = pt_mink(pt, v3_);
+  v3 r;
+  if (project_origin_plane(p3, p2, p1, &r)) return 0.f;
+  if (dot(r, p1 - pt.center) < 0.f) r = r * -1.0f;
+  pt.face[idx] = (unsigned)(v1 + (v2 << 10) + (v3_ << 20));
+  st3(pt.face_pr + 3 * idx, r);
+  const float n2 = dot(r, r);
+  pt.face_norm2[idx] = n2;
+  return n2;
+}
+__device__ void epa_support(Polytope& pt, int idx, const CGeom& g1, const CGeom& g2, v3 dir) {
+  st3(pt.vert + 6 * idx, ccd_support(g1, dir));
+  st3(pt.vert + 6 * idx + 3, ccd_support(g2, dir * -1.0f));
+}
+__device__ void replace_simplex3(const Polytope& pt, int v1, int v2, int v3_, GjkRes& r) {
+  const int v[3] = {v1, v2, v3_};
+  for (int k = 0; k < 3; k++) { r.s1[k] = pt_v1(pt, v[k]); r.s2[k] = pt_v2(pt, v[k]); r.s[k] = r.s1[k] - r.s2[k]; }
+}
+__device__ void load_simplex(Polytope& pt, const GjkRes& r, int n) {
+  for (int k = 0; k < n; k++) { st3(pt.vert + 6 * k, r.s1[k]); st3(pt.vert + 6 * k + 3, r.s2[k]); }
+}
+__device__ void polytope2(Polytope& pt, GjkRes& r, const CGeom& g1, const CGeom& g2) {
+  const v3 diff = r.s[1] - r.s[0];
+  pt.center = (r.s[0] + r.s[1]) * 0.5f;
+  float value = CCD_FLOAT_MAX;
+  int index = 0;
+  for (int i = 0; i < 3; i++) if (fabsf(comp(diff, i)) < value) { value = fabsf(comp(diff, i)); index = i; }
+  v3 e = mk3(0.f, 0.f, 0.f);
+  setcomp(e, index, 1.0f);
+  const v3 d1 = cross(e, diff);
+  float R[9];
+  { const float n = length(diff), u1 = diff.x / n, u2 = diff.y / n, u3 = diff.z / n, s = 0.86602540378f, c = -0.5f;  // rotation by 120 degrees (:885)
+    R[0] = c + u1 * u1 * (1.f - c); R[1] = u1 * u2 * (1.f - c) - u3 * s; R[2] = u1 * u3 * (1.f - c) + u2 * s;
+    R[3] = u2 * u1 * (1.f - c) + u3 * s; R[4] = c + u2 * u2 * (1.f - c); R[5] = u2 * u3 * (1.f - c) - u1 * s;
+    R[6] = u1 * u3 * (1.f - c) - u2 * s; R[7] = u2 * u3 * (1.f - c) + u1 * s; R[8] = c + u3 * u3 * (1.f - c); }
+  const v3 d2 = matvec(R, d1), d3 = matvec(R, d2);
+  load_simplex(pt, r, 2);
+  epa_support(pt, 2, g1, g2, d1 * (1.0f / length(d1)));
+  epa_support(pt, 3, g1, g2, d2 * (1.0f / length(d2)));
+  epa_support(pt, 4, g1, g2, d3 * (1.0f / length(d3)));
+  const int F[6][3] = {{0, 2, 3}, {0, 4, 2}, {0, 3, 4}, {1, 3, 2}, {1, 2, 4}, {1, 4, 3}};
+  for (int f = 0; f < 6; f++)
+    if (attach_face(pt, f, F[f][0], F[f][1], F[f][2]) < CCD_MIN_DIST2) { pt.status = -1; replace_simplex3(pt, F[f][0], F[f][1], F[f][2], r); return; }
+  {  // the hexahedron must enclose the segment (:907 _ray_triangle)
+    const v3 v1 = r.s[0], a = pt_mink(pt, 2) - v1, b = pt_mink(pt, 3) - v1, c = pt_mink(pt, 4) - v1, d = r.s[1] - v1;
+    const float vol1 = det3(a, b, d), vol2 = det3(b, c, d), vol3 = det3(c, a, d);
+    if (!((vol1 >= 0.f && vol2 >= 0.f && vol3 >= 0.f) || (vol1 <= 0.f && vol2 <= 0.f && vol3 <= 0.f))) { pt.status = 1; return; }
+  }
+  pt.nvert = 5; pt.nface = 6; pt.status = 0;
+}
+__device__ void polytope3(Polytope& pt, const GjkRes& r, const CGeom& g1, const CGeom& g2) {
+  pt.center = (r.s[0] + r.s[1] + r.s[2]) * (1.0f / 3.0f);
+  v3 n = cross(r.s[1] - r.s[0], r.s[2] - r.s[0]);
+  const float norm = length(n);
+  if (norm < CCD_MINVAL) { pt.status = 2; return; }
+  n = n * (1.0f / norm);
+  load_simplex(pt, r, 3);
+  epa_support(pt, 3, g1, g2, n * -1.0f);
+  epa_support(pt, 4, g1, g2, n);
+  const v3 v1 = r.s[0], v2 = r.s[1], v3_ = r.s[2], v4 = pt_mink(pt, 3), v5 = pt_mink(pt, 4);
+  if (tri_point_intersect(v1, v2, v3_, v4)) { pt.status = 3; return; }
+  if (tri_point_intersect(v1, v2, v3_, v5)) { pt.status = 4; return; }
+  if (r.dist > 1e-5f && !test_tetra(v1, v2, v3_, v4) && !test_tetra(v1, v2, v3_, v5)) { pt.status = 5; return; }
+  const int F[6][3] = {{4, 0, 1}, {4, 2, 0}, {4, 1, 2}, {3, 1, 0}, {3, 0, 2}, {3, 2, 1}};
+  for (int f = 0; f < 6; f++) if (attach_face(pt, f, F[f][0], F[f][1], F[f][2]) < CCD_MIN_DIST3) { pt.status = 6 + f; return; }
+  pt.nvert = 5; pt.nface = 6; pt.status = 0;
+}
+__device__ void polytope4(Polytope& pt, GjkRes& r) {
+  pt.center = (r.s[0] + r.s[1] + r.s[2] + r.s[3]) * 0.25f;
+  load_simplex(pt, r, 4);
+  const int F[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {3, 2, 1}};
+  float dist[4];
+  int idx = 0;
+  for (int f = 0; f < 4; f++) {
+    dist[f] = attach_face(pt, f, F[f][0], F[f][1], F[f][2]);
+    if (dist[f] < CCD_MIN_DIST4) { pt.status = -1; replace_simplex3(pt, F[f][0], F[f][1], F[f][2], r); return; }
+    if (f == 1) idx = dist[0] < dist[1] ? 0 : 1;
+    else if (f > 1) idx = dist[f] < dist[idx] ? f : idx;
+  }
+  if (!test_tetra(r.s[0], r.s[1], r.s[2], r.s[3])) {
+    if (dist[idx] > CCD_MINVAL) { pt.status = 12; return; }
+    pt.status = -1;
+    replace_simplex3(pt, F[idx][0], F[idx][1], F[idx][2], r);
+    return;
+  }
+  pt.nvert = 4; pt.nface = 4; pt.status = 0;
+}
+__device__ int add_edge(Polytope& pt, int e1, int e2) {
+  const int n = pt.nhorizon;
+  if (n < 0) return -1;
+  const int edge = (min(e1, e2) << 10) | max(e1, e2);
+  for (int i = 0; i < n; i++) if (edge == pt.horizon[i]) { pt.horizon[i] = pt.horizon[n - 1]; return n - 1; }
+  if (n == CCD_MAX_EPAHORIZON) return -1;
+  pt.horizon[n] = edge;
+  return n + 1;
+}
+// :1319 _epa + :947 witness points; returns the closest face index or -1
+__device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeom& g1, const CGeom& g2, float* dist, v3* x1, v3* x2, bool* ovf) {
+  float upper = CCD_FLOAT_MAX, upper2 = CCD_FLOAT_MAX;
+  int idx = -1, pidx = -1, nvalid = pt.nface;
+  iterations = min(iterations, 1000);
+#pragma unroll 1
+  for (int it = 0; it < iterations; it++) {
+    pidx = idx; idx = -1;
+    float lower2 = CCD_FLOAT_MAX;
+    for (int i = 0; i < pt.nface; i++) if (!(pt.face[i] & (CCD_FACE_DELETED | CCD_FACE_INVALID)) && pt.face_norm2[i] < lower2) { idx = i; lower2 = pt.face_norm2[i]; }
+    if (lower2 > upper2 || idx < 0) { idx = pidx; break; }
+    if (lower2 <= 0.f) break;
+    const float lower = sqrtf(lower2);
+    const int wi = pt.nvert;
+    const v3 fp = ld3(pt.face_pr + 3 * idx);
+    epa_support(pt, wi, g1, g2, fp * (1.0f / lower));
+    const v3 w = pt_mink(pt, wi);
+    pt.nvert++;
+    const float upper_k = dot(fp, w) / lower;
+    if (upper_k < upper) { upper = upper_k; upper2 = upper * upper; }
+    if (upper - lower < tolerance) break;
+    nvalid--;
+    pt.face[idx] |= CCD_FACE_DELETED;
+    { const unsigned f = pt.face[idx]; const int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
+      pt.nhorizon = add_edge(pt, a, b); pt.nhorizon = add_edge(pt, b, c); pt.nhorizon = add_edge(pt, c, a); }
+    if (pt.nhorizon == -1) { *ovf = true; idx = -1; break; }
+    for (int i = 0; i < pt.nface; i++) {
+      if (pt.face[i] & CCD_FACE_DELETED) continue;
+      if (dot(ld3(pt.face_pr + 3 * i), w) - pt.face_norm2[i] > 1e-10f) {
+        if (!(pt.face[i] & CCD_FACE_INVALID)) nvalid--;
+        pt.face[i] |= CCD_FACE_DELETED;
+        const unsigned f = pt.face[i]; const int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
+        pt.nhorizon = add_edge(pt, a, b); pt.nhorizon = add_edge(pt, b, c); pt.nhorizon = add_edge(pt, c, a);
+        if (pt.nhorizon == -1) { *ovf = true; idx = -1; break; }
+      }
+    }
+    for (int i = 0; i < pt.nhorizon; i++) {
+      const int e = pt.horizon[i];
+      const float dist2 = attach_face(pt, pt.nface, wi, e & 0x3FF, (e >> 10) & 0x3FF);
+      if (dist2 == 0.f) { idx = -1; break; }
+      pt.nface++;
+      if (dist2 >= lower2 && dist2 <= upper2) nvalid++; else pt.face[pt.nface - 1] |= CCD_FACE_INVALID;
+    }
+    if (nvalid == 0 || idx == -1) break;
+    pt.nhorizon = 0;
+  }
+  if (idx > -1) {
+    const unsigned f = pt.face[idx]; const int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
+    float C[3];
+    const float Mmax = tri_cofactors(pt_mink(pt, a), pt_mink(pt, b), pt_mink(pt, c), ld3(pt.face_pr + 3 * idx), C);
+    const float l1 = C[0] / Mmax, l2 = C[1] / Mmax, l3 = C[2] / Mmax;
+    *x2 = pt_v2(pt, a) * l1 + pt_v2(pt, b) * l2 + pt_v2(pt, c) * l3;
+    *x1 = pt_v1(pt, a) * l1 + pt_v1(pt, b) * l2 + pt_v1(pt, c) * l3;
+    *dist = -sqrtf(pt.face_norm2[idx]);
+    return idx;
+  }
+  *dist = 0.f; *x1 = *x2 = mk3(0.f, 0.f, 0.f);
+  return -1;
+}
+
+// gjk_phase (:2350) + epa_phase (:2421).  Returns the number of contacts (0 / 1); *dist is relative to the margin-inflated shapes.
+__device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int iterations, CGeom g1, CGeom g2, float* scratch, float* dist, v3* x1, v3* x2, bool* ovf) {
+  const CGeom o1 = g1, o2 = g2;
+  float full1 = 0.f, full2 = 0.f, size1 = 0.f, size2 = 0.f;
+  GjkRes r;
+  if (g1.type == GEOM_SPHERE || g1.type == GEOM_CAPSULE) { size1 = g1.size.x; full1 = size1 + 0.5f * g1.margin; g1.margin = 0.f; g1.size.x = 0.f; }
+  if (g2.type == GEOM_SPHERE || g2.type == GEOM_CAPSULE) { size2 = g2.size.x; full2 = size2 + 0.5f * g2.margin; g2.margin = 0.f; g2.size.x = 0.f; }
+  if (size1 + size2 > 0.f) {
+    cutoff += full1 + full2;
+    ccd_gjk(tolerance, iterations, g1, g2, cutoff, r);
+    if (r.dist > tolerance) {
+      *x1 = r.x1; *x2 = r.x2;
+      if (r.dist == CCD_FLOAT_MAX) { *dist = r.dist; return 1; }
+      const v3 n = normalize(*x2 - *x1);  // :2303 _inflate
+      if (full1 > 0.f) *x1 = *x1 + n * full1;
+      if (full2 > 0.f) *x2 = *x2 - n * full2;
+      *dist = r.dist - (full1 + full2);
+      return 1;
+    }
+    g1 = o1; g2 = o2;
+    cutoff -= full1 + full2;
+  }
+  ccd_gjk(tolerance, iterations, g1, g2, cutoff, r);
+  if (r.dist > tolerance || r.dim < 2 || r.separated) { *dist = r.dist; *x1 = r.x1; *x2 = r.x2; return 1; }
+  Polytope pt;
+  const int maxvert = 10 + 2 * iterations;
+  pt.maxface = 6 + CCD_MAX_EPAFACES * iterations;
+  pt.status = 0; pt.nvert = 0; pt.nface = 0; pt.nhorizon = 0;
+  pt.vert = scratch;
+  pt.face = (unsigned*)(scratch + 3 * maxvert);
+  pt.face_pr = scratch + 3 * maxvert + pt.maxface;
+  pt.face_norm2 = pt.face_pr + 3 * pt.maxface;
+  pt.horizon = (int*)(pt.face_norm2 + pt.maxface);
+  if (r.dim == 2) { polytope2(pt, r, g1, g2); if (pt.status == -1) r.dim = 3; }
+  else if (r.dim == 4) { polytope4(pt, r); if (pt.status == -1) r.dim = 3; }
+  if (r.dim == 3) { pt.status = 0; polytope3(pt, r, g1, g2); }
+  if (pt.status) { *dist = r.dist; *x1 = r.x1; *x2 = r.x2; return 1; }
+  if (ccd_epa(tolerance, iterations, pt, g1, g2, dist, x1, x2, ovf) == -1) { *dist = CCD_FLOAT_MAX; return 0; }
+  return 1;
+}
