@@ -154,15 +154,15 @@ def test_unsupported_features_raise():
   xml = """<mujoco><option integrator="RK4"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
   with pytest.raises(NotImplementedError, match="integrator"):
     mio._validate(mjcf.load_string(xml))
-  # box-box is a primitive pair only with nativeccd disabled; cylinder-box always needs the (unimplemented) convex path
+  # box-box is a primitive pair only with nativeccd disabled (the convex path's multi-contact clipping is not built)
   two = '<body pos="0 0 1"><freejoint/><geom type="box" size=".1 .1 .1"/></body><body pos="0 0 2"><freejoint/><geom type="{t}" size=".1 .1 .1"/></body>'
   xml = "<mujoco><worldbody>" + two.format(t="box") + "</worldbody></mujoco>"
   with pytest.raises(NotImplementedError, match="nativeccd"):
     mio.derive_tables(mjcf.load_string(xml))
   mio.derive_tables(mjcf.load_string(xml.replace("<worldbody>", '<option><flag nativeccd="disable"/></option><worldbody>')))
+  # cylinder-box goes through the GJK / EPA pass
   xml = "<mujoco><worldbody>" + two.format(t="cylinder") + "</worldbody></mujoco>"
-  with pytest.raises(NotImplementedError, match="collision between geom types"):
-    mio.derive_tables(mjcf.load_string(xml))
+  assert mio.derive_tables(mjcf.load_string(xml))["has_convex_pair"] == 1
 
 
 def test_shard_worlds():
