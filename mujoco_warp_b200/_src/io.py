@@ -190,19 +190,32 @@ def derive_tables(mjm) -> dict:
     return (i * (2 * C.NGEOMTYPES - i - 1)) // 2 + j
 
   t["has_convex_pair"] = 0
+  nboxbox = nconvex = 0
   counts = np.zeros(C.NGEOMTYPES * (C.NGEOMTYPES + 1) // 2, dtype=int)
   for a, b in t["nxn_geom_pair_filtered"]:
     counts[trid(gt[a], gt[b])] += 1
     key = (min(gt[a], gt[b]), max(gt[a], gt[b]))
     if key == (C.GEOM_BOX, C.GEOM_BOX):
-      # box-box is a primitive pair only with native CCD disabled (collision_driver.py:868-870); GJK/EPA is not implemented here
+      # box-box is a primitive pair only with native CCD disabled (collision_driver.py:868-870); otherwise GJK / EPA + multi-contact
       if not (int(mjm.opt.disableflags) & C.DSBL_NATIVECCD):
-        raise NotImplementedError('box-box collisions need <flag nativeccd="disable"/> (primitive box-box); the GJK/EPA convex path is not implemented')
+        t["has_convex_pair"] = 1
+        nboxbox += 1
+        nconvex += 1
     elif key in _CONVEX_PAIRS:
       t["has_convex_pair"] = 1
+      nconvex += 1
     elif key not in _SUPPORTED_PAIRS:
       raise NotImplementedError(f"collision between geom types {key} is not implemented in this version (supported: {sorted(_SUPPORTED_PAIRS | _CONVEX_PAIRS)})")
   t["geom_pair_type_count"] = tuple(int(c) for c in counts)
+  # EPA gets 16 iterations when every convex pair of the model is box-box (collision_convex.py:1223)
+  t["epa_iterations"] = 16 if nboxbox == nconvex else int(getattr(mjm.opt, "ccd_iterations", 35))
+  if nboxbox:  # reference io.py:685-712: native box-box CCD does not support margins
+    for a, b in t["nxn_geom_pair_filtered"]:
+      if gt[a] == C.GEOM_BOX and gt[b] == C.GEOM_BOX and (float(mjm.geom_margin[a]) != 0.0 or float(mjm.geom_margin[b]) != 0.0):
+        raise NotImplementedError("box-box geom pair has non-zero margin with NATIVECCD enabled. Set margin to 0 or disable NATIVECCD.")
+    for i in range(int(getattr(mjm, "npair", 0))):
+      if gt[mjm.pair_geom1[i]] == C.GEOM_BOX and gt[mjm.pair_geom2[i]] == C.GEOM_BOX and float(mjm.pair_margin[i]) != 0.0:
+        raise NotImplementedError("box-box contact pair has non-zero margin with NATIVECCD enabled. Set margin to 0 or disable NATIVECCD.")
   # constraint source lists
   jt = _np(mjm, "jnt_type")
   lim = np.asarray(_np(mjm, "jnt_limited")).astype(bool)
@@ -375,7 +388,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
-    nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
+    nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), epa_iterations=t["epa_iterations"], neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))

@@ -36,7 +36,7 @@ __host__ __device__ inline ColLayout col_layout(const ModelDev& m, const DataDev
   L.surv = take(surv_cap(m));
   L.stage = take(STAGE_WORDS * world_con_cap(d));
   L.sgeom = take(4 * world_con_cap(d));  // g1, g2, geomcollisionid, pairid
-  L.ccd = take(m.has_convex_pair ? CCD_LANES * ccd_scratch_words(m.ccd_iterations) : 0);
+  L.ccd = take(m.has_convex_pair ? CCD_LANES * ccd_scratch_words(m.epa_iterations) : 0);
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -203,9 +203,10 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
   int ncon = 0;
   if (MAXC >= 8 && m.has_convex_pair) {
     float* ccd_scratch = S + L.ccd;
-    const int sw = ccd_scratch_words(m.ccd_iterations);
+    const int sw = ccd_scratch_words(m.epa_iterations);
+    const bool nativeccd = !(m.disableflags & DSBL_NATIVECCD);
 #pragma unroll 1
-    for (int rank = 0; rank < 8; rank++) {
+    for (int rank = 0; rank < CCD_NRANK; rank++) {
 #pragma unroll 1
       for (int s0 = 0; s0 < nsurv; s0 += 32) {
         const int si = s0 + lane;
@@ -215,7 +216,7 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
           const int e = surv[si];
           g1 = m.nxn_geom_pair[2 * e]; g2 = m.nxn_geom_pair[2 * e + 1];
           if (m.geom_type[g1] > m.geom_type[g2]) { const int t = g1; g1 = g2; g2 = t; }
-          mine = convex_rank(m.geom_type[g1], m.geom_type[g2]) == rank;
+          mine = convex_rank(m.geom_type[g1], m.geom_type[g2], nativeccd) == rank;
           pid = m.npair > 0 ? m.nxn_pairid[2 * e] : -1;
         }
         unsigned todo = __ballot_sync(FULL_MASK, mine);
@@ -224,9 +225,9 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
           for (int k = 0; k < CCD_LANES && t; k++) { batch |= t & (0u - t); t &= t - 1; }
           todo &= ~batch;
           const bool active = (batch >> lane) & 1u;
-          bool hit = false;
+          int nhit = 0;  // contacts of this lane's pair (box pairs recover up to 4)
           float dist = 0.f;
-          v3 pos = mk3(0.f, 0.f, 0.f), nrm = mk3(1.f, 0.f, 0.f);
+          v3 w1[4], w2[4], nrm = mk3(1.f, 0.f, 0.f);
           if (active) {
             const int slot = __popc(batch & ((1u << lane) - 1u));
             const float margin = pid > -1 ? m.pair_margin[pid] : m.geom_margin[g1] + m.geom_margin[g2];
@@ -234,28 +235,33 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
             CGeom a, b;
             a.pos = ld3(gxpos + 3 * g1); a.rot = gxmat + 9 * g1; a.size = ld3(m.geom_size + 3 * g1); a.margin = margin; a.type = m.geom_type[g1];
             b.pos = ld3(gxpos + 3 * g2); b.rot = gxmat + 9 * g2; b.size = ld3(m.geom_size + 3 * g2); b.margin = margin; b.type = m.geom_type[g2];
-            v3 x1, x2;
             bool eovf = false;
-            const int nc = ccd_pair(m.ccd_tolerance, gap, m.ccd_iterations, a, b, ccd_scratch + slot * sw, &dist, &x1, &x2, &eovf);
+            const int nc = ccd_pair(m.ccd_tolerance, gap, m.ccd_iterations, m.epa_iterations, a, b, ccd_scratch + slot * sw, &dist, w1, w2, &eovf);
             if (eovf) ovf |= OVF_EPA_HORIZON;
-            if (nc > 0 && dist < gap) {  // collision_convex.py:860-868, 935-940
+            if (nc > 0 && dist < gap) {  // collision_convex.py:860-868, 935-943
               dist += margin;
-              nrm = dist <= margin ? x1 - x2 : x2 - x1;
-              pos = (x1 + x2) * 0.5f;
-              hit = dist < margin + gap;  // write_contact
+              nrm = dist <= margin ? w1[0] - w2[0] : w2[0] - w1[0];
+              if (dist < margin + gap) nhit = nc;  // write_contact
             }
           }
-          const unsigned hb = __ballot_sync(FULL_MASK, hit);
-          if (hit) {
-            const int off = ncon + __popc(hb & ((1u << lane) - 1u));
+          // pairs keep their list order: exclusive scan of the per-lane contact counts over the batch
+          int before = 0, total = 0;
+          for (unsigned bb = batch; bb; bb &= bb - 1) {
+            const int src = __ffs(bb) - 1;
+            const int c = __shfl_sync(FULL_MASK, nhit, src);
+            if (src < lane) before += c;
+            total += c;
+          }
+          for (int k = 0; k < nhit; k++) {
+            const int off = ncon + before + k;
             if (off < ccap) {
               float* st = stage + STAGE_WORDS * off;
-              st[0] = dist; st3(st + 1, pos);
+              st[0] = dist; st3(st + 1, (w1[k] + w2[k]) * 0.5f);
               make_frame(nrm, st + 4);
-              sgeom[4 * off] = g1; sgeom[4 * off + 1] = g2; sgeom[4 * off + 2] = 0; sgeom[4 * off + 3] = pid;
+              sgeom[4 * off] = g1; sgeom[4 * off + 1] = g2; sgeom[4 * off + 2] = k; sgeom[4 * off + 3] = pid;
             }
           }
-          ncon += __popc(hb);
+          ncon += total;
         }
       }
     }
@@ -345,7 +351,7 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
           cd[0] = sphere_box(pos1, size1.x, pos2, rot2, size2, &cp[0], &cn[0]);
         } else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) {
           capsule_box(pos1, ax1, size1.x, size1.y, pos2, rot2, size2, cd, cp, cn);
-        } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {  // primitive box-box: put_model requires the nativeccd disable flag
+        } else if (t1 == GEOM_BOX && t2 == GEOM_BOX && (m.disableflags & DSBL_NATIVECCD)) {  // primitive box-box only with native CCD disabled
           v3 nn;
           const int nc = box_box(pos1, rot1, size1, pos2, rot2, size2, margin, cd, cp, &nn);
           for (int k = 0; k < MAXC; k++) { cn[k] = nn; if (k >= nc) cd[k] = INFINITY; }

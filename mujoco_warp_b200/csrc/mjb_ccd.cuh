@@ -2,8 +2,9 @@
 //
 // Replaces /root/reference/mujoco_warp/_src/collision_gjk.py: :115 support, :281-594 distance sub-algorithm (S1D / S2D / S3D),
 // :635 gjk, :1021-1286 polytope construction, :1319 _epa, :947 _epa_witness, :2303 _inflate, :2350 gjk_phase,
-// :2421 epa_phase (sphere, capsule, ellipsoid, cylinder, box; meshes, height fields and the multi-contact clipping of
-// box / mesh pairs are not built yet).  The EPA polytope lives in a per-lane slice of shared memory supplied by the caller.
+// :2421 epa_phase, :2076 multicontact (sphere, capsule, ellipsoid, cylinder, box; meshes and height fields are not built).
+// The EPA polytope lives in a per-lane slice of shared memory supplied by the caller; the multi-contact clipping of box
+// pairs reuses that slice for its polygon buffers once EPA has finished.
 #pragma once
 #include "mjb_colliders.cuh"
 #include "mjb_math.cuh"
@@ -18,11 +19,16 @@
 #define CCD_MAX_EPAHORIZON 24
 #define CCD_FACE_DELETED 0x80000000u
 #define CCD_FACE_INVALID 0x40000000u
+#define CCD_MIN_EPATOL 1e-7f
+#define CCD_MINVAL2 1e-30f
+#define CCD_FACE_TOL 0.99999872f       // cos(0.0016)
+#define CCD_EDGE_TOL 0.00159999931f    // sin(0.0016)
+#define CCD_INTERSECT_TOL 0.0000003f
 
 // Geom-type pairs the reference routes to the convex path (collision_driver.py:47-81), analytic geoms only, in table order.
-// Box-box is convex there too but needs the multi-contact clipping; put_model only admits it with nativeccd disabled
-// (primitive box_box).
-__host__ __device__ inline int convex_rank(int t1, int t2) {
+// Box-box is convex unless the nativeccd disable flag routes it to the primitive box_box.
+#define CCD_NRANK 9
+__host__ __device__ inline int convex_rank(int t1, int t2, bool nativeccd) {
   if (t1 == GEOM_SPHERE && t2 == GEOM_ELLIPSOID) return 0;
   if (t1 == GEOM_CAPSULE && t2 == GEOM_ELLIPSOID) return 1;
   if (t1 == GEOM_CAPSULE && t2 == GEOM_CYLINDER) return 2;
@@ -31,14 +37,15 @@ __host__ __device__ inline int convex_rank(int t1, int t2) {
   if (t1 == GEOM_ELLIPSOID && t2 == GEOM_BOX) return 5;
   if (t1 == GEOM_CYLINDER && t2 == GEOM_CYLINDER) return 6;
   if (t1 == GEOM_CYLINDER && t2 == GEOM_BOX) return 7;
+  if (t1 == GEOM_BOX && t2 == GEOM_BOX && nativeccd) return 8;
   return -1;
 }
 
 struct CGeom { v3 pos; const float* rot; v3 size; float margin; int type; };
-struct GjkRes { bool separated; int dim; float dist; v3 x1, x2, s[4], s1[4], s2[4]; };
+struct GjkRes { bool separated; int dim; float dist; v3 x1, x2, s[4], s1[4], s2[4]; int vi[4]; };  // vi: box corner ids, geom1 | geom2 << 4
 // words of shared memory one lane's polytope needs: vertices (2 per support pair), faces, face projections, squared norms, horizon
 __host__ __device__ inline int ccd_scratch_words(int iterations) {
-  return 3 * (10 + 2 * iterations) + 5 * (6 + CCD_MAX_EPAFACES * iterations) + CCD_MAX_EPAHORIZON;
+  return 3 * (10 + 2 * iterations) + 5 * (6 + CCD_MAX_EPAFACES * iterations) + CCD_MAX_EPAHORIZON + (5 + iterations);
 }
 struct Polytope {
   int status, nvert, nface, nhorizon, maxface;
@@ -48,15 +55,19 @@ struct Polytope {
   float* face_pr;    // 3 * maxface
   float* face_norm2; // maxface
   int* horizon;      // CCD_MAX_EPAHORIZON
+  int* vidx;         // 5 + it: box corner ids of each support pair (geom1 | geom2 << 4)
 };
 
 __device__ __forceinline__ float csign(float x) { return x < 0.f ? -1.f : 1.f; }  // wp.sign(0) = +1
 
-__device__ v3 ccd_support(const CGeom& g, v3 dir) {
+__device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr) {
   if (g.type == GEOM_SPHERE) return g.pos + dir * (g.size.x + 0.5f * g.margin);
   const v3 ld = mat_t_vec(g.rot, dir);
   v3 res = mk3(0.f, 0.f, 0.f);
-  if (g.type == GEOM_BOX) res = mk3(csign(ld.x) * g.size.x, csign(ld.y) * g.size.y, csign(ld.z) * g.size.z);
+  if (g.type == GEOM_BOX) {
+    res = mk3(csign(ld.x) * g.size.x, csign(ld.y) * g.size.y, csign(ld.z) * g.size.z);
+    if (vindex) *vindex = (ld.x >= 0.f ? 1 : 0) | (ld.y >= 0.f ? 2 : 0) | (ld.z >= 0.f ? 4 : 0);  // :128-137 corner id
+  }
   else if (g.type == GEOM_CAPSULE) { res = ld * g.size.x; res.z += csign(ld.z) * g.size.y; }
   else if (g.type == GEOM_ELLIPSOID) res = cw_mul(normalize(cw_mul(ld, g.size)), g.size);
   else if (g.type == GEOM_CYLINDER) {
@@ -146,20 +157,37 @@ __device__ __forceinline__ v3 lin_comb(int n, const float* l, const v3* m) {
   return o;
 }
 
-// collision_gjk.py:635 with is_discrete = false (analytic geoms)
-__device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const CGeom& g2, float cutoff, GjkRes& r) {
+// collision_gjk.py:635; discrete (box pairs without margin) drops the tolerances and tracks box corner ids (:662-663)
+__device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const CGeom& g2, float cutoff, bool discrete, GjkRes& r) {
   float lmbda[4] = {1.f, 0.f, 0.f, 0.f};
-  const float epsilon = 0.5f * tolerance * tolerance;
+  const float epsilon = discrete ? 0.f : 0.5f * tolerance * tolerance, min_norm = discrete ? CCD_MINVAL : tolerance;
   int n = 0;
   v3 x_k = g1.pos - g2.pos;
   float xnorm = sqrtf(dot(x_k, x_k)), xnorm_prev = 0.f;
   r.separated = false; r.dim = 0; r.dist = 0.f; r.x1 = r.x2 = mk3(0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int it = 0; it < iterations; it++) {
-    if (xnorm < tolerance || fabsf(xnorm_prev - xnorm) < CCD_MINVAL) break;
-    const v3 dir_neg = x_k * (1.0f / xnorm);
-    r.s1[n] = ccd_support(g1, dir_neg * -1.0f);
-    r.s2[n] = ccd_support(g2, dir_neg);
+    if (xnorm < min_norm || fabsf(xnorm_prev - xnorm) < CCD_MINVAL) break;
+    v3 dir_neg = x_k * (1.0f / xnorm);
+    if (discrete && xnorm < 1e-4f) {  // :609-627 the search direction is noisy near the origin: rebuild it from the simplex
+      if (n == 2) {
+        const v3 edge = r.s[1] - r.s[0];
+        const float en2 = dot(edge, edge);
+        if (en2 > CCD_MINVAL2) {
+          dir_neg = dir_neg - edge * (dot(dir_neg, edge) / en2);
+          const float dn = length(dir_neg);
+          if (dn > CCD_MINVAL) dir_neg = dir_neg * (1.0f / dn);
+        }
+      } else if (n == 3) {
+        const v3 nrm = cross(r.s[1] - r.s[0], r.s[2] - r.s[0]);
+        const float nn = length(nrm);
+        if (nn > CCD_MINVAL) dir_neg = nrm * (csign(dot(dir_neg, nrm)) / nn);
+      }
+    }
+    int i1 = 0, i2 = 0;
+    r.s1[n] = ccd_support(g1, dir_neg * -1.0f, &i1);
+    r.s2[n] = ccd_support(g2, dir_neg, &i2);
+    r.vi[n] = i1 | (i2 << 4);
     r.s[n] = r.s1[n] - r.s2[n];
     if (dot(x_k, x_k - r.s[n]) < epsilon) break;
     const float lower = dot(x_k, r.s[n]);
@@ -173,7 +201,7 @@ __device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const 
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (lmbda[i] == 0.f) continue;
-      r.s[n] = r.s[i]; r.s1[n] = r.s1[i]; r.s2[n] = r.s2[i]; lmbda[n] = lmbda[i];
+      r.s[n] = r.s[i]; r.s1[n] = r.s1[i]; r.s2[n] = r.s2[i]; r.vi[n] = r.vi[i]; lmbda[n] = lmbda[i];
       n++;
     }
     if (n < 1) break;
@@ -222,15 +250,17 @@ __device__ float attach_face(Polytope& pt, int idx, int v1, int v2, int v3_) {
   return n2;
 }
 __device__ void epa_support(Polytope& pt, int idx, const CGeom& g1, const CGeom& g2, v3 dir) {
-  st3(pt.vert + 6 * idx, ccd_support(g1, dir));
-  st3(pt.vert + 6 * idx + 3, ccd_support(g2, dir * -1.0f));
+  int i1 = 0, i2 = 0;
+  st3(pt.vert + 6 * idx, ccd_support(g1, dir, &i1));
+  st3(pt.vert + 6 * idx + 3, ccd_support(g2, dir * -1.0f, &i2));
+  pt.vidx[idx] = i1 | (i2 << 4);
 }
 __device__ void replace_simplex3(const Polytope& pt, int v1, int v2, int v3_, GjkRes& r) {
   const int v[3] = {v1, v2, v3_};
-  for (int k = 0; k < 3; k++) { r.s1[k] = pt_v1(pt, v[k]); r.s2[k] = pt_v2(pt, v[k]); r.s[k] = r.s1[k] - r.s2[k]; }
+  for (int k = 0; k < 3; k++) { r.s1[k] = pt_v1(pt, v[k]); r.s2[k] = pt_v2(pt, v[k]); r.s[k] = r.s1[k] - r.s2[k]; r.vi[k] = pt.vidx[v[k]]; }
 }
 __device__ void load_simplex(Polytope& pt, const GjkRes& r, int n) {
-  for (int k = 0; k < n; k++) { st3(pt.vert + 6 * k, r.s1[k]); st3(pt.vert + 6 * k + 3, r.s2[k]); }
+  for (int k = 0; k < n; k++) { st3(pt.vert + 6 * k, r.s1[k]); st3(pt.vert + 6 * k + 3, r.s2[k]); pt.vidx[k] = r.vi[k]; }
 }
 __device__ void polytope2(Polytope& pt, GjkRes& r, const CGeom& g1, const CGeom& g2) {
   const v3 diff = r.s[1] - r.s[0];
@@ -308,8 +338,9 @@ __device__ int add_edge(Polytope& pt, int e1, int e2) {
   return n + 1;
 }
 // :1319 _epa + :947 witness points; returns the closest face index or -1
-__device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeom& g1, const CGeom& g2, float* dist, v3* x1, v3* x2, bool* ovf) {
+__device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeom& g1, const CGeom& g2, bool discrete, float* dist, v3* x1, v3* x2, bool* ovf) {
   float upper = CCD_FLOAT_MAX, upper2 = CCD_FLOAT_MAX;
+  const float epsilon = discrete ? CCD_MIN_EPATOL : tolerance;
   int idx = -1, pidx = -1, nvalid = pt.nface;
   iterations = min(iterations, 1000);
 #pragma unroll 1
@@ -327,7 +358,12 @@ __device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeo
     pt.nvert++;
     const float upper_k = dot(fp, w) / lower;
     if (upper_k < upper) { upper = upper_k; upper2 = upper * upper; }
-    if (upper - lower < tolerance) break;
+    if (upper - lower < epsilon) break;
+    if (discrete) {  // :1377-1385 a repeated support point ends the expansion
+      bool rep = false;
+      for (int i = 0; i < wi; i++) if (pt.vidx[i] == pt.vidx[wi]) { rep = true; break; }
+      if (rep) break;
+    }
     nvalid--;
     pt.face[idx] |= CCD_FACE_DELETED;
     { const unsigned f = pt.face[idx]; const int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
@@ -367,43 +403,244 @@ __device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeo
   return -1;
 }
 
-// gjk_phase (:2350) + epa_phase (:2421).  Returns the number of contacts (0 / 1); *dist is relative to the margin-inflated shapes.
-__device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int iterations, CGeom g1, CGeom g2, float* scratch, float* dist, v3* x1, v3* x2, bool* ovf) {
+// ---- multi-contact recovery for box pairs (collision_gjk.py:1503 _feature_dim, :1703-1888 box normals / edges / faces,
+// :1916-2056 polygon clipping, :2076 multicontact; mesh branches not built)
+struct BoxFeat { int dim, idx[3]; v3 v0, v1; };
+__device__ BoxFeat feature_dim(const Polytope& pt, const int* face, int which) {
+  BoxFeat f;
+  const int sh = which ? 4 : 0;
+  const int a = (pt.vidx[face[0]] >> sh) & 15, b = (pt.vidx[face[1]] >> sh) & 15, c = (pt.vidx[face[2]] >> sh) & 15;
+  f.idx[0] = a; f.idx[1] = b; f.idx[2] = c;
+  f.v0 = ld3(pt.vert + 6 * face[0] + 3 * which);
+  f.v1 = ld3(pt.vert + 6 * face[1] + 3 * which);
+  if (a != b) { f.dim = (c == a || c == b) ? 2 : 3; return f; }
+  f.idx[1] = c; f.v1 = ld3(pt.vert + 6 * face[2] + 3 * which);
+  f.dim = a != c ? 2 : 1;
+  return f;
+}
+__device__ __forceinline__ v3 box_face_normal(int i) { return mk3(i == 0 ? 1.f : (i == 1 ? -1.f : 0.f), i == 2 ? 1.f : (i == 3 ? -1.f : 0.f), i == 4 ? 1.f : (i == 5 ? -1.f : 0.f)); }
+__device__ int box_normals2(const float* mat, v3 n, v3* nout, int* iout) {
+  const v3 ln = normalize(mat_t_vec(mat, n));
+  for (int i = 0; i < 6; i++) if (dot(ln, box_face_normal(i)) > CCD_FACE_TOL) { nout[0] = matvec(mat, box_face_normal(i)); iout[0] = i; return 1; }
+  return 0;
+}
+__device__ __forceinline__ float bit_axis(int a, int b, int c, int bit) {  // +1 when every corner has the bit, -1 when none has it
+  return (float)(((a & bit) && (b & bit) && (c & bit)) ? 1 : 0) - (float)((!(a & bit) && !(b & bit) && !(c & bit)) ? 1 : 0);
+}
+__device__ int box_normals(const BoxFeat& f, const float* mat, v3 dir, v3* nout, int* iout) {
+  const int v1 = f.idx[0], v2 = f.idx[1], v3i = f.idx[2];
+  if (f.dim == 3) {
+    int c = 0;
+    const float x = bit_axis(v1, v2, v3i, 1), y = bit_axis(v1, v2, v3i, 2), z = bit_axis(v1, v2, v3i, 4);
+    nout[0] = matvec(mat, mk3(x, y, z));
+    if (x != 0.f) iout[c++] = 0;
+    if (y != 0.f) iout[c++] = 2;
+    if (z != 0.f) iout[c++] = 4;
+    if (x + y + z == -1.f) iout[0] = iout[0] + 1;
+    if (c == 1) return 1;
+    return box_normals2(mat, dir, nout, iout);
+  }
+  if (f.dim == 2) {
+    int c = 0;
+    const float x = bit_axis(v1, v2, v2, 1), y = bit_axis(v1, v2, v2, 2), z = bit_axis(v1, v2, v2, 4);
+    if (x != 0.f) { nout[c] = matvec(mat, mk3(x, 0.f, 0.f)); iout[c] = x > 0.f ? 0 : 1; c++; }
+    if (y != 0.f) { nout[c] = matvec(mat, mk3(0.f, y, 0.f)); iout[c] = y > 0.f ? 2 : 3; c++; }
+    if (z != 0.f) { nout[c] = matvec(mat, mk3(0.f, 0.f, z)); iout[c] = z > 0.f ? 4 : 5; c++; }
+    if (c == 1 || c == 2) return c;  // 1: diagonal of a face, 2: an edge of the box
+    return box_normals2(mat, dir, nout, iout);
+  }
+  if (f.dim == 1) {
+    const float x = (v1 & 1) ? 1.f : -1.f, y = (v1 & 2) ? 1.f : -1.f, z = (v1 & 4) ? 1.f : -1.f;
+    nout[0] = matvec(mat, mk3(x, 0.f, 0.f)); nout[1] = matvec(mat, mk3(0.f, y, 0.f)); nout[2] = matvec(mat, mk3(0.f, 0.f, z));
+    iout[0] = x > 0.f ? 0 : 1; iout[1] = y > 0.f ? 2 : 3; iout[2] = z > 0.f ? 4 : 5;
+    return 3;
+  }
+  return 0;
+}
+__device__ int box_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3* endvert) {
+  if (f.dim == 2) { endvert[0] = f.v1; nout[0] = normalize(f.v1 - f.v0); return 1; }
+  if (f.dim == 1) {
+    const int vi = f.idx[0];
+    const float x = (vi & 1) ? g.size.x : -g.size.x, y = (vi & 2) ? g.size.y : -g.size.y, z = (vi & 4) ? g.size.z : -g.size.z;
+    endvert[0] = matvec(g.rot, mk3(-x, y, z)) + g.pos; nout[0] = normalize(endvert[0] - f.v0);
+    endvert[1] = matvec(g.rot, mk3(x, -y, z)) + g.pos; nout[1] = normalize(endvert[1] - f.v0);
+    endvert[2] = matvec(g.rot, mk3(x, y, -z)) + g.pos; nout[2] = normalize(endvert[2] - f.v0);
+    return 3;
+  }
+  return 0;
+}
+__device__ int box_face(const CGeom& g, int idx, v3* face) {
+  if (idx < 0 || idx > 5) return 0;
+  // corner k of face idx, as signs of (x, y, z): one byte per face, bit (3 k + axis)
+  const float sx = g.size.x, sy = g.size.y, sz = g.size.z;
+  v3 l[4];
+  switch (idx) {
+    case 0: l[0] = mk3(sx, sy, sz); l[1] = mk3(sx, sy, -sz); l[2] = mk3(sx, -sy, -sz); l[3] = mk3(sx, -sy, sz); break;
+    case 1: l[0] = mk3(-sx, sy, -sz); l[1] = mk3(-sx, sy, sz); l[2] = mk3(-sx, -sy, sz); l[3] = mk3(-sx, -sy, -sz); break;
+    case 2: l[0] = mk3(-sx, sy, -sz); l[1] = mk3(sx, sy, -sz); l[2] = mk3(sx, sy, sz); l[3] = mk3(-sx, sy, sz); break;
+    case 3: l[0] = mk3(-sx, -sy, sz); l[1] = mk3(sx, -sy, sz); l[2] = mk3(sx, -sy, -sz); l[3] = mk3(-sx, -sy, -sz); break;
+    case 4: l[0] = mk3(-sx, sy, sz); l[1] = mk3(sx, sy, sz); l[2] = mk3(sx, -sy, sz); l[3] = mk3(-sx, -sy, sz); break;
+    default: l[0] = mk3(sx, sy, -sz); l[1] = mk3(-sx, sy, -sz); l[2] = mk3(-sx, -sy, -sz); l[3] = mk3(sx, -sy, -sz); break;
+  }
+  for (int k = 0; k < 4; k++) face[k] = matvec(g.rot, l[k]) + g.pos;
+  return 4;
+}
+__device__ __forceinline__ float area4(v3 a, v3 b, v3 c, v3 d) { return 0.5f * length(cross(a - d, d - b) + cross(b - c, c - a)); }
+__device__ void polygon_quad(const float* poly, int np, int* res) {  // :1463 maximum-area quadrilateral of a convex polygon
+  int b = 1, c = 2, d = 3;
+  res[0] = 0; res[1] = b; res[2] = c; res[3] = d;
+  float m = area4(ld3(poly), ld3(poly + 3 * b), ld3(poly + 3 * c), ld3(poly + 3 * d));
+  for (int a = 0; a < np; a++) {
+    for (int guard = 0; guard < 64; guard++) {
+      float mn = area4(ld3(poly + 3 * a), ld3(poly + 3 * b), ld3(poly + 3 * c), ld3(poly + 3 * ((d + 1) % np)));
+      if (mn <= m) break;
+      m = mn; d = (d + 1) % np; res[0] = a; res[1] = b; res[2] = c; res[3] = d;
+      for (int g2 = 0; g2 < 64; g2++) {
+        mn = area4(ld3(poly + 3 * a), ld3(poly + 3 * b), ld3(poly + 3 * ((c + 1) % np)), ld3(poly + 3 * d));
+        if (mn <= m) break;
+        m = mn; c = (c + 1) % np; res[0] = a; res[1] = b; res[2] = c; res[3] = d;
+      }
+      for (int g3 = 0; g3 < 64; g3++) {
+        mn = area4(ld3(poly + 3 * a), ld3(poly + 3 * ((b + 1) % np)), ld3(poly + 3 * c), ld3(poly + 3 * d));
+        if (mn <= m) break;
+        m = mn; b = (b + 1) % np; res[0] = a; res[1] = b; res[2] = c; res[3] = d;
+      }
+    }
+    if (b == a) { b = (b + 1) % np; if (c == b) { c = (c + 1) % np; if (d == c) d = (d + 1) % np; } }
+  }
+}
+// :1941 clip polygon face2 against the side planes of face1 (extruded along n).  witness2 lies on the clipped polygon,
+// witness1 = witness2 - dir.  buf: 48 words (two 8-vertex polygons).
+__device__ int polygon_clip(const v3* face1, int nface1, const v3* face2, int nface2, v3 n, v3 dir, float* buf, v3* w1, v3* w2) {
+  if (nface1 < 3) return 0;
+  float* poly = buf;
+  float* clip = buf + 24;
+  int np = nface2, nc = 0;
+  for (int i = 0; i < nface2; i++) st3(poly + 3 * i, face2[i]);
+  for (int e = 0; e < nface1; e++) {
+    const v3 a = face1[e], b = face1[(e + 1) % nface1];
+    const v3 pn = cross(b - a, (a + n) - a);  // :1916 _plane_normal
+    const float pd = dot(pn, a);
+    for (int i = 0; i < np; i++) {
+      const v3 P = ld3(poly + 3 * i), Q = ld3(poly + 3 * ((i + 1) % np));
+      const bool in1 = dot(P - a, pn) > -1e-10f, in2 = dot(Q - a, pn) > -1e-10f;
+      if (!in1 && !in2) continue;
+      if (in1 && in2) { if (nc < 8) st3(clip + 3 * nc, Q); nc++; continue; }
+      const v3 pq = Q - P;
+      const float dt = dot(pn, pq);
+      float t = fabsf(dt) < 1e-10f ? CCD_FLOAT_MAX : (pd - dot(pn, P)) / dt;
+      if (t > -CCD_INTERSECT_TOL && t < 1.f + CCD_INTERSECT_TOL) {
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        if (nc < 8) st3(clip + 3 * nc, P + pq * t);
+        nc++;
+      }
+      if (in2) { if (nc < 8) st3(clip + 3 * nc, Q); nc++; }
+    }
+    float* tmp = poly; poly = clip; clip = tmp;
+    np = min(nc, 8); nc = 0;
+  }
+  if (np < 1) return 0;
+  if (nface2 == 2 && np > 2) {  // an edge: keep the two points farthest apart
+    int b1 = 0, b2 = 1;
+    float maxd = 0.f;
+    for (int i = 0; i < np; i++) for (int j = i + 1; j < np; j++) {
+      const v3 df = ld3(poly + 3 * j) - ld3(poly + 3 * i);
+      const float d2 = dot(df, df);
+      if (d2 > maxd) { maxd = d2; b1 = i; b2 = j; }
+    }
+    w2[0] = ld3(poly + 3 * b1); w1[0] = w2[0] - dir; w2[1] = ld3(poly + 3 * b2); w1[1] = w2[1] - dir;
+    return 2;
+  }
+  if (np > 4) {
+    int q[4];
+    polygon_quad(poly, np, q);
+    for (int i = 0; i < 4; i++) { w2[i] = ld3(poly + 3 * q[i]); w1[i] = w2[i] - dir; }
+    return 4;
+  }
+  for (int i = 0; i < np; i++) { w2[i] = ld3(poly + 3 * i); w1[i] = w2[i] - dir; }
+  return np;
+}
+// :2076 for two boxes.  Overwrites the witness arrays (4 each) and returns the contact count; buf must not alias pt.vert / pt.vidx.
+__device__ int ccd_multicontact(const Polytope& pt, int epa_face, const CGeom& g1, const CGeom& g2, float* buf, v3* w1, v3* w2) {
+  const v3 x1 = w1[0], x2 = w2[0];
+  for (int k = 1; k < 4; k++) w1[k] = w2[k] = mk3(0.f, 0.f, 0.f);
+  const unsigned fw = pt.face[epa_face];
+  const int face[3] = {(int)(fw & 0x3FF), (int)((fw >> 10) & 0x3FF), (int)((fw >> 20) & 0x3FF)};
+  const BoxFeat f1 = feature_dim(pt, face, 0), f2 = feature_dim(pt, face, 1);
+  const v3 ev1 = ld3(pt.vert + 6 * face[0]), ev2 = ld3(pt.vert + 6 * face[0] + 3);
+  const v3 dir = x2 - x1;
+  v3 n1[3], n2[3], endvert[3];
+  int idx1[3] = {0, 0, 0}, idx2[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++) n1[k] = n2[k] = endvert[k] = mk3(0.f, 0.f, 0.f);
+  int nn1 = box_normals(f1, g1.rot, dir * -1.0f, n1, idx1), nn2 = box_normals(f2, g2.rot, dir, n2, idx2);
+  bool edge1 = false, edge2 = false, found = false;
+  int ri = 0, rj = 0;
+  for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (dot(n1[i], n2[j]) < -CCD_FACE_TOL) { ri = i; rj = j; found = true; break; }
+  if (!found) {
+    if (f1.dim < 3 && f1.dim <= f2.dim) {  // edge of geom1 against a face of geom2
+      nn1 = box_edge_normals(f1, g1, n1, endvert);
+      for (int i = 0; i < nn2 && !found; i++) for (int j = 0; j < nn1; j++) if (fabsf(dot(n1[j], n2[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = true; break; }
+      if (!found) return 1;
+      edge1 = true;
+    } else if (f2.dim < 3) {  // face of geom1 against an edge of geom2
+      nn2 = box_edge_normals(f2, g2, n2, endvert);
+      for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (fabsf(dot(n2[j], n1[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = true; break; }
+      if (!found) return 1;
+      edge2 = true;
+    } else return 1;
+  }
+  v3 face1[4], face2[4];
+  int nface1, nface2;
+  if (edge1) { face1[0] = ev1; face1[1] = endvert[ri]; nface1 = 2; } else nface1 = box_face(g1, edge2 ? idx1[rj] : idx1[ri], face1);
+  if (edge2) { face2[0] = ev2; face2[1] = endvert[ri]; nface2 = 2; } else nface2 = box_face(g2, idx2[rj], face2);
+  const float dl = length(dir);
+  if (edge1) return polygon_clip(face2, nface2, face1, nface1, n2[rj], n2[rj] * -dl, buf, w2, w1);  // roles flipped, witnesses flipped back
+  if (edge2) return polygon_clip(face1, nface1, face2, nface2, n1[rj], n1[rj] * -dl, buf, w1, w2);
+  return polygon_clip(face1, nface1, face2, nface2, n1[ri], n2[rj] * dl, buf, w1, w2);
+}
+
+// gjk_phase (:2350) + epa_phase (:2421) + multicontact for box pairs.  Returns the number of contacts (0..4, witnesses in
+// w1 / w2, 4 each); *dist is relative to the margin-inflated shapes.
+__device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iterations, int epa_iterations, CGeom g1, CGeom g2, float* scratch, float* dist, v3* w1, v3* w2, bool* ovf) {
   const CGeom o1 = g1, o2 = g2;
   float full1 = 0.f, full2 = 0.f, size1 = 0.f, size2 = 0.f;
+  const bool boxes = g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0.f && g2.margin == 0.f;  // :109 _discrete_geoms
   GjkRes r;
   if (g1.type == GEOM_SPHERE || g1.type == GEOM_CAPSULE) { size1 = g1.size.x; full1 = size1 + 0.5f * g1.margin; g1.margin = 0.f; g1.size.x = 0.f; }
   if (g2.type == GEOM_SPHERE || g2.type == GEOM_CAPSULE) { size2 = g2.size.x; full2 = size2 + 0.5f * g2.margin; g2.margin = 0.f; g2.size.x = 0.f; }
   if (size1 + size2 > 0.f) {
     cutoff += full1 + full2;
-    ccd_gjk(tolerance, iterations, g1, g2, cutoff, r);
+    ccd_gjk(tolerance, gjk_iterations, g1, g2, cutoff, boxes, r);
     if (r.dist > tolerance) {
-      *x1 = r.x1; *x2 = r.x2;
+      w1[0] = r.x1; w2[0] = r.x2;
       if (r.dist == CCD_FLOAT_MAX) { *dist = r.dist; return 1; }
-      const v3 n = normalize(*x2 - *x1);  // :2303 _inflate
-      if (full1 > 0.f) *x1 = *x1 + n * full1;
-      if (full2 > 0.f) *x2 = *x2 - n * full2;
+      const v3 n = normalize(w2[0] - w1[0]);  // :2303 _inflate
+      if (full1 > 0.f) w1[0] = w1[0] + n * full1;
+      if (full2 > 0.f) w2[0] = w2[0] - n * full2;
       *dist = r.dist - (full1 + full2);
       return 1;
     }
     g1 = o1; g2 = o2;
     cutoff -= full1 + full2;
   }
-  ccd_gjk(tolerance, iterations, g1, g2, cutoff, r);
-  if (r.dist > tolerance || r.dim < 2 || r.separated) { *dist = r.dist; *x1 = r.x1; *x2 = r.x2; return 1; }
+  ccd_gjk(tolerance, gjk_iterations, g1, g2, cutoff, boxes, r);
+  if (r.dist > tolerance || r.dim < 2 || r.separated) { *dist = r.dist; w1[0] = r.x1; w2[0] = r.x2; return 1; }
   Polytope pt;
-  const int maxvert = 10 + 2 * iterations;
-  pt.maxface = 6 + CCD_MAX_EPAFACES * iterations;
+  const int maxvert = 10 + 2 * epa_iterations;
+  pt.maxface = 6 + CCD_MAX_EPAFACES * epa_iterations;
   pt.status = 0; pt.nvert = 0; pt.nface = 0; pt.nhorizon = 0;
   pt.vert = scratch;
   pt.face = (unsigned*)(scratch + 3 * maxvert);
   pt.face_pr = scratch + 3 * maxvert + pt.maxface;
   pt.face_norm2 = pt.face_pr + 3 * pt.maxface;
   pt.horizon = (int*)(pt.face_norm2 + pt.maxface);
+  pt.vidx = pt.horizon + CCD_MAX_EPAHORIZON;
   if (r.dim == 2) { polytope2(pt, r, g1, g2); if (pt.status == -1) r.dim = 3; }
   else if (r.dim == 4) { polytope4(pt, r); if (pt.status == -1) r.dim = 3; }
   if (r.dim == 3) { pt.status = 0; polytope3(pt, r, g1, g2); }
-  if (pt.status) { *dist = r.dist; *x1 = r.x1; *x2 = r.x2; return 1; }
-  if (ccd_epa(tolerance, iterations, pt, g1, g2, dist, x1, x2, ovf) == -1) { *dist = CCD_FLOAT_MAX; return 0; }
+  if (pt.status) { *dist = r.dist; w1[0] = r.x1; w2[0] = r.x2; return 1; }
+  const int fidx = ccd_epa(tolerance, epa_iterations, pt, g1, g2, boxes, dist, &w1[0], &w2[0], ovf);
+  if (fidx == -1) { *dist = CCD_FLOAT_MAX; return 0; }
+  if (boxes) return ccd_multicontact(pt, fidx, g1, g2, pt.face_pr, w1, w2);  // face_pr (>= 108 words) is free once EPA is done
   return 1;
 }

@@ -43,7 +43,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
-  X(disableflags) X(enableflags) X(broadphase_filter) X(ccd_iterations)
+  X(disableflags) X(enableflags) X(broadphase_filter) X(ccd_iterations) X(epa_iterations)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(ccd_tolerance)
 #define MODEL_IARRS(X) \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
@@ -1256,9 +1256,11 @@ static int box_box(const real* pos1, const real* rot1, const real* size1, const 
  * restricted to analytic geoms.  Box-box is convex unless the nativeccd disable flag routes it to the primitive. */
 static const int CONVEX_PAIRS[][2] = {{GEOM_SPHERE, GEOM_ELLIPSOID}, {GEOM_CAPSULE, GEOM_ELLIPSOID}, {GEOM_CAPSULE, GEOM_CYLINDER},
   {GEOM_ELLIPSOID, GEOM_ELLIPSOID}, {GEOM_ELLIPSOID, GEOM_CYLINDER}, {GEOM_ELLIPSOID, GEOM_BOX}, {GEOM_CYLINDER, GEOM_CYLINDER},
-  {GEOM_CYLINDER, GEOM_BOX}};
+  {GEOM_CYLINDER, GEOM_BOX}, {GEOM_BOX, GEOM_BOX}};
 #define N_CONVEX_PAIRS ((int)(sizeof CONVEX_PAIRS / sizeof CONVEX_PAIRS[0]))
+static int g_nativeccd = 1; /* set per model in collision(): box-box is convex unless the nativeccd disable flag is set */
 static int convex_pair_rank(int t1, int t2) {
+  if (t1 == GEOM_BOX && t2 == GEOM_BOX && !g_nativeccd) return -1;
   for (int i = 0; i < N_CONVEX_PAIRS; i++) if (CONVEX_PAIRS[i][0] == t1 && CONVEX_PAIRS[i][1] == t2) return i;
   return -1;
 }
@@ -1272,15 +1274,18 @@ static void convex_pair(W* w, int g1, int g2, int pairid) {
   memcpy(b.pos, w->geom_xpos + 3 * g2, sizeof b.pos); memcpy(b.rot, w->geom_xmat + 9 * g2, sizeof b.rot); memcpy(b.size, m->geom_size + 3 * g2, sizeof b.size);
   a.type = m->geom_type[g1]; b.type = m->geom_type[g2];
   a.margin = b.margin = p.margin;
-  real dist, x1[3], x2[3], frame[9], nrm[3], pos[3]; int ovf = 0;
-  int ncon = ccd_pair(m->ccd_tolerance, p.gap, m->ccd_iterations, a, b, &dist, x1, x2, &ovf);
+  real dist, w1[4][3], w2[4][3], frame[9], nrm[3], pos[3]; int ovf = 0;
+  memset(w1, 0, sizeof w1); memset(w2, 0, sizeof w2);
+  int ncon = ccd_pair(m->ccd_tolerance, p.gap, m->ccd_iterations, m->epa_iterations, a, b, &dist, w1, w2, &ovf);
   if (ovf) w->overflow[0] |= OVF_EPA_HORIZON;
   if (ncon == 0 || dist >= p.gap) return;
   dist += p.margin; /* back to the distance between the un-inflated surfaces (collision_convex.py:862-868) */
-  if (dist <= p.margin) v3sub(x1, x2, nrm); else v3sub(x2, x1, nrm);
+  if (dist <= p.margin) v3sub(w1[0], w2[0], nrm); else v3sub(w2[0], w1[0], nrm);
   make_frame(nrm, frame);
-  for (int i = 0; i < 3; i++) pos[i] = (real)0.5 * (x1[i] + x2[i]);
-  write_contact(w, 0, dist, pos, frame, &p, g1, g2);
+  for (int k = 0; k < ncon; k++) {
+    for (int i = 0; i < 3; i++) pos[i] = (real)0.5 * (w1[k][i] + w2[k][i]);
+    write_contact(w, k, dist, pos, frame, &p, g1, g2);
+  }
 }
 
 static void narrowphase_pair(W* w, int g1, int g2, int pairid) {
@@ -1406,6 +1411,7 @@ static void collision(W* w) {
   /* Contact order of the reference under sequential execution: the convex narrowphase runs first, one launch per pair type
    * in table order (collision_driver.py:877, collision_convex.py:1369), then the primitive narrowphase; within a launch,
    * broadphase (pair-list) order.  Pass -1 is the broadphase itself. */
+  g_nativeccd = !(m->disableflags & DSBL_NATIVECCD);
   unsigned char* pass = (unsigned char*)calloc((size_t)(m->nxn_npair > 0 ? m->nxn_npair : 1), 1);
   for (int e = 0; e < m->nxn_npair; e++) {
     int g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];

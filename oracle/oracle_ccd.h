@@ -9,6 +9,11 @@
 #define CCD_MIN_DIST2 ((real)1e-10)
 #define CCD_MIN_DIST3 ((real)1e-10)
 #define CCD_MIN_DIST4 ((real)1e-17)
+#define CCD_MIN_EPATOL ((real)1e-7)
+#define CCD_MINVAL2 ((real)1e-30)
+#define CCD_FACE_TOL ((real)0.99999872) /* cos(0.0016) */
+#define CCD_EDGE_TOL ((real)0.00159999931) /* sin(0.0016) */
+#define CCD_INTERSECT_TOL ((real)0.0000003)
 #define CCD_MAX_EPAFACES 5
 #define CCD_MAX_EPAHORIZON 24
 
@@ -136,15 +141,34 @@ static void linear_combine(int n, const real* l, real m[4][3], real* o) {
 }
 
 /* collision_gjk.py:635 (is_discrete = false for analytic geoms: no direction tuning, tolerance-based stop) */
-static void ccd_gjk(real tolerance, int iterations, const CGeom* g1, const CGeom* g2, const real* x1_0, const real* x2_0, real cutoff, GjkResult* r) {
-  real lmbda[4] = {1, 0, 0, 0}, x_k[3], epsilon = (real)0.5 * tolerance * tolerance, min_norm = tolerance;
+static void ccd_gjk(real tolerance, int iterations, const CGeom* g1, const CGeom* g2, const real* x1_0, const real* x2_0, real cutoff, int discrete, GjkResult* r) {
+  /* discrete pairs (box / mesh, no margin) converge in finitely many steps: no tolerance (collision_gjk.py:662-663) */
+  real lmbda[4] = {1, 0, 0, 0}, x_k[3], epsilon = discrete ? 0 : (real)0.5 * tolerance * tolerance, min_norm = discrete ? CCD_MINVAL : tolerance;
   int n = 0;
   memset(r, 0, sizeof *r);
   v3sub(x1_0, x2_0, x_k);
   real xnorm = (real)sqrt((double)dot3(x_k, x_k)), xnorm_prev = 0;
   for (int it = 0; it < iterations; it++) {
     if (xnorm < min_norm || rabs(xnorm_prev - xnorm) < CCD_MINVAL) break;
-    real dir_neg[3] = {x_k[0] / xnorm, x_k[1] / xnorm, x_k[2] / xnorm}, dpos[3] = {-dir_neg[0], -dir_neg[1], -dir_neg[2]};
+    real dir_neg[3] = {x_k[0] / xnorm, x_k[1] / xnorm, x_k[2] / xnorm};
+    if (discrete && xnorm < (real)1e-4) { /* :609-627 direction tuning when the search direction is noisy */
+      if (n == 2) {
+        real edge[3]; v3sub(r->simplex[1], r->simplex[0], edge);
+        real en2 = dot3(edge, edge);
+        if (en2 > CCD_MINVAL2) {
+          real proj = dot3(dir_neg, edge) / en2;
+          for (int i = 0; i < 3; i++) dir_neg[i] -= proj * edge[i];
+          real dn = len3(dir_neg);
+          if (dn > CCD_MINVAL) for (int i = 0; i < 3; i++) dir_neg[i] /= dn;
+        }
+      } else if (n == 3) {
+        real e1[3], e2[3], nrm[3];
+        v3sub(r->simplex[1], r->simplex[0], e1); v3sub(r->simplex[2], r->simplex[0], e2); cross3(e1, e2, nrm);
+        real nn = len3(nrm);
+        if (nn > CCD_MINVAL) { real sg = csign(dot3(dir_neg, nrm)); for (int i = 0; i < 3; i++) dir_neg[i] = sg * nrm[i] / nn; }
+      }
+    }
+    real dpos[3] = {-dir_neg[0], -dir_neg[1], -dir_neg[2]};
     ccd_support(g1, dpos, r->simplex1[n], &r->index1[n]);
     ccd_support(g2, dir_neg, r->simplex2[n], &r->index2[n]);
     v3sub(r->simplex1[n], r->simplex2[n], r->simplex[n]);
@@ -317,8 +341,8 @@ static int add_edge(Polytope* pt, int e1, int e2) {
   return n + 1;
 }
 /* :1319; returns the index of the closest face (or -1) and writes the witness points / distance */
-static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1, const CGeom* g2, real* dist, real* x1, real* x2, int* ovf) {
-  real upper = CCD_FLOAT_MAX, upper2 = CCD_FLOAT_MAX, epsilon = tolerance;
+static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1, const CGeom* g2, int discrete, real* dist, real* x1, real* x2, int* ovf) {
+  real upper = CCD_FLOAT_MAX, upper2 = CCD_FLOAT_MAX, epsilon = discrete ? CCD_MIN_EPATOL : tolerance;
   int idx = -1, pidx = -1, nvalid = pt->nface;
   if (iterations > 1000) iterations = 1000;
   for (int it = 0; it < iterations; it++) {
@@ -337,6 +361,11 @@ static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1
     real upper_k = dot3(fp, w) / lower;
     if (upper_k < upper) { upper = upper_k; upper2 = upper * upper; }
     if (upper - lower < epsilon) break;
+    if (discrete) { /* :1377-1385 a repeated support point ends the expansion */
+      int rep = 0;
+      for (int i = 0; i < pt->nvert - 1; i++) if (pt->vert_index[2 * i] == pt->vert_index[2 * wi] && pt->vert_index[2 * i + 1] == pt->vert_index[2 * wi + 1]) { rep = 1; break; }
+      if (rep) break;
+    }
     nvalid--;
     pt->face[idx] |= FACE_DELETED;
     { unsigned f = pt->face[idx]; int a = f & 0x3FF, b = (f >> 10) & 0x3FF, c = (f >> 20) & 0x3FF;
@@ -378,16 +407,209 @@ static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1
   return -1;
 }
 
+/* ---- multi-contact recovery for box pairs (collision_gjk.py:1503 _feature_dim, :1703-1888 box normals / edges / faces,
+ * :1916-2056 polygon clipping, :2076 multicontact; mesh branches omitted) */
+static int feature_dim(const Polytope* pt, const int face[3], int offset, int fidx[3], real fvert[3][3]) {
+  int v1i = pt->vert_index[2 * face[0] + offset], v2i = pt->vert_index[2 * face[1] + offset], v3i = pt->vert_index[2 * face[2] + offset];
+  fidx[0] = v1i; fidx[1] = v2i; fidx[2] = v3i;
+  for (int k = 0; k < 3; k++) v3cpy(fvert[k], pt->vert[2 * face[k] + offset]);
+  if (v1i != v2i) return (v3i == v1i || v3i == v2i) ? 2 : 3;
+  fidx[1] = v3i; v3cpy(fvert[1], pt->vert[2 * face[2] + offset]);
+  return v1i != v3i ? 2 : 1;
+}
+static int box_normals2(const real* mat, const real* n, real nout[3][3], int* iout) {
+  static const real FN[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+  real ln[3]; matT_vec3(mat, n, ln); normalize3(ln);
+  for (int i = 0; i < 6; i++) if (dot3(ln, FN[i]) > CCD_FACE_TOL) { matvec3(mat, FN[i], nout[0]); iout[0] = i; return 1; }
+  return 0;
+}
+static int box_normals(int fdim, const int* fi, const real* mat, const real* dir, real nout[3][3], int* iout) {
+  int v1 = fi[0], v2 = fi[1], v3 = fi[2];
+  if (fdim == 3) {
+    int c = 0;
+    real x = (real)(((v1 & 1) && (v2 & 1) && (v3 & 1)) ? 1 : 0) - (real)((!(v1 & 1) && !(v2 & 1) && !(v3 & 1)) ? 1 : 0);
+    real y = (real)(((v1 & 2) && (v2 & 2) && (v3 & 2)) ? 1 : 0) - (real)((!(v1 & 2) && !(v2 & 2) && !(v3 & 2)) ? 1 : 0);
+    real z = (real)(((v1 & 4) && (v2 & 4) && (v3 & 4)) ? 1 : 0) - (real)((!(v1 & 4) && !(v2 & 4) && !(v3 & 4)) ? 1 : 0);
+    real l[3] = {x, y, z}; matvec3(mat, l, nout[0]);
+    real sgn = x + y + z;
+    if (x != 0) iout[c++] = 0;
+    if (y != 0) iout[c++] = 2;
+    if (z != 0) iout[c++] = 4;
+    if (sgn == -1) iout[0] = iout[0] + 1;
+    if (c == 1) return 1;
+    return box_normals2(mat, dir, nout, iout);
+  }
+  if (fdim == 2) {
+    int c = 0;
+    real x = (real)(((v1 & 1) && (v2 & 1)) ? 1 : 0) - (real)((!(v1 & 1) && !(v2 & 1)) ? 1 : 0);
+    real y = (real)(((v1 & 2) && (v2 & 2)) ? 1 : 0) - (real)((!(v1 & 2) && !(v2 & 2)) ? 1 : 0);
+    real z = (real)(((v1 & 4) && (v2 & 4)) ? 1 : 0) - (real)((!(v1 & 4) && !(v2 & 4)) ? 1 : 0);
+    if (x != 0) { real l[3] = {x, 0, 0}; matvec3(mat, l, nout[c]); iout[c] = x > 0 ? 0 : 1; c++; }
+    if (y != 0) { real l[3] = {0, y, 0}; matvec3(mat, l, nout[c]); iout[c] = y > 0 ? 2 : 3; c++; }
+    if (z != 0) { real l[3] = {0, 0, z}; matvec3(mat, l, nout[c]); iout[c] = z > 0 ? 4 : 5; c++; }
+    if (c == 1 || c == 2) return c;
+    return box_normals2(mat, dir, nout, iout);
+  }
+  if (fdim == 1) {
+    real x = (v1 & 1) ? (real)1 : (real)-1, y = (v1 & 2) ? (real)1 : (real)-1, z = (v1 & 4) ? (real)1 : (real)-1;
+    real lx[3] = {x, 0, 0}, ly[3] = {0, y, 0}, lz[3] = {0, 0, z};
+    matvec3(mat, lx, nout[0]); matvec3(mat, ly, nout[1]); matvec3(mat, lz, nout[2]);
+    iout[0] = x > 0 ? 0 : 1; iout[1] = y > 0 ? 2 : 3; iout[2] = z > 0 ? 4 : 5;
+    return 3;
+  }
+  return 0;
+}
+static int box_edge_normals(int dim, const CGeom* g, const real* v1, const real* v2, int v1i, real nout[3][3], real endvert[3][3]) {
+  if (dim == 2) { v3cpy(endvert[0], v2); v3sub(v2, v1, nout[0]); normalize3(nout[0]); return 1; }
+  if (dim == 1) {
+    real x = (v1i & 1) ? g->size[0] : -g->size[0], y = (v1i & 2) ? g->size[1] : -g->size[1], z = (v1i & 4) ? g->size[2] : -g->size[2];
+    real l[3][3] = {{-x, y, z}, {x, -y, z}, {x, y, -z}};
+    for (int k = 0; k < 3; k++) {
+      matvec3(g->rot, l[k], endvert[k]);
+      for (int i = 0; i < 3; i++) endvert[k][i] += g->pos[i];
+      v3sub(endvert[k], v1, nout[k]); normalize3(nout[k]);
+    }
+    return 3;
+  }
+  return 0;
+}
+static int box_face(const CGeom* g, int idx, real face[4][3]) {
+  const real sx = g->size[0], sy = g->size[1], sz = g->size[2];
+  const real L[6][4][3] = {
+    {{sx, sy, sz}, {sx, sy, -sz}, {sx, -sy, -sz}, {sx, -sy, sz}}, {{-sx, sy, -sz}, {-sx, sy, sz}, {-sx, -sy, sz}, {-sx, -sy, -sz}},
+    {{-sx, sy, -sz}, {sx, sy, -sz}, {sx, sy, sz}, {-sx, sy, sz}}, {{-sx, -sy, sz}, {sx, -sy, sz}, {sx, -sy, -sz}, {-sx, -sy, -sz}},
+    {{-sx, sy, sz}, {sx, sy, sz}, {sx, -sy, sz}, {-sx, -sy, sz}}, {{sx, sy, -sz}, {-sx, sy, -sz}, {-sx, -sy, -sz}, {sx, -sy, -sz}}};
+  if (idx < 0 || idx > 5) return 0;
+  for (int k = 0; k < 4; k++) { matvec3(g->rot, L[idx][k], face[k]); for (int i = 0; i < 3; i++) face[k][i] += g->pos[i]; }
+  return 4;
+}
+static real area4(const real* a, const real* b, const real* c, const real* d) {
+  real ad[3], db[3], bc[3], ca[3], c1[3], c2[3], s[3];
+  v3sub(a, d, ad); v3sub(d, b, db); v3sub(b, c, bc); v3sub(c, a, ca);
+  cross3(ad, db, c1); cross3(bc, ca, c2);
+  for (int i = 0; i < 3; i++) s[i] = c1[i] + c2[i];
+  return (real)0.5 * len3(s);
+}
+static void polygon_quad(real poly[][3], int np, int res[4]) { /* :1463 maximum-area quadrilateral of a convex polygon */
+  int b = 1, c = 2, d = 3;
+  res[0] = 0; res[1] = b; res[2] = c; res[3] = d;
+  real m = area4(poly[0], poly[b], poly[c], poly[d]);
+  for (int a = 0; a < np; a++) {
+    for (;;) {
+      real mn = area4(poly[a], poly[b], poly[c], poly[(d + 1) % np]);
+      if (mn <= m) break;
+      m = mn; d = (d + 1) % np; res[0] = a; res[1] = b; res[2] = c; res[3] = d;
+      for (;;) {
+        mn = area4(poly[a], poly[b], poly[(c + 1) % np], poly[d]);
+        if (mn <= m) break;
+        m = mn; c = (c + 1) % np; res[0] = a; res[1] = b; res[2] = c; res[3] = d;
+      }
+      for (;;) {
+        mn = area4(poly[a], poly[(b + 1) % np], poly[c], poly[d]);
+        if (mn <= m) break;
+        m = mn; b = (b + 1) % np; res[0] = a; res[1] = b; res[2] = c; res[3] = d;
+      }
+    }
+    if (b == a) { b = (b + 1) % np; if (c == b) { c = (c + 1) % np; if (d == c) d = (d + 1) % np; } }
+  }
+}
+/* :1941 clip polygon face2 against the side planes of face1 (extruded along n); witness2 on the clipped polygon, witness1 = witness2 - dir */
+static int polygon_clip(real face1[][3], int nface1, real face2[][3], int nface2, const real* n, const real* dir, real w1[4][3], real w2[4][3]) {
+  if (nface1 < 3) return 0;
+  real pn[4][3], pd[4], bufA[8][3], bufB[8][3];
+  for (int i = 0; i < nface1; i++) { /* :1916 _plane_normal */
+    const real *a = face1[i], *b = face1[(i + 1) % nface1];
+    real ba[3], res[3]; v3sub(b, a, ba); cross3(ba, n, res);
+    pd[i] = dot3(res, a); v3cpy(pn[i], res);
+  }
+  real (*poly)[3] = bufA, (*clip)[3] = bufB;
+  int np = nface2, nc = 0;
+  for (int i = 0; i < nface2; i++) v3cpy(poly[i], face2[i]);
+  for (int e = 0; e < nface1; e++) {
+    for (int i = 0; i < np; i++) {
+      const real *P = poly[i], *Q = poly[(i + 1) % np];
+      real dP[3], dQ[3]; v3sub(P, face1[e], dP); v3sub(Q, face1[e], dQ);
+      int in1 = dot3(dP, pn[e]) > (real)-1e-10, in2 = dot3(dQ, pn[e]) > (real)-1e-10;
+      if (!in1 && !in2) continue;
+      if (in1 && in2) { if (nc < 8) v3cpy(clip[nc], Q); nc++; continue; }
+      real pq[3]; v3sub(Q, P, pq);
+      real dt = dot3(pn[e], pq), t = rabs(dt) < (real)1e-10 ? CCD_FLOAT_MAX : (pd[e] - dot3(pn[e], P)) / dt;
+      if (t > -CCD_INTERSECT_TOL && t < 1 + CCD_INTERSECT_TOL) {
+        t = rclamp(t, 0, 1);
+        if (nc < 8) for (int k = 0; k < 3; k++) clip[nc][k] = P[k] + t * pq[k];
+        nc++;
+      }
+      if (in2) { if (nc < 8) v3cpy(clip[nc], Q); nc++; }
+    }
+    if (nc > 8) nc = 8;
+    real (*tmp)[3] = poly; poly = clip; clip = tmp;
+    np = nc; nc = 0;
+  }
+  if (np < 1) return 0;
+  if (nface2 == 2 && np > 2) { /* an edge: keep the two farthest points */
+    int b1 = 0, b2 = 1; real maxd = 0;
+    for (int i = 0; i < np; i++) for (int j = i + 1; j < np; j++) { real df[3]; v3sub(poly[j], poly[i], df); real d2 = dot3(df, df); if (d2 > maxd) { maxd = d2; b1 = i; b2 = j; } }
+    v3cpy(w2[0], poly[b1]); v3sub(w2[0], dir, w1[0]); v3cpy(w2[1], poly[b2]); v3sub(w2[1], dir, w1[1]);
+    return 2;
+  }
+  if (np > 4) {
+    int q[4]; polygon_quad(poly, np, q);
+    for (int i = 0; i < 4; i++) { v3cpy(w2[i], poly[q[i]]); v3sub(w2[i], dir, w1[i]); }
+    return 4;
+  }
+  for (int i = 0; i < np; i++) { v3cpy(w2[i], poly[i]); v3sub(w2[i], dir, w1[i]); }
+  return np;
+}
+/* :2076 (both geoms boxes); returns the contact count and overwrites the witness arrays */
+static int ccd_multicontact(const Polytope* pt, int epa_face_idx, const real* x1, const real* x2, const CGeom* g1, const CGeom* g2, real w1[4][3], real w2[4][3]) {
+  memset(w1, 0, 12 * sizeof(real)); memset(w2, 0, 12 * sizeof(real));
+  v3cpy(w1[0], x1); v3cpy(w2[0], x2);
+  unsigned f = pt->face[epa_face_idx]; int face[3] = {(int)(f & 0x3FF), (int)((f >> 10) & 0x3FF), (int)((f >> 20) & 0x3FF)};
+  int fi1[3], fi2[3]; real fv1[3][3], fv2[3][3];
+  int nface1 = feature_dim(pt, face, 0, fi1, fv1), nface2 = feature_dim(pt, face, 1, fi2, fv2);
+  real dir[3], dneg[3]; v3sub(x2, x1, dir); for (int i = 0; i < 3; i++) dneg[i] = -dir[i];
+  real n1[3][3], n2[3][3], endvert[3][3]; int idx1[3] = {0, 0, 0}, idx2[3] = {0, 0, 0};
+  memset(n1, 0, sizeof n1); memset(n2, 0, sizeof n2); memset(endvert, 0, sizeof endvert);
+  int nn1 = box_normals(nface1, fi1, g1->rot, dneg, n1, idx1), nn2 = box_normals(nface2, fi2, g2->rot, dir, n2, idx2);
+  int edge1 = 0, edge2 = 0, ri = 0, rj = 0, found = 0;
+  for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (dot3(n1[i], n2[j]) < -CCD_FACE_TOL) { ri = i; rj = j; found = 1; break; }
+  if (!found) {
+    if (nface1 < 3 && nface1 <= nface2) {
+      nn1 = box_edge_normals(nface1, g1, fv1[0], fv1[1], fi1[0], n1, endvert);
+      for (int i = 0; i < nn2 && !found; i++) for (int j = 0; j < nn1; j++) if (rabs(dot3(n1[j], n2[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = 1; break; }
+      if (!found) return 1;
+      edge1 = 1;
+    } else if (nface2 < 3) {
+      nn2 = box_edge_normals(nface2, g2, fv2[0], fv2[1], fi2[0], n2, endvert);
+      for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (rabs(dot3(n2[j], n1[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = 1; break; }
+      if (!found) return 1;
+      edge2 = 1;
+    } else return 1;
+  }
+  int i = ri, j = rj;
+  real face1[4][3], face2[4][3];
+  if (edge1) { v3cpy(face1[0], pt->vert[2 * face[0]]); v3cpy(face1[1], endvert[i]); nface1 = 2; }
+  else nface1 = box_face(g1, edge2 ? idx1[j] : idx1[i], face1);
+  if (edge2) { v3cpy(face2[0], pt->vert[2 * face[0] + 1]); v3cpy(face2[1], endvert[i]); nface2 = 2; }
+  else nface2 = box_face(g2, idx2[j], face2);
+  real dl = len3(dir), ad[3];
+  if (edge1) { for (int k = 0; k < 3; k++) ad[k] = -dl * n2[j][k]; return polygon_clip(face2, nface2, face1, nface1, n2[j], ad, w2, w1); } /* faces flipped, flip the witnesses back */
+  if (edge2) { for (int k = 0; k < 3; k++) ad[k] = -dl * n1[j][k]; return polygon_clip(face1, nface1, face2, nface2, n1[j], ad, w1, w2); }
+  for (int k = 0; k < 3; k++) ad[k] = dl * n2[j][k];
+  return polygon_clip(face1, nface1, face2, nface2, n1[i], ad, w1, w2);
+}
+
 /* gjk_phase (:2350) + epa_phase (:2421): returns the number of contacts (0 or 1); dist is relative to the margin-inflated shapes */
-static int ccd_pair(real tolerance, real cutoff, int iterations, CGeom g1, CGeom g2, real* dist, real* x1, real* x2, int* ovf) {
+static int ccd_pair(real tolerance, real cutoff, int gjk_iterations, int epa_iterations, CGeom g1, CGeom g2, real* dist, real w1[4][3], real w2[4][3], int* ovf) {
   const CGeom o1 = g1, o2 = g2;
-  real full1 = 0, full2 = 0, size1 = 0, size2 = 0;
+  real full1 = 0, full2 = 0, size1 = 0, size2 = 0, *x1 = w1[0], *x2 = w2[0];
+  const int discrete = g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0 && g2.margin == 0; /* :109 _discrete_geoms */
   GjkResult r;
   if (g1.type == GEOM_SPHERE || g1.type == GEOM_CAPSULE) { size1 = g1.size[0]; full1 = size1 + (real)0.5 * g1.margin; g1.margin = 0; g1.size[0] = 0; }
   if (g2.type == GEOM_SPHERE || g2.type == GEOM_CAPSULE) { size2 = g2.size[0]; full2 = size2 + (real)0.5 * g2.margin; g2.margin = 0; g2.size[0] = 0; }
   if (size1 + size2 > 0) {
     cutoff += full1 + full2;
-    ccd_gjk(tolerance, iterations, &g1, &g2, g1.pos, g2.pos, cutoff, &r);
+    ccd_gjk(tolerance, gjk_iterations, &g1, &g2, g1.pos, g2.pos, cutoff, discrete, &r);
     if (r.dist > tolerance) {
       v3cpy(x1, r.x1); v3cpy(x2, r.x2);
       if (r.dist == CCD_FLOAT_MAX) { *dist = r.dist; return 1; }
@@ -400,11 +622,10 @@ static int ccd_pair(real tolerance, real cutoff, int iterations, CGeom g1, CGeom
     g1 = o1; g2 = o2;
     cutoff -= full1 + full2;
   }
-  ccd_gjk(tolerance, iterations, &g1, &g2, g1.pos, g2.pos, cutoff, &r);
+  ccd_gjk(tolerance, gjk_iterations, &g1, &g2, g1.pos, g2.pos, cutoff, discrete, &r);
   if (r.dist > tolerance || r.dim < 2 || r.separated) { *dist = r.dist; v3cpy(x1, r.x1); v3cpy(x2, r.x2); return 1; }
   /* epa_phase */
-  enum { MAXV = 10 + 2 * 1000 };
-  int maxvert = 10 + 2 * iterations, maxface = 6 + CCD_MAX_EPAFACES * iterations;
+  int maxvert = 10 + 2 * epa_iterations, maxface = 6 + CCD_MAX_EPAFACES * epa_iterations;
   Polytope pt; memset(&pt, 0, sizeof pt);
   pt.maxvert = maxvert; pt.maxface = maxface;
   pt.vert = (real(*)[3])calloc((size_t)maxvert, 3 * sizeof(real)); pt.vert_index = (int*)calloc((size_t)maxvert, sizeof(int));
@@ -415,7 +636,16 @@ static int ccd_pair(real tolerance, real cutoff, int iterations, CGeom g1, CGeom
   else if (r.dim == 4) { polytope4(&pt, &r); if (pt.status == -1) r.dim = 3; }
   if (r.dim == 3) { pt.status = 0; polytope3(&pt, &r, &g1, &g2); }
   if (pt.status) { *dist = r.dist; v3cpy(x1, r.x1); v3cpy(x2, r.x2); }
-  else if (ccd_epa(tolerance, iterations, &pt, &g1, &g2, dist, x1, x2, ovf) == -1) { *dist = CCD_FLOAT_MAX; ncon = 0; }
+  else {
+    real e1[3], e2[3];
+    int fidx = ccd_epa(tolerance, epa_iterations, &pt, &g1, &g2, discrete, dist, e1, e2, ovf);
+    if (fidx == -1) { *dist = CCD_FLOAT_MAX; ncon = 0; }
+    else {
+      v3cpy(x1, e1); v3cpy(x2, e2);
+      /* multi-contact: boxes without margin only (epa_phase :2517-2525, collision_convex.py:875-912) */
+      if (g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0 && g2.margin == 0) ncon = ccd_multicontact(&pt, fidx, e1, e2, &g1, &g2, w1, w2);
+    }
+  }
   free(pt.vert); free(pt.vert_index); free(pt.face); free(pt.face_pr); free(pt.face_norm2);
   return ncon;
 }

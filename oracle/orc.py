@@ -25,7 +25,7 @@ def build(force: bool = False):
   src = os.path.join(_HERE, "oracle.c")
   for name, flags in (("liborc64.so", []), ("liborc32.so", ["-DORC_FLOAT"])):
     out = os.path.join(_HERE, name)
-    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "oracle.h"))):
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "oracle.h")), os.path.getmtime(os.path.join(_HERE, "oracle_ccd.h"))):
       continue
     cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-std=c99", "-fno-fast-math", "-ffp-contract=off", *flags, src, "-o", out, "-lm"]
     subprocess.check_call(cmd)
@@ -120,7 +120,16 @@ def derived_tables(mjm):
   nmaxcondim = int(mjm.geom_condim.max()) if ngeom else 1
   if getattr(mjm, "npair", 0):
     nmaxcondim = max(nmaxcondim, int(np.asarray(mjm.pair_dim).max()))
-  return dict(body_isdofancestor=anc, nxn_geom_pair=pairs, nxn_pairid=pid, jnt_limited_slide_hinge_adr=limited, jnt_limited_ball_adr=limited_ball,
+  # collision_convex.py:1209-1223: EPA gets 16 iterations when every convex pair of the model is box-box
+  convex = {(2, 4), (3, 4), (3, 5), (4, 4), (4, 5), (4, 6), (5, 5), (5, 6)}
+  if not (int(mjm.opt.disableflags) & (1 << 17)):
+    convex.add((6, 6))
+  gt = np.asarray(mjm.geom_type)
+  keys = [(min(int(gt[a]), int(gt[b])), max(int(gt[a]), int(gt[b]))) for a, b in pairs]
+  nconvex = sum(k in convex for k in keys)
+  nboxbox = sum(k == (6, 6) and k in convex for k in keys)
+  epa_iterations = 16 if nboxbox == nconvex else int(getattr(mjm.opt, "ccd_iterations", 35))
+  return dict(epa_iterations=epa_iterations, body_isdofancestor=anc, nxn_geom_pair=pairs, nxn_pairid=pid, jnt_limited_slide_hinge_adr=limited, jnt_limited_ball_adr=limited_ball,
               qLD_block_adr=blk, qld_total=off, nJmom=nJmom, nmaxpyramid=max(1, 2 * (nmaxcondim - 1)))
 
 
@@ -197,6 +206,7 @@ class Oracle:
     seti("ls_iterations", o.ls_iterations); seti("disableflags", o.disableflags); seti("enableflags", o.enableflags)
     seti("broadphase_filter", getattr(o, "broadphase_filter", 1 | 2 | 8))  # io.py:405 default PLANE|SPHERE|OBB
     seti("ccd_iterations", getattr(o, "ccd_iterations", 35)); setr("ccd_tolerance", getattr(o, "ccd_tolerance", 1e-6))
+    seti("epa_iterations", self.tabs["epa_iterations"])
     tol = float(o.tolerance)
     if clamp_tolerance:
       tol = max(tol, 1e-6)  # io.py:401: put_model clamps the solver tolerance (chosen for float32) whatever the host precision;

@@ -154,15 +154,20 @@ def test_unsupported_features_raise():
   xml = """<mujoco><option integrator="RK4"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
   with pytest.raises(NotImplementedError, match="integrator"):
     mio._validate(mjcf.load_string(xml))
-  # box-box is a primitive pair only with nativeccd disabled (the convex path's multi-contact clipping is not built)
-  two = '<body pos="0 0 1"><freejoint/><geom type="box" size=".1 .1 .1"/></body><body pos="0 0 2"><freejoint/><geom type="{t}" size=".1 .1 .1"/></body>'
-  xml = "<mujoco><worldbody>" + two.format(t="box") + "</worldbody></mujoco>"
-  with pytest.raises(NotImplementedError, match="nativeccd"):
-    mio.derive_tables(mjcf.load_string(xml))
-  mio.derive_tables(mjcf.load_string(xml.replace("<worldbody>", '<option><flag nativeccd="disable"/></option><worldbody>')))
+  # box-box goes through GJK / EPA + multi-contact recovery (16 EPA iterations when it is the only convex pair type);
+  # with nativeccd disabled it is a primitive pair.  The convex box path does not support margins (reference io.py:693-717).
+  two = '<body pos="0 0 1"><freejoint/><geom type="box" size=".1 .1 .1"{m}/></body><body pos="0 0 2"><freejoint/><geom type="{t}" size=".1 .1 .1"/></body>'
+  xml = "<mujoco><worldbody>" + two.format(t="box", m="") + "</worldbody></mujoco>"
+  t = mio.derive_tables(mjcf.load_string(xml))
+  assert t["has_convex_pair"] == 1 and t["epa_iterations"] == 16
+  t = mio.derive_tables(mjcf.load_string(xml.replace("<worldbody>", '<option><flag nativeccd="disable"/></option><worldbody>')))
+  assert t["has_convex_pair"] == 0
+  with pytest.raises(NotImplementedError, match="margin"):
+    mio.derive_tables(mjcf.load_string("<mujoco><worldbody>" + two.format(t="box", m=' margin="0.01"') + "</worldbody></mujoco>"))
   # cylinder-box goes through the GJK / EPA pass
-  xml = "<mujoco><worldbody>" + two.format(t="cylinder") + "</worldbody></mujoco>"
-  assert mio.derive_tables(mjcf.load_string(xml))["has_convex_pair"] == 1
+  xml = "<mujoco><worldbody>" + two.format(t="cylinder", m="") + "</worldbody></mujoco>"
+  t = mio.derive_tables(mjcf.load_string(xml))
+  assert t["has_convex_pair"] == 1 and t["epa_iterations"] == 35
 
 
 def test_shard_worlds():

@@ -37,6 +37,8 @@ def load_scene(name):
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"'))
   elif name == "boxes":
     mjm = mjcf.load_string(BOX_XML)
+  elif name in ("boxccd", "boxccd_mixed"):
+    mjm = mjcf.load_string(util.boxccd_xml(name.endswith("mixed")))
   elif name == "convex":
     mjm = mjcf.load_string(util.CONVEX_XML)
   elif name == "pairs":

@@ -232,3 +232,30 @@ CONVEX_XML = """
   </worldbody>
 </mujoco>
 """
+
+
+def boxccd_xml(mixed=False):
+  """Boxes under default options: box-box goes through GJK / EPA + multi-contact recovery (collision_convex.py:875-912).
+  Face-face (full, overhanging and 45-degree octagon overlap), edge-face with the edge on either geom, vertex-face and crossed edges.
+  mixed=True swaps the corner-down box for a cylinder so the model has a non-box convex pair (EPA keeps ccd_iterations instead of 16)."""
+  corner = ('<body pos="-0.3 0 0.1836" euler="45 35.264 0"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>' if not mixed else
+            '<body pos="-0.3 0 0.159"><freejoint/><geom type="cylinder" size="0.05 0.06"/></body>')
+  return f"""
+<mujoco>
+  <option timestep="0.002" iterations="50"/>
+  <default><geom friction="0.9 0.01 0.002" density="400"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05"/>
+    <geom name="platform" type="box" size="0.5 0.5 0.05" pos="0 0 0.05"/>
+    <body pos="-0.3 -0.3 0.149"><freejoint/><geom type="box" size="0.08 0.08 0.05"/></body>
+    <body pos="-0.25 -0.27 0.238"><freejoint/><geom type="box" size="0.06 0.06 0.04"/></body>
+    <body pos="0 -0.3 0.149" euler="0 0 45"><freejoint/><geom type="box" size="0.07 0.07 0.05"/></body>
+    <body pos="0 -0.3 0.228"><freejoint/><geom type="box" size="0.07 0.07 0.03"/></body>
+    <body pos="0.3 -0.3 0.1697" euler="45 0 0"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>
+    {corner}
+    <body pos="0.3 0.2 0.2346" euler="45 0 0"><freejoint/><geom type="box" size="0.04 0.04 0.04"/></body>
+    <body pos="0.3 0.2 0.139"><freejoint/><geom type="box" size="0.1 0.1 0.04"/></body>
+    <body pos="0 0.3 0.1697" euler="45 0 0"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>
+    <body pos="0 0.3 0.3101" euler="0 45 0"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>
+  </worldbody>
+</mujoco>"""

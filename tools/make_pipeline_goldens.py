@@ -53,6 +53,8 @@ def scenes():
   yield "passive", mjcf.load_string(util.passive_xml()), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   yield "convex", mjcf.load_string(util.CONVEX_XML), dict(nconmax=64, njmax=256, key=None, qpos_noise=0.004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "boxes", mjcf.load_string(BOX_XML), dict(nconmax=48, njmax=200, key=None, qpos_noise=0.003, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
+  yield "boxccd", mjcf.load_string(util.boxccd_xml()), dict(nconmax=48, njmax=256, key=None, qpos_noise=0.0004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
+  yield "boxccd_mixed", mjcf.load_string(util.boxccd_xml(True)), dict(nconmax=48, njmax=256, key=None, qpos_noise=0.0004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
   yield "g1", mjcf.load_any(util.G1), dict(nconmax=48, njmax=192, key=0, qpos_noise=0.02, qvel_noise=0.2, ctrl_noise=0.3)
 
@@ -118,4 +120,13 @@ def main(only=None):
 
 
 if __name__ == "__main__":
-  main(sys.argv[1:])
+  # One process per scene: the reference keeps process-global kernel state (collision_primitive.py:1516 accumulates the
+  # primitive pair types of every model the process has seen, so a box-box primitive from one model would also run for the next).
+  names = sys.argv[1:] or [n for n, _, _ in scenes()]
+  if len(names) == 1:
+    main(names)
+  else:
+    import subprocess
+
+    for n in names:
+      subprocess.check_call([sys.executable, os.path.abspath(__file__), n])

@@ -795,8 +795,8 @@ def _is_wp_decorator(dec):
 
 class _WarpSemantics(ast.NodeTransformer):
   """Applied in memory to device code only (functions decorated with @wp.func / @wp.kernel, including nested ones): the
-  source files are read unmodified from the reference tree; this restores the two places where Python's semantics differ
-  from warp's typed semantics -- integer `/` and `%`, and value (copy) semantics of vector/matrix assignment."""
+  source files are read unmodified from the reference tree; this restores the places where Python's semantics differ
+  from warp's typed semantics -- integer `/` and `%`, boolean-valued `and` / `or`, and value (copy) semantics of vector/matrix assignment."""
 
   def __init__(self):
     self.depth = 0
@@ -815,6 +815,13 @@ class _WarpSemantics(ast.NodeTransformer):
     if self.depth and isinstance(node.op, (ast.Div, ast.Mod)):
       fn = "__wp_div__" if isinstance(node.op, ast.Div) else "__wp_mod__"
       return ast.copy_location(ast.Call(func=ast.Name(id=fn, ctx=ast.Load()), args=[node.left, node.right], keywords=[]), node)
+    return node
+
+  def visit_BoolOp(self, node):
+    # warp's `and` / `or` yield a bool (float(a & 2 and b & 2) is 1.0); Python's yield one of the operands
+    self.generic_visit(node)
+    if self.depth:
+      return ast.copy_location(ast.Call(func=ast.Name(id="bool", ctx=ast.Load()), args=[node], keywords=[]), node)
     return node
 
   def visit_AugAssign(self, node):
