@@ -9,7 +9,7 @@
  * PARITY PINNING: pinned against outputs of the reference itself.  The reference's unmodified
  * Python sources are executed on the CPU through tools/warp_shim.py (a pure-Python stand-in for the warp API), which
  * yields (i) tests/golden/reference_colliders.json -- every primitive pair function of collision_primitive_core.py --
- * and (ii) tests/golden/pipeline_*.npz -- io.put_model -> make_data -> forward()/step() on six scenes.  The fp64 build
+ * and (ii) tests/golden/pipeline_*.npz -- io.put_model -> make_data -> forward()/step() on fourteen scenes.  The fp64 build
  * of this file reproduces them to 1e-9 (tests/test_oracle_golden_colliders.py, tests/test_oracle_golden_pipeline.py).
  * Also kept: the reference's hard-coded vectors that need no MuJoCo and physical invariants (tests/test_oracle_*.py).
  * Outside the pin: the MJCF compiler (MuJoCo's C compiler is absent; the fixtures pin step(m, d) given the model arrays).
