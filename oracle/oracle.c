@@ -1276,7 +1276,7 @@ static void convex_pair(W* w, int g1, int g2, int pairid) {
   a.margin = b.margin = p.margin;
   real dist, w1[4][3], w2[4][3], frame[9], nrm[3], pos[3]; int ovf = 0;
   memset(w1, 0, sizeof w1); memset(w2, 0, sizeof w2);
-  int ncon = ccd_pair(m->ccd_tolerance, p.gap, m->ccd_iterations, m->epa_iterations, a, b, &dist, w1, w2, &ovf);
+  int ncon = ccd_pair(m->ccd_tolerance, p.gap, m->ccd_iterations, m->epa_iterations, 1, a, b, &dist, w1, w2, &ovf);
   if (ovf) w->overflow[0] |= OVF_EPA_HORIZON;
   if (ncon == 0 || dist >= p.gap) return;
   dist += p.margin; /* back to the distance between the un-inflated surfaces (collision_convex.py:862-868) */
@@ -1286,6 +1286,21 @@ static void convex_pair(W* w, int g1, int g2, int pairid) {
     for (int i = 0; i < 3; i++) pos[i] = (real)0.5 * (w1[k][i] + w2[k][i]);
     write_contact(w, k, dist, pos, frame, &p, g1, g2);
   }
+}
+
+/* Direct entry to the convex pair routine, shaped like the harness of the reference's own GJK tests
+ * (collision_gjk_test.py:35-303 _geom_dist: ccd() with the same iteration count for GJK and EPA, optional multicontact). */
+int orc_ccd(int type1, const real* size1, const real* pos1, const real* mat1, int type2, const real* size2, const real* pos2, const real* mat2,
+            real margin, real tolerance, real cutoff, int iterations, int multi, real* dist, real* w1, real* w2, int* overflow) {
+  CGeom a, b;
+  memcpy(a.pos, pos1, sizeof a.pos); memcpy(a.rot, mat1, sizeof a.rot); memcpy(a.size, size1, sizeof a.size); a.type = type1; a.margin = margin;
+  memcpy(b.pos, pos2, sizeof b.pos); memcpy(b.rot, mat2, sizeof b.rot); memcpy(b.size, size2, sizeof b.size); b.type = type2; b.margin = margin;
+  real x1[4][3], x2[4][3]; int ovf = 0;
+  memset(x1, 0, sizeof x1); memset(x2, 0, sizeof x2);
+  int n = ccd_pair(tolerance, cutoff, iterations, iterations, multi, a, b, dist, x1, x2, &ovf);
+  memcpy(w1, x1, sizeof x1); memcpy(w2, x2, sizeof x2);
+  *overflow = ovf;
+  return n;
 }
 
 static void narrowphase_pair(W* w, int g1, int g2, int pairid) {

@@ -59,6 +59,9 @@ void orc_closest_segment_to_segment_points(const real a0[3], const real a1[3], c
 int orc_upper_tri_index(int n, int i, int j);
 int orc_upper_trid_index(int n, int i, int j);
 double orc_halton(int index, int base);
+/* convex pair (GJK / EPA / box multi-contact) on two posed geoms; returns the contact count, witnesses in w1 / w2 (4 x 3 each) */
+int orc_ccd(int type1, const real* size1, const real* pos1, const real* mat1, int type2, const real* size2, const real* pos2, const real* mat2,
+            real margin, real tolerance, real cutoff, int iterations, int multi, real* dist, real* w1, real* w2, int* overflow);
 
 #ifdef __cplusplus
 }

@@ -600,7 +600,7 @@ static int ccd_multicontact(const Polytope* pt, int epa_face_idx, const real* x1
 }
 
 /* gjk_phase (:2350) + epa_phase (:2421): returns the number of contacts (0 or 1); dist is relative to the margin-inflated shapes */
-static int ccd_pair(real tolerance, real cutoff, int gjk_iterations, int epa_iterations, CGeom g1, CGeom g2, real* dist, real w1[4][3], real w2[4][3], int* ovf) {
+static int ccd_pair(real tolerance, real cutoff, int gjk_iterations, int epa_iterations, int multi, CGeom g1, CGeom g2, real* dist, real w1[4][3], real w2[4][3], int* ovf) {
   const CGeom o1 = g1, o2 = g2;
   real full1 = 0, full2 = 0, size1 = 0, size2 = 0, *x1 = w1[0], *x2 = w2[0];
   const int discrete = g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0 && g2.margin == 0; /* :109 _discrete_geoms */
@@ -643,7 +643,7 @@ static int ccd_pair(real tolerance, real cutoff, int gjk_iterations, int epa_ite
     else {
       v3cpy(x1, e1); v3cpy(x2, e2);
       /* multi-contact: boxes without margin only (epa_phase :2517-2525, collision_convex.py:875-912) */
-      if (g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0 && g2.margin == 0) ncon = ccd_multicontact(&pt, fidx, e1, e2, &g1, &g2, w1, w2);
+      if (multi && g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0 && g2.margin == 0) ncon = ccd_multicontact(&pt, fidx, e1, e2, &g1, &g2, w1, w2);
     }
   }
   free(pt.vert); free(pt.vert_index); free(pt.face); free(pt.face_pr); free(pt.face_norm2);

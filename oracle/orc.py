@@ -274,3 +274,21 @@ class Oracle:
 
 def halton(index, base):
   return _lib(8).orc_halton(int(index), int(base))
+
+
+def ccd(type1, size1, pos1, mat1, type2, size2, pos2, mat2, margin=0.0, tolerance=1e-6, cutoff=1e30, iterations=35, multiccd=False, dtype=np.float64):
+  """Convex pair routine on two posed geoms -> (dist, ncon, witness1[4,3], witness2[4,3], overflow).
+  Mirrors the harness of the reference's GJK tests (collision_gjk_test.py:35-303 `_geom_dist`)."""
+  real = np.dtype(dtype)
+  lib = _lib(real.itemsize)
+  c_real = ctypes.c_double if real.itemsize == 8 else ctypes.c_float
+  arr = lambda a, n: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1)[:n].astype(real))
+  s1, p1, m1, s2, p2, m2 = arr(size1, 3), arr(pos1, 3), arr(mat1, 9), arr(size2, 3), arr(pos2, 3), arr(mat2, 9)
+  dist = np.zeros(1, dtype=real); w1 = np.zeros((4, 3), dtype=real); w2 = np.zeros((4, 3), dtype=real); ovf = np.zeros(1, dtype=np.int32)
+  P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+  lib.orc_ccd.restype = ctypes.c_int
+  lib.orc_ccd.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                          c_real, c_real, c_real, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+  n = lib.orc_ccd(int(type1), P(s1), P(p1), P(m1), int(type2), P(s2), P(p2), P(m2), margin, tolerance, cutoff, int(iterations), int(bool(multiccd)),
+                  P(dist), P(w1), P(w2), P(ovf))
+  return float(dist[0]), int(n), w1, w2, int(ovf[0])
