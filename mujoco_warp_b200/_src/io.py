@@ -319,11 +319,13 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     timestep=f32(o.timestep), tolerance=f32(tol), ls_tolerance=f32(o.ls_tolerance), gravity=f32(np.asarray(o.gravity)),
     integrator=int(o.integrator), cone=int(o.cone), solver=int(o.solver), iterations=int(o.iterations), ls_iterations=int(o.ls_iterations),
     disableflags=int(o.disableflags), enableflags=int(o.enableflags), impratio_invsqrt=f32(1.0 / np.sqrt(o.impratio)),
-    broadphase=types.BroadphaseType.NXN, broadphase_filter=int(getattr(o, "broadphase_filter", C.BF_PLANE | C.BF_SPHERE | C.BF_OBB)),
+    broadphase=types.BroadphaseType(int(getattr(o, "broadphase", 0))), broadphase_filter=int(getattr(o, "broadphase_filter", C.BF_PLANE | C.BF_SPHERE | C.BF_OBB)),
     graph_conditional=False, run_collision_detection=True, warn_overflow=False,
   )
   if len(t["nxn_geom_pair_filtered"]) >= 250_000:
-    raise NotImplementedError("SAP broadphase (>= 250k candidate pairs) is not implemented in this version")
+    # the reference switches to sweep-and-prune here (io.py:631-636); this build keeps one world's geoms and pair list in one
+    # warp's shared memory, which such a model does not fit.  opt.broadphase = SAP_* is honoured for models that do fit.
+    raise NotImplementedError("models with >= 250k candidate geom pairs are not supported in this version")
   m.stat = types.Statistic(meaninertia=f32(mjm.stat.meaninertia))
 
   keep = []
@@ -386,7 +388,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     nJmom=m.nJmom, nlevel=t["nlevel"], nxn_npair=len(t["nxn_geom_pair_filtered"]), nlimit=len(t["jnt_limited_slide_hinge_adr"]),
     nfricdof=len(t["dof_fricloss_adr"]), nmaxpyramid=m.nmaxpyramid, integrator=m.opt.integrator, cone=m.opt.cone, solver=m.opt.solver,
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
-    broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
+    broadphase=int(m.opt.broadphase), broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
     nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), epa_iterations=t["epa_iterations"], neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )

@@ -27,7 +27,7 @@ __host__ __device__ inline int surv_cap(const ModelDev& m) { return m.nxn_npair 
 
 constexpr int CCD_LANES = 4;  // geom pairs that run GJK / EPA concurrently in one warp (each needs a polytope in shared memory)
 
-struct ColLayout { int gxpos, gxmat, surv, stage, sgeom, ccd, total; };
+struct ColLayout { int gxpos, gxmat, surv, stage, sgeom, ccd, sap, total; };
 __host__ __device__ inline ColLayout col_layout(const ModelDev& m, const DataDev& d) {
   ColLayout L;
   int o = 0;
@@ -37,6 +37,7 @@ __host__ __device__ inline ColLayout col_layout(const ModelDev& m, const DataDev
   L.stage = take(STAGE_WORDS * world_con_cap(d));
   L.sgeom = take(4 * world_con_cap(d));  // g1, g2, geomcollisionid, pairid
   L.ccd = take(m.has_convex_pair ? CCD_LANES * ccd_scratch_words(m.epa_iterations) : 0);
+  L.sap = take(m.broadphase != 0 ? 4 * m.ngeom : 0);  // sweep-and-prune: projection bounds, sorted lower bounds, ranks
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -157,6 +158,33 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
   warp_copy(gxmat, d.geom_xmat + wb * 9 * ng, 9 * ng, lane);
   __syncwarp();
 
+  // ---- sweep-and-prune option (collision_driver.py:582-682): bounding-sphere projections on the reference's fixed axis, each
+  // geom's position in the sort by lower bound.  A pair is a sweep candidate when every geom sorted between the two starts
+  // below the earlier geom's upper bound (the reference's range also takes in the first neighbour past it,
+  // collision_core.py:516-519); candidates then go through the same filters.  Survivors keep pair-list order here (the
+  // reference's own order comes out of atomics).
+  float *sap_lo = S + L.sap, *sap_hi = sap_lo + ng, *sap_sorted = sap_hi + ng;
+  int* sap_rank = (int*)(sap_sorted + ng);
+  const bool sap = m.broadphase != 0;
+  if (sap) {
+    const v3 dir = normalize(mk3(0.5935f, 0.7790f, 0.1235f));
+    for (int g = lane; g < ng; g += 32) {
+      float rb = m.geom_rbound[g];
+      if (rb == 0.f) rb = MJ_MAXVAL;
+      const float radius = rb + m.geom_margin[g] + m.geom_gap[g], center = dot(dir, ld3(gxpos + 3 * g));
+      const bool ok = center == center;
+      sap_lo[g] = ok ? center - radius : MJ_MAXVAL; sap_hi[g] = ok ? center + radius : MJ_MAXVAL;
+    }
+    __syncwarp();
+    for (int g = lane; g < ng; g += 32) {
+      const float lo = sap_lo[g];
+      int r = 0;
+      for (int h = 0; h < ng; h++) { const float lh = sap_lo[h]; r += (lh < lo || (lh == lo && h < g)) ? 1 : 0; }
+      sap_rank[g] = r; sap_sorted[r] = lo;
+    }
+    __syncwarp();
+  }
+
   // ---- broadphase: lanes over the filtered pair list, ordered compaction of survivors
   int nsurv = 0, ntotal = 0;
 #pragma unroll 1
@@ -181,6 +209,10 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
         }
       }
       pass = pass || m.nxn_pairid[2 * e + 1] >= 0;
+      if (sap) {
+        const int ra = sap_rank[g1], rb_ = sap_rank[g2], ri = min(ra, rb_), rj = max(ra, rb_);
+        pass = pass && (rj == ri + 1 || sap_sorted[rj - 1] <= sap_hi[ra < rb_ ? g1 : g2]);
+      }
     }
     const unsigned bal = __ballot_sync(FULL_MASK, pass);
     ntotal += __popc(bal);

@@ -43,7 +43,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
-  X(disableflags) X(enableflags) X(broadphase_filter) X(ccd_iterations) X(epa_iterations)
+  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(ccd_tolerance)
 #define MODEL_IARRS(X) \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
@@ -1418,34 +1418,82 @@ static void narrowphase_pair(W* w, int g1, int g2, int pairid) {
     w->overflow[0] |= OVF_UNSUPPORTED;
   }
 }
-/* collision_driver.py:884-942 with NXN broadphase (:684-770); contacts are written in filtered-pair order */
+/* collision_driver.py:582-682 sap_broadphase: candidate pairs from a sort of the bounding-sphere projections on a fixed axis
+ * (:602-603), in the order the reference's sweep kernel visits them when its threads run one after the other: by world,
+ * sorted position of the first geom, sorted position of the second.  Returns the candidate count; cand holds indices into
+ * the filtered pair list. */
+typedef struct { real lower; int geom; } SapKey;
+static int sap_cmp(const void* a, const void* b) {
+  const SapKey *x = (const SapKey*)a, *y = (const SapKey*)b;
+  if (x->lower < y->lower) return -1;
+  if (x->lower > y->lower) return 1;
+  return x->geom - y->geom; /* stable */
+}
+static int sap_candidates(const W* w, int* cand) {
+  const OrcModel* m = w->m;
+  const int ng = m->ngeom;
+  real dir[3] = {(real)0.5935, (real)0.7790, (real)0.1235};
+  normalize3(dir);
+  SapKey* keys = (SapKey*)malloc((size_t)(ng > 0 ? ng : 1) * sizeof(SapKey));
+  real* upper = (real*)malloc((size_t)(ng > 0 ? ng : 1) * sizeof(real));
+  int* lookup = (int*)malloc((size_t)(ng > 0 ? ng * ng : 1) * sizeof(int));
+  for (int k = 0; k < ng * ng; k++) lookup[k] = -1;
+  for (int e = 0; e < m->nxn_npair; e++) lookup[m->nxn_geom_pair[2 * e] * ng + m->nxn_geom_pair[2 * e + 1]] = e;
+  for (int g = 0; g < ng; g++) { /* :373-413 sap_project */
+    real rbound = m->geom_rbound[g];
+    if (rbound == 0) rbound = MJ_MAXVAL;
+    real radius = rbound + m->geom_margin[g] + m->geom_gap[g], center = dot3(dir, w->geom_xpos + 3 * g);
+    keys[g].geom = g;
+    if (center == center) { keys[g].lower = center - radius; upper[g] = center + radius; } else { keys[g].lower = MJ_MAXVAL; upper[g] = MJ_MAXVAL; }
+  }
+  qsort(keys, (size_t)ng, sizeof(SapKey), sap_cmp);
+  int n = 0;
+  for (int si = 0; si < ng; si++) {
+    /* collision_core.py:489-519: first sorted position past si whose lower bound exceeds this geom's upper bound, clamped to ng - 1
+     * (the sweep therefore also visits that first non-overlapping neighbour; the pair filters discard it) */
+    int lo = si + 1, hi = ng;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid].lower > upper[keys[si].geom]) hi = mid; else lo = mid + 1; }
+    int limit = hi < ng - 1 ? hi : ng - 1;
+    for (int sj = si + 1; sj <= limit; sj++) {
+      int g1 = keys[si].geom, g2 = keys[sj].geom;
+      if (g2 < g1) { int t = g1; g1 = g2; g2 = t; }
+      int e = lookup[g1 * ng + g2];
+      if (e >= 0) cand[n++] = e;
+    }
+  }
+  free(keys); free(upper); free(lookup);
+  return n;
+}
+/* collision_driver.py:884-942 with the NXN (:684-770) or SAP broadphase; contacts are written in candidate order */
 static void collision(W* w) {
   const OrcModel* m = w->m;
   w->ncon[0] = 0; w->ncollision[0] = 0;
   if (w->nconmax == 0 || (m->disableflags & (DSBL_CONSTRAINT | DSBL_CONTACT))) return;
   /* Contact order of the reference under sequential execution: the convex narrowphase runs first, one launch per pair type
    * in table order (collision_driver.py:877, collision_convex.py:1369), then the primitive narrowphase; within a launch,
-   * broadphase (pair-list) order.  Pass -1 is the broadphase itself. */
+   * broadphase output order. */
   g_nativeccd = !(m->disableflags & DSBL_NATIVECCD);
-  unsigned char* pass = (unsigned char*)calloc((size_t)(m->nxn_npair > 0 ? m->nxn_npair : 1), 1);
-  for (int e = 0; e < m->nxn_npair; e++) {
-    int g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
+  int* cand = (int*)malloc((size_t)(m->nxn_npair > 0 ? m->nxn_npair : 1) * sizeof(int));
+  int ncand = 0, npass = 0;
+  if (m->broadphase == 0) for (int e = 0; e < m->nxn_npair; e++) cand[ncand++] = e;
+  else ncand = sap_candidates(w, cand);
+  for (int k = 0; k < ncand; k++) {
+    int e = cand[k], g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
     if (!(broadphase_filter(w, g1, g2) || m->nxn_pairid[2 * e + 1] >= 0)) continue;
     w->ncollision[0]++;
     if (m->nxn_pairid[2 * e] == -2) continue; /* sensor-only pair: no constraint contact */
-    pass[e] = 1;
+    cand[npass++] = e;
   }
   for (int rank = 0; rank <= N_CONVEX_PAIRS; rank++) {
-    for (int e = 0; e < m->nxn_npair; e++) {
-      if (!pass[e]) continue;
-      int g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
+    for (int k = 0; k < npass; k++) {
+      int e = cand[k], g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
       if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
       int cr = convex_pair_rank(m->geom_type[g1], m->geom_type[g2]);
       if (rank < N_CONVEX_PAIRS) { if (cr == rank) convex_pair(w, g1, g2, m->nxn_pairid[2 * e]); }
       else if (cr < 0) narrowphase_pair(w, g1, g2, m->nxn_pairid[2 * e]);
     }
   }
-  free(pass);
+  free(cand);
   if (w->ncon[0] > w->nconmax) w->ncon[0] = w->nconmax;
 }
 

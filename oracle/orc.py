@@ -205,6 +205,7 @@ class Oracle:
     seti("integrator", o.integrator); seti("cone", o.cone); seti("solver", o.solver); seti("iterations", o.iterations)
     seti("ls_iterations", o.ls_iterations); seti("disableflags", o.disableflags); seti("enableflags", o.enableflags)
     seti("broadphase_filter", getattr(o, "broadphase_filter", 1 | 2 | 8))  # io.py:405 default PLANE|SPHERE|OBB
+    seti("broadphase", getattr(o, "broadphase", 0))  # 0 NXN (io.py:404), 1 / 2 sweep-and-prune
     seti("ccd_iterations", getattr(o, "ccd_iterations", 35)); setr("ccd_tolerance", getattr(o, "ccd_tolerance", 1e-6))
     seti("epa_iterations", self.tabs["epa_iterations"])
     tol = float(o.tolerance)

@@ -39,6 +39,12 @@ def load_scene(name):
     mjm = mjcf.load_string(BOX_XML)
   elif name in ("boxccd", "boxccd_mixed"):
     mjm = mjcf.load_string(util.boxccd_xml(name.endswith("mixed")))
+  elif name == "mixed_sap":
+    mjm = mjcf.load_string(util.MIXED_XML)
+    mjm.opt.broadphase = 1
+  elif name == "convex_sap":
+    mjm = mjcf.load_string(util.CONVEX_XML)
+    mjm.opt.broadphase, mjm.opt.broadphase_filter = 2, 1 | 8
   elif name == "convex":
     mjm = mjcf.load_string(util.CONVEX_XML)
   elif name == "pairs":

@@ -55,6 +55,14 @@ def scenes():
   yield "boxes", mjcf.load_string(BOX_XML), dict(nconmax=48, njmax=200, key=None, qpos_noise=0.003, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "boxccd", mjcf.load_string(util.boxccd_xml()), dict(nconmax=48, njmax=256, key=None, qpos_noise=0.0004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "boxccd_mixed", mjcf.load_string(util.boxccd_xml(True)), dict(nconmax=48, njmax=256, key=None, qpos_noise=0.0004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
+  # sweep-and-prune broadphase (collision_driver.py:582): same scenes, tile sort with the default filters and segmented sort
+  # without the bounding-sphere filter (so the sweep's own pruning decides which pairs reach the OBB test)
+  sap = mjcf.load_string(util.MIXED_XML)
+  sap.opt.broadphase = 1
+  yield "mixed_sap", sap, dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  sap2 = mjcf.load_string(util.CONVEX_XML)
+  sap2.opt.broadphase, sap2.opt.broadphase_filter = 2, 1 | 8
+  yield "convex_sap", sap2, dict(nconmax=64, njmax=256, key=None, qpos_noise=0.004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
   yield "g1", mjcf.load_any(util.G1), dict(nconmax=48, njmax=192, key=0, qpos_noise=0.02, qvel_noise=0.2, ctrl_noise=0.3)
 
@@ -95,6 +103,10 @@ def main(only=None):
     qpos, qvel, ctrl, warm = f32(qpos), f32(qvel), f32(ctrl), f32(warm)
     ad = ref_runner.MjModelAdapter(mjm)
     m = io.put_model(ad)
+    if getattr(mjm.opt, "broadphase", 0):  # put_model picks the broadphase from the pair count (io.py:631-636); override like a user would
+      m.opt.broadphase = int(mjm.opt.broadphase)
+    if hasattr(mjm.opt, "broadphase_filter"):
+      m.opt.broadphase_filter = int(mjm.opt.broadphase_filter)
     d = io.make_data(ad, nworld=NWORLD, nconmax=nconmax, njmax=njmax)
     d.qpos.a[...] = qpos; d.qvel.a[...] = qvel; d.qacc_warmstart.a[...] = warm
     if mjm.nu:

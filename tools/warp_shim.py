@@ -586,6 +586,28 @@ def _install_runtime(wp):
     arr.a[tuple(sl_dst)] = block
 
   wp.tile_load, wp.tile_store = tile_load, tile_store
+
+  def tile_sort(keys, values):
+    order = _np.argsort(keys.a, kind="stable")
+    keys.a[...] = keys.a[order]; values.a[...] = values.a[order]
+
+  wp.tile_sort = tile_sort
+
+  class _Utils:
+    @staticmethod
+    def array_scan(src, dst, inclusive=True):
+      c = _np.cumsum(src.a.reshape(-1))
+      dst.a.reshape(-1)[...] = c if inclusive else _np.concatenate(([0], c[:-1]))
+
+    @staticmethod
+    def segmented_sort_pairs(keys, values, count, segment_start_indices, segment_end_indices=None):
+      k, v, seg = keys.a.reshape(-1), values.a.reshape(-1), segment_start_indices.a.reshape(-1)
+      for i in range(len(seg) - 1):
+        lo, hi = int(seg[i]), int(seg[i + 1])
+        order = _np.argsort(k[lo:hi], kind="stable")
+        k[lo:hi] = k[lo:hi][order]; v[lo:hi] = v[lo:hi][order]
+
+  wp.utils = _Utils
   wp.tile_zeros = lambda shape=None, dtype=float, **kw: Tile(_np.zeros(_shape_t(shape)))
   wp.tile_ones = lambda shape=None, dtype=float, **kw: Tile(_np.ones(_shape_t(shape)))
   wp.tile_arange = lambda *a, dtype=int, **kw: Tile(_np.arange(*a).astype(float))
