@@ -260,8 +260,8 @@ def derive_tables(mjm) -> dict:
 def _validate(mjm):
   """Feature checks in the spirit of io.py:284-363: fail loudly on anything the kernels do not cover."""
   o = mjm.opt
-  if o.integrator not in (C.INT_EULER, C.INT_IMPLICITFAST):
-    raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler and implicitfast only in this version)")
+  if o.integrator not in (C.INT_EULER, C.INT_RK4, C.INT_IMPLICITFAST):
+    raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler, RK4 and implicitfast in this version; the fully implicit integrator is not)")
   if o.cone not in (C.CONE_PYRAMIDAL, C.CONE_ELLIPTIC):
     raise NotImplementedError(f"unknown friction cone {o.cone}")
   if o.solver not in (C.SOL_NEWTON, C.SOL_CG):

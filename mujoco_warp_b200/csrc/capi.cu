@@ -22,6 +22,7 @@ struct mjbData {
   cudaStream_t aux[8];
   cudaEvent_t ev_fork, ev_join[8];
   int nsplit;
+  float* rk;  // Runge-Kutta scratch, (nworld, nq + 3 nv); allocated by mjb_data_finalize for RK4 models only
 };
 
 namespace {
@@ -92,12 +93,14 @@ mjbData* mjb_data_create(int nworld, int nconmax, int naconmax, int njmax, int n
   d->dev.w0 = 0; d->dev.wn = nworld;
   d->finalized = false;
   d->nsplit = 1;
+  d->rk = nullptr;
   return d;
 }
 void mjb_data_destroy(mjbData* d) {
   if (!d) return;
   if (d->dev.world_conadr) cudaFree(d->dev.world_conadr);
   if (d->dev.world_ncon) cudaFree(d->dev.world_ncon);
+  if (d->rk) cudaFree(d->rk);
   if (d->nsplit > 1) {
     for (int i = 0; i < d->nsplit; i++) { cudaStreamDestroy(d->aux[i]); cudaEventDestroy(d->ev_join[i]); }
     cudaEventDestroy(d->ev_fork);
@@ -124,6 +127,8 @@ int mjb_data_finalize(mjbData* d, const mjbModel* m) {
   if (check(cudaMalloc(&d->dev.world_ncon, sizeof(int) * (size_t)d->dev.nworld), "cudaMalloc(world_ncon)")) return -1;
   if (check(cudaMemset(d->dev.world_conadr, 0, sizeof(int) * (size_t)d->dev.nworld), "memset")) return -1;
   if (check(cudaMemset(d->dev.world_ncon, 0, sizeof(int) * (size_t)d->dev.nworld), "memset")) return -1;
+  if (m->dev.integrator == INT_RK4 && !d->rk &&
+      check(cudaMalloc(&d->rk, sizeof(float) * (size_t)d->dev.nworld * (size_t)(m->dev.nq + 3 * m->dev.nv + 1)), "cudaMalloc(rk)")) return -1;
   d->smem[0] = smem_position(m->dev); d->smem[1] = smem_collision(m->dev, d->dev); d->smem[2] = smem_constraint(m->dev, d->dev);
   d->smem[3] = smem_velocity(m->dev); d->smem[4] = smem_solver(m->dev, d->dev); d->smem[5] = smem_integrate(m->dev);
   static const char* names[6] = {"position", "collision", "constraint", "velocity", "solver", "integrate"};
@@ -223,6 +228,14 @@ int mjb_fwd_position(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER();
 int mjb_forward(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER, s); }
 int mjb_step(const mjbModel* m, mjbData* d, void* stream) {
   MJB_ENTER();
+  if (m->dev.integrator == INT_RK4) {  // forward.py:523-555: four forward() evaluations with the state bookkeeping in between
+    if (!d->rk) return fail("Runge-Kutta scratch missing: data was finalized against a model with another integrator");
+    for (int stage = 0; stage < 4; stage++) {
+      if (pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER, s)) return -1;
+      MJB_LAUNCH(launch_rk_stage(m->dev, d->dev, d->rk, stage, s), 1);
+    }
+    return 0;
+  }
   return pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER | RUN_EULER, s);
 }
 int mjb_step_profile(const mjbModel* m, mjbData* d, void* stream, float* ms_out) {

@@ -145,6 +145,61 @@ __global__ void k_ctrl_noise(const __grid_constant__ ModelDev m, const __grid_co
   d.ctrl[i] = ctrl;
 }
 
+// forward.py:53-115 _next_position for one joint: qpos <- integrate(qpos_in, scale * qvel) over dt
+__device__ __forceinline__ void next_position_jnt(const ModelDev& m, int j, const float* qpos_in, const float* qvel, float scale, float dt, float* qpos) {
+  const int t = m.jnt_type[j], qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+  if (t == JNT_FREE) {
+    for (int k = 0; k < 3; k++) qpos[qa + k] = qpos_in[qa + k] + dt * (qvel[da + k] * scale);
+    stq(qpos + qa + 3, quat_integrate(ldq(qpos_in + qa + 3), ld3(qvel + da + 3) * scale, dt));
+  } else if (t == JNT_BALL) {
+    stq(qpos + qa, quat_integrate(ldq(qpos_in + qa), ld3(qvel + da) * scale, dt));
+  } else {
+    qpos[qa] = qpos_in[qa] + dt * qvel[da] * scale;
+  }
+}
+
+// One Runge-Kutta bookkeeping step after the stage-th forward() of the step (forward.py:523-555 rungekutta4, stateless
+// actuators): accumulate B[stage] * (qvel, qacc); stages 0..2 then perturb the state for the next forward
+// (_rk_perturb_state: position from the current stage velocity, velocity from qvel_t0 + A dt qacc); stage 3 restores the
+// state and advances it with the accumulated velocity / acceleration (_advance with qvel = qvel_rk).
+// rk: per world [qpos_t0 (nq) | qvel_t0 (nv) | qvel_rk (nv) | qacc_rk (nv)].  One warp per world.
+__global__ void __launch_bounds__(32)
+k_rk_stage(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, float* __restrict__ rk, int stage) {
+  const int lane = threadIdx.x, w = blockIdx.x;
+  if (w >= d.nworld) return;
+  const int nq = m.nq, nv = m.nv;
+  const size_t wb = (size_t)w;
+  float *qpos_t0 = rk + wb * (nq + 3 * nv), *qvel_t0 = qpos_t0 + nq, *qvel_rk = qvel_t0 + nv, *qacc_rk = qvel_rk + nv;
+  float *qpos = d.qpos + wb * nq, *qvel = d.qvel + wb * nv;
+  const float* qacc = d.qacc + wb * nv;
+  const float dt = m.timestep;
+  const float B = (stage == 0 || stage == 3) ? (1.0f / 6.0f) : (1.0f / 3.0f), A = stage == 2 ? 1.0f : 0.5f;
+  if (stage == 0) {
+    for (int i = lane; i < nq; i += 32) qpos_t0[i] = qpos[i];
+    for (int i = lane; i < nv; i += 32) { const float v = qvel[i]; qvel_t0[i] = v; qvel_rk[i] = B * v; qacc_rk[i] = B * qacc[i]; }
+  } else {
+    for (int i = lane; i < nv; i += 32) { qvel_rk[i] += B * qvel[i]; qacc_rk[i] += B * qacc[i]; }
+  }
+  __syncwarp();
+  if (stage < 3) {
+    for (int j = lane; j < m.njnt; j += 32) next_position_jnt(m, j, qpos_t0, qvel, A, dt, qpos);
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) qvel[i] = qvel_t0[i] + A * qacc[i] * dt;
+    return;
+  }
+  for (int i = lane; i < nv; i += 32) { qvel[i] = qvel_t0[i] + qacc_rk[i] * dt; d.qacc_warmstart[wb * nv + i] = qacc[i]; }
+  for (int j = lane; j < m.njnt; j += 32) next_position_jnt(m, j, qpos_t0, qvel_rk, 1.0f, dt, qpos);
+  if (lane == 0) {  // _next_time (forward.py:221-271)
+    d.time[w] += dt;
+    int ovf = 0;
+    if (d.nefc[w] > d.njmax) ovf |= OVF_NEFC;
+    if (d.ncollision[0] > d.naconmax) ovf |= OVF_BROADPHASE;
+    if (d.nacon[0] > d.naconmax) ovf |= OVF_NARROWPHASE;
+    if (ovf) d.overflow[w] |= ovf;
+  }
+}
+
+
 }  // namespace
 
 size_t smem_integrate(const ModelDev& m) { return (size_t)int_words(m) * sizeof(float) * MJB_WARPS_PER_BLOCK; }
@@ -166,5 +221,10 @@ cudaError_t launch_ctrl_noise(const ModelDev& m, const DataDev& d, const float* 
   const int n = d.nworld * m.nu;
   if (n == 0) return cudaSuccess;
   k_ctrl_noise<<<(n + 255) / 256, 256, 0, s>>>(m, d, ctrl_center, step, std, rate);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rk_stage(const ModelDev& m, const DataDev& d, float* rk, int stage, cudaStream_t s) {
+  k_rk_stage<<<d.nworld, 32, 0, s>>>(m, d, rk, stage);
   return cudaGetLastError();
 }

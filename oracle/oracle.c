@@ -2296,24 +2296,34 @@ static void solve(W* w) {
 }
 
 /* ------------------------------------------------------------------ integrators (forward.py:53-131,221-349,387-417) */
-static void advance(W* w, const real* qacc) {
-  const OrcModel* m = w->m;
-  for (int d = 0; d < m->nv; d++) w->qvel[d] += qacc[d] * m->timestep;
+/* forward.py:53-115 _next_position: qpos <- integrate(qpos_in, scale * qvel) over one timestep */
+static void next_position(const OrcModel* m, const real* qpos_in, const real* qvel, real scale, real* qpos) {
   for (int j = 0; j < m->njnt; j++) {
     int t = m->jnt_type[j], qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
     if (t == JNT_FREE) {
-      for (int i = 0; i < 3; i++) w->qpos[qa + i] += m->timestep * w->qvel[da + i];
-      quat_integrate(w->qpos + qa + 3, w->qvel + da + 3, m->timestep);
+      real ang[3] = {qvel[da + 3] * scale, qvel[da + 4] * scale, qvel[da + 5] * scale};
+      for (int i = 0; i < 3; i++) qpos[qa + i] = qpos_in[qa + i] + m->timestep * (qvel[da + i] * scale);
+      for (int i = 3; i < 7; i++) qpos[qa + i] = qpos_in[qa + i];
+      quat_integrate(qpos + qa + 3, ang, m->timestep);
     } else if (t == JNT_BALL) {
-      quat_integrate(w->qpos + qa, w->qvel + da, m->timestep);
+      real ang[3] = {qvel[da] * scale, qvel[da + 1] * scale, qvel[da + 2] * scale};
+      for (int i = 0; i < 4; i++) qpos[qa + i] = qpos_in[qa + i];
+      quat_integrate(qpos + qa, ang, m->timestep);
     } else {
-      w->qpos[qa] += m->timestep * w->qvel[da];
+      qpos[qa] = qpos_in[qa] + m->timestep * qvel[da] * scale;
     }
   }
+}
+/* forward.py:276-349 _advance: velocity from qacc, position from qvel_pos (the new velocity when NULL: semi-implicit) */
+static void advance2(W* w, const real* qacc, const real* qvel_pos) {
+  const OrcModel* m = w->m;
+  for (int d = 0; d < m->nv; d++) w->qvel[d] += qacc[d] * m->timestep;
+  next_position(m, w->qpos, qvel_pos ? qvel_pos : w->qvel, 1, w->qpos);
   w->time[0] += m->timestep;
   if (w->nefc[0] > w->njmax) w->overflow[0] |= OVF_NEFC;
   memcpy(w->qacc_warmstart, w->qacc, m->nv * sizeof(real));
 }
+static void advance(W* w, const real* qacc) { advance2(w, qacc, NULL); }
 static void euler(W* w) {
   const OrcModel* m = w->m;
   if (!(m->disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
@@ -2372,9 +2382,31 @@ static void forward_world(W* w) {
   solve(w);
 }
 
+/* forward.py:523-555 rungekutta4 (stateless actuators): called after the first forward() of the step */
+static void rungekutta4(W* w) {
+  const OrcModel* m = w->m;
+  const int nq = m->nq, nv = m->nv;
+  const real A[3] = {(real)0.5, (real)0.5, (real)1.0}, B[4] = {(real)(1.0 / 6.0), (real)(1.0 / 3.0), (real)(1.0 / 3.0), (real)(1.0 / 6.0)};
+  real* buf = (real*)calloc((size_t)2 * nq + 3 * nv, sizeof(real));
+  real *qpos_t0 = buf, *qpos_new = buf + nq, *qvel_t0 = buf + 2 * nq, *qvel_rk = qvel_t0 + nv, *qacc_rk = qvel_rk + nv;
+  memcpy(qpos_t0, w->qpos, nq * sizeof(real)); memcpy(qvel_t0, w->qvel, nv * sizeof(real));
+  for (int d = 0; d < nv; d++) { qvel_rk[d] += B[0] * w->qvel[d]; qacc_rk[d] += B[0] * w->qacc[d]; }
+  for (int i = 0; i < 3; i++) {
+    /* _rk_perturb_state: the position step uses the current stage velocity, then the velocity is perturbed */
+    next_position(m, qpos_t0, w->qvel, A[i], qpos_new);
+    memcpy(w->qpos, qpos_new, nq * sizeof(real));
+    for (int d = 0; d < nv; d++) w->qvel[d] = qvel_t0[d] + A[i] * w->qacc[d] * m->timestep;
+    forward_world(w);
+    for (int d = 0; d < nv; d++) { qvel_rk[d] += B[i + 1] * w->qvel[d]; qacc_rk[d] += B[i + 1] * w->qacc[d]; }
+  }
+  memcpy(w->qpos, qpos_t0, nq * sizeof(real)); memcpy(w->qvel, qvel_t0, nv * sizeof(real));
+  advance2(w, qacc_rk, qvel_rk);
+  free(buf);
+}
+
 static int run(const OrcModel* m, OrcData* d, int nthreads, int do_step) {
   if (check_fields(m, d)) return -1;
-  if (do_step && m->integrator != INT_EULER && m->integrator != INT_IMPLICITFAST) { snprintf(g_err, sizeof g_err, "oracle: only the Euler and implicitfast integrators are restated"); return -1; }
+  if (do_step && m->integrator != INT_EULER && m->integrator != INT_IMPLICITFAST && m->integrator != INT_RK4) { snprintf(g_err, sizeof g_err, "oracle: the fully implicit integrator is not restated"); return -1; }
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -2383,7 +2415,7 @@ static int run(const OrcModel* m, OrcData* d, int nthreads, int do_step) {
     W w;
     make_view(m, d, wi, &w);
     forward_world(&w);
-    if (do_step) { if (m->integrator == INT_IMPLICITFAST) implicitfast(&w); else euler(&w); }
+    if (do_step) { if (m->integrator == INT_IMPLICITFAST) implicitfast(&w); else if (m->integrator == INT_RK4) rungekutta4(&w); else euler(&w); }
   }
   return 0;
 }

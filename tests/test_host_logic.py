@@ -151,7 +151,7 @@ def test_unsupported_features_raise():
   from mujoco_warp_b200._src import io as mio
   from mujoco_warp_b200._src import mjcf
 
-  xml = """<mujoco><option integrator="RK4"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
+  xml = """<mujoco><option integrator="implicit"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
   with pytest.raises(NotImplementedError, match="integrator"):
     mio._validate(mjcf.load_string(xml))
   # box-box goes through GJK / EPA + multi-contact recovery (16 EPA iterations when it is the only convex pair type);

@@ -39,6 +39,8 @@ def load_scene(name):
     mjm = mjcf.load_string(BOX_XML)
   elif name in ("boxccd", "boxccd_mixed"):
     mjm = mjcf.load_string(util.boxccd_xml(name.endswith("mixed")))
+  elif name == "mixed_rk4":
+    mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"'))
   elif name == "mixed_sap":
     mjm = mjcf.load_string(util.MIXED_XML)
     mjm.opt.broadphase = 1
