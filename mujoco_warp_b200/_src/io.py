@@ -266,8 +266,9 @@ def _validate(mjm):
     raise NotImplementedError(f"unknown friction cone {o.cone}")
   if o.solver not in (C.SOL_NEWTON, C.SOL_CG):
     raise NotImplementedError("only the Newton and CG solvers are implemented in this version (no PGS)")
-  if mjm.nv > 64:
-    raise NotImplementedError("nv > 64 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
+  if mjm.nv > 128:
+    # the dense per-world Hessian and its factor live in one warp's shared memory; make_data reports the exact per-kernel need
+    raise NotImplementedError("nv > 128 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
   for n in ("na", "ntendon", "nflex"):
     if getattr(mjm, n, 0):
       raise NotImplementedError(f"{n} > 0 is not supported in this version")

@@ -276,6 +276,172 @@ def _expand_includes(root, basedir):
   return root
 
 
+# ----------------------------------------------------------------------------------------------
+# composite elements: <frame>, <replicate>, <attach model=...> are expanded into plain bodies before compilation
+# ----------------------------------------------------------------------------------------------
+
+_ORIENT_ATTRS = ("quat", "axisangle", "euler", "xyaxes", "zaxis")
+_NAME_REFS = ("joint", "body1", "body2", "geom1", "geom2", "target", "site", "body", "objname", "refname", "joint1", "joint2")
+
+
+def _fmt(v):
+  return " ".join(repr(float(x)) for x in np.asarray(v).reshape(-1))
+
+
+def _bake_frame(elem, fpos, fquat, compiler):
+  """Express a body / geom / site / camera / light given in a frame (fpos, fquat) in the frame's parent."""
+  a = elem.attrib
+  if elem.tag == "light":
+    a["pos"] = _fmt(fpos + rot_vec(fquat, _vec(a.get("pos"), default=[0, 0, 0])))
+    a["dir"] = _fmt(rot_vec(fquat, _vec(a.get("dir"), default=[0, 0, -1])))
+    return
+  if "fromto" in a:
+    ft = _vec(a["fromto"])
+    a["fromto"] = _fmt(np.concatenate([fpos + rot_vec(fquat, ft[:3]), fpos + rot_vec(fquat, ft[3:])]))
+    return
+  q = quat_mul(fquat, _frame_quat(a, compiler))
+  for k in _ORIENT_ATTRS:
+    a.pop(k, None)
+  a["pos"] = _fmt(fpos + rot_vec(fquat, _vec(a.get("pos"), default=[0, 0, 0])))
+  a["quat"] = _fmt(q / np.linalg.norm(q))
+
+
+def _rename(elem, prefix, suffix):
+  """prefix + name + suffix on every name and name reference of a subtree."""
+  if not prefix and not suffix:
+    return
+  for e in elem.iter():
+    for k in ("name",) + _NAME_REFS:
+      if k in e.attrib:
+        e.set(k, prefix + e.get(k) + suffix)
+
+
+def _expand_composites(root, basedir):
+  """<frame> children are re-expressed in the parent frame; <replicate> repeats its children `count` times with cumulative
+  offset / euler increments and a name suffix `sep + index`; <attach model= body= prefix=> grafts a body subtree of another
+  MJCF file (declared in <asset><model/>) together with the actuators, contact pairs / excludes and keyframes that refer to it.
+  The attached file's <default> tree is adopted when the host file has none (anything else raises); its <option> is not
+  imported (as in MuJoCo).  Keyframes: each attachment contributes its file's keyframes, the rest of qpos keeps qpos0."""
+  if not any(e.tag in ("frame", "replicate", "attach") for e in root.iter()):
+    return root
+  compiler = {"angle": "degree", "eulerseq": "xyz"}
+  for ce in root.findall("compiler"):
+    compiler["angle"] = ce.get("angle", compiler["angle"]); compiler["eulerseq"] = ce.get("eulerseq", compiler["eulerseq"])
+  models = {}
+  for asset in root.findall("asset"):
+    for me in list(asset.findall("model")):
+      models[me.get("name")] = os.path.join(basedir or "", me.get("file"))
+      asset.remove(me)
+  ident = (np.zeros(3), np.array([1.0, 0, 0, 0]))
+  extra = {"actuator": [], "contact": [], "keyframe": []}
+
+  def section(tag):
+    sec = root.find(tag)
+    if sec is None:
+      sec = ET.SubElement(root, tag)
+    return sec
+
+  def attach(elem, fpos, fquat, suffix):
+    import copy
+
+    if elem.get("model") not in models:
+      raise NotImplementedError("<attach> needs model= naming an <asset><model file=.../> entry")
+    path = models[elem.get("model")]
+    child = ET.parse(path).getroot()
+    _expand_includes(child, os.path.dirname(os.path.abspath(path)))
+    for tag in ("tendon", "equality", "sensor"):
+      if child.find(tag) is not None and len(child.find(tag)):
+        raise NotImplementedError(f"<attach>: <{tag}> of the attached model is not supported")
+    for ce in child.findall("compiler"):
+      if ce.get("angle", "degree") != compiler["angle"] or ce.get("eulerseq", "xyz") != compiler["eulerseq"]:
+        raise NotImplementedError("<attach>: the attached model uses different compiler angle / eulerseq settings")
+    body = next((b for b in child.iter("body") if b.get("name") == elem.get("body")), None)
+    if body is None:
+      raise ValueError(f"<attach>: body {elem.get('body')} not found in {path}")
+    if child.find("default") is not None:
+      if root.find("default") is not None and root.find("default") is not child.find("default") and not root.find("default").get("_adopted"):
+        raise NotImplementedError("<attach>: both files define <default>s")
+      if root.find("default") is None:
+        d = copy.deepcopy(child.find("default")); d.set("_adopted", "1"); root.append(d)
+    prefix = elem.get("prefix", "")
+    graft = copy.deepcopy(body)
+    _bake_frame(graft, fpos, fquat, compiler)
+    _rename(graft, prefix, suffix)
+    for tag in ("actuator", "contact"):
+      sec = child.find(tag)
+      for e in (list(sec) if sec is not None else []):
+        e2 = copy.deepcopy(e); _rename(e2, prefix, suffix); extra[tag].append(e2)
+    # keyframes of the attached file, restricted to the grafted subtree's joints (free-joint root poses move with the frame)
+    def qsize(j):
+      return {"free": 7, "ball": 4}.get(j.get("type", "hinge") if j.tag == "joint" else "free", 1)
+
+    off, found = 0, False
+    for b in child.iter("body"):  # document order = qpos order
+      if b is body:
+        found = True
+        break
+      if any(anc is b for anc in []) :
+        pass
+      off += sum(qsize(j) for j in b if j.tag in ("joint", "freejoint"))
+    sub_joints = [j for b in body.iter("body") for j in b if j.tag in ("joint", "freejoint")]
+    size = sum(qsize(j) for j in sub_joints)
+    free_root = bool(sub_joints) and sub_joints[0] in list(body) and qsize(sub_joints[0]) == 7
+    ke = child.find("keyframe")
+    for k in (ke.findall("key") if ke is not None and found else []):
+      if "qpos" not in k.attrib:
+        continue
+      q = _vec(k.get("qpos"))[off : off + size].copy()
+      if free_root:
+        q[:3] = fpos + rot_vec(fquat, q[:3]); q[3:7] = quat_mul(fquat, q[3:7] / np.linalg.norm(q[3:7]))
+      pk = ET.Element("key", {"name": prefix + k.get("name", "key") + suffix, "_part_body": graft.get("name"), "_part_qpos": _fmt(q)})
+      extra["keyframe"].append(pk)
+    return graft
+
+  def expand(parent, fpos, fquat, suffix):
+    """children of `parent`, with frames / replicates / attaches resolved; (fpos, fquat) is the pending frame of `parent`'s children."""
+    import copy
+
+    out = []
+    for ch in list(parent):
+      if ch.tag == "frame":
+        p = fpos + rot_vec(fquat, _vec(ch.get("pos"), default=[0, 0, 0])); q = quat_mul(fquat, _frame_quat(ch.attrib, compiler))
+        out += expand(ch, p, q, suffix)
+      elif ch.tag == "replicate":
+        n = int(ch.get("count")); sep = ch.get("sep", ""); width = len(str(n - 1))
+        off = _vec(ch.get("offset"), default=[0, 0, 0]); rq = _frame_quat({k: v for k, v in ch.attrib.items() if k == "euler"}, compiler)
+        p, q = fpos.copy(), fquat.copy()
+        for i in range(n):
+          out += expand(copy.deepcopy(ch), p, q, suffix + sep + str(i).zfill(width))
+          p = p + rot_vec(q, off); q = quat_mul(q, rq)
+      elif ch.tag == "attach":
+        g = attach(ch, fpos, fquat, suffix)
+        g[:] = expand(g, *ident, "")
+        out.append(g)
+      else:
+        if ch.tag in ("body", "geom", "site", "camera", "light") and (fpos.any() or not np.allclose(fquat, ident[1])):
+          _bake_frame(ch, fpos, fquat, compiler)
+        if suffix:
+          for k in ("name",) + _NAME_REFS:
+            if k in ch.attrib:
+              ch.set(k, ch.get(k) + suffix)
+        if ch.tag == "body":
+          ch[:] = expand(ch, *ident, suffix)
+        out.append(ch)
+    return out
+
+  for wb in root.findall("worldbody"):
+    wb[:] = expand(wb, *ident, "")
+  for tag, elems in extra.items():
+    if elems:
+      sec = section(tag)
+      for e in elems:
+        sec.append(e)
+  d = root.find("default")
+  if d is not None:
+    d.attrib.pop("_adopted", None)
+  return root
+
+
 def _merge_toplevel(root):
   """Merge repeated top-level sections (from includes) into one element per tag."""
   merged = {}
@@ -294,6 +460,7 @@ def load(path: str):
   """Compile an MJCF file into an MjModel-like object."""
   root = ET.parse(path).getroot()
   _expand_includes(root, os.path.dirname(os.path.abspath(path)))
+  _expand_composites(root, os.path.dirname(os.path.abspath(path)))
   return compile_xml(root)
 
 
@@ -972,6 +1139,12 @@ def compile_xml(root):
     m.names.key.append(k.get("name", f"key{i}"))
     if "time" in k.attrib:
       m.key_time[i] = float(k.get("time"))
+    if "_part_body" in k.attrib:  # keyframe of an attached model: only that subtree's joints, the rest stays at qpos0
+      v = _vec(k.get("_part_qpos"))
+      b0 = m.names.body.index(k.get("_part_body"))
+      adr = int(m.jnt_qposadr[m.body_jntadr[b0]])
+      m.key_qpos[i, adr : adr + v.size] = v
+      continue
     for nm_, arr in (("qpos", m.key_qpos), ("qvel", m.key_qvel), ("ctrl", m.key_ctrl)):
       if nm_ in k.attrib:
         v = _vec(k.get(nm_))

@@ -55,6 +55,8 @@ def load_scene(name):
     mjm = mjcf.load_string(util.passive_xml())
   elif name == "equality":
     mjm = mjcf.load_string(util.EQUALITY_XML)
+  elif name == "three_humanoids":
+    mjm = mjcf.load_any(util.THREE_HUMANOIDS)
   elif name == "g1":
     mjm = mjcf.load_any(util.G1)
   else:

@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = os.path.join(ROOT, "mujoco_warp_b200", "test_data")
 HUMANOID = os.path.join(SCENES, "humanoid.npz")
 G1 = os.path.join(SCENES, "unitree_g1_flat.npz")
+THREE_HUMANOIDS = os.path.join(SCENES, "three_humanoids.npz")
 G1_TRAJ = os.path.join(SCENES, "unitree_g1_shuffle_dance.npz")
 
 

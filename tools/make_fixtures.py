@@ -18,6 +18,7 @@ OUT = os.path.join(ROOT, "mujoco_warp_b200", "test_data")
 
 SCENES = {
   "humanoid": "benchmarks/humanoid/humanoid.xml",  # BASELINE configs[1]: iterations=100, ls_iterations=50
+  "three_humanoids": "benchmarks/humanoid/three_humanoids.xml",  # benchmarks/humanoid/__init__.py second entry: nv 81, <replicate> + <attach>
   "unitree_g1_flat": "benchmarks/unitree_g1/scene_flat.xml",  # BASELINE configs[2] (visual mesh geoms skipped: STL not in tree)
 }
 # replay trajectories are benchmark INPUT data (ctrl sequences), copied verbatim

@@ -66,6 +66,9 @@ def scenes():
   rk = util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"')
   yield "mixed_rk4", mjcf.load_string(rk), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
+  three = mjcf.load_any(util.THREE_HUMANOIDS)
+  three.opt.jacobian = 1  # sparse: the reference does not run dense above nv = 60; snapshot() stores efc_J densified
+  yield "three_humanoids", three, dict(nconmax=100, njmax=192, key=0, qpos_noise=0.003, qvel_noise=0.05, ctrl_noise=0.3, exact_world0=False)
   yield "g1", mjcf.load_any(util.G1), dict(nconmax=48, njmax=192, key=0, qpos_noise=0.02, qvel_noise=0.2, ctrl_noise=0.3)
 
 
@@ -78,6 +81,17 @@ def snapshot(mjm, d, out, tag):
     a = getattr(d.efc, f)
     if a is not None and a.a is not None:
       out[f"{tag}/efc_{f}"] = a.numpy()
+  if getattr(d.efc, "J_rownnz", None) is not None and d.efc.J_rownnz.a is not None and d.efc.J_rownnz.a.size and d.efc.J.numpy().shape[1] == 1:
+    # CSR Jacobian (types.py:2021-2072) -> dense (nworld, njmax, nv) so that fixtures have one layout
+    J, nnz, adr, col = d.efc.J.numpy(), d.efc.J_rownnz.numpy(), d.efc.J_rowadr.numpy(), d.efc.J_colind.numpy()
+    nworld, njmax = nnz.shape
+    dense = np.zeros((nworld, njmax, mjm.nv))
+    nefc = d.nefc.numpy()
+    for w in range(nworld):
+      for r in range(int(nefc[w])):
+        for k in range(int(nnz[w, r])):
+          dense[w, r, col[w, 0, adr[w, r] + k]] = J[w, 0, adr[w, r] + k]
+    out[f"{tag}/efc_J"] = dense
   nacon = int(d.nacon.numpy()[0])
   out[f"{tag}/nacon"] = np.array(nacon)
   for f in CON:
@@ -101,6 +115,12 @@ def main(only=None):
     if name.startswith("humanoid"):  # keep the feet on the floor: exact root pose, pushed 0.5 mm deeper per world
       qpos[:, :7] = mjm.key_qpos[0][:7]
       qpos[:, 2] -= 0.0005 * np.arange(NWORLD)
+    if name == "three_humanoids":  # all three in the squat pose (keys 0, 3, 6 each pose one of them), roots exact, feet on the floor
+      for i in range(3):
+        sl = slice(28 * i, 28 * (i + 1))
+        qpos[:, sl] += mjm.key_qpos[3 * i][sl] - mjm.key_qpos[0][sl]
+        qpos[:, 28 * i : 28 * i + 7] = mjm.key_qpos[3 * i][28 * i : 28 * i + 7]
+        qpos[:, 28 * i + 2] -= 0.0005 * np.arange(NWORLD)
     f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)  # inputs exactly representable in fp32
     qpos, qvel, ctrl, warm = f32(qpos), f32(qvel), f32(ctrl), f32(warm)
     ad = ref_runner.MjModelAdapter(mjm)

@@ -185,8 +185,8 @@ class OptAdapter:
 
   def __getattr__(self, name):
     o = object.__getattribute__(self, "_o")
-    if name == "jacobian":
-      return OPT_DEFAULTS["jacobian"]
+    if name == "jacobian":  # dense unless the model asks otherwise (the reference refuses dense above nv = 60)
+      return int(getattr(o, "jacobian", OPT_DEFAULTS["jacobian"]))
     if hasattr(o, name):
       return getattr(o, name)
     if name in OPT_DEFAULTS:

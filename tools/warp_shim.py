@@ -544,6 +544,7 @@ def _install_runtime(wp):
   wp.get_device = lambda *a: _t.SimpleNamespace(is_cuda=False, is_cpu=True, sm_count=1, arch=0, ordinal=0)
   wp.is_conditional_graph_supported = lambda: False
   wp.ScopedDevice = lambda *a, **k: _Null()
+  wp.get_suggested_block_size = lambda kernel, *a, **k: (256, 1184)  # (block size, min grid): only used to partition work
   wp.config = _t.SimpleNamespace(enable_backward=False, quiet=True)
 
   def capture_while(cond, while_body=None, **kw):
