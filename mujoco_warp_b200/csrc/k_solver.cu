@@ -1,4 +1,5 @@
-// k_solver.cu -- Newton constraint solver as ONE persistent launch (one warp per world, all state in shared memory).
+// k_solver.cu -- Newton constraint solver as ONE persistent launch (one warp per world -- a team of 2 or 4 warps above
+// nv = 32 -- with all state in shared memory).
 //
 // Replaces (reference, /root/reference/mujoco_warp/_src/solver.py): :3671 solve / :3689 _solve, :3622 init_context,
 // :1566 _solve_init_dof, :1609 _solve_init_jaref, support.py:153 mul_m, :1698 _update_constraint_efc,
@@ -14,6 +15,8 @@
 // shifted (cost(alpha) - cost(0)) piecewise-quadratic 1-D cost.  Pyramidal / frictionless / limit / dof-friction rows
 // in the default instantiation; k_solver<true> adds elliptic cones (solver.py:286-477 zones, :957-1015 per-contact
 // quads, :2443-2565 cone Hessian) with the Hessian rebuilt from M every iteration like the reference's elliptic path.
+#include <cstdlib>
+
 #include "mjb_chol.cuh"
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
@@ -23,7 +26,7 @@ namespace {
 // Shared-memory slice of one world.  J rows keep the global stride nv_pad (a multiple of 4 floats), so a row is 16-byte
 // aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
 // rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
-struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, cgv, total; };
+struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, cgv, red, env, total; };
 __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d) {
   SolLayout L;
   int o = 0;
@@ -47,6 +50,9 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   L.nrowf = (m.nfricdof > 0 ? 5 : 4);
   L.rowf = take((L.nrowf + (ell ? 4 : 0)) * d.njmax);
   L.rowi = take((ell ? 3 : 2) * d.njmax);
+  L.red = take(m.nv > 32 ? 9 * 8 : 0);  // cross-warp reduction scratch of the multi-warp (nv > 32) instantiations
+  // nv > 32: nonzero column range of every Jacobian row (lo | hi << 16) and the Hessian's row envelope (first column per row)
+  L.env = take(m.nv > 32 ? d.njmax + L.nvp : 0);
   L.total = o;
   return L;
 }
@@ -54,7 +60,34 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
 struct P3 { float c, g, h; };
 __device__ __forceinline__ P3 mkp(float c, float g, float h) { P3 p; p.c = c; p.g = g; p.h = h; return p; }
 __device__ __forceinline__ P3 operator+(P3 a, P3 b) { return mkp(a.c + b.c, a.g + b.g, a.h + b.h); }
-__device__ __forceinline__ P3 warp_sum3(P3 p) { return mkp(warp_sum(p.c), warp_sum(p.g), warp_sum(p.h)); }
+
+// ---- team = the NW warps (one block) that own a world.  NW = 1: plain warp primitives.  NW > 1 (models with nv > 32, where a
+// world's slice of shared memory caps the SM at a few resident worlds): block barriers, and reductions that finish in shared
+// memory in a fixed order so every thread sees the same bits.
+template <int NW> __device__ __forceinline__ void tsync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
+template <int NW, int N>
+__device__ __forceinline__ void tsum_n(float (&v)[N], float* red) {
+#pragma unroll
+  for (int k = 0; k < N; k++) v[k] = warp_sum(v[k]);
+  if (NW == 1) return;
+  const int warp = threadIdx.x >> 5;
+  __syncthreads();  // the previous reduction's readers are done with `red`
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < N; k++) red[warp * N + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    float t = red[k];
+#pragma unroll
+    for (int w = 1; w < NW; w++) t += red[w * N + k];
+    v[k] = t;
+  }
+}
+template <int NW> __device__ __forceinline__ float tsum(float v, float* red) { float a[1] = {v}; tsum_n<NW, 1>(a, red); return a[0]; }
+template <int NW> __device__ __forceinline__ P3 tsum3(P3 p, float* red) { float a[3] = {p.c, p.g, p.h}; tsum_n<NW, 3>(a, red); return mkp(a[0], a[1], a[2]); }
+template <int NW> __device__ __forceinline__ void tcopy(float* dst, const float* src, int n, int tid) { for (int i = tid; i < n; i += 32 * NW) dst[i] = src[i]; }
 
 // row kinds by position (solver.py:1751-1755): [0,ne) equality, [ne,ne+nf) friction loss, rest inequality
 // shifted evaluation: (cost(alpha) - cost(0), grad, hess) -- solver.py:479-517
@@ -171,6 +204,9 @@ struct Ctx {
   int* rinfo; float *rfri, *quad; int njmax, ncone;
   const float* Jg; int jcap;  // big models: rows >= jcap live in global memory (same leading dimension)
   float* cgv;                 // CG only: Mgrad, prev_grad, prev_Mgrad (nvp each)
+  float* red;                 // NW > 1: cross-warp reduction scratch (9 floats per warp)
+  int *rng, *fz;              // nv > 32: Jacobian row ranges, Hessian row envelope
+  bool env;                   // ranges / envelope in use (several kinematic trees: the Hessian is close to block diagonal)
 };
 template <bool BIG>
 __device__ __forceinline__ const float* jrow(const Ctx& c, int r) {
@@ -184,10 +220,11 @@ __device__ __forceinline__ EllQ ell_load(const Ctx& c, int r) {
 }
 
 // res = M vec via the symmetric gather tables (support.py:153 mul_m; tables io.py:1029-1050)
+template <int NW>
 __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res) {
   const ModelDev& m = *c.m;
 #pragma unroll 1
-  for (int i = c.lane; i < c.nv; i += 32) {
+  for (int i = c.lane; i < c.nv; i += 32 * NW) {
     float acc = 0.f;
 #pragma unroll 4
     for (int k = m.mulm_rowadr[i]; k < m.mulm_rowadr[i + 1]; k++) acc += c.M[m.mulm_madr[k]] * vec[m.mulm_col[k]];
@@ -197,12 +234,13 @@ __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res
 
 // force/state per row, qfrc_constraint = J^T force, and the list of rows whose QUADRATIC flag changed
 // (init=true: list every QUADRATIC row with weight +D).  Returns the list length.
-template <bool ELL, bool BIG>
+template <bool ELL, bool BIG, int NW>
 __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
   int nlist = 0, ncone = 0;
   if (ELL) init = true;  // elliptic: H is rebuilt from M, so every QUADRATIC row is listed
+  // the row pass (a handful of flops per row, ordered compaction by ballot) stays on the first warp of the team
 #pragma unroll 1
-  for (int r0 = 0; r0 < c.nefc; r0 += 32) {
+  for (int r0 = 0; r0 < ((NW == 1 || c.lane < 32) ? c.nefc : 0); r0 += 32) {
     const int r = r0 + c.lane;
     bool flip = false, cone0 = false;
     float wgt = 0.f;
@@ -248,26 +286,32 @@ __device__ __forceinline__ int update_constraint(Ctx& c, bool init) {
       ncone += __popc(cb);
     }
   }
+  if (NW > 1) {  // hand the two counts to the other warps
+    if (c.lane == 0) { c.red[0] = __int_as_float(nlist); c.red[1] = __int_as_float(ncone); }
+    __syncthreads();
+    nlist = __float_as_int(c.red[0]); ncone = __float_as_int(c.red[1]);
+  }
   c.ncone = ncone;
-  __syncwarp();
+  tsync<NW>();
 #pragma unroll 1
-  for (int dd = c.lane; dd < c.nv; dd += 32) {
+  for (int dd = c.lane; dd < c.nv; dd += 32 * NW) {
     float s = 0.f;
 #pragma unroll 8
     for (int r = 0; r < c.nefc; r++) s += jrow<BIG>(c, r)[dd] * c.force[r];
     c.qfc[dd] = s;
   }
-  __syncwarp();
+  tsync<NW>();
   return nlist;
 }
 
 // grad = Ma - qfrc_smooth - qfrc_constraint and its squared norm
+template <int NW>
 __device__ __forceinline__ void update_grad(Ctx& c) {
   float gd = 0.f;
 #pragma unroll 1
-  for (int dd = c.lane; dd < c.nv; dd += 32) { const float g = c.Ma[dd] - c.qfs[dd] - c.qfc[dd]; c.grad[dd] = g; gd += g * g; }
-  c.grad_dot = warp_sum(gd);
-  __syncwarp();
+  for (int dd = c.lane; dd < c.nv; dd += 32 * NW) { const float g = c.Ma[dd] - c.qfs[dd] - c.qfc[dd]; c.grad[dd] = g; gd += g * g; }
+  c.grad_dot = tsum<NW>(gd, c.red);
+  tsync<NW>();
 }
 
 // Newton direction for nv <= 32: lane i keeps row i of H in registers, adds w * J_r[i] * J_r[:] for every listed row r
@@ -350,7 +394,7 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
-template <bool ELL, bool BIG>
+template <bool ELL, bool BIG, int NW>
 __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   const int nv = c.nv;
   float sd = 0.f, nd = 0.f;
@@ -365,28 +409,45 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
     sd = xx * xx; nd = g * xx;
     if (c.lane < nv) c.search[c.lane] = -xx;
   } else {
-    // 32 < nv <= 64: lane owns Hessian rows `lane` and `lane + 32` of the packed lower triangle in shared memory
+    // nv > 32: packed lower triangle in shared memory, worked on by the whole team
+    constexpr int NT = 32 * NW;
     const int ntri = nv * (nv + 1) / 2;
     float* Hd = ELL ? c.Lf : c.H;  // elliptic: rebuild into Lf from M (c.H) every iteration
     if (ELL) {
 #pragma unroll 1
-      for (int e = c.lane; e < ntri; e += 32) c.Lf[e] = c.H[e];
-      __syncwarp();
+      for (int e = c.lane; e < ntri; e += NT) c.Lf[e] = c.H[e];
+      tsync<NW>();
     }
+    if (NW == 1) {  // one warp: lane owns rows lane, lane + 32, ...
 #pragma unroll 1
-    for (int t = 0; t < nlist; t++) {
-      const float* Jr = jrow<true>(c, c.hidx[t]);
-      const float wt = c.hw[t];
+      for (int t = 0; t < nlist; t++) {
+        const float* Jr = jrow<true>(c, c.hidx[t]);
+        const float wt = c.hw[t];
+        const int lo = c.env ? (c.rng[c.hidx[t]] & 0xFFFF) : 0, hi = c.env ? (c.rng[c.hidx[t]] >> 16) : nv;  // the row is zero outside [lo, hi)
 #pragma unroll 1
-      for (int i = c.lane; i < nv; i += 32) {
-        const float sc = wt * Jr[i];
-        float* Hi = Hd + (i * (i + 1)) / 2;
-        if (sc != 0.f)
+        for (int i = lo + c.lane; i < hi; i += 32) {
+          const float sc = wt * Jr[i];
+          float* Hi = Hd + (i * (i + 1)) / 2;
+          if (sc != 0.f)
 #pragma unroll 4
-          for (int k = 0; k <= i; k++) Hi[k] += sc * Jr[k];
+            for (int k = lo; k <= i; k++) Hi[k] += sc * Jr[k];
+        }
+      }
+    } else if (nlist > 0) {  // team: every thread owns entries (i, k) of the triangle and sums the listed rows' contributions
+#pragma unroll 1
+      for (int e = c.lane; e < ntri; e += NT) {
+        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= e) i++;
+        while (i * (i + 1) / 2 > e) i--;
+        const int k = e - i * (i + 1) / 2;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int t = 0; t < nlist; t++) { const float* Jr = jrow<true>(c, c.hidx[t]); acc += c.hw[t] * Jr[i] * Jr[k]; }
+        Hd[e] += acc;
       }
     }
     if (ELL) {
+      tsync<NW>();
 #pragma unroll 1
       for (int t = 0; t < c.ncone; t++) {
         const int e0 = c.hidx[c.njmax - 1 - t];
@@ -394,7 +455,7 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
         if (k.dm == 0.f) continue;
         const float* J0 = jrow<true>(c, e0);
 #pragma unroll 1
-        for (int i = c.lane; i < nv; i += 32) {
+        for (int i = c.lane; i < nv; i += NT) {
           float pi = 0.f;
           for (int q = 1; q < k.dim; q++) pi += c.Jaref[e0 + q] * c.rfri[e0 + q] * c.rfri[e0 + q] * jrow<true>(c, e0 + q)[i];
           float* Hi = Hd + (i * (i + 1)) / 2;
@@ -406,53 +467,63 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
         }
       }
     }
-    __syncwarp();
+    tsync<NW>();
     if (!ELL) {
 #pragma unroll 1
-      for (int e = c.lane; e < ntri; e += 32) c.Lf[e] = c.H[e];
+      for (int e = c.lane; e < ntri; e += NT) c.Lf[e] = c.H[e];
     }
 #pragma unroll 1
-    for (int dd = c.lane; dd < nv; dd += 32) c.x[dd] = c.grad[dd];
-    __syncwarp();
-    warp_cholesky_packed(c.Lf, nv, c.lane);
-    warp_chol_solve_packed(c.Lf, nv, c.x, c.lane);
+    for (int dd = c.lane; dd < nv; dd += NT) c.x[dd] = c.grad[dd];
+    tsync<NW>();
+    if (NW == 1) {
+      if (c.env) {
+        warp_cholesky_packed_env(c.Lf, nv, c.fz, c.lane);
+        warp_chol_solve_packed_env(c.Lf, nv, c.fz, c.x, c.lane);
+      } else {
+        warp_cholesky_packed(c.Lf, nv, c.lane);
+        warp_chol_solve_packed(c.Lf, nv, c.x, c.lane);
+      }
+    } else {
+      team_cholesky_packed<NW>(c.Lf, nv, c.lane);
+      team_chol_solve_packed<NW>(c.Lf, nv, c.x, c.lane);
+    }
 #pragma unroll 1
-    for (int dd = c.lane; dd < nv; dd += 32) { const float xx = c.x[dd]; sd += xx * xx; nd += c.grad[dd] * xx; c.search[dd] = -xx; }
+    for (int dd = c.lane; dd < nv; dd += NT) { const float xx = c.x[dd]; sd += xx * xx; nd += c.grad[dd] * xx; c.search[dd] = -xx; }
   }
-  c.search_dot = warp_sum(sd);
-  c.newton_decrement = warp_sum(nd);
-  __syncwarp();
+  { float a[2] = {sd, nd}; tsum_n<NW, 2>(a, c.red); c.search_dot = a[0]; c.newton_decrement = a[1]; }
+  tsync<NW>();
 }
 
-template <bool ELL>
+template <bool ELL, int NW>
 __device__ __forceinline__ P3 eval_total(const Ctx& c, float alpha, float q0, float q1, float q2) {
   P3 s = mkp(0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int r = c.lane; r < c.nefc; r += 32) {
+  for (int r = c.lane; r < c.nefc; r += 32 * NW) {
     if (ELL && c.rinfo[r] != -1) {
       if (c.rinfo[r] >= 0 && (c.rinfo[r] & 15) == 0) { const EllQ q = ell_load(c, r); const float mu = c.rfri[r]; s = s + ell_shifted(mu, q, ell_reference(mu, q), alpha); }
     } else s = s + eval_row(r, alpha, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
   }
-  return eval_gauss(q0, q1, q2, alpha) + warp_sum3(s);
+  return eval_gauss(q0, q1, q2, alpha) + tsum3<NW>(s, c.red);
 }
 
 // solver.py:836-1347; returns true when the line search converged
-template <bool ELL, bool BIG>
+template <bool ELL, bool BIG, int NW>
 __device__ __forceinline__ bool linesearch(Ctx& c) {
   const ModelDev& m = *c.m;
   const int nv = c.nv;
-  mul_m(c, c.search, c.mv);
+  constexpr int NT = 32 * NW;
+  mul_m<NW>(c, c.search, c.mv);
 #pragma unroll 1
-  for (int r = c.lane; r < c.nefc; r += 32) {
+  for (int r = c.lane; r < c.nefc; r += NT) {
     c.jv[r] = row_dot(jrow<BIG>(c, r), c.search, c.nvp);
   }
-  __syncwarp();
+  tsync<NW>();
   const float snorm = sqrtf(c.search_dot), scale = m.meaninertia * (float)nv;
   const float gtol = fmaxf(m.tolerance * m.ls_tolerance * snorm * scale, 1e-6f);
   P3 p0s = mkp(0.f, 0.f, 0.f);
   if (ELL) {  // per-contact quads at the primary rows (solver.py:957-1015)
 #pragma unroll 1
-    for (int r = c.lane; r < c.nefc; r += 32) {
+    for (int r = c.lane; r < c.nefc; r += NT) {
       const int info = c.rinfo[r];
       if (info < 0 || (info & 15) != 0) continue;
       const int dim = info >> 4;
@@ -468,23 +539,24 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
       const float mu2 = mu * mu;
       q[0] = q0; q[1] = q1; q[2] = q2; q[3] = ja * mu; q[4] = jv * mu; q[5] = uu; q[6] = uv; q[7] = vv; q[8] = D / (mu2 * (1.0f + mu2));
     }
-    __syncwarp();
+    tsync<NW>();
   }
 #pragma unroll 1
-  for (int r = c.lane; r < c.nefc; r += 32) {
+  for (int r = c.lane; r < c.nefc; r += NT) {
     if (ELL && c.rinfo[r] != -1) {
       if (c.rinfo[r] >= 0 && (c.rinfo[r] & 15) == 0) p0s = p0s + ell_zero(c.rfri[r], ell_load(c, r));
     } else p0s = p0s + eval_row_zero(r, c.ne, c.nf, c.D[r], c.floss[r], c.Jaref[r], c.jv[r]);
   }
-  p0s = warp_sum3(p0s);
   float g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
-  for (int dd = c.lane; dd < nv; dd += 32) { const float s = c.search[dd]; g1 += s * (c.Ma[dd] - c.qfs[dd]); g2 += 0.5f * s * c.mv[dd]; }
-  const float q0 = 0.f, q1 = warp_sum(g1), q2 = warp_sum(g2);
+  for (int dd = c.lane; dd < nv; dd += NT) { const float s = c.search[dd]; g1 += s * (c.Ma[dd] - c.qfs[dd]); g2 += 0.5f * s * c.mv[dd]; }
+  float q1, q2;
+  { float a[5] = {p0s.c, p0s.g, p0s.h, g1, g2}; tsum_n<NW, 5>(a, c.red); p0s = mkp(a[0], a[1], a[2]); q1 = a[3]; q2 = a[4]; }
+  const float q0 = 0.f;
   const P3 p0 = mkp(q0 + p0s.c, q1 + p0s.g, 2.0f * q2 + p0s.h);
   const P3 p0_delta = mkp(0.f, p0.g, p0.h);
   const float lo_alpha_in = -safe_div(p0.g, p0.h);
-  const P3 lo_in = eval_total<ELL>(c, lo_alpha_in, q0, q1, q2);
+  const P3 lo_in = eval_total<ELL, NW>(c, lo_alpha_in, q0, q1, q2);
   const bool initial_converged = fabsf(lo_in.g) < gtol && lo_in.c < 0.f;
   bool ls_converged = initial_converged;
   float alpha = 0.f, improvement = 0.f;
@@ -497,7 +569,7 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
       const float lo_next_alpha = lo_alpha - safe_div(lo.g, lo.h), hi_next_alpha = hi_alpha - safe_div(hi.g, hi.h), mid_alpha = 0.5f * (lo_alpha + hi_alpha);
       P3 sl = mkp(0.f, 0.f, 0.f), sh = sl, sm = sl;
 #pragma unroll 1
-      for (int r = c.lane; r < c.nefc; r += 32) {
+      for (int r = c.lane; r < c.nefc; r += NT) {
         if (ELL && c.rinfo[r] != -1) {
           if (c.rinfo[r] >= 0 && (c.rinfo[r] & 15) == 0) {
             const EllQ q = ell_load(c, r); const float mu = c.rfri[r]; const EllRef e = ell_reference(mu, q);
@@ -510,9 +582,14 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
         sh = sh + eval_row(r, hi_next_alpha, c.ne, c.nf, D, f, ja, jv);
         sm = sm + eval_row(r, mid_alpha, c.ne, c.nf, D, f, ja, jv);
       }
-      const P3 lo_next = eval_gauss(q0, q1, q2, lo_next_alpha) + warp_sum3(sl);
-      const P3 hi_next = eval_gauss(q0, q1, q2, hi_next_alpha) + warp_sum3(sh);
-      const P3 mid = eval_gauss(q0, q1, q2, mid_alpha) + warp_sum3(sm);
+      {
+        float a[9] = {sl.c, sl.g, sl.h, sh.c, sh.g, sh.h, sm.c, sm.g, sm.h};
+        tsum_n<NW, 9>(a, c.red);
+        sl = mkp(a[0], a[1], a[2]); sh = mkp(a[3], a[4], a[5]); sm = mkp(a[6], a[7], a[8]);
+      }
+      const P3 lo_next = eval_gauss(q0, q1, q2, lo_next_alpha) + sl;
+      const P3 hi_next = eval_gauss(q0, q1, q2, hi_next_alpha) + sh;
+      const P3 mid = eval_gauss(q0, q1, q2, mid_alpha) + sm;
       const bool s1 = in_bracket(lo, lo_next); if (s1) { lo = lo_next; lo_alpha = lo_next_alpha; }
       const bool s2 = in_bracket(lo, mid); if (s2) { lo = mid; lo_alpha = mid_alpha; }
       const bool s3 = in_bracket(lo, hi_next); if (s3) { lo = hi_next; lo_alpha = hi_next_alpha; }
@@ -529,11 +606,11 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
     alpha = lo_alpha_in; improvement = -lo_in.c;
   }
 #pragma unroll 1
-  for (int dd = c.lane; dd < nv; dd += 32) { c.qacc[dd] += alpha * c.search[dd]; c.Ma[dd] += alpha * c.mv[dd]; }
+  for (int dd = c.lane; dd < nv; dd += NT) { c.qacc[dd] += alpha * c.search[dd]; c.Ma[dd] += alpha * c.mv[dd]; }
 #pragma unroll 1
-  for (int r = c.lane; r < c.nefc; r += 32) c.Jaref[r] += alpha * c.jv[r];
+  for (int r = c.lane; r < c.nefc; r += NT) c.Jaref[r] += alpha * c.jv[r];
   c.improvement = improvement;
-  __syncwarp();
+  tsync<NW>();
   return ls_converged;
 }
 
@@ -586,15 +663,16 @@ __device__ __forceinline__ void cg_direction(Ctx& c, const ModelDev& m, const Da
   __syncwarp();
 }
 
-template <bool ELL, bool BIG, bool CG>
-__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
+template <bool ELL, bool BIG, bool CG, int NW>
+__global__ void __launch_bounds__(NW * 32)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
+  constexpr int NT = 32 * NW;
+  const int lane = threadIdx.x;  // index inside the team of NW warps (one block) that owns the world
   const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   const SolLayout L = sol_layout(m, d);
-  float* S = smem + warp * L.total;
+  float* S = smem;
   const int nv = m.nv, njmax = d.njmax, nvp = d.nv_pad;
   const size_t wb = (size_t)w;
   Ctx c;
@@ -611,11 +689,15 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   c.njmax = njmax; c.ncone = 0;
   c.jcap = L.jcap; c.Jg = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
   c.cgv = S + L.cgv;
+  c.red = S + L.red;
+  c.rng = (int*)(S + L.env); c.fz = c.rng + njmax;
+  // a single tree with a floating base has a dense envelope (every row reaches the root dofs): bookkeeping would only cost
+  c.env = BIG && m.ntree > 1;
   c.rfri = rf + L.nrowf * njmax; c.quad = c.rfri + njmax; c.rinfo = ri + 2 * njmax;
 
   if (njmax == 0 || nv == 0) {
 #pragma unroll 1
-    for (int dd = lane; dd < nv; dd += 32) d.qacc[wb * nv + dd] = d.qacc_smooth[wb * nv + dd];
+    for (int dd = lane; dd < nv; dd += NT) d.qacc[wb * nv + dd] = d.qacc_smooth[wb * nv + dd];
     if (lane == 0) d.solver_niter[w] = 0;
     return;
   }
@@ -627,11 +709,11 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     const float4* Jg = reinterpret_cast<const float4*>(d.efc_J + wb * (size_t)d.njmax_pad * nvp);
     float4* Js = reinterpret_cast<float4*>(c.J);
 #pragma unroll 1
-    for (int i = lane; i < min(nefc, L.jcap) * nvp / 4; i += 32) Js[i] = Jg[i];
-    for (int i = lane; i < 7 * vp; i += 32) v[i] = 0.f;  // zero padding of every per-dof vector
-    __syncwarp();
+    for (int i = lane; i < min(nefc, L.jcap) * nvp / 4; i += NT) Js[i] = Jg[i];
+    for (int i = lane; i < 7 * vp; i += NT) v[i] = 0.f;  // zero padding of every per-dof vector
+    tsync<NW>();
 #pragma unroll 1
-    for (int r = lane; r < nefc; r += 32) {
+    for (int r = lane; r < nefc; r += NT) {
       c.D[r] = d.efc_D[wb * d.njmax_pad + r];
       if (m.nfricdof > 0) c.floss[r] = d.efc_frictionloss[wb * njmax + r];
       c.state[r] = ST_SATISFIED;
@@ -645,26 +727,63 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
         c.rinfo[r] = info; c.rfri[r] = fr;
       }
     }
-    warp_copy(c.M, d.M + wb * m.nC, m.nC, lane);
-    warp_copy(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
+    tcopy<NW>(c.M, d.M + wb * m.nC, m.nC, lane);
+    tcopy<NW>(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
     const float* start = (m.disableflags & DSBL_WARMSTART) ? d.qacc_smooth : d.qacc_warmstart;
-    warp_copy(c.qacc, start + wb * nv, nv, lane);
+    tcopy<NW>(c.qacc, start + wb * nv, nv, lane);
     const int hsz = nv * (nv + 1) / 2;
 #pragma unroll 1
-    for (int e = lane; e < hsz; e += 32) c.H[e] = 0.f;
+    for (int e = lane; e < hsz; e += NT) c.H[e] = 0.f;
   }
-  __syncwarp();
+  tsync<NW>();
+  if (c.env) {
 #pragma unroll 1
-  for (int e = lane; e < m.nC; e += 32) {  // lower triangle of M
+    for (int i = lane; i < nv; i += NT) c.fz[i] = i;
+    tsync<NW>();
+  }
+#pragma unroll 1
+  for (int e = lane; e < m.nC; e += NT) {  // lower triangle of M
     const int r = m.M_entry_row[e], col = m.M_colind[e];
     c.H[(r * (r + 1)) / 2 + col] = c.M[e];
+    if (c.env) atomicMin(&c.fz[r], col);
+  }
+  if (c.env) {
+    // nonzero column range [lo, hi) of every Jacobian row; rows of one elliptic contact share the union of their ranges (the cone
+    // Hessian mixes them); every dof inside a row's range gets that row's lo into its envelope (H = M + sum of w J_r J_r^T terms)
+#pragma unroll 1
+    for (int r = lane; r < nefc; r += NT) {
+      const float* Jr = jrow<BIG>(c, r);
+      int lo = nv, hi = 0;
+      for (int k = 0; k < nv; k++) if (Jr[k] != 0.f) { lo = min(lo, k); hi = k + 1; }
+      if (hi == 0) lo = 0;
+      c.rng[r] = lo | (hi << 16);
+    }
+    tsync<NW>();
+    if (ELL) {
+#pragma unroll 1
+      for (int r = lane; r < nefc; r += NT) {
+        const int info = c.rinfo[r];
+        if (info < 0 || (info & 15) != 0) continue;
+        const int dim = info >> 4;
+        int lo = nv, hi = 0;
+        for (int j = 0; j < dim; j++) { const int g = c.rng[r + j]; if ((g >> 16) > 0) { lo = min(lo, g & 0xFFFF); hi = max(hi, g >> 16); } }
+        if (hi == 0) lo = 0;
+        for (int j = 0; j < dim; j++) c.rng[r + j] = lo | (hi << 16);
+      }
+      tsync<NW>();
+    }
+#pragma unroll 1
+    for (int r = lane; r < nefc; r += NT) {
+      const int lo = c.rng[r] & 0xFFFF, hi = c.rng[r] >> 16;
+      for (int i = lo; i < hi; i++) atomicMin(&c.fz[i], lo);
+    }
   }
 #pragma unroll 1
-  for (int r = lane; r < nefc; r += 32) {  // Jaref = J qacc - aref
+  for (int r = lane; r < nefc; r += NT) {  // Jaref = J qacc - aref
     c.Jaref[r] = row_dot(jrow<BIG>(c, r), c.qacc, c.nvp) - d.efc_aref[wb * njmax + r];
   }
-  mul_m(c, c.qacc, c.Ma);
-  __syncwarp();
+  mul_m<NW>(c, c.qacc, c.Ma);
+  tsync<NW>();
 
   // One call site per phase: iteration -1 is init_context (solver.py:3622), iterations >= 0 are _solver_iteration (:3526).
   // _solve_done's three criteria are OR-ed (:3483-3486), so when `improvement` or `gradient` already satisfies the
@@ -672,9 +791,9 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const float scale = m.meaninertia * (float)nv;
   int niter = 0, ovf = 0;
   for (int it = -1;; it++) {
-    if (it >= 0 && !linesearch<ELL, BIG>(c)) ovf |= OVF_LS_ITERATIONS;
-    const int nlist = update_constraint<ELL, BIG>(c, it < 0);
-    update_grad(c);
+    if (it >= 0 && !linesearch<ELL, BIG, NW>(c)) ovf |= OVF_LS_ITERATIONS;
+    const int nlist = update_constraint<ELL, BIG, NW>(c, it < 0);
+    update_grad<NW>(c);
     if (it >= 0) {
       niter++;
       const float improvement = c.improvement / scale, gradient = sqrtf(c.grad_dot) / scale;
@@ -685,7 +804,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
       cg_direction(c, m, d, wb, it < 0);
       continue;
     }
-    if (!CG) update_search<ELL, BIG>(c, nlist);
+    if (!CG) update_search<ELL, BIG, NW>(c, nlist);
     if (it >= 0) {
       if (0.5f * c.newton_decrement / scale < m.tolerance) break;
       if (niter == m.iterations) { ovf |= OVF_ITERATIONS; break; }
@@ -693,25 +812,40 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   }
 
   // ---- results
-  warp_copy(d.qacc + wb * nv, c.qacc, nv, lane);
-  warp_copy(d.efc_Ma + wb * nv, c.Ma, nv, lane);
-  warp_copy(d.qfrc_constraint + wb * nv, c.qfc, nv, lane);
+  tcopy<NW>(d.qacc + wb * nv, c.qacc, nv, lane);
+  tcopy<NW>(d.efc_Ma + wb * nv, c.Ma, nv, lane);
+  tcopy<NW>(d.qfrc_constraint + wb * nv, c.qfc, nv, lane);
 #pragma unroll 1
-  for (int r = lane; r < nefc; r += 32) { d.efc_force[wb * njmax + r] = c.force[r]; d.efc_state[wb * d.njmax_pad + r] = c.state[r]; }
+  for (int r = lane; r < nefc; r += NT) { d.efc_force[wb * njmax + r] = c.force[r]; d.efc_state[wb * d.njmax_pad + r] = c.state[r]; }
   if (lane == 0) { d.solver_niter[w] = niter; if (ovf) d.overflow[w] |= ovf; }
 }
 
 }  // namespace
 
-size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_layout(m, d).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_layout(m, d).total * sizeof(float); }
+
+// Warps per world: 1.  For nv > 32 the per-world slice of shared memory (packed Hessian + factor + Jacobian rows) limits an SM to
+// a few resident worlds; teams of 2 or 4 warps per world (block barriers, right-looking team Cholesky) are implemented and
+// parity-tested but measured slower than one warp per world, so they stay an experiment knob: MJB_SOLVER_WARPS = 1, 2 or 4.
+static int solver_warps(const ModelDev& m) {
+  if (m.nv <= 32 || m.solver == SOL_CG) return 1;
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MJB_SOLVER_WARPS"); forced = e ? atoi(e) : 0; }
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  return 1;  // measured on B200: teams of 2 / 4 warps are slower on unitree G1 (3.2 M vs 3.6 M steps/s) and three_humanoids
+}
 
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_solver(m, d);
-  static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = m.nv > 32 ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0, which = 4 * cg + 2 * big + ell;
-  static void (*const kerns[8])(ModelDev, DataDev) = {
-    k_solver<false, false, false>, k_solver<true, false, false>, k_solver<false, true, false>, k_solver<true, true, false>,
-    k_solver<false, false, true>,  k_solver<true, false, true>,  k_solver<false, true, true>,  k_solver<true, true, true>};
+  const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = m.nv > 32 ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0;
+  const int nw = solver_warps(m), team = nw == 4 ? 2 : (nw == 2 ? 1 : 0);
+  const int which = cg ? 4 + 2 * big + ell : (big ? 8 + 2 * team + ell : ell);
+  static size_t configured[14] = {0};
+  static void (*const kerns[14])(ModelDev, DataDev) = {
+    k_solver<false, false, false, 1>, k_solver<true, false, false, 1>, nullptr, nullptr,
+    k_solver<false, false, true, 1>,  k_solver<true, false, true, 1>,  k_solver<false, true, true, 1>,  k_solver<true, true, true, 1>,
+    k_solver<false, true, false, 1>,  k_solver<true, true, false, 1>,  k_solver<false, true, false, 2>, k_solver<true, true, false, 2>,
+    k_solver<false, true, false, 4>,  k_solver<true, true, false, 4>};
   void (*kern)(ModelDev, DataDev) = kerns[which];
   if (smem > 48 * 1024 && smem > configured[which]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -719,6 +853,6 @@ cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
     configured[which] = smem;
   }
   const int grid = d.wn;
-  kern<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  kern<<<grid, nw * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

@@ -85,6 +85,95 @@ __device__ __forceinline__ void warp_chol_solve_packed(const float* L, int n, fl
   }
 }
 
+// Envelope (skyline) variants: fz[i] <= i is the first column of row i that can be nonzero (the factor keeps the envelope of the
+// matrix), so inner products start at max(fz[i], fz[j]) and rows whose envelope starts past column j are skipped.  For a
+// block-diagonal Hessian (independent kinematic trees without a coupling constraint) this is one small factorisation per block.
+__device__ __forceinline__ void warp_cholesky_packed_env(float* A, int n, const int* fz, int lane) {
+  for (int j = 0; j < n; j++) {
+    const float* rj = A + (j * (j + 1)) / 2;
+    const int fj = fz[j];
+    float s = 0.f;
+    for (int k = fj + lane; k < j; k += 32) s += rj[k] * rj[k];
+    s = warp_sum(s);
+    const float ljj = sqrtf(fmaxf(rj[j] - s, MJ_MINVAL));
+    const float inv = 1.0f / ljj;
+    for (int i = j + 1 + lane; i < n; i += 32) {
+      const int fi = fz[i];
+      if (fi > j) continue;  // A[i][j] is outside the envelope: stays 0
+      float* ri = A + (i * (i + 1)) / 2;
+      float t = ri[j];
+#pragma unroll 4
+      for (int k = max(fi, fj); k < j; k++) t -= ri[k] * rj[k];
+      ri[j] = t * inv;
+    }
+    __syncwarp();
+    if (lane == 0) A[(j * (j + 1)) / 2 + j] = ljj;
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void warp_chol_solve_packed_env(const float* L, int n, const int* fz, float* x, int lane) {
+  for (int j = 0; j < n; j++) {  // forward: L y = b
+    const float yj = x[j] / L[(j * (j + 1)) / 2 + j];
+    __syncwarp();
+    for (int i = j + 1 + lane; i < n; i += 32) if (fz[i] <= j) x[i] -= L[(i * (i + 1)) / 2 + j] * yj;
+    if (lane == 0) x[j] = yj;
+    __syncwarp();
+  }
+  for (int j = n - 1; j >= 0; j--) {  // backward: L^T x = y
+    const float* rj = L + (j * (j + 1)) / 2;
+    const float xj = x[j] / rj[j];
+    __syncwarp();
+    for (int i = fz[j] + lane; i < j; i += 32) x[i] -= rj[i] * xj;
+    if (lane == 0) x[j] = xj;
+    __syncwarp();
+  }
+}
+
+// Team (NW warps = one block) variants of the packed factor / solve for the multi-warp solver: right-looking, so that the
+// O(n^2) trailing update of every column is spread over all 32 NW threads (entry (a, b) of the trailing triangle is decoded
+// from a flat index); three block barriers per column.
+template <int NW>
+__device__ __forceinline__ void team_cholesky_packed(float* A, int n, int tid) {
+  constexpr int NT = 32 * NW;
+  for (int j = 0; j < n; j++) {
+    const int jj = (j * (j + 1)) / 2 + j;
+    if (tid == 0) A[jj] = sqrtf(fmaxf(A[jj], MJ_MINVAL));
+    __syncthreads();
+    const float inv = 1.0f / A[jj];
+    for (int i = j + 1 + tid; i < n; i += NT) A[(i * (i + 1)) / 2 + j] *= inv;
+    __syncthreads();
+    const int mrem = n - 1 - j, cnt = mrem * (mrem + 1) / 2;
+    for (int e = tid; e < cnt; e += NT) {
+      int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((a + 1) * (a + 2) / 2 <= e) a++;
+      while (a * (a + 1) / 2 > e) a--;
+      const int b = e - a * (a + 1) / 2, i = j + 1 + a, k = j + 1 + b;
+      const int ri = (i * (i + 1)) / 2;
+      A[ri + k] -= A[ri + j] * A[(k * (k + 1)) / 2 + j];
+    }
+    __syncthreads();
+  }
+}
+template <int NW>
+__device__ __forceinline__ void team_chol_solve_packed(const float* L, int n, float* x, int tid) {
+  constexpr int NT = 32 * NW;
+  for (int j = 0; j < n; j++) {  // forward: L y = b
+    const float yj = x[j] / L[(j * (j + 1)) / 2 + j];
+    __syncthreads();
+    for (int i = j + 1 + tid; i < n; i += NT) x[i] -= L[(i * (i + 1)) / 2 + j] * yj;
+    if (tid == 0) x[j] = yj;
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; j--) {  // backward: L^T x = y
+    const float* rj = L + (j * (j + 1)) / 2;
+    const float xj = x[j] / rj[j];
+    __syncthreads();
+    for (int i = tid; i < j; i += NT) x[i] -= rj[i] * xj;
+    if (tid == 0) x[j] = xj;
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Register-resident Cholesky for n <= 32: lane i keeps row i of the matrix in registers, columns are eliminated
 // right-looking with warp shuffles (no shared-memory round trips, no __syncwarp per column), the forward substitution of
