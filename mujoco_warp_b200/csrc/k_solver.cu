@@ -32,10 +32,9 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   L.nvp = d.nv_pad; L.ldJ = d.nv_pad; L.ldH = m.nv | 1;
-  // nv > 32 ("big" models, e.g. unitree G1): only the first jcap Jacobian rows are staged in shared memory, later rows are
-  // read from global memory (they are L2 hits; nefc is usually far below njmax) -- keeps the per-world slice small enough for
-  // >= 12 resident warps per SM instead of 5
-  L.jcap = m.nv > 32 ? (d.njmax < 48 ? d.njmax : 48) : d.njmax;
+  // nv > 32 ("big" models, e.g. unitree G1, three_humanoids): only the first d.jcap Jacobian rows are staged in shared memory,
+  // the rest is read from global memory (L2 hits).  d.jcap defaults to 0: occupancy beats the shorter access (see capi.cu).
+  L.jcap = m.nv > 32 ? (d.njmax < d.jcap ? d.njmax : d.jcap) : d.njmax;
   L.J = take(L.jcap * L.ldJ);
   L.vec = take(7 * L.nvp);  // qacc, Ma, grad, search, mv (= x scratch of the nv > 32 path), qfs, qfc
   L.cgv = take(m.solver == SOL_CG ? 3 * L.nvp : 0);  // CG only: Mgrad, prev_grad, prev_Mgrad

@@ -66,6 +66,7 @@ struct ModelDev {
 struct DataDev {
   int nworld, nconmax, naconmax, njmax, njmax_pad, nv_pad;
   int w0, wn;  // world range [w0, w0 + wn) processed by one launch (the step is pipelined over two world halves)
+  int jcap;    // nv > 32: Jacobian rows the solver stages in shared memory (the rest is read from global memory / L2)
 #define X(n) float* __restrict__ n;
   MJB_DATA_FARRS(X)
 #undef X
