@@ -24,6 +24,8 @@
  *   mjb_rne                    <- _src/smooth.py:1499  rne(flg_acc=False)
  *   mjb_solve_m                <- _src/smooth.py:3214  solve_m(m, d, x, y): x = M^-1 y through Data.qLD
  *   mjb_mul_m                  <- _src/support.py:153  mul_m(m, d, res, vec): res = M vec
+ *   mjb_contact_force          <- _src/support.py:445  contact_force(m, d, contact_ids, to_world_frame, force)
+ *   mjb_rungekutta4            <- _src/forward.py:523  rungekutta4(m, d)
  *   mjb_solve                  <- _src/solver.py:3671  solve
  *   mjb_euler                  <- _src/forward.py:387  euler
  *   mjb_ctrl_noise             <- _src/cli.py:103      _ctrl_noise (harness kernel, untimed in testspeed)
@@ -82,6 +84,10 @@ int mjb_rne(const mjbModel* m, mjbData* d, void* stream);
 /* x, y, res, vec: device arrays (nworld, nv) fp32 */
 int mjb_solve_m(const mjbModel* m, mjbData* d, float* x, const float* y, void* stream);
 int mjb_mul_m(const mjbModel* m, mjbData* d, float* res, const float* vec, void* stream);
+/* support.py:445 contact_force(m, d, contact_ids, to_world_frame, force): force is (n, 6) floats, device pointers */
+int mjb_contact_force(const mjbModel* m, mjbData* d, const int* contact_ids, int n, int to_world_frame, float* force, void* stream);
+/* forward.py:523 rungekutta4(m, d): the integrator alone, after forward() (models compiled with the RK4 integrator) */
+int mjb_rungekutta4(const mjbModel* m, mjbData* d, void* stream);
 int mjb_solve(const mjbModel* m, mjbData* d, void* stream);
 int mjb_euler(const mjbModel* m, mjbData* d, void* stream);
 /* ctrl <- OU noise around ctrl_center (device array of nu floats, or NULL), reference cli.py:103-145 */

@@ -78,6 +78,8 @@ def lib():
   for f in ("mjb_solve_m", "mjb_mul_m"):
     getattr(L, f).argtypes = [vp, vp, vp, vp, vp]
     getattr(L, f).restype = ci
+  L.mjb_contact_force.argtypes = [vp, vp, vp, ci, ci, vp, vp]
+  L.mjb_contact_force.restype = ci
   L.mjb_step_profile.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_float)]
   L.mjb_last_launch_count.restype = ci
   _lib = L
@@ -87,7 +89,7 @@ def lib():
 STAGE_FUNCS = [
   "mjb_step", "mjb_forward", "mjb_fwd_position", "mjb_kinematics", "mjb_com_pos", "mjb_camlight", "mjb_crb", "mjb_transmission",
   "mjb_collision", "mjb_make_constraint", "mjb_fwd_velocity", "mjb_fwd_actuation", "mjb_fwd_acceleration", "mjb_factor_m",
-  "mjb_solve", "mjb_euler", "mjb_com_vel", "mjb_passive", "mjb_rne",
+  "mjb_solve", "mjb_euler", "mjb_com_vel", "mjb_passive", "mjb_rne", "mjb_rungekutta4",
 ]
 
 

@@ -89,6 +89,15 @@ def euler(m: Model, d: Data):
   _call("mjb_euler", m, d)
 
 
+def rungekutta4(m: Model, d: Data):
+  """Runge-Kutta 4 integrator, to be called after forward() (reference forward.py:523); the model must use the RK4 integrator."""
+  from . import constants as C
+
+  if m.opt.integrator != C.INT_RK4:
+    raise NotImplementedError("rungekutta4(): the model was put with another integrator (the RK scratch is allocated per model)")
+  _call("mjb_rungekutta4", m, d)
+
+
 def implicit(m: Model, d: Data):
   """Integrates with the implicit-in-velocity scheme the model selects (reference forward.py:578; implicitfast only here)."""
   from . import constants as C
@@ -138,6 +147,64 @@ def solve_m(m: Model, d: Data, x: torch.Tensor, y: torch.Tensor):
 def mul_m(m: Model, d: Data, res: torch.Tensor, vec: torch.Tensor):
   """res = M vec (reference support.py:153)."""
   _vec_call("mjb_mul_m", m, d, res, vec)
+
+
+def contact_force(m: Model, d: Data, contact_ids: torch.Tensor, to_world_frame: bool, force: torch.Tensor):
+  """6D force / torque of the listed contacts into force (n, 6), in the contact frame unless to_world_frame
+  (reference support.py:445; contact ids index the global contact pool)."""
+  n = int(contact_ids.numel())
+  if contact_ids.dtype != torch.int32 or not contact_ids.is_cuda or not contact_ids.is_contiguous():
+    raise ValueError("contact_ids: expected a contiguous CUDA int32 tensor")
+  if force.dtype != torch.float32 or not force.is_cuda or not force.is_contiguous() or tuple(force.shape) != (n, 6):
+    raise ValueError(f"force: expected a contiguous CUDA float32 tensor of shape ({n}, 6)")
+  stream = torch.cuda.current_stream().cuda_stream
+  _lib.check(_lib.lib().mjb_contact_force(m._handle, d._handle, contact_ids.data_ptr(), n, int(bool(to_world_frame)), force.data_ptr(), stream))
+
+
+_STATE_ORDER = ("TIME", "QPOS", "QVEL", "ACT", "HISTORY", "WARMSTART", "CTRL", "QFRC_APPLIED", "XFRC_APPLIED", "EQ_ACTIVE", "MOCAP_POS", "MOCAP_QUAT", "USERDATA")
+
+
+def _state_fields(m: Model, d: Data, sig: int):
+  """(tensor, width) of every state component selected by sig, in bit order (reference support.py:722-790)."""
+  from .types import State
+
+  if sig >= (1 << int(State.NSTATE)):
+    raise ValueError(f"invalid state signature {sig} >= 2^mjNSTATE")
+  nw = d.nworld
+  out = []
+  for name in _STATE_ORDER:
+    if not (int(getattr(State, name)) & sig):
+      continue
+    t = {
+      "TIME": lambda: d.time.reshape(nw, 1), "QPOS": lambda: d.qpos, "QVEL": lambda: d.qvel, "WARMSTART": lambda: d.qacc_warmstart,
+      "CTRL": lambda: d.ctrl, "QFRC_APPLIED": lambda: d.qfrc_applied, "XFRC_APPLIED": lambda: d.xfrc_applied.reshape(nw, -1),
+      "EQ_ACTIVE": lambda: d.eq_active.reshape(nw, -1), "MOCAP_POS": lambda: d.mocap_pos.reshape(nw, -1), "MOCAP_QUAT": lambda: d.mocap_quat.reshape(nw, -1),
+    }.get(name)
+    if t is None:  # ACT / HISTORY / USERDATA: stateless actuators only, no history buffers, no user data in this build (width 0)
+      continue
+    out.append(t())
+  return out
+
+
+def get_state(m: Model, d: Data, state: torch.Tensor, sig: int, active: torch.Tensor = None):
+  """Copy the state components selected by the State bit flags in sig from Data into state (nworld, size), concatenated in
+  bit order; worlds whose `active` entry is False are left untouched (reference support.py:674)."""
+  fields = _state_fields(m, d, int(sig))
+  if not fields:
+    return
+  cat = torch.cat([f.to(torch.float32) for f in fields], dim=1)
+  dst = state[:, : cat.shape[1]]
+  dst.copy_(cat if active is None else torch.where(active.reshape(-1, 1).bool(), cat, dst))
+
+
+def set_state(m: Model, d: Data, state: torch.Tensor, sig: int, active: torch.Tensor = None):
+  """Inverse of get_state (reference support.py:829)."""
+  adr = 0
+  for f in _state_fields(m, d, int(sig)):
+    w = f.shape[1]
+    src = state[:, adr : adr + w].to(f.dtype)
+    f.copy_(src if active is None else torch.where(active.reshape(-1, 1).bool(), src, f))
+    adr += w
 
 
 def step1(m: Model, d: Data):

@@ -115,6 +115,59 @@ class BroadphaseType(enum.IntEnum):
   SAP_SEGMENTED = 2
 
 
+class State(enum.IntEnum):
+  """State components as bit flags (reference types.py:712; MuJoCo mjtState with the history element after ACT)."""
+
+  TIME = 1 << 0
+  QPOS = 1 << 1
+  QVEL = 1 << 2
+  ACT = 1 << 3
+  HISTORY = 1 << 4
+  WARMSTART = 1 << 5
+  CTRL = 1 << 6
+  QFRC_APPLIED = 1 << 7
+  XFRC_APPLIED = 1 << 8
+  EQ_ACTIVE = 1 << 9
+  MOCAP_POS = 1 << 10
+  MOCAP_QUAT = 1 << 11
+  USERDATA = 1 << 12
+  PLUGIN = 1 << 13
+  NSTATE = 14
+  PHYSICS = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4)
+  FULLPHYSICS = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4) | (1 << 13)
+  USER = (1 << 6) | (1 << 7) | (1 << 8) | (1 << 9) | (1 << 10) | (1 << 11) | (1 << 12)
+  INTEGRATION = FULLPHYSICS | USER | (1 << 5)
+
+
+class TrnType(enum.IntEnum):
+  JOINT = 0
+  JOINTINPARENT = 1
+  SLIDERCRANK = 2
+  TENDON = 3
+  SITE = 4
+  BODY = 5
+
+
+class DynType(enum.IntEnum):
+  NONE = 0
+  INTEGRATOR = 1
+  FILTER = 2
+  FILTEREXACT = 3
+  MUSCLE = 4
+
+
+class GainType(enum.IntEnum):
+  FIXED = 0
+  AFFINE = 1
+  MUSCLE = 2
+
+
+class BiasType(enum.IntEnum):
+  NONE = 0
+  AFFINE = 1
+  MUSCLE = 2
+
+
 class BroadphaseFilter(enum.IntFlag):
   PLANE = 1
   SPHERE = 2

@@ -190,6 +190,12 @@ int mjb_mul_m(const mjbModel* m, mjbData* d, float* res, const float* vec, void*
   MJB_LAUNCH(launch_mul_m(m->dev, d->dev, res, vec, s), 1);
   return 0;
 }
+int mjb_contact_force(const mjbModel* m, mjbData* d, const int* contact_ids, int n, int to_world_frame, float* force, void* stream) {
+  MJB_ENTER();
+  if (n > 0 && (!contact_ids || !force)) return fail("mjb_contact_force: null array");
+  MJB_LAUNCH(launch_contact_force(m->dev, d->dev, contact_ids, n, to_world_frame, force, s), 1);
+  return 0;
+}
 int mjb_solve(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1); return 0; }
 int mjb_euler(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1); return 0; }
 
@@ -229,15 +235,21 @@ static int pipeline(const mjbModel* m, mjbData* d, int what, cudaStream_t s) {
 }
 int mjb_fwd_position(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return pipeline(m, d, RUN_POSITION, s); }
 int mjb_forward(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER, s); }
+// forward.py:523-555 rungekutta4, called after forward(): three more forward() evaluations with the state bookkeeping in between
+static int rk4_after_forward(const mjbModel* m, mjbData* d, cudaStream_t s) {
+  if (!d->rk) return fail("Runge-Kutta scratch missing: data was finalized against a model whose integrator is not RK4");
+  for (int stage = 0; stage < 4; stage++) {
+    if (stage > 0 && pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER, s)) return -1;
+    MJB_LAUNCH(launch_rk_stage(m->dev, d->dev, d->rk, stage, s), 1);
+  }
+  return 0;
+}
+int mjb_rungekutta4(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); return rk4_after_forward(m, d, s); }
 int mjb_step(const mjbModel* m, mjbData* d, void* stream) {
   MJB_ENTER();
-  if (m->dev.integrator == INT_RK4) {  // forward.py:523-555: four forward() evaluations with the state bookkeeping in between
-    if (!d->rk) return fail("Runge-Kutta scratch missing: data was finalized against a model with another integrator");
-    for (int stage = 0; stage < 4; stage++) {
-      if (pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER, s)) return -1;
-      MJB_LAUNCH(launch_rk_stage(m->dev, d->dev, d->rk, stage, s), 1);
-    }
-    return 0;
+  if (m->dev.integrator == INT_RK4) {
+    if (pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER, s)) return -1;
+    return rk4_after_forward(m, d, s);
   }
   return pipeline(m, d, RUN_POSITION | RUN_VELOCITY | RUN_SOLVER | RUN_EULER, s);
 }

@@ -60,6 +60,43 @@ k_mul_m(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, f
   }
 }
 
+// support.py:326-442 contact_force: 6D force / torque of the listed contacts, in the contact frame unless to_world is set
+// (pyramid decode :326-348; elliptic rows are the force components themselves).  No adhesion in this build.
+__global__ void k_contact_force(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, const int* __restrict__ contact_ids, int n, int to_world,
+                                float* __restrict__ out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  const int cid = contact_ids[tid];
+  if (cid >= d.nacon[0]) return;
+  float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (cid >= 0) {
+    const int w = d.contact_worldid[cid], dim = d.contact_dim[cid];
+    const int* adr = d.contact_efc_address + (size_t)cid * m.nmaxpyramid;
+    const float* force = d.efc_force + (size_t)w * d.njmax;
+    if (adr[0] >= 0) {
+      if (m.cone == CONE_PYRAMIDAL) {
+        if (dim == 1) f[0] = force[adr[0]];
+        else
+          for (int i = 0; i < dim - 1; i++) {
+            const int a = 2 * i + adr[0];
+            const float d1 = a < d.njmax ? force[a] : 0.f, d2 = a + 1 < d.njmax ? force[a + 1] : 0.f;
+            f[0] += d1 + d2;
+            f[i + 1] = (d1 - d2) * d.contact_friction[5 * (size_t)cid + i];
+          }
+      } else {
+        for (int i = 0; i < dim; i++) if (adr[i] < d.njmax) f[i] = force[adr[i]];
+      }
+    }
+    if (to_world) {  // row vector times the frame matrix, for the force and the torque part
+      const float* R = d.contact_frame + 9 * (size_t)cid;
+      float t[6];
+      for (int k = 0; k < 3; k++) { t[k] = f[0] * R[k] + f[1] * R[3 + k] + f[2] * R[6 + k]; t[3 + k] = f[3] * R[k] + f[4] * R[3 + k] + f[5] * R[6 + k]; }
+      for (int k = 0; k < 6; k++) f[k] = t[k];
+    }
+  }
+  for (int k = 0; k < 6; k++) out[6 * (size_t)tid + k] = f[k];
+}
+
 }  // namespace
 
 cudaError_t launch_solve_m(const ModelDev& m, const DataDev& d, float* x, const float* y, cudaStream_t s) {
@@ -68,5 +105,10 @@ cudaError_t launch_solve_m(const ModelDev& m, const DataDev& d, float* x, const 
 }
 cudaError_t launch_mul_m(const ModelDev& m, const DataDev& d, float* res, const float* vec, cudaStream_t s) {
   k_mul_m<<<d.wn, 32, (m.nv + 4) * sizeof(float), s>>>(m, d, res, vec);
+  return cudaGetLastError();
+}
+cudaError_t launch_contact_force(const ModelDev& m, const DataDev& d, const int* contact_ids, int n, int to_world, float* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_contact_force<<<(n + 127) / 128, 128, 0, s>>>(m, d, contact_ids, n, to_world, out);
   return cudaGetLastError();
 }

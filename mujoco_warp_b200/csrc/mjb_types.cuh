@@ -125,6 +125,7 @@ cudaError_t launch_solve_m(const ModelDev& m, const DataDev& d, float* x, const 
 cudaError_t launch_mul_m(const ModelDev& m, const DataDev& d, float* res, const float* vec, cudaStream_t s);
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s);
 cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s);
+cudaError_t launch_contact_force(const ModelDev& m, const DataDev& d, const int* contact_ids, int n, int to_world, float* out, cudaStream_t s);
 cudaError_t launch_rk_stage(const ModelDev& m, const DataDev& d, float* rk, int stage, cudaStream_t s);
 cudaError_t launch_ctrl_noise(const ModelDev& m, const DataDev& d, const float* ctrl_center, int step, float std, float rate, cudaStream_t s);
 size_t smem_position(const ModelDev& m);

@@ -103,3 +103,112 @@ def test_reset_data_keyframe_and_get_data_into(scene):
   assert res.ncon == 8 and res.nefc == 32 and res.efc_J.shape == (32, mjm.nv) and res.contact["geom"].shape == (8, 2)
   np.testing.assert_allclose(res.qpos, mjm.key_qpos[0], atol=1e-6)
   np.testing.assert_allclose(res.qacc, d.qacc[3].cpu().numpy(), atol=0)
+
+
+@pytest.mark.parametrize("cone", ["pyramidal", "elliptic"])
+def test_contact_force_matches_decode(built, cone):
+  """contact_force (reference support.py:326-442): pyramid / elliptic decode of efc.force per contact, contact and world frame;
+  the normal forces of the humanoid's foot contacts carry its weight once it has settled for a few steps."""
+  import mujoco_warp_b200 as mjw
+  from mujoco_warp_b200._src import constants as C
+
+  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  if cone == "elliptic":
+    mjm.opt.cone = C.CONE_ELLIPTIC
+  m = mjw.put_model(mjm)
+  nworld = 4
+  d = mjw.make_data(mjm, nworld=nworld, nconmax=24, njmax=128, m=m)
+  mjw.reset_data_keyframe(m, d, 0)
+  for _ in range(3):
+    mjw.step(m, d)
+  mjw.forward(m, d)
+  nacon = int(d.nacon.cpu()[0])
+  assert nacon > 0
+  ids = torch.arange(nacon + 3, dtype=torch.int32, device="cuda")  # three ids past the pool end: left untouched
+  out = torch.full((nacon + 3, 6), -7.0, device="cuda")
+  outw = torch.full((nacon + 3, 6), -7.0, device="cuda")
+  mjw.contact_force(m, d, ids, False, out)
+  mjw.contact_force(m, d, ids, True, outw)
+  torch.cuda.synchronize()
+  out, outw = out.cpu().numpy(), outw.cpu().numpy()
+  assert (out[nacon:] == -7.0).all()
+  force = d.efc.force.cpu().numpy()
+  adr = d.contact.efc_address[:nacon].cpu().numpy()
+  dim = d.contact.dim[:nacon].cpu().numpy()
+  wid = d.contact.worldid[:nacon].cpu().numpy()
+  fri = d.contact.friction[:nacon].cpu().numpy()
+  frame = d.contact.frame[:nacon].cpu().numpy().reshape(nacon, 3, 3)
+  want = np.zeros((nacon, 6))
+  for c in range(nacon):
+    a0 = adr[c, 0]
+    if a0 < 0:
+      continue
+    f = force[wid[c]]
+    if cone == "pyramidal":
+      if dim[c] == 1:
+        want[c, 0] = f[a0]
+      else:
+        for i in range(dim[c] - 1):
+          d1, d2 = f[a0 + 2 * i], f[a0 + 2 * i + 1]
+          want[c, 0] += d1 + d2
+          want[c, i + 1] = (d1 - d2) * fri[c, i]
+    else:
+      for i in range(dim[c]):
+        want[c, i] = f[adr[c, i]]
+  np.testing.assert_allclose(out[:nacon], want, rtol=1e-6, atol=1e-6)
+  wantw = np.concatenate([np.einsum("ci,cik->ck", want[:, :3], frame), np.einsum("ci,cik->ck", want[:, 3:], frame)], axis=1)
+  np.testing.assert_allclose(outw[:nacon], wantw, rtol=1e-5, atol=1e-5)
+  assert (out[:nacon, 0] >= 0).all() and out[:nacon, 0].sum() > 0  # normal forces push
+
+
+def test_get_set_state_roundtrip(built):
+  import mujoco_warp_b200 as mjw
+
+  mjm = mjw.mjcf.load_string(util.EQUALITY_XML)
+  m = mjw.put_model(mjm)
+  nworld = 3
+  d = mjw.make_data(mjm, nworld=nworld, nconmax=16, njmax=64, m=m)
+  g = torch.Generator(device="cuda").manual_seed(0)
+  d.qvel.copy_(torch.randn(d.qvel.shape, device="cuda", generator=g))
+  d.ctrl.copy_(torch.randn(d.ctrl.shape, device="cuda", generator=g))
+  mjw.step(m, d)
+  sig = int(mjw.State.INTEGRATION)
+  size = 1 + mjm.nq + 2 * mjm.nv + mjm.nu + mjm.nv + 6 * mjm.nbody + mjm.neq + 7 * mjm.nmocap
+  state = torch.zeros((nworld, size), device="cuda")
+  mjw.get_state(m, d, state, sig)
+  s = state.cpu().numpy()
+  np.testing.assert_array_equal(s[:, 0], d.time.cpu().numpy())
+  np.testing.assert_array_equal(s[:, 1 : 1 + mjm.nq], d.qpos.cpu().numpy())
+  np.testing.assert_array_equal(s[:, 1 + mjm.nq : 1 + mjm.nq + mjm.nv], d.qvel.cpu().numpy())
+  np.testing.assert_array_equal(s[:, 1 + mjm.nq + mjm.nv : 1 + mjm.nq + 2 * mjm.nv], d.qacc_warmstart.cpu().numpy())  # ACT, HISTORY are empty
+  ref = {k: getattr(d, k).clone() for k in ("time", "qpos", "qvel", "qacc_warmstart", "ctrl", "mocap_pos", "mocap_quat")}
+  for _ in range(3):
+    mjw.step(m, d)
+  active = torch.tensor([True, False, True], device="cuda")
+  moved = d.qpos.clone()
+  mjw.set_state(m, d, state, sig, active)
+  for k, v in ref.items():
+    got = getattr(d, k)
+    assert torch.equal(got[0], v[0]) and torch.equal(got[2], v[2]), k
+  assert torch.equal(d.qpos[1], moved[1])  # the inactive world keeps its state
+  with pytest.raises(ValueError):
+    mjw.get_state(m, d, state, 1 << 14)
+
+
+def test_rungekutta4_equals_step(built):
+  """forward() followed by rungekutta4() is step() for an RK4 model (reference forward.py:1368-1381)."""
+  import mujoco_warp_b200 as mjw
+
+  xml = util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"')
+  mjm = mjw.mjcf.load_string(xml)
+  m = mjw.put_model(mjm)
+  da = mjw.make_data(mjm, nworld=4, nconmax=32, njmax=128, m=m)
+  db = mjw.make_data(mjm, nworld=4, nconmax=32, njmax=128, m=m)
+  qpos, qvel, ctrl, _ = util.seeded_state(mjm, 4, key=0, seed=5, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.0)
+  for d in (da, db):
+    d.qpos.copy_(torch.from_numpy(qpos.astype(np.float32))); d.qvel.copy_(torch.from_numpy(qvel.astype(np.float32))); d.ctrl.copy_(torch.from_numpy(ctrl.astype(np.float32)))
+  for _ in range(3):
+    mjw.step(m, da)
+    mjw.forward(m, db); mjw.rungekutta4(m, db)
+  torch.cuda.synchronize()
+  assert torch.equal(da.qpos, db.qpos) and torch.equal(da.qvel, db.qvel) and torch.equal(da.time, db.time)
