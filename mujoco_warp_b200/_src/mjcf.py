@@ -1118,9 +1118,50 @@ def compile_xml(root):
   m.eq_data = np.array([e["data"] for e in eqs], dtype=np.float64).reshape(m.neq, 11)
 
   # unused families (sizes only)
-  m.ntendon = m.nflex = m.nmesh = m.nhfield = m.nsensor = m.nsensordata = 0
+  m.ntendon = m.nflex = m.nmesh = m.nhfield = 0
+
+  # ---- sensors (MuJoCo mjtSensor / mjtDataType / mjtStage values; element tag -> type, object kind, dim, datatype, stage)
+  S = C
+  table = {
+    "jointpos": (S.SENS_JOINTPOS, "joint", 1, 0, 1), "jointvel": (S.SENS_JOINTVEL, "joint", 1, 0, 2),
+    "actuatorpos": (S.SENS_ACTUATORPOS, "actuator", 1, 0, 1), "actuatorvel": (S.SENS_ACTUATORVEL, "actuator", 1, 0, 2),
+    "actuatorfrc": (S.SENS_ACTUATORFRC, "actuator", 1, 0, 3), "jointactuatorfrc": (S.SENS_JOINTACTFRC, "joint", 1, 0, 3),
+    "ballquat": (S.SENS_BALLQUAT, "joint", 4, 3, 1), "ballangvel": (S.SENS_BALLANGVEL, "joint", 3, 0, 2),
+    "gyro": (S.SENS_GYRO, "site", 3, 0, 2), "velocimeter": (S.SENS_VELOCIMETER, "site", 3, 0, 2), "accelerometer": (S.SENS_ACCELEROMETER, "site", 3, 0, 3),
+    "subtreecom": (S.SENS_SUBTREECOM, "body", 3, 0, 1), "subtreelinvel": (S.SENS_SUBTREELINVEL, "body", 3, 0, 2),
+    "subtreeangmom": (S.SENS_SUBTREEANGMOM, "body", 3, 0, 2), "clock": (S.SENS_CLOCK, None, 1, 0, 1),
+    "framepos": (S.SENS_FRAMEPOS, "obj", 3, 0, 1), "framexaxis": (S.SENS_FRAMEXAXIS, "obj", 3, 2, 1), "frameyaxis": (S.SENS_FRAMEYAXIS, "obj", 3, 2, 1),
+    "framezaxis": (S.SENS_FRAMEZAXIS, "obj", 3, 2, 1),
+  }
+  objkind = {"joint": (C.OBJ_JOINT, "joint"), "actuator": (C.OBJ_ACTUATOR, "actuator"), "site": (C.OBJ_SITE, "site"), "body": (C.OBJ_BODY, "body")}
+  objtypes = {"body": (C.OBJ_BODY, "body"), "xbody": (C.OBJ_XBODY, "body"), "geom": (C.OBJ_GEOM, "geom"), "site": (C.OBJ_SITE, "site"), "camera": (C.OBJ_CAMERA, "camera")}
+  sens, unsupported = [], []
   nsens = root.find("sensor")
-  m.nsensor_ignored = 0 if nsens is None else len(list(nsens))
+  for e in (list(nsens) if nsens is not None else []):
+    if e.tag not in table or "reftype" in e.attrib or "refname" in e.attrib:
+      unsupported.append(e.tag)
+      continue
+    stype, kind, dim, datatype, stage = table[e.tag]
+    if kind is None:
+      otype, oid = C.OBJ_UNKNOWN, -1
+    elif kind == "obj":
+      otype, lst = objtypes[e.get("objtype")]
+      oid = getattr(m.names, lst).index(e.get("objname"))
+    else:
+      otype, lst = objkind[kind]
+      oid = getattr(m.names, lst).index(e.get(kind))
+    sens.append(dict(name=e.get("name", f"sensor{len(sens)}"), type=stype, objtype=otype, objid=oid, dim=dim, datatype=datatype, needstage=stage,
+                     cutoff=float(e.get("cutoff", 0.0)), noise=float(e.get("noise", 0.0))))
+  m.nsensor = len(sens)
+  m.sensor_unsupported = unsupported  # put_model refuses these (they would silently read zero otherwise)
+  m.names.sensor = [x["name"] for x in sens]
+  for key in ("type", "objtype", "objid", "dim", "datatype", "needstage"):
+    setattr(m, "sensor_" + key, np.array([x[key] for x in sens], dtype=np.int32).reshape(m.nsensor))
+  m.sensor_reftype = np.zeros(m.nsensor, dtype=np.int32); m.sensor_refid = -np.ones(m.nsensor, dtype=np.int32)
+  m.sensor_cutoff = np.array([x["cutoff"] for x in sens], dtype=np.float64).reshape(m.nsensor)
+  m.sensor_noise = np.array([x["noise"] for x in sens], dtype=np.float64).reshape(m.nsensor)
+  m.sensor_adr = (np.concatenate(([0], np.cumsum(m.sensor_dim)[:-1])) if m.nsensor else np.zeros(0)).astype(np.int32)
+  m.nsensordata = int(m.sensor_dim.sum()) if m.nsensor else 0
 
   # ---- keyframes
   keys = []

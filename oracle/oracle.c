@@ -43,7 +43,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
-  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations)
+  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations) X(nsensor) X(nsensordata)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(ccd_tolerance)
 #define MODEL_IARRS(X) \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
@@ -54,7 +54,8 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
-  X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim)
+  X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim) \
+  X(sensor_type) X(sensor_datatype) X(sensor_needstage) X(sensor_objtype) X(sensor_objid) X(sensor_dim) X(sensor_adr)
 #define MODEL_RARRS(X) \
   X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
   X(body_inertia) X(body_invweight0) X(body_gravcomp) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
@@ -63,7 +64,8 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(geom_gap) X(geom_solmix) X(geom_solref) X(geom_solimp) X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) \
   X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
   X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat) \
-  X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap)
+  X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap) \
+  X(sensor_cutoff)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -72,7 +74,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(cam_xpos) X(cam_xmat) X(light_xpos) X(light_xdir) X(subtree_com) X(cdof) X(cinert) X(crb) X(M) X(qLD) \
   X(actuator_length) X(actuator_moment) X(actuator_velocity) X(cvel) X(cdof_dot) X(qfrc_bias) X(qfrc_spring) \
   X(qfrc_damper) X(qfrc_gravcomp) X(qfrc_passive) X(actuator_force) X(qfrc_actuator) X(qfrc_smooth) X(qacc_smooth) \
-  X(qfrc_constraint) X(cacc) X(cfrc_int) \
+  X(qfrc_constraint) X(cacc) X(cfrc_int) X(sensordata) X(subtree_linvel) X(subtree_angmom) \
   X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
   X(con_dist) X(con_pos) X(con_frame) X(con_includemargin) X(con_friction) X(con_solref) X(con_solreffriction) X(con_solimp)
 #define DATA_IARRS(X) \
@@ -337,6 +339,7 @@ static void make_view(const OrcModel* m, const OrcData* d, int w, W* v) {
   R(efc_type, njm); R(efc_id, njm); R(efc_state, njm); R(moment_rownnz, nu); R(moment_rowadr, nu); R(moment_colind, m->nJmom);
   R(con_dim, ncm); R(con_geom, 2 * ncm); R(con_efc_address, m->nmaxpyramid * ncm); R(con_geomcollisionid, ncm);
   R(eq_active, m->neq);
+  R(sensordata, m->nsensordata); R(subtree_linvel, 3 * nb); R(subtree_angmom, 3 * nb);
 #undef R
 }
 
@@ -2375,11 +2378,165 @@ static void implicitfast(W* w) {
   free(buf);
 }
 
+/* ------------------------------------------------------------------ sensors (sensor.py; smooth.py:3500-3612 subtree_vel, :1743 rne_postconstraint) */
+enum { SENS_TOUCH = 0, SENS_ACCELEROMETER, SENS_VELOCIMETER, SENS_GYRO, SENS_FORCE, SENS_TORQUE, SENS_MAGNETOMETER, SENS_RANGEFINDER, SENS_CAMPROJECTION,
+  SENS_JOINTPOS, SENS_JOINTVEL, SENS_TENDONPOS, SENS_TENDONVEL, SENS_ACTUATORPOS, SENS_ACTUATORVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_TENDONACTFRC,
+  SENS_BALLQUAT, SENS_BALLANGVEL, SENS_JOINTLIMITPOS, SENS_JOINTLIMITVEL, SENS_JOINTLIMITFRC, SENS_TENDONLIMITPOS, SENS_TENDONLIMITVEL, SENS_TENDONLIMITFRC,
+  SENS_FRAMEPOS, SENS_FRAMEQUAT, SENS_FRAMEXAXIS, SENS_FRAMEYAXIS, SENS_FRAMEZAXIS, SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_FRAMELINACC, SENS_FRAMEANGACC,
+  SENS_SUBTREECOM, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM, SENS_INSIDESITE, SENS_GEOMDIST, SENS_GEOMNORMAL, SENS_GEOMFROMTO, SENS_CONTACT, SENS_E_POTENTIAL,
+  SENS_E_KINETIC, SENS_CLOCK };
+enum { STAGE_POS = 1, STAGE_VEL = 2, STAGE_ACC = 3 };
+enum { DATATYPE_REAL = 0, DATATYPE_POSITIVE = 1 };
+enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5, OBJ_SITE = 6, OBJ_CAMERA = 7 };
+#define DSBL_SENSOR (1 << 13)
+
+/* sensor.py:56-113 _write_scalar / _write_vector: cutoff clamps REAL data to [-c, c] and POSITIVE data to (-inf, c] */
+static void sensor_write(W* w, int s, int dim, const real* v) {
+  const OrcModel* m = w->m;
+  real cutoff = m->sensor_cutoff[s];
+  for (int i = 0; i < dim; i++) {
+    real x = v[i];
+    if (cutoff > 0) {
+      if (m->sensor_datatype[s] == DATATYPE_REAL) x = rclamp(x, -cutoff, cutoff);
+      else if (m->sensor_datatype[s] == DATATYPE_POSITIVE) x = rmin(x, cutoff);
+    }
+    w->sensordata[m->sensor_adr[s] + i] = x;
+  }
+}
+/* smooth.py:3500-3612: subtree linear velocity and angular momentum about the subtree centre of mass */
+static void subtree_vel(W* w) {
+  const OrcModel* m = w->m;
+  const int nb = m->nbody;
+  real* bodyvel = (real*)malloc((size_t)6 * nb * sizeof(real));
+  for (int b = 0; b < nb; b++) {
+    const real *cv = w->cvel + 6 * b, *ximat = w->ximat + 9 * b;
+    real dif[3], cr[3], lin[3], dv[3];
+    v3sub(w->xipos + 3 * b, w->subtree_com + 3 * m->body_rootid[b], dif);
+    cross3(dif, cv, cr);
+    for (int i = 0; i < 3; i++) lin[i] = cv[3 + i] - cr[i];
+    for (int i = 0; i < 3; i++) w->subtree_linvel[3 * b + i] = m->body_mass[b] * lin[i];
+    matT_vec3(ximat, cv, dv);
+    for (int i = 0; i < 3; i++) dv[i] *= m->body_inertia[3 * b + i];
+    matvec3(ximat, dv, w->subtree_angmom + 3 * b);
+    for (int i = 0; i < 3; i++) { bodyvel[6 * b + i] = cv[i]; bodyvel[6 * b + 3 + i] = lin[i]; }
+  }
+  for (int b = nb - 1; b >= 0; b--) { /* _linear_momentum, deepest bodies first */
+    if (b) for (int i = 0; i < 3; i++) w->subtree_linvel[3 * m->body_parentid[b] + i] += w->subtree_linvel[3 * b + i];
+    for (int i = 0; i < 3; i++) w->subtree_linvel[3 * b + i] /= rmax(MJ_MINVAL, m->body_subtreemass[b]);
+  }
+  for (int b = nb - 1; b >= 1; b--) { /* _angular_momentum */
+    const int pid = m->body_parentid[b];
+    real dx[3], dv[3], dL[3];
+    v3sub(w->xipos + 3 * b, w->subtree_com + 3 * b, dx);
+    for (int i = 0; i < 3; i++) dv[i] = (bodyvel[6 * b + 3 + i] - w->subtree_linvel[3 * b + i]) * m->body_mass[b];
+    cross3(dx, dv, dL);
+    for (int i = 0; i < 3; i++) w->subtree_angmom[3 * b + i] += dL[i];
+    for (int i = 0; i < 3; i++) w->subtree_angmom[3 * pid + i] += w->subtree_angmom[3 * b + i];
+    v3sub(w->subtree_com + 3 * b, w->subtree_com + 3 * pid, dx);
+    for (int i = 0; i < 3; i++) dv[i] = (w->subtree_linvel[3 * b + i] - w->subtree_linvel[3 * pid + i]) * m->body_subtreemass[b];
+    cross3(dx, dv, dL);
+    for (int i = 0; i < 3; i++) w->subtree_angmom[3 * pid + i] += dL[i];
+  }
+  free(bodyvel);
+}
+/* smooth.py:1743 rne_postconstraint, acceleration part (:1364-1425 with flg_acc): cacc including qacc.  The external / internal
+ * force accumulation (cfrc_ext, cfrc_int) that only force / torque sensors read is not restated. */
+static void rne_postconstraint_cacc(W* w) {
+  const OrcModel* m = w->m;
+  memset(w->cacc, 0, 6 * sizeof(real));
+  if (!(m->disableflags & DSBL_GRAVITY)) for (int i = 0; i < 3; i++) w->cacc[3 + i] = -m->gravity[i];
+  for (int b = 1; b < m->nbody; b++) {
+    real a[6];
+    memcpy(a, w->cacc + 6 * m->body_parentid[b], sizeof a);
+    for (int k = 0; k < m->body_dofnum[b]; k++) {
+      int d = m->body_dofadr[b] + k;
+      for (int i = 0; i < 6; i++) a[i] += w->cdof_dot[6 * d + i] * w->qvel[d];
+      for (int i = 0; i < 6; i++) a[i] += w->cdof[6 * d + i] * w->qacc[d];
+    }
+    memcpy(w->cacc + 6 * b, a, sizeof a);
+  }
+}
+/* object frame position / orientation (sensor.py:266-317 _get_pos / _get_mat) */
+static const real* obj_pos(const W* w, int objtype, int id) {
+  switch (objtype) {
+    case OBJ_BODY: return w->xipos + 3 * id;
+    case OBJ_XBODY: return w->xpos + 3 * id;
+    case OBJ_GEOM: return w->geom_xpos + 3 * id;
+    case OBJ_SITE: return w->site_xpos + 3 * id;
+    default: return w->cam_xpos + 3 * id;
+  }
+}
+static const real* obj_mat(const W* w, int objtype, int id) {
+  switch (objtype) {
+    case OBJ_BODY: return w->ximat + 9 * id;
+    case OBJ_XBODY: return w->xmat + 9 * id;
+    case OBJ_GEOM: return w->geom_xmat + 9 * id;
+    case OBJ_SITE: return w->site_xmat + 9 * id;
+    default: return w->cam_xmat + 9 * id;
+  }
+}
+/* sensor.py:810 sensor_pos, :1432 sensor_vel, :2512 sensor_acc for the sensor types this build carries */
+static void sensors(W* w, int stage) {
+  const OrcModel* m = w->m;
+  if (!m->nsensor || (m->disableflags & DSBL_SENSOR)) return;
+  int need_subtree = 0, need_cacc = 0;
+  for (int s = 0; s < m->nsensor; s++) {
+    int t = m->sensor_type[s];
+    if (t == SENS_SUBTREELINVEL || t == SENS_SUBTREEANGMOM) need_subtree = 1;
+    if (t == SENS_ACCELEROMETER) need_cacc = 1;
+  }
+  if (stage == STAGE_VEL && need_subtree) subtree_vel(w);
+  if (stage == STAGE_ACC && need_cacc) rne_postconstraint_cacc(w);
+  for (int s = 0; s < m->nsensor; s++) {
+    if (m->sensor_needstage[s] != stage) continue;
+    const int t = m->sensor_type[s], id = m->sensor_objid[s];
+    real v[4] = {0, 0, 0, 0};
+    switch (t) {
+      case SENS_JOINTPOS: v[0] = w->qpos[m->jnt_qposadr[id]]; break;
+      case SENS_ACTUATORPOS: v[0] = w->actuator_length[id]; break;
+      case SENS_BALLQUAT: { memcpy(v, w->qpos + m->jnt_qposadr[id], 4 * sizeof(real)); normalize4(v); break; }
+      case SENS_FRAMEPOS: memcpy(v, obj_pos(w, m->sensor_objtype[s], id), 3 * sizeof(real)); break;
+      case SENS_FRAMEXAXIS: case SENS_FRAMEYAXIS: case SENS_FRAMEZAXIS: {
+        const real* R = obj_mat(w, m->sensor_objtype[s], id); int c = t - SENS_FRAMEXAXIS;
+        v[0] = R[c]; v[1] = R[3 + c]; v[2] = R[6 + c]; break; }
+      case SENS_SUBTREECOM: memcpy(v, w->subtree_com + 3 * id, 3 * sizeof(real)); break;
+      case SENS_CLOCK: v[0] = w->time[0]; break;
+      case SENS_JOINTVEL: v[0] = w->qvel[m->jnt_dofadr[id]]; break;
+      case SENS_ACTUATORVEL: v[0] = w->actuator_velocity[id]; break;
+      case SENS_BALLANGVEL: memcpy(v, w->qvel + m->jnt_dofadr[id], 3 * sizeof(real)); break;
+      case SENS_SUBTREELINVEL: memcpy(v, w->subtree_linvel + 3 * id, 3 * sizeof(real)); break;
+      case SENS_SUBTREEANGMOM: memcpy(v, w->subtree_angmom + 3 * id, 3 * sizeof(real)); break;
+      case SENS_GYRO: matT_vec3(w->site_xmat + 9 * id, w->cvel + 6 * m->site_bodyid[id], v); break; /* sensor.py:989 */
+      case SENS_VELOCIMETER: { /* sensor.py:964 */
+        const int b = m->site_bodyid[id]; const real* cv = w->cvel + 6 * b;
+        real dif[3], cr[3], lin[3];
+        v3sub(w->site_xpos + 3 * id, w->subtree_com + 3 * m->body_rootid[b], dif); cross3(dif, cv, cr);
+        for (int i = 0; i < 3; i++) lin[i] = cv[3 + i] - cr[i];
+        matT_vec3(w->site_xmat + 9 * id, lin, v); break; }
+      case SENS_ACCELEROMETER: { /* sensor.py:1510 */
+        const int b = m->site_bodyid[id]; const real *cv = w->cvel + 6 * b, *ca = w->cacc + 6 * b, *R = w->site_xmat + 9 * id;
+        real dif[3], cr[3], t1[3], ang[3], lin[3], acc[3], corr[3];
+        v3sub(w->site_xpos + 3 * id, w->subtree_com + 3 * m->body_rootid[b], dif);
+        matT_vec3(R, cv, ang);
+        cross3(dif, cv, cr); for (int i = 0; i < 3; i++) t1[i] = cv[3 + i] - cr[i]; matT_vec3(R, t1, lin);
+        cross3(dif, ca, cr); for (int i = 0; i < 3; i++) t1[i] = ca[3 + i] - cr[i]; matT_vec3(R, t1, acc);
+        cross3(ang, lin, corr);
+        for (int i = 0; i < 3; i++) v[i] = acc[i] + corr[i]; break; }
+      case SENS_ACTUATORFRC: v[0] = w->actuator_force[id]; break;
+      case SENS_JOINTACTFRC: v[0] = w->qfrc_actuator[m->jnt_dofadr[id]]; break;
+      default: continue; /* put_model rejects other types */
+    }
+    sensor_write(w, s, m->sensor_dim[s], v);
+  }
+}
+
 static void forward_world(W* w) {
   kinematics(w); com_pos(w); camlight(w); crb(w);
   collision(w); make_constraint(w); transmission(w);
-  fwd_velocity(w); fwd_actuation(w); fwd_acceleration(w);
+  sensors(w, STAGE_POS);
+  fwd_velocity(w); sensors(w, STAGE_VEL); fwd_actuation(w); fwd_acceleration(w);
   solve(w);
+  sensors(w, STAGE_ACC);
 }
 
 /* forward.py:523-555 rungekutta4 (stateless actuators): called after the first forward() of the step */

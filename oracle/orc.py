@@ -152,6 +152,7 @@ def data_spec(mjm, tabs, nconmax, njmax):
     "cvel": (R, (nb, 6)), "cdof_dot": (R, (nv, 6)), "qfrc_bias": (R, (nv,)), "qfrc_spring": (R, (nv,)), "qfrc_damper": (R, (nv,)),
     "qfrc_gravcomp": (R, (nv,)), "qfrc_passive": (R, (nv,)), "actuator_force": (R, (nu,)), "qfrc_actuator": (R, (nv,)),
     "qfrc_smooth": (R, (nv,)), "qacc_smooth": (R, (nv,)), "qfrc_constraint": (R, (nv,)), "cacc": (R, (nb, 6)), "cfrc_int": (R, (nb, 6)),
+    "sensordata": (R, (int(getattr(mjm, "nsensordata", 0)) if int(getattr(mjm, "nsensor", 0)) else 0,)), "subtree_linvel": (R, (nb, 3)), "subtree_angmom": (R, (nb, 3)),
     "efc_J": (R, (njmax, nv)), "efc_pos": (R, (njmax,)), "efc_margin": (R, (njmax,)), "efc_D": (R, (njmax,)), "efc_vel": (R, (njmax,)),
     "efc_aref": (R, (njmax,)), "efc_frictionloss": (R, (njmax,)), "efc_force": (R, (njmax,)), "efc_Ma": (R, (nv,)),
     "con_dist": (R, (nconmax,)), "con_pos": (R, (nconmax, 3)), "con_frame": (R, (nconmax, 3, 3)), "con_includemargin": (R, (nconmax,)),
@@ -230,6 +231,11 @@ class Oracle:
       setra(n, getattr(mjm, n) if npair else np.zeros(k))
     for n, k in (("eq_solref", 2), ("eq_solimp", 5), ("eq_data", 11)):
       setra(n, getattr(mjm, n) if neq else np.zeros(k))
+    nsensor = int(getattr(mjm, "nsensor", 0))
+    seti("nsensor", nsensor); seti("nsensordata", int(getattr(mjm, "nsensordata", 0)) if nsensor else 0)
+    for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_dim", "sensor_adr"):
+      setia(n, getattr(mjm, n) if nsensor else np.zeros(1, dtype=np.int32))
+    setra("sensor_cutoff", mjm.sensor_cutoff if nsensor else np.zeros(1))
 
     self.spec = data_spec(mjm, self.tabs, nconmax, njmax)
     self.dptr = ctypes.c_void_p(lib.orc_data_create(nworld, nconmax, njmax))

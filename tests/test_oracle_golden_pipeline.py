@@ -39,6 +39,8 @@ def load_scene(name):
     mjm = mjcf.load_string(BOX_XML)
   elif name in ("boxccd", "boxccd_mixed"):
     mjm = mjcf.load_string(util.boxccd_xml(name.endswith("mixed")))
+  elif name == "sensors":
+    mjm = mjcf.load_string(util.sensor_xml())
   elif name == "mixed_rk4":
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"'))
   elif name == "mixed_sap":
@@ -111,6 +113,10 @@ def compare(tag, g, od, mjm, nworld, tol, solver_tol=1e-7, exact_iterations=True
     close(f"{tag}/efc_force[w{w}]", od["efc_force"][w, :ne], g[f"{tag}/efc_force"][w, :ne], solver_tol)
     if exact_iterations:
       np.testing.assert_array_equal(od["efc_state"][w, :ne], g[f"{tag}/efc_state"][w, :ne])
+  if f"{tag}/sensordata" in g and g[f"{tag}/sensordata"].size:  # position / velocity sensors to tol, acceleration-stage ones follow qacc
+    close(f"{tag}/sensordata", od["sensordata"], g[f"{tag}/sensordata"], solver_tol)
+    for f in ("subtree_linvel", "subtree_angmom"):
+      close(f"{tag}/{f}", od[f].reshape(nworld, -1), g[f"{tag}/{f}"].reshape(nworld, -1), tol)
   close(f"{tag}/qacc", od["qacc"], g[f"{tag}/qacc"], solver_tol)
   close(f"{tag}/qfrc_constraint", od["qfrc_constraint"], g[f"{tag}/qfrc_constraint"], solver_tol)
   if exact_iterations:

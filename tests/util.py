@@ -260,3 +260,23 @@ def boxccd_xml(mixed=False):
     <body pos="0 0.3 0.3101" euler="0 45 0"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>
   </worldbody>
 </mujoco>"""
+
+
+def sensor_xml():
+  """MIXED_XML with one sensor of every type this build carries (two with cutoffs), sites on a free body and on the arm chain."""
+  x = MIXED_XML.replace('<geom name="tip" type="sphere" pos="0 0 -0.22" size="0.04" mass="0.2"/>',
+                        '<geom name="tip" type="sphere" pos="0 0 -0.22" size="0.04" mass="0.2"/>\n          <site name="imu" pos="0.01 0.02 -0.1" euler="10 20 30"/>')
+  sensors = """
+  <sensor>
+    <jointpos name="jp" joint="hinge"/> <jointvel name="jv" joint="slide"/> <ballquat name="bq" joint="ball"/> <ballangvel name="bv" joint="ball"/>
+    <actuatorpos name="ap" actuator="p_hinge"/> <actuatorvel name="av" actuator="v_hinge"/> <actuatorfrc name="af" actuator="p_hinge" cutoff="2"/>
+    <jointactuatorfrc name="jaf" joint="hinge"/>
+    <gyro name="gy" site="imu"/> <velocimeter name="vm" site="imu"/> <accelerometer name="ac" site="imu" cutoff="50"/>
+    <gyro name="gy0" site="st0"/> <accelerometer name="ac0" site="st0"/>
+    <subtreecom name="sc" body="arm"/> <subtreelinvel name="sl" body="fore"/> <subtreeangmom name="sa" body="arm"/> <subtreeangmom name="sa0" body="cap0"/>
+    <framepos name="fp" objtype="site" objname="imu"/> <framexaxis name="fx" objtype="geom" objname="tip"/> <frameyaxis name="fy" objtype="body" objname="pend"/>
+    <framezaxis name="fz" objtype="xbody" objname="fore"/> <framepos name="fc" objtype="camera" objname="c0"/>
+    <clock name="clk"/>
+  </sensor>
+"""
+  return x.replace("  <actuator>", sensors + "  <actuator>")

@@ -29,7 +29,7 @@ FIELDS = [
   "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
   "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert", "crb", "M", "actuator_length", "actuator_moment", "actuator_velocity", "cvel",
   "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper", "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth",
-  "qacc", "qfrc_constraint", "ne", "nf", "nl", "nefc", "solver_niter",
+  "qacc", "qfrc_constraint", "ne", "nf", "nl", "nefc", "solver_niter", "sensordata", "subtree_linvel", "subtree_angmom",
 ]
 EFC = ["type", "id", "J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "state"]
 CON = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "geomcollisionid"]
@@ -65,6 +65,7 @@ def scenes():
   yield "convex_sap", sap2, dict(nconmax=64, njmax=256, key=None, qpos_noise=0.004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   rk = util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"')
   yield "mixed_rk4", mjcf.load_string(rk), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  yield "sensors", mjcf.load_string(util.sensor_xml()), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
   three = mjcf.load_any(util.THREE_HUMANOIDS)
   three.opt.jacobian = 1  # sparse: the reference does not run dense above nv = 60; snapshot() stores efc_J densified

@@ -126,6 +126,10 @@ class Mat:
     cols = list(zip(*o.m))
     return _mat_cls(len(self.m), len(cols))._from_rows([[sum(a * b for a, b in zip(row, col)) for col in cols] for row in self.m])
 
+  def __rmatmul__(self, o):  # row vector times matrix
+    cols = list(zip(*self.m))
+    return _vec_cls(len(cols))([sum(a * b for a, b in zip(o.v, col)) for col in cols])
+
   def __mul__(self, o):  # warp allows mat * vec as well as scalar scaling
     if isinstance(o, (Vec, Mat)):
       return self.__matmul__(o)
@@ -171,12 +175,22 @@ def _mat_cls(r, c):
 
 def _build_warp():
   wp = _t.ModuleType("warp")
+  _overloads = {}
+
   def func(f):
+    """@wp.func: arguments are passed by value; functions of one module that share a name are overloads, picked by arity."""
     import functools
+
+    cands = _overloads.setdefault((f.__module__, f.__qualname__), [])
+    cands.append(f)
 
     @functools.wraps(f)
     def by_value(*a, **k):
-      return f(*[_wp_copy(x) for x in a], **{n: _wp_copy(x) for n, x in k.items()})
+      g = f
+      if len(cands) > 1:
+        n = len(a) + len(k)
+        g = next((c for c in reversed(cands) if c.__code__.co_argcount == n), f)
+      return g(*[_wp_copy(x) for x in a], **{n_: _wp_copy(x) for n_, x in k.items()})
 
     return by_value
 
