@@ -24,6 +24,7 @@
  *   mjb_rne                    <- _src/smooth.py:1499  rne(flg_acc=False)
  *   mjb_solve_m                <- _src/smooth.py:3214  solve_m(m, d, x, y): x = M^-1 y through Data.qLD
  *   mjb_mul_m                  <- _src/support.py:153  mul_m(m, d, res, vec): res = M vec
+ *   mjb_sensor_pos/vel/acc     <- _src/sensor.py:810, :1432, :2512  sensor_pos / sensor_vel / sensor_acc(m, d)
  *   mjb_contact_force          <- _src/support.py:445  contact_force(m, d, contact_ids, to_world_frame, force)
  *   mjb_rungekutta4            <- _src/forward.py:523  rungekutta4(m, d)
  *   mjb_solve                  <- _src/solver.py:3671  solve
@@ -84,6 +85,10 @@ int mjb_rne(const mjbModel* m, mjbData* d, void* stream);
 /* x, y, res, vec: device arrays (nworld, nv) fp32 */
 int mjb_solve_m(const mjbModel* m, mjbData* d, float* x, const float* y, void* stream);
 int mjb_mul_m(const mjbModel* m, mjbData* d, float* res, const float* vec, void* stream);
+/* sensor.py:810 / :1432 / :2512: the sensors of one stage (forward and step already evaluate all of them after the solver) */
+int mjb_sensor_pos(const mjbModel* m, mjbData* d, void* stream);
+int mjb_sensor_vel(const mjbModel* m, mjbData* d, void* stream);
+int mjb_sensor_acc(const mjbModel* m, mjbData* d, void* stream);
 /* support.py:445 contact_force(m, d, contact_ids, to_world_frame, force): force is (n, 6) floats, device pointers */
 int mjb_contact_force(const mjbModel* m, mjbData* d, const int* contact_ids, int n, int to_world_frame, float* force, void* stream);
 /* forward.py:523 rungekutta4(m, d): the integrator alone, after forward() (models compiled with the RK4 integrator) */

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("MJB_LIB", os.path.join(_PKG, "libmjb200.so"))  # MJB_LIB: A/B-test an alternative build
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "mjb200.h")
-SOURCES = ["capi.cu", "k_position.cu", "k_collision.cu", "k_constraint.cu", "k_velocity.cu", "k_solver.cu", "k_integrate.cu", "k_support.cu"]
+SOURCES = ["capi.cu", "k_position.cu", "k_collision.cu", "k_constraint.cu", "k_velocity.cu", "k_solver.cu", "k_integrate.cu", "k_support.cu", "k_sensor.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "--extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
 
 _lib = None
@@ -89,7 +89,7 @@ def lib():
 STAGE_FUNCS = [
   "mjb_step", "mjb_forward", "mjb_fwd_position", "mjb_kinematics", "mjb_com_pos", "mjb_camlight", "mjb_crb", "mjb_transmission",
   "mjb_collision", "mjb_make_constraint", "mjb_fwd_velocity", "mjb_fwd_actuation", "mjb_fwd_acceleration", "mjb_factor_m",
-  "mjb_solve", "mjb_euler", "mjb_com_vel", "mjb_passive", "mjb_rne", "mjb_rungekutta4",
+  "mjb_solve", "mjb_euler", "mjb_com_vel", "mjb_passive", "mjb_rne", "mjb_rungekutta4", "mjb_sensor_pos", "mjb_sensor_vel", "mjb_sensor_acc",
 ]
 
 

@@ -89,6 +89,21 @@ def euler(m: Model, d: Data):
   _call("mjb_euler", m, d)
 
 
+def sensor_pos(m: Model, d: Data):
+  """Position-stage sensors (reference sensor.py:810); forward() / step() already evaluate every stage after the solver."""
+  _call("mjb_sensor_pos", m, d)
+
+
+def sensor_vel(m: Model, d: Data):
+  """Velocity-stage sensors, with subtree_vel when a sensor needs it (reference sensor.py:1432)."""
+  _call("mjb_sensor_vel", m, d)
+
+
+def sensor_acc(m: Model, d: Data):
+  """Acceleration-stage sensors, with the cacc part of rne_postconstraint when an accelerometer needs it (reference sensor.py:2512)."""
+  _call("mjb_sensor_acc", m, d)
+
+
 def rungekutta4(m: Model, d: Data):
   """Runge-Kutta 4 integrator, to be called after forward() (reference forward.py:523); the model must use the RK4 integrator."""
   from . import constants as C

@@ -355,6 +355,16 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   # equality constraints (connect / weld / joint): eq_* as in the reference Model (types.py), data per world-batch slot 0
   neq = int(getattr(mjm, "neq", 0))
   m.neq = neq
+  nsensor = int(getattr(mjm, "nsensor", 0))
+  if getattr(mjm, "sensor_unsupported", None):
+    raise NotImplementedError(f"sensor types not implemented in this version: {sorted(set(mjm.sensor_unsupported))}")
+  m.nsensor, m.nsensordata = nsensor, int(getattr(mjm, "nsensordata", 0)) if nsensor else 0
+  for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_dim", "sensor_adr"):
+    setattr(m, n, dev_i(getattr(mjm, n) if nsensor else np.zeros(0)))
+  m.sensor_cutoff = dev_f(np.asarray(mjm.sensor_cutoff) if nsensor else np.zeros(0), batched=False)
+  stype = np.asarray(mjm.sensor_type) if nsensor else np.zeros(0, dtype=int)
+  m.sensor_subtree_vel = bool(np.isin(stype, (C.SENS_SUBTREELINVEL, C.SENS_SUBTREEANGMOM)).any())  # reference io.py:896-897
+  m.sensor_rne_postconstraint = bool((stype == C.SENS_ACCELEROMETER).any())  # :900 (force / torque / frame accelerations are not carried)
   m.eq_type = dev_i(mjm.eq_type if neq else np.zeros(0))
   m.eq_obj1id = dev_i(mjm.eq_obj1id if neq else np.zeros(0))
   m.eq_obj2id = dev_i(mjm.eq_obj2id if neq else np.zeros(0))
@@ -391,7 +401,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase=int(m.opt.broadphase), broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
     has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
-    nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), epa_iterations=t["epa_iterations"], neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
+    nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), epa_iterations=t["epa_iterations"], nsensor=m.nsensor, nsensordata=m.nsensordata, sensor_subtree_vel=int(m.sensor_subtree_vel), sensor_rne_postconstraint=int(m.sensor_rne_postconstraint), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
     _lib.check(L.mjb_model_set_int(h, k.encode(), int(v)))
@@ -408,7 +418,8 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                                          "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
                                          "dofact_adr", "dofact_act", "dofact_mom", "eq_type", "eq_obj1id", "eq_obj2id", "eq_solref", "eq_solimp", "eq_data",
                                          "jnt_limited_ball_adr", "pair_dim", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp",
-                                         "pair_margin", "pair_gap"]:
+                                         "pair_margin", "pair_gap", "sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid",
+                                         "sensor_dim", "sensor_adr", "sensor_cutoff"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)
@@ -430,7 +441,7 @@ def _data_spec(m: types.Model, nworld, naconmax, njmax, njmax_pad):
     "solver_niter": (i, (nworld,)), "ne": (i, (nworld,)), "nf": (i, (nworld,)), "nl": (i, (nworld,)), "nefc": (i, (nworld,)),
     "time": (f, (nworld,)), "qpos": (f, (nworld, nq)), "qvel": (f, (nworld, nv)), "act": (f, (nworld, m.na)),
     "qacc_warmstart": (f, (nworld, nv)), "ctrl": (f, (nworld, nu)), "qfrc_applied": (f, (nworld, nv)), "xfrc_applied": (f, (nworld, nb, 6)),
-    "qacc": (f, (nworld, nv)), "act_dot": (f, (nworld, m.na)), "sensordata": (f, (nworld, 0)),
+    "qacc": (f, (nworld, nv)), "act_dot": (f, (nworld, m.na)), "sensordata": (f, (nworld, getattr(m, "nsensordata", 0))), "subtree_linvel": (f, (nworld, nb, 3)), "subtree_angmom": (f, (nworld, nb, 3)),
     "xpos": (f, (nworld, nb, 3)), "xquat": (f, (nworld, nb, 4)), "xmat": (f, (nworld, nb, 3, 3)), "xipos": (f, (nworld, nb, 3)),
     "ximat": (f, (nworld, nb, 3, 3)), "xanchor": (f, (nworld, nj, 3)), "xaxis": (f, (nworld, nj, 3)),
     "geom_xpos": (f, (nworld, ng, 3)), "geom_xmat": (f, (nworld, ng, 3, 3)), "site_xpos": (f, (nworld, m.nsite, 3)), "site_xmat": (f, (nworld, m.nsite, 3, 3)),
@@ -480,7 +491,7 @@ _BOUND_TOP = [
   "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat", "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert",
   "crb", "M", "qLD", "actuator_length", "actuator_moment", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
   "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int",
-  "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active", "mocap_pos", "mocap_quat",
+  "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active", "mocap_pos", "mocap_quat", "sensordata", "subtree_linvel", "subtree_angmom",
 ]
 _BOUND_EFC = ["J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "Ma", "type", "id", "state"]
 _BOUND_CONTACT = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "type", "geomcollisionid"]

@@ -1,0 +1,179 @@
+// k_sensor.cu -- sensors of one world by one warp.
+//
+// Replaces (reference, /root/reference/mujoco_warp/_src/): sensor.py:810 sensor_pos, :1432 sensor_vel, :2512 sensor_acc for the sensor
+// types this build carries (joint / actuator / ball readings, gyro, velocimeter, accelerometer, subtree com / linvel / angmom, frame
+// position and axes, clock), with their prerequisites smooth.py:3500-3612 subtree_vel (subtree linear velocity and angular momentum) and
+// the acceleration part of smooth.py:1743 rne_postconstraint (cacc including qacc; cfrc_ext / cfrc_int, read only by force / torque
+// sensors, are not built).  Every input a position- or velocity-stage sensor reads is final once its stage has run, so one launch after
+// the solver evaluates all three stages (the stage mask lets sensor_pos / sensor_vel / sensor_acc be called on their own).
+#include "mjb_math.cuh"
+#include "mjb_types.cuh"
+
+namespace {
+
+__device__ __forceinline__ v3 mat_t_vec(const float* m, v3 v) {  // m^T v
+  return mk3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z);
+}
+
+enum { STAGE_POS = 1, STAGE_VEL = 2, STAGE_ACC = 4 };
+
+__device__ __forceinline__ const float* obj_pos(const DataDev& d, const ModelDev& m, size_t wb, int objtype, int id) {
+  switch (objtype) {
+    case OBJ_BODY: return d.xipos + (wb * m.nbody + id) * 3;
+    case OBJ_XBODY: return d.xpos + (wb * m.nbody + id) * 3;
+    case OBJ_GEOM: return d.geom_xpos + (wb * m.ngeom + id) * 3;
+    case OBJ_SITE: return d.site_xpos + (wb * m.nsite + id) * 3;
+    default: return d.cam_xpos + (wb * m.ncam + id) * 3;
+  }
+}
+__device__ __forceinline__ const float* obj_mat(const DataDev& d, const ModelDev& m, size_t wb, int objtype, int id) {
+  switch (objtype) {
+    case OBJ_BODY: return d.ximat + (wb * m.nbody + id) * 9;
+    case OBJ_XBODY: return d.xmat + (wb * m.nbody + id) * 9;
+    case OBJ_GEOM: return d.geom_xmat + (wb * m.ngeom + id) * 9;
+    case OBJ_SITE: return d.site_xmat + (wb * m.nsite + id) * 9;
+    default: return d.cam_xmat + (wb * m.ncam + id) * 9;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int stages) {
+  extern __shared__ float smem[];  // nbody x (linvel 3 | angmom 3 | bodyvel lin 3) or nbody x cacc 6
+  const int lane = threadIdx.x, w = blockIdx.x + d.w0;
+  if (w >= d.nworld) return;
+  const size_t wb = (size_t)w;
+  const int nb = m.nbody, nv = m.nv;
+
+  if ((stages & STAGE_VEL) && m.sensor_subtree_vel) {  // smooth.py:3500-3612
+    float *linvel = smem, *angmom = smem + 3 * nb, *blin = smem + 6 * nb;
+    for (int b = lane; b < nb; b += 32) {
+      const float* cv = d.cvel + (wb * nb + b) * 6;
+      const float* ximat = d.ximat + (wb * nb + b) * 9;
+      const v3 ang = ld3(cv), dif = ld3(d.xipos + (wb * nb + b) * 3) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3);
+      const v3 lin = ld3(cv + 3) - cross(dif, ang);
+      st3(linvel + 3 * b, lin * m.body_mass[b]);
+      v3 dv = mat_t_vec(ximat, ang);
+      dv.x *= m.body_inertia[3 * b]; dv.y *= m.body_inertia[3 * b + 1]; dv.z *= m.body_inertia[3 * b + 2];
+      st3(angmom + 3 * b, matvec(ximat, dv));
+      st3(blin + 3 * b, lin);
+    }
+    __syncwarp();
+    // _linear_momentum: children into parents, deepest level first (fixed child order: no float atomics), then divide by the subtree mass
+    for (int lv = m.nlevel - 1; lv >= 0; lv--) {
+      for (int i = m.level_adr[lv] + lane; i < m.level_adr[lv + 1]; i += 32) {
+        const int b = m.level_body[i];
+        v3 s = ld3(linvel + 3 * b);
+        for (int c = m.body_childadr[b]; c < m.body_childadr[b + 1]; c++) { const int ch = m.body_childid[c]; s = s + ld3(linvel + 3 * ch) * m.body_subtreemass[ch]; }
+        st3(linvel + 3 * b, s * (1.0f / fmaxf(MJ_MINVAL, m.body_subtreemass[b])));
+      }
+      __syncwarp();
+    }
+    // _angular_momentum: a body's own term, then its (finished) subtree momentum and the orbital term go to the parent
+    for (int b = lane; b < nb; b += 32) {
+      if (b == 0) continue;
+      const v3 dx = ld3(d.xipos + (wb * nb + b) * 3) - ld3(d.subtree_com + (wb * nb + b) * 3);
+      const v3 dp = (ld3(blin + 3 * b) - ld3(linvel + 3 * b)) * m.body_mass[b];
+      st3(angmom + 3 * b, ld3(angmom + 3 * b) + cross(dx, dp));
+    }
+    __syncwarp();
+    for (int lv = m.nlevel - 1; lv >= 0; lv--) {
+      for (int i = m.level_adr[lv] + lane; i < m.level_adr[lv + 1]; i += 32) {
+        const int b = m.level_body[i];
+        v3 s = ld3(angmom + 3 * b);
+        const v3 com = ld3(d.subtree_com + (wb * nb + b) * 3), lv_b = ld3(linvel + 3 * b);
+        for (int c = m.body_childadr[b]; c < m.body_childadr[b + 1]; c++) {
+          const int ch = m.body_childid[c];
+          const v3 dx = ld3(d.subtree_com + (wb * nb + ch) * 3) - com, dv = (ld3(linvel + 3 * ch) - lv_b) * m.body_subtreemass[ch];
+          s = s + ld3(angmom + 3 * ch) + cross(dx, dv);
+        }
+        st3(angmom + 3 * b, s);
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < 3 * nb; i += 32) { d.subtree_linvel[wb * 3 * nb + i] = linvel[i]; d.subtree_angmom[wb * 3 * nb + i] = angmom[i]; }
+    __syncwarp();
+  }
+
+  if ((stages & STAGE_ACC) && m.sensor_rne_postconstraint) {  // smooth.py:1364-1425 with flg_acc
+    float* cacc = smem;
+    if (lane < 6) cacc[lane] = (lane >= 3 && !(m.disableflags & DSBL_GRAVITY)) ? -(lane == 3 ? m.gravity_x : (lane == 4 ? m.gravity_y : m.gravity_z)) : 0.f;
+    __syncwarp();
+    for (int lv = 1; lv < m.nlevel; lv++) {
+      for (int i = m.level_adr[lv] + lane; i < m.level_adr[lv + 1]; i += 32) {
+        const int b = m.level_body[i], pid = m.body_parentid[b];
+        float a[6];
+        for (int k = 0; k < 6; k++) a[k] = cacc[6 * pid + k];
+        for (int j = 0; j < m.body_dofnum[b]; j++) {
+          const int dof = m.body_dofadr[b] + j;
+          const float qv = d.qvel[wb * nv + dof], qa = d.qacc[wb * nv + dof];
+          const float *cd = d.cdof + (wb * nv + dof) * 6, *cdd = d.cdof_dot + (wb * nv + dof) * 6;
+          for (int k = 0; k < 6; k++) { a[k] += cdd[k] * qv; a[k] += cd[k] * qa; }
+        }
+        for (int k = 0; k < 6; k++) cacc[6 * b + k] = a[k];
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < 6 * nb; i += 32) d.cacc[wb * 6 * nb + i] = cacc[i];
+    __syncwarp();
+  }
+
+  if (m.disableflags & DSBL_SENSOR) return;
+  float* out = d.sensordata + wb * m.nsensordata;
+  for (int s = lane; s < m.nsensor; s += 32) {
+    const int st = m.sensor_needstage[s];
+    if (!(stages & (st == 1 ? STAGE_POS : (st == 2 ? STAGE_VEL : STAGE_ACC)))) continue;
+    const int t = m.sensor_type[s], id = m.sensor_objid[s];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    switch (t) {
+      case SENS_JOINTPOS: v[0] = d.qpos[wb * m.nq + m.jnt_qposadr[id]]; break;
+      case SENS_ACTUATORPOS: v[0] = d.actuator_length[wb * m.nu + id]; break;
+      case SENS_BALLQUAT: { const q4 q = qnormalize(ldq(d.qpos + wb * m.nq + m.jnt_qposadr[id])); v[0] = q.w; v[1] = q.x; v[2] = q.y; v[3] = q.z; break; }
+      case SENS_FRAMEPOS: { const float* p = obj_pos(d, m, wb, m.sensor_objtype[s], id); v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
+      case SENS_FRAMEXAXIS: case SENS_FRAMEYAXIS: case SENS_FRAMEZAXIS: {
+        const float* R = obj_mat(d, m, wb, m.sensor_objtype[s], id); const int c = t - SENS_FRAMEXAXIS;
+        v[0] = R[c]; v[1] = R[3 + c]; v[2] = R[6 + c]; break; }
+      case SENS_SUBTREECOM: { const float* p = d.subtree_com + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
+      case SENS_CLOCK: v[0] = d.time[w]; break;
+      case SENS_JOINTVEL: v[0] = d.qvel[wb * nv + m.jnt_dofadr[id]]; break;
+      case SENS_ACTUATORVEL: v[0] = d.actuator_velocity[wb * m.nu + id]; break;
+      case SENS_BALLANGVEL: { const float* p = d.qvel + wb * nv + m.jnt_dofadr[id]; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
+      case SENS_SUBTREELINVEL: { const float* p = d.subtree_linvel + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
+      case SENS_SUBTREEANGMOM: { const float* p = d.subtree_angmom + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
+      case SENS_GYRO: {  // sensor.py:989
+        const v3 r = mat_t_vec(d.site_xmat + (wb * m.nsite + id) * 9, ld3(d.cvel + (wb * nb + m.site_bodyid[id]) * 6));
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
+      case SENS_VELOCIMETER: {  // sensor.py:964
+        const int b = m.site_bodyid[id];
+        const float* cv = d.cvel + (wb * nb + b) * 6;
+        const v3 dif = ld3(d.site_xpos + (wb * m.nsite + id) * 3) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3);
+        const v3 r = mat_t_vec(d.site_xmat + (wb * m.nsite + id) * 9, ld3(cv + 3) - cross(dif, ld3(cv)));
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
+      case SENS_ACCELEROMETER: {  // sensor.py:1510
+        const int b = m.site_bodyid[id];
+        const float *cv = d.cvel + (wb * nb + b) * 6, *ca = d.cacc + (wb * nb + b) * 6, *R = d.site_xmat + (wb * m.nsite + id) * 9;
+        const v3 dif = ld3(d.site_xpos + (wb * m.nsite + id) * 3) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3);
+        const v3 ang = mat_t_vec(R, ld3(cv)), lin = mat_t_vec(R, ld3(cv + 3) - cross(dif, ld3(cv)));
+        const v3 acc = mat_t_vec(R, ld3(ca + 3) - cross(dif, ld3(ca))), r = acc + cross(ang, lin);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
+      case SENS_ACTUATORFRC: v[0] = d.actuator_force[wb * m.nu + id]; break;
+      case SENS_JOINTACTFRC: v[0] = d.qfrc_actuator[wb * nv + m.jnt_dofadr[id]]; break;
+      default: continue;
+    }
+    // sensor.py:56-113: cutoff clamps REAL data to [-c, c] and POSITIVE data from above
+    const float cutoff = m.sensor_cutoff[s];
+    const int dt = m.sensor_datatype[s], adr = m.sensor_adr[s];
+    for (int k = 0; k < m.sensor_dim[s]; k++) {
+      float x = v[k];
+      if (cutoff > 0.f) { if (dt == 0) x = fminf(fmaxf(x, -cutoff), cutoff); else if (dt == 1) x = fminf(x, cutoff); }
+      out[adr + k] = x;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_sensor(const ModelDev& m, const DataDev& d, int stages, cudaStream_t s) {
+  if (m.nsensor == 0) return cudaSuccess;
+  k_sensor<<<d.wn, 32, (size_t)9 * m.nbody * sizeof(float), s>>>(m, d, stages);
+  return cudaGetLastError();
+}

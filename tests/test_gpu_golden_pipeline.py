@@ -83,6 +83,14 @@ def test_gpu_matches_reference_pipeline(built, name):
     close(f"efc_force[w{w}]", d.efc.force[w, :ne].cpu().numpy(), g[f"{tag}/efc_force"][w, :ne], atol=(5e-2 if flat else 5e-3) * fscale)
   scale = max(1.0, float(np.abs(g[f"{tag}/qacc"]).max()))
   close("qacc", d.qacc.cpu().numpy(), g[f"{tag}/qacc"], atol=(5e-2 if flat else 5e-3) * scale)
+  if f"{tag}/sensordata" in g and g[f"{tag}/sensordata"].size:
+    # position / velocity sensors at the smooth-field tolerance; accelerometers inherit the solver's qacc band times the lever arm
+    stage = np.repeat(np.asarray(mjm.sensor_needstage), np.asarray(mjm.sensor_dim))
+    got, want = d.sensordata.cpu().numpy(), g[f"{tag}/sensordata"]
+    close("sensordata[pos, vel]", got[:, stage < 3], want[:, stage < 3], atol=5e-4, rtol=5e-4)
+    close("sensordata[acc]", got[:, stage == 3], want[:, stage == 3], atol=5e-3 * scale, rtol=5e-3)
+    for f in ("subtree_linvel", "subtree_angmom"):
+      close(f, getattr(d, f).cpu().numpy().reshape(nworld, -1), g[f"{tag}/{f}"].reshape(nworld, -1), atol=5e-4, rtol=5e-4)
   s = 0
   while f"step{s}/qpos" in g:
     mjw.step(m, d)
