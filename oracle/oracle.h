@@ -9,7 +9,7 @@
  * PARITY PINNING: pinned against outputs of the reference itself.  The reference's unmodified
  * Python sources are executed on the CPU through tools/warp_shim.py (a pure-Python stand-in for the warp API), which
  * yields (i) tests/golden/reference_colliders.json -- every primitive pair function of collision_primitive_core.py --
- * and (ii) tests/golden/pipeline_*.npz -- io.put_model -> make_data -> forward()/step() on seventeen scenes.  The fp64 build
+ * and (ii) tests/golden/pipeline_*.npz -- io.put_model -> make_data -> forward()/step() on nineteen scenes.  The fp64 build
  * of this file reproduces them to 1e-9 (tests/test_oracle_golden_colliders.py, tests/test_oracle_golden_pipeline.py).
  * (iii) The reference's own GJK / EPA known-answer tests (collision_gjk_test.py:307-1002, non-mesh cases) are transcribed in
  * tests/test_oracle_gjk_vectors.py and met by both builds through orc_ccd().
