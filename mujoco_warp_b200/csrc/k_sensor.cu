@@ -3,14 +3,15 @@
 // Replaces (reference, /root/reference/mujoco_warp/_src/): sensor.py:810 sensor_pos, :1432 sensor_vel, :2512 sensor_acc for the sensor
 // types this build carries (joint / actuator / ball readings, gyro, velocimeter, accelerometer, subtree com / linvel / angmom, frame
 // position and axes, clock), with their prerequisites smooth.py:3500-3612 subtree_vel (subtree linear velocity and angular momentum) and
-// the acceleration part of smooth.py:1743 rne_postconstraint (cacc including qacc; cfrc_ext / cfrc_int, read only by force / torque
-// sensors, are not built).  Every input a position- or velocity-stage sensor reads is final once its stage has run, so one launch after
+// smooth.py:1743 rne_postconstraint (cfrc_ext from applied wrenches, body-to-body connect / weld equalities and contacts; cacc including
+// qacc; cfrc_int accumulated up the tree).  Every input a position- or velocity-stage sensor reads is final once its stage has run, so one launch after
 // the solver evaluates all three stages (the stage mask lets sensor_pos / sensor_vel / sensor_acc be called on their own).
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
 
 namespace {
 
+__device__ __forceinline__ float comp3(v3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 __device__ __forceinline__ v3 mat_t_vec(const float* m, v3 v) {  // m^T v
   return mk3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z);
 }
@@ -38,7 +39,7 @@ __device__ __forceinline__ const float* obj_mat(const DataDev& d, const ModelDev
 
 __global__ void __launch_bounds__(32)
 k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int stages) {
-  extern __shared__ float smem[];  // nbody x (linvel 3 | angmom 3 | bodyvel lin 3) or nbody x cacc 6
+  extern __shared__ float smem[];  // nbody x (linvel 3 | angmom 3 | bodyvel lin 3) or nbody x (cfrc_ext 6 | cacc / cfrc_int 6)
   const int lane = threadIdx.x, w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
   const size_t wb = (size_t)w;
@@ -94,8 +95,76 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
     __syncwarp();
   }
 
-  if ((stages & STAGE_ACC) && m.sensor_rne_postconstraint) {  // smooth.py:1364-1425 with flg_acc
-    float* cacc = smem;
+  if ((stages & STAGE_ACC) && m.sensor_rne_postconstraint) {  // smooth.py:1743 rne_postconstraint
+    float *cext = smem, *cacc = smem + 6 * nb;  // cfrc_int later reuses the cacc rows
+    // cfrc_ext: applied wrenches (:1518) ...
+    for (int b = lane; b < nb; b += 32) {
+      float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (b) {
+        const float* x = d.xfrc_applied + (wb * nb + b) * 6;
+        const v3 off = ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3) - ld3(d.xipos + (wb * nb + b) * 3);
+        const v3 f = ld3(x), t = ld3(x + 3) - cross(off, f);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = f.x; o[4] = f.y; o[5] = f.z;
+      }
+      for (int k = 0; k < 6; k++) cext[6 * b + k] = o[k];
+    }
+    __syncwarp();
+    // ... connect / weld equalities between bodies (:1562; rows are ordered connect, weld, joint) and contacts (:1660), one after the
+    // other in row / pool order so that the sums are reproducible; lanes 0-5 own the six components
+    const float* force = d.efc_force + wb * d.njmax;
+#pragma unroll 1
+    for (int e = 0; e < d.ne[w];) {
+      const int id = d.efc_id[wb * d.njmax + e], type = m.eq_type[id];
+      if (type != EQ_CONNECT && type != EQ_WELD) break;
+      const int nrow = type == EQ_CONNECT ? 3 : 6, b1 = m.eq_obj1id[id], b2 = m.eq_obj2id[id];
+      const v3 f = mk3(force[e], force[e + 1], force[e + 2]);
+      const v3 tq = type == EQ_WELD ? mk3(force[e + 3], force[e + 4], force[e + 5]) : mk3(0.f, 0.f, 0.f);
+      const float* data = m.eq_data + 11 * id;
+      for (int side = 0; side < 2; side++) {
+        const int b = side ? b2 : b1;
+        if (!b) continue;
+        const v3 anchor = ld3(data + (((type == EQ_CONNECT) == (side == 0)) ? 0 : 3));
+        const v3 pos = matvec(d.xmat + (wb * nb + b) * 9, anchor) + ld3(d.xpos + (wb * nb + b) * 3);
+        const v3 dif = ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3) - pos, t = tq - cross(dif, f);
+        if (lane < 6) { const float c = lane < 3 ? comp3(t, lane) : comp3(f, lane - 3); cext[6 * b + lane] += side ? -c : c; }
+      }
+      __syncwarp();
+      e += nrow;
+    }
+    const int c0 = d.world_conadr[w], c1 = c0 + min(d.world_ncon[w], d.nconmax);
+#pragma unroll 1
+    for (int c = c0; c < c1; c++) {
+      const int id1 = m.geom_bodyid[d.contact_geom[2 * c]], id2 = m.geom_bodyid[d.contact_geom[2 * c + 1]];
+      if (id1 == 0 && id2 == 0) continue;
+      float fc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // support.py:326-397 contact_force_fn
+      const int dim = d.contact_dim[c];
+      const int* adr = d.contact_efc_address + (size_t)c * m.nmaxpyramid;
+      if (adr[0] >= 0) {
+        if (m.cone == CONE_PYRAMIDAL) {
+          if (dim == 1) fc[0] = force[adr[0]];
+          else
+            for (int i = 0; i < dim - 1; i++) {
+              const int a = 2 * i + adr[0];
+              const float d1 = a < d.njmax ? force[a] : 0.f, d2 = a + 1 < d.njmax ? force[a + 1] : 0.f;
+              fc[0] += d1 + d2; fc[i + 1] = (d1 - d2) * d.contact_friction[5 * (size_t)c + i];
+            }
+        } else {
+          for (int i = 0; i < dim; i++) if (adr[i] < d.njmax) fc[i] = force[adr[i]];
+        }
+      }
+      const float* R = d.contact_frame + 9 * (size_t)c;
+      const v3 fw = mk3(fc[0] * R[0] + fc[1] * R[3] + fc[2] * R[6], fc[0] * R[1] + fc[1] * R[4] + fc[2] * R[7], fc[0] * R[2] + fc[1] * R[5] + fc[2] * R[8]);
+      const v3 tw = mk3(fc[3] * R[0] + fc[4] * R[3] + fc[5] * R[6], fc[3] * R[1] + fc[4] * R[4] + fc[5] * R[7], fc[3] * R[2] + fc[4] * R[5] + fc[5] * R[8]);
+      const v3 pos = ld3(d.contact_pos + 3 * (size_t)c);
+      for (int side = 0; side < 2; side++) {
+        const int b = side ? id2 : id1;
+        if (!b) continue;
+        const v3 off = ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3) - pos, t = tw - cross(off, fw);
+        if (lane < 6) { const float cc = lane < 3 ? comp3(t, lane) : comp3(fw, lane - 3); cext[6 * b + lane] += side ? cc : -cc; }
+      }
+      __syncwarp();
+    }
+    // cacc including qacc (:1364-1425 with flg_acc)
     if (lane < 6) cacc[lane] = (lane >= 3 && !(m.disableflags & DSBL_GRAVITY)) ? -(lane == 3 ? m.gravity_x : (lane == 4 ? m.gravity_y : m.gravity_z)) : 0.f;
     __syncwarp();
     for (int lv = 1; lv < m.nlevel; lv++) {
@@ -113,7 +182,33 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
       }
       __syncwarp();
     }
-    for (int i = lane; i < 6 * nb; i += 32) d.cacc[wb * 6 * nb + i] = cacc[i];
+    for (int i = lane; i < 6 * nb; i += 32) { d.cacc[wb * 6 * nb + i] = cacc[i]; d.cfrc_ext[wb * 6 * nb + i] = cext[i]; }
+    __syncwarp();
+    // cfrc_int = I cacc + cvel x* (I cvel) - cfrc_ext (:1428), then children into parents, deepest level first (:1453)
+    float* cint = cacc;
+    for (int b = lane; b < nb; b += 32) {
+      float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (b) {
+        float f[6], iv[6], g[6];
+        const float *ci = d.cinert + (wb * nb + b) * 10, *cv = d.cvel + (wb * nb + b) * 6;
+        inert_vec(ci, cacc + 6 * b, f); inert_vec(ci, cv, iv); motion_cross_force(cv, iv, g);
+        for (int k = 0; k < 6; k++) o[k] = f[k] + g[k] - cext[6 * b + k];
+      }
+      // (a lane only reads and then overwrites its own body's row)
+      for (int k = 0; k < 6; k++) cint[6 * b + k] = o[k];
+    }
+    __syncwarp();
+    for (int lv = m.nlevel - 2; lv >= 0; lv--) {
+      for (int i = m.level_adr[lv] + lane; i < m.level_adr[lv + 1]; i += 32) {
+        const int b = m.level_body[i];
+        float a[6];
+        for (int k = 0; k < 6; k++) a[k] = cint[6 * b + k];
+        for (int c = m.body_childadr[b]; c < m.body_childadr[b + 1]; c++) { const int ch = m.body_childid[c]; for (int k = 0; k < 6; k++) a[k] += cint[6 * ch + k]; }
+        for (int k = 0; k < 6; k++) cint[6 * b + k] = a[k];
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < 6 * nb; i += 32) d.cfrc_int[wb * 6 * nb + i] = cint[i];
     __syncwarp();
   }
 
@@ -155,6 +250,15 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
         const v3 ang = mat_t_vec(R, ld3(cv)), lin = mat_t_vec(R, ld3(cv + 3) - cross(dif, ld3(cv)));
         const v3 acc = mat_t_vec(R, ld3(ca + 3) - cross(dif, ld3(ca))), r = acc + cross(ang, lin);
         v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
+      case SENS_FORCE: {  // sensor.py:1542
+        const v3 r = mat_t_vec(d.site_xmat + (wb * m.nsite + id) * 9, ld3(d.cfrc_int + (wb * nb + m.site_bodyid[id]) * 6 + 3));
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
+      case SENS_TORQUE: {  // sensor.py:1559
+        const int b = m.site_bodyid[id];
+        const float* cf = d.cfrc_int + (wb * nb + b) * 6;
+        const v3 dif = ld3(d.site_xpos + (wb * m.nsite + id) * 3) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3);
+        const v3 r = mat_t_vec(d.site_xmat + (wb * m.nsite + id) * 9, ld3(cf) - cross(dif, ld3(cf + 3)));
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
       case SENS_ACTUATORFRC: v[0] = d.actuator_force[wb * m.nu + id]; break;
       case SENS_JOINTACTFRC: v[0] = d.qfrc_actuator[wb * nv + m.jnt_dofadr[id]]; break;
       default: continue;
@@ -174,6 +278,6 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
 
 cudaError_t launch_sensor(const ModelDev& m, const DataDev& d, int stages, cudaStream_t s) {
   if (m.nsensor == 0) return cudaSuccess;
-  k_sensor<<<d.wn, 32, (size_t)9 * m.nbody * sizeof(float), s>>>(m, d, stages);
+  k_sensor<<<d.wn, 32, (size_t)12 * m.nbody * sizeof(float), s>>>(m, d, stages);
   return cudaGetLastError();
 }

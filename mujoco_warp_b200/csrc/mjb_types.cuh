@@ -59,7 +59,7 @@ struct ModelDev {
   X(qfrc_constraint) X(cacc) X(cfrc_int) \
   X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
   X(contact_dist) X(contact_pos) X(contact_frame) X(contact_includemargin) X(contact_friction) X(contact_solref) \
-  X(contact_solreffriction) X(contact_solimp) X(mocap_pos) X(mocap_quat) X(sensordata) X(subtree_linvel) X(subtree_angmom)
+  X(contact_solreffriction) X(contact_solimp) X(mocap_pos) X(mocap_quat) X(sensordata) X(subtree_linvel) X(subtree_angmom) X(cfrc_ext)
 #define MJB_DATA_IARRS(X) \
   X(ne) X(nf) X(nl) X(nefc) X(nacon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
   X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(contact_dim) X(contact_geom) X(contact_efc_address) \
@@ -89,7 +89,7 @@ enum { SOL_CG = 1, SOL_NEWTON = 2 };
 enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
 enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5, OBJ_SITE = 6, OBJ_CAMERA = 7 };
 // mjtSensor values of the sensor types carried here (MuJoCo order, as in _src/constants.py)
-enum { SENS_ACCELEROMETER = 1, SENS_VELOCIMETER = 2, SENS_GYRO = 3, SENS_JOINTPOS = 9, SENS_JOINTVEL = 10, SENS_ACTUATORPOS = 13, SENS_ACTUATORVEL = 14,
+enum { SENS_ACCELEROMETER = 1, SENS_VELOCIMETER = 2, SENS_GYRO = 3, SENS_FORCE = 4, SENS_TORQUE = 5, SENS_JOINTPOS = 9, SENS_JOINTVEL = 10, SENS_ACTUATORPOS = 13, SENS_ACTUATORVEL = 14,
        SENS_ACTUATORFRC = 15, SENS_JOINTACTFRC = 16, SENS_BALLQUAT = 18, SENS_BALLANGVEL = 19, SENS_FRAMEPOS = 26, SENS_FRAMEXAXIS = 28,
        SENS_FRAMEYAXIS = 29, SENS_FRAMEZAXIS = 30, SENS_SUBTREECOM = 35, SENS_SUBTREELINVEL = 36, SENS_SUBTREEANGMOM = 37, SENS_CLOCK = 45 };
 enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_LIMIT_JOINT = 3, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6, CNSTR_CONTACT_ELLIPTIC = 7 };

@@ -74,7 +74,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(cam_xpos) X(cam_xmat) X(light_xpos) X(light_xdir) X(subtree_com) X(cdof) X(cinert) X(crb) X(M) X(qLD) \
   X(actuator_length) X(actuator_moment) X(actuator_velocity) X(cvel) X(cdof_dot) X(qfrc_bias) X(qfrc_spring) \
   X(qfrc_damper) X(qfrc_gravcomp) X(qfrc_passive) X(actuator_force) X(qfrc_actuator) X(qfrc_smooth) X(qacc_smooth) \
-  X(qfrc_constraint) X(cacc) X(cfrc_int) X(sensordata) X(subtree_linvel) X(subtree_angmom) \
+  X(qfrc_constraint) X(cacc) X(cfrc_int) X(cfrc_ext) X(sensordata) X(subtree_linvel) X(subtree_angmom) \
   X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
   X(con_dist) X(con_pos) X(con_frame) X(con_includemargin) X(con_friction) X(con_solref) X(con_solreffriction) X(con_solimp)
 #define DATA_IARRS(X) \
@@ -339,7 +339,7 @@ static void make_view(const OrcModel* m, const OrcData* d, int w, W* v) {
   R(efc_type, njm); R(efc_id, njm); R(efc_state, njm); R(moment_rownnz, nu); R(moment_rowadr, nu); R(moment_colind, m->nJmom);
   R(con_dim, ncm); R(con_geom, 2 * ncm); R(con_efc_address, m->nmaxpyramid * ncm); R(con_geomcollisionid, ncm);
   R(eq_active, m->neq);
-  R(sensordata, m->nsensordata); R(subtree_linvel, 3 * nb); R(subtree_angmom, 3 * nb);
+  R(cfrc_ext, 6 * nb); R(sensordata, m->nsensordata); R(subtree_linvel, 3 * nb); R(subtree_angmom, 3 * nb);
 #undef R
 }
 
@@ -2439,13 +2439,74 @@ static void subtree_vel(W* w) {
   }
   free(bodyvel);
 }
-/* smooth.py:1743 rne_postconstraint, acceleration part (:1364-1425 with flg_acc): cacc including qacc.  The external / internal
- * force accumulation (cfrc_ext, cfrc_int) that only force / torque sensors read is not restated. */
-static void rne_postconstraint_cacc(W* w) {
+/* support.py:326-397 contact_force_fn with to_world_frame: 6D (force, torque) of one contact in the world frame */
+static void contact_wrench_world(const W* w, int c, real* out) {
   const OrcModel* m = w->m;
+  real f[6] = {0, 0, 0, 0, 0, 0};
+  const int dim = w->con_dim[c], *adr = w->con_efc_address + m->nmaxpyramid * c;
+  if (adr[0] >= 0) {
+    if (m->cone == CONE_PYRAMIDAL) {
+      if (dim == 1) f[0] = w->efc_force[adr[0]];
+      else for (int i = 0; i < dim - 1; i++) {
+        int a = 2 * i + adr[0];
+        real d1 = a < w->njmax ? w->efc_force[a] : 0, d2 = a + 1 < w->njmax ? w->efc_force[a + 1] : 0;
+        f[0] += d1 + d2; f[i + 1] = (d1 - d2) * w->con_friction[5 * c + i];
+      }
+    } else for (int i = 0; i < dim; i++) if (adr[i] < w->njmax) f[i] = w->efc_force[adr[i]];
+  }
+  const real* R = w->con_frame + 9 * c;
+  for (int k = 0; k < 3; k++) { out[k] = f[0] * R[k] + f[1] * R[3 + k] + f[2] * R[6 + k]; out[3 + k] = f[3] * R[k] + f[4] * R[3 + k] + f[5] * R[6 + k]; }
+}
+/* support.py:476-485 transform_force: (torque - offset x force, force) as a spatial (angular, linear) vector */
+static void transform_force(const real* force, const real* torque, const real* offset, real* o) {
+  real cr[3]; cross3(offset, force, cr);
+  for (int i = 0; i < 3; i++) { o[i] = torque[i] - cr[i]; o[3 + i] = force[i]; }
+}
+/* smooth.py:1743 rne_postconstraint: cfrc_ext from applied wrenches (:1518), connect / weld equalities between bodies (:1562) and
+ * contacts (:1660); cacc including qacc (:1364-1425 with flg_acc); cfrc_int (:1428) accumulated up the tree (:1453) */
+static void rne_postconstraint(W* w) {
+  const OrcModel* m = w->m;
+  const int nb = m->nbody;
+  memset(w->cfrc_ext, 0, 6 * sizeof(real));
+  for (int b = 1; b < nb; b++) {
+    real off[3]; v3sub(w->subtree_com + 3 * m->body_rootid[b], w->xipos + 3 * b, off);
+    transform_force(w->xfrc_applied + 6 * b, w->xfrc_applied + 6 * b + 3, off, w->cfrc_ext + 6 * b);
+  }
+  for (int e = 0; e < w->ne[0];) { /* rows are ordered connect (3 rows each), weld (6), joint (1): constraint.py:4909-5010 */
+    const int id = w->efc_id[e], type = m->eq_type[id];
+    if (type != EQ_CONNECT && type != EQ_WELD) break;
+    const int nrow = type == EQ_CONNECT ? 3 : 6, b1 = m->eq_obj1id[id], b2 = m->eq_obj2id[id];
+    real force[3] = {w->efc_force[e], w->efc_force[e + 1], w->efc_force[e + 2]}, torque[3] = {0, 0, 0}, c6[6], pos[3], dif[3], t[3];
+    if (type == EQ_WELD) for (int i = 0; i < 3; i++) torque[i] = w->efc_force[e + 3 + i];
+    const real* data = m->eq_data + 11 * id;
+    if (b1) {
+      matvec3(w->xmat + 9 * b1, type == EQ_CONNECT ? data : data + 3, t);
+      for (int i = 0; i < 3; i++) pos[i] = t[i] + w->xpos[3 * b1 + i];
+      v3sub(w->subtree_com + 3 * m->body_rootid[b1], pos, dif);
+      transform_force(force, torque, dif, c6);
+      for (int i = 0; i < 6; i++) w->cfrc_ext[6 * b1 + i] += c6[i];
+    }
+    if (b2) {
+      matvec3(w->xmat + 9 * b2, type == EQ_CONNECT ? data + 3 : data, t);
+      for (int i = 0; i < 3; i++) pos[i] = t[i] + w->xpos[3 * b2 + i];
+      v3sub(w->subtree_com + 3 * m->body_rootid[b2], pos, dif);
+      transform_force(force, torque, dif, c6);
+      for (int i = 0; i < 6; i++) w->cfrc_ext[6 * b2 + i] -= c6[i];
+    }
+    e += nrow;
+  }
+  const int ncon = w->ncon[0] < w->nconmax ? w->ncon[0] : w->nconmax;
+  for (int c = 0; c < ncon; c++) {
+    const int id1 = m->geom_bodyid[w->con_geom[2 * c]], id2 = m->geom_bodyid[w->con_geom[2 * c + 1]];
+    if (id1 == 0 && id2 == 0) continue;
+    real wr[6], off[3], c6[6];
+    contact_wrench_world(w, c, wr);
+    if (id1) { v3sub(w->subtree_com + 3 * m->body_rootid[id1], w->con_pos + 3 * c, off); transform_force(wr, wr + 3, off, c6); for (int i = 0; i < 6; i++) w->cfrc_ext[6 * id1 + i] -= c6[i]; }
+    if (id2) { v3sub(w->subtree_com + 3 * m->body_rootid[id2], w->con_pos + 3 * c, off); transform_force(wr, wr + 3, off, c6); for (int i = 0; i < 6; i++) w->cfrc_ext[6 * id2 + i] += c6[i]; }
+  }
   memset(w->cacc, 0, 6 * sizeof(real));
   if (!(m->disableflags & DSBL_GRAVITY)) for (int i = 0; i < 3; i++) w->cacc[3 + i] = -m->gravity[i];
-  for (int b = 1; b < m->nbody; b++) {
+  for (int b = 1; b < nb; b++) {
     real a[6];
     memcpy(a, w->cacc + 6 * m->body_parentid[b], sizeof a);
     for (int k = 0; k < m->body_dofnum[b]; k++) {
@@ -2455,6 +2516,15 @@ static void rne_postconstraint_cacc(W* w) {
     }
     memcpy(w->cacc + 6 * b, a, sizeof a);
   }
+  memset(w->cfrc_int, 0, 6 * sizeof(real));
+  for (int b = 1; b < nb; b++) {
+    real f[6], iv[6], g[6];
+    inert_vec(w->cinert + 10 * b, w->cacc + 6 * b, f);
+    inert_vec(w->cinert + 10 * b, w->cvel + 6 * b, iv);
+    motion_cross_force(w->cvel + 6 * b, iv, g);
+    for (int i = 0; i < 6; i++) w->cfrc_int[6 * b + i] = f[i] + g[i] - w->cfrc_ext[6 * b + i];
+  }
+  for (int b = nb - 1; b >= 1; b--) { int p = m->body_parentid[b]; for (int i = 0; i < 6; i++) w->cfrc_int[6 * p + i] += w->cfrc_int[6 * b + i]; }
 }
 /* object frame position / orientation (sensor.py:266-317 _get_pos / _get_mat) */
 static const real* obj_pos(const W* w, int objtype, int id) {
@@ -2483,10 +2553,10 @@ static void sensors(W* w, int stage) {
   for (int s = 0; s < m->nsensor; s++) {
     int t = m->sensor_type[s];
     if (t == SENS_SUBTREELINVEL || t == SENS_SUBTREEANGMOM) need_subtree = 1;
-    if (t == SENS_ACCELEROMETER) need_cacc = 1;
+    if (t == SENS_ACCELEROMETER || t == SENS_FORCE || t == SENS_TORQUE) need_cacc = 1;
   }
   if (stage == STAGE_VEL && need_subtree) subtree_vel(w);
-  if (stage == STAGE_ACC && need_cacc) rne_postconstraint_cacc(w);
+  if (stage == STAGE_ACC && need_cacc) rne_postconstraint(w);
   for (int s = 0; s < m->nsensor; s++) {
     if (m->sensor_needstage[s] != stage) continue;
     const int t = m->sensor_type[s], id = m->sensor_objid[s];
@@ -2522,6 +2592,13 @@ static void sensors(W* w, int stage) {
         cross3(dif, ca, cr); for (int i = 0; i < 3; i++) t1[i] = ca[3 + i] - cr[i]; matT_vec3(R, t1, acc);
         cross3(ang, lin, corr);
         for (int i = 0; i < 3; i++) v[i] = acc[i] + corr[i]; break; }
+      case SENS_FORCE: matT_vec3(w->site_xmat + 9 * id, w->cfrc_int + 6 * m->site_bodyid[id] + 3, v); break; /* sensor.py:1542 */
+      case SENS_TORQUE: { /* sensor.py:1559 */
+        const int b = m->site_bodyid[id]; const real* cf = w->cfrc_int + 6 * b;
+        real dif[3], cr[3], t1[3];
+        v3sub(w->site_xpos + 3 * id, w->subtree_com + 3 * m->body_rootid[b], dif); cross3(dif, cf + 3, cr);
+        for (int i = 0; i < 3; i++) t1[i] = cf[i] - cr[i];
+        matT_vec3(w->site_xmat + 9 * id, t1, v); break; }
       case SENS_ACTUATORFRC: v[0] = w->actuator_force[id]; break;
       case SENS_JOINTACTFRC: v[0] = w->qfrc_actuator[m->jnt_dofadr[id]]; break;
       default: continue; /* put_model rejects other types */

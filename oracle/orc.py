@@ -151,7 +151,7 @@ def data_spec(mjm, tabs, nconmax, njmax):
     "actuator_length": (R, (nu,)), "actuator_moment": (R, (tabs["nJmom"],)), "actuator_velocity": (R, (nu,)),
     "cvel": (R, (nb, 6)), "cdof_dot": (R, (nv, 6)), "qfrc_bias": (R, (nv,)), "qfrc_spring": (R, (nv,)), "qfrc_damper": (R, (nv,)),
     "qfrc_gravcomp": (R, (nv,)), "qfrc_passive": (R, (nv,)), "actuator_force": (R, (nu,)), "qfrc_actuator": (R, (nv,)),
-    "qfrc_smooth": (R, (nv,)), "qacc_smooth": (R, (nv,)), "qfrc_constraint": (R, (nv,)), "cacc": (R, (nb, 6)), "cfrc_int": (R, (nb, 6)),
+    "qfrc_smooth": (R, (nv,)), "qacc_smooth": (R, (nv,)), "qfrc_constraint": (R, (nv,)), "cacc": (R, (nb, 6)), "cfrc_int": (R, (nb, 6)), "cfrc_ext": (R, (nb, 6)),
     "sensordata": (R, (int(getattr(mjm, "nsensordata", 0)) if int(getattr(mjm, "nsensor", 0)) else 0,)), "subtree_linvel": (R, (nb, 3)), "subtree_angmom": (R, (nb, 3)),
     "efc_J": (R, (njmax, nv)), "efc_pos": (R, (njmax,)), "efc_margin": (R, (njmax,)), "efc_D": (R, (njmax,)), "efc_vel": (R, (njmax,)),
     "efc_aref": (R, (njmax,)), "efc_frictionloss": (R, (njmax,)), "efc_force": (R, (njmax,)), "efc_Ma": (R, (nv,)),

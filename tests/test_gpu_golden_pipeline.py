@@ -91,6 +91,9 @@ def test_gpu_matches_reference_pipeline(built, name):
     close("sensordata[acc]", got[:, stage == 3], want[:, stage == 3], atol=5e-3 * scale, rtol=5e-3)
     for f in ("subtree_linvel", "subtree_angmom"):
       close(f, getattr(d, f).cpu().numpy().reshape(nworld, -1), g[f"{tag}/{f}"].reshape(nworld, -1), atol=5e-4, rtol=5e-4)
+    if f"{tag}/cfrc_ext" in g and np.abs(g[f"{tag}/cfrc_ext"]).max() > 0:
+      fs = max(1.0, float(np.abs(g[f"{tag}/cfrc_ext"]).max()))
+      close("cfrc_ext", d.cfrc_ext.cpu().numpy().reshape(nworld, -1), g[f"{tag}/cfrc_ext"].reshape(nworld, -1), atol=5e-3 * fs, rtol=5e-3)
   s = 0
   while f"step{s}/qpos" in g:
     mjw.step(m, d)

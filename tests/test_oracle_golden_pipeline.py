@@ -117,6 +117,8 @@ def compare(tag, g, od, mjm, nworld, tol, solver_tol=1e-7, exact_iterations=True
     close(f"{tag}/sensordata", od["sensordata"], g[f"{tag}/sensordata"], solver_tol)
     for f in ("subtree_linvel", "subtree_angmom"):
       close(f"{tag}/{f}", od[f].reshape(nworld, -1), g[f"{tag}/{f}"].reshape(nworld, -1), tol)
+    if f"{tag}/cfrc_ext" in g and np.abs(g[f"{tag}/cfrc_ext"]).max() > 0:  # rne_postconstraint ran (force / torque / accelerometer sensors)
+      close(f"{tag}/cfrc_ext", od["cfrc_ext"].reshape(nworld, -1), g[f"{tag}/cfrc_ext"].reshape(nworld, -1), solver_tol * 10)
   close(f"{tag}/qacc", od["qacc"], g[f"{tag}/qacc"], solver_tol)
   close(f"{tag}/qfrc_constraint", od["qfrc_constraint"], g[f"{tag}/qfrc_constraint"], solver_tol)
   if exact_iterations:

@@ -139,6 +139,7 @@ EQUALITY_XML = """
       <body name="a2" pos="0.3 0 0">
         <joint name="h2" type="hinge" axis="0 1 0" damping="0.1"/>
         <geom type="capsule" fromto="0 0 0 0 0 -0.3" size="0.02"/>
+        <site name="sa2" pos="0 0.01 -0.1" euler="20 0 40"/>
       </body>
     </body>
     <body name="b1" pos="0 0 0.7">
@@ -150,7 +151,7 @@ EQUALITY_XML = """
       <geom type="capsule" fromto="0 0 0 0 0 -0.3" size="0.03"/>
     </body>
     <body name="f1" pos="0.6 0.5 0.5"><freejoint/><geom type="sphere" size="0.05"/></body>
-    <body name="f2" pos="0.8 0.5 0.5"><freejoint/><geom type="box" size="0.04 0.04 0.04"/></body>
+    <body name="f2" pos="0.8 0.5 0.5"><freejoint/><geom type="box" size="0.04 0.04 0.04"/><site name="sf2" pos="0.01 0 0.02"/></body>
     <body name="s1" pos="-0.5 0 0.5"><joint name="sl1" type="slide" axis="0 0 1"/><geom type="sphere" size="0.04"/></body>
     <body name="s2" pos="-0.7 0 0.5"><joint name="sl2" type="slide" axis="0 0 1" damping="1"/><geom type="sphere" size="0.04"/></body>
     <body name="s3" pos="-0.9 0 0.5"><joint name="sl3" type="slide" axis="1 0 0"/><geom type="sphere" size="0.04"/></body>
@@ -159,7 +160,7 @@ EQUALITY_XML = """
       <body name="target_child" pos="0 0 0.1"><geom type="sphere" size="0.03" contype="0" conaffinity="0"/></body>
     </body>
     <body name="puck" pos="0.3 -0.5 0.47"><freejoint/><geom type="sphere" size="0.05" contype="2" conaffinity="2"/></body>
-    <body name="follower" pos="0.3 -0.9 0.4"><freejoint/><geom type="sphere" size="0.04" contype="0" conaffinity="0"/></body>
+    <body name="follower" pos="0.3 -0.9 0.4"><freejoint/><geom type="sphere" size="0.04" contype="0" conaffinity="0"/><site name="sfol" pos="0 0.02 0"/></body>
   </worldbody>
   <equality>
     <connect body1="a2" body2="b1" anchor="0 0 -0.3"/>
@@ -170,6 +171,10 @@ EQUALITY_XML = """
     <weld body1="s1" body2="s3" active="false"/>
     <weld body1="follower" body2="target_child" solref="0.01 1"/>
   </equality>
+  <sensor>
+    <force name="fa2" site="sa2"/> <torque name="ta2" site="sa2"/> <force name="ff2" site="sf2"/> <torque name="tf2" site="sf2"/>
+    <force name="ffol" site="sfol"/> <torque name="tfol" site="sfol"/>
+  </sensor>
   <actuator>
     <motor joint="h1" gear="2"/>
     <motor joint="sl1" gear="5"/>
@@ -273,6 +278,7 @@ def sensor_xml():
     <jointactuatorfrc name="jaf" joint="hinge"/>
     <gyro name="gy" site="imu"/> <velocimeter name="vm" site="imu"/> <accelerometer name="ac" site="imu" cutoff="50"/>
     <gyro name="gy0" site="st0"/> <accelerometer name="ac0" site="st0"/>
+    <force name="ft_f" site="imu"/> <torque name="ft_t" site="imu"/> <force name="f0" site="st0"/> <torque name="t0" site="st0"/>
     <subtreecom name="sc" body="arm"/> <subtreelinvel name="sl" body="fore"/> <subtreeangmom name="sa" body="arm"/> <subtreeangmom name="sa0" body="cap0"/>
     <framepos name="fp" objtype="site" objname="imu"/> <framexaxis name="fx" objtype="geom" objname="tip"/> <frameyaxis name="fy" objtype="body" objname="pend"/>
     <framezaxis name="fz" objtype="xbody" objname="fore"/> <framepos name="fc" objtype="camera" objname="c0"/>

@@ -29,7 +29,7 @@ FIELDS = [
   "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
   "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert", "crb", "M", "actuator_length", "actuator_moment", "actuator_velocity", "cvel",
   "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper", "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth",
-  "qacc", "qfrc_constraint", "ne", "nf", "nl", "nefc", "solver_niter", "sensordata", "subtree_linvel", "subtree_angmom",
+  "qacc", "qfrc_constraint", "ne", "nf", "nl", "nefc", "solver_niter", "sensordata", "subtree_linvel", "subtree_angmom", "cfrc_ext",
 ]
 EFC = ["type", "id", "J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "state"]
 CON = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "geomcollisionid"]
