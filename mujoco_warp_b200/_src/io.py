@@ -356,8 +356,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   neq = int(getattr(mjm, "neq", 0))
   m.neq = neq
   nsensor = int(getattr(mjm, "nsensor", 0))
-  if getattr(mjm, "sensor_unsupported", None):
-    raise NotImplementedError(f"sensor types not implemented in this version: {sorted(set(mjm.sensor_unsupported))}")
+  unsupported = [str(x) for x in np.asarray(getattr(mjm, "sensor_unsupported", []), dtype=object).reshape(-1)]
+  if unsupported:
+    raise NotImplementedError(f"sensor types not implemented in this version: {sorted(set(unsupported))}")
   m.nsensor, m.nsensordata = nsensor, int(getattr(mjm, "nsensordata", 0)) if nsensor else 0
   for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_dim", "sensor_adr"):
     setattr(m, n, dev_i(getattr(mjm, n) if nsensor else np.zeros(0)))

@@ -179,3 +179,39 @@ def test_shard_worlds():
     assert all(blocks[r][0] + blocks[r][1] == blocks[r + 1][0] for r in range(ws - 1))
     assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
   assert shard.whole_job_rate(8192 * 100, 0.5, world_size=8) == 8 * 8192 * 100 / 0.5
+
+
+def test_put_model_and_make_data_host_path(monkeypatch):
+  """The Python side of put_model / make_data (table derivation, field specs, C-ABI registration order) runs for every fixture
+  model against a stub of the C library: no device, no compute -- it catches host-logic slips the GPU tests would only show later."""
+  import torch
+
+  from mujoco_warp_b200._src import _lib
+  from mujoco_warp_b200._src import io as mio
+  from mujoco_warp_b200._src import mjcf
+
+  calls = []
+
+  class Stub:
+    def __getattr__(self, name):
+      def f(*a, **k):
+        calls.append(name)
+        return 1 if name in ("mjb_model_create", "mjb_data_create") else 0
+
+      return f
+
+  monkeypatch.setattr(mio, "_require_cuda", lambda: torch.device("cpu"))
+  monkeypatch.setattr(_lib, "lib", lambda: Stub())
+  scenes = {
+    "humanoid": mjcf.load_any(util.HUMANOID), "g1": mjcf.load_any(util.G1), "three_humanoids": mjcf.load_any(util.THREE_HUMANOIDS),
+    "sensors": mjcf.load_string(util.sensor_xml()), "equality": mjcf.load_string(util.EQUALITY_XML), "boxccd": mjcf.load_string(util.boxccd_xml()),
+  }
+  for name, mjm in scenes.items():
+    m = mio.put_model(mjm)
+    d = mio.make_data(mjm, nworld=3, nconmax=32, njmax=128, m=m)
+    assert d.sensordata.shape == (3, getattr(mjm, "nsensordata", 0) if getattr(mjm, "nsensor", 0) else 0), name
+    assert d.qpos.shape == (3, mjm.nq) and d.efc.J.shape[0] == 3, name
+  assert "mjb_model_finalize" in calls and "mjb_data_finalize" in calls
+  bad = mjcf.load_string(util.sensor_xml().replace('<clock name="clk"/>', '<touch name="tch" site="imu"/>'))
+  with pytest.raises(NotImplementedError, match="touch"):
+    mio.put_model(bad)
