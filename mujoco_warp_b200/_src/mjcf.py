@@ -1133,6 +1133,8 @@ def compile_xml(root):
     "subtreeangmom": (S.SENS_SUBTREEANGMOM, "body", 3, 0, 2), "clock": (S.SENS_CLOCK, None, 1, 0, 1),
     "framepos": (S.SENS_FRAMEPOS, "obj", 3, 0, 1), "framexaxis": (S.SENS_FRAMEXAXIS, "obj", 3, 2, 1), "frameyaxis": (S.SENS_FRAMEYAXIS, "obj", 3, 2, 1),
     "framezaxis": (S.SENS_FRAMEZAXIS, "obj", 3, 2, 1),
+    "framequat": (S.SENS_FRAMEQUAT, "obj", 4, 3, 1), "framelinvel": (S.SENS_FRAMELINVEL, "obj", 3, 0, 2), "frameangvel": (S.SENS_FRAMEANGVEL, "obj", 3, 0, 2),
+    "framelinacc": (S.SENS_FRAMELINACC, "obj", 3, 0, 3), "frameangacc": (S.SENS_FRAMEANGACC, "obj", 3, 0, 3),
   }
   objkind = {"joint": (C.OBJ_JOINT, "joint"), "actuator": (C.OBJ_ACTUATOR, "actuator"), "site": (C.OBJ_SITE, "site"), "body": (C.OBJ_BODY, "body")}
   objtypes = {"body": (C.OBJ_BODY, "body"), "xbody": (C.OBJ_XBODY, "body"), "geom": (C.OBJ_GEOM, "geom"), "site": (C.OBJ_SITE, "site"), "camera": (C.OBJ_CAMERA, "camera")}

@@ -37,6 +37,16 @@ __device__ __forceinline__ const float* obj_mat(const DataDev& d, const ModelDev
   }
 }
 
+__device__ __forceinline__ int obj_body(const ModelDev& m, int objtype, int id) {  // sensor.py:1066 / :320
+  switch (objtype) {
+    case OBJ_BODY: case OBJ_XBODY: return id;
+    case OBJ_GEOM: return m.geom_bodyid[id];
+    case OBJ_SITE: return m.site_bodyid[id];
+    case OBJ_CAMERA: return m.cam_bodyid[id];
+    default: return 0;
+  }
+}
+
 __global__ void __launch_bounds__(32)
 k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int stages) {
   extern __shared__ float smem[];  // nbody x (linvel 3 | angmom 3 | bodyvel lin 3) or nbody x (cfrc_ext 6 | cacc / cfrc_int 6)
@@ -227,11 +237,23 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
       case SENS_FRAMEXAXIS: case SENS_FRAMEYAXIS: case SENS_FRAMEZAXIS: {
         const float* R = obj_mat(d, m, wb, m.sensor_objtype[s], id); const int c = t - SENS_FRAMEXAXIS;
         v[0] = R[c]; v[1] = R[3 + c]; v[2] = R[6 + c]; break; }
+      case SENS_FRAMEQUAT: {  // sensor.py:342-374 _get_quat
+        const int ot = m.sensor_objtype[s];
+        const float* local = ot == OBJ_BODY ? m.body_iquat + 4 * id : ot == OBJ_GEOM ? m.geom_quat + 4 * id : ot == OBJ_SITE ? m.site_quat + 4 * id : ot == OBJ_CAMERA ? m.cam_quat + 4 * id : nullptr;
+        q4 q = ldq(d.xquat + (wb * nb + obj_body(m, ot, id)) * 4);
+        if (local) q = qmul(q, ldq(local));
+        v[0] = q.w; v[1] = q.x; v[2] = q.y; v[3] = q.z; break; }
       case SENS_SUBTREECOM: { const float* p = d.subtree_com + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
       case SENS_CLOCK: v[0] = d.time[w]; break;
       case SENS_JOINTVEL: v[0] = d.qvel[wb * nv + m.jnt_dofadr[id]]; break;
       case SENS_ACTUATORVEL: v[0] = d.actuator_velocity[wb * m.nu + id]; break;
       case SENS_BALLANGVEL: { const float* p = d.qvel + wb * nv + m.jnt_dofadr[id]; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
+      case SENS_FRAMELINVEL: case SENS_FRAMEANGVEL: {  // sensor.py:1108-1293 without a reference frame
+        const int ot = m.sensor_objtype[s], b = obj_body(m, ot, id);
+        const float* cv = d.cvel + (wb * nb + b) * 6;
+        v3 r = ld3(cv);
+        if (t == SENS_FRAMELINVEL) r = ld3(cv + 3) - cross(ld3(obj_pos(d, m, wb, ot, id)) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3), r);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
       case SENS_SUBTREELINVEL: { const float* p = d.subtree_linvel + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
       case SENS_SUBTREEANGMOM: { const float* p = d.subtree_angmom + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
       case SENS_GYRO: {  // sensor.py:989
@@ -249,6 +271,16 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
         const v3 dif = ld3(d.site_xpos + (wb * m.nsite + id) * 3) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3);
         const v3 ang = mat_t_vec(R, ld3(cv)), lin = mat_t_vec(R, ld3(cv + 3) - cross(dif, ld3(cv)));
         const v3 acc = mat_t_vec(R, ld3(ca + 3) - cross(dif, ld3(ca))), r = acc + cross(ang, lin);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
+      case SENS_FRAMELINACC: case SENS_FRAMEANGACC: {  // sensor.py:1678-1753
+        const int ot = m.sensor_objtype[s], b = obj_body(m, ot, id);
+        const float *cv = d.cvel + (wb * nb + b) * 6, *ca = d.cacc + (wb * nb + b) * 6;
+        v3 r = ld3(ca);
+        if (t == SENS_FRAMELINACC) {
+          const v3 off = ld3(obj_pos(d, m, wb, ot, id)) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3);
+          const v3 ang = ld3(cv), lin = ld3(cv + 3) - cross(off, ang);
+          r = ld3(ca + 3) - cross(off, r) + cross(ang, lin);
+        }
         v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
       case SENS_FORCE: {  // sensor.py:1542
         const v3 r = mat_t_vec(d.site_xmat + (wb * m.nsite + id) * 9, ld3(d.cfrc_int + (wb * nb + m.site_bodyid[id]) * 6 + 3));

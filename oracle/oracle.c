@@ -2545,6 +2545,16 @@ static const real* obj_mat(const W* w, int objtype, int id) {
     default: return w->cam_xmat + 9 * id;
   }
 }
+/* body that carries an object (sensor.py:1066-1105 _cvel_offset / :320 _get_body_id) */
+static int obj_body(const OrcModel* m, int objtype, int id) {
+  switch (objtype) {
+    case OBJ_BODY: case OBJ_XBODY: return id;
+    case OBJ_GEOM: return m->geom_bodyid[id];
+    case OBJ_SITE: return m->site_bodyid[id];
+    case OBJ_CAMERA: return m->cam_bodyid[id];
+    default: return 0;
+  }
+}
 /* sensor.py:810 sensor_pos, :1432 sensor_vel, :2512 sensor_acc for the sensor types this build carries */
 static void sensors(W* w, int stage) {
   const OrcModel* m = w->m;
@@ -2553,7 +2563,7 @@ static void sensors(W* w, int stage) {
   for (int s = 0; s < m->nsensor; s++) {
     int t = m->sensor_type[s];
     if (t == SENS_SUBTREELINVEL || t == SENS_SUBTREEANGMOM) need_subtree = 1;
-    if (t == SENS_ACCELEROMETER || t == SENS_FORCE || t == SENS_TORQUE) need_cacc = 1;
+    if (t == SENS_ACCELEROMETER || t == SENS_FORCE || t == SENS_TORQUE || t == SENS_FRAMELINACC || t == SENS_FRAMEANGACC) need_cacc = 1;
   }
   if (stage == STAGE_VEL && need_subtree) subtree_vel(w);
   if (stage == STAGE_ACC && need_cacc) rne_postconstraint(w);
@@ -2569,11 +2579,23 @@ static void sensors(W* w, int stage) {
       case SENS_FRAMEXAXIS: case SENS_FRAMEYAXIS: case SENS_FRAMEZAXIS: {
         const real* R = obj_mat(w, m->sensor_objtype[s], id); int c = t - SENS_FRAMEXAXIS;
         v[0] = R[c]; v[1] = R[3 + c]; v[2] = R[6 + c]; break; }
+      case SENS_FRAMEQUAT: { /* sensor.py:342-374 _get_quat */
+        const int ot = m->sensor_objtype[s];
+        const real* local = ot == OBJ_BODY ? m->body_iquat + 4 * id : ot == OBJ_GEOM ? m->geom_quat + 4 * id : ot == OBJ_SITE ? m->site_quat + 4 * id : ot == OBJ_CAMERA ? m->cam_quat + 4 * id : NULL;
+        const real* xq = w->xquat + 4 * obj_body(m, ot, id);
+        if (local) mul_quat(xq, local, v); else memcpy(v, xq, 4 * sizeof(real));
+        break; }
       case SENS_SUBTREECOM: memcpy(v, w->subtree_com + 3 * id, 3 * sizeof(real)); break;
       case SENS_CLOCK: v[0] = w->time[0]; break;
       case SENS_JOINTVEL: v[0] = w->qvel[m->jnt_dofadr[id]]; break;
       case SENS_ACTUATORVEL: v[0] = w->actuator_velocity[id]; break;
       case SENS_BALLANGVEL: memcpy(v, w->qvel + m->jnt_dofadr[id], 3 * sizeof(real)); break;
+      case SENS_FRAMELINVEL: case SENS_FRAMEANGVEL: { /* sensor.py:1108-1293 without a reference frame */
+        const int ot = m->sensor_objtype[s], b = obj_body(m, ot, id); const real* cv = w->cvel + 6 * b;
+        if (t == SENS_FRAMEANGVEL) { memcpy(v, cv, 3 * sizeof(real)); break; }
+        real off[3], cr[3]; v3sub(obj_pos(w, ot, id), w->subtree_com + 3 * m->body_rootid[b], off); cross3(off, cv, cr);
+        for (int i = 0; i < 3; i++) v[i] = cv[3 + i] - cr[i];
+        break; }
       case SENS_SUBTREELINVEL: memcpy(v, w->subtree_linvel + 3 * id, 3 * sizeof(real)); break;
       case SENS_SUBTREEANGMOM: memcpy(v, w->subtree_angmom + 3 * id, 3 * sizeof(real)); break;
       case SENS_GYRO: matT_vec3(w->site_xmat + 9 * id, w->cvel + 6 * m->site_bodyid[id], v); break; /* sensor.py:989 */
@@ -2592,6 +2614,16 @@ static void sensors(W* w, int stage) {
         cross3(dif, ca, cr); for (int i = 0; i < 3; i++) t1[i] = ca[3 + i] - cr[i]; matT_vec3(R, t1, acc);
         cross3(ang, lin, corr);
         for (int i = 0; i < 3; i++) v[i] = acc[i] + corr[i]; break; }
+      case SENS_FRAMELINACC: case SENS_FRAMEANGACC: { /* sensor.py:1678-1753 */
+        const int ot = m->sensor_objtype[s], b = obj_body(m, ot, id); const real *cv = w->cvel + 6 * b, *ca = w->cacc + 6 * b;
+        if (t == SENS_FRAMEANGACC) { memcpy(v, ca, 3 * sizeof(real)); break; }
+        real off[3], cr[3], lin[3], acc[3], corr[3];
+        v3sub(obj_pos(w, ot, id), w->subtree_com + 3 * m->body_rootid[b], off);
+        cross3(off, cv, cr); for (int i = 0; i < 3; i++) lin[i] = cv[3 + i] - cr[i];
+        cross3(off, ca, cr); for (int i = 0; i < 3; i++) acc[i] = ca[3 + i] - cr[i];
+        cross3(cv, lin, corr);
+        for (int i = 0; i < 3; i++) v[i] = acc[i] + corr[i];
+        break; }
       case SENS_FORCE: matT_vec3(w->site_xmat + 9 * id, w->cfrc_int + 6 * m->site_bodyid[id] + 3, v); break; /* sensor.py:1542 */
       case SENS_TORQUE: { /* sensor.py:1559 */
         const int b = m->site_bodyid[id]; const real* cf = w->cfrc_int + 6 * b;

@@ -282,6 +282,10 @@ def sensor_xml():
     <subtreecom name="sc" body="arm"/> <subtreelinvel name="sl" body="fore"/> <subtreeangmom name="sa" body="arm"/> <subtreeangmom name="sa0" body="cap0"/>
     <framepos name="fp" objtype="site" objname="imu"/> <framexaxis name="fx" objtype="geom" objname="tip"/> <frameyaxis name="fy" objtype="body" objname="pend"/>
     <framezaxis name="fz" objtype="xbody" objname="fore"/> <framepos name="fc" objtype="camera" objname="c0"/>
+    <framequat name="fq" objtype="site" objname="imu"/> <framequat name="fqb" objtype="body" objname="pend"/> <framequat name="fqx" objtype="xbody" objname="cap0"/>
+    <framequat name="fqg" objtype="geom" objname="c1"/> <framequat name="fqc" objtype="camera" objname="c0"/>
+    <framelinvel name="flv" objtype="site" objname="imu"/> <frameangvel name="fav" objtype="geom" objname="tip"/> <framelinvel name="flvb" objtype="body" objname="cap1"/>
+    <framelinacc name="fla" objtype="site" objname="imu"/> <frameangacc name="faa" objtype="xbody" objname="pend"/> <framelinacc name="flab" objtype="body" objname="ball0"/>
     <clock name="clk"/>
   </sensor>
 """
