@@ -363,6 +363,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_dim", "sensor_adr"):
     setattr(m, n, dev_i(getattr(mjm, n) if nsensor else np.zeros(0)))
   m.sensor_cutoff = dev_f(np.asarray(mjm.sensor_cutoff) if nsensor else np.zeros(0), batched=False)
+  nsite = int(getattr(mjm, "nsite", 0))
+  m.site_type = dev_i(getattr(mjm, "site_type", np.full(nsite, C.GEOM_SPHERE)))  # fixtures compiled before sites carried a shape: MuJoCo's default
+  m.site_size = dev_f(getattr(mjm, "site_size", np.full((nsite, 3), 0.005)), batched=False)
   stype = np.asarray(mjm.sensor_type) if nsensor else np.zeros(0, dtype=int)
   m.sensor_subtree_vel = bool(np.isin(stype, (C.SENS_SUBTREELINVEL, C.SENS_SUBTREEANGMOM)).any())  # reference io.py:896-897
   m.sensor_rne_postconstraint = bool(np.isin(stype, (C.SENS_ACCELEROMETER, C.SENS_FORCE, C.SENS_TORQUE, C.SENS_FRAMELINACC, C.SENS_FRAMEANGACC)).any())  # :900
@@ -420,7 +423,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                                          "dofact_adr", "dofact_act", "dofact_mom", "eq_type", "eq_obj1id", "eq_obj2id", "eq_solref", "eq_solimp", "eq_data",
                                          "jnt_limited_ball_adr", "pair_dim", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp",
                                          "pair_margin", "pair_gap", "sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid",
-                                         "sensor_dim", "sensor_adr", "sensor_cutoff"]:
+                                         "sensor_dim", "sensor_adr", "sensor_cutoff", "site_type", "site_size"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)

@@ -690,7 +690,13 @@ def compile_xml(root):
         geoms.append(g)
       elif tag == "site":
         a = attrs(child, childclass)
-        sites.append(dict(name=a.get("name", f"site{len(sites)}"), bodyid=bid, pos=_vec(a.get("pos"), default=[0, 0, 0]), quat=_frame_quat(a, compiler)))
+        if "fromto" in a:
+          raise NotImplementedError("site fromto is not supported by this compiler")
+        ssize = np.full(3, 0.005)
+        sv = _vec(a.get("size"), default=[])
+        ssize[: len(sv)] = sv
+        sites.append(dict(name=a.get("name", f"site{len(sites)}"), bodyid=bid, pos=_vec(a.get("pos"), default=[0, 0, 0]), quat=_frame_quat(a, compiler),
+                          type=_GEOM_TYPES[a.get("type", "sphere")], size=ssize))
       elif tag == "camera":
         a = attrs(child, childclass)
         cams.append(dict(name=a.get("name", f"cam{len(cams)}"), bodyid=bid, pos=_vec(a.get("pos"), default=[0, 0, 0]), quat=_frame_quat(a, compiler), mode=C.CAMLIGHT_MODES[a.get("mode", "fixed")], target=a.get("target")))
@@ -943,6 +949,8 @@ def compile_xml(root):
   m.site_bodyid = np.array([s["bodyid"] for s in sites], dtype=np.int32)
   m.site_pos = np.array([s["pos"] for s in sites]).reshape(m.nsite, 3)
   m.site_quat = np.array([s["quat"] for s in sites]).reshape(m.nsite, 4)
+  m.site_type = np.array([s["type"] for s in sites], dtype=np.int32).reshape(m.nsite)
+  m.site_size = np.array([s["size"] for s in sites], dtype=np.float64).reshape(m.nsite, 3)
 
   def body_id(name):
     return m.names.body.index(name) if name is not None else -1
@@ -1128,7 +1136,7 @@ def compile_xml(root):
     "actuatorfrc": (S.SENS_ACTUATORFRC, "actuator", 1, 0, 3), "jointactuatorfrc": (S.SENS_JOINTACTFRC, "joint", 1, 0, 3),
     "ballquat": (S.SENS_BALLQUAT, "joint", 4, 3, 1), "ballangvel": (S.SENS_BALLANGVEL, "joint", 3, 0, 2),
     "gyro": (S.SENS_GYRO, "site", 3, 0, 2), "velocimeter": (S.SENS_VELOCIMETER, "site", 3, 0, 2), "accelerometer": (S.SENS_ACCELEROMETER, "site", 3, 0, 3),
-    "force": (S.SENS_FORCE, "site", 3, 0, 3), "torque": (S.SENS_TORQUE, "site", 3, 0, 3),
+    "touch": (S.SENS_TOUCH, "site", 1, 1, 3), "force": (S.SENS_FORCE, "site", 3, 0, 3), "torque": (S.SENS_TORQUE, "site", 3, 0, 3),
     "subtreecom": (S.SENS_SUBTREECOM, "body", 3, 0, 1), "subtreelinvel": (S.SENS_SUBTREELINVEL, "body", 3, 0, 2),
     "subtreeangmom": (S.SENS_SUBTREEANGMOM, "body", 3, 0, 2), "clock": (S.SENS_CLOCK, None, 1, 0, 1),
     "framepos": (S.SENS_FRAMEPOS, "obj", 3, 0, 1), "framexaxis": (S.SENS_FRAMEXAXIS, "obj", 3, 2, 1), "frameyaxis": (S.SENS_FRAMEYAXIS, "obj", 3, 2, 1),

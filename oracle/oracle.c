@@ -55,7 +55,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
   X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim) \
-  X(sensor_type) X(sensor_datatype) X(sensor_needstage) X(sensor_objtype) X(sensor_objid) X(sensor_dim) X(sensor_adr)
+  X(sensor_type) X(sensor_datatype) X(sensor_needstage) X(sensor_objtype) X(sensor_objid) X(sensor_dim) X(sensor_adr) X(site_type)
 #define MODEL_RARRS(X) \
   X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
   X(body_inertia) X(body_invweight0) X(body_gravcomp) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
@@ -65,7 +65,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
   X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat) \
   X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap) \
-  X(sensor_cutoff)
+  X(sensor_cutoff) X(site_size)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -2545,6 +2545,101 @@ static const real* obj_mat(const W* w, int objtype, int id) {
     default: return w->cam_xmat + 9 * id;
   }
 }
+/* ray.py:106 _ray_quad: smallest non-negative root of a x^2 + 2 b x + c = 0 (and both roots), -1 if none */
+static real ray_quad(real a, real b, real c, real* x2) {
+  real det = b * b - a * c;
+  x2[0] = x2[1] = -1;
+  if (det < MJ_MINVAL) return -1;
+  det = (real)sqrt((double)det);
+  real den = a != 0 ? 1 / a : 0; /* safe_div */
+  x2[0] = (-b - det) * den; x2[1] = (-b + det) * den;
+  return x2[0] >= 0 ? x2[0] : (x2[1] >= 0 ? x2[1] : -1);
+}
+static real ray_sphere(const real* pos, real dist_sqr, const real* pnt, const real* vec) { /* ray.py:238 */
+  real dif[3], xx[2]; v3sub(pnt, pos, dif);
+  return ray_quad(dot3(vec, vec), dot3(vec, dif), dot3(dif, dif) - dist_sqr, xx);
+}
+/* ray.py:799 ray_geom, distance only, for the shapes a site can have (sphere, capsule, ellipsoid, cylinder, box) */
+static real ray_geom_dist(const real* pos, const real* mat, const real* size, const real* pnt, const real* vec, int type) {
+  real xx[2];
+  if (type == GEOM_SPHERE) return ray_sphere(pos, size[0] * size[0], pnt, vec);
+  real d[3], lpnt[3], lvec[3];
+  v3sub(pnt, pos, d); matT_vec3(mat, d, lpnt); matT_vec3(mat, vec, lvec); /* :33 _ray_map */
+  if (type == GEOM_CAPSULE) { /* :255 */
+    real ssz = size[0] + size[1];
+    if (ray_sphere(pos, ssz * ssz, pnt, vec) < 0) return -1;
+    real x = -1, sq = size[0] * size[0];
+    real a = lvec[0] * lvec[0] + lvec[1] * lvec[1], b = lvec[0] * lpnt[0] + lvec[1] * lpnt[1], c = lpnt[0] * lpnt[0] + lpnt[1] * lpnt[1] - sq;
+    real sol = ray_quad(a, b, c, xx);
+    if (sol >= 0 && rabs(lpnt[2] + sol * lvec[2]) <= size[1]) if (x < 0 || sol < x) x = sol;
+    real ldif[3] = {lpnt[0], lpnt[1], lpnt[2] - size[1]};
+    a += lvec[2] * lvec[2]; b = dot3(lvec, ldif); c = dot3(ldif, ldif) - sq;
+    ray_quad(a, b, c, xx);
+    for (int i = 0; i < 2; i++) if (xx[i] >= 0 && lpnt[2] + xx[i] * lvec[2] >= size[1]) if (x < 0 || xx[i] < x) x = xx[i];
+    ldif[2] = lpnt[2] + size[1];
+    b = dot3(lvec, ldif); c = dot3(ldif, ldif) - sq;
+    ray_quad(a, b, c, xx);
+    for (int i = 0; i < 2; i++) if (xx[i] >= 0 && lpnt[2] + xx[i] * lvec[2] <= -size[1]) if (x < 0 || xx[i] < x) x = xx[i];
+    return x;
+  }
+  if (type == GEOM_ELLIPSOID) { /* :329 */
+    real sv[3], sp[3], a = 0, b = 0, c = -1;
+    for (int i = 0; i < 3; i++) { real q = size[i] * size[i], si = q != 0 ? 1 / q : 0; sv[i] = si * lvec[i]; sp[i] = si * lpnt[i]; }
+    a = dot3(sv, lvec); b = dot3(sv, lpnt); c = dot3(sp, lpnt) - 1;
+    return ray_quad(a, b, c, xx);
+  }
+  if (type == GEOM_CYLINDER) { /* :360 */
+    if (ray_sphere(pos, size[0] * size[0] + size[1] * size[1], pnt, vec) < 0) return -1;
+    real x = -1;
+    if (rabs(lvec[2]) > MJ_MINVAL)
+      for (int side = -1; side <= 1; side += 2) {
+        real sol = ((real)side * size[1] - lpnt[2]) / lvec[2];
+        if (sol >= 0) {
+          real p0 = lpnt[0] + sol * lvec[0], p1 = lpnt[1] + sol * lvec[1];
+          if (p0 * p0 + p1 * p1 <= size[0] * size[0]) if (x < 0 || sol < x) x = sol;
+        }
+      }
+    real a = lvec[0] * lvec[0] + lvec[1] * lvec[1], b = lvec[0] * lpnt[0] + lvec[1] * lpnt[1], c = lpnt[0] * lpnt[0] + lpnt[1] * lpnt[1] - size[0] * size[0];
+    real sol = ray_quad(a, b, c, xx);
+    if (sol >= 0 && rabs(lpnt[2] + sol * lvec[2]) <= size[1]) if (x < 0 || sol < x) x = sol;
+    return x;
+  }
+  if (type == GEOM_BOX) { /* :421 */
+    if (ray_sphere(pos, dot3(size, size), pnt, vec) < 0) return -1;
+    real x = -1;
+    for (int i = 0; i < 3; i++) {
+      if (rabs(lvec[i]) <= MJ_MINVAL) continue;
+      for (int side = -1; side <= 1; side += 2) {
+        real sol = ((real)side * size[i] - lpnt[i]) / lvec[i];
+        if (sol < 0) continue;
+        int id0 = i == 0 ? 1 : 0, id1 = i == 2 ? 1 : 2;
+        real p0 = lpnt[id0] + sol * lvec[id0], p1 = lpnt[id1] + sol * lvec[id1];
+        if (rabs(p0) <= size[id0] && rabs(p1) <= size[id1]) if (x < 0 || sol < x) x = sol;
+      }
+    }
+    return x;
+  }
+  return -1;
+}
+/* sensor.py:2063 _sensor_touch: sum of the normal forces of the sensorised body's contacts whose force ray meets the site volume */
+static real sensor_touch(const W* w, int site) {
+  const OrcModel* m = w->m;
+  const int body = m->site_bodyid[site], ncon = w->ncon[0] < w->nconmax ? w->ncon[0] : w->nconmax;
+  real total = 0;
+  for (int c = 0; c < ncon; c++) {
+    const int b1 = m->geom_bodyid[w->con_geom[2 * c]], b2 = m->geom_bodyid[w->con_geom[2 * c + 1]];
+    const int* adr = w->con_efc_address + m->nmaxpyramid * c;
+    if (adr[0] < 0 || (body != b1 && body != b2)) continue;
+    real nf = w->efc_force[adr[0]];
+    if (m->cone == CONE_PYRAMIDAL) for (int i = 1; i < 2 * (w->con_dim[c] - 1); i++) nf += w->efc_force[adr[i]];
+    if (nf <= 0) continue;
+    real ray[3] = {w->con_frame[9 * c] * nf, w->con_frame[9 * c + 1] * nf, w->con_frame[9 * c + 2] * nf};
+    normalize3(ray);
+    if (body == b2) for (int i = 0; i < 3; i++) ray[i] = -ray[i];
+    if (ray_geom_dist(w->site_xpos + 3 * site, w->site_xmat + 9 * site, m->site_size + 3 * site, w->con_pos + 3 * c, ray, m->site_type[site]) >= 0) total += nf;
+  }
+  return total;
+}
 /* body that carries an object (sensor.py:1066-1105 _cvel_offset / :320 _get_body_id) */
 static int obj_body(const OrcModel* m, int objtype, int id) {
   switch (objtype) {
@@ -2624,6 +2719,7 @@ static void sensors(W* w, int stage) {
         cross3(cv, lin, corr);
         for (int i = 0; i < 3; i++) v[i] = acc[i] + corr[i];
         break; }
+      case SENS_TOUCH: v[0] = sensor_touch(w, id); break;
       case SENS_FORCE: matT_vec3(w->site_xmat + 9 * id, w->cfrc_int + 6 * m->site_bodyid[id] + 3, v); break; /* sensor.py:1542 */
       case SENS_TORQUE: { /* sensor.py:1559 */
         const int b = m->site_bodyid[id]; const real* cf = w->cfrc_int + 6 * b;

@@ -236,6 +236,9 @@ class Oracle:
     for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_dim", "sensor_adr"):
       setia(n, getattr(mjm, n) if nsensor else np.zeros(1, dtype=np.int32))
     setra("sensor_cutoff", mjm.sensor_cutoff if nsensor else np.zeros(1))
+    nsite = int(getattr(mjm, "nsite", 0))
+    setia("site_type", getattr(mjm, "site_type", 2 * np.ones(nsite, dtype=np.int32)) if nsite else np.zeros(1, dtype=np.int32))
+    setra("site_size", getattr(mjm, "site_size", 0.005 * np.ones((nsite, 3))) if nsite else np.zeros(3))
 
     self.spec = data_spec(mjm, self.tabs, nconmax, njmax)
     self.dptr = ctypes.c_void_p(lib.orc_data_create(nworld, nconmax, njmax))

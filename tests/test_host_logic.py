@@ -212,6 +212,6 @@ def test_put_model_and_make_data_host_path(monkeypatch):
     assert d.sensordata.shape == (3, getattr(mjm, "nsensordata", 0) if getattr(mjm, "nsensor", 0) else 0), name
     assert d.qpos.shape == (3, mjm.nq) and d.efc.J.shape[0] == 3, name
   assert "mjb_model_finalize" in calls and "mjb_data_finalize" in calls
-  bad = mjcf.load_string(util.sensor_xml().replace('<clock name="clk"/>', '<touch name="tch" site="imu"/>'))
-  with pytest.raises(NotImplementedError, match="touch"):
+  bad = mjcf.load_string(util.sensor_xml().replace('<clock name="clk"/>', '<rangefinder name="rf" site="imu"/>'))
+  with pytest.raises(NotImplementedError, match="rangefinder"):
     mio.put_model(bad)

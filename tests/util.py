@@ -271,6 +271,10 @@ def sensor_xml():
   """MIXED_XML with one sensor of every type this build carries (two with cutoffs), sites on a free body and on the arm chain."""
   x = MIXED_XML.replace('<geom name="tip" type="sphere" pos="0 0 -0.22" size="0.04" mass="0.2"/>',
                         '<geom name="tip" type="sphere" pos="0 0 -0.22" size="0.04" mass="0.2"/>\n          <site name="imu" pos="0.01 0.02 -0.1" euler="10 20 30"/>')
+  x = x.replace('<site name="st0" pos="0.05 0 0"/>', '<site name="st0" pos="0.05 0 0"/>\n      <site name="tz_box" type="box" size="0.12 0.12 0.12"/>\n      <site name="tz_sph" pos="0 0 -0.08" size="0.05"/>')
+  x = x.replace('<geom name="c0" type="capsule" size="0.06 0.15" condim="6"/>', '<geom name="c0" type="capsule" size="0.06 0.15" condim="6"/>\n      <site name="tz_cap" type="capsule" size="0.07 0.16"/>')
+  x = x.replace('<geom name="c1" type="capsule" size="0.05 0.12" condim="3"/>', '<geom name="c1" type="capsule" size="0.05 0.12" condim="3"/>\n      <site name="tz_ell" type="ellipsoid" size="0.06 0.06 0.2"/>')
+  x = x.replace('<geom name="c2" type="capsule" size="0.04 0.1"/>', '<geom name="c2" type="capsule" size="0.04 0.1"/>\n      <site name="tz_cyl" type="cylinder" size="0.05 0.08"/>')
   sensors = """
   <sensor>
     <jointpos name="jp" joint="hinge"/> <jointvel name="jv" joint="slide"/> <ballquat name="bq" joint="ball"/> <ballangvel name="bv" joint="ball"/>
@@ -286,6 +290,7 @@ def sensor_xml():
     <framequat name="fqg" objtype="geom" objname="c1"/> <framequat name="fqc" objtype="camera" objname="c0"/>
     <framelinvel name="flv" objtype="site" objname="imu"/> <frameangvel name="fav" objtype="geom" objname="tip"/> <framelinvel name="flvb" objtype="body" objname="cap1"/>
     <framelinacc name="fla" objtype="site" objname="imu"/> <frameangacc name="faa" objtype="xbody" objname="pend"/> <framelinacc name="flab" objtype="body" objname="ball0"/>
+    <touch name="tb" site="tz_box"/> <touch name="ts" site="tz_sph"/> <touch name="tc" site="tz_cap"/> <touch name="te" site="tz_ell"/> <touch name="ty" site="tz_cyl" cutoff="30"/>
     <clock name="clk"/>
   </sensor>
 """
