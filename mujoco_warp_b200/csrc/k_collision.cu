@@ -294,6 +294,7 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
             }
           }
           ncon += total;
+          __syncwarp();  // the next batch hands the polytope slots to other lanes
         }
       }
     }

@@ -424,7 +424,7 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
         const float wt = c.hw[t];
         const int lo = c.env ? (c.rng[c.hidx[t]] & 0xFFFF) : 0, hi = c.env ? (c.rng[c.hidx[t]] >> 16) : nv;  // the row is zero outside [lo, hi)
 #pragma unroll 1
-        for (int i = lo + c.lane; i < hi; i += 32) {
+        for (int i = lo + ((c.lane - lo) & 31); i < hi; i += 32) {  // row i always belongs to lane i % 32, whatever the row range
           const float sc = wt * Jr[i];
           float* Hi = Hd + (i * (i + 1)) / 2;
           if (sc != 0.f)
