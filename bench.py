@@ -226,14 +226,20 @@ def run_ours(args):
       with torch.cuda.graph(g, stream=stream):
         mjw.step(m, d)
       graph = g
-    for _ in range(args.warmup):
-      one_step()
-    stream.synchronize()
-
-    # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
+    # nvidia-smi needs a few hundred ms before its first row: start it ahead of the warm-up and keep the same load running until it
+    # reports, so that samples exist before, during and after the (short) timed region
     sampler = ClockSampler(local)
     if rank == 0:
       sampler.start()
+    for _ in range(args.warmup):
+      one_step()
+    stream.synchronize()
+    t_wait = time.perf_counter() + 3.0
+    while rank == 0 and sampler.proc is not None and len(sampler.rows) < 1 and time.perf_counter() < t_wait:
+      one_step()
+      stream.synchronize()
+
+    # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     niter_sum = torch.zeros((), device="cuda", dtype=torch.float64)
@@ -243,8 +249,12 @@ def run_ours(args):
     e1.record(stream)
     stream.synchronize()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    n_rows, t_wait = len(sampler.rows), time.perf_counter() + 1.0
+    while rank == 0 and sampler.proc is not None and len(sampler.rows) <= n_rows and time.perf_counter() < t_wait:
+      one_step()  # same load, untimed, until one more 100 ms sample lands after the timed region
+      stream.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- statistics of the run (untimed)
     ncon_mean = float(d.nacon.cpu()[0]) / nworld
