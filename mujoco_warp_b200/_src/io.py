@@ -362,6 +362,8 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.nsensor, m.nsensordata = nsensor, int(getattr(mjm, "nsensordata", 0)) if nsensor else 0
   for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_dim", "sensor_adr"):
     setattr(m, n, dev_i(getattr(mjm, n) if nsensor else np.zeros(0)))
+  m.sensor_reftype = dev_i(getattr(mjm, "sensor_reftype", np.zeros(nsensor)) if nsensor else np.zeros(0))
+  m.sensor_refid = dev_i(getattr(mjm, "sensor_refid", -np.ones(nsensor)) if nsensor else np.zeros(0))
   m.sensor_cutoff = dev_f(np.asarray(mjm.sensor_cutoff) if nsensor else np.zeros(0), batched=False)
   nsite = int(getattr(mjm, "nsite", 0))
   m.site_type = dev_i(getattr(mjm, "site_type", np.full(nsite, C.GEOM_SPHERE)))  # fixtures compiled before sites carried a shape: MuJoCo's default
@@ -422,7 +424,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                                          "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
                                          "dofact_adr", "dofact_act", "dofact_mom", "eq_type", "eq_obj1id", "eq_obj2id", "eq_solref", "eq_solimp", "eq_data",
                                          "jnt_limited_ball_adr", "pair_dim", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp",
-                                         "pair_margin", "pair_gap", "sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid",
+                                         "pair_margin", "pair_gap", "sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_reftype", "sensor_refid",
                                          "sensor_dim", "sensor_adr", "sensor_cutoff", "site_type", "site_size"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():

@@ -1134,6 +1134,8 @@ def compile_xml(root):
     "jointpos": (S.SENS_JOINTPOS, "joint", 1, 0, 1), "jointvel": (S.SENS_JOINTVEL, "joint", 1, 0, 2),
     "actuatorpos": (S.SENS_ACTUATORPOS, "actuator", 1, 0, 1), "actuatorvel": (S.SENS_ACTUATORVEL, "actuator", 1, 0, 2),
     "actuatorfrc": (S.SENS_ACTUATORFRC, "actuator", 1, 0, 3), "jointactuatorfrc": (S.SENS_JOINTACTFRC, "joint", 1, 0, 3),
+    "jointlimitpos": (S.SENS_JOINTLIMITPOS, "joint", 1, 0, 1), "jointlimitvel": (S.SENS_JOINTLIMITVEL, "joint", 1, 0, 2),
+    "jointlimitfrc": (S.SENS_JOINTLIMITFRC, "joint", 1, 0, 3),
     "ballquat": (S.SENS_BALLQUAT, "joint", 4, 3, 1), "ballangvel": (S.SENS_BALLANGVEL, "joint", 3, 0, 2),
     "gyro": (S.SENS_GYRO, "site", 3, 0, 2), "velocimeter": (S.SENS_VELOCIMETER, "site", 3, 0, 2), "accelerometer": (S.SENS_ACCELEROMETER, "site", 3, 0, 3),
     "touch": (S.SENS_TOUCH, "site", 1, 1, 3), "force": (S.SENS_FORCE, "site", 3, 0, 3), "torque": (S.SENS_TORQUE, "site", 3, 0, 3),
@@ -1149,10 +1151,15 @@ def compile_xml(root):
   sens, unsupported = [], []
   nsens = root.find("sensor")
   for e in (list(nsens) if nsens is not None else []):
-    if e.tag not in table or "reftype" in e.attrib or "refname" in e.attrib:
+    has_ref = "reftype" in e.attrib or "refname" in e.attrib
+    if e.tag not in table or (has_ref and e.tag not in ("framepos", "framequat", "framexaxis", "frameyaxis", "framezaxis", "framelinvel", "frameangvel")):
       unsupported.append(e.tag)
       continue
     stype, kind, dim, datatype, stage = table[e.tag]
+    rtype, rid = C.OBJ_UNKNOWN, -1
+    if has_ref:
+      rtype, rlst = objtypes[e.get("reftype")]
+      rid = getattr(m.names, rlst).index(e.get("refname"))
     if kind is None:
       otype, oid = C.OBJ_UNKNOWN, -1
     elif kind == "obj":
@@ -1161,14 +1168,13 @@ def compile_xml(root):
     else:
       otype, lst = objkind[kind]
       oid = getattr(m.names, lst).index(e.get(kind))
-    sens.append(dict(name=e.get("name", f"sensor{len(sens)}"), type=stype, objtype=otype, objid=oid, dim=dim, datatype=datatype, needstage=stage,
+    sens.append(dict(name=e.get("name", f"sensor{len(sens)}"), type=stype, objtype=otype, objid=oid, reftype=rtype, refid=rid, dim=dim, datatype=datatype, needstage=stage,
                      cutoff=float(e.get("cutoff", 0.0)), noise=float(e.get("noise", 0.0))))
   m.nsensor = len(sens)
   m.sensor_unsupported = unsupported  # put_model refuses these (they would silently read zero otherwise)
   m.names.sensor = [x["name"] for x in sens]
-  for key in ("type", "objtype", "objid", "dim", "datatype", "needstage"):
+  for key in ("type", "objtype", "objid", "reftype", "refid", "dim", "datatype", "needstage"):
     setattr(m, "sensor_" + key, np.array([x[key] for x in sens], dtype=np.int32).reshape(m.nsensor))
-  m.sensor_reftype = np.zeros(m.nsensor, dtype=np.int32); m.sensor_refid = -np.ones(m.nsensor, dtype=np.int32)
   m.sensor_cutoff = np.array([x["cutoff"] for x in sens], dtype=np.float64).reshape(m.nsensor)
   m.sensor_noise = np.array([x["noise"] for x in sens], dtype=np.float64).reshape(m.nsensor)
   m.sensor_adr = (np.concatenate(([0], np.cumsum(m.sensor_dim)[:-1])) if m.nsensor else np.zeros(0)).astype(np.int32)

@@ -305,32 +305,59 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
   for (int s = lane; s < m.nsensor; s += 32) {
     const int st = m.sensor_needstage[s];
     if (!(stages & (st == 1 ? STAGE_POS : (st == 2 ? STAGE_VEL : STAGE_ACC)))) continue;
-    const int t = m.sensor_type[s], id = m.sensor_objid[s];
+    const int t = m.sensor_type[s], id = m.sensor_objid[s], rt = m.sensor_reftype[s], rid = m.sensor_refid[s];  // rid = -1: world frame
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     switch (t) {
       case SENS_JOINTPOS: v[0] = d.qpos[wb * m.nq + m.jnt_qposadr[id]]; break;
       case SENS_ACTUATORPOS: v[0] = d.actuator_length[wb * m.nu + id]; break;
       case SENS_BALLQUAT: { const q4 q = qnormalize(ldq(d.qpos + wb * m.nq + m.jnt_qposadr[id])); v[0] = q.w; v[1] = q.x; v[2] = q.y; v[3] = q.z; break; }
-      case SENS_FRAMEPOS: { const float* p = obj_pos(d, m, wb, m.sensor_objtype[s], id); v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
+      case SENS_FRAMEPOS: {  // sensor.py:377
+        v3 r = ld3(obj_pos(d, m, wb, m.sensor_objtype[s], id));
+        if (rid > -1) r = mat_t_vec(obj_mat(d, m, wb, rt, rid), r - ld3(obj_pos(d, m, wb, rt, rid)));
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
       case SENS_FRAMEXAXIS: case SENS_FRAMEYAXIS: case SENS_FRAMEZAXIS: {
         const float* R = obj_mat(d, m, wb, m.sensor_objtype[s], id); const int c = t - SENS_FRAMEXAXIS;
-        v[0] = R[c]; v[1] = R[3 + c]; v[2] = R[6 + c]; break; }
+        v3 r = mk3(R[c], R[3 + c], R[6 + c]);
+        if (rid > -1) r = mat_t_vec(obj_mat(d, m, wb, rt, rid), r);  // sensor.py:406
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
       case SENS_FRAMEQUAT: {  // sensor.py:342-374 _get_quat
         const int ot = m.sensor_objtype[s];
         const float* local = ot == OBJ_BODY ? m.body_iquat + 4 * id : ot == OBJ_GEOM ? m.geom_quat + 4 * id : ot == OBJ_SITE ? m.site_quat + 4 * id : ot == OBJ_CAMERA ? m.cam_quat + 4 * id : nullptr;
         q4 q = ldq(d.xquat + (wb * nb + obj_body(m, ot, id)) * 4);
         if (local) q = qmul(q, ldq(local));
+        if (rid > -1) {  // sensor.py:470-482: conj(refquat) * quat
+          const float* rl = rt == OBJ_BODY ? m.body_iquat + 4 * rid : rt == OBJ_GEOM ? m.geom_quat + 4 * rid : rt == OBJ_SITE ? m.site_quat + 4 * rid : rt == OBJ_CAMERA ? m.cam_quat + 4 * rid : nullptr;
+          q4 rq = ldq(d.xquat + (wb * nb + obj_body(m, rt, rid)) * 4);
+          if (rl) rq = qmul(rq, ldq(rl));
+          q = qmul(mkq(rq.w, -rq.x, -rq.y, -rq.z), q);
+        }
         v[0] = q.w; v[1] = q.x; v[2] = q.y; v[3] = q.z; break; }
       case SENS_SUBTREECOM: { const float* p = d.subtree_com + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
       case SENS_CLOCK: v[0] = d.time[w]; break;
+      case SENS_JOINTLIMITPOS: case SENS_JOINTLIMITVEL: case SENS_JOINTLIMITFRC: {  // sensor.py:228, :1028, :1640: the joint's active limit row, else 0
+        const int e0 = d.ne[w] + d.nf[w], e1 = min(e0 + d.nl[w], d.njmax);
+        for (int e = e0; e < e1; e++)
+          if (d.efc_id[wb * d.njmax + e] == id && d.efc_type[wb * d.njmax + e] == CNSTR_LIMIT_JOINT)
+            v[0] = t == SENS_JOINTLIMITPOS ? d.efc_pos[wb * d.njmax + e] - d.efc_margin[wb * d.njmax + e]
+                                           : (t == SENS_JOINTLIMITVEL ? d.efc_vel[wb * d.njmax + e] : d.efc_force[wb * d.njmax + e]);
+        break; }
       case SENS_JOINTVEL: v[0] = d.qvel[wb * nv + m.jnt_dofadr[id]]; break;
       case SENS_ACTUATORVEL: v[0] = d.actuator_velocity[wb * m.nu + id]; break;
       case SENS_BALLANGVEL: { const float* p = d.qvel + wb * nv + m.jnt_dofadr[id]; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
       case SENS_FRAMELINVEL: case SENS_FRAMEANGVEL: {  // sensor.py:1108-1293 without a reference frame
         const int ot = m.sensor_objtype[s], b = obj_body(m, ot, id);
         const float* cv = d.cvel + (wb * nb + b) * 6;
-        v3 r = ld3(cv);
-        if (t == SENS_FRAMELINVEL) r = ld3(cv + 3) - cross(ld3(obj_pos(d, m, wb, ot, id)) - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3), r);
+        const v3 ang = ld3(cv), pos = ld3(obj_pos(d, m, wb, ot, id));
+        const v3 lin = ld3(cv + 3) - cross(pos - ld3(d.subtree_com + (wb * nb + m.body_rootid[b]) * 3), ang);
+        v3 r = t == SENS_FRAMELINVEL ? lin : ang;
+        if (rid > -1) {  // sensor.py:1188-1210, :1255-1291: relative to, and expressed in, the reference frame
+          const int rb = obj_body(m, rt, rid);
+          const float* rv = d.cvel + (wb * nb + rb) * 6;
+          const v3 rang = ld3(rv), rpos = ld3(obj_pos(d, m, wb, rt, rid));
+          const v3 rlin = ld3(rv + 3) - cross(rpos - ld3(d.subtree_com + (wb * nb + m.body_rootid[rb]) * 3), rang);
+          const v3 rel = t == SENS_FRAMELINVEL ? lin - rlin + cross(pos - rpos, rang) : ang - rang;
+          r = mat_t_vec(obj_mat(d, m, wb, rt, rid), rel);
+        }
         v[0] = r.x; v[1] = r.y; v[2] = r.z; break; }
       case SENS_SUBTREELINVEL: { const float* p = d.subtree_linvel + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
       case SENS_SUBTREEANGMOM: { const float* p = d.subtree_angmom + (wb * nb + id) * 3; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }

@@ -55,7 +55,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
   X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim) \
-  X(sensor_type) X(sensor_datatype) X(sensor_needstage) X(sensor_objtype) X(sensor_objid) X(sensor_dim) X(sensor_adr) X(site_type)
+  X(sensor_type) X(sensor_datatype) X(sensor_needstage) X(sensor_objtype) X(sensor_objid) X(sensor_reftype) X(sensor_refid) X(sensor_dim) X(sensor_adr) X(site_type)
 #define MODEL_RARRS(X) \
   X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
   X(body_inertia) X(body_invweight0) X(body_gravcomp) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
@@ -2664,32 +2664,59 @@ static void sensors(W* w, int stage) {
   if (stage == STAGE_ACC && need_cacc) rne_postconstraint(w);
   for (int s = 0; s < m->nsensor; s++) {
     if (m->sensor_needstage[s] != stage) continue;
-    const int t = m->sensor_type[s], id = m->sensor_objid[s];
+    const int t = m->sensor_type[s], id = m->sensor_objid[s], rt = m->sensor_reftype[s], rid = m->sensor_refid[s];
     real v[4] = {0, 0, 0, 0};
     switch (t) {
       case SENS_JOINTPOS: v[0] = w->qpos[m->jnt_qposadr[id]]; break;
       case SENS_ACTUATORPOS: v[0] = w->actuator_length[id]; break;
       case SENS_BALLQUAT: { memcpy(v, w->qpos + m->jnt_qposadr[id], 4 * sizeof(real)); normalize4(v); break; }
-      case SENS_FRAMEPOS: memcpy(v, obj_pos(w, m->sensor_objtype[s], id), 3 * sizeof(real)); break;
+      case SENS_FRAMEPOS: { /* sensor.py:377: relative to the reference frame when one is given */
+        memcpy(v, obj_pos(w, m->sensor_objtype[s], id), 3 * sizeof(real));
+        if (rid > -1) { real dlt[3]; v3sub(v, obj_pos(w, rt, rid), dlt); matT_vec3(obj_mat(w, rt, rid), dlt, v); }
+        break; }
       case SENS_FRAMEXAXIS: case SENS_FRAMEYAXIS: case SENS_FRAMEZAXIS: {
         const real* R = obj_mat(w, m->sensor_objtype[s], id); int c = t - SENS_FRAMEXAXIS;
-        v[0] = R[c]; v[1] = R[3 + c]; v[2] = R[6 + c]; break; }
+        v[0] = R[c]; v[1] = R[3 + c]; v[2] = R[6 + c];
+        if (rid > -1) { real ax[3] = {v[0], v[1], v[2]}; matT_vec3(obj_mat(w, rt, rid), ax, v); } /* sensor.py:406 */
+        break; }
       case SENS_FRAMEQUAT: { /* sensor.py:342-374 _get_quat */
         const int ot = m->sensor_objtype[s];
         const real* local = ot == OBJ_BODY ? m->body_iquat + 4 * id : ot == OBJ_GEOM ? m->geom_quat + 4 * id : ot == OBJ_SITE ? m->site_quat + 4 * id : ot == OBJ_CAMERA ? m->cam_quat + 4 * id : NULL;
         const real* xq = w->xquat + 4 * obj_body(m, ot, id);
         if (local) mul_quat(xq, local, v); else memcpy(v, xq, 4 * sizeof(real));
+        if (rid > -1) { /* sensor.py:470-482: conj(refquat) * quat */
+          const real* rl = rt == OBJ_BODY ? m->body_iquat + 4 * rid : rt == OBJ_GEOM ? m->geom_quat + 4 * rid : rt == OBJ_SITE ? m->site_quat + 4 * rid : rt == OBJ_CAMERA ? m->cam_quat + 4 * rid : NULL;
+          const real* rx = w->xquat + 4 * obj_body(m, rt, rid);
+          real rq[4], q[4] = {v[0], v[1], v[2], v[3]};
+          if (rl) mul_quat(rx, rl, rq); else memcpy(rq, rx, sizeof rq);
+          rq[1] = -rq[1]; rq[2] = -rq[2]; rq[3] = -rq[3];
+          mul_quat(rq, q, v);
+        }
         break; }
       case SENS_SUBTREECOM: memcpy(v, w->subtree_com + 3 * id, 3 * sizeof(real)); break;
       case SENS_CLOCK: v[0] = w->time[0]; break;
+      case SENS_JOINTLIMITPOS: case SENS_JOINTLIMITVEL: case SENS_JOINTLIMITFRC: { /* sensor.py:228, :1028, :1640: the joint's active limit row, else 0 */
+        for (int e = w->ne[0] + w->nf[0]; e < w->ne[0] + w->nf[0] + w->nl[0] && e < w->njmax; e++)
+          if (w->efc_id[e] == id && w->efc_type[e] == CNSTR_LIMIT_JOINT)
+            v[0] = t == SENS_JOINTLIMITPOS ? w->efc_pos[e] - w->efc_margin[e] : (t == SENS_JOINTLIMITVEL ? w->efc_vel[e] : w->efc_force[e]);
+        break; }
       case SENS_JOINTVEL: v[0] = w->qvel[m->jnt_dofadr[id]]; break;
       case SENS_ACTUATORVEL: v[0] = w->actuator_velocity[id]; break;
       case SENS_BALLANGVEL: memcpy(v, w->qvel + m->jnt_dofadr[id], 3 * sizeof(real)); break;
       case SENS_FRAMELINVEL: case SENS_FRAMEANGVEL: { /* sensor.py:1108-1293 without a reference frame */
         const int ot = m->sensor_objtype[s], b = obj_body(m, ot, id); const real* cv = w->cvel + 6 * b;
-        if (t == SENS_FRAMEANGVEL) { memcpy(v, cv, 3 * sizeof(real)); break; }
-        real off[3], cr[3]; v3sub(obj_pos(w, ot, id), w->subtree_com + 3 * m->body_rootid[b], off); cross3(off, cv, cr);
-        for (int i = 0; i < 3; i++) v[i] = cv[3 + i] - cr[i];
+        real off[3], cr[3], lin[3];
+        v3sub(obj_pos(w, ot, id), w->subtree_com + 3 * m->body_rootid[b], off); cross3(off, cv, cr);
+        for (int i = 0; i < 3; i++) lin[i] = cv[3 + i] - cr[i];
+        if (rid > -1) { /* sensor.py:1188-1210, :1255-1291: velocity relative to, and expressed in, the reference frame */
+          const int rb = obj_body(m, rt, rid); const real* rv = w->cvel + 6 * rb;
+          real roff[3], rlin[3], rvec[3], cr2[3], rel[3];
+          v3sub(obj_pos(w, rt, rid), w->subtree_com + 3 * m->body_rootid[rb], roff); cross3(roff, rv, cr);
+          for (int i = 0; i < 3; i++) rlin[i] = rv[3 + i] - cr[i];
+          v3sub(obj_pos(w, ot, id), obj_pos(w, rt, rid), rvec); cross3(rvec, rv, cr2);
+          for (int i = 0; i < 3; i++) rel[i] = t == SENS_FRAMEANGVEL ? cv[i] - rv[i] : lin[i] - rlin[i] + cr2[i];
+          matT_vec3(obj_mat(w, rt, rid), rel, v);
+        } else memcpy(v, t == SENS_FRAMEANGVEL ? cv : lin, 3 * sizeof(real));
         break; }
       case SENS_SUBTREELINVEL: memcpy(v, w->subtree_linvel + 3 * id, 3 * sizeof(real)); break;
       case SENS_SUBTREEANGMOM: memcpy(v, w->subtree_angmom + 3 * id, 3 * sizeof(real)); break;

@@ -233,7 +233,7 @@ class Oracle:
       setra(n, getattr(mjm, n) if neq else np.zeros(k))
     nsensor = int(getattr(mjm, "nsensor", 0))
     seti("nsensor", nsensor); seti("nsensordata", int(getattr(mjm, "nsensordata", 0)) if nsensor else 0)
-    for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_dim", "sensor_adr"):
+    for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_reftype", "sensor_refid", "sensor_dim", "sensor_adr"):
       setia(n, getattr(mjm, n) if nsensor else np.zeros(1, dtype=np.int32))
     setra("sensor_cutoff", mjm.sensor_cutoff if nsensor else np.zeros(1))
     nsite = int(getattr(mjm, "nsite", 0))

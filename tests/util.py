@@ -291,6 +291,12 @@ def sensor_xml():
     <framelinvel name="flv" objtype="site" objname="imu"/> <frameangvel name="fav" objtype="geom" objname="tip"/> <framelinvel name="flvb" objtype="body" objname="cap1"/>
     <framelinacc name="fla" objtype="site" objname="imu"/> <frameangacc name="faa" objtype="xbody" objname="pend"/> <framelinacc name="flab" objtype="body" objname="ball0"/>
     <touch name="tb" site="tz_box"/> <touch name="ts" site="tz_sph"/> <touch name="tc" site="tz_cap"/> <touch name="te" site="tz_ell"/> <touch name="ty" site="tz_cyl" cutoff="30"/>
+    <jointlimitpos name="lp_s" joint="slide"/> <jointlimitvel name="lv_s" joint="slide"/> <jointlimitfrc name="lf_s" joint="slide"/>
+    <jointlimitpos name="lp_h" joint="hinge"/> <jointlimitfrc name="lf_h" joint="hinge"/>
+    <framepos name="rp" objtype="site" objname="imu" reftype="body" refname="ball0"/> <framequat name="rq" objtype="geom" objname="tip" reftype="site" refname="st0"/>
+    <framexaxis name="rx" objtype="xbody" objname="pend" reftype="xbody" refname="cap0"/> <framezaxis name="rz" objtype="site" objname="imu" reftype="camera" refname="c0"/>
+    <framelinvel name="rlv" objtype="site" objname="imu" reftype="geom" refname="c1"/> <frameangvel name="rav" objtype="body" objname="pend" reftype="site" refname="st0"/>
+    <framelinvel name="rlv2" objtype="body" objname="ball1" reftype="xbody" refname="fore"/>
     <clock name="clk"/>
   </sensor>
 """
