@@ -1261,9 +1261,9 @@ static const int CONVEX_PAIRS[][2] = {{GEOM_SPHERE, GEOM_ELLIPSOID}, {GEOM_CAPSU
   {GEOM_ELLIPSOID, GEOM_ELLIPSOID}, {GEOM_ELLIPSOID, GEOM_CYLINDER}, {GEOM_ELLIPSOID, GEOM_BOX}, {GEOM_CYLINDER, GEOM_CYLINDER},
   {GEOM_CYLINDER, GEOM_BOX}, {GEOM_BOX, GEOM_BOX}};
 #define N_CONVEX_PAIRS ((int)(sizeof CONVEX_PAIRS / sizeof CONVEX_PAIRS[0]))
-static int g_nativeccd = 1; /* set per model in collision(): box-box is convex unless the nativeccd disable flag is set */
-static int convex_pair_rank(int t1, int t2) {
-  if (t1 == GEOM_BOX && t2 == GEOM_BOX && !g_nativeccd) return -1;
+/* box-box is a convex pair unless the model's nativeccd disable flag is set */
+static int convex_pair_rank(int t1, int t2, int nativeccd) {
+  if (t1 == GEOM_BOX && t2 == GEOM_BOX && !nativeccd) return -1;
   for (int i = 0; i < N_CONVEX_PAIRS; i++) if (CONVEX_PAIRS[i][0] == t1 && CONVEX_PAIRS[i][1] == t2) return i;
   return -1;
 }
@@ -1475,7 +1475,7 @@ static void collision(W* w) {
   /* Contact order of the reference under sequential execution: the convex narrowphase runs first, one launch per pair type
    * in table order (collision_driver.py:877, collision_convex.py:1369), then the primitive narrowphase; within a launch,
    * broadphase output order. */
-  g_nativeccd = !(m->disableflags & DSBL_NATIVECCD);
+  const int nativeccd = !(m->disableflags & DSBL_NATIVECCD);
   int* cand = (int*)malloc((size_t)(m->nxn_npair > 0 ? m->nxn_npair : 1) * sizeof(int));
   int ncand = 0, npass = 0;
   if (m->broadphase == 0) for (int e = 0; e < m->nxn_npair; e++) cand[ncand++] = e;
@@ -1491,7 +1491,7 @@ static void collision(W* w) {
     for (int k = 0; k < npass; k++) {
       int e = cand[k], g1 = m->nxn_geom_pair[2 * e], g2 = m->nxn_geom_pair[2 * e + 1];
       if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
-      int cr = convex_pair_rank(m->geom_type[g1], m->geom_type[g2]);
+      int cr = convex_pair_rank(m->geom_type[g1], m->geom_type[g2], nativeccd);
       if (rank < N_CONVEX_PAIRS) { if (cr == rank) convex_pair(w, g1, g2, m->nxn_pairid[2 * e]); }
       else if (cr < 0) narrowphase_pair(w, g1, g2, m->nxn_pairid[2 * e]);
     }

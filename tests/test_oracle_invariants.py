@@ -235,3 +235,68 @@ def test_solver_elliptic_minimises_cone_cost(scene):
         assert f[r] >= -1e-9
         if od["efc_state"][w, r] == 4:
           np.testing.assert_allclose(np.sqrt((ft**2).sum()), f[r], rtol=1e-6, atol=1e-9)
+
+
+SENSOR_BALL = """
+<mujoco>
+  <option timestep="0.002" gravity="0 0 -9.81"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05"/>
+    <body name="ball" pos="0 0 {z}">
+      <freejoint/>
+      <geom type="sphere" size="0.1" mass="2"/>
+      <site name="s" pos="0.02 0.01 0" euler="30 20 10"/>
+      <site name="zone" type="box" size="0.2 0.2 0.2"/>
+    </body>
+  </worldbody>
+  <sensor>
+    <accelerometer name="acc" site="s"/> <gyro name="gyro" site="s"/> <velocimeter name="vel" site="s"/>
+    <touch name="touch" site="zone"/> <force name="frc" site="s"/>
+    <subtreelinvel name="lv" body="ball"/> <subtreeangmom name="am" body="ball"/> <framelinacc name="fla" objtype="site" objname="s"/>
+  </sensor>
+</mujoco>"""
+
+
+def _sens(mjm, od, name, w=0):
+  i = mjm.names.sensor.index(name)
+  return od["sensordata"][w, mjm.sensor_adr[i] : mjm.sensor_adr[i] + mjm.sensor_dim[i]]
+
+
+def test_sensor_physics_resting_and_free_fall(built):
+  """Implementation-independent facts about the sensors: a body resting on the floor has an accelerometer (and frame-acceleration) reading of +g along the
+  world vertical, a touch sensor reading its weight; in free fall both read the centripetal term of the offset site only (no gravity); the velocity sensors follow the rigid-body velocity field."""
+  from mujoco_warp_b200._src import mjcf
+
+  # resting: let the contact settle, then read
+  mjm = mjcf.load_string(SENSOR_BALL.format(z=0.0995))
+  o = util.make_oracle(mjm, 1, 8, 32, clamp_tolerance=False)
+  for _ in range(400):
+    o.step()
+  o.forward()
+  kin = mjcf.kinematics_np(mjm, o.d["qpos"][0])
+  R = np.asarray(kin.site_xmat).reshape(-1, 3, 3)[mjm.names.site.index("s")]
+  np.testing.assert_allclose(R @ _sens(mjm, o.d, "acc"), [0, 0, 9.81], atol=2e-3)
+  np.testing.assert_allclose(_sens(mjm, o.d, "touch"), [2 * 9.81], rtol=2e-3)
+  np.testing.assert_allclose(_sens(mjm, o.d, "fla"), [0, 0, 9.81], atol=2e-3)  # like the accelerometer (MuJoCo's cacc carries -gravity), world frame
+  # interaction force the body exerts on its parent (the world) through its joint: zero for a free joint
+  np.testing.assert_allclose(_sens(mjm, o.d, "frc"), [0, 0, 0], atol=2e-2)
+
+  # free fall with spin: accelerometer 0, frame acceleration = gravity + centripetal term, velocity field of a rigid body
+  mjm = mjcf.load_string(SENSOR_BALL.format(z=2.0))
+  o = util.make_oracle(mjm, 1, 8, 32)
+  wvec, vvec = np.array([0.3, -0.2, 0.5]), np.array([0.1, 0.2, -0.3])
+  qvel = np.concatenate([vvec, wvec])[None]  # free joint: linear velocity in the world frame, angular velocity in the body frame (identity here)
+  o.set_state(qvel=qvel)
+  o.forward()
+  kin = mjcf.kinematics_np(mjm, o.d["qpos"][0])
+  si = mjm.names.site.index("s")
+  R, p = np.asarray(kin.site_xmat).reshape(-1, 3, 3)[si], np.asarray(kin.site_xpos).reshape(-1, 3)[si]
+  r = p - o.d["qpos"][0, :3]
+  np.testing.assert_allclose(R @ _sens(mjm, o.d, "acc"), np.cross(wvec, np.cross(wvec, r)), atol=1e-9)  # no gravity felt: centripetal term of the offset site only
+  np.testing.assert_allclose(R @ _sens(mjm, o.d, "gyro"), wvec, atol=1e-12)
+  np.testing.assert_allclose(R @ _sens(mjm, o.d, "vel"), vvec + np.cross(wvec, r), atol=1e-12)
+  np.testing.assert_allclose(_sens(mjm, o.d, "fla"), np.cross(wvec, np.cross(wvec, r)), atol=1e-9)  # centripetal term only
+  np.testing.assert_allclose(_sens(mjm, o.d, "lv"), vvec, atol=1e-12)
+  inertia = 0.4 * 2 * 0.1**2  # solid sphere
+  np.testing.assert_allclose(_sens(mjm, o.d, "am"), inertia * wvec, rtol=1e-9)
+  np.testing.assert_allclose(_sens(mjm, o.d, "touch"), [0.0])
