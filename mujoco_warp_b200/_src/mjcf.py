@@ -549,6 +549,18 @@ def compile_xml(root):
 
   bodies, joints, geoms, sites, cams, lights = [], [], [], [], [], []
   skipped_mesh_geoms = 0
+  # mesh assets with inline vertex data (files are resolved by load(); assets whose data is unavailable stay unknown and
+  # only visual geoms may refer to them)
+  meshes, mesh_names = [], []
+  for asset in root.findall("asset"):
+    for me in asset.findall("mesh"):
+      if "vertex" not in me.attrib:
+        continue
+      from . import mesh as _mesh
+
+      faces = _vec(me.get("face")).astype(int).reshape(-1, 3) if "face" in me.attrib else None
+      meshes.append(_mesh.process(_vec(me.get("vertex")).reshape(-1, 3), faces, _vec(me.get("scale"), 3, default=[1, 1, 1])))
+      mesh_names.append(me.get("name", f"mesh{len(mesh_names)}"))
 
   def attrs(elem, childclass):
     cls = elem.get("class", childclass)
@@ -643,15 +655,23 @@ def compile_xml(root):
         gtype = _GEOM_TYPES[a.get("type", "sphere")]
         if "mesh" in a and "type" not in a:
           gtype = C.GEOM_MESH
-        if gtype == C.GEOM_MESH:
-          # mesh assets are not in the tree (visual STL); only visual (non-colliding, massless) ones can be skipped
+        dataid = -1
+        if gtype == C.GEOM_MESH and a.get("mesh") in mesh_names:
+          dataid = mesh_names.index(a.get("mesh"))
+        elif gtype == C.GEOM_MESH:
+          # the asset's data is not available (e.g. visual STL files outside the tree): only visual (non-colliding, massless) geoms can be skipped
           if int(a.get("contype", 1)) == 0 and int(a.get("conaffinity", 1)) == 0 and (float(a.get("density", 1000)) == 0 or "mass" in a and float(a["mass"]) == 0):
             skipped_mesh_geoms += 1
             continue
-          raise NotImplementedError("colliding / massive mesh geoms need mesh assets and convex hulls (SURVEY.md §7: out of scope offline)")
+          raise NotImplementedError("colliding / massive mesh geoms need the mesh asset's vertex data (inline `vertex=` or a readable file)")
         size = _vec(a.get("size"), 3, default=[0, 0, 0])
         pos = _vec(a.get("pos"), default=[0, 0, 0])
         quat = _frame_quat(a, compiler)
+        if dataid >= 0:  # the geom frame is the mesh frame (centre of mass, principal axes): compose with the asset's transform
+          md = meshes[dataid]
+          pos = pos + rot_vec(quat, md["pos"])
+          quat = quat_mul(quat, md["quat"])
+          size = md["aabb_size"].copy()
         if "fromto" in a:
           ft = _vec(a["fromto"])
           vec = ft[0:3] - ft[3:6]
@@ -683,6 +703,7 @@ def compile_xml(root):
           density=float(a.get("density", 1000.0)),
           mass=float(a["mass"]) if "mass" in a else None,
           group=int(a.get("group", 0)),
+          dataid=dataid,
         )
         if b["geomnum"] == 0:
           b["geomadr"] = len(geoms)
@@ -886,7 +907,7 @@ def compile_xml(root):
   m.geom_conaffinity = np.array([g["conaffinity"] for g in geoms], dtype=np.int32)
   m.geom_condim = np.array([g["condim"] for g in geoms], dtype=np.int32)
   m.geom_priority = np.array([g["priority"] for g in geoms], dtype=np.int32)
-  m.geom_dataid = -np.ones(ngeom, dtype=np.int32)
+  m.geom_dataid = np.array([g["dataid"] for g in geoms], dtype=np.int32).reshape(ngeom)
   m.geom_size = np.array([g["size"] for g in geoms]).reshape(ngeom, 3)
   m.geom_pos = np.array([g["pos"] for g in geoms]).reshape(ngeom, 3)
   m.geom_quat = np.array([g["quat"] for g in geoms]).reshape(ngeom, 4)
@@ -896,8 +917,9 @@ def compile_xml(root):
   m.geom_solimp = np.array([g["solimp"] for g in geoms]).reshape(ngeom, 5)
   m.geom_margin = np.array([g["margin"] for g in geoms])
   m.geom_gap = np.array([g["gap"] for g in geoms])
-  m.geom_rbound = np.array([_geom_rbound(g["type"], g["size"]) for g in geoms])
-  m.geom_aabb = np.array([_geom_aabb(g["type"], g["size"]) for g in geoms]).reshape(ngeom, 6)
+  m.geom_rbound = np.array([meshes[g["dataid"]]["rbound"] if g["dataid"] >= 0 else _geom_rbound(g["type"], g["size"]) for g in geoms])
+  m.geom_aabb = np.array([np.concatenate([meshes[g["dataid"]]["aabb_center"], meshes[g["dataid"]]["aabb_size"]]) if g["dataid"] >= 0
+                          else _geom_aabb(g["type"], g["size"]) for g in geoms]).reshape(ngeom, 6)
 
   # ---- body inertial properties
   mass = np.zeros(nbody)
@@ -916,7 +938,7 @@ def compile_xml(root):
     tot, com = 0.0, np.zeros(3)
     parts = []
     for g in gs:
-      vol, iu = _geom_volume_inertia(g["type"], g["size"])
+      vol, iu = (meshes[g["dataid"]]["volume"], meshes[g["dataid"]]["inertia"]) if g["dataid"] >= 0 else _geom_volume_inertia(g["type"], g["size"])
       if vol <= 0:
         continue
       gm = g["mass"] if g["mass"] is not None else g["density"] * vol
@@ -1126,7 +1148,28 @@ def compile_xml(root):
   m.eq_data = np.array([e["data"] for e in eqs], dtype=np.float64).reshape(m.neq, 11)
 
   # unused families (sizes only)
-  m.ntendon = m.nflex = m.nmesh = m.nhfield = 0
+  m.ntendon = m.nflex = m.nhfield = 0
+
+  # ---- mesh tables (reference types.py:1214-1235), concatenated over the assets
+  m.nmesh = len(meshes)
+  m.names.mesh = list(mesh_names)
+  cat = lambda key, dt, width=None: (np.concatenate([np.asarray(md[key]).reshape(-1, width) if width else np.asarray(md[key]).reshape(-1) for md in meshes]).astype(dt)
+                                     if meshes else np.zeros((0, width) if width else 0, dtype=dt))
+  count = lambda key, per=1: np.array([len(np.asarray(md[key]).reshape(-1)) // per for md in meshes], dtype=np.int32)
+  adr = lambda n: (np.concatenate(([0], np.cumsum(n)[:-1])) if len(n) else np.zeros(0)).astype(np.int32)
+  m.mesh_vertnum = count("vert", 3); m.mesh_vertadr = adr(m.mesh_vertnum); m.mesh_vert = cat("vert", np.float64, 3)
+  m.mesh_facenum = count("face", 3); m.mesh_faceadr = adr(m.mesh_facenum); m.mesh_face = cat("face", np.int32, 3)
+  m.mesh_graphadr = adr(count("graph")); m.mesh_graph = cat("graph", np.int32)
+  m.mesh_pos = cat("pos", np.float64, 3); m.mesh_quat = cat("quat", np.float64, 4)
+  m.mesh_polynum = count("polyvertnum"); m.mesh_polyadr = adr(m.mesh_polynum)
+  m.mesh_polynormal = cat("polynormal", np.float64, 3)
+  m.mesh_polyvertnum = cat("polyvertnum", np.int32)
+  m.mesh_polyvertadr = adr(m.mesh_polyvertnum)  # addresses into mesh_polyvert run over all meshes
+  m.mesh_polyvert = cat("polyvert", np.int32)
+  m.mesh_polymapnum = cat("polymapnum", np.int32)
+  m.mesh_polymapadr = adr(m.mesh_polymapnum)
+  m.mesh_polymap = cat("polymap", np.int32)
+  m.nmeshvert, m.nmeshface, m.nmeshgraph, m.nmeshpoly = len(m.mesh_vert), len(m.mesh_face), len(m.mesh_graph), len(m.mesh_polynormal)
 
   # ---- sensors (MuJoCo mjtSensor / mjtDataType / mjtStage values; element tag -> type, object kind, dim, datatype, stage)
   S = C
