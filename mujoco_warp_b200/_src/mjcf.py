@@ -1170,6 +1170,9 @@ def compile_xml(root):
   m.mesh_polymapadr = adr(m.mesh_polymapnum)
   m.mesh_polymap = cat("polymap", np.int32)
   m.nmeshvert, m.nmeshface, m.nmeshgraph, m.nmeshpoly = len(m.mesh_vert), len(m.mesh_face), len(m.mesh_graph), len(m.mesh_polynormal)
+  m.nmeshpolyvert, m.nmeshpolymap, m.nmeshnormal = len(m.mesh_polyvert), len(m.mesh_polymap), 0
+  m.npolygonmax = int(m.mesh_polyvertnum.max()) if m.nmesh else 0  # most vertices in one hull polygon / most polygons at one vertex
+  m.nmeshdegmax = int(m.mesh_polymapnum.max()) if m.nmesh else 0
 
   # ---- sensors (MuJoCo mjtSensor / mjtDataType / mjtStage values; element tag -> type, object kind, dim, datatype, stage)
   S = C

@@ -43,7 +43,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
-  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations) X(nsensor) X(nsensordata)
+  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations) X(nsensor) X(nsensordata) X(nmesh)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(ccd_tolerance)
 #define MODEL_IARRS(X) \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
@@ -55,7 +55,9 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
   X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim) \
-  X(sensor_type) X(sensor_datatype) X(sensor_needstage) X(sensor_objtype) X(sensor_objid) X(sensor_reftype) X(sensor_refid) X(sensor_dim) X(sensor_adr) X(site_type)
+  X(sensor_type) X(sensor_datatype) X(sensor_needstage) X(sensor_objtype) X(sensor_objid) X(sensor_reftype) X(sensor_refid) X(sensor_dim) X(sensor_adr) X(site_type) \
+  X(geom_dataid) X(mesh_vertadr) X(mesh_vertnum) X(mesh_graphadr) X(mesh_graph) X(mesh_polynum) X(mesh_polyadr) X(mesh_polyvertadr) X(mesh_polyvertnum) \
+  X(mesh_polyvert) X(mesh_polymapadr) X(mesh_polymapnum) X(mesh_polymap)
 #define MODEL_RARRS(X) \
   X(gravity) X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_subtreemass) \
   X(body_inertia) X(body_invweight0) X(body_gravcomp) X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_range) X(jnt_margin) X(jnt_solref) \
@@ -65,7 +67,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
   X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat) \
   X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap) \
-  X(sensor_cutoff) X(site_size)
+  X(sensor_cutoff) X(site_size) X(mesh_vert) X(mesh_polynormal)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -1257,9 +1259,9 @@ static int box_box(const real* pos1, const real* rot1, const real* size1, const 
 
 /* collision_driver.py:47-81: pair types the reference sends to the convex (GJK / EPA) path, in MJ_COLLISION_TABLE order,
  * restricted to analytic geoms.  Box-box is convex unless the nativeccd disable flag routes it to the primitive. */
-static const int CONVEX_PAIRS[][2] = {{GEOM_SPHERE, GEOM_ELLIPSOID}, {GEOM_CAPSULE, GEOM_ELLIPSOID}, {GEOM_CAPSULE, GEOM_CYLINDER},
-  {GEOM_ELLIPSOID, GEOM_ELLIPSOID}, {GEOM_ELLIPSOID, GEOM_CYLINDER}, {GEOM_ELLIPSOID, GEOM_BOX}, {GEOM_CYLINDER, GEOM_CYLINDER},
-  {GEOM_CYLINDER, GEOM_BOX}, {GEOM_BOX, GEOM_BOX}};
+static const int CONVEX_PAIRS[][2] = {{GEOM_SPHERE, GEOM_ELLIPSOID}, {GEOM_SPHERE, GEOM_MESH}, {GEOM_CAPSULE, GEOM_ELLIPSOID}, {GEOM_CAPSULE, GEOM_CYLINDER},
+  {GEOM_CAPSULE, GEOM_MESH}, {GEOM_ELLIPSOID, GEOM_ELLIPSOID}, {GEOM_ELLIPSOID, GEOM_CYLINDER}, {GEOM_ELLIPSOID, GEOM_BOX}, {GEOM_ELLIPSOID, GEOM_MESH},
+  {GEOM_CYLINDER, GEOM_CYLINDER}, {GEOM_CYLINDER, GEOM_BOX}, {GEOM_CYLINDER, GEOM_MESH}, {GEOM_BOX, GEOM_BOX}, {GEOM_BOX, GEOM_MESH}, {GEOM_MESH, GEOM_MESH}};
 #define N_CONVEX_PAIRS ((int)(sizeof CONVEX_PAIRS / sizeof CONVEX_PAIRS[0]))
 /* box-box is a convex pair unless the model's nativeccd disable flag is set */
 static int convex_pair_rank(int t1, int t2, int nativeccd) {
@@ -1267,16 +1269,28 @@ static int convex_pair_rank(int t1, int t2, int nativeccd) {
   for (int i = 0; i < N_CONVEX_PAIRS; i++) if (CONVEX_PAIRS[i][0] == t1 && CONVEX_PAIRS[i][1] == t2) return i;
   return -1;
 }
+/* collision_core.py:60-140 geom(): pose, size and -- for meshes -- the asset's vertex block, hull graph and polygon tables */
+static void fill_cgeom(const W* w, int g, real margin, CGeom* c) {
+  const OrcModel* m = w->m;
+  memset(c, 0, sizeof *c);
+  memcpy(c->pos, w->geom_xpos + 3 * g, sizeof c->pos); memcpy(c->rot, w->geom_xmat + 9 * g, sizeof c->rot); memcpy(c->size, m->geom_size + 3 * g, sizeof c->size);
+  c->type = m->geom_type[g]; c->margin = margin; c->index = -1;
+  if (c->type == GEOM_MESH && m->geom_dataid[g] >= 0) {
+    const int id = m->geom_dataid[g], vadr = m->mesh_vertadr[id], padr = m->mesh_polyadr[id];
+    c->vert = m->mesh_vert + 3 * vadr; c->vertnum = m->mesh_vertnum[id];
+    c->graph = m->mesh_graphadr[id] >= 0 ? m->mesh_graph + m->mesh_graphadr[id] : NULL;
+    c->polynum = m->mesh_polynum[id]; c->polynormal = m->mesh_polynormal + 3 * padr;
+    c->polyvertadr = m->mesh_polyvertadr + padr; c->polyvertnum = m->mesh_polyvertnum + padr; c->polyvert = m->mesh_polyvert;
+    c->polymapadr = m->mesh_polymapadr + vadr; c->polymapnum = m->mesh_polymapnum + vadr; c->polymap = m->mesh_polymap;
+  }
+}
 /* collision_convex.py:739-968 eval_ccd_write_contact (single contact; multi-contact applies to box / mesh pairs only) */
 static void convex_pair(W* w, int g1, int g2, int pairid) {
   const OrcModel* m = w->m;
   ConParams p;
   contact_params(m, g1, g2, pairid, &p);
   CGeom a, b;
-  memcpy(a.pos, w->geom_xpos + 3 * g1, sizeof a.pos); memcpy(a.rot, w->geom_xmat + 9 * g1, sizeof a.rot); memcpy(a.size, m->geom_size + 3 * g1, sizeof a.size);
-  memcpy(b.pos, w->geom_xpos + 3 * g2, sizeof b.pos); memcpy(b.rot, w->geom_xmat + 9 * g2, sizeof b.rot); memcpy(b.size, m->geom_size + 3 * g2, sizeof b.size);
-  a.type = m->geom_type[g1]; b.type = m->geom_type[g2];
-  a.margin = b.margin = p.margin;
+  fill_cgeom(w, g1, p.margin, &a); fill_cgeom(w, g2, p.margin, &b);
   real dist, w1[4][3], w2[4][3], frame[9], nrm[3], pos[3]; int ovf = 0;
   memset(w1, 0, sizeof w1); memset(w2, 0, sizeof w2);
   int ncon = ccd_pair(m->ccd_tolerance, p.gap, m->ccd_iterations, m->epa_iterations, 1, a, b, &dist, w1, w2, &ovf);
@@ -1296,6 +1310,7 @@ static void convex_pair(W* w, int g1, int g2, int pairid) {
 int orc_ccd(int type1, const real* size1, const real* pos1, const real* mat1, int type2, const real* size2, const real* pos2, const real* mat2,
             real margin, real tolerance, real cutoff, int iterations, int multi, real* dist, real* w1, real* w2, int* overflow) {
   CGeom a, b;
+  memset(&a, 0, sizeof a); memset(&b, 0, sizeof b); a.index = b.index = -1;
   memcpy(a.pos, pos1, sizeof a.pos); memcpy(a.rot, mat1, sizeof a.rot); memcpy(a.size, size1, sizeof a.size); a.type = type1; a.margin = margin;
   memcpy(b.pos, pos2, sizeof b.pos); memcpy(b.rot, mat2, sizeof b.rot); memcpy(b.size, size2, sizeof b.size); b.type = type2; b.margin = margin;
   real x1[4][3], x2[4][3]; int ovf = 0;
@@ -1304,6 +1319,107 @@ int orc_ccd(int type1, const real* size1, const real* pos1, const real* mat1, in
   memcpy(w1, x1, sizeof x1); memcpy(w2, x2, sizeof x2);
   *overflow = ovf;
   return n;
+}
+
+static real pc_support(const real* ppl, const real* v, const real* n) { real d[3]; v3sub(ppl, v, d); return dot3(d, n); }
+/* collision_primitive.py:52-277 plane_convex: up to four well-spread vertices of the convex geom that lie (nearly) deepest below the plane */
+static void plane_convex(const real* n_world, const real* plane_pos, const CGeom* c, real dist[4], real pos[4][3]) {
+  const real HUGE_V = (real)1e6;
+  real d[3], ppl[3], n[3];
+  int idx[4] = {-1, -1, -1, -1};
+  for (int i = 0; i < 4; i++) { dist[i] = MJ_MAXVAL; pos[i][0] = pos[i][1] = pos[i][2] = 0; }
+  v3sub(plane_pos, c->pos, d); matT_vec3(c->rot, d, ppl); matT_vec3(c->rot, n_world, n);
+#define PC_SUPPORT(v) pc_support(ppl, (v), n) /* dot(plane_pos_local - vert, n), evaluated in the reference's order */
+  if (!c->graph || c->vertnum < 10) {
+    real max_support = -HUGE_V; const real* a = NULL;
+    for (int i = 0; i < c->vertnum; i++) { real s = PC_SUPPORT(c->vert + 3 * i); if (s > max_support) { max_support = s; idx[0] = i; a = c->vert + 3 * i; } }
+    if (max_support < 0) return;
+    real threshold = max_support - (real)1e-3, best = -HUGE_V; const real* b = NULL;
+    for (int i = 0; i < c->vertnum; i++) {
+      const real* v = c->vert + 3 * i; real df[3]; v3sub(a, v, df);
+      real dd = dot3(df, df) + (PC_SUPPORT(v) > threshold ? 0 : -HUGE_V);
+      if (dd > best) { idx[1] = i; best = dd; b = v; }
+    }
+    real amb[3], ab[3]; v3sub(a, b, amb); cross3(n, amb, ab);
+    best = -HUGE_V; const real* cc = NULL;
+    for (int i = 0; i < c->vertnum; i++) {
+      const real* v = c->vert + 3 * i; real ap[3]; v3sub(a, v, ap);
+      real dd = rabs(dot3(ap, ab)) + (PC_SUPPORT(v) > threshold ? 0 : -HUGE_V);
+      if (dd > best) { idx[2] = i; best = dd; cc = v; }
+    }
+    real amc[3], bmc[3], ac[3], bc[3]; v3sub(a, cc, amc); v3sub(b, cc, bmc); cross3(n, amc, ac); cross3(n, bmc, bc);
+    best = -HUGE_V;
+    for (int i = 0; i < c->vertnum; i++) {
+      const real* v = c->vert + 3 * i; real ap[3], bp[3]; v3sub(a, v, ap); v3sub(b, v, bp);
+      real mask = PC_SUPPORT(v) > threshold ? 0 : -HUGE_V;
+      real dd = (rabs(dot3(ap, ac)) + mask) + (rabs(dot3(bp, bc)) + mask);
+      if (dd > best) { idx[3] = i; best = dd; }
+    }
+  } else {
+    const int numvert = c->graph[0], *vert_edgeadr = c->graph + 2, *vert_globalid = c->graph + 2 + numvert, *edge_localid = c->graph + 2 + 2 * numvert;
+    real max_support = -HUGE_V; int prev, imax = 0;
+    for (;;) { /* hill climb to the deepest vertex */
+      prev = imax;
+      for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) { int sub = edge_localid[i]; real s = PC_SUPPORT(c->vert + 3 * vert_globalid[sub]); if (s > max_support) { max_support = s; imax = sub; } }
+      if (imax == prev) break;
+    }
+    real threshold = rmax(0, max_support - (real)1e-3), best = -HUGE_V;
+    for (;;) {
+      prev = imax;
+      for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) { int sub = edge_localid[i]; real s = PC_SUPPORT(c->vert + 3 * vert_globalid[sub]); real dd = s > threshold ? s : -HUGE_V; if (dd > best) { best = dd; imax = sub; } }
+      if (imax == prev) break;
+    }
+    const real* a = c->vert + 3 * vert_globalid[imax]; idx[0] = vert_globalid[imax];
+    best = -HUGE_V;
+    for (;;) {
+      prev = imax;
+      for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) {
+        int sub = edge_localid[i]; const real* v = c->vert + 3 * vert_globalid[sub]; real df[3]; v3sub(a, v, df);
+        real dd = dot3(df, df) + (PC_SUPPORT(v) > threshold ? 0 : -HUGE_V);
+        if (dd > best) { best = dd; imax = sub; }
+      }
+      if (imax == prev) break;
+    }
+    const real* b = c->vert + 3 * vert_globalid[imax]; idx[1] = vert_globalid[imax];
+    real amb[3], ab[3]; v3sub(a, b, amb); cross3(n, amb, ab);
+    best = -HUGE_V;
+    for (;;) {
+      prev = imax;
+      for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) {
+        int sub = edge_localid[i]; const real* v = c->vert + 3 * vert_globalid[sub]; real ap[3]; v3sub(a, v, ap);
+        real dd = rabs(dot3(ap, ab)) + (PC_SUPPORT(v) > threshold ? 0 : -HUGE_V);
+        if (dd > best) { best = dd; imax = sub; }
+      }
+      if (imax == prev) break;
+    }
+    const real* cc = c->vert + 3 * vert_globalid[imax]; idx[2] = vert_globalid[imax];
+    real amc[3], bmc[3], ac[3], bc[3]; v3sub(a, cc, amc); v3sub(b, cc, bmc); cross3(n, amc, ac); cross3(n, bmc, bc);
+    best = -HUGE_V;
+    for (;;) {
+      prev = imax;
+      for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) {
+        int sub = edge_localid[i]; const real* v = c->vert + 3 * vert_globalid[sub]; real ap[3], bp[3]; v3sub(a, v, ap); v3sub(b, v, bp);
+        real mask = PC_SUPPORT(v) > threshold ? 0 : -HUGE_V;
+        real dd = (rabs(dot3(ap, ac)) + mask) + (rabs(dot3(bp, bc)) + mask);
+        if (dd > best) { best = dd; imax = sub; }
+      }
+      if (imax == prev) break;
+    }
+    idx[3] = vert_globalid[imax];
+  }
+  int count = 0;
+  for (int i = 3; i >= 0; i--) { /* unique indices, last first */
+    int uniq = 0;
+    for (int j = 0; j <= i; j++) if (idx[j] == idx[i]) uniq++;
+    if (uniq != 1) continue;
+    const real* v = c->vert + 3 * idx[i];
+    real wp[3]; matvec3(c->rot, v, wp);
+    real dd = -PC_SUPPORT(v);
+    for (int k = 0; k < 3; k++) pos[count][k] = c->pos[k] + wp[k] - (real)0.5 * dd * n_world[k];
+    dist[count] = dd;
+    count++;
+  }
+#undef PC_SUPPORT
 }
 
 static void narrowphase_pair(W* w, int g1, int g2, int pairid) {
@@ -1393,6 +1509,12 @@ static void narrowphase_pair(W* w, int g1, int g2, int pairid) {
   } else if (t1 == GEOM_PLANE && t2 == GEOM_CYLINDER) { /* collision_primitive.py:1000 */
     real d4[4], p4[4][3];
     plane_cylinder(ax1, pos1, pos2, ax2, size2[0], size2[1], d4, p4);
+    make_frame(ax1, frame);
+    for (int i = 0; i < 4; i++) write_contact(w, i, d4[i], p4[i], frame, &p, g1, g2);
+  } else if (t1 == GEOM_PLANE && t2 == GEOM_MESH) { /* collision_primitive.py:838 plane_convex_wrapper */
+    CGeom c; fill_cgeom(w, g2, 0, &c);
+    real d4[4], p4[4][3];
+    plane_convex(ax1, pos1, &c, d4, p4);
     make_frame(ax1, frame);
     for (int i = 0; i < 4; i++) write_contact(w, i, d4[i], p4[i], frame, &p, g1, g2);
   } else if (t1 == GEOM_PLANE && t2 == GEOM_BOX) { /* collision_primitive.py:761 */

@@ -17,10 +17,25 @@
 #define CCD_MAX_EPAFACES 5
 #define CCD_MAX_EPAHORIZON 24
 
-typedef struct { real pos[3], rot[9], size[3], margin; int type; } CGeom;
+/* mesh geoms carry their vertex block, the hull graph (NULL: exhaustive search) and the hull polygon tables (collision_core.py Geom);
+ * index = cached support vertex (vertex id for the exhaustive search, hull-local id for the hill climb; -1: none) */
+typedef struct {
+  real pos[3], rot[9], size[3], margin; int type;
+  int index, vertnum, polynum;
+  const real *vert, *polynormal;          /* vert / polynormal already offset to this mesh (vertadr / polyadr) */
+  const int *graph;                       /* this mesh's graph block */
+  const int *polyvertadr, *polyvertnum;   /* offset to this mesh's first polygon; the addresses they hold are global */
+  const int *polyvert;                    /* global */
+  const int *polymapadr, *polymapnum;     /* offset to this mesh's first vertex; addresses are global */
+  const int *polymap;                     /* global */
+} CGeom;
+#define CCD_FLOAT_MIN ((real)-1e30)
+#define CCD_MAXDEG 32    /* hull polygons meeting at one vertex (model nmeshdegmax) */
+#define CCD_MAXPOLY 64   /* vertices of one hull polygon (model npolygonmax) */
 typedef struct {
   int separated, dim; real dist, x1[3], x2[3];
   real simplex[4][3], simplex1[4][3], simplex2[4][3]; int index1[4], index2[4];
+  int cindex1, cindex2; /* cached support vertices of the two geoms when gjk returned */
 } GjkResult;
 typedef struct {
   int status, nvert, nface, nhorizon, maxvert, maxface;
@@ -32,9 +47,11 @@ static inline real csign(real x) { return x < 0 ? (real)-1 : (real)1; } /* warp:
 static inline void v3sub(const real* a, const real* b, real* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
 static inline void v3cpy(real* d, const real* s) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
 
-/* collision_gjk.py:115 support point of a geom inflated by half its margin; *vidx = box corner id or -1 */
-static void ccd_support(const CGeom* g, const real* dir, real* out, int* vidx) {
-  *vidx = -1;
+/* collision_gjk.py:115 support point of a geom inflated by half its margin; *vidx = box corner / mesh vertex id or -1,
+ * *cidx = the index to cache for the next query of this geom */
+static void ccd_support(const CGeom* g, const real* dir, real* out, int* vidx, int* cidx) {
+  const int cached = g->index; /* read first: callers may pass &g->index as cidx */
+  *vidx = -1; *cidx = -1;
   if (g->type == GEOM_SPHERE) { for (int i = 0; i < 3; i++) out[i] = g->pos[i] + (g->size[0] + (real)0.5 * g->margin) * dir[i]; return; }
   real ld[3], res[3] = {0, 0, 0};
   matT_vec3(g->rot, dir, ld);
@@ -53,6 +70,31 @@ static void ccd_support(const CGeom* g, const real* dir, real* out, int* vidx) {
     real d = (real)sqrt((double)(ld[0] * ld[0] + ld[1] * ld[1]));
     if (d > CCD_MINVAL) { real scl = g->size[0] / d; res[0] = ld[0] * scl; res[1] = ld[1] * scl; }
     res[2] = csign(ld[2]) * g->size[1];
+  } else if (g->type == GEOM_MESH) { /* :154-194 */
+    real max_dist = CCD_FLOAT_MIN;
+    if (!g->graph || g->vertnum < 10) {
+      if (cached > -1) { *cidx = cached; max_dist = dot3(g->vert + 3 * cached, ld); v3cpy(res, g->vert + 3 * cached); }
+      for (int i = 0; i < g->vertnum; i++) {
+        real dd = dot3(g->vert + 3 * i, ld);
+        if (dd > max_dist) { max_dist = dd; v3cpy(res, g->vert + 3 * i); *cidx = i; }
+      }
+      *vidx = *cidx;
+    } else {
+      const int numvert = g->graph[0], *vert_edgeadr = g->graph + 2, *vert_globalid = g->graph + 2 + numvert, *edge_localid = g->graph + 2 + 2 * numvert;
+      int prev = -1, imax = cached > -1 ? cached : 0;
+      max_dist = dot3(ld, g->vert + 3 * vert_globalid[imax]);
+      while (imax != prev) {
+        prev = imax;
+        int i = vert_edgeadr[imax], subidx = edge_localid[i];
+        while (subidx >= 0) {
+          real dd = dot3(ld, g->vert + 3 * vert_globalid[subidx]);
+          if (dd > max_dist) { imax = subidx; max_dist = dd; }
+          i++; subidx = edge_localid[i];
+        }
+      }
+      *cidx = imax; *vidx = vert_globalid[imax];
+      v3cpy(res, g->vert + 3 * *vidx);
+    }
   }
   matvec3(g->rot, res, out);
   for (int i = 0; i < 3; i++) out[i] += g->pos[i];
@@ -141,7 +183,8 @@ static void linear_combine(int n, const real* l, real m[4][3], real* o) {
 }
 
 /* collision_gjk.py:635 (is_discrete = false for analytic geoms: no direction tuning, tolerance-based stop) */
-static void ccd_gjk(real tolerance, int iterations, const CGeom* g1, const CGeom* g2, const real* x1_0, const real* x2_0, real cutoff, int discrete, GjkResult* r) {
+static void ccd_gjk(real tolerance, int iterations, const CGeom* g1_in, const CGeom* g2_in, const real* x1_0, const real* x2_0, real cutoff, int discrete, GjkResult* r) {
+  CGeom ga = *g1_in, gb = *g2_in, *g1 = &ga, *g2 = &gb; /* by value: the cached support indices advance with the iterations (:675-679) */
   /* discrete pairs (box / mesh, no margin) converge in finitely many steps: no tolerance (collision_gjk.py:662-663) */
   real lmbda[4] = {1, 0, 0, 0}, x_k[3], epsilon = discrete ? 0 : (real)0.5 * tolerance * tolerance, min_norm = discrete ? CCD_MINVAL : tolerance;
   int n = 0;
@@ -169,14 +212,14 @@ static void ccd_gjk(real tolerance, int iterations, const CGeom* g1, const CGeom
       }
     }
     real dpos[3] = {-dir_neg[0], -dir_neg[1], -dir_neg[2]};
-    ccd_support(g1, dpos, r->simplex1[n], &r->index1[n]);
-    ccd_support(g2, dir_neg, r->simplex2[n], &r->index2[n]);
+    ccd_support(g1, dpos, r->simplex1[n], &r->index1[n], &g1->index);
+    ccd_support(g2, dir_neg, r->simplex2[n], &r->index2[n], &g2->index);
     v3sub(r->simplex1[n], r->simplex2[n], r->simplex[n]);
     real dk[3]; v3sub(x_k, r->simplex[n], dk);
     if (dot3(x_k, dk) < epsilon) break;
     real lower = dot3(x_k, r->simplex[n]);
-    if (cutoff == 0) { if (lower > 0) { r->separated = 1; r->dim = 0; r->dist = CCD_FLOAT_MAX; return; } }
-    else if (cutoff < CCD_FLOAT_MAX) { if (lower > 0 && lower >= cutoff * xnorm) { r->separated = 1; r->dim = 0; r->dist = CCD_FLOAT_MAX; return; } }
+    if (cutoff == 0) { if (lower > 0) { r->separated = 1; r->dim = 0; r->dist = CCD_FLOAT_MAX; r->cindex1 = g1->index; r->cindex2 = g2->index; return; } }
+    else if (cutoff < CCD_FLOAT_MAX) { if (lower > 0 && lower >= cutoff * xnorm) { r->separated = 1; r->dim = 0; r->dist = CCD_FLOAT_MAX; r->cindex1 = g1->index; r->cindex2 = g2->index; return; } }
     subdistance(n + 1, r->simplex, lmbda);
     n = 0;
     for (int i = 0; i < 4; i++) {
@@ -194,13 +237,14 @@ static void ccd_gjk(real tolerance, int iterations, const CGeom* g1, const CGeom
   r->separated = 0;
   if (n == 0) { v3cpy(r->x1, x1_0); v3cpy(r->x2, x2_0); } else { linear_combine(n, lmbda, r->simplex1, r->x1); linear_combine(n, lmbda, r->simplex2, r->x2); }
   if (xnorm > 0) {
-    real dir[3] = {x_k[0] / xnorm, x_k[1] / xnorm, x_k[2] / xnorm}, nd[3] = {-dir[0], -dir[1], -dir[2]}, p1[3], p2[3], dd[3]; int vi;
-    ccd_support(g1, nd, p1, &vi); ccd_support(g2, dir, p2, &vi);
+    real dir[3] = {x_k[0] / xnorm, x_k[1] / xnorm, x_k[2] / xnorm}, nd[3] = {-dir[0], -dir[1], -dir[2]}, p1[3], p2[3], dd[3]; int vi, ci;
+    ccd_support(g1, nd, p1, &vi, &ci); ccd_support(g2, dir, p2, &vi, &ci);
     v3sub(p1, p2, dd);
     r->separated = dot3(x_k, dd) > 0;
   }
   r->dist = (n == 4 && !r->separated) ? 0 : xnorm;
   r->dim = n;
+  r->cindex1 = g1->index; r->cindex2 = g2->index;
 }
 
 /* ---- EPA */
@@ -238,11 +282,12 @@ static real attach_face(Polytope* pt, int idx, int v1, int v2, int v3) {
   pt->face_norm2[idx] = dot3(r, r);
   return pt->face_norm2[idx];
 }
-static void epa_support(Polytope* pt, int idx, const CGeom* g1, const CGeom* g2, const real* dir) {
+static void epa_support_c(Polytope* pt, int idx, const CGeom* g1, const CGeom* g2, const real* dir, int* c1, int* c2) {
   real nd[3] = {-dir[0], -dir[1], -dir[2]};
-  ccd_support(g1, dir, pt->vert[2 * idx], &pt->vert_index[2 * idx]);
-  ccd_support(g2, nd, pt->vert[2 * idx + 1], &pt->vert_index[2 * idx + 1]);
+  ccd_support(g1, dir, pt->vert[2 * idx], &pt->vert_index[2 * idx], c1);
+  ccd_support(g2, nd, pt->vert[2 * idx + 1], &pt->vert_index[2 * idx + 1], c2);
 }
+static void epa_support(Polytope* pt, int idx, const CGeom* g1, const CGeom* g2, const real* dir) { int c1, c2; epa_support_c(pt, idx, g1, g2, dir, &c1, &c2); }
 static void replace_simplex3(const Polytope* pt, int v1, int v2, int v3, GjkResult* r) {
   int v[3] = {v1, v2, v3};
   for (int k = 0; k < 3; k++) {
@@ -341,7 +386,8 @@ static int add_edge(Polytope* pt, int e1, int e2) {
   return n + 1;
 }
 /* :1319; returns the index of the closest face (or -1) and writes the witness points / distance */
-static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1, const CGeom* g2, int discrete, real* dist, real* x1, real* x2, int* ovf) {
+static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1_in, const CGeom* g2_in, int discrete, real* dist, real* x1, real* x2, int* ovf) {
+  CGeom ga = *g1_in, gb = *g2_in, *g1 = &ga, *g2 = &gb; /* :1372-1373 the cached indices follow the expansion */
   real upper = CCD_FLOAT_MAX, upper2 = CCD_FLOAT_MAX, epsilon = discrete ? CCD_MIN_EPATOL : tolerance;
   int idx = -1, pidx = -1, nvalid = pt->nface;
   if (iterations > 1000) iterations = 1000;
@@ -355,7 +401,7 @@ static int ccd_epa(real tolerance, int iterations, Polytope* pt, const CGeom* g1
     int wi = pt->nvert;
     v3cpy(fp, pt->face_pr[idx]);
     for (int i = 0; i < 3; i++) dir[i] = fp[i] / lower;
-    epa_support(pt, wi, g1, g2, dir);
+    epa_support_c(pt, wi, g1, g2, dir, &g1->index, &g2->index);
     pt_mink(pt, wi, w);
     pt->nvert++;
     real upper_k = dot3(fp, w) / lower;
@@ -516,7 +562,9 @@ static void polygon_quad(real poly[][3], int np, int res[4]) { /* :1463 maximum-
 /* :1941 clip polygon face2 against the side planes of face1 (extruded along n); witness2 on the clipped polygon, witness1 = witness2 - dir */
 static int polygon_clip(real face1[][3], int nface1, real face2[][3], int nface2, const real* n, const real* dir, real w1[4][3], real w2[4][3]) {
   if (nface1 < 3) return 0;
-  real pn[4][3], pd[4], bufA[8][3], bufB[8][3];
+  real pn[CCD_MAXPOLY][3], pd[CCD_MAXPOLY], bufA[2 * CCD_MAXPOLY][3], bufB[2 * CCD_MAXPOLY][3];
+  const int cap = 2 * CCD_MAXPOLY; /* the reference sizes these buffers 2 x the model's largest polygon (collision_convex.py:1229-1236) */
+  if (nface1 > CCD_MAXPOLY || nface2 > cap) return 0;
   for (int i = 0; i < nface1; i++) { /* :1916 _plane_normal */
     const real *a = face1[i], *b = face1[(i + 1) % nface1];
     real ba[3], res[3]; v3sub(b, a, ba); cross3(ba, n, res);
@@ -531,17 +579,17 @@ static int polygon_clip(real face1[][3], int nface1, real face2[][3], int nface2
       real dP[3], dQ[3]; v3sub(P, face1[e], dP); v3sub(Q, face1[e], dQ);
       int in1 = dot3(dP, pn[e]) > (real)-1e-10, in2 = dot3(dQ, pn[e]) > (real)-1e-10;
       if (!in1 && !in2) continue;
-      if (in1 && in2) { if (nc < 8) v3cpy(clip[nc], Q); nc++; continue; }
+      if (in1 && in2) { if (nc < cap) v3cpy(clip[nc], Q); nc++; continue; }
       real pq[3]; v3sub(Q, P, pq);
       real dt = dot3(pn[e], pq), t = rabs(dt) < (real)1e-10 ? CCD_FLOAT_MAX : (pd[e] - dot3(pn[e], P)) / dt;
       if (t > -CCD_INTERSECT_TOL && t < 1 + CCD_INTERSECT_TOL) {
         t = rclamp(t, 0, 1);
-        if (nc < 8) for (int k = 0; k < 3; k++) clip[nc][k] = P[k] + t * pq[k];
+        if (nc < cap) for (int k = 0; k < 3; k++) clip[nc][k] = P[k] + t * pq[k];
         nc++;
       }
-      if (in2) { if (nc < 8) v3cpy(clip[nc], Q); nc++; }
+      if (in2) { if (nc < cap) v3cpy(clip[nc], Q); nc++; }
     }
-    if (nc > 8) nc = 8;
+    if (nc > cap) nc = cap;
     real (*tmp)[3] = poly; poly = clip; clip = tmp;
     np = nc; nc = 0;
   }
@@ -560,7 +608,69 @@ static int polygon_clip(real face1[][3], int nface1, real face2[][3], int nface2
   for (int i = 0; i < np; i++) { v3cpy(w2[i], poly[i]); v3sub(w2[i], dir, w1[i]); }
   return np;
 }
-/* :2076 (both geoms boxes); returns the contact count and overwrites the witness arrays */
+/* collision_gjk.py:1556-1581 common polygon ids of two vertices' polygon lists (at most two) */
+static int mesh_intersect(const int* a1, int n1, const int* a2, int n2, int res[2]) {
+  int count = 0;
+  for (int i = 0; i < n1; i++) for (int j = 0; j < n2; j++) if (a1[i] == a2[j]) { res[count++] = a1[i]; if (count == 2) return 2; }
+  return count;
+}
+/* :1585-1651 possible hull-polygon normals of a mesh feature given by up to three vertices */
+static int mesh_normals(int fdim, const int* fi, const CGeom* g, real nout[][3], int* iout) {
+  const int *m1 = g->polymap + g->polymapadr[fi[0]], n1 = g->polymapnum[fi[0]];
+  if (fdim == 3) {
+    int e[2], f[2];
+    int n = mesh_intersect(m1, n1, g->polymap + g->polymapadr[fi[1]], g->polymapnum[fi[1]], e);
+    if (n == 0) return 0;
+    n = mesh_intersect(e, n, g->polymap + g->polymapadr[fi[2]], g->polymapnum[fi[2]], f);
+    if (n == 0) return 0;
+    matvec3(g->rot, g->polynormal + 3 * f[0], nout[0]); iout[0] = f[0];
+    return 1;
+  }
+  if (fdim == 2) {
+    int e[2];
+    int n = mesh_intersect(m1, n1, g->polymap + g->polymapadr[fi[1]], g->polymapnum[fi[1]], e);
+    for (int i = 0; i < n; i++) { matvec3(g->rot, g->polynormal + 3 * e[i], nout[i]); iout[i] = e[i]; }
+    return n;
+  }
+  if (fdim == 1) {
+    int n = n1 < CCD_MAXDEG ? n1 : CCD_MAXDEG;
+    for (int i = 0; i < n; i++) { matvec3(g->rot, g->polynormal + 3 * m1[i], nout[i]); iout[i] = m1[i]; }
+    return n;
+  }
+  return 0;
+}
+/* :1656-1699 edge directions of a mesh feature: the edge itself, or the edges entering the vertex in each of its polygons */
+static int mesh_edge_normals(int dim, const CGeom* g, const real* v1, const real* v2, int v1i, real nout[][3], real endvert[][3]) {
+  if (dim == 2) { v3cpy(endvert[0], v2); v3sub(v2, v1, nout[0]); normalize3(nout[0]); return 1; }
+  if (dim == 1) {
+    const int *m1 = g->polymap + g->polymapadr[v1i];
+    int n = g->polymapnum[v1i] < CCD_MAXDEG ? g->polymapnum[v1i] : CCD_MAXDEG;
+    for (int i = 0; i < n; i++) {
+      const int adr = g->polyvertadr[m1[i]], nvert = g->polyvertnum[m1[i]];
+      for (int j = 0; j < nvert; j++)
+        if (g->polyvert[adr + j] == v1i) {
+          int k = j == 0 ? nvert - 1 : j - 1;
+          matvec3(g->rot, g->vert + 3 * g->polyvert[adr + k], endvert[i]);
+          for (int c = 0; c < 3; c++) endvert[i][c] += g->pos[c];
+          v3sub(endvert[i], v1, nout[i]); normalize3(nout[i]);
+        }
+    }
+    return n;
+  }
+  return 0;
+}
+/* :1891-1912 a hull polygon in world coordinates, vertex order reversed */
+static int mesh_face(const CGeom* g, int idx, real face[][3]) {
+  const int adr = g->polyvertadr[idx], nvert = g->polyvertnum[idx];
+  if (nvert > CCD_MAXPOLY) return 0;
+  int j = 0;
+  for (int i = nvert - 1; i >= 0; i--, j++) {
+    matvec3(g->rot, g->vert + 3 * g->polyvert[adr + i], face[j]);
+    for (int c = 0; c < 3; c++) face[j][c] += g->pos[c];
+  }
+  return nvert;
+}
+/* :2076 multicontact for box / mesh pairs; returns the contact count and overwrites the witness arrays */
 static int ccd_multicontact(const Polytope* pt, int epa_face_idx, const real* x1, const real* x2, const CGeom* g1, const CGeom* g2, real w1[4][3], real w2[4][3]) {
   memset(w1, 0, 12 * sizeof(real)); memset(w2, 0, 12 * sizeof(real));
   v3cpy(w1[0], x1); v3cpy(w2[0], x2);
@@ -568,30 +678,33 @@ static int ccd_multicontact(const Polytope* pt, int epa_face_idx, const real* x1
   int fi1[3], fi2[3]; real fv1[3][3], fv2[3][3];
   int nface1 = feature_dim(pt, face, 0, fi1, fv1), nface2 = feature_dim(pt, face, 1, fi2, fv2);
   real dir[3], dneg[3]; v3sub(x2, x1, dir); for (int i = 0; i < 3; i++) dneg[i] = -dir[i];
-  real n1[3][3], n2[3][3], endvert[3][3]; int idx1[3] = {0, 0, 0}, idx2[3] = {0, 0, 0};
-  memset(n1, 0, sizeof n1); memset(n2, 0, sizeof n2); memset(endvert, 0, sizeof endvert);
-  int nn1 = box_normals(nface1, fi1, g1->rot, dneg, n1, idx1), nn2 = box_normals(nface2, fi2, g2->rot, dir, n2, idx2);
+  static const int ND = CCD_MAXDEG > 3 ? CCD_MAXDEG : 3;
+  real n1[CCD_MAXDEG][3], n2[CCD_MAXDEG][3], endvert[CCD_MAXDEG][3]; int idx1[CCD_MAXDEG], idx2[CCD_MAXDEG];
+  (void)ND;
+  memset(n1, 0, sizeof n1); memset(n2, 0, sizeof n2); memset(endvert, 0, sizeof endvert); memset(idx1, 0, sizeof idx1); memset(idx2, 0, sizeof idx2);
+  int nn1 = g1->type == GEOM_BOX ? box_normals(nface1, fi1, g1->rot, dneg, n1, idx1) : mesh_normals(nface1, fi1, g1, n1, idx1);
+  int nn2 = g2->type == GEOM_BOX ? box_normals(nface2, fi2, g2->rot, dir, n2, idx2) : mesh_normals(nface2, fi2, g2, n2, idx2);
   int edge1 = 0, edge2 = 0, ri = 0, rj = 0, found = 0;
   for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (dot3(n1[i], n2[j]) < -CCD_FACE_TOL) { ri = i; rj = j; found = 1; break; }
   if (!found) {
     if (nface1 < 3 && nface1 <= nface2) {
-      nn1 = box_edge_normals(nface1, g1, fv1[0], fv1[1], fi1[0], n1, endvert);
+      nn1 = g1->type == GEOM_BOX ? box_edge_normals(nface1, g1, fv1[0], fv1[1], fi1[0], n1, endvert) : mesh_edge_normals(nface1, g1, fv1[0], fv1[1], fi1[0], n1, endvert);
       for (int i = 0; i < nn2 && !found; i++) for (int j = 0; j < nn1; j++) if (rabs(dot3(n1[j], n2[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = 1; break; }
       if (!found) return 1;
       edge1 = 1;
     } else if (nface2 < 3) {
-      nn2 = box_edge_normals(nface2, g2, fv2[0], fv2[1], fi2[0], n2, endvert);
+      nn2 = g2->type == GEOM_BOX ? box_edge_normals(nface2, g2, fv2[0], fv2[1], fi2[0], n2, endvert) : mesh_edge_normals(nface2, g2, fv2[0], fv2[1], fi2[0], n2, endvert);
       for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (rabs(dot3(n2[j], n1[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = 1; break; }
       if (!found) return 1;
       edge2 = 1;
     } else return 1;
   }
   int i = ri, j = rj;
-  real face1[4][3], face2[4][3];
+  real face1[CCD_MAXPOLY][3], face2[CCD_MAXPOLY][3];
   if (edge1) { v3cpy(face1[0], pt->vert[2 * face[0]]); v3cpy(face1[1], endvert[i]); nface1 = 2; }
-  else nface1 = box_face(g1, edge2 ? idx1[j] : idx1[i], face1);
+  else { int ind = edge2 ? idx1[j] : idx1[i]; nface1 = g1->type == GEOM_BOX ? box_face(g1, ind, face1) : mesh_face(g1, ind, face1); }
   if (edge2) { v3cpy(face2[0], pt->vert[2 * face[0] + 1]); v3cpy(face2[1], endvert[i]); nface2 = 2; }
-  else nface2 = box_face(g2, idx2[j], face2);
+  else nface2 = g2->type == GEOM_BOX ? box_face(g2, idx2[j], face2) : mesh_face(g2, idx2[j], face2);
   real dl = len3(dir), ad[3];
   if (edge1) { for (int k = 0; k < 3; k++) ad[k] = -dl * n2[j][k]; return polygon_clip(face2, nface2, face1, nface1, n2[j], ad, w2, w1); } /* faces flipped, flip the witnesses back */
   if (edge2) { for (int k = 0; k < 3; k++) ad[k] = -dl * n1[j][k]; return polygon_clip(face1, nface1, face2, nface2, n1[j], ad, w1, w2); }
@@ -603,7 +716,8 @@ static int ccd_multicontact(const Polytope* pt, int epa_face_idx, const real* x1
 static int ccd_pair(real tolerance, real cutoff, int gjk_iterations, int epa_iterations, int multi, CGeom g1, CGeom g2, real* dist, real w1[4][3], real w2[4][3], int* ovf) {
   const CGeom o1 = g1, o2 = g2;
   real full1 = 0, full2 = 0, size1 = 0, size2 = 0, *x1 = w1[0], *x2 = w2[0];
-  const int discrete = g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0 && g2.margin == 0; /* :109 _discrete_geoms */
+  const int disc1 = g1.type == GEOM_BOX || g1.type == GEOM_MESH, disc2 = g2.type == GEOM_BOX || g2.type == GEOM_MESH;
+  const int discrete = disc1 && disc2 && g1.margin == 0 && g2.margin == 0; /* :109 _discrete_geoms */
   GjkResult r;
   if (g1.type == GEOM_SPHERE || g1.type == GEOM_CAPSULE) { size1 = g1.size[0]; full1 = size1 + (real)0.5 * g1.margin; g1.margin = 0; g1.size[0] = 0; }
   if (g2.type == GEOM_SPHERE || g2.type == GEOM_CAPSULE) { size2 = g2.size[0]; full2 = size2 + (real)0.5 * g2.margin; g2.margin = 0; g2.size[0] = 0; }
@@ -619,10 +733,12 @@ static int ccd_pair(real tolerance, real cutoff, int gjk_iterations, int epa_ite
       *dist = r.dist - (full1 + full2);
       return 1;
     }
-    g1 = o1; g2 = o2;
+    g1 = o1; g2 = o2; /* margin and size back; the cached support indices stay (:2392-2403) */
+    g1.index = r.cindex1; g2.index = r.cindex2;
     cutoff -= full1 + full2;
   }
   ccd_gjk(tolerance, gjk_iterations, &g1, &g2, g1.pos, g2.pos, cutoff, discrete, &r);
+  g1.index = r.cindex1; g2.index = r.cindex2;
   if (r.dist > tolerance || r.dim < 2 || r.separated) { *dist = r.dist; v3cpy(x1, r.x1); v3cpy(x2, r.x2); return 1; }
   /* epa_phase */
   int maxvert = 10 + 2 * epa_iterations, maxface = 6 + CCD_MAX_EPAFACES * epa_iterations;
@@ -642,8 +758,10 @@ static int ccd_pair(real tolerance, real cutoff, int gjk_iterations, int epa_ite
     if (fidx == -1) { *dist = CCD_FLOAT_MAX; ncon = 0; }
     else {
       v3cpy(x1, e1); v3cpy(x2, e2);
-      /* multi-contact: boxes without margin only (epa_phase :2517-2525, collision_convex.py:875-912) */
-      if (multi && g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0 && g2.margin == 0) ncon = ccd_multicontact(&pt, fidx, e1, e2, &g1, &g2, w1, w2);
+      /* multi-contact: box / mesh pairs without margin (epa_phase :2517-2525, collision_convex.py:875-912); a mesh without polygon
+       * data is left at one contact */
+      const int mesh_ok = (g1.type != GEOM_MESH || g1.polynum > 0) && (g2.type != GEOM_MESH || g2.polynum > 0);
+      if (multi && disc1 && disc2 && mesh_ok && g1.margin == 0 && g2.margin == 0) ncon = ccd_multicontact(&pt, fidx, e1, e2, &g1, &g2, w1, w2);
     }
   }
   free(pt.vert); free(pt.vert_index); free(pt.face); free(pt.face_pr); free(pt.face_norm2);

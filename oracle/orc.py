@@ -121,7 +121,7 @@ def derived_tables(mjm):
   if getattr(mjm, "npair", 0):
     nmaxcondim = max(nmaxcondim, int(np.asarray(mjm.pair_dim).max()))
   # collision_convex.py:1209-1223: EPA gets 16 iterations when every convex pair of the model is box-box
-  convex = {(2, 4), (3, 4), (3, 5), (4, 4), (4, 5), (4, 6), (5, 5), (5, 6)}
+  convex = {(2, 4), (3, 4), (3, 5), (4, 4), (4, 5), (4, 6), (5, 5), (5, 6), (2, 7), (3, 7), (4, 7), (5, 7), (6, 7), (7, 7)}
   if not (int(mjm.opt.disableflags) & (1 << 17)):
     convex.add((6, 6))
   gt = np.asarray(mjm.geom_type)
@@ -236,6 +236,13 @@ class Oracle:
     for n in ("sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_reftype", "sensor_refid", "sensor_dim", "sensor_adr"):
       setia(n, getattr(mjm, n) if nsensor else np.zeros(1, dtype=np.int32))
     setra("sensor_cutoff", mjm.sensor_cutoff if nsensor else np.zeros(1))
+    nmesh = int(getattr(mjm, "nmesh", 0))
+    seti("nmesh", nmesh)
+    setia("geom_dataid", getattr(mjm, "geom_dataid", -np.ones(mjm.ngeom, dtype=np.int32)))
+    for n in ("mesh_vertadr", "mesh_vertnum", "mesh_graphadr", "mesh_graph", "mesh_polynum", "mesh_polyadr", "mesh_polyvertadr", "mesh_polyvertnum",
+              "mesh_polyvert", "mesh_polymapadr", "mesh_polymapnum", "mesh_polymap"):
+      setia(n, getattr(mjm, n) if nmesh and len(np.asarray(getattr(mjm, n))) else np.zeros(1, dtype=np.int32))
+    setra("mesh_vert", mjm.mesh_vert if nmesh else np.zeros(3)); setra("mesh_polynormal", mjm.mesh_polynormal if nmesh else np.zeros(3))
     nsite = int(getattr(mjm, "nsite", 0))
     setia("site_type", getattr(mjm, "site_type", 2 * np.ones(nsite, dtype=np.int32)) if nsite else np.zeros(1, dtype=np.int32))
     setra("site_size", getattr(mjm, "site_size", 0.005 * np.ones((nsite, 3))) if nsite else np.zeros(3))

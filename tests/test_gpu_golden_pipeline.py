@@ -21,7 +21,12 @@ def close(name, got, want, atol, rtol=0.0):
   util.assert_close(name, got, want, atol=atol, rtol=rtol)
 
 
-@pytest.mark.parametrize("name", SCENES)
+# mesh geoms: compiled by the host side and covered by the oracle; the CUDA collision kernel has no mesh support function yet and
+# put_model() rejects such models loudly (tests/test_host_logic.py), so the scene is an oracle-only golden for now
+GPU_SCENES = [s for s in SCENES if not s.startswith("mesh")]
+
+
+@pytest.mark.parametrize("name", GPU_SCENES)
 def test_gpu_matches_reference_pipeline(built, name):
   import mujoco_warp_b200 as mjw
 

@@ -39,6 +39,8 @@ def load_scene(name):
     mjm = mjcf.load_string(BOX_XML)
   elif name in ("boxccd", "boxccd_mixed"):
     mjm = mjcf.load_string(util.boxccd_xml(name.endswith("mixed")))
+  elif name == "mesh":
+    mjm = mjcf.load_string(util.mesh_xml())
   elif name == "sensors":
     mjm = mjcf.load_string(util.sensor_xml())
   elif name == "mixed_rk4":
@@ -144,7 +146,10 @@ def test_oracle_matches_reference_pipeline(built, name):
   # CG takes tens of iterations: rounding differences grow along the conjugate directions, so iteration counts can differ by
   # a few and the two (equally converged) answers agree to the solver tolerance rather than to rounding
   cg = name.endswith("cg")
-  compare("forward", g, o.d, mjm, nworld, 1e-9, solver_tol=5e-3 if cg else 1e-7, exact_iterations=not cg)
+  # mesh scene: cubes resting flat on cubes give four redundant contacts per face, whose force split is not unique -- the two sides agree
+  # on it to the solver tolerance, not to rounding (geometry, Jacobians and every other constraint field still match to 1e-9)
+  loose = cg or name == "mesh"
+  compare("forward", g, o.d, mjm, nworld, 1e-9, solver_tol=5e-3 if cg else (2e-4 if loose else 1e-7), exact_iterations=not loose)
   if cg:
     assert (np.abs(o.d["solver_niter"].reshape(-1) - g["forward/solver_niter"].reshape(-1)) <= 5).all()
   s = 0

@@ -301,3 +301,37 @@ def sensor_xml():
   </sensor>
 """
   return x.replace("  <actuator>", sensors + "  <actuator>")
+
+
+def mesh_xml():
+  """Mesh geoms (inline vertex data): a 7-vertex wedge (exhaustive support search) and a cube resting on the floor, a cube stacked
+  on a cube (mesh-mesh multi-contact), a 26-vertex blob (hull-graph hill climbing) on the floor, and sphere / capsule / box /
+  ellipsoid / cylinder bodies resting on meshes.  Oracle-only fixture for now: the CUDA collision kernels do not take meshes."""
+  rng = np.random.default_rng(5)
+  blob = rng.normal(size=(26, 3))
+  blob = blob / np.linalg.norm(blob, axis=1, keepdims=True) * np.array([0.12, 0.1, 0.07])
+  blob_s = " ".join(f"{x:.6f}" for x in blob.reshape(-1))
+  return f"""
+<mujoco>
+  <option timestep="0.002" iterations="50"/>
+  <asset>
+    <mesh name="wedge" vertex="0 0 0  1 0 0  0 1 0  0 0 1  1 1 0  0.3 0.3 0.1  1 1 1" scale="0.2 0.2 0.2"/>
+    <mesh name="cube" vertex="-1 -1 -1  1 -1 -1  -1 1 -1  1 1 -1  -1 -1 1  1 -1 1  -1 1 1  1 1 1" scale="0.1 0.08 0.05"/>
+    <mesh name="blob" vertex="{blob_s}"/>
+  </asset>
+  <default><geom friction="0.9 0.01 0.002" density="600"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05"/>
+    <body pos="0 0 0.09" euler="180 0 0"><freejoint/><geom name="wedge" type="mesh" mesh="wedge"/></body>
+    <body pos="0.05 0.03 0.215"><freejoint/><geom name="ball_on_wedge" type="sphere" size="0.05"/></body>
+    <body pos="0.6 0 0.049"><freejoint/><geom name="cube_a" type="mesh" mesh="cube"/></body>
+    <body pos="0.62 0.01 0.147" euler="0 0 25"><freejoint/><geom name="cube_b" type="mesh" mesh="cube"/></body>
+    <body pos="0.6 0 0.2445"><freejoint/><geom name="box_on_cube" type="box" size="0.04 0.04 0.05"/></body>
+    <body pos="-0.5 0.3 0.068"><freejoint/><geom name="blob" type="mesh" mesh="blob"/></body>
+    <body pos="-0.5 0.3 0.176"><freejoint/><geom name="cap_on_blob" type="capsule" size="0.04 0.05" euler="90 0 0"/></body>
+    <body pos="-0.5 -0.4 0.049"><freejoint/><geom name="cube_c" type="mesh" mesh="cube"/></body>
+    <body pos="-0.48 -0.4 0.137"><freejoint/><geom name="ell_on_cube" type="ellipsoid" size="0.06 0.05 0.04"/></body>
+    <body pos="0.1 -0.6 0.049"><freejoint/><geom name="cube_d" type="mesh" mesh="cube"/></body>
+    <body pos="0.1 -0.59 0.137" euler="90 0 0"><freejoint/><geom name="cyl_on_cube" type="cylinder" size="0.04 0.06"/></body>
+  </worldbody>
+</mujoco>"""

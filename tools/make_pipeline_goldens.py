@@ -66,6 +66,7 @@ def scenes():
   rk = util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"')
   yield "mixed_rk4", mjcf.load_string(rk), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
   yield "sensors", mjcf.load_string(util.sensor_xml()), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=0.3, ctrl_noise=1.5, exact_world0=False)
+  yield "mesh", mjcf.load_string(util.mesh_xml()), dict(nconmax=64, njmax=256, key=None, qpos_noise=0.0004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
   three = mjcf.load_any(util.THREE_HUMANOIDS)
   three.opt.jacobian = 1  # sparse: the reference does not run dense above nv = 60; snapshot() stores efc_J densified

@@ -187,9 +187,9 @@ def _build_warp():
     @functools.wraps(f)
     def by_value(*a, **k):
       g = f
-      if len(cands) > 1:
-        n = len(a) + len(k)
-        g = next((c for c in reversed(cands) if c.__code__.co_argcount == n), f)
+      n = len(a) + len(k)
+      if len(cands) > 1 and f.__code__.co_argcount != n:  # an overload with another arity; a same-named function whose arity fits is itself
+        g = next((c for c in reversed(cands) if c.__code__.co_argcount == n), f)  # (kernel builders redefine their nested functions per build)
       return g(*[_wp_copy(x) for x in a], **{n_: _wp_copy(x) for n_, x in k.items()})
 
     return by_value
