@@ -24,6 +24,25 @@
 #define CCD_FACE_TOL 0.99999872f       // cos(0.0016)
 #define CCD_EDGE_TOL 0.00159999931f    // sin(0.0016)
 #define CCD_INTERSECT_TOL 0.0000003f
+// CCD_MESH = 1 adds mesh geoms (hull-vertex support function with a cached start vertex, mesh multi-contact).  The product library is built
+// without it until the collision kernel carries the mesh tables; tests/host_harness builds this header with it on the host.
+#ifndef CCD_MESH
+#define CCD_MESH 0
+#endif
+#if CCD_MESH
+#define CCD_VSHIFT 16        // support-vertex ids of the two geoms packed in one word: mesh vertex ids need 16 bits each
+#define CCD_VMASK 0xFFFF
+#define CCD_MAXDEG 16        // hull polygons meeting at one mesh vertex (model nmeshdegmax)
+#define CCD_MAXPOLY 32       // vertices of one hull polygon (model npolygonmax)
+#define CCD_CLIPCAP (2 * CCD_MAXPOLY)
+#define CCD_FLOAT_MIN -1e30f
+#else
+#define CCD_VSHIFT 4         // box corner ids
+#define CCD_VMASK 15
+#define CCD_MAXDEG 3
+#define CCD_MAXPOLY 4
+#define CCD_CLIPCAP 8
+#endif
 
 // Geom-type pairs the reference routes to the convex path (collision_driver.py:47-81), analytic geoms only, in table order.
 // Box-box is convex unless the nativeccd disable flag routes it to the primitive box_box.
@@ -41,7 +60,20 @@ __host__ __device__ inline int convex_rank(int t1, int t2, bool nativeccd) {
   return -1;
 }
 
+#if CCD_MESH
+// mesh geoms carry their vertex block, hull graph (nullptr: exhaustive search) and hull polygon tables, already offset to the mesh
+// (collision_core.py Geom); index = cached support vertex (vertex id, or hull-local id for the hill climb; -1: none)
+struct CGeom {
+  v3 pos; const float* rot; v3 size; float margin; int type;
+  mutable int index; int vertnum, polynum;
+  const float *vert, *polynormal;
+  const int *graph, *polyvertadr, *polyvertnum, *polyvert, *polymapadr, *polymapnum, *polymap;
+};
+#define CCD_CACHE , true
+#else
 struct CGeom { v3 pos; const float* rot; v3 size; float margin; int type; };
+#define CCD_CACHE
+#endif
 struct GjkRes { bool separated; int dim; float dist; v3 x1, x2, s[4], s1[4], s2[4]; int vi[4]; };  // vi: box corner ids, geom1 | geom2 << 4
 // words of shared memory one lane's polytope needs: vertices (2 per support pair), faces, face projections, squared norms, horizon
 __host__ __device__ inline int ccd_scratch_words(int iterations) {
@@ -60,7 +92,46 @@ struct Polytope {
 
 __device__ __forceinline__ float csign(float x) { return x < 0.f ? -1.f : 1.f; }  // wp.sign(0) = +1
 
+#if CCD_MESH
+// :154-194 support vertex of a mesh in its own frame.  cache: remember the vertex for the geom's next query (GJK / EPA main loops)
+__device__ v3 mesh_support_local(const CGeom& g, v3 ld, int* vindex, bool cache) {
+  const int cached = g.index;
+  v3 res = mk3(0.f, 0.f, 0.f);
+  int cidx = -1, vid = -1;
+  float max_dist = CCD_FLOAT_MIN;
+  if (!g.graph || g.vertnum < 10) {
+    if (cached > -1) { cidx = cached; res = ld3(g.vert + 3 * cached); max_dist = dot(res, ld); }
+    for (int i = 0; i < g.vertnum; i++) {
+      const v3 p = ld3(g.vert + 3 * i);
+      const float dd = dot(p, ld);
+      if (dd > max_dist) { max_dist = dd; res = p; cidx = i; }
+    }
+    vid = cidx;
+  } else {
+    const int numvert = g.graph[0];
+    const int *vert_edgeadr = g.graph + 2, *vert_globalid = g.graph + 2 + numvert, *edge_localid = g.graph + 2 + 2 * numvert;
+    int prev = -1, imax = cached > -1 ? cached : 0;
+    max_dist = dot(ld, ld3(g.vert + 3 * vert_globalid[imax]));
+    while (imax != prev) {
+      prev = imax;
+      int i = vert_edgeadr[imax], subidx = edge_localid[i];
+      while (subidx >= 0) {
+        const float dd = dot(ld, ld3(g.vert + 3 * vert_globalid[subidx]));
+        if (dd > max_dist) { imax = subidx; max_dist = dd; }
+        i++; subidx = edge_localid[i];
+      }
+    }
+    cidx = imax; vid = vert_globalid[imax];
+    res = ld3(g.vert + 3 * vid);
+  }
+  if (vindex) *vindex = vid;
+  if (cache) g.index = cidx;
+  return res;
+}
+__device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr, bool cache = false) {
+#else
 __device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr) {
+#endif
   if (g.type == GEOM_SPHERE) return g.pos + dir * (g.size.x + 0.5f * g.margin);
   const v3 ld = mat_t_vec(g.rot, dir);
   v3 res = mk3(0.f, 0.f, 0.f);
@@ -75,6 +146,9 @@ __device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr) {
     if (d > CCD_MINVAL) { const float scl = g.size.x / d; res.x = ld.x * scl; res.y = ld.y * scl; }
     res.z = csign(ld.z) * g.size.y;
   }
+#if CCD_MESH
+  else if (g.type == GEOM_MESH) res = mesh_support_local(g, ld, vindex, cache);
+#endif
   v3 out = matvec(g.rot, res) + g.pos;
   if (g.margin > 0.f) out = out + dir * (0.5f * g.margin);
   return out;
@@ -185,9 +259,9 @@ __device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const 
       }
     }
     int i1 = 0, i2 = 0;
-    r.s1[n] = ccd_support(g1, dir_neg * -1.0f, &i1);
-    r.s2[n] = ccd_support(g2, dir_neg, &i2);
-    r.vi[n] = i1 | (i2 << 4);
+    r.s1[n] = ccd_support(g1, dir_neg * -1.0f, &i1 CCD_CACHE);
+    r.s2[n] = ccd_support(g2, dir_neg, &i2 CCD_CACHE);
+    r.vi[n] = i1 | (i2 << CCD_VSHIFT);
     r.s[n] = r.s1[n] - r.s2[n];
     if (dot(x_k, x_k - r.s[n]) < epsilon) break;
     const float lower = dot(x_k, r.s[n]);
@@ -253,8 +327,18 @@ __device__ void epa_support(Polytope& pt, int idx, const CGeom& g1, const CGeom&
   int i1 = 0, i2 = 0;
   st3(pt.vert + 6 * idx, ccd_support(g1, dir, &i1));
   st3(pt.vert + 6 * idx + 3, ccd_support(g2, dir * -1.0f, &i2));
-  pt.vidx[idx] = i1 | (i2 << 4);
+  pt.vidx[idx] = i1 | (i2 << CCD_VSHIFT);
 }
+#if CCD_MESH
+__device__ void epa_support_cached(Polytope& pt, int idx, const CGeom& g1, const CGeom& g2, v3 dir) {  // :1372-1373 the cached vertices follow the expansion
+  int i1 = 0, i2 = 0;
+  st3(pt.vert + 6 * idx, ccd_support(g1, dir, &i1, true));
+  st3(pt.vert + 6 * idx + 3, ccd_support(g2, dir * -1.0f, &i2, true));
+  pt.vidx[idx] = i1 | (i2 << CCD_VSHIFT);
+}
+#else
+#define epa_support_cached epa_support
+#endif
 __device__ void replace_simplex3(const Polytope& pt, int v1, int v2, int v3_, GjkRes& r) {
   const int v[3] = {v1, v2, v3_};
   for (int k = 0; k < 3; k++) { r.s1[k] = pt_v1(pt, v[k]); r.s2[k] = pt_v2(pt, v[k]); r.s[k] = r.s1[k] - r.s2[k]; r.vi[k] = pt.vidx[v[k]]; }
@@ -353,7 +437,7 @@ __device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeo
     const float lower = sqrtf(lower2);
     const int wi = pt.nvert;
     const v3 fp = ld3(pt.face_pr + 3 * idx);
-    epa_support(pt, wi, g1, g2, fp * (1.0f / lower));
+    epa_support_cached(pt, wi, g1, g2, fp * (1.0f / lower));
     const v3 w = pt_mink(pt, wi);
     pt.nvert++;
     const float upper_k = dot(fp, w) / lower;
@@ -408,8 +492,8 @@ __device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeo
 struct BoxFeat { int dim, idx[3]; v3 v0, v1; };
 __device__ BoxFeat feature_dim(const Polytope& pt, const int* face, int which) {
   BoxFeat f;
-  const int sh = which ? 4 : 0;
-  const int a = (pt.vidx[face[0]] >> sh) & 15, b = (pt.vidx[face[1]] >> sh) & 15, c = (pt.vidx[face[2]] >> sh) & 15;
+  const int sh = which ? CCD_VSHIFT : 0;
+  const int a = (pt.vidx[face[0]] >> sh) & CCD_VMASK, b = (pt.vidx[face[1]] >> sh) & CCD_VMASK, c = (pt.vidx[face[2]] >> sh) & CCD_VMASK;
   f.idx[0] = a; f.idx[1] = b; f.idx[2] = c;
   f.v0 = ld3(pt.vert + 6 * face[0] + 3 * which);
   f.v1 = ld3(pt.vert + 6 * face[1] + 3 * which);
@@ -514,7 +598,7 @@ __device__ void polygon_quad(const float* poly, int np, int* res) {  // :1463 ma
 __device__ int polygon_clip(const v3* face1, int nface1, const v3* face2, int nface2, v3 n, v3 dir, float* buf, v3* w1, v3* w2) {
   if (nface1 < 3) return 0;
   float* poly = buf;
-  float* clip = buf + 24;
+  float* clip = buf + 3 * CCD_CLIPCAP;
   int np = nface2, nc = 0;
   for (int i = 0; i < nface2; i++) st3(poly + 3 * i, face2[i]);
   for (int e = 0; e < nface1; e++) {
@@ -525,19 +609,19 @@ __device__ int polygon_clip(const v3* face1, int nface1, const v3* face2, int nf
       const v3 P = ld3(poly + 3 * i), Q = ld3(poly + 3 * ((i + 1) % np));
       const bool in1 = dot(P - a, pn) > -1e-10f, in2 = dot(Q - a, pn) > -1e-10f;
       if (!in1 && !in2) continue;
-      if (in1 && in2) { if (nc < 8) st3(clip + 3 * nc, Q); nc++; continue; }
+      if (in1 && in2) { if (nc < CCD_CLIPCAP) st3(clip + 3 * nc, Q); nc++; continue; }
       const v3 pq = Q - P;
       const float dt = dot(pn, pq);
       float t = fabsf(dt) < 1e-10f ? CCD_FLOAT_MAX : (pd - dot(pn, P)) / dt;
       if (t > -CCD_INTERSECT_TOL && t < 1.f + CCD_INTERSECT_TOL) {
         t = fminf(fmaxf(t, 0.f), 1.f);
-        if (nc < 8) st3(clip + 3 * nc, P + pq * t);
+        if (nc < CCD_CLIPCAP) st3(clip + 3 * nc, P + pq * t);
         nc++;
       }
-      if (in2) { if (nc < 8) st3(clip + 3 * nc, Q); nc++; }
+      if (in2) { if (nc < CCD_CLIPCAP) st3(clip + 3 * nc, Q); nc++; }
     }
     float* tmp = poly; poly = clip; clip = tmp;
-    np = min(nc, 8); nc = 0;
+    np = min(nc, CCD_CLIPCAP); nc = 0;
   }
   if (np < 1) return 0;
   if (nface2 == 2 && np > 2) {  // an edge: keep the two points farthest apart
@@ -560,7 +644,77 @@ __device__ int polygon_clip(const v3* face1, int nface1, const v3* face2, int nf
   for (int i = 0; i < np; i++) { w2[i] = ld3(poly + 3 * i); w1[i] = w2[i] - dir; }
   return np;
 }
-// :2076 for two boxes.  Overwrites the witness arrays (4 each) and returns the contact count; buf must not alias pt.vert / pt.vidx.
+#if CCD_MESH
+// :1556-1581 common polygon ids of two vertices' polygon lists (at most two)
+__device__ int mesh_intersect(const int* a1, int n1, const int* a2, int n2, int* res) {
+  int count = 0;
+  for (int i = 0; i < n1; i++) for (int j = 0; j < n2; j++) if (a1[i] == a2[j]) { res[count++] = a1[i]; if (count == 2) return 2; }
+  return count;
+}
+// :1585-1651 candidate hull-polygon normals of a mesh feature given by up to three vertices
+__device__ int mesh_normals(const BoxFeat& f, const CGeom& g, v3* nout, int* iout) {
+  const int* m1 = g.polymap + g.polymapadr[f.idx[0]];
+  const int n1 = g.polymapnum[f.idx[0]];
+  if (f.dim == 3) {
+    int e[2], ff[2];
+    int n = mesh_intersect(m1, n1, g.polymap + g.polymapadr[f.idx[1]], g.polymapnum[f.idx[1]], e);
+    if (n == 0) return 0;
+    n = mesh_intersect(e, n, g.polymap + g.polymapadr[f.idx[2]], g.polymapnum[f.idx[2]], ff);
+    if (n == 0) return 0;
+    nout[0] = matvec(g.rot, ld3(g.polynormal + 3 * ff[0])); iout[0] = ff[0];
+    return 1;
+  }
+  if (f.dim == 2) {
+    int e[2];
+    const int n = mesh_intersect(m1, n1, g.polymap + g.polymapadr[f.idx[1]], g.polymapnum[f.idx[1]], e);
+    for (int i = 0; i < n; i++) { nout[i] = matvec(g.rot, ld3(g.polynormal + 3 * e[i])); iout[i] = e[i]; }
+    return n;
+  }
+  if (f.dim == 1) {
+    const int n = min(n1, CCD_MAXDEG);
+    for (int i = 0; i < n; i++) { nout[i] = matvec(g.rot, ld3(g.polynormal + 3 * m1[i])); iout[i] = m1[i]; }
+    return n;
+  }
+  return 0;
+}
+// :1656-1699 edge directions of a mesh feature: the edge itself, or the edge entering the vertex in each of its polygons
+__device__ int mesh_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3* endvert) {
+  if (f.dim == 2) { endvert[0] = f.v1; nout[0] = normalize(f.v1 - f.v0); return 1; }
+  if (f.dim == 1) {
+    const int v1i = f.idx[0];
+    const int* m1 = g.polymap + g.polymapadr[v1i];
+    const int n = min(g.polymapnum[v1i], CCD_MAXDEG);
+    for (int i = 0; i < n; i++) {
+      const int adr = g.polyvertadr[m1[i]], nvert = g.polyvertnum[m1[i]];
+      for (int j = 0; j < nvert; j++)
+        if (g.polyvert[adr + j] == v1i) {
+          const int k = j == 0 ? nvert - 1 : j - 1;
+          endvert[i] = matvec(g.rot, ld3(g.vert + 3 * g.polyvert[adr + k])) + g.pos;
+          nout[i] = normalize(endvert[i] - f.v0);
+        }
+    }
+    return n;
+  }
+  return 0;
+}
+// :1891-1912 a hull polygon in world coordinates, vertex order reversed
+__device__ int mesh_face(const CGeom& g, int idx, v3* face) {
+  const int adr = g.polyvertadr[idx], nvert = g.polyvertnum[idx];
+  if (nvert > CCD_MAXPOLY) return 0;
+  int j = 0;
+  for (int i = nvert - 1; i >= 0; i--, j++) face[j] = matvec(g.rot, ld3(g.vert + 3 * g.polyvert[adr + i])) + g.pos;
+  return nvert;
+}
+#define CCD_NORMALS(f, g, dir, n, idx) ((g).type == GEOM_BOX ? box_normals(f, (g).rot, dir, n, idx) : mesh_normals(f, g, n, idx))
+#define CCD_EDGE_NORMALS(f, g, n, ev) ((g).type == GEOM_BOX ? box_edge_normals(f, g, n, ev) : mesh_edge_normals(f, g, n, ev))
+#define CCD_FACE(g, idx, face) ((g).type == GEOM_BOX ? box_face(g, idx, face) : mesh_face(g, idx, face))
+#else
+#define CCD_NORMALS(f, g, dir, n, idx) box_normals(f, (g).rot, dir, n, idx)
+#define CCD_EDGE_NORMALS(f, g, n, ev) box_edge_normals(f, g, n, ev)
+#define CCD_FACE(g, idx, face) box_face(g, idx, face)
+#endif
+// :2076 for two boxes (CCD_MESH: boxes and meshes).  Overwrites the witness arrays (4 each) and returns the contact count; buf must not alias
+// pt.vert / pt.vidx.
 __device__ int ccd_multicontact(const Polytope& pt, int epa_face, const CGeom& g1, const CGeom& g2, float* buf, v3* w1, v3* w2) {
   const v3 x1 = w1[0], x2 = w2[0];
   for (int k = 1; k < 4; k++) w1[k] = w2[k] = mk3(0.f, 0.f, 0.f);
@@ -569,30 +723,35 @@ __device__ int ccd_multicontact(const Polytope& pt, int epa_face, const CGeom& g
   const BoxFeat f1 = feature_dim(pt, face, 0), f2 = feature_dim(pt, face, 1);
   const v3 ev1 = ld3(pt.vert + 6 * face[0]), ev2 = ld3(pt.vert + 6 * face[0] + 3);
   const v3 dir = x2 - x1;
-  v3 n1[3], n2[3], endvert[3];
+  v3 n1[CCD_MAXDEG], n2[CCD_MAXDEG], endvert[CCD_MAXDEG];
+#if CCD_MESH
+  int idx1[CCD_MAXDEG], idx2[CCD_MAXDEG];
+  for (int k = 0; k < CCD_MAXDEG; k++) idx1[k] = idx2[k] = 0;
+#else
   int idx1[3] = {0, 0, 0}, idx2[3] = {0, 0, 0};
-  for (int k = 0; k < 3; k++) n1[k] = n2[k] = endvert[k] = mk3(0.f, 0.f, 0.f);
-  int nn1 = box_normals(f1, g1.rot, dir * -1.0f, n1, idx1), nn2 = box_normals(f2, g2.rot, dir, n2, idx2);
+#endif
+  for (int k = 0; k < CCD_MAXDEG; k++) n1[k] = n2[k] = endvert[k] = mk3(0.f, 0.f, 0.f);
+  int nn1 = CCD_NORMALS(f1, g1, dir * -1.0f, n1, idx1), nn2 = CCD_NORMALS(f2, g2, dir, n2, idx2);
   bool edge1 = false, edge2 = false, found = false;
   int ri = 0, rj = 0;
   for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (dot(n1[i], n2[j]) < -CCD_FACE_TOL) { ri = i; rj = j; found = true; break; }
   if (!found) {
     if (f1.dim < 3 && f1.dim <= f2.dim) {  // edge of geom1 against a face of geom2
-      nn1 = box_edge_normals(f1, g1, n1, endvert);
+      nn1 = CCD_EDGE_NORMALS(f1, g1, n1, endvert);
       for (int i = 0; i < nn2 && !found; i++) for (int j = 0; j < nn1; j++) if (fabsf(dot(n1[j], n2[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = true; break; }
       if (!found) return 1;
       edge1 = true;
     } else if (f2.dim < 3) {  // face of geom1 against an edge of geom2
-      nn2 = box_edge_normals(f2, g2, n2, endvert);
+      nn2 = CCD_EDGE_NORMALS(f2, g2, n2, endvert);
       for (int i = 0; i < nn1 && !found; i++) for (int j = 0; j < nn2; j++) if (fabsf(dot(n2[j], n1[i])) < CCD_EDGE_TOL) { ri = j; rj = i; found = true; break; }
       if (!found) return 1;
       edge2 = true;
     } else return 1;
   }
-  v3 face1[4], face2[4];
+  v3 face1[CCD_MAXPOLY], face2[CCD_MAXPOLY];
   int nface1, nface2;
-  if (edge1) { face1[0] = ev1; face1[1] = endvert[ri]; nface1 = 2; } else nface1 = box_face(g1, edge2 ? idx1[rj] : idx1[ri], face1);
-  if (edge2) { face2[0] = ev2; face2[1] = endvert[ri]; nface2 = 2; } else nface2 = box_face(g2, idx2[rj], face2);
+  if (edge1) { face1[0] = ev1; face1[1] = endvert[ri]; nface1 = 2; } else nface1 = CCD_FACE(g1, edge2 ? idx1[rj] : idx1[ri], face1);
+  if (edge2) { face2[0] = ev2; face2[1] = endvert[ri]; nface2 = 2; } else nface2 = CCD_FACE(g2, idx2[rj], face2);
   const float dl = length(dir);
   if (edge1) return polygon_clip(face2, nface2, face1, nface1, n2[rj], n2[rj] * -dl, buf, w2, w1);  // roles flipped, witnesses flipped back
   if (edge2) return polygon_clip(face1, nface1, face2, nface2, n1[rj], n1[rj] * -dl, buf, w1, w2);
@@ -604,7 +763,12 @@ __device__ int ccd_multicontact(const Polytope& pt, int epa_face, const CGeom& g
 __device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iterations, int epa_iterations, CGeom g1, CGeom g2, float* scratch, float* dist, v3* w1, v3* w2, bool* ovf) {
   const CGeom o1 = g1, o2 = g2;
   float full1 = 0.f, full2 = 0.f, size1 = 0.f, size2 = 0.f;
+#if CCD_MESH
+  const bool disc1 = g1.type == GEOM_BOX || g1.type == GEOM_MESH, disc2 = g2.type == GEOM_BOX || g2.type == GEOM_MESH;
+  const bool boxes = disc1 && disc2 && g1.margin == 0.f && g2.margin == 0.f;  // :109 _discrete_geoms
+#else
   const bool boxes = g1.type == GEOM_BOX && g2.type == GEOM_BOX && g1.margin == 0.f && g2.margin == 0.f;  // :109 _discrete_geoms
+#endif
   GjkRes r;
   if (g1.type == GEOM_SPHERE || g1.type == GEOM_CAPSULE) { size1 = g1.size.x; full1 = size1 + 0.5f * g1.margin; g1.margin = 0.f; g1.size.x = 0.f; }
   if (g2.type == GEOM_SPHERE || g2.type == GEOM_CAPSULE) { size2 = g2.size.x; full2 = size2 + 0.5f * g2.margin; g2.margin = 0.f; g2.size.x = 0.f; }
@@ -620,7 +784,11 @@ __device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iter
       *dist = r.dist - (full1 + full2);
       return 1;
     }
+#if CCD_MESH
+    { const int c1 = g1.index, c2 = g2.index; g1 = o1; g2 = o2; g1.index = c1; g2.index = c2; }  // :2392-2403 the cached support vertices stay
+#else
     g1 = o1; g2 = o2;
+#endif
     cutoff -= full1 + full2;
   }
   ccd_gjk(tolerance, gjk_iterations, g1, g2, cutoff, boxes, r);
@@ -641,6 +809,13 @@ __device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iter
   if (pt.status) { *dist = r.dist; w1[0] = r.x1; w2[0] = r.x2; return 1; }
   const int fidx = ccd_epa(tolerance, epa_iterations, pt, g1, g2, boxes, dist, &w1[0], &w2[0], ovf);
   if (fidx == -1) { *dist = CCD_FLOAT_MAX; return 0; }
+#if CCD_MESH
+  if (boxes && (g1.type != GEOM_MESH || g1.polynum > 0) && (g2.type != GEOM_MESH || g2.polynum > 0)) {  // a mesh without polygon data keeps one contact
+    float clipbuf[2 * 3 * CCD_CLIPCAP];
+    return ccd_multicontact(pt, fidx, g1, g2, clipbuf, w1, w2);
+  }
+#else
   if (boxes) return ccd_multicontact(pt, fidx, g1, g2, pt.face_pr, w1, w2);  // face_pr (>= 108 words) is free once EPA is done
+#endif
   return 1;
 }

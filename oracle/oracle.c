@@ -1321,6 +1321,33 @@ int orc_ccd(int type1, const real* size1, const real* pos1, const real* mat1, in
   return n;
 }
 
+/* Same, with the geoms given by descriptor so that mesh geoms (vertex block, hull graph, polygon tables -- already offset to the mesh the way
+ * fill_cgeom does it) can be passed; separate GJK / EPA iteration counts. */
+typedef struct {
+  int type, vertnum, polynum, pad;
+  const real *size, *pos, *mat, *vert, *polynormal;
+  const int *graph, *polyvertadr, *polyvertnum, *polyvert, *polymapadr, *polymapnum, *polymap;
+} OrcGeomDesc;
+static void desc_cgeom(const OrcGeomDesc* d, real margin, CGeom* c) {
+  memset(c, 0, sizeof *c);
+  memcpy(c->pos, d->pos, sizeof c->pos); memcpy(c->rot, d->mat, sizeof c->rot); memcpy(c->size, d->size, sizeof c->size);
+  c->type = d->type; c->margin = margin; c->index = -1;
+  c->vertnum = d->vertnum; c->polynum = d->polynum; c->vert = d->vert; c->polynormal = d->polynormal; c->graph = d->graph;
+  c->polyvertadr = d->polyvertadr; c->polyvertnum = d->polyvertnum; c->polyvert = d->polyvert;
+  c->polymapadr = d->polymapadr; c->polymapnum = d->polymapnum; c->polymap = d->polymap;
+}
+int orc_ccd_desc(const OrcGeomDesc* d1, const OrcGeomDesc* d2, real margin, real tolerance, real cutoff, int gjk_iterations, int epa_iterations, int multi,
+                 real* dist, real* w1, real* w2, int* overflow) {
+  CGeom a, b;
+  desc_cgeom(d1, margin, &a); desc_cgeom(d2, margin, &b);
+  real x1[4][3], x2[4][3]; int ovf = 0;
+  memset(x1, 0, sizeof x1); memset(x2, 0, sizeof x2);
+  int n = ccd_pair(tolerance, cutoff, gjk_iterations, epa_iterations, multi, a, b, dist, x1, x2, &ovf);
+  memcpy(w1, x1, sizeof x1); memcpy(w2, x2, sizeof x2);
+  *overflow = ovf;
+  return n;
+}
+
 static real pc_support(const real* ppl, const real* v, const real* n) { real d[3]; v3sub(ppl, v, d); return dot3(d, n); }
 /* collision_primitive.py:52-277 plane_convex: up to four well-spread vertices of the convex geom that lie (nearly) deepest below the plane */
 static void plane_convex(const real* n_world, const real* plane_pos, const CGeom* c, real dist[4], real pos[4][3]) {

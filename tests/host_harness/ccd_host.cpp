@@ -28,6 +28,9 @@ extern "C" int hccd_pair(int type1, const float* size1, const float* pos1, const
   memset(&a, 0, sizeof a); memset(&b, 0, sizeof b);
   a.pos = ld3(pos1); a.rot = mat1; a.size = ld3(size1); a.margin = margin; a.type = type1;
   b.pos = ld3(pos2); b.rot = mat2; b.size = ld3(size2); b.margin = margin; b.type = type2;
+#if CCD_MESH
+  a.index = b.index = -1;
+#endif
   const int it = std::max(gjk_iterations, epa_iterations);
   float* scratch = new float[ccd_scratch_words(it) + 64]();
   v3 x1[4], x2[4];
@@ -39,3 +42,35 @@ extern "C" int hccd_pair(int type1, const float* size1, const float* pos1, const
   delete[] scratch;
   return n;
 }
+
+#if CCD_MESH
+// descriptor entry, same layout as the oracle's OrcGeomDesc / orc_ccd_desc (fp32): mesh tables already offset to the geom's mesh
+struct HGeomDesc {
+  int type, vertnum, polynum, pad;
+  const float *size, *pos, *mat, *vert, *polynormal;
+  const int *graph, *polyvertadr, *polyvertnum, *polyvert, *polymapadr, *polymapnum, *polymap;
+};
+static CGeom from_desc(const HGeomDesc* d, float margin) {
+  CGeom c;
+  memset(&c, 0, sizeof c);
+  c.pos = ld3(d->pos); c.rot = d->mat; c.size = ld3(d->size); c.margin = margin; c.type = d->type;
+  c.index = -1; c.vertnum = d->vertnum; c.polynum = d->polynum; c.vert = d->vert; c.polynormal = d->polynormal; c.graph = d->graph;
+  c.polyvertadr = d->polyvertadr; c.polyvertnum = d->polyvertnum; c.polyvert = d->polyvert;
+  c.polymapadr = d->polymapadr; c.polymapnum = d->polymapnum; c.polymap = d->polymap;
+  return c;
+}
+extern "C" int hccd_desc(const HGeomDesc* d1, const HGeomDesc* d2, float margin, float tolerance, float cutoff, int gjk_iterations, int epa_iterations,
+                         float* dist, float* w1, float* w2, int* overflow) {
+  const CGeom a = from_desc(d1, margin), b = from_desc(d2, margin);
+  const int it = std::max(gjk_iterations, epa_iterations);
+  float* scratch = new float[ccd_scratch_words(it) + 64]();
+  v3 x1[4], x2[4];
+  memset(x1, 0, sizeof x1); memset(x2, 0, sizeof x2);
+  bool ovf = false;
+  const int n = ccd_pair(tolerance, cutoff, gjk_iterations, epa_iterations, a, b, scratch, dist, x1, x2, &ovf);
+  for (int k = 0; k < 4; k++) { st3(w1 + 3 * k, x1[k]); st3(w2 + 3 * k, x2[k]); }
+  *overflow = ovf ? 1 : 0;
+  delete[] scratch;
+  return n;
+}
+#endif
