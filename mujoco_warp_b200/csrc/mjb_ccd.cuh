@@ -819,3 +819,96 @@ __device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iter
 #endif
   return 1;
 }
+
+#if CCD_MESH
+// collision_primitive.py:52-277 plane_convex for a mesh: up to four well-spread hull vertices that lie (nearly) deepest below the plane.
+// pass 0: deepest vertex a; 1: farthest from a; 2: farthest from the line a-b; 3: farthest from the triangle's other two edges -- candidates
+// restricted to vertices within 1e-3 of the deepest.  Exhaustive over the vertex block, or hill climbing on the hull graph.
+#define PM_HUGE 1e6f
+__device__ __forceinline__ float pm_support(v3 ppl, v3 v, v3 n) { return dot(ppl - v, n); }
+__device__ __forceinline__ float pm_score(int pass, v3 v, v3 a, v3 b, v3 ab, v3 ac, v3 bc, float sup, float threshold) {
+  const float mask = sup > threshold ? 0.f : -PM_HUGE;
+  if (pass == 1) { const v3 df = a - v; return dot(df, df) + mask; }
+  if (pass == 2) return fabsf(dot(a - v, ab)) + mask;
+  return (fabsf(dot(a - v, ac)) + mask) + (fabsf(dot(b - v, bc)) + mask);
+}
+__device__ int plane_mesh(v3 n_world, v3 plane_pos, const CGeom& c, float* dist, v3* pos) {
+  int idx[4] = {-1, -1, -1, -1};
+  for (int i = 0; i < 4; i++) { dist[i] = MJ_MAXVAL; pos[i] = mk3(0.f, 0.f, 0.f); }
+  const v3 ppl = mat_t_vec(c.rot, plane_pos - c.pos), n = mat_t_vec(c.rot, n_world);
+  v3 a = mk3(0.f, 0.f, 0.f), b = a, cc = a, ab = a, ac = a, bc = a;
+  if (!c.graph || c.vertnum < 10) {
+    float max_support = -PM_HUGE;
+    for (int i = 0; i < c.vertnum; i++) { const v3 v = ld3(c.vert + 3 * i); const float s = pm_support(ppl, v, n); if (s > max_support) { max_support = s; idx[0] = i; a = v; } }
+    if (max_support < 0.f) return 0;
+    const float threshold = max_support - 1e-3f;
+    for (int pass = 1; pass < 4; pass++) {
+      float best = -PM_HUGE;
+      v3 pick = mk3(0.f, 0.f, 0.f);
+      for (int i = 0; i < c.vertnum; i++) {
+        const v3 v = ld3(c.vert + 3 * i);
+        const float dd = pm_score(pass, v, a, b, ab, ac, bc, pm_support(ppl, v, n), threshold);
+        if (dd > best) { idx[pass] = i; best = dd; pick = v; }
+      }
+      if (pass == 1) { b = pick; ab = cross(n, a - b); }
+      else if (pass == 2) { cc = pick; ac = cross(n, a - cc); bc = cross(n, b - cc); }
+    }
+  } else {
+    const int numvert = c.graph[0];
+    const int *vert_edgeadr = c.graph + 2, *vert_globalid = c.graph + 2 + numvert, *edge_localid = c.graph + 2 + 2 * numvert;
+    float max_support = -PM_HUGE;
+    int prev, imax = 0;
+    for (;;) {  // hill climb to the deepest vertex
+      prev = imax;
+      for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) {
+        const int sub = edge_localid[i];
+        const float s = pm_support(ppl, ld3(c.vert + 3 * vert_globalid[sub]), n);
+        if (s > max_support) { max_support = s; imax = sub; }
+      }
+      if (imax == prev) break;
+    }
+    const float threshold = fmaxf(0.f, max_support - 1e-3f);
+    float best = -PM_HUGE;
+    for (;;) {
+      prev = imax;
+      for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) {
+        const int sub = edge_localid[i];
+        const float s = pm_support(ppl, ld3(c.vert + 3 * vert_globalid[sub]), n);
+        const float dd = s > threshold ? s : -PM_HUGE;
+        if (dd > best) { best = dd; imax = sub; }
+      }
+      if (imax == prev) break;
+    }
+    a = ld3(c.vert + 3 * vert_globalid[imax]); idx[0] = vert_globalid[imax];
+    for (int pass = 1; pass < 4; pass++) {
+      best = -PM_HUGE;
+      for (;;) {
+        prev = imax;
+        for (int i = vert_edgeadr[imax]; edge_localid[i] >= 0; i++) {
+          const int sub = edge_localid[i];
+          const v3 v = ld3(c.vert + 3 * vert_globalid[sub]);
+          const float dd = pm_score(pass, v, a, b, ab, ac, bc, pm_support(ppl, v, n), threshold);
+          if (dd > best) { best = dd; imax = sub; }
+        }
+        if (imax == prev) break;
+      }
+      idx[pass] = vert_globalid[imax];
+      const v3 pick = ld3(c.vert + 3 * vert_globalid[imax]);
+      if (pass == 1) { b = pick; ab = cross(n, a - b); }
+      else if (pass == 2) { cc = pick; ac = cross(n, a - cc); bc = cross(n, b - cc); }
+    }
+  }
+  int count = 0;
+  for (int i = 3; i >= 0; i--) {  // unique vertices, last first
+    int uniq = 0;
+    for (int j = 0; j <= i; j++) if (idx[j] == idx[i]) uniq++;
+    if (uniq != 1) continue;
+    const v3 v = ld3(c.vert + 3 * idx[i]);
+    const float dd = -pm_support(ppl, v, n);
+    pos[count] = c.pos + matvec(c.rot, v) - n_world * (0.5f * dd);
+    dist[count] = dd;
+    count++;
+  }
+  return count;
+}
+#endif

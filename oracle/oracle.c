@@ -1449,6 +1449,14 @@ static void plane_convex(const real* n_world, const real* plane_pos, const CGeom
 #undef PC_SUPPORT
 }
 
+/* plane_convex on a described geom (tests of the device routine on the host) */
+void orc_plane_convex_desc(const real* n_world, const real* plane_pos, const OrcGeomDesc* d, real* dist, real* pos) {
+  CGeom c; desc_cgeom(d, 0, &c);
+  real d4[4], p4[4][3];
+  plane_convex(n_world, plane_pos, &c, d4, p4);
+  memcpy(dist, d4, sizeof d4); memcpy(pos, p4, sizeof p4);
+}
+
 static void narrowphase_pair(W* w, int g1, int g2, int pairid) {
   const OrcModel* m = w->m;
   int t1 = m->geom_type[g1], t2 = m->geom_type[g2];

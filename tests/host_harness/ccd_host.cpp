@@ -73,4 +73,10 @@ extern "C" int hccd_desc(const HGeomDesc* d1, const HGeomDesc* d2, float margin,
   delete[] scratch;
   return n;
 }
+extern "C" void hplane_mesh(const float* n_world, const float* plane_pos, const HGeomDesc* d, float* dist, float* pos) {
+  const CGeom c = from_desc(d, 0.f);
+  v3 p4[4];
+  plane_mesh(ld3(n_world), ld3(plane_pos), c, dist, p4);
+  for (int k = 0; k < 4; k++) st3(pos + 3 * k, p4[k]);
+}
 #endif

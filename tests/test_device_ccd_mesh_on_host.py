@@ -194,3 +194,46 @@ def test_mesh_build_compiles_for_sm_100a(tmp_path):
   r = subprocess.run([nvcc, "-c", "-gencode", "arch=compute_100a,code=sm_100a", "-Xptxas", "-v", "-o", str(tmp_path / "check.o"), src], capture_output=True, text=True)
   assert r.returncode == 0, r.stderr[-2000:]
   assert "k_ccd_mesh_pairs" in r.stderr and "0 bytes spill stores" in r.stderr
+
+
+def test_plane_mesh_matches_oracle(hlib, model):
+  """plane_convex for mesh geoms (exhaustive and hull-graph variants): same vertices picked, same depths / positions as the oracle."""
+  mjm = model
+  types = np.asarray(mjm.geom_type)
+  rng = np.random.default_rng(3)
+  hlib.hplane_mesh.restype = None
+  hlib.hplane_mesh.argtypes = [V, V, V, V, V]
+  ncontact = nfour = 0
+  for g in [g for g in range(mjm.ngeom) if types[g] == GEOM_MESH]:
+    for trial in range(40):
+      # half the trials rest a face / edge nearly flat on the plane (several vertices within the 1e-3 band), the others are random tilts
+      mat = rand_rot(rng) if trial % 2 else np.eye(3).reshape(-1)
+      if trial % 4 == 0:
+        mat = np.array([[1, 0, 0], [0, -1, 0], [0, 0, -1]], dtype=np.float64).reshape(-1)
+      pos = np.array([0.0, 0.0, rng.uniform(-0.02, 0.06)])
+      n_world, plane_pos = np.array([0.0, 0.0, 1.0]), np.zeros(3)
+      res = {}
+      for tag, real in (("dev", np.float32), ("o32", np.float32), ("o64", np.float64)):
+        d, keep = make_desc(mjm, g, pos, mat, real)
+        dist = np.zeros(4, real); p4 = np.zeros((4, 3), real)
+        nw, pp = np.ascontiguousarray(n_world.astype(real)), np.ascontiguousarray(plane_pos.astype(real))
+        P = lambda a: a.ctypes.data_as(V)
+        if tag == "dev":
+          hlib.hplane_mesh(P(nw), P(pp), ctypes.byref(d), P(dist), P(p4))
+        else:
+          lib = orc._lib(np.dtype(real).itemsize)
+          lib.orc_plane_convex_desc.restype = None
+          lib.orc_plane_convex_desc.argtypes = [V, V, V, V, V]
+          lib.orc_plane_convex_desc(P(nw), P(pp), ctypes.byref(d), P(dist), P(p4))
+        res[tag] = (dist.astype(np.float64), p4.astype(np.float64))
+      dd, dp = res["dev"]
+      ok = False
+      for tag in ("o64", "o32"):  # near-ties between vertices in the band can resolve differently in fp32 and fp64
+        od, op = res[tag]
+        if np.array_equal(dd < 1e9, od < 1e9) and np.allclose(dd[dd < 1e9], od[od < 1e9], atol=2e-6) and np.allclose(dp, op, atol=2e-6):
+          ok = True
+      assert ok, (g, trial, res)
+      ncontact += int((dd < 1e9).sum() > 0)
+      nfour += int((dd < 1e9).sum() == 4)
+  print("plane-mesh trials with contacts:", ncontact, "with four:", nfour)
+  assert ncontact >= 60 and nfour >= 10
