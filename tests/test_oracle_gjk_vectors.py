@@ -1,7 +1,7 @@
 """The reference's own known-answer tests for the convex path (collision_gjk_test.py:307-1002), transcribed as data:
 geoms, poses and the expected distance / contact count / witness points are the reference's; the harness calls the oracle's
-convex pair routine the way `_geom_dist` (collision_gjk_test.py:35-303) calls `ccd` + `multicontact`.  Mesh and height-field
-cases are left out (no mesh geoms in this build).  `tests/test_gpu_gjk_vectors.py` runs the penetrating cases on the GPU."""
+convex pair routine the way `_geom_dist` (collision_gjk_test.py:35-303) calls `ccd` + `multicontact`.  The mesh cases live in
+tests/test_mesh_gjk_vectors.py; height-field cases are left out (no height fields in this build).  `tests/test_gpu_gjk_vectors.py` runs the penetrating cases on the GPU."""
 import numpy as np
 import pytest
 
