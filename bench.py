@@ -39,6 +39,7 @@ def parse():
   p.add_argument("--nworld", type=int, default=8192, help="worlds per GPU")
   p.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
   p.add_argument("--cpu-sample-worlds", type=int, default=8192)
+  p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel A/B sweeps)")
   return p.parse_args()
 
 
@@ -207,6 +208,7 @@ def run_ours(args):
   stream = torch.cuda.Stream()
   graph = None
   step_idx = [0]
+  initial = {n: getattr(d, n).clone() for n in ("qpos", "qvel", "ctrl", "qacc_warmstart", "time", "qacc")}
 
   def one_step():
     mjw.ctrl_noise(m, d, step_idx[0] + world_offset, center)
@@ -226,18 +228,33 @@ def run_ours(args):
       with torch.cuda.graph(g, stream=stream):
         mjw.step(m, d)
       graph = g
-    # nvidia-smi needs a few hundred ms before its first row: start it ahead of the warm-up and keep the same load running until it
-    # reports, so that samples exist before, during and after the (short) timed region
+    # The simulated state inside the timed window is deterministic: the state is put back to the keyframe after graph capture,
+    # advanced by exactly `warmup` steps, snapshotted, and restored right before the timed region.  nvidia-smi needs a few hundred
+    # ms before its first row, so the same load keeps running (on the live state) until it reports; those extra steps are undone
+    # by the restore.
+    def snapshot():
+      return {n: getattr(d, n).clone() for n in ("qpos", "qvel", "ctrl", "qacc_warmstart", "time", "qacc")}
+
+    def restore(snap):
+      for n, v in snap.items():
+        getattr(d, n).copy_(v)
+
+    restore(initial)
+    step_idx[0] = 0
     sampler = ClockSampler(local)
     if rank == 0:
       sampler.start()
     for _ in range(args.warmup):
       one_step()
     stream.synchronize()
+    snap, snap_idx = snapshot(), step_idx[0]
     t_wait = time.perf_counter() + 3.0
     while rank == 0 and sampler.proc is not None and len(sampler.rows) < 1 and time.perf_counter() < t_wait:
       one_step()
       stream.synchronize()
+    restore(snap)
+    step_idx[0] = snap_idx
+    sim_steps_before_timed = snap_idx
 
     # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
     barrier()
@@ -250,18 +267,19 @@ def run_ours(args):
     stream.synchronize()
     barrier()
     ms = e0.elapsed_time(e1)
-    n_rows, t_wait = len(sampler.rows), time.perf_counter() + 1.0
-    while rank == 0 and sampler.proc is not None and len(sampler.rows) <= n_rows and time.perf_counter() < t_wait:
-      one_step()  # same load, untimed, until one more 100 ms sample lands after the timed region
-      stream.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- statistics of the run (untimed)
+    # ---- statistics of the run (untimed), taken from the last timed step
     ncon_mean = float(d.nacon.cpu()[0]) / nworld
     nefc_mean = float(d.nefc.float().mean().cpu())
     niter_mean = float(d.solver_niter.float().mean().cpu())
     ovf = int((d.overflow != 0).sum().cpu())
     nan_worlds = int(torch.isnan(d.qpos).any(dim=1).sum().cpu())
+    n_rows, t_wait = len(sampler.rows), time.perf_counter() + 1.0
+    while rank == 0 and sampler.proc is not None and len(sampler.rows) <= n_rows and time.perf_counter() < t_wait:
+      one_step()  # same load, untimed, until one more 100 ms sample lands after the timed region
+      stream.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    restore(snap)  # the per-kernel pass and the e2e loop below start from the same state as the timed region
+    step_idx[0] = snap_idx
 
     # ---- per-kernel durations (separate pass with event pairs around each kernel)
     nprof = 20
@@ -322,7 +340,7 @@ def run_ours(args):
       pass
     step_bytes = 4.0 * sum(words.values()) * nworld
     cpu = None
-    if world == 1:  # reported baseline, rank 0 at N = 1 only: a bounded sample of the same workload on the host cores
+    if world == 1 and not args.no_cpu:  # reported baseline, rank 0 at N = 1 only: a bounded sample of the same workload on the host cores
       cores = usable_cores()
       cpu_steps = 50
       rate, dt = cpu_run(mjm, args.cpu_sample_worlds, cpu_steps, cores)
@@ -336,7 +354,7 @@ def run_ours(args):
         "workload": f"humanoid.xml nworld={nworld}/GPU nconmax={NCONMAX} njmax={NJMAX} keyframe=squat Newton/pyramidal/Euler, OU ctrl noise (Halton)",
         "cuda_graph": graph is not None, "l2": "per-step Data working set (~175 MB at 8192 worlds incl. efc.J rows) exceeds the 126 MB L2; no explicit flush",
         "vs_baseline_note": "2,729,192 steps/s is the reference's only published number (benchmarks/README.md:48), hardware unstated",
-        "ncon_mean": ncon_mean, "nefc_mean": nefc_mean, "solver_niter_mean": niter_mean, "overflow_worlds": ovf, "nan_worlds": nan_worlds,
+        "sim_steps_before_timed": sim_steps_before_timed, "ncon_mean": ncon_mean, "nefc_mean": nefc_mean, "solver_niter_mean": niter_mean, "overflow_worlds": ovf, "nan_worlds": nan_worlds,
       },
       "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(nworld * mjm.nu * 4), "d2h_bytes_per_step": int(nworld * (mjm.nq + mjm.nv) * 4), "steps": e2e_steps},
       "gpu_launches": launches_per_step * args.steps,

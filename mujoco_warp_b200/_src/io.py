@@ -11,6 +11,8 @@ symmetric gather tables for M*v, per-tree factor offsets, filtered NXN pairs, li
 
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -433,7 +435,66 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     _lib.check(L.mjb_model_set_array(h, n.encode(), x.data_ptr(), 1))
   _lib.check(L.mjb_model_finalize(h))
   m._keep = keep
+  weakref.finalize(m, L.mjb_model_destroy, h)
+  _install_model_rebind(m, L, set(dev_names) - {"jnt_limited_adr", "nxn_geom_pair", "nxn_pairid", "body_isdofancestor"}, set(ints))
   return m
+
+
+_OPT_FLOATS = {"timestep": "timestep", "tolerance": "tolerance", "ls_tolerance": "ls_tolerance", "impratio_invsqrt": "impratio_invsqrt", "ccd_tolerance": "ccd_tolerance"}
+_OPT_INTS = ("integrator", "cone", "solver", "iterations", "ls_iterations", "disableflags", "enableflags", "broadphase", "broadphase_filter", "ccd_iterations")
+
+
+def _check_like(name, new, old):
+  if not isinstance(new, torch.Tensor):
+    raise TypeError(f"{name}: expected a torch.Tensor like the bound one ({tuple(old.shape)}, {old.dtype}), got {type(new).__name__}; use .copy_() to write values")
+  if new.shape != old.shape or new.dtype != old.dtype or new.device != old.device:
+    raise ValueError(f"{name}: replacement must match the bound tensor: shape {tuple(old.shape)} {old.dtype} on {old.device}, got {tuple(new.shape)} {new.dtype} on {new.device}")
+  return new.contiguous()
+
+
+def _install_model_rebind(m: types.Model, L, arrays, ints):
+  """Assignments to bound Model / Option / Statistic fields reach the C handle (they used to be silent no-ops)."""
+  h = m._handle
+
+  def model_hook(name, value):
+    if name in arrays and name in m.__dict__:
+      value = _check_like("Model." + name, value, m.__dict__[name])
+      x = _ptr_tensor(value)
+      m._keep.append(x)
+      _lib.check(L.mjb_model_set_array(h, name.encode(), x.data_ptr(), 1))
+    elif name in ints and name in m.__dict__ and isinstance(m.__dict__[name], int):
+      raise AttributeError(f"Model.{name} is a compiled size / table constant and cannot be reassigned; build a new Model with put_model")
+    return value
+
+  def opt_hook(name, value):
+    if name in _OPT_FLOATS:
+      v = float(value.reshape(-1)[0]) if isinstance(value, torch.Tensor) else float(value)
+      if name == "tolerance":
+        v = max(v, 1e-6)
+      _lib.check(L.mjb_model_set_float(h, _OPT_FLOATS[name].encode(), v))
+      return torch.full((1,), v, dtype=torch.float32, device=m.opt.__dict__[name].device) if not isinstance(value, torch.Tensor) else value
+    if name == "gravity":
+      g = value.reshape(-1)[:3].tolist() if isinstance(value, torch.Tensor) else [float(x) for x in value]
+      for k, v in zip(("gravity_x", "gravity_y", "gravity_z"), g):
+        _lib.check(L.mjb_model_set_float(h, k.encode(), float(v)))
+      return value if isinstance(value, torch.Tensor) else torch.tensor([g], dtype=torch.float32, device=m.opt.__dict__["gravity"].device)
+    if name in _OPT_INTS:
+      if name == "integrator" and int(value) not in (C.INT_EULER, C.INT_IMPLICITFAST, C.INT_RK4):
+        raise NotImplementedError(f"integrator {value} not implemented")
+      if name in ("integrator", "cone", "solver") and int(value) != int(m.opt.__dict__[name]):
+        raise NotImplementedError(f"opt.{name} selects kernel instantiations and scratch sizes fixed at put_model / make_data; rebuild the Model to change it")
+      _lib.check(L.mjb_model_set_int(h, name.encode(), int(value)))
+    return value
+
+  def stat_hook(name, value):
+    if name == "meaninertia":
+      v = float(value.reshape(-1)[0]) if isinstance(value, torch.Tensor) else float(value)
+      _lib.check(L.mjb_model_set_float(h, b"meaninertia", v))
+    return value
+
+  object.__setattr__(m, "_rebind", model_hook)
+  object.__setattr__(m.opt, "_rebind", opt_hook)
+  object.__setattr__(m.stat, "_rebind", stat_hook)
 
 
 # --------------------------------------------------------------------------------------------- Data
@@ -583,6 +644,22 @@ def _bind(m: types.Model, d: types.Data, L):
   for n in _BOUND_CONTACT:
     reg("contact_" + n, getattr(d.contact, n))
   _lib.check(L.mjb_data_finalize(h, m._handle))
+  weakref.finalize(d, L.mjb_data_destroy, h)
+
+  def make_hook(struct, prefix, names):
+    def hook(name, value):
+      if name in names and name in struct.__dict__:
+        value = _check_like(f"{type(struct).__name__}.{name}", value, struct.__dict__[name])
+        x = _ptr_tensor(value)
+        d._keep.append(x)
+        _lib.check(L.mjb_data_set_array(h, (prefix + name).encode(), x.data_ptr()))
+      return value
+
+    return hook
+
+  object.__setattr__(d, "_rebind", make_hook(d, "", set(_BOUND_TOP)))
+  object.__setattr__(d.efc, "_rebind", make_hook(d.efc, "efc_", set(_BOUND_EFC)))
+  object.__setattr__(d.contact, "_rebind", make_hook(d.contact, "contact_", set(_BOUND_CONTACT)))
 
 
 def put_data(mjm, mjd, nworld: int = 1, nconmax=None, nccdmax=None, njmax=None, njmax_nnz=None, naconmax=None, naccdmax=None, nvmax=None, m: types.Model = None) -> types.Data:

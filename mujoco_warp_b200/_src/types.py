@@ -181,10 +181,23 @@ class ContactType(enum.IntFlag):
 
 
 class _Struct:
-  """Attribute bag with a stable field listing (stands in for the reference's dataclasses)."""
+  """Attribute bag with a stable field listing (stands in for the reference's dataclasses).
+
+  The C handle holds raw device pointers / scalar options, so once a struct is bound (io.put_model / io._bind install
+  `_rebind`) assigning a field re-registers the new pointer or scalar with the handle after validating shape, dtype and
+  device -- `d.qpos = t`, `m.opt.timestep = 0.002`, `m.geom_friction = t` take effect on the next launch exactly like the
+  reference, whose kernels read the dataclass fields at launch time.  (A captured CUDA graph keeps the old pointers, the
+  same hazard the reference has.)
+  """
 
   def __init__(self, **kw):
     self.__dict__.update(kw)
+
+  def __setattr__(self, name, value):
+    hook = self.__dict__.get("_rebind")
+    if hook is not None and not name.startswith("_"):
+      value = hook(name, value)
+    object.__setattr__(self, name, value)
 
   def fields(self):
     return [k for k in self.__dict__ if not k.startswith("_")]

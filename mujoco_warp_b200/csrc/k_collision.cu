@@ -15,6 +15,8 @@
 // pool layout (types.py:1975-2018) so [0, nacon) is densely packed.
 #include "mjb_ccd.cuh"
 #include "mjb_colliders.cuh"
+#include <cstdlib>
+
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
 
@@ -137,12 +139,12 @@ __device__ void contact_params(const ModelDev& m, int g1, int g2, int pairid, Co
 // MAXC = contacts one geom pair can produce: 2 for plane/sphere/capsule-only models (everything stays in registers),
 // 8 once boxes, cylinders or ellipsoids are present.
 template <int MAXC>
-__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(64, MAXC == 2 ? 16 : 8)
 k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x + d.w0;
-  if (w >= d.nworld) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // every warp of the block owns one world (its own shared-memory slice)
+  const int w = blockIdx.x * (blockDim.x >> 5) + warp + d.w0;
+  if (w >= d.nworld || w >= d.w0 + d.wn) return;
   const ColLayout L = col_layout(m, d);
   float* S = smem + warp * L.total;
   float *gxpos = S + L.gxpos, *gxmat = S + L.gxmat, *stage = S + L.stage;
@@ -451,7 +453,14 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
 
 }  // namespace
 
-size_t smem_collision(const ModelDev& m, const DataDev& d) { return (size_t)col_layout(m, d).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+// warps (= worlds) per block: one-warp blocks cap an SM at 32 resident worlds (CTA limit); MJB_WPB_COL overrides
+static int collision_wpb() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("MJB_WPB_COL"); v = e ? atoi(e) : 2; if (v < 1 || v > 2) v = 2; }
+  return v;
+}
+
+size_t smem_collision(const ModelDev& m, const DataDev& d) { return (size_t)col_layout(m, d).total * sizeof(float) * collision_wpb(); }
 
 cudaError_t reset_contact_counters(const DataDev& d, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(d.nacon, 0, sizeof(int), s);
@@ -470,8 +479,8 @@ cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s
     if (e != cudaSuccess) return e;
     configured[full] = smem;
   }
-  const int grid = d.wn;
-  if (full) k_collision<8><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
-  else k_collision<2><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  const int grid = (d.wn + collision_wpb() - 1) / collision_wpb();
+  if (full) k_collision<8><<<grid, collision_wpb() * 32, smem, s>>>(m, d);
+  else k_collision<2><<<grid, collision_wpb() * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

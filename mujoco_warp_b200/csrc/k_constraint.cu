@@ -11,6 +11,8 @@
 // atomics-dependent; its own tests sort before comparing, constraint_test.py:40-59).  Lanes map to dofs: a J row is a
 // single coalesced store, J*qvel is a warp-shuffle reduction, and the per-row impedance/reference math runs on the lane
 // whose index equals the row's dimension id.
+#include <cstdlib>
+
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
 
@@ -102,12 +104,12 @@ __device__ __forceinline__ v3 warp_sum3v(v3 a) { return mk3(warp_sum(a.x), warp_
 // EQ = the model has equality constraints or limited ball joints; plain articulated models (humanoid) use the leaner
 // instantiation without that code.
 template <bool EQ>
-__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32, 28)
+__global__ void __launch_bounds__(64, EQ ? 12 : 16)
 k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x + d.w0;
-  if (w >= d.nworld) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // every warp of the block owns one world (its own shared-memory slice)
+  const int w = blockIdx.x * (blockDim.x >> 5) + warp + d.w0;
+  if (w >= d.nworld || w >= d.w0 + d.wn) return;
   const ConLayout L = con_layout(m, d);
   float* S = smem + warp * L.total;
   float *cdof = S + L.cdof, *scom = S + L.scom, *qvel = S + L.qvel, *rec = S + L.rec;
@@ -426,7 +428,14 @@ k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
 
 }  // namespace
 
-size_t smem_constraint(const ModelDev& m, const DataDev& d) { return (size_t)con_layout(m, d).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+// warps (= worlds) per block: one-warp blocks cap an SM at 32 resident worlds (CTA limit); MJB_WPB_CON overrides
+static int constraint_wpb() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("MJB_WPB_CON"); v = e ? atoi(e) : 2; if (v < 1 || v > 2) v = 2; }
+  return v;
+}
+
+size_t smem_constraint(const ModelDev& m, const DataDev& d) { return (size_t)con_layout(m, d).total * sizeof(float) * constraint_wpb(); }
 
 cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_constraint(m, d);
@@ -438,7 +447,7 @@ cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t 
     if (e != cudaSuccess) return e;
     configured[eq] = smem;
   }
-  const int grid = d.wn;
-  kern<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  const int grid = (d.wn + constraint_wpb() - 1) / constraint_wpb();
+  kern<<<grid, constraint_wpb() * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

@@ -158,6 +158,50 @@ __device__ __forceinline__ void next_position_jnt(const ModelDev& m, int j, cons
   }
 }
 
+// Plain Euler without the implicit-damping solve (eulerdamp disabled or no dampers: the benchmark humanoid): nothing couples
+// the dofs, so the stage is an elementwise pass -- one THREAD per (world, joint) advances the joint's velocities, warm start
+// and position (forward.py:276-349 _advance); consecutive threads touch consecutive addresses, no shared memory, and the
+// grid is sized by joints instead of worlds.  k_euler (one warp per world) remains for the factor-and-solve variants.
+__global__ void __launch_bounds__(256)
+k_euler_flat(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wl = idx / m.njnt, j = idx - wl * m.njnt;
+  if (wl >= d.wn) return;
+  const int w = wl + d.w0;
+  if (w >= d.nworld) return;
+  const size_t wb = (size_t)w;
+  const float dt = m.timestep;
+  const int t = m.jnt_type[j], qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+  const int nd = t == JNT_FREE ? 6 : (t == JNT_BALL ? 3 : 1);
+  float v[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    if (k < nd) {
+      const float a = d.qacc[wb * m.nv + da + k];
+      v[k] = d.qvel[wb * m.nv + da + k] + a * dt;
+      d.qvel[wb * m.nv + da + k] = v[k];
+      d.qacc_warmstart[wb * m.nv + da + k] = a;  // warmstart <- solver qacc (forward.py:343)
+    }
+  }
+  float* qpos = d.qpos + wb * m.nq;
+  if (t == JNT_FREE) {
+    for (int k = 0; k < 3; k++) qpos[qa + k] += dt * v[k];
+    stq(qpos + qa + 3, quat_integrate(ldq(qpos + qa + 3), mk3(v[3], v[4], v[5]), dt));
+  } else if (t == JNT_BALL) {
+    stq(qpos + qa, quat_integrate(ldq(qpos + qa), mk3(v[0], v[1], v[2]), dt));
+  } else {
+    qpos[qa] += dt * v[0];
+  }
+  if (j == 0) {  // _next_time (forward.py:221-271)
+    d.time[w] += dt;
+    int ovf = 0;
+    if (d.nefc[w] > d.njmax) ovf |= OVF_NEFC;
+    if (d.ncollision[0] > d.naconmax) ovf |= OVF_BROADPHASE;
+    if (d.nacon[0] > d.naconmax) ovf |= OVF_NARROWPHASE;
+    if (ovf) d.overflow[w] |= ovf;
+  }
+}
+
 // One Runge-Kutta bookkeeping step after the stage-th forward() of the step (forward.py:523-555 rungekutta4, stateless
 // actuators): accumulate B[stage] * (qvel, qacc); stages 0..2 then perturb the state for the next forward
 // (_rk_perturb_state: position from the current stage velocity, velocity from qvel_t0 + A dt qacc); stage 3 restores the
@@ -205,6 +249,12 @@ k_rk_stage(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 size_t smem_integrate(const ModelDev& m) { return (size_t)int_words(m) * sizeof(float) * MJB_WARPS_PER_BLOCK; }
 
 cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s) {
+  const bool solve = m.integrator == INT_IMPLICITFAST || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
+  if (!solve && m.njnt > 0) {
+    const long n = (long)d.wn * m.njnt;
+    k_euler_flat<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, d);
+    return cudaGetLastError();
+  }
   const size_t smem = smem_integrate(m);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {

@@ -7,57 +7,96 @@
 // parents gather their children in fixed order (deterministic; no float atomics), and every Data field is written
 // once with coalesced row stores.  `mask` selects sub-stages so each public stage function stays individually callable;
 // inputs a skipped sub-stage would have produced are re-loaded from Data.
+#include <cstdlib>
+
 #include "mjb_math.cuh"
+#include "mjb_team.cuh"
 #include "mjb_types.cuh"
 
 namespace {
 
 struct PosLayout {
-  int qpos, xpos, xquat, xmat, xipos, ximat, xanchor, xaxis, gxpos, gxmat, scom, cinert, crb, cdof, buf, M, total;
+  int qpos, xpos, xquat, xipos, xanchor, xaxis, scom, cinert, cdof, buf, arena, a_gxmat, total;
 };
 
+// Per-world words of shared memory.  Only what later phases read stays resident (body poses, joint anchors / axes, subtree
+// com, cinert -> crb in place, cdof); pure outputs (xmat, ximat, geom poses, M) pass one after the other through one arena
+// that is reused once the bulk store that read it has drained; qpos sits in the arena until the tree pass is done, and the
+// crb * cdof scratch takes the place of the body / joint poses once those have left.  3.8 KB per humanoid world: an SM holds
+// its 55 worlds at once.  That is what the kernel time hangs on -- it is latency bound (ncu: one instruction issued per ~13
+// cycles per warp, long-scoreboard stalls on dependent table lookups), so time ~ rounds of resident worlds x per-warp chain.
+__host__ __device__ inline int pad4(int n) { return (n + 3) & ~3; }
 __host__ __device__ inline PosLayout pos_layout(const ModelDev& m) {
   PosLayout L;
   int o = 0;
-  auto take = [&](int n) { int r = o; o += n; return r; };
-  L.qpos = take(m.nq);
-  L.xpos = take(3 * m.nbody); L.xquat = take(4 * m.nbody); L.xmat = take(9 * m.nbody);
-  L.xipos = take(3 * m.nbody); L.ximat = take(9 * m.nbody);
+  auto take = [&](int n) { int r = o; o += pad4(n); return r; };  // padded: a field's group block [G][n] starts 16 B aligned
+  L.xpos = take(3 * m.nbody); L.xquat = take(4 * m.nbody); L.xipos = take(3 * m.nbody);
   L.xanchor = take(3 * m.njnt); L.xaxis = take(3 * m.njnt);
-  L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom);
-  L.scom = take(3 * m.nbody); L.cinert = take(10 * m.nbody); L.crb = take(10 * m.nbody);
-  L.cdof = take(6 * m.nv); L.M = take(m.nC);
-  // crb*cdof scratch (6 nv) reuses the geom_xmat staging area, which is dead once kinematics has been written out
-  L.buf = L.gxmat;
-  if (6 * m.nv > 9 * m.ngeom) L.buf = take(6 * m.nv);
-  L.total = (o + 3) & ~3;
+  L.buf = L.xpos;
+  if (o < pad4(6 * m.nv)) o = pad4(6 * m.nv);
+  L.scom = take(3 * m.nbody); L.cinert = take(10 * m.nbody); L.cdof = take(6 * m.nv);
+  // arena uses, in time order: qpos (tree pass, transmission), xmat, ximat, [geom_xpos | geom_xmat], M
+  L.a_gxmat = pad4(3 * m.ngeom);
+  int a = pad4(9 * m.nbody);
+  if (L.a_gxmat + pad4(9 * m.ngeom) > a) a = L.a_gxmat + pad4(9 * m.ngeom);
+  if (pad4(m.nC) > a) a = pad4(m.nC);
+  if (pad4(m.nq) > a) a = pad4(m.nq);
+  L.arena = take(a);
+  L.qpos = L.arena;
+  L.total = o;
   return L;
 }
 
-__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
+// LPW lanes per world, G = 32 / LPW worlds per warp (one warp per block).  Shared layout of field f: [G][n_f] at S + L.f * G.
+template <int LPW>
+__global__ void __launch_bounds__(256)
 k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x + d.w0;
-  if (w >= d.nworld) return;
+  extern __shared__ __align__(16) float smem[];
+  constexpr int G = 32 / LPW;
+  Team<LPW> T;
+  T.init(d.w0, d.wn, d.nworld);
+  if (T.nvalid <= 0) return;
+  const int lane = T.lane, sub = T.sub, g = T.g, nval = T.nvalid;
+  const bool valid = T.valid;
   const PosLayout L = pos_layout(m);
-  float* S = smem + warp * L.total;
-  float *qpos = S + L.qpos, *xpos = S + L.xpos, *xquat = S + L.xquat, *xmat = S + L.xmat, *xipos = S + L.xipos,
-        *ximat = S + L.ximat, *xanchor = S + L.xanchor, *xaxis = S + L.xaxis, *gxpos = S + L.gxpos, *gxmat = S + L.gxmat,
-        *scom = S + L.scom, *cinert = S + L.cinert, *crb = S + L.crb, *cdof = S + L.cdof, *buf = S + L.buf, *Ms = S + L.M;
+  float* S = smem + (size_t)(threadIdx.x >> 5) * ((size_t)L.total * G + 4);  // this warp's slice (+ its mbarrier)
+  Stager st;
+  st.init(reinterpret_cast<uint64_t*>(S + (size_t)L.total * G), lane);
   const int nb = m.nbody, nj = m.njnt, ng = m.ngeom, nv = m.nv;
-  const size_t wb = (size_t)w;
+  // block (all G worlds) and this team's row of a resident field / of an arena slot at per-world offset `off`
+#define BLK(f) (S + (size_t)L.f * G)
+#define ABLK(off) (S + (size_t)(L.arena + (off)) * G)
+#define ROW(blk, n) ((blk) + (size_t)g * (n))
+  float *qpos = ROW(BLK(qpos), m.nq), *xpos = ROW(BLK(xpos), 3 * nb), *xquat = ROW(BLK(xquat), 4 * nb), *xipos = ROW(BLK(xipos), 3 * nb),
+        *xanchor = ROW(BLK(xanchor), 3 * nj), *xaxis = ROW(BLK(xaxis), 3 * nj), *scom = ROW(BLK(scom), 3 * nb), *cinert = ROW(BLK(cinert), 10 * nb),
+        *cdof = ROW(BLK(cdof), 6 * nv);
+  float *xmat = ROW(ABLK(0), 9 * nb), *ximat = ROW(ABLK(0), 9 * nb), *gxpos = ROW(ABLK(0), 3 * ng), *gxmat = ROW(ABLK(L.a_gxmat), 9 * ng),
+        *buf = ROW(BLK(buf), 6 * nv), *Ms = ROW(ABLK(0), m.nC);
+  float* crb = cinert;  // accumulated in place once cinert has been stored
+  // the G worlds' rows of a Data field are one contiguous block in global memory
+  const size_t wg = (size_t)T.wg0;
+#define GLOAD(blk, field, n) st.load(blk, d.field + wg * (size_t)(n), nval * (n))
+#define GSTORE(field, blk, n) st.store(d.field + wg * (size_t)(n), blk, nval * (n))
+  const size_t wb = (size_t)T.w;
+  const bool kin = mask & STG_KINEMATICS, com = mask & STG_COM_POS, cam = mask & STG_CAMLIGHT, crbm = mask & STG_CRB;
 
-  warp_copy(qpos, d.qpos + wb * m.nq, m.nq, lane);
+  // ------------------------------------------------------------------ inputs
+  if (mask & (STG_KINEMATICS | STG_TRANSMISSION)) GLOAD(BLK(qpos), qpos, m.nq);
+  if (!kin && (com || cam)) {  // a skipped kinematics stage: its outputs come from Data
+    GLOAD(BLK(xpos), xpos, 3 * nb); GLOAD(BLK(xquat), xquat, 4 * nb); GLOAD(BLK(xipos), xipos, 3 * nb);
+    GLOAD(BLK(xanchor), xanchor, 3 * nj); GLOAD(BLK(xaxis), xaxis, 3 * nj);
+  }
+  if (!com && (cam || crbm)) { GLOAD(BLK(scom), subtree_com, 3 * nb); GLOAD(BLK(cinert), cinert, 10 * nb); GLOAD(BLK(cdof), cdof, 6 * nv); }
+  st.load_wait();
 
-  // ------------------------------------------------------------------ kinematics
-  if (mask & STG_KINEMATICS) {
-    if (lane == 0) { xpos[0] = xpos[1] = xpos[2] = 0.f; xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f; }
+  // ------------------------------------------------------------------ kinematics: tree pass (smooth.py:46-145)
+  if (kin) {
+    if (sub == 0) { xpos[0] = xpos[1] = xpos[2] = 0.f; xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f; }
     __syncwarp();
 #pragma unroll 1
     for (int l = 1; l < m.nlevel; l++) {
 #pragma unroll 1
-      for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
+      for (int i = m.level_adr[l] + sub; i < m.level_adr[l + 1]; i += LPW) {
         const int b = m.level_body[i], pid = m.body_parentid[b], jntadr = m.body_jntadr[b], jntnum = m.body_jntnum[b];
         if (jntnum == 1 && m.jnt_type[jntadr] == JNT_FREE) {
           const int qa = m.jnt_qposadr[jntadr];
@@ -94,27 +133,35 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
+  }
+
+  // ------------------------------------------------------------------ transmission (joint transmission; smooth.py:2288-2396)
+  if (mask & STG_TRANSMISSION) {
 #pragma unroll 1
-    for (int b = lane; b < nb; b += 32) {
+    for (int a = valid ? sub : m.nu; a < m.nu; a += LPW) {
+      const int j = m.actuator_trnid[2 * a], t = m.jnt_type[j], adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a];
+      const float* gear = m.actuator_gear + 6 * a;
+      d.actuator_length[wb * m.nu + a] = (t == JNT_SLIDE || t == JNT_HINGE) ? qpos[m.jnt_qposadr[j]] * gear[0] : 0.f;
+      d.moment_rownnz[wb * m.nu + a] = nnz;
+      d.moment_rowadr[wb * m.nu + a] = adr;
+#pragma unroll 1
+      for (int k = 0; k < nnz; k++) {
+        d.moment_colind[wb * m.nJmom + adr + k] = m.moment_colind0[adr + k];
+        d.actuator_moment[wb * m.nJmom + adr + k] = gear[k];
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ kinematics: per-body frames, sites
+  if (kin) {
+#pragma unroll 2
+    for (int b = sub; b < nb; b += LPW) {
       q4 q = ldq(xquat + 4 * b);
       quat_to_mat(q, xmat + 9 * b);
       st3(xipos + 3 * b, ld3(xpos + 3 * b) + qrot(q, ld3(m.body_ipos + 3 * b)));
-      quat_to_mat(qmul(q, ldq(m.body_iquat + 4 * b)), ximat + 9 * b);
     }
 #pragma unroll 1
-    for (int g = lane; g < ng; g += 32) {
-      const int b = m.geom_bodyid[g];
-      if (m.body_weldid[b] == 0 && (m.nmocap == 0 || m.body_mocapid[m.body_rootid[b]] == -1)) {  // static geom: keeps the pose computed at make_data (smooth.py:197-200)
-        for (int k = 0; k < 3; k++) gxpos[3 * g + k] = d.geom_xpos[(wb * ng + g) * 3 + k];
-        for (int k = 0; k < 9; k++) gxmat[9 * g + k] = d.geom_xmat[(wb * ng + g) * 9 + k];
-      } else {
-        q4 q = ldq(xquat + 4 * b);
-        st3(gxpos + 3 * g, ld3(xpos + 3 * b) + qrot(q, ld3(m.geom_pos + 3 * g)));
-        quat_to_mat(qmul(q, ldq(m.geom_quat + 4 * g)), gxmat + 9 * g);
-      }
-    }
-#pragma unroll 1
-    for (int s = lane; s < m.nsite; s += 32) {
+    for (int s = valid ? sub : m.nsite; s < m.nsite; s += LPW) {
       const int b = m.site_bodyid[s];
       q4 q = ldq(xquat + 4 * b);
       float mat[9];
@@ -122,36 +169,30 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       quat_to_mat(qmul(q, ldq(m.site_quat + 4 * s)), mat);
       for (int k = 0; k < 9; k++) d.site_xmat[(wb * m.nsite + s) * 9 + k] = mat[k];
     }
-    __syncwarp();
-    warp_copy(d.xpos + wb * 3 * nb, xpos, 3 * nb, lane);
-    warp_copy(d.xquat + wb * 4 * nb, xquat, 4 * nb, lane);
-    warp_copy(d.xmat + wb * 9 * nb, xmat, 9 * nb, lane);
-    warp_copy(d.xipos + wb * 3 * nb, xipos, 3 * nb, lane);
-    warp_copy(d.ximat + wb * 9 * nb, ximat, 9 * nb, lane);
-    warp_copy(d.xanchor + wb * 3 * nj, xanchor, 3 * nj, lane);
-    warp_copy(d.xaxis + wb * 3 * nj, xaxis, 3 * nj, lane);
-    warp_copy(d.geom_xpos + wb * 3 * ng, gxpos, 3 * ng, lane);
-    warp_copy(d.geom_xmat + wb * 9 * ng, gxmat, 9 * ng, lane);
-  } else if (mask & (STG_COM_POS | STG_CAMLIGHT)) {
-    warp_copy(xpos, d.xpos + wb * 3 * nb, 3 * nb, lane);
-    warp_copy(xquat, d.xquat + wb * 4 * nb, 4 * nb, lane);
-    warp_copy(xmat, d.xmat + wb * 9 * nb, 9 * nb, lane);
-    warp_copy(xipos, d.xipos + wb * 3 * nb, 3 * nb, lane);
-    warp_copy(ximat, d.ximat + wb * 9 * nb, 9 * nb, lane);
-    warp_copy(xanchor, d.xanchor + wb * 3 * nj, 3 * nj, lane);
-    warp_copy(xaxis, d.xaxis + wb * 3 * nj, 3 * nj, lane);
+    st.store_fence();
+    GSTORE(xpos, BLK(xpos), 3 * nb); GSTORE(xquat, BLK(xquat), 4 * nb); GSTORE(xmat, ABLK(0), 9 * nb); GSTORE(xipos, BLK(xipos), 3 * nb);
+    GSTORE(xanchor, BLK(xanchor), 3 * nj); GSTORE(xaxis, BLK(xaxis), 3 * nj);
+    st.store_commit();
+    if (!com) {  // kinematics alone: the inertial frames follow xmat through the arena (otherwise the cinert loop below produces them)
+      st.store_wait_read();
+#pragma unroll 2
+      for (int b = sub; b < nb; b += LPW) quat_to_mat(qmul(ldq(xquat + 4 * b), ldq(m.body_iquat + 4 * b)), ximat + 9 * b);
+      st.store_fence();
+      GSTORE(ximat, ABLK(0), 9 * nb);
+      st.store_commit();
+    }
   }
   __syncwarp();
 
-  // ------------------------------------------------------------------ com_pos
-  if (mask & STG_COM_POS) {
-#pragma unroll 1
-    for (int b = lane; b < nb; b += 32) st3(scom + 3 * b, ld3(xipos + 3 * b) * m.body_mass[b]);
+  // ------------------------------------------------------------------ com_pos (smooth.py:686-855)
+  if (com) {
+#pragma unroll 2
+    for (int b = sub; b < nb; b += LPW) st3(scom + 3 * b, ld3(xipos + 3 * b) * m.body_mass[b]);
     __syncwarp();
 #pragma unroll 1
     for (int l = m.nlevel - 2; l >= 0; l--) {
 #pragma unroll 1
-      for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
+      for (int i = m.level_adr[l] + sub; i < m.level_adr[l + 1]; i += LPW) {
         const int b = m.level_body[i];
         v3 acc = ld3(scom + 3 * b);
         for (int c = m.body_childadr[b]; c < m.body_childadr[b + 1]; c++) acc = acc + ld3(scom + 3 * m.body_childid[c]);
@@ -159,15 +200,17 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
-#pragma unroll 1
-    for (int b = lane; b < nb; b += 32) {
+#pragma unroll 2
+    for (int b = sub; b < nb; b += LPW) {
       const float ms = m.body_subtreemass[b];
       if (ms != 0.f) st3(scom + 3 * b, ld3(scom + 3 * b) * (1.0f / ms));
     }
     __syncwarp();
-#pragma unroll 1
-    for (int b = lane; b < nb; b += 32) {  // cinert (smooth.py:733)
-      const float* mat = ximat + 9 * b;
+    if (kin) st.store_wait_read();  // xmat has left the arena (long ago: the subtree-com passes ran in between); ximat takes its place
+#pragma unroll 2
+    for (int b = sub; b < nb; b += LPW) {  // cinert (smooth.py:733); the inertial frame is built here, on its way out through the arena
+      float* mat = ximat + 9 * b;
+      quat_to_mat(qmul(ldq(xquat + 4 * b), ldq(m.body_iquat + 4 * b)), mat);
       const v3 inert = ld3(m.body_inertia + 3 * b);
       const float mass = m.body_mass[b];
       const v3 dif = ld3(xipos + 3 * b) - ld3(scom + 3 * m.body_rootid[b]);
@@ -184,13 +227,14 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       r[5] = b0 * mat[6] + b1 * mat[7] + b2 * mat[8] - mass * dif.y * dif.z;
       r[6] = mass * dif.x; r[7] = mass * dif.y; r[8] = mass * dif.z; r[9] = mass;
     }
-#pragma unroll 1
-    for (int j = lane; j < nj; j += 32) {  // cdof (smooth.py:779)
+#pragma unroll 2
+    for (int j = sub; j < nj; j += LPW) {  // cdof (smooth.py:779)
       const int b = m.jnt_bodyid[j], t = m.jnt_type[j];
       int dof = m.jnt_dofadr[j];
       const v3 offset = ld3(scom + 3 * m.body_rootid[b]) - ld3(xanchor + 3 * j);
-      const float* xm = xmat + 9 * b;
       if (t == JNT_FREE || t == JNT_BALL) {
+        float xm[9];
+        quat_to_mat(ldq(xquat + 4 * b), xm);
         if (t == JNT_FREE) {
           for (int k = 0; k < 18; k++) cdof[6 * dof + k] = 0.f;
           cdof[6 * dof + 3] = 1.f; cdof[6 * (dof + 1) + 4] = 1.f; cdof[6 * (dof + 2) + 5] = 1.f;
@@ -207,21 +251,17 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         st3(cdof + 6 * dof, ax); st3(cdof + 6 * dof + 3, cross(ax, offset));
       }
     }
-    __syncwarp();
-    warp_copy(d.subtree_com + wb * 3 * nb, scom, 3 * nb, lane);
-    warp_copy(d.cinert + wb * 10 * nb, cinert, 10 * nb, lane);
-    warp_copy(d.cdof + wb * 6 * nv, cdof, 6 * nv, lane);
-  } else if (mask & (STG_CAMLIGHT | STG_CRB)) {
-    warp_copy(scom, d.subtree_com + wb * 3 * nb, 3 * nb, lane);
-    warp_copy(cinert, d.cinert + wb * 10 * nb, 10 * nb, lane);
-    warp_copy(cdof, d.cdof + wb * 6 * nv, 6 * nv, lane);
+    st.store_fence();
+    GSTORE(subtree_com, BLK(scom), 3 * nb); GSTORE(cinert, BLK(cinert), 10 * nb); GSTORE(cdof, BLK(cdof), 6 * nv);
+    if (kin) GSTORE(ximat, ABLK(0), 9 * nb);
+    st.store_commit();
   }
   __syncwarp();
 
   // ------------------------------------------------------------------ camlight (smooth.py:858-1027)
   if (mask & STG_CAMLIGHT) {
 #pragma unroll 1
-    for (int c = lane; c < m.ncam; c += 32) {
+    for (int c = valid ? sub : m.ncam; c < m.ncam; c += LPW) {
       const int mode = m.cam_mode[c], b = m.cam_bodyid[c], tb = m.cam_targetbodyid[c];
       const bool is_target = mode == CAM_TARGETBODY || mode == CAM_TARGETBODYCOM;
       v3 p; float mat[9];
@@ -246,7 +286,7 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       for (int k = 0; k < 9; k++) d.cam_xmat[(wb * m.ncam + c) * 9 + k] = mat[k];
     }
 #pragma unroll 1
-    for (int l = lane; l < m.nlight; l += 32) {
+    for (int l = valid ? sub : m.nlight; l < m.nlight; l += LPW) {
       const int mode = m.light_mode[l], b = m.light_bodyid[l], tb = m.light_targetbodyid[l];
       const bool is_target = mode == CAM_TARGETBODY || mode == CAM_TARGETBODYCOM;
       v3 p, dir;
@@ -271,15 +311,34 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     }
   }
 
+
+  // ------------------------------------------------------------------ kinematics: geom poses (through the arena, once xmat / ximat have left)
+  if (kin) {
+    st.store_wait_read();
+#pragma unroll 2
+    for (int gi = sub; gi < ng; gi += LPW) {
+      const int b = m.geom_bodyid[gi];
+      if (m.body_weldid[b] == 0 && (m.nmocap == 0 || m.body_mocapid[m.body_rootid[b]] == -1)) {  // static geom: keeps the pose computed at make_data (smooth.py:197-200)
+        for (int k = 0; k < 3; k++) gxpos[3 * gi + k] = d.geom_xpos[(wb * ng + gi) * 3 + k];
+        for (int k = 0; k < 9; k++) gxmat[9 * gi + k] = d.geom_xmat[(wb * ng + gi) * 9 + k];
+      } else {
+        q4 q = ldq(xquat + 4 * b);
+        st3(gxpos + 3 * gi, ld3(xpos + 3 * b) + qrot(q, ld3(m.geom_pos + 3 * gi)));
+        quat_to_mat(qmul(q, ldq(m.geom_quat + 4 * gi)), gxmat + 9 * gi);
+      }
+    }
+    st.store_fence();
+    GSTORE(geom_xpos, ABLK(0), 3 * ng); GSTORE(geom_xmat, ABLK(L.a_gxmat), 9 * ng);
+    st.store_commit();
+  }
+
   // ------------------------------------------------------------------ crb + M (smooth.py:1029-1098)
-  if (mask & STG_CRB) {
-#pragma unroll 1
-    for (int i = lane; i < 10 * nb; i += 32) crb[i] = cinert[i];
-    __syncwarp();
+  if (crbm) {
+    st.store_wait_read();  // cinert has been stored: crb accumulates in place; the arena and the pose fields (-> buf) are free
 #pragma unroll 1
     for (int l = m.nlevel - 2; l >= 1; l--) {
 #pragma unroll 1
-      for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
+      for (int i = m.level_adr[l] + sub; i < m.level_adr[l + 1]; i += LPW) {
         const int b = m.level_body[i];
         float acc[10];
 #pragma unroll
@@ -295,52 +354,51 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
-#pragma unroll 1
-    for (int dd = lane; dd < nv; dd += 32) inert_vec(crb + 10 * m.dof_bodyid[dd], cdof + 6 * dd, buf + 6 * dd);
+#pragma unroll 2
+    for (int dd = sub; dd < nv; dd += LPW) inert_vec(crb + 10 * m.dof_bodyid[dd], cdof + 6 * dd, buf + 6 * dd);
     __syncwarp();
-#pragma unroll 1
-    for (int e = lane; e < m.nC; e += 32) {
+#pragma unroll 4
+    for (int e = sub; e < m.nC; e += LPW) {
       const int i = m.M_entry_row[e], j = m.M_colind[e];
       float v = dot6(cdof + 6 * j, buf + 6 * i);
       if (i == j) v += m.dof_armature[i];
       Ms[e] = v;
     }
-    __syncwarp();
-    warp_copy(d.crb + wb * 10 * nb, crb, 10 * nb, lane);
-    warp_copy(d.M + wb * m.nC, Ms, m.nC, lane);
+    st.store_fence();
+    GSTORE(crb, BLK(cinert), 10 * nb); GSTORE(M, ABLK(0), m.nC);
+    st.store_commit();
   }
-
-  // ------------------------------------------------------------------ transmission (joint transmission; smooth.py:2288-2396)
-  if (mask & STG_TRANSMISSION) {
-#pragma unroll 1
-    for (int a = lane; a < m.nu; a += 32) {
-      const int j = m.actuator_trnid[2 * a], t = m.jnt_type[j], adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a];
-      const float* gear = m.actuator_gear + 6 * a;
-      d.actuator_length[wb * m.nu + a] = (t == JNT_SLIDE || t == JNT_HINGE) ? qpos[m.jnt_qposadr[j]] * gear[0] : 0.f;
-      d.moment_rownnz[wb * m.nu + a] = nnz;
-      d.moment_rowadr[wb * m.nu + a] = adr;
-#pragma unroll 1
-      for (int k = 0; k < nnz; k++) {
-        d.moment_colind[wb * m.nJmom + adr + k] = m.moment_colind0[adr + k];
-        d.actuator_moment[wb * m.nJmom + adr + k] = gear[k];
-      }
-    }
-  }
+  st.store_wait_read();  // shared memory must outlive the bulk stores that read it
+#undef GLOAD
+#undef GSTORE
+#undef BLK
+#undef ABLK
+#undef ROW
 }
 
 }  // namespace
 
-size_t smem_position(const ModelDev& m) { return (size_t)pos_layout(m).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+// lanes per world of the position kernel (MJB_LPW_POS = 4 | 8 | 16 | 32 overrides; measured on B200)
+int position_lpw() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("MJB_LPW_POS"); v = e ? atoi(e) : 8; if (v != 4 && v != 8 && v != 16 && v != 32) v = 8; }
+  return v;
+}
+
+static size_t pos_warp_bytes(const ModelDev& m) { return ((size_t)pos_layout(m).total * (32 / position_lpw()) + 4) * sizeof(float); }
+size_t smem_position(const ModelDev& m) { return pos_warp_bytes(m) * team_warps_per_block(position_lpw(), "MJB_WPB_POS"); }
 
 cudaError_t launch_position(const ModelDev& m, const DataDev& d, int mask, cudaStream_t s) {
   const size_t smem = smem_position(m);
+  const int lpw = position_lpw(), G = 32 / lpw, wpb = team_warps_per_block(lpw, "MJB_WPB_POS");
+  void (*kern)(ModelDev, DataDev, int) = lpw == 4 ? k_position<4> : lpw == 8 ? k_position<8> : lpw == 16 ? k_position<16> : k_position<32>;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int grid = d.wn;
-  k_position<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, mask);
+  const int ngroups = (d.wn + G - 1) / G, grid = (ngroups + wpb - 1) / wpb;
+  kern<<<grid, 32 * wpb, smem, s>>>(m, d, mask);
   return cudaGetLastError();
 }

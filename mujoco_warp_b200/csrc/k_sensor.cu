@@ -219,7 +219,7 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
       __syncwarp();
       e += nrow;
     }
-    const int c0 = d.world_conadr[w], c1 = c0 + min(d.world_ncon[w], d.nconmax);
+    const int c0 = d.world_conadr[w], c1 = c0 + d.world_ncon[w];  // already clamped by k_collision to the per-world cap and the pool
 #pragma unroll 1
     for (int c = c0; c < c1; c++) {
       const int id1 = m.geom_bodyid[d.contact_geom[2 * c]], id2 = m.geom_bodyid[d.contact_geom[2 * c + 1]];
@@ -229,7 +229,7 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
       const int* adr = d.contact_efc_address + (size_t)c * m.nmaxpyramid;
       if (adr[0] >= 0) {
         if (m.cone == CONE_PYRAMIDAL) {
-          if (dim == 1) fc[0] = force[adr[0]];
+          if (dim == 1) fc[0] = adr[0] < d.njmax ? force[adr[0]] : 0.f;
           else
             for (int i = 0; i < dim - 1; i++) {
               const int a = 2 * i + adr[0];
@@ -237,7 +237,7 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
               fc[0] += d1 + d2; fc[i + 1] = (d1 - d2) * d.contact_friction[5 * (size_t)c + i];
             }
         } else {
-          for (int i = 0; i < dim; i++) if (adr[i] < d.njmax) fc[i] = force[adr[i]];
+          for (int i = 0; i < dim; i++) if (adr[i] >= 0 && adr[i] < d.njmax) fc[i] = force[adr[i]];
         }
       }
       const float* R = d.contact_frame + 9 * (size_t)c;
@@ -390,14 +390,14 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
       case SENS_TOUCH: {  // sensor.py:2063: normal forces of the sensorised body's contacts whose force ray meets the site volume
         const int body = m.site_bodyid[id];
         const float* force = d.efc_force + wb * d.njmax;
-        const int c0 = d.world_conadr[w], c1 = c0 + min(d.world_ncon[w], d.nconmax);
+        const int c0 = d.world_conadr[w], c1 = c0 + d.world_ncon[w];  // already clamped by k_collision to the per-world cap and the pool
         float total = 0.f;
         for (int c = c0; c < c1; c++) {
           const int b1 = m.geom_bodyid[d.contact_geom[2 * c]], b2 = m.geom_bodyid[d.contact_geom[2 * c + 1]];
           const int* adr = d.contact_efc_address + (size_t)c * m.nmaxpyramid;
           if (adr[0] < 0 || (body != b1 && body != b2)) continue;
-          float nf = force[adr[0]];
-          if (m.cone == CONE_PYRAMIDAL) for (int i = 1; i < 2 * (d.contact_dim[c] - 1); i++) nf += force[adr[i]];
+          float nf = adr[0] < d.njmax ? force[adr[0]] : 0.f;  // rows cut by njmax carry address -1 (k_constraint)
+          if (m.cone == CONE_PYRAMIDAL) for (int i = 1; i < 2 * (d.contact_dim[c] - 1); i++) nf += (adr[i] >= 0 && adr[i] < d.njmax) ? force[adr[i]] : 0.f;
           if (nf <= 0.f) continue;
           v3 ray = normalize(ld3(d.contact_frame + 9 * (size_t)c) * nf);
           if (body == b2) ray = ray * -1.0f;

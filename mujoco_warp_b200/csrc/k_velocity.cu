@@ -6,56 +6,137 @@
 // transmission); forward.py:1255-1324 fwd_acceleration with support.py:259-324 xfrc_accumulate and the per-tree dense
 // Cholesky factor+solve of M (smooth.py:3227-3265) -- about 30 launches there, one here.
 //
-// One warp owns one world; tree passes are level-synchronous in shared memory, children are gathered by the parent in a
-// fixed order (no float atomics => bit-reproducible), the inertia block is factored by the warp in shared memory.
-#include "mjb_chol.cuh"
+// A team of LPW lanes owns one world, a warp owns G = 32 / LPW consecutive worlds (mjb_team.cuh); inputs and outputs move as
+// bulk-async (TMA) copies of the contiguous [G][n] blocks.  Tree passes are level-synchronous in shared memory, children
+// are gathered by the parent in a fixed order (no float atomics => bit-reproducible), the inertia blocks are factored by the
+// team in shared memory directly in the qLD layout (upper factor, row-major), so qLD leaves as one bulk store.
+#include <cstdlib>
+
 #include "mjb_math.cuh"
+#include "mjb_team.cuh"
 #include "mjb_types.cuh"
 
 namespace {
 
-struct VelLayout { int qvel, cdof, cinert, cvel, cdofdot, cacc, cfrc, qf, A, x, af, total; };
-__host__ __device__ inline int chol_ld(int n) { return (n | 1); }  // odd leading dimension
+struct VelLayout { int qvel, cdof, cinert, cvel, cdofdot, cacc, cfrc, qpas, qbias, qact, qsm, qld, x, af, total; };
+// Per-world words of shared memory (3.9 KB for the humanoid, so that an SM's 55 worlds are resident together: the kernel is
+// latency bound).  The n x n factor (Data.qLD layout) is built where the tree-pass fields (cdof .. cfrc_int) lived, once the
+// bulk stores that read them have drained; M is scattered into it straight from global memory.
 __host__ __device__ inline VelLayout vel_layout(const ModelDev& m) {
   VelLayout L;
   int o = 0;
-  auto take = [&](int n) { int r = o; o += n; return r; };
-  L.qvel = take(m.nv); L.cdof = take(6 * m.nv); L.cinert = take(10 * m.nbody); L.cvel = take(6 * m.nbody);
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };  // padded: a field's group block [G][n] starts 16 B aligned
+  L.qvel = take(m.nv);
+  const int a0 = o;
+  L.cdof = take(6 * m.nv); L.cinert = take(10 * m.nbody); L.cvel = take(6 * m.nbody);
   L.cdofdot = take(6 * m.nv); L.cacc = take(6 * m.nbody); L.cfrc = take(6 * m.nbody);
-  L.qf = take(4 * m.nv);  // passive, bias, actuator, smooth
-  L.A = take(m.maxtree * chol_ld(m.maxtree)); L.x = take(m.maxtree); L.af = take(m.nu);
-  L.total = (o + 3) & ~3;
+  L.qld = a0;
+  if (o - a0 < ((m.qld_total + 3) & ~3)) o = a0 + ((m.qld_total + 3) & ~3);
+  L.qpas = take(m.nv); L.qbias = take(m.nv); L.qact = take(m.nv); L.qsm = take(m.nv);
+  // the solve's right-hand side / solution takes qfrc_passive's slot once qfrc_smooth has been formed (qfrc_passive is written
+  // straight to global memory); actuator forces live in their own small slot
+  L.x = L.qpas; L.af = take(m.nu);
+  L.total = o;
   return L;
 }
 
-// 28 resident one-warp blocks per SM make 8192 worlds exactly two full waves on 148 SMs (caps registers at 72)
-// PEXT = the model uses gravity compensation or free / ball joint springs (kept out of the plain instantiation)
-template <bool PEXT>
-__global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32, 28)
-k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
-  const int w = blockIdx.x + d.w0;
-  if (w >= d.nworld) return;
-  const VelLayout L = vel_layout(m);
-  float* S = smem + warp * L.total;
-  float *qvel = S + L.qvel, *cdof = S + L.cdof, *cinert = S + L.cinert, *cvel = S + L.cvel, *cdofdot = S + L.cdofdot,
-        *cacc = S + L.cacc, *cfrc = S + L.cfrc, *A = S + L.A, *x = S + L.x, *aforce = S + L.af;
-  float *q_passive = S + L.qf, *q_bias = q_passive + m.nv, *q_act = q_bias + m.nv, *q_smooth = q_act + m.nv;
-  const int nv = m.nv, nb = m.nbody, nu = m.nu;
-  const size_t wb = (size_t)w;
+// Dense Cholesky of one tree's inertia block by a team, in the qLD layout: U (n x n, row-major, ld = n) starts as the upper
+// triangle of M with zeros below and ends as the factor U with U^T U = M (= the reference's L^T, smooth.py:3227-3265).
+// Row j of U needs the columns above it: U[j][i] = (M[j][i] - sum_{k<j} U[k][j] U[k][i]) / U[j][j]; lanes take the entries
+// i = j + sub, j + sub + LPW, ... .  The right-hand side rides along as a virtual column i = n (y = U^-T b comes out of the
+// same sweep), then the backward substitution U x = y runs column by column.  x holds b on entry, the solution on exit.
+template <int LPW>
+__device__ __forceinline__ void team_chol_upper(float* U, int n, float* x, bool solve, int sub) {
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    const int iend = solve ? n + 1 : n;
+#pragma unroll 1
+    for (int i = j + sub; i < iend; i += LPW) {
+      const bool rhs = i == n;
+      const float* col = rhs ? x : U + i;
+      const int cs = rhs ? 1 : n;
+      float s0 = rhs ? x[j] : U[j * n + i], s1 = 0.f;
+      int k = 0;
+#pragma unroll 4
+      for (; k + 1 < j; k += 2) {
+        s0 -= U[k * n + j] * col[k * cs];
+        s1 -= U[(k + 1) * n + j] * col[(k + 1) * cs];
+      }
+      if (k < j) s0 -= U[k * n + j] * col[k * cs];
+      if (rhs) x[j] = s0 + s1; else U[j * n + i] = s0 + s1;
+    }
+    __syncwarp();
+    const float piv = sqrtf(fmaxf(U[j * n + j], MJ_MINVAL)), inv = 1.0f / piv;
+    __syncwarp();
+#pragma unroll 1
+    for (int i = j + sub; i < iend; i += LPW) {
+      if (i == n) x[j] *= inv;
+      else U[j * n + i] = i == j ? piv : U[j * n + i] * inv;
+    }
+    __syncwarp();
+  }
+  if (!solve) return;
+#pragma unroll 1
+  for (int j = n - 1; j >= 0; j--) {  // backward: U x = y, column j of U
+    const float xj = x[j] / U[j * n + j];
+    __syncwarp();
+#pragma unroll 1
+    for (int k = sub; k < j; k += LPW) x[k] -= U[k * n + j] * xj;
+    if (sub == 0) x[j] = xj;
+    __syncwarp();
+  }
+}
 
-  warp_copy(qvel, d.qvel + wb * nv, nv, lane);
-  warp_copy(cdof, d.cdof + wb * 6 * nv, 6 * nv, lane);
-  __syncwarp();
+// PEXT = the model uses gravity compensation or free / ball joint springs (kept out of the plain instantiation)
+template <bool PEXT, int LPW>
+__global__ void __launch_bounds__(256)
+k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int G = 32 / LPW;
+  Team<LPW> T;
+  T.init(d.w0, d.wn, d.nworld);
+  if (T.nvalid <= 0) return;
+  const int lane = T.lane, sub = T.sub, g = T.g, nval = T.nvalid;
+  const bool valid = T.valid;
+  const VelLayout L = vel_layout(m);
+  float* S = smem + (size_t)(threadIdx.x >> 5) * ((size_t)L.total * G + 4);  // this warp's slice (+ its mbarrier)
+  Stager st;
+  st.init(reinterpret_cast<uint64_t*>(S + (size_t)L.total * G), lane);
+  const int nv = m.nv, nb = m.nbody, nu = m.nu;
+#define FLD(f, n) (S + (size_t)L.f * G + (size_t)g * (n))
+  float *qvel = FLD(qvel, nv), *cdof = FLD(cdof, 6 * nv), *cinert = FLD(cinert, 10 * nb), *cvel = FLD(cvel, 6 * nb), *cdofdot = FLD(cdofdot, 6 * nv),
+        *cacc = FLD(cacc, 6 * nb), *cfrc = FLD(cfrc, 6 * nb), *q_passive = FLD(qpas, nv), *q_bias = FLD(qbias, nv), *q_act = FLD(qact, nv),
+        *q_smooth = FLD(qsm, nv), *qld = FLD(qld, m.qld_total), *x = FLD(x, nv), *aforce = FLD(af, nu);
+  const float* Mw = d.M + (size_t)T.w * m.nC;
+#undef FLD
+  const size_t wg = (size_t)T.wg0;
+#define GLOAD(f, field, n) st.load(S + (size_t)L.f * G, d.field + wg * (size_t)(n), nval * (n))
+#define GSTORE(field, f, n) st.store(d.field + wg * (size_t)(n), S + (size_t)L.f * G, nval * (n))
+  const size_t wb = (size_t)T.w;
+  const bool v_all = mask & STG_VELOCITY;  // the sub-stage bits serve the individually callable com_vel / passive / rne
+
+  GLOAD(qvel, qvel, nv); GLOAD(cdof, cdof, 6 * nv);
+  if (v_all || (mask & STG_RNE)) GLOAD(cinert, cinert, 10 * nb);
+  // Long-latency global reads whose consumers come much later are issued now, into registers: the world's inertia entries
+  // (scattered into the factor's layout by the Cholesky phase; MREG * LPW entries are prefetched, the rest is read in place)
+  // and the "any applied wrench?" test of fwd_acceleration.
+  constexpr int MREG = 32;
+  float mreg[MREG];
+  const bool fac = mask & (STG_ACCELERATION | STG_FACTOR_ONLY);
+#pragma unroll
+  for (int k = 0; k < MREG; k++) { const int e = sub + k * LPW; mreg[k] = (fac && e < m.nC) ? Mw[e] : 0.f; }
+  bool any_xfrc = false;
+  if (mask & STG_ACCELERATION) {
+#pragma unroll 4
+    for (int i = sub; i < 6 * nb; i += LPW) any_xfrc |= d.xfrc_applied[wb * 6 * nb + i] != 0.f;
+  }
+  st.load_wait();
 
   // ------------------------------------------------------------------ fwd_velocity
-  const bool v_all = mask & STG_VELOCITY;  // the sub-stage bits serve the individually callable com_vel / passive / rne
   if (mask & (STG_VELOCITY | STG_COMVEL | STG_PASSIVE | STG_RNE)) {
-    if (v_all || (mask & STG_RNE)) warp_copy(cinert, d.cinert + wb * 10 * nb, 10 * nb, lane);
     if (v_all)
 #pragma unroll 1
-    for (int a = lane; a < nu; a += 32) {  // actuator velocity = moment . qvel
+    for (int a = valid ? sub : nu; a < nu; a += LPW) {  // actuator velocity = moment . qvel
       const int nnz = d.moment_rownnz[wb * nu + a], adr = d.moment_rowadr[wb * nu + a];
       float vel = 0.f;
       for (int k = 0; k < nnz; k++) vel += d.actuator_moment[wb * m.nJmom + adr + k] * qvel[d.moment_colind[wb * m.nJmom + adr + k]];
@@ -63,12 +144,13 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
     }
     // com_vel: level-synchronous forward pass
     if (v_all || (mask & STG_COMVEL)) {
-    if (lane < 6) cvel[lane] = 0.f;
+    if (sub < 6) cvel[sub] = 0.f;
+    if (LPW < 6 && sub == 0) { cvel[4] = 0.f; cvel[5] = 0.f; }
     __syncwarp();
 #pragma unroll 1
     for (int l = 1; l < m.nlevel; l++) {
 #pragma unroll 1
-      for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
+      for (int i = m.level_adr[l] + sub; i < m.level_adr[l + 1]; i += LPW) {
         const int b = m.level_body[i], pid = m.body_parentid[b], jntadr = m.body_jntadr[b], jntnum = m.body_jntnum[b];
         int dof = m.body_dofadr[b];
         float cv[6];
@@ -98,12 +180,12 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
-    warp_copy(d.cvel + wb * 6 * nb, cvel, 6 * nb, lane);
-    warp_copy(d.cdof_dot + wb * 6 * nv, cdofdot, 6 * nv, lane);
+    st.store_fence();
+    GSTORE(cvel, cvel, 6 * nb); GSTORE(cdof_dot, cdofdot, 6 * nv);
+    st.store_commit();
     } else if (mask & STG_RNE) {
-      warp_copy(cvel, d.cvel + wb * 6 * nb, 6 * nb, lane);
-      warp_copy(cdofdot, d.cdof_dot + wb * 6 * nv, 6 * nv, lane);
-      __syncwarp();
+      GLOAD(cvel, cvel, 6 * nb); GLOAD(cdofdot, cdof_dot, 6 * nv);
+      st.load_wait();
     }
 
     // passive: joint springs (slide / hinge; ball and free joints through quat_sub) and dampers, gravity compensation
@@ -111,7 +193,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       const bool dsbl_spring = m.disableflags & DSBL_SPRING, dsbl_damper = m.disableflags & DSBL_DAMPER;
       const bool gravcomp = PEXT && m.has_gravcomp && !(m.disableflags & DSBL_GRAVITY) && !(dsbl_spring && dsbl_damper);
 #pragma unroll 1
-      for (int dd = lane; dd < nv; dd += 32) {
+      for (int dd = sub; dd < nv; dd += LPW) {
         const int j = m.dof_jntid[dd], t = m.jnt_type[j];
         float spring = 0.f, damper = 0.f, gc = 0.f;
         if (!(dsbl_spring && dsbl_damper)) {
@@ -147,22 +229,24 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
             gc += sc * (jp.x * m.gravity_x + jp.y * m.gravity_y + jp.z * m.gravity_z);
           }
         }
-        d.qfrc_spring[wb * nv + dd] = spring;
-        d.qfrc_damper[wb * nv + dd] = damper;
-        d.qfrc_gravcomp[wb * nv + dd] = gc;
         const float passive = spring + damper + (m.jnt_actgravcomp[j] ? 0.f : gc);
         q_passive[dd] = passive;
-        d.qfrc_passive[wb * nv + dd] = passive;
+        if (valid) {
+          d.qfrc_spring[wb * nv + dd] = spring;
+          d.qfrc_damper[wb * nv + dd] = damper;
+          d.qfrc_gravcomp[wb * nv + dd] = gc;
+          d.qfrc_passive[wb * nv + dd] = passive;
+        }
       }
     }
     // rne: cacc forward, cfrc per body, backward accumulation, projection
     if (v_all || (mask & STG_RNE)) {
-    if (lane < 6) cacc[lane] = lane < 3 ? 0.f : ((m.disableflags & DSBL_GRAVITY) ? 0.f : -(lane == 3 ? m.gravity_x : lane == 4 ? m.gravity_y : m.gravity_z));
+    for (int k = sub; k < 6; k += LPW) cacc[k] = k < 3 ? 0.f : ((m.disableflags & DSBL_GRAVITY) ? 0.f : -(k == 3 ? m.gravity_x : k == 4 ? m.gravity_y : m.gravity_z));
     __syncwarp();
 #pragma unroll 1
     for (int l = 1; l < m.nlevel; l++) {
 #pragma unroll 1
-      for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
+      for (int i = m.level_adr[l] + sub; i < m.level_adr[l + 1]; i += LPW) {
         const int b = m.level_body[i], pid = m.body_parentid[b];
         float a[6];
 #pragma unroll
@@ -179,8 +263,8 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       }
       __syncwarp();
     }
-#pragma unroll 1
-    for (int b = lane; b < nb; b += 32) {
+#pragma unroll 2
+    for (int b = sub; b < nb; b += LPW) {
       float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (b > 0) {
         float iv[6], g[6];
@@ -197,7 +281,7 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 #pragma unroll 1
     for (int l = m.nlevel - 2; l >= 0; l--) {
 #pragma unroll 1
-      for (int i = m.level_adr[l] + lane; i < m.level_adr[l + 1]; i += 32) {
+      for (int i = m.level_adr[l] + sub; i < m.level_adr[l + 1]; i += LPW) {
         const int b = m.level_body[i];
         float acc[6];
 #pragma unroll
@@ -214,29 +298,29 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
       __syncwarp();
     }
 #pragma unroll 1
-    for (int dd = lane; dd < nv; dd += 32) {
+    for (int dd = sub; dd < nv; dd += LPW) {
       const float v = dot6(cdof + 6 * dd, cfrc + 6 * m.dof_bodyid[dd]);
       q_bias[dd] = v;
-      d.qfrc_bias[wb * nv + dd] = v;
     }
-    warp_copy(d.cacc + wb * 6 * nb, cacc, 6 * nb, lane);
-    warp_copy(d.cfrc_int + wb * 6 * nb, cfrc, 6 * nb, lane);
+    st.store_fence();
+    GSTORE(cacc, cacc, 6 * nb); GSTORE(cfrc_int, cfrc, 6 * nb); GSTORE(qfrc_bias, qbias, nv);
+    st.store_commit();
     }
   } else if (mask & STG_ACCELERATION) {
-    warp_copy(q_passive, d.qfrc_passive + wb * nv, nv, lane);
-    warp_copy(q_bias, d.qfrc_bias + wb * nv, nv, lane);
+    GLOAD(qpas, qfrc_passive, nv); GLOAD(qbias, qfrc_bias, nv);
+    st.load_wait();
   }
   __syncwarp();
 
   // ------------------------------------------------------------------ fwd_actuation
   if (mask & STG_ACTUATION) {
 #pragma unroll 1
-    for (int dd = lane; dd < nv; dd += 32) q_act[dd] = 0.f;
+    for (int dd = sub; dd < nv; dd += LPW) q_act[dd] = 0.f;
     __syncwarp();
     const bool enabled = nu > 0 && !(m.disableflags & DSBL_ACTUATION);
     // actuator forces; scatter moment^T force by a per-dof gather loop over actuators (deterministic, no atomics)
 #pragma unroll 1
-    for (int a = lane; a < nu; a += 32) {
+    for (int a = sub; a < nu; a += LPW) {
       float force = 0.f;
       if (enabled) {
         float ctrl = d.ctrl[wb * nu + a];
@@ -250,13 +334,13 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         force = gain * ctrl + bias;
         if (m.actuator_forcelimited[a]) force = clampf(force, m.actuator_forcerange[2 * a], m.actuator_forcerange[2 * a + 1]);
       }
-      d.actuator_force[wb * nu + a] = force;
+      if (valid) d.actuator_force[wb * nu + a] = force;
       aforce[a] = force;
     }
     __syncwarp();
     if (enabled) {
 #pragma unroll 1
-      for (int dd = lane; dd < nv; dd += 32) {
+      for (int dd = sub; dd < nv; dd += LPW) {
         float q = 0.f;
         // moment^T force through the per-dof reverse table (entries in actuator order -> fixed summation order, no atomics)
         for (int k = m.dofact_adr[dd]; k < m.dofact_adr[dd + 1]; k++) q += d.actuator_moment[wb * m.nJmom + m.dofact_mom[k]] * aforce[m.dofact_act[k]];
@@ -266,10 +350,12 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         q_act[dd] = q;
       }
     }
-    __syncwarp();
-    warp_copy(d.qfrc_actuator + wb * nv, q_act, nv, lane);
+    st.store_fence();
+    GSTORE(qfrc_actuator, qact, nv);
+    st.store_commit();
   } else if (mask & STG_ACCELERATION) {
-    warp_copy(q_act, d.qfrc_actuator + wb * nv, nv, lane);
+    GLOAD(qact, qfrc_actuator, nv);
+    st.load_wait();
   }
   __syncwarp();
 
@@ -277,14 +363,11 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
   if (mask & (STG_ACCELERATION | STG_FACTOR_ONLY)) {
     if (mask & STG_ACCELERATION) {
 #pragma unroll 1
-      for (int dd = lane; dd < nv; dd += 32) q_smooth[dd] = q_passive[dd] - q_bias[dd] + q_act[dd] + d.qfrc_applied[wb * nv + dd];
+      for (int dd = sub; dd < nv; dd += LPW) q_smooth[dd] = q_passive[dd] - q_bias[dd] + q_act[dd] + d.qfrc_applied[wb * nv + dd];
       // xfrc_applied: skipped entirely when the world's applied wrenches are all zero (the common case)
-      bool any = false;
+      if (team_any<LPW>(any_xfrc, g)) {
 #pragma unroll 1
-      for (int i = lane; i < 6 * nb; i += 32) any |= d.xfrc_applied[wb * 6 * nb + i] != 0.f;
-      if (__any_sync(FULL_MASK, any)) {
-#pragma unroll 1
-        for (int dd = lane; dd < nv; dd += 32) {
+        for (int dd = sub; dd < nv; dd += LPW) {
           const float* cd = cdof + 6 * dd;
           const int db = m.dof_bodyid[dd];
           float acc = 0.f;
@@ -302,60 +385,72 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
         }
       }
       __syncwarp();
-      warp_copy(d.qfrc_smooth + wb * nv, q_smooth, nv, lane);
     }
-    // per-tree dense Cholesky of M, qLD block = upper factor U (row-major, zeros below), qacc_smooth = M^-1 qfrc_smooth
-    const float* Mw = d.M + wb * m.nC;
+    // per-tree dense Cholesky of M in the qLD layout (upper factor U, row-major, zeros below), qacc_smooth = M^-1 qfrc_smooth
+    const bool acc = mask & STG_ACCELERATION;
+    st.store_wait_read();  // the factor is built where cdof .. cfrc_int lived: their bulk stores must have read them
+#pragma unroll 1
+    for (int i = sub; i < m.qld_total; i += LPW) qld[i] = 0.f;
+    if (acc)
+#pragma unroll 1
+      for (int i = sub; i < nv; i += LPW) x[i] = q_smooth[i];
+    __syncwarp();
 #pragma unroll 1
     for (int t = 0; t < m.ntree; t++) {
-      const int start = m.tree_dofadr[t], n = m.tree_dofnum[t], ld = chol_ld(n);
-#pragma unroll 1
-      for (int i = lane; i < n * ld; i += 32) A[i] = 0.f;
-      __syncwarp();
+      const int start = m.tree_dofadr[t], n = m.tree_dofnum[t];
+      float* U = qld + m.tree_qLDadr[t];
       const int e0 = m.M_rowadr[start], e1 = m.M_rowadr[start + n - 1] + m.M_rownnz[start + n - 1];
-#pragma unroll 1
-      for (int e = e0 + lane; e < e1; e += 32) A[(m.M_entry_row[e] - start) * ld + (m.M_colind[e] - start)] = Mw[e];
-      __syncwarp();
-      float* qld = d.qLD + wb * m.qld_total + m.tree_qLDadr[t];
-      if (n <= 32) {
-        const float b = ((mask & STG_ACCELERATION) && lane < n) ? q_smooth[start + lane] : 0.f;
-        const float xx = chol_solve_reg_any(A, ld, n, b, A, ld, lane);
-        __syncwarp();
-        if ((mask & STG_ACCELERATION) && lane < n) d.qacc_smooth[wb * nv + start + lane] = xx;
-      } else {
-        warp_cholesky(A, n, ld, lane);
-        if (mask & STG_ACCELERATION) {
-#pragma unroll 1
-          for (int i = lane; i < n; i += 32) x[i] = q_smooth[start + i];
-          __syncwarp();
-          warp_chol_solve(A, n, ld, x, lane);
-#pragma unroll 1
-          for (int i = lane; i < n; i += 32) d.qacc_smooth[wb * nv + start + i] = x[i];
-        }
+      // lower entry (r, c) -> U[c][r]; entries e = sub + k * LPW with k < MREG come from the registers loaded at kernel start
+#pragma unroll
+      for (int k = 0; k < MREG; k++) {
+        const int e = sub + k * LPW;
+        if (e >= e0 && e < e1) U[(m.M_colind[e] - start) * n + (m.M_entry_row[e] - start)] = mreg[k];
       }
 #pragma unroll 1
-      for (int r = 0; r < n; r++)
-        for (int c = lane; c < n; c += 32) qld[r * n + c] = c >= r ? A[c * ld + r] : 0.f;
+      for (int e = max(e0, MREG * LPW) + ((sub - max(e0, MREG * LPW)) % LPW + LPW) % LPW; e < e1; e += LPW)
+        U[(m.M_colind[e] - start) * n + (m.M_entry_row[e] - start)] = Mw[e];
       __syncwarp();
+      team_chol_upper<LPW>(U, n, x + start, acc, sub);
     }
+    st.store_fence();
+    if (acc) { GSTORE(qfrc_smooth, qsm, nv); GSTORE(qacc_smooth, x, nv); }
+    GSTORE(qLD, qld, m.qld_total);
+    st.store_commit();
   }
+  st.store_wait_read();  // shared memory must outlive the bulk stores that read it
+#undef GLOAD
+#undef GSTORE
 }
 
 }  // namespace
 
-size_t smem_velocity(const ModelDev& m) { return (size_t)vel_layout(m).total * sizeof(float) * MJB_WARPS_PER_BLOCK; }
+// lanes per world of the velocity kernel (MJB_LPW_VEL = 4 | 8 | 16 | 32 overrides; measured on B200)
+int velocity_lpw() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("MJB_LPW_VEL"); v = e ? atoi(e) : 8; if (v != 4 && v != 8 && v != 16 && v != 32) v = 8; }
+  return v;
+}
+
+static size_t vel_warp_bytes(const ModelDev& m) { return ((size_t)vel_layout(m).total * (32 / velocity_lpw()) + 4) * sizeof(float); }
+size_t smem_velocity(const ModelDev& m) { return vel_warp_bytes(m) * team_warps_per_block(velocity_lpw(), "MJB_WPB_VEL"); }
+
+template <bool PEXT>
+static void (*vel_kernel(int lpw))(ModelDev, DataDev, int) {
+  return lpw == 4 ? k_velocity<PEXT, 4> : lpw == 8 ? k_velocity<PEXT, 8> : lpw == 16 ? k_velocity<PEXT, 16> : k_velocity<PEXT, 32>;
+}
 
 cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int mask, cudaStream_t s) {
   const size_t smem = smem_velocity(m);
   static size_t configured[2] = {0, 0};
   const int ext = m.has_gravcomp ? 1 : 0;  // has_gravcomp also flags free / ball joint springs (io.py put_model)
-  void (*kern)(ModelDev, DataDev, int) = ext ? k_velocity<true> : k_velocity<false>;
+  const int lpw = velocity_lpw(), G = 32 / lpw, wpb = team_warps_per_block(lpw, "MJB_WPB_VEL");
+  void (*kern)(ModelDev, DataDev, int) = ext ? vel_kernel<true>(lpw) : vel_kernel<false>(lpw);
   if (smem > 48 * 1024 && smem > configured[ext]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[ext] = smem;
   }
-  const int grid = d.wn;
-  kern<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, mask);
+  const int ngroups = (d.wn + G - 1) / G, grid = (ngroups + wpb - 1) / wpb;
+  kern<<<grid, 32 * wpb, smem, s>>>(m, d, mask);
   return cudaGetLastError();
 }
