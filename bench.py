@@ -26,8 +26,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCONMAX, NJMAX = 24, 64
-METRIC = "env-steps/sec (whole box) on humanoid.xml at nworld=8192 per GPU"
+from mujoco_warp_b200.scenes import WORKLOADS  # noqa: E402  (paths + sizes only; the package imports torch lazily)
+
+
+def metric_name(wl):
+  return "env-steps/sec (whole box) on humanoid.xml at nworld=8192 per GPU" if wl == "humanoid" else f"env-steps/sec (whole box) on {wl} at nworld={WORKLOADS[wl]['nworld']} per GPU"
 
 
 def parse():
@@ -36,9 +39,10 @@ def parse():
   p.add_argument("--steps", type=int, default=200)
   p.add_argument("--warmup", type=int, default=20)
   p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  p.add_argument("--nworld", type=int, default=8192, help="worlds per GPU")
+  p.add_argument("--workload", default="humanoid", choices=sorted(WORKLOADS), help="BASELINE configs[1] (default), [2] g1, [3] convex_mesh stand-in, three_humanoids")
+  p.add_argument("--nworld", type=int, default=None, help="worlds per GPU (default: the workload's)")
   p.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
-  p.add_argument("--cpu-sample-worlds", type=int, default=8192)
+  p.add_argument("--cpu-sample-worlds", type=int, default=None)
   p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel A/B sweeps)")
   return p.parse_args()
 
@@ -121,18 +125,39 @@ def algorithmic_words(mjm, tabs, ncon_mean, nefc_mean, nv_pad):
 # --------------------------------------------------------------------------------------------- CPU arm (oracle)
 
 
-def cpu_run(mjm, nworld, nsteps, nthreads):
+def load_workload(name):
+  """Model + initial host state + (optional) control trajectory of a workload."""
+  from mujoco_warp_b200._src import io as mio
+  from mujoco_warp_b200._src import mjcf
+  from mujoco_warp_b200._src.mjcf import MjDataLite, reset_data_keyframe
+
+  wl = WORKLOADS[name]
+  mjm = mjcf.load_any(wl["model"])
+  mjd = MjDataLite(mjm)
+  ctrls = None
+  if wl["replay"]:
+    ctrls = mio.load_trajectory(wl["replay"], mjm, mjd)
+  elif mjm.nkey > 0:
+    reset_data_keyframe(mjm, mjd, 0)
+  return wl, mjm, mjd, ctrls
+
+
+def cpu_run(name, nworld, nsteps, nthreads):
   """Times the CPU restatement (oracle, fp64, OpenMP over worlds) on a bounded sample; returns env-steps/s."""
   from tests import util
   from oracle import orc  # noqa: F401  (bench.py's cpu_baseline / --impl reference legs are allowed to use the oracle)
 
-  o = util.make_oracle(mjm, nworld, NCONMAX, NJMAX)
-  o.set_state(qpos=mjm.key_qpos[0], ctrl=mjm.key_ctrl[0])
+  wl, mjm, mjd, ctrls = load_workload(name)
+  o = util.make_oracle(mjm, nworld, wl["nconmax"], wl["njmax"])
+  o.set_state(qpos=np.asarray(mjd.qpos), qvel=np.asarray(mjd.qvel), ctrl=np.asarray(mjd.ctrl))
   rng = np.random.default_rng(0)
   o.step(nthreads)
   t0 = time.perf_counter()
-  for _ in range(nsteps):
-    o.d["ctrl"][:] = np.clip(o.d["ctrl"] + 0.01 * rng.uniform(-1, 1, o.d["ctrl"].shape), -1, 1)
+  for i in range(nsteps):
+    if ctrls is not None:
+      o.d["ctrl"][:] = ctrls[i % len(ctrls)]
+    elif mjm.nu:
+      o.d["ctrl"][:] = np.clip(o.d["ctrl"] + 0.01 * rng.uniform(-1, 1, o.d["ctrl"].shape), -1, 1)
     o.step(nthreads)
   dt = time.perf_counter() - t0
   return nworld * nsteps / dt, dt
@@ -144,21 +169,18 @@ def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  from mujoco_warp_b200._src import mjcf
-  from tests import util
-
-  mjm = mjcf.load_any(util.HUMANOID)
+  wl = WORKLOADS[args.workload]
+  nworld = args.nworld or wl["nworld"]
   cores = usable_cores()
-  nw = args.cpu_sample_worlds
+  nw = args.cpu_sample_worlds or nworld
   for _ in range(max(1, min(args.warmup, 3))):
-    cpu_run(mjm, nw, 1, cores)
-  t0 = time.perf_counter()
-  rate, dt = cpu_run(mjm, nw, args.steps, cores)
+    cpu_run(args.workload, nw, 1, cores)
+  rate, dt = cpu_run(args.workload, nw, args.steps, cores)
   sample = f"{nw} worlds x {args.steps} steps of the oracle (fp64 C, OpenMP {cores} threads) per run"
   line = {
-    "impl": "reference", "metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    "impl": "reference", "metric": metric_name(args.workload), "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
     "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-    "config": {"workload": f"humanoid nworld={nw} per CPU step (bounded sample of nworld={args.nworld}/GPU), nconmax={NCONMAX}, njmax={NJMAX}, keyframe squat, random-walk ctrl"},
+    "config": {"workload": f"{wl['label']}; CPU sample of {nw} worlds per step (bounded sample of nworld={nworld}/GPU), random-walk ctrl" if not wl["replay"] else f"{wl['label']}; CPU sample of {nw} worlds per step"},
     "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
     "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,
@@ -175,7 +197,6 @@ def run_ours(args):
   torch.set_num_threads(max(1, min(4, usable_cores())))  # host-side tensor ops in the e2e loop stay within the cpu quota
   import mujoco_warp_b200 as mjw
   from mujoco_warp_b200._src import io as mio
-  from tests import util
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
@@ -192,16 +213,17 @@ def run_ours(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  wl, mjm, mjd, ctrls = load_workload(args.workload)
   tabs = mio.derive_tables(mjm)
   m = mjw.put_model(mjm)
-  nworld = args.nworld
-  from mujoco_warp_b200._src.mjcf import MjDataLite, reset_data_keyframe
-
-  mjd = MjDataLite(mjm)
-  reset_data_keyframe(mjm, mjd, 0)
+  nworld = args.nworld or wl["nworld"]
+  NCONMAX, NJMAX = wl["nconmax"], wl["njmax"]
   d = mjw.put_data(mjm, mjd, nworld=nworld, nconmax=NCONMAX, njmax=NJMAX, m=m)
-  center = torch.from_numpy(np.asarray(mjm.key_ctrl[0], dtype=np.float32)).cuda()
+  center = torch.from_numpy(np.asarray(mjd.ctrl, dtype=np.float32)).cuda()
+  traj = torch.from_numpy(np.asarray(ctrls, dtype=np.float32)).cuda() if ctrls is not None else None  # (nstep, nu), device resident
+  data_mb = sum(t.numel() * t.element_size() for o in (d, d.efc, d.contact) for t in vars(o).values() if isinstance(t, torch.Tensor)) / 2**20
+  # timing rule: a per-step working set below the 126 MB L2 is flushed between timed steps (each step then gets its own event pair)
+  flush = torch.empty(256 * 2**20 // 4, dtype=torch.float32, device="cuda") if data_mb <= 126 else None
   # ranks use shifted Halton step indices so their noise streams differ
   world_offset = rank * nworld
 
@@ -210,8 +232,14 @@ def run_ours(args):
   step_idx = [0]
   initial = {n: getattr(d, n).clone() for n in ("qpos", "qvel", "ctrl", "qacc_warmstart", "time", "qacc")}
 
+  def set_ctrl():
+    if traj is not None:  # trajectory replay, zero-order hold (cli.py:154-158): every world gets the step's control row
+      d.ctrl.copy_(traj[step_idx[0] % traj.shape[0]].unsqueeze(0).expand(nworld, -1))
+    elif mjm.nu:
+      mjw.ctrl_noise(m, d, step_idx[0] + world_offset, center)
+
   def one_step():
-    mjw.ctrl_noise(m, d, step_idx[0] + world_offset, center)
+    set_ctrl()
     if graph is not None:
       graph.replay()
     else:
@@ -259,19 +287,29 @@ def run_ours(args):
     # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    niter_sum = torch.zeros((), device="cuda", dtype=torch.float64)
-    e0.record(stream)
-    for _ in range(args.steps):
-      one_step()
-    e1.record(stream)
-    stream.synchronize()
+    if flush is None:
+      e0.record(stream)
+      for _ in range(args.steps):
+        one_step()
+      e1.record(stream)
+      stream.synchronize()
+      ms = e0.elapsed_time(e1)
+    else:
+      evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+      for a, b in evs:
+        flush.fill_(0.0)
+        a.record(stream)
+        one_step()
+        b.record(stream)
+      stream.synchronize()
+      ms = sum(a.elapsed_time(b) for a, b in evs)
     barrier()
-    ms = e0.elapsed_time(e1)
     # ---- statistics of the run (untimed), taken from the last timed step
     ncon_mean = float(d.nacon.cpu()[0]) / nworld
     nefc_mean = float(d.nefc.float().mean().cpu())
     niter_mean = float(d.solver_niter.float().mean().cpu())
     ovf = int((d.overflow != 0).sum().cpu())
+    ovf_bits = int(np.bitwise_or.reduce(d.overflow.cpu().numpy().astype(np.int64))) if nworld else 0
     nan_worlds = int(torch.isnan(d.qpos).any(dim=1).sum().cpu())
     n_rows, t_wait = len(sampler.rows), time.perf_counter() + 1.0
     while rank == 0 and sampler.proc is not None and len(sampler.rows) <= n_rows and time.perf_counter() < t_wait:
@@ -285,7 +323,7 @@ def run_ours(args):
     nprof = 20
     acc = None
     for _ in range(nprof):
-      mjw.ctrl_noise(m, d, step_idx[0] + world_offset, center)
+      set_ctrl()
       step_idx[0] += 1
       r = mjw.step_profile(m, d)
       acc = r if acc is None else {k: acc[k] + r[k] for k in r}
@@ -313,13 +351,12 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier()
 
-  t_max = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
-  if dist is not None:
-    dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-  ms_max, e2e_ms_max = float(t_max[0]), float(t_max[1])
+  from mujoco_warp_b200._src import shard  # the measurement path's only collectives: MAX over ranks of the device-timed durations
+
+  ms_max, e2e_ms_max = shard.reduce_max_elapsed(ms, dist), shard.reduce_max_elapsed(e2e_s * 1e3, dist)
   total_worlds = nworld * world
-  value = total_worlds * args.steps / (ms_max * 1e-3)
-  e2e_value = total_worlds * e2e_steps / (e2e_ms_max * 1e-3)
+  value = shard.whole_job_rate(nworld * args.steps, ms_max * 1e-3, world)
+  e2e_value = shard.whole_job_rate(nworld * e2e_steps, e2e_ms_max * 1e-3, world)
 
   if rank == 0:
     peaks = {}
@@ -343,18 +380,19 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:  # reported baseline, rank 0 at N = 1 only: a bounded sample of the same workload on the host cores
       cores = usable_cores()
       cpu_steps = 50
-      rate, dt = cpu_run(mjm, args.cpu_sample_worlds, cpu_steps, cores)
+      nws = args.cpu_sample_worlds or nworld
+      rate, dt = cpu_run(args.workload, nws, cpu_steps, cores)
       cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-             "sample": f"{args.cpu_sample_worlds} worlds x {cpu_steps} steps of the fp64 C oracle (OpenMP {cores} threads), {dt:.1f} s wall"}
+             "sample": f"{nws} worlds x {cpu_steps} steps of the fp64 C oracle (OpenMP {cores} threads), {dt:.1f} s wall"}
     line = {
-      "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-      "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 2729192.0,
+      "metric": metric_name(args.workload), "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 2729192.0 if args.workload == "humanoid" else None,
       "dtype": "f32", "data": "synthetic",
       "config": {
-        "workload": f"humanoid.xml nworld={nworld}/GPU nconmax={NCONMAX} njmax={NJMAX} keyframe=squat Newton/pyramidal/Euler, OU ctrl noise (Halton)",
-        "cuda_graph": graph is not None, "l2": "per-step Data working set (~175 MB at 8192 worlds incl. efc.J rows) exceeds the 126 MB L2; no explicit flush",
+        "workload": wl["label"] if nworld == wl["nworld"] else wl["label"].replace(f"nworld={wl['nworld']}", f"nworld={nworld}"),
+        "cuda_graph": graph is not None, "l2": f"per-step Data working set ({data_mb:.0f} MB of Data tensors at {nworld} worlds) exceeds the 126 MB L2; no explicit flush" if data_mb > 126 else f"Data tensors are {data_mb:.0f} MB (< 126 MB L2): 256 MB scratch buffer written between timed steps",
         "vs_baseline_note": "2,729,192 steps/s is the reference's only published number (benchmarks/README.md:48), hardware unstated",
-        "sim_steps_before_timed": sim_steps_before_timed, "ncon_mean": ncon_mean, "nefc_mean": nefc_mean, "solver_niter_mean": niter_mean, "overflow_worlds": ovf, "nan_worlds": nan_worlds,
+        "sim_steps_before_timed": sim_steps_before_timed, "ncon_mean": ncon_mean, "nefc_mean": nefc_mean, "solver_niter_mean": niter_mean, "overflow_worlds": ovf, "overflow_bits_or": hex(ovf_bits), "nan_worlds": nan_worlds,
       },
       "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(nworld * mjm.nu * 4), "d2h_bytes_per_step": int(nworld * (mjm.nq + mjm.nv) * 4), "steps": e2e_steps},
       "gpu_launches": launches_per_step * args.steps,

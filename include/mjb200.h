@@ -28,7 +28,8 @@
  *   mjb_contact_force          <- _src/support.py:445  contact_force(m, d, contact_ids, to_world_frame, force)
  *   mjb_rungekutta4            <- _src/forward.py:523  rungekutta4(m, d)
  *   mjb_solve                  <- _src/solver.py:3671  solve
- *   mjb_euler                  <- _src/forward.py:387  euler
+ *   mjb_euler                  <- _src/forward.py:387  euler (always the semi-implicit Euler update, whatever the model's integrator)
+ *   mjb_implicit               <- _src/forward.py:578  implicit (implicitfast: M - dt * qDeriv factor-and-solve, then advance)
  *   mjb_ctrl_noise             <- _src/cli.py:103      _ctrl_noise (harness kernel, untimed in testspeed)
  *
  * Conventions: plain pointers and sizes only (no torch / warp types).  All array pointers are DEVICE
@@ -62,6 +63,8 @@ int mjb_model_finalize(mjbModel* m);
 mjbData* mjb_data_create(int nworld, int nconmax, int naconmax, int njmax, int njmax_pad, int nv_pad);
 void mjb_data_destroy(mjbData* d);
 int mjb_data_set_array(mjbData* d, const char* name, void* dev_ptr);
+/* optional sizes set before finalize: "njmax_nnz" = capacity of the CSR view of efc.J (models the reference treats as sparse, io.py:153) */
+int mjb_data_set_int(mjbData* d, const char* name, int value);
 int mjb_data_finalize(mjbData* d, const mjbModel* m);
 
 /* ---- pipeline */
@@ -95,6 +98,7 @@ int mjb_contact_force(const mjbModel* m, mjbData* d, const int* contact_ids, int
 int mjb_rungekutta4(const mjbModel* m, mjbData* d, void* stream);
 int mjb_solve(const mjbModel* m, mjbData* d, void* stream);
 int mjb_euler(const mjbModel* m, mjbData* d, void* stream);
+int mjb_implicit(const mjbModel* m, mjbData* d, void* stream);
 /* ctrl <- OU noise around ctrl_center (device array of nu floats, or NULL), reference cli.py:103-145 */
 int mjb_ctrl_noise(const mjbModel* m, mjbData* d, const float* ctrl_center, int step, float noise_std, float noise_rate, void* stream);
 

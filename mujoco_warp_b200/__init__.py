@@ -4,6 +4,7 @@ Public surface mirrors /root/reference/mujoco_warp/__init__.py for the step path
 reset_data, step, forward and the individually callable stages; `mjcf.load` stands in for mujoco's MJCF compiler.
 """
 
+from . import scenes
 from ._src import mjcf
 from ._src._lib import build
 from ._src.forward import camlight, collision, com_pos, crb, ctrl_noise, euler, factor_m, forward, fwd_acceleration, fwd_actuation

@@ -15,10 +15,14 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("MJB_LIB", os.path.join(_PKG, "libmjb200.so"))  # MJB_LIB: A/B-test an alternative build
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "mjb200.h")
-SOURCES = ["capi.cu", "k_position.cu", "k_collision.cu", "k_constraint.cu", "k_velocity.cu", "k_solver.cu", "k_integrate.cu", "k_support.cu", "k_sensor.cu"]
+SOURCES = ["capi.cu", "k_position.cu", "k_collision.cu", "k_collision_mesh.cu", "k_constraint.cu", "k_velocity.cu", "k_solver.cu", "k_integrate.cu", "k_support.cu", "k_sensor.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "--extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
 
 _lib = None
+
+
+def _headers():
+  return [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")] + [HEADER_PATH]
 
 
 def _stale() -> bool:
@@ -30,13 +34,31 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-  """Compile every CUDA source for sm_100a into libmjb200.so (nvcc cross-compiles without a GPU)."""
-  if force or _stale():
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(_CSRC, s) for s in SOURCES]]
-    if verbose:
-      cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+  """Compile every CUDA source for sm_100a into libmjb200.so (nvcc cross-compiles without a GPU).
+
+  One object per translation unit, compiled in parallel and only when the source or a header changed, then linked."""
+  if not (force or _stale()):
+    return LIB_PATH
+  from concurrent.futures import ThreadPoolExecutor
+
+  nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+  objdir = os.path.join(_CSRC, "_obj")
+  os.makedirs(objdir, exist_ok=True)
+  hdr_t = max(os.path.getmtime(p) for p in _headers())
+  flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas=-v"] if verbose else [])
+  # k_collision_mesh.cu includes k_collision.cu
+  extra_dep = {"k_collision_mesh.cu": [os.path.join(_CSRC, "k_collision.cu")]}
+
+  def compile_one(src):
+    path, obj = os.path.join(_CSRC, src), os.path.join(objdir, src[:-3] + ".o")
+    newest = max([os.path.getmtime(path), hdr_t] + [os.path.getmtime(p) for p in extra_dep.get(src, [])])
+    if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
+      subprocess.check_call([nvcc, *flags, "-c", path, "-o", obj])
+    return obj
+
+  with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+    objs = list(ex.map(compile_one, SOURCES))
+  subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs])
   return LIB_PATH
 
 
@@ -70,6 +92,7 @@ def lib():
   L.mjb_data_create.argtypes = [ci] * 6
   L.mjb_data_destroy.argtypes = [vp]
   L.mjb_data_set_array.argtypes = [vp, cp, vp]
+  L.mjb_data_set_int.argtypes = [vp, cp, ci]
   L.mjb_data_finalize.argtypes = [vp, vp]
   for f in STAGE_FUNCS:
     getattr(L, f).argtypes = [vp, vp, vp]
@@ -89,7 +112,7 @@ def lib():
 STAGE_FUNCS = [
   "mjb_step", "mjb_forward", "mjb_fwd_position", "mjb_kinematics", "mjb_com_pos", "mjb_camlight", "mjb_crb", "mjb_transmission",
   "mjb_collision", "mjb_make_constraint", "mjb_fwd_velocity", "mjb_fwd_actuation", "mjb_fwd_acceleration", "mjb_factor_m",
-  "mjb_solve", "mjb_euler", "mjb_com_vel", "mjb_passive", "mjb_rne", "mjb_rungekutta4", "mjb_sensor_pos", "mjb_sensor_vel", "mjb_sensor_acc",
+  "mjb_solve", "mjb_euler", "mjb_implicit", "mjb_com_vel", "mjb_passive", "mjb_rne", "mjb_rungekutta4", "mjb_sensor_pos", "mjb_sensor_vel", "mjb_sensor_acc",
 ]
 
 

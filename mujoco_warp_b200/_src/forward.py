@@ -119,7 +119,7 @@ def implicit(m: Model, d: Data):
 
   if m.opt.integrator != C.INT_IMPLICITFAST:
     raise NotImplementedError("implicit(): only the implicitfast integrator is implemented")
-  _call("mjb_euler", m, d)  # the integrate kernel dispatches on m.opt.integrator
+  _call("mjb_implicit", m, d)
 
 
 def fwd_kinematics(m: Model, d: Data):
@@ -223,9 +223,15 @@ def set_state(m: Model, d: Data, state: torch.Tensor, sig: int, active: torch.Te
 
 
 def step1(m: Model, d: Data):
-  """First half of a split step, before the user sets controls (reference forward.py step1; no sensors / energy here)."""
+  """First half of a split step, before the user sets controls (reference forward.py:1384 step1: position and velocity stages
+  with their sensors; energy is not computed in this build)."""
   fwd_position(m, d)
+  if getattr(m, "nsensor", 0):
+    d.sensordata.zero_()
+    sensor_pos(m, d)
   fwd_velocity(m, d)
+  if getattr(m, "nsensor", 0):
+    sensor_vel(m, d)
 
 
 def step2(m: Model, d: Data):
@@ -235,6 +241,8 @@ def step2(m: Model, d: Data):
   fwd_actuation(m, d)
   fwd_acceleration(m, d)
   solve(m, d)
+  if getattr(m, "nsensor", 0):
+    sensor_acc(m, d)
   if m.opt.integrator == C.INT_IMPLICITFAST:
     implicit(m, d)
   else:

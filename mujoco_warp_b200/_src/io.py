@@ -46,11 +46,15 @@ _SUPPORTED_PAIRS = {
   # box / cylinder / ellipsoid primitives (collision_driver.py:47-81: the pairs the reference routes to primitive functions)
   (C.GEOM_PLANE, C.GEOM_ELLIPSOID), (C.GEOM_PLANE, C.GEOM_CYLINDER), (C.GEOM_PLANE, C.GEOM_BOX),
   (C.GEOM_SPHERE, C.GEOM_CYLINDER), (C.GEOM_SPHERE, C.GEOM_BOX), (C.GEOM_CAPSULE, C.GEOM_BOX),
+  (C.GEOM_PLANE, C.GEOM_MESH),  # plane_convex (collision_primitive.py:52), in the mesh build of the collision kernel
 }
 # pairs the reference sends to GJK / EPA (collision_driver.py:47-81) that are built here: analytic convex geoms, single contact
 _CONVEX_PAIRS = {
   (C.GEOM_SPHERE, C.GEOM_ELLIPSOID), (C.GEOM_CAPSULE, C.GEOM_ELLIPSOID), (C.GEOM_CAPSULE, C.GEOM_CYLINDER), (C.GEOM_ELLIPSOID, C.GEOM_ELLIPSOID),
   (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER), (C.GEOM_ELLIPSOID, C.GEOM_BOX), (C.GEOM_CYLINDER, C.GEOM_CYLINDER), (C.GEOM_CYLINDER, C.GEOM_BOX),
+  # mesh geoms (hull-vertex support function, mesh multi-contact): collision_gjk.py:116, collision_convex.py:1190
+  (C.GEOM_SPHERE, C.GEOM_MESH), (C.GEOM_CAPSULE, C.GEOM_MESH), (C.GEOM_ELLIPSOID, C.GEOM_MESH), (C.GEOM_CYLINDER, C.GEOM_MESH),
+  (C.GEOM_BOX, C.GEOM_MESH), (C.GEOM_MESH, C.GEOM_MESH),
 }
 
 
@@ -143,6 +147,12 @@ def derive_tables(mjm) -> dict:
   t["tree_qLDadr"] = np.array(qadr if qadr else [0], dtype=np.int32)
   t["qld_total"] = off
   t["maxtree"] = int(tnum.max()) if len(tnum) else 0
+  # longest dof chain (a dof and its ancestors): bounds the nonzeros of one constraint Jacobian row (two bodies' chains)
+  dpar = _np(mjm, "dof_parentid")
+  depth = np.zeros(max(nv, 1), dtype=np.int64)
+  for i in range(nv):
+    depth[i] = 1 + (depth[dpar[i]] if dpar[i] >= 0 else 0)
+  t["max_dof_chain"] = int(depth.max()) if nv else 0
   blk = np.zeros(max(nv, 1), dtype=np.int32)
   for a, n, q in zip(tadr, tnum, qadr):
     blk[a : a + n] = q
@@ -268,6 +278,26 @@ def _validate(mjm):
     raise NotImplementedError(f"unknown friction cone {o.cone}")
   if o.solver not in (C.SOL_NEWTON, C.SOL_CG):
     raise NotImplementedError("only the Newton and CG solvers are implemented in this version (no PGS)")
+  # features the kernels do not evaluate must fail here, not silently change the simulation
+  if float(getattr(o, "density", 0.0)) != 0.0 or float(getattr(o, "viscosity", 0.0)) != 0.0 or np.any(np.asarray(getattr(o, "wind", 0.0)) != 0.0):
+    raise NotImplementedError("fluid forces (opt.density / viscosity / wind) are not implemented")
+  if int(getattr(o, "noslip_iterations", 0)) > 0:
+    raise NotImplementedError("the noslip solver (opt.noslip_iterations > 0) is not implemented")
+  unsupported_enable = int(o.enableflags) & (C.ENBL_OVERRIDE | C.ENBL_ENERGY | C.ENBL_FWDINV | C.ENBL_INVDISCRETE | C.ENBL_SLEEP)
+  if unsupported_enable:
+    names = [n for n, b in C.ENABLE_FLAGS.items() if unsupported_enable & b]
+    raise NotImplementedError(f"enable flag(s) {names} are not implemented (contact override, energy, fwdinv / invdiscrete, sleeping)")
+  if getattr(mjm, "nu", 0):
+    gt, bt = np.asarray(mjm.actuator_gaintype), np.asarray(mjm.actuator_biastype)
+    if not np.isin(gt, (C.GAIN_FIXED, C.GAIN_AFFINE)).all():
+      raise NotImplementedError(f"actuator gain type(s) {sorted(set(gt[~np.isin(gt, (C.GAIN_FIXED, C.GAIN_AFFINE))].tolist()))} are not implemented (fixed and affine are)")
+    if not np.isin(bt, (C.BIAS_NONE, C.BIAS_AFFINE)).all():
+      raise NotImplementedError(f"actuator bias type(s) {sorted(set(bt[~np.isin(bt, (C.BIAS_NONE, C.BIAS_AFFINE))].tolist()))} are not implemented (none and affine are)")
+    if hasattr(mjm, "actuator_dyntype") and np.any(np.asarray(mjm.actuator_dyntype) != 0):
+      raise NotImplementedError("stateful actuators (dyntype != none) are not implemented")
+  for n in ("dof_dampingpoly", "jnt_stiffnesspoly"):
+    if hasattr(mjm, n) and np.any(np.asarray(getattr(mjm, n)) != 0):
+      raise NotImplementedError(f"{n}: polynomial stiffness / damping is not implemented")
   if mjm.nv > 128:
     # the dense per-world Hessian and its factor live in one warp's shared memory; make_data reports the exact per-kernel need
     raise NotImplementedError("nv > 128 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
@@ -300,9 +330,10 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   L = _lib.lib()
   _validate(mjm)
   t = derive_tables(mjm)
-  # The reference switches to a CSR constraint Jacobian for nv > 32 (io.py:153-160).  This version keeps the DENSE efc.J
-  # layout for every supported nv (<= 64); Model.is_sparse is therefore always False (documented deviation for e.g. the G1).
-  sparse = False
+  # The reference switches to a CSR constraint Jacobian for nv > 32 (io.py:153-160).  The kernels here always work on dense rows;
+  # for a sparse model Data.efc carries the reference's CSR arrays (J_rownnz / J_rowadr / J_colind / J) written by k_efc_csr after
+  # make_constraint, and the dense rows live in Data.efc.J_dense.
+  sparse = is_sparse(mjm)
   m = types.Model()
   for n in _SIZES:
     setattr(m, n, int(getattr(mjm, n, 0)))
@@ -310,7 +341,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.nJmom = t["nJmom"]
   m.nmaxcondim, m.nmaxpyramid = t["nmaxcondim"], t["nmaxpyramid"]
   m.is_sparse = sparse
-  m.nv_pad = _get_padded_sizes(m.nv, 0, sparse)[1]
+  m.nv_pad = _get_padded_sizes(m.nv, 0, False)[1]  # row stride of the dense working Jacobian
   m.qLD_block_total = t["qld_total"]
   m.geom_pair_type_count = t["geom_pair_type_count"]
   m.nbranch = int((t["body_childadr"][1:] - t["body_childadr"][:-1] == 0)[1:].sum()) if m.nbody > 1 else 0
@@ -390,6 +421,17 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     setattr(m, n, dev_f(np.asarray(getattr(mjm, n)).reshape(npair, k) if npair else np.zeros((0, k))))
   for n in ("pair_margin", "pair_gap"):
     setattr(m, n, dev_f(np.asarray(getattr(mjm, n)) if npair else np.zeros(0)))
+  # mesh assets (reference Model.mesh_*, types.py): vertex blocks, hull graphs for hill-climbing support queries, hull polygons
+  nmesh = int(getattr(mjm, "nmesh", 0))
+  m.nmesh = nmesh
+  if nmesh and (int(getattr(mjm, "npolygonmax", 0)) > 32 or int(getattr(mjm, "nmeshdegmax", 0)) > 16):
+    raise NotImplementedError(f"mesh hull with {mjm.npolygonmax} vertices in one polygon / {mjm.nmeshdegmax} polygons at one vertex: the mesh multi-contact buffers hold 32 / 16")
+  m.geom_dataid = dev_i(getattr(mjm, "geom_dataid", -np.ones(m.ngeom)))
+  for n in ("mesh_vertadr", "mesh_vertnum", "mesh_graphadr", "mesh_graph", "mesh_polynum", "mesh_polyadr", "mesh_polyvertadr", "mesh_polyvertnum",
+            "mesh_polyvert", "mesh_polymapadr", "mesh_polymapnum", "mesh_polymap"):
+    setattr(m, n, dev_i(getattr(mjm, n) if nmesh else np.zeros(0)))
+  m.mesh_vert = dev_f(np.asarray(mjm.mesh_vert).reshape(-1, 3) if nmesh else np.zeros((0, 3)), batched=False)
+  m.mesh_polynormal = dev_f(np.asarray(mjm.mesh_polynormal).reshape(-1, 3) if nmesh else np.zeros((0, 3)), batched=False)
   m.M_mulm_rowadr, m.M_mulm_col, m.M_mulm_madr = m.mulm_rowadr, m.mulm_col, m.mulm_madr
   anc_pad = np.zeros((m.nbody, m.nv_pad), dtype=np.int32)
   anc_pad[:, : m.nv] = t["body_isdofancestor"]
@@ -408,7 +450,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     nfricdof=len(t["dof_fricloss_adr"]), nmaxpyramid=m.nmaxpyramid, integrator=m.opt.integrator, cone=m.opt.cone, solver=m.opt.solver,
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase=int(m.opt.broadphase), broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
-    has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX)).any()),
+    has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX, C.GEOM_MESH)).any()), nmesh=nmesh,
     nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), epa_iterations=t["epa_iterations"], nsensor=m.nsensor, nsensordata=m.nsensordata, sensor_subtree_vel=int(m.sensor_subtree_vel), sensor_rne_postconstraint=int(m.sensor_rne_postconstraint), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
@@ -427,7 +469,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                                          "dofact_adr", "dofact_act", "dofact_mom", "eq_type", "eq_obj1id", "eq_obj2id", "eq_solref", "eq_solimp", "eq_data",
                                          "jnt_limited_ball_adr", "pair_dim", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp",
                                          "pair_margin", "pair_gap", "sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_reftype", "sensor_refid",
-                                         "sensor_dim", "sensor_adr", "sensor_cutoff", "site_type", "site_size"]:
+                                         "sensor_dim", "sensor_adr", "sensor_cutoff", "site_type", "site_size", "geom_dataid", "mesh_vertadr", "mesh_vertnum", "mesh_graphadr", "mesh_graph",
+                                         "mesh_polynum", "mesh_polyadr", "mesh_polyvertadr", "mesh_polyvertnum", "mesh_polyvert", "mesh_polymapadr", "mesh_polymapnum",
+                                         "mesh_polymap", "mesh_vert", "mesh_polynormal"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)
@@ -584,12 +628,32 @@ def make_data(mjm, nworld: int = 1, nconmax=None, nccdmax=None, njmax=None, njma
   if nconmax < 0 or njmax < 0:
     raise ValueError("nconmax and njmax must be >= 0")
   naconmax = nworld * nconmax if naconmax is None else int(naconmax)
-  njmax_pad, nv_pad = _get_padded_sizes(m.nv, njmax, m.is_sparse)
-  d = types.Data(nworld=nworld, naconmax=naconmax, naccdmax=0, njmax=njmax, njmax_pad=njmax_pad, njmax_nnz=0, nvmax=m.nv, nconmax=nconmax)
+  njmax_pad, nv_pad = _get_padded_sizes(m.nv, njmax, False)
+  if m.is_sparse:
+    if njmax_nnz is None:
+      # every row fits: a row touches at most the dof chains of two bodies (the reference's default is a tighter heuristic,
+      # io.py:1468; pass njmax_nnz to reproduce a particular capacity)
+      t = m._tables
+      njmax_nnz = njmax * min(m.nv, 2 * int(t["max_dof_chain"]))
+    njmax_nnz = int(njmax_nnz)
+  else:
+    njmax_nnz = 0
+  d = types.Data(nworld=nworld, naconmax=naconmax, naccdmax=0, njmax=njmax, njmax_pad=njmax_pad, njmax_nnz=njmax_nnz, nvmax=m.nv, nconmax=nconmax)
   for k, v in _alloc(_data_spec(m, nworld, naconmax, njmax, njmax_pad), dev).items():
     setattr(d, k, v)
   d.contact = types.Contact(**_alloc(_contact_spec(m, max(naconmax, 1)), dev))
   d.efc = types.Constraint(**_alloc(_efc_spec(m, nworld, max(njmax, 1), max(njmax_pad, 1)), dev))
+  i32 = torch.int32
+  if m.is_sparse:  # reference io.py:1803-1812: J becomes the CSR value array; the dense rows stay available as J_dense
+    d.efc.J_dense = d.efc.J
+    d.efc.J = torch.zeros((nworld, 1, max(njmax_nnz, 1)), dtype=torch.float32, device=dev)
+    d.efc.J_rownnz = torch.zeros((nworld, max(njmax, 1)), dtype=i32, device=dev)
+    d.efc.J_rowadr = torch.zeros((nworld, max(njmax, 1)), dtype=i32, device=dev)
+    d.efc.J_colind = torch.zeros((nworld, 1, max(njmax_nnz, 1)), dtype=i32, device=dev)
+  else:
+    d.efc.J_rownnz = torch.zeros((nworld, 0), dtype=i32, device=dev)
+    d.efc.J_rowadr = torch.zeros((nworld, 0), dtype=i32, device=dev)
+    d.efc.J_colind = torch.zeros((nworld, 0, 0), dtype=i32, device=dev)
   # state at qpos0; static geom poses from one host kinematics pass (io.py:1815-1848)
   qpos0 = np.asarray(mjm.qpos0, dtype=np.float64)
   d.qpos.copy_(torch.from_numpy(np.tile(qpos0.astype(np.float32), (nworld, 1))))
@@ -640,7 +704,11 @@ def _bind(m: types.Model, d: types.Data, L):
   for n in _BOUND_TOP:
     reg(n, getattr(d, n))
   for n in _BOUND_EFC:
+    reg("efc_" + n, d.efc.J_dense if (n == "J" and m.is_sparse) else getattr(d.efc, n))
+  reg("efc_Jsp", d.efc.J if m.is_sparse else torch.zeros(1, dtype=torch.float32, device=d.efc.J.device))
+  for n in ("J_rownnz", "J_rowadr", "J_colind"):
     reg("efc_" + n, getattr(d.efc, n))
+  _lib.check(L.mjb_data_set_int(h, b"njmax_nnz", int(d.njmax_nnz)))
   for n in _BOUND_CONTACT:
     reg("contact_" + n, getattr(d.contact, n))
   _lib.check(L.mjb_data_finalize(h, m._handle))
@@ -658,7 +726,7 @@ def _bind(m: types.Model, d: types.Data, L):
     return hook
 
   object.__setattr__(d, "_rebind", make_hook(d, "", set(_BOUND_TOP)))
-  object.__setattr__(d.efc, "_rebind", make_hook(d.efc, "efc_", set(_BOUND_EFC)))
+  object.__setattr__(d.efc, "_rebind", make_hook(d.efc, "efc_", (set(_BOUND_EFC) - {"J"}) if m.is_sparse else set(_BOUND_EFC)))
   object.__setattr__(d.contact, "_rebind", make_hook(d.contact, "contact_", set(_BOUND_CONTACT)))
 
 
@@ -757,7 +825,7 @@ def get_data_into(result, mjm, d: types.Data, world_id: int = 0):
     con[name] = getattr(d.contact, name)[ids].cpu().numpy()
   result.contact = con
   nv = mjm.nv
-  result.efc_J = d.efc.J[w, :nefc, :nv].cpu().numpy().astype(np.float64)
+  result.efc_J = (d.efc.J_dense if hasattr(d.efc, "J_dense") else d.efc.J)[w, :nefc, :nv].cpu().numpy().astype(np.float64)
   for name in ("pos", "margin", "D", "vel", "aref", "frictionloss", "force"):
     setattr(result, "efc_" + name, getattr(d.efc, name)[w, :nefc].cpu().numpy().astype(np.float64))
   for name in ("type", "id", "state"):

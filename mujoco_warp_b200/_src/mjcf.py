@@ -512,9 +512,30 @@ def compile_xml(root):
     enableflags=0,
     impratio=1.0,
     jacobian=C.JAC_AUTO,
+    density=0.0,
+    viscosity=0.0,
+    wind=np.zeros(3),
+    magnetic=np.array([0.0, -0.5, 0.0]),
+    noslip_iterations=0,
+    noslip_tolerance=1e-6,
+    o_margin=0.0,
   )
+  known_option = {"timestep", "tolerance", "ls_tolerance", "impratio", "ccd_tolerance", "iterations", "ls_iterations", "ccd_iterations", "gravity", "integrator",
+                  "cone", "solver", "jacobian", "density", "viscosity", "wind", "magnetic", "noslip_iterations", "noslip_tolerance", "o_margin", "o_solref",
+                  "o_solimp", "o_friction", "sdf_iterations", "sdf_initpoints", "actuatorgroupdisable", "apirate", "mpr_iterations", "mpr_tolerance"}
   for oe in root.findall("option"):
     a = oe.attrib
+    unknown = sorted(set(a) - known_option)
+    if unknown:
+      raise ValueError(f"<option>: unknown attribute(s) {unknown}")
+    for k in ("density", "viscosity", "noslip_tolerance", "o_margin"):
+      if k in a:
+        setattr(opt, k, float(a[k]))
+    if "noslip_iterations" in a:
+      opt.noslip_iterations = int(a["noslip_iterations"])
+    for k in ("wind", "magnetic"):
+      if k in a:
+        setattr(opt, k, _vec(a[k]))
     if "ccd_iterations" in a:
       opt.ccd_iterations = int(a["ccd_iterations"])
     for k in ("timestep", "tolerance", "ls_tolerance", "impratio", "ccd_tolerance"):

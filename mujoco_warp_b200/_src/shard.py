@@ -16,8 +16,14 @@ def shard_worlds(nworld_total: int, world_size: int, rank: int) -> tuple[int, in
 
 
 def whole_job_rate(units_per_rank: list[int] | int, elapsed_s_max: float, world_size: int | None = None) -> float:
-  """Whole-job throughput = units all ranks processed / max-over-ranks elapsed time."""
-  total = units_per_rank * world_size if isinstance(units_per_rank, int) else sum(units_per_rank)
+  """Whole-job throughput = units all ranks processed / max-over-ranks elapsed time.  An int means the same count on every
+  rank and needs world_size."""
+  if isinstance(units_per_rank, int):
+    if world_size is None:
+      raise ValueError("whole_job_rate: world_size is required when units_per_rank is a single count")
+    total = units_per_rank * world_size
+  else:
+    total = sum(units_per_rank)
   return total / elapsed_s_max
 
 
@@ -27,7 +33,9 @@ def reduce_max_elapsed(elapsed_ms: float, dist=None, device=None) -> float:
     return float(elapsed_ms)
   import torch
 
-  t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device or "cpu")
+  if device is None:  # NCCL reduces device tensors only; gloo takes CPU tensors
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+  t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
   dist.all_reduce(t, op=dist.ReduceOp.MAX)
   return float(t[0])
 

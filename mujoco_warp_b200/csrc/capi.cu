@@ -107,6 +107,10 @@ void mjb_data_destroy(mjbData* d) {
   }
   delete d;
 }
+int mjb_data_set_int(mjbData* d, const char* name, int v) {
+  if (!strcmp(name, "njmax_nnz")) { d->dev.njmax_nnz = v; return 0; }
+  return fail(std::string("unknown data int field: ") + name);
+}
 int mjb_data_set_array(mjbData* d, const char* name, void* p) {
 #define X(n) if (!strcmp(name, #n)) { d->dev.n = (float*)p; return 0; }
   MJB_DATA_FARRS(X)
@@ -170,7 +174,12 @@ int mjb_camlight(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB
 int mjb_crb(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_CRB, s), 1); return 0; }
 int mjb_transmission(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_position(m->dev, d->dev, STG_TRANSMISSION, s), 1); return 0; }
 int mjb_collision(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(reset_contact_counters(d->dev, s), 0); MJB_LAUNCH(launch_collision(m->dev, d->dev, s), 1); return 0; }
-int mjb_make_constraint(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1); return 0; }
+int mjb_make_constraint(const mjbModel* m, mjbData* d, void* stream) {
+  MJB_ENTER();
+  MJB_LAUNCH(launch_constraint(m->dev, d->dev, s), 1);
+  if (d->dev.njmax_nnz > 0) MJB_LAUNCH(launch_efc_csr(m->dev, d->dev, s), 1);
+  return 0;
+}
 int mjb_fwd_velocity(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_VELOCITY, s), 1); return 0; }
 int mjb_fwd_actuation(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_ACTUATION, s), 1); return 0; }
 int mjb_fwd_acceleration(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_velocity(m->dev, d->dev, STG_ACCELERATION, s), 1); return 0; }
@@ -200,7 +209,8 @@ int mjb_sensor_pos(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); M
 int mjb_sensor_vel(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_sensor(m->dev, d->dev, 2, s), 1); return 0; }
 int mjb_sensor_acc(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_sensor(m->dev, d->dev, 4, s), 1); return 0; }
 int mjb_solve(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1); return 0; }
-int mjb_euler(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1); return 0; }
+int mjb_euler(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, INT_EULER, s), 1); return 0; }
+int mjb_implicit(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, INT_IMPLICITFAST, s), 1); return 0; }
 
 // which stages a pipeline call runs
 enum { RUN_POSITION = 1, RUN_VELOCITY = 2, RUN_SOLVER = 4, RUN_EULER = 8 };
@@ -211,12 +221,13 @@ static int chain(const mjbModel* m, const DataDev& dd, int what, cudaStream_t s)
     MJB_LAUNCH(launch_position(m->dev, dd, STG_KINEMATICS | STG_COM_POS | STG_CAMLIGHT | STG_CRB | STG_TRANSMISSION, s), 1);
     MJB_LAUNCH(launch_collision(m->dev, dd, s), 1);
     MJB_LAUNCH(launch_constraint(m->dev, dd, s), 1);
+    if (dd.njmax_nnz > 0) MJB_LAUNCH(launch_efc_csr(m->dev, dd, s), 1);  // sparse models: the reference's CSR arrays next to the dense rows
   }
   if (what & RUN_VELOCITY) MJB_LAUNCH(launch_velocity(m->dev, dd, STG_VELOCITY | STG_ACTUATION | STG_ACCELERATION, s), 1);
   if (what & RUN_SOLVER) MJB_LAUNCH(launch_solver(m->dev, dd, s), 1);
   // sensors of all three stages in one launch after the solver (forward.py:1350-1365 interleaves them; their inputs are final by now)
   if ((what & RUN_SOLVER) && m->dev.nsensor > 0) MJB_LAUNCH(launch_sensor(m->dev, dd, 7, s), 1);
-  if (what & RUN_EULER) MJB_LAUNCH(launch_integrate(m->dev, dd, s), 1);
+  if (what & RUN_EULER) MJB_LAUNCH(launch_integrate(m->dev, dd, -1, s), 1);
   return 0;
 }
 
@@ -275,7 +286,7 @@ int mjb_step_profile(const mjbModel* m, mjbData* d, void* stream, float* ms_out)
   cudaEventRecord(ev[4], s);
   MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1);
   cudaEventRecord(ev[5], s);
-  MJB_LAUNCH(launch_integrate(m->dev, d->dev, s), 1);
+  MJB_LAUNCH(launch_integrate(m->dev, d->dev, -1, s), 1);
   cudaEventRecord(ev[6], s);
   if (check(cudaEventSynchronize(ev[6]), "cudaEventSynchronize")) return -1;
   for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);

@@ -136,6 +136,23 @@ __device__ void contact_params(const ModelDev& m, int g1, int g2, int pairid, Co
   for (int i = 0; i < 5; i++) p->solimp[i] = mix * m.geom_solimp[5 * g1 + i] + (1.f - mix) * m.geom_solimp[5 * g2 + i];
 }
 
+#if CCD_MESH
+// collision_core.py:60-140 geom(): a mesh geom carries its asset's vertex block, hull graph and hull polygon tables
+__device__ __forceinline__ void fill_mesh(const ModelDev& m, int g, CGeom& c) {
+  c.index = -1; c.vertnum = 0; c.polynum = 0; c.vert = nullptr; c.polynormal = nullptr; c.graph = nullptr;
+  c.polyvertadr = c.polyvertnum = c.polyvert = c.polymapadr = c.polymapnum = c.polymap = nullptr;
+  if (c.type != GEOM_MESH) return;
+  const int id = m.geom_dataid[g];
+  if (id < 0) return;
+  const int vadr = m.mesh_vertadr[id], padr = m.mesh_polyadr[id];
+  c.vert = m.mesh_vert + 3 * vadr; c.vertnum = m.mesh_vertnum[id];
+  c.graph = m.mesh_graphadr[id] >= 0 ? m.mesh_graph + m.mesh_graphadr[id] : nullptr;
+  c.polynum = m.mesh_polynum[id]; c.polynormal = m.mesh_polynormal + 3 * padr;
+  c.polyvertadr = m.mesh_polyvertadr + padr; c.polyvertnum = m.mesh_polyvertnum + padr; c.polyvert = m.mesh_polyvert;
+  c.polymapadr = m.mesh_polymapadr + vadr; c.polymapnum = m.mesh_polymapnum + vadr; c.polymap = m.mesh_polymap;
+}
+#endif
+
 // MAXC = contacts one geom pair can produce: 2 for plane/sphere/capsule-only models (everything stays in registers),
 // 8 once boxes, cylinders or ellipsoids are present.
 template <int MAXC>
@@ -269,6 +286,9 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
             CGeom a, b;
             a.pos = ld3(gxpos + 3 * g1); a.rot = gxmat + 9 * g1; a.size = ld3(m.geom_size + 3 * g1); a.margin = margin; a.type = m.geom_type[g1];
             b.pos = ld3(gxpos + 3 * g2); b.rot = gxmat + 9 * g2; b.size = ld3(m.geom_size + 3 * g2); b.margin = margin; b.type = m.geom_type[g2];
+#if CCD_MESH
+            fill_mesh(m, g1, a); fill_mesh(m, g2, b);
+#endif
             bool eovf = false;
             const int nc = ccd_pair(m.ccd_tolerance, gap, m.ccd_iterations, m.epa_iterations, a, b, ccd_scratch + slot * sw, &dist, w1, w2, &eovf);
             if (eovf) ovf |= OVF_EPA_HORIZON;
@@ -380,6 +400,15 @@ k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev 
         } else if (t1 == GEOM_PLANE && t2 == GEOM_BOX) {
           plane_box(ax1, pos1, pos2, rot2, size2, cd, cp);
           for (int k = 0; k < MAXC; k++) cn[k] = ax1;
+#if CCD_MESH
+        } else if (t1 == GEOM_PLANE && t2 == GEOM_MESH) {  // collision_primitive.py:838 plane_convex: up to four hull vertices below the plane
+          CGeom c;
+          c.pos = pos2; c.rot = rot2; c.size = size2; c.margin = 0.f; c.type = GEOM_MESH;
+          fill_mesh(m, g2, c);
+          float d4[4]; v3 p4[4];
+          plane_mesh(ax1, pos1, c, d4, p4);
+          for (int k = 0; k < 4; k++) { cd[k] = d4[k] < MJ_MAXVAL ? d4[k] : INFINITY; cp[k] = p4[k]; cn[k] = ax1; }
+#endif
         } else if (t1 == GEOM_SPHERE && t2 == GEOM_CYLINDER) {
           cd[0] = sphere_cylinder(pos1, size1.x, pos2, ax2, size2.x, size2.y, &cp[0], &cn[0]);
         } else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) {
@@ -460,27 +489,48 @@ static int collision_wpb() {
   return v;
 }
 
-size_t smem_collision(const ModelDev& m, const DataDev& d) { return (size_t)col_layout(m, d).total * sizeof(float) * collision_wpb(); }
+#ifdef MJB_COLLISION_MESH_TU
+#define LAUNCH_NAME launch_collision_mesh
+#define SMEM_NAME smem_collision_mesh
+#else
+#define LAUNCH_NAME launch_collision
+#define SMEM_NAME smem_collision
+#endif
 
+size_t SMEM_NAME(const ModelDev& m, const DataDev& d) {
+#ifndef MJB_COLLISION_MESH_TU
+  if (m.nmesh > 0) return smem_collision_mesh(m, d);
+#endif
+  return (size_t)col_layout(m, d).total * sizeof(float) * collision_wpb();
+}
+
+#ifndef MJB_COLLISION_MESH_TU
 cudaError_t reset_contact_counters(const DataDev& d, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(d.nacon, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
   return cudaMemsetAsync(d.ncollision, 0, sizeof(int), s);
 }
+#endif
 
-cudaError_t launch_collision(const ModelDev& m, const DataDev& d, cudaStream_t s) {
-  cudaError_t e;
-  const size_t smem = smem_collision(m, d);
+cudaError_t LAUNCH_NAME(const ModelDev& m, const DataDev& d, cudaStream_t s) {
+#ifndef MJB_COLLISION_MESH_TU
+  if (m.nmesh > 0) return launch_collision_mesh(m, d, s);  // models with mesh geoms run the CCD_MESH build of this kernel
+#endif
+  const size_t smem = SMEM_NAME(m, d);
   static size_t configured[2] = {0, 0};
+#ifdef MJB_COLLISION_MESH_TU
+  const int full = 1;
+  void (*kern)(ModelDev, DataDev) = k_collision<8>;
+#else
   const int full = m.has_multicontact_geom ? 1 : 0;
+  void (*kern)(ModelDev, DataDev) = full ? k_collision<8> : k_collision<2>;
+#endif
   if (smem > 48 * 1024 && smem > configured[full]) {
-    e = full ? cudaFuncSetAttribute(k_collision<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-             : cudaFuncSetAttribute(k_collision<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[full] = smem;
   }
   const int grid = (d.wn + collision_wpb() - 1) / collision_wpb();
-  if (full) k_collision<8><<<grid, collision_wpb() * 32, smem, s>>>(m, d);
-  else k_collision<2><<<grid, collision_wpb() * 32, smem, s>>>(m, d);
+  kern<<<grid, collision_wpb() * 32, smem, s>>>(m, d);
   return cudaGetLastError();
 }

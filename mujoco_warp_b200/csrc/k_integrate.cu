@@ -20,7 +20,7 @@ __host__ __device__ inline int int_words(const ModelDev& m) {
 }
 
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
-k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
+k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int integrator) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
   const int w = blockIdx.x + d.w0;
@@ -36,7 +36,7 @@ k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   __syncwarp();
   warp_copy(d.qacc_warmstart + wb * nv, qacc, nv, lane);  // warmstart <- solver qacc (forward.py:343)
 
-  const bool implicitfast = m.integrator == INT_IMPLICITFAST;
+  const bool implicitfast = integrator == INT_IMPLICITFAST;
   if (implicitfast || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
     // Euler: qacc <- (M + dt*diag(damping))^-1 * Ma  (forward.py:391-415); implicitfast: (M - dt*qDeriv)^-1 * Ma
     const bool damper = !(m.disableflags & DSBL_DAMPER);
@@ -248,8 +248,10 @@ k_rk_stage(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
 size_t smem_integrate(const ModelDev& m) { return (size_t)int_words(m) * sizeof(float) * MJB_WARPS_PER_BLOCK; }
 
-cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s) {
-  const bool solve = m.integrator == INT_IMPLICITFAST || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
+// integrator: INT_EULER / INT_IMPLICITFAST, or -1 for the model's own (RK4 models advance with Euler here, forward.py:1411)
+cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, int integrator, cudaStream_t s) {
+  if (integrator < 0) integrator = m.integrator == INT_IMPLICITFAST ? INT_IMPLICITFAST : INT_EULER;
+  const bool solve = integrator == INT_IMPLICITFAST || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
   if (!solve && m.njnt > 0) {
     const long n = (long)d.wn * m.njnt;
     k_euler_flat<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, d);
@@ -263,7 +265,7 @@ cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, cudaStream_t s
     configured = smem;
   }
   const int grid = d.wn;
-  k_euler<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d);
+  k_euler<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, integrator);
   return cudaGetLastError();
 }
 

@@ -378,25 +378,20 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
 }  // namespace
 
-// lanes per world of the position kernel (MJB_LPW_POS = 4 | 8 | 16 | 32 overrides; measured on B200)
-int position_lpw() {
-  static int v = 0;
-  if (!v) { const char* e = getenv("MJB_LPW_POS"); v = e ? atoi(e) : 8; if (v != 4 && v != 8 && v != 16 && v != 32) v = 8; }
-  return v;
-}
-
-static size_t pos_warp_bytes(const ModelDev& m) { return ((size_t)pos_layout(m).total * (32 / position_lpw()) + 4) * sizeof(float); }
-size_t smem_position(const ModelDev& m) { return pos_warp_bytes(m) * team_warps_per_block(position_lpw(), "MJB_WPB_POS"); }
+static TeamShape pos_shape(const ModelDev& m) { return team_shape((size_t)pos_layout(m).total, "MJB_LPW_POS", "MJB_WPB_POS"); }
+size_t smem_position(const ModelDev& m) { return pos_shape(m).block_bytes; }
 
 cudaError_t launch_position(const ModelDev& m, const DataDev& d, int mask, cudaStream_t s) {
-  const size_t smem = smem_position(m);
-  const int lpw = position_lpw(), G = 32 / lpw, wpb = team_warps_per_block(lpw, "MJB_WPB_POS");
+  const TeamShape t = pos_shape(m);
+  const size_t smem = t.block_bytes;
+  const int lpw = t.lpw, G = 32 / lpw, wpb = t.wpb;
   void (*kern)(ModelDev, DataDev, int) = lpw == 4 ? k_position<4> : lpw == 8 ? k_position<8> : lpw == 16 ? k_position<16> : k_position<32>;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[4] = {0, 0, 0, 0};
+  const int ki = lpw == 4 ? 0 : lpw == 8 ? 1 : lpw == 16 ? 2 : 3;
+  if (smem > 48 * 1024 && smem > configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[ki] = smem;
   }
   const int ngroups = (d.wn + G - 1) / G, grid = (ngroups + wpb - 1) / wpb;
   kern<<<grid, 32 * wpb, smem, s>>>(m, d, mask);

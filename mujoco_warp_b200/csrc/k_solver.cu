@@ -41,8 +41,11 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   // nv <= 32: H and its factor are stored as packed lower triangles (register Cholesky path); larger nv keeps nv x ldH
   // H and its factor are packed lower triangles (register Cholesky for nv <= 32, shared-memory Cholesky above)
   const int hsz = m.nv * (m.nv + 1) / 2;
-  L.H = take(hsz); L.Lf = take(hsz);
-  L.M = take(m.nC);
+  L.H = take(hsz);
+  // nv <= 32: the factor lives in the padded column layout of chol_solve_rows_bcast, and M is kept as a dense packed lower
+  // triangle (H starts as a copy of it, M * v needs no index tables); nv > 32: packed factor, CSR M with gather tables
+  L.Lf = take(m.nv > 32 ? hsz : colsub_off(m.nv));
+  L.M = take(m.nv > 32 ? m.nC : hsz);
   // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
   // elliptic cones add: per-row friction scale, 3 quad words per row (solver.py:1008-1015 layout), row->contact info
   const bool ell = m.cone == CONE_ELLIPTIC;
@@ -218,10 +221,28 @@ __device__ __forceinline__ EllQ ell_load(const Ctx& c, int r) {
   return e;
 }
 
-// res = M vec via the symmetric gather tables (support.py:153 mul_m; tables io.py:1029-1050)
-template <int NW>
+// res = M vec (support.py:153 mul_m).  nv <= 32: M is a dense packed lower triangle in shared memory, lane i walks row i up to the
+// diagonal and column i below it -- no index tables, no global loads (the CSR gather's table lookups were the top
+// long-scoreboard line of the solver).  nv > 32: the symmetric gather tables (io.py:1029-1050).
+template <int NW, bool BIG>
 __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res) {
   const ModelDev& m = *c.m;
+  if (!BIG) {
+    const int i = c.lane, nv = c.nv;
+    if (i < nv) {
+      const float* Mi = c.M + (i * (i + 1)) / 2;
+      float acc = 0.f;
+      int tk = 0;  // k (k + 1) / 2
+#pragma unroll 4
+      for (int k = 0; k < nv; k++) {
+        const float mk = k <= i ? Mi[k] : c.M[tk + i];
+        acc += mk * vec[k];
+        tk += k + 1;
+      }
+      res[i] = acc;
+    }
+    return;
+  }
 #pragma unroll 1
   for (int i = c.lane; i < c.nv; i += 32 * NW) {
     float acc = 0.f;
@@ -385,11 +406,7 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
       }
     }
   }
-#ifdef MJB_CHOL_UNROLLED
-  return chol_solve_rows<N, true>(a, nv, g, c.Lf, c.ldH, lane);
-#else
-  return chol_solve_rows_rolled<N, true>(a, nv, g, c.Lf, c.ldH, lane);
-#endif
+  return chol_solve_rows_bcast<N>(a, nv, g, c.Lf, lane);
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
@@ -511,7 +528,7 @@ __device__ __forceinline__ bool linesearch(Ctx& c) {
   const ModelDev& m = *c.m;
   const int nv = c.nv;
   constexpr int NT = 32 * NW;
-  mul_m<NW>(c, c.search, c.mv);
+  mul_m<NW, BIG>(c, c.search, c.mv);
 #pragma unroll 1
   for (int r = c.lane; r < c.nefc; r += NT) {
     c.jv[r] = row_dot(jrow<BIG>(c, r), c.search, c.nvp);
@@ -726,13 +743,13 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
         c.rinfo[r] = info; c.rfri[r] = fr;
       }
     }
-    tcopy<NW>(c.M, d.M + wb * m.nC, m.nC, lane);
+    if (BIG) tcopy<NW>(c.M, d.M + wb * m.nC, m.nC, lane);
     tcopy<NW>(c.qfs, d.qfrc_smooth + wb * nv, nv, lane);
     const float* start = (m.disableflags & DSBL_WARMSTART) ? d.qacc_smooth : d.qacc_warmstart;
     tcopy<NW>(c.qacc, start + wb * nv, nv, lane);
     const int hsz = nv * (nv + 1) / 2;
 #pragma unroll 1
-    for (int e = lane; e < hsz; e += NT) c.H[e] = 0.f;
+    for (int e = lane; e < hsz; e += NT) { c.H[e] = 0.f; if (!BIG) c.M[e] = 0.f; }
   }
   tsync<NW>();
   if (c.env) {
@@ -740,11 +757,22 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     for (int i = lane; i < nv; i += NT) c.fz[i] = i;
     tsync<NW>();
   }
+  if (!BIG) {  // dense packed M from the CSR values in global memory; H = M
+    const float* Mg = d.M + wb * m.nC;
+#pragma unroll 4
+    for (int e = lane; e < m.nC; e += NT) {
+      const int r = m.M_entry_row[e], col = m.M_colind[e];
+      const float v = Mg[e];
+      c.M[(r * (r + 1)) / 2 + col] = v;
+      c.H[(r * (r + 1)) / 2 + col] = v;
+    }
+  } else {
 #pragma unroll 1
-  for (int e = lane; e < m.nC; e += NT) {  // lower triangle of M
-    const int r = m.M_entry_row[e], col = m.M_colind[e];
-    c.H[(r * (r + 1)) / 2 + col] = c.M[e];
-    if (c.env) atomicMin(&c.fz[r], col);
+    for (int e = lane; e < m.nC; e += NT) {  // lower triangle of M
+      const int r = m.M_entry_row[e], col = m.M_colind[e];
+      c.H[(r * (r + 1)) / 2 + col] = c.M[e];
+      if (c.env) atomicMin(&c.fz[r], col);
+    }
   }
   if (c.env) {
     // nonzero column range [lo, hi) of every Jacobian row; rows of one elliptic contact share the union of their ranges (the cone
@@ -781,7 +809,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   for (int r = lane; r < nefc; r += NT) {  // Jaref = J qacc - aref
     c.Jaref[r] = row_dot(jrow<BIG>(c, r), c.qacc, c.nvp) - d.efc_aref[wb * njmax + r];
   }
-  mul_m<NW>(c, c.qacc, c.Ma);
+  mul_m<NW, BIG>(c, c.qacc, c.Ma);
   tsync<NW>();
 
   // One call site per phase: iteration -1 is init_context (solver.py:3622), iterations >= 0 are _solver_iteration (:3526).

@@ -8,6 +8,73 @@
 
 namespace {
 
+// ---- CSR view of the constraint Jacobian for models the reference treats as sparse (io.py:153 is_sparse: nv > 32 under jacobian = auto).
+// The kernels of this library build and consume a dense efc.J; this pass writes the reference's arrays next to it (types.py:2021-2072:
+// J_rownnz, J_rowadr (nworld, njmax), J_colind, J (nworld, 1, njmax_nnz)) with the reference's own sparsity pattern and column order:
+//   contact rows      constraint.py:2728-2753 / :3100-3250  dof chains of the two (weld) bodies, descending dof, stopping at the first common dof
+//   connect / weld    :262-370 / :1130-1240                  union of the two chains, descending (common ancestors kept)
+//   joint equality    :570-606  dof1 [, dof2];   dof friction :1821  dof;   slide / hinge limit :2041  dof;   ball limit :2182  dof, dof + 1, dof + 2
+// Row addresses are the running sum of rownnz in row order (the reference hands them out with an atomic, i.e. in its launch order; run
+// sequentially that is the same sequence).  A row that does not fit in njmax_nnz raises OVF_NJMAX_NNZ and stays empty.
+__device__ __forceinline__ int chain_start(const ModelDev& m, int body) {
+  const int b = m.body_weldid[body];
+  return m.body_dofadr[b] + m.body_dofnum[b] - 1;
+}
+// walks the two dof chains downwards; emit(da) per visited dof.  stop_common: contact rows end at the first dof both chains share.
+template <typename F>
+__device__ __forceinline__ int chain_walk(const ModelDev& m, int da1, int da2, bool stop_common, F emit) {
+  int n = 0;
+  while (da1 >= 0 || da2 >= 0) {
+    const int da = max(da1, da2);
+    if (stop_common && da1 == da && da2 == da) break;
+    if (da1 == da) da1 = m.dof_parentid[da1];
+    if (da2 == da) da2 = m.dof_parentid[da2];
+    emit(da, n);
+    n++;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(32)
+k_efc_csr(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
+  const int lane = threadIdx.x, w = blockIdx.x + d.w0;
+  if (w >= d.nworld || w >= d.w0 + d.wn) return;
+  const size_t wb = (size_t)w;
+  const int njmax = d.njmax, nvp = d.nv_pad, nrow = min(d.nefc[w], njmax);
+  const float* Jd = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
+  float* Jv = d.efc_Jsp + wb * (size_t)d.njmax_nnz;
+  int* col = d.efc_J_colind + wb * (size_t)d.njmax_nnz;
+  int base = 0;
+  bool ovf = false;
+#pragma unroll 1
+  for (int r0 = 0; r0 < nrow; r0 += 32) {
+    const int r = r0 + lane;
+    int kind = 0, a1 = -1, a2 = -1, nnz = 0;  // kind 0: listed dofs a1 [, a2] / ball triple; 1: chain union; 2: chain difference
+    if (r < nrow) {
+      const int type = d.efc_type[wb * njmax + r], id = d.efc_id[wb * njmax + r];
+      if (type == CNSTR_EQUALITY) {
+        if (m.eq_type[id] == EQ_JOINT) { a1 = m.jnt_dofadr[m.eq_obj1id[id]]; a2 = m.eq_obj2id[id] > -1 ? m.jnt_dofadr[m.eq_obj2id[id]] : -1; nnz = a2 >= 0 ? 2 : 1; }
+        else { kind = 1; a1 = chain_start(m, m.eq_obj1id[id]); a2 = chain_start(m, m.eq_obj2id[id]); }
+      } else if (type == CNSTR_FRICTION_DOF) { a1 = id; nnz = 1; }
+      else if (type == CNSTR_LIMIT_JOINT) { a1 = m.jnt_dofadr[id]; if (m.jnt_type[id] == JNT_BALL) { kind = 3; nnz = 3; } else nnz = 1; }
+      else { kind = 2; a1 = chain_start(m, m.geom_bodyid[d.contact_geom[2 * (size_t)id]]); a2 = chain_start(m, m.geom_bodyid[d.contact_geom[2 * (size_t)id + 1]]); }
+      if (kind == 1 || kind == 2) nnz = chain_walk(m, a1, a2, kind == 2, [](int, int) {});
+    }
+    const int adr = base + warp_excl_scan(nnz, lane);
+    base += warp_sum_i(nnz);
+    if (r < nrow) {
+      d.efc_J_rownnz[wb * njmax + r] = nnz;
+      if (adr + nnz > d.njmax_nnz) { ovf = true; continue; }
+      d.efc_J_rowadr[wb * njmax + r] = adr;
+      const float* Jr = Jd + (size_t)r * nvp;
+      if (kind == 1 || kind == 2) chain_walk(m, a1, a2, kind == 2, [&](int da, int k) { col[adr + k] = da; Jv[adr + k] = Jr[da]; });
+      else if (kind == 3) { for (int k = 0; k < 3; k++) { col[adr + k] = a1 + k; Jv[adr + k] = Jr[a1 + k]; } }
+      else { col[adr] = a1; Jv[adr] = Jr[a1]; if (nnz == 2) { col[adr + 1] = a2; Jv[adr + 1] = Jr[a2]; } }
+    }
+  }
+  if (__any_sync(FULL_MASK, ovf) && lane == 0) d.overflow[w] |= OVF_NJMAX_NNZ;
+}
+
 // qLD holds, per kinematic tree, the dense upper factor U (row-major n x n, zeros below the diagonal) with M = U^T U.
 __global__ void __launch_bounds__(32)
 k_solve_m(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, float* __restrict__ xo, const float* __restrict__ yi) {
@@ -110,5 +177,10 @@ cudaError_t launch_mul_m(const ModelDev& m, const DataDev& d, float* res, const 
 cudaError_t launch_contact_force(const ModelDev& m, const DataDev& d, const int* contact_ids, int n, int to_world, float* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   k_contact_force<<<(n + 127) / 128, 128, 0, s>>>(m, d, contact_ids, n, to_world, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_efc_csr(const ModelDev& m, const DataDev& d, cudaStream_t s) {
+  k_efc_csr<<<d.wn, 32, 0, s>>>(m, d);
   return cudaGetLastError();
 }

@@ -424,15 +424,8 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
 }  // namespace
 
-// lanes per world of the velocity kernel (MJB_LPW_VEL = 4 | 8 | 16 | 32 overrides; measured on B200)
-int velocity_lpw() {
-  static int v = 0;
-  if (!v) { const char* e = getenv("MJB_LPW_VEL"); v = e ? atoi(e) : 8; if (v != 4 && v != 8 && v != 16 && v != 32) v = 8; }
-  return v;
-}
-
-static size_t vel_warp_bytes(const ModelDev& m) { return ((size_t)vel_layout(m).total * (32 / velocity_lpw()) + 4) * sizeof(float); }
-size_t smem_velocity(const ModelDev& m) { return vel_warp_bytes(m) * team_warps_per_block(velocity_lpw(), "MJB_WPB_VEL"); }
+static TeamShape vel_shape(const ModelDev& m) { return team_shape((size_t)vel_layout(m).total, "MJB_LPW_VEL", "MJB_WPB_VEL"); }
+size_t smem_velocity(const ModelDev& m) { return vel_shape(m).block_bytes; }
 
 template <bool PEXT>
 static void (*vel_kernel(int lpw))(ModelDev, DataDev, int) {
@@ -440,15 +433,16 @@ static void (*vel_kernel(int lpw))(ModelDev, DataDev, int) {
 }
 
 cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int mask, cudaStream_t s) {
-  const size_t smem = smem_velocity(m);
-  static size_t configured[2] = {0, 0};
+  const TeamShape t = vel_shape(m);
+  const size_t smem = t.block_bytes;
+  static size_t configured[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
   const int ext = m.has_gravcomp ? 1 : 0;  // has_gravcomp also flags free / ball joint springs (io.py put_model)
-  const int lpw = velocity_lpw(), G = 32 / lpw, wpb = team_warps_per_block(lpw, "MJB_WPB_VEL");
+  const int lpw = t.lpw, G = 32 / lpw, wpb = t.wpb, ki = lpw == 4 ? 0 : lpw == 8 ? 1 : lpw == 16 ? 2 : 3;
   void (*kern)(ModelDev, DataDev, int) = ext ? vel_kernel<true>(lpw) : vel_kernel<false>(lpw);
-  if (smem > 48 * 1024 && smem > configured[ext]) {
+  if (smem > 48 * 1024 && smem > configured[ext][ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[ext] = smem;
+    configured[ext][ki] = smem;
   }
   const int ngroups = (d.wn + G - 1) / G, grid = (ngroups + wpb - 1) / wpb;
   kern<<<grid, 32 * wpb, smem, s>>>(m, d, mask);

@@ -24,8 +24,9 @@
 #define CCD_FACE_TOL 0.99999872f       // cos(0.0016)
 #define CCD_EDGE_TOL 0.00159999931f    // sin(0.0016)
 #define CCD_INTERSECT_TOL 0.0000003f
-// CCD_MESH = 1 adds mesh geoms (hull-vertex support function with a cached start vertex, mesh multi-contact).  The product library is built
-// without it until the collision kernel carries the mesh tables; tests/host_harness builds this header with it on the host.
+// CCD_MESH = 1 adds mesh geoms (hull-vertex support function with a cached start vertex, mesh multi-contact).  The product library carries
+// both builds of the collision kernel: k_collision.cu without it (models without mesh geoms keep the lean box / analytic code and its small
+// stack), k_collision_mesh.cu with it; tests/host_harness also builds this header with it on the host.
 #ifndef CCD_MESH
 #define CCD_MESH 0
 #endif
@@ -46,8 +47,30 @@
 
 // Geom-type pairs the reference routes to the convex path (collision_driver.py:47-81), analytic geoms only, in table order.
 // Box-box is convex unless the nativeccd disable flag routes it to the primitive box_box.
+#if CCD_MESH
+// with mesh geoms: the reference's full table order (sphere-mesh after sphere-ellipsoid, ... mesh-mesh last)
+#define CCD_NRANK 15
+static __host__ __device__ inline int convex_rank(int t1, int t2, bool nativeccd) {
+  if (t1 == GEOM_SPHERE && t2 == GEOM_ELLIPSOID) return 0;
+  if (t1 == GEOM_SPHERE && t2 == GEOM_MESH) return 1;
+  if (t1 == GEOM_CAPSULE && t2 == GEOM_ELLIPSOID) return 2;
+  if (t1 == GEOM_CAPSULE && t2 == GEOM_CYLINDER) return 3;
+  if (t1 == GEOM_CAPSULE && t2 == GEOM_MESH) return 4;
+  if (t1 == GEOM_ELLIPSOID && t2 == GEOM_ELLIPSOID) return 5;
+  if (t1 == GEOM_ELLIPSOID && t2 == GEOM_CYLINDER) return 6;
+  if (t1 == GEOM_ELLIPSOID && t2 == GEOM_BOX) return 7;
+  if (t1 == GEOM_ELLIPSOID && t2 == GEOM_MESH) return 8;
+  if (t1 == GEOM_CYLINDER && t2 == GEOM_CYLINDER) return 9;
+  if (t1 == GEOM_CYLINDER && t2 == GEOM_BOX) return 10;
+  if (t1 == GEOM_CYLINDER && t2 == GEOM_MESH) return 11;
+  if (t1 == GEOM_BOX && t2 == GEOM_BOX && nativeccd) return 12;
+  if (t1 == GEOM_BOX && t2 == GEOM_MESH) return 13;
+  if (t1 == GEOM_MESH && t2 == GEOM_MESH) return 14;
+  return -1;
+}
+#else
 #define CCD_NRANK 9
-__host__ __device__ inline int convex_rank(int t1, int t2, bool nativeccd) {
+static __host__ __device__ inline int convex_rank(int t1, int t2, bool nativeccd) {
   if (t1 == GEOM_SPHERE && t2 == GEOM_ELLIPSOID) return 0;
   if (t1 == GEOM_CAPSULE && t2 == GEOM_ELLIPSOID) return 1;
   if (t1 == GEOM_CAPSULE && t2 == GEOM_CYLINDER) return 2;
@@ -59,6 +82,7 @@ __host__ __device__ inline int convex_rank(int t1, int t2, bool nativeccd) {
   if (t1 == GEOM_BOX && t2 == GEOM_BOX && nativeccd) return 8;
   return -1;
 }
+#endif
 
 #if CCD_MESH
 // mesh geoms carry their vertex block, hull graph (nullptr: exhaustive search) and hull polygon tables, already offset to the mesh
@@ -76,7 +100,7 @@ struct CGeom { v3 pos; const float* rot; v3 size; float margin; int type; };
 #endif
 struct GjkRes { bool separated; int dim; float dist; v3 x1, x2, s[4], s1[4], s2[4]; int vi[4]; };  // vi: box corner ids, geom1 | geom2 << 4
 // words of shared memory one lane's polytope needs: vertices (2 per support pair), faces, face projections, squared norms, horizon
-__host__ __device__ inline int ccd_scratch_words(int iterations) {
+static __host__ __device__ inline int ccd_scratch_words(int iterations) {
   return 3 * (10 + 2 * iterations) + 5 * (6 + CCD_MAX_EPAFACES * iterations) + CCD_MAX_EPAHORIZON + (5 + iterations);
 }
 struct Polytope {
@@ -90,11 +114,11 @@ struct Polytope {
   int* vidx;         // 5 + it: box corner ids of each support pair (geom1 | geom2 << 4)
 };
 
-__device__ __forceinline__ float csign(float x) { return x < 0.f ? -1.f : 1.f; }  // wp.sign(0) = +1
+static __device__ __forceinline__ float csign(float x) { return x < 0.f ? -1.f : 1.f; }  // wp.sign(0) = +1
 
 #if CCD_MESH
 // :154-194 support vertex of a mesh in its own frame.  cache: remember the vertex for the geom's next query (GJK / EPA main loops)
-__device__ v3 mesh_support_local(const CGeom& g, v3 ld, int* vindex, bool cache) {
+static __device__ v3 mesh_support_local(const CGeom& g, v3 ld, int* vindex, bool cache) {
   const int cached = g.index;
   v3 res = mk3(0.f, 0.f, 0.f);
   int cidx = -1, vid = -1;
@@ -128,9 +152,9 @@ __device__ v3 mesh_support_local(const CGeom& g, v3 ld, int* vindex, bool cache)
   if (cache) g.index = cidx;
   return res;
 }
-__device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr, bool cache = false) {
+static __device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr, bool cache = false) {
 #else
-__device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr) {
+static __device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr) {
 #endif
   if (g.type == GEOM_SPHERE) return g.pos + dir * (g.size.x + 0.5f * g.margin);
   const v3 ld = mat_t_vec(g.rot, dir);
@@ -154,13 +178,13 @@ __device__ v3 ccd_support(const CGeom& g, v3 dir, int* vindex = nullptr) {
   return out;
 }
 
-__device__ __forceinline__ float det3(v3 a, v3 b, v3 c) { return dot(a, cross(b, c)); }
-__device__ __forceinline__ int same_sign(float a, float b) { return (a > 0.f && b > 0.f) ? 1 : ((a < 0.f && b < 0.f) ? -1 : 0); }
-__device__ __forceinline__ v3 project_origin_line(v3 v1, v3 v2) {
+static __device__ __forceinline__ float det3(v3 a, v3 b, v3 c) { return dot(a, cross(b, c)); }
+static __device__ __forceinline__ int same_sign(float a, float b) { return (a > 0.f && b > 0.f) ? 1 : ((a < 0.f && b < 0.f) ? -1 : 0); }
+static __device__ __forceinline__ v3 project_origin_line(v3 v1, v3 v2) {
   const v3 diff = v2 - v1;
   return v2 + diff * (-(dot(v2, diff) / dot(diff, diff)));
 }
-__device__ int project_origin_plane(v3 v1, v3 v2, v3 v3_, v3* o) {
+static __device__ int project_origin_plane(v3 v1, v3 v2, v3 v3_, v3* o) {
   const v3 d21 = v2 - v1, d31 = v3_ - v1, d32 = v3_ - v2;
   *o = mk3(0.f, 0.f, 0.f);
   v3 n = cross(d32, d21);
@@ -174,7 +198,7 @@ __device__ int project_origin_plane(v3 v1, v3 v2, v3 v3_, v3* o) {
   *o = n * (nv / nn);
   return 0;
 }
-__device__ void S1D(v3 s1, v3 s2, float* l) {
+static __device__ void S1D(v3 s1, v3 s2, float* l) {
   const v3 po = project_origin_line(s1, s2);
   float mu_max = s1.x - s2.x;
   int index = 0;
@@ -187,7 +211,7 @@ __device__ void S1D(v3 s1, v3 s2, float* l) {
   l[0] = 0.f; l[1] = 1.f;
 }
 // signed areas of (p, s2, s3), (p, s1, s3), (p, s1, s2) in the projection that drops the axis with the largest minor; returns that minor
-__device__ float tri_cofactors(v3 s1, v3 s2, v3 s3, v3 p, float* C) {
+static __device__ float tri_cofactors(v3 s1, v3 s2, v3 s3, v3 p, float* C) {
   const float M14 = s2.y * s3.z - s2.z * s3.y - s1.y * s3.z + s1.z * s3.y + s1.y * s2.z - s1.z * s2.y;
   const float M24 = s2.x * s3.z - s2.z * s3.x - s1.x * s3.z + s1.z * s3.x + s1.x * s2.z - s1.z * s2.x;
   const float M34 = s2.x * s3.y - s2.y * s3.x - s1.x * s3.y + s1.y * s3.x + s1.x * s2.y - s1.y * s2.x;
@@ -200,7 +224,7 @@ __device__ float tri_cofactors(v3 s1, v3 s2, v3 s3, v3 p, float* C) {
   C[2] = px * ay + py * bx + ax * by - px * by - py * ax - bx * ay;
   return Mmax;
 }
-__device__ void S2D(v3 s1, v3 s2, v3 s3, float* l) {
+static __device__ void S2D(v3 s1, v3 s2, v3 s3, float* l) {
   v3 po;
   if (project_origin_plane(s1, s2, s3, &po)) { S1D(s1, s2, l); l[2] = 0.f; return; }
   float C[3];
@@ -213,7 +237,7 @@ __device__ void S2D(v3 s1, v3 s2, v3 s3, float* l) {
   if (!c2) { S1D(s1, s3, sub); const v3 x = s1 * sub[0] + s3 * sub[1]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = 0.f; l[2] = sub[1]; dmin = d; } }
   if (!c3) { S1D(s1, s2, sub); const v3 x = s1 * sub[0] + s2 * sub[1]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = 0.f; } }
 }
-__device__ void S3D(v3 s1, v3 s2, v3 s3, v3 s4, float* l) {
+static __device__ void S3D(v3 s1, v3 s2, v3 s3, v3 s4, float* l) {
   const float C41 = -det3(s2, s3, s4), C42 = det3(s1, s3, s4), C43 = -det3(s1, s2, s4), C44 = det3(s1, s2, s3);
   const float m_det = C41 + C42 + C43 + C44;
   const int c1 = same_sign(m_det, C41), c2 = same_sign(m_det, C42), c3 = same_sign(m_det, C43), c4 = same_sign(m_det, C44);
@@ -225,14 +249,14 @@ __device__ void S3D(v3 s1, v3 s2, v3 s3, v3 s4, float* l) {
   if (!c3) { S2D(s1, s2, s4, sub); const v3 x = s1 * sub[0] + s2 * sub[1] + s4 * sub[2]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = 0.f; l[3] = sub[2]; dmin = d; } }
   if (!c4) { S2D(s1, s2, s3, sub); const v3 x = s1 * sub[0] + s2 * sub[1] + s3 * sub[2]; const float d = dot(x, x); if (d < dmin) { l[0] = sub[0]; l[1] = sub[1]; l[2] = sub[2]; l[3] = 0.f; } }
 }
-__device__ __forceinline__ v3 lin_comb(int n, const float* l, const v3* m) {
+static __device__ __forceinline__ v3 lin_comb(int n, const float* l, const v3* m) {
   v3 o = m[0] * l[0];
   for (int k = 1; k < n; k++) o = o + m[k] * l[k];
   return o;
 }
 
 // collision_gjk.py:635; discrete (box pairs without margin) drops the tolerances and tracks box corner ids (:662-663)
-__device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const CGeom& g2, float cutoff, bool discrete, GjkRes& r) {
+static __device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const CGeom& g2, float cutoff, bool discrete, GjkRes& r) {
   float lmbda[4] = {1.f, 0.f, 0.f, 0.f};
   const float epsilon = discrete ? 0.f : 0.5f * tolerance * tolerance, min_norm = discrete ? CCD_MINVAL : tolerance;
   int n = 0;
@@ -293,25 +317,25 @@ __device__ void ccd_gjk(float tolerance, int iterations, const CGeom& g1, const 
   r.dim = n;
 }
 
-__device__ __forceinline__ v3 pt_v1(const Polytope& pt, int v) { return ld3(pt.vert + 6 * v); }
-__device__ __forceinline__ v3 pt_v2(const Polytope& pt, int v) { return ld3(pt.vert + 6 * v + 3); }
-__device__ __forceinline__ v3 pt_mink(const Polytope& pt, int v) { return pt_v1(pt, v) - pt_v2(pt, v); }
-__device__ bool same_side(v3 p0, v3 p1, v3 p2, v3 p3) {
+static __device__ __forceinline__ v3 pt_v1(const Polytope& pt, int v) { return ld3(pt.vert + 6 * v); }
+static __device__ __forceinline__ v3 pt_v2(const Polytope& pt, int v) { return ld3(pt.vert + 6 * v + 3); }
+static __device__ __forceinline__ v3 pt_mink(const Polytope& pt, int v) { return pt_v1(pt, v) - pt_v2(pt, v); }
+static __device__ bool same_side(v3 p0, v3 p1, v3 p2, v3 p3) {
   const v3 n = cross(p1 - p0, p2 - p0);
   const float d1 = dot(n, p3 - p0), d2 = dot(n, p0 * -1.0f);
   return (d1 > 0.f && d2 > 0.f) || (d1 < 0.f && d2 < 0.f);
 }
-__device__ bool test_tetra(v3 p0, v3 p1, v3 p2, v3 p3) {
+static __device__ bool test_tetra(v3 p0, v3 p1, v3 p2, v3 p3) {
   return same_side(p0, p1, p2, p3) && same_side(p1, p2, p3, p0) && same_side(p2, p3, p0, p1) && same_side(p3, p0, p1, p2);
 }
-__device__ bool tri_point_intersect(v3 v1, v3 v2, v3 v3_, v3 p) {
+static __device__ bool tri_point_intersect(v3 v1, v3 v2, v3 v3_, v3 p) {
   float C[3];
   const float Mmax = tri_cofactors(v1, v2, v3_, p, C);
   const float l1 = C[0] / Mmax, l2 = C[1] / Mmax, l3 = C[2] / Mmax;
   if (l1 < 0.f || l2 < 0.f || l3 < 0.f) return false;
   return length(v1 * l1 + v2 * l2 + v3_ * l3 - p) < CCD_MINVAL;
 }
-__device__ float attach_face(Polytope& pt, int idx, int v1, int v2, int v3_) {
+static __device__ float attach_face(Polytope& pt, int idx, int v1, int v2, int v3_) {
   if (pt.nface == pt.maxface) return 0.f;
   const v3 p1 = pt_mink(pt, v1), p2 = pt_mink(pt, v2), p3 = pt_mink(pt, v3_);
   v3 r;
@@ -323,14 +347,14 @@ __device__ float attach_face(Polytope& pt, int idx, int v1, int v2, int v3_) {
   pt.face_norm2[idx] = n2;
   return n2;
 }
-__device__ void epa_support(Polytope& pt, int idx, const CGeom& g1, const CGeom& g2, v3 dir) {
+static __device__ void epa_support(Polytope& pt, int idx, const CGeom& g1, const CGeom& g2, v3 dir) {
   int i1 = 0, i2 = 0;
   st3(pt.vert + 6 * idx, ccd_support(g1, dir, &i1));
   st3(pt.vert + 6 * idx + 3, ccd_support(g2, dir * -1.0f, &i2));
   pt.vidx[idx] = i1 | (i2 << CCD_VSHIFT);
 }
 #if CCD_MESH
-__device__ void epa_support_cached(Polytope& pt, int idx, const CGeom& g1, const CGeom& g2, v3 dir) {  // :1372-1373 the cached vertices follow the expansion
+static __device__ void epa_support_cached(Polytope& pt, int idx, const CGeom& g1, const CGeom& g2, v3 dir) {  // :1372-1373 the cached vertices follow the expansion
   int i1 = 0, i2 = 0;
   st3(pt.vert + 6 * idx, ccd_support(g1, dir, &i1, true));
   st3(pt.vert + 6 * idx + 3, ccd_support(g2, dir * -1.0f, &i2, true));
@@ -339,14 +363,14 @@ __device__ void epa_support_cached(Polytope& pt, int idx, const CGeom& g1, const
 #else
 #define epa_support_cached epa_support
 #endif
-__device__ void replace_simplex3(const Polytope& pt, int v1, int v2, int v3_, GjkRes& r) {
+static __device__ void replace_simplex3(const Polytope& pt, int v1, int v2, int v3_, GjkRes& r) {
   const int v[3] = {v1, v2, v3_};
   for (int k = 0; k < 3; k++) { r.s1[k] = pt_v1(pt, v[k]); r.s2[k] = pt_v2(pt, v[k]); r.s[k] = r.s1[k] - r.s2[k]; r.vi[k] = pt.vidx[v[k]]; }
 }
-__device__ void load_simplex(Polytope& pt, const GjkRes& r, int n) {
+static __device__ void load_simplex(Polytope& pt, const GjkRes& r, int n) {
   for (int k = 0; k < n; k++) { st3(pt.vert + 6 * k, r.s1[k]); st3(pt.vert + 6 * k + 3, r.s2[k]); pt.vidx[k] = r.vi[k]; }
 }
-__device__ void polytope2(Polytope& pt, GjkRes& r, const CGeom& g1, const CGeom& g2) {
+static __device__ void polytope2(Polytope& pt, GjkRes& r, const CGeom& g1, const CGeom& g2) {
   const v3 diff = r.s[1] - r.s[0];
   pt.center = (r.s[0] + r.s[1]) * 0.5f;
   float value = CCD_FLOAT_MAX;
@@ -375,7 +399,7 @@ __device__ void polytope2(Polytope& pt, GjkRes& r, const CGeom& g1, const CGeom&
   }
   pt.nvert = 5; pt.nface = 6; pt.status = 0;
 }
-__device__ void polytope3(Polytope& pt, const GjkRes& r, const CGeom& g1, const CGeom& g2) {
+static __device__ void polytope3(Polytope& pt, const GjkRes& r, const CGeom& g1, const CGeom& g2) {
   pt.center = (r.s[0] + r.s[1] + r.s[2]) * (1.0f / 3.0f);
   v3 n = cross(r.s[1] - r.s[0], r.s[2] - r.s[0]);
   const float norm = length(n);
@@ -392,7 +416,7 @@ __device__ void polytope3(Polytope& pt, const GjkRes& r, const CGeom& g1, const 
   for (int f = 0; f < 6; f++) if (attach_face(pt, f, F[f][0], F[f][1], F[f][2]) < CCD_MIN_DIST3) { pt.status = 6 + f; return; }
   pt.nvert = 5; pt.nface = 6; pt.status = 0;
 }
-__device__ void polytope4(Polytope& pt, GjkRes& r) {
+static __device__ void polytope4(Polytope& pt, GjkRes& r) {
   pt.center = (r.s[0] + r.s[1] + r.s[2] + r.s[3]) * 0.25f;
   load_simplex(pt, r, 4);
   const int F[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {3, 2, 1}};
@@ -412,7 +436,7 @@ __device__ void polytope4(Polytope& pt, GjkRes& r) {
   }
   pt.nvert = 4; pt.nface = 4; pt.status = 0;
 }
-__device__ int add_edge(Polytope& pt, int e1, int e2) {
+static __device__ int add_edge(Polytope& pt, int e1, int e2) {
   const int n = pt.nhorizon;
   if (n < 0) return -1;
   const int edge = (min(e1, e2) << 10) | max(e1, e2);
@@ -422,7 +446,7 @@ __device__ int add_edge(Polytope& pt, int e1, int e2) {
   return n + 1;
 }
 // :1319 _epa + :947 witness points; returns the closest face index or -1
-__device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeom& g1, const CGeom& g2, bool discrete, float* dist, v3* x1, v3* x2, bool* ovf) {
+static __device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeom& g1, const CGeom& g2, bool discrete, float* dist, v3* x1, v3* x2, bool* ovf) {
   float upper = CCD_FLOAT_MAX, upper2 = CCD_FLOAT_MAX;
   const float epsilon = discrete ? CCD_MIN_EPATOL : tolerance;
   int idx = -1, pidx = -1, nvalid = pt.nface;
@@ -490,7 +514,7 @@ __device__ int ccd_epa(float tolerance, int iterations, Polytope& pt, const CGeo
 // ---- multi-contact recovery for box pairs (collision_gjk.py:1503 _feature_dim, :1703-1888 box normals / edges / faces,
 // :1916-2056 polygon clipping, :2076 multicontact; mesh branches not built)
 struct BoxFeat { int dim, idx[3]; v3 v0, v1; };
-__device__ BoxFeat feature_dim(const Polytope& pt, const int* face, int which) {
+static __device__ BoxFeat feature_dim(const Polytope& pt, const int* face, int which) {
   BoxFeat f;
   const int sh = which ? CCD_VSHIFT : 0;
   const int a = (pt.vidx[face[0]] >> sh) & CCD_VMASK, b = (pt.vidx[face[1]] >> sh) & CCD_VMASK, c = (pt.vidx[face[2]] >> sh) & CCD_VMASK;
@@ -502,16 +526,16 @@ __device__ BoxFeat feature_dim(const Polytope& pt, const int* face, int which) {
   f.dim = a != c ? 2 : 1;
   return f;
 }
-__device__ __forceinline__ v3 box_face_normal(int i) { return mk3(i == 0 ? 1.f : (i == 1 ? -1.f : 0.f), i == 2 ? 1.f : (i == 3 ? -1.f : 0.f), i == 4 ? 1.f : (i == 5 ? -1.f : 0.f)); }
-__device__ int box_normals2(const float* mat, v3 n, v3* nout, int* iout) {
+static __device__ __forceinline__ v3 box_face_normal(int i) { return mk3(i == 0 ? 1.f : (i == 1 ? -1.f : 0.f), i == 2 ? 1.f : (i == 3 ? -1.f : 0.f), i == 4 ? 1.f : (i == 5 ? -1.f : 0.f)); }
+static __device__ int box_normals2(const float* mat, v3 n, v3* nout, int* iout) {
   const v3 ln = normalize(mat_t_vec(mat, n));
   for (int i = 0; i < 6; i++) if (dot(ln, box_face_normal(i)) > CCD_FACE_TOL) { nout[0] = matvec(mat, box_face_normal(i)); iout[0] = i; return 1; }
   return 0;
 }
-__device__ __forceinline__ float bit_axis(int a, int b, int c, int bit) {  // +1 when every corner has the bit, -1 when none has it
+static __device__ __forceinline__ float bit_axis(int a, int b, int c, int bit) {  // +1 when every corner has the bit, -1 when none has it
   return (float)(((a & bit) && (b & bit) && (c & bit)) ? 1 : 0) - (float)((!(a & bit) && !(b & bit) && !(c & bit)) ? 1 : 0);
 }
-__device__ int box_normals(const BoxFeat& f, const float* mat, v3 dir, v3* nout, int* iout) {
+static __device__ int box_normals(const BoxFeat& f, const float* mat, v3 dir, v3* nout, int* iout) {
   const int v1 = f.idx[0], v2 = f.idx[1], v3i = f.idx[2];
   if (f.dim == 3) {
     int c = 0;
@@ -541,7 +565,7 @@ __device__ int box_normals(const BoxFeat& f, const float* mat, v3 dir, v3* nout,
   }
   return 0;
 }
-__device__ int box_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3* endvert) {
+static __device__ int box_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3* endvert) {
   if (f.dim == 2) { endvert[0] = f.v1; nout[0] = normalize(f.v1 - f.v0); return 1; }
   if (f.dim == 1) {
     const int vi = f.idx[0];
@@ -553,7 +577,7 @@ __device__ int box_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3* 
   }
   return 0;
 }
-__device__ int box_face(const CGeom& g, int idx, v3* face) {
+static __device__ int box_face(const CGeom& g, int idx, v3* face) {
   if (idx < 0 || idx > 5) return 0;
   // corner k of face idx, as signs of (x, y, z): one byte per face, bit (3 k + axis)
   const float sx = g.size.x, sy = g.size.y, sz = g.size.z;
@@ -569,8 +593,8 @@ __device__ int box_face(const CGeom& g, int idx, v3* face) {
   for (int k = 0; k < 4; k++) face[k] = matvec(g.rot, l[k]) + g.pos;
   return 4;
 }
-__device__ __forceinline__ float area4(v3 a, v3 b, v3 c, v3 d) { return 0.5f * length(cross(a - d, d - b) + cross(b - c, c - a)); }
-__device__ void polygon_quad(const float* poly, int np, int* res) {  // :1463 maximum-area quadrilateral of a convex polygon
+static __device__ __forceinline__ float area4(v3 a, v3 b, v3 c, v3 d) { return 0.5f * length(cross(a - d, d - b) + cross(b - c, c - a)); }
+static __device__ void polygon_quad(const float* poly, int np, int* res) {  // :1463 maximum-area quadrilateral of a convex polygon
   int b = 1, c = 2, d = 3;
   res[0] = 0; res[1] = b; res[2] = c; res[3] = d;
   float m = area4(ld3(poly), ld3(poly + 3 * b), ld3(poly + 3 * c), ld3(poly + 3 * d));
@@ -595,7 +619,7 @@ __device__ void polygon_quad(const float* poly, int np, int* res) {  // :1463 ma
 }
 // :1941 clip polygon face2 against the side planes of face1 (extruded along n).  witness2 lies on the clipped polygon,
 // witness1 = witness2 - dir.  buf: 48 words (two 8-vertex polygons).
-__device__ int polygon_clip(const v3* face1, int nface1, const v3* face2, int nface2, v3 n, v3 dir, float* buf, v3* w1, v3* w2) {
+static __device__ int polygon_clip(const v3* face1, int nface1, const v3* face2, int nface2, v3 n, v3 dir, float* buf, v3* w1, v3* w2) {
   if (nface1 < 3) return 0;
   float* poly = buf;
   float* clip = buf + 3 * CCD_CLIPCAP;
@@ -646,13 +670,13 @@ __device__ int polygon_clip(const v3* face1, int nface1, const v3* face2, int nf
 }
 #if CCD_MESH
 // :1556-1581 common polygon ids of two vertices' polygon lists (at most two)
-__device__ int mesh_intersect(const int* a1, int n1, const int* a2, int n2, int* res) {
+static __device__ int mesh_intersect(const int* a1, int n1, const int* a2, int n2, int* res) {
   int count = 0;
   for (int i = 0; i < n1; i++) for (int j = 0; j < n2; j++) if (a1[i] == a2[j]) { res[count++] = a1[i]; if (count == 2) return 2; }
   return count;
 }
 // :1585-1651 candidate hull-polygon normals of a mesh feature given by up to three vertices
-__device__ int mesh_normals(const BoxFeat& f, const CGeom& g, v3* nout, int* iout) {
+static __device__ int mesh_normals(const BoxFeat& f, const CGeom& g, v3* nout, int* iout) {
   const int* m1 = g.polymap + g.polymapadr[f.idx[0]];
   const int n1 = g.polymapnum[f.idx[0]];
   if (f.dim == 3) {
@@ -678,7 +702,7 @@ __device__ int mesh_normals(const BoxFeat& f, const CGeom& g, v3* nout, int* iou
   return 0;
 }
 // :1656-1699 edge directions of a mesh feature: the edge itself, or the edge entering the vertex in each of its polygons
-__device__ int mesh_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3* endvert) {
+static __device__ int mesh_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3* endvert) {
   if (f.dim == 2) { endvert[0] = f.v1; nout[0] = normalize(f.v1 - f.v0); return 1; }
   if (f.dim == 1) {
     const int v1i = f.idx[0];
@@ -698,7 +722,7 @@ __device__ int mesh_edge_normals(const BoxFeat& f, const CGeom& g, v3* nout, v3*
   return 0;
 }
 // :1891-1912 a hull polygon in world coordinates, vertex order reversed
-__device__ int mesh_face(const CGeom& g, int idx, v3* face) {
+static __device__ int mesh_face(const CGeom& g, int idx, v3* face) {
   const int adr = g.polyvertadr[idx], nvert = g.polyvertnum[idx];
   if (nvert > CCD_MAXPOLY) return 0;
   int j = 0;
@@ -715,7 +739,7 @@ __device__ int mesh_face(const CGeom& g, int idx, v3* face) {
 #endif
 // :2076 for two boxes (CCD_MESH: boxes and meshes).  Overwrites the witness arrays (4 each) and returns the contact count; buf must not alias
 // pt.vert / pt.vidx.
-__device__ int ccd_multicontact(const Polytope& pt, int epa_face, const CGeom& g1, const CGeom& g2, float* buf, v3* w1, v3* w2) {
+static __device__ int ccd_multicontact(const Polytope& pt, int epa_face, const CGeom& g1, const CGeom& g2, float* buf, v3* w1, v3* w2) {
   const v3 x1 = w1[0], x2 = w2[0];
   for (int k = 1; k < 4; k++) w1[k] = w2[k] = mk3(0.f, 0.f, 0.f);
   const unsigned fw = pt.face[epa_face];
@@ -760,7 +784,7 @@ __device__ int ccd_multicontact(const Polytope& pt, int epa_face, const CGeom& g
 
 // gjk_phase (:2350) + epa_phase (:2421) + multicontact for box pairs.  Returns the number of contacts (0..4, witnesses in
 // w1 / w2, 4 each); *dist is relative to the margin-inflated shapes.
-__device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iterations, int epa_iterations, CGeom g1, CGeom g2, float* scratch, float* dist, v3* w1, v3* w2, bool* ovf) {
+static __device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iterations, int epa_iterations, CGeom g1, CGeom g2, float* scratch, float* dist, v3* w1, v3* w2, bool* ovf) {
   const CGeom o1 = g1, o2 = g2;
   float full1 = 0.f, full2 = 0.f, size1 = 0.f, size2 = 0.f;
 #if CCD_MESH
@@ -825,14 +849,14 @@ __device__ __noinline__ int ccd_pair(float tolerance, float cutoff, int gjk_iter
 // pass 0: deepest vertex a; 1: farthest from a; 2: farthest from the line a-b; 3: farthest from the triangle's other two edges -- candidates
 // restricted to vertices within 1e-3 of the deepest.  Exhaustive over the vertex block, or hill climbing on the hull graph.
 #define PM_HUGE 1e6f
-__device__ __forceinline__ float pm_support(v3 ppl, v3 v, v3 n) { return dot(ppl - v, n); }
-__device__ __forceinline__ float pm_score(int pass, v3 v, v3 a, v3 b, v3 ab, v3 ac, v3 bc, float sup, float threshold) {
+static __device__ __forceinline__ float pm_support(v3 ppl, v3 v, v3 n) { return dot(ppl - v, n); }
+static __device__ __forceinline__ float pm_score(int pass, v3 v, v3 a, v3 b, v3 ab, v3 ac, v3 bc, float sup, float threshold) {
   const float mask = sup > threshold ? 0.f : -PM_HUGE;
   if (pass == 1) { const v3 df = a - v; return dot(df, df) + mask; }
   if (pass == 2) return fabsf(dot(a - v, ab)) + mask;
   return (fabsf(dot(a - v, ac)) + mask) + (fabsf(dot(b - v, bc)) + mask);
 }
-__device__ int plane_mesh(v3 n_world, v3 plane_pos, const CGeom& c, float* dist, v3* pos) {
+static __device__ int plane_mesh(v3 n_world, v3 plane_pos, const CGeom& c, float* dist, v3* pos) {
   int idx[4] = {-1, -1, -1, -1};
   for (int i = 0; i < 4; i++) { dist[i] = MJ_MAXVAL; pos[i] = mk3(0.f, 0.f, 0.f); }
   const v3 ppl = mat_t_vec(c.rot, plane_pos - c.pos), n = mat_t_vec(c.rot, n_world);

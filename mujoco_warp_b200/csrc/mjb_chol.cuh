@@ -278,6 +278,58 @@ __device__ __forceinline__ float chol_solve_rows_rolled(float (&a)[N], int n, fl
   return b;
 }
 
+// Column-major storage of the factor's sub-diagonal part for the broadcast variant below: column j keeps its c = n - 1 - j
+// entries L[j+1 .. n-1][j] contiguously, padded to a multiple of 4 floats, columns ordered by increasing c, so that every
+// column starts 16-byte aligned.  colsub_off(c) = sum_{t < c} pad4(t); the whole factor takes colsub_off(n) floats (420 for n = 28).
+__host__ __device__ __forceinline__ int colsub_off(int c) {
+  if (c <= 0) return 0;
+  const int U = (c - 1) >> 2;
+  return 8 * U * (U + 1) + 4 * (U + 1) * (c - 1 - 4 * U);
+}
+
+// Factor + solve with the rolled column loop as above, but the pivot column is broadcast through shared memory instead of
+// one SHFL per trailing column: every lane stores its l_ij into the column's (16-byte aligned) slot, then all lanes read
+// four multipliers per LDS.128 (same address in every lane: a broadcast, one wavefront).  ncu on the humanoid: the SHFL
+// sweep was 44 % of the solver's instructions (30 % of those the SHFL + lane arithmetic, 16 % the FMA); this version issues
+// a quarter of the data-movement instructions and leaves the SHFL pipe to the two per-column broadcasts.
+//   a[]  : row `lane` of the matrix (consumed);  Lc : colsub_off(n) floats of scratch, receives the factor (layout above)
+template <int N>
+__device__ __forceinline__ float chol_solve_rows_bcast(float (&a)[N], int n, float b, float* Lc, int lane) {
+  float myinv = 1.0f;
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    const float ajj = __shfl_sync(FULL_MASK, a[0], j);
+    const float inv = rsqrtf(fmaxf(ajj, MJ_MINVAL));
+    const float lij = a[0] * inv;  // column j of L (meaningful for lanes >= j)
+    if (lane == j) myinv = inv;
+    const float yj = __shfl_sync(FULL_MASK, b, j) * inv;
+    b = lane > j ? b - lij * yj : (lane == j ? yj : b);
+    const int rem = n - 1 - j;
+    float* col = Lc + colsub_off(rem);
+    if (lane > j && lane < n) col[lane - j - 1] = lij;
+    __syncwarp();
+    // trailing update of the rem columns to the right; registers are rotated by one so the next pivot sits in a[0]
+#pragma unroll
+    for (int k0 = 1; k0 < N; k0 += 4) {
+      if (k0 > rem) break;
+      const float4 l = *reinterpret_cast<const float4*>(col + (k0 - 1));
+      a[k0 - 1] = a[k0] - lij * l.x;
+      if (k0 + 1 < N) a[k0] = a[k0 + 1] - lij * l.y;
+      if (k0 + 2 < N) a[k0 + 1] = a[k0 + 2] - lij * l.z;
+      if (k0 + 3 < N) a[k0 + 2] = a[k0 + 3] - lij * l.w;
+    }
+  }
+  // backward substitution: L[j][lane] for lane < j sits in column `lane`, slot j - lane - 1
+  const float* mycol = Lc + colsub_off(n - 1 - lane) - lane - 1;
+#pragma unroll 1
+  for (int j = n - 1; j >= 0; j--) {
+    const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
+    const float ltj = lane < j ? mycol[j] : 0.f;
+    b = lane < j ? b - ltj * xj : (lane == j ? xj : b);
+  }
+  return b;
+}
+
 template <int N>
 __device__ __forceinline__ float chol_solve_reg(const float* Hs, int ld, int n, float b, float* Ls, int ldL, int lane) {
   float a[N];

@@ -9,32 +9,32 @@
 
 #define MJB_MAXVAL 1e10f
 
-__device__ __forceinline__ v3 mat_t_vec(const float* m, v3 v) {  // m^T v
+static __device__ __forceinline__ v3 mat_t_vec(const float* m, v3 v) {  // m^T v
   return mk3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z);
 }
-__device__ __forceinline__ void mat_mul33(const float* a, const float* b, float* c) {
+static __device__ __forceinline__ void mat_mul33(const float* a, const float* b, float* c) {
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
 }
-__device__ __forceinline__ void mat_t33(const float* a, float* t) {
+static __device__ __forceinline__ void mat_t33(const float* a, float* t) {
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * j + i];
 }
-__device__ __forceinline__ float comp(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
-__device__ __forceinline__ void setcomp(v3& a, int i, float x) { if (i == 0) a.x = x; else if (i == 1) a.y = x; else a.z = x; }
-__device__ __forceinline__ v3 cw_mul(v3 a, v3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
-__device__ __forceinline__ v3 vabs(v3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+static __device__ __forceinline__ float comp(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+static __device__ __forceinline__ void setcomp(v3& a, int i, float x) { if (i == 0) a.x = x; else if (i == 1) a.y = x; else a.z = x; }
+static __device__ __forceinline__ v3 cw_mul(v3 a, v3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static __device__ __forceinline__ v3 vabs(v3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
 
-__device__ __forceinline__ float col_plane_sphere(v3 n, v3 ppos, v3 spos, float r, v3* pos) {
+static __device__ __forceinline__ float col_plane_sphere(v3 n, v3 ppos, v3 spos, float r, v3* pos) {
   const float dist = dot(spos - ppos, n) - r;
   *pos = spos - n * (r + 0.5f * dist);
   return dist;
 }
-__device__ __forceinline__ float col_sphere_sphere(v3 pos1, float r1, v3 pos2, float r2, v3* pos, v3* n) {
+static __device__ __forceinline__ float col_sphere_sphere(v3 pos1, float r1, v3 pos2, float r2, v3* pos, v3* n) {
   const v3 dir = pos2 - pos1;
   float dist = length(dir);
   *n = dist == 0.f ? mk3(1.f, 0.f, 0.f) : dir * (1.0f / dist);
@@ -43,7 +43,7 @@ __device__ __forceinline__ float col_sphere_sphere(v3 pos1, float r1, v3 pos2, f
   return dist;
 }
 
-__device__ __forceinline__ float plane_ellipsoid(v3 n, v3 ppos, v3 epos, const float* erot, v3 esize, v3* pos) {
+static __device__ __forceinline__ float plane_ellipsoid(v3 n, v3 ppos, v3 epos, const float* erot, v3 esize, v3* pos) {
   const v3 sup = normalize(cw_mul(mat_t_vec(erot, n), esize)) * -1.0f;
   v3 p = epos + matvec(erot, cw_mul(sup, esize));
   const float dist = dot(n, p - ppos);
@@ -51,7 +51,7 @@ __device__ __forceinline__ float plane_ellipsoid(v3 n, v3 ppos, v3 epos, const f
   return dist;
 }
 
-__device__ __forceinline__ void plane_box(v3 n, v3 ppos, v3 bpos, const float* brot, v3 bsize, float* dist, v3* pos) {
+static __device__ __forceinline__ void plane_box(v3 n, v3 ppos, v3 bpos, const float* brot, v3 bsize, float* dist, v3* pos) {
   const float center_dist = dot(bpos - ppos, n);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -62,7 +62,7 @@ __device__ __forceinline__ void plane_box(v3 n, v3 ppos, v3 bpos, const float* b
   }
 }
 
-__device__ __forceinline__ float sphere_cylinder(v3 spos, float sr, v3 cpos, v3 caxis, float cr, float chh, v3* pos, v3* nrm) {
+static __device__ __forceinline__ float sphere_cylinder(v3 spos, float sr, v3 cpos, v3 caxis, float cr, float chh, v3* pos, v3* nrm) {
   const v3 vec = spos - cpos;
   const float x = dot(vec, caxis);
   const v3 a_proj = caxis * x, p_proj = vec - a_proj;
@@ -83,7 +83,7 @@ __device__ __forceinline__ float sphere_cylinder(v3 spos, float sr, v3 cpos, v3 
   return col_sphere_sphere(spos, sr, cpos + caxis * (sgn * chh) + p_proj * (cr * inv_len), 0.f, pos, nrm);
 }
 
-__device__ __forceinline__ void plane_cylinder(v3 n, v3 ppos, v3 center, v3 caxis, float cr, float chh, float* dist, v3* pos) {
+static __device__ __forceinline__ void plane_cylinder(v3 n, v3 ppos, v3 center, v3 caxis, float cr, float chh, float* dist, v3* pos) {
   v3 axis = caxis;
   float prjaxis = dot(n, axis);
   if (prjaxis > 0.f) { axis = axis * -1.0f; prjaxis = -prjaxis; }
@@ -102,7 +102,7 @@ __device__ __forceinline__ void plane_cylinder(v3 n, v3 ppos, v3 center, v3 caxi
   dist[3] = dist3; pos[3] = center - vec1 + axis - vec * 0.5f - n * (dist3 * 0.5f);
 }
 
-__device__ __noinline__ float sphere_box(v3 spos, float sr, v3 bpos, const float* brot, v3 bsize, v3* cpos, v3* nrm) {
+static __device__ __noinline__ float sphere_box(v3 spos, float sr, v3 bpos, const float* brot, v3 bsize, v3* cpos, v3* nrm) {
   const v3 center = mat_t_vec(brot, spos - bpos);
   const v3 clamped = mk3(fmaxf(-bsize.x, fminf(bsize.x, center.x)), fmaxf(-bsize.y, fminf(bsize.y, center.y)), fmaxf(-bsize.z, fminf(bsize.z, center.z)));
   const v3 dif = clamped - center;
@@ -134,7 +134,7 @@ __device__ __noinline__ float sphere_box(v3 spos, float sr, v3 bpos, const float
 
 // closest-feature search between the capsule segment and the box (faces, then the 12 edges), an optional second point
 // further along the segment, and one sphere-box test per point
-__device__ __noinline__ void capsule_box(v3 cpos_in, v3 caxis, float crad, float chl, v3 bpos, const float* brot, v3 bsize, float* dist, v3* cpos, v3* cnrm) {
+static __device__ __noinline__ void capsule_box(v3 cpos_in, v3 caxis, float crad, float chl, v3 bpos, const float* brot, v3 bsize, float* dist, v3* cpos, v3* cnrm) {
   const v3 pos = mat_t_vec(brot, cpos_in - bpos), axis = mat_t_vec(brot, caxis), halfaxis = axis * chl;
   const int axisdir = (halfaxis.x > 0.f ? 1 : 0) + (halfaxis.y > 0.f ? 2 : 0) + (halfaxis.z > 0.f ? 4 : 0);
   float bestdist = 1.0e32f, bestsegmentpos = -12.f, bestboxpos = 0.f;
@@ -238,7 +238,7 @@ __device__ __noinline__ void capsule_box(v3 cpos_in, v3 caxis, float crad, float
   if (secondpos > -3.f) dist[1] = sphere_box(matvec(brot, pos + halfaxis * (secondpos + bestsegmentpos)) + bpos, crad, bpos, brot, bsize, &cpos[1], &cnrm[1]);
 }
 
-__device__ __forceinline__ void rotmore_of(int face, float* r) {
+static __device__ __forceinline__ void rotmore_of(int face, float* r) {
 #pragma unroll
   for (int i = 0; i < 9; i++) r[i] = 0.f;
   if (face == 0) { r[2] = -1.f; r[4] = 1.f; r[6] = 1.f; }
@@ -248,11 +248,11 @@ __device__ __forceinline__ void rotmore_of(int face, float* r) {
   else if (face == 4) { r[0] = 1.f; r[5] = 1.f; r[7] = -1.f; }
   else { r[0] = -1.f; r[4] = 1.f; r[8] = -1.f; }
 }
-__device__ __forceinline__ v3 row3(const float* m, int i) { return mk3(m[3 * i], m[3 * i + 1], m[3 * i + 2]); }
+static __device__ __forceinline__ v3 row3(const float* m, int i) { return mk3(m[3 * i], m[3 * i + 1], m[3 * i + 2]); }
 
 // 15-axis separating-axis search, then clipping of the incident face (face-vertex case) or of box2's closest face against
 // box1's (edge-edge case); at most 8 contacts sharing one normal.  Returns the contact count.
-__device__ __noinline__ int box_box(v3 pos1, const float* rot1, v3 size1, v3 pos2, const float* rot2, v3 size2, float margin, float* cdist, v3* cpos, v3* cnormal) {
+static __device__ __noinline__ int box_box(v3 pos1, const float* rot1, v3 size1, v3 pos2, const float* rot2, v3 size2, float margin, float* cdist, v3* cpos, v3* cnormal) {
   const v3 pos21 = mat_t_vec(rot1, pos2 - pos1), pos12 = mat_t_vec(rot2, pos1 - pos2);
   float rot1T[9], rot21[9], rot12[9], rot21abs[9], rot12abs[9];
   mat_t33(rot1, rot1T);

@@ -103,12 +103,25 @@ struct Stager {
   }
 };
 
-// Warps per block for a kernel whose warps each own `per_warp_bytes` of shared memory: one-warp blocks cap an SM at 32
-// resident warps (the CTA limit), so kernels that run one world per warp use two-warp blocks.
-inline int team_warps_per_block(int lpw, const char* env) {
-  const char* e = getenv(env);
-  int v = e ? atoi(e) : (lpw == 32 ? 2 : 1);
-  return v < 1 ? 1 : (v > 8 ? 8 : v);
+// Launch shape of a team kernel: lanes per world and warps per block, from the per-world shared-memory footprint.
+// Default 8 lanes per world (4 worlds per warp) and two-warp blocks: measured best on B200 for the humanoid; models
+// whose worlds are too large for that fall back to fewer worlds per warp / one-warp blocks.  MJB_LPW_* / MJB_WPB_* override.
+struct TeamShape { int lpw, wpb; size_t warp_bytes, block_bytes; };
+inline TeamShape team_shape(size_t world_words, const char* env_lpw, const char* env_wpb) {
+  constexpr size_t kBlockMax = 200 * 1024;  // leaves room for a second resident block's reserve
+  auto bytes = [&](int lpw) { return (world_words * (size_t)(32 / lpw) + 4) * sizeof(float); };
+  const char* e = getenv(env_lpw);
+  int lpw = e ? atoi(e) : 8;
+  if (lpw != 4 && lpw != 8 && lpw != 16 && lpw != 32) lpw = 8;
+  while (lpw < 32 && bytes(lpw) > kBlockMax / 2) lpw *= 2;
+  e = getenv(env_wpb);
+  int wpb = e ? atoi(e) : 2;
+  if (wpb < 1) wpb = 1;
+  if (wpb > 8) wpb = 8;
+  while (wpb > 1 && bytes(lpw) * wpb > kBlockMax) wpb--;
+  TeamShape t;
+  t.lpw = lpw; t.wpb = wpb; t.warp_bytes = bytes(lpw); t.block_bytes = t.warp_bytes * wpb;
+  return t;
 }
 
 // World team of the calling lane.

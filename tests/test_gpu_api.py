@@ -212,3 +212,54 @@ def test_rungekutta4_equals_step(built):
     mjw.forward(m, db); mjw.rungekutta4(m, db)
   torch.cuda.synchronize()
   assert torch.equal(da.qpos, db.qpos) and torch.equal(da.qvel, db.qvel) and torch.equal(da.time, db.time)
+
+
+def test_sparse_models_expose_the_reference_csr_jacobian(built):
+  """Models the reference treats as sparse (nv > 32 under jacobian = auto, io.py:153): Model.is_sparse is honest and Data.efc carries
+  the reference's CSR arrays (types.py:2021-2072) -- rows in efc order, row addresses the running sum of rownnz, contact rows listing the
+  dof chains of the two bodies in descending order up to their first common dof (constraint.py:2728-2753), single-dof rows for dof
+  friction / joint limits.  Expanding them reproduces the dense rows the solver works on."""
+  import mujoco_warp_b200 as mjw
+  from mujoco_warp_b200._src.mjcf import MjDataLite, reset_data_keyframe
+
+  mjm = mjw.mjcf.load_any(util.THREE_HUMANOIDS)
+  m = mjw.put_model(mjm)
+  assert m.is_sparse and mjm.nv > 32
+  nworld = 4
+  mjd = MjDataLite(mjm)
+  reset_data_keyframe(mjm, mjd, 0)
+  d = mjw.put_data(mjm, mjd, nworld=nworld, nconmax=100, njmax=192, m=m)
+  assert d.efc.J.shape == (nworld, 1, d.njmax_nnz) and d.efc.J_rownnz.shape == (nworld, 192) and d.efc.J_colind.shape == (nworld, 1, d.njmax_nnz)
+  for _ in range(3):
+    mjw.step(m, d)
+  mjw.forward(m, d)
+  torch.cuda.synchronize()
+  assert not (d.overflow.cpu().numpy() & int(mjw.OverflowType.NJMAX_NNZ)).any()
+  nefc = d.nefc.cpu().numpy()
+  assert nefc.min() > 8
+  dense = d.efc.J_dense.cpu().numpy()
+  np.testing.assert_array_equal(util.dense_J(d)[:, :, : mjm.nv] != 0, (dense[:, :, : mjm.nv] != 0) & (np.arange(192)[None, :, None] < nefc[:, None, None]))
+  np.testing.assert_array_equal(util.dense_J(d)[0, : nefc[0]], dense[0, : nefc[0]])
+  nnz, adr, col = d.efc.J_rownnz.cpu().numpy(), d.efc.J_rowadr.cpu().numpy(), d.efc.J_colind.cpu().numpy()[:, 0]
+  typ = d.efc.type.cpu().numpy()
+  dpar = np.asarray(mjm.dof_parentid)
+  for w in range(nworld):
+    ne = int(nefc[w])
+    np.testing.assert_array_equal(adr[w, :ne], np.concatenate([[0], np.cumsum(nnz[w, : ne - 1])]))  # running sum in row order
+    for r in range(ne):
+      c = col[w, adr[w, r] : adr[w, r] + nnz[w, r]]
+      if typ[w, r] in (int(mjw.ConstraintType.FRICTION_DOF), int(mjw.ConstraintType.LIMIT_JOINT)):
+        assert len(c) in (1, 3)
+      else:  # contact row: strictly descending dofs, every listed dof's parent chain stays inside one of at most two chains
+        assert (np.diff(c) < 0).all() and len(c) >= 1
+        heads = [x for x in c if not any(dpar[y] == x for y in c)]
+        assert 1 <= len(heads) <= 2
+
+
+def test_dense_models_keep_the_dense_layout(built):
+  import mujoco_warp_b200 as mjw
+
+  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  m = mjw.put_model(mjm)
+  d = mjw.make_data(mjm, nworld=2, nconmax=24, njmax=64, m=m)
+  assert not m.is_sparse and d.njmax_nnz == 0 and d.efc.J.shape == (2, 64, m.nv_pad) and d.efc.J_rownnz.shape == (2, 0) and d.efc.J_colind.shape == (2, 0, 0)

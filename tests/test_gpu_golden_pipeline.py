@@ -21,9 +21,7 @@ def close(name, got, want, atol, rtol=0.0):
   util.assert_close(name, got, want, atol=atol, rtol=rtol)
 
 
-# mesh geoms: compiled by the host side and covered by the oracle; the CUDA collision kernel has no mesh support function yet and
-# put_model() rejects such models loudly (tests/test_host_logic.py), so the scene is an oracle-only golden for now
-GPU_SCENES = [s for s in SCENES if not s.startswith("mesh")]
+GPU_SCENES = list(SCENES)  # incl. `mesh`: hull-vertex support function, hill climbing, mesh multi-contact, plane-mesh (k_collision_mesh.cu)
 
 
 @pytest.mark.parametrize("name", GPU_SCENES)
@@ -43,11 +41,12 @@ def test_gpu_matches_reference_pipeline(built, name):
     d.mocap_pos.copy_(f32(g["in/mocap_pos"])); d.mocap_quat.copy_(f32(g["in/mocap_quat"]))
   mjw.forward(m, d)
   torch.cuda.synchronize()
-  assert (d.overflow.cpu().numpy() == 0).all()
+  trunc = "step0/overflow" in g and int(g["step0/overflow"].max()) != 0  # capacity-overflow scene: bits are raised where the truncation happens
+  assert trunc or (d.overflow.cpu().numpy() == 0).all()
   nv, tag = mjm.nv, "forward"
   # flat-on-flat convex contacts (cylinder cap on a box face, crossed cylinders ...) have a whole patch of valid witness points:
   # EPA in fp32 and in double stop at different ones, so positions (and everything downstream of the torque arm) get a looser band
-  flat = name.startswith("convex") or name.startswith("boxccd")
+  flat = name.startswith("convex") or name.startswith("boxccd") or name.startswith("mesh")
   ptol = 5e-3 if flat else 5e-4
   for f in SMOOTH:
     k = f"{tag}/{f}"
@@ -64,28 +63,51 @@ def test_gpu_matches_reference_pipeline(built, name):
     np.testing.assert_array_equal(getattr(d, f).cpu().numpy().reshape(-1), g[f"{tag}/{f}"].reshape(-1), err_msg=f)
   assert int(d.nacon.cpu()[0]) == int(g[f"{tag}/nacon"])
   wid = g[f"{tag}/con_worldid"]
-  J = d.efc.J.cpu().numpy()
+  J = util.dense_J(d)
   fscale = max(1.0, float(np.abs(g[f"{tag}/efc_force"]).max()))
   for w in range(nworld):
     ids = util.world_contacts(d, w)
     ref_ids = np.nonzero(wid == w)[0]
     assert len(ids) == len(ref_ids)
     c = d.contact
+    ne = min(int(g[f"{tag}/nefc"].reshape(-1)[w]), int(g["in/njmax"]))  # rows beyond njmax are dropped (constraint.py:2048,2712)
+    rows = np.arange(ne)  # got row that corresponds to reference row i
+    if name.startswith("mesh") and len(ids):
+      # a mesh lying flat on the floor has several hull vertices within rounding of the deepest one: plane_convex then picks the same
+      # set of (up to four) vertices in fp32 and in double, but may start from a different one.  Contacts of one geom pair are
+      # therefore matched by position, and their constraint rows are permuted accordingly, before the field-by-field comparison.
+      gg, wg = c.geom[ids].cpu().numpy(), g[f"{tag}/con_geom"][ref_ids]
+      gp, wp = c.pos[ids].cpu().numpy().astype(np.float64), g[f"{tag}/con_pos"][ref_ids]
+      perm, used = [], set()
+      for i in range(len(ref_ids)):
+        cand = [j for j in range(len(ids)) if j not in used and (gg[j] == wg[i]).all()]
+        assert cand, f"world {w}: no contact left for geom pair {wg[i]}"
+        j = min(cand, key=lambda j: float(np.abs(gp[j] - wp[i]).sum()))
+        used.add(j); perm.append(j)
+      perm = np.asarray(perm)
+      gadr = c.efc_address[ids].cpu().numpy()[perm]
+      wadr = g[f"{tag}/con_efc_address"][ref_ids]
+      for a_got, a_want in zip(gadr, wadr):
+        for r_got, r_want in zip(a_got, a_want):
+          assert (r_got >= 0) == (r_want >= 0)
+          if r_want >= 0:
+            rows[r_want] = r_got
+      ids = ids[torch.as_tensor(perm, device=ids.device)] if isinstance(ids, torch.Tensor) else np.asarray(ids)[perm]
+    else:
+      np.testing.assert_array_equal(c.geomcollisionid[ids].cpu().numpy(), g[f"{tag}/con_geomcollisionid"][ref_ids])
     np.testing.assert_array_equal(c.geom[ids].cpu().numpy(), g[f"{tag}/con_geom"][ref_ids])
     np.testing.assert_array_equal(c.dim[ids].cpu().numpy(), g[f"{tag}/con_dim"][ref_ids])
-    np.testing.assert_array_equal(c.geomcollisionid[ids].cpu().numpy(), g[f"{tag}/con_geomcollisionid"][ref_ids])
     for f in ("dist", "pos", "frame", "includemargin", "friction", "solref", "solimp") if len(ids) else ():
       tol = ptol if f in ("pos", "frame") else 5e-4
       close(f"con_{f}[w{w}]", getattr(c, f)[ids].cpu().numpy().reshape(len(ids), -1), g[f"{tag}/con_{f}"][ref_ids].reshape(len(ids), -1), atol=tol, rtol=5e-4)
-    ne = int(g[f"{tag}/nefc"].reshape(-1)[w])
-    np.testing.assert_array_equal(d.efc.type[w, :ne].cpu().numpy(), g[f"{tag}/efc_type"][w, :ne])
-    close(f"efc_J[w{w}]", J[w, :ne, :nv], g[f"{tag}/efc_J"][w, :ne, :nv], atol=ptol, rtol=5e-4)
+    np.testing.assert_array_equal(d.efc.type[w, :ne].cpu().numpy()[rows], g[f"{tag}/efc_type"][w, :ne])
+    close(f"efc_J[w{w}]", J[w, :ne, :nv][rows], g[f"{tag}/efc_J"][w, :ne, :nv], atol=ptol, rtol=5e-4)
     for f in ("pos", "margin", "vel", "frictionloss"):
-      close(f"efc_{f}[w{w}]", getattr(d.efc, f)[w, :ne].cpu().numpy(), g[f"{tag}/efc_{f}"][w, :ne], atol=5e-4, rtol=5e-4)
-    close(f"efc_D[w{w}]", d.efc.D[w, :ne].cpu().numpy(), g[f"{tag}/efc_D"][w, :ne], atol=1e-3, rtol=2e-3)
+      close(f"efc_{f}[w{w}]", getattr(d.efc, f)[w, :ne].cpu().numpy()[rows], g[f"{tag}/efc_{f}"][w, :ne], atol=5e-4, rtol=5e-4)
+    close(f"efc_D[w{w}]", d.efc.D[w, :ne].cpu().numpy()[rows], g[f"{tag}/efc_D"][w, :ne], atol=1e-3, rtol=2e-3)
     # aref = -k imp pos - b vel with k ~ 1e4: an fp32 penetration depth (error ~2e-6) moves aref by ~1e-2
-    close(f"efc_aref[w{w}]", d.efc.aref[w, :ne].cpu().numpy(), g[f"{tag}/efc_aref"][w, :ne], atol=2e-3, rtol=1e-2)
-    close(f"efc_force[w{w}]", d.efc.force[w, :ne].cpu().numpy(), g[f"{tag}/efc_force"][w, :ne], atol=(5e-2 if flat else 5e-3) * fscale)
+    close(f"efc_aref[w{w}]", d.efc.aref[w, :ne].cpu().numpy()[rows], g[f"{tag}/efc_aref"][w, :ne], atol=2e-3, rtol=1e-2)
+    close(f"efc_force[w{w}]", d.efc.force[w, :ne].cpu().numpy()[rows], g[f"{tag}/efc_force"][w, :ne], atol=(5e-2 if flat else 5e-3) * fscale)
   scale = max(1.0, float(np.abs(g[f"{tag}/qacc"]).max()))
   close("qacc", d.qacc.cpu().numpy(), g[f"{tag}/qacc"], atol=(5e-2 if flat else 5e-3) * scale)
   if f"{tag}/sensordata" in g and g[f"{tag}/sensordata"].size:
@@ -109,4 +131,8 @@ def test_gpu_matches_reference_pipeline(built, name):
   # the line-search budget flag (1 << 10) may be raised in fp32 when the bracketing stalls at rounding level; nothing else may
   # (CG scenes run close to their iteration cap -- 41..48 of 50 in double -- so fp32 may also raise the iteration flag, 1 << 9)
   allowed = (1 << 10) | ((1 << 9) if name.endswith("cg") else 0)
+  if f"step{s - 1}/overflow" in g:  # capacity-overflow scene: the reference's own overflow bits must be raised (njmax truncation -> NEFC)
+    want_ovf = g[f"step{s - 1}/overflow"].reshape(-1).astype(np.int64)
+    np.testing.assert_array_equal(d.overflow.cpu().numpy().astype(np.int64) & ~allowed, want_ovf & ~allowed)
+    allowed |= int(want_ovf.max())
   assert s >= 3 and ((d.overflow.cpu().numpy() & ~allowed) == 0).all()

@@ -51,7 +51,7 @@ def _compare_forward(scene, d, o, solver_tol=5e-3):
   nacon = int(d.nacon.cpu()[0])
   assert nacon == int(od["ncon"].sum())
   assert int(d.ncollision.cpu()[0]) == int(od["ncollision"].sum())
-  J = d.efc.J.cpu().numpy()
+  J = util.dense_J(d)
   for w in range(d.nworld):
     ids = util.world_contacts(d, w)
     n = int(od["ncon"][w])
@@ -264,7 +264,7 @@ def test_mixed_scene_forward_and_rollout(mixed):
     util.assert_close(name, getattr(d, name).cpu().numpy().reshape(od[name].shape), od[name], atol=5e-4, rtol=5e-4)
   for name in ("ne", "nf", "nl", "nefc"):
     np.testing.assert_array_equal(getattr(d, name).cpu().numpy(), od[name], err_msg=name)
-  J = d.efc.J.cpu().numpy()
+  J = util.dense_J(d)
   for w in range(nworld):
     ids = util.world_contacts(d, w)
     n = int(od["ncon"][w])

@@ -168,12 +168,11 @@ def test_unsupported_features_raise():
   xml = "<mujoco><worldbody>" + two.format(t="cylinder", m="") + "</worldbody></mujoco>"
   t = mio.derive_tables(mjcf.load_string(xml))
   assert t["has_convex_pair"] == 1 and t["epa_iterations"] == 35
-  # mesh geoms compile (hull, graph, polygons) and run in the oracle, but the CUDA collision kernel has no mesh support function yet:
-  # the product path refuses the model instead of dropping the pairs
+  # mesh geoms go through the convex pass of the mesh build of the collision kernel (k_collision_mesh.cu); height fields are refused
   from tests import util
 
-  with pytest.raises(NotImplementedError, match="geom types"):
-    mio.derive_tables(mjcf.load_string(util.mesh_xml()))
+  t = mio.derive_tables(mjcf.load_string(util.mesh_xml()))
+  assert t["has_convex_pair"] == 1 and t["epa_iterations"] == 35
 
 
 def test_shard_worlds():

@@ -88,7 +88,7 @@ MESH_XML = """<mujoco><asset>
 
 def test_mesh_geom_compiles_like_the_equivalent_box():
   """A cube given as a mesh asset yields the mass, inertia, centre of mass and bounds of the same box primitive; the mesh tables
-  of the Model are filled; models whose mesh geoms can collide are refused by put_model's table derivation (no mesh colliders yet)."""
+  of the Model are filled; colliding mesh geoms are routed to the convex pass of the mesh build of the collision kernel."""
   from mujoco_warp_b200._src import io as mio
   from mujoco_warp_b200._src import mjcf
 
@@ -109,6 +109,5 @@ def test_mesh_geom_compiles_like_the_equivalent_box():
   box_corners = (gR[2] @ box_corners.T).T + gx[2] - [2, 0, 0]
   d = np.linalg.norm(mesh_corners[:, None] - box_corners[None], axis=2)
   assert d.min(axis=1).max() < 1e-12 and d.min(axis=0).max() < 1e-12
-  mio.derive_tables(m)  # visual only: fine
-  with pytest.raises(NotImplementedError, match="not implemented"):
-    mio.derive_tables(mjcf.load_string(MESH_XML.format(col="")))
+  assert mio.derive_tables(m)["has_convex_pair"] == 0  # visual only
+  assert mio.derive_tables(mjcf.load_string(MESH_XML.format(col="")))["has_convex_pair"] == 1  # box - mesh goes through GJK / EPA

@@ -142,7 +142,10 @@ def test_oracle_matches_reference_pipeline(built, name):
   if "in/mocap_pos" in g:
     o.d["mocap_pos"][:] = g["in/mocap_pos"]; o.d["mocap_quat"][:] = g["in/mocap_quat"]
   o.forward()
-  assert (o.d["overflow"] == 0).all()
+  # capacity-overflow scenes: the oracle (like the CUDA collision kernel) raises the bit where the truncation happens, the reference
+  # at the end of step() (forward.py:247-271); the bits are sticky, so both agree after a step (checked below)
+  trunc = "step0/overflow" in g and int(g["step0/overflow"].max()) != 0
+  assert trunc or (o.d["overflow"] == 0).all()
   # CG takes tens of iterations: rounding differences grow along the conjugate directions, so iteration counts can differ by
   # a few and the two (equally converged) answers agree to the solver tolerance rather than to rounding
   cg = name.endswith("cg")
@@ -162,5 +165,7 @@ def test_oracle_matches_reference_pipeline(built, name):
     close(f"step{s}/qacc_warmstart", o.d["qacc_warmstart"], g[f"step{s}/qacc_warmstart"], 5e-3 if cg else 2e-4)
     close(f"step{s}/time", o.d["time"], g[f"step{s}/time"], 1e-12)
     np.testing.assert_array_equal(o.d["nefc"].reshape(-1), g[f"step{s}/nefc"].reshape(-1), err_msg=f"step{s}/nefc")
+    if trunc:
+      np.testing.assert_array_equal(o.d["overflow"].reshape(-1) & ~(1 << 10), g[f"step{s}/overflow"].reshape(-1) & ~(1 << 10), err_msg=f"step{s}/overflow")
     s += 1
   assert s >= 3

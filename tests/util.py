@@ -5,11 +5,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SCENES = os.path.join(ROOT, "mujoco_warp_b200", "test_data")
-HUMANOID = os.path.join(SCENES, "humanoid.npz")
-G1 = os.path.join(SCENES, "unitree_g1_flat.npz")
-THREE_HUMANOIDS = os.path.join(SCENES, "three_humanoids.npz")
-G1_TRAJ = os.path.join(SCENES, "unitree_g1_shuffle_dance.npz")
+from mujoco_warp_b200.scenes import DATA as SCENES, G1, G1_TRAJ, HUMANOID, THREE_HUMANOIDS  # noqa: E402,F401
 
 
 def seeded_state(mjm, nworld, key=0, seed=42, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=True):
@@ -41,6 +37,21 @@ def make_oracle(mjm, nworld, nconmax, njmax, dtype=np.float64, clamp_tolerance=T
 
   kin = mjcf.kinematics_np(mjm, mjm.qpos0)
   return orc.Oracle(mjm, nworld=nworld, nconmax=nconmax, njmax=njmax, dtype=dtype, static_kin=kin, clamp_tolerance=clamp_tolerance)
+
+
+def dense_J(d):
+  """Constraint Jacobian as dense (nworld, njmax, nv_pad) rows: Data.efc.J itself, or -- for models the reference treats as sparse --
+  the CSR arrays (J_rownnz / J_rowadr / J_colind / J, reference types.py:2021-2072) expanded row by row."""
+  if not hasattr(d.efc, "J_dense"):
+    return d.efc.J.cpu().numpy()
+  J, nnz, adr, col = d.efc.J.cpu().numpy()[:, 0], d.efc.J_rownnz.cpu().numpy(), d.efc.J_rowadr.cpu().numpy(), d.efc.J_colind.cpu().numpy()[:, 0]
+  nefc = np.minimum(d.nefc.cpu().numpy(), d.njmax)
+  out = np.zeros_like(d.efc.J_dense.cpu().numpy())
+  for w in range(d.nworld):
+    for r in range(int(nefc[w])):
+      k = np.arange(adr[w, r], adr[w, r] + nnz[w, r])
+      out[w, r, col[w, k]] = J[w, k]
+  return out
 
 
 def world_contacts(d, w):

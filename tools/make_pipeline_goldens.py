@@ -23,7 +23,7 @@ from tests import util  # noqa: E402
 from tests.test_gpu_colliders import BOX_XML  # noqa: E402
 from tools import ref_runner  # noqa: E402
 
-NWORLD, NSTEP = 3, 4
+NSTEP = 4
 
 FIELDS = [
   "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
@@ -38,6 +38,10 @@ CON = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffri
 def scenes():
   hum = mjcf.load_any(util.HUMANOID)
   yield "humanoid", hum, dict(nconmax=24, njmax=128, key=0, qpos_noise=0.003, exact_world0=False)
+  # capacity overflow (collision_core.py:271-291, constraint.py:2048,2712): one world lying flat on the floor detects 25 contacts / 100
+  # rows but the pool holds 20 contacts (19 broadphase candidates fit) and njmax is 64 -> 5 contacts dropped, the last kept contacts lose rows, overflow bits set.
+  # One world, because the contact pool is global: which WORLD loses contacts depends on the order worlds reach the atomic counter.
+  yield "humanoid_trunc", mjcf.load_any(util.HUMANOID), dict(nconmax=20, njmax=64, key=None, qpos_noise=0.0, qvel_noise=0.2, ctrl_noise=0.3, exact_world0=True, nworld=1)
   hum_e = mjcf.load_any(util.HUMANOID)
   hum_e.opt.cone = C.CONE_ELLIPTIC
   yield "humanoid_elliptic", hum_e, dict(nconmax=24, njmax=128, key=0, qpos_noise=0.003, exact_world0=False)
@@ -113,8 +117,12 @@ def main(only=None):
     t0 = time.time()
     nconmax, njmax = cfg.pop("nconmax"), cfg.pop("njmax")
     key = cfg.pop("key")
+    NWORLD = cfg.pop("nworld", 3)
     qpos, qvel, ctrl, warm = util.seeded_state(mjm, NWORLD, key=key, seed=1234, **cfg)
-    if name.startswith("humanoid"):  # keep the feet on the floor: exact root pose, pushed 0.5 mm deeper per world
+    if name == "humanoid_trunc":  # lying on its back, torso 4.6 cm above the floor (no geom exactly tangent to it): head, torso, arms and legs all touch
+      qpos[:, :3] = [0.0, 0.0, 0.046]
+      qpos[:, 3:7] = [np.cos(np.pi / 4), 0.0, np.sin(np.pi / 4), 0.0]
+    elif name.startswith("humanoid"):  # keep the feet on the floor: exact root pose, pushed 0.5 mm deeper per world
       qpos[:, :7] = mjm.key_qpos[0][:7]
       qpos[:, 2] -= 0.0005 * np.arange(NWORLD)
     if name == "three_humanoids":  # all three in the squat pose (keys 0, 3, 6 each pose one of them), roots exact, feet on the floor
@@ -146,9 +154,11 @@ def main(only=None):
     out = {**extra, "in/qpos": qpos, "in/qvel": qvel, "in/ctrl": ctrl, "in/qacc_warmstart": warm, "in/nconmax": np.array(nconmax), "in/njmax": np.array(njmax)}
     fwd.forward(m, d)
     snapshot(mjm, d, out, "forward")
+    out["forward/overflow"] = d.overflow.numpy() if getattr(d, "overflow", None) is not None else np.zeros(NWORLD, dtype=np.int32)
     for s in range(NSTEP):
       fwd.step(m, d)
       snapshot(mjm, d, out, f"step{s}")
+      out[f"step{s}/overflow"] = d.overflow.numpy()
     path = os.path.join(ROOT, "tests", "golden", f"pipeline_{name}.npz")
     np.savez_compressed(path, **out)
     print(f"{name}: nefc {out['forward/nefc'].ravel()}, nacon {int(out['forward/nacon'])}, niter {out['forward/solver_niter'].ravel()}, "
