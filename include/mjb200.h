@@ -55,8 +55,12 @@ mjbModel* mjb_model_create(void);
 void mjb_model_destroy(mjbModel* m);
 int mjb_model_set_int(mjbModel* m, const char* name, int value);
 int mjb_model_set_float(mjbModel* m, const char* name, float value);
-/* dev_ptr: device array; nbatch: leading (domain-randomisation) dimension, must be 1 in this version */
+/* dev_ptr: device array shared by all worlds (nbatch must be 1) */
 int mjb_model_set_array(mjbModel* m, const char* name, const void* dev_ptr, int nbatch);
+/* per-world (batched) float field, the reference's `*` leading dimension (types.py:822-833, io.py:259-282): nbatch entries of
+ * batch_stride floats each, world w reads entry w % nbatch.  May be called again after finalize (e.g. when a field is re-randomised
+ * into a new buffer); integer tables cannot be batched. */
+int mjb_model_set_array_batched(mjbModel* m, const char* name, const void* dev_ptr, int nbatch, int batch_stride);
 int mjb_model_finalize(mjbModel* m);
 
 /* ---- Data */

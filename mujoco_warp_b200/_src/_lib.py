@@ -87,6 +87,7 @@ def lib():
   L.mjb_model_set_int.argtypes = [vp, cp, ci]
   L.mjb_model_set_float.argtypes = [vp, cp, cf]
   L.mjb_model_set_array.argtypes = [vp, cp, vp, ci]
+  L.mjb_model_set_array_batched.argtypes = [vp, cp, vp, ci, ci]
   L.mjb_model_finalize.argtypes = [vp]
   L.mjb_data_create.restype = vp
   L.mjb_data_create.argtypes = [ci] * 6

@@ -38,6 +38,8 @@ _INT_FIELDS = [
   "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
   "cam_mode", "cam_bodyid", "cam_targetbodyid", "light_mode", "light_bodyid", "light_targetbodyid", "site_bodyid",
 ]
+# float fields outside _FLOAT_FIELDS that carry the reference's `*` leading dimension as well
+_BATCHABLE_EXTRA = ("eq_solref", "eq_solimp", "eq_data", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp", "pair_margin", "pair_gap")
 _SIZES = ["nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "nsite", "ncam", "nlight", "ntree", "nkey", "nmocap", "neq", "ntendon", "nflex"]
 
 _SUPPORTED_PAIRS = {
@@ -323,9 +325,17 @@ def _ptr_tensor(x: torch.Tensor) -> torch.Tensor:
 
 
 def put_model(mjm, batch_sizes=None) -> types.Model:
-  """Creates a device Model from an MjModel-like object (reference io.py:259)."""
-  if batch_sizes:
-    raise NotImplementedError("per-world (batched) Model fields are not supported in this version")
+  """Creates a device Model from an MjModel-like object (reference io.py:259).
+
+  batch_sizes: optional {field: n} for the float Model fields the reference marks with a `*` leading dimension (types.py:822-833):
+  the field is allocated with n entries (each a copy of the model's value) and world w reads entry w % n -- write per-world values
+  into `m.<field>` (in place, or by assigning a tensor with a different leading size) for domain randomisation."""
+  batch_sizes = dict(batch_sizes or {})
+  for name, size in batch_sizes.items():
+    if name not in _FLOAT_FIELDS and name not in _BATCHABLE_EXTRA:
+      raise ValueError(f"Model field {name!r} is not a batched array field.")
+    if int(size) < 1:
+      raise ValueError(f"batch_sizes[{name!r}] must be positive, got {size}.")
   dev = _require_cuda()
   L = _lib.lib()
   _validate(mjm)
@@ -364,17 +374,20 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
 
   keep = []
 
-  def dev_f(arr, batched=True):
+  def dev_f(arr, batched=True, name=None):
     a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
     x = torch.from_numpy(a).to(dev)
-    return x.unsqueeze(0).contiguous() if batched else x
+    if not batched:
+      return x
+    nb = int(batch_sizes.get(name, 1)) if name else 1
+    return x.unsqueeze(0).repeat(nb, *([1] * x.dim())).contiguous()
 
   def dev_i(arr):
     a = np.ascontiguousarray(np.asarray(arr).astype(np.int32))
     return torch.from_numpy(a).to(dev)
 
   for n in _FLOAT_FIELDS:
-    setattr(m, n, dev_f(getattr(mjm, n)))
+    setattr(m, n, dev_f(getattr(mjm, n), name=n))
   for n in _INT_FIELDS:
     setattr(m, n, dev_i(getattr(mjm, n)))
   m.jnt_limited = dev_i(np.asarray(mjm.jnt_limited).astype(np.int32))
@@ -408,9 +421,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.eq_obj1id = dev_i(mjm.eq_obj1id if neq else np.zeros(0))
   m.eq_obj2id = dev_i(mjm.eq_obj2id if neq else np.zeros(0))
   m.eq_objtype = dev_i(mjm.eq_objtype if neq else np.zeros(0))
-  m.eq_solref = dev_f(np.asarray(mjm.eq_solref).reshape(neq, 2) if neq else np.zeros((0, 2)))
-  m.eq_solimp = dev_f(np.asarray(mjm.eq_solimp).reshape(neq, 5) if neq else np.zeros((0, 5)))
-  m.eq_data = dev_f(np.asarray(mjm.eq_data).reshape(neq, 11) if neq else np.zeros((0, 11)))
+  m.eq_solref = dev_f(np.asarray(mjm.eq_solref).reshape(neq, 2) if neq else np.zeros((0, 2)), name="eq_solref")
+  m.eq_solimp = dev_f(np.asarray(mjm.eq_solimp).reshape(neq, 5) if neq else np.zeros((0, 5)), name="eq_solimp")
+  m.eq_data = dev_f(np.asarray(mjm.eq_data).reshape(neq, 11) if neq else np.zeros((0, 11)), name="eq_data")
   # explicit contact pairs (reference Model.pair_*)
   npair = int(getattr(mjm, "npair", 0))
   m.npair = npair
@@ -418,9 +431,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.pair_geom1 = dev_i(mjm.pair_geom1 if npair else np.zeros(0))
   m.pair_geom2 = dev_i(mjm.pair_geom2 if npair else np.zeros(0))
   for n, k in (("pair_friction", 5), ("pair_solref", 2), ("pair_solreffriction", 2), ("pair_solimp", 5)):
-    setattr(m, n, dev_f(np.asarray(getattr(mjm, n)).reshape(npair, k) if npair else np.zeros((0, k))))
+    setattr(m, n, dev_f(np.asarray(getattr(mjm, n)).reshape(npair, k) if npair else np.zeros((0, k)), name=n))
   for n in ("pair_margin", "pair_gap"):
-    setattr(m, n, dev_f(np.asarray(getattr(mjm, n)) if npair else np.zeros(0)))
+    setattr(m, n, dev_f(np.asarray(getattr(mjm, n)) if npair else np.zeros(0), name=n))
   # mesh assets (reference Model.mesh_*, types.py): vertex blocks, hull graphs for hill-climbing support queries, hull polygons
   nmesh = int(getattr(mjm, "nmesh", 0))
   m.nmesh = nmesh
@@ -476,7 +489,8 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   for n, x in dev_names.items():
     x = _ptr_tensor(x)
     keep.append(x)
-    _lib.check(L.mjb_model_set_array(h, n.encode(), x.data_ptr(), 1))
+    nb = int(x.shape[0]) if (n in _FLOAT_FIELDS or n in _BATCHABLE_EXTRA) and x.dim() >= 1 and x.numel() > 0 else 1
+    _lib.check(L.mjb_model_set_array_batched(h, n.encode(), x.data_ptr(), nb, int(x.numel() // max(nb, 1))))
   _lib.check(L.mjb_model_finalize(h))
   m._keep = keep
   weakref.finalize(m, L.mjb_model_destroy, h)
@@ -502,10 +516,19 @@ def _install_model_rebind(m: types.Model, L, arrays, ints):
 
   def model_hook(name, value):
     if name in arrays and name in m.__dict__:
-      value = _check_like("Model." + name, value, m.__dict__[name])
+      old = m.__dict__[name]
+      batchable = name in _FLOAT_FIELDS or name in _BATCHABLE_EXTRA
+      if batchable and isinstance(value, torch.Tensor) and value.dim() == old.dim() and value.shape[1:] == old.shape[1:] and value.shape[0] >= 1:
+        # a per-world (batched) field may change its leading size: world w reads entry w % size (reference types.py:822-833)
+        if value.dtype != old.dtype or value.device != old.device:
+          raise ValueError(f"Model.{name}: replacement must be {old.dtype} on {old.device}")
+        value = value.contiguous()
+      else:
+        value = _check_like("Model." + name, value, old)
       x = _ptr_tensor(value)
       m._keep.append(x)
-      _lib.check(L.mjb_model_set_array(h, name.encode(), x.data_ptr(), 1))
+      nb = int(x.shape[0]) if batchable and x.numel() > 0 else 1
+      _lib.check(L.mjb_model_set_array_batched(h, name.encode(), x.data_ptr(), nb, int(x.numel() // max(nb, 1))))
     elif name in ints and name in m.__dict__ and isinstance(m.__dict__[name], int):
       raise AttributeError(f"Model.{name} is a compiled size / table constant and cannot be reassigned; build a new Model with put_model")
     return value
@@ -831,6 +854,69 @@ def get_data_into(result, mjm, d: types.Data, world_id: int = 0):
   for name in ("type", "id", "state"):
     setattr(result, "efc_" + name, getattr(d.efc, name)[w, :nefc].cpu().numpy())
   return result
+
+
+def override_model(model, overrides):
+  """Overrides model parameters (reference io.py:2933): `overrides` is a dict or a sequence of "key = value" strings such as
+  "opt.iterations = 1", "opt.cone = pyramidal", "opt.disableflags = contact | spring".  Works on a device Model (the assignment goes
+  through the rebinding hooks, so the C handle follows) and on a host MjModel-like object; fields that exist only on the other kind
+  are skipped like in the reference."""
+  enum_fields = {
+    "opt.broadphase": types.BroadphaseType, "opt.broadphase_filter": types.BroadphaseFilter, "opt.cone": types.ConeType,
+    "opt.disableflags": types.DisableBit, "opt.enableflags": types.EnableBit, "opt.integrator": types.IntegratorType, "opt.solver": types.SolverType,
+  }
+  mj_enum_fields = {"opt.jacobian": {"DENSE": C.JAC_DENSE, "SPARSE": C.JAC_SPARSE, "AUTO": C.JAC_AUTO}}
+  mjw_only = {"opt.broadphase", "opt.broadphase_filter", "opt.graph_conditional", "opt.contact_sensor_maxmatch"}
+  mj_only = {"opt.jacobian", "vis.quality.offsamples"}
+  is_device = isinstance(model, types.Model)
+  if not isinstance(overrides, dict):
+    parsed = {}
+    for o in overrides:
+      if "=" not in o:
+        raise ValueError(f"Invalid override format: {o}")
+      k, v = o.split("=", 1)
+      parsed[k.strip()] = v.strip()
+    overrides = parsed
+  for key, val in overrides.items():
+    if key in ("opt.ls_parallel", "opt.ls_parallel_min_step"):
+      raise ValueError(f"{key.split('.')[1]} was removed in MuJoCo Warp 3.9.1.")
+    if (key in mjw_only and not is_device) or (key in mj_only and is_device):
+      continue
+    obj, attrs = model, key.split(".")
+    for i, attr in enumerate(attrs):
+      if not hasattr(obj, attr):
+        raise ValueError(f"Unrecognized model field: {key}")
+      if i < len(attrs) - 1:
+        obj = getattr(obj, attr)
+        continue
+      cur = getattr(obj, attr)
+      if key in mj_enum_fields and isinstance(val, str):
+        member = val.strip().upper()
+        if member not in mj_enum_fields[key]:
+          raise ValueError(f"Unrecognized enum value for {key}: {member}")
+        val = mj_enum_fields[key][member]
+      elif key in enum_fields and isinstance(val, str):
+        acc = 0
+        for member in val.split("|"):
+          member = member.strip().upper()
+          if member not in enum_fields[key].__members__:
+            raise ValueError(f"Unrecognized enum value for {enum_fields[key].__name__}: {member}")
+          acc |= int(enum_fields[key][member])
+        val = acc
+      elif isinstance(cur, bool) and isinstance(val, str):
+        if val.upper() not in ("TRUE", "FALSE"):
+          raise ValueError(f"Unrecognized value for field: {key}")
+        val = val.upper() == "TRUE"
+      elif isinstance(cur, torch.Tensor) and isinstance(val, str):
+        floats = [float(p) for p in val.strip("[]").split()]
+        val = torch.tensor(floats, dtype=cur.dtype, device=cur.device).reshape(cur.shape)
+      elif isinstance(cur, np.ndarray) and isinstance(val, str):
+        val = np.array([float(p) for p in val.strip("[]").split()], dtype=cur.dtype)
+      elif isinstance(cur, torch.Tensor):
+        val = torch.as_tensor(val, dtype=cur.dtype, device=cur.device).reshape(cur.shape)
+      else:
+        val = type(cur)(val)
+      setattr(obj, attr, val)
 
 
 def load_trajectory(npz_path: str, mjm, mjd) -> np.ndarray:

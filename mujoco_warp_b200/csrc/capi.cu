@@ -62,15 +62,25 @@ int mjb_model_set_float(mjbModel* m, const char* name, float v) {
 #undef X
   return fail(std::string("unknown model float field: ") + name);
 }
-int mjb_model_set_array(mjbModel* m, const char* name, const void* p, int nbatch) {
-  if (nbatch != 1) return fail(std::string("per-world (batched) Model fields are not supported yet: ") + name);
-#define X(n) if (!strcmp(name, #n)) { m->dev.n = (const int*)p; return 0; }
+int mjb_model_set_array_batched(mjbModel* m, const char* name, const void* p, int nbatch, int batch_stride) {
+  if (nbatch < 1) return fail(std::string("nbatch must be >= 1: ") + name);
+#define X(n) if (!strcmp(name, #n)) { if (nbatch != 1) return fail(std::string("integer Model tables are shared by all worlds (not batched): ") + name); m->dev.n = (const int*)p; return 0; }
   MJB_MODEL_IARRS(X)
 #undef X
-#define X(n) if (!strcmp(name, #n)) { m->dev.n = (const float*)p; return 0; }
+#define X(n) if (!strcmp(name, #n)) { m->dev.n = (const float*)p; m->dev.nb_##n = nbatch; m->dev.bs_##n = batch_stride; goto done; }
   MJB_MODEL_FARRS(X)
 #undef X
   return fail(std::string("unknown model array field: ") + name);
+done:
+  m->dev.batched = 0;
+#define X(n) if (m->dev.nb_##n > 1) m->dev.batched = 1;
+  MJB_MODEL_FARRS(X)
+#undef X
+  return 0;
+}
+int mjb_model_set_array(mjbModel* m, const char* name, const void* p, int nbatch) {
+  if (nbatch != 1) return fail(std::string("use mjb_model_set_array_batched (needs the per-entry stride) for a per-world field: ") + name);
+  return mjb_model_set_array_batched(m, name, p, 1, 0);
 }
 int mjb_model_finalize(mjbModel* m) {
 #define X(n) if (!m->dev.n) return fail(std::string("model array not set: ") + #n);

@@ -155,14 +155,15 @@ __device__ __forceinline__ void fill_mesh(const ModelDev& m, int g, CGeom& c) {
 
 // MAXC = contacts one geom pair can produce: 2 for plane/sphere/capsule-only models (everything stays in registers),
 // 8 once boxes, cylinders or ellipsoids are present.
-template <int MAXC>
+template <int MAXC, bool BAT>
 __global__ void __launch_bounds__(64, MAXC == 2 ? 16 : 8)
-k_collision(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
+k_collision(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // every warp of the block owns one world (its own shared-memory slice)
   const int w = blockIdx.x * (blockDim.x >> 5) + warp + d.w0;
   if (w >= d.nworld || w >= d.w0 + d.wn) return;
-  const ColLayout L = col_layout(m, d);
+  MJB_WORLD_MODEL(w)
+  const ColLayout L = col_layout(mp, d);
   float* S = smem + warp * L.total;
   float *gxpos = S + L.gxpos, *gxmat = S + L.gxmat, *stage = S + L.stage;
   int *surv = (int*)(S + L.surv), *sgeom = (int*)(S + L.sgeom);
@@ -517,18 +518,19 @@ cudaError_t LAUNCH_NAME(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   if (m.nmesh > 0) return launch_collision_mesh(m, d, s);  // models with mesh geoms run the CCD_MESH build of this kernel
 #endif
   const size_t smem = SMEM_NAME(m, d);
-  static size_t configured[2] = {0, 0};
+  static size_t configured4[4] = {0, 0, 0, 0};
 #ifdef MJB_COLLISION_MESH_TU
   const int full = 1;
-  void (*kern)(ModelDev, DataDev) = k_collision<8>;
+  void (*kern)(ModelDev, DataDev) = m.batched ? k_collision<8, true> : k_collision<8, false>;
 #else
   const int full = m.has_multicontact_geom ? 1 : 0;
-  void (*kern)(ModelDev, DataDev) = full ? k_collision<8> : k_collision<2>;
+  void (*kern)(ModelDev, DataDev) = full ? (m.batched ? k_collision<8, true> : k_collision<8, false>) : (m.batched ? k_collision<2, true> : k_collision<2, false>);
 #endif
-  if (smem > 48 * 1024 && smem > configured[full]) {
+  const int ci = full + 2 * (m.batched ? 1 : 0);
+  if (smem > 48 * 1024 && smem > configured4[ci]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[full] = smem;
+    configured4[ci] = smem;
   }
   const int grid = (d.wn + collision_wpb() - 1) / collision_wpb();
   kern<<<grid, collision_wpb() * 32, smem, s>>>(m, d);

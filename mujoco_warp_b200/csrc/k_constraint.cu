@@ -103,14 +103,15 @@ __device__ __forceinline__ v3 warp_sum3v(v3 a) { return mk3(warp_sum(a.x), warp_
 
 // EQ = the model has equality constraints or limited ball joints; plain articulated models (humanoid) use the leaner
 // instantiation without that code.
-template <bool EQ>
+template <bool EQ, bool BAT>
 __global__ void __launch_bounds__(64, EQ ? 12 : 16)
-k_constraint(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
+k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // every warp of the block owns one world (its own shared-memory slice)
   const int w = blockIdx.x * (blockDim.x >> 5) + warp + d.w0;
   if (w >= d.nworld || w >= d.w0 + d.wn) return;
-  const ConLayout L = con_layout(m, d);
+  MJB_WORLD_MODEL(w)
+  const ConLayout L = con_layout(mp, d);
   float* S = smem + warp * L.total;
   float *cdof = S + L.cdof, *scom = S + L.scom, *qvel = S + L.qvel, *rec = S + L.rec;
   const int nv = m.nv, nb = m.nbody, njmax = d.njmax, nvp = d.nv_pad;
@@ -439,13 +440,14 @@ size_t smem_constraint(const ModelDev& m, const DataDev& d) { return (size_t)con
 
 cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_constraint(m, d);
-  static size_t configured[2] = {0, 0};
+  static size_t configured[4] = {0, 0, 0, 0};
   const int eq = (m.neq > 0 || m.nlimit_ball > 0) ? 1 : 0;
-  void (*kern)(ModelDev, DataDev) = eq ? k_constraint<true> : k_constraint<false>;
-  if (smem > 48 * 1024 && smem > configured[eq]) {
+  void (*kern)(ModelDev, DataDev) = eq ? (m.batched ? k_constraint<true, true> : k_constraint<true, false>) : (m.batched ? k_constraint<false, true> : k_constraint<false, false>);
+  const int ci = eq + 2 * (m.batched ? 1 : 0);
+  if (smem > 48 * 1024 && smem > configured[ci]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[eq] = smem;
+    configured[ci] = smem;
   }
   const int grid = (d.wn + constraint_wpb() - 1) / constraint_wpb();
   kern<<<grid, constraint_wpb() * 32, smem, s>>>(m, d);

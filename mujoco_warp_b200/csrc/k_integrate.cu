@@ -19,13 +19,15 @@ __host__ __device__ inline int int_words(const ModelDev& m) {
   return (o + 3) & ~3;
 }
 
+template <bool BAT>
 __global__ void __launch_bounds__(MJB_WARPS_PER_BLOCK * 32)
-k_euler(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int integrator) {
+k_euler(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, int integrator) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x, warp = 0;  // one warp per block: the world index is block-uniform
   const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
-  float* S = smem + warp * int_words(m);
+  MJB_WORLD_MODEL(w)
+  float* S = smem + warp * int_words(mp);
   float *qacc = S, *qvel = S + m.nv, *A = S + 2 * m.nv, *x = A + m.maxtree * chol_ld(m.maxtree);
   const int nv = m.nv;
   const size_t wb = (size_t)w;
@@ -129,10 +131,12 @@ __device__ __forceinline__ float halton(int index, int base) {
   return hn;
 }
 
-__global__ void k_ctrl_noise(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, const float* __restrict__ ctrl_center, int step, float noise_std, float noise_rate) {
+template <bool BAT>
+__global__ void k_ctrl_noise(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, const float* __restrict__ ctrl_center, int step, float noise_std, float noise_rate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.nworld * m.nu) return;
-  const int w = i / m.nu, a = i - w * m.nu;
+  if (i >= d.nworld * mp.nu) return;
+  const int w = i / mp.nu, a = i - w * mp.nu;
+  MJB_WORLD_MODEL(w)
   const float rate = expf(-m.timestep / noise_rate), scale = noise_std * sqrtf(1.0f - rate * rate);
   float midpoint = 0.f, halfrange = 1.f;
   const float lo = m.actuator_ctrlrange[2 * a], hi = m.actuator_ctrlrange[2 * a + 1];
@@ -258,21 +262,24 @@ cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, int integrator
     return cudaGetLastError();
   }
   const size_t smem = smem_integrate(m);
-  static size_t configured = 0;
+  static size_t configured2[2] = {0, 0};
+  size_t& configured = configured2[m.batched ? 1 : 0];
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_euler, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(m.batched ? k_euler<true> : k_euler<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   const int grid = d.wn;
-  k_euler<<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, integrator);
+  if (m.batched) k_euler<true><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, integrator);
+  else k_euler<false><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, integrator);
   return cudaGetLastError();
 }
 
 cudaError_t launch_ctrl_noise(const ModelDev& m, const DataDev& d, const float* ctrl_center, int step, float std, float rate, cudaStream_t s) {
   const int n = d.nworld * m.nu;
   if (n == 0) return cudaSuccess;
-  k_ctrl_noise<<<(n + 255) / 256, 256, 0, s>>>(m, d, ctrl_center, step, std, rate);
+  if (m.batched) k_ctrl_noise<true><<<(n + 255) / 256, 256, 0, s>>>(m, d, ctrl_center, step, std, rate);
+  else k_ctrl_noise<false><<<(n + 255) / 256, 256, 0, s>>>(m, d, ctrl_center, step, std, rate);
   return cudaGetLastError();
 }
 

@@ -48,17 +48,19 @@ __host__ __device__ inline PosLayout pos_layout(const ModelDev& m) {
 }
 
 // LPW lanes per world, G = 32 / LPW worlds per warp (one warp per block).  Shared layout of field f: [G][n_f] at S + L.f * G.
-template <int LPW>
+// BAT: per-world (batched) Model fields -- the launcher then uses one world per warp so the world's offsets stay uniform
+template <int LPW, bool BAT>
 __global__ void __launch_bounds__(256)
-k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
+k_position(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, int mask) {
   extern __shared__ __align__(16) float smem[];
   constexpr int G = 32 / LPW;
   Team<LPW> T;
   T.init(d.w0, d.wn, d.nworld);
   if (T.nvalid <= 0) return;
+  MJB_WORLD_MODEL(T.w)
   const int lane = T.lane, sub = T.sub, g = T.g, nval = T.nvalid;
   const bool valid = T.valid;
-  const PosLayout L = pos_layout(m);
+  const PosLayout L = pos_layout(mp);
   float* S = smem + (size_t)(threadIdx.x >> 5) * ((size_t)L.total * G + 4);  // this warp's slice (+ its mbarrier)
   Stager st;
   st.init(reinterpret_cast<uint64_t*>(S + (size_t)L.total * G), lane);
@@ -378,16 +380,20 @@ k_position(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
 }  // namespace
 
-static TeamShape pos_shape(const ModelDev& m) { return team_shape((size_t)pos_layout(m).total, "MJB_LPW_POS", "MJB_WPB_POS"); }
+static TeamShape pos_shape(const ModelDev& m) {
+  TeamShape t = team_shape((size_t)pos_layout(m).total, "MJB_LPW_POS", "MJB_WPB_POS");
+  if (m.batched && t.lpw != 32) { t = team_shape_fixed((size_t)pos_layout(m).total, 32, 2); }
+  return t;
+}
 size_t smem_position(const ModelDev& m) { return pos_shape(m).block_bytes; }
 
 cudaError_t launch_position(const ModelDev& m, const DataDev& d, int mask, cudaStream_t s) {
   const TeamShape t = pos_shape(m);
   const size_t smem = t.block_bytes;
   const int lpw = t.lpw, G = 32 / lpw, wpb = t.wpb;
-  void (*kern)(ModelDev, DataDev, int) = lpw == 4 ? k_position<4> : lpw == 8 ? k_position<8> : lpw == 16 ? k_position<16> : k_position<32>;
-  static size_t configured[4] = {0, 0, 0, 0};
-  const int ki = lpw == 4 ? 0 : lpw == 8 ? 1 : lpw == 16 ? 2 : 3;
+  void (*kern)(ModelDev, DataDev, int) = m.batched ? k_position<32, true> : lpw == 4 ? k_position<4, false> : lpw == 8 ? k_position<8, false> : lpw == 16 ? k_position<16, false> : k_position<32, false>;
+  static size_t configured[5] = {0, 0, 0, 0, 0};
+  const int ki = m.batched ? 4 : lpw == 4 ? 0 : lpw == 8 ? 1 : lpw == 16 ? 2 : 3;
   if (smem > 48 * 1024 && smem > configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

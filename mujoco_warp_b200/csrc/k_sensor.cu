@@ -125,11 +125,13 @@ __device__ __forceinline__ int obj_body(const ModelDev& m, int objtype, int id) 
   }
 }
 
+template <bool BAT>
 __global__ void __launch_bounds__(32)
-k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int stages) {
+k_sensor(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, int stages) {
   extern __shared__ float smem[];  // nbody x (linvel 3 | angmom 3 | bodyvel lin 3) or nbody x (cfrc_ext 6 | cacc / cfrc_int 6)
   const int lane = threadIdx.x, w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
+  MJB_WORLD_MODEL(w)
   const size_t wb = (size_t)w;
   const int nb = m.nbody, nv = m.nv;
 
@@ -433,6 +435,7 @@ k_sensor(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, 
 
 cudaError_t launch_sensor(const ModelDev& m, const DataDev& d, int stages, cudaStream_t s) {
   if (m.nsensor == 0) return cudaSuccess;
-  k_sensor<<<d.wn, 32, (size_t)12 * m.nbody * sizeof(float), s>>>(m, d, stages);
+  if (m.batched) k_sensor<true><<<d.wn, 32, (size_t)12 * m.nbody * sizeof(float), s>>>(m, d, stages);
+  else k_sensor<false><<<d.wn, 32, (size_t)12 * m.nbody * sizeof(float), s>>>(m, d, stages);
   return cudaGetLastError();
 }

@@ -27,14 +27,14 @@ namespace {
 // aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
 // rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
 struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, cgv, red, env, total; };
-__host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d) {
+__host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d, bool big) {
   SolLayout L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   L.nvp = d.nv_pad; L.ldJ = d.nv_pad; L.ldH = m.nv | 1;
   // nv > 32 ("big" models, e.g. unitree G1, three_humanoids): only the first d.jcap Jacobian rows are staged in shared memory,
   // the rest is read from global memory (L2 hits).  d.jcap defaults to 0: occupancy beats the shorter access (see capi.cu).
-  L.jcap = m.nv > 32 ? (d.njmax < d.jcap ? d.njmax : d.jcap) : d.njmax;
+  L.jcap = big ? (d.njmax < d.jcap ? d.njmax : d.jcap) : d.njmax;
   L.J = take(L.jcap * L.ldJ);
   L.vec = take(7 * L.nvp);  // qacc, Ma, grad, search, mv (= x scratch of the nv > 32 path), qfs, qfc
   L.cgv = take(m.solver == SOL_CG ? 3 * L.nvp : 0);  // CG only: Mgrad, prev_grad, prev_Mgrad
@@ -44,17 +44,17 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   L.H = take(hsz);
   // nv <= 32: the factor lives in the padded column layout of chol_solve_rows_bcast, and M is kept as a dense packed lower
   // triangle (H starts as a copy of it, M * v needs no index tables); nv > 32: packed factor, CSR M with gather tables
-  L.Lf = take(m.nv > 32 ? hsz : colsub_off(m.nv));
-  L.M = take(m.nv > 32 ? m.nC : hsz);
+  L.Lf = take(big ? hsz : colsub_off(m.nv));
+  L.M = take(big ? m.nC : hsz);
   // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
   // elliptic cones add: per-row friction scale, 3 quad words per row (solver.py:1008-1015 layout), row->contact info
   const bool ell = m.cone == CONE_ELLIPTIC;
   L.nrowf = (m.nfricdof > 0 ? 5 : 4);
   L.rowf = take((L.nrowf + (ell ? 4 : 0)) * d.njmax);
   L.rowi = take((ell ? 3 : 2) * d.njmax);
-  L.red = take(m.nv > 32 ? 9 * 8 : 0);  // cross-warp reduction scratch of the multi-warp (nv > 32) instantiations
+  L.red = take(big ? 9 * 8 : 0);  // cross-warp reduction scratch of the multi-warp (nv > 32) instantiations
   // nv > 32: nonzero column range of every Jacobian row (lo | hi << 16) and the Hessian's row envelope (first column per row)
-  L.env = take(m.nv > 32 ? d.njmax + L.nvp : 0);
+  L.env = take(big ? d.njmax + L.nvp : 0);
   L.total = o;
   return L;
 }
@@ -687,7 +687,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const int lane = threadIdx.x;  // index inside the team of NW warps (one block) that owns the world
   const int w = blockIdx.x + d.w0;
   if (w >= d.nworld) return;
-  const SolLayout L = sol_layout(m, d);
+  const SolLayout L = sol_layout(m, d, BIG);
   float* S = smem;
   const int nv = m.nv, njmax = d.njmax, nvp = d.nv_pad;
   const size_t wb = (size_t)w;
@@ -849,7 +849,14 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
 
 }  // namespace
 
-size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_layout(m, d).total * sizeof(float); }
+// The "big" instantiation (packed Hessian and factor worked on in shared memory, Jacobian rows read through L2, CSR inertia) is mandatory
+// above nv = 32; MJB_SOLVER_BIG = 1 selects it for small models too (62 instead of 127 registers, 6.4 instead of 14 KB per world).
+static bool solver_big(const ModelDev& m) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MJB_SOLVER_BIG"); forced = e ? atoi(e) : 0; }
+  return m.nv > 32 || forced == 1;
+}
+size_t smem_solver(const ModelDev& m, const DataDev& d) { return (size_t)sol_layout(m, d, solver_big(m)).total * sizeof(float); }
 
 // Warps per world: 1.  For nv > 32 the per-world slice of shared memory (packed Hessian + factor + Jacobian rows) limits an SM to
 // a few resident worlds; teams of 2 or 4 warps per world (block barriers, right-looking team Cholesky) are implemented and
@@ -864,7 +871,7 @@ static int solver_warps(const ModelDev& m) {
 
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_solver(m, d);
-  const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = m.nv > 32 ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0;
+  const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = solver_big(m) ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0;
   const int nw = solver_warps(m), team = nw == 4 ? 2 : (nw == 2 ? 1 : 0);
   const int which = cg ? 4 + 2 * big + ell : (big ? 8 + 2 * team + ell : ell);
   static size_t configured[14] = {0};

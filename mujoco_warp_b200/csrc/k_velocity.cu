@@ -88,17 +88,18 @@ __device__ __forceinline__ void team_chol_upper(float* U, int n, float* x, bool 
 }
 
 // PEXT = the model uses gravity compensation or free / ball joint springs (kept out of the plain instantiation)
-template <bool PEXT, int LPW>
+template <bool PEXT, int LPW, bool BAT>
 __global__ void __launch_bounds__(256)
-k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, int mask) {
+k_velocity(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, int mask) {
   extern __shared__ __align__(16) float smem[];
   constexpr int G = 32 / LPW;
   Team<LPW> T;
   T.init(d.w0, d.wn, d.nworld);
   if (T.nvalid <= 0) return;
+  MJB_WORLD_MODEL(T.w)
   const int lane = T.lane, sub = T.sub, g = T.g, nval = T.nvalid;
   const bool valid = T.valid;
-  const VelLayout L = vel_layout(m);
+  const VelLayout L = vel_layout(mp);
   float* S = smem + (size_t)(threadIdx.x >> 5) * ((size_t)L.total * G + 4);  // this warp's slice (+ its mbarrier)
   Stager st;
   st.init(reinterpret_cast<uint64_t*>(S + (size_t)L.total * G), lane);
@@ -424,21 +425,26 @@ k_velocity(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
 }  // namespace
 
-static TeamShape vel_shape(const ModelDev& m) { return team_shape((size_t)vel_layout(m).total, "MJB_LPW_VEL", "MJB_WPB_VEL"); }
+static TeamShape vel_shape(const ModelDev& m) {
+  TeamShape t = team_shape((size_t)vel_layout(m).total, "MJB_LPW_VEL", "MJB_WPB_VEL");
+  if (m.batched && t.lpw != 32) t = team_shape_fixed((size_t)vel_layout(m).total, 32, 2);
+  return t;
+}
 size_t smem_velocity(const ModelDev& m) { return vel_shape(m).block_bytes; }
 
 template <bool PEXT>
-static void (*vel_kernel(int lpw))(ModelDev, DataDev, int) {
-  return lpw == 4 ? k_velocity<PEXT, 4> : lpw == 8 ? k_velocity<PEXT, 8> : lpw == 16 ? k_velocity<PEXT, 16> : k_velocity<PEXT, 32>;
+static void (*vel_kernel(int lpw, bool bat))(ModelDev, DataDev, int) {
+  if (bat) return k_velocity<PEXT, 32, true>;
+  return lpw == 4 ? k_velocity<PEXT, 4, false> : lpw == 8 ? k_velocity<PEXT, 8, false> : lpw == 16 ? k_velocity<PEXT, 16, false> : k_velocity<PEXT, 32, false>;
 }
 
 cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int mask, cudaStream_t s) {
   const TeamShape t = vel_shape(m);
   const size_t smem = t.block_bytes;
-  static size_t configured[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  static size_t configured[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
   const int ext = m.has_gravcomp ? 1 : 0;  // has_gravcomp also flags free / ball joint springs (io.py put_model)
-  const int lpw = t.lpw, G = 32 / lpw, wpb = t.wpb, ki = lpw == 4 ? 0 : lpw == 8 ? 1 : lpw == 16 ? 2 : 3;
-  void (*kern)(ModelDev, DataDev, int) = ext ? vel_kernel<true>(lpw) : vel_kernel<false>(lpw);
+  const int lpw = t.lpw, G = 32 / lpw, wpb = t.wpb, ki = m.batched ? 4 : lpw == 4 ? 0 : lpw == 8 ? 1 : lpw == 16 ? 2 : 3;
+  void (*kern)(ModelDev, DataDev, int) = ext ? vel_kernel<true>(lpw, m.batched) : vel_kernel<false>(lpw, m.batched);
   if (smem > 48 * 1024 && smem > configured[ext][ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

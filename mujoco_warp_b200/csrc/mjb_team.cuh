@@ -124,6 +124,14 @@ inline TeamShape team_shape(size_t world_words, const char* env_lpw, const char*
   return t;
 }
 
+inline TeamShape team_shape_fixed(size_t world_words, int lpw, int wpb) {
+  TeamShape t;
+  t.lpw = lpw; t.wpb = wpb; t.warp_bytes = (world_words * (size_t)(32 / lpw) + 4) * sizeof(float);
+  while (t.wpb > 1 && t.warp_bytes * t.wpb > 200 * 1024) t.wpb--;
+  t.block_bytes = t.warp_bytes * t.wpb;
+  return t;
+}
+
 // World team of the calling lane.
 template <int LPW>
 struct Team {

@@ -49,7 +49,30 @@ struct ModelDev {
 #define X(n) const float* __restrict__ n;
   MJB_MODEL_FARRS(X)
 #undef X
+  // per-world (batched) float fields, the reference's `*` leading dimension (types.py:822-833, io.py:259-282): world w reads entry
+  // w % nb of a field with nb > 1 entries of bs floats each.  batched = any field has nb > 1 (selects the BAT kernel instantiations).
+  int batched;
+#define X(n) int nb_##n, bs_##n;
+  MJB_MODEL_FARRS(X)
+#undef X
 };
+
+#ifdef __CUDACC__
+// The model as world w sees it: every batched float field already offset to the world's entry.  Unused fields cost nothing (the
+// copy is scalar-replaced); with one world per warp the offsets stay in uniform registers.
+__device__ __forceinline__ ModelDev world_model(const ModelDev& m, int w, int nworld) {
+  ModelDev r = m;
+#define X(n) if (m.nb_##n > 1) r.n = m.n + (size_t)(m.nb_##n == nworld ? w : w % m.nb_##n) * (size_t)m.bs_##n;
+  MJB_MODEL_FARRS(X)
+#undef X
+  return r;
+}
+// Inside a kernel template with `bool BAT` whose Model parameter is `mp`: defines `m`, the model of world `w`.
+#define MJB_WORLD_MODEL(w)                                         \
+  ModelDev m_world_;                                               \
+  if (BAT) m_world_ = world_model(mp, (w), d.nworld);              \
+  const ModelDev& m = BAT ? m_world_ : mp;
+#endif
 
 // ---------------------------------------------------------------- Data
 #define MJB_DATA_FARRS(X) \

@@ -40,6 +40,7 @@ def _parse(argv):
   p.add_argument("--measure_alloc", nargs="?", const="true", default="false")
   p.add_argument("--memory", nargs="?", const="true", default="false")
   p.add_argument("--device", default="cuda:0")
+  p.add_argument("-o", "--override", action="append", default=[], help='model overrides, e.g. -o "opt.iterations = 10" (reference io.py:2933)')
   a = p.parse_args(argv)
   for k in ("event_trace", "measure_solver", "measure_alloc", "memory"):
     setattr(a, k, str(getattr(a, k)).lower() in ("1", "true", "yes"))
@@ -89,7 +90,9 @@ def main(argv=None):
   if a.nstep is None:
     a.nstep = 1000
   free0 = torch.cuda.mem_get_info()[0]
+  mjw.override_model(mjm, a.override)
   m = mjw.put_model(mjm)
+  mjw.override_model(m, a.override)
   d = mjw.put_data(mjm, mjd, nworld=a.nworld, nconmax=a.nconmax, njmax=a.njmax, m=m)
   timestep = float(m.opt.timestep.cpu()[0])
   if a.format == "human":
@@ -133,18 +136,19 @@ def main(argv=None):
       nefc.append(float(d.nefc.float().mean().cpu()))
       niter.append(float(d.solver_niter.float().mean().cpu()))
     if a.event_trace and a.function == "step":
+      # the reference's nested stage keys (warp_util.py:51-145, testspeed.py:75-89), from stage-wise steps (see _src/trace.py)
       acc = None
+      ntrace = 10
+      for i in range(ntrace):
+        fl = mjw.flatten_trace(mjw.event_trace_step(m, d), scale=1e6 / a.nworld)  # ms -> ns per env-step
+        acc = fl if acc is None else {k: acc[k] + fl[k] for k in fl}
+      trace = {k: v / ntrace for k, v in acc.items()}
+      # the fused production step for comparison (kernels of mjb_step timed one by one)
+      accp = None
       for i in range(20):
         r = mjw.step_profile(m, d)
-        acc = r if acc is None else {k: acc[k] + r[k] for k in r}
-      ns = {k: 1e6 * v / 20 / a.nworld for k, v in acc.items()}  # ns per env-step, like testspeed.py:75-89
-      trace = {
-        "step": sum(ns.values()), "step.forward": sum(ns.values()) - ns["integrate"],
-        "step.forward.fwd_position": ns["position"] + ns["collision"] + ns["constraint"],
-        "step.forward.fwd_position.kinematics_com_pos_camlight_crb_transmission": ns["position"],
-        "step.forward.fwd_position.collision": ns["collision"], "step.forward.fwd_position.make_constraint": ns["constraint"],
-        "step.forward.fwd_velocity_actuation_acceleration": ns["velocity"], "step.forward.solve": ns["solver"], "step.euler": ns["integrate"],
-      }
+        accp = r if accp is None else {k: accp[k] + r[k] for k in r}
+      trace.update({f"fused.{k}": 1e6 * v / 20 / a.nworld for k, v in accp.items()})
 
   nconverged = int((~torch.isnan(d.qpos).any(dim=1)).sum().cpu())
   steps = a.nworld * a.nstep

@@ -263,3 +263,115 @@ def test_dense_models_keep_the_dense_layout(built):
   m = mjw.put_model(mjm)
   d = mjw.make_data(mjm, nworld=2, nconmax=24, njmax=64, m=m)
   assert not m.is_sparse and d.njmax_nnz == 0 and d.efc.J.shape == (2, 64, m.nv_pad) and d.efc.J_rownnz.shape == (2, 0) and d.efc.J_colind.shape == (2, 0, 0)
+
+
+def test_event_trace_has_the_reference_keys_and_the_traced_step_is_the_fused_step(built):
+  """testspeed --event_trace: nested keys of the reference's EventTracer (warp_util.py:51-145 flattened by testspeed.py:75-89); the
+  stage-wise step that produces them must leave exactly the state the fused step leaves."""
+  import mujoco_warp_b200 as mjw
+
+  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  m = mjw.put_model(mjm)
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, 16, key=0, seed=3)
+  f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+  ds = []
+  for _ in range(2):
+    d = mjw.make_data(mjm, nworld=16, nconmax=24, njmax=64, m=m)
+    d.qpos.copy_(f32(qpos)); d.qvel.copy_(f32(qvel)); d.ctrl.copy_(f32(ctrl)); d.qacc_warmstart.copy_(f32(warm))
+    ds.append(d)
+  tr = mjw.flatten_trace(mjw.event_trace_step(m, ds[0]))
+  mjw.step(m, ds[1])
+  torch.cuda.synchronize()
+  for k in ("step", "step.forward", "step.forward.fwd_position", "step.forward.fwd_position.fwd_kinematics.kinematics", "step.forward.fwd_position.fwd_kinematics.com_pos",
+            "step.forward.fwd_position.crb", "step.forward.fwd_position.collision", "step.forward.fwd_position.make_constraint", "step.forward.fwd_position.transmission",
+            "step.forward.fwd_velocity", "step.forward.fwd_actuation", "step.forward.fwd_acceleration", "step.forward.solve", "step.euler"):
+    assert k in tr and tr[k] >= 0.0, k
+  assert tr["step"] >= tr["step.forward"] >= tr["step.forward.fwd_position"]
+  for f in ("qpos", "qvel", "qacc", "qacc_warmstart"):
+    np.testing.assert_array_equal(getattr(ds[0], f).cpu().numpy(), getattr(ds[1], f).cpu().numpy(), err_msg=f)
+
+
+def test_override_model_reaches_the_kernels(built):
+  import mujoco_warp_b200 as mjw
+
+  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  m = mjw.put_model(mjm)
+  d = mjw.make_data(mjm, nworld=4, nconmax=24, njmax=64, m=m)
+  from mujoco_warp_b200._src.mjcf import MjDataLite, reset_data_keyframe
+  mjd = MjDataLite(mjm); reset_data_keyframe(mjm, mjd, 0)
+  d = mjw.put_data(mjm, mjd, nworld=4, nconmax=24, njmax=64, m=m)
+  mjw.forward(m, d)
+  torch.cuda.synchronize()
+  assert int(d.nacon.cpu()[0]) > 0 and int(d.solver_niter.max().cpu()) >= 1
+  mjw.override_model(m, ["opt.disableflags = contact", "opt.iterations = 0"])
+  assert m.opt.disableflags == int(mjw.DisableBit.CONTACT) and m.opt.iterations == 0
+  mjw.forward(m, d)
+  torch.cuda.synchronize()
+  assert int(d.nacon.cpu()[0]) == 0 and int(d.solver_niter.max().cpu()) == 0
+  with pytest.raises(ValueError, match="Unrecognized model field"):
+    mjw.override_model(m, {"opt.nonsense": 1})
+  # direct assignment goes through the same rebinding hook (ADVICE r1: used to be a silent no-op)
+  m.opt.disableflags = 0
+  m.opt.iterations = 100
+  m.opt.timestep = 0.001
+  mjw.step(m, d)
+  torch.cuda.synchronize()
+  assert int(d.nacon.cpu()[0]) > 0 and abs(float(d.time[0].cpu()) - 0.001) < 1e-9
+  with pytest.raises(ValueError, match="must match"):
+    d.qpos = torch.zeros(3, 3, device="cuda")
+  new_qpos = d.qpos.clone()
+  new_qpos[:, 2] += 1.0  # lift every humanoid off the floor
+  d.qpos = new_qpos
+  mjw.forward(m, d)
+  torch.cuda.synchronize()
+  assert int(d.nacon.cpu()[0]) == 0
+
+
+def test_batched_model_fields_match_per_world_models(built):
+  """put_model(batch_sizes=...) (reference io.py:259-282): per-world masses, inertias, dof damping / armature, geom friction, actuator
+  gains and gear.  World w must evolve exactly like a single-world run on a Model that holds w's values in its shared fields; a field
+  batched with fewer entries than worlds wraps around (w % n)."""
+  import mujoco_warp_b200 as mjw
+  from mujoco_warp_b200._src.mjcf import MjDataLite, reset_data_keyframe
+
+  mjm = mjw.mjcf.load_any(util.HUMANOID)
+  mjm.opt.disableflags = int(mjm.opt.disableflags) & ~int(mjw.DisableBit.EULERDAMP)  # make dof_damping matter in the integrator too
+  nworld = 6
+  fields = {"body_mass": nworld, "body_inertia": nworld, "dof_damping": nworld, "dof_armature": 3, "geom_friction": nworld, "actuator_gainprm": 2, "actuator_gear": nworld}
+  m = mjw.put_model(mjm, batch_sizes=fields)
+  with pytest.raises(ValueError, match="not a batched array field"):
+    mjw.put_model(mjm, batch_sizes={"body_parentid": 2})
+  rng = np.random.default_rng(0)
+  scale = {}
+  for f, n in fields.items():
+    t = getattr(m, f)
+    assert t.shape[0] == n
+    sc = torch.from_numpy(rng.uniform(0.7, 1.4, size=(n,) + (1,) * (t.dim() - 1)).astype(np.float32)).cuda()
+    scale[f] = sc.cpu().numpy()
+    t.mul_(sc)  # in place: the kernels read the registered buffer
+  mjd = MjDataLite(mjm)
+  reset_data_keyframe(mjm, mjd, 0)
+  d = mjw.put_data(mjm, mjd, nworld=nworld, nconmax=24, njmax=64, m=m)
+  ctrl = torch.from_numpy(rng.uniform(-0.5, 0.5, (nworld, mjm.nu)).astype(np.float32)).cuda()
+  d.ctrl.copy_(ctrl)
+  for _ in range(5):
+    mjw.step(m, d)
+  torch.cuda.synchronize()
+  batched = {f: getattr(d, f).cpu().numpy() for f in ("qpos", "qvel", "qacc", "qfrc_bias", "actuator_force", "nefc")}
+  for w in range(nworld):
+    m1 = mjw.put_model(mjm)
+    for f, n in fields.items():
+      getattr(m1, f).mul_(torch.from_numpy(scale[f][w % n : w % n + 1]).cuda())
+    d1 = mjw.put_data(mjm, mjd, nworld=1, nconmax=24, njmax=64, m=m1)
+    d1.ctrl.copy_(ctrl[w : w + 1])
+    for _ in range(5):
+      mjw.step(m1, d1)
+    torch.cuda.synchronize()
+    for f, got in batched.items():
+      np.testing.assert_allclose(got[w], getattr(d1, f).cpu().numpy()[0], rtol=2e-5, atol=2e-6, err_msg=f"world {w}: {f}")
+  assert np.abs(batched["qpos"] - batched["qpos"][0]).max() > 1e-4  # the worlds really differ
+  # assigning a tensor with another leading size re-registers the field (w % size)
+  m.dof_damping = m.dof_damping[:2].clone()
+  mjw.step(m, d)
+  torch.cuda.synchronize()
+  assert not np.isnan(d.qpos.cpu().numpy()).any()
