@@ -39,7 +39,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
   One object per translation unit, compiled in parallel and only when the source or a header changed, then linked."""
   if not (force or _stale()):
     return LIB_PATH
+  import fcntl
   from concurrent.futures import ThreadPoolExecutor
+
+  lock = open(os.path.join(_CSRC, ".build.lock"), "w")
+  fcntl.flock(lock, fcntl.LOCK_EX)  # concurrent builders (pytest-xdist workers) take turns; the later ones find a fresh library
+  if not (force or _stale()):
+    return LIB_PATH
 
   nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
   objdir = os.path.join(_CSRC, "_obj")

@@ -22,6 +22,8 @@ struct mjbData {
   cudaStream_t aux[8];
   cudaEvent_t ev_fork, ev_join[8];
   int nsplit;
+  cudaStream_t sol_aux[8];        // solver row-capacity classes: second class of each world range runs here
+  cudaEvent_t sol_fork[8], sol_join[8];
   float* rk;  // Runge-Kutta scratch, (nworld, nq + 3 nv); allocated by mjb_data_finalize for RK4 models only
 };
 
@@ -110,6 +112,11 @@ void mjb_data_destroy(mjbData* d) {
   if (!d) return;
   if (d->dev.world_conadr) cudaFree(d->dev.world_conadr);
   if (d->dev.world_ncon) cudaFree(d->dev.world_ncon);
+  if (d->dev.sol_list) cudaFree(d->dev.sol_list);
+  if (d->dev.sol_count) {
+    cudaFree(d->dev.sol_count);
+    for (int i = 0; i < 8; i++) { cudaStreamDestroy(d->sol_aux[i]); cudaEventDestroy(d->sol_fork[i]); cudaEventDestroy(d->sol_join[i]); }
+  }
   if (d->rk) cudaFree(d->rk);
   if (d->nsplit > 1) {
     for (int i = 0; i < d->nsplit; i++) { cudaStreamDestroy(d->aux[i]); cudaEventDestroy(d->ev_join[i]); }
@@ -144,6 +151,15 @@ int mjb_data_finalize(mjbData* d, const mjbModel* m) {
   if (check(cudaMalloc(&d->dev.world_ncon, sizeof(int) * (size_t)d->dev.nworld), "cudaMalloc(world_ncon)")) return -1;
   if (check(cudaMemset(d->dev.world_conadr, 0, sizeof(int) * (size_t)d->dev.nworld), "memset")) return -1;
   if (check(cudaMemset(d->dev.world_ncon, 0, sizeof(int) * (size_t)d->dev.nworld), "memset")) return -1;
+  if (check(cudaMalloc(&d->dev.sol_list, sizeof(int) * 2 * (size_t)d->dev.nworld), "cudaMalloc(sol_list)")) return -1;
+  if (check(cudaMalloc(&d->dev.sol_count, sizeof(int) * 16), "cudaMalloc(sol_count)")) return -1;
+  if (check(cudaMemset(d->dev.sol_count, 0, sizeof(int) * 16), "memset")) return -1;
+  for (int i = 0; i < 8; i++) {
+    if (check(cudaStreamCreateWithFlags(&d->sol_aux[i], cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
+    if (check(cudaEventCreateWithFlags(&d->sol_fork[i], cudaEventDisableTiming), "cudaEventCreate")) return -1;
+    if (check(cudaEventCreateWithFlags(&d->sol_join[i], cudaEventDisableTiming), "cudaEventCreate")) return -1;
+  }
+  d->dev.sol_stream = d->sol_aux[0]; d->dev.sol_fork = d->sol_fork[0]; d->dev.sol_join = d->sol_join[0];
   if (m->dev.integrator == INT_RK4 && !d->rk &&
       check(cudaMalloc(&d->rk, sizeof(float) * (size_t)d->dev.nworld * (size_t)(m->dev.nq + 3 * m->dev.nv + 1)), "cudaMalloc(rk)")) return -1;
   d->smem[0] = smem_position(m->dev); d->smem[1] = smem_collision(m->dev, d->dev); d->smem[2] = smem_constraint(m->dev, d->dev);
@@ -218,7 +234,7 @@ int mjb_contact_force(const mjbModel* m, mjbData* d, const int* contact_ids, int
 int mjb_sensor_pos(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_sensor(m->dev, d->dev, 1, s), 1); return 0; }
 int mjb_sensor_vel(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_sensor(m->dev, d->dev, 2, s), 1); return 0; }
 int mjb_sensor_acc(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_sensor(m->dev, d->dev, 4, s), 1); return 0; }
-int mjb_solve(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_solver(m->dev, d->dev, s), 1); return 0; }
+int mjb_solve(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_solver(m->dev, d->dev, s), solver_launch_count(m->dev, d->dev)); return 0; }
 int mjb_euler(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, INT_EULER, s), 1); return 0; }
 int mjb_implicit(const mjbModel* m, mjbData* d, void* stream) { MJB_ENTER(); MJB_LAUNCH(launch_integrate(m->dev, d->dev, INT_IMPLICITFAST, s), 1); return 0; }
 
@@ -234,7 +250,7 @@ static int chain(const mjbModel* m, const DataDev& dd, int what, cudaStream_t s)
     if (dd.njmax_nnz > 0) MJB_LAUNCH(launch_efc_csr(m->dev, dd, s), 1);  // sparse models: the reference's CSR arrays next to the dense rows
   }
   if (what & RUN_VELOCITY) MJB_LAUNCH(launch_velocity(m->dev, dd, STG_VELOCITY | STG_ACTUATION | STG_ACCELERATION, s), 1);
-  if (what & RUN_SOLVER) MJB_LAUNCH(launch_solver(m->dev, dd, s), 1);
+  if (what & RUN_SOLVER) MJB_LAUNCH(launch_solver(m->dev, dd, s), solver_launch_count(m->dev, dd));
   // sensors of all three stages in one launch after the solver (forward.py:1350-1365 interleaves them; their inputs are final by now)
   if ((what & RUN_SOLVER) && m->dev.nsensor > 0) MJB_LAUNCH(launch_sensor(m->dev, dd, 7, s), 1);
   if (what & RUN_EULER) MJB_LAUNCH(launch_integrate(m->dev, dd, -1, s), 1);
@@ -251,6 +267,8 @@ static int pipeline(const mjbModel* m, mjbData* d, int what, cudaStream_t s) {
     DataDev dd = d->dev;
     dd.w0 = h * part;
     dd.wn = min(part, d->dev.nworld - dd.w0);
+    dd.split_id = h;
+    dd.sol_stream = d->sol_aux[h]; dd.sol_fork = d->sol_fork[h]; dd.sol_join = d->sol_join[h];
     if (dd.wn <= 0) break;
     if (check(cudaStreamWaitEvent(d->aux[h], d->ev_fork, 0), "cudaStreamWaitEvent")) return -1;
     if (chain(m, dd, what, d->aux[h])) return -1;

@@ -27,14 +27,17 @@ namespace {
 // aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
 // rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
 struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, cgv, red, env, total; };
+// rows of shared memory a world gets: d.rowcap for a row-capacity class launch (see launch_solver), else njmax
+__host__ __device__ inline int sol_rowcap(const DataDev& d) { return d.rowcap > 0 ? d.rowcap : d.njmax; }
 __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d, bool big) {
   SolLayout L;
+  const int cap = sol_rowcap(d);
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   L.nvp = d.nv_pad; L.ldJ = d.nv_pad; L.ldH = m.nv | 1;
   // nv > 32 ("big" models, e.g. unitree G1, three_humanoids): only the first d.jcap Jacobian rows are staged in shared memory,
   // the rest is read from global memory (L2 hits).  d.jcap defaults to 0: occupancy beats the shorter access (see capi.cu).
-  L.jcap = big ? (d.njmax < d.jcap ? d.njmax : d.jcap) : d.njmax;
+  L.jcap = big ? (cap < d.jcap ? cap : d.jcap) : cap;
   L.J = take(L.jcap * L.ldJ);
   L.vec = take(7 * L.nvp);  // qacc, Ma, grad, search, mv (= x scratch of the nv > 32 path), qfs, qfc
   L.cgv = take(m.solver == SOL_CG ? 3 * L.nvp : 0);  // CG only: Mgrad, prev_grad, prev_Mgrad
@@ -50,11 +53,11 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   // elliptic cones add: per-row friction scale, 3 quad words per row (solver.py:1008-1015 layout), row->contact info
   const bool ell = m.cone == CONE_ELLIPTIC;
   L.nrowf = (m.nfricdof > 0 ? 5 : 4);
-  L.rowf = take((L.nrowf + (ell ? 4 : 0)) * d.njmax);
-  L.rowi = take((ell ? 3 : 2) * d.njmax);
+  L.rowf = take((L.nrowf + (ell ? 4 : 0)) * cap);
+  L.rowi = take((ell ? 3 : 2) * cap);
   L.red = take(big ? 9 * 8 : 0);  // cross-warp reduction scratch of the multi-warp (nv > 32) instantiations
   // nv > 32: nonzero column range of every Jacobian row (lo | hi << 16) and the Hessian's row envelope (first column per row)
-  L.env = take(big ? d.njmax + L.nvp : 0);
+  L.env = take(big ? cap + L.nvp : 0);
   L.total = o;
   return L;
 }
@@ -685,11 +688,16 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   extern __shared__ float smem[];
   constexpr int NT = 32 * NW;
   const int lane = threadIdx.x;  // index inside the team of NW warps (one block) that owns the world
-  const int w = blockIdx.x + d.w0;
+  int w = blockIdx.x + d.w0;
+  if (d.rowcap > 0) {  // row-capacity class launch: the block's world comes from the class list
+    if ((int)blockIdx.x >= d.sol_count[2 * d.split_id + d.sol_class]) return;
+    w = d.sol_list[(size_t)d.sol_class * d.nworld + d.w0 + blockIdx.x];
+  }
   if (w >= d.nworld) return;
   const SolLayout L = sol_layout(m, d, BIG);
   float* S = smem;
   const int nv = m.nv, njmax = d.njmax, nvp = d.nv_pad;
+  const int cap = sol_rowcap(d);  // rows of this world's shared-memory slice (njmax, or the row-capacity class of this launch)
   const size_t wb = (size_t)w;
   Ctx c;
   c.m = &m; c.lane = lane; c.nv = nv; c.nvp = L.nvp; c.ldJ = L.ldJ; c.ldH = L.ldH;
@@ -698,18 +706,18 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const int vp = L.nvp;
   c.qacc = v; c.Ma = v + vp; c.grad = v + 2 * vp; c.search = v + 3 * vp; c.mv = v + 4 * vp; c.x = c.mv; c.qfs = v + 5 * vp; c.qfc = v + 6 * vp;
   float* rf = S + L.rowf;
-  c.Jaref = rf; c.jv = rf + njmax; c.hw = c.jv; c.D = rf + 2 * njmax; c.force = rf + 3 * njmax;
-  c.floss = m.nfricdof > 0 ? rf + 4 * njmax : c.D;  // never interpreted when the world has no friction rows
+  c.Jaref = rf; c.jv = rf + cap; c.hw = c.jv; c.D = rf + 2 * cap; c.force = rf + 3 * cap;
+  c.floss = m.nfricdof > 0 ? rf + 4 * cap : c.D;  // never interpreted when the world has no friction rows
   int* ri = (int*)(S + L.rowi);
-  c.state = ri; c.hidx = ri + njmax;
-  c.njmax = njmax; c.ncone = 0;
+  c.state = ri; c.hidx = ri + cap;
+  c.njmax = cap; c.ncone = 0;
   c.jcap = L.jcap; c.Jg = d.efc_J + wb * (size_t)d.njmax_pad * nvp;
   c.cgv = S + L.cgv;
   c.red = S + L.red;
-  c.rng = (int*)(S + L.env); c.fz = c.rng + njmax;
+  c.rng = (int*)(S + L.env); c.fz = c.rng + cap;
   // a single tree with a floating base has a dense envelope (every row reaches the root dofs): bookkeeping would only cost
   c.env = BIG && m.ntree > 1;
-  c.rfri = rf + L.nrowf * njmax; c.quad = c.rfri + njmax; c.rinfo = ri + 2 * njmax;
+  c.rfri = rf + L.nrowf * cap; c.quad = c.rfri + cap; c.rinfo = ri + 2 * cap;
 
   if (njmax == 0 || nv == 0) {
 #pragma unroll 1
@@ -717,7 +725,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     if (lane == 0) d.solver_niter[w] = 0;
     return;
   }
-  const int nefc = min(d.nefc[w], njmax);
+  const int nefc = min(min(d.nefc[w], njmax), cap);
   c.nefc = nefc; c.ne = d.ne[w]; c.nf = d.nf[w];
 
   // ---- stage the world's problem in shared memory
@@ -847,6 +855,27 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   if (lane == 0) { d.solver_niter[w] = niter; if (ovf) d.overflow[w] |= ovf; }
 }
 
+// Row-capacity classes.  A world's shared-memory slice is dominated by its staged Jacobian, sized for njmax rows although most worlds
+// hold far fewer (benchmark humanoid: njmax 64, ~18 rows while it stands): worlds whose row count fits rowcap = njmax / 2 are listed
+// here and solved by a launch with the smaller slice -- more of them are resident per SM, which is what the latency-bound solver's
+// time hangs on -- the rest by a launch with the full slice.  Lists are filled with one warp-aggregated atomic per warp; the order
+// inside a list depends on scheduling, the per-world results do not.
+__global__ void __launch_bounds__(256)
+k_solver_classify(const __grid_constant__ DataDev d, int cap0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const bool in = i < d.wn && i + d.w0 < d.nworld;
+  const int w = i + d.w0;
+  const int cls = in ? (min(d.nefc[w], d.njmax) <= cap0 ? 0 : 1) : -1;
+  for (int c = 0; c < 2; c++) {
+    const unsigned bal = __ballot_sync(FULL_MASK, cls == c);
+    if (!bal) continue;
+    int base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(&d.sol_count[2 * d.split_id + c], __popc(bal));
+    base = __shfl_sync(FULL_MASK, base, __ffs(bal) - 1);
+    if (cls == c) d.sol_list[(size_t)c * d.nworld + d.w0 + base + __popc(bal & ((1u << lane) - 1u))] = w;
+  }
+}
+
 }  // namespace
 
 // The "big" instantiation (packed Hessian and factor worked on in shared memory, Jacobian rows read through L2, CSR inertia) is mandatory
@@ -869,6 +898,17 @@ static int solver_warps(const ModelDev& m) {
   return 1;  // measured on B200: teams of 2 / 4 warps are slower on unitree G1 (3.2 M vs 3.6 M steps/s) and three_humanoids
 }
 
+// row-capacity classes (see k_solver_classify): small-model path with a staged Jacobian, enough rows and worlds to matter
+static bool solver_uses_classes(const ModelDev& m, const DataDev& d) {
+  static int classes = -1;
+  // off by default: measured slower on B200 (humanoid 8192 worlds: solver 237 -> 247 us with every world in the small class, 217 -> 255 us
+  // with a mixed population) -- the extra resident worlds do not speed the solve up, so its time is not set by the number of worlds in
+  // flight the way the position / velocity kernels' is; kept as an experiment knob (MJB_SOLVER_CLASSES=1), parity-tested
+  if (classes < 0) { const char* e = getenv("MJB_SOLVER_CLASSES"); classes = e ? atoi(e) : 0; }
+  return classes && !solver_big(m) && d.rowcap == 0 && d.njmax >= 32 && d.wn >= 256 && d.sol_list;
+}
+int solver_launch_count(const ModelDev& m, const DataDev& d) { return solver_uses_classes(m, d) ? 3 : 1; }
+
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_solver(m, d);
   const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = solver_big(m) ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0;
@@ -885,6 +925,26 @@ cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[which] = smem;
+  }
+  const int cap0 = ((d.njmax / 2) + 3) & ~3;
+  if (solver_uses_classes(m, d)) {
+    cudaError_t e = cudaMemsetAsync(d.sol_count + 2 * d.split_id, 0, 2 * sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    k_solver_classify<<<(d.wn + 255) / 256, 256, 0, s>>>(d, cap0);
+    // the two classes run concurrently (fork / join on the range's auxiliary stream): with different slice sizes they cannot share a
+    // launch, and back to back each would pay its own last, partly empty round of resident blocks
+    cudaStream_t aux = (cudaStream_t)d.sol_stream;
+    cudaEvent_t fork = (cudaEvent_t)d.sol_fork, join = (cudaEvent_t)d.sol_join;
+    if ((e = cudaEventRecord(fork, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
+    DataDev dc = d;
+    dc.rowcap = d.njmax; dc.sol_class = 1;
+    kern<<<d.wn, nw * 32, smem, aux>>>(m, dc);  // blocks beyond the class count exit at once
+    if ((e = cudaEventRecord(join, aux)) != cudaSuccess) return e;
+    dc.rowcap = cap0; dc.sol_class = 0;
+    kern<<<d.wn, nw * 32, smem_solver(m, dc), s>>>(m, dc);
+    if ((e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) return e;
+    return cudaGetLastError();
   }
   const int grid = d.wn;
   kern<<<grid, nw * 32, smem, s>>>(m, d);

@@ -104,6 +104,15 @@ struct DataDev {
   // internal scratch (allocated by mjb_data_finalize; not part of the reference's Data)
   int* world_conadr;  // (nworld) first contact-pool slot of each world's contiguous block
   int* world_ncon;    // (nworld) number of contacts the world wrote this step
+  // solver row-capacity classes (k_solver.cu): worlds whose constraint count fits rowcap rows run with a smaller shared-memory slice
+  int* sol_list;      // (2, nworld) world ids per class, each launch range [w0, w0 + wn) owns that sub-range of both rows
+  int* sol_count;     // (8, 2) worlds per (split, class)
+  int split_id;       // which of the pipelined world ranges this launch covers
+  int rowcap;         // > 0: the solver launch stages at most this many rows per world and takes its worlds from sol_list[sol_class]
+  int sol_class;
+  // host-side handles of this launch range (opaque to kernels): auxiliary stream + fork / join events on which the second
+  // row-capacity class of the solver runs concurrently with the first
+  void *sol_stream, *sol_fork, *sol_join;
 };
 
 // ---------------------------------------------------------------- enums (MuJoCo values; see constants.py)
@@ -160,6 +169,7 @@ cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int stage_mask,
 cudaError_t launch_solve_m(const ModelDev& m, const DataDev& d, float* x, const float* y, cudaStream_t s);
 cudaError_t launch_mul_m(const ModelDev& m, const DataDev& d, float* res, const float* vec, cudaStream_t s);
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s);
+int solver_launch_count(const ModelDev& m, const DataDev& d);  // kernels launch_solver issues (row-capacity classes: classify + two solves)
 cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, int integrator, cudaStream_t s);
 cudaError_t launch_sensor(const ModelDev& m, const DataDev& d, int stages, cudaStream_t s);
 cudaError_t launch_contact_force(const ModelDev& m, const DataDev& d, const int* contact_ids, int n, int to_world, float* out, cudaStream_t s);
