@@ -47,7 +47,7 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   L.H = take(hsz);
   // nv <= 32: the factor lives in the padded column layout of chol_solve_rows_bcast, and M is kept as a dense packed lower
   // triangle (H starts as a copy of it, M * v needs no index tables); nv > 32: packed factor, CSR M with gather tables
-  L.Lf = take(big ? hsz : colsub_off(m.nv));
+  L.Lf = take(big ? hsz : colsub_off(m.nv <= 8 ? 8 : m.nv <= 16 ? 16 : m.nv <= 24 ? 24 : m.nv <= 28 ? 28 : 32));  // padded size of the register path
   L.M = take(big ? m.nC : hsz);
   // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
   // elliptic cones add: per-row friction scale, 3 quad words per row (solver.py:1008-1015 layout), row->contact info
@@ -409,7 +409,11 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
       }
     }
   }
+#ifdef MJB_CHOL_UNROLLED  // measured slower on B200 (humanoid solver 237 -> 290 us): the straight-line sweep misses the instruction cache
+  return chol_solve_rows_unrolled<N>(a, nv, g, c.Lf, lane);
+#else
   return chol_solve_rows_bcast<N>(a, nv, g, c.Lf, lane);
+#endif
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement

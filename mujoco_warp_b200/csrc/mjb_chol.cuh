@@ -296,17 +296,21 @@ __host__ __device__ __forceinline__ int colsub_off(int c) {
 template <int N>
 __device__ __forceinline__ float chol_solve_rows_bcast(float (&a)[N], int n, float b, float* Lc, int lane) {
   float myinv = 1.0f;
+  int coff = colsub_off(n - 1);      // slot offset of column j (rem = n - 1 - j entries), updated incrementally
+  float* lanecol = Lc + lane - 1;    // lane's slot in column j is lanecol[coff - j]
+  const bool row = lane < n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
     const float ajj = __shfl_sync(FULL_MASK, a[0], j);
     const float inv = rsqrtf(fmaxf(ajj, MJ_MINVAL));
     const float lij = a[0] * inv;  // column j of L (meaningful for lanes >= j)
     if (lane == j) myinv = inv;
+    // forward substitution folded in: lanes below the pivot subtract l_ij y_j; the pivot lane keeps its unscaled b (y_j = b * myinv)
     const float yj = __shfl_sync(FULL_MASK, b, j) * inv;
-    b = lane > j ? b - lij * yj : (lane == j ? yj : b);
+    b -= lane > j ? lij * yj : 0.f;
     const int rem = n - 1 - j;
-    float* col = Lc + colsub_off(rem);
-    if (lane > j && lane < n) col[lane - j - 1] = lij;
+    const float* col = Lc + coff;
+    if (lane > j && row) lanecol[coff - j] = lij;
     __syncwarp();
     // trailing update of the rem columns to the right; registers are rotated by one so the next pivot sits in a[0]
 #pragma unroll
@@ -318,14 +322,64 @@ __device__ __forceinline__ float chol_solve_rows_bcast(float (&a)[N], int n, flo
       if (k0 + 2 < N) a[k0 + 1] = a[k0 + 2] - lij * l.z;
       if (k0 + 3 < N) a[k0 + 2] = a[k0 + 3] - lij * l.w;
     }
+    coff -= (rem + 2) & ~3;  // colsub_off(rem) - colsub_off(rem - 1) = pad4(rem - 1)
   }
   // backward substitution: L[j][lane] for lane < j sits in column `lane`, slot j - lane - 1
   const float* mycol = Lc + colsub_off(n - 1 - lane) - lane - 1;
+  b *= myinv;  // y
 #pragma unroll 1
-  for (int j = n - 1; j >= 0; j--) {
+  for (int j = n - 1; j >= 0; j--) {  // x_j = (y_j - sum_{i > j} L_ij x_i) / L_jj; lane i < j accumulates -L_ji x_j, lanes >= j hold ltj = 0
     const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
     const float ltj = lane < j ? mycol[j] : 0.f;
-    b = lane < j ? b - ltj * xj : (lane == j ? xj : b);
+    b -= ltj * xj;
+  }
+  return b * myinv;
+}
+
+// The same factor + solve with the column loop fully unrolled: row registers are addressed statically (no rotation), column slots and
+// chunk counts are compile-time, the per-column bookkeeping of the rolled loop (offsets, trip counts, register moves: ~40 of its ~65
+// instructions per column) disappears.  ~1000 instructions for N = 28 instead of ~2300 -- and yet measured SLOWER on B200 (humanoid
+// solver 237 -> 290 us, 150 registers): every warp streams ~16 KB of straight-line code per factorisation through the instruction
+// cache.  Kept behind MJB_CHOL_UNROLLED for reference; the rolled loop above is what ships.  Lc holds colsub_off(N) floats,
+// laid out for the padded size N (rows >= n are identity padding and produce zero multipliers).
+template <int N>
+__device__ __forceinline__ float chol_solve_rows_unrolled(float (&a)[N], int n, float b, float* Lc, int lane) {
+  float myinv = 1.0f;
+  float* lanecol = Lc + lane - 1;  // lane's slot in column j is lanecol[colsub_off(N - 1 - j) - j]
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    if (j < n) {
+      const float ajj = __shfl_sync(FULL_MASK, a[j], j);
+      const float inv = rsqrtf(fmaxf(ajj, MJ_MINVAL));
+      const float lij = a[j] * inv;  // column j of L (meaningful for lanes >= j)
+      if (lane == j) myinv = inv;
+      const float yj = __shfl_sync(FULL_MASK, b, j) * inv;
+      b = lane > j ? b - lij * yj : (lane == j ? yj : b);
+      if (j + 1 < N) {
+        constexpr int dummy = 0; (void)dummy;
+        float* col = Lc + colsub_off(N - 1 - j);
+        if (lane > j && lane < N) lanecol[colsub_off(N - 1 - j) - j] = lij;
+        __syncwarp();
+#pragma unroll
+        for (int k0 = j + 1; k0 < N; k0 += 4) {
+          const float4 l = *reinterpret_cast<const float4*>(col + (k0 - j - 1));
+          a[k0] -= lij * l.x;
+          if (k0 + 1 < N) a[k0 + 1] -= lij * l.y;
+          if (k0 + 2 < N) a[k0 + 2] -= lij * l.z;
+          if (k0 + 3 < N) a[k0 + 3] -= lij * l.w;
+        }
+      }
+    }
+  }
+  // backward substitution: L[j][lane] for lane < j sits in column `lane`, slot j - lane - 1
+  const float* mycol = Lc + colsub_off(N - 1 - lane) - lane - 1;
+#pragma unroll
+  for (int j = N - 1; j >= 0; j--) {
+    if (j < n) {
+      const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
+      const float ltj = lane < j ? mycol[j] : 0.f;
+      b = lane < j ? b - ltj * xj : (lane == j ? xj : b);
+    }
   }
   return b;
 }
