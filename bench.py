@@ -380,9 +380,10 @@ def run_ours(args):
     bytes_launch = 4.0 * words[top] * nworld
     achieved = bytes_launch / (kms[top] * 1e-3) / 1e9
     traffic = None
-    try:  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/r01_final_kernels.md)
-      traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["traffic_bytes"].get("k_" + top)
-      traffic = traffic * nworld / 8192.0 if traffic is not None else None
+    try:  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/r02_kernels.md); humanoid only
+      if args.workload == "humanoid":
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["traffic_bytes"].get("k_" + top)
+        traffic = traffic * nworld / 8192.0 if traffic is not None else None
     except Exception:
       pass
     step_bytes = 4.0 * sum(words.values()) * nworld
