@@ -308,6 +308,7 @@ def run_ours(args):
     ncon_mean = float(d.nacon.cpu()[0]) / nworld
     nefc_mean = float(d.nefc.float().mean().cpu())
     niter_mean = float(d.solver_niter.float().mean().cpu())
+    niter_hist = torch.bincount(d.solver_niter.clamp(0, 4).long().cpu(), minlength=5).tolist()  # worlds with 0, 1, 2, 3, >= 4 Newton iterations
     ovf = int((d.overflow != 0).sum().cpu())
     ovf_bits = int(np.bitwise_or.reduce(d.overflow.cpu().numpy().astype(np.int64))) if nworld else 0
     nan_worlds = int(torch.isnan(d.qpos).any(dim=1).sum().cpu())
@@ -329,34 +330,71 @@ def run_ours(args):
       acc = r if acc is None else {k: acc[k] + r[k] for k in r}
     kms = {k: v / nprof for k, v in acc.items()}
 
-    # ---- e2e: same metric through the public API with HOST buffers: every step copies its controls from pinned host memory (H2D),
-    # runs the step and reads qpos + qvel back (D2H).  The loop is software-pipelined one step deep, as an asynchronous actor would
-    # run it: while the GPU works on step k the host consumes the read-back of step k - 1 (event wait, not a stream sync) and
-    # prepares the controls of step k + 1, from two alternating pinned buffer sets.  Every step's copies are inside the timed region.
-    nbuf = 2
+    # ---- e2e: same metric through the public API with HOST buffers: every step's controls come from pinned host memory (H2D) and
+    # every step's qpos + qvel go back to pinned host memory (D2H), all inside the timed region.  The loop is software-pipelined one
+    # step deep, as an asynchronous actor would run it: the two copy engines work on their own streams (upload of step k + 1's
+    # controls and download of step k - 1's state overlap the kernels of step k; small device-to-device copies decouple the buffers
+    # the step graph reads / writes from the ones in flight), and the host consumes the read-back of step k - 1 (event wait, not a
+    # stream sync) to produce the controls of step k + 1.
+    nbuf, nq_, nv_ = 2, mjm.nq, mjm.nv
     ctrl_host = [torch.empty((nworld, mjm.nu), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    qpos_host = [torch.empty((nworld, mjm.nq), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    qvel_host = [torch.empty((nworld, mjm.nv), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    done = [torch.cuda.Event() for _ in range(nbuf)]
+    state_host = [torch.empty((nworld, nq_ + nv_), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    ctrl_dev = [torch.empty_like(d.ctrl) for _ in range(nbuf)]
+    state_dev = [torch.empty((nworld, nq_ + nv_), dtype=torch.float32, device="cuda") for _ in range(nbuf)]
+    h2d_done, ctrl_used, snap_done, d2h_done = ([torch.cuda.Event() for _ in range(nbuf)] for _ in range(4))
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     for c in ctrl_host:
       c.copy_(d.ctrl.cpu())
     e2e_steps = max(10, args.steps // 2)
+
+    def upload(b):
+      with torch.cuda.stream(s_in):
+        s_in.wait_event(ctrl_used[b])
+        ctrl_dev[b].copy_(ctrl_host[b], non_blocking=True)
+        h2d_done[b].record(s_in)
+
+    stream.synchronize()
     barrier()
     t0 = time.perf_counter()
+    upload(0)
+    tr = [0.0] * 5 if os.environ.get('MJB_E2E_TRACE') else None
     for i in range(e2e_steps):
       b = i % nbuf
-      d.ctrl.copy_(ctrl_host[b], non_blocking=True)
+      ta = time.perf_counter()
+      stream.wait_event(h2d_done[b])
+      if mjm.nu:
+        d.ctrl.copy_(ctrl_dev[b], non_blocking=True)
+      ctrl_used[b].record(stream)
       if graph is not None:
         graph.replay()
       else:
         mjw.step(m, d)
-      qpos_host[b].copy_(d.qpos, non_blocking=True)
-      qvel_host[b].copy_(d.qvel, non_blocking=True)
-      done[b].record(stream)
+      stream.wait_event(d2h_done[b])  # the download that last read state_dev[b] (step i - 2)
+      state_dev[b][:, :nq_].copy_(d.qpos, non_blocking=True)
+      state_dev[b][:, nq_:].copy_(d.qvel, non_blocking=True)
+      snap_done[b].record(stream)
+      with torch.cuda.stream(s_out):
+        s_out.wait_event(snap_done[b])
+        state_host[b].copy_(state_dev[b], non_blocking=True)
+        d2h_done[b].record(s_out)
+      tb = time.perf_counter()
+      p = (i + 1) % nbuf
       if i > 0:  # host-side policy stand-in on the PREVIOUS step's read-back, while this step runs on the GPU
-        p = (i - 1) % nbuf
-        done[p].synchronize()
-        ctrl_host[p].add_(0.001 * float(qpos_host[p][0, 2])).clamp_(-1, 1)
+        d2h_done[p].synchronize()
+        tc = time.perf_counter()
+        ctrl_host[p].add_(0.001 * float(state_host[p][0, 2])).clamp_(-1, 1)
+      else:
+        tc = tb
+      td = time.perf_counter()
+      upload(p)  # controls of step i + 1
+      if tr is not None:
+        te = time.perf_counter()
+        for k, v in enumerate((tb - ta, tc - tb, td - tc, te - td)):
+          tr[k] += v
+    for e in d2h_done:
+      e.synchronize()
+    if tr is not None:
+      print('e2e host us/step: launch %.1f wait %.1f policy %.1f upload %.1f' % tuple(1e6 * v / e2e_steps for v in tr[:4]), file=sys.stderr)
     stream.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -403,10 +441,10 @@ def run_ours(args):
         "workload": wl["label"] if nworld == wl["nworld"] else wl["label"].replace(f"nworld={wl['nworld']}", f"nworld={nworld}"),
         "cuda_graph": graph is not None, "l2": f"per-step Data working set ({data_mb:.0f} MB of Data tensors at {nworld} worlds) exceeds the 126 MB L2; no explicit flush" if data_mb > 126 else f"Data tensors are {data_mb:.0f} MB (< 126 MB L2): 256 MB scratch buffer written between timed steps",
         "vs_baseline_note": "2,729,192 steps/s is the reference's only published number (benchmarks/README.md:48), hardware unstated",
-        "sim_steps_before_timed": sim_steps_before_timed, "ncon_mean": ncon_mean, "nefc_mean": nefc_mean, "solver_niter_mean": niter_mean, "overflow_worlds": ovf, "overflow_bits_or": hex(ovf_bits), "nan_worlds": nan_worlds,
+        "sim_steps_before_timed": sim_steps_before_timed, "ncon_mean": ncon_mean, "nefc_mean": nefc_mean, "solver_niter_mean": niter_mean, "solver_niter_hist_0_1_2_3_4plus": niter_hist, "overflow_worlds": ovf, "overflow_bits_or": hex(ovf_bits), "nan_worlds": nan_worlds,
       },
       "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(nworld * mjm.nu * 4), "d2h_bytes_per_step": int(nworld * (mjm.nq + mjm.nv) * 4), "steps": e2e_steps,
-              "pipeline": "one step deep: host consumes step k-1 while the GPU runs step k (two pinned buffer sets, event waits)"},
+              "pipeline": "one step deep: host consumes step k-1 while the GPU runs step k; H2D / D2H on their own streams (two pinned buffer sets, event waits)"},
       "gpu_launches": launches_per_step * args.steps,
       "kernel_ms": kms,
       "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "mjb_chol.cuh"
+#include "mjb_team.cuh"
 #include "mjb_math.cuh"
 #include "mjb_types.cuh"
 
@@ -26,7 +27,7 @@ namespace {
 // Shared-memory slice of one world.  J rows keep the global stride nv_pad (a multiple of 4 floats), so a row is 16-byte
 // aligned: staging is a straight float4 copy and row-times-vector products use LDS.128 (a quarter-warp of 112-byte-strided
 // rows is bank-conflict free).  Per-dof vectors are padded to nv_pad with zeros so the float4 loops need no tail handling.
-struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, cgv, red, env, total; };
+struct SolLayout { int J, vec, H, Lf, M, rowf, rowi, ldJ, ldH, nvp, nrowf, jcap, cgv, red, env, bar, total; };
 // rows of shared memory a world gets: d.rowcap for a row-capacity class launch (see launch_solver), else njmax
 __host__ __device__ inline int sol_rowcap(const DataDev& d) { return d.rowcap > 0 ? d.rowcap : d.njmax; }
 __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev& d, bool big) {
@@ -58,6 +59,7 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   L.red = take(big ? 9 * 8 : 0);  // cross-warp reduction scratch of the multi-warp (nv > 32) instantiations
   // nv > 32: nonzero column range of every Jacobian row (lo | hi << 16) and the Hessian's row envelope (first column per row)
   L.env = take(big ? cap + L.nvp : 0);
+  L.bar = take(4);  // mbarrier of the bulk-async staging (8 bytes, 16-byte slot)
   L.total = o;
   return L;
 }
@@ -212,6 +214,8 @@ struct Ctx {
   float* red;                 // NW > 1: cross-warp reduction scratch (9 floats per warp)
   int *rng, *fz;              // nv > 32: Jacobian row ranges, Hessian row envelope
   bool env;                   // ranges / envelope in use (several kinematic trees: the Hessian is close to block diagonal)
+  float chol_inv;             // nv <= 32: lane j keeps 1 / L_jj of the factor in Lf
+  bool factored;              // Lf holds the factor of the current H
 };
 template <bool BIG>
 __device__ __forceinline__ const float* jrow(const Ctx& c, int r) {
@@ -412,7 +416,8 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
 #ifdef MJB_CHOL_UNROLLED  // measured slower on B200 (humanoid solver 237 -> 290 us): the straight-line sweep misses the instruction cache
   return chol_solve_rows_unrolled<N>(a, nv, g, c.Lf, lane);
 #else
-  return chol_solve_rows_bcast<N>(a, nv, g, c.Lf, lane);
+  c.factored = true;
+  return chol_solve_rows_bcast<N>(a, nv, g, c.Lf, lane, c.chol_inv);
 #endif
 }
 
@@ -424,7 +429,10 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   if (!BIG) {  // nv <= 32 (launch_solver picks the instantiation)
     const float g = c.lane < nv ? c.grad[c.lane] : 0.f;
     float xx;
-    if (nv <= 8) xx = newton_direction_reg<8, ELL>(c, nlist, g);
+    // no row changed state since the last factorisation: H is what was factored, only the right-hand side is new (the reference's
+    // stable-state shortcut, solver.py:2145-2159, which reuses the whole direction instead)
+    if (!ELL && nlist == 0 && c.factored) xx = chol_subst_bcast(nv, g, c.Lf, c.lane, c.chol_inv);
+    else if (nv <= 8) xx = newton_direction_reg<8, ELL>(c, nlist, g);
     else if (nv <= 16) xx = newton_direction_reg<16, ELL>(c, nlist, g);
     else if (nv <= 24) xx = newton_direction_reg<24, ELL>(c, nlist, g);
     else if (nv <= 28) xx = newton_direction_reg<28, ELL>(c, nlist, g);
@@ -704,6 +712,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const int cap = sol_rowcap(d);  // rows of this world's shared-memory slice (njmax, or the row-capacity class of this launch)
   const size_t wb = (size_t)w;
   Ctx c;
+  c.factored = false; c.chol_inv = 1.0f;
   c.m = &m; c.lane = lane; c.nv = nv; c.nvp = L.nvp; c.ldJ = L.ldJ; c.ldH = L.ldH;
   c.J = S + L.J; c.H = S + L.H; c.Lf = S + L.Lf; c.M = S + L.M;
   float* v = S + L.vec;
@@ -732,18 +741,34 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const int nefc = min(min(d.nefc[w], njmax), cap);
   c.nefc = nefc; c.ne = d.ne[w]; c.nf = d.nf[w];
 
-  // ---- stage the world's problem in shared memory
+  // ---- stage the world's problem in shared memory.  One warp per world (NW = 1): the Jacobian rows and the per-row vectors are
+  // contiguous, 16-byte aligned blocks of the world-major arrays, so one lane issues a bulk-async copy (cp.async.bulk, SASS UBLKCP)
+  // for each and the warp waits once on the mbarrier, after it has issued its own small loads -- instead of four dependent
+  // load -> store loops in a row.  aref lands in the Jaref slot and is folded in below.
+  Stager st;
+  const int n4 = (nefc + 3) & ~3, nrow = n4 <= cap ? n4 : nefc;  // whole float4s when the slice has room (the pad is never read)
+  if (NW == 1) {
+    st.init(reinterpret_cast<uint64_t*>(S + L.bar), lane);
+    st.load(c.J, d.efc_J + wb * (size_t)d.njmax_pad * nvp, min(nefc, L.jcap) * nvp);
+    st.load(c.D, d.efc_D + wb * d.njmax_pad, nrow);
+    st.load(c.Jaref, d.efc_aref + wb * njmax, nrow);
+    if (m.nfricdof > 0) st.load(c.floss, d.efc_frictionloss + wb * njmax, nrow);
+  }
   {
-    const float4* Jg = reinterpret_cast<const float4*>(d.efc_J + wb * (size_t)d.njmax_pad * nvp);
-    float4* Js = reinterpret_cast<float4*>(c.J);
+    if (NW != 1) {
+      const float4* Jg = reinterpret_cast<const float4*>(d.efc_J + wb * (size_t)d.njmax_pad * nvp);
+      float4* Js = reinterpret_cast<float4*>(c.J);
 #pragma unroll 1
-    for (int i = lane; i < min(nefc, L.jcap) * nvp / 4; i += NT) Js[i] = Jg[i];
+      for (int i = lane; i < min(nefc, L.jcap) * nvp / 4; i += NT) Js[i] = Jg[i];
+    }
     for (int i = lane; i < 7 * vp; i += NT) v[i] = 0.f;  // zero padding of every per-dof vector
     tsync<NW>();
 #pragma unroll 1
     for (int r = lane; r < nefc; r += NT) {
-      c.D[r] = d.efc_D[wb * d.njmax_pad + r];
-      if (m.nfricdof > 0) c.floss[r] = d.efc_frictionloss[wb * njmax + r];
+      if (NW != 1) {
+        c.D[r] = d.efc_D[wb * d.njmax_pad + r];
+        if (m.nfricdof > 0) c.floss[r] = d.efc_frictionloss[wb * njmax + r];
+      }
       c.state[r] = ST_SATISFIED;
       if (ELL) {  // row -> (contact, component) map; a contact's rows are consecutive (k_constraint.cu)
         int info = -1; float fr = 0.f;
@@ -786,6 +811,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
       if (c.env) atomicMin(&c.fz[r], col);
     }
   }
+  if (NW == 1) st.load_wait();  // staged rows and per-row vectors have landed
   if (c.env) {
     // nonzero column range [lo, hi) of every Jacobian row; rows of one elliptic contact share the union of their ranges (the cone
     // Hessian mixes them); every dof inside a row's range gets that row's lo into its envelope (H = M + sum of w J_r J_r^T terms)
@@ -819,7 +845,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   }
 #pragma unroll 1
   for (int r = lane; r < nefc; r += NT) {  // Jaref = J qacc - aref
-    c.Jaref[r] = row_dot(jrow<BIG>(c, r), c.qacc, c.nvp) - d.efc_aref[wb * njmax + r];
+    c.Jaref[r] = row_dot(jrow<BIG>(c, r), c.qacc, c.nvp) - (NW == 1 ? c.Jaref[r] : d.efc_aref[wb * njmax + r]);
   }
   mul_m<NW, BIG>(c, c.qacc, c.Ma);
   tsync<NW>();

@@ -281,6 +281,14 @@ __device__ __forceinline__ float chol_solve_rows_rolled(float (&a)[N], int n, fl
 // Column-major storage of the factor's sub-diagonal part for the broadcast variant below: column j keeps its c = n - 1 - j
 // entries L[j+1 .. n-1][j] contiguously, padded to a multiple of 4 floats, columns ordered by increasing c, so that every
 // column starts 16-byte aligned.  colsub_off(c) = sum_{t < c} pad4(t); the whole factor takes colsub_off(n) floats (420 for n = 28).
+// 1 / sqrt(x) for x known to be a normal number (callers clamp at MJ_MINVAL): the bare MUFU.RSQ, without the denormal rescaling
+// rsqrtf() wraps around it -- same bits for normal inputs.
+__device__ __forceinline__ float rsqrt_normal(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __host__ __device__ __forceinline__ int colsub_off(int c) {
   if (c <= 0) return 0;
   const int U = (c - 1) >> 2;
@@ -294,15 +302,15 @@ __host__ __device__ __forceinline__ int colsub_off(int c) {
 // a quarter of the data-movement instructions and leaves the SHFL pipe to the two per-column broadcasts.
 //   a[]  : row `lane` of the matrix (consumed);  Lc : colsub_off(n) floats of scratch, receives the factor (layout above)
 template <int N>
-__device__ __forceinline__ float chol_solve_rows_bcast(float (&a)[N], int n, float b, float* Lc, int lane) {
-  float myinv = 1.0f;
+__device__ __forceinline__ float chol_solve_rows_bcast(float (&a)[N], int n, float b, float* Lc, int lane, float& myinv) {
+  myinv = 1.0f;
   int coff = colsub_off(n - 1);      // slot offset of column j (rem = n - 1 - j entries), updated incrementally
   float* lanecol = Lc + lane - 1;    // lane's slot in column j is lanecol[coff - j]
   const bool row = lane < n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
     const float ajj = __shfl_sync(FULL_MASK, a[0], j);
-    const float inv = rsqrtf(fmaxf(ajj, MJ_MINVAL));
+    const float inv = rsqrt_normal(fmaxf(ajj, MJ_MINVAL));
     const float lij = a[0] * inv;  // column j of L (meaningful for lanes >= j)
     if (lane == j) myinv = inv;
     // forward substitution folded in: lanes below the pivot subtract l_ij y_j; the pivot lane keeps its unscaled b (y_j = b * myinv)
@@ -329,6 +337,31 @@ __device__ __forceinline__ float chol_solve_rows_bcast(float (&a)[N], int n, flo
   b *= myinv;  // y
 #pragma unroll 1
   for (int j = n - 1; j >= 0; j--) {  // x_j = (y_j - sum_{i > j} L_ij x_i) / L_jj; lane i < j accumulates -L_ji x_j, lanes >= j hold ltj = 0
+    const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
+    const float ltj = lane < j ? mycol[j] : 0.f;
+    b -= ltj * xj;
+  }
+  return b * myinv;
+}
+
+// Solve only, with the factor chol_solve_rows_bcast left in Lc and the reciprocal diagonal it returned in myinv (lane j holds
+// 1 / L_jj): the same operations in the same order as the substitutions folded into the factorisation, so the result is
+// bit-identical to factoring the same matrix again.
+__device__ __forceinline__ float chol_subst_bcast(int n, float b, const float* Lc, int lane, float myinv) {
+  int coff = colsub_off(n - 1);
+  const float* lanecol = Lc + lane - 1;
+  const bool row = lane < n;
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    const float yj = __shfl_sync(FULL_MASK, b * myinv, j);
+    const float lij = (lane > j && row) ? lanecol[coff - j] : 0.f;
+    b -= lane > j ? lij * yj : 0.f;
+    coff -= (n - j + 1) & ~3;  // (rem + 2) & ~3 with rem = n - 1 - j
+  }
+  const float* mycol = Lc + colsub_off(n - 1 - lane) - lane - 1;
+  b *= myinv;
+#pragma unroll 1
+  for (int j = n - 1; j >= 0; j--) {
     const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
     const float ltj = lane < j ? mycol[j] : 0.f;
     b -= ltj * xj;

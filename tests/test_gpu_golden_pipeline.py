@@ -123,9 +123,13 @@ def test_gpu_matches_reference_pipeline(built, name):
       close("cfrc_ext", d.cfrc_ext.cpu().numpy().reshape(nworld, -1), g[f"{tag}/cfrc_ext"].reshape(nworld, -1), atol=5e-3 * fs, rtol=5e-3)
   # Stepped states, teacher-forced: step s starts from the REFERENCE's state after step s-1 (qpos, qvel, warm start, time), so a
   # rounding-level difference cannot grow chaotically over the steps and the band is one step's worth of the qacc band above:
-  # |dqvel| <= dt * |dqacc|, |dqpos| <= dt * |dqvel|.
+  # |dqvel| <= dt * |dqacc|, |dqpos| <= dt * |dqvel|.  A world is compared when its row count equals the reference's for that step:
+  # the box scenes sit on multi-contact decisions (a face patch of 4 contacts vs an edge of 2) that fp32 with fused multiply-add
+  # takes one step earlier than double does (boxccd world 0: 104 rows at step 1, the reference reaches 104 at step 2; the device
+  # routine built for the host without FMA contraction agrees with the reference there) -- at most one world-step per scene may
+  # differ that way, and only in the flat-contact scenes.
   dt = float(np.asarray(mjm.opt.timestep))
-  s = 0
+  s, skipped = 0, 0
   while f"step{s}/qpos" in g:
     if s > 0 and f"step{s - 1}/qacc_warmstart" in g:
       d.qpos.copy_(f32(g[f"step{s - 1}/qpos"])); d.qvel.copy_(f32(g[f"step{s - 1}/qvel"]))
@@ -133,11 +137,16 @@ def test_gpu_matches_reference_pipeline(built, name):
       d.time.copy_(f32(np.asarray(g[f"step{s - 1}/time"]).reshape(-1)))
     mjw.step(m, d)
     torch.cuda.synchronize()
+    same = np.ones(nworld, dtype=bool)
+    if f"step{s}/nefc" in g and not trunc:
+      same = d.nefc.cpu().numpy().reshape(-1) == g[f"step{s}/nefc"].reshape(-1)
+      skipped += int((~same).sum())
     ascale = max(1.0, float(np.abs(g[f"step{s}/qacc"]).max())) if f"step{s}/qacc" in g else scale
-    vtol = dt * (5e-2 if flat else 5e-3) * ascale + 1e-4
-    close(f"step{s}/qvel", d.qvel.cpu().numpy(), g[f"step{s}/qvel"], atol=vtol, rtol=1e-3)
-    close(f"step{s}/qpos", d.qpos.cpu().numpy(), g[f"step{s}/qpos"], atol=dt * vtol + 2e-5, rtol=1e-5)
+    vtol = dt * (1e-2 if flat else 5e-3) * ascale + 1e-4
+    close(f"step{s}/qvel", d.qvel.cpu().numpy()[same], g[f"step{s}/qvel"][same], atol=vtol, rtol=1e-3)
+    close(f"step{s}/qpos", d.qpos.cpu().numpy()[same], g[f"step{s}/qpos"][same], atol=dt * vtol + 2e-5, rtol=1e-5)
     s += 1
+  assert skipped <= (1 if flat else 0), f"{skipped} world-steps with a row count different from the reference's"
   # the line-search budget flag (1 << 10) may be raised in fp32 when the bracketing stalls at rounding level; nothing else may
   # (CG scenes run close to their iteration cap -- 41..48 of 50 in double -- so fp32 may also raise the iteration flag, 1 << 9)
   allowed = (1 << 10) | ((1 << 9) if name.endswith("cg") else 0)
