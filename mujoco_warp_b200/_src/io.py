@@ -39,7 +39,8 @@ _INT_FIELDS = [
   "cam_mode", "cam_bodyid", "cam_targetbodyid", "light_mode", "light_bodyid", "light_targetbodyid", "site_bodyid",
 ]
 # float fields outside _FLOAT_FIELDS that carry the reference's `*` leading dimension as well
-_BATCHABLE_EXTRA = ("eq_solref", "eq_solimp", "eq_data", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp", "pair_margin", "pair_gap")
+_BATCHABLE_EXTRA = ("eq_solref", "eq_solimp", "eq_data", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp", "pair_margin", "pair_gap",
+                    "actuator_dynprm", "actuator_actrange")
 _SIZES = ["nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "nsite", "ncam", "nlight", "ntree", "nkey", "nmocap", "neq", "ntendon", "nflex"]
 
 _SUPPORTED_PAIRS = {
@@ -295,15 +296,16 @@ def _validate(mjm):
       raise NotImplementedError(f"actuator gain type(s) {sorted(set(gt[~np.isin(gt, (C.GAIN_FIXED, C.GAIN_AFFINE))].tolist()))} are not implemented (fixed and affine are)")
     if not np.isin(bt, (C.BIAS_NONE, C.BIAS_AFFINE)).all():
       raise NotImplementedError(f"actuator bias type(s) {sorted(set(bt[~np.isin(bt, (C.BIAS_NONE, C.BIAS_AFFINE))].tolist()))} are not implemented (none and affine are)")
-    if hasattr(mjm, "actuator_dyntype") and np.any(np.asarray(mjm.actuator_dyntype) != 0):
-      raise NotImplementedError("stateful actuators (dyntype != none) are not implemented")
+    dyn = np.asarray(getattr(mjm, "actuator_dyntype", np.zeros(mjm.nu)))
+    if not np.isin(dyn, (C.DYN_NONE, C.DYN_INTEGRATOR, C.DYN_FILTER, C.DYN_FILTEREXACT)).all():
+      raise NotImplementedError(f"actuator dynamics type(s) {sorted(set(dyn[~np.isin(dyn, (0, 1, 2, 3))].tolist()))} are not implemented (none, integrator, filter, filterexact are)")
   for n in ("dof_dampingpoly", "jnt_stiffnesspoly"):
     if hasattr(mjm, n) and np.any(np.asarray(getattr(mjm, n)) != 0):
       raise NotImplementedError(f"{n}: polynomial stiffness / damping is not implemented")
   if mjm.nv > 128:
     # the dense per-world Hessian and its factor live in one warp's shared memory; make_data reports the exact per-kernel need
     raise NotImplementedError("nv > 128 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
-  for n in ("na", "ntendon", "nflex"):
+  for n in ("ntendon", "nflex"):
     if getattr(mjm, n, 0):
       raise NotImplementedError(f"{n} > 0 is not supported in this version")
   if getattr(mjm, "neq", 0):
@@ -390,6 +392,15 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     setattr(m, n, dev_f(getattr(mjm, n), name=n))
   for n in _INT_FIELDS:
     setattr(m, n, dev_i(getattr(mjm, n)))
+  # stateful actuators (forward.py:135-218, 800-963): activation layout and dynamics parameters
+  nu_ = int(mjm.nu)
+  m.actuator_dyntype = dev_i(getattr(mjm, "actuator_dyntype", np.zeros(nu_)))
+  m.actuator_actadr = dev_i(getattr(mjm, "actuator_actadr", -np.ones(nu_)))
+  m.actuator_actnum = dev_i(getattr(mjm, "actuator_actnum", np.zeros(nu_)))
+  m.actuator_actlimited = dev_i(np.asarray(getattr(mjm, "actuator_actlimited", np.zeros(nu_))).astype(np.int32))
+  m.actuator_actearly = dev_i(np.asarray(getattr(mjm, "actuator_actearly", np.zeros(nu_))).astype(np.int32))
+  m.actuator_dynprm = dev_f(np.asarray(getattr(mjm, "actuator_dynprm", np.zeros((nu_, 10)))).reshape(nu_, 10), name="actuator_dynprm")
+  m.actuator_actrange = dev_f(np.asarray(getattr(mjm, "actuator_actrange", np.zeros((nu_, 2)))).reshape(nu_, 2), name="actuator_actrange")
   m.jnt_limited = dev_i(np.asarray(mjm.jnt_limited).astype(np.int32))
   m.body_tree = tuple(dev_i(x) for x in t["body_tree"])
   for n in ("body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col", "mulm_madr", "tree_qLDadr",
@@ -463,7 +474,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     nfricdof=len(t["dof_fricloss_adr"]), nmaxpyramid=m.nmaxpyramid, integrator=m.opt.integrator, cone=m.opt.cone, solver=m.opt.solver,
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase=int(m.opt.broadphase), broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
-    has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX, C.GEOM_MESH)).any()), nmesh=nmesh,
+    has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX, C.GEOM_MESH)).any()), nmesh=nmesh, na=m.na,
     nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), epa_iterations=t["epa_iterations"], nsensor=m.nsensor, nsensordata=m.nsensordata, sensor_subtree_vel=int(m.sensor_subtree_vel), sensor_rne_postconstraint=int(m.sensor_rne_postconstraint), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
@@ -484,7 +495,8 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                                          "pair_margin", "pair_gap", "sensor_type", "sensor_datatype", "sensor_needstage", "sensor_objtype", "sensor_objid", "sensor_reftype", "sensor_refid",
                                          "sensor_dim", "sensor_adr", "sensor_cutoff", "site_type", "site_size", "geom_dataid", "mesh_vertadr", "mesh_vertnum", "mesh_graphadr", "mesh_graph",
                                          "mesh_polynum", "mesh_polyadr", "mesh_polyvertadr", "mesh_polyvertnum", "mesh_polyvert", "mesh_polymapadr", "mesh_polymapnum",
-                                         "mesh_polymap", "mesh_vert", "mesh_polynormal"]:
+                                         "mesh_polymap", "mesh_vert", "mesh_polynormal", "actuator_dyntype", "actuator_actadr", "actuator_actnum",
+                                         "actuator_actlimited", "actuator_actearly", "actuator_dynprm", "actuator_actrange"]:
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)
@@ -626,6 +638,7 @@ _BOUND_TOP = [
   "crb", "M", "qLD", "actuator_length", "actuator_moment", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
   "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int",
   "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active", "mocap_pos", "mocap_quat", "sensordata", "subtree_linvel", "subtree_angmom", "cfrc_ext",
+  "act", "act_dot",
 ]
 _BOUND_EFC = ["J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "Ma", "type", "id", "state"]
 _BOUND_CONTACT = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "type", "geomcollisionid"]
@@ -756,8 +769,8 @@ def _bind(m: types.Model, d: types.Data, L):
 def put_data(mjm, mjd, nworld: int = 1, nconmax=None, nccdmax=None, njmax=None, njmax_nnz=None, naconmax=None, naccdmax=None, nvmax=None, m: types.Model = None) -> types.Data:
   """Moves host state (MjData-like: qpos, qvel, ctrl, qacc_warmstart, time, ...) to a device Data tiled over nworld (io.py:1890)."""
   d = make_data(mjm, nworld, nconmax, nccdmax, njmax, njmax_nnz, naconmax, naccdmax, nvmax, m=m)
-  for name in ("qpos", "qvel", "ctrl", "qacc_warmstart", "qfrc_applied", "xfrc_applied"):
-    if hasattr(mjd, name):
+  for name in ("qpos", "qvel", "ctrl", "qacc_warmstart", "qfrc_applied", "xfrc_applied", "act"):
+    if hasattr(mjd, name) and getattr(d, name).numel():
       src = np.asarray(getattr(mjd, name), dtype=np.float32)
       dst = getattr(d, name)
       dst.copy_(torch.from_numpy(np.broadcast_to(src, (nworld,) + src.shape).copy()).reshape(dst.shape))
@@ -769,7 +782,7 @@ def reset_data(m: types.Model, d: types.Data):
   """Resets every world to qpos0 with zero velocity/ctrl/time (reference io.py:2435, all worlds)."""
   mjm = m._mjm
   d.qpos.copy_(torch.from_numpy(np.tile(np.asarray(mjm.qpos0, dtype=np.float32), (d.nworld, 1))))
-  for n in ("qvel", "ctrl", "qacc_warmstart", "qacc", "qfrc_applied", "xfrc_applied", "time"):
+  for n in ("qvel", "ctrl", "qacc_warmstart", "qacc", "qfrc_applied", "xfrc_applied", "time", "act", "act_dot"):
     getattr(d, n).zero_()
   for n in ("overflow", "solver_niter", "nefc", "ne", "nf", "nl", "nacon", "ncollision"):
     getattr(d, n).zero_()
@@ -807,7 +820,9 @@ def reset_data_keyframe(m: types.Model, d: types.Data, key):
   if m.nu:
     d.ctrl.copy_(sel(f32(mjm.key_ctrl)[idx], d.ctrl))
   d.time.copy_(sel(f32(mjm.key_time)[idx], d.time))
-  for n in ("qacc_warmstart", "qacc", "qfrc_applied", "xfrc_applied"):
+  if m.na:
+    d.act.copy_(sel(f32(np.asarray(mjm.key_act).reshape(nkey, m.na))[idx], d.act))
+  for n in ("qacc_warmstart", "qacc", "qfrc_applied", "xfrc_applied", "act_dot"):
     t = getattr(d, n)
     t.copy_(sel(torch.zeros_like(t), t))
   for n in ("overflow", "solver_niter", "nefc", "ne", "nf", "nl"):

@@ -1041,7 +1041,9 @@ def compile_xml(root):
   m.actuator_actrange = np.zeros((nu, 2))
   m.actuator_actadr = -np.ones(nu, dtype=np.int32)
   m.actuator_actnum = np.zeros(nu, dtype=np.int32)
+  m.actuator_actearly = np.zeros(nu, dtype=bool)
   m.names.actuator = []
+  dyn_names = {"none": C.DYN_NONE, "integrator": C.DYN_INTEGRATOR, "filter": C.DYN_FILTER, "filterexact": C.DYN_FILTEREXACT}
   for i, (tag, a) in enumerate(acts):
     m.names.actuator.append(a.get("name", f"actuator{i}"))
     if "joint" not in a:
@@ -1051,9 +1053,16 @@ def compile_xml(root):
     gear = _vec(a.get("gear"), 6, default=[1, 0, 0, 0, 0, 0])
     m.actuator_gear[i] = gear
     m.actuator_gainprm[i, 0] = 1.0
+    m.actuator_dynprm[i, 0] = 1.0
     if tag == "general":
-      if a.get("dyntype", "none") != "none":
-        raise NotImplementedError("stateful actuators (na>0) are not supported")
+      dyn = a.get("dyntype", "none")
+      if dyn not in dyn_names:
+        raise NotImplementedError(f"actuator dyntype '{dyn}' is not supported (none, integrator, filter, filterexact are)")
+      m.actuator_dyntype[i] = dyn_names[dyn]
+      if "dynprm" in a:
+        dp = _vec(a["dynprm"])
+        m.actuator_dynprm[i, :] = 0
+        m.actuator_dynprm[i, : dp.size] = dp
       m.actuator_gaintype[i] = {"fixed": C.GAIN_FIXED, "affine": C.GAIN_AFFINE}[a.get("gaintype", "fixed")]
       m.actuator_biastype[i] = {"none": C.BIAS_NONE, "affine": C.BIAS_AFFINE}[a.get("biastype", "none")]
       if "gainprm" in a:
@@ -1072,6 +1081,31 @@ def compile_xml(root):
       m.actuator_biastype[i] = C.BIAS_AFFINE
       m.actuator_biasprm[i, 1] = -kp
       m.actuator_biasprm[i, 2] = -kv
+      if "dampratio" in a:
+        raise NotImplementedError("<position dampratio> is not supported")
+      tc = float(a.get("timeconst", 0.0))
+      if tc > 0:  # first-order filter on the target, integrated exactly
+        m.actuator_dyntype[i] = C.DYN_FILTEREXACT
+        m.actuator_dynprm[i, 0] = tc
+    elif tag == "intvelocity":  # integrated-velocity servo: the activation is the position target
+      kp = float(a.get("kp", 1.0))
+      kv = float(a.get("kv", 0.0))
+      m.actuator_dyntype[i] = C.DYN_INTEGRATOR
+      m.actuator_gainprm[i, 0] = kp
+      m.actuator_biastype[i] = C.BIAS_AFFINE
+      m.actuator_biasprm[i, 1] = -kp
+      m.actuator_biasprm[i, 2] = -kv
+      if "actrange" not in a:
+        raise ValueError("<intvelocity> requires actrange")
+      a.setdefault("actlimited", "true")
+    elif tag == "damper":  # force = -kv * velocity * ctrl
+      kv = float(a.get("kv", 1.0))
+      m.actuator_gaintype[i] = C.GAIN_AFFINE
+      m.actuator_gainprm[i, :] = 0
+      m.actuator_gainprm[i, 2] = -kv
+      if "ctrlrange" not in a:
+        raise ValueError("<damper> requires ctrlrange")
+      a.setdefault("ctrllimited", "true")
     elif tag == "velocity":
       kv = float(a.get("kv", 1.0))
       m.actuator_gainprm[i, 0] = kv
@@ -1079,7 +1113,12 @@ def compile_xml(root):
       m.actuator_biasprm[i, 2] = -kv
     else:
       raise NotImplementedError(f"actuator shortcut <{tag}> is not supported")
-    for rng, lim in (("ctrlrange", "ctrllimited"), ("forcerange", "forcelimited")):
+    m.actuator_actearly[i] = a.get("actearly", "false") == "true"
+    if m.actuator_dyntype[i] != C.DYN_NONE or int(a.get("actdim", -1)) > 0:
+      m.actuator_actnum[i] = int(a.get("actdim", -1)) if int(a.get("actdim", -1)) > 0 else 1
+      m.actuator_actadr[i] = m.na
+      m.na += int(m.actuator_actnum[i])
+    for rng, lim in (("ctrlrange", "ctrllimited"), ("forcerange", "forcelimited"), ("actrange", "actlimited")):
       if rng in a:
         getattr(m, "actuator_" + rng)[i] = _vec(a[rng])
       l = a.get(lim, "auto")
@@ -1258,7 +1297,7 @@ def compile_xml(root):
   m.key_qpos = np.tile(qpos0, (m.nkey, 1)).reshape(m.nkey, nq)
   m.key_qvel = np.zeros((m.nkey, nv))
   m.key_ctrl = np.zeros((m.nkey, nu))
-  m.key_act = np.zeros((m.nkey, 0))
+  m.key_act = np.zeros((m.nkey, m.na))
   m.names.key = []
   for i, k in enumerate(keys):
     m.names.key.append(k.get("name", f"key{i}"))
@@ -1270,7 +1309,7 @@ def compile_xml(root):
       adr = int(m.jnt_qposadr[m.body_jntadr[b0]])
       m.key_qpos[i, adr : adr + v.size] = v
       continue
-    for nm_, arr in (("qpos", m.key_qpos), ("qvel", m.key_qvel), ("ctrl", m.key_ctrl)):
+    for nm_, arr in (("qpos", m.key_qpos), ("qvel", m.key_qvel), ("ctrl", m.key_ctrl), ("act", m.key_act)):
       if nm_ in k.attrib:
         v = _vec(k.get(nm_))
         if v.size != arr.shape[1]:
@@ -1486,6 +1525,8 @@ def reset_data_keyframe(m, d: MjDataLite, key: int):
   d.qpos[:] = m.key_qpos[key]
   d.qvel[:] = m.key_qvel[key]
   d.ctrl[:] = m.key_ctrl[key]
+  if getattr(m, "na", 0):
+    d.act[:] = np.asarray(m.key_act)[key]
   d.time = float(m.key_time[key])
   d.qacc_warmstart[:] = 0
 

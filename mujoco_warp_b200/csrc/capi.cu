@@ -24,7 +24,7 @@ struct mjbData {
   int nsplit;
   cudaStream_t sol_aux[8];        // solver row-capacity classes: second class of each world range runs here
   cudaEvent_t sol_fork[8], sol_join[8];
-  float* rk;  // Runge-Kutta scratch, (nworld, nq + 3 nv); allocated by mjb_data_finalize for RK4 models only
+  float* rk;  // Runge-Kutta scratch, (nworld, nq + 3 nv + 2 na); allocated by mjb_data_finalize for RK4 models only
 };
 
 namespace {
@@ -161,7 +161,7 @@ int mjb_data_finalize(mjbData* d, const mjbModel* m) {
   }
   d->dev.sol_stream = d->sol_aux[0]; d->dev.sol_fork = d->sol_fork[0]; d->dev.sol_join = d->sol_join[0];
   if (m->dev.integrator == INT_RK4 && !d->rk &&
-      check(cudaMalloc(&d->rk, sizeof(float) * (size_t)d->dev.nworld * (size_t)(m->dev.nq + 3 * m->dev.nv + 1)), "cudaMalloc(rk)")) return -1;
+      check(cudaMalloc(&d->rk, sizeof(float) * (size_t)d->dev.nworld * (size_t)(m->dev.nq + 3 * m->dev.nv + 2 * m->dev.na + 1)), "cudaMalloc(rk)")) return -1;
   d->smem[0] = smem_position(m->dev); d->smem[1] = smem_collision(m->dev, d->dev); d->smem[2] = smem_constraint(m->dev, d->dev);
   d->smem[3] = smem_velocity(m->dev); d->smem[4] = smem_solver(m->dev, d->dev); d->smem[5] = smem_integrate(m->dev);
   static const char* names[6] = {"position", "collision", "constraint", "velocity", "solver", "integrate"};

@@ -68,7 +68,14 @@ k_euler(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, 
             const float f = d.actuator_force[wb * m.nu + a];
             if (f <= m.actuator_forcerange[2 * a] || f >= m.actuator_forcerange[2 * a + 1]) continue;
           }
-          const float vel = bias + (gain != 0.f ? gain * d.ctrl[wb * m.nu + a] : 0.f);
+          float vel = bias;
+          if (gain != 0.f) {  // derivative.py:142-164: the gain multiplies the activation of a stateful actuator
+            if (m.na > 0 && m.actuator_dyntype[a] != DYN_NONE) {
+              const int last = m.actuator_actadr[a] + m.actuator_actnum[a] - 1;
+              const float act = d.act[wb * m.na + last];
+              vel += gain * (m.actuator_actearly[a] ? next_act(m, a, act, d.act_dot[wb * m.na + last], 1.0f, m.actuator_actlimited[a] != 0) : act);
+            } else vel += gain * d.ctrl[wb * m.nu + a];
+          }
           for (int p = lane; p < nnz * nnz; p += 32) {
             const int i = p / nnz, j = p - i * nnz;
             if (j <= i) {
@@ -206,18 +213,41 @@ k_euler_flat(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev
   }
 }
 
+// forward.py:135-218 _next_activation (dyntype NONE / INTEGRATOR / FILTER / FILTEREXACT): one thread per (world, actuator)
+// advances the actuator's activations from act_dot; launched after the integrator kernel (which still reads the old ones).
+template <bool BAT>
+__global__ void __launch_bounds__(256)
+k_next_act(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wl = idx / mp.nu, a = idx - wl * mp.nu;
+  if (wl >= d.wn) return;
+  const int w = wl + d.w0;
+  if (w >= d.nworld) return;
+  MJB_WORLD_MODEL(w)
+  const int adr = m.actuator_actadr[a];
+  if (adr < 0) return;
+  for (int j = adr; j < adr + m.actuator_actnum[a]; j++) {
+    const size_t k = (size_t)w * m.na + j;
+    d.act[k] = next_act(m, a, d.act[k], d.act_dot[k], 1.0f, m.actuator_actlimited[a] != 0);
+  }
+}
+
 // One Runge-Kutta bookkeeping step after the stage-th forward() of the step (forward.py:523-555 rungekutta4, stateless
 // actuators): accumulate B[stage] * (qvel, qacc); stages 0..2 then perturb the state for the next forward
 // (_rk_perturb_state: position from the current stage velocity, velocity from qvel_t0 + A dt qacc); stage 3 restores the
 // state and advances it with the accumulated velocity / acceleration (_advance with qvel = qvel_rk).
-// rk: per world [qpos_t0 (nq) | qvel_t0 (nv) | qvel_rk (nv) | qacc_rk (nv)].  One warp per world.
+// rk: per world [qpos_t0 (nq) | qvel_t0 (nv) | qvel_rk (nv) | qacc_rk (nv) | act_t0 (na) | act_dot_rk (na)].  One warp per world.
+// Stateful actuators (forward.py:445-463, 514-519, 553-555): stage activations are next_act(act_t0, act_dot, A) without the range
+// clamp, the final ones next_act(act_t0, sum B act_dot, 1) with it.
 __global__ void __launch_bounds__(32)
 k_rk_stage(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d, float* __restrict__ rk, int stage) {
   const int lane = threadIdx.x, w = blockIdx.x;
   if (w >= d.nworld) return;
   const int nq = m.nq, nv = m.nv;
   const size_t wb = (size_t)w;
-  float *qpos_t0 = rk + wb * (nq + 3 * nv), *qvel_t0 = qpos_t0 + nq, *qvel_rk = qvel_t0 + nv, *qacc_rk = qvel_rk + nv;
+  const int na = m.na;
+  float *qpos_t0 = rk + wb * (nq + 3 * nv + 2 * na), *qvel_t0 = qpos_t0 + nq, *qvel_rk = qvel_t0 + nv, *qacc_rk = qvel_rk + nv, *act_t0 = qacc_rk + nv, *act_dot_rk = act_t0 + na;
+  float *act = d.act + wb * na, *act_dot = d.act_dot + wb * na;
   float *qpos = d.qpos + wb * nq, *qvel = d.qvel + wb * nv;
   const float* qacc = d.qacc + wb * nv;
   const float dt = m.timestep;
@@ -225,15 +255,27 @@ k_rk_stage(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
   if (stage == 0) {
     for (int i = lane; i < nq; i += 32) qpos_t0[i] = qpos[i];
     for (int i = lane; i < nv; i += 32) { const float v = qvel[i]; qvel_t0[i] = v; qvel_rk[i] = B * v; qacc_rk[i] = B * qacc[i]; }
+    for (int i = lane; i < na; i += 32) { act_t0[i] = act[i]; act_dot_rk[i] = B * act_dot[i]; }
   } else {
     for (int i = lane; i < nv; i += 32) { qvel_rk[i] += B * qvel[i]; qacc_rk[i] += B * qacc[i]; }
+    for (int i = lane; i < na; i += 32) act_dot_rk[i] += B * act_dot[i];
   }
   __syncwarp();
   if (stage < 3) {
     for (int j = lane; j < m.njnt; j += 32) next_position_jnt(m, j, qpos_t0, qvel, A, dt, qpos);
     __syncwarp();
     for (int i = lane; i < nv; i += 32) qvel[i] = qvel_t0[i] + A * qacc[i] * dt;
+    if (na > 0)
+      for (int a = lane; a < m.nu; a += 32)
+        for (int j = m.actuator_actadr[a]; j >= 0 && j < m.actuator_actadr[a] + m.actuator_actnum[a]; j++) act[j] = next_act(m, a, act_t0[j], act_dot[j], A, false);
     return;
+  }
+  if (na > 0) {
+    for (int a = lane; a < m.nu; a += 32)
+      for (int j = m.actuator_actadr[a]; j >= 0 && j < m.actuator_actadr[a] + m.actuator_actnum[a]; j++) {
+        act_dot[j] = act_dot_rk[j];
+        act[j] = next_act(m, a, act_t0[j], act_dot_rk[j], 1.0f, m.actuator_actlimited[a] != 0);
+      }
   }
   for (int i = lane; i < nv; i += 32) { qvel[i] = qvel_t0[i] + qacc_rk[i] * dt; d.qacc_warmstart[wb * nv + i] = qacc[i]; }
   for (int j = lane; j < m.njnt; j += 32) next_position_jnt(m, j, qpos_t0, qvel_rk, 1.0f, dt, qpos);
@@ -256,10 +298,17 @@ size_t smem_integrate(const ModelDev& m) { return (size_t)int_words(m) * sizeof(
 cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, int integrator, cudaStream_t s) {
   if (integrator < 0) integrator = m.integrator == INT_IMPLICITFAST ? INT_IMPLICITFAST : INT_EULER;
   const bool solve = integrator == INT_IMPLICITFAST || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
+  auto next_activation = [&]() -> cudaError_t {  // after the integrator kernel: it reads the activations of the step
+    if (m.na <= 0 || m.nu <= 0) return cudaGetLastError();
+    const long n = (long)d.wn * m.nu;
+    if (m.batched) k_next_act<true><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, d);
+    else k_next_act<false><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, d);
+    return cudaGetLastError();
+  };
   if (!solve && m.njnt > 0) {
     const long n = (long)d.wn * m.njnt;
     k_euler_flat<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, d);
-    return cudaGetLastError();
+    return next_activation();
   }
   const size_t smem = smem_integrate(m);
   static size_t configured2[2] = {0, 0};
@@ -272,7 +321,7 @@ cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, int integrator
   const int grid = d.wn;
   if (m.batched) k_euler<true><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, integrator);
   else k_euler<false><<<grid, MJB_WARPS_PER_BLOCK * 32, smem, s>>>(m, d, integrator);
-  return cudaGetLastError();
+  return next_activation();
 }
 
 cudaError_t launch_ctrl_noise(const ModelDev& m, const DataDev& d, const float* ctrl_center, int step, float std, float rate, cudaStream_t s) {

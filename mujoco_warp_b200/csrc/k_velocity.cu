@@ -332,8 +332,20 @@ k_velocity(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev 
         if (m.actuator_gaintype[a] == GAIN_FIXED) gain = gp[0];
         else if (m.actuator_gaintype[a] == GAIN_AFFINE) gain = gp[0] + gp[1] * length + gp[2] * velocity;
         if (m.actuator_biastype[a] == BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
-        force = gain * ctrl + bias;
+        float ctrl_act = ctrl;
+        if (m.na > 0 && m.actuator_actadr[a] >= 0) {  // stateful actuator (forward.py:800-963): INTEGRATOR / FILTER / FILTEREXACT
+          const int last = m.actuator_actadr[a] + m.actuator_actnum[a] - 1, dyn = m.actuator_dyntype[a];
+          const float act = d.act[wb * m.na + last];
+          float act_dot = 0.f;
+          if (dyn == DYN_INTEGRATOR) act_dot = ctrl;
+          else if (dyn == DYN_FILTER || dyn == DYN_FILTEREXACT) act_dot = (ctrl - act) / fmaxf(m.actuator_dynprm[10 * a], MJ_MINVAL);
+          if (valid) d.act_dot[wb * m.na + last] = act_dot;
+          ctrl_act = m.actuator_actearly[a] ? next_act(m, a, act, act_dot, 1.0f, m.actuator_actlimited[a] != 0) : act;
+        }
+        force = gain * ctrl_act + bias;
         if (m.actuator_forcelimited[a]) force = clampf(force, m.actuator_forcerange[2 * a], m.actuator_forcerange[2 * a + 1]);
+      } else if (m.na > 0 && m.actuator_actadr[a] >= 0 && valid) {
+        d.act_dot[wb * m.na + m.actuator_actadr[a] + m.actuator_actnum[a] - 1] = 0.f;  // forward.py:1155: actuation disabled
       }
       if (valid) d.actuator_force[wb * nu + a] = force;
       aforce[a] = force;

@@ -98,6 +98,16 @@ __device__ __forceinline__ void make_frame(v3 a_in, float* frame) {
 }
 __device__ __forceinline__ float safe_div(float x, float y) { return x / (y != 0.f ? y : MJ_MINVAL); }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// support.py:38-64 next_act: one integration step of actuator a's activation (exact for FILTEREXACT), optionally clamped to actrange
+__device__ __forceinline__ float next_act(const ModelDev& m, int a, float act, float act_dot, float scale, bool clamp) {
+  float r;
+  if (m.actuator_dyntype[a] == DYN_FILTEREXACT) {
+    const float tau = fmaxf(MJ_MINVAL, m.actuator_dynprm[10 * a]);
+    r = act + scale * act_dot * tau * (1.0f - expf(-m.timestep / tau));
+  } else r = act + scale * act_dot * m.timestep;
+  if (clamp) r = clampf(r, m.actuator_actrange[2 * a], m.actuator_actrange[2 * a + 1]);
+  return r;
+}
 __device__ __forceinline__ v3 closest_segment_point(v3 a, v3 b, v3 pt) {
   v3 ab = b - a;
   float t = dot(pt - a, ab) / (dot(ab, ab) + 1e-6f);

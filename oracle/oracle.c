@@ -43,7 +43,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
-  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations) X(nsensor) X(nsensordata) X(nmesh)
+  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations) X(nsensor) X(nsensordata) X(nmesh) X(na)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(ccd_tolerance)
 #define MODEL_IARRS(X) \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
@@ -52,6 +52,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(tree_dofadr) X(tree_dofnum) X(qLD_block_adr) \
   X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
+  X(actuator_dyntype) X(actuator_actadr) X(actuator_actnum) X(actuator_actlimited) X(actuator_actearly) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
   X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim) \
@@ -67,7 +68,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
   X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat) \
   X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap) \
-  X(sensor_cutoff) X(site_size) X(mesh_vert) X(mesh_polynormal)
+  X(sensor_cutoff) X(site_size) X(mesh_vert) X(mesh_polynormal) X(actuator_dynprm) X(actuator_actrange)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -78,7 +79,8 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(qfrc_damper) X(qfrc_gravcomp) X(qfrc_passive) X(actuator_force) X(qfrc_actuator) X(qfrc_smooth) X(qacc_smooth) \
   X(qfrc_constraint) X(cacc) X(cfrc_int) X(cfrc_ext) X(sensordata) X(subtree_linvel) X(subtree_angmom) \
   X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
-  X(con_dist) X(con_pos) X(con_frame) X(con_includemargin) X(con_friction) X(con_solref) X(con_solreffriction) X(con_solimp)
+  X(con_dist) X(con_pos) X(con_frame) X(con_includemargin) X(con_friction) X(con_solref) X(con_solreffriction) X(con_solimp) \
+  X(act) X(act_dot)
 #define DATA_IARRS(X) \
   X(ne) X(nf) X(nl) X(nefc) X(ncon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
   X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(con_dim) X(con_geom) X(con_efc_address) X(con_geomcollisionid) \
@@ -341,6 +343,7 @@ static void make_view(const OrcModel* m, const OrcData* d, int w, W* v) {
   R(efc_type, njm); R(efc_id, njm); R(efc_state, njm); R(moment_rownnz, nu); R(moment_rowadr, nu); R(moment_colind, m->nJmom);
   R(con_dim, ncm); R(con_geom, 2 * ncm); R(con_efc_address, m->nmaxpyramid * ncm); R(con_geomcollisionid, ncm);
   R(eq_active, m->neq);
+  R(act, m->na); R(act_dot, m->na);
   R(cfrc_ext, 6 * nb); R(sensordata, m->nsensordata); R(subtree_linvel, 3 * nb); R(subtree_angmom, 3 * nb);
 #undef R
 }
@@ -2065,21 +2068,54 @@ static void fwd_velocity(W* w) {
   for (int d = 0; d < nv; d++) { real s = 0; int b = m->dof_bodyid[d]; for (int i = 0; i < 6; i++) s += w->cdof[6 * d + i] * w->cfrc_int[6 * b + i]; w->qfrc_bias[d] = s; }
 }
 
-/* ------------------------------------------------------------------ fwd_actuation (forward.py:756-1252; stateless actuators) */
+/* support.py:38-64 next_act: one integration step of an activation (exact for FILTEREXACT), optionally clamped to actrange */
+enum { DYN_NONE = 0, DYN_INTEGRATOR = 1, DYN_FILTER = 2, DYN_FILTEREXACT = 3 };
+static real next_act(const OrcModel* m, int a, real act, real act_dot, real scale, int clamp) {
+  real r;
+  if (m->actuator_dyntype[a] == DYN_FILTEREXACT) {
+    real tau = rmax(MJ_MINVAL, m->actuator_dynprm[10 * a]);
+    r = act + scale * act_dot * tau * ((real)1 - (real)exp((double)(-m->timestep / tau)));
+  } else r = act + scale * act_dot * m->timestep;
+  if (clamp) r = rclamp(r, m->actuator_actrange[2 * a], m->actuator_actrange[2 * a + 1]);
+  return r;
+}
+/* forward.py:135-218 _next_activation (INTEGRATOR / FILTER / FILTEREXACT / NONE): act <- next_act(act0, act_dot) */
+static void next_activation(W* w, const real* act0, real scale, int limit) {
+  const OrcModel* m = w->m;
+  for (int a = 0; a < m->nu; a++)
+    for (int j = m->actuator_actadr[a]; j >= 0 && j < m->actuator_actadr[a] + m->actuator_actnum[a]; j++)
+      w->act[j] = next_act(m, a, act0[j], w->act_dot[j], scale, limit && m->actuator_actlimited[a]);
+}
+
+/* ------------------------------------------------------------------ fwd_actuation (forward.py:756-1252; dyntype NONE / INTEGRATOR / FILTER / FILTEREXACT) */
 static void fwd_actuation(W* w) {
   const OrcModel* m = w->m;
   for (int d = 0; d < m->nv; d++) w->qfrc_actuator[d] = 0;
-  if (!m->nu || (m->disableflags & DSBL_ACTUATION)) { for (int a = 0; a < m->nu; a++) w->actuator_force[a] = 0; return; }
+  if (!m->nu || (m->disableflags & DSBL_ACTUATION)) {
+    for (int a = 0; a < m->nu; a++) w->actuator_force[a] = 0;
+    for (int j = 0; j < m->na; j++) w->act_dot[j] = 0;
+    return;
+  }
   for (int a = 0; a < m->nu; a++) {
     real ctrl = w->ctrl[a];
     if (m->actuator_ctrllimited[a] && !(m->disableflags & DSBL_CLAMPCTRL)) ctrl = rclamp(ctrl, m->actuator_ctrlrange[2 * a], m->actuator_ctrlrange[2 * a + 1]);
+    real ctrl_act = ctrl;
+    if (m->na && m->actuator_actadr[a] >= 0) { /* forward.py:800-963 */
+      const int last = m->actuator_actadr[a] + m->actuator_actnum[a] - 1, dyn = m->actuator_dyntype[a];
+      const real act = w->act[last];
+      real act_dot = 0;
+      if (dyn == DYN_INTEGRATOR) act_dot = ctrl;
+      else if (dyn == DYN_FILTER || dyn == DYN_FILTEREXACT) act_dot = (ctrl - act) / rmax(m->actuator_dynprm[10 * a], MJ_MINVAL);
+      w->act_dot[last] = act_dot;
+      ctrl_act = m->actuator_actearly[a] ? next_act(m, a, act, act_dot, 1, m->actuator_actlimited[a]) : act;
+    }
     real length = w->actuator_length[a], velocity = w->actuator_velocity[a];
     const real *gp = m->actuator_gainprm + 10 * a, *bp = m->actuator_biasprm + 10 * a;
     real gain = 0, bias = 0;
     if (m->actuator_gaintype[a] == GAIN_FIXED) gain = gp[0];
     else if (m->actuator_gaintype[a] == GAIN_AFFINE) gain = gp[0] + gp[1] * length + gp[2] * velocity;
     if (m->actuator_biastype[a] == BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
-    real force = gain * ctrl + bias;
+    real force = gain * ctrl_act + bias;
     if (m->actuator_forcelimited[a]) force = rclamp(force, m->actuator_forcerange[2 * a], m->actuator_forcerange[2 * a + 1]);
     w->actuator_force[a] = force;
   }
@@ -2477,6 +2513,7 @@ static void next_position(const OrcModel* m, const real* qpos_in, const real* qv
 /* forward.py:276-349 _advance: velocity from qacc, position from qvel_pos (the new velocity when NULL: semi-implicit) */
 static void advance2(W* w, const real* qacc, const real* qvel_pos) {
   const OrcModel* m = w->m;
+  if (m->na) next_activation(w, w->act, 1, 1); /* forward.py:280-300 */
   for (int d = 0; d < m->nv; d++) w->qvel[d] += qacc[d] * m->timestep;
   next_position(m, w->qpos, qvel_pos ? qvel_pos : w->qvel, 1, w->qpos);
   w->time[0] += m->timestep;
@@ -2517,7 +2554,13 @@ static void implicitfast(W* w) {
         real f = w->actuator_force[a];
         if (f <= m->actuator_forcerange[2 * a] || f >= m->actuator_forcerange[2 * a + 1]) continue;
       }
-      real vel = bias + (gain != 0 ? gain * w->ctrl[a] : 0);
+      real vel = bias;
+      if (gain != 0) { /* derivative.py:142-164: the input the gain multiplies is the activation for a stateful actuator */
+        if (m->actuator_dyntype[a] != DYN_NONE) {
+          const int last = m->actuator_actadr[a] + m->actuator_actnum[a] - 1;
+          vel += gain * (m->actuator_actearly[a] ? next_act(m, a, w->act[last], w->act_dot[last], 1, m->actuator_actlimited[a]) : w->act[last]);
+        } else vel += gain * w->ctrl[a];
+      }
       if (vel == 0) continue;
       int adr = w->moment_rowadr[a], nnz = w->moment_rownnz[a];
       for (int i = 0; i < nnz; i++) for (int j = 0; j <= i; j++) {
@@ -2933,19 +2976,24 @@ static void rungekutta4(W* w) {
   const OrcModel* m = w->m;
   const int nq = m->nq, nv = m->nv;
   const real A[3] = {(real)0.5, (real)0.5, (real)1.0}, B[4] = {(real)(1.0 / 6.0), (real)(1.0 / 3.0), (real)(1.0 / 3.0), (real)(1.0 / 6.0)};
-  real* buf = (real*)calloc((size_t)2 * nq + 3 * nv, sizeof(real));
-  real *qpos_t0 = buf, *qpos_new = buf + nq, *qvel_t0 = buf + 2 * nq, *qvel_rk = qvel_t0 + nv, *qacc_rk = qvel_rk + nv;
-  memcpy(qpos_t0, w->qpos, nq * sizeof(real)); memcpy(qvel_t0, w->qvel, nv * sizeof(real));
+  const int na = m->na;
+  real* buf = (real*)calloc((size_t)2 * nq + 3 * nv + 2 * na, sizeof(real));
+  real *qpos_t0 = buf, *qpos_new = buf + nq, *qvel_t0 = buf + 2 * nq, *qvel_rk = qvel_t0 + nv, *qacc_rk = qvel_rk + nv, *act_t0 = qacc_rk + nv, *act_dot_rk = act_t0 + na;
+  memcpy(qpos_t0, w->qpos, nq * sizeof(real)); memcpy(qvel_t0, w->qvel, nv * sizeof(real)); memcpy(act_t0, w->act, na * sizeof(real));
   for (int d = 0; d < nv; d++) { qvel_rk[d] += B[0] * w->qvel[d]; qacc_rk[d] += B[0] * w->qacc[d]; }
+  for (int j = 0; j < na; j++) act_dot_rk[j] += B[0] * w->act_dot[j];
   for (int i = 0; i < 3; i++) {
     /* _rk_perturb_state: the position step uses the current stage velocity, then the velocity is perturbed */
     next_position(m, qpos_t0, w->qvel, A[i], qpos_new);
     memcpy(w->qpos, qpos_new, nq * sizeof(real));
     for (int d = 0; d < nv; d++) w->qvel[d] = qvel_t0[d] + A[i] * w->qacc[d] * m->timestep;
+    if (na) next_activation(w, act_t0, A[i], 0); /* forward.py:445-463: unclamped stage activations */
     forward_world(w);
     for (int d = 0; d < nv; d++) { qvel_rk[d] += B[i + 1] * w->qvel[d]; qacc_rk[d] += B[i + 1] * w->qacc[d]; }
+    for (int j = 0; j < na; j++) act_dot_rk[j] += B[i + 1] * w->act_dot[j];
   }
   memcpy(w->qpos, qpos_t0, nq * sizeof(real)); memcpy(w->qvel, qvel_t0, nv * sizeof(real));
+  if (na) { memcpy(w->act, act_t0, na * sizeof(real)); memcpy(w->act_dot, act_dot_rk, na * sizeof(real)); } /* forward.py:553-555 */
   advance2(w, qacc_rk, qvel_rk);
   free(buf);
 }

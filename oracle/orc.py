@@ -140,6 +140,7 @@ def data_spec(mjm, tabs, nconmax, njmax):
   R, I = False, True
   return {
     "time": (R, ()), "qpos": (R, (nq,)), "qvel": (R, (nv,)), "ctrl": (R, (nu,)), "qacc_warmstart": (R, (nv,)),
+    "act": (R, (int(getattr(mjm, "na", 0)),)), "act_dot": (R, (int(getattr(mjm, "na", 0)),)),
     "qfrc_applied": (R, (nv,)), "xfrc_applied": (R, (nb, 6)), "qacc": (R, (nv,)),
     "mocap_pos": (R, (int(getattr(mjm, "nmocap", 0)), 3)), "mocap_quat": (R, (int(getattr(mjm, "nmocap", 0)), 4)),
     "xpos": (R, (nb, 3)), "xquat": (R, (nb, 4)), "xmat": (R, (nb, 3, 3)), "xipos": (R, (nb, 3)), "ximat": (R, (nb, 3, 3)),
@@ -243,6 +244,14 @@ class Oracle:
               "mesh_polyvert", "mesh_polymapadr", "mesh_polymapnum", "mesh_polymap"):
       setia(n, getattr(mjm, n) if nmesh and len(np.asarray(getattr(mjm, n))) else np.zeros(1, dtype=np.int32))
     setra("mesh_vert", mjm.mesh_vert if nmesh else np.zeros(3)); setra("mesh_polynormal", mjm.mesh_polynormal if nmesh else np.zeros(3))
+    na, nu = int(getattr(mjm, "na", 0)), int(mjm.nu)
+    seti("na", na)
+    adr_default = -np.ones(max(nu, 1), dtype=np.int32)
+    for n, dflt in (("actuator_dyntype", np.zeros(max(nu, 1))), ("actuator_actadr", adr_default), ("actuator_actnum", np.zeros(max(nu, 1))),
+                    ("actuator_actlimited", np.zeros(max(nu, 1))), ("actuator_actearly", np.zeros(max(nu, 1)))):
+      setia(n, getattr(mjm, n, dflt) if nu else dflt)
+    setra("actuator_dynprm", getattr(mjm, "actuator_dynprm", np.zeros((max(nu, 1), 10))) if nu else np.zeros(10))
+    setra("actuator_actrange", getattr(mjm, "actuator_actrange", np.zeros((max(nu, 1), 2))) if nu else np.zeros(2))
     nsite = int(getattr(mjm, "nsite", 0))
     setia("site_type", getattr(mjm, "site_type", 2 * np.ones(nsite, dtype=np.int32)) if nsite else np.zeros(1, dtype=np.int32))
     setra("site_size", getattr(mjm, "site_size", 0.005 * np.ones((nsite, 3))) if nsite else np.zeros(3))
@@ -268,8 +277,8 @@ class Oracle:
       self.d["geom_xpos"][:] = static_kin.geom_xpos
       self.d["geom_xmat"][:] = static_kin.geom_xmat
 
-  def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, time=None):
-    for k, v in (("qpos", qpos), ("qvel", qvel), ("ctrl", ctrl), ("qacc_warmstart", qacc_warmstart), ("time", time)):
+  def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, time=None, act=None):
+    for k, v in (("qpos", qpos), ("qvel", qvel), ("ctrl", ctrl), ("qacc_warmstart", qacc_warmstart), ("time", time), ("act", act)):
       if v is not None:
         self.d[k][...] = np.asarray(v)
 

@@ -43,6 +43,8 @@ def load_scene(name):
     mjm = mjcf.load_string(util.mesh_xml())
   elif name == "sensors":
     mjm = mjcf.load_string(util.sensor_xml())
+  elif name.startswith("actuators"):
+    mjm = mjcf.load_string(util.actuators_xml({"actuators": "Euler", "actuators_implicitfast": "implicitfast", "actuators_rk4": "RK4"}[name]))
   elif name == "mixed_rk4":
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"'))
   elif name == "mixed_sap":
@@ -141,6 +143,8 @@ def test_oracle_matches_reference_pipeline(built, name):
     o.set_state(ctrl=g["in/ctrl"])
   if "in/mocap_pos" in g:
     o.d["mocap_pos"][:] = g["in/mocap_pos"]; o.d["mocap_quat"][:] = g["in/mocap_quat"]
+  if "in/act" in g:
+    o.set_state(act=g["in/act"])
   o.forward()
   # capacity-overflow scenes: the oracle (like the CUDA collision kernel) raises the bit where the truncation happens, the reference
   # at the end of step() (forward.py:247-271); the bits are sticky, so both agree after a step (checked below)
@@ -153,6 +157,8 @@ def test_oracle_matches_reference_pipeline(built, name):
   # on it to the solver tolerance, not to rounding (geometry, Jacobians and every other constraint field still match to 1e-9)
   loose = cg or name == "mesh"
   compare("forward", g, o.d, mjm, nworld, 1e-9, solver_tol=5e-3 if cg else (2e-4 if loose else 1e-7), exact_iterations=not loose)
+  if "in/act" in g:  # stateful actuators: activation derivatives of forward(), activations after every step
+    close("forward/act_dot", o.d["act_dot"], g["forward/act_dot"], 1e-9)
   if cg:
     assert (np.abs(o.d["solver_niter"].reshape(-1) - g["forward/solver_niter"].reshape(-1)) <= 5).all()
   s = 0
@@ -164,6 +170,8 @@ def test_oracle_matches_reference_pipeline(built, name):
     close(f"step{s}/qvel", o.d["qvel"], g[f"step{s}/qvel"], 2e-3 if cg else 1e-4)
     close(f"step{s}/qacc_warmstart", o.d["qacc_warmstart"], g[f"step{s}/qacc_warmstart"], 5e-3 if cg else 2e-4)
     close(f"step{s}/time", o.d["time"], g[f"step{s}/time"], 1e-12)
+    if "in/act" in g:
+      close(f"step{s}/act", o.d["act"], g[f"step{s}/act"], 1e-7)
     np.testing.assert_array_equal(o.d["nefc"].reshape(-1), g[f"step{s}/nefc"].reshape(-1), err_msg=f"step{s}/nefc")
     if trunc:
       np.testing.assert_array_equal(o.d["overflow"].reshape(-1) & ~(1 << 10), g[f"step{s}/overflow"].reshape(-1) & ~(1 << 10), err_msg=f"step{s}/overflow")

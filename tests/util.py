@@ -31,6 +31,12 @@ def seeded_state(mjm, nworld, key=0, seed=42, qpos_noise=0.05, qvel_noise=0.5, c
   return qpos, qvel, ctrl, warm
 
 
+def seeded_act(mjm, nworld, seed=4321, scale=0.4):
+  """Per-world activations of a model with stateful actuators (na > 0), fp32-representable."""
+  rng = np.random.default_rng(seed)
+  return (scale * rng.uniform(-1, 1, (nworld, int(getattr(mjm, "na", 0))))).astype(np.float32).astype(np.float64)
+
+
 def make_oracle(mjm, nworld, nconmax, njmax, dtype=np.float64, clamp_tolerance=True):
   from mujoco_warp_b200._src import mjcf
   from oracle import orc
@@ -312,6 +318,55 @@ def sensor_xml():
   </sensor>
 """
   return x.replace("  <actuator>", sensors + "  <actuator>")
+
+
+def actuators_xml(integrator="Euler"):
+  """Stateful actuators (na > 0) on a three-link arm above a floor: integrator, filter, exact filter (general and <position timeconst>),
+  <intvelocity>, <damper>, early activation (actearly), activation limits, a velocity-dependent gain on a filtered actuator (the
+  implicit integrators' d force / d velocity path), next to stateless motors."""
+  return f"""
+<mujoco model="actuators">
+  <option timestep="0.004" integrator="{integrator}" iterations="50" ls_iterations="30"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05" condim="3"/>
+    <body name="base" pos="0 0 0.5">
+      <joint name="j0" type="hinge" axis="0 1 0" damping="0.2" armature="0.01"/>
+      <geom type="capsule" fromto="0 0 0 0.25 0 0" size="0.03" mass="0.6"/>
+      <body name="l1" pos="0.25 0 0">
+        <joint name="j1" type="hinge" axis="0 1 0" damping="0.1" range="-100 100" limited="true"/>
+        <geom type="capsule" fromto="0 0 0 0.2 0 0" size="0.025" mass="0.4"/>
+        <body name="l2" pos="0.2 0 0">
+          <joint name="j2" type="hinge" axis="0 0 1" damping="0.05"/>
+          <joint name="j3" type="slide" axis="1 0 0" damping="0.5" range="-0.05 0.1" limited="true"/>
+          <geom type="capsule" fromto="0 0 0 0.15 0 0" size="0.02" mass="0.2"/>
+          <geom name="tip" type="sphere" pos="0.17 0 0" size="0.03" mass="0.1"/>
+        </body>
+      </body>
+    </body>
+    <body name="cart" pos="-0.4 0 0.06">
+      <joint name="cx" type="slide" axis="1 0 0" damping="1"/>
+      <joint name="cz" type="slide" axis="0 0 1"/>
+      <geom type="box" size="0.08 0.05 0.05" mass="1"/>
+      <body name="pole" pos="0 0 0.05">
+        <joint name="cp" type="hinge" axis="0 1 0" damping="0.02"/>
+        <geom type="capsule" fromto="0 0 0 0 0 0.3" size="0.015" mass="0.2"/>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <general name="a_int" joint="j0" dyntype="integrator" gainprm="4" actlimited="true" actrange="-0.6 0.6" ctrlrange="-2 2" ctrllimited="true"/>
+    <general name="a_filt" joint="j1" dyntype="filter" dynprm="0.05" gaintype="affine" gainprm="6 0.5 -0.3" biastype="affine" biasprm="0.1 -2 -0.2"/>
+    <general name="a_fex" joint="j2" dyntype="filterexact" dynprm="0.02" gainprm="1.5" actearly="true" forcerange="-1 1" forcelimited="true"/>
+    <position name="a_pos" joint="j3" kp="60" kv="3" timeconst="0.03"/>
+    <intvelocity name="a_iv" joint="cx" kp="30" kv="2" actrange="-0.3 0.3"/>
+    <damper name="a_damp" joint="cp" kv="0.4" ctrlrange="0 1"/>
+    <motor name="a_mot" joint="cz" gear="3"/>
+    <general name="a_int_early" joint="cp" dyntype="integrator" gainprm="0.5" actearly="true" actlimited="true" actrange="-0.2 0.2"/>
+  </actuator>
+  <keyframe>
+    <key name="k0" qpos="0.3 -0.5 0.2 0.01 0 0 0.1"/>
+  </keyframe>
+</mujoco>"""
 
 
 def mesh_xml():

@@ -37,3 +37,18 @@ for w in range(nworld):
   e = np.abs(J[w, :ne, :mjm.nv] - o.d["efc_J"][w][:ne, :mjm.nv]); print(f"w{w} efc_J max err {e.max():.4g}")
   st_g, st_o = d.efc.state[w, :ne].cpu().numpy(), o.d["efc_state"][w][:ne]
   print(f"w{w} efc_state differs in {int((st_g != st_o).sum())} rows")
+# ---- contacts per geom pair, GPU vs oracle
+import collections
+for w in range(nworld):
+  ids = util.world_contacts(d, w)
+  gg = d.contact.geom[ids].cpu().numpy(); gd = d.contact.dist[ids].cpu().numpy()
+  nc = int(o.d["ncon"][w]); og = o.d["con_geom"][w][:nc]; od_ = o.d["con_dist"][w][:nc]
+  cg, co = collections.Counter(map(tuple, gg.tolist())), collections.Counter(map(tuple, og.tolist()))
+  for pair in sorted(set(cg) | set(co)):
+    if cg[pair] != co[pair]:
+      a, b = pair
+      print(f"w{w} pair {pair}: gpu {cg[pair]} contacts dist {gd[[i for i in range(len(gg)) if tuple(gg[i]) == pair]]}, oracle {co[pair]} dist {od_[[i for i in range(nc) if tuple(og[i]) == pair]]}")
+      for gi in pair:
+        print(f"   geom {gi} type {int(mjm.geom_type[gi])} size {np.asarray(mjm.geom_size[gi]).tolist()}")
+        print("   gpu xpos", repr(d.geom_xpos[w, gi].cpu().numpy().astype(np.float64).tolist()), "xmat", repr(d.geom_xmat[w, gi].cpu().numpy().reshape(-1).astype(np.float64).tolist()))
+        print("   orc xpos", repr(np.asarray(o.d["geom_xpos"][w, gi], dtype=np.float64).tolist()), "xmat", repr(np.asarray(o.d["geom_xmat"][w, gi], dtype=np.float64).reshape(-1).tolist()))
