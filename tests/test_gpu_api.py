@@ -375,3 +375,55 @@ def test_batched_model_fields_match_per_world_models(built):
   mjw.step(m, d)
   torch.cuda.synchronize()
   assert not np.isnan(d.qpos.cpu().numpy()).any()
+
+
+def test_stateful_actuators_state_keyframe_and_analytic_response(built):
+  """na > 0 through the public API: the ACT component of get_state / set_state, keyframe activations, the activation limit of an
+  integrator, the closed-form response of an exact filter (act -> ctrl with time constant tau, forward.py:135-218 / support.py:38),
+  and per-world (batched) dynprm."""
+  import mujoco_warp_b200 as mjw
+
+  xml = util.actuators_xml().replace('<key name="k0" qpos="0.3 -0.5 0.2 0.01 0 0 0.1"/>', '<key name="k0" qpos="0.3 -0.5 0.2 0.01 0 0 0.1" act="0.1 0.2 0.3 0.02 -0.1 0.05"/>')
+  mjm = mjw.mjcf.load_string(xml)
+  assert mjm.na == 6
+  nworld = 4
+  m = mjw.put_model(mjm, batch_sizes={"actuator_dynprm": nworld})
+  tau = torch.tensor([0.02, 0.04, 0.08, 0.16], device="cuda")
+  dp = m.actuator_dynprm.clone()
+  dp[:, 2, 0] = tau  # a_fex (filterexact): one time constant per world
+  m.actuator_dynprm = dp
+  d = mjw.make_data(mjm, nworld=nworld, nconmax=16, njmax=64, m=m)
+  mjw.reset_data_keyframe(m, d, 0)
+  np.testing.assert_allclose(d.act.cpu().numpy(), np.tile([0.1, 0.2, 0.3, 0.02, -0.1, 0.05], (nworld, 1)), rtol=1e-6)
+  ctrl = torch.zeros_like(d.ctrl)
+  ctrl[:, 0] = 2.0   # a_int: integrates ctrl, clamped at actrange 0.6
+  ctrl[:, 2] = 1.0   # a_fex
+  d.ctrl.copy_(ctrl)
+  nstep, dt = 100, float(mjm.opt.timestep)
+  for _ in range(nstep):
+    mjw.step(m, d)
+  torch.cuda.synchronize()
+  act = d.act.cpu().numpy()
+  np.testing.assert_allclose(act[:, 0], 0.6, rtol=1e-6)  # 0.1 + 100 * 0.004 * 2 = 0.9 without the activation limit
+  want = 1.0 + (0.3 - 1.0) * np.exp(-nstep * dt / tau.cpu().numpy())
+  np.testing.assert_allclose(act[:, 2], want, rtol=2e-5, atol=2e-6)
+  assert not np.isnan(d.qpos.cpu().numpy()).any()
+  # ACT is part of the integration state
+  sig = int(mjw.State.INTEGRATION)
+  size = 1 + mjm.nq + 2 * mjm.nv + mjm.na + mjm.nu + mjm.nv + 6 * mjm.nbody
+  state = torch.zeros((nworld, size), device="cuda")
+  mjw.get_state(m, d, state, sig)
+  off = 1 + mjm.nq + mjm.nv
+  np.testing.assert_array_equal(state[:, off : off + mjm.na].cpu().numpy(), act)
+  saved = {k: getattr(d, k).clone() for k in ("qpos", "qvel", "act", "time")}
+  for _ in range(5):
+    mjw.step(m, d)
+  after = {k: getattr(d, k).clone() for k in saved}
+  mjw.set_state(m, d, state, sig)
+  for k, v in saved.items():
+    assert torch.equal(getattr(d, k), v), k
+  d.qacc_warmstart.copy_(state[:, 1 + mjm.nq + mjm.nv + mjm.na : 1 + mjm.nq + 2 * mjm.nv + mjm.na])
+  for _ in range(5):
+    mjw.step(m, d)
+  for k, v in after.items():  # the restored state replays the same trajectory bit for bit
+    assert torch.equal(getattr(d, k), v), k
