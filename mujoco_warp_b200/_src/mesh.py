@@ -96,9 +96,9 @@ def hull_polygons(points: np.ndarray, tris: np.ndarray, tol: float = 1e-6):
     keep = []
     for i, v in enumerate(loop):
       p, q, r = pts[loop[i - 1]], pts[v], pts[loop[(i + 1) % len(loop)]]
-      if np.linalg.norm(np.cross(q - p, r - q)) > tol * max(1.0, np.linalg.norm(q - p) * np.linalg.norm(r - q)):
+      if np.linalg.norm(np.cross(q - p, r - q)) > tol * np.linalg.norm(q - p) * np.linalg.norm(r - q):  # sine of the turn angle
         keep.append(v)
-    polys.append((n, keep))
+    polys.append((n, keep if len(keep) >= 3 else loop))
   polys.sort(key=lambda pv: min(pv[1]))
   return polys
 
@@ -148,3 +148,46 @@ def process(vertices, faces=None, scale=(1.0, 1.0, 1.0)):
     aabb_center=0.5 * (local.max(axis=0) + local.min(axis=0)), aabb_size=0.5 * (local.max(axis=0) - local.min(axis=0)),
     rbound=float(np.linalg.norm(local, axis=1).max()),
   )
+
+
+def read_obj(path: str):
+  """Vertices and triangles of a Wavefront OBJ file (`v` and `f` records; polygons are fanned, texture / normal indices dropped)."""
+  verts, faces = [], []
+  with open(path, "r", errors="replace") as f:
+    for line in f:
+      t = line.split()
+      if not t:
+        continue
+      if t[0] == "v":
+        verts.append([float(t[1]), float(t[2]), float(t[3])])
+      elif t[0] == "f":
+        idx = [int(x.split("/")[0]) for x in t[1:]]
+        idx = [i - 1 if i > 0 else len(verts) + i for i in idx]
+        for k in range(1, len(idx) - 1):
+          faces.append([idx[0], idx[k], idx[k + 1]])
+  return np.asarray(verts, dtype=np.float64).reshape(-1, 3), np.asarray(faces, dtype=np.int32).reshape(-1, 3)
+
+
+def read_stl(path: str):
+  """Vertices and triangles of an STL file (binary or ASCII); coincident vertices are merged like MuJoCo's loader does."""
+  raw = open(path, "rb").read()
+  tri = None
+  if len(raw) >= 84:
+    n = int(np.frombuffer(raw[80:84], dtype="<u4")[0])
+    if len(raw) == 84 + 50 * n:
+      rec = np.frombuffer(raw[84:], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=n)
+      tri = rec["v"].astype(np.float64)
+  if tri is None:
+    pts = [[float(x) for x in line.split()[1:4]] for line in raw.decode("ascii", errors="replace").splitlines() if line.strip().startswith("vertex")]
+    tri = np.asarray(pts, dtype=np.float64).reshape(-1, 3, 3)
+  verts, inv = np.unique(tri.reshape(-1, 3), axis=0, return_inverse=True)
+  return verts, inv.reshape(-1, 3).astype(np.int32)
+
+
+def read_file(path: str):
+  ext = path.lower().rsplit(".", 1)[-1]
+  if ext == "obj":
+    return read_obj(path)
+  if ext == "stl":
+    return read_stl(path)
+  raise NotImplementedError(f"mesh file format .{ext} is not supported (OBJ and STL are): {path}")

@@ -461,7 +461,32 @@ def load(path: str):
   root = ET.parse(path).getroot()
   _expand_includes(root, os.path.dirname(os.path.abspath(path)))
   _expand_composites(root, os.path.dirname(os.path.abspath(path)))
+  _load_mesh_files(root, os.path.dirname(os.path.abspath(path)))
   return compile_xml(root)
+
+
+def _load_mesh_files(root, basedir):
+  """Mesh assets given by `file=` (OBJ / STL under <compiler meshdir>): the vertex / face data is read here and attached to the
+  element as inline `vertex=` / `face=` data, which is what the compiler consumes.  Files that do not exist are left alone (only
+  visual geoms may then refer to the asset)."""
+  from . import mesh as _mesh
+
+  meshdir = ""
+  for ce in root.iter("compiler"):
+    meshdir = ce.get("meshdir", ce.get("assetdir", meshdir))
+  for asset in root.iter("asset"):
+    for me in asset.findall("mesh"):
+      if "vertex" in me.attrib or "file" not in me.attrib:
+        continue
+      path = os.path.join(basedir, meshdir, me.get("file"))
+      if not os.path.exists(path):
+        continue
+      v, f = _mesh.read_file(path)
+      me.set("vertex", " ".join(repr(float(x)) for x in v.reshape(-1)))
+      if len(f):
+        me.set("face", " ".join(str(int(x)) for x in f.reshape(-1)))
+      if "name" not in me.attrib:
+        me.set("name", os.path.splitext(os.path.basename(me.get("file")))[0])
 
 
 def load_string(xml: str):
@@ -580,7 +605,12 @@ def compile_xml(root):
       from . import mesh as _mesh
 
       faces = _vec(me.get("face")).astype(int).reshape(-1, 3) if "face" in me.attrib else None
-      meshes.append(_mesh.process(_vec(me.get("vertex")).reshape(-1, 3), faces, _vec(me.get("scale"), 3, default=[1, 1, 1])))
+      ma = dflt.resolve("mesh", me.get("class", "main"))
+      ma.update(me.attrib)
+      if ma.get("inertia", "convex") not in ("convex", "legacy", "exact"):
+        raise NotImplementedError(f"mesh inertia='{ma.get('inertia')}' is not supported")
+      # inertia="convex": mass properties of the hull; otherwise those of the given faces (closed, outward-oriented surfaces)
+      meshes.append(_mesh.process(_vec(me.get("vertex")).reshape(-1, 3), None if ma.get("inertia") == "convex" else faces, _vec(ma.get("scale"), 3, default=[1, 1, 1])))
       mesh_names.append(me.get("name", f"mesh{len(mesh_names)}"))
 
   def attrs(elem, childclass):

@@ -48,7 +48,7 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   L.H = take(hsz);
   // nv <= 32: the factor lives in the padded column layout of chol_solve_rows_bcast, and M is kept as a dense packed lower
   // triangle (H starts as a copy of it, M * v needs no index tables); nv > 32: packed factor, CSR M with gather tables
-  L.Lf = take(big ? hsz : colsub_off(m.nv <= 8 ? 8 : m.nv <= 16 ? 16 : m.nv <= 24 ? 24 : m.nv <= 28 ? 28 : 32));  // padded size of the register path
+  L.Lf = take(big ? hsz : cholpair_size(m.nv <= 8 ? 8 : m.nv <= 16 ? 16 : m.nv <= 24 ? 24 : m.nv <= 28 ? 28 : 32));  // padded size of the register path (>= colsub_off of the same size)
   L.M = take(big ? m.nC : hsz);
   // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
   // elliptic cones add: per-row friction scale, 3 quad words per row (solver.py:1008-1015 layout), row->contact info
@@ -215,6 +215,7 @@ struct Ctx {
   int *rng, *fz;              // nv > 32: Jacobian row ranges, Hessian row envelope
   bool env;                   // ranges / envelope in use (several kinematic trees: the Hessian is close to block diagonal)
   float chol_inv;             // nv <= 32: lane j keeps 1 / L_jj of the factor in Lf
+  int chol_off;               // nv <= 32: where lane j's column of the factor starts in Lf (paired-column layout)
   bool factored;              // Lf holds the factor of the current H
 };
 template <bool BIG>
@@ -417,7 +418,11 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
   return chol_solve_rows_unrolled<N>(a, nv, g, c.Lf, lane);
 #else
   c.factored = true;
+#ifdef MJB_CHOL_SINGLE  // one column per sweep (humanoid solver 216 us)
   return chol_solve_rows_bcast<N>(a, nv, g, c.Lf, lane, c.chol_inv);
+#else
+  return chol_solve_rows_pair<N>(a, nv, g, c.Lf, lane, c.chol_inv, c.chol_off);
+#endif
 #endif
 }
 
@@ -431,7 +436,11 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
     float xx;
     // no row changed state since the last factorisation: H is what was factored, only the right-hand side is new (the reference's
     // stable-state shortcut, solver.py:2145-2159, which reuses the whole direction instead)
+#ifdef MJB_CHOL_SINGLE
     if (!ELL && nlist == 0 && c.factored) xx = chol_subst_bcast(nv, g, c.Lf, c.lane, c.chol_inv);
+#else
+    if (!ELL && nlist == 0 && c.factored) xx = chol_subst_pair(nv, g, c.Lf, c.lane, c.chol_inv, c.chol_off);
+#endif
     else if (nv <= 8) xx = newton_direction_reg<8, ELL>(c, nlist, g);
     else if (nv <= 16) xx = newton_direction_reg<16, ELL>(c, nlist, g);
     else if (nv <= 24) xx = newton_direction_reg<24, ELL>(c, nlist, g);
@@ -712,7 +721,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   const int cap = sol_rowcap(d);  // rows of this world's shared-memory slice (njmax, or the row-capacity class of this launch)
   const size_t wb = (size_t)w;
   Ctx c;
-  c.factored = false; c.chol_inv = 1.0f;
+  c.factored = false; c.chol_inv = 1.0f; c.chol_off = 0;
   c.m = &m; c.lane = lane; c.nv = nv; c.nvp = L.nvp; c.ldJ = L.ldJ; c.ldH = L.ldH;
   c.J = S + L.J; c.H = S + L.H; c.Lf = S + L.Lf; c.M = S + L.M;
   float* v = S + L.vec;

@@ -369,6 +369,106 @@ __device__ __forceinline__ float chol_subst_bcast(int n, float b, const float* L
   return b * myinv;
 }
 
+// ---- Two columns per sweep.  The per-column bookkeeping of chol_solve_rows_bcast (pivot broadcast, reciprocal square root, slot
+// arithmetic, barrier, loop control: about half of its ~90 instructions per column) is paid once per PAIR of columns here, and a row
+// makes one shared-memory round trip per pair instead of one per column.  Columns (j, j+1) are eliminated together:
+//   l0 = a[0] / sqrt(a00);  l10 = l0 of row j+1;  t1 = a[1] - l0 l10;  l1 = t1 / sqrt(t1 of row j+1)
+//   a[k-2] <- a[k] - l0 L[j+k][j] - l1 L[j+k][j+1]     (registers rotate by two)
+// Storage of the factor, per pair p (columns 2p, 2p+1, cnt = ne - 2p - 2 rows below the pair, ne = n rounded up to even):
+//   [3 pad, L[2p+1][2p]] [P0: L[2p+2+t][2p], pad4(cnt)] [P1: L[2p+2+t][2p+1], pad4(cnt)]
+// so both column pieces start 16-byte aligned (LDS.128 broadcasts in the trailing update) and P0[-1] is the in-pair entry.
+__host__ __device__ __forceinline__ int cholpair_size(int n) {
+  const int ne = (n + 1) & ~1;
+  int o = 0;
+  for (int c = ne - 2; c >= 0; c -= 2) o += 4 + 2 * ((c + 3) & ~3);
+  return o;
+}
+template <int N>
+__device__ __forceinline__ float chol_solve_rows_pair(float (&a)[N], int n, float b, float* Lc, int lane, float& myinv, int& mycol_off) {
+  static_assert((N & 1) == 0, "register rows come in even sizes");
+  myinv = 1.0f;
+  mycol_off = 0;
+  const int ne = (n + 1) & ~1;
+  int cnt = ne - 2;      // rows below the current pair
+  float* P0 = Lc + 4;    // pair block: P0[-1] = in-pair entry, P0[t], P1[t] = P0[pad4(cnt) + t]
+#pragma unroll 1
+  for (int j = 0; j < ne; j += 2) {
+    const int pc = (cnt + 3) & ~3;
+    const float a00 = __shfl_sync(FULL_MASK, a[0], j);
+    const float inv0 = rsqrt_normal(fmaxf(a00, MJ_MINVAL));
+    const float l0 = a[0] * inv0;                       // L[lane][j], lanes >= j
+    const float l10 = __shfl_sync(FULL_MASK, l0, j + 1);
+    const float t1 = a[1] - l0 * l10;                   // column j+1 after eliminating column j
+    const float a11 = __shfl_sync(FULL_MASK, t1, j + 1);
+    const float inv1 = rsqrt_normal(fmaxf(a11, MJ_MINVAL));
+    const float l1 = t1 * inv1;                         // L[lane][j+1], lanes >= j+1
+    if (lane == j) myinv = inv0;
+    if (lane == j + 1) myinv = inv1;
+    // forward substitution folded in (pivot lanes keep their unscaled b: y = b * myinv)
+    const float y0 = __shfl_sync(FULL_MASK, b, j) * inv0;
+    b -= lane > j ? l0 * y0 : 0.f;
+    const float y1 = __shfl_sync(FULL_MASK, b, j + 1) * inv1;
+    b -= lane > j + 1 ? l1 * y1 : 0.f;
+    // this lane's column of the factor starts in this pair's block: remember where (backward substitution reads mycol[row])
+    if ((lane >> 1) == (j >> 1)) mycol_off = (int)(P0 - Lc) + ((lane & 1) ? pc - (lane + 1) : -(lane + 2));
+    if (lane > j && lane < ne) {
+      P0[lane - j - 2] = l0;                            // lane j+1 lands on P0[-1]
+      if (lane > j + 1) P0[pc + lane - j - 2] = l1;
+    }
+    __syncwarp();
+    const float* P1 = P0 + pc;
+#pragma unroll
+    for (int k0 = 2; k0 < N; k0 += 4) {
+      if (k0 - 2 >= cnt) break;
+      const float4 p = *reinterpret_cast<const float4*>(P0 + (k0 - 2));
+      const float4 q = *reinterpret_cast<const float4*>(P1 + (k0 - 2));
+      a[k0 - 2] = a[k0] - l0 * p.x - l1 * q.x;
+      if (k0 + 1 < N) a[k0 - 1] = a[k0 + 1] - l0 * p.y - l1 * q.y;
+      if (k0 + 2 < N) a[k0] = a[k0 + 2] - l0 * p.z - l1 * q.z;
+      if (k0 + 3 < N) a[k0 + 1] = a[k0 + 3] - l0 * p.w - l1 * q.w;
+    }
+    P0 += 4 + 2 * pc;
+    cnt -= 2;
+  }
+  // backward substitution: L[j][lane] for lane < j is mycol[j]
+  const float* mycol = Lc + mycol_off;
+  b *= myinv;  // y
+#pragma unroll 1
+  for (int j = n - 1; j >= 0; j--) {
+    const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
+    const float ltj = lane < j ? mycol[j] : 0.f;
+    b -= ltj * xj;
+  }
+  return b * myinv;
+}
+// Solve only, on the factor chol_solve_rows_pair left in Lc (same operations in the same order as the folded substitutions).
+__device__ __forceinline__ float chol_subst_pair(int n, float b, const float* Lc, int lane, float myinv, int mycol_off) {
+  const int ne = (n + 1) & ~1;
+  int cnt = ne - 2;
+  const float* P0 = Lc + 4;
+#pragma unroll 1
+  for (int j = 0; j < ne; j += 2) {
+    const int pc = (cnt + 3) & ~3;
+    const float l0 = (lane > j && lane < ne) ? P0[lane - j - 2] : 0.f;
+    const float l1 = (lane > j + 1 && lane < ne) ? P0[pc + lane - j - 2] : 0.f;
+    const float y0 = __shfl_sync(FULL_MASK, b * myinv, j);
+    b -= lane > j ? l0 * y0 : 0.f;
+    const float y1 = __shfl_sync(FULL_MASK, b * myinv, j + 1);
+    b -= lane > j + 1 ? l1 * y1 : 0.f;
+    P0 += 4 + 2 * pc;
+    cnt -= 2;
+  }
+  const float* mycol = Lc + mycol_off;
+  b *= myinv;
+#pragma unroll 1
+  for (int j = n - 1; j >= 0; j--) {
+    const float xj = __shfl_sync(FULL_MASK, b * myinv, j);
+    const float ltj = lane < j ? mycol[j] : 0.f;
+    b -= ltj * xj;
+  }
+  return b * myinv;
+}
+
 // The same factor + solve with the column loop fully unrolled: row registers are addressed statically (no rotation), column slots and
 // chunk counts are compile-time, the per-column bookkeeping of the rolled loop (offsets, trip counts, register moves: ~40 of its ~65
 // instructions per column) disappears.  ~1000 instructions for N = 28 instead of ~2300 -- and yet measured SLOWER on B200 (humanoid

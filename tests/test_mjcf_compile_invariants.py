@@ -168,3 +168,40 @@ def test_geom_bounds_against_support_sampling(model):
     assert (np.abs(pts - c) <= h * (1 + 1e-9) + 1e-12).all(), g
     assert (np.abs(pts - c).max(axis=0) >= h * 0.98 - 1e-9).all(), g
   assert checked >= m.ngeom - 2
+
+
+def test_mesh_files_obj_and_stl_compile_like_inline_vertices(tmp_path):
+  """<mesh file=...> (OBJ, binary STL, ASCII STL under <compiler meshdir>) gives the same asset tables as the same vertices inline;
+  a default-class scale applies; a missing file only breaks the model when a colliding geom needs it."""
+  import struct
+
+  from mujoco_warp_b200._src import mjcf
+
+  v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [0.3, 0.3, 0.1], [1, 1, 1]], dtype=np.float64)
+  from mujoco_warp_b200._src.mesh import convex_hull
+
+  _, tris = convex_hull(v)
+  d = tmp_path / "assets"
+  d.mkdir()
+  (d / "w.obj").write_text("".join(f"v {a} {b} {c}\n" for a, b, c in v) + "".join(f"f {a + 1}/1/1 {b + 1}/1/1 {c + 1}/1/1\n" for a, b, c in tris))
+  with open(d / "w_bin.stl", "wb") as f:
+    f.write(b"\0" * 80 + struct.pack("<I", len(tris)))
+    for t in tris:
+      f.write(struct.pack("<12fH", 0, 0, 0, *v[t].reshape(-1), 0))
+  (d / "w_ascii.stl").write_text("solid w\n" + "".join("facet normal 0 0 0\nouter loop\n" + "".join(f"vertex {a} {b} {c}\n" for a, b, c in v[t]) + "endloop\nendfacet\n" for t in tris) + "endsolid w\n")
+  body = '<worldbody><geom type="plane" size="0 0 .05"/><body pos="0 0 0.2"><freejoint/><geom type="mesh" mesh="{}"/></body></worldbody>'
+  inline = mjcf.load_string(f'<mujoco><asset><mesh name="w" vertex="{" ".join(str(x) for x in v.reshape(-1))}" scale="0.1 0.1 0.1"/></asset>{body.format("w")}</mujoco>')
+  for fn in ("w.obj", "w_bin.stl", "w_ascii.stl"):
+    p = tmp_path / f"m_{fn}.xml"
+    p.write_text(f'<mujoco><compiler meshdir="assets"/><default><default class="c"><mesh scale="0.1 0.1 0.1"/></default></default>'
+                 f'<asset><mesh name="w" class="c" file="{fn}"/></asset>{body.format("w")}</mujoco>')
+    m = mjcf.load(str(p))
+    assert m.nmesh == 1 and int(m.mesh_vertnum[0]) == (7 if fn.endswith("obj") else len(np.unique(v[np.unique(tris)], axis=0)))
+    np.testing.assert_allclose(m.body_mass, inline.body_mass, rtol=1e-9)
+    np.testing.assert_allclose(m.body_inertia, inline.body_inertia, rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(m.geom_rbound, inline.geom_rbound, rtol=1e-9)
+    np.testing.assert_allclose(np.sort(m.mesh_polynormal, axis=0), np.sort(inline.mesh_polynormal, axis=0), atol=1e-9)
+  p = tmp_path / "missing.xml"
+  p.write_text(f'<mujoco><compiler meshdir="assets"/><asset><mesh name="w" file="nope.obj"/></asset>{body.format("w")}</mujoco>')
+  with pytest.raises(NotImplementedError):
+    mjcf.load(str(p))
