@@ -1041,6 +1041,69 @@ def compile_xml(root):
   m.light_pos = np.array([l["pos"] for l in lights]).reshape(m.nlight, 3)
   m.light_dir = np.array([l["dir"] for l in lights]).reshape(m.nlight, 3)
 
+  # ---- tendons: fixed tendons (linear combinations of scalar joint positions); spatial tendons are not compiled
+  tens = []
+  te = root.find("tendon")
+  for child in (list(te) if te is not None else []):
+    if child.tag != "fixed":
+      raise NotImplementedError(f"<tendon><{child.tag}>: only fixed tendons are supported")
+    a = dflt.resolve("tendon", child.get("class", "main"))
+    a.update(child.attrib)
+    path = []
+    for w in child:
+      if w.tag != "joint":
+        raise NotImplementedError(f"fixed tendon element <{w.tag}>")
+      j = m.names.joint.index(w.get("joint"))
+      if m.jnt_type[j] not in (C.JNT_SLIDE, C.JNT_HINGE):
+        raise ValueError("fixed tendons combine slide / hinge joints")
+      path.append((j, float(w.get("coef", 1.0))))
+    if float(a.get("armature", 0.0)) != 0.0:
+      raise NotImplementedError("tendon armature is not supported")
+    rng = _vec(a.get("range"), 2, default=[0, 0])
+    lim = a.get("limited", "auto")
+    sl = _vec(a.get("springlength"), default=[-1.0])
+    tens.append(dict(
+      name=a.get("name", f"tendon{len(tens)}"), path=path, range=rng,
+      limited=(lim == "true") or (lim == "auto" and compiler["autolimits"] and "range" in a),
+      margin=float(a.get("margin", 0.0)), stiffness=float(a.get("stiffness", 0.0)), damping=float(a.get("damping", 0.0)),
+      frictionloss=float(a.get("frictionloss", 0.0)), springlength=(sl if sl.size == 2 else np.array([sl[0], sl[0]])),
+      solref_lim=_vec(a.get("solreflimit", "0.02 1")), solimp_lim=_vec(a.get("solimplimit", "0.9 0.95 0.001 0.5 2")),
+      solref_fri=_vec(a.get("solreffriction", "0.02 1")), solimp_fri=_vec(a.get("solimpfriction", "0.9 0.95 0.001 0.5 2")),
+      actfrcrange=_vec(a.get("actuatorfrcrange"), 2, default=[0, 0]),
+      actfrclimited=(a.get("actuatorfrclimited", "auto") == "true") or (a.get("actuatorfrclimited", "auto") == "auto" and compiler["autolimits"] and "actuatorfrcrange" in a),
+    ))
+  nt = len(tens)
+  m.ntendon = nt
+  m.names.tendon = [t["name"] for t in tens]
+  m.tendon_num = np.array([len(t["path"]) for t in tens], dtype=np.int32)
+  m.tendon_adr = (np.concatenate(([0], np.cumsum(m.tendon_num)[:-1])) if nt else np.zeros(0)).astype(np.int32)
+  m.nwrap = int(m.tendon_num.sum()) if nt else 0
+  m.wrap_type = np.full(m.nwrap, C.WRAP_JOINT, dtype=np.int32)
+  m.wrap_objid = np.array([j for t in tens for j, _ in t["path"]], dtype=np.int32)
+  m.wrap_prm = np.array([c for t in tens for _, c in t["path"]], dtype=np.float64)
+  m.tendon_limited = np.array([t["limited"] for t in tens], dtype=bool)
+  m.tendon_range = np.array([t["range"] for t in tens], dtype=np.float64).reshape(nt, 2)
+  m.tendon_margin = np.array([t["margin"] for t in tens], dtype=np.float64)
+  m.tendon_stiffness = np.array([t["stiffness"] for t in tens], dtype=np.float64)
+  m.tendon_damping = np.array([t["damping"] for t in tens], dtype=np.float64)
+  m.tendon_armature = np.zeros(nt)
+  m.tendon_frictionloss = np.array([t["frictionloss"] for t in tens], dtype=np.float64)
+  m.tendon_lengthspring = np.array([t["springlength"] for t in tens], dtype=np.float64).reshape(nt, 2)  # (-1, -1) -> length0 in _set_const
+  m.tendon_solref_lim = np.array([t["solref_lim"] for t in tens], dtype=np.float64).reshape(nt, 2)
+  m.tendon_solimp_lim = np.array([t["solimp_lim"] for t in tens], dtype=np.float64).reshape(nt, 5)
+  m.tendon_solref_fri = np.array([t["solref_fri"] for t in tens], dtype=np.float64).reshape(nt, 2)
+  m.tendon_solimp_fri = np.array([t["solimp_fri"] for t in tens], dtype=np.float64).reshape(nt, 5)
+  m.tendon_actfrclimited = np.array([t["actfrclimited"] for t in tens], dtype=bool)
+  m.tendon_actfrcrange = np.array([t["actfrcrange"] for t in tens], dtype=np.float64).reshape(nt, 2)
+  m.tendon_length0 = np.zeros(nt)
+  m.tendon_invweight0 = np.zeros(nt)
+  # sparsity of the tendon Jacobian (MjModel ten_J_rownnz / rowadr / colind): the dofs of a fixed tendon's joints, ascending
+  rows = [sorted({int(m.jnt_dofadr[j]) for j, _ in t["path"]}) for t in tens]
+  m.ten_J_rownnz = np.array([len(r) for r in rows], dtype=np.int32)
+  m.ten_J_rowadr = (np.concatenate(([0], np.cumsum(m.ten_J_rownnz)[:-1])) if nt else np.zeros(0)).astype(np.int32)
+  m.ten_J_colind = np.array([c for r in rows for c in r], dtype=np.int32)
+  m.nJten = int(m.ten_J_rownnz.sum()) if nt else 0
+
   # ---- actuators
   acts = []
   ae = root.find("actuator")
@@ -1076,10 +1139,14 @@ def compile_xml(root):
   dyn_names = {"none": C.DYN_NONE, "integrator": C.DYN_INTEGRATOR, "filter": C.DYN_FILTER, "filterexact": C.DYN_FILTEREXACT}
   for i, (tag, a) in enumerate(acts):
     m.names.actuator.append(a.get("name", f"actuator{i}"))
-    if "joint" not in a:
-      raise NotImplementedError(f"actuator transmission other than joint is not supported: {a}")
-    m.actuator_trntype[i] = C.TRN_JOINT
-    m.actuator_trnid[i, 0] = m.names.joint.index(a["joint"])
+    if "tendon" in a:
+      m.actuator_trntype[i] = C.TRN_TENDON
+      m.actuator_trnid[i, 0] = m.names.tendon.index(a["tendon"])
+    elif "joint" in a:
+      m.actuator_trntype[i] = C.TRN_JOINT
+      m.actuator_trnid[i, 0] = m.names.joint.index(a["joint"])
+    else:
+      raise NotImplementedError(f"actuator transmission other than joint / tendon is not supported: {a}")
     gear = _vec(a.get("gear"), 6, default=[1, 0, 0, 0, 0, 0])
     m.actuator_gear[i] = gear
     m.actuator_gainprm[i, 0] = 1.0
@@ -1201,7 +1268,7 @@ def compile_xml(root):
   ee = root.find("equality")
   if ee is not None:
     for child in ee:
-      if child.tag not in ("connect", "weld", "joint"):
+      if child.tag not in ("connect", "weld", "joint", "tendon"):
         raise NotImplementedError(f"equality type <{child.tag}> is not supported")
       a = dflt.resolve("equality", child.get("class", "main"))
       a.update(child.attrib)
@@ -1210,6 +1277,11 @@ def compile_xml(root):
         etype, otype = C.EQ_JOINT, C.OBJ_JOINT
         o1 = m.names.joint.index(a["joint1"])
         o2 = m.names.joint.index(a["joint2"]) if "joint2" in a else -1
+        data[:5] = _vec(a.get("polycoef", "0 1 0 0 0"))
+      elif child.tag == "tendon":
+        etype, otype = C.EQ_TENDON, C.OBJ_TENDON
+        o1 = m.names.tendon.index(a["tendon1"])
+        o2 = m.names.tendon.index(a["tendon2"]) if "tendon2" in a else -1
         data[:5] = _vec(a.get("polycoef", "0 1 0 0 0"))
       else:
         if "site1" in a:
@@ -1238,7 +1310,7 @@ def compile_xml(root):
   m.eq_data = np.array([e["data"] for e in eqs], dtype=np.float64).reshape(m.neq, 11)
 
   # unused families (sizes only)
-  m.ntendon = m.nflex = m.nhfield = 0
+  m.nflex = m.nhfield = 0
 
   # ---- mesh tables (reference types.py:1214-1235), concatenated over the assets
   m.nmesh = len(meshes)
@@ -1268,6 +1340,7 @@ def compile_xml(root):
   S = C
   table = {
     "jointpos": (S.SENS_JOINTPOS, "joint", 1, 0, 1), "jointvel": (S.SENS_JOINTVEL, "joint", 1, 0, 2),
+    "tendonpos": (S.SENS_TENDONPOS, "tendon", 1, 0, 1), "tendonvel": (S.SENS_TENDONVEL, "tendon", 1, 0, 2),
     "actuatorpos": (S.SENS_ACTUATORPOS, "actuator", 1, 0, 1), "actuatorvel": (S.SENS_ACTUATORVEL, "actuator", 1, 0, 2),
     "actuatorfrc": (S.SENS_ACTUATORFRC, "actuator", 1, 0, 3), "jointactuatorfrc": (S.SENS_JOINTACTFRC, "joint", 1, 0, 3),
     "jointlimitpos": (S.SENS_JOINTLIMITPOS, "joint", 1, 0, 1), "jointlimitvel": (S.SENS_JOINTLIMITVEL, "joint", 1, 0, 2),
@@ -1282,7 +1355,7 @@ def compile_xml(root):
     "framequat": (S.SENS_FRAMEQUAT, "obj", 4, 3, 1), "framelinvel": (S.SENS_FRAMELINVEL, "obj", 3, 0, 2), "frameangvel": (S.SENS_FRAMEANGVEL, "obj", 3, 0, 2),
     "framelinacc": (S.SENS_FRAMELINACC, "obj", 3, 0, 3), "frameangacc": (S.SENS_FRAMEANGACC, "obj", 3, 0, 3),
   }
-  objkind = {"joint": (C.OBJ_JOINT, "joint"), "actuator": (C.OBJ_ACTUATOR, "actuator"), "site": (C.OBJ_SITE, "site"), "body": (C.OBJ_BODY, "body")}
+  objkind = {"tendon": (C.OBJ_TENDON, "tendon"), "joint": (C.OBJ_JOINT, "joint"), "actuator": (C.OBJ_ACTUATOR, "actuator"), "site": (C.OBJ_SITE, "site"), "body": (C.OBJ_BODY, "body")}
   objtypes = {"body": (C.OBJ_BODY, "body"), "xbody": (C.OBJ_XBODY, "body"), "geom": (C.OBJ_GEOM, "geom"), "site": (C.OBJ_SITE, "site"), "camera": (C.OBJ_CAMERA, "camera")}
   sens, unsupported = [], []
   nsens = root.find("sensor")
@@ -1486,6 +1559,14 @@ def _set_eq_data0(m, kin):
         data[6:10] = quat_mul(np.array([q1[0], -q1[1], -q1[2], -q1[3]]), kin.xquat[o2])
 
 
+def _tendon_row(m, t):
+  """Dense moment row (nv) of fixed tendon t."""
+  J = np.zeros(m.nv)
+  for k in range(m.tendon_adr[t], m.tendon_adr[t] + m.tendon_num[t]):
+    J[m.jnt_dofadr[m.wrap_objid[k]]] += m.wrap_prm[k]
+  return J
+
+
 def _set_const(m):
   kin = kinematics_np(m, m.qpos0)
   nv = m.nv
@@ -1516,10 +1597,19 @@ def _set_const(m):
         m.dof_invweight0[d : d + 3] = dg[d : d + 3].mean()
       else:
         m.dof_invweight0[d] = dg[d]
+    for t in range(getattr(m, "ntendon", 0)):  # fixed tendons: length and moment are linear in the joint positions
+      J = _tendon_row(m, t)
+      m.tendon_length0[t] = sum(m.wrap_prm[k] * m.qpos0[m.jnt_qposadr[m.wrap_objid[k]]] for k in range(m.tendon_adr[t], m.tendon_adr[t] + m.tendon_num[t]))
+      m.tendon_invweight0[t] = float(J @ Minv @ J)
+      if m.tendon_lengthspring[t, 0] == -1.0 and m.tendon_lengthspring[t, 1] == -1.0:
+        m.tendon_lengthspring[t] = m.tendon_length0[t]
     for i in range(m.nu):
       mom = np.zeros(nv)
       j = m.actuator_trnid[i, 0]
-      mom[m.jnt_dofadr[j]] = m.actuator_gear[i, 0]
+      if m.actuator_trntype[i] == C.TRN_TENDON:
+        mom = m.actuator_gear[i, 0] * _tendon_row(m, j)
+      else:
+        mom[m.jnt_dofadr[j]] = m.actuator_gear[i, 0]
       m.actuator_acc0[i] = np.linalg.norm(Minv @ mom)
   else:
     m.stat = SimpleNamespace(meaninertia=1.0)

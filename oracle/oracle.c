@@ -25,8 +25,9 @@ enum { GEOM_PLANE = 0, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, G
 enum { INT_EULER = 0, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST };
 enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
 enum { SOL_CG = 1, SOL_NEWTON = 2 };
-enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
-enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_LIMIT_JOINT = 3, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6, CNSTR_CONTACT_ELLIPTIC = 7 };
+enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2, EQ_TENDON = 3 };
+enum { TRN_JOINT = 0, TRN_TENDON = 3 };
+enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_FRICTION_TENDON = 2, CNSTR_LIMIT_JOINT = 3, CNSTR_LIMIT_TENDON = 4, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6, CNSTR_CONTACT_ELLIPTIC = 7 };
 enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
 enum { CAM_FIXED = 0, CAM_TRACK, CAM_TRACKCOM, CAM_TARGETBODY, CAM_TARGETBODYCOM };
 enum { GAIN_FIXED = 0, GAIN_AFFINE = 1 };
@@ -43,7 +44,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
 #define MODEL_INTS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(nmocap) X(njnt) X(ngeom) X(nsite) X(ncam) X(nlight) X(nC) X(ntree) X(nJmom) \
   X(nxn_npair) X(nlimit) X(nlimit_ball) X(neq) X(nmaxpyramid) X(integrator) X(cone) X(solver) X(iterations) X(ls_iterations) \
-  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations) X(nsensor) X(nsensordata) X(nmesh) X(na)
+  X(disableflags) X(enableflags) X(broadphase) X(broadphase_filter) X(ccd_iterations) X(epa_iterations) X(nsensor) X(nsensordata) X(nmesh) X(na) X(ntendon) X(nJten)
 #define MODEL_REALS(X) X(timestep) X(tolerance) X(ls_tolerance) X(impratio_invsqrt) X(meaninertia) X(ccd_tolerance)
 #define MODEL_IARRS(X) \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) \
@@ -52,7 +53,8 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(tree_dofadr) X(tree_dofnum) X(qLD_block_adr) \
   X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
-  X(actuator_dyntype) X(actuator_actadr) X(actuator_actnum) X(actuator_actlimited) X(actuator_actearly) \
+  X(actuator_dyntype) X(actuator_actadr) X(actuator_actnum) X(actuator_actlimited) X(actuator_actearly) X(actuator_trntype) \
+  X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind) X(tendon_adr) X(tendon_num) X(wrap_objid) X(tendon_limited) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
   X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim) \
@@ -68,7 +70,9 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(actuator_ctrlrange) X(actuator_forcerange) X(cam_pos) X(cam_quat) X(cam_poscom0) X(cam_pos0) X(cam_mat0) \
   X(light_pos) X(light_dir) X(light_poscom0) X(light_pos0) X(light_dir0) X(site_pos) X(site_quat) \
   X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap) \
-  X(sensor_cutoff) X(site_size) X(mesh_vert) X(mesh_polynormal) X(actuator_dynprm) X(actuator_actrange)
+  X(sensor_cutoff) X(site_size) X(mesh_vert) X(mesh_polynormal) X(actuator_dynprm) X(actuator_actrange) \
+  X(wrap_prm) X(tendon_range) X(tendon_margin) X(tendon_stiffness) X(tendon_damping) X(tendon_frictionloss) X(tendon_lengthspring) \
+  X(tendon_length0) X(tendon_invweight0) X(tendon_solref_lim) X(tendon_solimp_lim) X(tendon_solref_fri) X(tendon_solimp_fri)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -80,7 +84,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(qfrc_constraint) X(cacc) X(cfrc_int) X(cfrc_ext) X(sensordata) X(subtree_linvel) X(subtree_angmom) \
   X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
   X(con_dist) X(con_pos) X(con_frame) X(con_includemargin) X(con_friction) X(con_solref) X(con_solreffriction) X(con_solimp) \
-  X(act) X(act_dot)
+  X(act) X(act_dot) X(ten_length) X(ten_J) X(ten_velocity)
 #define DATA_IARRS(X) \
   X(ne) X(nf) X(nl) X(nefc) X(ncon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
   X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(con_dim) X(con_geom) X(con_efc_address) X(con_geomcollisionid) \
@@ -343,7 +347,7 @@ static void make_view(const OrcModel* m, const OrcData* d, int w, W* v) {
   R(efc_type, njm); R(efc_id, njm); R(efc_state, njm); R(moment_rownnz, nu); R(moment_rowadr, nu); R(moment_colind, m->nJmom);
   R(con_dim, ncm); R(con_geom, 2 * ncm); R(con_efc_address, m->nmaxpyramid * ncm); R(con_geomcollisionid, ncm);
   R(eq_active, m->neq);
-  R(act, m->na); R(act_dot, m->na);
+  R(act, m->na); R(act_dot, m->na); R(ten_length, m->ntendon); R(ten_J, m->nJten); R(ten_velocity, m->ntendon);
   R(cfrc_ext, 6 * nb); R(sensordata, m->nsensordata); R(subtree_linvel, 3 * nb); R(subtree_angmom, 3 * nb);
 #undef R
 }
@@ -615,11 +619,39 @@ static void mul_m(const OrcModel* m, const real* Mcsr, const real* vec, real* re
   }
 }
 
-/* ------------------------------------------------------------------ transmission (smooth.py:2288-2396; joint transmission only) */
+/* ------------------------------------------------------------------ tendon (smooth.py:3658-3692, 4197; fixed tendons: joint wraps) */
+static void tendon(W* w) {
+  const OrcModel* m = w->m;
+  for (int t = 0; t < m->ntendon; t++) w->ten_length[t] = 0;
+  for (int i = 0; i < m->nJten; i++) w->ten_J[i] = 0;
+  for (int t = 0; t < m->ntendon; t++)
+    for (int k = m->tendon_adr[t]; k < m->tendon_adr[t] + m->tendon_num[t]; k++) {
+      const int j = m->wrap_objid[k], dof = m->jnt_dofadr[j];
+      const real prm = m->wrap_prm[k];
+      w->ten_length[t] += prm * w->qpos[m->jnt_qposadr[j]];
+      for (int c = 0; c < m->ten_J_rownnz[t]; c++)
+        if (m->ten_J_colind[m->ten_J_rowadr[t] + c] == dof) { w->ten_J[m->ten_J_rowadr[t] + c] = prm; break; }
+    }
+}
+/* dense row (nv) of tendon t's Jacobian times scale, added into out */
+static void tendon_row(const W* w, int t, real scale, real* out) {
+  const OrcModel* m = w->m;
+  for (int c = 0; c < m->ten_J_rownnz[t]; c++) { const int s = m->ten_J_rowadr[t] + c; out[m->ten_J_colind[s]] += scale * w->ten_J[s]; }
+}
+
+/* ------------------------------------------------------------------ transmission (smooth.py:2288-2396, :2508-2525; joint and tendon transmission) */
 static void transmission(W* w) {
   const OrcModel* m = w->m;
   int nnz = 0;
   for (int a = 0; a < m->nu; a++) {
+    if (m->actuator_trntype[a] == TRN_TENDON) {
+      const int t = m->actuator_trnid[2 * a];
+      const real gear0 = m->actuator_gear[6 * a];
+      w->actuator_length[a] = w->ten_length[t] * gear0;
+      w->moment_rownnz[a] = m->ten_J_rownnz[t]; w->moment_rowadr[a] = nnz;
+      for (int c = 0; c < m->ten_J_rownnz[t]; c++) { w->moment_colind[nnz] = m->ten_J_colind[m->ten_J_rowadr[t] + c]; w->actuator_moment[nnz] = w->ten_J[m->ten_J_rowadr[t] + c] * gear0; nnz++; }
+      continue;
+    }
     int j = m->actuator_trnid[2 * a], t = m->jnt_type[j], qa = m->jnt_qposadr[j], va = m->jnt_dofadr[j];
     const real* gear = m->actuator_gear + 6 * a;
     if (t == JNT_SLIDE || t == JNT_HINGE) {
@@ -1726,11 +1758,33 @@ static inline void quat_mul_axis(const real* q, const real* a, real* o) { /* mat
 /* constraint.py:156 connect (3 rows), :966 weld (6 rows), :500 joint (1 row); body-based anchors only */
 static int equality_rows(W* w, int nefc) {
   const OrcModel* m = w->m; const int nv = m->nv, njmax = w->njmax;
-  for (int pass = 0; pass < 3; pass++) for (int e = 0; e < m->neq; e++) { /* launch order: connect, weld, joint */
+  for (int pass = 0; pass < 4; pass++) for (int e = 0; e < m->neq; e++) { /* launch order: connect, weld, joint, tendon */
     int type = m->eq_type[e];
-    if (type != (pass == 0 ? EQ_CONNECT : pass == 1 ? EQ_WELD : EQ_JOINT) || !w->eq_active[e]) continue;
+    if (type != (pass == 0 ? EQ_CONNECT : pass == 1 ? EQ_WELD : pass == 2 ? EQ_JOINT : EQ_TENDON) || !w->eq_active[e]) continue;
     const real* data = m->eq_data + 11 * e; const real* solref = m->eq_solref + 2 * e; const real* solimp = m->eq_solimp + 5 * e;
     int o1 = m->eq_obj1id[e], o2 = m->eq_obj2id[e];
+    if (type == EQ_TENDON) { /* constraint.py:642-826 */
+      w->ne[0] += 1;
+      int efcid = nefc; nefc += 1;
+      if (efcid >= njmax) continue;
+      real* J = w->efc_J + (size_t)efcid * nv, pos, invweight, deriv = 0, Jqvel = 0;
+      for (int i = 0; i < nv; i++) J[i] = 0;
+      const real pos1 = w->ten_length[o1] - m->tendon_length0[o1];
+      if (o2 > -1) {
+        invweight = m->tendon_invweight0[o1] + m->tendon_invweight0[o2];
+        const real dif = w->ten_length[o2] - m->tendon_length0[o2], dif2 = dif * dif, dif3 = dif2 * dif, dif4 = dif3 * dif;
+        pos = pos1 - (data[0] + data[1] * dif + data[2] * dif2 + data[3] * dif3 + data[4] * dif4);
+        deriv = data[1] + 2 * data[2] * dif + 3 * data[3] * dif2 + 4 * data[4] * dif3;
+      } else {
+        invweight = m->tendon_invweight0[o1];
+        pos = pos1 - data[0];
+      }
+      tendon_row(w, o1, 1, J);
+      if (deriv != 0) tendon_row(w, o2, -deriv, J);
+      for (int i = 0; i < nv; i++) Jqvel += J[i] * w->qvel[i];
+      efc_row(w, efcid, pos, pos, invweight, solref, solimp, 0, Jqvel, 0, CNSTR_EQUALITY, e);
+      continue;
+    }
     if (type == EQ_JOINT) {
       w->ne[0] += 1;
       int efcid = nefc; nefc += 1;
@@ -1848,6 +1902,17 @@ static void make_constraint(W* w) {
       w->efc_J[efcid * nv + d] = 1;
       efc_row(w, efcid, 0, 0, m->dof_invweight0[d], m->dof_solref + 2 * d, m->dof_solimp + 5 * d, 0, w->qvel[d], m->dof_frictionloss[d], CNSTR_FRICTION_DOF, d);
     }
+    for (int t = 0; t < m->ntendon; t++) { /* constraint.py:1867-1985 */
+      if (m->tendon_frictionloss[t] <= 0) continue;
+      w->nf[0]++;
+      int efcid = nefc++;
+      if (efcid >= njmax) continue;
+      real* J = w->efc_J + (size_t)efcid * nv, Jqvel = 0;
+      for (int i = 0; i < nv; i++) J[i] = 0;
+      tendon_row(w, t, 1, J);
+      for (int i = 0; i < nv; i++) Jqvel += J[i] * w->qvel[i];
+      efc_row(w, efcid, 0, 0, m->tendon_invweight0[t], m->tendon_solref_fri + 2 * t, m->tendon_solimp_fri + 5 * t, 0, Jqvel, m->tendon_frictionloss[t], CNSTR_FRICTION_TENDON, t);
+    }
   }
   /* joint limits: ball (constraint.py:2107) first, then slide/hinge (:1990) -- the reference's launch order */
   if (!(m->disableflags & DSBL_LIMIT)) {
@@ -1888,6 +1953,22 @@ static void make_constraint(W* w) {
       for (int i = 0; i < nv; i++) w->efc_J[efcid * nv + i] = 0;
       w->efc_J[efcid * nv + d] = J;
       efc_row(w, efcid, pos, pos, m->dof_invweight0[d], m->jnt_solref + 2 * j, m->jnt_solimp + 5 * j, margin, J * w->qvel[d], 0, CNSTR_LIMIT_JOINT, j);
+    }
+    for (int t = 0; t < m->ntendon; t++) { /* constraint.py:2243-2375 */
+      if (!m->tendon_limited[t]) continue;
+      const real length = w->ten_length[t], margin = m->tendon_margin[t];
+      const real dist_min = length - m->tendon_range[2 * t], dist_max = m->tendon_range[2 * t + 1] - length;
+      const real pos = rmin(dist_min, dist_max) - margin;
+      if (!(pos < 0)) continue;
+      w->nl[0]++;
+      int efcid = nefc++;
+      if (efcid >= njmax) continue;
+      const real scl = (dist_min < dist_max ? (real)1 : (real)0) * 2 - 1;
+      real* J = w->efc_J + (size_t)efcid * nv, Jqvel = 0;
+      for (int i = 0; i < nv; i++) J[i] = 0;
+      tendon_row(w, t, scl, J);
+      for (int i = 0; i < nv; i++) Jqvel += J[i] * w->qvel[i];
+      efc_row(w, efcid, pos, pos, m->tendon_invweight0[t], m->tendon_solref_lim + 2 * t, m->tendon_solimp_lim + 5 * t, margin, Jqvel, 0, CNSTR_LIMIT_TENDON, t);
     }
   }
   /* contacts (constraint.py:2641 init, :3751 dense jac, :4197 update) */
@@ -1964,6 +2045,11 @@ static void fwd_velocity(W* w) {
     for (int i = 0; i < w->moment_rownnz[a]; i++) { int s = w->moment_rowadr[a] + i; vel += w->actuator_moment[s] * w->qvel[w->moment_colind[s]]; }
     w->actuator_velocity[a] = vel;
   }
+  for (int t = 0; t < m->ntendon; t++) { /* forward.py:706-729 */
+    real vel = 0;
+    for (int c = 0; c < m->ten_J_rownnz[t]; c++) { const int s = m->ten_J_rowadr[t] + c; vel += w->ten_J[s] * w->qvel[m->ten_J_colind[s]]; }
+    w->ten_velocity[t] = vel;
+  }
   /* com_vel (smooth.py:2179-2285) */
   memset(w->cvel, 0, 6 * sizeof(real));
   for (int b = 1; b < nb; b++) {
@@ -2024,6 +2110,15 @@ static void fwd_velocity(W* w) {
         real damping = m->dof_damping[d + k];
         if (damping != 0 && !dsbl_damper) w->qfrc_damper[d + k] = -w->qvel[d + k] * damping;
       }
+    }
+    for (int t = 0; t < m->ntendon; t++) { /* passive.py:208-272 (polynomial terms zero) */
+      const real stiffness = m->tendon_stiffness[t], damping = m->tendon_damping[t];
+      if (stiffness != 0 && !dsbl_spring) {
+        const real length = w->ten_length[t], lower = m->tendon_lengthspring[2 * t], upper = m->tendon_lengthspring[2 * t + 1];
+        const real x = length > upper ? length - upper : (length < lower ? length - lower : 0);
+        tendon_row(w, t, -x * stiffness, w->qfrc_spring);
+      }
+      if (damping != 0 && !dsbl_damper) tendon_row(w, t, -w->ten_velocity[t] * damping, w->qfrc_damper);
     }
     for (int d = 0; d < nv; d++) w->qfrc_passive[d] = w->qfrc_spring[d] + w->qfrc_damper[d];
   }
@@ -2573,6 +2668,15 @@ static void implicitfast(W* w) {
   }
   if (!(m->disableflags & DSBL_DAMPER))
     for (int d = 0; d < nv; d++) Mi[m->M_rowadr[d] + m->M_rownnz[d] - 1] += m->timestep * m->dof_damping[d];
+  if (!(m->disableflags & DSBL_DAMPER)) /* derivative.py:262-318: tendon damping, entries of the M sparsity pattern only */
+    for (int t = 0; t < m->ntendon; t++) {
+      if (m->tendon_damping[t] == 0) continue;
+      for (int a = 0; a < m->ten_J_rownnz[t]; a++) for (int b = 0; b < m->ten_J_rownnz[t]; b++) {
+        const int di = m->ten_J_colind[m->ten_J_rowadr[t] + a], dj = m->ten_J_colind[m->ten_J_rowadr[t] + b];
+        for (int k = 0; k < m->M_rownnz[di]; k++)
+          if (m->M_colind[m->M_rowadr[di] + k] == dj) Mi[m->M_rowadr[di] + k] += m->timestep * w->ten_J[m->ten_J_rowadr[t] + a] * w->ten_J[m->ten_J_rowadr[t] + b] * m->tendon_damping[t];
+      }
+    }
   factor_solve_i(w, Mi, NULL, L, qacc, w->efc_Ma);
   advance(w, qacc);
   free(buf);
@@ -2868,6 +2972,7 @@ static void sensors(W* w, int stage) {
     real v[4] = {0, 0, 0, 0};
     switch (t) {
       case SENS_JOINTPOS: v[0] = w->qpos[m->jnt_qposadr[id]]; break;
+      case SENS_TENDONPOS: v[0] = w->ten_length[id]; break;
       case SENS_ACTUATORPOS: v[0] = w->actuator_length[id]; break;
       case SENS_BALLQUAT: { memcpy(v, w->qpos + m->jnt_qposadr[id], 4 * sizeof(real)); normalize4(v); break; }
       case SENS_FRAMEPOS: { /* sensor.py:377: relative to the reference frame when one is given */
@@ -2901,6 +3006,7 @@ static void sensors(W* w, int stage) {
             v[0] = t == SENS_JOINTLIMITPOS ? w->efc_pos[e] - w->efc_margin[e] : (t == SENS_JOINTLIMITVEL ? w->efc_vel[e] : w->efc_force[e]);
         break; }
       case SENS_JOINTVEL: v[0] = w->qvel[m->jnt_dofadr[id]]; break;
+      case SENS_TENDONVEL: v[0] = w->ten_velocity[id]; break;
       case SENS_ACTUATORVEL: v[0] = w->actuator_velocity[id]; break;
       case SENS_BALLANGVEL: memcpy(v, w->qvel + m->jnt_dofadr[id], 3 * sizeof(real)); break;
       case SENS_FRAMELINVEL: case SENS_FRAMEANGVEL: { /* sensor.py:1108-1293 without a reference frame */
@@ -2963,7 +3069,7 @@ static void sensors(W* w, int stage) {
 }
 
 static void forward_world(W* w) {
-  kinematics(w); com_pos(w); camlight(w); crb(w);
+  kinematics(w); com_pos(w); camlight(w); tendon(w); crb(w);
   collision(w); make_constraint(w); transmission(w);
   sensors(w, STAGE_POS);
   fwd_velocity(w); sensors(w, STAGE_VEL); fwd_actuation(w); fwd_acceleration(w);

@@ -115,6 +115,9 @@ def derived_tables(mjm):
     off += int(num) * int(num)
   nJmom = 0
   for i in range(mjm.nu):
+    if int(np.asarray(getattr(mjm, "actuator_trntype", np.zeros(mjm.nu)))[i]) == 3:  # tendon transmission: the tendon's Jacobian row
+      nJmom += int(mjm.ten_J_rownnz[mjm.actuator_trnid[i, 0]])
+      continue
     t = mjm.jnt_type[mjm.actuator_trnid[i, 0]]
     nJmom += {0: 6, 1: 3, 2: 1, 3: 1}[int(t)]
   nmaxcondim = int(mjm.geom_condim.max()) if ngeom else 1
@@ -141,6 +144,8 @@ def data_spec(mjm, tabs, nconmax, njmax):
   return {
     "time": (R, ()), "qpos": (R, (nq,)), "qvel": (R, (nv,)), "ctrl": (R, (nu,)), "qacc_warmstart": (R, (nv,)),
     "act": (R, (int(getattr(mjm, "na", 0)),)), "act_dot": (R, (int(getattr(mjm, "na", 0)),)),
+    "ten_length": (R, (int(getattr(mjm, "ntendon", 0)),)), "ten_velocity": (R, (int(getattr(mjm, "ntendon", 0)),)),
+    "ten_J": (R, (int(getattr(mjm, "nJten", 0)) if int(getattr(mjm, "ntendon", 0)) else 0,)),
     "qfrc_applied": (R, (nv,)), "xfrc_applied": (R, (nb, 6)), "qacc": (R, (nv,)),
     "mocap_pos": (R, (int(getattr(mjm, "nmocap", 0)), 3)), "mocap_quat": (R, (int(getattr(mjm, "nmocap", 0)), 4)),
     "xpos": (R, (nb, 3)), "xquat": (R, (nb, 4)), "xmat": (R, (nb, 3, 3)), "xipos": (R, (nb, 3)), "ximat": (R, (nb, 3, 3)),
@@ -252,6 +257,17 @@ class Oracle:
       setia(n, getattr(mjm, n, dflt) if nu else dflt)
     setra("actuator_dynprm", getattr(mjm, "actuator_dynprm", np.zeros((max(nu, 1), 10))) if nu else np.zeros(10))
     setra("actuator_actrange", getattr(mjm, "actuator_actrange", np.zeros((max(nu, 1), 2))) if nu else np.zeros(2))
+    nt = int(getattr(mjm, "ntendon", 0))
+    seti("ntendon", nt); seti("nJten", int(getattr(mjm, "nJten", 0)) if nt else 0)
+    setia("actuator_trntype", getattr(mjm, "actuator_trntype", np.zeros(max(nu, 1))) if nu else np.zeros(1))
+    for n in ("ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid", "tendon_limited"):
+      setia(n, np.asarray(getattr(mjm, n)).astype(np.int32) if nt else np.zeros(1, dtype=np.int32))
+    for n, k in (("wrap_prm", 1), ("tendon_range", 2), ("tendon_margin", 1), ("tendon_stiffness", 1), ("tendon_damping", 1), ("tendon_frictionloss", 1),
+                 ("tendon_lengthspring", 2), ("tendon_length0", 1), ("tendon_invweight0", 1), ("tendon_solref_lim", 2), ("tendon_solimp_lim", 5),
+                 ("tendon_solref_fri", 2), ("tendon_solimp_fri", 5)):
+      setra(n, getattr(mjm, n) if nt else np.zeros(k))
+    if nt and (np.any(np.asarray(getattr(mjm, "tendon_actfrclimited", 0))) or np.any(np.asarray(getattr(mjm, "tendon_armature", 0)) != 0)):
+      raise NotImplementedError("oracle: tendon actuator force limits / tendon armature are not restated")
     nsite = int(getattr(mjm, "nsite", 0))
     setia("site_type", getattr(mjm, "site_type", 2 * np.ones(nsite, dtype=np.int32)) if nsite else np.zeros(1, dtype=np.int32))
     setra("site_size", getattr(mjm, "site_size", 0.005 * np.ones((nsite, 3))) if nsite else np.zeros(3))

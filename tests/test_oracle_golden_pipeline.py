@@ -13,7 +13,7 @@ from tests import util
 GOLD_DIR = os.path.join(os.path.dirname(__file__), "golden")
 SCENES = sorted(os.path.basename(p)[len("pipeline_"):-4] for p in glob.glob(os.path.join(GOLD_DIR, "pipeline_*.npz")))
 
-SMOOTH = ["xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
+SMOOTH = ["ten_length", "ten_velocity", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
           "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert", "crb", "M", "actuator_length", "actuator_moment", "actuator_velocity", "cvel",
           "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper", "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth"]
 
@@ -43,6 +43,8 @@ def load_scene(name):
     mjm = mjcf.load_string(util.mesh_xml())
   elif name == "sensors":
     mjm = mjcf.load_string(util.sensor_xml())
+  elif name.startswith("tendons"):
+    mjm = mjcf.load_string(util.tendon_xml("implicitfast" if name.endswith("implicitfast") else "Euler"))
   elif name.startswith("actuators"):
     mjm = mjcf.load_string(util.actuators_xml({"actuators": "Euler", "actuators_implicitfast": "implicitfast", "actuators_rk4": "RK4"}[name]))
   elif name == "mixed_rk4":

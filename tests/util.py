@@ -401,3 +401,66 @@ def mesh_xml():
     <body pos="0.1 -0.59 0.137" euler="90 0 0"><freejoint/><geom name="cyl_on_cube" type="cylinder" size="0.04 0.06"/></body>
   </worldbody>
 </mujoco>"""
+
+
+def tendon_xml(integrator="Euler"):
+  """Fixed tendons on two planar arms and a gripper: a limited tendon (both sides reachable), tendon spring (with a dead band) and
+  damper, tendon friction loss, a tendon equality coupling two fingers (with a polynomial) and a single-tendon equality, tendon
+  transmissions (motor and position servo on a tendon), next to joint actuators, limits and a contact."""
+  return f"""
+<mujoco model="tendons">
+  <option timestep="0.004" integrator="{integrator}" iterations="50" ls_iterations="30"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05" condim="3"/>
+    <body name="a0" pos="0 0 0.6">
+      <joint name="a0" type="hinge" axis="0 1 0" damping="0.1" armature="0.01"/>
+      <geom type="capsule" fromto="0 0 0 0.2 0 0" size="0.03" mass="0.5"/>
+      <body name="a1" pos="0.2 0 0">
+        <joint name="a1" type="hinge" axis="0 1 0" damping="0.05" range="-120 120" limited="true"/>
+        <geom type="capsule" fromto="0 0 0 0.2 0 0" size="0.025" mass="0.3"/>
+        <body name="a2" pos="0.2 0 0">
+          <joint name="a2" type="hinge" axis="0 1 0" damping="0.05"/>
+          <geom type="capsule" fromto="0 0 0 0.15 0 0" size="0.02" mass="0.2"/>
+        </body>
+      </body>
+    </body>
+    <body name="palm" pos="-0.4 0 0.3">
+      <joint name="pz" type="slide" axis="0 0 1" damping="2"/>
+      <geom type="box" size="0.05 0.04 0.02" mass="0.4"/>
+      <body name="f1" pos="0.04 0 -0.02">
+        <joint name="f1" type="slide" axis="1 0 0" damping="1" range="-0.03 0.03" limited="true"/>
+        <geom type="box" size="0.008 0.03 0.04" pos="0 0 -0.04" mass="0.05"/>
+      </body>
+      <body name="f2" pos="-0.04 0 -0.02">
+        <joint name="f2" type="slide" axis="-1 0 0" damping="1" range="-0.03 0.03" limited="true"/>
+        <geom type="box" size="0.008 0.03 0.04" pos="0 0 -0.04" mass="0.05"/>
+      </body>
+    </body>
+    <body name="ball" pos="0.3 0.4 0.049"><freejoint/><geom type="sphere" size="0.05" mass="0.2"/></body>
+  </worldbody>
+  <tendon>
+    <fixed name="t_lim" limited="true" range="-0.4 0.5" margin="0.01" solreflimit="0.01 1"><joint joint="a0" coef="0.5"/><joint joint="a1" coef="-0.5"/></fixed>
+    <fixed name="t_spring" stiffness="8" damping="0.3" springlength="-0.1 0.2"><joint joint="a1" coef="1"/><joint joint="a2" coef="0.7"/></fixed>
+    <fixed name="t_fric" frictionloss="0.2" solreffriction="0.015 1"><joint joint="a2" coef="1.5"/></fixed>
+    <fixed name="t_f1"><joint joint="f1" coef="1"/></fixed>
+    <fixed name="t_f2"><joint joint="f2" coef="1"/></fixed>
+    <fixed name="t_grip" stiffness="20"><joint joint="f1" coef="1"/><joint joint="f2" coef="1"/></fixed>
+    <fixed name="t_lift" limited="true" range="-0.05 0.2"><joint joint="pz" coef="1"/></fixed>
+  </tendon>
+  <equality>
+    <tendon name="e_couple" tendon1="t_f1" tendon2="t_f2" polycoef="0 1 0.5 0 0" solref="0.01 1"/>
+    <tendon name="e_single" tendon1="t_lift" polycoef="0.02 0 0 0 0" active="false"/>
+  </equality>
+  <actuator>
+    <motor name="m_ten" tendon="t_lim" gear="2" ctrlrange="-1 1"/>
+    <position name="p_grip" tendon="t_grip" kp="40" kv="1"/>
+    <motor name="m_a0" joint="a0" gear="1.5"/>
+    <general name="g_lift" tendon="t_lift" gainprm="5" biastype="affine" biasprm="0 -10 -1"/>
+  </actuator>
+  <sensor>
+    <tendonpos name="tp" tendon="t_lim"/> <tendonvel name="tv" tendon="t_spring"/> <actuatorpos name="ap" actuator="p_grip"/> <actuatorfrc name="af" actuator="m_ten"/>
+  </sensor>
+  <keyframe>
+    <key name="k0" qpos="0.9 -0.6 0.4  0 0.01 -0.005  0.3 0.4 0.049 1 0 0 0"/>
+  </keyframe>
+</mujoco>"""
