@@ -38,9 +38,11 @@ _INT_FIELDS = [
   "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
   "cam_mode", "cam_bodyid", "cam_targetbodyid", "light_mode", "light_bodyid", "light_targetbodyid", "site_bodyid",
 ]
+_TENDON_FLOATS = (("tendon_range", 2), ("tendon_margin", 1), ("tendon_stiffness", 1), ("tendon_damping", 1), ("tendon_frictionloss", 1), ("tendon_lengthspring", 2),
+                  ("tendon_length0", 1), ("tendon_invweight0", 1), ("tendon_solref_lim", 2), ("tendon_solimp_lim", 5), ("tendon_solref_fri", 2), ("tendon_solimp_fri", 5))
 # float fields outside _FLOAT_FIELDS that carry the reference's `*` leading dimension as well
 _BATCHABLE_EXTRA = ("eq_solref", "eq_solimp", "eq_data", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp", "pair_margin", "pair_gap",
-                    "actuator_dynprm", "actuator_actrange")
+                    "actuator_dynprm", "actuator_actrange") + tuple(n for n, _ in _TENDON_FLOATS)
 _SIZES = ["nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "nsite", "ncam", "nlight", "ntree", "nkey", "nmocap", "neq", "ntendon", "nflex"]
 
 _SUPPORTED_PAIRS = {
@@ -243,8 +245,15 @@ def derive_tables(mjm) -> dict:
   nnz_of = {C.JNT_FREE: 6, C.JNT_BALL: 3, C.JNT_SLIDE: 1, C.JNT_HINGE: 1}
   rn, ra, ci = [], [], []
   for a in range(nu):
-    if int(_np(mjm, "actuator_trntype")[a]) != C.TRN_JOINT:
-      raise NotImplementedError("only joint transmission is implemented")
+    trn = int(_np(mjm, "actuator_trntype")[a])
+    if trn == C.TRN_TENDON:  # the moment row is the tendon's Jacobian row (smooth.py:2508-2525)
+      t_ = int(trnid[a, 0])
+      adr_, n = int(_np(mjm, "ten_J_rowadr")[t_]), int(_np(mjm, "ten_J_rownnz")[t_])
+      ra.append(len(ci)); rn.append(n)
+      ci.extend(int(x) for x in _np(mjm, "ten_J_colind")[adr_ : adr_ + n])
+      continue
+    if trn != C.TRN_JOINT:
+      raise NotImplementedError("only joint and tendon transmissions are implemented")
     jtype = int(jt[trnid[a, 0]])
     if jtype == C.JNT_BALL:
       raise NotImplementedError("ball-joint actuator transmission is not implemented")
@@ -305,13 +314,21 @@ def _validate(mjm):
   if mjm.nv > 128:
     # the dense per-world Hessian and its factor live in one warp's shared memory; make_data reports the exact per-kernel need
     raise NotImplementedError("nv > 128 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")
-  for n in ("ntendon", "nflex"):
+  if getattr(mjm, "ntendon", 0):
+    if not np.all(np.asarray(mjm.wrap_type) == C.WRAP_JOINT):
+      raise NotImplementedError("spatial tendons (site / geom / pulley wraps) are not implemented; fixed tendons are")
+    for n in ("tendon_armature", "tendon_stiffnesspoly", "tendon_dampingpoly"):
+      if hasattr(mjm, n) and np.any(np.asarray(getattr(mjm, n)) != 0):
+        raise NotImplementedError(f"{n} is not implemented")
+    if np.any(np.asarray(getattr(mjm, "tendon_actfrclimited", False))):
+      raise NotImplementedError("tendon actuator force limits (tendon_actfrclimited) are not implemented")
+  for n in ("nflex",):
     if getattr(mjm, n, 0):
       raise NotImplementedError(f"{n} > 0 is not supported in this version")
   if getattr(mjm, "neq", 0):
     et, ot = np.asarray(mjm.eq_type), np.asarray(mjm.eq_objtype)
-    if not np.isin(et, (C.EQ_CONNECT, C.EQ_WELD, C.EQ_JOINT)).all():
-      raise NotImplementedError("only connect / weld / joint equality constraints are implemented")
+    if not np.isin(et, (C.EQ_CONNECT, C.EQ_WELD, C.EQ_JOINT, C.EQ_TENDON)).all():
+      raise NotImplementedError("only connect / weld / joint / tendon equality constraints are implemented")
     if (ot[np.isin(et, (C.EQ_CONNECT, C.EQ_WELD))] != C.OBJ_BODY).any():
       raise NotImplementedError("site-based connect / weld equality constraints are not implemented")
   if int(np.asarray(mjm.tree_dofnum).max(initial=0)) > 64:
@@ -401,6 +418,24 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   m.actuator_actearly = dev_i(np.asarray(getattr(mjm, "actuator_actearly", np.zeros(nu_))).astype(np.int32))
   m.actuator_dynprm = dev_f(np.asarray(getattr(mjm, "actuator_dynprm", np.zeros((nu_, 10)))).reshape(nu_, 10), name="actuator_dynprm")
   m.actuator_actrange = dev_f(np.asarray(getattr(mjm, "actuator_actrange", np.zeros((nu_, 2)))).reshape(nu_, 2), name="actuator_actrange")
+  # fixed tendons (smooth.py:3658; constraint.py:642, 1867, 2243; passive.py:208): path, Jacobian sparsity and constant entries
+  nt = int(getattr(mjm, "ntendon", 0))
+  m.ntendon, m.nJten, m.nwrap = nt, (int(getattr(mjm, "nJten", 0)) if nt else 0), (int(getattr(mjm, "nwrap", 0)) if nt else 0)
+  m.actuator_trntype = dev_i(getattr(mjm, "actuator_trntype", np.zeros(nu_)))
+  for n in ("ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid"):
+    setattr(m, n, dev_i(getattr(mjm, n) if nt else np.zeros(0)))
+  m.tendon_limited = dev_i(np.asarray(mjm.tendon_limited).astype(np.int32) if nt else np.zeros(0))
+  m.wrap_prm = dev_f(mjm.wrap_prm if nt else np.zeros(0), batched=False)
+  tenJ0 = np.zeros(m.nJten)
+  for t_ in range(nt):  # the last joint wrap that hits a dof sets the entry (the reference assigns, it does not accumulate)
+    for k in range(int(mjm.tendon_adr[t_]), int(mjm.tendon_adr[t_]) + int(mjm.tendon_num[t_])):
+      dof = int(mjm.jnt_dofadr[int(mjm.wrap_objid[k])])
+      row = np.asarray(mjm.ten_J_colind)[int(mjm.ten_J_rowadr[t_]) : int(mjm.ten_J_rowadr[t_]) + int(mjm.ten_J_rownnz[t_])]
+      tenJ0[int(mjm.ten_J_rowadr[t_]) + int(np.nonzero(row == dof)[0][0])] = float(mjm.wrap_prm[k])
+  m.ten_J0 = dev_f(tenJ0, batched=False)
+  for n, k in _TENDON_FLOATS:
+    setattr(m, n, dev_f(np.asarray(getattr(mjm, n)).reshape((nt, k) if k > 1 else (nt,)) if nt else np.zeros((0, k) if k > 1 else 0), name=n))
+  m.ntenfric = int((np.asarray(mjm.tendon_frictionloss) > 0).sum()) if nt else 0
   m.jnt_limited = dev_i(np.asarray(mjm.jnt_limited).astype(np.int32))
   m.body_tree = tuple(dev_i(x) for x in t["body_tree"])
   for n in ("body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col", "mulm_madr", "tree_qLDadr",
@@ -474,7 +509,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     nfricdof=len(t["dof_fricloss_adr"]), nmaxpyramid=m.nmaxpyramid, integrator=m.opt.integrator, cone=m.opt.cone, solver=m.opt.solver,
     iterations=m.opt.iterations, ls_iterations=m.opt.ls_iterations, disableflags=m.opt.disableflags, enableflags=m.opt.enableflags,
     broadphase=int(m.opt.broadphase), broadphase_filter=m.opt.broadphase_filter, qld_total=t["qld_total"], maxtree=t["maxtree"],
-    has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX, C.GEOM_MESH)).any()), nmesh=nmesh, na=m.na,
+    has_multicontact_geom=int(np.isin(_np(mjm, "geom_type"), (C.GEOM_ELLIPSOID, C.GEOM_CYLINDER, C.GEOM_BOX, C.GEOM_MESH)).any()), nmesh=nmesh, na=m.na, ntendon=m.ntendon, nJten=m.nJten, ntenfric=m.ntenfric, nwrap=m.nwrap,
     nmocap=int(getattr(mjm, "nmocap", 0)), npair=npair, has_convex_pair=t["has_convex_pair"], ccd_iterations=int(getattr(o, "ccd_iterations", 35)), epa_iterations=t["epa_iterations"], nsensor=m.nsensor, nsensordata=m.nsensordata, sensor_subtree_vel=int(m.sensor_subtree_vel), sensor_rne_postconstraint=int(m.sensor_rne_postconstraint), neq=neq, nlimit_ball=len(t["jnt_limited_ball_adr"]), has_gravcomp=int((np.asarray(mjm.body_gravcomp) != 0).any() or (np.asarray(mjm.jnt_stiffness)[np.isin(np.asarray(mjm.jnt_type), (C.JNT_FREE, C.JNT_BALL))] != 0).any()),
   )
   for k, v in ints.items():
@@ -488,7 +523,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
     "jnt_limited_adr": m.jnt_limited_slide_hinge_adr, "nxn_geom_pair": m.nxn_geom_pair_filtered, "nxn_pairid": m.nxn_pairid_filtered,
     "body_isdofancestor": m._isdofancestor_nv,
   }
-  for n in _FLOAT_FIELDS + _INT_FIELDS + ["body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col",
+  for n in (_FLOAT_FIELDS + _INT_FIELDS + ["body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col",
                                          "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
                                          "dofact_adr", "dofact_act", "dofact_mom", "eq_type", "eq_obj1id", "eq_obj2id", "eq_solref", "eq_solimp", "eq_data",
                                          "jnt_limited_ball_adr", "pair_dim", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp",
@@ -496,7 +531,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                                          "sensor_dim", "sensor_adr", "sensor_cutoff", "site_type", "site_size", "geom_dataid", "mesh_vertadr", "mesh_vertnum", "mesh_graphadr", "mesh_graph",
                                          "mesh_polynum", "mesh_polyadr", "mesh_polyvertadr", "mesh_polyvertnum", "mesh_polyvert", "mesh_polymapadr", "mesh_polymapnum",
                                          "mesh_polymap", "mesh_vert", "mesh_polynormal", "actuator_dyntype", "actuator_actadr", "actuator_actnum",
-                                         "actuator_actlimited", "actuator_actearly", "actuator_dynprm", "actuator_actrange"]:
+                                         "actuator_actlimited", "actuator_actearly", "actuator_dynprm", "actuator_actrange", "actuator_trntype",
+                                         "ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid", "tendon_limited", "wrap_prm", "ten_J0"]
+                                        + [n for n, _ in _TENDON_FLOATS]):
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():
     x = _ptr_tensor(x)
@@ -585,6 +622,7 @@ def _data_spec(m: types.Model, nworld, naconmax, njmax, njmax_pad):
   nb, nv, nq, nu, nj, ng = m.nbody, m.nv, m.nq, m.nu, m.njnt, m.ngeom
   return {
     "solver_niter": (i, (nworld,)), "ne": (i, (nworld,)), "nf": (i, (nworld,)), "nl": (i, (nworld,)), "nefc": (i, (nworld,)),
+    "ten_length": (f, (nworld, m.ntendon)), "ten_J": (f, (nworld, m.nJten)), "ten_velocity": (f, (nworld, m.ntendon)),
     "time": (f, (nworld,)), "qpos": (f, (nworld, nq)), "qvel": (f, (nworld, nv)), "act": (f, (nworld, m.na)),
     "qacc_warmstart": (f, (nworld, nv)), "ctrl": (f, (nworld, nu)), "qfrc_applied": (f, (nworld, nv)), "xfrc_applied": (f, (nworld, nb, 6)),
     "qacc": (f, (nworld, nv)), "act_dot": (f, (nworld, m.na)), "sensordata": (f, (nworld, getattr(m, "nsensordata", 0))), "subtree_linvel": (f, (nworld, nb, 3)), "subtree_angmom": (f, (nworld, nb, 3)),
@@ -638,7 +676,7 @@ _BOUND_TOP = [
   "crb", "M", "qLD", "actuator_length", "actuator_moment", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
   "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int",
   "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active", "mocap_pos", "mocap_quat", "sensordata", "subtree_linvel", "subtree_angmom", "cfrc_ext",
-  "act", "act_dot",
+  "act", "act_dot", "ten_length", "ten_J", "ten_velocity",
 ]
 _BOUND_EFC = ["J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "Ma", "type", "id", "state"]
 _BOUND_CONTACT = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "type", "geomcollisionid"]

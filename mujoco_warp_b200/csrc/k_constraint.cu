@@ -133,13 +133,39 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
   // the (few) equalities together; lanes map to dofs for the Jacobian rows and the J*qvel / Jdot*qvel reductions.
   if (EQ && m.neq > 0 && !(m.disableflags & DSBL_EQUALITY)) {
 #pragma unroll 1
-    for (int pass = 0; pass < 3; pass++) {
+    for (int pass = 0; pass < 4; pass++) {
 #pragma unroll 1
       for (int e = 0; e < m.neq; e++) {
         const int type = m.eq_type[e];
-        if (type != (pass == 0 ? EQ_CONNECT : pass == 1 ? EQ_WELD : EQ_JOINT) || !d.eq_active[wb * m.neq + e]) continue;
+        if (type != (pass == 0 ? EQ_CONNECT : pass == 1 ? EQ_WELD : pass == 2 ? EQ_JOINT : EQ_TENDON) || !d.eq_active[wb * m.neq + e]) continue;
         const float* data = m.eq_data + 11 * e;
         const int o1 = m.eq_obj1id[e], o2 = m.eq_obj2id[e];
+        if (type == EQ_TENDON) {  // constraint.py:642-826: tendon length (coupled to a second tendon through a quartic)
+          const int efcid = nefc;
+          nefc += 1; ne += 1;
+          if (efcid >= njmax) continue;
+          const float pos1 = d.ten_length[wb * m.ntendon + o1] - m.tendon_length0[o1];
+          float pos, invweight, deriv = 0.f;
+          if (o2 > -1) {
+            invweight = m.tendon_invweight0[o1] + m.tendon_invweight0[o2];
+            const float dif = d.ten_length[wb * m.ntendon + o2] - m.tendon_length0[o2], dif2 = dif * dif, dif3 = dif2 * dif, dif4 = dif3 * dif;
+            pos = pos1 - (data[0] + data[1] * dif + data[2] * dif2 + data[3] * dif3 + data[4] * dif4);
+            deriv = data[1] + 2.0f * data[2] * dif + 3.0f * data[3] * dif2 + 4.0f * data[4] * dif3;
+          } else {
+            invweight = m.tendon_invweight0[o1];
+            pos = pos1 - data[0];
+          }
+          float Jqvel = 0.f;
+#pragma unroll 1
+          for (int c = lane; c < nvp; c += 32) {
+            float J = 0.f;
+            if (c < nv) { J = tendon_J_at(m, o1, c); if (deriv != 0.f) J -= deriv * tendon_J_at(m, o2, c); Jqvel += J * qvel[c]; }
+            Jw[(size_t)efcid * nvp + c] = J;
+          }
+          Jqvel = warp_sum(Jqvel);
+          if (lane == 0) efc_row(m, d, w, efcid, pos, pos, invweight, m.eq_solref + 2 * e, m.eq_solimp + 5 * e, 0.f, Jqvel, 0.f, CNSTR_EQUALITY, e);
+          continue;
+        }
         if (type == EQ_JOINT) {
           const int efcid = nefc;
           nefc += 1; ne += 1;
@@ -237,6 +263,26 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
                 m.dof_frictionloss[dof], CNSTR_FRICTION_DOF, dof);
     }
     nefc += nf;
+    if (EQ && m.ntenfric > 0) {  // tendon friction loss (constraint.py:1867-1985)
+#pragma unroll 1
+      for (int t = 0; t < m.ntendon; t++) {
+        if (!(m.tendon_frictionloss[t] > 0.f)) continue;
+        const int efcid = nefc;
+        nefc += 1; nf += 1;
+        if (efcid >= njmax) continue;
+        float Jqvel = 0.f;
+#pragma unroll 1
+        for (int c = lane; c < nvp; c += 32) {
+          const float J = c < nv ? tendon_J_at(m, t, c) : 0.f;
+          if (c < nv) Jqvel += J * qvel[c];
+          Jw[(size_t)efcid * nvp + c] = J;
+        }
+        Jqvel = warp_sum(Jqvel);
+        if (lane == 0)
+          efc_row(m, d, w, efcid, 0.f, 0.f, m.tendon_invweight0[t], m.tendon_solref_fri + 2 * t, m.tendon_solimp_fri + 5 * t, 0.f, Jqvel,
+                  m.tendon_frictionloss[t], CNSTR_FRICTION_TENDON, t);
+      }
+    }
   }
 
   // ---- joint limits: ball joints first (constraint.py:2107), then slide / hinge -- the reference's launch order
@@ -299,6 +345,31 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
       }
       const int n = __popc(bal);
       nefc += n; nl += n;
+    }
+    if (EQ && m.ntendon > 0) {  // tendon limits (constraint.py:2243-2375)
+#pragma unroll 1
+      for (int t = 0; t < m.ntendon; t++) {
+        if (!m.tendon_limited[t]) continue;
+        const float len = d.ten_length[wb * m.ntendon + t], margin = m.tendon_margin[t];
+        const float dist_min = len - m.tendon_range[2 * t], dist_max = m.tendon_range[2 * t + 1] - len;
+        const float pos = fminf(dist_min, dist_max) - margin;
+        if (!(pos < 0.f)) continue;
+        const int efcid = nefc;
+        nefc += 1; nl += 1;
+        if (efcid >= njmax) continue;
+        const float scl = dist_min < dist_max ? 1.0f : -1.0f;
+        float Jqvel = 0.f;
+#pragma unroll 1
+        for (int c = lane; c < nvp; c += 32) {
+          const float J = c < nv ? scl * tendon_J_at(m, t, c) : 0.f;
+          if (c < nv) Jqvel += J * qvel[c];
+          Jw[(size_t)efcid * nvp + c] = J;
+        }
+        Jqvel = warp_sum(Jqvel);
+        if (lane == 0)
+          efc_row(m, d, w, efcid, pos, pos, m.tendon_invweight0[t], m.tendon_solref_lim + 2 * t, m.tendon_solimp_lim + 5 * t, margin, Jqvel, 0.f,
+                  CNSTR_LIMIT_TENDON, t);
+      }
     }
   }
 
@@ -441,7 +512,7 @@ size_t smem_constraint(const ModelDev& m, const DataDev& d) { return (size_t)con
 cudaError_t launch_constraint(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const size_t smem = smem_constraint(m, d);
   static size_t configured[4] = {0, 0, 0, 0};
-  const int eq = (m.neq > 0 || m.nlimit_ball > 0) ? 1 : 0;
+  const int eq = (m.neq > 0 || m.nlimit_ball > 0 || m.ntendon > 0) ? 1 : 0;
   void (*kern)(ModelDev, DataDev) = eq ? (m.batched ? k_constraint<true, true> : k_constraint<true, false>) : (m.batched ? k_constraint<false, true> : k_constraint<false, false>);
   const int ci = eq + 2 * (m.batched ? 1 : 0);
   if (smem > 48 * 1024 && smem > configured[ci]) {

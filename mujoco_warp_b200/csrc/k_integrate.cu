@@ -78,10 +78,27 @@ k_euler(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, 
           }
           for (int p = lane; p < nnz * nnz; p += 32) {
             const int i = p / nnz, j = p - i * nnz;
-            if (j <= i) {
+            const int di = m.moment_colind0[adr + i], dj = m.moment_colind0[adr + j];
+            // entries of the M sparsity pattern only (derivative.py:178-218: M_elemid < 0 is skipped): dj is di or an ancestor dof
+            // of it -- a tendon transmission may couple dofs of sibling bodies, which M does not
+            if (j <= i && m.body_isdofancestor[m.dof_bodyid[di] * nv + dj]) {
               const float mi = d.actuator_moment[wb * m.nJmom + adr + i], mj = d.actuator_moment[wb * m.nJmom + adr + j];
-              A[(m.moment_colind0[adr + i] - start) * ld + (m.moment_colind0[adr + j] - start)] -= dt * mi * mj * vel;
+              A[(di - start) * ld + (dj - start)] -= dt * mi * mj * vel;
             }
+          }
+          __syncwarp();
+        }
+      }
+      if (implicitfast && m.ntendon > 0 && damper) {  // derivative.py:262-318: tendon damping on the entries of the M sparsity pattern
+#pragma unroll 1
+        for (int t = 0; t < m.ntendon; t++) {
+          const float kd = m.tendon_damping[t];
+          const int adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
+          if (kd == 0.f) continue;
+          for (int p = lane; p < nnz * nnz; p += 32) {
+            const int i = p / nnz, j = p - i * nnz, di = m.ten_J_colind[adr + i], dj = m.ten_J_colind[adr + j];
+            if (di >= start && di < start + n && dj <= di && m.body_isdofancestor[m.dof_bodyid[di] * nv + dj])  // dj: di itself or an ancestor dof, i.e. an entry of M
+              A[(di - start) * ld + (dj - start)] += dt * m.ten_J0[adr + i] * m.ten_J0[adr + j] * kd;
           }
           __syncwarp();
         }

@@ -137,10 +137,31 @@ k_position(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev 
     }
   }
 
-  // ------------------------------------------------------------------ transmission (joint transmission; smooth.py:2288-2396)
+  // ------------------------------------------------------------------ tendon (smooth.py:3658-3692, 4197: fixed tendons)
+  if (kin && m.ntendon > 0) {
+#pragma unroll 1
+    for (int t = valid ? sub : m.ntendon; t < m.ntendon; t += LPW) {
+      d.ten_length[wb * m.ntendon + t] = tendon_length(m, t, qpos);
+      for (int k = m.ten_J_rowadr[t]; k < m.ten_J_rowadr[t] + m.ten_J_rownnz[t]; k++) d.ten_J[wb * m.nJten + k] = m.ten_J0[k];
+    }
+  }
+
+  // ------------------------------------------------------------------ transmission (joint / tendon transmission; smooth.py:2288-2396)
   if (mask & STG_TRANSMISSION) {
 #pragma unroll 1
     for (int a = valid ? sub : m.nu; a < m.nu; a += LPW) {
+      if (m.ntendon > 0 && m.actuator_trntype[a] == TRN_TENDON) {  // smooth.py:2508-2525: length and moment of the tendon, times gear[0]
+        const int t = m.actuator_trnid[2 * a], adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a], tadr = m.ten_J_rowadr[t];
+        const float gear0 = m.actuator_gear[6 * a];
+        d.actuator_length[wb * m.nu + a] = tendon_length(m, t, qpos) * gear0;
+        d.moment_rownnz[wb * m.nu + a] = nnz;
+        d.moment_rowadr[wb * m.nu + a] = adr;
+        for (int k = 0; k < nnz; k++) {
+          d.moment_colind[wb * m.nJmom + adr + k] = m.moment_colind0[adr + k];
+          d.actuator_moment[wb * m.nJmom + adr + k] = m.ten_J0[tadr + k] * gear0;
+        }
+        continue;
+      }
       const int j = m.actuator_trnid[2 * a], t = m.jnt_type[j], adr = m.moment_rowadr0[a], nnz = m.moment_rownnz0[a];
       const float* gear = m.actuator_gear + 6 * a;
       d.actuator_length[wb * m.nu + a] = (t == JNT_SLIDE || t == JNT_HINGE) ? qpos[m.jnt_qposadr[j]] * gear[0] : 0.f;

@@ -311,6 +311,7 @@ k_sensor(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d,
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     switch (t) {
       case SENS_JOINTPOS: v[0] = d.qpos[wb * m.nq + m.jnt_qposadr[id]]; break;
+      case SENS_TENDONPOS: v[0] = d.ten_length[wb * m.ntendon + id]; break;
       case SENS_ACTUATORPOS: v[0] = d.actuator_length[wb * m.nu + id]; break;
       case SENS_BALLQUAT: { const q4 q = qnormalize(ldq(d.qpos + wb * m.nq + m.jnt_qposadr[id])); v[0] = q.w; v[1] = q.x; v[2] = q.y; v[3] = q.z; break; }
       case SENS_FRAMEPOS: {  // sensor.py:377
@@ -344,6 +345,7 @@ k_sensor(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d,
                                            : (t == SENS_JOINTLIMITVEL ? d.efc_vel[wb * d.njmax + e] : d.efc_force[wb * d.njmax + e]);
         break; }
       case SENS_JOINTVEL: v[0] = d.qvel[wb * nv + m.jnt_dofadr[id]]; break;
+      case SENS_TENDONVEL: v[0] = d.ten_velocity[wb * m.ntendon + id]; break;
       case SENS_ACTUATORVEL: v[0] = d.actuator_velocity[wb * m.nu + id]; break;
       case SENS_BALLANGVEL: { const float* p = d.qvel + wb * nv + m.jnt_dofadr[id]; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; break; }
       case SENS_FRAMELINVEL: case SENS_FRAMEANGVEL: {  // sensor.py:1108-1293 without a reference frame

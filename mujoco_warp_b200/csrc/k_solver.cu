@@ -53,7 +53,7 @@ __host__ __device__ inline SolLayout sol_layout(const ModelDev& m, const DataDev
   // Jaref, jv (= hw: the H-update weights live only between update_constraint and update_search), D, force [, floss]
   // elliptic cones add: per-row friction scale, 3 quad words per row (solver.py:1008-1015 layout), row->contact info
   const bool ell = m.cone == CONE_ELLIPTIC;
-  L.nrowf = (m.nfricdof > 0 ? 5 : 4);
+  L.nrowf = ((m.nfricdof + m.ntenfric) > 0 ? 5 : 4);
   L.rowf = take((L.nrowf + (ell ? 4 : 0)) * cap);
   L.rowi = take((ell ? 3 : 2) * cap);
   L.red = take(big ? 9 * 8 : 0);  // cross-warp reduction scratch of the multi-warp (nv > 32) instantiations
@@ -729,7 +729,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   c.qacc = v; c.Ma = v + vp; c.grad = v + 2 * vp; c.search = v + 3 * vp; c.mv = v + 4 * vp; c.x = c.mv; c.qfs = v + 5 * vp; c.qfc = v + 6 * vp;
   float* rf = S + L.rowf;
   c.Jaref = rf; c.jv = rf + cap; c.hw = c.jv; c.D = rf + 2 * cap; c.force = rf + 3 * cap;
-  c.floss = m.nfricdof > 0 ? rf + 4 * cap : c.D;  // never interpreted when the world has no friction rows
+  c.floss = (m.nfricdof + m.ntenfric) > 0 ? rf + 4 * cap : c.D;  // never interpreted when the world has no friction rows
   int* ri = (int*)(S + L.rowi);
   c.state = ri; c.hidx = ri + cap;
   c.njmax = cap; c.ncone = 0;
@@ -761,7 +761,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     st.load(c.J, d.efc_J + wb * (size_t)d.njmax_pad * nvp, min(nefc, L.jcap) * nvp);
     st.load(c.D, d.efc_D + wb * d.njmax_pad, nrow);
     st.load(c.Jaref, d.efc_aref + wb * njmax, nrow);
-    if (m.nfricdof > 0) st.load(c.floss, d.efc_frictionloss + wb * njmax, nrow);
+    if ((m.nfricdof + m.ntenfric) > 0) st.load(c.floss, d.efc_frictionloss + wb * njmax, nrow);
   }
   {
     if (NW != 1) {
@@ -776,7 +776,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     for (int r = lane; r < nefc; r += NT) {
       if (NW != 1) {
         c.D[r] = d.efc_D[wb * d.njmax_pad + r];
-        if (m.nfricdof > 0) c.floss[r] = d.efc_frictionloss[wb * njmax + r];
+        if ((m.nfricdof + m.ntenfric) > 0) c.floss[r] = d.efc_frictionloss[wb * njmax + r];
       }
       c.state[r] = ST_SATISFIED;
       if (ELL) {  // row -> (contact, component) map; a contact's rows are consecutive (k_constraint.cu)

@@ -143,6 +143,14 @@ k_velocity(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev 
       for (int k = 0; k < nnz; k++) vel += d.actuator_moment[wb * m.nJmom + adr + k] * qvel[d.moment_colind[wb * m.nJmom + adr + k]];
       d.actuator_velocity[wb * nu + a] = vel;
     }
+    if (PEXT && v_all && m.ntendon > 0) {  // forward.py:706-729 tendon velocity
+#pragma unroll 1
+      for (int t = valid ? sub : m.ntendon; t < m.ntendon; t += LPW) {
+        float vel = 0.f;
+        for (int k = m.ten_J_rowadr[t]; k < m.ten_J_rowadr[t] + m.ten_J_rownnz[t]; k++) vel += m.ten_J0[k] * qvel[m.ten_J_colind[k]];
+        d.ten_velocity[wb * m.ntendon + t] = vel;
+      }
+    }
     // com_vel: level-synchronous forward pass
     if (v_all || (mask & STG_COMVEL)) {
     if (sub < 6) cvel[sub] = 0.f;
@@ -218,6 +226,25 @@ k_velocity(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev 
           }
           const float damping = m.dof_damping[dd];
           if (damping != 0.f && !dsbl_damper) damper = -qvel[dd] * damping;
+          if (PEXT && m.ntendon > 0) {  // tendon springs (dead band lengthspring) and dampers, J^T force gathered per dof (passive.py:208-272)
+#pragma unroll 1
+            for (int tn = 0; tn < m.ntendon; tn++) {
+              const float ks = m.tendon_stiffness[tn], kd = m.tendon_damping[tn];
+              if ((ks == 0.f || dsbl_spring) && (kd == 0.f || dsbl_damper)) continue;
+              const float J = tendon_J_at(m, tn, dd);
+              if (J == 0.f) continue;
+              if (ks != 0.f && !dsbl_spring) {
+                const float len = d.ten_length[wb * m.ntendon + tn], lo = m.tendon_lengthspring[2 * tn], hi = m.tendon_lengthspring[2 * tn + 1];
+                const float x = len > hi ? len - hi : (len < lo ? len - lo : 0.f);
+                spring += J * (-x * ks);
+              }
+              if (kd != 0.f && !dsbl_damper) {
+                float vel = 0.f;
+                for (int k = m.ten_J_rowadr[tn]; k < m.ten_J_rowadr[tn] + m.ten_J_rownnz[tn]; k++) vel += m.ten_J0[k] * qvel[m.ten_J_colind[k]];
+                damper += J * (-vel * kd);
+              }
+            }
+          }
         }
         if (gravcomp) {  // passive.py:275-303: -gravity * mass * gravcomp at the body's inertial origin, projected on this dof
 #pragma unroll 1
@@ -454,7 +481,7 @@ cudaError_t launch_velocity(const ModelDev& m, const DataDev& d, int mask, cudaS
   const TeamShape t = vel_shape(m);
   const size_t smem = t.block_bytes;
   static size_t configured[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
-  const int ext = m.has_gravcomp ? 1 : 0;  // has_gravcomp also flags free / ball joint springs (io.py put_model)
+  const int ext = (m.has_gravcomp || m.ntendon > 0) ? 1 : 0;  // has_gravcomp also flags free / ball joint springs (io.py put_model); tendons live in the same instantiation
   const int lpw = t.lpw, G = 32 / lpw, wpb = t.wpb, ki = m.batched ? 4 : lpw == 4 ? 0 : lpw == 8 ? 1 : lpw == 16 ? 2 : 3;
   void (*kern)(ModelDev, DataDev, int) = ext ? vel_kernel<true>(lpw, m.batched) : vel_kernel<false>(lpw, m.batched);
   if (smem > 48 * 1024 && smem > configured[ext][ki]) {

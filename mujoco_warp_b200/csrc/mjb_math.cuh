@@ -98,6 +98,19 @@ __device__ __forceinline__ void make_frame(v3 a_in, float* frame) {
 }
 __device__ __forceinline__ float safe_div(float x, float y) { return x / (y != 0.f ? y : MJ_MINVAL); }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// smooth.py:3658-3692 (fixed tendons): length = sum of coef * joint position over the tendon's joint wraps; the Jacobian entries are
+// the constant coefficients (Model.ten_J0, in the sparsity of ten_J_colind)
+__device__ __forceinline__ float tendon_length(const ModelDev& m, int t, const float* qpos) {
+  float len = 0.f;
+  for (int k = m.tendon_adr[t]; k < m.tendon_adr[t] + m.tendon_num[t]; k++) len += m.wrap_prm[k] * qpos[m.jnt_qposadr[m.wrap_objid[k]]];
+  return len;
+}
+// entry of tendon t's Jacobian row at dof c (0 outside the row's sparsity)
+__device__ __forceinline__ float tendon_J_at(const ModelDev& m, int t, int c) {
+  const int adr = m.ten_J_rowadr[t], n = m.ten_J_rownnz[t];
+  for (int k = 0; k < n; k++) if (m.ten_J_colind[adr + k] == c) return m.ten_J0[adr + k];
+  return 0.f;
+}
 // support.py:38-64 next_act: one integration step of actuator a's activation (exact for FILTEREXACT), optionally clamped to actrange
 __device__ __forceinline__ float next_act(const ModelDev& m, int a, float act, float act_dot, float scale, bool clamp) {
   float r;
