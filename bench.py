@@ -142,6 +142,27 @@ def load_workload(name):
   return wl, mjm, mjd, ctrls
 
 
+def ctrl_noise_np(mjm, ctrl, step, center, noise_std=0.01, noise_rate=0.1):
+  """numpy restatement of the harness control noise (reference cli.py:103-145; the GPU arm's k_ctrl_noise): per (world, actuator)
+  ctrl <- rate ctrl + (1 - rate) centre + scale halfrange (2 halton((step + 1)(world + 1), actuator + 2) - 1), clipped to ctrlrange."""
+  nworld, nu = ctrl.shape
+  rate = np.exp(-float(mjm.opt.timestep) / noise_rate)
+  scale = noise_std * np.sqrt(1.0 - rate * rate)
+  limited = np.asarray(mjm.actuator_ctrllimited).astype(bool)
+  lo, hi = np.asarray(mjm.actuator_ctrlrange)[:, 0], np.asarray(mjm.actuator_ctrlrange)[:, 1]
+  halfrange = np.where(limited, 0.5 * (hi - lo), 1.0)
+  n = np.tile(((step + 1) * (np.arange(nworld, dtype=np.int64) + 1))[:, None], (1, nu))
+  base = (np.arange(nu, dtype=np.int64) + 2)[None, :]
+  f = 1.0 / base
+  h = np.zeros((nworld, nu))
+  while (n > 0).any():  # radical inverse, all (world, actuator) pairs at once
+    h += f * (n % base)
+    n //= base
+    f = f / base
+  out = rate * ctrl + (1.0 - rate) * center[None, :] + scale * halfrange[None, :] * (2.0 * h - 1.0)
+  return np.where(limited[None, :], np.clip(out, lo[None, :], hi[None, :]), out)
+
+
 def cpu_run(name, nworld, nsteps, nthreads):
   """Times the CPU restatement (oracle, fp64, OpenMP over worlds) on a bounded sample; returns env-steps/s."""
   from tests import util
@@ -150,14 +171,14 @@ def cpu_run(name, nworld, nsteps, nthreads):
   wl, mjm, mjd, ctrls = load_workload(name)
   o = util.make_oracle(mjm, nworld, wl["nconmax"], wl["njmax"])
   o.set_state(qpos=np.asarray(mjd.qpos), qvel=np.asarray(mjd.qvel), ctrl=np.asarray(mjd.ctrl))
-  rng = np.random.default_rng(0)
+  center = np.asarray(mjd.ctrl, dtype=np.float64)
   o.step(nthreads)
   t0 = time.perf_counter()
   for i in range(nsteps):
     if ctrls is not None:
       o.d["ctrl"][:] = ctrls[i % len(ctrls)]
-    elif mjm.nu:
-      o.d["ctrl"][:] = np.clip(o.d["ctrl"] + 0.01 * rng.uniform(-1, 1, o.d["ctrl"].shape), -1, 1)
+    elif mjm.nu:  # the same control process as the GPU arm: OU noise around the keyframe controls, Halton sequence (cli.py:103-145)
+      o.d["ctrl"][:] = ctrl_noise_np(mjm, o.d["ctrl"], i, center)
     o.step(nthreads)
   dt = time.perf_counter() - t0
   return nworld * nsteps / dt, dt
@@ -180,7 +201,7 @@ def run_reference(args):
   line = {
     "impl": "reference", "metric": metric_name(args.workload), "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
     "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-    "config": {"workload": f"{wl['label']}; CPU sample of {nw} worlds per step (bounded sample of nworld={nworld}/GPU), random-walk ctrl" if not wl["replay"] else f"{wl['label']}; CPU sample of {nw} worlds per step"},
+    "config": {"workload": f"{wl['label']}; CPU sample of {nw} worlds per step (bounded sample of nworld={nworld}/GPU), same OU / Halton ctrl noise as the GPU arm" if not wl["replay"] else f"{wl['label']}; CPU sample of {nw} worlds per step"},
     "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
     "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,

@@ -39,7 +39,7 @@ _INT_FIELDS = [
   "cam_mode", "cam_bodyid", "cam_targetbodyid", "light_mode", "light_bodyid", "light_targetbodyid", "site_bodyid",
 ]
 _TENDON_FLOATS = (("tendon_range", 2), ("tendon_margin", 1), ("tendon_stiffness", 1), ("tendon_damping", 1), ("tendon_frictionloss", 1), ("tendon_lengthspring", 2),
-                  ("tendon_length0", 1), ("tendon_invweight0", 1), ("tendon_solref_lim", 2), ("tendon_solimp_lim", 5), ("tendon_solref_fri", 2), ("tendon_solimp_fri", 5))
+                  ("tendon_length0", 1), ("tendon_invweight0", 1), ("tendon_solref_lim", 2), ("tendon_solimp_lim", 5), ("tendon_solref_fri", 2), ("tendon_solimp_fri", 5), ("tendon_actfrcrange", 2))
 # float fields outside _FLOAT_FIELDS that carry the reference's `*` leading dimension as well
 _BATCHABLE_EXTRA = ("eq_solref", "eq_solimp", "eq_data", "pair_friction", "pair_solref", "pair_solreffriction", "pair_solimp", "pair_margin", "pair_gap",
                     "actuator_dynprm", "actuator_actrange") + tuple(n for n, _ in _TENDON_FLOATS)
@@ -320,8 +320,6 @@ def _validate(mjm):
     for n in ("tendon_armature", "tendon_stiffnesspoly", "tendon_dampingpoly"):
       if hasattr(mjm, n) and np.any(np.asarray(getattr(mjm, n)) != 0):
         raise NotImplementedError(f"{n} is not implemented")
-    if np.any(np.asarray(getattr(mjm, "tendon_actfrclimited", False))):
-      raise NotImplementedError("tendon actuator force limits (tendon_actfrclimited) are not implemented")
   for n in ("nflex",):
     if getattr(mjm, n, 0):
       raise NotImplementedError(f"{n} > 0 is not supported in this version")
@@ -425,6 +423,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   for n in ("ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid"):
     setattr(m, n, dev_i(getattr(mjm, n) if nt else np.zeros(0)))
   m.tendon_limited = dev_i(np.asarray(mjm.tendon_limited).astype(np.int32) if nt else np.zeros(0))
+  m.tendon_actfrclimited = dev_i(np.asarray(getattr(mjm, "tendon_actfrclimited", np.zeros(nt))).astype(np.int32) if nt else np.zeros(0))
   m.wrap_prm = dev_f(mjm.wrap_prm if nt else np.zeros(0), batched=False)
   tenJ0 = np.zeros(m.nJten)
   for t_ in range(nt):  # the last joint wrap that hits a dof sets the entry (the reference assigns, it does not accumulate)
@@ -532,7 +531,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                                          "mesh_polynum", "mesh_polyadr", "mesh_polyvertadr", "mesh_polyvertnum", "mesh_polyvert", "mesh_polymapadr", "mesh_polymapnum",
                                          "mesh_polymap", "mesh_vert", "mesh_polynormal", "actuator_dyntype", "actuator_actadr", "actuator_actnum",
                                          "actuator_actlimited", "actuator_actearly", "actuator_dynprm", "actuator_actrange", "actuator_trntype",
-                                         "ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid", "tendon_limited", "wrap_prm", "ten_J0"]
+                                         "ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid", "tendon_limited", "tendon_actfrclimited", "wrap_prm", "ten_J0"]
                                         + [n for n, _ in _TENDON_FLOATS]):
     dev_names.setdefault(n, getattr(m, n))
   for n, x in dev_names.items():

@@ -175,6 +175,8 @@ k_position(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev 
     }
   }
 
+  __syncwarp();  // tendon / transmission lanes are done reading qpos: the arena it lives in is about to take xmat (found by racecheck)
+
   // ------------------------------------------------------------------ kinematics: per-body frames, sites
   if (kin) {
 #pragma unroll 2

@@ -378,6 +378,20 @@ k_velocity(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev 
       aforce[a] = force;
     }
     __syncwarp();
+    if (PEXT && enabled && m.ntendon > 0) {  // forward.py:1054-1094: the actuators of a force-limited tendon share the tendon's range
+#pragma unroll 1
+      for (int t = sub; t < m.ntendon; t += LPW) {  // one lane per tendon: the actuator sets of different tendons are disjoint
+        if (!m.tendon_actfrclimited[t]) continue;
+        float total = 0.f;
+        for (int b = 0; b < nu; b++) if (m.actuator_trntype[b] == TRN_TENDON && m.actuator_trnid[2 * b] == t) total += aforce[b];
+        const float lo = m.tendon_actfrcrange[2 * t], hi = m.tendon_actfrcrange[2 * t + 1];
+        const float sc = total < lo ? lo / total : (total > hi ? hi / total : 1.0f);
+        if (sc == 1.0f) continue;
+        for (int b = 0; b < nu; b++)
+          if (m.actuator_trntype[b] == TRN_TENDON && m.actuator_trnid[2 * b] == t) { aforce[b] *= sc; if (valid) d.actuator_force[wb * nu + b] = aforce[b]; }
+      }
+      __syncwarp();
+    }
     if (enabled) {
 #pragma unroll 1
       for (int dd = sub; dd < nv; dd += LPW) {

@@ -20,7 +20,7 @@
   X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
   X(actuator_dyntype) X(actuator_actadr) X(actuator_actnum) X(actuator_actlimited) X(actuator_actearly) X(actuator_trntype) \
-  X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind) X(tendon_adr) X(tendon_num) X(wrap_objid) X(tendon_limited) \
+  X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind) X(tendon_adr) X(tendon_num) X(wrap_objid) X(tendon_limited) X(tendon_actfrclimited) \
   X(moment_rownnz0) X(moment_rowadr0) X(moment_colind0) X(dofact_adr) X(dofact_act) X(dofact_mom) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(body_isdofancestor) X(eq_type) X(eq_obj1id) X(eq_obj2id) X(jnt_limited_ball_adr) X(pair_dim) \
@@ -38,7 +38,7 @@
   X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap) \
   X(sensor_cutoff) X(site_size) X(mesh_vert) X(mesh_polynormal) X(actuator_dynprm) X(actuator_actrange) \
   X(wrap_prm) X(ten_J0) X(tendon_range) X(tendon_margin) X(tendon_stiffness) X(tendon_damping) X(tendon_frictionloss) X(tendon_lengthspring) \
-  X(tendon_length0) X(tendon_invweight0) X(tendon_solref_lim) X(tendon_solimp_lim) X(tendon_solref_fri) X(tendon_solimp_fri)
+  X(tendon_length0) X(tendon_invweight0) X(tendon_solref_lim) X(tendon_solimp_lim) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)
 
 struct ModelDev {
 #define X(n) int n;

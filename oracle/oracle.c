@@ -54,7 +54,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(geom_type) X(geom_condim) X(geom_bodyid) X(geom_priority) \
   X(actuator_trnid) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) \
   X(actuator_dyntype) X(actuator_actadr) X(actuator_actnum) X(actuator_actlimited) X(actuator_actearly) X(actuator_trntype) \
-  X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind) X(tendon_adr) X(tendon_num) X(wrap_objid) X(tendon_limited) \
+  X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind) X(tendon_adr) X(tendon_num) X(wrap_objid) X(tendon_limited) X(tendon_actfrclimited) \
   X(cam_mode) X(cam_bodyid) X(cam_targetbodyid) X(light_mode) X(light_bodyid) X(light_targetbodyid) X(site_bodyid) \
   X(nxn_geom_pair) X(nxn_pairid) X(jnt_limited_slide_hinge_adr) X(jnt_limited_ball_adr) X(body_isdofancestor) \
   X(eq_type) X(eq_obj1id) X(eq_obj2id) X(pair_dim) \
@@ -72,7 +72,7 @@ enum { BF_PLANE = 1, BF_SPHERE = 2, BF_AABB = 4, BF_OBB = 8 };
   X(eq_solref) X(eq_solimp) X(eq_data) X(pair_friction) X(pair_solref) X(pair_solreffriction) X(pair_solimp) X(pair_margin) X(pair_gap) \
   X(sensor_cutoff) X(site_size) X(mesh_vert) X(mesh_polynormal) X(actuator_dynprm) X(actuator_actrange) \
   X(wrap_prm) X(tendon_range) X(tendon_margin) X(tendon_stiffness) X(tendon_damping) X(tendon_frictionloss) X(tendon_lengthspring) \
-  X(tendon_length0) X(tendon_invweight0) X(tendon_solref_lim) X(tendon_solimp_lim) X(tendon_solref_fri) X(tendon_solimp_fri)
+  X(tendon_length0) X(tendon_invweight0) X(tendon_solref_lim) X(tendon_solimp_lim) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)
 
 /* Data arrays: (nworld, per-world size) row-major; per-world sizes are implied by the model dims. */
 #define DATA_RARRS(X) \
@@ -2213,6 +2213,14 @@ static void fwd_actuation(W* w) {
     real force = gain * ctrl_act + bias;
     if (m->actuator_forcelimited[a]) force = rclamp(force, m->actuator_forcerange[2 * a], m->actuator_forcerange[2 * a + 1]);
     w->actuator_force[a] = force;
+  }
+  for (int t = 0; t < m->ntendon; t++) { /* forward.py:1054-1094: the actuators of a force-limited tendon share its range */
+    if (!m->tendon_actfrclimited[t]) continue;
+    real total = 0;
+    for (int a = 0; a < m->nu; a++) if (m->actuator_trntype[a] == TRN_TENDON && m->actuator_trnid[2 * a] == t) total += w->actuator_force[a];
+    const real lo = m->tendon_actfrcrange[2 * t], hi = m->tendon_actfrcrange[2 * t + 1];
+    const real sc = total < lo ? lo / total : (total > hi ? hi / total : 1);
+    if (sc != 1) for (int a = 0; a < m->nu; a++) if (m->actuator_trntype[a] == TRN_TENDON && m->actuator_trnid[2 * a] == t) w->actuator_force[a] *= sc;
   }
   for (int a = 0; a < m->nu; a++) /* forward.py:1097 */
     for (int i = 0; i < w->moment_rownnz[a]; i++) { int s = w->moment_rowadr[a] + i; w->qfrc_actuator[w->moment_colind[s]] += w->actuator_moment[s] * w->actuator_force[a]; }

@@ -260,14 +260,14 @@ class Oracle:
     nt = int(getattr(mjm, "ntendon", 0))
     seti("ntendon", nt); seti("nJten", int(getattr(mjm, "nJten", 0)) if nt else 0)
     setia("actuator_trntype", getattr(mjm, "actuator_trntype", np.zeros(max(nu, 1))) if nu else np.zeros(1))
-    for n in ("ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid", "tendon_limited"):
+    for n in ("ten_J_rownnz", "ten_J_rowadr", "ten_J_colind", "tendon_adr", "tendon_num", "wrap_objid", "tendon_limited", "tendon_actfrclimited"):
       setia(n, np.asarray(getattr(mjm, n)).astype(np.int32) if nt else np.zeros(1, dtype=np.int32))
     for n, k in (("wrap_prm", 1), ("tendon_range", 2), ("tendon_margin", 1), ("tendon_stiffness", 1), ("tendon_damping", 1), ("tendon_frictionloss", 1),
                  ("tendon_lengthspring", 2), ("tendon_length0", 1), ("tendon_invweight0", 1), ("tendon_solref_lim", 2), ("tendon_solimp_lim", 5),
-                 ("tendon_solref_fri", 2), ("tendon_solimp_fri", 5)):
+                 ("tendon_solref_fri", 2), ("tendon_solimp_fri", 5), ("tendon_actfrcrange", 2)):
       setra(n, getattr(mjm, n) if nt else np.zeros(k))
-    if nt and (np.any(np.asarray(getattr(mjm, "tendon_actfrclimited", 0))) or np.any(np.asarray(getattr(mjm, "tendon_armature", 0)) != 0)):
-      raise NotImplementedError("oracle: tendon actuator force limits / tendon armature are not restated")
+    if nt and np.any(np.asarray(getattr(mjm, "tendon_armature", 0)) != 0):
+      raise NotImplementedError("oracle: tendon armature is not restated")
     nsite = int(getattr(mjm, "nsite", 0))
     setia("site_type", getattr(mjm, "site_type", 2 * np.ones(nsite, dtype=np.int32)) if nsite else np.zeros(1, dtype=np.int32))
     setra("site_size", getattr(mjm, "site_size", 0.005 * np.ones((nsite, 3))) if nsite else np.zeros(3))

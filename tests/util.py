@@ -439,7 +439,7 @@ def tendon_xml(integrator="Euler"):
     <body name="ball" pos="0.3 0.4 0.049"><freejoint/><geom type="sphere" size="0.05" mass="0.2"/></body>
   </worldbody>
   <tendon>
-    <fixed name="t_lim" limited="true" range="-0.4 0.5" margin="0.01" solreflimit="0.01 1"><joint joint="a0" coef="0.5"/><joint joint="a1" coef="-0.5"/></fixed>
+    <fixed name="t_lim" limited="true" range="-0.4 0.5" margin="0.01" solreflimit="0.01 1" actuatorfrcrange="-1.2 0.4"><joint joint="a0" coef="0.5"/><joint joint="a1" coef="-0.5"/></fixed>
     <fixed name="t_spring" stiffness="8" damping="0.3" springlength="-0.1 0.2"><joint joint="a1" coef="1"/><joint joint="a2" coef="0.7"/></fixed>
     <fixed name="t_fric" frictionloss="0.2" solreffriction="0.015 1"><joint joint="a2" coef="1.5"/></fixed>
     <fixed name="t_f1"><joint joint="f1" coef="1"/></fixed>
@@ -453,6 +453,7 @@ def tendon_xml(integrator="Euler"):
   </equality>
   <actuator>
     <motor name="m_ten" tendon="t_lim" gear="2" ctrlrange="-1 1"/>
+    <motor name="m_ten2" tendon="t_lim" gear="-1.5"/>
     <position name="p_grip" tendon="t_grip" kp="40" kv="1"/>
     <motor name="m_a0" joint="a0" gear="1.5"/>
     <general name="g_lift" tendon="t_lift" gainprm="5" biastype="affine" biasprm="0 -10 -1"/>
