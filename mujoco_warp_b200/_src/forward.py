@@ -114,11 +114,13 @@ def rungekutta4(m: Model, d: Data):
 
 
 def implicit(m: Model, d: Data):
-  """Integrates with the implicit-in-velocity scheme the model selects (reference forward.py:578; implicitfast only here)."""
+  """Integrates implicitly in velocity (reference forward.py:578): the full velocity derivative with an LU solve when the model's
+  integrator is IMPLICIT, the symmetric implicitfast variant when it is IMPLICITFAST.  (The reference also runs the implicitfast branch
+  for Euler / RK4 models; here the factor-and-solve scratch is sized by the model's integrator at put_model, so those raise.)"""
   from . import constants as C
 
-  if m.opt.integrator != C.INT_IMPLICITFAST:
-    raise NotImplementedError("implicit(): only the implicitfast integrator is implemented")
+  if m.opt.integrator not in (C.INT_IMPLICITFAST, C.INT_IMPLICIT):
+    raise NotImplementedError("implicit(): the model was put with the Euler / RK4 integrator (scratch is sized per integrator)")
   _call("mjb_implicit", m, d)
 
 
@@ -243,7 +245,7 @@ def step2(m: Model, d: Data):
   solve(m, d)
   if getattr(m, "nsensor", 0):
     sensor_acc(m, d)
-  if m.opt.integrator == C.INT_IMPLICITFAST:
+  if m.opt.integrator in (C.INT_IMPLICITFAST, C.INT_IMPLICIT):
     implicit(m, d)
   else:
     euler(m, d)

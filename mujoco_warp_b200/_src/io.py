@@ -284,8 +284,10 @@ def derive_tables(mjm) -> dict:
 def _validate(mjm):
   """Feature checks in the spirit of io.py:284-363: fail loudly on anything the kernels do not cover."""
   o = mjm.opt
-  if o.integrator not in (C.INT_EULER, C.INT_RK4, C.INT_IMPLICITFAST):
-    raise NotImplementedError(f"integrator {o.integrator} not implemented (Euler, RK4 and implicitfast in this version; the fully implicit integrator is not)")
+  if o.integrator not in (C.INT_EULER, C.INT_RK4, C.INT_IMPLICIT, C.INT_IMPLICITFAST):
+    raise NotImplementedError(f"unknown integrator {o.integrator}")
+  if o.integrator == C.INT_IMPLICIT and 18 * mjm.nbody * 32 * 4 > 200 * 1024:
+    raise NotImplementedError(f"implicit integrator: the velocity-derivative scratch of {mjm.nbody} bodies exceeds one block's shared memory (use implicitfast)")
   if o.cone not in (C.CONE_PYRAMIDAL, C.CONE_ELLIPTIC):
     raise NotImplementedError(f"unknown friction cone {o.cone}")
   if o.solver not in (C.SOL_NEWTON, C.SOL_CG):
@@ -443,6 +445,11 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
             "nxn_geom_pair", "nxn_pairid", "nxn_geom_pair_filtered", "nxn_pairid_filtered"):
     setattr(m, n, dev_i(t[n]))
   m.M_hinit_i = m.M_entry_row
+  # D-structure (types.py:1343-1347): the dofs coupled to each dof, both triangles; identical to the symmetric gather rows of mul_m
+  m.D_rowadr, m.D_colind, m.mapM2D = m.mulm_rowadr[:-1], m.mulm_col, m.mulm_madr
+  m.D_rownnz = dev_i(np.diff(t["mulm_rowadr"]))
+  m.D_diag = dev_i(np.array([list(t["mulm_col"][t["mulm_rowadr"][i] : t["mulm_rowadr"][i + 1]]).index(i) for i in range(m.nv)], dtype=np.int32))
+  m.nD = int(t["mulm_rowadr"][-1])
   # equality constraints (connect / weld / joint): eq_* as in the reference Model (types.py), data per world-batch slot 0
   neq = int(getattr(mjm, "neq", 0))
   m.neq = neq
@@ -594,7 +601,7 @@ def _install_model_rebind(m: types.Model, L, arrays, ints):
         _lib.check(L.mjb_model_set_float(h, k.encode(), float(v)))
       return value if isinstance(value, torch.Tensor) else torch.tensor([g], dtype=torch.float32, device=m.opt.__dict__["gravity"].device)
     if name in _OPT_INTS:
-      if name == "integrator" and int(value) not in (C.INT_EULER, C.INT_IMPLICITFAST, C.INT_RK4):
+      if name == "integrator" and int(value) not in (C.INT_EULER, C.INT_IMPLICIT, C.INT_IMPLICITFAST, C.INT_RK4):
         raise NotImplementedError(f"integrator {value} not implemented")
       if name in ("integrator", "cone", "solver") and int(value) != int(m.opt.__dict__[name]):
         raise NotImplementedError(f"opt.{name} selects kernel instantiations and scratch sizes fixed at put_model / make_data; rebuild the Model to change it")
@@ -632,7 +639,7 @@ def _data_spec(m: types.Model, nworld, naconmax, njmax, njmax_pad):
     "subtree_com": (f, (nworld, nb, 3)), "cdof": (f, (nworld, nv, 6)), "cinert": (f, (nworld, nb, 10)),
     "actuator_length": (f, (nworld, nu)), "moment_rownnz": (i, (nworld, nu)), "moment_rowadr": (i, (nworld, nu)),
     "moment_colind": (i, (nworld, m.nJmom)), "actuator_moment": (f, (nworld, m.nJmom)),
-    "crb": (f, (nworld, nb, 10)), "M": (f, (nworld, m.nC)), "qLD": (f, (nworld, m.qLD_block_total)), "qLDiagInv": (f, (nworld, nv)),
+    "crb": (f, (nworld, nb, 10)), "M": (f, (nworld, m.nC)), "qLD": (f, (nworld, m.qLD_block_total)), "qLDiagInv": (f, (nworld, nv)), "qLU": (f, (nworld, m.nD)),
     "actuator_velocity": (f, (nworld, nu)), "cvel": (f, (nworld, nb, 6)), "cdof_dot": (f, (nworld, nv, 6)),
     "qfrc_bias": (f, (nworld, nv)), "qfrc_spring": (f, (nworld, nv)), "qfrc_damper": (f, (nworld, nv)), "qfrc_gravcomp": (f, (nworld, nv)),
     "qfrc_fluid": (f, (nworld, nv)), "qfrc_adhesion": (f, (nworld, nv)), "qfrc_passive": (f, (nworld, nv)),
@@ -675,7 +682,7 @@ _BOUND_TOP = [
   "crb", "M", "qLD", "actuator_length", "actuator_moment", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
   "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "cacc", "cfrc_int",
   "ne", "nf", "nl", "nefc", "nacon", "ncollision", "solver_niter", "overflow", "moment_rownnz", "moment_rowadr", "moment_colind", "eq_active", "mocap_pos", "mocap_quat", "sensordata", "subtree_linvel", "subtree_angmom", "cfrc_ext",
-  "act", "act_dot", "ten_length", "ten_J", "ten_velocity",
+  "act", "act_dot", "ten_length", "ten_J", "ten_velocity", "qLU",
 ]
 _BOUND_EFC = ["J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "Ma", "type", "id", "state"]
 _BOUND_CONTACT = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "type", "geomcollisionid"]

@@ -949,6 +949,7 @@ def compile_xml(root):
   m.M_colind = np.array(colind, dtype=np.int32)
   m.nC = m.nM = adr
   m.dof_Madr = (m.M_rowadr + m.M_rownnz - 1).astype(np.int32)
+  d_structure(m)
 
   # ---- geoms
   m.ngeom = ngeom
@@ -1657,6 +1658,27 @@ def reset_data_keyframe(m, d: MjDataLite, key: int):
 # ----------------------------------------------------------------------------------------------
 
 
+def d_structure(m):
+  """MjModel's D-structure (dof-dof sparsity of the velocity derivatives, both triangles): row i lists the dofs coupled to dof i --
+  ancestors, itself, descendants -- in ascending order; mapM2D sends entry (i, j) to the entry (max, min) of the lower-triangular M."""
+  nv = int(m.nv)
+  rows = [[] for _ in range(nv)]
+  for i in range(nv):
+    for k in range(int(m.M_rownnz[i])):
+      e = int(m.M_rowadr[i]) + k
+      j = int(m.M_colind[e])
+      rows[i].append((j, e))
+      if j != i:
+        rows[j].append((i, e))
+  rows = [sorted(r) for r in rows]
+  m.D_rownnz = np.array([len(r) for r in rows], dtype=np.int32)
+  m.D_rowadr = np.concatenate([[0], np.cumsum(m.D_rownnz)[:-1]]).astype(np.int32) if nv else np.zeros(0, np.int32)
+  m.D_diag = np.array([[c for c, _ in r].index(i) for i, r in enumerate(rows)], dtype=np.int32)
+  m.D_colind = np.array([c for r in rows for c, _ in r], dtype=np.int32)
+  m.mapM2D = np.array([e for r in rows for _, e in r], dtype=np.int32)
+  m.nD = int(m.D_rownnz.sum())
+
+
 def save_npz(m, path: str):
   out = {}
   for k, v in vars(m).items():
@@ -1682,6 +1704,8 @@ def load_npz(path: str):
     elif v.ndim == 0:
       v = v.item()
     setattr(tgt, name, v)
+  if not hasattr(m, "D_rownnz"):  # files written before the compiler stored the D-structure
+    d_structure(m)
   return m
 
 

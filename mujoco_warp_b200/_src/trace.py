@@ -27,7 +27,7 @@ def _tree(m):
   fwd += [("sensor_acc", F.sensor_acc, [])] if sens else []
   if m.opt.integrator == C.INT_RK4:
     integ = ("rungekutta4", F.rungekutta4, [])
-  elif m.opt.integrator == C.INT_IMPLICITFAST:
+  elif m.opt.integrator in (C.INT_IMPLICITFAST, C.INT_IMPLICIT):
     integ = ("implicit", F.implicit, [])
   else:
     integ = ("euler", F.euler, [])

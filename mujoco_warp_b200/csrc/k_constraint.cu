@@ -9,8 +9,8 @@
 // One warp owns one world.  Rows are allocated in a fixed order (friction dofs by dof id, limits by joint id via
 // ballot/prefix, contacts in the world's contact order), so efc row order is deterministic (the reference's is
 // atomics-dependent; its own tests sort before comparing, constraint_test.py:40-59).  Lanes map to dofs: a J row is a
-// single coalesced store, J*qvel is a warp-shuffle reduction, and the per-row impedance/reference math runs on the lane
-// whose index equals the row's dimension id.
+// single coalesced store, J*qvel is a warp-shuffle reduction; the per-row impedance / reference math of the contact rows runs
+// afterwards with lanes = rows of the 32-contact batch (phase C), so its eight per-row stores are coalesced over consecutive rows.
 #include <cstdlib>
 
 #include "mjb_math.cuh"
@@ -24,14 +24,17 @@ namespace {
 // (_efc_contact_jac_dense), re-reading the pool from global memory in every kernel.
 constexpr int CR_FRAME = 0, CR_FRI = 9, CR_OFF1 = 14, CR_OFF2 = 17, CR_POS = 20, CR_INC = 21, CR_INVW = 22, CR_SOLREF = 23,
               CR_SOLREFF = 25, CR_SOLIMP = 27, CR_B1 = 32, CR_B2 = 33, CR_BASE = 34, CR_NDIM = 35, CR_CONDIM = 36, CR_WORDS = 37;
+// phase B leaves J qvel of the contact's (up to ten) rows where its frame and first offset were: slots 0..8 and 14
+__device__ __forceinline__ int cr_vel(int k) { return k < 9 ? CR_FRAME + k : CR_OFF1 + (k - 9); }
 __host__ __device__ inline int con_cap(const DataDev& d) { return 2 * d.nconmax > 32 ? 2 * d.nconmax : 32; }  // = collision's per-world cap
 
-struct ConLayout { int cdof, scom, qvel, rec, total; };
+struct ConLayout { int cdof, scom, qvel, rec, rowmap, total; };
 __host__ __device__ inline ConLayout con_layout(const ModelDev& m, const DataDev& d) {
   ConLayout L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
   L.cdof = take(6 * m.nv); L.scom = take(3 * m.nbody); L.qvel = take(m.nv); L.rec = take(CR_WORDS * 32);  // one 32-contact batch at a time
+  L.rowmap = take(d.njmax < 320 ? d.njmax : 320);  // row of the batch -> contact | dimension << 8 (a batch holds <= 32 x 10 rows, njmax caps them)
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -114,6 +117,7 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
   const ConLayout L = con_layout(mp, d);
   float* S = smem + warp * L.total;
   float *cdof = S + L.cdof, *scom = S + L.scom, *qvel = S + L.qvel, *rec = S + L.rec;
+  int* rowmap = (int*)(S + L.rowmap);
   const int nv = m.nv, nb = m.nbody, njmax = d.njmax, nvp = d.nv_pad;
   const size_t wb = (size_t)w;
   float* Jw = d.efc_J + wb * (size_t)d.njmax_pad * nvp;   // (nworld, njmax_pad, nv_pad)
@@ -389,6 +393,7 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
         condim = d.contact_dim[cid];
         if (pos < 0.f) ndim = elliptic ? condim : (condim == 1 ? 1 : 2 * (condim - 1));
       }
+      const int bstart = nefc;  // first row of this batch
       const int base = nefc + warp_excl_scan(ndim, lane);
       nefc += warp_sum_i(ndim);
       if (c < ncon) {
@@ -407,7 +412,10 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
           r[CR_SOLREFF] = d.contact_solreffriction[2 * cid]; r[CR_SOLREFF + 1] = d.contact_solreffriction[2 * cid + 1];
           r[CR_B1] = __int_as_float(b1); r[CR_B2] = __int_as_float(b2);
           r[CR_BASE] = __int_as_float(base); r[CR_CONDIM] = __int_as_float(condim);
-          for (int k = 0; k < ndim; k++) d.contact_efc_address[np * cid + k] = base + k < njmax ? base + k : -1;
+          for (int k = 0; k < ndim; k++) {
+            d.contact_efc_address[np * cid + k] = base + k < njmax ? base + k : -1;
+            if (base + k < njmax) rowmap[base + k - bstart] = lane | (k << 8);
+          }
         }
       }
       __syncwarp();
@@ -418,9 +426,8 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
       const float* r = rec + CR_WORDS * cb;
       const int ndim = __float_as_int(r[CR_NDIM]);
       if (ndim == 0) continue;
-      const int cid = cbase + c0 + cb, base = __float_as_int(r[CR_BASE]), condim = __float_as_int(r[CR_CONDIM]);
+      const int base = __float_as_int(r[CR_BASE]), condim = __float_as_int(r[CR_CONDIM]);
       const int b1 = __float_as_int(r[CR_B1]), b2 = __float_as_int(r[CR_B2]);
-      const float pos = r[CR_POS], includemargin = r[CR_INC];
       float frame[9], fri[5];
       for (int k = 0; k < 9; k++) frame[k] = r[CR_FRAME + k];
       for (int k = 0; k < 5; k++) fri[k] = r[CR_FRI + k];
@@ -441,6 +448,18 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
         }
         const float p0 = dot(jpd, ld3(frame)), p1 = dot(jpd, ld3(frame + 3)), p2 = dot(jpd, ld3(frame + 6));
         const float r0 = dot(jrd, ld3(frame)), r1 = dot(jrd, ld3(frame + 3)), r2 = dot(jrd, ld3(frame + 6));
+        if (!elliptic && ndim == 4) {
+          // the common contact (pyramidal, condim 3): rows n + mu1 t1, n - mu1 t1, n + mu2 t2, n - mu2 t2 written out, without the
+          // ten-way predicated generic loop below (constraint.py:3851-3868)
+          const float J0 = p0 + p1 * fri[0], J1 = p0 + p1 * -fri[0], J2 = p0 + p2 * fri[1], J3 = p0 + p2 * -fri[1];
+          float* Jr = Jw + (size_t)base * nvp + dd;
+          if (base < njmax) Jr[0] = J0;
+          if (base + 1 < njmax) Jr[nvp] = J1;
+          if (base + 2 < njmax) Jr[2 * nvp] = J2;
+          if (base + 3 < njmax) Jr[3 * nvp] = J3;
+          velp[0] += J0 * qv; velp[1] += J1 * qv; velp[2] += J2 * qv; velp[3] += J3 * qv;
+          continue;
+        }
 #pragma unroll
         for (int dim = 0; dim < 10; dim++) {
           if (dim < ndim) {
@@ -461,36 +480,56 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
           }
         }
       }
-      float myvel = 0.f;
+      // J qvel of the contact's rows, left in the record for phase C (the frame / offset slots are free again: every lane holds its
+      // copy in registers).  Four rows -- a pyramidal condim-3 contact -- go through the halving butterfly: 6 SHFL instead of 20.
+      __syncwarp();
+      float* rv = rec + CR_WORDS * cb;
+      if (ndim == 4) {
+        const bool b4 = lane & 16, b3 = lane & 8;
+        const float w0 = (b4 ? velp[2] : velp[0]) + __shfl_xor_sync(FULL_MASK, b4 ? velp[0] : velp[2], 16);
+        const float w1 = (b4 ? velp[3] : velp[1]) + __shfl_xor_sync(FULL_MASK, b4 ? velp[1] : velp[3], 16);
+        float t = (b3 ? w1 : w0) + __shfl_xor_sync(FULL_MASK, b3 ? w0 : w1, 8);
+        t += __shfl_xor_sync(FULL_MASK, t, 4);
+        t += __shfl_xor_sync(FULL_MASK, t, 2);
+        t += __shfl_xor_sync(FULL_MASK, t, 1);
+        if ((lane & 7) == 0) rv[cr_vel(lane >> 3)] = t;  // row 2 b4 + b3 ended up in lanes 8 (2 b4 + b3) ..
+      } else {
 #pragma unroll
-      for (int dim = 0; dim < 10; dim++) {
-        if (dim < ndim) { const float s = warp_sum(velp[dim]); if (lane == dim) myvel = s; }
-      }
-      if (lane < ndim) {  // constraint.py:4197-4343
-        const int dim = lane, efcid = base + dim;
-        if (efcid < njmax) {
-          float invweight = r[CR_INVW];
-          float pos_aref = pos;
-          float ref[2] = {r[CR_SOLREF], r[CR_SOLREF + 1]};
-          float imp5[5];
-          for (int k = 0; k < 5; k++) imp5[k] = r[CR_SOLIMP + k];
-          if (elliptic) {
-            if (dim > 0) {
-              const float s0 = r[CR_SOLREFF], s1 = r[CR_SOLREFF + 1];
-              if (s0 != 0.f || s1 != 0.f) { ref[0] = s0; ref[1] = s1; }
-              invweight = invweight * m.impratio_invsqrt * m.impratio_invsqrt;
-              if (dim > 1) invweight *= fri[0] * fri[0] / (fri[dim - 1] * fri[dim - 1]);
-              pos_aref = 0.f;
-            }
-          } else if (condim > 1) {
-            const float f0 = fri[0];
-            invweight = invweight + f0 * f0 * invweight;
-            invweight = invweight * 2.0f * f0 * f0 * m.impratio_invsqrt * m.impratio_invsqrt;
-          }
-          const int type = condim == 1 ? CNSTR_CONTACT_FRICTIONLESS : (elliptic ? CNSTR_CONTACT_ELLIPTIC : CNSTR_CONTACT_PYRAMIDAL);
-          efc_row(m, d, w, efcid, pos_aref, pos, invweight, ref, imp5, includemargin, myvel, 0.f, type, cid);
+        for (int dim = 0; dim < 10; dim++) {
+          if (dim < ndim) { const float s = warp_sum(velp[dim]); if (lane == dim) rv[cr_vel(dim)] = s; }
         }
       }
+      }
+      __syncwarp();
+      // ---- phase C: lane = row of the batch (constraint.py:4197-4343): impedance / reference of up to 32 rows at a time, the
+      // per-row stores coalesced over consecutive rows
+      const int nrows_b = min(nefc, njmax) - bstart;
+#pragma unroll 1
+      for (int rr = lane; rr < nrows_b; rr += 32) {
+        const int rm = rowmap[rr], cb = rm & 255, dim = rm >> 8, efcid = bstart + rr;
+        const float* r = rec + CR_WORDS * cb;
+        const int cid = cbase + c0 + cb, condim = __float_as_int(r[CR_CONDIM]);
+        const float pos = r[CR_POS], includemargin = r[CR_INC], myvel = r[cr_vel(dim)];
+        float invweight = r[CR_INVW];
+        float pos_aref = pos;
+        float ref[2] = {r[CR_SOLREF], r[CR_SOLREF + 1]};
+        float imp5[5];
+        for (int k = 0; k < 5; k++) imp5[k] = r[CR_SOLIMP + k];
+        if (elliptic) {
+          if (dim > 0) {
+            const float s0 = r[CR_SOLREFF], s1 = r[CR_SOLREFF + 1];
+            if (s0 != 0.f || s1 != 0.f) { ref[0] = s0; ref[1] = s1; }
+            invweight = invweight * m.impratio_invsqrt * m.impratio_invsqrt;
+            if (dim > 1) invweight *= r[CR_FRI] * r[CR_FRI] / (r[CR_FRI + dim - 1] * r[CR_FRI + dim - 1]);
+            pos_aref = 0.f;
+          }
+        } else if (condim > 1) {
+          const float f0 = r[CR_FRI];
+          invweight = invweight + f0 * f0 * invweight;
+          invweight = invweight * 2.0f * f0 * f0 * m.impratio_invsqrt * m.impratio_invsqrt;
+        }
+        const int type = condim == 1 ? CNSTR_CONTACT_FRICTIONLESS : (elliptic ? CNSTR_CONTACT_ELLIPTIC : CNSTR_CONTACT_PYRAMIDAL);
+        efc_row(m, d, w, efcid, pos_aref, pos, invweight, ref, imp5, includemargin, myvel, 0.f, type, cid);
       }
       __syncwarp();
     }

@@ -39,7 +39,11 @@ k_euler(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev d, 
   warp_copy(d.qacc_warmstart + wb * nv, qacc, nv, lane);  // warmstart <- solver qacc (forward.py:343)
 
   const bool implicitfast = integrator == INT_IMPLICITFAST;
-  if (implicitfast || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
+  if (integrator == INT_IMPLICIT) {  // forward.py:578-600: the acceleration k_implicit solved for with the full velocity derivative
+    __syncwarp();
+    warp_copy(qacc, d.imp_qacc + wb * nv, nv, lane);
+    __syncwarp();
+  } else if (implicitfast || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER))) {
     // Euler: qacc <- (M + dt*diag(damping))^-1 * Ma  (forward.py:391-415); implicitfast: (M - dt*qDeriv)^-1 * Ma
     const bool damper = !(m.disableflags & DSBL_DAMPER);
     const float* Mw = d.M + wb * m.nC;
@@ -311,10 +315,14 @@ k_rk_stage(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d
 
 size_t smem_integrate(const ModelDev& m) { return (size_t)int_words(m) * sizeof(float) * MJB_WARPS_PER_BLOCK; }
 
-// integrator: INT_EULER / INT_IMPLICITFAST, or -1 for the model's own (RK4 models advance with Euler here, forward.py:1411)
+// integrator: INT_EULER / INT_IMPLICITFAST / INT_IMPLICIT, or -1 for the model's own (RK4 models advance with Euler here, forward.py:1411)
 cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, int integrator, cudaStream_t s) {
-  if (integrator < 0) integrator = m.integrator == INT_IMPLICITFAST ? INT_IMPLICITFAST : INT_EULER;
-  const bool solve = integrator == INT_IMPLICITFAST || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
+  if (integrator < 0) integrator = (m.integrator == INT_IMPLICITFAST || m.integrator == INT_IMPLICIT) ? m.integrator : INT_EULER;
+  const bool solve = integrator == INT_IMPLICITFAST || integrator == INT_IMPLICIT || !(m.disableflags & (DSBL_EULERDAMP | DSBL_DAMPER));
+  if (integrator == INT_IMPLICIT) {
+    cudaError_t e = launch_implicit_solve(m, d, d.imp_qacc, s);
+    if (e != cudaSuccess) return e;
+  }
   auto next_activation = [&]() -> cudaError_t {  // after the integrator kernel: it reads the activations of the step
     if (m.na <= 0 || m.nu <= 0) return cudaGetLastError();
     const long n = (long)d.wn * m.nu;

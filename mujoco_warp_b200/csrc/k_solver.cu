@@ -94,7 +94,10 @@ __device__ __forceinline__ void tsum_n(float (&v)[N], float* red) {
 }
 template <int NW> __device__ __forceinline__ float tsum(float v, float* red) { float a[1] = {v}; tsum_n<NW, 1>(a, red); return a[0]; }
 template <int NW> __device__ __forceinline__ P3 tsum3(P3 p, float* red) { float a[3] = {p.c, p.g, p.h}; tsum_n<NW, 3>(a, red); return mkp(a[0], a[1], a[2]); }
-template <int NW> __device__ __forceinline__ void tcopy(float* dst, const float* src, int n, int tid) { for (int i = tid; i < n; i += 32 * NW) dst[i] = src[i]; }
+template <int NW> __device__ __forceinline__ void tcopy(float* dst, const float* src, int n, int tid) {
+#pragma unroll 1  // n is a per-dof count: one or two trips; the unrolled-by-16 form the compiler picks costs ~45 instructions per call (solver 206 -> 202 us)
+  for (int i = tid; i < n; i += 32 * NW) dst[i] = src[i];
+}
 
 // row kinds by position (solver.py:1751-1755): [0,ne) equality, [ne,ne+nf) friction loss, rest inequality
 // shifted evaluation: (cost(alpha) - cost(0), grad, hess) -- solver.py:479-517
@@ -230,8 +233,9 @@ __device__ __forceinline__ EllQ ell_load(const Ctx& c, int r) {
 }
 
 // res = M vec (support.py:153 mul_m).  nv <= 32: M is a dense packed lower triangle in shared memory, lane i walks row i up to the
-// diagonal and column i below it -- no index tables, no global loads (the CSR gather's table lookups were the top
-// long-scoreboard line of the solver).  nv > 32: the symmetric gather tables (io.py:1029-1050).
+// diagonal and column i below it -- no index tables, no global loads (the CSR gather's table lookups were the top long-scoreboard line
+// of the solver).  A fully unrolled variant with predicated loads (4 instead of 9 instructions per entry) measured SLOWER: 245 vs 206 us.
+// nv > 32: the symmetric gather tables (io.py:1029-1050).
 template <int NW, bool BIG>
 __device__ __forceinline__ void mul_m(const Ctx& c, const float* vec, float* res) {
   const ModelDev& m = *c.m;
@@ -703,8 +707,10 @@ __device__ __forceinline__ void cg_direction(Ctx& c, const ModelDev& m, const Da
   __syncwarp();
 }
 
+// nv <= 32: 16 one-warp blocks per SM need <= 128 registers per thread (the register file is split per scheduler: 136 registers
+// already drop an SM from 16 to 12 resident worlds -- measured 206 -> 250 us on the humanoid)
 template <bool ELL, bool BIG, bool CG, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (NW == 1 && !BIG) ? 16 : 1)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
   constexpr int NT = 32 * NW;

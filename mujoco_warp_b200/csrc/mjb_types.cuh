@@ -88,7 +88,7 @@ __device__ __forceinline__ ModelDev world_model(const ModelDev& m, int w, int nw
   X(qfrc_constraint) X(cacc) X(cfrc_int) \
   X(efc_J) X(efc_pos) X(efc_margin) X(efc_D) X(efc_vel) X(efc_aref) X(efc_frictionloss) X(efc_force) X(efc_Ma) \
   X(contact_dist) X(contact_pos) X(contact_frame) X(contact_includemargin) X(contact_friction) X(contact_solref) \
-  X(contact_solreffriction) X(contact_solimp) X(mocap_pos) X(mocap_quat) X(sensordata) X(subtree_linvel) X(subtree_angmom) X(cfrc_ext) X(efc_Jsp) X(act) X(act_dot) X(ten_length) X(ten_J) X(ten_velocity)
+  X(contact_solreffriction) X(contact_solimp) X(mocap_pos) X(mocap_quat) X(sensordata) X(subtree_linvel) X(subtree_angmom) X(cfrc_ext) X(efc_Jsp) X(act) X(act_dot) X(ten_length) X(ten_J) X(ten_velocity) X(qLU)
 #define MJB_DATA_IARRS(X) \
   X(ne) X(nf) X(nl) X(nefc) X(nacon) X(ncollision) X(solver_niter) X(overflow) X(efc_type) X(efc_id) X(efc_state) \
   X(moment_rownnz) X(moment_rowadr) X(moment_colind) X(contact_dim) X(contact_geom) X(contact_efc_address) \
@@ -108,6 +108,7 @@ struct DataDev {
   // internal scratch (allocated by mjb_data_finalize; not part of the reference's Data)
   int* world_conadr;  // (nworld) first contact-pool slot of each world's contiguous block
   int* world_ncon;    // (nworld) number of contacts the world wrote this step
+  float* imp_qacc;    // (nworld, nv) acceleration solved by the fully implicit integrator (k_implicit.cu), consumed by the advance kernel
   // solver row-capacity classes (k_solver.cu): worlds whose constraint count fits rowcap rows run with a smaller shared-memory slice
   int* sol_list;      // (2, nworld) world ids per class, each launch range [w0, w0 + wn) owns that sub-range of both rows
   int* sol_count;     // (8, 2) worlds per (split, class)
@@ -177,6 +178,8 @@ cudaError_t launch_mul_m(const ModelDev& m, const DataDev& d, float* res, const 
 cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s);
 int solver_launch_count(const ModelDev& m, const DataDev& d);  // kernels launch_solver issues (row-capacity classes: classify + two solves)
 cudaError_t launch_integrate(const ModelDev& m, const DataDev& d, int integrator, cudaStream_t s);
+cudaError_t launch_implicit_solve(const ModelDev& m, const DataDev& d, float* qacc_out, cudaStream_t s);  // fully implicit integrator: qLU and its solve
+size_t smem_implicit(const ModelDev& m);
 cudaError_t launch_sensor(const ModelDev& m, const DataDev& d, int stages, cudaStream_t s);
 cudaError_t launch_contact_force(const ModelDev& m, const DataDev& d, const int* contact_ids, int n, int to_world, float* out, cudaStream_t s);
 cudaError_t launch_rk_stage(const ModelDev& m, const DataDev& d, float* rk, int stage, cudaStream_t s);

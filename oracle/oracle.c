@@ -2641,12 +2641,10 @@ static void euler(W* w) {
 
 /* implicitfast (forward.py:602-610; derivative.py:38-176,178-245,1116-1200): qacc = (M - dt*qDeriv)^-1 Ma with
  * qDeriv = sum_act moment^T (d force / d velocity) moment  -  diag(damping), stateless actuators only */
-static void implicitfast(W* w) {
+/* derivative.py:1117-1213 deriv_smooth_vel: Mi = M - dt * qDeriv in the sparsity of M (lower triangle, CSR) */
+static void deriv_smooth_vel(W* w, real* Mi) {
   const OrcModel* m = w->m;
   const int nv = m->nv;
-  int qld = 0; for (int t = 0; t < m->ntree; t++) qld += m->tree_dofnum[t] * m->tree_dofnum[t];
-  real* buf = (real*)calloc((size_t)qld + nv + m->nC, sizeof(real));
-  real *L = buf, *qacc = buf + qld, *Mi = qacc + nv;
   memcpy(Mi, w->M, m->nC * sizeof(real));
   if (m->nu && !(m->disableflags & DSBL_ACTUATION)) {
     for (int a = 0; a < m->nu; a++) {
@@ -2685,9 +2683,170 @@ static void implicitfast(W* w) {
           if (m->M_colind[m->M_rowadr[di] + k] == dj) Mi[m->M_rowadr[di] + k] += m->timestep * w->ten_J[m->ten_J_rowadr[t] + a] * w->ten_J[m->ten_J_rowadr[t] + b] * m->tendon_damping[t];
       }
     }
+}
+static void implicitfast(W* w) {
+  const OrcModel* m = w->m;
+  const int nv = m->nv;
+  int qld = 0; for (int t = 0; t < m->ntree; t++) qld += m->tree_dofnum[t] * m->tree_dofnum[t];
+  real* buf = (real*)calloc((size_t)qld + nv + m->nC, sizeof(real));
+  real *L = buf, *qacc = buf + qld, *Mi = qacc + nv;
+  deriv_smooth_vel(w, Mi);
   factor_solve_i(w, Mi, NULL, L, qacc, w->efc_Ma);
   advance(w, qacc);
   free(buf);
+}
+
+/* D-structure (types.py:1343-1347): row i holds the dofs coupled to dof i -- its ancestors, itself, its descendants -- in ascending
+ * order; mapM2D sends an entry (i, j) to the entry (max, min) of the lower-triangular M.  Derived here from the M-structure. */
+typedef struct { int nD; int *rownnz, *rowadr, *diag, *colind, *mapM2D; } DStruct;
+static DStruct dstruct_make(const OrcModel* m) {
+  const int nv = m->nv;
+  DStruct D;
+  int* cnt = (int*)calloc((size_t)nv + 1, sizeof(int));
+  for (int i = 0; i < nv; i++)
+    for (int k = 0; k < m->M_rownnz[i]; k++) { const int j = m->M_colind[m->M_rowadr[i] + k]; cnt[i]++; if (j != i) cnt[j]++; }
+  D.rownnz = (int*)malloc((size_t)(nv + 1) * sizeof(int)); D.rowadr = (int*)malloc((size_t)(nv + 1) * sizeof(int)); D.diag = (int*)malloc((size_t)(nv + 1) * sizeof(int));
+  int adr = 0;
+  for (int i = 0; i < nv; i++) { D.rownnz[i] = cnt[i]; D.rowadr[i] = adr; adr += cnt[i]; }
+  D.nD = adr;
+  D.colind = (int*)malloc((size_t)(adr + 1) * sizeof(int)); D.mapM2D = (int*)malloc((size_t)(adr + 1) * sizeof(int));
+  memset(cnt, 0, (size_t)(nv + 1) * sizeof(int));
+  /* ascending columns: first the row's own M entries (ancestors, then the diagonal), then rows j > i that hold i, in order of j */
+  for (int i = 0; i < nv; i++)
+    for (int k = 0; k < m->M_rownnz[i]; k++) {
+      const int e = m->M_rowadr[i] + k, j = m->M_colind[e];
+      if (j == i) D.diag[i] = cnt[i];
+      D.colind[D.rowadr[i] + cnt[i]] = j; D.mapM2D[D.rowadr[i] + cnt[i]] = e; cnt[i]++;
+    }
+  for (int j = 0; j < nv; j++)
+    for (int k = 0; k < m->M_rownnz[j] - 1; k++) {
+      const int e = m->M_rowadr[j] + k, i = m->M_colind[e];
+      D.colind[D.rowadr[i] + cnt[i]] = j; D.mapM2D[D.rowadr[i] + cnt[i]] = e; cnt[i]++;
+    }
+  free(cnt);
+  return D;
+}
+static void dstruct_free(DStruct* D) { free(D->rownnz); free(D->rowadr); free(D->diag); free(D->colind); free(D->mapM2D); }
+
+/* derivative.py:321-584 deriv_rne_vel: qLU -= dt * d(qfrc_bias) / d(qvel), column by column (dof k), in the D-structure.
+ * Forward pass 1 (cvel, cdof_dot), forward pass 2 (cacc, body force), backward accumulation, projection on the joint axes. */
+static void deriv_rne_vel_sub(W* w, const DStruct* D, real* qLU) {
+  const OrcModel* m = w->m;
+  const int nv = m->nv, nb = m->nbody;
+  real* Dcvel = (real*)malloc((size_t)6 * (3 * nb + nv) * sizeof(real));
+  real *Dcdd = Dcvel + 6 * nb, *Dcacc = Dcdd + 6 * nv, *Dcfrc = Dcacc + 6 * nb;
+  for (int k = 0; k < nv; k++) {
+    memset(Dcvel, 0, (size_t)6 * (3 * nb + nv) * sizeof(real));
+    for (int b = 1; b < nb; b++) {  /* bodies are numbered parents first (derivative.py:336-402) */
+      const int pid = m->body_parentid[b];
+      real cv[6];
+      memcpy(cv, Dcvel + 6 * pid, sizeof cv);
+      int dof = m->body_dofadr[b];
+      for (int j = m->body_jntadr[b]; j < m->body_jntadr[b] + m->body_jntnum[b]; j++) {
+        const int t = m->jnt_type[j];
+        if (t == JNT_FREE) {
+          if (k >= dof && k < dof + 3) for (int c = 0; c < 6; c++) cv[c] += w->cdof[6 * k + c];
+          for (int a = 3; a < 6; a++) motion_cross(cv, w->cdof + 6 * (dof + a), Dcdd + 6 * (dof + a));
+          if (k >= dof + 3 && k < dof + 6) for (int c = 0; c < 6; c++) cv[c] += w->cdof[6 * k + c];
+          dof += 6;
+        } else if (t == JNT_BALL) {
+          for (int a = 0; a < 3; a++) motion_cross(cv, w->cdof + 6 * (dof + a), Dcdd + 6 * (dof + a));
+          if (k >= dof && k < dof + 3) for (int c = 0; c < 6; c++) cv[c] += w->cdof[6 * k + c];
+          dof += 3;
+        } else {
+          motion_cross(cv, w->cdof + 6 * dof, Dcdd + 6 * dof);
+          if (k == dof) for (int c = 0; c < 6; c++) cv[c] += w->cdof[6 * dof + c];
+          dof += 1;
+        }
+      }
+      memcpy(Dcvel + 6 * b, cv, sizeof cv);
+    }
+    for (int b = 1; b < nb; b++) {  /* derivative.py:405-459 */
+      const int pid = m->body_parentid[b];
+      real dca[6];
+      memcpy(dca, Dcacc + 6 * pid, sizeof dca);
+      for (int j = m->body_dofadr[b]; j < m->body_dofadr[b] + m->body_dofnum[b]; j++) {
+        if (j == k) for (int c = 0; c < 6; c++) dca[c] += w->cdof_dot[6 * j + c];
+        for (int c = 0; c < 6; c++) dca[c] += Dcdd[6 * j + c] * w->qvel[j];
+      }
+      memcpy(Dcacc + 6 * b, dca, sizeof dca);
+      real t1[6], icv[6], idcv[6], x1[6], x2[6];
+      inert_vec(w->cinert + 10 * b, dca, t1);
+      inert_vec(w->cinert + 10 * b, w->cvel + 6 * b, icv);
+      inert_vec(w->cinert + 10 * b, Dcvel + 6 * b, idcv);
+      motion_cross_force(Dcvel + 6 * b, icv, x1);
+      motion_cross_force(w->cvel + 6 * b, idcv, x2);
+      for (int c = 0; c < 6; c++) Dcfrc[6 * b + c] = t1[c] + x1[c] + x2[c];
+    }
+    for (int b = nb - 1; b > 0; b--) {  /* derivative.py:462-479: children into parents */
+      const int pid = m->body_parentid[b];
+      for (int c = 0; c < 6; c++) Dcfrc[6 * pid + c] += Dcfrc[6 * b + c];
+    }
+    for (int i = 0; i < nv; i++)  /* derivative.py:482-511: entries (i, k) of the D-structure */
+      for (int e = D->rowadr[i]; e < D->rowadr[i] + D->rownnz[i]; e++)
+        if (D->colind[e] == k) {
+          real s = 0;
+          for (int c = 0; c < 6; c++) s += w->cdof[6 * i + c] * Dcfrc[6 * m->dof_bodyid[i] + c];
+          qLU[e] -= m->timestep * s;
+        }
+  }
+  free(Dcvel);
+}
+
+/* smooth.py:3376-3478 _factor_solve_lu_sparse_fused: in-place sparse LU without fill-in (rows from the last to the first; the part of a
+ * row right of the diagonal becomes U with a unit diagonal, the part left of and on the diagonal L), then (U + I) y = b, L x = y */
+static void factor_solve_lu(const OrcModel* m, const DStruct* D, real* qLU, real* x, const real* b) {
+  const int nv = m->nv;
+  int* rem = (int*)malloc((size_t)(nv + 1) * sizeof(int));
+  for (int i = 0; i < nv; i++) rem[i] = D->rownnz[i];
+  for (int i = nv - 1; i >= 0; i--) {
+    const int ii = D->rowadr[i] + rem[i] - 1;
+    rem[i]--;
+    const real LUii = qLU[ii];
+    for (int j = i - 1; j >= 0; j--) {
+      const int ji = D->rowadr[j] + rem[j] - 1;
+      if (rem[j] > 0 && D->colind[ji] == i) {
+        rem[j]--;
+        const real LUji = qLU[ji] / LUii;
+        qLU[ji] = LUji;
+        int ic = D->rowadr[i], jc = D->rowadr[j];
+        const int jend = D->rowadr[j] + rem[j], iend = D->rowadr[i] + D->rownnz[i];
+        while (jc < jend && ic < iend) {
+          const int ci = D->colind[ic], cj = D->colind[jc];
+          if (ci == cj) { qLU[jc] -= qLU[ic] * LUji; ic++; jc++; }
+          else if (ci > cj) jc++;
+          else ic++;
+        }
+      }
+    }
+  }
+  for (int i = nv - 1; i >= 0; i--) {
+    real acc = b[i];
+    for (int e = D->rowadr[i] + D->diag[i] + 1; e < D->rowadr[i] + D->rownnz[i]; e++) acc -= qLU[e] * x[D->colind[e]];
+    x[i] = acc;
+  }
+  for (int i = 0; i < nv; i++) {
+    real acc = x[i];
+    for (int e = D->rowadr[i]; e < D->rowadr[i] + D->diag[i]; e++) acc -= qLU[e] * x[D->colind[e]];
+    x[i] = acc / qLU[D->rowadr[i] + D->diag[i]];
+  }
+  free(rem);
+}
+
+/* forward.py:578-600 implicit, IMPLICIT branch: qLU = M - dt (qDeriv_smooth + d RNE / d qvel) in the D-structure, qacc = qLU \ Ma */
+static void implicit_full(W* w) {
+  const OrcModel* m = w->m;
+  const int nv = m->nv;
+  DStruct D = dstruct_make(m);
+  real* Mi = (real*)calloc((size_t)m->nC + D.nD + nv + 1, sizeof(real));
+  real *qLU = Mi + m->nC, *qacc = qLU + D.nD;
+  deriv_smooth_vel(w, Mi);
+  for (int e = 0; e < D.nD; e++) qLU[e] = Mi[D.mapM2D[e]];
+  deriv_rne_vel_sub(w, &D, qLU);
+  factor_solve_lu(m, &D, qLU, qacc, w->efc_Ma);
+  advance(w, qacc);
+  free(Mi);
+  dstruct_free(&D);
 }
 
 /* ------------------------------------------------------------------ sensors (sensor.py; smooth.py:3500-3612 subtree_vel, :1743 rne_postconstraint) */
@@ -3114,7 +3273,6 @@ static void rungekutta4(W* w) {
 
 static int run(const OrcModel* m, OrcData* d, int nthreads, int do_step) {
   if (check_fields(m, d)) return -1;
-  if (do_step && m->integrator != INT_EULER && m->integrator != INT_IMPLICITFAST && m->integrator != INT_RK4) { snprintf(g_err, sizeof g_err, "oracle: the fully implicit integrator is not restated"); return -1; }
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -3123,7 +3281,7 @@ static int run(const OrcModel* m, OrcData* d, int nthreads, int do_step) {
     W w;
     make_view(m, d, wi, &w);
     forward_world(&w);
-    if (do_step) { if (m->integrator == INT_IMPLICITFAST) implicitfast(&w); else if (m->integrator == INT_RK4) rungekutta4(&w); else euler(&w); }
+    if (do_step) { if (m->integrator == INT_IMPLICITFAST) implicitfast(&w); else if (m->integrator == INT_IMPLICIT) implicit_full(&w); else if (m->integrator == INT_RK4) rungekutta4(&w); else euler(&w); }
   }
   return 0;
 }

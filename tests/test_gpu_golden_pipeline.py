@@ -154,6 +154,10 @@ def test_gpu_matches_reference_pipeline(built, name):
     close(f"step{s}/qpos", d.qpos.cpu().numpy()[same], g[f"step{s}/qpos"][same], atol=dt * vtol + 2e-5, rtol=1e-5)
     if "in/act" in g:
       close(f"step{s}/act", d.act.cpu().numpy()[same], g[f"step{s}/act"][same], atol=1e-5, rtol=1e-5)
+    if name.endswith("_implicit"):  # fully implicit integrator: the LU factors of M - dt (qDeriv_smooth + d RNE / d qvel), D-structure
+      want = g[f"step{s}/qLU"]
+      assert d.qLU.shape == want.shape and np.abs(want).max() > 0
+      close(f"step{s}/qLU", d.qLU.cpu().numpy()[same], want[same], atol=2e-3 * max(1.0, float(np.abs(want).max())), rtol=2e-3)
     s += 1
   assert skipped <= (nworld * s // 4 if flat else 0), f"{skipped} world-steps with a row count different from the reference's"
   # the line-search budget flag (1 << 10) may be raised in fp32 when the bracketing stalls at rounding level; nothing else may

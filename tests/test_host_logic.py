@@ -151,9 +151,12 @@ def test_unsupported_features_raise():
   from mujoco_warp_b200._src import io as mio
   from mujoco_warp_b200._src import mjcf
 
+  # the fully implicit integrator is carried (k_implicit.cu) up to the body count whose derivative scratch fits one block's shared memory
   xml = """<mujoco><option integrator="implicit"/><worldbody><body><joint type="hinge"/><geom size="0.1"/></body></worldbody></mujoco>"""
-  with pytest.raises(NotImplementedError, match="integrator"):
-    mio._validate(mjcf.load_string(xml))
+  mio._validate(mjcf.load_string(xml))
+  many = "".join(f'<body pos="{i} 0 0"><joint type="hinge"/><geom size="0.1"/></body>' for i in range(100))
+  with pytest.raises(NotImplementedError, match="implicit integrator"):
+    mio._validate(mjcf.load_string(f'<mujoco><option integrator="implicit"/><worldbody>{many}</worldbody></mujoco>'))
   # box-box goes through GJK / EPA + multi-contact recovery (16 EPA iterations when it is the only convex pair type);
   # with nativeccd disabled it is a primitive pair.  The convex box path does not support margins (reference io.py:693-717).
   two = '<body pos="0 0 1"><freejoint/><geom type="box" size=".1 .1 .1"{m}/></body><body pos="0 0 2"><freejoint/><geom type="{t}" size=".1 .1 .1"/></body>'
@@ -220,3 +223,37 @@ def test_put_model_and_make_data_host_path(monkeypatch):
   bad = mjcf.load_string(util.sensor_xml().replace('<clock name="clk"/>', '<rangefinder name="rf" site="imu"/>'))
   with pytest.raises(NotImplementedError, match="rangefinder"):
     mio.put_model(bad)
+
+
+def test_d_structure_of_the_compiled_model():
+  """MjModel's D-structure as the MJCF compiler writes it (types.py:1343-1347): symmetric tree sparsity, ascending columns, the diagonal
+  index, mapM2D onto the lower-triangular M -- and the same rows as the symmetric gather tables put_model derives for mul_m."""
+  from mujoco_warp_b200._src import io as mio
+  from mujoco_warp_b200._src import mjcf
+
+  for path in (util.HUMANOID, util.G1, util.THREE_HUMANOIDS):
+    mjm = mjcf.load_any(path)
+    nv = mjm.nv
+    assert mjm.nD == 2 * mjm.nC - nv == int(mjm.D_rownnz.sum())
+    pat = np.zeros((nv, nv), dtype=bool)
+    for i in range(nv):
+      cols = mjm.D_colind[mjm.D_rowadr[i] : mjm.D_rowadr[i] + mjm.D_rownnz[i]]
+      assert (np.diff(cols) > 0).all() and cols[mjm.D_diag[i]] == i
+      pat[i, cols] = True
+      for k, j in enumerate(cols):
+        e = mjm.mapM2D[mjm.D_rowadr[i] + k]
+        r = int(np.searchsorted(mjm.M_rowadr, e, side="right") - 1)
+        assert (r, int(mjm.M_colind[e])) == (max(i, j), min(i, j))
+    assert (pat == pat.T).all()
+    # coupled <=> one dof is an ancestor of the other
+    anc = np.zeros((nv, nv), dtype=bool)
+    for i in range(nv):
+      d = i
+      while d >= 0:
+        anc[i, d] = True
+        d = mjm.dof_parentid[d]
+    assert (pat == (anc | anc.T)).all()
+    t = mio.derive_tables(mjm)
+    np.testing.assert_array_equal(t["mulm_col"], mjm.D_colind)
+    np.testing.assert_array_equal(t["mulm_madr"], mjm.mapM2D)
+    np.testing.assert_array_equal(t["mulm_rowadr"][:-1], mjm.D_rowadr)

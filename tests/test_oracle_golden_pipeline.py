@@ -33,6 +33,8 @@ def load_scene(name):
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option solver="CG" cone="elliptic" timestep="0.004"'))
   elif name == "mixed":
     mjm = mjcf.load_string(util.MIXED_XML)
+  elif name == "mixed_implicit":
+    mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="implicit" timestep="0.004"'))
   elif name == "mixed_elliptic":
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option cone="elliptic" impratio="2" timestep="0.004"'))
   elif name == "boxes":
@@ -44,9 +46,9 @@ def load_scene(name):
   elif name == "sensors":
     mjm = mjcf.load_string(util.sensor_xml())
   elif name.startswith("tendons"):
-    mjm = mjcf.load_string(util.tendon_xml("implicitfast" if name.endswith("implicitfast") else "Euler"))
+    mjm = mjcf.load_string(util.tendon_xml("implicitfast" if name.endswith("implicitfast") else "implicit" if name.endswith("implicit") else "Euler"))
   elif name.startswith("actuators"):
-    mjm = mjcf.load_string(util.actuators_xml({"actuators": "Euler", "actuators_implicitfast": "implicitfast", "actuators_rk4": "RK4"}[name]))
+    mjm = mjcf.load_string(util.actuators_xml({"actuators": "Euler", "actuators_implicitfast": "implicitfast", "actuators_rk4": "RK4", "actuators_implicit": "implicit"}[name]))
   elif name == "mixed_rk4":
     mjm = mjcf.load_string(util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="RK4" timestep="0.004"'))
   elif name == "mixed_sap":

@@ -29,7 +29,7 @@ FIELDS = [
   "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "cam_xpos", "cam_xmat",
   "light_xpos", "light_xdir", "subtree_com", "cdof", "cinert", "crb", "M", "actuator_length", "actuator_moment", "actuator_velocity", "cvel",
   "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper", "qfrc_gravcomp", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth",
-  "qacc", "qfrc_constraint", "ne", "nf", "nl", "nefc", "solver_niter", "sensordata", "subtree_linvel", "subtree_angmom", "cfrc_ext", "act_dot", "ten_length", "ten_velocity",
+  "qacc", "qfrc_constraint", "ne", "nf", "nl", "nefc", "solver_niter", "qLU", "sensordata", "subtree_linvel", "subtree_angmom", "cfrc_ext", "act_dot", "ten_length", "ten_velocity",
 ]
 EFC = ["type", "id", "J", "pos", "margin", "D", "vel", "aref", "frictionloss", "force", "state"]
 CON = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom", "efc_address", "worldid", "geomcollisionid"]
@@ -74,6 +74,13 @@ def scenes():
     yield "actuators" + ("" if integ == "Euler" else "_" + integ.lower()), mjcf.load_string(util.actuators_xml(integ)), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=1.2, exact_world0=False)
   for integ in ("Euler", "implicitfast"):  # fixed tendons: limits, spring / damper, friction loss, equalities, tendon transmissions
     yield "tendons" + ("" if integ == "Euler" else "_" + integ.lower()), mjcf.load_string(util.tendon_xml(integ)), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=1.0, exact_world0=False)
+  # fully implicit integrator (forward.py:578-600, derivative.py:321-584 RNE velocity derivative, smooth.py:3376 sparse LU): the mixed scene
+  # has free / ball / slide / hinge joints with several joints on one body, the actuator scene velocity-dependent actuator forces, the
+  # tendon scene tendon damping
+  imp = util.MIXED_XML.replace('<option timestep="0.004"', '<option integrator="implicit" timestep="0.004"')
+  yield "mixed_implicit", mjcf.load_string(imp), dict(nconmax=32, njmax=128, key=0, qpos_noise=0.01, qvel_noise=1.0, ctrl_noise=1.5, exact_world0=False)
+  yield "actuators_implicit", mjcf.load_string(util.actuators_xml("implicit")), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=1.2, exact_world0=False)
+  yield "tendons_implicit", mjcf.load_string(util.tendon_xml("implicit")), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.05, qvel_noise=0.5, ctrl_noise=1.0, exact_world0=False)
   yield "mesh", mjcf.load_string(util.mesh_xml()), dict(nconmax=64, njmax=256, key=None, qpos_noise=0.0004, qvel_noise=0.05, ctrl_noise=0.0, exact_world0=False)
   yield "equality", mjcf.load_string(util.EQUALITY_XML), dict(nconmax=16, njmax=64, key=0, qpos_noise=0.02, qvel_noise=0.5, ctrl_noise=0.5, exact_world0=False)
   three = mjcf.load_any(util.THREE_HUMANOIDS)
