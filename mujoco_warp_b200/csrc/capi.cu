@@ -97,7 +97,7 @@ int mjb_model_finalize(mjbModel* m) {
   if (m->dev.nv <= 0 || m->dev.nbody <= 0) return fail("model has no dofs/bodies");
   if (m->dev.solver != SOL_NEWTON && m->dev.solver != SOL_CG) return fail("only the Newton and CG solvers are implemented");
   if (m->dev.cone != CONE_PYRAMIDAL && m->dev.cone != CONE_ELLIPTIC) return fail("unknown friction cone type");
-  if (m->dev.integrator != INT_EULER && m->dev.integrator != INT_RK4 && m->dev.integrator != INT_IMPLICITFAST) return fail("only the Euler, RK4 and implicitfast integrators are implemented");
+  if (m->dev.integrator != INT_EULER && m->dev.integrator != INT_RK4 && m->dev.integrator != INT_IMPLICITFAST && m->dev.integrator != INT_IMPLICIT) return fail("unknown integrator");
   m->finalized = true;
   return 0;
 }
