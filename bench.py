@@ -438,11 +438,20 @@ def run_ours(args):
     top = max(kms, key=kms.get)
     bytes_launch = 4.0 * words[top] * nworld
     achieved = bytes_launch / (kms[top] * 1e-3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     try:  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/r02_kernels.md); humanoid only
       if args.workload == "humanoid":
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["traffic_bytes"].get("k_" + top)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        traffic = prof["traffic_bytes"].get("k_" + top)
         traffic = traffic * nworld / 8192.0 if traffic is not None else None
+        # second roofline (context; the kernels are issue / latency bound): warp instructions of the same capture
+        # against the SM's issue rate -- 148 SMs x 4 schedulers x one warp instruction per cycle at the SM clock sampled under load
+        winst = prof.get("warp_inst", {}).get("k_" + top)
+        mhz = float((clocks or {}).get("sm_mhz") or 0.0)
+        if winst and mhz > 0:
+          rate = winst * nworld / 8192.0 / (kms[top] * 1e-3)
+          issue = {"warp_inst_per_launch": winst * nworld / 8192.0, "achieved_warp_inst_per_s": rate, "peak_warp_inst_per_s": 148 * 4 * mhz * 1e6,
+                   "frac": rate / (148 * 4 * mhz * 1e6), "source": "smsp__inst_executed.sum of profiles/r02_kernels.md"}
     except Exception:
       pass
     step_bytes = 4.0 * sum(words.values()) * nworld
@@ -471,7 +480,7 @@ def run_ours(args):
       "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                    "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                    "algorithmic_bytes_per_launch": bytes_launch, "step_algorithmic_bytes": step_bytes,
-                   "step_frac": step_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak},
+                   "step_frac": step_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak, "issue": issue},
       "cpu_baseline": cpu,
       "clocks": clocks,
     }

@@ -525,13 +525,9 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
                 meaninertia=mjm.stat.meaninertia, gravity_x=g[0], gravity_y=g[1], gravity_z=g[2], ccd_tolerance=float(getattr(o, "ccd_tolerance", 1e-6)))
   for k, v in floats.items():
     _lib.check(L.mjb_model_set_float(h, k.encode(), float(v)))
-  # nv <= 32: a body's ancestor dofs as one bit mask (the contact-row builder tests bits instead of loading table entries)
-  anc_bits = np.asarray(t["body_isdofancestor"]).reshape(m.nbody, m.nv)[:, :32].astype(np.uint64)
-  dofmask = (anc_bits << np.arange(anc_bits.shape[1], dtype=np.uint64)).sum(axis=1).astype(np.uint32).view(np.int32) if m.nv <= 32 else np.zeros(m.nbody, dtype=np.int32)
-  m._body_dofmask = dev_i(dofmask)
   dev_names = {
     "jnt_limited_adr": m.jnt_limited_slide_hinge_adr, "nxn_geom_pair": m.nxn_geom_pair_filtered, "nxn_pairid": m.nxn_pairid_filtered,
-    "body_isdofancestor": m._isdofancestor_nv, "body_dofmask": m._body_dofmask,
+    "body_isdofancestor": m._isdofancestor_nv,
   }
   for n in (_FLOAT_FIELDS + _INT_FIELDS + ["body_childadr", "body_childid", "level_adr", "level_body", "M_entry_row", "mulm_rowadr", "mulm_col",
                                          "mulm_madr", "tree_qLDadr", "dof_fricloss_adr", "moment_rownnz0", "moment_rowadr0", "moment_colind0",
@@ -553,7 +549,7 @@ def put_model(mjm, batch_sizes=None) -> types.Model:
   _lib.check(L.mjb_model_finalize(h))
   m._keep = keep
   weakref.finalize(m, L.mjb_model_destroy, h)
-  _install_model_rebind(m, L, set(dev_names) - {"jnt_limited_adr", "nxn_geom_pair", "nxn_pairid", "body_isdofancestor", "body_dofmask"}, set(ints))
+  _install_model_rebind(m, L, set(dev_names) - {"jnt_limited_adr", "nxn_geom_pair", "nxn_pairid", "body_isdofancestor"}, set(ints))
   return m
 
 

@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "mjb_math.cuh"
+#include "mjb_team.cuh"
 #include "mjb_types.cuh"
 
 namespace {
@@ -29,17 +30,20 @@ __host__ __device__ inline int surv_cap(const ModelDev& m) { return m.nxn_npair 
 
 constexpr int CCD_LANES = 4;  // geom pairs that run GJK / EPA concurrently in one warp (each needs a polytope in shared memory)
 
-struct ColLayout { int gxpos, gxmat, surv, stage, sgeom, ccd, sap, total; };
+struct ColLayout { int gxpos, gxmat, surv, stage, sgeom, ccd, sap, bar, total; };
 __host__ __device__ inline ColLayout col_layout(const ModelDev& m, const DataDev& d) {
   ColLayout L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
-  L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom);
+  // geom poses first, each on a 16-byte boundary: staged with one bulk-async copy apiece when the world's rows are aligned in global memory
+  L.gxpos = take((3 * m.ngeom + 3) & ~3); L.gxmat = take((9 * m.ngeom + 3) & ~3);
   L.surv = take(surv_cap(m));
   L.stage = take(STAGE_WORDS * world_con_cap(d));
   L.sgeom = take(4 * world_con_cap(d));  // g1, g2, geomcollisionid, pairid
   L.ccd = take(m.has_convex_pair ? CCD_LANES * ccd_scratch_words(m.epa_iterations) : 0);
   L.sap = take(m.broadphase != 0 ? 4 * m.ngeom : 0);  // sweep-and-prune: projection bounds, sorted lower bounds, ranks
+  o = (o + 3) & ~3;
+  L.bar = take(4);  // mbarrier of the staging copies (8 bytes in a 16-byte slot)
   L.total = (o + 3) & ~3;
   return L;
 }
@@ -174,9 +178,13 @@ k_collision(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDev
     if (lane == 0) { d.world_conadr[w] = 0; d.world_ncon[w] = 0; }
     return;
   }
-  warp_copy(gxpos, d.geom_xpos + wb * 3 * ng, 3 * ng, lane);
-  warp_copy(gxmat, d.geom_xmat + wb * 9 * ng, 9 * ng, lane);
-  __syncwarp();
+  {  // cp.async.bulk (SASS UBLKCP) when both rows are 16-byte aligned (ngeom a multiple of 4), a lane loop otherwise
+    Stager st;
+    st.init(reinterpret_cast<uint64_t*>(S + L.bar), lane);
+    st.load(gxpos, d.geom_xpos + wb * 3 * ng, 3 * ng);
+    st.load(gxmat, d.geom_xmat + wb * 9 * ng, 9 * ng);
+    st.load_wait();
+  }
 
   // ---- sweep-and-prune option (collision_driver.py:582-682): bounding-sphere projections on the reference's fixed axis, each
   // geom's position in the sort by lower bound.  A pair is a sweep candidate when every geom sorted between the two starts

@@ -410,8 +410,7 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
           r[CR_INVW] = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
           r[CR_SOLREF] = d.contact_solref[2 * cid]; r[CR_SOLREF + 1] = d.contact_solref[2 * cid + 1];
           r[CR_SOLREFF] = d.contact_solreffriction[2 * cid]; r[CR_SOLREFF + 1] = d.contact_solreffriction[2 * cid + 1];
-          // nv <= 32: the bodies' ancestor-dof bit masks instead of their ids (phase B tests a bit instead of loading a table entry)
-          r[CR_B1] = __int_as_float(nv <= 32 ? m.body_dofmask[b1] : b1); r[CR_B2] = __int_as_float(nv <= 32 ? m.body_dofmask[b2] : b2);
+          r[CR_B1] = __int_as_float(b1); r[CR_B2] = __int_as_float(b2);
           r[CR_BASE] = __int_as_float(base); r[CR_CONDIM] = __int_as_float(condim);
           for (int k = 0; k < ndim; k++) {
             d.contact_efc_address[np * cid + k] = base + k < njmax ? base + k : -1;
@@ -422,9 +421,6 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
       __syncwarp();
       // ---- phase B: lanes = dofs, the batch's contacts one after the other, every operand already in shared memory
       const int nb_ = min(32, ncon - c0);
-      // this lane's (first) dof: its cdof and velocity are the same for every contact of the batch
-      const v3 ang_l = lane < nv ? ld3(cdof + 6 * lane) : mk3(0.f, 0.f, 0.f), lin_l = lane < nv ? ld3(cdof + 6 * lane + 3) : mk3(0.f, 0.f, 0.f);
-      const float qv_l = lane < nv ? qvel[lane] : 0.f;
 #pragma unroll 1
       for (int cb = 0; cb < nb_; cb++) {
       const float* r = rec + CR_WORDS * cb;
@@ -444,14 +440,9 @@ k_constraint(const __grid_constant__ ModelDev mp, const __grid_constant__ DataDe
         v3 jpd = mk3(0.f, 0.f, 0.f), jrd = mk3(0.f, 0.f, 0.f);
         float qv = 0.f;
         if (dd < nv) {
-          v3 ang = ang_l, lin = lin_l;
-          qv = qv_l;
-          int a1, a2;
-          if (nv <= 32) { a1 = (b1 >> dd) & 1; a2 = (b2 >> dd) & 1; }  // b1 / b2 hold the ancestor-dof masks
-          else {
-            if (dd != lane) { ang = ld3(cdof + 6 * dd); lin = ld3(cdof + 6 * dd + 3); qv = qvel[dd]; }
-            a1 = m.body_isdofancestor[b1 * nv + dd]; a2 = m.body_isdofancestor[b2 * nv + dd];
-          }
+          const v3 ang = ld3(cdof + 6 * dd), lin = ld3(cdof + 6 * dd + 3);
+          qv = qvel[dd];
+          const int a1 = m.body_isdofancestor[b1 * nv + dd], a2 = m.body_isdofancestor[b2 * nv + dd];
           if (a2) { jpd = lin + cross(ang, off2); jrd = ang; }
           if (a1) { jpd = jpd - (lin + cross(ang, off1)); jrd = jrd - ang; }
         }

@@ -709,7 +709,9 @@ __device__ __forceinline__ void cg_direction(Ctx& c, const ModelDev& m, const Da
 
 // nv <= 32: 16 one-warp blocks per SM need <= 128 registers per thread (the register file is split per scheduler: 136 registers
 // already drop an SM from 16 to 12 resident worlds -- measured 206 -> 250 us on the humanoid)
-template <bool ELL, bool BIG, bool CG, int NW>
+// PLAIN: the model can produce neither equality nor friction-loss rows (no equalities, no dof / tendon frictionloss), so every row is
+// an inequality: ne = nf = 0 become compile-time constants and the two other row kinds drop out of the line search and the row pass
+template <bool ELL, bool BIG, bool CG, int NW, bool PLAIN = false>
 __global__ void __launch_bounds__(NW * 32, (NW == 1 && !BIG) ? 16 : 1)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -754,7 +756,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
     return;
   }
   const int nefc = min(min(d.nefc[w], njmax), cap);
-  c.nefc = nefc; c.ne = d.ne[w]; c.nf = d.nf[w];
+  c.nefc = nefc; c.ne = PLAIN ? 0 : d.ne[w]; c.nf = PLAIN ? 0 : d.nf[w];
 
   // ---- stage the world's problem in shared memory.  One warp per world (NW = 1): the Jacobian rows and the per-row vectors are
   // contiguous, 16-byte aligned blocks of the world-major arrays, so one lane issues a bulk-async copy (cp.async.bulk, SASS UBLKCP)
@@ -959,17 +961,22 @@ cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = solver_big(m) ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0;
   const int nw = solver_warps(m), team = nw == 4 ? 2 : (nw == 2 ? 1 : 0);
   const int which = cg ? 4 + 2 * big + ell : (big ? 8 + 2 * team + ell : ell);
-  static size_t configured[14] = {0};
+  static size_t configured[15] = {0};
   static void (*const kerns[14])(ModelDev, DataDev) = {
     k_solver<false, false, false, 1>, k_solver<true, false, false, 1>, nullptr, nullptr,
     k_solver<false, false, true, 1>,  k_solver<true, false, true, 1>,  k_solver<false, true, true, 1>,  k_solver<true, true, true, 1>,
     k_solver<false, true, false, 1>,  k_solver<true, true, false, 1>,  k_solver<false, true, false, 2>, k_solver<true, true, false, 2>,
     k_solver<false, true, false, 4>,  k_solver<true, true, false, 4>};
   void (*kern)(ModelDev, DataDev) = kerns[which];
-  if (smem > 48 * 1024 && smem > configured[which]) {
+  int ci = which;
+#ifdef MJB_SOL_PLAIN
+  const bool plain = m.neq == 0 && m.nfricdof == 0 && m.ntenfric == 0 && m.ntendon == 0;
+  if (which == 0 && plain) { kern = k_solver<false, false, false, 1, true>; ci = 14; }
+#endif
+  if (smem > 48 * 1024 && smem > configured[ci]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[which] = smem;
+    configured[ci] = smem;
   }
   const int cap0 = ((d.njmax / 2) + 3) & ~3;
   if (solver_uses_classes(m, d)) {
