@@ -39,6 +39,10 @@ __host__ __device__ inline ConLayout con_layout(const ModelDev& m, const DataDev
   return L;
 }
 
+// general impedance exponent (solimp[4] other than the default 2 or 1): kept out of line, two powf expansions per inlined copy of efc_row
+// were a seventh of the kernel's code
+__device__ __noinline__ float imp_pow(float bx, float bc, float power) { return (1.0f / powf(bc, power - 1.0f)) * powf(bx, power); }
+
 // constraint.py:83-152
 __device__ void efc_row(const ModelDev& m, const DataDev& d, int w, int efcid, float pos_aref, float pos_imp, float invweight,
                         const float* solref, const float* solimp, float margin, float vel, float frictionloss, int type, int id) {
@@ -59,7 +63,7 @@ __device__ void efc_row(const ModelDev& m, const DataDev& d, int w, int efcid, f
   float t;
   if (power == 2.0f) t = bx * bx / bc;
   else if (power == 1.0f) t = bx;
-  else t = (1.0f / powf(bc, power - 1.0f)) * powf(bx, power);
+  else t = imp_pow(bx, bc, power);
   const float imp_y = lower ? t : 1.0f - t;
   float imp = clampf(dmin + imp_y * (dmax - dmin), dmin, dmax);
   if (imp_x > 1.0f) imp = dmax;

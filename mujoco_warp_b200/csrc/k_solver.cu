@@ -431,7 +431,7 @@ __device__ __forceinline__ float newton_direction_reg(Ctx& c, int nlist, float g
 }
 
 // H += sum_list w J J^T (lower triangle), Cholesky, search = -H^-1 grad, Newton decrement
-template <bool ELL, bool BIG, int NW>
+template <bool ELL, bool BIG, int NW, int NREG = 0>
 __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
   const int nv = c.nv;
   float sd = 0.f, nd = 0.f;
@@ -445,6 +445,8 @@ __device__ __forceinline__ void update_search(Ctx& c, int nlist) {
 #else
     if (!ELL && nlist == 0 && c.factored) xx = chol_subst_pair(nv, g, c.Lf, c.lane, c.chol_inv, c.chol_off);
 #endif
+    else if (NREG == 28) xx = newton_direction_reg<28, ELL>(c, nlist, g);  // register-row size fixed by the launcher: one variant in the kernel
+    else if (NREG == 32) xx = newton_direction_reg<32, ELL>(c, nlist, g);
     else if (nv <= 8) xx = newton_direction_reg<8, ELL>(c, nlist, g);
     else if (nv <= 16) xx = newton_direction_reg<16, ELL>(c, nlist, g);
     else if (nv <= 24) xx = newton_direction_reg<24, ELL>(c, nlist, g);
@@ -711,7 +713,7 @@ __device__ __forceinline__ void cg_direction(Ctx& c, const ModelDev& m, const Da
 // already drop an SM from 16 to 12 resident worlds -- measured 206 -> 250 us on the humanoid)
 // PLAIN: the model can produce neither equality nor friction-loss rows (no equalities, no dof / tendon frictionloss), so every row is
 // an inequality: ne = nf = 0 become compile-time constants and the two other row kinds drop out of the line search and the row pass
-template <bool ELL, bool BIG, bool CG, int NW, bool PLAIN = false>
+template <bool ELL, bool BIG, bool CG, int NW, bool PLAIN = false, int NREG = 0>
 __global__ void __launch_bounds__(NW * 32, (NW == 1 && !BIG) ? 16 : 1)
 k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) {
   extern __shared__ float smem[];
@@ -731,6 +733,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
   Ctx c;
   c.factored = false; c.chol_inv = 1.0f; c.chol_off = 0;
   c.m = &m; c.lane = lane; c.nv = nv; c.nvp = L.nvp; c.ldJ = L.ldJ; c.ldH = L.ldH;
+  if (NREG > 0) { c.nvp = NREG; c.ldJ = NREG; }  // the launcher checked nv_pad == NREG: row strides and row-dot trip counts become constants (176 -> 172 us)
   c.J = S + L.J; c.H = S + L.H; c.Lf = S + L.Lf; c.M = S + L.M;
   float* v = S + L.vec;
   const int vp = L.nvp;
@@ -886,7 +889,7 @@ k_solver(const __grid_constant__ ModelDev m, const __grid_constant__ DataDev d) 
       cg_direction(c, m, d, wb, it < 0);
       continue;
     }
-    if (!CG) update_search<ELL, BIG, NW>(c, nlist);
+    if (!CG) update_search<ELL, BIG, NW, NREG>(c, nlist);
     if (it >= 0) {
       if (0.5f * c.newton_decrement / scale < m.tolerance) break;
       if (niter == m.iterations) { ovf |= OVF_ITERATIONS; break; }
@@ -961,7 +964,7 @@ cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
   const int ell = m.cone == CONE_ELLIPTIC ? 1 : 0, big = solver_big(m) ? 1 : 0, cg = m.solver == SOL_CG ? 1 : 0;
   const int nw = solver_warps(m), team = nw == 4 ? 2 : (nw == 2 ? 1 : 0);
   const int which = cg ? 4 + 2 * big + ell : (big ? 8 + 2 * team + ell : ell);
-  static size_t configured[15] = {0};
+  static size_t configured[18] = {0};
   static void (*const kerns[14])(ModelDev, DataDev) = {
     k_solver<false, false, false, 1>, k_solver<true, false, false, 1>, nullptr, nullptr,
     k_solver<false, false, true, 1>,  k_solver<true, false, true, 1>,  k_solver<false, true, true, 1>,  k_solver<true, true, true, 1>,
@@ -969,10 +972,16 @@ cudaError_t launch_solver(const ModelDev& m, const DataDev& d, cudaStream_t s) {
     k_solver<false, true, false, 4>,  k_solver<true, true, false, 4>};
   void (*kern)(ModelDev, DataDev) = kerns[which];
   int ci = which;
-#ifdef MJB_SOL_PLAIN
+  // no equality and no friction-loss rows possible: the instantiation with ne = nf = 0 compiled in (humanoid solver 202 -> 181 us: the
+  // line-search loops lose two of their three row kinds, and with them instructions and instruction-cache footprint)
   const bool plain = m.neq == 0 && m.nfricdof == 0 && m.ntenfric == 0 && m.ntendon == 0;
-  if (which == 0 && plain) { kern = k_solver<false, false, false, 1, true>; ci = 14; }
-#endif
+  if (which == 0 && plain) {
+    kern = k_solver<false, false, false, 1, true>; ci = 14;
+    // ... and the register-row size fixed (one Hessian / Cholesky variant in the kernel instead of five: 182 -> 178 us)
+    if (m.nv > 24 && m.nv <= 28 && d.nv_pad == 28) { kern = k_solver<false, false, false, 1, true, 28>; ci = 15; }
+    else if (m.nv > 28 && d.nv_pad == 32) { kern = k_solver<false, false, false, 1, true, 32>; ci = 16; }
+  }
+  if (which == 8 && plain) { kern = k_solver<false, true, false, 1, true>; ci = 17; }  // nv > 32 (unitree G1, three_humanoids)
   if (smem > 48 * 1024 && smem > configured[ci]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -102,6 +102,7 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // the constant coefficients (Model.ten_J0, in the sparsity of ten_J_colind)
 __device__ __forceinline__ float tendon_length(const ModelDev& m, int t, const float* qpos) {
   float len = 0.f;
+#pragma unroll 1
   for (int k = m.tendon_adr[t]; k < m.tendon_adr[t] + m.tendon_num[t]; k++) len += m.wrap_prm[k] * qpos[m.jnt_qposadr[m.wrap_objid[k]]];
   return len;
 }
