@@ -1,8 +1,9 @@
 #!/bin/bash
+# PLAIN instantiation of the nv > 32 solver path: parity + bench lines of the two workloads it serves
 cd "${GRAFT_REPO_ROOT:-.}"
-for warm in 20 200; do
-  echo "== pre (plain, unrolled stager fallbacks) $warm"; MJB_LIB=build_ab/libmjb200_pre.so python tools/ktime.py 8192 $warm 60 2>/dev/null | cut -c1-330
-  echo "== default (nreg, rolled stager fallbacks) $warm"; python tools/ktime.py 8192 $warm 60 2>/dev/null | cut -c1-330
-  echo "== constpad $warm"; MJB_LIB=build_ab/libmjb200_constpad.so python tools/ktime.py 8192 $warm 60 2>/dev/null | cut -c1-330
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_golden_pipeline.py tests/test_gpu_api.py tests/test_gpu_parity.py -m gpu -q -k "g1 or three or sparse or G1 or replay" 2>&1 | tail -4
+for wl in g1 three_humanoids; do
+  timeout 400 python bench.py --workload $wl --steps 100 --warmup 20 > gpurun_out/r02_bench_$wl.json 2>> gpurun_out/r02_bench.err; echo "$wl rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_$wl.json')); print(d['value'], d['e2e']['value'], d['kernel_ms'])"
 done
-MJB_LIB=build_ab/libmjb200_constpad.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3
