@@ -29,7 +29,9 @@
  *   mjb_rungekutta4            <- _src/forward.py:523  rungekutta4(m, d)
  *   mjb_solve                  <- _src/solver.py:3671  solve
  *   mjb_euler                  <- _src/forward.py:387  euler (always the semi-implicit Euler update, whatever the model's integrator)
- *   mjb_implicit               <- _src/forward.py:578  implicit (implicitfast: M - dt * qDeriv factor-and-solve, then advance)
+ *   mjb_implicit               <- _src/forward.py:578  implicit (integrator IMPLICIT: qLU = M - dt (qDeriv_smooth + d RNE / d qvel) in the
+ *                                                      D-structure, LU solve, Data.qLU written; IMPLICITFAST: symmetric M - dt qDeriv, Cholesky;
+ *                                                      then advance.  Error for Euler / RK4 models: the scratch is sized per integrator)
  *   mjb_ctrl_noise             <- _src/cli.py:103      _ctrl_noise (harness kernel, untimed in testspeed)
  *
  * Conventions: plain pointers and sizes only (no torch / warp types).  All array pointers are DEVICE

@@ -313,6 +313,9 @@ def _validate(mjm):
   for n in ("dof_dampingpoly", "jnt_stiffnesspoly"):
     if hasattr(mjm, n) and np.any(np.asarray(getattr(mjm, n)) != 0):
       raise NotImplementedError(f"{n}: polynomial stiffness / damping is not implemented")
+  gt_ = np.asarray(mjm.geom_type)
+  if np.isin(gt_, (C.GEOM_HFIELD, C.GEOM_SDF)).any():
+    raise NotImplementedError("height-field / SDF geoms are not implemented (plane, sphere, capsule, ellipsoid, cylinder, box and mesh geoms are)")
   if mjm.nv > 128:
     # the dense per-world Hessian and its factor live in one warp's shared memory; make_data reports the exact per-kernel need
     raise NotImplementedError("nv > 128 is not supported in this version (dense per-world Jacobian/Hessian in shared memory)")

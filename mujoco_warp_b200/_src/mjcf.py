@@ -504,6 +504,17 @@ def compile_xml(root):
       flat.append(child)
   root = _merge_toplevel(flat)
 
+  # top-level sections: the ones compiled below, the ones without influence on the dynamics (visual, statistic, custom, size), and the ones
+  # whose content cannot be dropped without changing the simulation
+  for child in root:
+    if not isinstance(child.tag, str):
+      continue
+    if child.tag in ("deformable", "extension"):
+      if len(child):
+        raise NotImplementedError(f"<{child.tag}> (flex / skin / plugin declarations) is not supported by this compiler")
+    elif child.tag not in ("compiler", "option", "size", "visual", "statistic", "default", "asset", "worldbody", "contact", "equality", "tendon",
+                           "actuator", "sensor", "keyframe", "custom"):
+      raise NotImplementedError(f"unknown top-level element <{child.tag}>")
   compiler = {"angle": "degree", "eulerseq": "xyz", "autolimits": True, "inertiafromgeom": "auto", "boundmass": 0.0, "boundinertia": 0.0}
   for ce in root.findall("compiler"):
     if "angle" in ce.attrib:
@@ -778,6 +789,13 @@ def compile_xml(root):
         lights.append(dict(name=a.get("name", f"light{len(lights)}"), bodyid=bid, pos=_vec(a.get("pos"), default=[0, 0, 0]), dir=d / np.linalg.norm(d), mode=C.CAMLIGHT_MODES[a.get("mode", "fixed")], target=a.get("target")))
       elif tag == "body":
         pass
+      elif tag in ("flexcomp", "composite", "plugin"):
+        # deformable / procedurally generated bodies would change the dynamics if they were dropped: say so instead
+        raise NotImplementedError(f"<{tag}> inside <body> is not supported by this compiler (flex / composite / plugin bodies)")
+      elif not isinstance(tag, str) or tag in ("frame", "replicate", "attach"):
+        pass  # comments; composite wrappers are expanded before this pass
+      else:
+        raise NotImplementedError(f"unknown element <{tag}> inside <body>")
     for child in elem:
       if child.tag == "body":
         add_body(child, bid, childclass)
