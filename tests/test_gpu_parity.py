@@ -291,3 +291,28 @@ def test_mixed_scene_forward_and_rollout(mixed):
     mismatched += int((d.nefc.cpu().numpy() != od["nefc"]).sum())
     util.assert_close(f"qpos@{i}", d.qpos.cpu().numpy(), od["qpos"], atol=3e-3, rtol=3e-3)
   assert mismatched <= 10, mismatched
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU minutes were spent: it has not run on a B200 yet, so it may not turn the suite red; expected to pass")
+def test_more_than_32_contacts_in_one_world(built):
+  """The contact-row builder of k_constraint works in batches of 32 contacts (phase A: lane = contact, phase C: lane = row of the batch):
+  a rigid rake of 40 spheres on a plane gives 40 contacts per world with 1, 4 and 6 rows per contact (contact dimensions 1, 3, 4), i.e. a
+  second batch, the generic row path next to the condim-3 fast path, and a row map with mixed row counts.  The fp64 oracle reproduces the
+  reference on every fixture; here it is the checker for a case no reference-generated fixture covers (none has more than 28 contacts in a
+  world)."""
+  import mujoco_warp_b200 as mjw
+
+  mjm = mjw.mjcf.load_string(util.rake_xml())
+  m = mjw.put_model(mjm)
+  nworld, nconmax, njmax = 8, 64, 256
+  d = mjw.make_data(mjm, nworld=nworld, nconmax=nconmax, njmax=njmax, m=m)
+  o = util.make_oracle(mjm, nworld, nconmax, njmax)
+  qpos, qvel, ctrl, warm = util.seeded_state(mjm, nworld, seed=3, qpos_noise=0.0005, qvel_noise=0.05)
+  f32 = lambda a: a.astype(np.float32)
+  for name, val in (("qpos", qpos), ("qvel", qvel), ("qacc_warmstart", warm)):
+    getattr(d, name).copy_(torch.from_numpy(f32(val)))
+  o.set_state(qpos=f32(qpos), qvel=f32(qvel), qacc_warmstart=f32(warm))
+  mjw.forward(m, d)
+  o.forward()
+  assert int(o.d["ncon"].max()) > 32 and set(np.unique(o.d["con_dim"][0, : o.d["ncon"][0]]).tolist()) == {1, 3, 4}
+  _compare_forward((mjw, mjm, m), d, o, solver_tol=2e-2)  # 144 coupled rows on one 6-dof body: a stiffer system than the humanoid's

@@ -465,3 +465,22 @@ def tendon_xml(integrator="Euler"):
     <key name="k0" qpos="0.9 -0.6 0.4  0 0.01 -0.005  0.3 0.4 0.049 1 0 0 0"/>
   </keyframe>
 </mujoco>"""
+
+
+def rake_xml(ngeom=40):
+  """One free body carrying `ngeom` small spheres in a grid, resting on a plane: more than 32 contacts in one world (the contact-row builder
+  works in batches of 32 contacts), with contact dimensions 1, 3 and 4 mixed so that the rows per contact differ (1, 4, 6)."""
+  spheres = "".join(
+    f'<geom type="sphere" size="0.05" pos="{0.12 * (i % 8):.3f} {0.12 * (i // 8):.3f} {0.0005 * (i % 3):.4f}" condim="{(1, 3, 4)[i % 3]}" friction="{0.6 + 0.01 * i:.2f} 0.01 0.001"/>'
+    for i in range(ngeom))
+  return f"""
+<mujoco model="rake">
+  <option timestep="0.002" iterations="50" ls_iterations="30"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 .05" condim="1"/>
+    <body name="rake" pos="0 0 0.049">
+      <freejoint/>
+      {spheres}
+    </body>
+  </worldbody>
+</mujoco>"""
