@@ -1,4 +1,4 @@
-"""Summarise an `ncu --set full` capture exported with --page raw / --page source (see tools/gpu_r2_e.sh).
+"""Summarise an `ncu --set full` capture exported with --page raw / --page source (see tools/final_gpu_run.sh).
 usage: python tools/ncu_summary.py <raw.csv> <src.csv> [topN]"""
 import collections
 import csv
