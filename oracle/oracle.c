@@ -2444,6 +2444,13 @@ static void ell_alpha_zero(real mu, const real* q, const real* q1, const real* q
     out[0] = cost0; out[1] = dm * r0 * r1; out[2] = dm * (r1 * r1 - mu * r0 * T2);
   }
 }
+/* exported for the reference's known-answer vectors (solver_test.py:296-350): _compute_efc_eval_pt_elliptic on a primary row */
+void orc_elliptic_eval_pt(double alpha, const real* quad, const real* quad1, const real* quad2, double mu, real* out) {
+  real cost0, T0, r0; int st;
+  ell_reference((real)mu, quad, quad1, quad2, &cost0, &T0, &r0, &st);
+  ell_shifted((real)mu, quad, quad1, quad2, (real)alpha, cost0, T0, r0, st, out);
+}
+void orc_elliptic_zero(const real* quad, const real* quad1, const real* quad2, double mu, real* out) { ell_alpha_zero((real)mu, quad, quad1, quad2, out); }
 /* per-contact quad / quad1 / quad2 for the current (Jaref, jv) -- solver.py:957-1015 */
 static void ell_prepare(W* w, SCtx* c, int nefc) {
   const OrcModel* m = w->m; const int np = m->nmaxpyramid;

@@ -61,6 +61,10 @@ void orc_closest_segment_to_segment_points(const real a0[3], const real a1[3], c
 int orc_upper_tri_index(int n, int i, int j);
 int orc_upper_trid_index(int n, int i, int j);
 double orc_halton(int index, int base);
+/* solver.py:521-551 shifted cost / gradient / curvature of one elliptic contact at step alpha (quad = (q0, q1, q2), quad1 = (u0, v0, uu),
+ * quad2 = (uv, vv, dm)); orc_elliptic_zero: the absolute value at alpha = 0 (solver.py:308-320) */
+void orc_elliptic_eval_pt(double alpha, const real* quad, const real* quad1, const real* quad2, double mu, real* out);
+void orc_elliptic_zero(const real* quad, const real* quad1, const real* quad2, double mu, real* out);
 /* convex pair (GJK / EPA / box multi-contact) on two posed geoms; returns the contact count, witnesses in w1 / w2 (4 x 3 each) */
 int orc_ccd(int type1, const real* size1, const real* pos1, const real* mat1, int type2, const real* size2, const real* pos2, const real* mat2,
             real margin, real tolerance, real cutoff, int iterations, int multi, real* dist, real* w1, real* w2, int* overflow);
